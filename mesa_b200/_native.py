@@ -1,0 +1,94 @@
+"""ctypes binding of libmesa_b200.so — the C-ABI boundary (include/mesa_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a symbol cannot be
+resolved the import of any compute entry point raises.  Argument errors reported by
+the library (MB_ERR_INVALID) surface as ``ValueError`` like the reference's own
+parameter validation (mesa/discrete_space/grid.py:280-286).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_uint32, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmesa_b200.so")
+
+MB_OK = 0
+MB_ERR_INVALID = -1
+MB_ERR_CUDA = -2
+MB_ERR_WORKSPACE = -3
+MB_ERR_UNSUPPORTED = -4
+
+
+class NativeLibraryMissing(ImportError):
+    """libmesa_b200.so has not been built (python -m mesa_b200.build)."""
+
+
+class MesaB200Error(RuntimeError):
+    """A CUDA/runtime failure reported through the C ABI."""
+
+
+_P = c_void_p  # device or host pointer
+_S = c_void_p  # cudaStream_t
+
+# name -> (restype, argtypes).  Kept in the same order as include/mesa_b200.h.
+SIGNATURES: dict[str, tuple] = {
+    "mb_version": (c_int, []),
+    "mb_last_error": (c_char_p, []),
+    "mb_sm_count": (c_int, []),
+    # Game of Life
+    "mb_gol_step_u8": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, _S]),
+}
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) and return the shared library with typed entry points."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryMissing(
+            f"{LIB_PATH} not found: build it with `python -m mesa_b200.build` "
+            "(mesa_b200 has no CPU fallback)"
+        )
+    handle = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(handle, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = handle
+    return _lib
+
+
+def last_error() -> str:
+    msg = lib().mb_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc: int) -> None:
+    """Map a C-ABI return code to the exception the reference would raise."""
+    if rc == MB_OK:
+        return
+    msg = last_error()
+    if rc == MB_ERR_INVALID:
+        raise ValueError(msg)
+    if rc == MB_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise MesaB200Error(f"[{rc}] {msg}")
+
+
+def ptr(t) -> int | None:
+    """Device (or pinned host) address of a torch tensor; None passes NULL."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr(device=None) -> int:
+    """cudaStream_t of torch's current stream on `device`."""
+    import torch
+
+    return torch.cuda.current_stream(device).cuda_stream
