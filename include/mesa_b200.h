@@ -51,6 +51,36 @@ int mb_sm_count(void);
 int mb_gol_step_u8(const uint8_t* in, const uint8_t* halo_top, const uint8_t* halo_bot, uint8_t* out,
                    int64_t rows, int64_t cols, int col_torus, mb_stream_t stream);
 
+/* ---- Schelling happiness (replaces AgentSet.do("assign_state") over
+ * examples/basic/schelling/agents.py:24-42; neighbourhood = cell.py:225-276, Moore radius r) ----
+ * type: int8 layer, -1 = empty cell, >= 0 = agent type (capacity-1 grid).  happy: uint8 layer out
+ * (1 = happy agent; 0 = unhappy agent or empty cell).  halo_top / halo_bot: [radius, cols] rows
+ * above / below the block (NULL = outside the grid).  min_similar_host: HOST table of
+ * (2r+1)^2 entries, entry v = smallest `similar` with `not (similar / v < homophily)` in the
+ * reference's float arithmetic (> v = never happy).  binary_types != 0 promises types in {0,1}
+ * (enables the packed-byte kernel).  happy_count: device uint64, receives model.happy. */
+int mb_schelling_happy_i8(const int8_t* type, const int8_t* halo_top, const int8_t* halo_bot, uint8_t* happy,
+                          int64_t rows, int64_t cols, int radius, int col_torus,
+                          const uint8_t* min_similar_host, int binary_types,
+                          unsigned long long* happy_count, mb_stream_t stream);
+
+/* ---- Schelling relocation (replaces AgentSet.shuffle_do("step"), agentset.py:772-787, over
+ * agents.py:44-47 -> Grid.select_random_empty_cell grid.py:288-316 -> HasCell.cell setter
+ * cell_agent.py:39-54).  Activation order = ascending Philox priority64(seed, epoch, agent);
+ * probes = the agent's keyed _randbelow(ncells) draws; result identical to the sequential
+ * reference driven with the same numbers (csrc/relocate.cu explains the fixed point).
+ * agent_id: uint32 layer, agent index sitting in each occupied cell; agent_cell: optional
+ * [nagents] uint32 inverse map (NULL to skip).  The workspace persists between calls
+ * (init once).  mb_schelling_relocate synchronises `stream`.  A full grid with an unhappy
+ * agent returns MB_ERR_INVALID (ValueError, grid.py:311-315). */
+int mb_relocate_workspace_bytes(int64_t ncells, int64_t max_movers, size_t* out);
+int mb_relocate_workspace_init(void* workspace, size_t workspace_bytes, int64_t ncells, int64_t max_movers,
+                               mb_stream_t stream);
+int mb_schelling_relocate(int8_t* type, uint8_t* happy, uint32_t* agent_id, uint32_t* agent_cell,
+                          int64_t ncells, uint64_t seed, uint32_t epoch, void* workspace,
+                          size_t workspace_bytes, int64_t max_movers, int64_t* out_movers,
+                          int* out_iterations, mb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

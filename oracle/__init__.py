@@ -66,3 +66,90 @@ def gol_step(state: np.ndarray, torus: bool = True) -> np.ndarray:
     if rc != 0:
         raise ValueError("gol_step: torus needs both dimensions >= 3")
     return out
+
+
+# ----------------------------------------------------------------------------- draw protocol
+def priority64(seed: int, epoch: int, agent: int) -> int:
+    f = lib().orc_priority64
+    f.restype = c_uint64
+    return int(f(c_uint64(seed), c_uint32(epoch), c_uint64(agent)))
+
+
+def activation_order(seed: int, epoch: int, n: int) -> np.ndarray:
+    order = np.empty(n, dtype=np.int64)
+    rc = lib().orc_activation_order(c_uint64(seed), c_uint32(epoch), c_int64(n), _p(order))
+    assert rc == 0
+    return order
+
+
+# ----------------------------------------------------------------------------- Schelling
+class SchellingState:
+    """Reference-shaped Schelling state: per-agent (registration order) cell/type/happy + occupancy."""
+
+    def __init__(self, rows: int, cols: int, cell, atype, happy=None):
+        self.rows, self.cols = int(rows), int(cols)
+        self.cell = np.ascontiguousarray(cell, dtype=np.int64).copy()
+        self.atype = np.ascontiguousarray(atype, dtype=np.int8).copy()
+        n = len(self.cell)
+        self.happy = np.zeros(n, np.uint8) if happy is None else np.ascontiguousarray(happy, dtype=np.uint8).copy()
+        self.occ = np.full(self.rows * self.cols, -1, dtype=np.int64)
+        self.occ[self.cell] = np.arange(n)
+        assert (self.occ >= 0).sum() == n, "capacity-1 grid: two agents share a cell"
+
+    @classmethod
+    def from_type_grid(cls, grid: np.ndarray):
+        """Agents registered row-major over occupied cells (schelling/model.py:72-81)."""
+        grid = np.asarray(grid)
+        flat = np.flatnonzero(grid.reshape(-1) >= 0)
+        return cls(grid.shape[0], grid.shape[1], flat, grid.reshape(-1)[flat])
+
+    @property
+    def n(self) -> int:
+        return len(self.cell)
+
+    def type_grid(self) -> np.ndarray:
+        g = np.full(self.rows * self.cols, -1, dtype=np.int8)
+        g[self.cell] = self.atype
+        return g.reshape(self.rows, self.cols)
+
+    def happy_grid(self) -> np.ndarray:
+        g = np.zeros(self.rows * self.cols, dtype=np.uint8)
+        g[self.cell] = self.happy
+        return g.reshape(self.rows, self.cols)
+
+    def id_grid(self) -> np.ndarray:
+        return self.occ.reshape(self.rows, self.cols).copy()
+
+    def assign_state(self, homophily: float, radius: int = 1, torus: bool = False) -> int:
+        f = lib().orc_schelling_assign
+        f.restype = c_int64
+        return int(f(c_int64(self.rows), c_int64(self.cols), c_int(radius), c_int(bool(torus)),
+                     c_double(homophily), c_int64(self.n), _p(self.cell), _p(self.atype), _p(self.happy),
+                     _p(self.occ)))
+
+    def move_unhappy(self, seed: int, epoch: int) -> tuple[int, int]:
+        """shuffle_do("step"); returns (movers, argwhere fallbacks)."""
+        f = lib().orc_schelling_move
+        f.restype = c_int64
+        nfb = c_int64(0)
+        movers = int(f(c_int64(self.rows * self.cols), c_int64(self.n), _p(self.cell), _p(self.happy),
+                       _p(self.occ), c_uint64(seed), c_uint32(epoch), ctypes.byref(nfb)))
+        if movers == -1:
+            raise ValueError("Grid is completely full. No empty cells available. Cannot select a random empty cell.")
+        assert movers >= 0
+        return movers, int(nfb.value)
+
+
+def happy_threshold_table(homophily: float, radius: int) -> np.ndarray:
+    """min_similar[valid] with the reference's float arithmetic (agents.py:31-39)."""
+    nmax = (2 * radius + 1) ** 2 - 1
+    tbl = np.zeros(nmax + 1, dtype=np.uint8)
+    for valid in range(nmax + 1):
+        t = valid + 1  # never happy
+        for similar in range(valid + 1):
+            frac = similar / valid if valid > 0 else 0.0
+            if not (frac < homophily):
+                t = similar
+                break
+        tbl[valid] = t
+    return tbl

@@ -110,3 +110,149 @@ ORC_API int orc_gol_step_u8(const uint8_t* in, uint8_t* out, int64_t rows, int64
     parallel_for(rows, gol_rows, &a);
     return 0;
 }
+
+/* ------------------------------------------------------------------ keyed draw protocol
+ * Same layout as oracle/philox.py and mesa_b200/csrc/philox.cuh. */
+enum { STREAM_PRIORITY = 0, STREAM_DRAW = 1, STREAM_INIT = 2 };
+
+static void philox_keyed(uint64_t seed, uint32_t epoch, uint64_t agent, uint32_t stream, uint32_t block,
+                         uint32_t out[4]) {
+    const uint32_t ctr[4] = {block, (uint32_t)agent, (uint32_t)((agent >> 32) & 0xffffu) | (stream << 16), epoch};
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    orc_philox4x32_10(ctr, key, out);
+}
+
+ORC_API uint64_t orc_priority64(uint64_t seed, uint32_t epoch, uint64_t agent) {
+    uint32_t o[4];
+    philox_keyed(seed, epoch, agent, STREAM_PRIORITY, 0, o);
+    return ((uint64_t)o[0] << 32) | (uint32_t)agent;
+}
+
+typedef struct {
+    uint64_t seed, agent;
+    uint32_t epoch, stream, c;
+    uint32_t cache[4];
+} draw_stream;
+
+static void ds_init(draw_stream* s, uint64_t seed, uint32_t epoch, uint64_t agent, uint32_t stream) {
+    s->seed = seed; s->agent = agent; s->epoch = epoch; s->stream = stream; s->c = 0;
+}
+static uint64_t ds_next64(draw_stream* s) {
+    uint64_t v;
+    if ((s->c & 1u) == 0) {
+        philox_keyed(s->seed, s->epoch, s->agent, s->stream, s->c >> 1, s->cache);
+        v = ((uint64_t)s->cache[0] << 32) | s->cache[1];
+    } else {
+        v = ((uint64_t)s->cache[2] << 32) | s->cache[3];
+    }
+    s->c++;
+    return v;
+}
+/* CPython 3.12 Lib/random.py:242-250 _randbelow_with_getrandbits */
+static uint64_t ds_randbelow(draw_stream* s, uint64_t n) {
+    int k = 0;
+    for (uint64_t t = n; t; t >>= 1) ++k; /* n.bit_length() */
+    uint64_t r = ds_next64(s) >> (64 - k);
+    while (r >= n) r = ds_next64(s) >> (64 - k);
+    return r;
+}
+
+typedef struct { uint64_t pri; int64_t idx; } pri_item;
+static int pri_cmp(const void* a, const void* b) {
+    const uint64_t x = ((const pri_item*)a)->pri, y = ((const pri_item*)b)->pri;
+    return (x > y) - (x < y);
+}
+/* activation order of agents 0..n-1 for shuffle number `epoch` (ascending priority64);
+ * replaces random.shuffle in mesa/agentset.py:772-787. */
+ORC_API int orc_activation_order(uint64_t seed, uint32_t epoch, int64_t n, int64_t* order) {
+    pri_item* it = (pri_item*)malloc(sizeof(pri_item) * (size_t)(n > 0 ? n : 1));
+    if (!it) return -1;
+    for (int64_t a = 0; a < n; ++a) { it[a].pri = orc_priority64(seed, epoch, (uint64_t)a); it[a].idx = a; }
+    qsort(it, (size_t)n, sizeof(pri_item), pri_cmp);
+    for (int64_t a = 0; a < n; ++a) order[a] = it[a].idx;
+    free(it);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ Schelling
+ * State mirrors the reference's objects: per agent (registration order = index) its flat
+ * cell id, type and happy flag; per cell the occupying agent index or -1 (capacity 1,
+ * examples/basic/schelling/model.py:45-47). */
+
+/* examples/basic/schelling/agents.py:24-42 assign_state for every agent
+ * (AgentSet.do, agentset.py:756-770); neighbourhood = cell.py:225-276 Moore radius r
+ * (Chebyshev square minus centre; clamped edges drop cells, torus wraps, grid.py:390-399).
+ * Returns model.happy. */
+ORC_API int64_t orc_schelling_assign(int64_t rows, int64_t cols, int radius, int torus, double homophily,
+                                     int64_t n, const int64_t* cell, const int8_t* atype, uint8_t* happy,
+                                     const int64_t* occ) {
+    int64_t total = 0;
+    for (int64_t a = 0; a < n; ++a) {
+        const int64_t i = cell[a] / cols, j = cell[a] % cols;
+        int64_t similar = 0, valid = 0;
+        for (int di = -radius; di <= radius; ++di) {
+            for (int dj = -radius; dj <= radius; ++dj) {
+                if (di == 0 && dj == 0) continue;
+                int64_t ni = i + di, nj = j + dj;
+                if (torus) {
+                    ni = ((ni % rows) + rows) % rows;
+                    nj = ((nj % cols) + cols) % cols;
+                } else if (ni < 0 || ni >= rows || nj < 0 || nj >= cols) {
+                    continue;
+                }
+                const int64_t b = occ[ni * cols + nj];
+                if (b < 0) continue;
+                ++valid;
+                similar += atype[b] == atype[a];
+            }
+        }
+        double frac = 0.0;
+        if (valid > 0) frac = (double)similar / (double)valid;
+        if (frac < homophily) {
+            happy[a] = 0;
+        } else {
+            happy[a] = 1;
+            ++total;
+        }
+    }
+    return total;
+}
+
+/* AgentSet.shuffle_do("step") (agentset.py:772-787) over agents.py:44-47:
+ * unhappy agents, in activation order, call Grid.select_random_empty_cell (grid.py:288-316:
+ * <= 50 probes random.choice(_celllist), first empty wins; else argwhere(empty) + choice)
+ * and move (cell_agent.py:39-54).  Returns the number of movers, or -1 on a full grid
+ * (ValueError in the reference).  *nfallback counts argwhere fallbacks. */
+ORC_API int64_t orc_schelling_move(int64_t ncells, int64_t n, int64_t* cell, const uint8_t* happy, int64_t* occ,
+                                   uint64_t seed, uint32_t epoch, int64_t* nfallback) {
+    int64_t* order = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+    if (!order || orc_activation_order(seed, epoch, n, order) != 0) { free(order); return -2; }
+    int64_t movers = 0, fb = 0;
+    for (int64_t q = 0; q < n; ++q) {
+        const int64_t a = order[q];
+        if (happy[a]) continue;
+        draw_stream ds;
+        ds_init(&ds, seed, epoch, (uint64_t)a, STREAM_DRAW);
+        int64_t dest = -1;
+        for (int p = 0; p < 50; ++p) {
+            const int64_t c = (int64_t)ds_randbelow(&ds, (uint64_t)ncells);
+            if (occ[c] < 0) { dest = c; break; }
+        }
+        if (dest < 0) {
+            int64_t nempty = 0;
+            for (int64_t c = 0; c < ncells; ++c) nempty += occ[c] < 0;
+            if (nempty == 0) { free(order); return -1; }
+            int64_t k = (int64_t)ds_randbelow(&ds, (uint64_t)nempty);
+            for (int64_t c = 0; c < ncells; ++c)
+                if (occ[c] < 0 && k-- == 0) { dest = c; break; }
+            ++fb;
+        }
+        occ[dest] = a;          /* add to the new cell first ... */
+        occ[cell[a]] = -1;      /* ... then leave the old one */
+        cell[a] = dest;
+        ++movers;
+    }
+    free(order);
+    if (nfallback) *nfallback = fb;
+    return movers;
+}
