@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the mesa_b200 hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[1], Conway's Game of Life on a 16384 x 16384
+uint8 torus layer; one "step" = one synchronous generation = 16384^2 agent-updates per GPU.
+With N GPUs the grid is row-sharded weak-scaling style: N blocks of 16384 x 16384 stacked into a
+[16384*N, 16384] torus, one block per rank, the two edge rows exchanged with the ring
+neighbours every step over NCCL (mesa_b200/sharding.py).
+
+Prints ONE JSON line (rank 0): `value` = agent-updates/s over all ranks with inputs resident in
+HBM (CUDA events, max over ranks); `e2e` = the same metric through the host-buffer API (pinned
+host -> device copy of the layer, one generation, device -> host copy, every step);
+`roofline` = algorithmic bytes (2 B per cell-update) / measured kernel time against
+MEASURED_PEAKS.json; `cpu_baseline` = the CPU oracle port on a bounded sample (rank 0, N=1).
+
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/, the reference
+itself is pure Python and is not on the GPU box) with all host threads on the same metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GRID = 16384
+ALG_BYTES_PER_UPDATE = 2  # uint8 read + uint8 write per cell-update
+L2_NOTE = "ping-pong layers 2 x 268 MB per GPU > 126 MB L2 (inputs larger than L2, no flush needed)"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU during the timed region (NVML)."""
+
+    def __init__(self, index: int, period: float = 0.02):
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+
+    def __enter__(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {
+                pynvml.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                pynvml.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                pynvml.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                pynvml.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            }
+
+            def run():
+                while not self._stop.is_set():
+                    try:
+                        self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for bit, nm in names.items():
+                            if mask & bit:
+                                self.reasons.add(nm)
+                    except Exception:
+                        pass
+                    self._stop.wait(self.period)
+
+            self._thr = threading.Thread(target=run, daemon=True)
+            self._thr.start()
+        except Exception:
+            self._thr = None
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=1.0)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def _physical_gpu_index(local_index: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_index])
+        except Exception:
+            return local_index
+    return local_index
+
+
+# --------------------------------------------------------------------------------------------
+# CPU side (oracle port): cpu_baseline leg and --impl reference
+# --------------------------------------------------------------------------------------------
+def cpu_gol_rate(rows: int, cols: int, steps: int, warmup: int, threads: int):
+    import numpy as np
+
+    import oracle
+
+    oracle.set_threads(threads)
+    rng = np.random.Generator(np.random.Philox(0))
+    a = (rng.random((rows, cols)) < 0.2).astype(np.uint8)
+    for _ in range(warmup):
+        a = oracle.gol_step(a, True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        a = oracle.gol_step(a, True)
+    dt = time.perf_counter() - t0
+    return rows * cols * steps / dt, dt / steps
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference's GoL step, all host threads, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    # calibrate on a small slab, then size the per-step sample so K+W steps fit in ~100 s
+    rate, _ = cpu_gol_rate(256, GRID, 1, 1, threads)
+    budget = 100.0 / max(1, args.steps + args.warmup)
+    rows = int(max(64, min(GRID, rate * budget / GRID)))
+    rows = max(64, rows // 64 * 64)
+    value, sec_per_step = cpu_gol_rate(rows, GRID, args.steps, args.warmup, threads)
+    sample = f"gol torus slab {rows}x{GRID} uint8 per step (of the {GRID}x{GRID} layer), C oracle port, {threads} threads"
+    line = {
+        "impl": "reference", "metric": "agent_updates_per_sec", "value": value, "unit": "agent-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "gol_16384x16384_u8_torus", "grid": [GRID, GRID], "torus": True, "sample_rows": rows},
+        "cpu_baseline": {"value": value, "unit": "agent-updates/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "agent-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# GPU side
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from mesa_b200 import ops
+    from mesa_b200.sharding import HaloExchanger
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (mesa_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    # synthetic initial state: alive with p=0.2 (conways_game_of_life/model.py:9-15), Philox-seeded
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    a = (torch.rand((GRID, GRID), device=dev, generator=g) < 0.2).to(torch.uint8)
+    b = torch.empty_like(a)
+    hx = HaloExchanger(GRID, torch.uint8, 1, True, dev) if world > 1 else None
+
+    def step(src, dst):
+        if hx is None:
+            ops.gol_step(src, out=dst, torus=True)
+        else:
+            top, bot = hx.exchange(src)
+            ops.gol_step(src, out=dst, torus=True, halo_top=top[0], halo_bot=bot[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(a, b)
+        a, b = b, a
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(_physical_gpu_index(local)) as clocks:
+        e0.record()
+        for _ in range(args.steps):
+            step(a, b)
+            a, b = b, a
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    updates = GRID * GRID * args.steps * world
+    value = updates / (ms * 1e-3)
+    ms_per_step = ms / args.steps
+
+    # ---- e2e: host buffers in, host buffers out, every step (public API: ops.gol_step) ----
+    e2e_steps = max(3, min(args.steps, 20))
+    h_in = torch.empty((GRID, GRID), dtype=torch.uint8).pin_memory()
+    h_out = torch.empty((GRID, GRID), dtype=torch.uint8).pin_memory()
+    h_in.copy_(a.cpu())
+    d_in = torch.empty_like(a)
+
+    def e2e_step():
+        d_in.copy_(h_in, non_blocking=True)
+        step(d_in, b)
+        h_out.copy_(b, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t.item())
+    e2e_value = GRID * GRID * e2e_steps * world / e2e_dt
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        achieved = ALG_BYTES_PER_UPDATE * GRID * GRID / (ms_per_step * 1e-3) / 1e9
+        line = {
+            "metric": "agent_updates_per_sec", "value": value, "unit": "agent-updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "gol_16384x16384_u8_torus", "grid_per_gpu": [GRID, GRID],
+                       "global_grid": [GRID * world, GRID], "torus": True,
+                       "parallelism": f"row-sharded x{world}, ring halo exchange (NCCL)" if world > 1 else "single GPU",
+                       "l2": L2_NOTE},
+            "e2e": {"value": e2e_value, "unit": "agent-updates/s", "h2d_bytes_per_step": GRID * GRID,
+                    "d2h_bytes_per_step": GRID * GRID, "steps": e2e_steps},
+            "gpu_launches": args.steps,
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": _ncu_traffic(), "peak_source": peak_src,
+                         "kernel": "gol_step_u8_vec", "algorithmic_bytes_per_launch": ALG_BYTES_PER_UPDATE * GRID * GRID},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            rate, _ = cpu_gol_rate(256, GRID, 1, 1, threads)
+            rows = max(64, min(GRID, int(rate * 5.0 / GRID)) // 64 * 64)  # ~5 s per step, 3 steps
+            v, _ = cpu_gol_rate(rows, GRID, 3, 1, threads)
+            line["cpu_baseline"] = {"value": v, "unit": "agent-updates/s", "cores": threads, "kind": "port",
+                                    "sample": f"gol torus slab {rows}x{GRID} uint8, 3 steps, C oracle port"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _ncu_traffic():
+    """dram bytes per launch of the GoL kernel from the committed ncu capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get("gol_step_u8_vec")
+    except Exception:
+        return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

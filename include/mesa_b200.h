@@ -81,6 +81,38 @@ int mb_schelling_relocate(int8_t* type, uint8_t* happy, uint32_t* agent_id, uint
                           size_t workspace_bytes, int64_t max_movers, int64_t* out_movers,
                           int* out_iterations, mb_stream_t stream);
 
+/* ---- stable LSD radix sort of (key, uint32) pairs (cell lists; no reference counterpart: the
+ * reference scans all agents per query, continuous_space.py:202-235) --------------------------
+ * Sorts on key bits [begin_bit, end_bit), 8 bits per pass, ping-ponging between buffer 0 and 1;
+ * *result_buffer tells which pair of buffers holds the result.  Equal keys keep input order. */
+int mb_sort_workspace_bytes(int64_t n, size_t* out);
+int mb_sort_pairs_u32(uint32_t* keys0, uint32_t* vals0, uint32_t* keys1, uint32_t* vals1, int64_t n,
+                      int begin_bit, int end_bit, void* workspace, size_t workspace_bytes, int* result_buffer,
+                      mb_stream_t stream);
+int mb_sort_pairs_u64(uint64_t* keys0, uint32_t* vals0, uint64_t* keys1, uint32_t* vals1, int64_t n,
+                      int begin_bit, int end_bit, void* workspace, size_t workspace_bytes, int* result_buffer,
+                      mb_stream_t stream);
+
+/* ---- continuous space (replaces experimental/continuous_space/continuous_space.py:169-298 and
+ * examples/basic/boid_flockers/agents.py:63-92 for all agents at once) -------------------------
+ * Positions / directions are float32 [n, 2] in storage-index order (ContinuousSpace._agent_positions
+ * rows, continuous_space.py:85-101).  The space is [x0, x0+size_x] x [y0, y0+size_y].
+ * mb_boids_step_f32 is one SYNCHRONOUS Boid.step of every agent (activation modes);
+ * neighbor_count (optional, [n]) receives len(neighbors).
+ * mb_radius_query_f32 is a batched get_agents_in_radius (dist <= radius, inclusive): first call
+ * with out_idx == NULL fills counts[nq]; the caller prefix-sums them into offsets[nq] and calls
+ * again to fill out_idx / out_dist (float64, the reference's distances) in ascending agent index.
+ * exclude[q] >= 0 drops that agent (ContinuousSpaceAgent.get_neighbors_in_radius). */
+int mb_celllist_workspace_bytes(int64_t n, double size_x, double size_y, double radius, size_t* out);
+int mb_boids_step_f32(const float* pos_in, const float* dir_in, float* pos_out, float* dir_out, int64_t n,
+                      double x0, double y0, double size_x, double size_y, int torus, double vision,
+                      double separation, double cohere, double separate, double match, double speed,
+                      uint32_t* neighbor_count, void* workspace, size_t workspace_bytes, mb_stream_t stream);
+int mb_radius_query_f32(const float* pos, int64_t n, double x0, double y0, double size_x, double size_y,
+                        int torus, const float* queries, const int32_t* exclude, int64_t nq, double radius,
+                        uint32_t* counts, const int64_t* offsets, int32_t* out_idx, double* out_dist,
+                        void* workspace, size_t workspace_bytes, int reuse_cell_list, mb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,19 @@ SIGNATURES: dict[str, tuple] = {
     "mb_relocate_workspace_init": (c_int, [_P, ctypes.c_size_t, c_int64, c_int64, _S]),
     "mb_schelling_relocate": (c_int, [_P, _P, _P, _P, c_int64, c_uint64, c_uint32, _P, ctypes.c_size_t,
                                       c_int64, ctypes.POINTER(c_int64), ctypes.POINTER(c_int), _S]),
+    # radix sort
+    "mb_sort_workspace_bytes": (c_int, [c_int64, ctypes.POINTER(ctypes.c_size_t)]),
+    "mb_sort_pairs_u32": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, _P, ctypes.c_size_t,
+                                  ctypes.POINTER(c_int), _S]),
+    "mb_sort_pairs_u64": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, _P, ctypes.c_size_t,
+                                  ctypes.POINTER(c_int), _S]),
+    # continuous space
+    "mb_celllist_workspace_bytes": (c_int, [c_int64, c_double, c_double, c_double, ctypes.POINTER(ctypes.c_size_t)]),
+    "mb_boids_step_f32": (c_int, [_P, _P, _P, _P, c_int64, c_double, c_double, c_double, c_double, c_int,
+                                  c_double, c_double, c_double, c_double, c_double, c_double, _P, _P,
+                                  ctypes.c_size_t, _S]),
+    "mb_radius_query_f32": (c_int, [_P, c_int64, c_double, c_double, c_double, c_double, c_int, _P, _P, c_int64,
+                                    c_double, _P, _P, _P, _P, _P, ctypes.c_size_t, c_int, _S]),
 }
 
 _lib = None

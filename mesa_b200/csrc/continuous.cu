@@ -1,0 +1,363 @@
+// Continuous space: cell list build, radius-neighbour search and the Boids step (K7+K8 of
+// SURVEY.md §2.4).
+//
+// Replaces, for all agents at once,
+//   mesa/experimental/continuous_space/continuous_space.py:202-235  calculate_distances
+//       torus: delta = abs(point - positions); delta = minimum(delta, size - delta);
+//              dists = sqrt(delta[:,0]**2 + delta[:,1]**2)
+//       non-torus: scipy cdist (Euclidean)
+//   continuous_space.py:237-247   get_agents_in_radius: dists <= radius (INCLUSIVE)
+//   continuous_space_agents.py:66-78   get_neighbors_in_radius: drops self
+//   continuous_space.py:169-200   calculate_difference_vector (torus: pick delta or
+//                                 delta - sign(delta)*size, whichever is STRICTLY smaller in magnitude)
+//   mesa/examples/basic/boid_flockers/agents.py:63-92   Boid.step
+//   continuous_space_agents.py:36-44 + continuous_space.py:285-298   position setter (wrap)
+//
+// The reference scans all N agents per query (O(N^2) per step).  Here agents are binned into
+// a uniform cell grid with edge >= radius (radix sort by cell id + boundary detection), and a
+// query only visits the 3x3 cells around it.
+//
+// State is fp32 (positions, directions); every pair predicate and the update arithmetic are
+// evaluated in fp64 with the reference's operation order (no FMA contraction), so for inputs
+// that are fp32-representable the neighbour SETS are bit-identical to the reference's and
+// the new position/direction differ only by the final fp32 rounding.
+//
+// The Boids step is SYNCHRONOUS (every boid reads the pre-step state), whereas
+// AgentSet.shuffle_do is sequential; DESIGN.md discusses the mode and how parity is checked
+// (reference Boid.step driven on frozen snapshots).
+#include "common.cuh"
+#include "sort.cuh"
+
+namespace {
+
+struct Geometry {
+    double x0, y0;      // lower corner (dimensions[:,0])
+    double sx, sy;      // size = dimensions[:,1] - dimensions[:,0]
+    int ncx, ncy;       // cells per axis (edge >= radius)
+    int torus;
+};
+
+__device__ __forceinline__ int cell_coord(double p, double lo, double size, int nc) {
+    int c = (int)floor((p - lo) * (double)nc / size);
+    return c < 0 ? 0 : (c >= nc ? nc - 1 : c);
+}
+
+__device__ __forceinline__ unsigned cell_of(const Geometry& g, float x, float y) {
+    return (unsigned)(cell_coord((double)y, g.y0, g.sy, g.ncy) * g.ncx + cell_coord((double)x, g.x0, g.sx, g.ncx));
+}
+
+__global__ void cell_keys(const float2* __restrict__ pos, int64_t n, Geometry g, uint32_t* __restrict__ keys,
+                          uint32_t* __restrict__ vals) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float2 p = pos[i];
+    keys[i] = cell_of(g, p.x, p.y);
+    vals[i] = (uint32_t)i;
+}
+
+__global__ void cell_ranges(const uint32_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ cell_start,
+                            uint32_t* __restrict__ cell_end) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t k = keys[i];
+    if (i == 0 || keys[i - 1] != k) cell_start[k] = (uint32_t)i;
+    if (i == n - 1 || keys[i + 1] != k) cell_end[k] = (uint32_t)(i + 1);
+}
+
+// packed[i] = (x, y, dx, dy) of the agent at sorted slot i
+__global__ void gather_state(const float2* __restrict__ pos, const float2* __restrict__ dir,
+                             const uint32_t* __restrict__ order, int64_t n, float4* __restrict__ packed) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t a = order[i];
+    const float2 p = pos[a];
+    const float2 d = dir != nullptr ? dir[a] : make_float2(0.f, 0.f);
+    packed[i] = make_float4(p.x, p.y, d.x, d.y);
+}
+
+// distance exactly as calculate_distances (continuous_space.py:223-235)
+__device__ __forceinline__ double ref_distance(const Geometry& g, double px, double py, double qx, double qy) {
+    double dx = fabs(px - qx), dy = fabs(py - qy);
+    if (g.torus) {
+        dx = fmin(dx, g.sx - dx);
+        dy = fmin(dy, g.sy - dy);
+    }
+    return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+}
+
+// one component of calculate_difference_vector (continuous_space.py:186-200)
+__device__ __forceinline__ double ref_delta(double q, double p, double size, int torus) {
+    const double d = q - p;
+    if (!torus) return d;
+    const double sgn = d > 0.0 ? 1.0 : (d < 0.0 ? -1.0 : 0.0);
+    const double inv = d - sgn * size;
+    return fabs(d) < fabs(inv) ? d : inv;
+}
+
+// visit the distinct cells of the 3x3 block around (cx, cy)
+template <typename F>
+__device__ __forceinline__ void for_neighbor_cells(const Geometry& g, int cx, int cy, F&& f) {
+    const int nx = g.ncx < 3 ? g.ncx : 3, ny = g.ncy < 3 ? g.ncy : 3;
+    for (int iy = 0; iy < ny; ++iy) {
+        int yy = g.ncy < 3 ? iy : cy + iy - 1;
+        if (yy < 0 || yy >= g.ncy) {
+            if (!g.torus) continue;
+            yy = (yy + g.ncy) % g.ncy;
+        }
+        for (int ix = 0; ix < nx; ++ix) {
+            int xx = g.ncx < 3 ? ix : cx + ix - 1;
+            if (xx < 0 || xx >= g.ncx) {
+                if (!g.torus) continue;
+                xx = (xx + g.ncx) % g.ncx;
+            }
+            f((unsigned)(yy * g.ncx + xx));
+        }
+    }
+}
+
+struct BoidParams {
+    double vision, separation, cohere, separate, match, speed;
+};
+
+__global__ void __launch_bounds__(128)
+boids_update(const float4* __restrict__ packed, const uint32_t* __restrict__ order,
+             const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end, int64_t n, Geometry g,
+             BoidParams bp, float2* __restrict__ pos_out, float2* __restrict__ dir_out,
+             uint32_t* __restrict__ nbr_count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 me = packed[i];
+    const double px = me.x, py = me.y;
+    const int cx = cell_coord(px, g.x0, g.sx, g.ncx), cy = cell_coord(py, g.y0, g.sy, g.ncy);
+    double cohx = 0.0, cohy = 0.0, sepx = 0.0, sepy = 0.0, mx = 0.0, my = 0.0;
+    unsigned k = 0;
+    for_neighbor_cells(g, cx, cy, [&](unsigned c) {
+        const uint32_t e = cell_end[c];
+        for (uint32_t j = cell_start[c]; j < e; ++j) {
+            if ((int64_t)j == i) continue;  // get_neighbors_in_radius drops self
+            const float4 o = packed[j];
+            const double d = ref_distance(g, px, py, (double)o.x, (double)o.y);
+            if (d <= bp.vision) {
+                const double ddx = ref_delta((double)o.x, px, g.sx, g.torus);
+                const double ddy = ref_delta((double)o.y, py, g.sy, g.torus);
+                cohx += ddx; cohy += ddy;
+                if (d < bp.separation) { sepx += ddx; sepy += ddy; }
+                mx += (double)o.z; my += (double)o.w;
+                ++k;
+            }
+        }
+    });
+    double dirx = me.z, diry = me.w;
+    double nx = px, ny = py;
+    if (k > 0) {
+        // agents.py:75-89
+        const double kk = (double)k;
+        dirx += (cohx * bp.cohere + (-1.0 * sepx * bp.separate) + mx * bp.match) / kk;
+        diry += (cohy * bp.cohere + (-1.0 * sepy * bp.separate) + my * bp.match) / kk;
+        const double norm = __dsqrt_rn(__dadd_rn(__dmul_rn(dirx, dirx), __dmul_rn(diry, diry)));
+        dirx /= norm;
+        diry /= norm;
+    }
+    nx += dirx * bp.speed;
+    ny += diry * bp.speed;
+    // position setter: in_bounds is inclusive on both ends (continuous_space.py:285-292)
+    const bool inb = nx >= g.x0 && nx <= g.x0 + g.sx && ny >= g.y0 && ny <= g.y0 + g.sy;
+    if (!inb && g.torus) {
+        // torus_correct: lo + np.mod(p - lo, size)  (floored modulo)
+        double rx = fmod(nx - g.x0, g.sx); if (rx != 0.0 && rx < 0.0) rx += g.sx;
+        double ry = fmod(ny - g.y0, g.sy); if (ry != 0.0 && ry < 0.0) ry += g.sy;
+        nx = g.x0 + rx;
+        ny = g.y0 + ry;
+    }
+    const uint32_t a = order[i];
+    pos_out[a] = make_float2((float)nx, (float)ny);
+    dir_out[a] = make_float2((float)dirx, (float)diry);
+    if (nbr_count != nullptr) nbr_count[a] = k;
+}
+
+// ---- radius queries (get_agents_in_radius for a batch of points) ---------------------------
+// pass 0 (out_idx == nullptr): counts[q] = #{agents with dist <= radius} (minus `exclude[q]` if given)
+// pass 1: fills out_idx/out_dist at offsets[q] .. in ascending agent index (storage order)
+__global__ void radius_query(const float4* __restrict__ packed, const uint32_t* __restrict__ order,
+                             const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end,
+                             Geometry g, const float2* __restrict__ queries, const int32_t* __restrict__ exclude,
+                             int64_t nq, double radius, uint32_t* __restrict__ counts,
+                             const int64_t* __restrict__ offsets, int32_t* __restrict__ out_idx,
+                             double* __restrict__ out_dist) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const float2 p = queries[q];
+    const double px = p.x, py = p.y;
+    const int cx = cell_coord(px, g.x0, g.sx, g.ncx), cy = cell_coord(py, g.y0, g.sy, g.ncy);
+    const int32_t skip = exclude != nullptr ? exclude[q] : -1;
+    unsigned k = 0;
+    const int64_t off = offsets != nullptr ? offsets[q] : 0;
+    for_neighbor_cells(g, cx, cy, [&](unsigned c) {
+        const uint32_t e = cell_end[c];
+        for (uint32_t j = cell_start[c]; j < e; ++j) {
+            const int32_t a = (int32_t)order[j];
+            if (a == skip) continue;
+            const float4 o = packed[j];
+            const double d = ref_distance(g, px, py, (double)o.x, (double)o.y);
+            if (d <= radius) {
+                if (out_idx != nullptr) {
+                    // insertion keeps the row sorted by agent index (rows are short)
+                    int64_t w = off + k;
+                    while (w > off && out_idx[w - 1] > a) {
+                        out_idx[w] = out_idx[w - 1];
+                        out_dist[w] = out_dist[w - 1];
+                        --w;
+                    }
+                    out_idx[w] = a;
+                    out_dist[w] = d;
+                }
+                ++k;
+            }
+        }
+    });
+    if (counts != nullptr) counts[q] = k;
+}
+
+struct CellListWs {
+    uint32_t *keys0, *vals0, *keys1, *vals1, *cell_start, *cell_end;
+    float4* packed;
+    void* sort_ws;
+    size_t sort_ws_bytes;
+};
+
+size_t carve(CellListWs* ws, char* base, int64_t n, int64_t ncells) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char* p = base ? base + off : nullptr;
+        off += (bytes + 255) & ~(size_t)255;
+        return p;
+    };
+    CellListWs t;
+    t.keys0 = (uint32_t*)take(4 * n);
+    t.vals0 = (uint32_t*)take(4 * n);
+    t.keys1 = (uint32_t*)take(4 * n);
+    t.vals1 = (uint32_t*)take(4 * n);
+    t.cell_start = (uint32_t*)take(4 * ncells);
+    t.cell_end = (uint32_t*)take(4 * ncells);
+    t.packed = (float4*)take(16 * n);
+    t.sort_ws_bytes = mb::sort_workspace_bytes(n);
+    t.sort_ws = take(t.sort_ws_bytes);
+    if (ws) *ws = t;
+    return off;
+}
+
+int make_geometry(Geometry* g, double x0, double y0, double sx, double sy, double radius, int torus) {
+    MB_REQUIRE(sx > 0.0 && sy > 0.0, "continuous space: size must be positive");
+    MB_REQUIRE(radius > 0.0, "continuous space: radius must be positive");
+    g->x0 = x0; g->y0 = y0; g->sx = sx; g->sy = sy; g->torus = torus;
+    // cell edge strictly larger than the radius so rounding can never push a neighbour two cells away
+    const double edge = radius * (1.0 + 1e-6);
+    int64_t ncx = (int64_t)floor(sx / edge), ncy = (int64_t)floor(sy / edge);
+    // cap the cell count: at most 2^26 cells (a few agents per cell is the useful regime)
+    while (ncx * ncy > (1ll << 26)) { ncx = (ncx + 1) / 2; ncy = (ncy + 1) / 2; }
+    g->ncx = (int)(ncx < 1 ? 1 : ncx);
+    g->ncy = (int)(ncy < 1 ? 1 : ncy);
+    return MB_OK;
+}
+
+// bins the agents; leaves order = vals (sorted slot -> agent), ranges and packed state in ws
+int build_cell_list(const float2* pos, const float2* dir, int64_t n, const Geometry& g, CellListWs& ws,
+                    uint32_t** order_out, cudaStream_t stream) {
+    const int64_t ncells = (int64_t)g.ncx * g.ncy;
+    int rc = mb::check_cuda(cudaMemsetAsync(ws.cell_start, 0, 4 * ncells, stream), "memset");
+    if (rc) return rc;
+    rc = mb::check_cuda(cudaMemsetAsync(ws.cell_end, 0, 4 * ncells, stream), "memset");
+    if (rc) return rc;
+    if (n == 0) { *order_out = ws.vals0; return MB_OK; }
+    const unsigned blocks = (unsigned)mb::ceil_div(n, 256);
+    cell_keys<<<blocks, 256, 0, stream>>>(pos, n, g, ws.keys0, ws.vals0);
+    int bits = 1;
+    while ((1ll << bits) < ncells) ++bits;
+    bits = (bits + 7) / 8 * 8;
+    const int where = mb::radix_sort_pairs<uint32_t>(ws.keys0, ws.vals0, ws.keys1, ws.vals1, n, 0, bits, ws.sort_ws,
+                                                     ws.sort_ws_bytes, stream);
+    if (where < 0) return where;
+    uint32_t* keys = where ? ws.keys1 : ws.keys0;
+    uint32_t* vals = where ? ws.vals1 : ws.vals0;
+    cell_ranges<<<blocks, 256, 0, stream>>>(keys, n, ws.cell_start, ws.cell_end);
+    gather_state<<<blocks, 256, 0, stream>>>(pos, dir, vals, n, ws.packed);
+    MB_LAUNCH_CHECK("build_cell_list");
+    *order_out = vals;
+    return MB_OK;
+}
+
+}  // namespace
+
+MB_API int mb_celllist_workspace_bytes(int64_t n, double size_x, double size_y, double radius, size_t* out) {
+    MB_REQUIRE(out != nullptr && n >= 0, "mb_celllist_workspace_bytes: bad argument");
+    Geometry g;
+    int rc = make_geometry(&g, 0.0, 0.0, size_x, size_y, radius, 1);
+    if (rc) return rc;
+    *out = carve(nullptr, nullptr, n, (int64_t)g.ncx * g.ncy);
+    return MB_OK;
+}
+
+MB_API int mb_boids_step_f32(const float* pos_in, const float* dir_in, float* pos_out, float* dir_out, int64_t n,
+                             double x0, double y0, double size_x, double size_y, int torus, double vision,
+                             double separation, double cohere, double separate, double match, double speed,
+                             uint32_t* neighbor_count, void* workspace, size_t workspace_bytes,
+                             cudaStream_t stream) {
+    MB_REQUIRE(n >= 0 && n < (1ll << 31), "mb_boids_step_f32: n out of range");
+    if (n == 0) return MB_OK;
+    MB_REQUIRE(pos_in && dir_in && pos_out && dir_out && workspace, "mb_boids_step_f32: null buffer");
+    MB_REQUIRE(pos_in != pos_out && dir_in != dir_out, "mb_boids_step_f32: in/out must not alias (synchronous step)");
+    Geometry g;
+    int rc = make_geometry(&g, x0, y0, size_x, size_y, vision, torus);
+    if (rc) return rc;
+    CellListWs ws;
+    if (carve(&ws, (char*)workspace, n, (int64_t)g.ncx * g.ncy) > workspace_bytes) {
+        mb::set_error("mb_boids_step_f32: workspace too small");
+        return MB_ERR_WORKSPACE;
+    }
+    uint32_t* order = nullptr;
+    rc = build_cell_list((const float2*)pos_in, (const float2*)dir_in, n, g, ws, &order, stream);
+    if (rc) return rc;
+    const BoidParams bp{vision, separation, cohere, separate, match, speed};
+    boids_update<<<(unsigned)mb::ceil_div(n, 128), 128, 0, stream>>>(ws.packed, order, ws.cell_start, ws.cell_end, n, g, bp,
+                                                                     (float2*)pos_out, (float2*)dir_out, neighbor_count);
+    MB_LAUNCH_CHECK("mb_boids_step_f32");
+    return MB_OK;
+}
+
+// Batched get_agents_in_radius.  Call with out_idx == NULL to get counts[nq]; prefix-sum them into
+// offsets[nq] (int64) and call again with out_idx/out_dist to fill the CSR rows (ascending agent index,
+// the reference's storage order).  exclude[q] >= 0 drops that agent (get_neighbors_in_radius).
+MB_API int mb_radius_query_f32(const float* pos, int64_t n, double x0, double y0, double size_x, double size_y,
+                               int torus, const float* queries, const int32_t* exclude, int64_t nq, double radius,
+                               uint32_t* counts, const int64_t* offsets, int32_t* out_idx, double* out_dist,
+                               void* workspace, size_t workspace_bytes, int reuse_cell_list, cudaStream_t stream) {
+    MB_REQUIRE(n >= 0 && n < (1ll << 31) && nq >= 0, "mb_radius_query_f32: size out of range");
+    if (nq == 0) return MB_OK;
+    MB_REQUIRE(queries && workspace && (n == 0 || pos), "mb_radius_query_f32: null buffer");
+    MB_REQUIRE((out_idx == nullptr) == (out_dist == nullptr), "mb_radius_query_f32: out_idx and out_dist go together");
+    MB_REQUIRE(out_idx == nullptr || offsets != nullptr, "mb_radius_query_f32: fill pass needs offsets");
+    Geometry g;
+    int rc = make_geometry(&g, x0, y0, size_x, size_y, radius, torus);
+    if (rc) return rc;
+    CellListWs ws;
+    if (carve(&ws, (char*)workspace, n, (int64_t)g.ncx * g.ncy) > workspace_bytes) {
+        mb::set_error("mb_radius_query_f32: workspace too small");
+        return MB_ERR_WORKSPACE;
+    }
+    uint32_t* order = ws.vals0;
+    if (!reuse_cell_list) {
+        rc = build_cell_list((const float2*)pos, nullptr, n, g, ws, &order, stream);
+        if (rc) return rc;
+        // keep the order in vals0 so a later call with reuse_cell_list finds it
+        if (order != ws.vals0) {
+            rc = mb::check_cuda(cudaMemcpyAsync(ws.vals0, order, 4 * n, cudaMemcpyDeviceToDevice, stream), "copy order");
+            if (rc) return rc;
+            order = ws.vals0;
+        }
+    }
+    radius_query<<<(unsigned)mb::ceil_div(nq, 128), 128, 0, stream>>>(ws.packed, order, ws.cell_start, ws.cell_end, g,
+                                                                      (const float2*)queries, exclude, nq, radius, counts,
+                                                                      offsets, out_idx, out_dist);
+    MB_LAUNCH_CHECK("mb_radius_query_f32");
+    return MB_OK;
+}

@@ -18,16 +18,15 @@
 // packed bytes (4 cells per 32-bit ALU op).
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 constexpr int kWarps = 8;       // warps per CTA
-constexpr int kRowsPerWarp = 64;  // rows walked by one warp (2 halo rows re-read per segment)
-constexpr int kUnroll = 4;      // rows loaded ahead of the compute (16 B x 4 in flight per lane)
-
-struct Row {
-    uint4 v;        // 16 cells of this lane
-    unsigned l, r;  // cell left of v / right of v (only meaningful on strip-edge lanes)
-};
+// Tunables (template parameters of the vector kernel):
+//   kRowsPerWarp  rows walked by one warp (2 halo rows re-read per segment)
+//   kUnroll       rows loaded ahead of the compute (16 B x kUnroll in flight per lane)
+//   kMinBlocks    CTAs per SM the register budget is capped for
 
 __device__ __forceinline__ const uint8_t* row_ptr(const uint8_t* __restrict__ in,
                                                   const uint8_t* __restrict__ halo_top,
@@ -38,93 +37,136 @@ __device__ __forceinline__ const uint8_t* row_ptr(const uint8_t* __restrict__ in
     return in + r * cols;
 }
 
-__device__ __forceinline__ Row load_row(const uint8_t* __restrict__ p, int64_t col, bool active,
-                                        bool ld_left, bool ld_right, int64_t lcol, int64_t rcol) {
+// 16 cells of one lane plus the cell left / right of them (edge lanes only).
+struct Row {
+    uint4 v;
+    unsigned l, r;
+};
+
+// is-equal-to-3 on packed bytes whose values are < 0x80: 1 per byte where (n | c) == 3.
+// alive' = (n == 3) || (c && n == 2)  <=>  (n | c) == 3   (n = 0..8 neighbours, c = 0/1).
+__device__ __forceinline__ unsigned rule4(unsigned n, unsigned c) {
+    const unsigned x = (n | c) ^ 0x03030303u;             // 0 where equal
+    return (~((x + 0x7f7f7f7fu) >> 7)) & 0x01010101u;     // bit7 of x+0x7f is set iff x != 0
+}
+
+// Per-lane addressing of one strip: the lane's 16 cells and, on strip-edge lanes, the byte left /
+// right of them (torus wrap or absent).
+struct LaneAddr {
+    unsigned col, lcol, rcol;
+    bool active, ld_left, ld_right;
+};
+
+__device__ __forceinline__ Row load_row(const uint8_t* __restrict__ row, const LaneAddr& la) {
     Row x;
     x.v = make_uint4(0u, 0u, 0u, 0u);
     x.l = 0u;
     x.r = 0u;
-    if (p != nullptr) {
-        if (active) x.v = __ldg(reinterpret_cast<const uint4*>(p + col));
-        if (ld_left) x.l = __ldg(p + lcol);
-        if (ld_right) x.r = __ldg(p + rcol);
-    }
+    if (la.active) x.v = __ldg(reinterpret_cast<const uint4*>(row + la.col));
+    if (la.ld_left) x.l = __ldg(row + la.lcol);
+    if (la.ld_right) x.r = __ldg(row + la.rcol);
     return x;
 }
 
-// next state of 4 packed cells: n = neighbour count (0..8) per byte, c = current (0/1) per byte.
-// alive' = (n == 3) || (c && n == 2)  <=>  (n | c) == 3.
-__device__ __forceinline__ unsigned rule4(unsigned n, unsigned c) {
-    return __vcmpeq4(n | c, 0x03030303u) & 0x01010101u;
+__device__ __forceinline__ Row load_row_checked(const uint8_t* __restrict__ row, const LaneAddr& la) {
+    if (row == nullptr) {
+        Row x;
+        x.v = make_uint4(0u, 0u, 0u, 0u);
+        x.l = 0u;
+        x.r = 0u;
+        return x;
+    }
+    return load_row(row, la);
 }
 
-__global__ void __launch_bounds__(kWarps * 32)
+// next generation of the 16 cells of row b given the rows above (a) and below (c)
+__device__ __forceinline__ uint4 gol_rows(const Row& a, const Row& b, const Row& c, bool edge_l, bool edge_r) {
+    // vertical 3-sums per byte (<= 3)
+    uint4 s;
+    s.x = a.v.x + b.v.x + c.v.x;
+    s.y = a.v.y + b.v.y + c.v.y;
+    s.z = a.v.z + b.v.z + c.v.z;
+    s.w = a.v.w + b.v.w + c.v.w;
+    unsigned sl = __shfl_up_sync(0xffffffffu, s.w, 1) >> 24;
+    unsigned sr = __shfl_down_sync(0xffffffffu, s.x, 1) << 24;
+    if (edge_l) sl = a.l + b.l + c.l;
+    if (edge_r) sr = (a.r + b.r + c.r) << 24;
+    // horizontal 3-sums: left neighbour of byte k is byte k-1, crossing words
+    uint4 h;
+    h.x = s.x + ((s.x << 8) | sl) + __funnelshift_r(s.x, s.y, 8);
+    h.y = s.y + __funnelshift_l(s.x, s.y, 8) + __funnelshift_r(s.y, s.z, 8);
+    h.z = s.z + __funnelshift_l(s.y, s.z, 8) + __funnelshift_r(s.z, s.w, 8);
+    h.w = s.w + __funnelshift_l(s.z, s.w, 8) + ((s.w >> 8) | sr);
+    uint4 o;
+    o.x = rule4(h.x - b.v.x, b.v.x);
+    o.y = rule4(h.y - b.v.y, b.v.y);
+    o.z = rule4(h.z - b.v.z, b.v.z);
+    o.w = rule4(h.w - b.v.w, b.v.w);
+    return o;
+}
+
+template <int kRowsPerWarp, int kUnroll, int kMinBlocks>
+__global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 gol_step_u8_vec(const uint8_t* __restrict__ in, const uint8_t* __restrict__ halo_top,
-                const uint8_t* __restrict__ halo_bot, uint8_t* __restrict__ out, int64_t rows,
-                int64_t cols, int col_torus, int nstrips) {
+                const uint8_t* __restrict__ halo_bot, uint8_t* __restrict__ out, int rows, int cols,
+                int col_torus, int nstrips) {
     const int lane = threadIdx.x & 31;
-    const int64_t task = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
-    const int64_t strip = task % nstrips;
-    const int64_t seg = task / nstrips;
-    const int64_t row0 = seg * kRowsPerWarp;
+    const unsigned task = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const unsigned strip = task % (unsigned)nstrips;
+    const int row0 = (int)(task / (unsigned)nstrips) * kRowsPerWarp;
     if (row0 >= rows) return;  // whole warp exits together
 
-    const int64_t col = strip * 512 + lane * 16;
-    const bool active = col < cols;
+    LaneAddr la;
+    la.col = strip * 512u + lane * 16u;
+    la.active = la.col < (unsigned)cols;
     // Neighbours across the lane boundary come from the adjacent lane (shuffle) except at
     // the strip edges, where one extra byte per row is loaded.
-    bool ld_left = active && lane == 0;
-    bool ld_right = active && (lane == 31 || col + 16 >= cols);
-    int64_t lcol = col - 1, rcol = col + 16;
-    if (ld_left && lcol < 0) {
-        if (col_torus) lcol = cols - 1; else ld_left = false;
-    }
-    if (ld_right && rcol >= cols) {
-        if (col_torus) rcol = 0; else ld_right = false;
-    }
     const bool edge_l = lane == 0;
-    const bool edge_r = (lane == 31) || (col + 16 >= cols);
+    const bool edge_r = (lane == 31) || (la.col + 16u >= (unsigned)cols);
+    la.ld_left = la.active && edge_l;
+    la.ld_right = la.active && edge_r;
+    la.lcol = la.col - 1u;
+    la.rcol = la.col + 16u;
+    if (la.ld_left && la.col == 0u) {
+        if (col_torus) la.lcol = cols - 1; else la.ld_left = false;
+    }
+    if (la.ld_right && la.rcol >= (unsigned)cols) {
+        if (col_torus) la.rcol = 0u; else la.ld_right = false;
+    }
 
-    Row a = load_row(row_ptr(in, halo_top, halo_bot, row0 - 1, rows, cols), col, active, ld_left,
-                     ld_right, lcol, rcol);
-    Row b = load_row(row_ptr(in, halo_top, halo_bot, row0, rows, cols), col, active, ld_left,
-                     ld_right, lcol, rcol);
+    const int rend = min(row0 + kRowsPerWarp, rows);
+    const size_t pitch = (size_t)cols;
+    const uint8_t* rp = in + (size_t)row0 * pitch;                      // row r
+    Row a = load_row_checked(row0 > 0 ? rp - pitch : halo_top, la);     // row r-1
+    Row b = load_row(rp, la);
+    uint8_t* op = out + (size_t)row0 * pitch + la.col;
 
-    const int64_t rend = min(row0 + (int64_t)kRowsPerWarp, rows);
-    for (int64_t r = row0; r < rend; r += kUnroll) {
+    int r = row0;
+    // full groups whose look-ahead rows r+1 .. r+kUnroll all lie inside this block: no checks
+    for (; r + kUnroll <= rend && r + kUnroll < rows; r += kUnroll) {
         Row nx[kUnroll];
 #pragma unroll
-        for (int k = 0; k < kUnroll; ++k)
-            nx[k] = load_row(row_ptr(in, halo_top, halo_bot, r + k + 1, rows, cols), col, active,
-                             ld_left, ld_right, lcol, rcol);
+        for (int k = 0; k < kUnroll; ++k) nx[k] = load_row(rp + (size_t)(k + 1) * pitch, la);
+        rp += (size_t)kUnroll * pitch;
 #pragma unroll
         for (int k = 0; k < kUnroll; ++k) {
-            const Row c = nx[k];
-            // vertical 3-sums per byte (<= 3)
-            uint4 s;
-            s.x = a.v.x + b.v.x + c.v.x;
-            s.y = a.v.y + b.v.y + c.v.y;
-            s.z = a.v.z + b.v.z + c.v.z;
-            s.w = a.v.w + b.v.w + c.v.w;
-            unsigned sl = __shfl_up_sync(0xffffffffu, s.w >> 24, 1);
-            unsigned sr = __shfl_down_sync(0xffffffffu, s.x & 0xffu, 1);
-            if (edge_l) sl = a.l + b.l + c.l;
-            if (edge_r) sr = a.r + b.r + c.r;
-            // horizontal 3-sums: left neighbour of byte k is byte k-1, crossing words
-            uint4 h;
-            h.x = s.x + ((s.x << 8) | sl) + __funnelshift_r(s.x, s.y, 8);
-            h.y = s.y + __funnelshift_l(s.x, s.y, 8) + __funnelshift_r(s.y, s.z, 8);
-            h.z = s.z + __funnelshift_l(s.y, s.z, 8) + __funnelshift_r(s.z, s.w, 8);
-            h.w = s.w + __funnelshift_l(s.z, s.w, 8) + ((s.w >> 8) | (sr << 24));
-            uint4 o;
-            o.x = rule4(h.x - b.v.x, b.v.x);
-            o.y = rule4(h.y - b.v.y, b.v.y);
-            o.z = rule4(h.z - b.v.z, b.v.z);
-            o.w = rule4(h.w - b.v.w, b.v.w);
-            if (active && r + k < rend) __stcs(reinterpret_cast<uint4*>(out + (r + k) * cols + col), o);
+            const uint4 o = gol_rows(a, b, nx[k], edge_l, edge_r);
+            if (la.active) __stcs(reinterpret_cast<uint4*>(op), o);
+            op += pitch;
             a = b;
-            b = c;
+            b = nx[k];
         }
+    }
+    // remainder (at most kUnroll rows; touches the bottom halo when the block ends here)
+    for (; r < rend; ++r) {
+        const int rr = r + 1;
+        const Row c = load_row_checked(rr < rows ? rp + pitch : (rr == rows ? halo_bot : nullptr), la);
+        rp += pitch;
+        const uint4 o = gol_rows(a, b, c, edge_l, edge_r);
+        if (la.active) __stcs(reinterpret_cast<uint4*>(op), o);
+        op += pitch;
+        a = b;
+        b = c;
     }
 }
 
@@ -167,16 +209,30 @@ MB_API int mb_gol_step_u8(const uint8_t* in, const uint8_t* halo_top, const uint
     // A torus narrower than 3 cells aliases neighbours (cell.py:239-241 dedups them); the
     // stencil would double count, so reject instead of silently differing.
     MB_REQUIRE(!(col_torus && cols < 3), "mb_gol_step_u8: torus needs cols >= 3");
-    const bool aligned = (cols % 16 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0) &&
+    const bool aligned = (cols % 16 == 0) && rows < (1ll << 30) && cols < (1ll << 30) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
                          (halo_top == nullptr || (reinterpret_cast<uintptr_t>(halo_top) & 15) == 0) &&
                          (halo_bot == nullptr || (reinterpret_cast<uintptr_t>(halo_bot) & 15) == 0);
     if (aligned) {
         const int nstrips = (int)mb::ceil_div(cols, 512);
-        const int64_t tasks = (int64_t)nstrips * mb::ceil_div(rows, kRowsPerWarp);
-        const int64_t blocks = mb::ceil_div(tasks, kWarps);
-        gol_step_u8_vec<<<(unsigned)blocks, kWarps * 32, 0, stream>>>(in, halo_top, halo_bot, out, rows,
-                                                                      cols, col_torus, nstrips);
+        static const int variant = getenv("MB_GOL_VARIANT") ? atoi(getenv("MB_GOL_VARIANT")) : 0;
+#define MB_GOL_LAUNCH(RPW, UNR, MINB)                                                                     \
+    do {                                                                                                  \
+        const int64_t tasks = (int64_t)nstrips * mb::ceil_div(rows, RPW);                                 \
+        gol_step_u8_vec<RPW, UNR, MINB><<<(unsigned)mb::ceil_div(tasks, kWarps), kWarps * 32, 0, stream>>>( \
+            in, halo_top, halo_bot, out, (int)rows, (int)cols, col_torus, nstrips);                       \
+    } while (0)
+        switch (variant) {
+            case 1: MB_GOL_LAUNCH(32, 4, 3); break;
+            case 2: MB_GOL_LAUNCH(128, 4, 3); break;
+            case 3: MB_GOL_LAUNCH(64, 2, 4); break;
+            case 4: MB_GOL_LAUNCH(64, 4, 4); break;
+            case 5: MB_GOL_LAUNCH(64, 8, 2); break;
+            case 6: MB_GOL_LAUNCH(32, 2, 5); break;
+            case 7: MB_GOL_LAUNCH(128, 2, 5); break;
+            default: MB_GOL_LAUNCH(64, 4, 3); break;
+        }
+#undef MB_GOL_LAUNCH
     } else {
         const int64_t n = rows * cols;
         gol_step_u8_scalar<<<(unsigned)mb::ceil_div(n, 256), 256, 0, stream>>>(in, halo_top, halo_bot, out,

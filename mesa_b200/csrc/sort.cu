@@ -1,0 +1,176 @@
+// Stable LSD radix sort of (key, uint32) pairs -- see sort.cuh.
+#include "sort.cuh"
+
+namespace mb {
+namespace {
+
+constexpr int kWarpsPerCta = kSortThreads / 32;
+
+template <typename K>
+__global__ void __launch_bounds__(kSortThreads)
+sort_hist(const K* __restrict__ keys, int64_t n, int bit, uint32_t* __restrict__ hist, int64_t tiles) {
+    __shared__ unsigned sh[kRadix];
+    sh[threadIdx.x] = 0u;  // kSortThreads == kRadix
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * kSortTile;
+#pragma unroll
+    for (int i = 0; i < kSortItems; ++i) {
+        const int64_t idx = base + (int64_t)i * kSortThreads + threadIdx.x;
+        if (idx < n) atomicAdd(&sh[(unsigned)(keys[idx] >> bit) & 0xffu], 1u);
+    }
+    __syncthreads();
+    hist[(int64_t)threadIdx.x * tiles + blockIdx.x] = sh[threadIdx.x];
+}
+
+// exclusive scan of `total` uint32 counters in place, one CTA
+__global__ void __launch_bounds__(1024) sort_scan(uint32_t* __restrict__ hist, int64_t total) {
+    __shared__ unsigned warp_sum[32];
+    __shared__ unsigned carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0u;
+    __syncthreads();
+    // chunks of 1024*4 elements: thread handles 4 consecutive counters
+    for (int64_t c0 = 0; c0 < total; c0 += 4096) {
+        const int64_t i0 = c0 + (int64_t)tid * 4;
+        unsigned v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (i0 + k < total) ? hist[i0 + k] : 0u;
+        const unsigned tsum = v[0] + v[1] + v[2] + v[3];
+        unsigned incl = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned w = warp_sum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            warp_sum[lane] = w;  // inclusive
+        }
+        __syncthreads();
+        unsigned excl = carry + (warp > 0 ? warp_sum[warp - 1] : 0u) + incl - tsum;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i0 + k < total) hist[i0 + k] = excl;
+            excl += v[k];
+        }
+        __syncthreads();
+        if (tid == 1023) carry = excl;
+        __syncthreads();
+    }
+}
+
+template <typename K>
+__global__ void __launch_bounds__(kSortThreads)
+sort_scatter(const K* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, K* __restrict__ keys_out,
+             uint32_t* __restrict__ vals_out, int64_t n, int bit, const uint32_t* __restrict__ hist,
+             int64_t tiles) {
+    __shared__ unsigned base[kRadix];                   // next output slot of each digit for this CTA
+    __shared__ unsigned wcount[kWarpsPerCta][kRadix];   // per-warp digit counts of the current sub-chunk
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    base[tid] = hist[(int64_t)tid * tiles + blockIdx.x];
+    const int64_t tile0 = (int64_t)blockIdx.x * kSortTile;
+    for (int i = 0; i < kSortItems; ++i) {
+#pragma unroll
+        for (int w = 0; w < kWarpsPerCta; ++w) wcount[w][tid] = 0u;
+        __syncthreads();
+        const int64_t idx = tile0 + (int64_t)i * kSortThreads + tid;
+        const bool valid = idx < n;
+        K key = 0;
+        unsigned digit = 0xffffffffu;  // invalid lanes never match a real digit
+        if (valid) {
+            key = keys_in[idx];
+            digit = (unsigned)(key >> bit) & 0xffu;
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, digit);
+        const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+        if (valid && rank == 0) wcount[warp][digit] = __popc(peers);
+        __syncthreads();
+        if (valid) {
+            unsigned off = base[digit] + rank;
+            for (int w = 0; w < warp; ++w) off += wcount[w][digit];
+            keys_out[off] = key;
+            vals_out[off] = vals_in[idx];
+        }
+        __syncthreads();
+        unsigned add = 0;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerCta; ++w) add += wcount[w][tid];
+        base[tid] += add;
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+template <typename K>
+int radix_sort_pairs(K* k0, uint32_t* v0, K* k1, uint32_t* v1, int64_t n, int begin_bit, int end_bit,
+                     void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (n < 0 || begin_bit < 0 || end_bit > (int)(8 * sizeof(K)) || begin_bit > end_bit) {
+        set_error("radix_sort_pairs: bad argument");
+        return MB_ERR_INVALID;
+    }
+    if (n >= (1ll << 32)) {
+        set_error("radix_sort_pairs: n must be < 2^32");
+        return MB_ERR_UNSUPPORTED;
+    }
+    if (n == 0 || begin_bit == end_bit) return 0;
+    if (workspace == nullptr || workspace_bytes < sort_workspace_bytes(n)) {
+        set_error("radix_sort_pairs: workspace too small");
+        return MB_ERR_WORKSPACE;
+    }
+    const int64_t tiles = sort_num_tiles(n);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(workspace);
+    K* ks[2] = {k0, k1};
+    uint32_t* vs[2] = {v0, v1};
+    int cur = 0;
+    for (int bit = begin_bit; bit < end_bit; bit += 8) {
+        sort_hist<K><<<(unsigned)tiles, kSortThreads, 0, stream>>>(ks[cur], n, bit, hist, tiles);
+        sort_scan<<<1, 1024, 0, stream>>>(hist, (int64_t)kRadix * tiles);
+        sort_scatter<K><<<(unsigned)tiles, kSortThreads, 0, stream>>>(ks[cur], vs[cur], ks[cur ^ 1], vs[cur ^ 1], n,
+                                                                     bit, hist, tiles);
+        cur ^= 1;
+    }
+    if (check_cuda(cudaGetLastError(), "radix_sort_pairs") != MB_OK) return MB_ERR_CUDA;
+    return cur;
+}
+
+template int radix_sort_pairs<uint32_t>(uint32_t*, uint32_t*, uint32_t*, uint32_t*, int64_t, int, int, void*, size_t,
+                                        cudaStream_t);
+template int radix_sort_pairs<uint64_t>(uint64_t*, uint32_t*, uint64_t*, uint32_t*, int64_t, int, int, void*, size_t,
+                                        cudaStream_t);
+
+}  // namespace mb
+
+// ---- C ABI ---------------------------------------------------------------------------------
+MB_API int mb_sort_workspace_bytes(int64_t n, size_t* out) {
+    MB_REQUIRE(out != nullptr && n >= 0, "mb_sort_workspace_bytes: bad argument");
+    *out = mb::sort_workspace_bytes(n);
+    return MB_OK;
+}
+
+MB_API int mb_sort_pairs_u32(uint32_t* keys0, uint32_t* vals0, uint32_t* keys1, uint32_t* vals1, int64_t n,
+                             int begin_bit, int end_bit, void* workspace, size_t workspace_bytes,
+                             int* result_buffer, cudaStream_t stream) {
+    const int rc = mb::radix_sort_pairs<uint32_t>(keys0, vals0, keys1, vals1, n, begin_bit, end_bit, workspace,
+                                                  workspace_bytes, stream);
+    if (rc < 0) return rc;
+    if (result_buffer) *result_buffer = rc;
+    return MB_OK;
+}
+
+MB_API int mb_sort_pairs_u64(uint64_t* keys0, uint32_t* vals0, uint64_t* keys1, uint32_t* vals1, int64_t n,
+                             int begin_bit, int end_bit, void* workspace, size_t workspace_bytes,
+                             int* result_buffer, cudaStream_t stream) {
+    const int rc = mb::radix_sort_pairs<uint64_t>(keys0, vals0, keys1, vals1, n, begin_bit, end_bit, workspace,
+                                                  workspace_bytes, stream);
+    if (rc < 0) return rc;
+    if (result_buffer) *result_buffer = rc;
+    return MB_OK;
+}

@@ -1,0 +1,33 @@
+// Stable LSD radix sort of (key, uint32 value) pairs, 8 bits per pass: warp-level multi-split
+// (match_any ranks) + per-CTA digit histograms + one prefix scan per pass (K7 of SURVEY.md §2.4).
+//
+// Used for the cell list of the continuous space (key = cell id) and for the per-cell arrival
+// order of the Boltzmann model (key = cell id << 32 | Philox priority).  The reference has no
+// counterpart: it scans all agents per query (continuous_space.py:202-235) and keeps Python
+// lists per cell (cell.py:143-170).
+//
+// Stability matters: pairs enter in agent-index order, so equal keys keep ascending agent
+// index -- exactly the tie-break of priority64 (philox.cuh).
+#pragma once
+
+#include "common.cuh"
+
+namespace mb {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;                         // items per thread
+constexpr int kSortTile = kSortThreads * kSortItems;   // items per CTA
+constexpr int kRadix = 256;
+
+inline int64_t sort_num_tiles(int64_t n) { return ceil_div(n > 0 ? n : 1, kSortTile); }
+
+// workspace: histogram [kRadix][tiles] uint32 (digit-major so one scan orders digits first)
+inline size_t sort_workspace_bytes(int64_t n) { return sizeof(uint32_t) * kRadix * (size_t)sort_num_tiles(n) + 256; }
+
+// Sort n pairs on key bits [begin_bit, end_bit).  Ping-pongs between (k0,v0) and (k1,v1);
+// returns 0 if the result is in (k0,v0), 1 if in (k1,v1), negative on error.
+template <typename K>
+int radix_sort_pairs(K* k0, uint32_t* v0, K* k1, uint32_t* v1, int64_t n, int begin_bit, int end_bit,
+                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+}  // namespace mb

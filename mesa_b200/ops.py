@@ -133,3 +133,90 @@ def schelling_relocate(type_layer: torch.Tensor, happy: torch.Tensor, agent_id: 
             int(seed) & 0xFFFFFFFFFFFFFFFF, int(epoch) & 0xFFFFFFFF, N.ptr(ws.buf), ws.nbytes, ws.max_movers,
             ctypes.byref(movers), ctypes.byref(iters), N.stream_ptr(type_layer.device)))
     return int(movers.value), int(iters.value)
+
+
+# ----------------------------------------------------------------------------- sort
+def sort_pairs(keys: torch.Tensor, vals: torch.Tensor, begin_bit: int = 0, end_bit: int | None = None):
+    """Stable radix sort of (keys, vals); keys int32/int64 viewed as unsigned, vals int32.  Returns new tensors."""
+    import ctypes
+
+    _need_cuda(keys, vals)
+    n = keys.numel()
+    wide = keys.dtype in (torch.int64, torch.uint64)
+    if end_bit is None:
+        end_bit = 64 if wide else 32
+    k0, v0 = keys.clone(), vals.clone()
+    k1, v1 = torch.empty_like(k0), torch.empty_like(v0)
+    nbytes = ctypes.c_size_t(0)
+    N.check(N.lib().mb_sort_workspace_bytes(n, ctypes.byref(nbytes)))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=keys.device)
+    which = ctypes.c_int(0)
+    fn = N.lib().mb_sort_pairs_u64 if wide else N.lib().mb_sort_pairs_u32
+    with torch.cuda.device(keys.device):
+        N.check(fn(N.ptr(k0), N.ptr(v0), N.ptr(k1), N.ptr(v1), n, begin_bit, end_bit, N.ptr(ws), nbytes.value,
+                   ctypes.byref(which), N.stream_ptr(keys.device)))
+    return (k1, v1) if which.value else (k0, v0)
+
+
+# ----------------------------------------------------------------------------- continuous space
+class CellListWorkspace:
+    """Scratch of the cell-list kernels for up to `n` agents and query radius >= `radius`."""
+
+    def __init__(self, n: int, size, radius: float, device):
+        import ctypes
+
+        nbytes = ctypes.c_size_t(0)
+        N.check(N.lib().mb_celllist_workspace_bytes(int(n), float(size[0]), float(size[1]), float(radius),
+                                                    ctypes.byref(nbytes)))
+        self.n, self.radius, self.nbytes = int(n), float(radius), int(nbytes.value)
+        self.buf = torch.empty(max(self.nbytes, 1), dtype=torch.uint8, device=device)
+
+
+def boids_step(pos: torch.Tensor, direction: torch.Tensor, size, *, vision: float, separation: float,
+               cohere: float = 0.03, separate: float = 0.015, match: float = 0.05, speed: float = 1.0,
+               torus: bool = True, origin=(0.0, 0.0), ws: CellListWorkspace | None = None,
+               pos_out: torch.Tensor | None = None, dir_out: torch.Tensor | None = None,
+               neighbor_count: torch.Tensor | None = None):
+    """One synchronous Boid.step of all agents (float32 [n,2] state).  Returns (pos_out, dir_out)."""
+    _need_cuda(pos, direction, pos_out, dir_out, neighbor_count)
+    if pos.dtype != torch.float32 or direction.dtype != torch.float32 or pos.shape != direction.shape or pos.dim() != 2 or pos.shape[1] != 2:
+        raise ValueError("boids_step expects float32 [n, 2] positions and directions")
+    n = pos.shape[0]
+    if ws is None:
+        ws = CellListWorkspace(n, size, vision, pos.device)
+    if pos_out is None:
+        pos_out = torch.empty_like(pos)
+    if dir_out is None:
+        dir_out = torch.empty_like(direction)
+    with torch.cuda.device(pos.device):
+        N.check(N.lib().mb_boids_step_f32(
+            N.ptr(_c(pos)), N.ptr(_c(direction)), N.ptr(_c(pos_out)), N.ptr(_c(dir_out)), n, float(origin[0]),
+            float(origin[1]), float(size[0]), float(size[1]), int(bool(torus)), float(vision), float(separation),
+            float(cohere), float(separate), float(match), float(speed), N.ptr(neighbor_count), N.ptr(ws.buf),
+            ws.nbytes, N.stream_ptr(pos.device)))
+    return pos_out, dir_out
+
+
+def radius_query(pos: torch.Tensor, queries: torch.Tensor, size, radius: float, torus: bool = True,
+                 origin=(0.0, 0.0), exclude: torch.Tensor | None = None, ws: CellListWorkspace | None = None):
+    """Batched get_agents_in_radius: CSR (offsets[nq+1] int64, indices int32, distances float64)."""
+    _need_cuda(pos, queries, exclude)
+    n, nq = pos.shape[0], queries.shape[0]
+    if ws is None:
+        ws = CellListWorkspace(n, size, radius, pos.device)
+    counts = torch.zeros(nq, dtype=torch.int32, device=pos.device)
+    args = (float(origin[0]), float(origin[1]), float(size[0]), float(size[1]), int(bool(torus)))
+    with torch.cuda.device(pos.device):
+        st = N.stream_ptr(pos.device)
+        N.check(N.lib().mb_radius_query_f32(N.ptr(_c(pos)), n, *args, N.ptr(_c(queries)), N.ptr(exclude), nq,
+                                            float(radius), N.ptr(counts), None, None, None, N.ptr(ws.buf), ws.nbytes,
+                                            0, st))
+        offsets = torch.zeros(nq + 1, dtype=torch.int64, device=pos.device)
+        torch.cumsum(counts, 0, out=offsets[1:])
+        total = int(offsets[-1].item())
+        idx = torch.empty(total, dtype=torch.int32, device=pos.device)
+        dist = torch.empty(total, dtype=torch.float64, device=pos.device)
+        N.check(N.lib().mb_radius_query_f32(N.ptr(pos), n, *args, N.ptr(queries), N.ptr(exclude), nq, float(radius),
+                                            None, N.ptr(offsets), N.ptr(idx), N.ptr(dist), N.ptr(ws.buf), ws.nbytes,
+                                            1, st))
+    return offsets, idx, dist

@@ -153,3 +153,35 @@ def happy_threshold_table(homophily: float, radius: int) -> np.ndarray:
                 break
         tbl[valid] = t
     return tbl
+
+
+# ----------------------------------------------------------------------------- continuous space / Boids
+def boids_step(pos, direction, size, *, vision, separation, cohere=0.03, separate=0.015, match=0.05, speed=1.0,
+               torus=True, origin=(0.0, 0.0), order=None):
+    """One BoidFlockers step.  order=None -> synchronous (frozen snapshot); order=array -> the reference's
+    sequential shuffle_do in that activation order.  Returns (pos, dir, neighbour counts), float64."""
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    direction = np.ascontiguousarray(direction, dtype=np.float64)
+    n = pos.shape[0]
+    po, do = np.empty_like(pos), np.empty_like(direction)
+    cnt = np.zeros(n, dtype=np.int64)
+    od = None if order is None else np.ascontiguousarray(order, dtype=np.int64)
+    rc = lib().orc_boids_step(c_int64(n), _p(pos), _p(direction), _p(po), _p(do), c_double(origin[0]),
+                              c_double(origin[1]), c_double(size[0]), c_double(size[1]), c_int(bool(torus)),
+                              c_double(vision), c_double(separation), c_double(cohere), c_double(separate),
+                              c_double(match), c_double(speed), None if od is None else _p(od), _p(cnt))
+    assert rc == 0
+    return po, do, cnt
+
+
+def radius_query(pos, point, size, radius, torus=True, exclude=-1):
+    """(indices ascending, distances) of agents within `radius` (inclusive) of `point`."""
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    n = pos.shape[0]
+    idx = np.empty(n, dtype=np.int64)
+    dist = np.empty(n, dtype=np.float64)
+    f = lib().orc_radius_query
+    f.restype = c_int64
+    k = int(f(c_int64(n), _p(pos), c_double(point[0]), c_double(point[1]), c_double(size[0]), c_double(size[1]),
+              c_int(bool(torus)), c_double(radius), c_int64(exclude), _p(idx), _p(dist)))
+    return idx[:k].copy(), dist[:k].copy()

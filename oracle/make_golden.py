@@ -97,13 +97,81 @@ def schelling_fixture(name, width, height, density, homophily, radius, steps, mt
     print(name, "agents", len(agents), "happy", happy_counts[:5], "...", happy_counts[-1], "movers", movers[:5])
 
 
+# ------------------------------------------------------------------------------ Boids
+def boids_fixture(name, n, width, height, vision, separation, steps, seed, philox_seed):
+    """Synchronous goldens: the UNMODIFIED Boid.step of every agent driven on a frozen snapshot
+    (call, record, restore).  Inputs are fp32-representable so the device's fp32 state is exact.
+    Also a sequential golden: model.step() with the replayed activation order."""
+    from mesa.examples.basic.boid_flockers.model import BoidFlockers, BoidsScenario
+
+    def make():
+        with patched_model_random(philox_seed):
+            m = BoidFlockers(BoidsScenario(population_size=n, width=width, height=height, vision=vision,
+                                           separation=separation, rng=seed))
+        agents = sorted(m.agents, key=lambda a: a.unique_id)
+        assert [a._mesa_index for a in agents] == list(range(n))
+        m.space._agent_positions[:n] = m.space._agent_positions[:n].astype(np.float32)
+        for a in agents:
+            a.direction = np.asarray(a.direction, dtype=np.float64).astype(np.float32).astype(np.float64)
+        return m, agents
+
+    m, agents = make()
+    out = {"n": n, "size": np.array([width, height], dtype=np.float64), "vision": vision,
+           "separation": separation, "cohere": 0.03, "separate": 0.015, "match": 0.05, "speed": 1.0,
+           "philox_seed": np.uint64(philox_seed), "steps": steps}
+    for t in range(steps):
+        pos0 = m.space.agent_positions.copy()
+        dir0 = np.array([a.direction for a in agents])
+        assert np.array_equal(pos0, pos0.astype(np.float32)) and np.array_equal(dir0, dir0.astype(np.float32))
+        pos1, dir1 = np.empty_like(pos0), np.empty_like(dir0)
+        counts, idx = [], []
+        for i, a in enumerate(agents):
+            nb, _ = a.get_neighbors_in_radius(radius=vision)
+            counts.append(len(nb))
+            idx.extend(b._mesa_index for b in nb)
+            a.step()
+            pos1[i] = a.position
+            dir1[i] = a.direction
+            a.position = pos0[i]          # restore the snapshot
+            a.direction = dir0[i].copy()
+        out[f"pos_in_{t}"] = pos0.astype(np.float32)
+        out[f"dir_in_{t}"] = dir0.astype(np.float32)
+        out[f"pos_out_{t}"] = pos1
+        out[f"dir_out_{t}"] = dir1
+        out[f"nbr_count_{t}"] = np.array(counts, dtype=np.int32)
+        out[f"nbr_idx_{t}"] = np.array(idx, dtype=np.int32)
+        # next snapshot = what an fp32 state would hold
+        m.space._agent_positions[:n] = pos1.astype(np.float32)
+        for i, a in enumerate(agents):
+            a.direction = dir1[i].astype(np.float32).astype(np.float64)
+
+    # sequential (the reference's own shuffle_do semantics) with the replayed activation order
+    m, agents = make()
+    m.random.replay = True
+    out["seq_pos_0"] = m.space.agent_positions.copy()
+    out["seq_dir_0"] = np.array([a.direction for a in agents])
+    for t in range(1, 4):
+        m.step()
+        out[f"seq_pos_{t}"] = m.space.agent_positions.copy()
+        out[f"seq_dir_{t}"] = np.array([a.direction for a in agents])
+    np.savez_compressed(os.path.join(GOLDEN, name), **out)
+    print(name, "mean neighbours", float(np.mean(out["nbr_count_0"])))
+
+
 def main():
     import_reference()
     os.makedirs(GOLDEN, exist_ok=True)
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
+    if only == "boids":
+        boids_fixture("boids_300.npz", 300, 100, 100, 10.0, 2.0, 3, 42, 5)
+        boids_fixture("boids_120_wrap.npz", 120, 40, 30, 6.0, 2.0, 3, 1, 6)
+        return
     gol_fixture(37, 23, 42, 6, "gol_37x23.npz")
     gol_fixture(64, 48, 7, 20, "gol_64x48.npz")
     schelling_fixture("schelling_20x20_r1.npz", 20, 20, 0.8, 0.4, 1, 30, 42, 2024, full_steps=range(1, 31))
     schelling_fixture("schelling_16x48_r2.npz", 16, 48, 0.9, 0.6, 2, 12, 5, 99, full_steps=range(1, 13))
+    boids_fixture("boids_300.npz", 300, 100, 100, 10.0, 2.0, 3, 42, 5)
+    boids_fixture("boids_120_wrap.npz", 120, 40, 30, 6.0, 2.0, 3, 1, 6)
     # BASELINE.json configs[0]: 100x100, density 0.8, 100 steps (h=0.4, r=1)
     schelling_fixture("schelling_100x100_c1.npz", 100, 100, 0.8, 0.4, 1, 100, 42, 7, full_steps=[1, 2, 10, 50, 100])
     # the reference's own "large" benchmark variant (benchmarks/configurations.py:42-49)

@@ -256,3 +256,121 @@ ORC_API int64_t orc_schelling_move(int64_t ncells, int64_t n, int64_t* cell, con
     if (nfallback) *nfallback = fb;
     return movers;
 }
+
+/* ------------------------------------------------------------------ continuous space / Boids
+ * experimental/continuous_space/continuous_space.py:202-235 calculate_distances (torus branch),
+ * :237-247 get_agents_in_radius (dist <= radius, inclusive), continuous_space_agents.py:66-78
+ * (drop self), continuous_space.py:169-200 calculate_difference_vector,
+ * examples/basic/boid_flockers/agents.py:63-92 Boid.step, position setter
+ * continuous_space_agents.py:36-44 + continuous_space.py:285-298. */
+static double boid_dist(const double* p, const double* q, const double* size, int torus) {
+    double dx = fabs(p[0] - q[0]), dy = fabs(p[1] - q[1]);
+    if (torus) {
+        dx = fmin(dx, size[0] - dx);
+        dy = fmin(dy, size[1] - dy);
+    }
+    const double a = dx * dx, b = dy * dy;
+    return sqrt(a + b);
+}
+static double boid_delta(double q, double p, double size, int torus) {
+    const double d = q - p;
+    if (!torus) return d;
+    const double sgn = d > 0 ? 1.0 : (d < 0 ? -1.0 : 0.0);
+    const double inv = d - sgn * size;
+    return fabs(d) < fabs(inv) ? d : inv;
+}
+static double np_mod(double a, double b) {
+    double m = fmod(a, b);
+    if (m != 0.0 && ((b < 0) != (m < 0))) m += b;
+    return m;
+}
+
+typedef struct {
+    int64_t n; const double *pos, *dir; double *pos_out, *dir_out;
+    double lo[2], size[2]; int torus;
+    double vision, separation, cohere, separate, match, speed;
+    int64_t* nbr_count;
+} boid_args;
+
+/* one Boid.step for agent a reading (pos, dir), writing (po, dout) */
+static void boid_one(const boid_args* g, int64_t a, const double* pos, const double* dir, double* po, double* dout) {
+    const double* p = pos + 2 * a;
+    double coh[2] = {0, 0}, sep[2] = {0, 0}, mat[2] = {0, 0};
+    int64_t k = 0;
+    for (int64_t b = 0; b < g->n; ++b) {  /* storage-index order, like the reference */
+        if (b == a) continue;
+        const double d = boid_dist(p, pos + 2 * b, g->size, g->torus);
+        if (d <= g->vision) {
+            const double dx = boid_delta(pos[2 * b], p[0], g->size[0], g->torus);
+            const double dy = boid_delta(pos[2 * b + 1], p[1], g->size[1], g->torus);
+            coh[0] += dx; coh[1] += dy;
+            if (d < g->separation) { sep[0] += dx; sep[1] += dy; }
+            mat[0] += dir[2 * b]; mat[1] += dir[2 * b + 1];
+            ++k;
+        }
+    }
+    double d0 = dir[2 * a], d1 = dir[2 * a + 1];
+    if (k > 0) {
+        d0 += (coh[0] * g->cohere + (-1 * sep[0] * g->separate) + mat[0] * g->match) / (double)k;
+        d1 += (coh[1] * g->cohere + (-1 * sep[1] * g->separate) + mat[1] * g->match) / (double)k;
+        const double q0 = d0 * d0, q1 = d1 * d1;
+        const double norm = sqrt(q0 + q1);
+        d0 /= norm; d1 /= norm;
+    }
+    double x = p[0] + d0 * g->speed, y = p[1] + d1 * g->speed;
+    const int inb = x >= g->lo[0] && x <= g->lo[0] + g->size[0] && y >= g->lo[1] && y <= g->lo[1] + g->size[1];
+    if (!inb && g->torus) {
+        x = g->lo[0] + np_mod(x - g->lo[0], g->size[0]);
+        y = g->lo[1] + np_mod(y - g->lo[1], g->size[1]);
+    }
+    po[0] = x; po[1] = y; dout[0] = d0; dout[1] = d1;
+    if (g->nbr_count) g->nbr_count[a] = k;
+}
+
+static void boid_range(int64_t lo, int64_t hi, void* p) {
+    const boid_args* g = (const boid_args*)p;
+    for (int64_t a = lo; a < hi; ++a) boid_one(g, a, g->pos, g->dir, g->pos_out + 2 * a, g->dir_out + 2 * a);
+}
+
+/* order == NULL: synchronous (every boid reads the pre-step snapshot; what the device computes).
+ * order != NULL: sequential Gauss-Seidel in that activation order, in place semantics
+ *                (AgentSet.shuffle_do, agentset.py:772-787) -- the reference's own mode. */
+ORC_API int orc_boids_step(int64_t n, const double* pos, const double* dir, double* pos_out, double* dir_out,
+                           double x0, double y0, double size_x, double size_y, int torus, double vision,
+                           double separation, double cohere, double separate, double match, double speed,
+                           const int64_t* order, int64_t* nbr_count) {
+    boid_args g = {n, pos, dir, pos_out, dir_out, {x0, y0}, {size_x, size_y}, torus,
+                   vision, separation, cohere, separate, match, speed, nbr_count};
+    if (order == NULL) {
+        parallel_for(n, boid_range, &g);
+        return 0;
+    }
+    memcpy(pos_out, pos, sizeof(double) * 2 * (size_t)n);
+    memcpy(dir_out, dir, sizeof(double) * 2 * (size_t)n);
+    for (int64_t q = 0; q < n; ++q) {
+        const int64_t a = order[q];
+        double np_[2], nd[2];
+        boid_one(&g, a, pos_out, dir_out, np_, nd);
+        pos_out[2 * a] = np_[0]; pos_out[2 * a + 1] = np_[1];
+        dir_out[2 * a] = nd[0]; dir_out[2 * a + 1] = nd[1];
+    }
+    return 0;
+}
+
+/* get_agents_in_radius / get_neighbors_in_radius for one point: indices (ascending) and
+ * distances of agents with dist <= radius, skipping `exclude` (-1: none).  Returns the count. */
+ORC_API int64_t orc_radius_query(int64_t n, const double* pos, double px, double py, double size_x, double size_y,
+                                 int torus, double radius, int64_t exclude, int64_t* out_idx, double* out_dist) {
+    const double p[2] = {px, py}, size[2] = {size_x, size_y};
+    int64_t k = 0;
+    for (int64_t b = 0; b < n; ++b) {
+        if (b == exclude) continue;
+        const double d = boid_dist(p, pos + 2 * b, size, torus);
+        if (d <= radius) {
+            if (out_idx) out_idx[k] = b;
+            if (out_dist) out_dist[k] = d;
+            ++k;
+        }
+    }
+    return k;
+}

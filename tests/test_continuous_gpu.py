@@ -1,0 +1,88 @@
+"""GPU parity: radix sort, cell-list radius queries and the Boids step vs golden fixtures / oracle."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+BOIDS = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "boids_*.npz")))
+RTOL = 1e-5  # north_star: fp32 Boids position/velocity within 1e-5 relative of the float64 reference
+
+
+def _kw(g):
+    return dict(vision=float(g["vision"]), separation=float(g["separation"]), cohere=float(g["cohere"]),
+                separate=float(g["separate"]), match=float(g["match"]), speed=float(g["speed"]), torus=True)
+
+
+@pytest.mark.parametrize("n,bits", [(1, 32), (1000, 32), (4096, 16), (100_003, 24), (70_000, 64)])
+def test_radix_sort_is_stable_and_sorted(n, bits):
+    from mesa_b200 import ops
+
+    rng = np.random.default_rng(n)
+    if bits == 64:
+        keys = rng.integers(0, 2**62, size=n, dtype=np.int64)
+        keys[::3] = keys[0]  # many duplicates
+    else:
+        keys = rng.integers(0, min(2**bits, 2**31 - 1), size=n, dtype=np.int64).astype(np.int32)
+        keys[::5] = 7 % (2**bits)
+    vals = np.arange(n, dtype=np.int32)
+    k, v = ops.sort_pairs(torch.from_numpy(keys).cuda(), torch.from_numpy(vals).cuda(), 0, bits)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(k.cpu().numpy(), keys[order])
+    assert np.array_equal(v.cpu().numpy(), vals[order])
+
+
+@pytest.mark.parametrize("name", BOIDS)
+def test_boids_step_matches_reference(name):
+    from mesa_b200 import ops
+
+    g = np.load(os.path.join(GOLDEN, name))
+    size = g["size"]
+    for t in range(int(g["steps"])):
+        pos = torch.from_numpy(g[f"pos_in_{t}"]).cuda()
+        dirs = torch.from_numpy(g[f"dir_in_{t}"]).cuda()
+        cnt = torch.zeros(int(g["n"]), dtype=torch.int32, device="cuda")
+        po, do = ops.boids_step(pos, dirs, size, neighbor_count=cnt, **_kw(g))
+        # neighbour sets are bit-exact (counts here, full CSR below)
+        assert np.array_equal(cnt.cpu().numpy(), g[f"nbr_count_{t}"])
+        want_p, want_d = g[f"pos_out_{t}"], g[f"dir_out_{t}"]
+        # norm-wise relative error: |dp| / size, |dd| / |d| (unit vectors)
+        assert np.max(np.abs(po.cpu().numpy().astype(np.float64) - want_p) / size) <= RTOL
+        assert np.max(np.abs(do.cpu().numpy().astype(np.float64) - want_d)) <= RTOL
+        off, idx, dist = ops.radius_query(pos, pos, size, float(g["vision"]), True,
+                                          exclude=torch.arange(int(g["n"]), dtype=torch.int32, device="cuda"))
+        assert np.array_equal(np.diff(off.cpu().numpy()), g[f"nbr_count_{t}"])
+        assert np.array_equal(idx.cpu().numpy(), g[f"nbr_idx_{t}"])
+
+
+@pytest.mark.parametrize("n,side,vision,torus", [(2000, 200.0, 10.0, True), (500, 25.0, 10.0, True),
+                                                 (3000, 300.0, 7.5, False), (64, 8.0, 5.0, True), (1, 10.0, 3.0, True)])
+def test_boids_and_radius_match_oracle(n, side, vision, torus):
+    from mesa_b200 import ops
+
+    rng = np.random.default_rng(n)
+    size = np.array([side, side * 0.75])
+    pos = (rng.random((n, 2)) * size).astype(np.float32)
+    pos[: min(n, 4)] = [[0.0, 0.0], [side, 0.0], [0.0, side * 0.75], [side, side * 0.75]][: min(n, 4)]
+    dirs = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+    kw = dict(vision=vision, separation=2.0, torus=torus)
+    wp, wd, wc = oracle.boids_step(pos, dirs, size, **kw) if torus else (None, None, None)
+    cnt = torch.zeros(n, dtype=torch.int32, device="cuda")
+    if torus:
+        po, do = ops.boids_step(torch.from_numpy(pos).cuda(), torch.from_numpy(dirs).cuda(), size,
+                                neighbor_count=cnt, **kw)
+        assert np.array_equal(cnt.cpu().numpy(), wc)
+        assert np.max(np.abs(po.cpu().numpy() - wp) / size) <= RTOL
+        assert np.max(np.abs(do.cpu().numpy() - wd)) <= RTOL
+    q = pos[:: max(1, n // 50)]
+    off, idx, dist = ops.radius_query(torch.from_numpy(pos).cuda(), torch.from_numpy(q.copy()).cuda(), size, vision, torus)
+    off, idx, dist = off.cpu().numpy(), idx.cpu().numpy(), dist.cpu().numpy()
+    for i, p in enumerate(q):
+        wi, wdist = oracle.radius_query(pos.astype(np.float64), p.astype(np.float64), size, vision, torus)
+        assert np.array_equal(idx[off[i]:off[i + 1]], wi)
+        assert np.array_equal(dist[off[i]:off[i + 1]], wdist)  # float64 distances are bit-exact

@@ -1,0 +1,29 @@
+"""Developer micro-benchmark: Boids step at BASELINE.json config 4 scale (N agents, reference 'large' density)."""
+import sys, os, json, math
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from mesa_b200 import ops
+
+n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 10_000_000
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+side = 150.0 * math.sqrt(n / 400.0)
+vision = 15.0
+g = torch.Generator(device="cuda").manual_seed(0)
+pos = torch.rand((n, 2), device="cuda", generator=g) * side
+dirs = torch.rand((n, 2), device="cuda", generator=g) * 2 - 1
+ws = ops.CellListWorkspace(n, (side, side), vision, "cuda")
+po, do = torch.empty_like(pos), torch.empty_like(dirs)
+cnt = torch.zeros(n, dtype=torch.int32, device="cuda")
+for _ in range(3):
+    ops.boids_step(pos, dirs, (side, side), vision=vision, separation=2.0, ws=ws, pos_out=po, dir_out=do, neighbor_count=cnt)
+    pos, po = po, pos; dirs, do = do, dirs
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(steps):
+    ops.boids_step(pos, dirs, (side, side), vision=vision, separation=2.0, ws=ws, pos_out=po, dir_out=do)
+    pos, po = po, pos; dirs, do = do, dirs
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / steps
+print(json.dumps({"n": n, "side": side, "ms_per_step": ms, "agent_updates_per_s": n / ms * 1e3,
+                  "mean_neighbors": float(cnt.float().mean()), "ws_MB": ws.nbytes / 1e6}))
