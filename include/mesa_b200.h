@@ -113,6 +113,21 @@ int mb_radius_query_f32(const float* pos, int64_t n, double x0, double y0, doubl
                         uint32_t* counts, const int64_t* offsets, int32_t* out_idx, double* out_dist,
                         void* workspace, size_t workspace_bytes, int reuse_cell_list, mb_stream_t stream);
 
+/* ---- Boltzmann wealth (replaces AgentSet.shuffle_do("step") over
+ * examples/basic/boltzmann_wealth_model/agents.py:24-44: Moore random walk, then give one unit to
+ * a random cell mate) ---------------------------------------------------------------------------
+ * cell: [n] uint32 flat cell id per agent (agent index = registration order), wealth: [n] int32.
+ * The workspace carries the per-cell list order (arrival order, cell.py:143-170) between steps:
+ * call mb_boltzmann_init after placing agents, then mb_boltzmann_step once per model step with
+ * epoch = number of shuffles so far.  Result identical to the sequential reference driven with the
+ * same keyed draws (csrc/boltzmann.cu).  mb_boltzmann_step synchronises `stream`. */
+int mb_boltzmann_workspace_bytes(int64_t n, size_t* out);
+int mb_boltzmann_init(const uint32_t* cell, int64_t n, int64_t rows, int64_t cols, void* workspace,
+                      size_t workspace_bytes, mb_stream_t stream);
+int mb_boltzmann_step(uint32_t* cell, int32_t* wealth, int64_t n, int64_t rows, int64_t cols, int torus,
+                      uint64_t seed, uint32_t epoch, void* workspace, size_t workspace_bytes,
+                      int* out_iterations, mb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,11 @@ SIGNATURES: dict[str, tuple] = {
                                   ctypes.c_size_t, _S]),
     "mb_radius_query_f32": (c_int, [_P, c_int64, c_double, c_double, c_double, c_double, c_int, _P, _P, c_int64,
                                     c_double, _P, _P, _P, _P, _P, ctypes.c_size_t, c_int, _S]),
+    # Boltzmann wealth
+    "mb_boltzmann_workspace_bytes": (c_int, [c_int64, ctypes.POINTER(ctypes.c_size_t)]),
+    "mb_boltzmann_init": (c_int, [_P, c_int64, c_int64, c_int64, _P, ctypes.c_size_t, _S]),
+    "mb_boltzmann_step": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int, c_uint64, c_uint32, _P,
+                                  ctypes.c_size_t, ctypes.POINTER(c_int), _S]),
 }
 
 _lib = None

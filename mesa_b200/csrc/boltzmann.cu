@@ -1,0 +1,296 @@
+// Boltzmann wealth model: Moore random walk + same-cell exchange, order-exact (K9 of SURVEY.md §2.4).
+//
+// Replaces AgentSet.shuffle_do("step") (mesa/agentset.py:772-787) over
+//   mesa/examples/basic/boltzmann_wealth_model/agents.py:24-26  move:
+//        self.cell = self.cell.neighborhood.select_random_cell()
+//        (cell_collection.py:101-119: random.choice over the connection-order cell list,
+//         grid.py:447-451 Moore offsets filtered by bounds on a clamped grid)
+//   agents.py:28-35  give_money: cellmates = cell.agents minus self (list = arrival order,
+//        cell.py:143-170); if any: other = random.choice(cellmates); other.wealth += 1; self.wealth -= 1
+//   agents.py:37-44  step: move(); if self.wealth > 0: give_money()
+//
+// The reference is sequential.  The same result is obtained in parallel because
+//   * every agent moves exactly once per step and its destination depends only on its own cell
+//     and its own keyed draws (philox.cuh), so all moves are independent;
+//   * at the time t_a of agent a, its new cell c holds, in list order, the agents whose OLD cell is c
+//     and act later (t_b > t_a; they have not left yet; kept in last step's arrival order) followed
+//     by the agents whose NEW cell is c and acted earlier (t_b < t_a; in arrival = priority order).
+//     Both groups are contiguous runs of two sorted arrays: last step's agents sorted by
+//     (cell, arrival priority) and this step's agents sorted by (new cell, priority);
+//   * whom a would give to is therefore state-independent; WHETHER it gives depends on
+//     wealth(a) at t_a = w0 + gifts received earlier, resolved by a monotone fixed point
+//     (an agent with w0 == 0 gives iff some earlier giver targets it).
+#include "common.cuh"
+#include "philox.cuh"
+#include "sort.cuh"
+
+namespace {
+
+constexpr unsigned long long kNever = ~0ull;
+constexpr uint32_t kNoTarget = 0xffffffffu;
+constexpr int kIterBatch = 4;
+constexpr int kMaxIterSlots = 4096;
+
+struct BoltzWs {
+    uint64_t* keysA;      // [n] sorted (cell << 32 | arrival priority hi32) of the PREVIOUS step (persistent)
+    uint32_t* valsA;      // [n] agent at each sorted slot (persistent)
+    uint64_t* keys0;      // [n] sort ping
+    uint32_t* vals0;
+    uint64_t* keys1;      // [n] sort pong
+    uint32_t* vals1;
+    uint64_t* prio;       // [n] priority64 of this epoch
+    uint32_t* new_cell;   // [n]
+    uint32_t* rankB;      // [n] slot of agent in this step's sorted order
+    uint32_t* target;     // [n] agent that would receive the gift, or kNoTarget
+    unsigned long long* first_gift;  // [n] earliest time a gift reaches the agent
+    uint8_t* gives;       // [n]
+    uint8_t* draws;       // [n] draws consumed by move()
+    unsigned long long* counters;    // [kMaxIterSlots] changed flags
+    void* sort_ws;
+    size_t sort_ws_bytes;
+};
+
+size_t carve(BoltzWs* ws, char* base, int64_t n) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char* p = base ? base + off : nullptr;
+        off += (bytes + 255) & ~(size_t)255;
+        return p;
+    };
+    BoltzWs t;
+    t.keysA = (uint64_t*)take(8 * n);
+    t.valsA = (uint32_t*)take(4 * n);
+    t.keys0 = (uint64_t*)take(8 * n);
+    t.vals0 = (uint32_t*)take(4 * n);
+    t.keys1 = (uint64_t*)take(8 * n);
+    t.vals1 = (uint32_t*)take(4 * n);
+    t.prio = (uint64_t*)take(8 * n);
+    t.new_cell = (uint32_t*)take(4 * n);
+    t.rankB = (uint32_t*)take(4 * n);
+    t.target = (uint32_t*)take(4 * n);
+    t.first_gift = (unsigned long long*)take(8 * n);
+    t.gives = (uint8_t*)take(n);
+    t.draws = (uint8_t*)take(n);
+    t.counters = (unsigned long long*)take(8 * kMaxIterSlots);
+    t.sort_ws_bytes = mb::sort_workspace_bytes(n);
+    t.sort_ws = take(t.sort_ws_bytes);
+    if (ws) *ws = t;
+    return off;
+}
+
+__global__ void init_keys(const uint32_t* __restrict__ cell, int64_t n, uint64_t* __restrict__ keys,
+                          uint32_t* __restrict__ vals) {
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    keys[a] = (uint64_t)cell[a] << 32;  // initial list order = registration order (stable sort)
+    vals[a] = (uint32_t)a;
+}
+
+// move(): destination = connection-order neighbour list [k], k = _randbelow(len)
+__global__ void boltz_move(const uint32_t* __restrict__ cell, int64_t n, int rows, int cols, int torus,
+                           uint64_t seed, uint32_t epoch, BoltzWs ws) {
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const uint32_t c = cell[a];
+    const int i = (int)(c / (uint32_t)cols), j = (int)(c % (uint32_t)cols);
+    // grid.py:447-451 offsets in order; clamped grids drop out-of-range cells (grid.py:398)
+    uint32_t nbr[8];
+    int cnt = 0;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        if (q == 4) continue;
+        int ni = i + q / 3 - 1, nj = j + q % 3 - 1;
+        if (torus) {
+            ni = (ni + rows) % rows;
+            nj = (nj + cols) % cols;
+        } else if (ni < 0 || ni >= rows || nj < 0 || nj >= cols) {
+            continue;
+        }
+        nbr[cnt++] = (uint32_t)ni * (uint32_t)cols + (uint32_t)nj;
+    }
+    mb::DrawStream ds(seed, epoch, (uint64_t)a);
+    const uint32_t k = (uint32_t)ds.randbelow((uint64_t)cnt);
+    uint32_t dest = nbr[0];
+#pragma unroll
+    for (int q = 1; q < 8; ++q)
+        if ((uint32_t)q == k) dest = nbr[q];
+    const uint64_t t = mb::priority64(seed, epoch, (uint64_t)a);
+    ws.new_cell[a] = dest;
+    ws.prio[a] = t;
+    ws.draws[a] = (uint8_t)ds.c;
+    ws.keys0[a] = ((uint64_t)dest << 32) | (t >> 32);
+    ws.vals0[a] = (uint32_t)a;
+}
+
+__global__ void boltz_rank(const uint32_t* __restrict__ valsB, int64_t n, uint32_t* __restrict__ rankB) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rankB[valsB[i]] = (uint32_t)i;
+}
+
+__device__ __forceinline__ int64_t lower_bound_u64(const uint64_t* __restrict__ a, int64_t n, uint64_t v) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (a[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// give_money() target of every agent (state independent) + initial give decision
+__global__ void boltz_target(const int32_t* __restrict__ wealth, int64_t n, uint64_t seed, uint32_t epoch,
+                             const uint64_t* __restrict__ keysB, const uint32_t* __restrict__ valsB, BoltzWs ws) {
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const uint32_t c = ws.new_cell[a];
+    const uint64_t t = ws.prio[a];
+    // agents still sitting in c (old cell == c, acting later), in last step's arrival order
+    const int64_t a0 = lower_bound_u64(ws.keysA, n, (uint64_t)c << 32);
+    int64_t cntA = 0;
+    for (int64_t s = a0; s < n && (uint32_t)(ws.keysA[s] >> 32) == c; ++s) cntA += ws.prio[ws.valsA[s]] > t;
+    // agents that already arrived in c, in arrival order: the run of this step's order before me
+    const int64_t me = ws.rankB[a];
+    int64_t b0 = me;
+    while (b0 > 0 && (uint32_t)(keysB[b0 - 1] >> 32) == c) --b0;
+    const int64_t cntB = me - b0;
+    const int64_t mates = cntA + cntB;
+    uint32_t tgt = kNoTarget;
+    if (mates > 0) {
+        mb::DrawStream ds(seed, epoch, (uint64_t)a);
+        ds.seek(ws.draws[a]);
+        int64_t m = (int64_t)ds.randbelow((uint64_t)mates);
+        if (m < cntA) {
+            for (int64_t s = a0;; ++s) {
+                const uint32_t b = ws.valsA[s];
+                if (ws.prio[b] > t && m-- == 0) { tgt = b; break; }
+            }
+        } else {
+            tgt = valsB[b0 + (m - cntA)];
+        }
+    }
+    ws.target[a] = tgt;
+    ws.gives[a] = (tgt != kNoTarget && wealth[a] > 0) ? 1 : 0;
+    ws.first_gift[a] = kNever;
+}
+
+// every giver announces the time of its gift to the receiver
+__global__ void boltz_push(int64_t n, BoltzWs ws) {
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n || !ws.gives[a]) return;
+    atomicMin(&ws.first_gift[ws.target[a]], (unsigned long long)ws.prio[a]);
+}
+
+// an agent that started the step broke gives iff a gift reached it before its turn
+__global__ void boltz_pull(int64_t n, BoltzWs ws, int iter) {
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n || ws.gives[a] || ws.target[a] == kNoTarget) return;
+    if (ws.first_gift[a] < ws.prio[a]) {
+        ws.gives[a] = 1;
+        atomicAdd(&ws.counters[iter], 1ull);
+    }
+}
+
+__global__ void boltz_apply(int32_t* __restrict__ wealth, uint32_t* __restrict__ cell, int64_t n, BoltzWs ws) {
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    cell[a] = ws.new_cell[a];
+    if (ws.gives[a]) {
+        atomicAdd(&wealth[ws.target[a]], 1);
+        atomicSub(&wealth[a], 1);
+    }
+}
+
+int sort_bits(int64_t ncells) {
+    int b = 1;
+    while ((1ll << b) < ncells) ++b;
+    return 32 + b;
+}
+
+}  // namespace
+
+MB_API int mb_boltzmann_workspace_bytes(int64_t n, size_t* out) {
+    MB_REQUIRE(out != nullptr && n >= 0, "mb_boltzmann_workspace_bytes: bad argument");
+    *out = carve(nullptr, nullptr, n);
+    return MB_OK;
+}
+
+// (Re)builds the per-cell arrival order from the current cells: list order = agent index
+// (registration order, boltzmann_wealth_model/model.py:70-74).  Call once after placing agents.
+MB_API int mb_boltzmann_init(const uint32_t* cell, int64_t n, int64_t rows, int64_t cols, void* workspace,
+                             size_t workspace_bytes, cudaStream_t stream) {
+    MB_REQUIRE(n >= 0 && n < (1ll << 31), "mb_boltzmann_init: n out of range");
+    MB_REQUIRE(rows > 0 && cols > 0 && rows * cols < (1ll << 32), "mb_boltzmann_init: grid must have < 2^32 cells");
+    if (n == 0) return MB_OK;
+    MB_REQUIRE(cell && workspace, "mb_boltzmann_init: null buffer");
+    BoltzWs ws;
+    if (carve(&ws, (char*)workspace, n) > workspace_bytes) {
+        mb::set_error("mb_boltzmann_init: workspace too small");
+        return MB_ERR_WORKSPACE;
+    }
+    const unsigned blocks = (unsigned)mb::ceil_div(n, 256);
+    init_keys<<<blocks, 256, 0, stream>>>(cell, n, ws.keys0, ws.vals0);
+    const int where = mb::radix_sort_pairs<uint64_t>(ws.keys0, ws.vals0, ws.keys1, ws.vals1, n, 32, sort_bits(rows * cols),
+                                                     ws.sort_ws, ws.sort_ws_bytes, stream);
+    if (where < 0) return where;
+    int rc = mb::check_cuda(cudaMemcpyAsync(ws.keysA, where ? ws.keys1 : ws.keys0, 8 * n, cudaMemcpyDeviceToDevice, stream), "copy");
+    if (rc) return rc;
+    return mb::check_cuda(cudaMemcpyAsync(ws.valsA, where ? ws.vals1 : ws.vals0, 4 * n, cudaMemcpyDeviceToDevice, stream), "copy");
+}
+
+// One model step (shuffle number `epoch`).  Synchronises `stream` (convergence flag).
+MB_API int mb_boltzmann_step(uint32_t* cell, int32_t* wealth, int64_t n, int64_t rows, int64_t cols, int torus,
+                             uint64_t seed, uint32_t epoch, void* workspace, size_t workspace_bytes,
+                             int* out_iterations, cudaStream_t stream) {
+    MB_REQUIRE(n >= 0 && n < (1ll << 31), "mb_boltzmann_step: n out of range");
+    MB_REQUIRE(rows > 0 && cols > 0 && rows * cols < (1ll << 32), "mb_boltzmann_step: grid must have < 2^32 cells");
+    // a 1x1 grid has an empty neighbourhood: select_random_cell raises LookupError (cell_collection.py:114-117)
+    MB_REQUIRE(rows * cols >= 2, "Cannot select random cell from empty collection");
+    MB_REQUIRE(!torus || (rows >= 3 && cols >= 3), "mb_boltzmann_step: torus needs dims >= 3 (SURVEY A.2)");
+    if (out_iterations) *out_iterations = 0;
+    if (n == 0) return MB_OK;
+    MB_REQUIRE(cell && wealth && workspace, "mb_boltzmann_step: null buffer");
+    BoltzWs ws;
+    if (carve(&ws, (char*)workspace, n) > workspace_bytes) {
+        mb::set_error("mb_boltzmann_step: workspace too small");
+        return MB_ERR_WORKSPACE;
+    }
+    int rc = mb::check_cuda(cudaMemsetAsync(ws.counters, 0, 8 * kMaxIterSlots, stream), "memset");
+    if (rc) return rc;
+    const unsigned blocks = (unsigned)mb::ceil_div(n, 256);
+    boltz_move<<<blocks, 256, 0, stream>>>(cell, n, (int)rows, (int)cols, torus, seed, epoch, ws);
+    const int where = mb::radix_sort_pairs<uint64_t>(ws.keys0, ws.vals0, ws.keys1, ws.vals1, n, 0, sort_bits(rows * cols),
+                                                     ws.sort_ws, ws.sort_ws_bytes, stream);
+    if (where < 0) return where;
+    const uint64_t* keysB = where ? ws.keys1 : ws.keys0;
+    const uint32_t* valsB = where ? ws.vals1 : ws.vals0;
+    boltz_rank<<<blocks, 256, 0, stream>>>(valsB, n, ws.rankB);
+    boltz_target<<<blocks, 256, 0, stream>>>(wealth, n, seed, epoch, keysB, valsB, ws);
+    MB_LAUNCH_CHECK("boltz_target");
+    int iter = 0;
+    for (bool done = false; !done;) {
+        if (iter + kIterBatch >= kMaxIterSlots) {
+            mb::set_error("mb_boltzmann_step: no convergence after %d iterations", iter);
+            return MB_ERR_CUDA;
+        }
+        const int first = iter;
+        for (int b = 0; b < kIterBatch; ++b, ++iter) {
+            boltz_push<<<blocks, 256, 0, stream>>>(n, ws);
+            boltz_pull<<<blocks, 256, 0, stream>>>(n, ws, iter);
+        }
+        MB_LAUNCH_CHECK("boltz_iterate");
+        unsigned long long changed[kIterBatch];
+        rc = mb::check_cuda(cudaMemcpyAsync(changed, ws.counters + first, sizeof(changed), cudaMemcpyDeviceToHost, stream), "read");
+        if (rc) return rc;
+        rc = mb::check_cuda(cudaStreamSynchronize(stream), "sync");
+        if (rc) return rc;
+        done = changed[kIterBatch - 1] == 0;
+    }
+    boltz_apply<<<blocks, 256, 0, stream>>>(wealth, cell, n, ws);
+    // this step's arrival order is next step's "still sitting here" order
+    rc = mb::check_cuda(cudaMemcpyAsync(ws.keysA, keysB, 8 * n, cudaMemcpyDeviceToDevice, stream), "copy");
+    if (rc) return rc;
+    rc = mb::check_cuda(cudaMemcpyAsync(ws.valsA, valsB, 4 * n, cudaMemcpyDeviceToDevice, stream), "copy");
+    if (rc) return rc;
+    MB_LAUNCH_CHECK("mb_boltzmann_step");
+    if (out_iterations) *out_iterations = iter;
+    return MB_OK;
+}

@@ -220,3 +220,43 @@ def radius_query(pos: torch.Tensor, queries: torch.Tensor, size, radius: float, 
                                             None, N.ptr(offsets), N.ptr(idx), N.ptr(dist), N.ptr(ws.buf), ws.nbytes,
                                             1, st))
     return offsets, idx, dist
+
+
+# ----------------------------------------------------------------------------- Boltzmann wealth
+class BoltzmannWorkspace:
+    """Scratch + per-cell list order of mb_boltzmann_step for `n` agents (persistent between steps)."""
+
+    def __init__(self, cell: torch.Tensor, rows: int, cols: int):
+        import ctypes
+
+        _need_cuda(cell)
+        if cell.dtype != torch.int32:
+            raise ValueError("cell must be int32 (uint32 bit pattern)")
+        self.n, self.rows, self.cols = cell.numel(), int(rows), int(cols)
+        nbytes = ctypes.c_size_t(0)
+        N.check(N.lib().mb_boltzmann_workspace_bytes(self.n, ctypes.byref(nbytes)))
+        self.nbytes = int(nbytes.value)
+        self.buf = torch.empty(max(self.nbytes, 1), dtype=torch.uint8, device=cell.device)
+        self.reset(cell)
+
+    def reset(self, cell: torch.Tensor) -> None:
+        """List order = registration order (after placing agents; model.py:70-74)."""
+        with torch.cuda.device(cell.device):
+            N.check(N.lib().mb_boltzmann_init(N.ptr(_c(cell)), self.n, self.rows, self.cols, N.ptr(self.buf),
+                                              self.nbytes, N.stream_ptr(cell.device)))
+
+
+def boltzmann_step(cell: torch.Tensor, wealth: torch.Tensor, ws: BoltzmannWorkspace, seed: int, epoch: int,
+                   torus: bool = False) -> int:
+    """shuffle_do("step") of all MoneyAgents; returns the number of give-resolution iterations."""
+    import ctypes
+
+    _need_cuda(cell, wealth)
+    if cell.dtype != torch.int32 or wealth.dtype != torch.int32 or cell.numel() != ws.n or wealth.numel() != ws.n:
+        raise ValueError("boltzmann_step expects int32 cell / wealth tensors matching the workspace")
+    iters = ctypes.c_int(0)
+    with torch.cuda.device(cell.device):
+        N.check(N.lib().mb_boltzmann_step(N.ptr(_c(cell)), N.ptr(_c(wealth)), ws.n, ws.rows, ws.cols,
+                                          int(bool(torus)), int(seed) & 0xFFFFFFFFFFFFFFFF, int(epoch) & 0xFFFFFFFF,
+                                          N.ptr(ws.buf), ws.nbytes, ctypes.byref(iters), N.stream_ptr(cell.device)))
+    return int(iters.value)

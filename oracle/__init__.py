@@ -185,3 +185,42 @@ def radius_query(pos, point, size, radius, torus=True, exclude=-1):
     k = int(f(c_int64(n), _p(pos), c_double(point[0]), c_double(point[1]), c_double(size[0]), c_double(size[1]),
               c_int(bool(torus)), c_double(radius), c_int64(exclude), _p(idx), _p(dist)))
     return idx[:k].copy(), dist[:k].copy()
+
+
+# ----------------------------------------------------------------------------- Boltzmann wealth
+class BoltzmannState:
+    """Reference-shaped Boltzmann state: per-agent cell/wealth + per-cell agent lists in list order."""
+
+    def __init__(self, rows: int, cols: int, cell, wealth=None, torus: bool = False):
+        self.rows, self.cols, self.torus = int(rows), int(cols), bool(torus)
+        self.cell = np.ascontiguousarray(cell, dtype=np.int64).copy()
+        n = len(self.cell)
+        self.wealth = (np.ones(n, np.int32) if wealth is None else np.ascontiguousarray(wealth, dtype=np.int32).copy())
+        nc = self.rows * self.cols
+        self.next, self.prev = np.empty(n, np.int64), np.empty(n, np.int64)
+        self.head, self.tail = np.empty(nc, np.int64), np.empty(nc, np.int64)
+        lib().orc_boltzmann_init_lists(c_int64(nc), c_int64(n), _p(self.cell), _p(self.next), _p(self.prev),
+                                       _p(self.head), _p(self.tail))
+
+    @property
+    def n(self) -> int:
+        return len(self.cell)
+
+    def step(self, seed: int, epoch: int) -> None:
+        rc = lib().orc_boltzmann_step(c_int64(self.rows), c_int64(self.cols), c_int(self.torus), c_int64(self.n),
+                                      _p(self.cell), _p(self.wealth), _p(self.next), _p(self.prev), _p(self.head),
+                                      _p(self.tail), c_uint64(seed), c_uint32(epoch))
+        if rc == -1:
+            raise LookupError("Cannot select random cell from empty collection")
+        assert rc == 0
+
+    def cell_lists(self) -> dict:
+        """{cell: [agents in list order]} for non-empty cells."""
+        out = {}
+        for c in np.flatnonzero(self.head >= 0):
+            lst, b = [], self.head[c]
+            while b >= 0:
+                lst.append(int(b))
+                b = self.next[b]
+            out[int(c)] = lst
+        return out

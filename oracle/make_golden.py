@@ -97,6 +97,44 @@ def schelling_fixture(name, width, height, density, homophily, radius, steps, mt
     print(name, "agents", len(agents), "happy", happy_counts[:5], "...", happy_counts[-1], "movers", movers[:5])
 
 
+# ------------------------------------------------------------------------------ Boltzmann
+def boltzmann_fixture(name, n, width, height, steps, mt_seed, philox_seed):
+    from mesa.examples.basic.boltzmann_wealth_model.agents import MoneyAgent
+    from mesa.examples.basic.boltzmann_wealth_model.model import BoltzmannScenario, BoltzmannWealth
+
+    with patched_model_random(philox_seed):
+        m = BoltzmannWealth(BoltzmannScenario(n=n, width=width, height=height, rng=mt_seed))
+    rng = m.random
+    agents = sorted(m.agents, key=lambda a: a.unique_id)
+    assert [a.unique_id for a in agents] == list(range(1, n + 1))
+
+    def cells():
+        return np.array([a.cell.coordinate[0] * height + a.cell.coordinate[1] for a in agents], dtype=np.uint32)
+
+    def wealth():
+        return np.array([a.wealth for a in agents], dtype=np.int32)
+
+    out = {"n": n, "width": width, "height": height, "philox_seed": np.uint64(philox_seed), "steps": steps,
+           "cell_0": cells(), "wealth_0": wealth()}
+    rng.replay = True
+    with activation_context(MoneyAgent, "step"):
+        for s in range(1, steps + 1):
+            m.step()
+            out[f"cell_{s}"] = cells()
+            out[f"wealth_{s}"] = wealth()
+            assert wealth().sum() == n
+    rng.replay = False
+    # per-cell list order after the last step (arrival order)
+    order = np.full(n, -1, dtype=np.int32)
+    for cell in m.grid.all_cells:
+        for pos, a in enumerate(cell._agents):
+            order[a.unique_id - 1] = pos
+    out["list_pos_last"] = order
+    np.savez_compressed(os.path.join(GOLDEN, name), **out)
+    w = wealth()
+    print(name, "max wealth", w.max(), "zero-wealth agents", int((w == 0).sum()))
+
+
 # ------------------------------------------------------------------------------ Boids
 def boids_fixture(name, n, width, height, vision, separation, steps, seed, philox_seed):
     """Synchronous goldens: the UNMODIFIED Boid.step of every agent driven on a frozen snapshot
@@ -162,6 +200,11 @@ def main():
     import_reference()
     os.makedirs(GOLDEN, exist_ok=True)
     only = sys.argv[1] if len(sys.argv) > 1 else ""
+    if only == "boltzmann":
+        boltzmann_fixture("boltzmann_100_10x10.npz", 100, 10, 10, 25, 42, 3)      # reference "small"
+        boltzmann_fixture("boltzmann_2000_20x30.npz", 2000, 20, 30, 10, 7, 4)     # crowded cells
+        boltzmann_fixture("boltzmann_10000_100x100.npz", 10000, 100, 100, 10, 1, 5)  # reference "large"
+        return
     if only == "boids":
         boids_fixture("boids_300.npz", 300, 100, 100, 10.0, 2.0, 3, 42, 5)
         boids_fixture("boids_120_wrap.npz", 120, 40, 30, 6.0, 2.0, 3, 1, 6)
@@ -172,6 +215,9 @@ def main():
     schelling_fixture("schelling_16x48_r2.npz", 16, 48, 0.9, 0.6, 2, 12, 5, 99, full_steps=range(1, 13))
     boids_fixture("boids_300.npz", 300, 100, 100, 10.0, 2.0, 3, 42, 5)
     boids_fixture("boids_120_wrap.npz", 120, 40, 30, 6.0, 2.0, 3, 1, 6)
+    boltzmann_fixture("boltzmann_100_10x10.npz", 100, 10, 10, 25, 42, 3)
+    boltzmann_fixture("boltzmann_2000_20x30.npz", 2000, 20, 30, 10, 7, 4)
+    boltzmann_fixture("boltzmann_10000_100x100.npz", 10000, 100, 100, 10, 1, 5)
     # BASELINE.json configs[0]: 100x100, density 0.8, 100 steps (h=0.4, r=1)
     schelling_fixture("schelling_100x100_c1.npz", 100, 100, 0.8, 0.4, 1, 100, 42, 7, full_steps=[1, 2, 10, 50, 100])
     # the reference's own "large" benchmark variant (benchmarks/configurations.py:42-49)

@@ -374,3 +374,70 @@ ORC_API int64_t orc_radius_query(int64_t n, const double* pos, double px, double
     }
     return k;
 }
+
+/* ------------------------------------------------------------------ Boltzmann wealth
+ * examples/basic/boltzmann_wealth_model/agents.py:24-44 (move / give_money / step) under
+ * AgentSet.shuffle_do (agentset.py:772-787).  Each cell keeps its agents in a doubly linked
+ * list in list order (cell.py:143-170: append on arrival, list.remove on departure).
+ * State: cell[n], wealth[n], and the list order: `next`/`prev` per agent, `head`/`tail` per cell
+ * (all -1 terminated), owned by the caller so it persists between steps. */
+ORC_API void orc_boltzmann_init_lists(int64_t ncells, int64_t n, const int64_t* cell, int64_t* next, int64_t* prev,
+                                      int64_t* head, int64_t* tail) {
+    for (int64_t c = 0; c < ncells; ++c) head[c] = tail[c] = -1;
+    for (int64_t a = 0; a < n; ++a) { /* registration order = initial list order (model.py:70-74) */
+        const int64_t c = cell[a];
+        next[a] = -1; prev[a] = tail[c];
+        if (tail[c] >= 0) next[tail[c]] = a; else head[c] = a;
+        tail[c] = a;
+    }
+}
+
+ORC_API int orc_boltzmann_step(int64_t rows, int64_t cols, int torus, int64_t n, int64_t* cell, int32_t* wealth,
+                               int64_t* next, int64_t* prev, int64_t* head, int64_t* tail, uint64_t seed,
+                               uint32_t epoch) {
+    int64_t* order = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+    if (!order || orc_activation_order(seed, epoch, n, order) != 0) { free(order); return -2; }
+    for (int64_t q = 0; q < n; ++q) {
+        const int64_t a = order[q];
+        draw_stream ds;
+        ds_init(&ds, seed, epoch, (uint64_t)a, STREAM_DRAW);
+        /* move(): neighbourhood in connection order (grid.py:447-451), clamped or torus */
+        const int64_t i = cell[a] / cols, j = cell[a] % cols;
+        int64_t nbr[8]; int cnt = 0;
+        for (int di = -1; di <= 1; ++di)
+            for (int dj = -1; dj <= 1; ++dj) {
+                if (di == 0 && dj == 0) continue;
+                int64_t ni = i + di, nj = j + dj;
+                if (torus) { ni = (ni + rows) % rows; nj = (nj + cols) % cols; }
+                else if (ni < 0 || ni >= rows || nj < 0 || nj >= cols) continue;
+                nbr[cnt++] = ni * cols + nj;
+            }
+        if (cnt == 0) { free(order); return -1; } /* LookupError in the reference */
+        const int64_t dest = nbr[ds_randbelow(&ds, (uint64_t)cnt)];
+        /* HasCell.cell setter (cell_agent.py:39-54): append to the new list, remove from the old */
+        const int64_t old = cell[a];
+        if (prev[a] >= 0) next[prev[a]] = next[a]; else head[old] = next[a];
+        if (next[a] >= 0) prev[next[a]] = prev[a]; else tail[old] = prev[a];
+        next[a] = -1; prev[a] = tail[dest];
+        if (tail[dest] >= 0) next[tail[dest]] = a; else head[dest] = a;
+        tail[dest] = a;
+        cell[a] = dest;
+        /* give_money() */
+        if (wealth[a] > 0) {
+            int64_t mates = 0;
+            for (int64_t b = head[dest]; b >= 0; b = next[b]) mates += b != a;
+            if (mates > 0) {
+                int64_t m = (int64_t)ds_randbelow(&ds, (uint64_t)mates);
+                int64_t other = -1;
+                for (int64_t b = head[dest]; b >= 0; b = next[b]) {
+                    if (b == a) continue;
+                    if (m-- == 0) { other = b; break; }
+                }
+                wealth[other] += 1;
+                wealth[a] -= 1;
+            }
+        }
+    }
+    free(order);
+    return 0;
+}
