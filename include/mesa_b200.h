@@ -128,6 +128,28 @@ int mb_boltzmann_step(uint32_t* cell, int32_t* wealth, int64_t n, int64_t rows, 
                       uint64_t seed, uint32_t epoch, void* workspace, size_t workspace_bytes,
                       int* out_iterations, mb_stream_t stream);
 
+/* ---- property layers (replace the numpy expressions users run on Grid.property_layers arrays,
+ * grid.py:112,130-220; e.g. sugarscape_g1mt/model.py:123-124, grid.py:146, grid.py:308) and the
+ * generic neighbourhood sum (cell.py:225-276: Moore = Chebyshev square, von Neumann = Manhattan
+ * diamond, centre excluded unless include_center) --------------------------------------------------
+ * dtype: 0 uint8, 1 int32, 2 float32, 3 float64.  op (binary): 0 add 1 sub 2 mul 3 min 4 max.
+ * op (reduce): 0 sum 1 min 2 max 3 count_nonzero; result is int64 for integer layers and
+ * count_nonzero, float64 otherwise; reductions are reproducible (fixed two-pass order).
+ * mb_neighborhood_sum writes int32 sums for integer layers, float64 for float layers.
+ * mb_layer_diffuse: out = in*(1 - rate*k/8) + rate/8 * sum(existing Moore neighbours), k = their
+ * number (NetLogo `diffuse`; the reference has no diffusion -- parity unpinned). */
+int mb_layer_fill(void* data, int64_t n, int dtype, double value, mb_stream_t stream);
+int mb_layer_affine_clamp(const void* in, void* out, int64_t n, int dtype, double alpha, double beta, double lo,
+                          double hi, mb_stream_t stream);
+int mb_layer_binary(const void* a, const void* b, void* out, int64_t n, int dtype, int op, mb_stream_t stream);
+int mb_layer_reduce(const void* in, int64_t n, int dtype, int op, void* result, void* workspace,
+                    size_t workspace_bytes, mb_stream_t stream);
+int mb_neighborhood_sum(const void* in, const void* halo_top, const void* halo_bot, void* out, int64_t rows,
+                        int64_t cols, int dtype, int radius, int von_neumann, int include_center, int col_torus,
+                        mb_stream_t stream);
+int mb_layer_diffuse(const void* in, const void* halo_top, const void* halo_bot, void* out, int64_t rows,
+                     int64_t cols, int dtype, double rate, int col_torus, mb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

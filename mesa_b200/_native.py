@@ -63,6 +63,13 @@ SIGNATURES: dict[str, tuple] = {
     "mb_boltzmann_init": (c_int, [_P, c_int64, c_int64, c_int64, _P, ctypes.c_size_t, _S]),
     "mb_boltzmann_step": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int, c_uint64, c_uint32, _P,
                                   ctypes.c_size_t, ctypes.POINTER(c_int), _S]),
+    # property layers / neighbourhood sums
+    "mb_layer_fill": (c_int, [_P, c_int64, c_int, c_double, _S]),
+    "mb_layer_affine_clamp": (c_int, [_P, _P, c_int64, c_int, c_double, c_double, c_double, c_double, _S]),
+    "mb_layer_binary": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _S]),
+    "mb_layer_reduce": (c_int, [_P, c_int64, c_int, c_int, _P, _P, ctypes.c_size_t, _S]),
+    "mb_neighborhood_sum": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, _S]),
+    "mb_layer_diffuse": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_double, c_int, _S]),
 }
 
 _lib = None

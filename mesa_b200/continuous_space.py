@@ -1,0 +1,167 @@
+"""DeviceContinuousSpace: device-resident mirror of mesa.experimental.continuous_space.ContinuousSpace.
+
+Mirrors mesa/experimental/continuous_space/continuous_space.py:48-298: `dimensions`, `size`, `center`,
+`torus`, `agent_positions`, `in_bounds`, `torus_correct`, `calculate_distances`,
+`calculate_difference_vector`, `get_agents_in_radius`, `get_k_nearest_agents` -- same argument meaning,
+same inclusive radius (`dist <= radius`), same errors.  Positions live in ONE float32 [n, 2] device
+tensor (storage-index order = the reference's `_agent_positions` rows); agents are identified by
+that index.  Distances are evaluated in float64 with the reference's operation order, so for
+fp32-representable positions they are bit-identical to the reference's (csrc/continuous.cu).
+
+Single-point queries launch one small kernel each; the batched `radius_query` /
+`neighbors_in_radius` are the hot-path entry points (one cell-list build + one query kernel).
+"""
+from __future__ import annotations
+
+import warnings
+from random import Random
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+class DeviceContinuousSpace:
+    def __init__(self, dimensions, torus: bool = False, random: Random | None = None, n_agents: int = 100,
+                 device="cuda"):
+        if random is None:
+            warnings.warn("Random number generator not specified, this can make models non-reproducible. "
+                          "Please pass a random number generator explicitly", UserWarning, stacklevel=2)
+            random = Random()
+        self.random = random
+        self.dimensions = np.asanyarray(dimensions, dtype=float)
+        self.ndims = int(self.dimensions.shape[0])
+        if self.ndims != 2:
+            raise NotImplementedError("mesa_b200 continuous spaces are two-dimensional")
+        self.size = self.dimensions[:, 1] - self.dimensions[:, 0]
+        self.center = np.sum(self.dimensions, axis=1) / 2
+        self.torus = bool(torus)
+        self.device = torch.device(device)
+        self._agent_positions = torch.empty((int(n_agents), 2), dtype=torch.float32, device=self.device)
+        self._n_agents = 0
+        self._ws = None
+
+    # -- storage (continuous_space.py:108-167) ---------------------------------
+    @property
+    def agent_positions(self) -> torch.Tensor:
+        return self._agent_positions[: self._n_agents]
+
+    @property
+    def width(self):
+        return self.size[0]
+
+    @property
+    def height(self):
+        return self.size[1]
+
+    def add_agents(self, positions) -> torch.Tensor:
+        """Append agents at `positions` ([k, 2]); returns their storage indices.  Out-of-bounds points wrap on
+        a torus and raise ValueError otherwise (continuous_space_agents.py:36-44)."""
+        pos = torch.as_tensor(np.asarray(positions, dtype=np.float64))
+        lo = torch.as_tensor(self.dimensions[:, 0])
+        hi = torch.as_tensor(self.dimensions[:, 1])
+        bad = ~((pos >= lo) & (pos <= hi)).all(dim=1)
+        if bad.any():
+            if not self.torus:
+                raise ValueError(f"point {pos[bad][0].tolist()} is outside the bounds of the space")
+            size = torch.as_tensor(self.size)
+            pos[bad] = lo + torch.remainder(pos[bad] - lo, size)
+        k = pos.shape[0]
+        need = self._n_agents + k
+        cap = self._agent_positions.shape[0]
+        if need > cap:
+            # growth +max(20 %, 20) rows like continuous_space.py:121-129, at least what is needed
+            new_cap = max(need, cap + max(int(cap * 0.2), 20))
+            grown = torch.empty((new_cap, 2), dtype=torch.float32, device=self.device)
+            grown[: self._n_agents] = self._agent_positions[: self._n_agents]
+            self._agent_positions = grown
+        self._agent_positions[self._n_agents:need] = pos.to(torch.float32).to(self.device)
+        idx = torch.arange(self._n_agents, need, device=self.device)
+        self._n_agents = need
+        self._ws = None
+        return idx
+
+    def remove_agent(self, index: int) -> int | None:
+        """Swap-with-last removal (continuous_space.py:141-167); returns the index that moved into `index`."""
+        last = self._n_agents - 1
+        if not 0 <= index <= last:
+            raise IndexError(index)
+        moved = None
+        if index != last:
+            self._agent_positions[index] = self._agent_positions[last]
+            moved = last
+        self._n_agents -= 1
+        self._ws = None
+        return moved
+
+    # -- geometry ---------------------------------------------------------------
+    def in_bounds(self, point) -> bool:
+        p = np.asanyarray(point)
+        return bool(((p >= self.dimensions[:, 0]) & (p <= self.dimensions[:, 1])).all())
+
+    def torus_correct(self, point) -> np.ndarray:
+        return self.dimensions[:, 0] + np.mod(np.asanyarray(point) - self.dimensions[:, 0], self.size)
+
+    # -- queries ------------------------------------------------------------------
+    def _workspace(self, radius: float) -> ops.CellListWorkspace:
+        if self._ws is None or self._ws.radius > radius or self._ws.n < self._n_agents:
+            self._ws = ops.CellListWorkspace(max(self._n_agents, 1), self.size, radius, self.device)
+        return self._ws
+
+    def radius_query(self, points, radius: float, exclude: torch.Tensor | None = None):
+        """Batched get_agents_in_radius for `points` [q, 2]: CSR (offsets, agent indices, float64 distances)."""
+        q = torch.as_tensor(np.asarray(points, dtype=np.float32)) if not isinstance(points, torch.Tensor) else points
+        q = q.to(self.device, torch.float32).contiguous()
+        return ops.radius_query(self.agent_positions.contiguous(), q, self.size, float(radius), self.torus,
+                                origin=self.dimensions[:, 0], exclude=exclude)
+
+    def neighbors_in_radius(self, radius: float):
+        """get_neighbors_in_radius of EVERY agent (self excluded) in one launch: CSR over agents."""
+        n = self._n_agents
+        me = torch.arange(n, dtype=torch.int32, device=self.device)
+        return self.radius_query(self.agent_positions, radius, exclude=me)
+
+    def get_agents_in_radius(self, point, radius: float | int = 1):
+        """continuous_space.py:237-247: (agent indices, distances) with dist <= radius, storage order."""
+        _, idx, dist = self.radius_query(np.asarray(point, dtype=np.float32)[None, :], radius)
+        return idx.cpu().tolist(), dist.cpu().numpy()
+
+    def calculate_distances(self, point, agents=None):
+        """continuous_space.py:202-235 for one point against all (or the given) agents; float64."""
+        pos = self.agent_positions if agents is None else self._agent_positions[torch.as_tensor(agents, device=self.device)]
+        p = torch.as_tensor(np.asarray(point, dtype=np.float64), device=self.device)
+        delta = torch.abs(p - pos.to(torch.float64))
+        if self.torus:
+            size = torch.as_tensor(self.size, device=self.device)
+            delta = torch.minimum(delta, size - delta)
+        dists = torch.sqrt(delta[:, 0] ** 2 + delta[:, 1] ** 2)
+        ids = list(range(self._n_agents)) if agents is None else list(agents)
+        return dists.cpu().numpy(), ids
+
+    def calculate_difference_vector(self, point, agents=None) -> np.ndarray:
+        """continuous_space.py:169-200 (torus: the strictly smaller of delta and delta - sign(delta)*size)."""
+        pos = self.agent_positions if agents is None else self._agent_positions[torch.as_tensor(agents, device=self.device)]
+        p = torch.as_tensor(np.asarray(point, dtype=np.float64), device=self.device)
+        delta = pos.to(torch.float64) - p
+        if self.torus:
+            size = torch.as_tensor(self.size, device=self.device)
+            inverse = delta - torch.sign(delta) * size
+            delta = torch.where(torch.abs(delta) < torch.abs(inverse), delta, inverse)
+        return delta.cpu().numpy()
+
+    def get_k_nearest_agents(self, point, k: int = 1):
+        """continuous_space.py:249-283 (ties: earlier storage index first)."""
+        dists, ids = self.calculate_distances(point)
+        n = len(dists)
+        if n == 0 or k <= 0:
+            return [], np.array([])
+        if k > n:
+            warnings.warn(f"Requested k={k} nearest agents but only {n} agent(s) are present in the space. "
+                          f"Returning all {n} agent(s).", UserWarning, stacklevel=2)
+            k = n
+        order = np.argsort(dists, kind="stable")[:k]
+        return [ids[i] for i in order], dists[order]
+
+
+ContinuousSpace = DeviceContinuousSpace

@@ -1,0 +1,9 @@
+"""Device versions of the four reference example models named by BASELINE.json
+(mesa/examples/basic/{schelling, conways_game_of_life, boltzmann_wealth_model, boid_flockers})."""
+from .boid_flockers import BoidFlockers, BoidsScenario
+from .boltzmann_wealth import BoltzmannScenario, BoltzmannWealth
+from .conways_game_of_life import ConwaysGameOfLife
+from .schelling import Schelling, SchellingScenario
+
+__all__ = ["Schelling", "SchellingScenario", "ConwaysGameOfLife", "BoltzmannWealth", "BoltzmannScenario",
+           "BoidFlockers", "BoidsScenario"]

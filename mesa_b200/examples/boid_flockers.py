@@ -1,0 +1,95 @@
+"""Boids flocking on the device (mirror of mesa/examples/basic/boid_flockers/model.py:22-120, agents.py:12-92).
+
+ACTIVATION MODE: the reference's `shuffle_do("step")` is sequential (each boid sees the boids moved
+before it); the device step is SYNCHRONOUS -- every boid reads the pre-step positions/directions --
+which is the reference's own `Boid.step` arithmetic applied to a frozen snapshot."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..agentset import DeviceAgent, DeviceAgentSet, batch_operator
+from ..continuous_space import DeviceContinuousSpace
+from ..model import DeviceModel
+from ._scenario import Scenario
+
+
+class BoidsScenario(Scenario):
+    """boid_flockers/model.py:22-46."""
+
+    population_size: int = 100
+    width: int = 100
+    height: int = 100
+    speed: float = 1.0
+    vision: float = 10.0
+    separation: float = 2.0
+    cohere: float = 0.03
+    separate: float = 0.015
+    match: float = 0.05
+
+
+class Boid(DeviceAgent):
+    """A Boid-style flocker agent (agents.py:12)."""
+
+
+@batch_operator(Boid, "step")
+def _step(agents: DeviceAgentSet, epoch: int | None = None, **_):
+    m = agents.model
+    s = m.scenario
+    pos, dirs = m.space._agent_positions, m._direction
+    ops.boids_step(pos[: m.space._n_agents], dirs, m.space.size, vision=s.vision, separation=s.separation,
+                   cohere=s.cohere, separate=s.separate, match=s.match, speed=s.speed, torus=m.space.torus,
+                   origin=m.space.dimensions[:, 0], ws=m._ws, pos_out=m._pos_next, dir_out=m._dir_next,
+                   neighbor_count=m._nbr_count)
+    # ping-pong: the new state becomes the space's positions / the agents' direction column
+    m.space._agent_positions, m._pos_next = m._pos_next, m.space._agent_positions
+    m._direction, m._dir_next = m._dir_next, m._direction
+    agents.columns["position"] = m.space._agent_positions
+    agents.columns["direction"] = m._direction
+
+
+class BoidFlockers(DeviceModel):
+    """Flocker model class. Handles agent creation, placement and scheduling."""
+
+    def __init__(self, scenario: BoidsScenario = BoidsScenario, initial_positions=None, initial_directions=None,
+                 device="cuda"):
+        if isinstance(scenario, type):
+            scenario = scenario()
+        super().__init__(scenario=scenario)
+        n = scenario.population_size
+        self.space = DeviceContinuousSpace([[0, scenario.width], [0, scenario.height]], torus=True,
+                                           random=self.random, n_agents=n, device=device)
+        dev = self.space.device
+        if initial_positions is None:
+            initial_positions = self.rng.random(size=(n, 2)) * self.space.size  # model.py:79-81
+        if initial_directions is None:
+            initial_directions = self.rng.uniform(-1, 1, size=(n, 2))           # model.py:82
+        self.space.add_agents(initial_positions)
+        self._direction = torch.as_tensor(np.asarray(initial_directions, dtype=np.float32)).to(dev).contiguous()
+        self._pos_next = torch.empty_like(self.space._agent_positions)
+        self._dir_next = torch.empty_like(self._direction)
+        self._nbr_count = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._ws = ops.CellListWorkspace(n, self.space.size, scenario.vision, dev)
+        self.agents = DeviceAgentSet(self, Boid, n, {"position": self.space._agent_positions,
+                                                     "direction": self._direction}, self.random)
+        self.agent_angles = torch.zeros(n, device=dev)
+        self.average_heading = None
+        self.update_average_heading()
+
+    def calculate_angles(self):
+        d = self._direction
+        self.agent_angles = torch.rad2deg(torch.atan2(d[:, 0], d[:, 1]))  # model.py:100-105
+
+    def update_average_heading(self):
+        if len(self.agents) == 0:
+            self.average_heading = 0
+            return
+        mean = self._direction.to(torch.float64).mean(dim=0)
+        self.average_heading = float(torch.atan2(mean[1], mean[0]))  # model.py:107-111
+
+    def step(self):
+        """model.py:113-120."""
+        self.agents.shuffle_do("step")
+        self.update_average_heading()
+        self.calculate_angles()

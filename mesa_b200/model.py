@@ -1,0 +1,57 @@
+"""DeviceModel: the part of mesa.Model the hot path needs (mesa/model.py:85-150, 296-422).
+
+Seeds: like the reference, `rng` / `seed` seed both a stdlib `random.Random` (`model.random`) and a
+numpy Generator (`model.rng`); in addition `model.philox_seed` keys the device draws and
+`model._next_epoch()` counts activations (`shuffle_do` / `shuffle` calls) so that every shuffle is a
+fresh, replayable permutation (csrc/philox.cuh).
+"""
+from __future__ import annotations
+
+import random
+
+import numpy as np
+
+
+class DeviceModel:
+    def __init__(self, *args, seed=None, rng=None, scenario=None, **kwargs):
+        if scenario is not None and rng is None and seed is None:
+            rng = getattr(scenario, "rng", None)
+        if rng is None:
+            rng = seed
+        self.scenario = scenario
+        if isinstance(rng, np.random.Generator):
+            self.rng = rng
+            stdlib_seed = int(rng.integers(0, 2**63))
+        else:
+            self.rng = np.random.default_rng(rng)
+            stdlib_seed = rng if rng is not None else int(self.rng.integers(0, 2**63))
+        self.random = random.Random(stdlib_seed)
+        self._seed = stdlib_seed
+        self.philox_seed = int(stdlib_seed) & 0xFFFFFFFFFFFFFFFF if isinstance(stdlib_seed, int) else hash(stdlib_seed) & 0xFFFFFFFFFFFFFFFF
+        self._epoch = 0
+        self.running = True
+        self.steps = 0
+        self.time = 0.0
+        self.agents = None  # set by the concrete model (a DeviceAgentSet)
+
+    def _next_epoch(self) -> int:
+        e = self._epoch
+        self._epoch += 1
+        return e
+
+    def step(self) -> None:  # pragma: no cover - user models override
+        """A single step. Fill in here."""
+
+    def _advance(self) -> None:
+        self.steps += 1
+        self.time += 1.0
+        self.step()
+
+    def run_for(self, duration: int) -> None:
+        """model.py:395-402: advance `duration` unit-interval steps."""
+        for _ in range(int(duration)):
+            self._advance()
+
+    def run_model(self) -> None:
+        while self.running:
+            self._advance()

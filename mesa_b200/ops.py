@@ -260,3 +260,103 @@ def boltzmann_step(cell: torch.Tensor, wealth: torch.Tensor, ws: BoltzmannWorksp
                                           int(bool(torus)), int(seed) & 0xFFFFFFFFFFFFFFFF, int(epoch) & 0xFFFFFFFF,
                                           N.ptr(ws.buf), ws.nbytes, ctypes.byref(iters), N.stream_ptr(cell.device)))
     return int(iters.value)
+
+
+# ----------------------------------------------------------------------------- property layers
+_DTYPES = {torch.uint8: 0, torch.bool: 0, torch.int32: 1, torch.float32: 2, torch.float64: 3}
+_BINARY = {"add": 0, "sub": 1, "mul": 2, "min": 3, "max": 4}
+_REDUCE = {"sum": 0, "min": 1, "max": 2, "count_nonzero": 3}
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError(f"property-layer kernels support uint8/bool/int32/float32/float64, not {t.dtype}") from None
+
+
+def layer_fill(layer: torch.Tensor, value) -> torch.Tensor:
+    """layer[:] = value  (np.full of grid.py:146 on an existing buffer)."""
+    _need_cuda(layer)
+    with torch.cuda.device(layer.device):
+        N.check(N.lib().mb_layer_fill(N.ptr(_c(layer)), layer.numel(), _dt(layer), float(value),
+                                      N.stream_ptr(layer.device)))
+    return layer
+
+
+def layer_affine_clamp(layer: torch.Tensor, alpha=1.0, beta=0.0, lo=float("-inf"), hi=float("inf"),
+                       out: torch.Tensor | None = None) -> torch.Tensor:
+    """out = clip(alpha * layer + beta, lo, hi); out defaults to in place."""
+    _need_cuda(layer, out)
+    out = layer if out is None else out
+    with torch.cuda.device(layer.device):
+        N.check(N.lib().mb_layer_affine_clamp(N.ptr(_c(layer)), N.ptr(_c(out)), layer.numel(), _dt(layer),
+                                              float(alpha), float(beta), float(lo), float(hi),
+                                              N.stream_ptr(layer.device)))
+    return out
+
+
+def layer_binary(a: torch.Tensor, b: torch.Tensor, op: str, out: torch.Tensor | None = None) -> torch.Tensor:
+    """out = a <op> b elementwise, op in add/sub/mul/min/max (e.g. np.minimum(sugar + 1, cap))."""
+    _need_cuda(a, b, out)
+    if a.shape != b.shape or a.dtype != b.dtype:
+        raise ValueError("layer_binary: shape / dtype mismatch")
+    out = torch.empty_like(a) if out is None else out
+    with torch.cuda.device(a.device):
+        N.check(N.lib().mb_layer_binary(N.ptr(_c(a)), N.ptr(_c(b)), N.ptr(_c(out)), a.numel(), _dt(a), _BINARY[op],
+                                        N.stream_ptr(a.device)))
+    return out
+
+
+def layer_reduce(layer: torch.Tensor, op: str = "sum") -> torch.Tensor:
+    """Aggregate a layer on the device; returns a 1-element tensor (int64 or float64)."""
+    _need_cuda(layer)
+    code = _REDUCE[op]
+    as_int = layer.dtype in (torch.uint8, torch.bool, torch.int32) or op == "count_nonzero"
+    res = torch.zeros(1, dtype=torch.int64 if as_int else torch.float64, device=layer.device)
+    ws = torch.empty(1024, dtype=torch.float64, device=layer.device)
+    with torch.cuda.device(layer.device):
+        N.check(N.lib().mb_layer_reduce(N.ptr(_c(layer)), layer.numel(), _dt(layer), code, N.ptr(res), N.ptr(ws),
+                                        ws.numel() * 8, N.stream_ptr(layer.device)))
+    return res
+
+
+def neighborhood_sum(layer: torch.Tensor, radius: int = 1, moore: bool = True, include_center: bool = False,
+                     torus: bool = False, halo_top: torch.Tensor | None = None,
+                     halo_bot: torch.Tensor | None = None) -> torch.Tensor:
+    """Sum of `layer` over each cell's radius-r neighbourhood (cell.py:225-276) for all cells at once."""
+    _need_cuda(layer, halo_top, halo_bot)
+    if layer.dim() != 2:
+        raise ValueError("neighborhood_sum expects a [rows, cols] layer")
+    if radius < 1:
+        raise ValueError("radius must be at least 1")
+    rows, cols = layer.shape
+    integer = layer.dtype in (torch.uint8, torch.bool, torch.int32)
+    out = torch.empty((rows, cols), dtype=torch.int32 if integer else torch.float64, device=layer.device)
+    if torus and halo_top is None and halo_bot is None and rows > 0:
+        if rows < 2 * radius + 1:
+            raise ValueError("torus needs rows >= 2*radius+1")
+        halo_top, halo_bot = layer[rows - radius:], layer[:radius]
+    with torch.cuda.device(layer.device):
+        N.check(N.lib().mb_neighborhood_sum(N.ptr(_c(layer)), N.ptr(halo_top), N.ptr(halo_bot), N.ptr(out), rows, cols,
+                                            _dt(layer), int(radius), int(not moore), int(bool(include_center)),
+                                            int(bool(torus)), N.stream_ptr(layer.device)))
+    return out
+
+
+def layer_diffuse(layer: torch.Tensor, rate: float, torus: bool = False, out: torch.Tensor | None = None,
+                  halo_top: torch.Tensor | None = None, halo_bot: torch.Tensor | None = None) -> torch.Tensor:
+    """One diffusion step (each cell shares `rate` of its value equally among its 8 neighbours)."""
+    _need_cuda(layer, out, halo_top, halo_bot)
+    if layer.dim() != 2 or layer.dtype not in (torch.float32, torch.float64):
+        raise ValueError("layer_diffuse expects a float32/float64 [rows, cols] layer")
+    rows, cols = layer.shape
+    out = torch.empty_like(layer) if out is None else out
+    if torus and halo_top is None and halo_bot is None and rows > 0:
+        if rows < 3:
+            raise ValueError("torus needs rows >= 3")
+        halo_top, halo_bot = layer[rows - 1], layer[0]
+    with torch.cuda.device(layer.device):
+        N.check(N.lib().mb_layer_diffuse(N.ptr(_c(layer)), N.ptr(halo_top), N.ptr(halo_bot), N.ptr(_c(out)), rows, cols,
+                                         _dt(layer), float(rate), int(bool(torus)), N.stream_ptr(layer.device)))
+    return out

@@ -1,0 +1,321 @@
+"""Device-resident orthogonal grids: the drop-in mirror of mesa.discrete_space.Grid for the hot path.
+
+Mirrors the public surface of
+    mesa/discrete_space/grid.py:59-128   Grid(dimensions, torus, capacity, random, cell_klass)
+    grid.py:434-501                      OrthogonalMooreGrid / OrthogonalVonNeumannGrid
+    grid.py:130-234                      create/add/remove_property_layer, get_neighborhood_mask
+    grid.py:288-316                      select_random_empty_cell
+    discrete_space.py:89-94, 169-183     find_nearest_cell, all_cells, __getitem__
+    cell.py:37, 192-276                  Cell.coordinate / is_empty / neighborhood / get_neighborhood
+with the same argument meaning and error behaviour (ValueError / TypeError / CellMissingException),
+but WITHOUT one Python object per cell: state is a set of [d0, d1] device layers (torch tensors),
+cells are lightweight proxies created on demand, and whole-grid neighbourhood work is one
+kernel launch (ops.neighborhood_sum, ops.schelling_happy, ops.gol_step).
+
+Two-dimensional grids only (the hot path of BASELINE.json; n-d grids are SURVEY §8f next-4).
+"""
+from __future__ import annotations
+
+from random import Random
+
+import numpy as np
+import torch
+
+from . import ops
+
+try:  # the reference's exception types when mesa is importable, same names otherwise
+    from mesa.exceptions import CellMissingException  # type: ignore
+except Exception:  # pragma: no cover - mesa is not installed on the GPU box
+    class CellMissingException(KeyError):
+        """Raised when a coordinate is not part of the grid (mesa/exceptions.py)."""
+
+        def __init__(self, coordinate):
+            super().__init__(f"Cell at coordinate {coordinate} does not exist.")
+            self.coordinate = coordinate
+
+
+_TORCH_DTYPES = {
+    float: torch.float64, int: torch.int32, bool: torch.bool,
+    np.float64: torch.float64, np.float32: torch.float32, np.int32: torch.int32, np.int64: torch.int64,
+    np.uint8: torch.uint8, np.int8: torch.int8, np.bool_: torch.bool,
+}
+
+
+def _torch_dtype(dtype):
+    if isinstance(dtype, torch.dtype):
+        return dtype
+    if dtype in _TORCH_DTYPES:
+        return _TORCH_DTYPES[dtype]
+    return _TORCH_DTYPES[np.dtype(dtype).type]
+
+
+class CellProxy:
+    """A cell of a DeviceGrid: coordinate + accessors that read the device layers (debug speed)."""
+
+    __slots__ = ("grid", "coordinate")
+
+    def __init__(self, grid: "DeviceGrid", coordinate: tuple[int, int]):
+        object.__setattr__(self, "grid", grid)
+        object.__setattr__(self, "coordinate", coordinate)
+
+    # property layers as attributes (grid.py:206-220)
+    def __getattr__(self, name):
+        layers = object.__getattribute__(self, "grid").property_layers
+        if name in layers:
+            return layers[name][self.coordinate].item()
+        raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        grid = self.grid
+        if name in grid.property_layers:
+            if name in grid._read_only_layers:
+                raise AttributeError(f"property_layer '{name}' is read-only")
+            grid.property_layers[name][self.coordinate] = value
+            return
+        raise AttributeError(name)
+
+    def __eq__(self, other):
+        return isinstance(other, CellProxy) and other.grid is self.grid and other.coordinate == self.coordinate
+
+    def __hash__(self):
+        return hash(self.coordinate)
+
+    def __repr__(self):
+        return f"Cell({self.coordinate})"
+
+    @property
+    def flat(self) -> int:
+        return self.coordinate[0] * self.grid.dimensions[1] + self.coordinate[1]
+
+    @property
+    def is_empty(self) -> bool:
+        return bool(self.grid.empty[self.coordinate].item())
+
+    @property
+    def neighborhood(self) -> list["CellProxy"]:
+        return self.get_neighborhood()
+
+    def get_neighborhood(self, radius: int = 1, include_center: bool = False) -> list["CellProxy"]:
+        """Neighbour cells in the reference's order for radius 1 (connection order)."""
+        return [CellProxy(self.grid, c) for c in self.grid.neighborhood_coordinates(self.coordinate, radius, include_center)]
+
+
+class DeviceGrid:
+    """Base class of the device grids (mirror of mesa.discrete_space.Grid)."""
+
+    _offsets: list[tuple[int, int]] = []
+    _moore = True
+
+    @property
+    def width(self) -> int:
+        return self.dimensions[0]
+
+    @property
+    def height(self) -> int:
+        return self.dimensions[1]
+
+    def __init__(self, dimensions, torus: bool = False, capacity: float | None = None,
+                 random: Random | None = None, device="cuda"):
+        self.torus = torus
+        self.dimensions = tuple(dimensions) if not isinstance(dimensions, tuple) else dimensions
+        self.capacity = capacity
+        self._validate_parameters()
+        if len(self.dimensions) != 2:
+            raise NotImplementedError("mesa_b200 device grids are two-dimensional")
+        self.random = random if random is not None else Random()
+        self.device = torch.device(device)
+        self.property_layers: dict[str, torch.Tensor] = {}
+        self._read_only_layers: set[str] = set()
+        self.create_property_layer("empty", default_value=True, dtype=bool)
+
+    # grid.py:280-286
+    def _validate_parameters(self):
+        if not all(isinstance(dim, int) and dim > 0 for dim in self.dimensions):
+            raise ValueError("Dimensions must be a list of positive integers.")
+        if not isinstance(self.torus, bool):
+            raise TypeError("Torus must be a boolean.")
+        if self.capacity is not None and not isinstance(self.capacity, float | int):
+            raise TypeError("Capacity must be a number or None.")
+
+    # ------------------------------------------------------------------ property layers
+    def create_property_layer(self, name: str, default_value=0.0, dtype=float, read_only: bool = False) -> torch.Tensor:
+        layer = torch.empty(self.dimensions, dtype=_torch_dtype(dtype), device=self.device)
+        if layer.dtype in (torch.bool, torch.uint8, torch.int32, torch.float32, torch.float64):
+            ops.layer_fill(layer.view(torch.uint8) if layer.dtype == torch.bool else layer, default_value)
+        else:
+            layer.fill_(default_value)
+        self._attach_property_layer(name, layer, read_only=read_only)
+        return layer
+
+    def add_property_layer(self, name: str, array, read_only: bool = False) -> None:
+        if tuple(array.shape) != tuple(self.dimensions):
+            raise ValueError(f"Array shape {tuple(array.shape)} does not match grid dimensions {self.dimensions}.")
+        if not isinstance(array, torch.Tensor):
+            array = torch.as_tensor(np.asarray(array)).to(self.device)
+        elif array.device != self.device:
+            array = array.to(self.device)
+        self._attach_property_layer(name, array, read_only=read_only)
+
+    def remove_property_layer(self, name: str) -> None:
+        if name not in self.property_layers:
+            raise KeyError(f"No property_layer named '{name}'.")
+        del self.property_layers[name]
+        self._read_only_layers.discard(name)
+
+    def _attach_property_layer(self, name: str, layer: torch.Tensor, read_only: bool = False) -> None:
+        if any(name in c.__dict__ for c in type(self).__mro__) or name in ("grid", "coordinate"):
+            raise ValueError(f"property_layer '{name}' conflicts with an existing Grid attribute.")
+        if name in self.property_layers:
+            raise ValueError(f"property_layer '{name}' already exists.")
+        self.property_layers[name] = layer
+        if read_only:
+            self._read_only_layers.add(name)
+
+    def __getattr__(self, name):
+        # grid.<layer> access (grid.py:205)
+        layers = self.__dict__.get("property_layers")
+        if layers is not None and name in layers:
+            return layers[name]
+        raise AttributeError(f"{type(self).__name__!s} has no attribute {name!r}")
+
+    # ------------------------------------------------------------------ cells
+    def _check(self, coordinate) -> tuple[int, int]:
+        try:
+            i, j = coordinate
+        except Exception:
+            raise CellMissingException(coordinate) from None
+        if not (isinstance(i, (int, np.integer)) and isinstance(j, (int, np.integer))
+                and 0 <= i < self.dimensions[0] and 0 <= j < self.dimensions[1]):
+            raise CellMissingException(coordinate)
+        return int(i), int(j)
+
+    def __getitem__(self, coordinate) -> CellProxy:
+        return CellProxy(self, self._check(coordinate))
+
+    @property
+    def all_cells(self):
+        """Row-major iterator over cell proxies (grid.py:120-126 order); lazy -- do not materialise large grids."""
+        d0, d1 = self.dimensions
+        return (CellProxy(self, (i, j)) for i in range(d0) for j in range(d1))
+
+    def __len__(self) -> int:
+        return self.dimensions[0] * self.dimensions[1]
+
+    @property
+    def empties(self):
+        idx = torch.nonzero(self.empty.reshape(-1)).reshape(-1).cpu().tolist()
+        d1 = self.dimensions[1]
+        return [CellProxy(self, (k // d1, k % d1)) for k in idx]
+
+    def find_nearest_cell(self, position) -> CellProxy:
+        """Floor of the position, wrapped on a torus (discrete_space tests test_spatial_lookups.py:20-44)."""
+        pos = np.asarray(position, dtype=float)
+        idx = np.floor(pos).astype(int)
+        if self.torus:
+            idx = idx % np.array(self.dimensions)
+        if np.any(idx < 0) or np.any(idx >= np.array(self.dimensions)):
+            raise ValueError(f"Position {position} is outside the grid bounds.")
+        return CellProxy(self, (int(idx[0]), int(idx[1])))
+
+    # ------------------------------------------------------------------ neighbourhoods
+    def neighborhood_coordinates(self, coordinate, radius: int = 1, include_center: bool = False) -> list[tuple[int, int]]:
+        """Distinct neighbour coordinates of one cell (Cell._neighborhood, cell.py:225-276): BFS over
+        the connection offsets, so Moore = Chebyshev, von Neumann = Manhattan; torus wraps and dedups."""
+        if radius < 1:
+            raise ValueError("radius must be at least 1")
+        start = self._check(coordinate)
+        d0, d1 = self.dimensions
+
+        def connections(c):
+            out = []
+            for di, dj in self._offsets:
+                ni, nj = c[0] + di, c[1] + dj
+                if self.torus:
+                    ni, nj = ni % d0, nj % d1
+                if 0 <= ni < d0 and 0 <= nj < d1:
+                    out.append((ni, nj))
+            return out
+
+        if radius == 1:
+            seen = dict.fromkeys(connections(start))
+            if include_center:
+                seen[start] = None
+            return list(seen)
+        visited = {start}
+        layer = connections(start)
+        found: dict = {}
+        for c in layer:
+            if c not in visited:
+                visited.add(c)
+                found[c] = None
+        for _ in range(radius - 1):
+            nxt = []
+            for c in layer:
+                for nb in connections(c):
+                    if nb not in visited:
+                        visited.add(nb)
+                        nxt.append(nb)
+                        found[nb] = None
+            layer = nxt
+            if not layer:
+                break
+        if include_center:
+            found[start] = None
+        else:
+            found.pop(start, None)
+        return list(found)
+
+    def get_neighborhood_mask(self, coordinate, include_center: bool = True, radius: int = 1) -> torch.Tensor:
+        mask = torch.zeros(self.dimensions, dtype=torch.bool, device=self.device)
+        coords = self.neighborhood_coordinates(coordinate, radius, include_center)
+        if coords:
+            idx = torch.tensor(coords, device=self.device)
+            mask[idx[:, 0], idx[:, 1]] = True
+        return mask
+
+    def neighborhood_sum(self, layer, radius: int = 1, include_center: bool = False) -> torch.Tensor:
+        """Sum of a property layer over every cell's neighbourhood in one launch."""
+        if isinstance(layer, str):
+            layer = self.property_layers[layer]
+        if layer.dtype == torch.bool:
+            layer = layer.view(torch.uint8)
+        return ops.neighborhood_sum(layer, radius, self._moore, include_center, self.torus)
+
+    # ------------------------------------------------------------------ empties
+    def select_random_empty_cell(self) -> CellProxy:
+        """grid.py:288-316: <= 50 uniform probes, first empty wins; else argwhere(empty) + one choice."""
+        d0, d1 = self.dimensions
+        ncells = d0 * d1
+        empty = self.empty
+        for _ in range(50):
+            k = self.random._randbelow(ncells)
+            if bool(empty.reshape(-1)[k].item()):
+                return CellProxy(self, (k // d1, k % d1))
+        empties = torch.nonzero(empty.reshape(-1)).reshape(-1)
+        if empties.numel() == 0:
+            raise ValueError("Grid is completely full. No empty cells available. Cannot select a random empty cell.")
+        k = int(empties[self.random._randbelow(empties.numel())].item())
+        return CellProxy(self, (k // d1, k % d1))
+
+
+class DeviceMooreGrid(DeviceGrid):
+    """8-connected grid (OrthogonalMooreGrid, grid.py:434-462)."""
+
+    # fmt: off
+    _offsets = [(-1, -1), (-1, 0), (-1, 1),
+                ( 0, -1),          ( 0, 1),
+                ( 1, -1), ( 1, 0), ( 1, 1)]
+    # fmt: on
+    _moore = True
+
+
+class DeviceVonNeumannGrid(DeviceGrid):
+    """4-connected grid (OrthogonalVonNeumannGrid, grid.py:465-501)."""
+
+    _offsets = [(-1, 0), (0, -1), (0, 1), (1, 0)]
+    _moore = False
+
+
+# names a Mesa user would look for
+OrthogonalMooreGrid = DeviceMooreGrid
+OrthogonalVonNeumannGrid = DeviceVonNeumannGrid

@@ -97,6 +97,41 @@ def schelling_fixture(name, width, height, density, homophily, radius, steps, mt
     print(name, "agents", len(agents), "happy", happy_counts[:5], "...", happy_counts[-1], "movers", movers[:5])
 
 
+# ------------------------------------------------------------------------------ neighbourhoods
+def neighborhood_fixture(name):
+    """Neighbourhood sums of a random integer layer computed cell by cell through the reference's
+    Cell.get_neighborhood (cell.py:202-276) for Moore / von Neumann grids, torus and clamped."""
+    import random
+
+    from mesa.discrete_space import OrthogonalMooreGrid, OrthogonalVonNeumannGrid
+
+    rng = np.random.default_rng(0)
+    out, cases = {}, []
+    k = 0
+    for moore in (True, False):
+        for torus in (False, True):
+            for (rows, cols) in [(7, 9), (5, 5), (12, 8)]:
+                for radius in (1, 2, 3):
+                    if torus and min(rows, cols) < 2 * radius + 1:
+                        continue
+                    for include_center in (False, True):
+                        klass = OrthogonalMooreGrid if moore else OrthogonalVonNeumannGrid
+                        grid = klass((rows, cols), torus=torus, random=random.Random(1))
+                        layer = rng.integers(0, 50, size=(rows, cols)).astype(np.int32)
+                        sums = np.zeros((rows, cols), dtype=np.int64)
+                        sizes = np.zeros((rows, cols), dtype=np.int64)
+                        for cell in grid.all_cells:
+                            nb = cell.get_neighborhood(radius=radius, include_center=include_center)
+                            sums[cell.coordinate] = sum(int(layer[c.coordinate]) for c in nb)
+                            sizes[cell.coordinate] = len(nb)
+                        out[f"layer_{k}"], out[f"sums_{k}"], out[f"sizes_{k}"] = layer, sums, sizes
+                        cases.append((int(moore), int(torus), rows, cols, radius, int(include_center)))
+                        k += 1
+    out["cases"] = np.array(cases, dtype=np.int64)
+    np.savez_compressed(os.path.join(GOLDEN, name), **out)
+    print(name, k, "cases")
+
+
 # ------------------------------------------------------------------------------ Boltzmann
 def boltzmann_fixture(name, n, width, height, steps, mt_seed, philox_seed):
     from mesa.examples.basic.boltzmann_wealth_model.agents import MoneyAgent
@@ -200,6 +235,9 @@ def main():
     import_reference()
     os.makedirs(GOLDEN, exist_ok=True)
     only = sys.argv[1] if len(sys.argv) > 1 else ""
+    if only == "neighborhoods":
+        neighborhood_fixture("neighborhoods.npz")
+        return
     if only == "boltzmann":
         boltzmann_fixture("boltzmann_100_10x10.npz", 100, 10, 10, 25, 42, 3)      # reference "small"
         boltzmann_fixture("boltzmann_2000_20x30.npz", 2000, 20, 30, 10, 7, 4)     # crowded cells
@@ -209,6 +247,7 @@ def main():
         boids_fixture("boids_300.npz", 300, 100, 100, 10.0, 2.0, 3, 42, 5)
         boids_fixture("boids_120_wrap.npz", 120, 40, 30, 6.0, 2.0, 3, 1, 6)
         return
+    neighborhood_fixture("neighborhoods.npz")
     gol_fixture(37, 23, 42, 6, "gol_37x23.npz")
     gol_fixture(64, 48, 7, 20, "gol_64x48.npz")
     schelling_fixture("schelling_20x20_r1.npz", 20, 20, 0.8, 0.4, 1, 30, 42, 2024, full_steps=range(1, 31))
