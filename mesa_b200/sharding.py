@@ -77,3 +77,88 @@ class HaloExchanger:
     def exchange(self, block: torch.Tensor):
         self.finish(self.start(block))
         return self.halo_top, self.halo_bot
+
+
+class PeerHaloLayer:
+    """Row block of a sharded uint8/int8 layer whose halos are READ IN PLACE from the neighbours' HBM.
+
+    Both ping-pong generations of the block live in torch symmetric memory (CUDA peer mappings over
+    NVLink 5 / NVSwitch, every peer one hop away), so the stencil kernel receives the neighbours' edge
+    rows as plain device pointers (`halo_top` / `halo_bot` of mb_gol_step_u8, mb_schelling_happy_i8):
+    no pack/unpack, no NCCL send/recv, no staging copy.  The default generation is one stencil
+    launch + one device-side barrier; the optional overlapped order is
+
+        edge kernel (rows 0..r-1 and R-r..R-1 of the new generation, reads the peers' old edges)
+        put_signal(up), put_signal(down)          "my new edges are written, your old ones are read"
+        interior kernel (rows r..R-r-1, needs no remote data)          <- hides the signal latency
+        wait_signal(up), wait_signal(down)
+
+    which also orders the write-after-read on the ping-pong buffers (a peer signals only after the
+    kernel that read my old edge rows has finished).  CUDA tensors + NCCL process group only; the
+    gloo/CPU path and the fallback use HaloExchanger.
+    """
+
+    def __init__(self, rows: int, cols: int, dtype: torch.dtype, radius: int, torus: bool, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.rows, self.cols, self.radius, self.torus = int(rows), int(cols), int(radius), bool(torus)
+        if self.rows < 2 * self.radius + 1:
+            raise ValueError("row block thinner than 2*radius+1")
+        self.buf = symm_mem.empty((2, self.rows, self.cols), dtype=dtype, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.up = self._peer(self.rank - 1)
+        self.down = self._peer(self.rank + 1)
+        shape = (2, self.rows, self.cols)
+        self.peer_up = self.hdl.get_buffer(self.up, shape, dtype) if self.up is not None else None
+        self.peer_down = self.hdl.get_buffer(self.down, shape, dtype) if self.down is not None else None
+        self.cur = 0
+        self.hdl.barrier()
+
+    def _peer(self, r: int):
+        if 0 <= r < self.world:
+            return r
+        return r % self.world if self.torus else None
+
+    @property
+    def state(self) -> torch.Tensor:
+        return self.buf[self.cur]
+
+    def halos(self):
+        """(rows above, rows below) of the current generation, living in the neighbours' memory."""
+        r, R = self.radius, self.rows
+        top = self.peer_up[self.cur, R - r:] if self.peer_up is not None else None
+        bot = self.peer_down[self.cur, :r] if self.peer_down is not None else None
+        return top, bot
+
+    def step(self, kernel, overlap: bool = False) -> None:
+        """Advance one generation.  `kernel(src_rows, dst_rows, halo_top, halo_bot)` runs the stencil on a
+        contiguous run of rows given the rows above / below it (None = outside the grid).
+
+        overlap=False (default): ONE launch over the whole block with the neighbours' rows as halo
+        pointers, then a device-side barrier over the group (measured 112 us/generation for 16384^2
+        per GPU at 2 GPUs against 96 us on one GPU).  overlap=True: edges / signals / interior /
+        waits as described in the class docstring; correct, but the six extra small launches cost
+        more than the barrier they hide (measured 130-138 us), so it is kept as an option only."""
+        r, R = self.radius, self.rows
+        src, dst = self.buf[self.cur], self.buf[1 - self.cur]
+        top, bot = self.halos()
+        if not overlap:
+            kernel(src, dst, top, bot)
+            self.hdl.barrier()
+            self.cur ^= 1
+            return
+        # edges first: they are what the neighbours wait for
+        kernel(src[:r], dst[:r], top, src[r:2 * r])
+        kernel(src[R - r:], dst[R - r:], src[R - 2 * r:R - r], bot)
+        if self.up is not None:
+            self.hdl.put_signal(self.up, 0)
+        if self.down is not None:
+            self.hdl.put_signal(self.down, 1)
+        kernel(src[r:R - r], dst[r:R - r], src[:r], src[R - r:])
+        if self.down is not None:
+            self.hdl.wait_signal(self.down, 0)   # the rank below signalled its "up" neighbour (me) on channel 0
+        if self.up is not None:
+            self.hdl.wait_signal(self.up, 1)
+        self.cur ^= 1

@@ -1,0 +1,102 @@
+"""Dev: row-sharded GoL with halos read directly from peer HBM over NVLink (symmetric memory) vs NCCL exchange."""
+import os, sys, json, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.distributed as dist
+import torch.distributed._symmetric_memory as symm_mem
+from mesa_b200 import ops
+from mesa_b200.sharding import HaloExchanger
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local); dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+R = C = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 500
+g = torch.Generator(device=dev).manual_seed(1234 + rank)
+init = (torch.rand((R, C), device=dev, generator=g) < 0.2).to(torch.uint8)
+
+# --- NCCL reference
+a, b = init.clone(), torch.empty_like(init)
+hx = HaloExchanger(C, torch.uint8, 1, True, dev)
+def nccl_step(a, b):
+    top, bot = hx.exchange(a)
+    ops.gol_step(a, out=b, torus=True, halo_top=top[0], halo_bot=bot[0])
+for _ in range(5):
+    nccl_step(a, b); a, b = b, a
+dist.barrier(); torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(steps):
+    nccl_step(a, b); a, b = b, a
+e1.record(); torch.cuda.synchronize()
+ms_nccl = e0.elapsed_time(e1) / steps
+ref = a.clone()
+
+# --- PeerHaloLayer: edges first, signals, interior overlapped
+from mesa_b200.sharding import PeerHaloLayer
+pl = PeerHaloLayer(R, C, torch.uint8, 1, True, dev)
+pl.state.copy_(init)
+def rows_kernel(src, dst, top, bot):
+    ops.gol_step(src, out=dst, torus=False, col_torus=True, halo_top=None if top is None else top[-1], halo_bot=None if bot is None else bot[0])
+for _ in range(5):
+    pl.step(rows_kernel)
+torch.cuda.synchronize(); dist.barrier()
+e0.record()
+for _ in range(steps):
+    pl.step(rows_kernel)
+e1.record(); torch.cuda.synchronize()
+ms_peer = e0.elapsed_time(e1) / steps
+same_peer = bool(torch.equal(pl.state, ref))
+
+# --- same, two generations captured in a CUDA graph
+pl2 = PeerHaloLayer(R, C, torch.uint8, 1, True, dev)
+pl2.state.copy_(init)
+for _ in range(6):
+    pl2.step(rows_kernel)      # warm-up (even number: cur back to 0)
+torch.cuda.synchronize(); dist.barrier()
+graph = torch.cuda.CUDAGraph()
+cap = torch.cuda.Stream()
+with torch.cuda.stream(cap):
+    with torch.cuda.graph(graph, stream=cap):
+        pl2.step(rows_kernel); pl2.step(rows_kernel)
+torch.cuda.synchronize(); dist.barrier()
+for _ in range(2):
+    graph.replay()
+torch.cuda.synchronize(); dist.barrier()
+e0.record()
+for _ in range(steps // 2):
+    graph.replay()
+e1.record(); torch.cuda.synchronize()
+ms_graph = e0.elapsed_time(e1) / (steps // 2 * 2)
+# compare against the NCCL path advanced to the same generation count
+gens_graph = 6 + 4 + steps // 2 * 2
+a2, b2 = init.clone(), torch.empty_like(init)
+for _ in range(gens_graph):
+    nccl_step(a2, b2); a2, b2 = b2, a2
+torch.cuda.synchronize()
+same_graph = bool(torch.equal(pl2.state, a2))
+
+# --- symmetric memory: peers' edge rows are read in place
+buf = symm_mem.empty((2, R, C), dtype=torch.uint8, device=dev)
+hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+up, down = (rank - 1) % world, (rank + 1) % world
+pu = hdl.get_buffer(up, (2, R, C), torch.uint8)
+pd = hdl.get_buffer(down, (2, R, C), torch.uint8)
+buf[0].copy_(init)
+hdl.barrier()
+cur = 0
+def symm_step(cur):
+    ops.gol_step(buf[cur], out=buf[1 - cur], torus=True, halo_top=pu[cur, R - 1], halo_bot=pd[cur, 0])
+    hdl.barrier()
+for _ in range(5):
+    symm_step(cur); cur ^= 1
+torch.cuda.synchronize(); dist.barrier()
+e0.record()
+for _ in range(steps):
+    symm_step(cur); cur ^= 1
+e1.record(); torch.cuda.synchronize()
+ms_symm = e0.elapsed_time(e1) / steps
+same = bool(torch.equal(buf[cur], ref))
+t = torch.tensor([ms_nccl, ms_symm, ms_peer, ms_graph], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+if rank == 0:
+    print(json.dumps({"world": world, "ms_nccl": t[0].item(), "ms_symm_barrier": t[1].item(), "ms_peer_overlap": t[2].item(), "ms_peer_graph": t[3].item(), "identical": same, "identical_peer": same_peer, "identical_graph": same_graph}))
+dist.destroy_process_group()
