@@ -30,145 +30,216 @@ constexpr int kWarps = 8;
 constexpr int kRowsPerWarp = 64;
 constexpr int kMaxRadius = 7;  // (2*7+1)^2 - 1 = 224 neighbours fit a byte
 
+enum { MODE_LINEAR = 0, MODE_T = 1, MODE_U = 2 };
+
+// How the vector kernel evaluates `similar >= min_similar[valid]` on packed bytes (all < 128):
+//   MODE_LINEAR  A*similar + C >= B*valid        (host-verified against the exact table, e.g. h=0.4 -> 5s >= 2v)
+//   MODE_T       similar >= base + #{k : valid >= steps[k]}
+//   MODE_U       valid - similar <= base + #{k : valid >= steps[k]}
+// valid == 0 is decided by happy_if_alone.  The scalar kernel reads min_similar[] directly.
 struct HappyRule {
-    int mode;      // 0: happy iff similar >= thr(valid); 1: happy iff (valid - similar) <= thr(valid)
-    int base;      // thr(valid) = base + #{k : valid >= steps[k]}  for valid >= 1
-    int nsteps;
-    int happy_if_alone;  // valid == 0 -> happy?
+    int mode;
+    int A, B, C;
+    int base, nsteps;
+    int happy_if_alone;
     uint8_t steps[24];
-    uint8_t min_similar[232];  // full table for the scalar kernel (index = valid)
+    uint8_t min_similar[232];
 };
 
 __device__ __forceinline__ unsigned splat(unsigned b) { return b * 0x01010101u; }
 
-// E[0..5] = word left of the lane, 4 words of the lane, word right of the lane.
-struct RowQ {
-    unsigned occ[6];
-    unsigned one[6];
+// One input row of a lane after the horizontal pass.
+//   R == 1: h[k] holds both box-row sums per byte: low nibble = #occupied, high nibble = #type-1 (each <= 3)
+//   R == 2: h[k] = #occupied, g[k] = #type-1 over the 5 columns (each <= 5)
+template <int R>
+struct RowH {
+    unsigned h[4];
+    unsigned g[R == 1 ? 1 : 4];
+    unsigned occ[4];  // centre cells: occupied (0/1 per byte)
+    unsigned one[4];  // centre cells: type 1
 };
 
-template <int R>
-__device__ __forceinline__ const int8_t* happy_row_ptr(const int8_t* __restrict__ in,
-                                                       const int8_t* __restrict__ halo_top,
-                                                       const int8_t* __restrict__ halo_bot, int64_t r,
-                                                       int64_t rows, int64_t cols) {
-    if (r < 0) return (halo_top != nullptr && r >= -R) ? halo_top + (R + r) * cols : nullptr;
-    if (r >= rows) return (halo_bot != nullptr && r - rows < R) ? halo_bot + (r - rows) * cols : nullptr;
-    return in + r * cols;
+struct LaneAddr {
+    unsigned col, lcol, rcol;
+    bool active, edge_l, edge_r, ld_left, ld_right;
+};
+
+struct RawRow {
+    uint4 v;
+    unsigned lw, rw;  // aligned word left / right of the lane's 16 cells (strip-edge lanes only)
+};
+
+template <bool kChecked>
+__device__ __forceinline__ RawRow load_raw(const int8_t* __restrict__ row, const LaneAddr& la) {
+    RawRow x;
+    x.v = make_uint4(~0u, ~0u, ~0u, ~0u);  // -1 = empty outside the grid
+    x.lw = ~0u;
+    x.rw = ~0u;
+    if (!kChecked || row != nullptr) {
+        if (la.active) x.v = __ldg(reinterpret_cast<const uint4*>(row + la.col));
+        if (la.ld_left) x.lw = __ldg(reinterpret_cast<const unsigned*>(row + la.lcol));
+        if (la.ld_right) x.rw = __ldg(reinterpret_cast<const unsigned*>(row + la.rcol));
+    }
+    return x;
 }
 
-__device__ __forceinline__ RowQ load_rowq(const int8_t* __restrict__ p, int64_t col, bool active, bool edge_l,
-                                          bool edge_r, bool ld_left, bool ld_right, int64_t lcol,
-                                          int64_t rcol) {
-    uint4 v = make_uint4(~0u, ~0u, ~0u, ~0u);  // -1 = empty outside the grid
-    unsigned lw = ~0u, rw = ~0u;
-    if (p != nullptr) {
-        if (active) v = __ldg(reinterpret_cast<const uint4*>(p + col));
-        if (ld_left) lw = __ldg(reinterpret_cast<const unsigned*>(p + lcol));
-        if (ld_right) rw = __ldg(reinterpret_cast<const unsigned*>(p + rcol));
-    }
+template <int R>
+__device__ __forceinline__ RowH<R> make_rowh(const RawRow& x, const LaneAddr& la) {
+    const uint4 v = x.v;
+    unsigned lw = x.lw, rw = x.rw;
     const unsigned sl = __shfl_up_sync(0xffffffffu, v.w, 1);
     const unsigned sr = __shfl_down_sync(0xffffffffu, v.x, 1);
-    if (!edge_l) lw = sl;
-    if (!edge_r) rw = sr;
+    if (!la.edge_l) lw = sl;
+    if (!la.edge_r) rw = sr;
     const unsigned raw[6] = {lw, v.x, v.y, v.z, v.w, rw};
-    RowQ q;
+    RowH<R> q;
+    if constexpr (R == 1) {
+        unsigned e[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        const unsigned occ = ~(raw[k] >> 7) & 0x01010101u;  // type >= 0
-        q.occ[k] = occ;
-        q.one[k] = raw[k] & occ;  // type == 1
+        for (int k = 0; k < 6; ++k) {
+            const unsigned occ = ~(raw[k] >> 7) & 0x01010101u;  // type >= 0
+            const unsigned one = raw[k] & occ;                  // type == 1
+            e[k] = occ + (one << 4);
+            if (k >= 1 && k <= 4) { q.occ[k - 1] = occ; q.one[k - 1] = one; }
+        }
+#pragma unroll
+        for (int k = 1; k <= 4; ++k)
+            q.h[k - 1] = e[k] + __funnelshift_r(e[k], e[k + 1], 8) + __funnelshift_l(e[k - 1], e[k], 8);
+        q.g[0] = 0u;
+    } else {
+        unsigned eo[6], e1[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            eo[k] = ~(raw[k] >> 7) & 0x01010101u;
+            e1[k] = raw[k] & eo[k];
+            if (k >= 1 && k <= 4) { q.occ[k - 1] = eo[k]; q.one[k - 1] = e1[k]; }
+        }
+#pragma unroll
+        for (int k = 1; k <= 4; ++k) {
+            unsigned a = eo[k], b = e1[k];
+#pragma unroll
+            for (int d = 1; d <= R; ++d) {
+                a += __funnelshift_r(eo[k], eo[k + 1], 8 * d) + __funnelshift_l(eo[k - 1], eo[k], 8 * d);
+                b += __funnelshift_r(e1[k], e1[k + 1], 8 * d) + __funnelshift_l(e1[k - 1], e1[k], 8 * d);
+            }
+            q.h[k - 1] = a;
+            q.g[k - 1] = b;
+        }
     }
     return q;
 }
 
 template <int R>
-__global__ void __launch_bounds__(kWarps * 32)
+__device__ __forceinline__ const int8_t* happy_row_ptr(const int8_t* __restrict__ in,
+                                                       const int8_t* __restrict__ halo_top,
+                                                       const int8_t* __restrict__ halo_bot, int r, int rows,
+                                                       size_t pitch) {
+    if (r < 0) return (halo_top != nullptr && r >= -R) ? halo_top + (size_t)(R + r) * pitch : nullptr;
+    if (r >= rows) return (halo_bot != nullptr && r - rows < R) ? halo_bot + (size_t)(r - rows) * pitch : nullptr;
+    return in + (size_t)r * pitch;
+}
+
+// happiness of 4 packed centre cells from the box sums (incl. the centre) of occupied / type-1 cells
+template <int MODE>
+__device__ __forceinline__ unsigned decide4(unsigned bocc, unsigned bone, unsigned occ_c, unsigned one_c,
+                                            const HappyRule& rule) {
+    const unsigned valid = bocc - occ_c;                       // occupied neighbours
+    const unsigned m1 = one_c * 0xffu;                         // 0xff where the centre is type 1
+    const unsigned same = (m1 & bone) | (~m1 & (bocc - bone)); // cells of the centre's type incl. itself
+    const unsigned similar = same - occ_c;
+    unsigned flag;  // bit 7 of each byte = happy
+    if (MODE == MODE_LINEAR) {
+        flag = (similar * (unsigned)rule.A + splat((unsigned)rule.C + 128u)) - valid * (unsigned)rule.B;
+    } else {
+        const unsigned vo = valid | 0x80808080u;
+        unsigned thr = splat((unsigned)rule.base);
+        for (int s = 0; s < rule.nsteps; ++s) thr += ((vo - splat(rule.steps[s])) >> 7) & 0x01010101u;
+        flag = MODE == MODE_T ? (similar | 0x80808080u) - thr : (thr | 0x80808080u) - (valid - similar);
+    }
+    const unsigned nonalone = valid + 0x7f7f7f7fu;             // bit 7 = valid != 0
+    flag = rule.happy_if_alone ? (flag | ~nonalone) : (flag & nonalone);
+    return (flag >> 7) & occ_c;
+}
+
+template <int R, int MODE>
+__global__ void __launch_bounds__(kWarps * 32, R == 1 ? 3 : 2)
 schelling_happy_vec(const int8_t* __restrict__ type, const int8_t* __restrict__ halo_top,
-                    const int8_t* __restrict__ halo_bot, uint8_t* __restrict__ happy, int64_t rows,
-                    int64_t cols, int col_torus, int nstrips, const HappyRule rule,
+                    const int8_t* __restrict__ halo_bot, uint8_t* __restrict__ happy, int rows, int cols,
+                    int col_torus, int nstrips, const HappyRule rule,
                     unsigned long long* __restrict__ happy_count) {
     const int lane = threadIdx.x & 31;
-    const int64_t task = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
-    const int64_t strip = task % nstrips;
-    const int64_t row0 = (task / nstrips) * kRowsPerWarp;
+    const unsigned task = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const unsigned strip = task % (unsigned)nstrips;
+    const int row0 = (int)(task / (unsigned)nstrips) * kRowsPerWarp;
     if (row0 >= rows) return;
 
-    const int64_t col = strip * 512 + lane * 16;
-    const bool active = col < cols;
-    const bool edge_l = lane == 0;
-    const bool edge_r = (lane == 31) || (col + 16 >= cols);
-    bool ld_left = active && edge_l, ld_right = active && edge_r;
-    int64_t lcol = col - 4, rcol = col + 16;
-    if (ld_left && lcol < 0) {
-        if (col_torus) lcol = cols - 4; else ld_left = false;
+    LaneAddr la;
+    la.col = strip * 512u + lane * 16u;
+    la.active = la.col < (unsigned)cols;
+    la.edge_l = lane == 0;
+    la.edge_r = (lane == 31) || (la.col + 16u >= (unsigned)cols);
+    la.ld_left = la.active && la.edge_l;
+    la.ld_right = la.active && la.edge_r;
+    la.lcol = la.col - 4u;
+    la.rcol = la.col + 16u;
+    if (la.ld_left && la.col == 0u) {
+        if (col_torus) la.lcol = cols - 4; else la.ld_left = false;
     }
-    if (ld_right && rcol >= cols) {
-        if (col_torus) rcol = 0; else ld_right = false;
+    if (la.ld_right && la.rcol >= (unsigned)cols) {
+        if (col_torus) la.rcol = 0u; else la.ld_right = false;
     }
+    const size_t pitch = (size_t)cols;
 
     constexpr int W = 2 * R + 1;
-    RowQ ring[W];
-    unsigned vocc[6], vone[6];
+    constexpr int kAhead = 2;  // rows fetched ahead of the compute
+    RowH<R> ring[W];  // ring[i] = row r - R + i while row r is being produced
 #pragma unroll
-    for (int k = 0; k < 6; ++k) vocc[k] = vone[k] = 0u;
-    // ring[0..W-2] = rows row0-R .. row0+R-1 ; the loop loads row r+R into ring[W-1]
-#pragma unroll
-    for (int i = 0; i < W - 1; ++i) {
-        ring[i] = load_rowq(happy_row_ptr<R>(type, halo_top, halo_bot, row0 - R + i, rows, cols), col, active,
-                            edge_l, edge_r, ld_left, ld_right, lcol, rcol);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            vocc[k] += ring[i].occ[k];
-            vone[k] += ring[i].one[k];
-        }
-    }
+    for (int i = 0; i < W - 1; ++i)
+        ring[i + 1] = make_rowh<R>(load_raw<true>(happy_row_ptr<R>(type, halo_top, halo_bot, row0 - R + i, rows, pitch), la), la);
 
     unsigned nhappy = 0;
-    const int64_t rend = min(row0 + (int64_t)kRowsPerWarp, rows);
-#pragma unroll 2
-    for (int64_t r = row0; r < rend; ++r) {
-        ring[W - 1] = load_rowq(happy_row_ptr<R>(type, halo_top, halo_bot, r + R, rows, cols), col, active,
-                                edge_l, edge_r, ld_left, ld_right, lcol, rcol);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            vocc[k] += ring[W - 1].occ[k];
-            vone[k] += ring[W - 1].one[k];
-        }
-        uint4 o;
-        unsigned* op = reinterpret_cast<unsigned*>(&o);
-#pragma unroll
-        for (int k = 1; k <= 4; ++k) {
-            unsigned bocc = vocc[k], bone = vone[k];
-#pragma unroll
-            for (int d = 1; d <= R; ++d) {
-                bocc += __funnelshift_r(vocc[k], vocc[k + 1], 8 * d) + __funnelshift_l(vocc[k - 1], vocc[k], 8 * d);
-                bone += __funnelshift_r(vone[k], vone[k + 1], 8 * d) + __funnelshift_l(vone[k - 1], vone[k], 8 * d);
-            }
-            const unsigned occ_c = ring[R].occ[k], one_c = ring[R].one[k];
-            const unsigned valid = bocc - occ_c;          // occupied neighbours (for occupied centres)
-            const unsigned m1 = one_c * 0xffu;            // 0xff where the centre is type 1
-            const unsigned sim1 = bone - one_c;           // type-1 neighbours
-            const unsigned similar = (m1 & sim1) | (~m1 & (valid - sim1));
-            unsigned thr = splat((unsigned)rule.base);
-            for (int s = 0; s < rule.nsteps; ++s) thr += __vsetgeu4(valid, splat(rule.steps[s]));
-            const unsigned cmp = rule.mode == 0 ? __vsetgeu4(similar, thr) : __vsetleu4(valid - similar, thr);
-            const unsigned alone = __vseteq4(valid, 0u);
-            const unsigned res = occ_c & ((cmp & ~alone) | (alone & splat((unsigned)rule.happy_if_alone)));
-            op[k - 1] = res;
-            nhappy += __popc(res);
-        }
-        if (active) __stcs(reinterpret_cast<uint4*>(happy + r * cols + col), o);
-        else nhappy = 0;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            vocc[k] -= ring[0].occ[k];
-            vone[k] -= ring[0].one[k];
-        }
+    const int rend = min(row0 + kRowsPerWarp, rows);
+    uint8_t* op = happy + (size_t)row0 * pitch + la.col;
+
+    auto produce = [&](const RawRow& fresh) {
 #pragma unroll
         for (int i = 0; i < W - 1; ++i) ring[i] = ring[i + 1];
+        ring[W - 1] = make_rowh<R>(fresh, la);
+        uint4 o;
+        unsigned* ow = reinterpret_cast<unsigned*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            unsigned bocc, bone;
+            if constexpr (R == 1) {
+                const unsigned b = ring[0].h[k] + ring[1].h[k] + ring[2].h[k];
+                bocc = b & 0x0f0f0f0fu;
+                bone = (b >> 4) & 0x0f0f0f0fu;
+            } else {
+                bocc = 0u; bone = 0u;
+#pragma unroll
+                for (int i = 0; i < W; ++i) { bocc += ring[i].h[k]; bone += ring[i].g[k]; }
+            }
+            const unsigned res = decide4<MODE>(bocc, bone, ring[R].occ[k], ring[R].one[k], rule);
+            ow[k] = res;
+            nhappy += __popc(res);
+        }
+        if (la.active) __stcs(reinterpret_cast<uint4*>(op), o);
+        op += pitch;
+    };
+
+    int r = row0;
+    const int8_t* fp = type + (size_t)(row0 + R) * pitch;  // row r + R
+    // groups whose look-ahead rows r+R .. r+R+kAhead-1 all lie inside this block: unchecked loads
+    for (; r + kAhead <= rend && r + R + kAhead <= rows; r += kAhead) {
+        RawRow nx[kAhead];
+#pragma unroll
+        for (int k = 0; k < kAhead; ++k) nx[k] = load_raw<false>(fp + (size_t)k * pitch, la);
+        fp += (size_t)kAhead * pitch;
+#pragma unroll
+        for (int k = 0; k < kAhead; ++k) produce(nx[k]);
     }
-    nhappy = warp_reduce_add(active ? nhappy : 0u);
+    for (; r < rend; ++r) produce(load_raw<true>(happy_row_ptr<R>(type, halo_top, halo_bot, r + R, rows, pitch), la));
+    nhappy = warp_reduce_add(la.active ? nhappy : 0u);
     if (lane == 0 && nhappy != 0 && happy_count != nullptr) atomicAdd(happy_count, (unsigned long long)nhappy);
 }
 
@@ -218,6 +289,20 @@ bool make_rule(const uint8_t* tbl, int nmax, HappyRule* rule) {
     for (int v = 0; v <= nmax; ++v) rule->min_similar[v] = tbl[v];
     rule->happy_if_alone = tbl[0] == 0;
     if (nmax < 1) return false;
+    // linear form A*s + C >= B*v, all byte quantities < 128, verified on every (s, v) with v >= 1
+    const int lim = 127 / nmax;
+    for (int A = 1; A <= lim; ++A)
+        for (int B = 0; B <= lim; ++B)
+            for (int C = 0; C <= (A < 8 ? A : 8) && A * nmax + C <= 127; ++C) {
+                bool ok = true;
+                for (int v = 1; v <= nmax && ok; ++v)
+                    for (int sim = 0; sim <= v; ++sim)
+                        if ((A * sim + C >= B * v) != (sim >= (int)tbl[v])) { ok = false; break; }
+                if (ok) {
+                    rule->mode = MODE_LINEAR; rule->A = A; rule->B = B; rule->C = C;
+                    return true;
+                }
+            }
     // representation T: similar >= T[v]
     bool okT = true, okU = true;
     int stepsT[256], nT = 0, stepsU[256], nU = 0;
@@ -232,12 +317,12 @@ bool make_rule(const uint8_t* tbl, int nmax, HappyRule* rule) {
     if (nT > 24) okT = false;
     if (nU > 24) okU = false;
     if (okU && (!okT || nU < nT)) {
-        rule->mode = 1; rule->base = baseU; rule->nsteps = nU;
+        rule->mode = MODE_U; rule->base = baseU; rule->nsteps = nU;
         for (int k = 0; k < nU; ++k) rule->steps[k] = (uint8_t)stepsU[k];
         return true;
     }
     if (okT) {
-        rule->mode = 0; rule->base = tbl[1]; rule->nsteps = nT;
+        rule->mode = MODE_T; rule->base = tbl[1]; rule->nsteps = nT;
         for (int k = 0; k < nT; ++k) rule->steps[k] = (uint8_t)stepsT[k];
         return true;
     }
@@ -270,18 +355,26 @@ MB_API int mb_schelling_happy_i8(const int8_t* type, const int8_t* halo_top, con
     HappyRule rule;
     const bool packed = make_rule(min_similar_host, nmax, &rule);
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-    const bool vec = packed && binary_types && radius <= 2 && cols % 16 == 0 && al16(type) && al16(happy) &&
+    const bool vec = packed && binary_types && radius <= 2 && cols % 16 == 0 && rows < (1ll << 30) &&
+                     cols < (1ll << 30) && al16(type) && al16(happy) &&
                      (halo_top == nullptr || al16(halo_top)) && (halo_bot == nullptr || al16(halo_bot));
     if (vec) {
         const int nstrips = (int)mb::ceil_div(cols, 512);
         const int64_t tasks = (int64_t)nstrips * mb::ceil_div(rows, kRowsPerWarp);
         const unsigned blocks = (unsigned)mb::ceil_div(tasks, kWarps);
-        if (radius == 1)
-            schelling_happy_vec<1><<<blocks, kWarps * 32, 0, stream>>>(type, halo_top, halo_bot, happy, rows, cols,
-                                                                       col_torus, nstrips, rule, happy_count);
-        else
-            schelling_happy_vec<2><<<blocks, kWarps * 32, 0, stream>>>(type, halo_top, halo_bot, happy, rows, cols,
-                                                                       col_torus, nstrips, rule, happy_count);
+#define MB_HAPPY_LAUNCH(RR, MM)                                                                              \
+    schelling_happy_vec<RR, MM><<<blocks, kWarps * 32, 0, stream>>>(type, halo_top, halo_bot, happy, (int)rows, \
+                                                                    (int)cols, col_torus, nstrips, rule, happy_count)
+        if (radius == 1) {
+            if (rule.mode == MODE_LINEAR) MB_HAPPY_LAUNCH(1, MODE_LINEAR);
+            else if (rule.mode == MODE_T) MB_HAPPY_LAUNCH(1, MODE_T);
+            else MB_HAPPY_LAUNCH(1, MODE_U);
+        } else {
+            if (rule.mode == MODE_LINEAR) MB_HAPPY_LAUNCH(2, MODE_LINEAR);
+            else if (rule.mode == MODE_T) MB_HAPPY_LAUNCH(2, MODE_T);
+            else MB_HAPPY_LAUNCH(2, MODE_U);
+        }
+#undef MB_HAPPY_LAUNCH
     } else {
         const int64_t n = rows * cols;
         schelling_happy_scalar<<<(unsigned)mb::ceil_div(n, 256), 256, 0, stream>>>(
