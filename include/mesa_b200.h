@@ -70,12 +70,14 @@ int mb_schelling_happy_i8(const int8_t* type, const int8_t* halo_top, const int8
  * probes = the agent's keyed _randbelow(ncells) draws; result identical to the sequential
  * reference driven with the same numbers (csrc/relocate.cu explains the fixed point).
  * agent_id: uint32 layer, agent index sitting in each occupied cell; agent_cell: optional
- * [nagents] uint32 inverse map (NULL to skip).  The workspace persists between calls
- * (init once).  mb_schelling_relocate synchronises `stream`.  A full grid with an unhappy
+ * [nagents] uint32 inverse map (NULL to skip).  The workspace holds a 16-byte slot per cell
+ * (when it empties / who arrives) that persists between calls: mb_relocate_workspace_init builds it
+ * from the type layer (once, and again if the layer is edited elsewhere).
+ * mb_schelling_relocate synchronises `stream`.  A full grid with an unhappy
  * agent returns MB_ERR_INVALID (ValueError, grid.py:311-315). */
 int mb_relocate_workspace_bytes(int64_t ncells, int64_t max_movers, size_t* out);
 int mb_relocate_workspace_init(void* workspace, size_t workspace_bytes, int64_t ncells, int64_t max_movers,
-                               mb_stream_t stream);
+                               const int8_t* type, mb_stream_t stream);
 int mb_schelling_relocate(int8_t* type, uint8_t* happy, uint32_t* agent_id, uint32_t* agent_cell,
                           int64_t ncells, uint64_t seed, uint32_t epoch, void* workspace,
                           size_t workspace_bytes, int64_t max_movers, int64_t* out_movers,

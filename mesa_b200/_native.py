@@ -42,7 +42,7 @@ SIGNATURES: dict[str, tuple] = {
     # Schelling
     "mb_schelling_happy_i8": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_int, _P, c_int, _P, _S]),
     "mb_relocate_workspace_bytes": (c_int, [c_int64, c_int64, ctypes.POINTER(ctypes.c_size_t)]),
-    "mb_relocate_workspace_init": (c_int, [_P, ctypes.c_size_t, c_int64, c_int64, _S]),
+    "mb_relocate_workspace_init": (c_int, [_P, ctypes.c_size_t, c_int64, c_int64, _P, _S]),
     "mb_schelling_relocate": (c_int, [_P, _P, _P, _P, c_int64, c_uint64, c_uint32, _P, ctypes.c_size_t,
                                       c_int64, ctypes.POINTER(c_int64), ctypes.POINTER(c_int), _S]),
     # radix sort

@@ -13,23 +13,28 @@
 //
 //   * every mover (occupied && !happy at step start) has a state-independent probe sequence
 //     p[0..49] = _randbelow(ncells) draws of its own DRAW stream;
-//   * a cell c is empty at time t (the priority of the acting mover) iff
-//         vacate(c) < t  and  not (arrive(c) < t)
-//     where vacate(c) = 0 for an initially empty cell, the occupant's priority if the
-//     occupant is a mover (it has left once its turn is over), +inf otherwise, and
-//     arrive(c) = min priority of the movers that choose c (+inf if none).  A cell receives
-//     at most one arrival per step (the arriving agent has already been activated);
-//   * iteration k recomputes every mover's choice (first probe that is empty at its time)
-//     from the arrive table of iteration k-1 and rebuilds the table with atomicMin.
-//     By induction on the rank, after k iterations the first k movers are final, so the
-//     iteration converges to exactly the sequential result; in practice it takes O(log M)
-//     rounds because conflicts are sparse.
-//   * the 50-probe miss (probability density^50) falls back to the k-th empty cell in
-//     row-major order at the mover's time, k = _randbelow(#empty), #empty = ncells - nagents
-//     at every instant (grid.py:308-316).
+//   * every cell has a 16-byte slot {vac, arr}: the cell is empty at time t (t = priority of
+//     the acting mover) iff  vac <= t <= arr, where
+//         vac = 0 (empty since the start of the step) | priority+1 of its occupant if the
+//               occupant moves this step (it is gone once its turn is over) | NEVER
+//         arr = min priority of the movers that currently choose the cell, NEVER if none
+//     (a cell receives at most one arrival per step: an arrived agent has already acted);
+//     one probe = ONE 16-byte load;
+//   * a pass lets every mover take its first probe that is empty at its own time and keep `arr`
+//     up to date in place (atomicMin to claim, compare-and-swap to release, re-asserted every
+//     pass).  The mover of lowest rank is right after one pass and its claim is never disturbed;
+//     by induction rank k is right one pass after ranks < k are, so the passes converge to
+//     exactly the sequential result (in practice a handful of passes: conflicts are sparse);
+//   * the 50-probe miss (probability density^50) falls back to the k-th empty cell in row-major
+//     order at the mover's time, k = _randbelow(#empty), #empty = ncells - nagents at every
+//     instant (grid.py:308-316).  All fallback movers of a pass are served by ONE pass over the
+//     slot table: their times are sorted, a cell's emptiness interval is a contiguous range of
+//     that order (two binary searches -> +1/-1 in a per-block difference array), per-block
+//     counts locate the block of the k-th empty cell and one warp scans that block.
 //
 // All state is caller-owned: the int8 type layer, the uint8 happy layer, the uint32
-// agent-id layer (who sits in each cell) and optionally the per-agent cell array.
+// agent-id layer (who sits in each cell), optionally the per-agent cell array, and the
+// workspace holding the slot table (persistent: initialise it from the type layer once).
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -37,19 +42,30 @@ namespace {
 
 constexpr unsigned long long kNever = ~0ull;
 constexpr uint32_t kNone = 0xffffffffu;
-constexpr int kMaxProbes = 50;  // grid.py:303 `for _ in range(50)`
-constexpr int kIterBatch = 4;   // iterations enqueued between convergence checks
-constexpr int kMaxIterSlots = 1024;
+constexpr int kMaxProbes = 50;   // grid.py:303 `for _ in range(50)`
+constexpr int kMaxPasses = 100000;
+constexpr int kFbBatch = 2048;   // fallback movers served per table pass
+constexpr int kFbBlocksMax = 4096;
+
+struct Slot {
+    unsigned long long vac, arr;
+};
 
 struct RelocWs {
-    unsigned long long* arrive[3];  // [ncells] each, all kNever between calls
+    Slot* slots;                    // [ncells]
     uint32_t* mv_cell;              // [cap] origin cell of mover m
-    uint32_t* mv_agent;             // [cap] agent index of mover m
+    uint32_t* mv_agent;             // [cap] agent index
+    unsigned long long* mv_prio;    // [cap] priority64
     int8_t* mv_type;                // [cap]
-    uint32_t* choice[3];            // [cap] destination chosen in iteration k % 3
-    uint32_t* fb_list;              // [cap] movers that missed all 50 probes this iteration
-    unsigned long long* counters;   // [0] movers, [1] occupied, [2] fallback count, [3] unused,
-                                    // [8 + k] choices changed in iteration k
+    uint32_t* choice;               // [cap] cell currently chosen (claimed) by mover m
+    uint32_t* fb_list;              // [cap] movers that missed all 50 probes in this pass
+    unsigned long long* fb_t;       // [kFbBatch] sorted times of the current fallback batch
+    uint32_t* fb_m;                 // [kFbBatch] mover of each sorted entry
+    unsigned long long* fb_k;       // [kFbBatch] rank of the empty cell to take
+    uint32_t* fb_block;             // [kFbBatch] table block holding it
+    uint32_t* fb_rem;               // [kFbBatch] rank inside that block
+    uint32_t* cnt;                  // [kFbBatch][kFbBlocksMax] empties per table block at each fallback time
+    unsigned long long* counters;   // [0] movers [1] occupied [2] fallback movers of the pass [3] changes of the pass
 };
 
 __host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -61,28 +77,46 @@ size_t carve(RelocWs* ws, char* base, int64_t ncells, int64_t cap) {
         off += align256(bytes);
         return p;
     };
-    RelocWs tmp;
-    for (int i = 0; i < 3; ++i) tmp.arrive[i] = (unsigned long long*)take(sizeof(unsigned long long) * ncells);
-    tmp.mv_cell = (uint32_t*)take(sizeof(uint32_t) * cap);
-    tmp.mv_agent = (uint32_t*)take(sizeof(uint32_t) * cap);
-    tmp.mv_type = (int8_t*)take(cap);
-    for (int i = 0; i < 3; ++i) tmp.choice[i] = (uint32_t*)take(sizeof(uint32_t) * cap);
-    tmp.fb_list = (uint32_t*)take(sizeof(uint32_t) * cap);
-    tmp.counters = (unsigned long long*)take(sizeof(unsigned long long) * (8 + kMaxIterSlots));
-    if (ws) *ws = tmp;
+    RelocWs t;
+    t.slots = (Slot*)take(sizeof(Slot) * ncells);
+    t.mv_cell = (uint32_t*)take(4 * cap);
+    t.mv_agent = (uint32_t*)take(4 * cap);
+    t.mv_prio = (unsigned long long*)take(8 * cap);
+    t.mv_type = (int8_t*)take(cap);
+    t.choice = (uint32_t*)take(4 * cap);
+    t.fb_list = (uint32_t*)take(4 * cap);
+    t.fb_t = (unsigned long long*)take(8 * kFbBatch);
+    t.fb_m = (uint32_t*)take(4 * kFbBatch);
+    t.fb_k = (unsigned long long*)take(8 * kFbBatch);
+    t.fb_block = (uint32_t*)take(4 * kFbBatch);
+    t.fb_rem = (uint32_t*)take(4 * kFbBatch);
+    t.cnt = (uint32_t*)take(4ull * kFbBlocksMax * kFbBatch);
+    t.counters = (unsigned long long*)take(8 * 8);
+    if (ws) *ws = t;
     return off;
 }
 
-__global__ void fill_u64(unsigned long long* p, int64_t n, unsigned long long v) {
+__device__ __forceinline__ Slot load_slot(const Slot* p) {
+    const ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(p));  // L2: sees other SMs' atomics
+    return Slot{v.x, v.y};
+}
+
+__device__ __forceinline__ bool empty_at(const Slot& s, unsigned long long t) { return s.vac <= t && t <= s.arr; }
+
+__global__ void init_slots(const int8_t* __restrict__ type, int64_t ncells, Slot* __restrict__ slots) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += stride) {
+        const bool occupied = type != nullptr && type[c] >= 0;
+        reinterpret_cast<ulonglong2*>(slots)[c] = make_ulonglong2(occupied ? kNever : 0ull, kNever);
+    }
 }
 
 // movers = occupied && !happy; appended in arbitrary order (the result does not depend on it).
 __global__ void collect_movers(const int8_t* __restrict__ type, const uint8_t* __restrict__ happy,
-                               const uint32_t* __restrict__ agent_id, int64_t ncells, RelocWs ws, int64_t cap) {
+                               const uint32_t* __restrict__ agent_id, int64_t ncells, RelocWs ws, int64_t cap,
+                               uint64_t seed, uint32_t epoch) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    unsigned long long occupied = 0;
+    unsigned occupied = 0;
     for (int64_t c0 = (int64_t)blockIdx.x * blockDim.x; c0 < ncells; c0 += stride) {
         const int64_t c = c0 + threadIdx.x;
         const int t = c < ncells ? type[c] : -1;
@@ -97,138 +131,213 @@ __global__ void collect_movers(const int8_t* __restrict__ type, const uint8_t* _
             if (mover) {
                 const unsigned long long slot = base + __popc(ballot & ((1u << lane) - 1u));
                 if ((int64_t)slot < cap) {
+                    const uint32_t agent = agent_id[c];
+                    const unsigned long long pr = mb::priority64(seed, epoch, agent);
                     ws.mv_cell[slot] = (uint32_t)c;
-                    ws.mv_agent[slot] = agent_id[c];
+                    ws.mv_agent[slot] = agent;
+                    ws.mv_prio[slot] = pr;
                     ws.mv_type[slot] = (int8_t)t;
-                    ws.choice[0][slot] = kNone;
-                    ws.choice[1][slot] = kNone;
-                    ws.choice[2][slot] = kNone;
+                    ws.choice[slot] = kNone;
+                    ws.slots[c].vac = pr + 1;  // empty for every mover that acts after this one
                 }
             }
         }
     }
-    occupied = warp_reduce_add((unsigned)occupied);  // per-thread counts are small
-    if ((threadIdx.x & 31) == 0 && occupied) atomicAdd(&ws.counters[1], occupied);
+    occupied = warp_reduce_add(occupied);
+    if ((threadIdx.x & 31) == 0 && occupied) atomicAdd(&ws.counters[1], (unsigned long long)occupied);
 }
 
-struct GridView {
-    const int8_t* type;
-    const uint8_t* happy;
-    const uint32_t* agent_id;
-    uint64_t seed;
-    uint32_t epoch;
-};
+// "the table changed in this pass": a plain store of a constant (millions of movers change in the
+// first pass; counting them with one atomic address would serialise the whole pass)
+__device__ __forceinline__ void mark_changed(RelocWs& ws) { *(volatile unsigned long long*)&ws.counters[3] = 1ull; }
 
-// Is cell c empty at time t, given the arrivals in `arrive`?
-__device__ __forceinline__ bool empty_at(const GridView& g, const unsigned long long* __restrict__ arrive,
-                                         int64_t c, unsigned long long t) {
-    if (arrive[c] < t) return false;  // somebody moved in earlier
-    if (g.type[c] < 0) return true;   // empty since the start of the step
-    if (g.happy[c]) return false;     // occupant does not move this step
-    return mb::priority64(g.seed, g.epoch, g.agent_id[c]) < t;  // occupant already left
+// claim `pick` for mover m (and release what it held before)
+__device__ __forceinline__ void commit_choice(RelocWs& ws, int64_t m, unsigned long long t, uint32_t pick) {
+    const uint32_t held = ws.choice[m];
+    if (held != pick) {
+        if (held != kNone) atomicCAS(&ws.slots[held].arr, t, kNever);  // release only if I am the registered arrival
+        ws.choice[m] = pick;
+        atomicMin(&ws.slots[pick].arr, t);
+        mark_changed(ws);
+    } else {
+        // re-assert: my registration may have been shadowed by an earlier arrival that has left since
+        if (atomicMin(&ws.slots[pick].arr, t) > t) mark_changed(ws);
+    }
 }
 
-__global__ void relocate_iterate(GridView g, RelocWs ws, int64_t ncells, int64_t nmovers, int iter) {
+__global__ void __launch_bounds__(128)
+relocate_pass(RelocWs ws, int64_t ncells, int64_t nmovers, uint64_t seed, uint32_t epoch) {
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= nmovers) return;
-    const unsigned long long* rd = ws.arrive[iter % 3];
-    unsigned long long* claim = ws.arrive[(iter + 1) % 3];
-    unsigned long long* reset = ws.arrive[(iter + 2) % 3];
-    const uint32_t agent = ws.mv_agent[m];
-    const unsigned long long t = mb::priority64(g.seed, g.epoch, agent);
-
-    const uint32_t two_ago = ws.choice[(iter + 1) % 3][m];
-    if (two_ago != kNone) reset[two_ago] = kNever;
-    const uint32_t prev = ws.choice[(iter + 2) % 3][m];
-
-    mb::DrawStream ds(g.seed, g.epoch, agent);
-    uint32_t pick = kNone;
+    const unsigned long long t = ws.mv_prio[m];
+    mb::DrawStream ds(seed, epoch, ws.mv_agent[m]);
     for (int j = 0; j < kMaxProbes; ++j) {
         const int64_t c = (int64_t)ds.randbelow((uint64_t)ncells);
-        if (empty_at(g, rd, c, t)) {
-            pick = (uint32_t)c;
+        if (empty_at(load_slot(ws.slots + c), t)) {
+            commit_choice(ws, m, t, (uint32_t)c);
+            return;
+        }
+    }
+    ws.fb_list[atomicAdd(&ws.counters[2], 1ull)] = (uint32_t)m;  // served by the fallback kernels of this pass
+}
+
+// ---- argwhere fallback, batched -----------------------------------------------------------------
+// sort the batch by time (bitonic, one CTA) and draw each mover's rank k = _randbelow(nempty)
+__global__ void __launch_bounds__(1024)
+fb_sort(RelocWs ws, int64_t first, int count, int64_t ncells, int64_t nempty, uint64_t seed, uint32_t epoch) {
+    __shared__ unsigned long long st[kFbBatch];
+    __shared__ uint32_t sm[kFbBatch];
+    for (int i = threadIdx.x; i < kFbBatch; i += blockDim.x) {
+        if (i < count) {
+            const uint32_t m = ws.fb_list[first + i];
+            st[i] = ws.mv_prio[m];
+            sm[i] = m;
+        } else {
+            st[i] = kNever;
+            sm[i] = kNone;
+        }
+    }
+    __syncthreads();
+    for (int k = 2; k <= kFbBatch; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < kFbBatch; i += blockDim.x) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const bool up = (i & k) == 0;
+                    if ((st[i] > st[p]) == up) {
+                        const unsigned long long a = st[i]; st[i] = st[p]; st[p] = a;
+                        const uint32_t b = sm[i]; sm[i] = sm[p]; sm[p] = b;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < count; i += blockDim.x) {
+        const uint32_t m = sm[i];
+        ws.fb_t[i] = st[i];
+        ws.fb_m[i] = m;
+        // replay the 50 accepted probes to position the stream, then draw the rank (grid.py:308-310)
+        mb::DrawStream ds(seed, epoch, ws.mv_agent[m]);
+        for (int j = 0; j < kMaxProbes; ++j) (void)ds.randbelow((uint64_t)ncells);
+        ws.fb_k[i] = ds.randbelow((uint64_t)nempty);
+    }
+}
+
+__device__ __forceinline__ int first_ge(const unsigned long long* __restrict__ a, int n, unsigned long long v) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// cnt[b][f] = number of cells of table block b that are empty at the time of fallback f
+__global__ void __launch_bounds__(256)
+fb_count(RelocWs ws, int64_t ncells, int64_t block_cells, int count) {
+    __shared__ int diff[kFbBatch + 1];
+    __shared__ unsigned long long times[kFbBatch];
+    __shared__ int warp_base[8];
+    for (int i = threadIdx.x; i <= kFbBatch; i += blockDim.x) diff[i] = 0;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) times[i] = ws.fb_t[i];
+    __syncthreads();
+    const int64_t lo_c = (int64_t)blockIdx.x * block_cells;
+    const int64_t hi_c = min(lo_c + block_cells, ncells);
+    int base = 0;
+    for (int64_t c = lo_c + threadIdx.x; c < hi_c; c += blockDim.x) {
+        const Slot s = load_slot(ws.slots + c);
+        if (s.vac == kNever) continue;                       // occupied during the whole step
+        if (s.vac == 0 && s.arr == kNever) { ++base; continue; }  // empty during the whole step
+        const int lo = first_ge(times, count, s.vac);        // first fallback with t >= vac
+        const int hi = s.arr == kNever ? count : first_ge(times, count, s.arr + 1);  // first with t > arr
+        if (lo < hi) {
+            atomicAdd(&diff[lo], 1);
+            atomicSub(&diff[hi], 1);
+        }
+    }
+    base = (int)warp_reduce_add((unsigned)base);
+    if ((threadIdx.x & 31) == 0) warp_base[threadIdx.x >> 5] = base;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int b = 0;
+        for (int w = 0; w < 8; ++w) b += warp_base[w];
+        int run = b;
+        for (int f = 0; f < count; ++f) {  // prefix sum of the difference array (count <= 2048)
+            run += diff[f];
+            diff[f] = run;
+        }
+    }
+    __syncthreads();
+    for (int f = threadIdx.x; f < count; f += blockDim.x) ws.cnt[(size_t)f * kFbBlocksMax + blockIdx.x] = (uint32_t)diff[f];
+}
+
+// one warp per fallback mover: walk the per-block counts 32 blocks at a time (coalesced, warp scan)
+__global__ void __launch_bounds__(256) fb_locate(RelocWs ws, int nblocks, int count) {
+    const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (f >= count) return;
+    unsigned long long k = ws.fb_k[f];
+    const uint32_t* __restrict__ row = ws.cnt + (size_t)f * kFbBlocksMax;
+    int block = nblocks - 1;
+    unsigned rem = 0;
+    bool done = false;
+    for (int b0 = 0; b0 < nblocks && !done; b0 += 32) {
+        const int b = b0 + lane;
+        const unsigned n = b < nblocks ? row[b] : 0u;
+        unsigned incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+        if (k < total) {
+            // first lane whose inclusive count exceeds k holds the block
+            const unsigned hit = __ballot_sync(0xffffffffu, k < incl);
+            const int l = __ffs(hit) - 1;
+            const unsigned before = __shfl_sync(0xffffffffu, incl - n, l);
+            block = b0 + l;
+            rem = (unsigned)(k - before);
+            done = true;
+        } else {
+            k -= total;
+        }
+    }
+    if (lane == 0) {
+        ws.fb_block[f] = (uint32_t)block;
+        ws.fb_rem[f] = done ? rem : 0xffffffffu;  // not found: fb_pick reports "changed" and the pass repeats
+    }
+}
+
+// one warp per fallback mover: the fb_rem-th empty cell of block fb_block at the mover's time
+__global__ void __launch_bounds__(256)
+fb_pick(RelocWs ws, int64_t ncells, int64_t block_cells, int count) {
+    const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (f >= count) return;
+    const unsigned long long t = ws.fb_t[f];
+    const int64_t lo_c = (int64_t)ws.fb_block[f] * block_cells;
+    const int64_t hi_c = min(lo_c + block_cells, ncells);
+    unsigned need = ws.fb_rem[f];
+    int64_t found = -1;
+    for (int64_t c0 = lo_c; c0 < hi_c; c0 += 32) {
+        const int64_t c = c0 + lane;
+        const bool e = c < hi_c && empty_at(load_slot(ws.slots + c), t);
+        const unsigned ballot = __ballot_sync(0xffffffffu, e);
+        const unsigned n = __popc(ballot);
+        if (need < n) {
+            unsigned b = ballot;
+            for (unsigned i = 0; i < need; ++i) b &= b - 1;  // drop the `need` lowest set bits
+            found = c0 + (__ffs(b) - 1);
             break;
         }
+        need -= n;
     }
-    if (pick == kNone) {
-        // resolved by relocate_fallback (same iteration); it also counts the change
-        const unsigned long long slot = atomicAdd(&ws.counters[2], 1ull);
-        ws.fb_list[slot] = (uint32_t)m;
-        ws.choice[iter % 3][m] = kNone;
-        return;
-    }
-    ws.choice[iter % 3][m] = pick;
-    atomicMin(&claim[pick], t);
-    if (pick != prev) atomicAdd(&ws.counters[8 + iter], 1ull);
-}
-
-// One CTA per fallback mover: k-th empty cell (row-major) at the mover's time.
-__global__ void __launch_bounds__(256)
-relocate_fallback(GridView g, RelocWs ws, int64_t ncells, int64_t nempty, int iter) {
-    __shared__ unsigned warp_tot[8];
-    __shared__ long long found;
-    const unsigned long long nfb = ws.counters[2];
-    const unsigned long long* rd = ws.arrive[iter % 3];
-    unsigned long long* claim = ws.arrive[(iter + 1) % 3];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (unsigned long long f = blockIdx.x; f < nfb; f += gridDim.x) {
-        const uint32_t m = ws.fb_list[f];
-        const uint32_t agent = ws.mv_agent[m];
-        const unsigned long long t = mb::priority64(g.seed, g.epoch, agent);
-        // replay the 50 accepted probes to position the stream, then draw the rank
-        mb::DrawStream ds(g.seed, g.epoch, agent);
-        for (int j = 0; j < kMaxProbes; ++j) (void)ds.randbelow((uint64_t)ncells);
-        const long long k = (long long)ds.randbelow((uint64_t)nempty);
-        if (threadIdx.x == 0) found = -1;
-        __syncthreads();
-        long long seen = 0;
-        constexpr int kPer = 8;
-        for (int64_t base = 0; base < ncells; base += 256 * kPer) {
-            const int64_t c0 = base + (int64_t)threadIdx.x * kPer;
-            unsigned bits = 0;
-#pragma unroll
-            for (int i = 0; i < kPer; ++i)
-                if (c0 + i < ncells && empty_at(g, rd, c0 + i, t)) bits |= 1u << i;
-            const unsigned cnt = __popc(bits);
-            unsigned incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            if (lane == 31) warp_tot[warp] = incl;
-            __syncthreads();
-            unsigned before = 0, total = 0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                if (w < warp) before += warp_tot[w];
-                total += warp_tot[w];
-            }
-            const long long lo = seen + before + incl - cnt;  // empties before this thread's cells
-            if (k >= lo && k < lo + cnt) {
-                int need = (int)(k - lo);
-                for (int i = 0; i < kPer; ++i)
-                    if (bits & (1u << i)) {
-                        if (need == 0) { found = c0 + i; break; }
-                        --need;
-                    }
-            }
-            seen += total;
-            __syncthreads();
-            if (found >= 0) break;
-        }
-        if (threadIdx.x == 0) {
-            const uint32_t pick = (uint32_t)found;  // always found: nempty counts exactly these cells
-            const uint32_t prev = ws.choice[(iter + 2) % 3][m];
-            ws.choice[iter % 3][m] = pick;
-            atomicMin(&claim[pick], t);
-            if (pick != prev) atomicAdd(&ws.counters[8 + iter], 1ull);
-        }
-        __syncthreads();
+    if (lane == 0) {
+        if (found >= 0) commit_choice(ws, ws.fb_m[f], t, (uint32_t)found);
+        else mark_changed(ws);  // table moved under the scan (concurrent commits): force another pass
     }
 }
-
-__global__ void reset_fallback_count(RelocWs ws) { ws.counters[2] = 0; }
 
 __global__ void relocate_vacate(RelocWs ws, int8_t* type, uint8_t* happy, int64_t nmovers) {
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -236,24 +345,27 @@ __global__ void relocate_vacate(RelocWs ws, int8_t* type, uint8_t* happy, int64_
     const uint32_t o = ws.mv_cell[m];
     type[o] = -1;
     happy[o] = 0;
+    reinterpret_cast<ulonglong2*>(ws.slots)[o] = make_ulonglong2(0ull, kNever);
 }
 
 __global__ void relocate_arrive(RelocWs ws, int8_t* type, uint8_t* happy, uint32_t* agent_id,
-                                uint32_t* agent_cell, int64_t nmovers, int last_iter) {
+                                uint32_t* agent_cell, int64_t nmovers) {
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= nmovers) return;
-    const uint32_t d = ws.choice[last_iter % 3][m];
+    const uint32_t d = ws.choice[m];
     const uint32_t agent = ws.mv_agent[m];
     type[d] = ws.mv_type[m];
     happy[d] = 0;  // the flag travels with the agent: movers are unhappy until the next assign_state
     agent_id[d] = agent;
     if (agent_cell != nullptr) agent_cell[agent] = d;
-    // restore the all-kNever invariant of the arrive tables
-    ws.arrive[(last_iter + 1) % 3][d] = kNever;
-    const uint32_t d1 = ws.choice[(last_iter + 2) % 3][m];  // iteration last_iter - 1
-    if (d1 != kNone) ws.arrive[last_iter % 3][d1] = kNever;
-    const uint32_t d2 = ws.choice[(last_iter + 1) % 3][m];  // iteration last_iter - 2 (normally reset already)
-    if (d2 != kNone) ws.arrive[(last_iter + 2) % 3][d2] = kNever;
+    reinterpret_cast<ulonglong2*>(ws.slots)[d] = make_ulonglong2(kNever, kNever);
+}
+
+int read_counters(const RelocWs& ws, unsigned long long* host4, cudaStream_t stream) {
+    int rc = mb::check_cuda(cudaMemcpyAsync(host4, ws.counters, 4 * sizeof(unsigned long long),
+                                            cudaMemcpyDeviceToHost, stream), "read counters");
+    if (rc) return rc;
+    return mb::check_cuda(cudaStreamSynchronize(stream), "sync");
 }
 
 }  // namespace
@@ -264,22 +376,22 @@ MB_API int mb_relocate_workspace_bytes(int64_t ncells, int64_t max_movers, size_
     return MB_OK;
 }
 
+// Builds the slot table from the occupancy (type[c] >= 0 = occupied; type == NULL = all empty).
+// Call once, and again whenever the type layer was modified outside mb_schelling_relocate.
 MB_API int mb_relocate_workspace_init(void* workspace, size_t workspace_bytes, int64_t ncells,
-                                      int64_t max_movers, cudaStream_t stream) {
+                                      int64_t max_movers, const int8_t* type, cudaStream_t stream) {
     RelocWs ws;
     MB_REQUIRE(workspace != nullptr, "mb_relocate_workspace_init: null workspace");
     if (carve(&ws, (char*)workspace, ncells, max_movers) > workspace_bytes) {
         mb::set_error("mb_relocate_workspace_init: workspace too small");
         return MB_ERR_WORKSPACE;
     }
-    const int blocks = mb::sm_count() * 8;
-    for (int i = 0; i < 3; ++i)
-        if (ncells > 0) fill_u64<<<blocks, 256, 0, stream>>>(ws.arrive[i], ncells, kNever);
+    if (ncells > 0) init_slots<<<mb::sm_count() * 8, 256, 0, stream>>>(type, ncells, ws.slots);
     MB_LAUNCH_CHECK("mb_relocate_workspace_init");
     return MB_OK;
 }
 
-// Synchronises `stream` (needs the mover count and the convergence flags on the host).
+// Synchronises `stream` (needs the mover count and the per-pass convergence flags on the host).
 MB_API int mb_schelling_relocate(int8_t* type, uint8_t* happy, uint32_t* agent_id, uint32_t* agent_cell,
                                  int64_t ncells, uint64_t seed, uint32_t epoch, void* workspace,
                                  size_t workspace_bytes, int64_t max_movers, int64_t* out_movers,
@@ -294,21 +406,17 @@ MB_API int mb_schelling_relocate(int8_t* type, uint8_t* happy, uint32_t* agent_i
         mb::set_error("mb_schelling_relocate: workspace too small");
         return MB_ERR_WORKSPACE;
     }
-    int rc;
-    rc = mb::check_cuda(cudaMemsetAsync(ws.counters, 0, sizeof(unsigned long long) * (8 + kMaxIterSlots), stream),
-                        "memset counters");
+    int rc = mb::check_cuda(cudaMemsetAsync(ws.counters, 0, 8 * sizeof(unsigned long long), stream), "memset");
     if (rc) return rc;
     const int sms = mb::sm_count();
     {
         const int64_t want = mb::ceil_div(ncells, 256);
         const unsigned blocks = (unsigned)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
-        collect_movers<<<blocks, 256, 0, stream>>>(type, happy, agent_id, ncells, ws, max_movers);
+        collect_movers<<<blocks, 256, 0, stream>>>(type, happy, agent_id, ncells, ws, max_movers, seed, epoch);
         MB_LAUNCH_CHECK("collect_movers");
     }
-    unsigned long long hc[2];
-    rc = mb::check_cuda(cudaMemcpyAsync(hc, ws.counters, sizeof(hc), cudaMemcpyDeviceToHost, stream), "read counters");
-    if (rc) return rc;
-    rc = mb::check_cuda(cudaStreamSynchronize(stream), "sync");
+    unsigned long long hc[4];
+    rc = read_counters(ws, hc, stream);
     if (rc) return rc;
     const int64_t nmovers = (int64_t)hc[0], noccupied = (int64_t)hc[1];
     if (out_movers) *out_movers = nmovers;
@@ -322,34 +430,40 @@ MB_API int mb_schelling_relocate(int8_t* type, uint8_t* happy, uint32_t* agent_i
     // grid.py:311-315: a completely full grid raises ValueError at the first unhappy agent
     MB_REQUIRE(nempty > 0, "Grid is completely full. No empty cells available. Cannot select a random empty cell.");
 
-    const GridView g{type, happy, agent_id, seed, epoch};
     const unsigned mblocks = (unsigned)mb::ceil_div(nmovers, 128);
-    int iter = 0;
-    bool converged = false;
-    while (!converged) {
-        if (iter + kIterBatch >= kMaxIterSlots) {
-            mb::set_error("mb_schelling_relocate: no convergence after %d iterations", iter);
+    int64_t fb_blocks = mb::ceil_div(ncells, 1024);
+    if (fb_blocks > kFbBlocksMax) fb_blocks = kFbBlocksMax;
+    const int64_t block_cells = mb::ceil_div(ncells, fb_blocks);
+    int pass = 0;
+    for (;; ++pass) {
+        if (pass >= kMaxPasses) {
+            mb::set_error("mb_schelling_relocate: no convergence after %d passes", pass);
             return MB_ERR_CUDA;
         }
-        const int first = iter;
-        for (int b = 0; b < kIterBatch; ++b, ++iter) {
-            reset_fallback_count<<<1, 1, 0, stream>>>(ws);
-            relocate_iterate<<<mblocks, 128, 0, stream>>>(g, ws, ncells, nmovers, iter);
-            relocate_fallback<<<sms, 256, 0, stream>>>(g, ws, ncells, nempty, iter);
+        rc = mb::check_cuda(cudaMemsetAsync(ws.counters + 2, 0, 2 * sizeof(unsigned long long), stream), "memset");
+        if (rc) return rc;
+        relocate_pass<<<mblocks, 128, 0, stream>>>(ws, ncells, nmovers, seed, epoch);
+        MB_LAUNCH_CHECK("relocate_pass");
+        rc = read_counters(ws, hc, stream);
+        if (rc) return rc;
+        const int64_t nfb = (int64_t)hc[2];
+        if (nfb > 0) {
+            for (int64_t first = 0; first < nfb; first += kFbBatch) {
+                const int count = (int)(nfb - first < kFbBatch ? nfb - first : kFbBatch);
+                fb_sort<<<1, 1024, 0, stream>>>(ws, first, count, ncells, nempty, seed, epoch);
+                fb_count<<<(unsigned)fb_blocks, 256, 0, stream>>>(ws, ncells, block_cells, count);
+                fb_locate<<<(unsigned)mb::ceil_div((int64_t)count * 32, 256), 256, 0, stream>>>(ws, (int)fb_blocks, count);
+                fb_pick<<<(unsigned)mb::ceil_div((int64_t)count * 32, 256), 256, 0, stream>>>(ws, ncells, block_cells, count);
+            }
+            MB_LAUNCH_CHECK("relocate_fallback");
+            rc = read_counters(ws, hc, stream);
+            if (rc) return rc;
         }
-        MB_LAUNCH_CHECK("relocate_iterate");
-        unsigned long long changed[kIterBatch];
-        rc = mb::check_cuda(cudaMemcpyAsync(changed, ws.counters + 8 + first, sizeof(changed),
-                                            cudaMemcpyDeviceToHost, stream), "read changed");
-        if (rc) return rc;
-        rc = mb::check_cuda(cudaStreamSynchronize(stream), "sync");
-        if (rc) return rc;
-        converged = changed[kIterBatch - 1] == 0;
+        if (hc[3] == 0) break;  // a pass without any change of the table: fixed point
     }
-    const int last = iter - 1;
     relocate_vacate<<<mblocks, 128, 0, stream>>>(ws, type, happy, nmovers);
-    relocate_arrive<<<mblocks, 128, 0, stream>>>(ws, type, happy, agent_id, agent_cell, nmovers, last);
+    relocate_arrive<<<mblocks, 128, 0, stream>>>(ws, type, happy, agent_id, agent_cell, nmovers);
     MB_LAUNCH_CHECK("relocate_apply");
-    if (out_iterations) *out_iterations = iter;
+    if (out_iterations) *out_iterations = pass + 1;
     return MB_OK;
 }

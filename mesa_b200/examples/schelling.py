@@ -95,7 +95,7 @@ class Schelling(DeviceModel):
         self.grid.add_property_layer("agent_id", agent_id.reshape(types.shape))
         self._table = ops.happy_threshold_table(self.homophily, self.radius)
         self._happy_count = torch.zeros(1, dtype=torch.int64, device=dev)
-        self._ws = ops.RelocationWorkspace(flat.numel(), n, dev)
+        self._ws = ops.RelocationWorkspace(types, n)
         self.last_movers = self.last_iterations = 0
         cols = _Columns(self, cell=cells.to(torch.int32), type=flat[cells].clone())
         self.agents = DeviceAgentSet(self, SchellingAgent, n, cols, self.random)

@@ -99,19 +99,28 @@ def schelling_happy(type_layer: torch.Tensor, homophily: float, radius: int = 1,
 
 
 class RelocationWorkspace:
-    """Persistent scratch of mb_schelling_relocate for a grid of `ncells` cells."""
+    """Persistent scratch of mb_schelling_relocate: the per-cell slot table + mover lists.
 
-    def __init__(self, ncells: int, max_movers: int, device):
+    Built from the int8 type layer; call `sync(type_layer)` again if the layer is edited outside
+    `schelling_relocate` (the slot table mirrors the occupancy)."""
+
+    def __init__(self, type_layer: torch.Tensor, max_movers: int):
         import ctypes
 
-        self.ncells, self.max_movers = int(ncells), int(max_movers)
+        _need_cuda(type_layer)
+        self.ncells, self.max_movers = int(type_layer.numel()), int(max_movers)
         nbytes = ctypes.c_size_t(0)
         N.check(N.lib().mb_relocate_workspace_bytes(self.ncells, self.max_movers, ctypes.byref(nbytes)))
         self.nbytes = int(nbytes.value)
-        self.buf = torch.empty(max(self.nbytes, 1), dtype=torch.uint8, device=device)
-        with torch.cuda.device(device):
-            N.check(N.lib().mb_relocate_workspace_init(N.ptr(self.buf), self.nbytes, self.ncells,
-                                                       self.max_movers, N.stream_ptr(device)))
+        self.buf = torch.empty(max(self.nbytes, 1), dtype=torch.uint8, device=type_layer.device)
+        self.sync(type_layer)
+
+    def sync(self, type_layer: torch.Tensor) -> None:
+        if type_layer.dtype != torch.int8 or type_layer.numel() != self.ncells:
+            raise ValueError("expected the int8 type layer this workspace was sized for")
+        with torch.cuda.device(type_layer.device):
+            N.check(N.lib().mb_relocate_workspace_init(N.ptr(self.buf), self.nbytes, self.ncells, self.max_movers,
+                                                       N.ptr(_c(type_layer)), N.stream_ptr(type_layer.device)))
 
 
 def schelling_relocate(type_layer: torch.Tensor, happy: torch.Tensor, agent_id: torch.Tensor,

@@ -29,7 +29,7 @@ class DeviceSchelling:
         self.agent_cell = torch.from_numpy(st.cell.astype(np.uint32).view(np.int32)).cuda().view(torch.uint32)
         self.happy = torch.zeros((self.rows, self.cols), dtype=torch.uint8, device="cuda")
         self.count = torch.zeros(1, dtype=torch.int64, device="cuda")
-        self.ws = ops.RelocationWorkspace(self.rows * self.cols, st.n, "cuda")
+        self.ws = ops.RelocationWorkspace(self.type, st.n)
 
     def assign(self):
         self.ops.schelling_happy(self.type, self.h, self.r, self.torus, out=self.happy, count=self.count)

@@ -30,7 +30,7 @@ for _ in range(20):
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 20
 print(json.dumps({"kernel": "happy", "n": n, "radius": radius, "ms": ms, "GBps": 2 * n * n / ms / 1e6, "happy": int(cnt.item()), "agents": nag}))
-ws = ops.RelocationWorkspace(n * n, nag, "cuda")
+ws = ops.RelocationWorkspace(t, nag)
 for s in range(steps):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     movers, iters = ops.schelling_relocate(t, happy, aid, ws, 1, s)
