@@ -69,19 +69,61 @@ int mb_schelling_happy_i8(const int8_t* type, const int8_t* halo_top, const int8
  * cell_agent.py:39-54).  Activation order = ascending Philox priority64(seed, epoch, agent);
  * probes = the agent's keyed _randbelow(ncells) draws; result identical to the sequential
  * reference driven with the same numbers (csrc/relocate.cu explains the fixed point).
- * agent_id: uint32 layer, agent index sitting in each occupied cell; agent_cell: optional
- * [nagents] uint32 inverse map (NULL to skip).  The workspace holds a 16-byte slot per cell
- * (when it empties / who arrives) that persists between calls: mb_relocate_workspace_init builds it
- * from the type layer (once, and again if the layer is edited elsewhere).
- * mb_schelling_relocate synchronises `stream`.  A full grid with an unhappy
- * agent returns MB_ERR_INVALID (ValueError, grid.py:311-315). */
-int mb_relocate_workspace_bytes(int64_t ncells, int64_t max_movers, size_t* out);
-int mb_relocate_workspace_init(void* workspace, size_t workspace_bytes, int64_t ncells, int64_t max_movers,
-                               const int8_t* type, mb_stream_t stream);
-int mb_schelling_relocate(int8_t* type, uint8_t* happy, uint32_t* agent_id, uint32_t* agent_cell,
-                          int64_t ncells, uint64_t seed, uint32_t epoch, void* workspace,
-                          size_t workspace_bytes, int64_t max_movers, int64_t* out_movers,
-                          int* out_iterations, mb_stream_t stream);
+ * Layers (row-major [rows, cols]): type int8 (-1 empty), happy uint8, agent_id uint32 (agent
+ * index sitting in each occupied cell), slots = 16 bytes per cell (when the cell empties / who
+ * arrives; persistent, built from the type layer by mb_reloc_slots_init and to be rebuilt if the
+ * type layer is edited elsewhere).  A full grid with an unhappy agent returns MB_ERR_INVALID
+ * (ValueError, grid.py:311-315).
+ *
+ * mb_schelling_relocate: the whole step on ONE GPU (synchronises `stream`); agent_cell is an
+ * optional [nagents] uint32 inverse map (NULL to skip).
+ *
+ * Row-sharded grids use the phase-level entry points with a shard descriptor whose per-rank
+ * base pointers are peer-mapped (symmetric memory): rank r owns the rows
+ * block_bounds(rows_total, world, r) of every layer; kernels read / claim remote slots and
+ * write arrivals over NVLink.  mesa_b200/sharded.py holds the (small) host protocol. */
+#define MB_MAX_PEERS 16
+typedef struct mb_shard {
+    int32_t world, rank;
+    int64_t rows_total, cols;
+    void* slots[MB_MAX_PEERS];    /* 16 B per cell */
+    void* type[MB_MAX_PEERS];     /* int8 */
+    void* happy[MB_MAX_PEERS];    /* uint8 */
+    void* agent_id[MB_MAX_PEERS]; /* uint32, global agent index */
+} mb_shard_t;
+
+int mb_schelling_relocate(int8_t* type, uint8_t* happy, uint32_t* agent_id, uint32_t* agent_cell, void* slots,
+                          int64_t rows, int64_t cols, uint64_t seed, uint32_t epoch, void* workspace,
+                          size_t workspace_bytes, int64_t max_movers, int64_t* out_movers, int* out_iterations,
+                          mb_stream_t stream);
+
+int mb_reloc_workspace_bytes(int64_t max_movers, size_t* out);
+int mb_reloc_slots_init(const void* shard /* mb_shard_t* */, mb_stream_t stream);
+/* movers = occupied && !happy of the local block; counters[0..1] = movers, occupied */
+int mb_reloc_collect(const void* shard, uint64_t seed, uint32_t epoch, void* workspace, size_t workspace_bytes,
+                     int64_t max_movers, mb_stream_t stream);
+/* host4 = {movers, occupied, fallback movers of the last pass, table changed in the last pass}; synchronises */
+int mb_reloc_counters(void* workspace, size_t workspace_bytes, int64_t max_movers, uint64_t* host4,
+                      mb_stream_t stream);
+int mb_reloc_pass(const void* shard, int64_t nmovers, uint64_t seed, uint32_t epoch, void* workspace,
+                  size_t workspace_bytes, int64_t max_movers, mb_stream_t stream);
+/* argwhere fallback (grid.py:308-316), batched: export (time, k = _randbelow(nempty), mover) of the local
+ * fallback movers; count the empties of the local table at <= 2048 ascending times; pick the k_local-th one;
+ * commit the picks of the local movers. */
+int mb_reloc_fb_export(const void* shard, int64_t first, int count, int64_t nempty, uint64_t seed, uint32_t epoch,
+                       uint64_t* out_t, uint64_t* out_k, uint32_t* out_m, void* workspace, size_t workspace_bytes,
+                       int64_t max_movers, mb_stream_t stream);
+int mb_reloc_fb_count(const void* shard, const uint64_t* times_sorted, int count, uint32_t* totals, void* workspace,
+                      size_t workspace_bytes, int64_t max_movers, mb_stream_t stream);
+int mb_reloc_fb_pick(const void* shard, const uint64_t* times_sorted, const uint64_t* k_local, int count,
+                     uint64_t* result, void* workspace, size_t workspace_bytes, int64_t max_movers,
+                     mb_stream_t stream);
+int mb_reloc_fb_commit(const void* shard, const uint64_t* times_sorted, const uint32_t* movers,
+                       const uint64_t* result, int count, void* workspace, size_t workspace_bytes,
+                       int64_t max_movers, mb_stream_t stream);
+/* phase 0: origins become empty; phase 1 (after ALL ranks did phase 0): arrivals are written */
+int mb_reloc_apply(const void* shard, int phase, int64_t nmovers, uint32_t* agent_cell, void* workspace,
+                   size_t workspace_bytes, int64_t max_movers, mb_stream_t stream);
 
 /* ---- stable LSD radix sort of (key, uint32) pairs (cell lists; no reference counterpart: the
  * reference scans all agents per query, continuous_space.py:202-235) --------------------------

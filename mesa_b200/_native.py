@@ -25,6 +25,17 @@ class NativeLibraryMissing(ImportError):
     """libmesa_b200.so has not been built (python -m mesa_b200.build)."""
 
 
+MB_MAX_PEERS = 16
+
+
+class Shard(ctypes.Structure):
+    """mb_shard_t: row-block partition + per-rank (peer-mapped) base pointers of the per-cell arrays."""
+
+    _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("rows_total", c_int64), ("cols", c_int64),
+                ("slots", c_void_p * MB_MAX_PEERS), ("type", c_void_p * MB_MAX_PEERS),
+                ("happy", c_void_p * MB_MAX_PEERS), ("agent_id", c_void_p * MB_MAX_PEERS)]
+
+
 class MesaB200Error(RuntimeError):
     """A CUDA/runtime failure reported through the C ABI."""
 
@@ -41,10 +52,19 @@ SIGNATURES: dict[str, tuple] = {
     "mb_gol_step_u8": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, _S]),
     # Schelling
     "mb_schelling_happy_i8": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_int, _P, c_int, _P, _S]),
-    "mb_relocate_workspace_bytes": (c_int, [c_int64, c_int64, ctypes.POINTER(ctypes.c_size_t)]),
-    "mb_relocate_workspace_init": (c_int, [_P, ctypes.c_size_t, c_int64, c_int64, _P, _S]),
-    "mb_schelling_relocate": (c_int, [_P, _P, _P, _P, c_int64, c_uint64, c_uint32, _P, ctypes.c_size_t,
+    "mb_schelling_relocate": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_uint64, c_uint32, _P, ctypes.c_size_t,
                                       c_int64, ctypes.POINTER(c_int64), ctypes.POINTER(c_int), _S]),
+    "mb_reloc_workspace_bytes": (c_int, [c_int64, ctypes.POINTER(ctypes.c_size_t)]),
+    "mb_reloc_slots_init": (c_int, [_P, _S]),
+    "mb_reloc_collect": (c_int, [_P, c_uint64, c_uint32, _P, ctypes.c_size_t, c_int64, _S]),
+    "mb_reloc_counters": (c_int, [_P, ctypes.c_size_t, c_int64, ctypes.POINTER(c_uint64), _S]),
+    "mb_reloc_pass": (c_int, [_P, c_int64, c_uint64, c_uint32, _P, ctypes.c_size_t, c_int64, _S]),
+    "mb_reloc_fb_export": (c_int, [_P, c_int64, c_int, c_int64, c_uint64, c_uint32, _P, _P, _P, _P, ctypes.c_size_t,
+                                   c_int64, _S]),
+    "mb_reloc_fb_count": (c_int, [_P, _P, c_int, _P, _P, ctypes.c_size_t, c_int64, _S]),
+    "mb_reloc_fb_pick": (c_int, [_P, _P, _P, c_int, _P, _P, ctypes.c_size_t, c_int64, _S]),
+    "mb_reloc_fb_commit": (c_int, [_P, _P, _P, _P, c_int, _P, ctypes.c_size_t, c_int64, _S]),
+    "mb_reloc_apply": (c_int, [_P, c_int, c_int64, _P, _P, ctypes.c_size_t, c_int64, _S]),
     # radix sort
     "mb_sort_workspace_bytes": (c_int, [c_int64, ctypes.POINTER(ctypes.c_size_t)]),
     "mb_sort_pairs_u32": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, _P, ctypes.c_size_t,

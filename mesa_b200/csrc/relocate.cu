@@ -33,67 +33,143 @@
 //     counts locate the block of the k-th empty cell and one warp scans that block.
 //
 // All state is caller-owned: the int8 type layer, the uint8 happy layer, the uint32
-// agent-id layer (who sits in each cell), optionally the per-agent cell array, and the
-// workspace holding the slot table (persistent: initialise it from the type layer once).
+// agent-id layer (who sits in each cell), the slot table (16 B per cell, persistent: built
+// from the type layer once), optionally the per-agent cell array, and a private workspace.
+//
+// ROW-SHARDED GRIDS (one process per GPU): a probe is a uniform draw over the
+// WHOLE grid, so most probes land on another rank's rows.  The per-cell arrays of every rank
+// are peer-mapped (torch symmetric memory over NVLink / NVSwitch) and described by mb_shard_t;
+// the same kernels then load remote slots, claim them with NVLink atomics and write arrivals
+// into the owner's layers directly -- no all-to-all of claims.  The host side
+// (mesa_b200/sharded.py) only all-reduces the per-pass flags and runs the small collectives of
+// the fallback (gather the fallback movers, all-gather per-rank empty counts).  Priorities and
+// draws are keyed on global agent ids, so the result is identical for every GPU count.
 #include "common.cuh"
 #include "philox.cuh"
+
+#include <string.h>
 
 namespace {
 
 constexpr unsigned long long kNever = ~0ull;
-constexpr uint32_t kNone = 0xffffffffu;
+constexpr unsigned long long kNoCell = ~0ull;
 constexpr int kMaxProbes = 50;   // grid.py:303 `for _ in range(50)`
 constexpr int kMaxPasses = 100000;
 constexpr int kFbBatch = 2048;   // fallback movers served per table pass
 constexpr int kFbBlocksMax = 4096;
+constexpr int kMaxPeers = 16;
 
 struct Slot {
     unsigned long long vac, arr;
 };
 
-struct RelocWs {
-    Slot* slots;                    // [ncells]
-    uint32_t* mv_cell;              // [cap] origin cell of mover m
-    uint32_t* mv_agent;             // [cap] agent index
-    unsigned long long* mv_prio;    // [cap] priority64
-    int8_t* mv_type;                // [cap]
-    uint32_t* choice;               // [cap] cell currently chosen (claimed) by mover m
-    uint32_t* fb_list;              // [cap] movers that missed all 50 probes in this pass
-    unsigned long long* fb_t;       // [kFbBatch] sorted times of the current fallback batch
-    uint32_t* fb_m;                 // [kFbBatch] mover of each sorted entry
-    unsigned long long* fb_k;       // [kFbBatch] rank of the empty cell to take
-    uint32_t* fb_block;             // [kFbBatch] table block holding it
-    uint32_t* fb_rem;               // [kFbBatch] rank inside that block
-    uint32_t* cnt;                  // [kFbBatch][kFbBlocksMax] empties per table block at each fallback time
-    unsigned long long* counters;   // [0] movers [1] occupied [2] fallback movers of the pass [3] changes of the pass
+// mirror of mb_shard_t (include/mesa_b200.h)
+struct ShardDesc {
+    int32_t world, rank;
+    int64_t rows_total, cols;
+    void* slots[kMaxPeers];
+    void* type[kMaxPeers];
+    void* happy[kMaxPeers];
+    void* agent_id[kMaxPeers];
 };
 
-__host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+// Row-block partition of the global grid (same rule as mesa_b200/sharding.py block_bounds): the first
+// `extra` ranks own base+1 rows.  Per-cell arrays of rank r are reached through peer-mapped base
+// pointers; with world == 1 everything is local.
+struct ShardView {
+    int world, rank;
+    long long cols, base, extra, ncells, local_lo, local_cells;  // local_lo / local_cells in cells
+    Slot* slots[kMaxPeers];
+    int8_t* type[kMaxPeers];
+    uint8_t* happy[kMaxPeers];
+    uint32_t* agent_id[kMaxPeers];
 
-size_t carve(RelocWs* ws, char* base, int64_t ncells, int64_t cap) {
+    __host__ __device__ long long row_lo(int r) const { return (long long)r * base + (r < extra ? r : extra); }
+    __device__ __forceinline__ void locate(unsigned long long c, int& owner, unsigned long long& local) const {
+        if (world == 1) { owner = 0; local = c; return; }
+        const long long row = (long long)(c / (unsigned long long)cols);
+        const long long cut = (base + 1) * extra;
+        owner = row < cut ? (int)(row / (base + 1)) : (int)(extra + (row - cut) / base);
+        local = c - (unsigned long long)(row_lo(owner) * cols);
+    }
+    __device__ __forceinline__ Slot* slot(unsigned long long c) const {
+        int o; unsigned long long l;
+        locate(c, o, l);
+        return slots[o] + l;
+    }
+};
+
+int make_view(const ShardDesc* d, ShardView* v) {
+    MB_REQUIRE(d != nullptr, "null shard descriptor");
+    MB_REQUIRE(d->world >= 1 && d->world <= kMaxPeers && d->rank >= 0 && d->rank < d->world, "bad world / rank");
+    MB_REQUIRE(d->rows_total >= d->world && d->cols > 0, "every rank needs at least one row");
+    v->world = d->world; v->rank = d->rank; v->cols = d->cols;
+    v->base = d->rows_total / d->world; v->extra = d->rows_total % d->world;
+    v->ncells = d->rows_total * d->cols;
+    v->local_lo = v->row_lo(d->rank) * d->cols;
+    v->local_cells = (v->row_lo(d->rank + 1) - v->row_lo(d->rank)) * d->cols;
+    MB_REQUIRE(v->local_cells < 0xffffffffll, "a rank's block must hold < 2^32 - 1 cells");
+    MB_REQUIRE(v->ncells <= (1ll << 32), "the grid must hold at most 2^32 cells");
+    for (int r = 0; r < d->world; ++r) {
+        MB_REQUIRE(d->slots[r] && d->type[r] && d->happy[r] && d->agent_id[r], "null peer pointer in shard descriptor");
+        v->slots[r] = (Slot*)d->slots[r]; v->type[r] = (int8_t*)d->type[r];
+        v->happy[r] = (uint8_t*)d->happy[r]; v->agent_id[r] = (uint32_t*)d->agent_id[r];
+    }
+    return MB_OK;
+}
+
+struct RelocWs {
+    uint32_t* mv_cell;              // [cap] LOCAL origin cell of mover m
+    uint32_t* mv_agent;             // [cap] global agent index
+    unsigned long long* mv_prio;    // [cap] priority64
+    int8_t* mv_type;                // [cap]
+    unsigned long long* choice;     // [cap] GLOBAL cell currently chosen (claimed) by mover m, kNoCell if none
+    uint32_t* fb_list;              // [cap] movers that missed all 50 probes in this pass
+    unsigned long long* fb_t;       // [kFbBatch] sorted times of the current fallback batch
+    uint32_t* fb_m;                 // [kFbBatch] local mover of each sorted entry
+    unsigned long long* fb_k;       // [kFbBatch] rank of the empty cell to take (within this rank's table)
+    unsigned long long* fb_res;     // [kFbBatch] chosen global cell + 1 (0 = not found here)
+    uint32_t* fb_tot;               // [kFbBatch] empties of the local table at each fallback time
+    uint32_t* fb_block;             // [kFbBatch]
+    uint32_t* fb_rem;               // [kFbBatch]
+    uint32_t* cnt;                  // [kFbBatch][kFbBlocksMax] empties per local table block
+    unsigned long long* counters;   // [0] movers [1] occupied [2] fallback movers of the pass [3] table changed
+};
+
+size_t carve(RelocWs* ws, char* base, int64_t cap) {
     size_t off = 0;
     auto take = [&](size_t bytes) {
         char* p = base ? base + off : nullptr;
-        off += align256(bytes);
+        off += (bytes + 255) & ~(size_t)255;
         return p;
     };
     RelocWs t;
-    t.slots = (Slot*)take(sizeof(Slot) * ncells);
     t.mv_cell = (uint32_t*)take(4 * cap);
     t.mv_agent = (uint32_t*)take(4 * cap);
     t.mv_prio = (unsigned long long*)take(8 * cap);
     t.mv_type = (int8_t*)take(cap);
-    t.choice = (uint32_t*)take(4 * cap);
+    t.choice = (unsigned long long*)take(8 * cap);
     t.fb_list = (uint32_t*)take(4 * cap);
     t.fb_t = (unsigned long long*)take(8 * kFbBatch);
     t.fb_m = (uint32_t*)take(4 * kFbBatch);
     t.fb_k = (unsigned long long*)take(8 * kFbBatch);
+    t.fb_res = (unsigned long long*)take(8 * kFbBatch);
+    t.fb_tot = (uint32_t*)take(4 * kFbBatch);
     t.fb_block = (uint32_t*)take(4 * kFbBatch);
     t.fb_rem = (uint32_t*)take(4 * kFbBatch);
     t.cnt = (uint32_t*)take(4ull * kFbBlocksMax * kFbBatch);
     t.counters = (unsigned long long*)take(8 * 8);
     if (ws) *ws = t;
     return off;
+}
+
+int get_ws(RelocWs* ws, void* workspace, size_t workspace_bytes, int64_t cap) {
+    MB_REQUIRE(workspace != nullptr && cap >= 0, "null relocation workspace");
+    if (carve(ws, (char*)workspace, cap) > workspace_bytes) {
+        mb::set_error("relocation workspace too small");
+        return MB_ERR_WORKSPACE;
+    }
+    return MB_OK;
 }
 
 __device__ __forceinline__ Slot load_slot(const Slot* p) {
@@ -103,18 +179,21 @@ __device__ __forceinline__ Slot load_slot(const Slot* p) {
 
 __device__ __forceinline__ bool empty_at(const Slot& s, unsigned long long t) { return s.vac <= t && t <= s.arr; }
 
-__global__ void init_slots(const int8_t* __restrict__ type, int64_t ncells, Slot* __restrict__ slots) {
+__global__ void init_slots(ShardView v) {
+    const int8_t* __restrict__ type = v.type[v.rank];
+    ulonglong2* __restrict__ slots = reinterpret_cast<ulonglong2*>(v.slots[v.rank]);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += stride) {
-        const bool occupied = type != nullptr && type[c] >= 0;
-        reinterpret_cast<ulonglong2*>(slots)[c] = make_ulonglong2(occupied ? kNever : 0ull, kNever);
-    }
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < v.local_cells; c += stride)
+        slots[c] = make_ulonglong2(type[c] >= 0 ? kNever : 0ull, kNever);
 }
 
 // movers = occupied && !happy; appended in arbitrary order (the result does not depend on it).
-__global__ void collect_movers(const int8_t* __restrict__ type, const uint8_t* __restrict__ happy,
-                               const uint32_t* __restrict__ agent_id, int64_t ncells, RelocWs ws, int64_t cap,
-                               uint64_t seed, uint32_t epoch) {
+__global__ void collect_movers(ShardView v, RelocWs ws, int64_t cap, uint64_t seed, uint32_t epoch) {
+    const int8_t* __restrict__ type = v.type[v.rank];
+    const uint8_t* __restrict__ happy = v.happy[v.rank];
+    const uint32_t* __restrict__ agent_id = v.agent_id[v.rank];
+    Slot* __restrict__ slots = v.slots[v.rank];
+    const int64_t ncells = v.local_cells;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     unsigned occupied = 0;
     for (int64_t c0 = (int64_t)blockIdx.x * blockDim.x; c0 < ncells; c0 += stride) {
@@ -137,8 +216,8 @@ __global__ void collect_movers(const int8_t* __restrict__ type, const uint8_t* _
                     ws.mv_agent[slot] = agent;
                     ws.mv_prio[slot] = pr;
                     ws.mv_type[slot] = (int8_t)t;
-                    ws.choice[slot] = kNone;
-                    ws.slots[c].vac = pr + 1;  // empty for every mover that acts after this one
+                    ws.choice[slot] = kNoCell;
+                    slots[c].vac = pr + 1;  // empty for every mover that acts after this one
                 }
             }
         }
@@ -152,50 +231,61 @@ __global__ void collect_movers(const int8_t* __restrict__ type, const uint8_t* _
 __device__ __forceinline__ void mark_changed(RelocWs& ws) { *(volatile unsigned long long*)&ws.counters[3] = 1ull; }
 
 // claim `pick` for mover m (and release what it held before)
-__device__ __forceinline__ void commit_choice(RelocWs& ws, int64_t m, unsigned long long t, uint32_t pick) {
-    const uint32_t held = ws.choice[m];
+__device__ __forceinline__ void commit_choice(const ShardView& v, RelocWs& ws, int64_t m, unsigned long long t,
+                                              unsigned long long pick) {
+    const unsigned long long held = ws.choice[m];
     if (held != pick) {
-        if (held != kNone) atomicCAS(&ws.slots[held].arr, t, kNever);  // release only if I am the registered arrival
+        if (held != kNoCell) atomicCAS(&v.slot(held)->arr, t, kNever);  // release only if I am the registered arrival
         ws.choice[m] = pick;
-        atomicMin(&ws.slots[pick].arr, t);
+        atomicMin(&v.slot(pick)->arr, t);
         mark_changed(ws);
     } else {
         // re-assert: my registration may have been shadowed by an earlier arrival that has left since
-        if (atomicMin(&ws.slots[pick].arr, t) > t) mark_changed(ws);
+        if (atomicMin(&v.slot(pick)->arr, t) > t) mark_changed(ws);
     }
 }
 
 __global__ void __launch_bounds__(128)
-relocate_pass(RelocWs ws, int64_t ncells, int64_t nmovers, uint64_t seed, uint32_t epoch) {
+relocate_pass(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, uint32_t epoch) {
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= nmovers) return;
     const unsigned long long t = ws.mv_prio[m];
     mb::DrawStream ds(seed, epoch, ws.mv_agent[m]);
     for (int j = 0; j < kMaxProbes; ++j) {
-        const int64_t c = (int64_t)ds.randbelow((uint64_t)ncells);
-        if (empty_at(load_slot(ws.slots + c), t)) {
-            commit_choice(ws, m, t, (uint32_t)c);
+        const unsigned long long c = ds.randbelow((uint64_t)v.ncells);
+        if (empty_at(load_slot(v.slot(c)), t)) {
+            commit_choice(v, ws, m, t, c);
             return;
         }
     }
-    ws.fb_list[atomicAdd(&ws.counters[2], 1ull)] = (uint32_t)m;  // served by the fallback kernels of this pass
+    ws.fb_list[atomicAdd(&ws.counters[2], 1ull)] = (uint32_t)m;  // served by the fallback phase of this pass
 }
 
 // ---- argwhere fallback, batched -----------------------------------------------------------------
-// sort the batch by time (bitonic, one CTA) and draw each mover's rank k = _randbelow(nempty)
+// (time, rank k = _randbelow(nempty)) of the local fallback movers [first, first+count) of this pass
+__global__ void fb_export(ShardView v, RelocWs ws, int64_t first, int count, int64_t nempty, uint64_t seed,
+                          uint32_t epoch, unsigned long long* __restrict__ out_t,
+                          unsigned long long* __restrict__ out_k, uint32_t* __restrict__ out_m) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t m = ws.fb_list[first + i];
+    // replay the 50 accepted probes to position the stream, then draw the rank (grid.py:308-310)
+    mb::DrawStream ds(seed, epoch, ws.mv_agent[m]);
+    for (int j = 0; j < kMaxProbes; ++j) (void)ds.randbelow((uint64_t)v.ncells);
+    out_t[i] = ws.mv_prio[m];
+    out_k[i] = ds.randbelow((uint64_t)nempty);
+    out_m[i] = m;
+}
+
+// sort a batch of (time, k, mover) by time (bitonic, one CTA) into fb_t / fb_k / fb_m
 __global__ void __launch_bounds__(1024)
-fb_sort(RelocWs ws, int64_t first, int count, int64_t ncells, int64_t nempty, uint64_t seed, uint32_t epoch) {
+fb_sort(RelocWs ws, const unsigned long long* __restrict__ in_t, const unsigned long long* __restrict__ in_k,
+        const uint32_t* __restrict__ in_m, int count) {
     __shared__ unsigned long long st[kFbBatch];
-    __shared__ uint32_t sm[kFbBatch];
+    __shared__ uint32_t si[kFbBatch];
     for (int i = threadIdx.x; i < kFbBatch; i += blockDim.x) {
-        if (i < count) {
-            const uint32_t m = ws.fb_list[first + i];
-            st[i] = ws.mv_prio[m];
-            sm[i] = m;
-        } else {
-            st[i] = kNever;
-            sm[i] = kNone;
-        }
+        st[i] = i < count ? in_t[i] : kNever;
+        si[i] = (uint32_t)i;
     }
     __syncthreads();
     for (int k = 2; k <= kFbBatch; k <<= 1)
@@ -206,49 +296,46 @@ fb_sort(RelocWs ws, int64_t first, int count, int64_t ncells, int64_t nempty, ui
                     const bool up = (i & k) == 0;
                     if ((st[i] > st[p]) == up) {
                         const unsigned long long a = st[i]; st[i] = st[p]; st[p] = a;
-                        const uint32_t b = sm[i]; sm[i] = sm[p]; sm[p] = b;
+                        const uint32_t b = si[i]; si[i] = si[p]; si[p] = b;
                     }
                 }
             }
             __syncthreads();
         }
     for (int i = threadIdx.x; i < count; i += blockDim.x) {
-        const uint32_t m = sm[i];
         ws.fb_t[i] = st[i];
-        ws.fb_m[i] = m;
-        // replay the 50 accepted probes to position the stream, then draw the rank (grid.py:308-310)
-        mb::DrawStream ds(seed, epoch, ws.mv_agent[m]);
-        for (int j = 0; j < kMaxProbes; ++j) (void)ds.randbelow((uint64_t)ncells);
-        ws.fb_k[i] = ds.randbelow((uint64_t)nempty);
+        ws.fb_k[i] = in_k[si[i]];
+        ws.fb_m[i] = in_m[si[i]];
     }
 }
 
-__device__ __forceinline__ int first_ge(const unsigned long long* __restrict__ a, int n, unsigned long long v) {
+__device__ __forceinline__ int first_ge(const unsigned long long* __restrict__ a, int n, unsigned long long x) {
     int lo = 0, hi = n;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (a[mid] < v) lo = mid + 1; else hi = mid;
+        if (a[mid] < x) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
 
-// cnt[b][f] = number of cells of table block b that are empty at the time of fallback f
+// cnt[f][b] = number of cells of LOCAL table block b that are empty at the time of fallback f
 __global__ void __launch_bounds__(256)
-fb_count(RelocWs ws, int64_t ncells, int64_t block_cells, int count) {
+fb_count(ShardView v, RelocWs ws, const unsigned long long* __restrict__ fb_t, int64_t block_cells, int count) {
     __shared__ int diff[kFbBatch + 1];
     __shared__ unsigned long long times[kFbBatch];
     __shared__ int warp_base[8];
     for (int i = threadIdx.x; i <= kFbBatch; i += blockDim.x) diff[i] = 0;
-    for (int i = threadIdx.x; i < count; i += blockDim.x) times[i] = ws.fb_t[i];
+    for (int i = threadIdx.x; i < count; i += blockDim.x) times[i] = fb_t[i];
     __syncthreads();
+    const Slot* __restrict__ slots = v.slots[v.rank];
     const int64_t lo_c = (int64_t)blockIdx.x * block_cells;
-    const int64_t hi_c = min(lo_c + block_cells, ncells);
+    const int64_t hi_c = min(lo_c + block_cells, (int64_t)v.local_cells);
     int base = 0;
     for (int64_t c = lo_c + threadIdx.x; c < hi_c; c += blockDim.x) {
-        const Slot s = load_slot(ws.slots + c);
-        if (s.vac == kNever) continue;                       // occupied during the whole step
+        const Slot s = load_slot(slots + c);
+        if (s.vac == kNever) continue;                            // occupied during the whole step
         if (s.vac == 0 && s.arr == kNever) { ++base; continue; }  // empty during the whole step
-        const int lo = first_ge(times, count, s.vac);        // first fallback with t >= vac
+        const int lo = first_ge(times, count, s.vac);             // first fallback with t >= vac
         const int hi = s.arr == kNever ? count : first_ge(times, count, s.arr + 1);  // first with t > arr
         if (lo < hi) {
             atomicAdd(&diff[lo], 1);
@@ -259,106 +346,106 @@ fb_count(RelocWs ws, int64_t ncells, int64_t block_cells, int count) {
     if ((threadIdx.x & 31) == 0) warp_base[threadIdx.x >> 5] = base;
     __syncthreads();
     if (threadIdx.x == 0) {
-        int b = 0;
-        for (int w = 0; w < 8; ++w) b += warp_base[w];
-        int run = b;
+        int run = 0;
+        for (int w = 0; w < 8; ++w) run += warp_base[w];
         for (int f = 0; f < count; ++f) {  // prefix sum of the difference array (count <= 2048)
             run += diff[f];
             diff[f] = run;
         }
     }
     __syncthreads();
-    for (int f = threadIdx.x; f < count; f += blockDim.x) ws.cnt[(size_t)f * kFbBlocksMax + blockIdx.x] = (uint32_t)diff[f];
+    for (int f = threadIdx.x; f < count; f += blockDim.x) {
+        ws.cnt[(size_t)f * kFbBlocksMax + blockIdx.x] = (uint32_t)diff[f];
+        if (diff[f]) atomicAdd(&ws.fb_tot[f], (uint32_t)diff[f]);
+    }
 }
 
-// one warp per fallback mover: walk the per-block counts 32 blocks at a time (coalesced, warp scan)
-__global__ void __launch_bounds__(256) fb_locate(RelocWs ws, int nblocks, int count) {
+// one warp per fallback mover whose k-th empty cell lies in the LOCAL table (k_local != kNoCell):
+// walk the per-block counts 32 blocks at a time, then scan the block; result = global cell + 1
+__global__ void __launch_bounds__(256)
+fb_pick(ShardView v, RelocWs ws, const unsigned long long* __restrict__ fb_t,
+        const unsigned long long* __restrict__ k_local, int nblocks, int64_t block_cells, int count,
+        unsigned long long* __restrict__ result) {
     const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (f >= count) return;
-    unsigned long long k = ws.fb_k[f];
+    unsigned long long k = k_local[f];
+    if (k == kNoCell) return;
     const uint32_t* __restrict__ row = ws.cnt + (size_t)f * kFbBlocksMax;
-    int block = nblocks - 1;
-    unsigned rem = 0;
-    bool done = false;
-    for (int b0 = 0; b0 < nblocks && !done; b0 += 32) {
+    int block = -1;
+    unsigned need = 0;
+    for (int b0 = 0; b0 < nblocks && block < 0; b0 += 32) {
         const int b = b0 + lane;
         const unsigned n = b < nblocks ? row[b] : 0u;
         unsigned incl = n;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
+            const unsigned x = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += x;
         }
         const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
         if (k < total) {
-            // first lane whose inclusive count exceeds k holds the block
-            const unsigned hit = __ballot_sync(0xffffffffu, k < incl);
-            const int l = __ffs(hit) - 1;
-            const unsigned before = __shfl_sync(0xffffffffu, incl - n, l);
+            const int l = __ffs(__ballot_sync(0xffffffffu, k < incl)) - 1;
+            need = (unsigned)(k - __shfl_sync(0xffffffffu, incl - n, l));
             block = b0 + l;
-            rem = (unsigned)(k - before);
-            done = true;
         } else {
             k -= total;
         }
     }
-    if (lane == 0) {
-        ws.fb_block[f] = (uint32_t)block;
-        ws.fb_rem[f] = done ? rem : 0xffffffffu;  // not found: fb_pick reports "changed" and the pass repeats
-    }
-}
-
-// one warp per fallback mover: the fb_rem-th empty cell of block fb_block at the mover's time
-__global__ void __launch_bounds__(256)
-fb_pick(RelocWs ws, int64_t ncells, int64_t block_cells, int count) {
-    const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (f >= count) return;
-    const unsigned long long t = ws.fb_t[f];
-    const int64_t lo_c = (int64_t)ws.fb_block[f] * block_cells;
-    const int64_t hi_c = min(lo_c + block_cells, ncells);
-    unsigned need = ws.fb_rem[f];
-    int64_t found = -1;
-    for (int64_t c0 = lo_c; c0 < hi_c; c0 += 32) {
-        const int64_t c = c0 + lane;
-        const bool e = c < hi_c && empty_at(load_slot(ws.slots + c), t);
-        const unsigned ballot = __ballot_sync(0xffffffffu, e);
-        const unsigned n = __popc(ballot);
-        if (need < n) {
-            unsigned b = ballot;
-            for (unsigned i = 0; i < need; ++i) b &= b - 1;  // drop the `need` lowest set bits
-            found = c0 + (__ffs(b) - 1);
-            break;
+    long long found = -1;
+    if (block >= 0) {
+        const unsigned long long t = fb_t[f];
+        const Slot* __restrict__ slots = v.slots[v.rank];
+        const int64_t lo_c = (int64_t)block * block_cells;
+        const int64_t hi_c = min(lo_c + block_cells, (int64_t)v.local_cells);
+        for (int64_t c0 = lo_c; c0 < hi_c; c0 += 32) {
+            const int64_t c = c0 + lane;
+            const bool e = c < hi_c && empty_at(load_slot(slots + c), t);
+            const unsigned ballot = __ballot_sync(0xffffffffu, e);
+            const unsigned n = __popc(ballot);
+            if (need < n) {
+                unsigned b = ballot;
+                for (unsigned i = 0; i < need; ++i) b &= b - 1;  // drop the `need` lowest set bits
+                found = c0 + (__ffs(b) - 1);
+                break;
+            }
+            need -= n;
         }
-        need -= n;
     }
-    if (lane == 0) {
-        if (found >= 0) commit_choice(ws, ws.fb_m[f], t, (uint32_t)found);
-        else mark_changed(ws);  // table moved under the scan (concurrent commits): force another pass
-    }
+    if (lane == 0) result[f] = found >= 0 ? (unsigned long long)(v.local_lo + found) + 1ull : 0ull;
 }
 
-__global__ void relocate_vacate(RelocWs ws, int8_t* type, uint8_t* happy, int64_t nmovers) {
+// commit the fallback picks of the movers that live on this rank (mover[f] != 0xffffffff)
+__global__ void fb_commit(ShardView v, RelocWs ws, const unsigned long long* __restrict__ fb_t,
+                          const uint32_t* __restrict__ mover, const unsigned long long* __restrict__ result, int count) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= count) return;
+    const uint32_t m = mover[f];
+    if (m == 0xffffffffu) return;
+    if (result[f] != 0ull) commit_choice(v, ws, m, fb_t[f], result[f] - 1ull);
+    else mark_changed(ws);  // the table moved under the scan (concurrent commits): force another pass
+}
+
+__global__ void relocate_vacate(ShardView v, RelocWs ws, int64_t nmovers) {
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= nmovers) return;
     const uint32_t o = ws.mv_cell[m];
-    type[o] = -1;
-    happy[o] = 0;
-    reinterpret_cast<ulonglong2*>(ws.slots)[o] = make_ulonglong2(0ull, kNever);
+    v.type[v.rank][o] = -1;
+    v.happy[v.rank][o] = 0;
+    reinterpret_cast<ulonglong2*>(v.slots[v.rank])[o] = make_ulonglong2(0ull, kNever);
 }
 
-__global__ void relocate_arrive(RelocWs ws, int8_t* type, uint8_t* happy, uint32_t* agent_id,
-                                uint32_t* agent_cell, int64_t nmovers) {
+__global__ void relocate_arrive(ShardView v, RelocWs ws, uint32_t* agent_cell, int64_t nmovers) {
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= nmovers) return;
-    const uint32_t d = ws.choice[m];
+    int o; unsigned long long d;
+    v.locate(ws.choice[m], o, d);
     const uint32_t agent = ws.mv_agent[m];
-    type[d] = ws.mv_type[m];
-    happy[d] = 0;  // the flag travels with the agent: movers are unhappy until the next assign_state
-    agent_id[d] = agent;
-    if (agent_cell != nullptr) agent_cell[agent] = d;
-    reinterpret_cast<ulonglong2*>(ws.slots)[d] = make_ulonglong2(kNever, kNever);
+    v.type[o][d] = ws.mv_type[m];
+    v.happy[o][d] = 0;  // the flag travels with the agent: movers are unhappy until the next assign_state
+    v.agent_id[o][d] = agent;
+    if (agent_cell != nullptr) agent_cell[agent] = (uint32_t)ws.choice[m];
+    reinterpret_cast<ulonglong2*>(v.slots[o])[d] = make_ulonglong2(kNever, kNever);
 }
 
 int read_counters(const RelocWs& ws, unsigned long long* host4, cudaStream_t stream) {
@@ -368,56 +455,204 @@ int read_counters(const RelocWs& ws, unsigned long long* host4, cudaStream_t str
     return mb::check_cuda(cudaStreamSynchronize(stream), "sync");
 }
 
+inline int64_t fb_num_blocks(int64_t local_cells) {
+    int64_t b = mb::ceil_div(local_cells > 0 ? local_cells : 1, 1024);
+    return b > kFbBlocksMax ? kFbBlocksMax : b;
+}
+
+// serve `count` (<= kFbBatch) fallback entries whose (t, k, m) sit in device arrays, single rank
+int serve_fallback_local(const ShardView& v, RelocWs& ws, const unsigned long long* in_t, const unsigned long long* in_k,
+                         const uint32_t* in_m, int count, cudaStream_t stream) {
+    const int64_t nblocks = fb_num_blocks(v.local_cells);
+    const int64_t block_cells = mb::ceil_div(v.local_cells, nblocks);
+    fb_sort<<<1, 1024, 0, stream>>>(ws, in_t, in_k, in_m, count);
+    int rc = mb::check_cuda(cudaMemsetAsync(ws.fb_tot, 0, 4 * kFbBatch, stream), "memset");
+    if (rc) return rc;
+    fb_count<<<(unsigned)nblocks, 256, 0, stream>>>(v, ws, ws.fb_t, block_cells, count);
+    const unsigned wblocks = (unsigned)mb::ceil_div((int64_t)count * 32, 256);
+    fb_pick<<<wblocks, 256, 0, stream>>>(v, ws, ws.fb_t, ws.fb_k, (int)nblocks, block_cells, count, ws.fb_res);
+    fb_commit<<<(unsigned)mb::ceil_div(count, 128), 128, 0, stream>>>(v, ws, ws.fb_t, ws.fb_m, ws.fb_res, count);
+    MB_LAUNCH_CHECK("relocate fallback");
+    return MB_OK;
+}
+
 }  // namespace
 
-MB_API int mb_relocate_workspace_bytes(int64_t ncells, int64_t max_movers, size_t* out) {
-    MB_REQUIRE(out != nullptr && ncells >= 0 && max_movers >= 0, "mb_relocate_workspace_bytes: bad argument");
-    *out = carve(nullptr, nullptr, ncells, max_movers);
+// ================================================================================================
+// C ABI: phase-level entry points (used one by one by the row-sharded driver, mesa_b200/sharded.py)
+// ================================================================================================
+MB_API int mb_reloc_workspace_bytes(int64_t max_movers, size_t* out) {
+    MB_REQUIRE(out != nullptr && max_movers >= 0, "mb_reloc_workspace_bytes: bad argument");
+    *out = carve(nullptr, nullptr, max_movers);
     return MB_OK;
 }
 
-// Builds the slot table from the occupancy (type[c] >= 0 = occupied; type == NULL = all empty).
-// Call once, and again whenever the type layer was modified outside mb_schelling_relocate.
-MB_API int mb_relocate_workspace_init(void* workspace, size_t workspace_bytes, int64_t ncells,
-                                      int64_t max_movers, const int8_t* type, cudaStream_t stream) {
+MB_API int mb_reloc_slots_init(const void* shard, cudaStream_t stream) {
+    ShardView v;
+    int rc = make_view((const ShardDesc*)shard, &v);
+    if (rc) return rc;
+    if (v.local_cells > 0) init_slots<<<mb::sm_count() * 8, 256, 0, stream>>>(v);
+    MB_LAUNCH_CHECK("mb_reloc_slots_init");
+    return MB_OK;
+}
+
+MB_API int mb_reloc_collect(const void* shard, uint64_t seed, uint32_t epoch, void* workspace, size_t workspace_bytes,
+                            int64_t max_movers, cudaStream_t stream) {
+    ShardView v;
     RelocWs ws;
-    MB_REQUIRE(workspace != nullptr, "mb_relocate_workspace_init: null workspace");
-    if (carve(&ws, (char*)workspace, ncells, max_movers) > workspace_bytes) {
-        mb::set_error("mb_relocate_workspace_init: workspace too small");
-        return MB_ERR_WORKSPACE;
+    int rc = make_view((const ShardDesc*)shard, &v);
+    if (rc) return rc;
+    if ((rc = get_ws(&ws, workspace, workspace_bytes, max_movers))) return rc;
+    if ((rc = mb::check_cuda(cudaMemsetAsync(ws.counters, 0, 8 * sizeof(unsigned long long), stream), "memset"))) return rc;
+    if (v.local_cells > 0) {
+        const int64_t want = mb::ceil_div(v.local_cells, 256);
+        const int64_t cap = (int64_t)mb::sm_count() * 16;
+        collect_movers<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(v, ws, max_movers, seed, epoch);
     }
-    if (ncells > 0) init_slots<<<mb::sm_count() * 8, 256, 0, stream>>>(type, ncells, ws.slots);
-    MB_LAUNCH_CHECK("mb_relocate_workspace_init");
+    MB_LAUNCH_CHECK("mb_reloc_collect");
     return MB_OK;
 }
 
-// Synchronises `stream` (needs the mover count and the per-pass convergence flags on the host).
-MB_API int mb_schelling_relocate(int8_t* type, uint8_t* happy, uint32_t* agent_id, uint32_t* agent_cell,
-                                 int64_t ncells, uint64_t seed, uint32_t epoch, void* workspace,
+// copies counters [movers, occupied, fallback movers of the pass, table changed] to the host; synchronises
+MB_API int mb_reloc_counters(void* workspace, size_t workspace_bytes, int64_t max_movers, uint64_t* host4,
+                             cudaStream_t stream) {
+    RelocWs ws;
+    int rc = get_ws(&ws, workspace, workspace_bytes, max_movers);
+    if (rc) return rc;
+    MB_REQUIRE(host4 != nullptr, "mb_reloc_counters: null output");
+    return read_counters(ws, (unsigned long long*)host4, stream);
+}
+
+MB_API int mb_reloc_pass(const void* shard, int64_t nmovers, uint64_t seed, uint32_t epoch, void* workspace,
+                         size_t workspace_bytes, int64_t max_movers, cudaStream_t stream) {
+    ShardView v;
+    RelocWs ws;
+    int rc = make_view((const ShardDesc*)shard, &v);
+    if (rc) return rc;
+    if ((rc = get_ws(&ws, workspace, workspace_bytes, max_movers))) return rc;
+    MB_REQUIRE(nmovers >= 0 && nmovers <= max_movers, "mb_reloc_pass: mover count exceeds the workspace");
+    if ((rc = mb::check_cuda(cudaMemsetAsync(ws.counters + 2, 0, 2 * sizeof(unsigned long long), stream), "memset"))) return rc;
+    if (nmovers > 0)
+        relocate_pass<<<(unsigned)mb::ceil_div(nmovers, 128), 128, 0, stream>>>(v, ws, nmovers, seed, epoch);
+    MB_LAUNCH_CHECK("mb_reloc_pass");
+    return MB_OK;
+}
+
+// (time, k = _randbelow(nempty), local mover) of this rank's fallback movers [first, first+count) of the pass
+MB_API int mb_reloc_fb_export(const void* shard, int64_t first, int count, int64_t nempty, uint64_t seed, uint32_t epoch,
+                              uint64_t* out_t, uint64_t* out_k, uint32_t* out_m, void* workspace, size_t workspace_bytes,
+                              int64_t max_movers, cudaStream_t stream) {
+    ShardView v;
+    RelocWs ws;
+    int rc = make_view((const ShardDesc*)shard, &v);
+    if (rc) return rc;
+    if ((rc = get_ws(&ws, workspace, workspace_bytes, max_movers))) return rc;
+    MB_REQUIRE(count >= 0 && nempty > 0 && out_t && out_k && out_m, "mb_reloc_fb_export: bad argument");
+    if (count > 0)
+        fb_export<<<(unsigned)mb::ceil_div(count, 128), 128, 0, stream>>>(v, ws, first, count, nempty, seed, epoch,
+                                                                           (unsigned long long*)out_t, (unsigned long long*)out_k, out_m);
+    MB_LAUNCH_CHECK("mb_reloc_fb_export");
+    return MB_OK;
+}
+
+// empties of the LOCAL table at each of `count` (<= 2048) ascending times -> totals[count]
+MB_API int mb_reloc_fb_count(const void* shard, const uint64_t* times_sorted, int count, uint32_t* totals, void* workspace,
+                             size_t workspace_bytes, int64_t max_movers, cudaStream_t stream) {
+    ShardView v;
+    RelocWs ws;
+    int rc = make_view((const ShardDesc*)shard, &v);
+    if (rc) return rc;
+    if ((rc = get_ws(&ws, workspace, workspace_bytes, max_movers))) return rc;
+    MB_REQUIRE(count >= 0 && count <= kFbBatch && times_sorted && totals, "mb_reloc_fb_count: bad argument");
+    if (count == 0) return MB_OK;
+    const int64_t nblocks = fb_num_blocks(v.local_cells);
+    if ((rc = mb::check_cuda(cudaMemsetAsync(ws.fb_tot, 0, 4 * kFbBatch, stream), "memset"))) return rc;
+    fb_count<<<(unsigned)nblocks, 256, 0, stream>>>(v, ws, (const unsigned long long*)times_sorted,
+                                                   mb::ceil_div(v.local_cells, nblocks), count);
+    if ((rc = mb::check_cuda(cudaMemcpyAsync(totals, ws.fb_tot, 4 * (size_t)count, cudaMemcpyDeviceToDevice, stream), "copy"))) return rc;
+    MB_LAUNCH_CHECK("mb_reloc_fb_count");
+    return MB_OK;
+}
+
+// after mb_reloc_fb_count with the same times: result[f] = global cell + 1 of the k_local[f]-th empty cell of the
+// LOCAL table at times_sorted[f] (k_local[f] == ~0: not on this rank -> untouched)
+MB_API int mb_reloc_fb_pick(const void* shard, const uint64_t* times_sorted, const uint64_t* k_local, int count,
+                            uint64_t* result, void* workspace, size_t workspace_bytes, int64_t max_movers,
+                            cudaStream_t stream) {
+    ShardView v;
+    RelocWs ws;
+    int rc = make_view((const ShardDesc*)shard, &v);
+    if (rc) return rc;
+    if ((rc = get_ws(&ws, workspace, workspace_bytes, max_movers))) return rc;
+    MB_REQUIRE(count >= 0 && count <= kFbBatch && times_sorted && k_local && result, "mb_reloc_fb_pick: bad argument");
+    if (count == 0) return MB_OK;
+    const int64_t nblocks = fb_num_blocks(v.local_cells);
+    fb_pick<<<(unsigned)mb::ceil_div((int64_t)count * 32, 256), 256, 0, stream>>>(
+        v, ws, (const unsigned long long*)times_sorted, (const unsigned long long*)k_local, (int)nblocks,
+        mb::ceil_div(v.local_cells, nblocks), count, (unsigned long long*)result);
+    MB_LAUNCH_CHECK("mb_reloc_fb_pick");
+    return MB_OK;
+}
+
+// claim result[f]-1 for the local mover movers[f] (0xffffffff = not mine) at times_sorted[f]
+MB_API int mb_reloc_fb_commit(const void* shard, const uint64_t* times_sorted, const uint32_t* movers,
+                              const uint64_t* result, int count, void* workspace, size_t workspace_bytes,
+                              int64_t max_movers, cudaStream_t stream) {
+    ShardView v;
+    RelocWs ws;
+    int rc = make_view((const ShardDesc*)shard, &v);
+    if (rc) return rc;
+    if ((rc = get_ws(&ws, workspace, workspace_bytes, max_movers))) return rc;
+    MB_REQUIRE(count >= 0 && times_sorted && movers && result, "mb_reloc_fb_commit: bad argument");
+    if (count > 0)
+        fb_commit<<<(unsigned)mb::ceil_div(count, 128), 128, 0, stream>>>(v, ws, (const unsigned long long*)times_sorted,
+                                                                           movers, (const unsigned long long*)result, count);
+    MB_LAUNCH_CHECK("mb_reloc_fb_commit");
+    return MB_OK;
+}
+
+// phase 0: every origin becomes empty; phase 1 (after ALL ranks finished phase 0): every arrival is written
+MB_API int mb_reloc_apply(const void* shard, int phase, int64_t nmovers, uint32_t* agent_cell, void* workspace,
+                          size_t workspace_bytes, int64_t max_movers, cudaStream_t stream) {
+    ShardView v;
+    RelocWs ws;
+    int rc = make_view((const ShardDesc*)shard, &v);
+    if (rc) return rc;
+    if ((rc = get_ws(&ws, workspace, workspace_bytes, max_movers))) return rc;
+    if (nmovers > 0) {
+        const unsigned blocks = (unsigned)mb::ceil_div(nmovers, 128);
+        if (phase == 0) relocate_vacate<<<blocks, 128, 0, stream>>>(v, ws, nmovers);
+        else relocate_arrive<<<blocks, 128, 0, stream>>>(v, ws, agent_cell, nmovers);
+    }
+    MB_LAUNCH_CHECK("mb_reloc_apply");
+    return MB_OK;
+}
+
+// ================================================================================================
+// Single-GPU driver: the whole shuffle_do("step") in one call.  Synchronises `stream` (needs the mover
+// count and the per-pass flags on the host).
+// ================================================================================================
+MB_API int mb_schelling_relocate(int8_t* type, uint8_t* happy, uint32_t* agent_id, uint32_t* agent_cell, void* slots,
+                                 int64_t rows, int64_t cols, uint64_t seed, uint32_t epoch, void* workspace,
                                  size_t workspace_bytes, int64_t max_movers, int64_t* out_movers,
                                  int* out_iterations, cudaStream_t stream) {
-    MB_REQUIRE(ncells >= 0 && ncells < 0xffffffffll, "mb_schelling_relocate: ncells must be < 2^32 - 1");
     if (out_movers) *out_movers = 0;
     if (out_iterations) *out_iterations = 0;
-    if (ncells == 0) return MB_OK;
-    MB_REQUIRE(type && happy && agent_id && workspace, "mb_schelling_relocate: null buffer");
+    MB_REQUIRE(rows >= 0 && cols >= 0, "mb_schelling_relocate: negative shape");
+    if (rows == 0 || cols == 0) return MB_OK;
+    MB_REQUIRE(type && happy && agent_id && slots && workspace, "mb_schelling_relocate: null buffer");
+    ShardDesc d;
+    memset(&d, 0, sizeof(d));
+    d.world = 1; d.rank = 0; d.rows_total = rows; d.cols = cols;
+    d.slots[0] = slots; d.type[0] = type; d.happy[0] = happy; d.agent_id[0] = agent_id;
+    ShardView v;
     RelocWs ws;
-    if (carve(&ws, (char*)workspace, ncells, max_movers) > workspace_bytes) {
-        mb::set_error("mb_schelling_relocate: workspace too small");
-        return MB_ERR_WORKSPACE;
-    }
-    int rc = mb::check_cuda(cudaMemsetAsync(ws.counters, 0, 8 * sizeof(unsigned long long), stream), "memset");
+    int rc = make_view(&d, &v);
     if (rc) return rc;
-    const int sms = mb::sm_count();
-    {
-        const int64_t want = mb::ceil_div(ncells, 256);
-        const unsigned blocks = (unsigned)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
-        collect_movers<<<blocks, 256, 0, stream>>>(type, happy, agent_id, ncells, ws, max_movers, seed, epoch);
-        MB_LAUNCH_CHECK("collect_movers");
-    }
+    if ((rc = get_ws(&ws, workspace, workspace_bytes, max_movers))) return rc;
+    if ((rc = mb_reloc_collect(&d, seed, epoch, workspace, workspace_bytes, max_movers, stream))) return rc;
     unsigned long long hc[4];
-    rc = read_counters(ws, hc, stream);
-    if (rc) return rc;
+    if ((rc = read_counters(ws, hc, stream))) return rc;
     const int64_t nmovers = (int64_t)hc[0], noccupied = (int64_t)hc[1];
     if (out_movers) *out_movers = nmovers;
     if (nmovers == 0) return MB_OK;
@@ -426,44 +661,37 @@ MB_API int mb_schelling_relocate(int8_t* type, uint8_t* happy, uint32_t* agent_i
                       (long long)max_movers);
         return MB_ERR_WORKSPACE;
     }
-    const int64_t nempty = ncells - noccupied;
+    const int64_t nempty = v.ncells - noccupied;
     // grid.py:311-315: a completely full grid raises ValueError at the first unhappy agent
     MB_REQUIRE(nempty > 0, "Grid is completely full. No empty cells available. Cannot select a random empty cell.");
-
-    const unsigned mblocks = (unsigned)mb::ceil_div(nmovers, 128);
-    int64_t fb_blocks = mb::ceil_div(ncells, 1024);
-    if (fb_blocks > kFbBlocksMax) fb_blocks = kFbBlocksMax;
-    const int64_t block_cells = mb::ceil_div(ncells, fb_blocks);
     int pass = 0;
     for (;; ++pass) {
         if (pass >= kMaxPasses) {
             mb::set_error("mb_schelling_relocate: no convergence after %d passes", pass);
             return MB_ERR_CUDA;
         }
-        rc = mb::check_cuda(cudaMemsetAsync(ws.counters + 2, 0, 2 * sizeof(unsigned long long), stream), "memset");
-        if (rc) return rc;
-        relocate_pass<<<mblocks, 128, 0, stream>>>(ws, ncells, nmovers, seed, epoch);
-        MB_LAUNCH_CHECK("relocate_pass");
-        rc = read_counters(ws, hc, stream);
-        if (rc) return rc;
+        if ((rc = mb_reloc_pass(&d, nmovers, seed, epoch, workspace, workspace_bytes, max_movers, stream))) return rc;
+        if ((rc = read_counters(ws, hc, stream))) return rc;
         const int64_t nfb = (int64_t)hc[2];
         if (nfb > 0) {
+            // scratch for the exported (t, k, m): the tail of the choice-independent arrays is free
             for (int64_t first = 0; first < nfb; first += kFbBatch) {
                 const int count = (int)(nfb - first < kFbBatch ? nfb - first : kFbBatch);
-                fb_sort<<<1, 1024, 0, stream>>>(ws, first, count, ncells, nempty, seed, epoch);
-                fb_count<<<(unsigned)fb_blocks, 256, 0, stream>>>(ws, ncells, block_cells, count);
-                fb_locate<<<(unsigned)mb::ceil_div((int64_t)count * 32, 256), 256, 0, stream>>>(ws, (int)fb_blocks, count);
-                fb_pick<<<(unsigned)mb::ceil_div((int64_t)count * 32, 256), 256, 0, stream>>>(ws, ncells, block_cells, count);
+                // fb_res / fb_k / fb_m double as the export buffers before the sort overwrites k and m
+                unsigned long long* tmp_t = ws.fb_res;
+                unsigned long long* tmp_k = reinterpret_cast<unsigned long long*>(ws.cnt);
+                uint32_t* tmp_m = ws.fb_block;
+                fb_export<<<(unsigned)mb::ceil_div(count, 128), 128, 0, stream>>>(v, ws, first, count, nempty, seed, epoch,
+                                                                                   tmp_t, tmp_k, tmp_m);
+                // the sort reads tmp_* and writes fb_t / fb_k / fb_m; cnt is rewritten by fb_count afterwards
+                if ((rc = serve_fallback_local(v, ws, tmp_t, tmp_k, tmp_m, count, stream))) return rc;
             }
-            MB_LAUNCH_CHECK("relocate_fallback");
-            rc = read_counters(ws, hc, stream);
-            if (rc) return rc;
+            if ((rc = read_counters(ws, hc, stream))) return rc;
         }
         if (hc[3] == 0) break;  // a pass without any change of the table: fixed point
     }
-    relocate_vacate<<<mblocks, 128, 0, stream>>>(ws, type, happy, nmovers);
-    relocate_arrive<<<mblocks, 128, 0, stream>>>(ws, type, happy, agent_id, agent_cell, nmovers);
-    MB_LAUNCH_CHECK("relocate_apply");
+    if ((rc = mb_reloc_apply(&d, 0, nmovers, agent_cell, workspace, workspace_bytes, max_movers, stream))) return rc;
+    if ((rc = mb_reloc_apply(&d, 1, nmovers, agent_cell, workspace, workspace_bytes, max_movers, stream))) return rc;
     if (out_iterations) *out_iterations = pass + 1;
     return MB_OK;
 }

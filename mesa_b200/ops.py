@@ -99,48 +99,59 @@ def schelling_happy(type_layer: torch.Tensor, homophily: float, radius: int = 1,
 
 
 class RelocationWorkspace:
-    """Persistent scratch of mb_schelling_relocate: the per-cell slot table + mover lists.
+    """Persistent state of mb_schelling_relocate on one GPU: the 16-byte-per-cell slot table (mirrors the
+    occupancy) + the private mover / fallback scratch.
 
     Built from the int8 type layer; call `sync(type_layer)` again if the layer is edited outside
-    `schelling_relocate` (the slot table mirrors the occupancy)."""
+    `schelling_relocate`."""
 
     def __init__(self, type_layer: torch.Tensor, max_movers: int):
         import ctypes
 
         _need_cuda(type_layer)
+        if type_layer.dtype != torch.int8 or type_layer.dim() != 2:
+            raise ValueError("expected the int8 [rows, cols] type layer")
+        self.rows, self.cols = type_layer.shape
         self.ncells, self.max_movers = int(type_layer.numel()), int(max_movers)
         nbytes = ctypes.c_size_t(0)
-        N.check(N.lib().mb_relocate_workspace_bytes(self.ncells, self.max_movers, ctypes.byref(nbytes)))
+        N.check(N.lib().mb_reloc_workspace_bytes(self.max_movers, ctypes.byref(nbytes)))
         self.nbytes = int(nbytes.value)
         self.buf = torch.empty(max(self.nbytes, 1), dtype=torch.uint8, device=type_layer.device)
+        self.slots = torch.empty((max(self.ncells, 1), 2), dtype=torch.int64, device=type_layer.device)
         self.sync(type_layer)
 
     def sync(self, type_layer: torch.Tensor) -> None:
         if type_layer.dtype != torch.int8 or type_layer.numel() != self.ncells:
             raise ValueError("expected the int8 type layer this workspace was sized for")
+        if self.ncells == 0:
+            return
+        d = N.Shard()
+        d.world, d.rank, d.rows_total, d.cols = 1, 0, self.rows, self.cols
+        d.slots[0], d.type[0] = self.slots.data_ptr(), _c(type_layer).data_ptr()
+        d.happy[0] = d.agent_id[0] = type_layer.data_ptr()  # unused by the init kernel, must be non-null
+        import ctypes
+
         with torch.cuda.device(type_layer.device):
-            N.check(N.lib().mb_relocate_workspace_init(N.ptr(self.buf), self.nbytes, self.ncells, self.max_movers,
-                                                       N.ptr(_c(type_layer)), N.stream_ptr(type_layer.device)))
+            N.check(N.lib().mb_reloc_slots_init(ctypes.byref(d), N.stream_ptr(type_layer.device)))
 
 
 def schelling_relocate(type_layer: torch.Tensor, happy: torch.Tensor, agent_id: torch.Tensor,
                        ws: RelocationWorkspace, seed: int, epoch: int,
                        agent_cell: torch.Tensor | None = None) -> tuple[int, int]:
-    """shuffle_do("step") of the Schelling agents; returns (movers, fixed-point iterations)."""
+    """shuffle_do("step") of the Schelling agents; returns (movers, fixed-point passes)."""
     import ctypes
 
     _need_cuda(type_layer, happy, agent_id, agent_cell)
     if type_layer.dtype != torch.int8 or happy.dtype != torch.uint8 or agent_id.dtype not in (torch.uint32, torch.int32):
         raise ValueError("schelling_relocate: expected int8 type, uint8 happy, uint32 agent_id layers")
-    ncells = type_layer.numel()
-    if ws.ncells != ncells:
+    if ws.ncells != type_layer.numel():
         raise ValueError("workspace was sized for a different grid")
     movers, iters = ctypes.c_int64(0), ctypes.c_int(0)
     with torch.cuda.device(type_layer.device):
         N.check(N.lib().mb_schelling_relocate(
-            N.ptr(_c(type_layer)), N.ptr(_c(happy)), N.ptr(_c(agent_id)), N.ptr(agent_cell), ncells,
-            int(seed) & 0xFFFFFFFFFFFFFFFF, int(epoch) & 0xFFFFFFFF, N.ptr(ws.buf), ws.nbytes, ws.max_movers,
-            ctypes.byref(movers), ctypes.byref(iters), N.stream_ptr(type_layer.device)))
+            N.ptr(_c(type_layer)), N.ptr(_c(happy)), N.ptr(_c(agent_id)), N.ptr(agent_cell), N.ptr(ws.slots),
+            ws.rows, ws.cols, int(seed) & 0xFFFFFFFFFFFFFFFF, int(epoch) & 0xFFFFFFFF, N.ptr(ws.buf), ws.nbytes,
+            ws.max_movers, ctypes.byref(movers), ctypes.byref(iters), N.stream_ptr(type_layer.device)))
     return int(movers.value), int(iters.value)
 
 
