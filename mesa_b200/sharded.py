@@ -1,0 +1,252 @@
+"""Row-sharded Schelling on several GPUs: BASELINE.json config 5 (65536^2 on 8 x B200), SURVEY section 8e.
+
+One process per GPU.  Rank k owns the contiguous row block `sharding.block_bounds(rows, world, k)` of
+every per-cell array (type int8, happy uint8, agent_id int32, 16-byte relocation slots).  All of them
+live in torch symmetric memory, i.e. they are peer-mapped over NVLink / NVSwitch, so
+
+* `assign_state` is the single-GPU stencil kernel whose halo pointers are the neighbours' own edge
+  rows (read in place, no exchange buffers), followed by a 1-element all-reduce of `model.happy`;
+* `shuffle_do("step")` runs the single-GPU relocation kernels unchanged: a probe is a uniform draw over
+  the WHOLE grid (grid.py:303-306), the kernels load the owner's slot, claim it with an NVLink
+  atomicMin and finally write the arrival into the owner's layers.  The host only all-reduces the
+  per-pass "changed" flag and runs the small collectives of the argwhere fallback
+  (gather the few fallback movers, all-gather per-rank empty counts).
+
+Agent ids are global (row-major over the whole grid, schelling/model.py:72-81), priorities and draws
+are keyed on them, so the trajectory is identical for every GPU count -- and equal to the reference's.
+The reference has no counterpart for any of this (single process).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _native as N
+from . import ops
+from .sharding import block_bounds
+
+_FB_BATCH = 2048
+_NONE64 = -1  # 0xffff_ffff_ffff_ffff as int64
+
+
+def _u64_sort_key(t: torch.Tensor) -> torch.Tensor:
+    """int64 bit patterns of uint64 values -> keys whose signed order is the unsigned order."""
+    return t ^ torch.iinfo(torch.int64).min
+
+
+class ShardedSchelling:
+    """Schelling model state + step on a row-sharded grid (mirror of schelling/model.py:31-93)."""
+
+    def __init__(self, rows_total: int, cols: int, local_types, homophily: float = 0.4, radius: int = 1,
+                 seed: int = 0, device=None, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        if not dist.is_initialized():
+            raise RuntimeError("ShardedSchelling needs an initialised torch.distributed process group (nccl)")
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.device = torch.device(device if device is not None else torch.cuda.current_device())
+        self.rows_total, self.cols = int(rows_total), int(cols)
+        self.homophily, self.radius, self.seed = float(homophily), int(radius), int(seed)
+        self.lo, self.hi = block_bounds(self.rows_total, self.world, self.rank)
+        self.rows = self.hi - self.lo
+        if self.rows < self.radius:
+            raise ValueError("row block thinner than the neighbourhood radius")
+        local_types = torch.as_tensor(local_types).to(torch.int8)
+        if tuple(local_types.shape) != (self.rows, self.cols):
+            raise ValueError(f"rank {self.rank} expects a [{self.rows}, {self.cols}] block of the type layer")
+        max_rows = -(-self.rows_total // self.world)
+
+        def symmetric(shape, dtype):
+            t = symm_mem.empty(shape, dtype=dtype, device=self.device)
+            return t, symm_mem.rendezvous(t, self.group)
+
+        self._type_buf, self._type_h = symmetric((max_rows, self.cols), torch.int8)
+        self._happy_buf, self._happy_h = symmetric((max_rows, self.cols), torch.uint8)
+        self._id_buf, self._id_h = symmetric((max_rows, self.cols), torch.int32)
+        self._slot_buf, self._slot_h = symmetric((max_rows * self.cols, 2), torch.int64)
+        self.type = self._type_buf[: self.rows]
+        self.happy = self._happy_buf[: self.rows]
+        self.agent_id = self._id_buf[: self.rows]
+        self.type.copy_(local_types.to(self.device))
+        self.happy.zero_()
+
+        # global agent ids: row-major over the whole grid
+        occupied = self.type.reshape(-1) >= 0
+        self.n_local = int(occupied.sum().item())
+        counts = torch.zeros(self.world, dtype=torch.int64, device=self.device)
+        counts[self.rank] = self.n_local
+        dist.all_reduce(counts, group=self.group)
+        self.n_agents = int(counts.sum().item())
+        if self.n_agents >= 2**32 - 1:
+            raise ValueError("agent ids must fit 32 bits")
+        first = int(counts[: self.rank].sum().item())
+        ids = torch.zeros(self.rows * self.cols, dtype=torch.int64, device=self.device)
+        ids[occupied] = torch.arange(first, first + self.n_local, dtype=torch.int64, device=self.device)
+        self.agent_id.copy_(ids.reshape(self.rows, self.cols).to(torch.int32))  # uint32 bit pattern
+
+        self.shard = N.Shard()
+        self.shard.world, self.shard.rank = self.world, self.rank
+        self.shard.rows_total, self.shard.cols = self.rows_total, self.cols
+        for r in range(self.world):
+            self.shard.slots[r] = self._slot_h.buffer_ptrs[r]
+            self.shard.type[r] = self._type_h.buffer_ptrs[r]
+            self.shard.happy[r] = self._happy_h.buffer_ptrs[r]
+            self.shard.agent_id[r] = self._id_h.buffer_ptrs[r]
+        self._shard_ref = ctypes.byref(self.shard)
+
+        # neighbours' edge rows, read in place by the stencil kernel (clamped grid: none outside)
+        self._halo_top = self._halo_bot = None
+        if self.rank > 0:
+            ulo, uhi = block_bounds(self.rows_total, self.world, self.rank - 1)
+            up = self._type_h.get_buffer(self.rank - 1, (max_rows, self.cols), torch.int8)
+            self._halo_top = up[uhi - ulo - self.radius: uhi - ulo]
+        if self.rank < self.world - 1:
+            down = self._type_h.get_buffer(self.rank + 1, (max_rows, self.cols), torch.int8)
+            self._halo_bot = down[: self.radius]
+
+        self.max_movers = max(self.n_local, 1)
+        nbytes = ctypes.c_size_t(0)
+        N.check(N.lib().mb_reloc_workspace_bytes(self.max_movers, ctypes.byref(nbytes)))
+        self._ws_bytes = int(nbytes.value)
+        self._ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=self.device)
+        self._table = ops.happy_threshold_table(self.homophily, self.radius)
+        self._count = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._host4 = (ctypes.c_uint64 * 4)()
+        self.epoch = 0
+        self.happy_count = 0
+        self.last_movers = self.last_passes = 0
+        self._stream = lambda: N.stream_ptr(self.device)
+        with torch.cuda.device(self.device):
+            N.check(N.lib().mb_reloc_slots_init(self._shard_ref, self._stream()))
+        self._barrier()
+        self.assign_state()
+
+    # ------------------------------------------------------------------ plumbing
+    def _barrier(self):
+        torch.cuda.current_stream(self.device).synchronize()
+        dist.barrier(group=self.group)
+
+    def _counters(self):
+        N.check(N.lib().mb_reloc_counters(N.ptr(self._ws), self._ws_bytes, self.max_movers, self._host4, self._stream()))
+        return [int(x) for x in self._host4]
+
+    def _allreduce(self, values, op=dist.ReduceOp.SUM):
+        t = torch.tensor(values, dtype=torch.int64, device=self.device)
+        dist.all_reduce(t, op=op, group=self.group)
+        return t.tolist()
+
+    # ------------------------------------------------------------------ do("assign_state")
+    def assign_state(self) -> int:
+        """agents.py:24-42 for every agent of the block; returns the global model.happy."""
+        ops.schelling_happy(self.type, self.homophily, self.radius, False, out=self.happy, count=self._count,
+                            halo_top=self._halo_top, halo_bot=self._halo_bot, table=self._table)
+        dist.all_reduce(self._count, group=self.group)
+        self.happy_count = int(self._count.item())
+        return self.happy_count
+
+    # ------------------------------------------------------------------ shuffle_do("step")
+    def move_unhappy(self) -> int:
+        lib, ws, wb, mm = N.lib(), N.ptr(self._ws), self._ws_bytes, self.max_movers
+        seed, epoch = self.seed & 0xFFFFFFFFFFFFFFFF, self.epoch & 0xFFFFFFFF
+        self.epoch += 1
+        with torch.cuda.device(self.device):
+            N.check(lib.mb_reloc_collect(self._shard_ref, seed, epoch, ws, wb, mm, self._stream()))
+            movers, occupied, _, _ = self._counters()
+            tot_movers, tot_occupied = self._allreduce([movers, occupied])   # also orders collect before any pass
+            self.last_movers, self.last_passes = tot_movers, 0
+            if tot_movers == 0:
+                return 0
+            nempty = self.rows_total * self.cols - tot_occupied
+            if nempty <= 0:
+                raise ValueError("Grid is completely full. No empty cells available. Cannot select a random empty cell.")
+            while True:
+                self.last_passes += 1
+                N.check(lib.mb_reloc_pass(self._shard_ref, movers, seed, epoch, ws, wb, mm, self._stream()))
+                _, _, nfb, changed = self._counters()
+                per_rank = torch.zeros(self.world, dtype=torch.int64, device=self.device)
+                per_rank[self.rank] = nfb
+                flags = torch.cat([per_rank, torch.tensor([changed], dtype=torch.int64, device=self.device)])
+                dist.all_reduce(flags, group=self.group)      # every rank's pass has finished past this point
+                nfb_all, changed = flags[:-1].tolist(), int(flags[-1].item())
+                if sum(nfb_all) > 0:
+                    self._serve_fallback(nfb, nfb_all, nempty, seed, epoch)
+                    _, _, _, changed2 = self._counters()
+                    changed += self._allreduce([changed2])[0]
+                if changed == 0:
+                    break
+            N.check(lib.mb_reloc_apply(self._shard_ref, 0, movers, None, ws, wb, mm, self._stream()))
+            self._barrier()      # every origin is empty before any arrival is written
+            N.check(lib.mb_reloc_apply(self._shard_ref, 1, movers, None, ws, wb, mm, self._stream()))
+            self._barrier()
+        return tot_movers
+
+    def _serve_fallback(self, nfb: int, nfb_all: list[int], nempty: int, seed: int, epoch: int) -> None:
+        """grid.py:308-316 for the movers that missed all 50 probes, across ranks."""
+        lib, ws, wb, mm = N.lib(), N.ptr(self._ws), self._ws_bytes, self.max_movers
+        dev, world = self.device, self.world
+        width = max(nfb_all)
+        mine = torch.zeros((width, 3), dtype=torch.int64, device=dev)     # (time, k, mover) uint64 bit patterns
+        if nfb > 0:
+            t = torch.empty(nfb, dtype=torch.int64, device=dev)
+            k = torch.empty(nfb, dtype=torch.int64, device=dev)
+            m = torch.empty(nfb, dtype=torch.int32, device=dev)
+            N.check(lib.mb_reloc_fb_export(self._shard_ref, 0, nfb, nempty, seed, epoch, N.ptr(t), N.ptr(k), N.ptr(m),
+                                           ws, wb, mm, self._stream()))
+            mine[:nfb, 0], mine[:nfb, 1], mine[:nfb, 2] = t, k, m.to(torch.int64) & 0xFFFFFFFF
+        everyone = torch.empty((world, width, 3), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(everyone, mine, group=self.group)
+        rows, homes = [], []
+        for r, n in enumerate(nfb_all):
+            rows.append(everyone[r, :n])
+            homes.append(torch.full((n,), r, dtype=torch.int64, device=dev))
+        entries, home = torch.cat(rows), torch.cat(homes)
+        order = torch.argsort(_u64_sort_key(entries[:, 0]))
+        entries, home = entries[order], home[order]
+        for first in range(0, entries.shape[0], _FB_BATCH):
+            batch = entries[first:first + _FB_BATCH]
+            count = batch.shape[0]
+            times = batch[:, 0].contiguous()
+            totals = torch.zeros(count, dtype=torch.int32, device=dev)
+            N.check(lib.mb_reloc_fb_count(self._shard_ref, N.ptr(times), count, N.ptr(totals), ws, wb, mm, self._stream()))
+            all_totals = torch.empty((world, count), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(all_totals, totals, group=self.group)
+            cum = torch.cumsum(all_totals.to(torch.int64), dim=0)            # empties in ranks 0..r at each time
+            kk = batch[:, 1]
+            owner = (cum <= kk.unsqueeze(0)).sum(dim=0)                        # first rank whose cumulative count exceeds k
+            before = torch.where(owner > 0, cum[(owner - 1).clamp(min=0), torch.arange(count, device=dev)], 0)
+            k_local = torch.where(owner == self.rank, kk - before, torch.full_like(kk, _NONE64)).contiguous()
+            result = torch.zeros(count, dtype=torch.int64, device=dev)
+            N.check(lib.mb_reloc_fb_pick(self._shard_ref, N.ptr(times), N.ptr(k_local), count, N.ptr(result),
+                                         ws, wb, mm, self._stream()))
+            dist.all_reduce(result, group=self.group)                          # exactly one rank wrote each entry
+            movers32 = torch.where(home[first:first + count] == self.rank, batch[:, 2],
+                                   torch.full_like(kk, -1)).to(torch.int32).contiguous()   # -1 = 0xffffffff: not mine
+            N.check(lib.mb_reloc_fb_commit(self._shard_ref, N.ptr(times), N.ptr(movers32), N.ptr(result),
+                                           count, ws, wb, mm, self._stream()))
+
+    # ------------------------------------------------------------------ model step
+    def step(self) -> int:
+        """schelling/model.py:87-93: shuffle_do("step") then do("assign_state"); returns model.happy."""
+        self.move_unhappy()
+        return self.assign_state()
+
+    def gather_types(self) -> torch.Tensor | None:
+        """Whole type layer on rank 0 (tests / readback)."""
+        max_rows = self._type_buf.shape[0]
+        out = torch.empty((self.world, max_rows, self.cols), dtype=torch.int8, device=self.device)
+        dist.all_gather_into_tensor(out, self._type_buf.contiguous(), group=self.group)
+        blocks = []
+        for r in range(self.world):
+            lo, hi = block_bounds(self.rows_total, self.world, r)
+            blocks.append(out[r, : hi - lo])
+        return torch.cat(blocks)
+
+    def gather_layer(self, buf: torch.Tensor) -> torch.Tensor:
+        max_rows = buf.shape[0]
+        out = torch.empty((self.world,) + tuple(buf.shape), dtype=buf.dtype, device=self.device)
+        dist.all_gather_into_tensor(out, buf.contiguous(), group=self.group)
+        return torch.cat([out[r, : block_bounds(self.rows_total, self.world, r)[1] - block_bounds(self.rows_total, self.world, r)[0]]
+                          for r in range(self.world)])
