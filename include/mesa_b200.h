@@ -105,8 +105,9 @@ int mb_reloc_collect(const void* shard, uint64_t seed, uint32_t epoch, void* wor
 /* host4 = {movers, occupied, fallback movers of the last pass, table changed in the last pass}; synchronises */
 int mb_reloc_counters(void* workspace, size_t workspace_bytes, int64_t max_movers, uint64_t* host4,
                       mb_stream_t stream);
-int mb_reloc_pass(const void* shard, int64_t nmovers, uint64_t seed, uint32_t epoch, void* workspace,
-                  size_t workspace_bytes, int64_t max_movers, mb_stream_t stream);
+/* one pass over the local movers whose priority lies in [t_lo, t_hi] (rank-ordered buckets, earliest first) */
+int mb_reloc_pass(const void* shard, int64_t nmovers, uint64_t seed, uint32_t epoch, uint64_t t_lo, uint64_t t_hi,
+                  void* workspace, size_t workspace_bytes, int64_t max_movers, mb_stream_t stream);
 /* argwhere fallback (grid.py:308-316), batched: export (time, k = _randbelow(nempty), mover) of the local
  * fallback movers; count the empties of the local table at <= 2048 ascending times; pick the k_local-th one;
  * commit the picks of the local movers. */

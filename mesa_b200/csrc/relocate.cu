@@ -245,11 +245,17 @@ __device__ __forceinline__ void commit_choice(const ShardView& v, RelocWs& ws, i
     }
 }
 
+// One pass over the movers whose time lies in [t_lo, t_hi].  Movers are processed in rank-ordered
+// buckets (earliest first, each to convergence): a mover only depends on earlier movers, so a
+// converged bucket is final, and conflicts inside a bucket are 1/K as dense as in the whole set --
+// far fewer passes touch far fewer movers (978 M movers on 65536^2: 88 passes over everyone without).
 __global__ void __launch_bounds__(128)
-relocate_pass(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, uint32_t epoch) {
+relocate_pass(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, uint32_t epoch, unsigned long long t_lo,
+              unsigned long long t_hi) {
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= nmovers) return;
     const unsigned long long t = ws.mv_prio[m];
+    if (t < t_lo || t > t_hi) return;
     mb::DrawStream ds(seed, epoch, ws.mv_agent[m]);
     for (int j = 0; j < kMaxProbes; ++j) {
         const unsigned long long c = ds.randbelow((uint64_t)v.ncells);
@@ -523,8 +529,8 @@ MB_API int mb_reloc_counters(void* workspace, size_t workspace_bytes, int64_t ma
     return read_counters(ws, (unsigned long long*)host4, stream);
 }
 
-MB_API int mb_reloc_pass(const void* shard, int64_t nmovers, uint64_t seed, uint32_t epoch, void* workspace,
-                         size_t workspace_bytes, int64_t max_movers, cudaStream_t stream) {
+MB_API int mb_reloc_pass(const void* shard, int64_t nmovers, uint64_t seed, uint32_t epoch, uint64_t t_lo, uint64_t t_hi,
+                         void* workspace, size_t workspace_bytes, int64_t max_movers, cudaStream_t stream) {
     ShardView v;
     RelocWs ws;
     int rc = make_view((const ShardDesc*)shard, &v);
@@ -533,7 +539,7 @@ MB_API int mb_reloc_pass(const void* shard, int64_t nmovers, uint64_t seed, uint
     MB_REQUIRE(nmovers >= 0 && nmovers <= max_movers, "mb_reloc_pass: mover count exceeds the workspace");
     if ((rc = mb::check_cuda(cudaMemsetAsync(ws.counters + 2, 0, 2 * sizeof(unsigned long long), stream), "memset"))) return rc;
     if (nmovers > 0)
-        relocate_pass<<<(unsigned)mb::ceil_div(nmovers, 128), 128, 0, stream>>>(v, ws, nmovers, seed, epoch);
+        relocate_pass<<<(unsigned)mb::ceil_div(nmovers, 128), 128, 0, stream>>>(v, ws, nmovers, seed, epoch, t_lo, t_hi);
     MB_LAUNCH_CHECK("mb_reloc_pass");
     return MB_OK;
 }
@@ -664,34 +670,42 @@ MB_API int mb_schelling_relocate(int8_t* type, uint8_t* happy, uint32_t* agent_i
     const int64_t nempty = v.ncells - noccupied;
     // grid.py:311-315: a completely full grid raises ValueError at the first unhappy agent
     MB_REQUIRE(nempty > 0, "Grid is completely full. No empty cells available. Cannot select a random empty cell.");
+    // rank-ordered buckets: a power of two, ~16 M movers each (smaller buckets lose to the fixed cost of a pass:
+    // measured on 8192^2 / 15 M movers, 1 bucket 79 ms, 8 buckets 96 ms)
+    int buckets = 1;
+    while (buckets < 256 && nmovers / buckets > (16ll << 20)) buckets <<= 1;
     int pass = 0;
-    for (;; ++pass) {
-        if (pass >= kMaxPasses) {
-            mb::set_error("mb_schelling_relocate: no convergence after %d passes", pass);
-            return MB_ERR_CUDA;
-        }
-        if ((rc = mb_reloc_pass(&d, nmovers, seed, epoch, workspace, workspace_bytes, max_movers, stream))) return rc;
-        if ((rc = read_counters(ws, hc, stream))) return rc;
-        const int64_t nfb = (int64_t)hc[2];
-        if (nfb > 0) {
-            // scratch for the exported (t, k, m): the tail of the choice-independent arrays is free
-            for (int64_t first = 0; first < nfb; first += kFbBatch) {
-                const int count = (int)(nfb - first < kFbBatch ? nfb - first : kFbBatch);
-                // fb_res / fb_k / fb_m double as the export buffers before the sort overwrites k and m
-                unsigned long long* tmp_t = ws.fb_res;
-                unsigned long long* tmp_k = reinterpret_cast<unsigned long long*>(ws.cnt);
-                uint32_t* tmp_m = ws.fb_block;
-                fb_export<<<(unsigned)mb::ceil_div(count, 128), 128, 0, stream>>>(v, ws, first, count, nempty, seed, epoch,
-                                                                                   tmp_t, tmp_k, tmp_m);
-                // the sort reads tmp_* and writes fb_t / fb_k / fb_m; cnt is rewritten by fb_count afterwards
-                if ((rc = serve_fallback_local(v, ws, tmp_t, tmp_k, tmp_m, count, stream))) return rc;
+    for (int b = 0; b < buckets; ++b) {
+        const unsigned long long width = buckets > 1 ? (1ull << 63) / (buckets / 2) : 0ull;  // 2^64 / buckets
+        const unsigned long long t_lo = buckets > 1 ? width * (unsigned long long)b : 0ull;
+        const unsigned long long t_hi = (buckets > 1 && b + 1 < buckets) ? t_lo + (width - 1) : kNever;
+        for (;; ++pass) {
+            if (pass >= kMaxPasses) {
+                mb::set_error("mb_schelling_relocate: no convergence after %d passes", pass);
+                return MB_ERR_CUDA;
             }
+            if ((rc = mb_reloc_pass(&d, nmovers, seed, epoch, t_lo, t_hi, workspace, workspace_bytes, max_movers, stream))) return rc;
             if ((rc = read_counters(ws, hc, stream))) return rc;
+            const int64_t nfb = (int64_t)hc[2];
+            if (nfb > 0) {
+                for (int64_t first = 0; first < nfb; first += kFbBatch) {
+                    const int count = (int)(nfb - first < kFbBatch ? nfb - first : kFbBatch);
+                    // fb_res / cnt / fb_block double as the export buffers: the sort consumes them before
+                    // fb_count / fb_pick overwrite them (same stream)
+                    unsigned long long* tmp_t = ws.fb_res;
+                    unsigned long long* tmp_k = reinterpret_cast<unsigned long long*>(ws.cnt);
+                    uint32_t* tmp_m = ws.fb_block;
+                    fb_export<<<(unsigned)mb::ceil_div(count, 128), 128, 0, stream>>>(v, ws, first, count, nempty, seed, epoch,
+                                                                                       tmp_t, tmp_k, tmp_m);
+                    if ((rc = serve_fallback_local(v, ws, tmp_t, tmp_k, tmp_m, count, stream))) return rc;
+                }
+                if ((rc = read_counters(ws, hc, stream))) return rc;
+            }
+            if (hc[3] == 0) { ++pass; break; }  // a pass without any change of the table: this bucket is final
         }
-        if (hc[3] == 0) break;  // a pass without any change of the table: fixed point
     }
     if ((rc = mb_reloc_apply(&d, 0, nmovers, agent_cell, workspace, workspace_bytes, max_movers, stream))) return rc;
     if ((rc = mb_reloc_apply(&d, 1, nmovers, agent_cell, workspace, workspace_bytes, max_movers, stream))) return rc;
-    if (out_iterations) *out_iterations = pass + 1;
+    if (out_iterations) *out_iterations = pass;
     return MB_OK;
 }

@@ -107,7 +107,8 @@ class ShardedSchelling:
             down = self._type_h.get_buffer(self.rank + 1, (max_rows, self.cols), torch.int8)
             self._halo_bot = down[: self.radius]
 
-        self.max_movers = max(self.n_local, 1)
+        # agents migrate between ranks: a block can hold up to one agent per cell
+        self.max_movers = max(self.rows * self.cols, 1)
         nbytes = ctypes.c_size_t(0)
         N.check(N.lib().mb_reloc_workspace_bytes(self.max_movers, ctypes.byref(nbytes)))
         self._ws_bytes = int(nbytes.value)
@@ -162,21 +163,29 @@ class ShardedSchelling:
             nempty = self.rows_total * self.cols - tot_occupied
             if nempty <= 0:
                 raise ValueError("Grid is completely full. No empty cells available. Cannot select a random empty cell.")
-            while True:
-                self.last_passes += 1
-                N.check(lib.mb_reloc_pass(self._shard_ref, movers, seed, epoch, ws, wb, mm, self._stream()))
-                _, _, nfb, changed = self._counters()
-                per_rank = torch.zeros(self.world, dtype=torch.int64, device=self.device)
-                per_rank[self.rank] = nfb
-                flags = torch.cat([per_rank, torch.tensor([changed], dtype=torch.int64, device=self.device)])
-                dist.all_reduce(flags, group=self.group)      # every rank's pass has finished past this point
-                nfb_all, changed = flags[:-1].tolist(), int(flags[-1].item())
-                if sum(nfb_all) > 0:
-                    self._serve_fallback(nfb, nfb_all, nempty, seed, epoch)
-                    _, _, _, changed2 = self._counters()
-                    changed += self._allreduce([changed2])[0]
-                if changed == 0:
-                    break
+            # rank-ordered buckets (earliest priorities first, each to convergence), ~16 M movers per GPU each
+            buckets = 1
+            while buckets < 256 and tot_movers // (buckets * self.world) > (16 << 20):
+                buckets <<= 1
+            width = (1 << 64) // buckets
+            for b in range(buckets):
+                t_lo = b * width
+                t_hi = (t_lo + width - 1) if b + 1 < buckets else (1 << 64) - 1
+                while True:
+                    self.last_passes += 1
+                    N.check(lib.mb_reloc_pass(self._shard_ref, movers, seed, epoch, t_lo, t_hi, ws, wb, mm, self._stream()))
+                    _, _, nfb, changed = self._counters()
+                    per_rank = torch.zeros(self.world, dtype=torch.int64, device=self.device)
+                    per_rank[self.rank] = nfb
+                    flags = torch.cat([per_rank, torch.tensor([changed], dtype=torch.int64, device=self.device)])
+                    dist.all_reduce(flags, group=self.group)      # every rank's pass has finished past this point
+                    nfb_all, changed = flags[:-1].tolist(), int(flags[-1].item())
+                    if sum(nfb_all) > 0:
+                        self._serve_fallback(nfb, nfb_all, nempty, seed, epoch)
+                        _, _, _, changed2 = self._counters()
+                        changed += self._allreduce([changed2])[0]
+                    if changed == 0:
+                        break
             N.check(lib.mb_reloc_apply(self._shard_ref, 0, movers, None, ws, wb, mm, self._stream()))
             self._barrier()      # every origin is empty before any arrival is written
             N.check(lib.mb_reloc_apply(self._shard_ref, 1, movers, None, ws, wb, mm, self._stream()))

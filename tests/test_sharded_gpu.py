@@ -1,0 +1,48 @@
+"""The row-sharded Schelling driver (mesa_b200/sharded.py) with a 1-rank NCCL group: exercises the
+phase-level C ABI + symmetric memory path on the single-GPU CI box.  Multi-GPU parity (2 GPUs, uneven
+blocks, argwhere fallback across ranks) is checked by tools/check_sharded_schelling.py under torchrun."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def one_rank_group():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    created = False
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1,
+                                device_id=torch.device("cuda", 0))
+        created = True
+    yield
+    if created:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("rows,cols,density,h,radius,steps", [(48, 64, 0.8, 0.4, 1, 8), (30, 32, 0.97, 0.9, 1, 4),
+                                                              (40, 48, 0.85, 0.6, 2, 5)])
+def test_sharded_driver_world1_matches_oracle(one_rank_group, rows, cols, density, h, radius, steps):
+    from mesa_b200.sharded import ShardedSchelling
+
+    rng = np.random.default_rng(rows)
+    grid = np.where(rng.random((rows, cols)) < density, (rng.random((rows, cols)) < 0.5).astype(np.int8), np.int8(-1)).astype(np.int8)
+    m = ShardedSchelling(rows, cols, grid, h, radius, seed=9)
+    st = oracle.SchellingState.from_type_grid(grid)
+    assert st.assign_state(h, radius) == m.happy_count
+    for s in range(steps):
+        happy = m.step()
+        movers, _ = st.move_unhappy(9, s)
+        assert movers == m.last_movers
+        assert st.assign_state(h, radius) == happy
+        assert np.array_equal(m.type.cpu().numpy(), st.type_grid())
+        assert np.array_equal(m.happy.cpu().numpy(), st.happy_grid())
