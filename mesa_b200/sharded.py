@@ -259,3 +259,128 @@ class ShardedSchelling:
         dist.all_gather_into_tensor(out, buf.contiguous(), group=self.group)
         return torch.cat([out[r, : block_bounds(self.rows_total, self.world, r)[1] - block_bounds(self.rows_total, self.world, r)[0]]
                           for r in range(self.world)])
+
+
+class ShardedBoids:
+    """BoidFlockers on a continuous torus sharded by spatial domain (BASELINE.json config 4).
+
+    Rank k owns the slab  y in [k, k+1) * height / world  and the boids inside it.  Per step:
+      1. halo: boids within `vision` of a slab edge are copied to the neighbouring rank (ghosts);
+      2. one synchronous Boid.step (ops.boids_step, csrc/continuous.cu) over owned + ghost boids -- ghosts keep
+         their global coordinates, the kernel's torus minimum-image arithmetic needs no shift; only the owned
+         results are kept (ghosts are ~2*vision/slab of the work);
+      3. migration: boids whose new y left the slab move to the neighbouring rank with their global id.
+    The exchanges are NCCL point-to-point messages with a counts exchange first (variable sizes).  The reference
+    has no counterpart (single process, O(N^2) scan per step: continuous_space.py:202-235)."""
+
+    def __init__(self, width: float, height: float, positions, directions, ids, *, vision=10.0, separation=2.0,
+                 cohere=0.03, separate=0.015, match=0.05, speed=1.0, device=None, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("ShardedBoids needs an initialised torch.distributed process group")
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.device = torch.device(device if device is not None else torch.cuda.current_device())
+        self.size = (float(width), float(height))
+        self.params = dict(vision=float(vision), separation=float(separation), cohere=float(cohere),
+                           separate=float(separate), match=float(match), speed=float(speed))
+        self.slab = self.size[1] / self.world
+        if self.world > 1 and self.slab < 2 * (vision + speed):
+            raise ValueError("slabs must be at least 2*(vision+speed) high")
+        self.y_lo, self.y_hi = self.rank * self.slab, (self.rank + 1) * self.slab
+        self.pos = torch.as_tensor(positions, dtype=torch.float32).to(self.device).contiguous()
+        self.dir = torch.as_tensor(directions, dtype=torch.float32).to(self.device).contiguous()
+        self.ids = torch.as_tensor(ids, dtype=torch.int64).to(self.device).contiguous()
+        self._ws = None
+        self._ws_n = 0
+
+    @staticmethod
+    def owner_of(y: torch.Tensor, height: float, world: int) -> torch.Tensor:
+        """Rank owning each y (slab index, the top edge y == height belongs to the last slab)."""
+        return torch.clamp((y.to(torch.float64) * world / height).floor().to(torch.int64), 0, world - 1)
+
+    @property
+    def n(self) -> int:
+        return int(self.pos.shape[0])
+
+    def _neighbours(self):
+        return (self.rank - 1) % self.world, (self.rank + 1) % self.world
+
+    def _exchange(self, to_down: torch.Tensor, to_up: torch.Tensor):
+        """Send rows to the rank below / above, receive theirs; returns (from_down, from_up)."""
+        down, up = self._neighbours()
+        width = to_down.shape[1]
+        counts = torch.zeros((self.world, 2), dtype=torch.int64, device=self.device)
+        counts[self.rank, 0], counts[self.rank, 1] = to_down.shape[0], to_up.shape[0]
+        dist.all_reduce(counts, group=self.group)
+        counts = counts.tolist()
+        n_from_down, n_from_up = counts[down][1], counts[up][0]   # what `down` sends up, what `up` sends down
+        from_down = torch.empty((n_from_down, width), dtype=to_down.dtype, device=self.device)
+        from_up = torch.empty((n_from_up, width), dtype=to_up.dtype, device=self.device)
+        g = lambda r: dist.get_global_rank(self.group, r) if self.group is not dist.group.WORLD else r
+        opsl = []
+        # identical pair order on both ends of each link (matters when world == 2: one peer, two messages)
+        first_up = self.rank % 2 == 0
+        pairs = [("up", to_up, from_up, up), ("down", to_down, from_down, down)]
+        if not first_up:
+            pairs.reverse()
+        for _, snd, rcv, peer in pairs:
+            if snd.shape[0] > 0:
+                opsl.append(dist.P2POp(dist.isend, snd.contiguous(), g(peer), self.group))
+            if rcv.shape[0] > 0:
+                opsl.append(dist.P2POp(dist.irecv, rcv, g(peer), self.group))
+        if opsl:
+            for q in dist.batch_isend_irecv(opsl):
+                q.wait()
+        return from_down, from_up
+
+    def step(self) -> None:
+        p = self.params
+        reach = p["vision"]
+        if self.world > 1:
+            y = self.pos[:, 1]
+            packed = torch.cat([self.pos, self.dir], dim=1)
+            ghosts_down, ghosts_up = self._exchange(packed[y < self.y_lo + reach], packed[y >= self.y_hi - reach])
+            allp = torch.cat([packed, ghosts_down, ghosts_up])
+            pos_all, dir_all = allp[:, :2].contiguous(), allp[:, 2:].contiguous()
+        else:
+            pos_all, dir_all = self.pos, self.dir
+        n_all = pos_all.shape[0]
+        if self._ws is None or self._ws_n < n_all:
+            self._ws_n = int(n_all * 1.2) + 1024
+            self._ws = ops.CellListWorkspace(self._ws_n, self.size, p["vision"], self.device)
+        new_pos, new_dir = ops.boids_step(pos_all, dir_all, self.size, torus=True, ws=self._ws, **p)
+        n = self.n
+        self.pos, self.dir = new_pos[:n], new_dir[:n]
+        if self.world > 1:
+            owner = self.owner_of(self.pos[:, 1], self.size[1], self.world)
+            down, up = self._neighbours()
+            stay = owner == self.rank
+            go_down = (owner == down) & ~stay
+            go_up = (owner == up) & ~stay & ~go_down
+            if bool((~(stay | go_down | go_up)).any()):
+                raise RuntimeError("a boid jumped over a whole slab (speed too large for this decomposition)")
+            # ids travel exactly: pack them as two float32-sized int32 words
+            idw = torch.stack([(self.ids & 0xFFFFFFFF).to(torch.int32), (self.ids >> 32).to(torch.int32)], dim=1).view(torch.float32)
+            rec = torch.cat([self.pos, self.dir, idw], dim=1)
+            from_down, from_up = self._exchange(rec[go_down], rec[go_up])
+            rec = torch.cat([rec[stay], from_down, from_up])
+            self.pos, self.dir = rec[:, :2].contiguous(), rec[:, 2:4].contiguous()
+            w = rec[:, 4:6].contiguous().view(torch.int32).to(torch.int64)
+            self.ids = (w[:, 0] & 0xFFFFFFFF) | (w[:, 1] << 32)
+        else:
+            self.pos, self.dir = self.pos.contiguous(), self.dir.contiguous()
+
+    def gather(self):
+        """(ids, pos, dir) of all boids on every rank, sorted by id (tests / readback)."""
+        n = torch.zeros(self.world, dtype=torch.int64, device=self.device)
+        n[self.rank] = self.n
+        dist.all_reduce(n, group=self.group)
+        width = int(n.max().item())
+        mine = torch.zeros((width, 5), dtype=torch.float64, device=self.device)
+        mine[: self.n, :2], mine[: self.n, 2:4], mine[: self.n, 4] = self.pos, self.dir, self.ids
+        everyone = torch.empty((self.world, width, 5), dtype=torch.float64, device=self.device)
+        dist.all_gather_into_tensor(everyone, mine, group=self.group)
+        rows = torch.cat([everyone[r, : int(n[r].item())] for r in range(self.world)])
+        order = torch.argsort(rows[:, 4])
+        rows = rows[order]
+        return rows[:, 4].to(torch.int64), rows[:, :2].to(torch.float32), rows[:, 2:4].to(torch.float32)
