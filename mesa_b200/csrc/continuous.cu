@@ -28,6 +28,8 @@
 #include "common.cuh"
 #include "sort.cuh"
 
+#include <math.h>
+
 namespace {
 
 struct Geometry {
@@ -75,14 +77,17 @@ __global__ void gather_state(const float2* __restrict__ pos, const float2* __res
     packed[i] = make_float4(p.x, p.y, d.x, d.y);
 }
 
-// distance exactly as calculate_distances (continuous_space.py:223-235)
-__device__ __forceinline__ double ref_distance(const Geometry& g, double px, double py, double qx, double qy) {
+// squared distance exactly as calculate_distances computes it before the sqrt (continuous_space.py:223-233).
+// The reference then tests sqrt(d2) <= radius; sqrt is monotone and correctly rounded, so that test equals
+// d2 <= T with T = the largest double whose rounded sqrt is <= radius (computed on the host,
+// sq_threshold_le) -- bit-identical neighbour sets without a double-precision sqrt per pair.
+__device__ __forceinline__ double ref_distance2(const Geometry& g, double px, double py, double qx, double qy) {
     double dx = fabs(px - qx), dy = fabs(py - qy);
     if (g.torus) {
         dx = fmin(dx, g.sx - dx);
         dy = fmin(dy, g.sy - dy);
     }
-    return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
 }
 
 // one component of calculate_difference_vector (continuous_space.py:186-200)
@@ -116,7 +121,9 @@ __device__ __forceinline__ void for_neighbor_cells(const Geometry& g, int cx, in
 }
 
 struct BoidParams {
-    double vision, separation, cohere, separate, match, speed;
+    double vision2_le;      // d <= vision      <=>  d2 <= vision2_le
+    double separation2_lt;  // d <  separation  <=>  d2 <  separation2_lt
+    double cohere, separate, match, speed;
 };
 
 __global__ void __launch_bounds__(128)
@@ -136,12 +143,12 @@ boids_update(const float4* __restrict__ packed, const uint32_t* __restrict__ ord
         for (uint32_t j = cell_start[c]; j < e; ++j) {
             if ((int64_t)j == i) continue;  // get_neighbors_in_radius drops self
             const float4 o = packed[j];
-            const double d = ref_distance(g, px, py, (double)o.x, (double)o.y);
-            if (d <= bp.vision) {
+            const double d2 = ref_distance2(g, px, py, (double)o.x, (double)o.y);
+            if (d2 <= bp.vision2_le) {
                 const double ddx = ref_delta((double)o.x, px, g.sx, g.torus);
                 const double ddy = ref_delta((double)o.y, py, g.sy, g.torus);
                 cohx += ddx; cohy += ddy;
-                if (d < bp.separation) { sepx += ddx; sepy += ddy; }
+                if (d2 < bp.separation2_lt) { sepx += ddx; sepy += ddy; }
                 mx += (double)o.z; my += (double)o.w;
                 ++k;
             }
@@ -181,7 +188,7 @@ boids_update(const float4* __restrict__ packed, const uint32_t* __restrict__ ord
 __global__ void radius_query(const float4* __restrict__ packed, const uint32_t* __restrict__ order,
                              const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end,
                              Geometry g, const float2* __restrict__ queries, const int32_t* __restrict__ exclude,
-                             int64_t nq, double radius, uint32_t* __restrict__ counts,
+                             int64_t nq, double radius2_le, uint32_t* __restrict__ counts,
                              const int64_t* __restrict__ offsets, int32_t* __restrict__ out_idx,
                              double* __restrict__ out_dist) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -198,9 +205,10 @@ __global__ void radius_query(const float4* __restrict__ packed, const uint32_t* 
             const int32_t a = (int32_t)order[j];
             if (a == skip) continue;
             const float4 o = packed[j];
-            const double d = ref_distance(g, px, py, (double)o.x, (double)o.y);
-            if (d <= radius) {
+            const double d2 = ref_distance2(g, px, py, (double)o.x, (double)o.y);
+            if (d2 <= radius2_le) {
                 if (out_idx != nullptr) {
+                    const double d = __dsqrt_rn(d2);
                     // insertion keeps the row sorted by agent index (rows are short)
                     int64_t w = off + k;
                     while (w > off && out_idx[w - 1] > a) {
@@ -244,6 +252,23 @@ size_t carve(CellListWs* ws, char* base, int64_t n, int64_t ncells) {
     t.sort_ws = take(t.sort_ws_bytes);
     if (ws) *ws = t;
     return off;
+}
+
+// largest double y with sqrt(y) <= r  (IEEE sqrt is correctly rounded and monotone)
+double sq_threshold_le(double r) {
+    if (!(r >= 0.0)) return -1.0;
+    double y = r * r;
+    while (y > 0.0 && sqrt(y) > r) y = nextafter(y, 0.0);
+    while (sqrt(nextafter(y, INFINITY)) <= r) y = nextafter(y, INFINITY);
+    return y;
+}
+// smallest double y with sqrt(y) >= s, so that  sqrt(d2) < s  <=>  d2 < y
+double sq_threshold_ge(double s) {
+    if (!(s > 0.0)) return 0.0;
+    double y = s * s;
+    while (sqrt(y) < s) y = nextafter(y, INFINITY);
+    while (y > 0.0 && sqrt(nextafter(y, 0.0)) >= s) y = nextafter(y, 0.0);
+    return y;
 }
 
 int make_geometry(Geometry* g, double x0, double y0, double sx, double sy, double radius, int torus) {
@@ -317,7 +342,7 @@ MB_API int mb_boids_step_f32(const float* pos_in, const float* dir_in, float* po
     uint32_t* order = nullptr;
     rc = build_cell_list((const float2*)pos_in, (const float2*)dir_in, n, g, ws, &order, stream);
     if (rc) return rc;
-    const BoidParams bp{vision, separation, cohere, separate, match, speed};
+    const BoidParams bp{sq_threshold_le(vision), sq_threshold_ge(separation), cohere, separate, match, speed};
     boids_update<<<(unsigned)mb::ceil_div(n, 128), 128, 0, stream>>>(ws.packed, order, ws.cell_start, ws.cell_end, n, g, bp,
                                                                      (float2*)pos_out, (float2*)dir_out, neighbor_count);
     MB_LAUNCH_CHECK("mb_boids_step_f32");
@@ -356,7 +381,7 @@ MB_API int mb_radius_query_f32(const float* pos, int64_t n, double x0, double y0
         }
     }
     radius_query<<<(unsigned)mb::ceil_div(nq, 128), 128, 0, stream>>>(ws.packed, order, ws.cell_start, ws.cell_end, g,
-                                                                      (const float2*)queries, exclude, nq, radius, counts,
+                                                                      (const float2*)queries, exclude, nq, sq_threshold_le(radius), counts,
                                                                       offsets, out_idx, out_dist);
     MB_LAUNCH_CHECK("mb_radius_query_f32");
     return MB_OK;

@@ -14,8 +14,8 @@
 //
 // Roofline: HBM-bound, 2 B per cell-update (1 B read + 1 B write).  The fast kernel
 // keeps a 3-row rolling window in registers (each row is loaded from HBM once per
-// 64-row segment), moves 16 cells per lane per LDG.128/STG.128 and does the rule on
-// packed bytes (4 cells per 32-bit ALU op).
+// 16-row segment; the two re-read halo rows hit L2), moves 16 cells per lane per LDG.128/STG.128
+// and does the rule on packed bytes (4 cells per 32-bit ALU op).
 #include "common.cuh"
 
 #include <stdlib.h>
@@ -223,14 +223,17 @@ MB_API int mb_gol_step_u8(const uint8_t* in, const uint8_t* halo_top, const uint
             in, halo_top, halo_bot, out, (int)rows, (int)cols, col_torus, nstrips);                       \
     } while (0)
         switch (variant) {
+            // developer variants (MB_GOL_VARIANT); the default is the best of the sweep in profiles/
             case 1: MB_GOL_LAUNCH(32, 4, 3); break;
-            case 2: MB_GOL_LAUNCH(128, 4, 3); break;
+            case 2: MB_GOL_LAUNCH(64, 4, 3); break;
             case 3: MB_GOL_LAUNCH(64, 2, 4); break;
-            case 4: MB_GOL_LAUNCH(64, 4, 4); break;
-            case 5: MB_GOL_LAUNCH(64, 8, 2); break;
-            case 6: MB_GOL_LAUNCH(32, 2, 5); break;
-            case 7: MB_GOL_LAUNCH(128, 2, 5); break;
-            default: MB_GOL_LAUNCH(64, 4, 3); break;
+            case 4: MB_GOL_LAUNCH(32, 4, 4); break;
+            case 5: MB_GOL_LAUNCH(64, 4, 4); break;
+            case 6: MB_GOL_LAUNCH(8, 4, 4); break;
+            case 7: MB_GOL_LAUNCH(8, 2, 4); break;
+            case 8: MB_GOL_LAUNCH(16, 2, 4); break;
+            case 9: MB_GOL_LAUNCH(16, 4, 5); break;
+            default: MB_GOL_LAUNCH(16, 4, 4); break;  // 90 us / 5.96 TB/s on 16384^2 (64 rows per warp: 95.7 us)
         }
 #undef MB_GOL_LAUNCH
     } else {

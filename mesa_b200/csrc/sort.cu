@@ -22,48 +22,75 @@ sort_hist(const K* __restrict__ keys, int64_t n, int bit, uint32_t* __restrict__
     hist[(int64_t)threadIdx.x * tiles + blockIdx.x] = sh[threadIdx.x];
 }
 
-// exclusive scan of `total` uint32 counters in place, one CTA
-__global__ void __launch_bounds__(1024) sort_scan(uint32_t* __restrict__ hist, int64_t total) {
-    __shared__ unsigned warp_sum[32];
-    __shared__ unsigned carry;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) carry = 0u;
-    __syncthreads();
-    // chunks of 1024*4 elements: thread handles 4 consecutive counters
-    for (int64_t c0 = 0; c0 < total; c0 += 4096) {
-        const int64_t i0 = c0 + (int64_t)tid * 4;
-        unsigned v[4];
+// Exclusive scan of `total` uint32 counters in place, three small kernels:
+//   scan_chunks  each CTA scans its 4096-counter chunk in place and writes the chunk sum
+//   scan_top     one CTA turns the chunk sums into exclusive offsets (<= 4096*... chunks, looped)
+//   scan_add     each CTA adds its chunk offset
+constexpr int kScanChunk = 4096;
+
+__device__ __forceinline__ unsigned block_excl_scan_1024(unsigned v, unsigned* warp_sum, unsigned& block_total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned incl = v;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = (i0 + k < total) ? hist[i0 + k] : 0u;
-        const unsigned tsum = v[0] + v[1] + v[2] + v[3];
-        unsigned incl = tsum;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned w = warp_sum[lane];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+            const unsigned t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
         }
-        if (lane == 31) warp_sum[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            unsigned w = warp_sum[lane];
+        warp_sum[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    block_total = warp_sum[31];
+    return (warp > 0 ? warp_sum[warp - 1] : 0u) + incl - v;
+}
+
+__global__ void __launch_bounds__(1024) scan_chunks(uint32_t* __restrict__ data, int64_t total, uint32_t* __restrict__ sums) {
+    __shared__ unsigned warp_sum[32];
+    const int64_t i0 = (int64_t)blockIdx.x * kScanChunk + (int64_t)threadIdx.x * 4;
+    unsigned v[4];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned t = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += t;
-            }
-            warp_sum[lane] = w;  // inclusive
-        }
-        __syncthreads();
-        unsigned excl = carry + (warp > 0 ? warp_sum[warp - 1] : 0u) + incl - tsum;
+    for (int k = 0; k < 4; ++k) v[k] = (i0 + k < total) ? data[i0 + k] : 0u;
+    unsigned block_total;
+    unsigned excl = block_excl_scan_1024(v[0] + v[1] + v[2] + v[3], warp_sum, block_total);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (i0 + k < total) hist[i0 + k] = excl;
-            excl += v[k];
-        }
+    for (int k = 0; k < 4; ++k) {
+        if (i0 + k < total) data[i0 + k] = excl;
+        excl += v[k];
+    }
+    if (threadIdx.x == 0) sums[blockIdx.x] = block_total;
+}
+
+__global__ void __launch_bounds__(1024) scan_top(uint32_t* __restrict__ sums, int64_t nchunks) {
+    __shared__ unsigned warp_sum[32];
+    __shared__ unsigned carry;
+    if (threadIdx.x == 0) carry = 0u;
+    __syncthreads();
+    for (int64_t c0 = 0; c0 < nchunks; c0 += 1024) {
+        const int64_t i = c0 + threadIdx.x;
+        const unsigned v = i < nchunks ? sums[i] : 0u;
+        unsigned block_total;
+        const unsigned excl = block_excl_scan_1024(v, warp_sum, block_total);
+        if (i < nchunks) sums[i] = carry + excl;
         __syncthreads();
-        if (tid == 1023) carry = excl;
+        if (threadIdx.x == 0) carry += block_total;
         __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(1024) scan_add(uint32_t* __restrict__ data, int64_t total, const uint32_t* __restrict__ sums) {
+    const unsigned off = sums[blockIdx.x];
+    const int64_t i0 = (int64_t)blockIdx.x * kScanChunk + (int64_t)threadIdx.x * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (i0 + k < total) data[i0 + k] += off;
 }
 
 template <typename K>
@@ -132,7 +159,14 @@ int radix_sort_pairs(K* k0, uint32_t* v0, K* k1, uint32_t* v1, int64_t n, int be
     int cur = 0;
     for (int bit = begin_bit; bit < end_bit; bit += 8) {
         sort_hist<K><<<(unsigned)tiles, kSortThreads, 0, stream>>>(ks[cur], n, bit, hist, tiles);
-        sort_scan<<<1, 1024, 0, stream>>>(hist, (int64_t)kRadix * tiles);
+        {
+            const int64_t total = (int64_t)kRadix * tiles;
+            const int64_t nchunks = ceil_div(total, kScanChunk);
+            uint32_t* sums = hist + total;
+            scan_chunks<<<(unsigned)nchunks, 1024, 0, stream>>>(hist, total, sums);
+            scan_top<<<1, 1024, 0, stream>>>(sums, nchunks);
+            scan_add<<<(unsigned)nchunks, 1024, 0, stream>>>(hist, total, sums);
+        }
         sort_scatter<K><<<(unsigned)tiles, kSortThreads, 0, stream>>>(ks[cur], vs[cur], ks[cur ^ 1], vs[cur ^ 1], n,
                                                                      bit, hist, tiles);
         cur ^= 1;

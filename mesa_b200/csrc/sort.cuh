@@ -21,8 +21,12 @@ constexpr int kRadix = 256;
 
 inline int64_t sort_num_tiles(int64_t n) { return ceil_div(n > 0 ? n : 1, kSortTile); }
 
-// workspace: histogram [kRadix][tiles] uint32 (digit-major so one scan orders digits first)
-inline size_t sort_workspace_bytes(int64_t n) { return sizeof(uint32_t) * kRadix * (size_t)sort_num_tiles(n) + 256; }
+// workspace: histogram [kRadix][tiles] uint32 (digit-major so one scan orders digits first) + one sum per
+// 4096-counter scan chunk
+inline size_t sort_workspace_bytes(int64_t n) {
+    const size_t total = (size_t)kRadix * (size_t)sort_num_tiles(n);
+    return sizeof(uint32_t) * (total + (total + 4095) / 4096 + 64) + 256;
+}
 
 // Sort n pairs on key bits [begin_bit, end_bit).  Ping-pongs between (k0,v0) and (k1,v1);
 // returns 0 if the result is in (k0,v0), 1 if in (k1,v1), negative on error.

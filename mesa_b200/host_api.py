@@ -1,0 +1,74 @@
+"""Host-buffer entry points: the call a Mesa user makes when the layer lives in host memory.
+
+The reference keeps property layers as numpy arrays (mesa/discrete_space/grid.py:112).  These functions
+take pinned host tensors (or numpy arrays), run the device kernels and return the result in host
+memory, pipelining host->device copies, compute and device->host copies over row chunks so that the two
+PCIe directions run concurrently."""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class GolHostStepper:
+    """One Game of Life generation of a uint8 [rows, cols] HOST layer per call (torus).
+
+    The layer is cut into `chunks` row blocks.  Chunk c is uploaded on the copy-in stream, computed on the
+    compute stream as soon as chunks c-1, c, c+1 are resident (a chunk needs one row of each neighbour; the
+    wrap-around rows of the torus are uploaded first), and downloaded on the copy-out stream, so H2D of
+    chunk c+2, the stencil of chunk c and D2H of chunk c-1 overlap."""
+
+    def __init__(self, rows: int, cols: int, device="cuda", chunks: int = 16):
+        self.rows, self.cols = int(rows), int(cols)
+        self.device = torch.device(device)
+        self.chunks = max(1, min(int(chunks), self.rows // 4 if self.rows >= 8 else 1))
+        self.d_in = torch.empty((self.rows, self.cols), dtype=torch.uint8, device=self.device)
+        self.d_out = torch.empty_like(self.d_in)
+        self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream(self.device) for _ in range(3))
+        base, extra = divmod(self.rows, self.chunks)
+        self.bounds, lo = [], 0
+        for c in range(self.chunks):
+            hi = lo + base + (1 if c < extra else 0)
+            self.bounds.append((lo, hi))
+            lo = hi
+
+    def step(self, h_in: torch.Tensor, h_out: torch.Tensor) -> torch.Tensor:
+        if h_in.shape != (self.rows, self.cols) or h_in.dtype != torch.uint8 or h_in.is_cuda or h_out.is_cuda:
+            raise ValueError("expected uint8 host tensors of the stepper's shape")
+        cur = torch.cuda.current_stream(self.device)
+        for s in (self.s_in, self.s_comp, self.s_out):
+            s.wait_stream(cur)
+        R = self.rows
+        ev_in = []
+        with torch.cuda.stream(self.s_in):
+            # torus wrap rows first: chunk 0 needs row R-1, the last chunk needs row 0
+            self.d_in[R - 1].copy_(h_in[R - 1], non_blocking=True)
+            for lo, hi in self.bounds:
+                self.d_in[lo:hi].copy_(h_in[lo:hi], non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(self.s_in)
+                ev_in.append(e)
+        for c, (lo, hi) in enumerate(self.bounds):
+            with torch.cuda.stream(self.s_comp):
+                self.s_comp.wait_event(ev_in[min(c + 1, self.chunks - 1)])   # chunk c+1 (and everything before) is resident
+                ops.gol_step(self.d_in[lo:hi], out=self.d_out[lo:hi], torus=False, col_torus=True,
+                             halo_top=self.d_in[(lo - 1) % R], halo_bot=self.d_in[hi % R])
+                done = torch.cuda.Event()
+                done.record(self.s_comp)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(done)
+                h_out[lo:hi].copy_(self.d_out[lo:hi], non_blocking=True)
+        cur.wait_stream(self.s_out)
+        return h_out
+
+
+def gol_step_host(h_in: torch.Tensor, h_out: torch.Tensor | None = None, stepper: GolHostStepper | None = None):
+    """Convenience wrapper: one generation of a host layer; synchronises before returning."""
+    if stepper is None:
+        stepper = GolHostStepper(h_in.shape[0], h_in.shape[1])
+    if h_out is None:
+        h_out = torch.empty_like(h_in).pin_memory()
+    stepper.step(h_in, h_out)
+    torch.cuda.current_stream(stepper.device).synchronize()
+    return h_out
