@@ -51,6 +51,17 @@ int mb_sm_count(void);
 int mb_gol_step_u8(const uint8_t* in, const uint8_t* halo_top, const uint8_t* halo_bot, uint8_t* out,
                    int64_t rows, int64_t cols, int col_torus, mb_stream_t stream);
 
+/* Row-sharded variant with the neighbour hand-shake fused into the stencil kernel: halo_top / halo_bot are
+ * PEER-MAPPED pointers to the neighbouring ranks' edge rows (read in place over NVLink); wait_top / wait_bot are
+ * this rank's generation flags, signal_up / signal_down the peer-mapped addresses of the neighbours' flags
+ * (NULL where halo_* is NULL), edge_done two zero-initialised local counters, error a local word that is set
+ * if a neighbour never shows up, gen = 1, 2, 3, ... the generation being written.  One launch per generation:
+ * no exchange, no barrier (csrc/gol.cu, PeerSync). */
+int mb_gol_step_u8_fused(const uint8_t* in, const uint8_t* halo_top, const uint8_t* halo_bot, uint8_t* out,
+                         int64_t rows, int64_t cols, int col_torus, unsigned* wait_top, unsigned* wait_bot,
+                         unsigned* signal_up, unsigned* signal_down, unsigned* edge_done, unsigned* error,
+                         unsigned gen, mb_stream_t stream);
+
 /* ---- Schelling happiness (replaces AgentSet.do("assign_state") over
  * examples/basic/schelling/agents.py:24-42; neighbourhood = cell.py:225-276, Moore radius r) ----
  * type: int8 layer, -1 = empty cell, >= 0 = agent type (capacity-1 grid).  happy: uint8 layer out

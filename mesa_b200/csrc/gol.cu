@@ -105,16 +105,76 @@ __device__ __forceinline__ uint4 gol_rows(const Row& a, const Row& b, const Row&
     return o;
 }
 
-template <int kRowsPerWarp, int kUnroll, int kMinBlocks>
+// ---- fused halo synchronisation for row-sharded grids (one process per GPU) ------------------------
+// The neighbours' edge rows are read IN PLACE from their HBM over NVLink (halo_top / halo_bot are
+// peer-mapped pointers) and the hand-shake that a separate exchange + barrier would do is done by
+// the stencil kernel itself with generation counters in peer-mapped memory:
+//   * the warps that own the first / last row segment wait (ld.acquire.sys) until the neighbour has
+//     published generation gen-1 of its edge rows, and only then touch the halo;
+//   * when all edge strips of the new generation are written, the last one publishes `gen` to the
+//     neighbour (threadfence_system + st.release.sys into ITS memory).
+// Edge segments are mapped to the lowest CTA indices, so the flags are published at the very start
+// of a launch and in steady state nobody waits: one launch per generation, no NCCL call, no barrier.
+// The same counters order the write-after-read on the ping-pong buffers (see PeerSync::gen).
+struct PeerSync {
+    unsigned* wait_top;     // local: generation of the upper neighbour's edge rows that is complete
+    unsigned* wait_bot;     // local: same for the lower neighbour
+    unsigned* signal_up;    // peer-mapped: the upper neighbour's wait_bot
+    unsigned* signal_down;  // peer-mapped: the lower neighbour's wait_top
+    unsigned* edge_done;    // local [2]: edge strips finished in this launch (top, bottom)
+    unsigned* error;        // local: set to 1 if a wait timed out
+    unsigned gen;           // generation being written (1, 2, ...): reads generation gen-1 everywhere
+};
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void wait_generation(const unsigned* flag, unsigned want, unsigned* error, int lane) {
+    if (flag != nullptr && lane == 0) {
+        unsigned spins = 0;
+        while ((int)(ld_acquire_sys(flag) - want) < 0) {
+            if (++spins > (1u << 26)) {  // ~ seconds: a peer died; do not hang the GPU
+                *error = 1u;
+                break;
+            }
+            __nanosleep(32);
+        }
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void publish_edge(unsigned* done, unsigned* peer_flag, unsigned nstrips, unsigned gen, int lane) {
+    if (peer_flag == nullptr) return;
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence_system();  // this strip's edge row is visible system-wide before it is counted
+        if (atomicAdd(done, 1u) == nstrips - 1u) {
+            *done = 0u;
+            __threadfence_system();
+            st_release_sys(peer_flag, gen);
+        }
+    }
+}
+
+template <int kRowsPerWarp, int kUnroll, int kMinBlocks, bool kSync>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 gol_step_u8_vec(const uint8_t* __restrict__ in, const uint8_t* __restrict__ halo_top,
                 const uint8_t* __restrict__ halo_bot, uint8_t* __restrict__ out, int rows, int cols,
-                int col_torus, int nstrips) {
+                int col_torus, int nstrips, const PeerSync sync) {
     const int lane = threadIdx.x & 31;
     const unsigned task = blockIdx.x * kWarps + (threadIdx.x >> 5);
     const unsigned strip = task % (unsigned)nstrips;
-    const int row0 = (int)(task / (unsigned)nstrips) * kRowsPerWarp;
-    if (row0 >= rows) return;  // whole warp exits together
+    unsigned seg = task / (unsigned)nstrips;
+    const unsigned nseg = (unsigned)((rows + kRowsPerWarp - 1) / kRowsPerWarp);
+    if (seg >= nseg) return;  // whole warp exits together
+    if (kSync && nseg >= 2u) seg = seg == 0u ? 0u : (seg == 1u ? nseg - 1u : seg - 1u);  // edge segments first
+    const int row0 = (int)seg * kRowsPerWarp;
+    const bool top_edge = kSync && seg == 0u, bot_edge = kSync && seg == nseg - 1u;
+    if (top_edge) wait_generation(sync.wait_top, sync.gen - 1u, sync.error, lane);
 
     LaneAddr la;
     la.col = strip * 512u + lane * 16u;
@@ -160,6 +220,7 @@ gol_step_u8_vec(const uint8_t* __restrict__ in, const uint8_t* __restrict__ halo
     // remainder (at most kUnroll rows; touches the bottom halo when the block ends here)
     for (; r < rend; ++r) {
         const int rr = r + 1;
+        if (bot_edge && rr == rows) wait_generation(sync.wait_bot, sync.gen - 1u, sync.error, lane);
         const Row c = load_row_checked(rr < rows ? rp + pitch : (rr == rows ? halo_bot : nullptr), la);
         rp += pitch;
         const uint4 o = gol_rows(a, b, c, edge_l, edge_r);
@@ -168,6 +229,8 @@ gol_step_u8_vec(const uint8_t* __restrict__ in, const uint8_t* __restrict__ halo
         a = b;
         b = c;
     }
+    if (top_edge) publish_edge(sync.edge_done, sync.signal_up, (unsigned)nstrips, sync.gen, lane);
+    if (bot_edge) publish_edge(sync.edge_done + 1, sync.signal_down, (unsigned)nstrips, sync.gen, lane);
 }
 
 // Any shape (cols not a multiple of 16, tiny grids): one thread per cell.
@@ -219,8 +282,8 @@ MB_API int mb_gol_step_u8(const uint8_t* in, const uint8_t* halo_top, const uint
 #define MB_GOL_LAUNCH(RPW, UNR, MINB)                                                                     \
     do {                                                                                                  \
         const int64_t tasks = (int64_t)nstrips * mb::ceil_div(rows, RPW);                                 \
-        gol_step_u8_vec<RPW, UNR, MINB><<<(unsigned)mb::ceil_div(tasks, kWarps), kWarps * 32, 0, stream>>>( \
-            in, halo_top, halo_bot, out, (int)rows, (int)cols, col_torus, nstrips);                       \
+        gol_step_u8_vec<RPW, UNR, MINB, false><<<(unsigned)mb::ceil_div(tasks, kWarps), kWarps * 32, 0, stream>>>( \
+            in, halo_top, halo_bot, out, (int)rows, (int)cols, col_torus, nstrips, PeerSync{});           \
     } while (0)
         switch (variant) {
             // developer variants (MB_GOL_VARIANT); the default is the best of the sweep in profiles/
@@ -242,5 +305,28 @@ MB_API int mb_gol_step_u8(const uint8_t* in, const uint8_t* halo_top, const uint
                                                                                rows, cols, col_torus);
     }
     MB_LAUNCH_CHECK("mb_gol_step_u8");
+    return MB_OK;
+}
+
+// One generation of a row block whose neighbours' edge rows (halo_top / halo_bot, peer-mapped) belong to other
+// GPUs; the hand-shake with the neighbours is fused into the kernel (see PeerSync).  wait_top / wait_bot are this
+// rank's flags, signal_up / signal_down the peer-mapped addresses of the neighbours' flags (NULL on a clamped
+// outer edge), edge_done two zero-initialised local counters, error a local word, gen = 1, 2, 3, ...
+MB_API int mb_gol_step_u8_fused(const uint8_t* in, const uint8_t* halo_top, const uint8_t* halo_bot, uint8_t* out,
+                                int64_t rows, int64_t cols, int col_torus, unsigned* wait_top, unsigned* wait_bot,
+                                unsigned* signal_up, unsigned* signal_down, unsigned* edge_done, unsigned* error,
+                                unsigned gen, cudaStream_t stream) {
+    MB_REQUIRE(rows > 0 && cols > 0 && rows < (1ll << 30) && cols < (1ll << 30), "mb_gol_step_u8_fused: bad shape");
+    MB_REQUIRE(cols % 16 == 0, "mb_gol_step_u8_fused: cols must be a multiple of 16");
+    MB_REQUIRE(in && out && in != out && edge_done && error, "mb_gol_step_u8_fused: null buffer");
+    MB_REQUIRE(!(col_torus && cols < 3), "mb_gol_step_u8_fused: torus needs cols >= 3");
+    const PeerSync sync{halo_top ? wait_top : nullptr, halo_bot ? wait_bot : nullptr, halo_top ? signal_up : nullptr,
+                        halo_bot ? signal_down : nullptr, edge_done, error, gen};
+    const int nstrips = (int)mb::ceil_div(cols, 512);
+    constexpr int kRpw = 16;
+    const int64_t tasks = (int64_t)nstrips * mb::ceil_div(rows, kRpw);
+    gol_step_u8_vec<kRpw, 4, 4, true><<<(unsigned)mb::ceil_div(tasks, kWarps), kWarps * 32, 0, stream>>>(
+        in, halo_top, halo_bot, out, (int)rows, (int)cols, col_torus, nstrips, sync);
+    MB_LAUNCH_CHECK("mb_gol_step_u8_fused");
     return MB_OK;
 }

@@ -162,3 +162,68 @@ class PeerHaloLayer:
         if self.up is not None:
             self.hdl.wait_signal(self.up, 1)
         self.cur ^= 1
+
+
+class FusedPeerGol:
+    """Row-sharded Game of Life with the halo hand-shake FUSED into the stencil kernel.
+
+    Like PeerHaloLayer the two ping-pong generations of the block live in symmetric memory and the kernel
+    reads the neighbours' edge rows in place over NVLink; unlike it there is no barrier and no exchange at
+    all: mb_gol_step_u8_fused waits on / publishes per-neighbour generation counters that also live in
+    peer-mapped memory (csrc/gol.cu, PeerSync).  One kernel launch per generation and per GPU."""
+
+    def __init__(self, rows: int, cols: int, torus: bool, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _native as N
+
+        self._N = N
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.rows, self.cols, self.torus = int(rows), int(cols), bool(torus)
+        self.device = torch.device(device)
+        self.buf = symm_mem.empty((2, self.rows, self.cols), dtype=torch.uint8, device=self.device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.flags = symm_mem.empty((4,), dtype=torch.int32, device=self.device)   # [wait_top, wait_bot, -, -]
+        self.flags.zero_()
+        self.fhdl = symm_mem.rendezvous(self.flags, self.group)
+        self.local = torch.zeros(4, dtype=torch.int32, device=self.device)          # [edge_done x2, error, -]
+        up = self.rank - 1 if self.rank > 0 else (self.world - 1 if self.torus else None)
+        down = self.rank + 1 if self.rank < self.world - 1 else (0 if self.torus else None)
+        shape = (2, self.rows, self.cols)
+        self.peer_up = self.hdl.get_buffer(up, shape, torch.uint8) if up is not None else None
+        self.peer_down = self.hdl.get_buffer(down, shape, torch.uint8) if down is not None else None
+        self.signal_up = self.fhdl.buffer_ptrs[up] + 4 if up is not None else None        # its wait_bot
+        self.signal_down = self.fhdl.buffer_ptrs[down] + 0 if down is not None else None  # its wait_top
+        self.cur, self.gen = 0, 0
+        torch.cuda.current_stream(self.device).synchronize()
+        dist.barrier(group=self.group)
+
+    @property
+    def state(self) -> torch.Tensor:
+        return self.buf[self.cur]
+
+    def load(self, block: torch.Tensor) -> None:
+        """Set the current generation (collective: every rank calls it before stepping)."""
+        self.buf[self.cur].copy_(block)
+        torch.cuda.current_stream(self.device).synchronize()
+        dist.barrier(group=self.group)
+
+    def step(self) -> None:
+        N = self._N
+        self.gen += 1
+        src, dst = self.buf[self.cur], self.buf[1 - self.cur]
+        top = self.peer_up[self.cur, self.rows - 1] if self.peer_up is not None else None
+        bot = self.peer_down[self.cur, 0] if self.peer_down is not None else None
+        f, l = self.flags.data_ptr(), self.local.data_ptr()
+        with torch.cuda.device(self.device):
+            N.check(N.lib().mb_gol_step_u8_fused(
+                src.data_ptr(), N.ptr(top), N.ptr(bot), dst.data_ptr(), self.rows, self.cols, 1,
+                f, f + 4, self.signal_up, self.signal_down, l, l + 8, self.gen & 0xFFFFFFFF,
+                N.stream_ptr(self.device)))
+        self.cur ^= 1
+
+    def check(self) -> None:
+        """Raise if a wait timed out (a neighbour never published its edge rows)."""
+        if int(self.local[2].item()) != 0:
+            raise RuntimeError("FusedPeerGol: timed out waiting for a neighbouring rank")

@@ -47,6 +47,21 @@ e1.record(); torch.cuda.synchronize()
 ms_peer = e0.elapsed_time(e1) / steps
 same_peer = bool(torch.equal(pl.state, ref))
 
+# --- fused: hand-shake inside the stencil kernel, one launch per generation
+from mesa_b200.sharding import FusedPeerGol
+fg = FusedPeerGol(R, C, True, dev)
+fg.load(init)
+for _ in range(5):
+    fg.step()
+torch.cuda.synchronize(); dist.barrier()
+e0.record()
+for _ in range(steps):
+    fg.step()
+e1.record(); torch.cuda.synchronize()
+ms_fused = e0.elapsed_time(e1) / steps
+fg.check()
+same_fused = bool(torch.equal(fg.state, ref))
+
 # --- same, two generations captured in a CUDA graph
 pl2 = PeerHaloLayer(R, C, torch.uint8, 1, True, dev)
 pl2.state.copy_(init)
@@ -96,7 +111,7 @@ for _ in range(steps):
 e1.record(); torch.cuda.synchronize()
 ms_symm = e0.elapsed_time(e1) / steps
 same = bool(torch.equal(buf[cur], ref))
-t = torch.tensor([ms_nccl, ms_symm, ms_peer, ms_graph], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+t = torch.tensor([ms_nccl, ms_symm, ms_peer, ms_graph, ms_fused], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
-    print(json.dumps({"world": world, "ms_nccl": t[0].item(), "ms_symm_barrier": t[1].item(), "ms_peer_overlap": t[2].item(), "ms_peer_graph": t[3].item(), "identical": same, "identical_peer": same_peer, "identical_graph": same_graph}))
+    print(json.dumps({"world": world, "ms_nccl": t[0].item(), "ms_symm_barrier": t[1].item(), "ms_peer_overlap": t[2].item(), "ms_peer_graph": t[3].item(), "ms_fused": t[4].item(), "identical_fused": same_fused, "identical": same, "identical_peer": same_peer, "identical_graph": same_graph}))
 dist.destroy_process_group()
