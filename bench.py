@@ -288,6 +288,8 @@ def run_ours(args):
                          "frac": achieved / peak, "traffic": _ncu_traffic(), "peak_source": peak_src,
                          "kernel": "gol_step_u8_vec", "algorithmic_bytes_per_launch": ALG_BYTES_PER_UPDATE * GRID * GRID},
         }
+        if world == 1 and not args.no_others:
+            line["workloads"] = other_workloads(dev)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             rate, _ = cpu_gol_rate(256, GRID, 1, 1, threads)
@@ -298,6 +300,82 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_workloads(dev):
+    """Short measurements of the other BASELINE.json configs on one GPU (same run, CUDA-event / wall timed).
+    The headline `value` stays the GoL line; these are reported for context (agent-updates/s)."""
+    import math
+
+    import torch
+
+    from mesa_b200 import ops
+    from mesa_b200.examples import BoltzmannScenario, BoltzmannWealth, Schelling, SchellingScenario
+
+    out = []
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / steps
+
+    # config 0: Schelling 100x100, density 0.8, 100 steps (launch-latency bound: 10 KB of state)
+    m = Schelling(SchellingScenario(width=100, height=100, density=0.8, homophily=0.4, radius=1, rng=42))
+    n = len(m.agents)
+    t = timed(m.step, 100)
+    out.append({"workload": "schelling_100x100_d0.8_h0.4_r1_100steps", "agents": n, "ms_per_step": t * 1e3,
+                "agent_updates_per_s": n / t, "note": "latency-bound (L2-resident); roofline fraction not meaningful"})
+    # Schelling happiness stencil alone on 16384^2 (the >= 60 % target of the north star)
+    g = torch.Generator(device=dev).manual_seed(0)
+    u = torch.rand((GRID, GRID), device=dev, generator=g)
+    types = torch.where(u < 0.2, -1, torch.where(u < 0.6, 0, 1)).to(torch.int8)
+    del u
+    happy = torch.empty((GRID, GRID), dtype=torch.uint8, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    tbl = ops.happy_threshold_table(0.4, 1)
+    for _ in range(3):
+        ops.schelling_happy(types, 0.4, 1, False, out=happy, count=cnt, table=tbl)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(50):
+        ops.schelling_happy(types, 0.4, 1, False, out=happy, count=cnt, table=tbl)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 50
+    peak, _ = _peaks()
+    occupied = int((types >= 0).sum().item())
+    out.append({"workload": "schelling_assign_state_16384x16384_r1", "ms_per_step": ms, "agents": occupied,
+                "agent_updates_per_s": occupied / ms * 1e3, "hbm_gbs": 2 * GRID * GRID / ms / 1e6,
+                "hbm_frac_of_measured_peak": 2 * GRID * GRID / ms / 1e6 / peak})
+    del types, happy
+    # config 2: Boltzmann wealth, 10^6 agents on 4096^2
+    m = BoltzmannWealth(BoltzmannScenario(n=1_000_000, width=4096, height=4096, rng=1))
+    m.run_for(3)
+    t = timed(m.step, 30)
+    out.append({"workload": "boltzmann_1e6_agents_4096x4096", "ms_per_step": t * 1e3, "agent_updates_per_s": 1e6 / t})
+    del m
+    # config 3: Boids, 10^7 agents at the reference "large" density (vision 15)
+    N = 10_000_000
+    side = 150.0 * math.sqrt(N / 400.0)
+    pos = torch.rand((N, 2), device=dev, generator=g) * side
+    dirs = torch.rand((N, 2), device=dev, generator=g) * 2 - 1
+    ws = ops.CellListWorkspace(N, (side, side), 15.0, dev)
+    po, do = torch.empty_like(pos), torch.empty_like(dirs)
+    state = [pos, dirs, po, do]
+
+    def boids():
+        ops.boids_step(state[0], state[1], (side, side), vision=15.0, separation=2.0, ws=ws, pos_out=state[2], dir_out=state[3])
+        state[0], state[2] = state[2], state[0]
+        state[1], state[3] = state[3], state[1]
+
+    for _ in range(2):
+        boids()
+    t = timed(boids, 10)
+    out.append({"workload": "boids_1e7_vision15_synchronous", "ms_per_step": t * 1e3, "agent_updates_per_s": N / t})
+    return out
 
 
 def _ncu_traffic():
@@ -317,6 +395,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the short Schelling / Boltzmann / Boids measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
