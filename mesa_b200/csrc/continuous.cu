@@ -29,6 +29,7 @@
 #include "sort.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -126,41 +127,36 @@ struct BoidParams {
     double cohere, separate, match, speed;
 };
 
-__global__ void __launch_bounds__(128)
-boids_update(const float4* __restrict__ packed, const uint32_t* __restrict__ order,
-             const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end, int64_t n, Geometry g,
-             BoidParams bp, float2* __restrict__ pos_out, float2* __restrict__ dir_out,
-             uint32_t* __restrict__ nbr_count) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 me = packed[i];
-    const double px = me.x, py = me.y;
-    const int cx = cell_coord(px, g.x0, g.sx, g.ncx), cy = cell_coord(py, g.y0, g.sy, g.ncy);
+// accumulators of one boid over its neighbours (agents.py:75-85)
+struct BoidAcc {
     double cohx = 0.0, cohy = 0.0, sepx = 0.0, sepy = 0.0, mx = 0.0, my = 0.0;
     unsigned k = 0;
-    for_neighbor_cells(g, cx, cy, [&](unsigned c) {
-        const uint32_t e = cell_end[c];
-        for (uint32_t j = cell_start[c]; j < e; ++j) {
-            if ((int64_t)j == i) continue;  // get_neighbors_in_radius drops self
-            const float4 o = packed[j];
-            const double d2 = ref_distance2(g, px, py, (double)o.x, (double)o.y);
-            if (d2 <= bp.vision2_le) {
-                const double ddx = ref_delta((double)o.x, px, g.sx, g.torus);
-                const double ddy = ref_delta((double)o.y, py, g.sy, g.torus);
-                cohx += ddx; cohy += ddy;
-                if (d2 < bp.separation2_lt) { sepx += ddx; sepy += ddy; }
-                mx += (double)o.z; my += (double)o.w;
-                ++k;
-            }
-        }
-    });
+};
+
+__device__ __forceinline__ void boid_pair(const Geometry& g, const BoidParams& bp, double px, double py,
+                                          const float4& o, BoidAcc& acc) {
+    const double d2 = ref_distance2(g, px, py, (double)o.x, (double)o.y);
+    if (d2 <= bp.vision2_le) {
+        const double ddx = ref_delta((double)o.x, px, g.sx, g.torus);
+        const double ddy = ref_delta((double)o.y, py, g.sy, g.torus);
+        acc.cohx += ddx; acc.cohy += ddy;
+        if (d2 < bp.separation2_lt) { acc.sepx += ddx; acc.sepy += ddy; }
+        acc.mx += (double)o.z; acc.my += (double)o.w;
+        ++acc.k;
+    }
+}
+
+// direction / position update of one boid from its accumulators, stored at agent index `a`
+__device__ __forceinline__ void boid_finish(const Geometry& g, const BoidParams& bp, const float4& me,
+                                            const BoidAcc& acc, uint32_t a, float2* __restrict__ pos_out,
+                                            float2* __restrict__ dir_out, uint32_t* __restrict__ nbr_count) {
     double dirx = me.z, diry = me.w;
-    double nx = px, ny = py;
-    if (k > 0) {
+    double nx = me.x, ny = me.y;
+    if (acc.k > 0) {
         // agents.py:75-89
-        const double kk = (double)k;
-        dirx += (cohx * bp.cohere + (-1.0 * sepx * bp.separate) + mx * bp.match) / kk;
-        diry += (cohy * bp.cohere + (-1.0 * sepy * bp.separate) + my * bp.match) / kk;
+        const double kk = (double)acc.k;
+        dirx += (acc.cohx * bp.cohere + (-1.0 * acc.sepx * bp.separate) + acc.mx * bp.match) / kk;
+        diry += (acc.cohy * bp.cohere + (-1.0 * acc.sepy * bp.separate) + acc.my * bp.match) / kk;
         const double norm = __dsqrt_rn(__dadd_rn(__dmul_rn(dirx, dirx), __dmul_rn(diry, diry)));
         dirx /= norm;
         diry /= norm;
@@ -176,10 +172,212 @@ boids_update(const float4* __restrict__ packed, const uint32_t* __restrict__ ord
         nx = g.x0 + rx;
         ny = g.y0 + ry;
     }
-    const uint32_t a = order[i];
     pos_out[a] = make_float2((float)nx, (float)ny);
     dir_out[a] = make_float2((float)dirx, (float)diry);
-    if (nbr_count != nullptr) nbr_count[a] = k;
+    if (nbr_count != nullptr) nbr_count[a] = acc.k;
+}
+
+// Generic path (any geometry): one thread per boid, neighbours through L1/L2.
+__global__ void __launch_bounds__(128)
+boids_update(const float4* __restrict__ packed, const uint32_t* __restrict__ order,
+             const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end, int64_t n, Geometry g,
+             BoidParams bp, float2* __restrict__ pos_out, float2* __restrict__ dir_out,
+             uint32_t* __restrict__ nbr_count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 me = packed[i];
+    const double px = me.x, py = me.y;
+    const int cx = cell_coord(px, g.x0, g.sx, g.ncx), cy = cell_coord(py, g.y0, g.sy, g.ncy);
+    BoidAcc acc;
+    for_neighbor_cells(g, cx, cy, [&](unsigned c) {
+        const uint32_t e = cell_end[c];
+        for (uint32_t j = cell_start[c]; j < e; ++j) {
+            if ((int64_t)j == i) continue;  // get_neighbors_in_radius drops self
+            boid_pair(g, bp, px, py, packed[j], acc);
+        }
+    });
+    boid_finish(g, bp, me, acc, order[i], pos_out, dir_out, nbr_count);
+}
+
+// Shared-memory tiled path: one CTA owns a tile of kTX x kTY cells.  The boids of the tile and of the
+// one-cell ring around it ((kTX+2) x (kTY+2) cells) are staged once in shared memory; every owned boid then
+// scans three contiguous shared-memory runs (the 3 cells of each of the 3 rows around it) in two phases:
+//   phase A  a float32 REJECT filter: d2 computed in fp32 (9 cheap instructions); a pair is dropped only if
+//            d2_f32 > vision^2 * (1 + margin), margin = a host-computed bound on the fp32 rounding error, so
+//            no pair the reference would accept is ever dropped; survivors (~36 %) go to a per-thread list
+//            in shared memory;
+//   phase B  the exact fp64 predicate + accumulation of the reference on the survivors only.
+// Without the compaction the fp64 path would be issued for every pair (SIMT: one passing lane is enough);
+// ncu on the first tiled version: 312 M warp-instructions per 2 M boids, issue slots 67 % busy, 15.9 of 32
+// lanes active -- instruction bound.  Tiles whose ring holds more than kTileCap boids (very dense regions)
+// report themselves and are redone by the generic kernel.
+constexpr int kTX = 8, kTY = 8;
+constexpr int kHX = kTX + 2, kHY = kTY + 2;
+constexpr int kTileCap = 1536;
+constexpr int kTileThreads = 256;
+constexpr int kListCap = 64;  // survivors kept per boid; further ones are evaluated on the spot
+
+struct TileSmem {
+    float4 cand[kTileCap];
+    uint32_t gidx[kTileCap];                  // cell-sorted index of each staged boid
+    uint16_t list[kListCap][kTileThreads];    // per-thread survivor lists, slot-major (conflict free)
+    uint32_t cell_off[kHX * kHY + 1];         // start of each ring cell in cand[]
+    uint32_t cell_src[kHX * kHY];             // start of each ring cell in the global sorted array
+    uint32_t own_off[kTY + 1];
+};
+
+__device__ __forceinline__ void boid_pair_exact(const Geometry& g, const BoidParams& bp, double px, double py,
+                                                const float4& o, BoidAcc& acc) {
+    boid_pair(g, bp, px, py, o, acc);
+}
+
+__global__ void __launch_bounds__(kTileThreads)
+boids_update_tiled(const float4* __restrict__ packed, const uint32_t* __restrict__ order,
+                   const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end, Geometry g,
+                   BoidParams bp, float reject2, int tiles_x, float2* __restrict__ pos_out,
+                   float2* __restrict__ dir_out, uint32_t* __restrict__ nbr_count,
+                   uint32_t* __restrict__ overflow_tiles, uint32_t* __restrict__ overflow_count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileSmem& sm = *reinterpret_cast<TileSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cx0 = (blockIdx.x % tiles_x) * kTX, cy0 = (blockIdx.x / tiles_x) * kTY;
+
+    // 1. sizes of the ring cells (wrapped on a torus, absent outside a clamped space)
+    if (tid < kHX * kHY) {
+        int cx = cx0 - 1 + tid % kHX, cy = cy0 - 1 + tid / kHX;
+        bool exists = true;
+        if (g.torus) {
+            cx = (cx + g.ncx) % g.ncx;
+            cy = (cy + g.ncy) % g.ncy;
+        } else {
+            exists = cx >= 0 && cx < g.ncx && cy >= 0 && cy < g.ncy;
+        }
+        uint32_t s = 0, e = 0;
+        if (exists) {
+            const unsigned c = (unsigned)cy * g.ncx + cx;
+            s = cell_start[c];
+            e = cell_end[c];
+        }
+        sm.cell_src[tid] = s;
+        sm.cell_off[tid + 1] = e - s;
+    }
+    if (tid == 0) sm.cell_off[0] = 0;
+    __syncthreads();
+    if (warp == 0) {  // inclusive scan of kHX*kHY = 100 counts, 4 per lane
+        unsigned v[4], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = lane * 4 + k;
+            v[k] = i < kHX * kHY ? sm.cell_off[i + 1] : 0u;
+            sum += v[k];
+        }
+        unsigned incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned x = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += x;
+        }
+        unsigned run = incl - sum;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = lane * 4 + k;
+            run += v[k];
+            if (i < kHX * kHY) sm.cell_off[i + 1] = run;
+        }
+    }
+    __syncthreads();
+    const unsigned total = sm.cell_off[kHX * kHY];
+    if (total > kTileCap) {  // too dense for the staging buffer: hand the tile to the generic kernel
+        if (tid == 0) overflow_tiles[atomicAdd(overflow_count, 1u)] = blockIdx.x;
+        return;
+    }
+    // 2. stage, flat over all ring boids (a ring cell holds only a few: per-cell loops would idle most lanes)
+    for (unsigned i = tid; i < total; i += kTileThreads) {
+        int lo = 0, hi = kHX * kHY;  // last cell with cell_off <= i
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (sm.cell_off[mid] <= i) lo = mid; else hi = mid;
+        }
+        const unsigned src = sm.cell_src[lo] + (i - sm.cell_off[lo]);
+        sm.cand[i] = packed[src];
+        sm.gidx[i] = src;
+    }
+    // 3. owned boids: the interior cells of ring row iy form the contiguous run
+    //    [cell_off[iy*kHX+1], cell_off[iy*kHX+kHX-1]); flatten the kTY runs so that all threads stay busy
+    if (tid == 0) {
+        unsigned run = 0;
+        for (int iy = 1; iy <= kTY; ++iy) {
+            sm.own_off[iy - 1] = run;
+            if (cy0 + iy - 1 < g.ncy) run += sm.cell_off[iy * kHX + kHX - 1] - sm.cell_off[iy * kHX + 1];
+        }
+        sm.own_off[kTY] = run;
+    }
+    __syncthreads();
+    const unsigned owned = sm.own_off[kTY];
+    const float fsx = (float)g.sx, fsy = (float)g.sy;
+    for (unsigned t = tid; t < owned; t += kTileThreads) {
+        int iy = 1;
+#pragma unroll
+        for (int k = 1; k < kTY; ++k) iy += t >= sm.own_off[k];
+        const unsigned p = sm.cell_off[iy * kHX + 1] + (t - sm.own_off[iy - 1]);
+        const float4 me = sm.cand[p];
+        const double px = me.x, py = me.y;
+        const int cx = cell_coord(px, g.x0, g.sx, g.ncx);
+        if (cx < cx0 || cx >= cx0 + kTX) continue;  // wrapped duplicate of a partial edge tile: owned elsewhere
+        const int ix = cx - cx0 + 1;                // ring column of my cell
+        BoidAcc acc;
+        // phase A: fp32 reject filter over the 3 runs
+        unsigned nlist = 0;
+#pragma unroll
+        for (int r = iy - 1; r <= iy + 1; ++r) {
+            const unsigned e = sm.cell_off[r * kHX + ix + 2];
+            for (unsigned q = sm.cell_off[r * kHX + ix - 1]; q < e; ++q) {
+                const float4 o = sm.cand[q];
+                float dx = fabsf(me.x - o.x), dy = fabsf(me.y - o.y);
+                if (g.torus) {
+                    dx = fminf(dx, fsx - dx);
+                    dy = fminf(dy, fsy - dy);
+                }
+                if (fmaf(dx, dx, dy * dy) > reject2 || q == p) continue;  // surely outside (or self)
+                if (nlist < (unsigned)kListCap) sm.list[nlist++][tid] = (uint16_t)q;
+                else boid_pair_exact(g, bp, px, py, o, acc);
+            }
+        }
+        // phase B: the reference's exact fp64 predicate and sums on the survivors
+        for (unsigned s = 0; s < nlist; ++s) boid_pair_exact(g, bp, px, py, sm.cand[sm.list[s][tid]], acc);
+        boid_finish(g, bp, me, acc, order[sm.gidx[p]], pos_out, dir_out, nbr_count);
+    }
+}
+
+// generic kernel restricted to the boids of the overflowed tiles (rare)
+__global__ void __launch_bounds__(128)
+boids_update_overflow(const float4* __restrict__ packed, const uint32_t* __restrict__ order,
+                      const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end, Geometry g,
+                      BoidParams bp, int tiles_x, const uint32_t* __restrict__ overflow_tiles,
+                      const uint32_t* __restrict__ overflow_count, float2* __restrict__ pos_out,
+                      float2* __restrict__ dir_out, uint32_t* __restrict__ nbr_count) {
+    for (unsigned t = blockIdx.x; t < *overflow_count; t += gridDim.x) {
+        const unsigned tile = overflow_tiles[t];
+        const int cx0 = (tile % tiles_x) * kTX, cy0 = (tile / tiles_x) * kTY;
+        for (int c = 0; c < kTX * kTY; ++c) {
+            const int cx = cx0 + c % kTX, cy = cy0 + c / kTX;
+            if (cx >= g.ncx || cy >= g.ncy) continue;
+            const unsigned cell = (unsigned)cy * g.ncx + cx;
+            const uint32_t e = cell_end[cell];
+            for (uint32_t i = cell_start[cell] + threadIdx.x; i < e; i += blockDim.x) {
+                const float4 me = packed[i];
+                BoidAcc acc;
+                for_neighbor_cells(g, cx, cy, [&](unsigned nc) {
+                    const uint32_t ne = cell_end[nc];
+                    for (uint32_t j = cell_start[nc]; j < ne; ++j) {
+                        if (j == i) continue;
+                        boid_pair(g, bp, (double)me.x, (double)me.y, packed[j], acc);
+                    }
+                });
+                boid_finish(g, bp, me, acc, order[i], pos_out, dir_out, nbr_count);
+            }
+        }
+    }
 }
 
 // ---- radius queries (get_agents_in_radius for a batch of points) ---------------------------
@@ -246,7 +444,7 @@ size_t carve(CellListWs* ws, char* base, int64_t n, int64_t ncells) {
     t.keys1 = (uint32_t*)take(4 * n);
     t.vals1 = (uint32_t*)take(4 * n);
     t.cell_start = (uint32_t*)take(4 * ncells);
-    t.cell_end = (uint32_t*)take(4 * ncells);
+    t.cell_end = (uint32_t*)take(4 * (ncells + 1));  // + 1 spare word (overflow-tile counter)
     t.packed = (float4*)take(16 * n);
     t.sort_ws_bytes = mb::sort_workspace_bytes(n);
     t.sort_ws = take(t.sort_ws_bytes);
@@ -343,6 +541,45 @@ MB_API int mb_boids_step_f32(const float* pos_in, const float* dir_in, float* po
     rc = build_cell_list((const float2*)pos_in, (const float2*)dir_in, n, g, ws, &order, stream);
     if (rc) return rc;
     const BoidParams bp{sq_threshold_le(vision), sq_threshold_ge(separation), cohere, separate, match, speed};
+    static const bool force_generic = getenv("MB_BOIDS_GENERIC") != nullptr;
+    if (!force_generic && g.ncx >= kHX && g.ncy >= kHY) {
+        // tiled path; keys0 is free after the sort when the order ended up in the other ping-pong buffer,
+        // keys1 otherwise: use whichever key buffer does not alias `order`'s partner for the overflow list
+        const int tiles_x = (int)mb::ceil_div(g.ncx, kTX), tiles_y = (int)mb::ceil_div(g.ncy, kTY);
+        uint32_t* ovf_tiles = (order == ws.vals0) ? ws.keys1 : ws.keys0;   // n entries >= tiles (checked below)
+        uint32_t* ovf_count = ws.cell_end + (int64_t)g.ncx * g.ncy;        // one spare word after the cell table
+        if ((int64_t)tiles_x * tiles_y <= n) {
+            rc = mb::check_cuda(cudaMemsetAsync(ovf_count, 0, 4, stream), "memset");
+            if (rc) return rc;
+            // fp32 reject threshold: vision^2 inflated by a bound on the fp32 error of d2 (positions up to the
+            // space size carry an absolute error of ~ulp(size); see the kernel comment).  A margin above 50 %
+            // means float32 cannot resolve the radius in this space: use the generic kernel.
+            const double smax = g.sx > g.sy ? g.sx : g.sy;
+            const double margin = 64.0 * 1.1920929e-7 * (smax / vision) + 1e-5;
+            static bool attr_set = false;
+            if (!attr_set) {
+                rc = mb::check_cuda(cudaFuncSetAttribute(boids_update_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         (int)sizeof(TileSmem)), "cudaFuncSetAttribute");
+                if (rc) return rc;
+                attr_set = true;
+            }
+            if (margin < 0.5) {
+                const float reject2 = (float)(vision * vision * (1.0 + margin));
+                boids_update_tiled<<<(unsigned)(tiles_x * tiles_y), kTileThreads, sizeof(TileSmem), stream>>>(
+                    ws.packed, order, ws.cell_start, ws.cell_end, g, bp, reject2, tiles_x, (float2*)pos_out,
+                    (float2*)dir_out, neighbor_count, ovf_tiles, ovf_count);
+            } else {
+                boids_update<<<(unsigned)mb::ceil_div(n, 128), 128, 0, stream>>>(ws.packed, order, ws.cell_start, ws.cell_end, n,
+                                                                             g, bp, (float2*)pos_out, (float2*)dir_out,
+                                                                             neighbor_count);
+            }
+            boids_update_overflow<<<mb::sm_count(), 128, 0, stream>>>(ws.packed, order, ws.cell_start, ws.cell_end, g, bp,
+                                                                    tiles_x, ovf_tiles, ovf_count, (float2*)pos_out,
+                                                                    (float2*)dir_out, neighbor_count);
+            MB_LAUNCH_CHECK("mb_boids_step_f32");
+            return MB_OK;
+        }
+    }
     boids_update<<<(unsigned)mb::ceil_div(n, 128), 128, 0, stream>>>(ws.packed, order, ws.cell_start, ws.cell_end, n, g, bp,
                                                                      (float2*)pos_out, (float2*)dir_out, neighbor_count);
     MB_LAUNCH_CHECK("mb_boids_step_f32");
