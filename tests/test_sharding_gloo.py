@@ -90,3 +90,44 @@ def test_block_bounds_cover_all_rows():
         assert spans[0][0] == 0 and spans[-1][1] == rows
         assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
         assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def _owner_worker(rank, world, port, out_dir):
+    """Host-side partition logic of the sharded drivers on a gloo group: every cell / boid has exactly one
+    owner, owners agree across ranks, and boids crossing a slab edge are routed to the adjacent rank."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mesa_b200.sharded import ShardedBoids
+    from mesa_b200.sharding import block_bounds
+
+    rows, cols = 37, 5
+    lo, hi = block_bounds(rows, world, rank)
+    owned = torch.zeros(rows * cols, dtype=torch.int64)
+    owned[lo * cols: hi * cols] = 1
+    dist.all_reduce(owned)
+    ok = bool((owned == 1).all())           # row blocks tile the grid exactly once
+    # global agent ids: exclusive scan of the local counts in rank order (ShardedSchelling.__init__)
+    rng = np.random.default_rng(1)
+    grid = rng.random((rows, cols)) < 0.7
+    counts = torch.zeros(world, dtype=torch.int64)
+    counts[rank] = int(grid[lo:hi].sum())
+    dist.all_reduce(counts)
+    first = int(counts[:rank].sum())
+    want_first = int(grid[:lo].sum())
+    ok &= first == want_first and int(counts.sum()) == int(grid.sum())
+    # slab ownership of boids (ShardedBoids.owner_of) incl. the inclusive top edge
+    height = 90.0
+    y = torch.tensor([0.0, 29.999, 30.0, 44.9, 45.0, 89.99, 90.0])
+    own = ShardedBoids.owner_of(y, height, world)
+    slab = height / world
+    ok &= bool(((own.double() * slab <= y.double()) | (own == 0)).all()) and int(own.max()) == world - 1
+    ok &= bool((own[1:] >= own[:-1]).all())
+    np.save(os.path.join(out_dir, f"ok_{rank}.npy"), np.array([ok]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_partition_logic_of_sharded_drivers(tmp_path, world):
+    mp.spawn(_owner_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(bool(np.load(tmp_path / f"ok_{r}.npy")[0]) for r in range(world))
