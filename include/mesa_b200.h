@@ -169,6 +169,24 @@ int mb_radius_query_f32(const float* pos, int64_t n, double x0, double y0, doubl
                         uint32_t* counts, const int64_t* offsets, int32_t* out_idx, double* out_dist,
                         void* workspace, size_t workspace_bytes, int reuse_cell_list, mb_stream_t stream);
 
+/* Domain-decomposed continuous space (one rank per slab of y, mesa_b200/sharded.py ShardedBoids): the exchange
+ * steps as kernels that append straight into the neighbouring ranks' peer-mapped inboxes (NVLink stores + an
+ * atomic slot counter in the receiver's memory) -- no pack / send / recv / unpack.  *_count are peer-mapped
+ * uint32 counters (NULL: no neighbour on that side), cap the inbox capacity, overflow / flags local words
+ * (flags[0] inbox overflow, flags[1] a boid jumped over a whole slab).  mb_boids_route also produces the stay
+ * flags and their exclusive scan for the stable compaction done by mb_boids_compact. */
+int mb_boids_send_ghosts(const float* pos, const float* dir, int64_t n, double y_lo, double y_hi, double reach,
+                         float* down_pos, float* down_dir, unsigned* down_count, float* up_pos, float* up_dir,
+                         unsigned* up_count, int64_t cap, unsigned* overflow, mb_stream_t stream);
+int mb_boids_route(const float* pos, const float* dir, const int64_t* ids, int64_t n, double height, int world,
+                   int rank, unsigned* stay_flags, unsigned* stay_offsets, unsigned* scratch, float* down_pos,
+                   float* down_dir, int64_t* down_ids, unsigned* down_count, float* up_pos, float* up_dir,
+                   int64_t* up_ids, unsigned* up_count, int64_t cap, unsigned* flags, mb_stream_t stream);
+int mb_boids_compact(const float* pos, const float* dir, const int64_t* ids, int64_t n, const unsigned* stay_flags,
+                     const unsigned* stay_offsets, float* pos_out, float* dir_out, int64_t* ids_out,
+                     mb_stream_t stream);
+int mb_scan_scratch_words(int64_t n, size_t* out);
+
 /* ---- Boltzmann wealth (replaces AgentSet.shuffle_do("step") over
  * examples/basic/boltzmann_wealth_model/agents.py:24-44: Moore random walk, then give one unit to
  * a random cell mate) ---------------------------------------------------------------------------

@@ -79,6 +79,11 @@ SIGNATURES: dict[str, tuple] = {
                                   ctypes.c_size_t, _S]),
     "mb_radius_query_f32": (c_int, [_P, c_int64, c_double, c_double, c_double, c_double, c_int, _P, _P, c_int64,
                                     c_double, _P, _P, _P, _P, _P, ctypes.c_size_t, c_int, _S]),
+    "mb_boids_send_ghosts": (c_int, [_P, _P, c_int64, c_double, c_double, c_double, _P, _P, _P, _P, _P, _P, c_int64, _P, _S]),
+    "mb_boids_route": (c_int, [_P, _P, _P, c_int64, c_double, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                               c_int64, _P, _S]),
+    "mb_boids_compact": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P, _P, _S]),
+    "mb_scan_scratch_words": (c_int, [c_int64, ctypes.POINTER(ctypes.c_size_t)]),
     # Boltzmann wealth
     "mb_boltzmann_workspace_bytes": (c_int, [c_int64, ctypes.POINTER(ctypes.c_size_t)]),
     "mb_boltzmann_init": (c_int, [_P, c_int64, c_int64, c_int64, _P, ctypes.c_size_t, _S]),

@@ -136,6 +136,15 @@ sort_scatter(const K* __restrict__ keys_in, const uint32_t* __restrict__ vals_in
 
 }  // namespace
 
+int exclusive_scan_u32(uint32_t* data, int64_t n, uint32_t* sums, cudaStream_t stream) {
+    if (n <= 0) return MB_OK;
+    const int64_t nchunks = ceil_div(n, kScanChunk);
+    scan_chunks<<<(unsigned)nchunks, 1024, 0, stream>>>(data, n, sums);
+    scan_top<<<1, 1024, 0, stream>>>(sums, nchunks);
+    scan_add<<<(unsigned)nchunks, 1024, 0, stream>>>(data, n, sums);
+    return check_cuda(cudaGetLastError(), "exclusive_scan_u32");
+}
+
 template <typename K>
 int radix_sort_pairs(K* k0, uint32_t* v0, K* k1, uint32_t* v1, int64_t n, int begin_bit, int end_bit,
                      void* workspace, size_t workspace_bytes, cudaStream_t stream) {
@@ -159,14 +168,7 @@ int radix_sort_pairs(K* k0, uint32_t* v0, K* k1, uint32_t* v1, int64_t n, int be
     int cur = 0;
     for (int bit = begin_bit; bit < end_bit; bit += 8) {
         sort_hist<K><<<(unsigned)tiles, kSortThreads, 0, stream>>>(ks[cur], n, bit, hist, tiles);
-        {
-            const int64_t total = (int64_t)kRadix * tiles;
-            const int64_t nchunks = ceil_div(total, kScanChunk);
-            uint32_t* sums = hist + total;
-            scan_chunks<<<(unsigned)nchunks, 1024, 0, stream>>>(hist, total, sums);
-            scan_top<<<1, 1024, 0, stream>>>(sums, nchunks);
-            scan_add<<<(unsigned)nchunks, 1024, 0, stream>>>(hist, total, sums);
-        }
+        if (exclusive_scan_u32(hist, (int64_t)kRadix * tiles, hist + (int64_t)kRadix * tiles, stream) != MB_OK) return MB_ERR_CUDA;
         sort_scatter<K><<<(unsigned)tiles, kSortThreads, 0, stream>>>(ks[cur], vs[cur], ks[cur ^ 1], vs[cur ^ 1], n,
                                                                      bit, hist, tiles);
         cur ^= 1;

@@ -34,4 +34,8 @@ template <typename K>
 int radix_sort_pairs(K* k0, uint32_t* v0, K* k1, uint32_t* v1, int64_t n, int begin_bit, int end_bit,
                      void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+// In-place exclusive prefix sum of n uint32 counters; `sums` needs ceil(n / 4096) + 1 words of scratch.
+inline size_t scan_scratch_words(int64_t n) { return (size_t)((n + 4095) / 4096) + 64; }
+int exclusive_scan_u32(uint32_t* data, int64_t n, uint32_t* sums, cudaStream_t stream);
+
 }  // namespace mb

@@ -261,8 +261,11 @@ class ShardedSchelling:
                           for r in range(self.world)])
 
 
-class ShardedBoids:
-    """BoidFlockers on a continuous torus sharded by spatial domain (BASELINE.json config 4).
+class ShardedBoidsNCCL:
+    """First version of the domain decomposition: torch-level packing + NCCL point-to-point (kept as the reference
+    implementation of the protocol and as a fallback; ShardedBoids below is the peer-memory version).
+
+    BoidFlockers on a continuous torus sharded by spatial domain (BASELINE.json config 4).
 
     Rank k owns the slab  y in [k, k+1) * height / world  and the boids inside it.  Per step:
       1. halo: boids within `vision` of a slab edge are copied to the neighbouring rank (ghosts);
@@ -383,4 +386,159 @@ class ShardedBoids:
         rows = torch.cat([everyone[r, : int(n[r].item())] for r in range(self.world)])
         order = torch.argsort(rows[:, 4])
         rows = rows[order]
+        return rows[:, 4].to(torch.int64), rows[:, :2].to(torch.float32), rows[:, 2:4].to(torch.float32)
+
+
+
+class ShardedBoids:
+    """BoidFlockers on a continuous torus sharded by spatial domain (BASELINE.json config 4),
+    with the exchanges done by kernels that write into the neighbours' memory over NVLink.
+
+    Rank k owns the slab  y in [k, k+1) * height / world.  Per step:
+      1. `mb_boids_send_ghosts`: boids within `vision` of a slab edge are appended to the neighbour's ghost inbox
+         (peer-mapped symmetric memory, atomic slot counter in the receiver's memory); device barrier;
+      2. one synchronous Boid.step (`ops.boids_step`) over owned + ghost boids (ghosts keep global coordinates:
+         the torus minimum-image arithmetic needs no shift); only the owned results are kept;
+      3. `mb_boids_route` / `mb_boids_compact`: boids whose new y left the slab are appended to their new owner's
+         migrant inbox with their global id, the others are compacted in place (stable); device barrier; the
+         migrants are appended.
+    No NCCL call and no torch-level packing on the step path; the host reads two small counter vectors per step."""
+
+    def __init__(self, width: float, height: float, positions, directions, ids, *, vision=10.0, separation=2.0,
+                 cohere=0.03, separate=0.015, match=0.05, speed=1.0, device=None, group=None, capacity=None,
+                 inbox=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        if not dist.is_initialized():
+            raise RuntimeError("ShardedBoids needs an initialised torch.distributed process group")
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.device = dev = torch.device(device if device is not None else torch.cuda.current_device())
+        self.size = (float(width), float(height))
+        self.params = dict(vision=float(vision), separation=float(separation), cohere=float(cohere),
+                           separate=float(separate), match=float(match), speed=float(speed))
+        self.slab = self.size[1] / self.world
+        if self.world > 1 and self.slab < 2 * (vision + speed):
+            raise ValueError("slabs must be at least 2*(vision+speed) high")
+        self.y_lo, self.y_hi = self.rank * self.slab, (self.rank + 1) * self.slab
+        pos = torch.as_tensor(positions, dtype=torch.float32).to(dev)
+        n = int(pos.shape[0])
+        nmax = torch.tensor([n], dtype=torch.int64, device=dev)
+        dist.all_reduce(nmax, op=dist.ReduceOp.MAX, group=self.group)
+        nmax = int(nmax.item())
+        # inbox capacity: 4x the boids expected within `vision` of an edge (uniform density), at least 4096
+        self.icap = int(inbox) if inbox is not None else max(4096, int(4 * nmax * vision / max(self.slab, vision)) + 1024)
+        self.cap = int(capacity) if capacity is not None else int(nmax * 1.5) + 4 * self.icap + 1024
+        self.n = n
+        self.pos = [torch.empty((self.cap, 2), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.dir = [torch.empty((self.cap, 2), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.ids = [torch.empty(self.cap, dtype=torch.int64, device=dev) for _ in range(2)]
+        self.pos[0][:n] = pos
+        self.dir[0][:n] = torch.as_tensor(directions, dtype=torch.float32).to(dev)
+        self.ids[0][:n] = torch.as_tensor(ids, dtype=torch.int64).to(dev)
+        # symmetric inboxes: rows [0, icap) are written by the rank below me, rows [icap, 2*icap) by the rank above
+        def symmetric(shape, dtype):
+            t = symm_mem.empty(shape, dtype=dtype, device=dev)
+            return t, symm_mem.rendezvous(t, self.group)
+
+        self.gpos, self._gpos_h = symmetric((2 * self.icap, 2), torch.float32)
+        self.gdir, self._gdir_h = symmetric((2 * self.icap, 2), torch.float32)
+        self.mpos, self._mpos_h = symmetric((2 * self.icap, 2), torch.float32)
+        self.mdir, self._mdir_h = symmetric((2 * self.icap, 2), torch.float32)
+        self.mids, self._mids_h = symmetric((2 * self.icap,), torch.int64)
+        self.cnt, self._cnt_h = symmetric((8,), torch.int32)   # [ghosts from below, ghosts from above, migrants ...]
+        self.cnt.zero_()
+        self.flags = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.stay = torch.empty(self.cap, dtype=torch.int32, device=dev)
+        self.offs = torch.empty(self.cap, dtype=torch.int32, device=dev)
+        words = ctypes.c_size_t(0)
+        N.check(N.lib().mb_scan_scratch_words(self.cap, ctypes.byref(words)))
+        self.scratch = torch.empty(int(words.value), dtype=torch.int32, device=dev)
+        self._ws = ops.CellListWorkspace(self.cap, self.size, self.params["vision"], dev)
+        down, up = (self.rank - 1) % self.world, (self.rank + 1) % self.world
+        row = self.icap * 2 * 4          # byte offset of the "from above" half of a [2*icap, 2] float32 inbox
+        P = lambda h, r, off=0: h.buffer_ptrs[r] + off
+        if self.world > 1:
+            # what I send DOWN lands in the lower neighbour's "from above" half, what I send UP in the upper one's "from below" half
+            self._g_down = (P(self._gpos_h, down, row), P(self._gdir_h, down, row), P(self._cnt_h, down, 4))
+            self._g_up = (P(self._gpos_h, up), P(self._gdir_h, up), P(self._cnt_h, up, 0))
+            self._m_down = (P(self._mpos_h, down, row), P(self._mdir_h, down, row), P(self._mids_h, down, self.icap * 8), P(self._cnt_h, down, 12))
+            self._m_up = (P(self._mpos_h, up), P(self._mdir_h, up), P(self._mids_h, up), P(self._cnt_h, up, 8))
+        self.cur = 0
+        torch.cuda.current_stream(dev).synchronize()
+        dist.barrier(group=self.group)
+
+    owner_of = staticmethod(ShardedBoidsNCCL.owner_of)
+
+    def _check_flags(self, flags):
+        if flags[0]:
+            raise RuntimeError("ShardedBoids: an inbox overflowed (raise `inbox=`)")
+        if flags[1]:
+            raise RuntimeError("a boid jumped over a whole slab (speed too large for this decomposition)")
+
+    def step(self) -> None:
+        p, lib, dev = self.params, N.lib(), self.device
+        cur, nxt = self.cur, 1 - self.cur
+        pos, dirs, ids, n = self.pos[cur], self.dir[cur], self.ids[cur], self.n
+        st = N.stream_ptr(dev)
+        with torch.cuda.device(dev):
+            g = 0
+            if self.world > 1:
+                N.check(lib.mb_boids_send_ghosts(pos.data_ptr(), dirs.data_ptr(), n, self.y_lo, self.y_hi, p["vision"],
+                                                 *self._g_down, *self._g_up, self.icap, self.flags.data_ptr(), st))
+                self._cnt_h.barrier()
+                c = self.cnt[:2].tolist()
+                gd, gu = int(c[0]), int(c[1])
+                if gd > self.icap or gu > self.icap:
+                    raise RuntimeError("ShardedBoids: a ghost inbox overflowed (raise `inbox=`)")
+                g = gd + gu
+                pos[n:n + gd] = self.gpos[:gd]
+                dirs[n:n + gd] = self.gdir[:gd]
+                pos[n + gd:n + g] = self.gpos[self.icap:self.icap + gu]
+                dirs[n + gd:n + g] = self.gdir[self.icap:self.icap + gu]
+                self.cnt[:2].zero_()
+            ops.boids_step(pos[:n + g], dirs[:n + g], self.size, torus=True, ws=self._ws,
+                           pos_out=self.pos[nxt][:n + g], dir_out=self.dir[nxt][:n + g], **p)
+            if self.world == 1:
+                self.ids[nxt][:n] = ids[:n]
+                self.cur = nxt
+                return
+            # route the owned results: stayers are compacted back into the `cur` buffers, leavers go to the inboxes
+            N.check(lib.mb_boids_route(self.pos[nxt].data_ptr(), self.dir[nxt].data_ptr(), ids.data_ptr(), n, self.size[1],
+                                       self.world, self.rank, self.stay.data_ptr(), self.offs.data_ptr(),
+                                       self.scratch.data_ptr(), *self._m_down, *self._m_up, self.icap,
+                                       self.flags.data_ptr(), st))
+            N.check(lib.mb_boids_compact(self.pos[nxt].data_ptr(), self.dir[nxt].data_ptr(), ids.data_ptr(), n,
+                                         self.stay.data_ptr(), self.offs.data_ptr(), pos.data_ptr(), dirs.data_ptr(),
+                                         self.ids[nxt].data_ptr(), st))
+            self._cnt_h.barrier()
+            info = torch.cat([self.cnt[2:4], self.flags[:2], self.offs[n - 1:n] + self.stay[n - 1:n]]).tolist() if n > 0 \
+                else torch.cat([self.cnt[2:4], self.flags[:2], torch.zeros(1, dtype=torch.int32, device=dev)]).tolist()
+            md, mu, ns = int(info[0]), int(info[1]), int(info[4])
+            self._check_flags(info[2:4])
+            if md > self.icap or mu > self.icap or ns + md + mu > self.cap - 2 * self.icap:
+                raise RuntimeError("ShardedBoids: capacity exceeded")
+            new_ids = self.ids[nxt]
+            pos[ns:ns + md], dirs[ns:ns + md], new_ids[ns:ns + md] = self.mpos[:md], self.mdir[:md], self.mids[:md]
+            lo = self.icap
+            pos[ns + md:ns + md + mu], dirs[ns + md:ns + md + mu] = self.mpos[lo:lo + mu], self.mdir[lo:lo + mu]
+            new_ids[ns + md:ns + md + mu] = self.mids[lo:lo + mu]
+            self.cnt[2:4].zero_()
+            self.n = ns + md + mu
+            # positions / directions stay in the `cur` buffers, ids moved to the other id buffer
+            self.ids[cur], self.ids[nxt] = self.ids[nxt], self.ids[cur]
+
+    def gather(self):
+        """(ids, pos, dir) of all boids on every rank, sorted by id (tests / readback)."""
+        n = torch.zeros(self.world, dtype=torch.int64, device=self.device)
+        n[self.rank] = self.n
+        dist.all_reduce(n, group=self.group)
+        width = int(n.max().item())
+        mine = torch.zeros((width, 5), dtype=torch.float64, device=self.device)
+        c = self.cur
+        mine[: self.n, :2], mine[: self.n, 2:4], mine[: self.n, 4] = self.pos[c][: self.n], self.dir[c][: self.n], self.ids[c][: self.n]
+        everyone = torch.empty((self.world, width, 5), dtype=torch.float64, device=self.device)
+        dist.all_gather_into_tensor(everyone, mine, group=self.group)
+        rows = torch.cat([everyone[r, : int(n[r].item())] for r in range(self.world)])
+        rows = rows[torch.argsort(rows[:, 4])]
         return rows[:, 4].to(torch.int64), rows[:, :2].to(torch.float32), rows[:, 2:4].to(torch.float32)

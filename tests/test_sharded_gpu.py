@@ -46,3 +46,22 @@ def test_sharded_driver_world1_matches_oracle(one_rank_group, rows, cols, densit
         assert st.assign_state(h, radius) == happy
         assert np.array_equal(m.type.cpu().numpy(), st.type_grid())
         assert np.array_equal(m.happy.cpu().numpy(), st.happy_grid())
+
+
+def test_sharded_boids_world1_matches_oracle(one_rank_group):
+    """Single-rank run of the domain-decomposed driver (no neighbours): the slab is the whole torus."""
+    from mesa_b200.sharded import ShardedBoids
+
+    rng = np.random.default_rng(3)
+    n, side = 1500, 200.0
+    pos = (rng.random((n, 2)) * side).astype(np.float32)
+    dirs = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+    m = ShardedBoids(side, side, pos, dirs, np.arange(n), vision=10.0, separation=2.0)
+    for _ in range(3):
+        m.step()
+        ids, gp, gd = m.gather()
+        wp, wd, _ = oracle.boids_step(pos, dirs, (side, side), vision=10.0, separation=2.0)
+        gp, gd = gp.cpu().numpy(), gd.cpu().numpy()
+        assert np.array_equal(ids.cpu().numpy(), np.arange(n))
+        assert np.max(np.abs(gp - wp)) / side <= 1e-5 and np.max(np.abs(gd - wd)) <= 1e-5
+        pos, dirs = gp.copy(), gd.copy()
