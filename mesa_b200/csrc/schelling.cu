@@ -22,12 +22,12 @@
 // Roofline: HBM-bound, 2 B per cell (1 B type read + 1 B happy write).
 #include "common.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
 
 constexpr int kWarps = 8;
-constexpr int kRowsPerWarp = 64;
 constexpr int kMaxRadius = 7;  // (2*7+1)^2 - 1 = 224 neighbours fit a byte
 
 enum { MODE_LINEAR = 0, MODE_T = 1, MODE_U = 2 };
@@ -161,8 +161,8 @@ __device__ __forceinline__ unsigned decide4(unsigned bocc, unsigned bone, unsign
     return (flag >> 7) & occ_c;
 }
 
-template <int R, int MODE>
-__global__ void __launch_bounds__(kWarps * 32, R == 1 ? 3 : 2)
+template <int R, int MODE, int kRowsPerWarp, int kMinBlocks>
+__global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 schelling_happy_vec(const int8_t* __restrict__ type, const int8_t* __restrict__ halo_top,
                     const int8_t* __restrict__ halo_bot, uint8_t* __restrict__ happy, int rows, int cols,
                     int col_torus, int nstrips, const HappyRule rule,
@@ -360,11 +360,31 @@ MB_API int mb_schelling_happy_i8(const int8_t* type, const int8_t* halo_top, con
                      (halo_top == nullptr || al16(halo_top)) && (halo_bot == nullptr || al16(halo_bot));
     if (vec) {
         const int nstrips = (int)mb::ceil_div(cols, 512);
-        const int64_t tasks = (int64_t)nstrips * mb::ceil_div(rows, kRowsPerWarp);
-        const unsigned blocks = (unsigned)mb::ceil_div(tasks, kWarps);
-#define MB_HAPPY_LAUNCH(RR, MM)                                                                              \
-    schelling_happy_vec<RR, MM><<<blocks, kWarps * 32, 0, stream>>>(type, halo_top, halo_bot, happy, (int)rows, \
-                                                                    (int)cols, col_torus, nstrips, rule, happy_count)
+        static const int variant = getenv("MB_HAPPY_VARIANT") ? atoi(getenv("MB_HAPPY_VARIANT")) : 0;
+#define MB_HAPPY_LAUNCH3(RR, MM, RPW, MINB)                                                                        \
+    schelling_happy_vec<RR, MM, RPW, MINB><<<(unsigned)mb::ceil_div((int64_t)nstrips * mb::ceil_div(rows, RPW), kWarps), \
+                                             kWarps * 32, 0, stream>>>(type, halo_top, halo_bot, happy, (int)rows,  \
+                                                                       (int)cols, col_torus, nstrips, rule, happy_count)
+#define MB_HAPPY_LAUNCH(RR, MM)                                              \
+    do {                                                                     \
+        if (RR == 1) {                                                       \
+            switch (variant) {                                               \
+                case 1: MB_HAPPY_LAUNCH3(1, MM, 64, 3); break;               \
+                case 2: MB_HAPPY_LAUNCH3(1, MM, 16, 3); break;               \
+                case 3: MB_HAPPY_LAUNCH3(1, MM, 16, 4); break;               \
+                case 4: MB_HAPPY_LAUNCH3(1, MM, 64, 4); break;               \
+                default: MB_HAPPY_LAUNCH3(1, MM, 32, 4); break; /* 115 us on 16384^2 (64 rows, 3 CTAs/SM: 134 us) */ \
+            }                                                                \
+        } else {                                                             \
+            switch (variant) {                                               \
+                case 1: MB_HAPPY_LAUNCH3(2, MM, 16, 3); break;               \
+                case 2: MB_HAPPY_LAUNCH3(2, MM, 32, 2); break;               \
+                case 3: MB_HAPPY_LAUNCH3(2, MM, 32, 3); break;               \
+                case 4: MB_HAPPY_LAUNCH3(2, MM, 64, 3); break;               \
+                default: MB_HAPPY_LAUNCH3(2, MM, 64, 2); break; /* 171 us; 3 CTAs/SM spills and is slower */ \
+            }                                                                \
+        }                                                                    \
+    } while (0)
         if (radius == 1) {
             if (rule.mode == MODE_LINEAR) MB_HAPPY_LAUNCH(1, MODE_LINEAR);
             else if (rule.mode == MODE_T) MB_HAPPY_LAUNCH(1, MODE_T);
@@ -374,6 +394,7 @@ MB_API int mb_schelling_happy_i8(const int8_t* type, const int8_t* halo_top, con
             else if (rule.mode == MODE_T) MB_HAPPY_LAUNCH(2, MODE_T);
             else MB_HAPPY_LAUNCH(2, MODE_U);
         }
+#undef MB_HAPPY_LAUNCH3
 #undef MB_HAPPY_LAUNCH
     } else {
         const int64_t n = rows * cols;
