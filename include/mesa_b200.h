@@ -62,6 +62,20 @@ int mb_gol_step_u8_fused(const uint8_t* in, const uint8_t* halo_top, const uint8
                          unsigned* signal_up, unsigned* signal_down, unsigned* edge_done, unsigned* error,
                          unsigned gen, mb_stream_t stream);
 
+/* Bit-packed Game of Life (same rule, same reference lines; csrc/gol_bits.cu).  While a model only steps, the
+ * uint8 layer is held as one bit per cell: word w of row i = cells (i, 32w .. 32w+31), bit k = column 32w+k
+ * (cols % 32 == 0).  mb_gol_pack_u8 / mb_gol_unpack_u8 convert a 0/1 uint8 layer to / from that form (what a
+ * read of the property layer costs).  mb_gol_step_bits advances `generations` (1..8) synchronous generations in
+ * ONE launch by chaining them through registers; halo_top / halo_bot are [generations, cols/32] packed rows
+ * above row 0 (last one adjacent) / below row rows-1 (first one adjacent), NULL = dead boundary: a single-GPU
+ * torus passes in + (rows-generations)*cols/32 and in (needs rows >= generations), a row-sharded grid the
+ * neighbours' edge rows.  rows_per_segment <= 0 picks the default tiling. */
+int mb_gol_pack_u8(const uint8_t* state, uint32_t* bits, int64_t rows, int64_t cols, mb_stream_t stream);
+int mb_gol_unpack_u8(const uint32_t* bits, uint8_t* state, int64_t rows, int64_t cols, mb_stream_t stream);
+int mb_gol_step_bits(const uint32_t* in, const uint32_t* halo_top, const uint32_t* halo_bot, uint32_t* out,
+                     int64_t rows, int64_t cols, int col_torus, int generations, int rows_per_segment,
+                     mb_stream_t stream);
+
 /* ---- Schelling happiness (replaces AgentSet.do("assign_state") over
  * examples/basic/schelling/agents.py:24-42; neighbourhood = cell.py:225-276, Moore radius r) ----
  * type: int8 layer, -1 = empty cell, >= 0 = agent type (capacity-1 grid).  happy: uint8 layer out

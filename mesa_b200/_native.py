@@ -51,6 +51,9 @@ SIGNATURES: dict[str, tuple] = {
     # Game of Life
     "mb_gol_step_u8": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, _S]),
     "mb_gol_step_u8_fused": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, _P, _P, _P, _P, _P, _P, c_uint32, _S]),
+    "mb_gol_pack_u8": (c_int, [_P, _P, c_int64, c_int64, _S]),
+    "mb_gol_unpack_u8": (c_int, [_P, _P, c_int64, c_int64, _S]),
+    "mb_gol_step_bits": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _S]),
     # Schelling
     "mb_schelling_happy_i8": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_int, _P, c_int, _P, _S]),
     "mb_schelling_relocate": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_uint64, c_uint32, _P, ctypes.c_size_t,

@@ -201,40 +201,49 @@ boids_update(const float4* __restrict__ packed, const uint32_t* __restrict__ ord
 
 // Shared-memory tiled path: one CTA owns a tile of kTX x kTY cells.  The boids of the tile and of the
 // one-cell ring around it ((kTX+2) x (kTY+2) cells) are staged once in shared memory; every owned boid then
-// scans three contiguous shared-memory runs (the 3 cells of each of the 3 rows around it) in two phases:
-//   phase A  a float32 REJECT filter: d2 computed in fp32 (9 cheap instructions); a pair is dropped only if
-//            d2_f32 > vision^2 * (1 + margin), margin = a host-computed bound on the fp32 rounding error, so
-//            no pair the reference would accept is ever dropped; survivors (~36 %) go to a per-thread list
-//            in shared memory;
-//   phase B  the exact fp64 predicate + accumulation of the reference on the survivors only.
-// Without the compaction the fp64 path would be issued for every pair (SIMT: one passing lane is enough);
-// ncu on the first tiled version: 312 M warp-instructions per 2 M boids, issue slots 67 % busy, 15.9 of 32
-// lanes active -- instruction bound.  Tiles whose ring holds more than kTileCap boids (very dense regions)
-// report themselves and are redone by the generic kernel.
+// scans three contiguous shared-memory runs (the 3 cells of each of the 3 rows around it).
+//
+// Arithmetic: the reference works in float64 on positions that are float32-representable here, and its result is
+// rounded to float32 at the end of the step.  What has to be EXACT is the membership of the neighbour set
+// (`dist <= vision`, inclusive) and of the separation set (`dist < separation`); the sums only have to be good
+// to float32.  So a pair is classified in float32 first -- d2 from the float32 differences carries a relative
+// error below 3e-7 -- and
+//   d2 <  vision^2 (1 - 1e-6)  surely a neighbour: its difference vector IS the float32 (dx, dy) (the unwrapped
+//                              image is the nearest one: a tiled space is at least 10 cells wide), accumulated
+//                              in float32 (5 adds);
+//   d2 >  vision^2 (1 + 1e-6)  surely not (unless the pair may straddle the torus seam);
+//   else                       the reference's float64 predicate and difference vector (boid_pair), ~1 pair in 1e5.
+// Pairs that may be neighbours across the torus seam (|dx| > size - vision, only in tiles whose ring wraps) also
+// take the float64 path: float32 cannot subtract the space size accurately.  The same three-way test is used for
+// `dist < separation`.  The float64 accumulators of the rare path and the float32 ones are added in boid_finish,
+// which is float64 throughout (normalisation, move, wrap) like the reference.
+// History (10^7 boids, B200): thread per boid through L1 2.50 ms -> threshold on d2 instead of sqrt 2.07 ms ->
+// shared-memory tiles 1.8 ms -> float32 reject filter + float64 survivor lists 1.73 ms -> this kernel.
+// Tiles whose ring holds more than kTileCap boids (very dense regions) report themselves and are redone by the
+// generic kernel.
 constexpr int kTX = 8, kTY = 8;
 constexpr int kHX = kTX + 2, kHY = kTY + 2;
 constexpr int kTileCap = 1536;
 constexpr int kTileThreads = 256;
-constexpr int kListCap = 64;  // survivors kept per boid; further ones are evaluated on the spot
 
 struct TileSmem {
     float4 cand[kTileCap];
     uint32_t gidx[kTileCap];                  // cell-sorted index of each staged boid
-    uint16_t list[kListCap][kTileThreads];    // per-thread survivor lists, slot-major (conflict free)
     uint32_t cell_off[kHX * kHY + 1];         // start of each ring cell in cand[]
     uint32_t cell_src[kHX * kHY];             // start of each ring cell in the global sorted array
     uint32_t own_off[kTY + 1];
 };
 
-__device__ __forceinline__ void boid_pair_exact(const Geometry& g, const BoidParams& bp, double px, double py,
-                                                const float4& o, BoidAcc& acc) {
-    boid_pair(g, bp, px, py, o, acc);
-}
+struct FastParams {
+    float vis_lo2, vis_hi2;   // float32 band around vision2_le
+    float sep_lo2, sep_hi2;   // float32 band around separation2_lt
+    float seam_x, seam_y;     // |dx| above this may be a neighbour across the torus seam
+};
 
 __global__ void __launch_bounds__(kTileThreads)
 boids_update_tiled(const float4* __restrict__ packed, const uint32_t* __restrict__ order,
                    const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end, Geometry g,
-                   BoidParams bp, float reject2, int tiles_x, float2* __restrict__ pos_out,
+                   BoidParams bp, FastParams fp, int tiles_x, float2* __restrict__ pos_out,
                    float2* __restrict__ dir_out, uint32_t* __restrict__ nbr_count,
                    uint32_t* __restrict__ overflow_tiles, uint32_t* __restrict__ overflow_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -314,7 +323,8 @@ boids_update_tiled(const float4* __restrict__ packed, const uint32_t* __restrict
     }
     __syncthreads();
     const unsigned owned = sm.own_off[kTY];
-    const float fsx = (float)g.sx, fsy = (float)g.sy;
+    // only tiles whose ring wraps around the space can hold pairs that are neighbours across the seam
+    const bool seam_tile = g.torus && (cx0 == 0 || cy0 == 0 || cx0 + kTX >= g.ncx || cy0 + kTY >= g.ncy);
     for (unsigned t = tid; t < owned; t += kTileThreads) {
         int iy = 1;
 #pragma unroll
@@ -325,26 +335,37 @@ boids_update_tiled(const float4* __restrict__ packed, const uint32_t* __restrict
         const int cx = cell_coord(px, g.x0, g.sx, g.ncx);
         if (cx < cx0 || cx >= cx0 + kTX) continue;  // wrapped duplicate of a partial edge tile: owned elsewhere
         const int ix = cx - cx0 + 1;                // ring column of my cell
-        BoidAcc acc;
-        // phase A: fp32 reject filter over the 3 runs
-        unsigned nlist = 0;
+        BoidAcc acc;                                // float64: the rare exact path
+        float cohx = 0.f, cohy = 0.f, sepx = 0.f, sepy = 0.f, mx = 0.f, my = 0.f;
+        unsigned k = 0;
 #pragma unroll
         for (int r = iy - 1; r <= iy + 1; ++r) {
             const unsigned e = sm.cell_off[r * kHX + ix + 2];
             for (unsigned q = sm.cell_off[r * kHX + ix - 1]; q < e; ++q) {
                 const float4 o = sm.cand[q];
-                float dx = fabsf(me.x - o.x), dy = fabsf(me.y - o.y);
-                if (g.torus) {
-                    dx = fminf(dx, fsx - dx);
-                    dy = fminf(dy, fsy - dy);
+                const float dx = o.x - me.x, dy = o.y - me.y;
+                const float d2 = fmaf(dx, dx, dy * dy);
+                if (d2 < fp.vis_lo2) {
+                    if (q == p) continue;  // get_neighbors_in_radius drops self
+                    cohx += dx; cohy += dy;
+                    mx += o.z; my += o.w;
+                    ++k;
+                    if (d2 < fp.sep_hi2) {
+                        if (d2 < fp.sep_lo2) {
+                            sepx += dx; sepy += dy;
+                        } else if (ref_distance2(g, px, py, (double)o.x, (double)o.y) < bp.separation2_lt) {
+                            sepx += dx; sepy += dy;
+                        }
+                    }
+                } else if (d2 <= fp.vis_hi2 || (seam_tile && (fabsf(dx) > fp.seam_x || fabsf(dy) > fp.seam_y))) {
+                    boid_pair(g, bp, px, py, o, acc);  // borderline or across the seam: the reference's float64 test
                 }
-                if (fmaf(dx, dx, dy * dy) > reject2 || q == p) continue;  // surely outside (or self)
-                if (nlist < (unsigned)kListCap) sm.list[nlist++][tid] = (uint16_t)q;
-                else boid_pair_exact(g, bp, px, py, o, acc);
             }
         }
-        // phase B: the reference's exact fp64 predicate and sums on the survivors
-        for (unsigned s = 0; s < nlist; ++s) boid_pair_exact(g, bp, px, py, sm.cand[sm.list[s][tid]], acc);
+        acc.cohx += (double)cohx; acc.cohy += (double)cohy;
+        acc.sepx += (double)sepx; acc.sepy += (double)sepy;
+        acc.mx += (double)mx; acc.my += (double)my;
+        acc.k += k;
         boid_finish(g, bp, me, acc, order[sm.gidx[p]], pos_out, dir_out, nbr_count);
     }
 }
@@ -551,11 +572,6 @@ MB_API int mb_boids_step_f32(const float* pos_in, const float* dir_in, float* po
         if ((int64_t)tiles_x * tiles_y <= n) {
             rc = mb::check_cuda(cudaMemsetAsync(ovf_count, 0, 4, stream), "memset");
             if (rc) return rc;
-            // fp32 reject threshold: vision^2 inflated by a bound on the fp32 error of d2 (positions up to the
-            // space size carry an absolute error of ~ulp(size); see the kernel comment).  A margin above 50 %
-            // means float32 cannot resolve the radius in this space: use the generic kernel.
-            const double smax = g.sx > g.sy ? g.sx : g.sy;
-            const double margin = 64.0 * 1.1920929e-7 * (smax / vision) + 1e-5;
             static bool attr_set = false;
             if (!attr_set) {
                 rc = mb::check_cuda(cudaFuncSetAttribute(boids_update_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -563,16 +579,20 @@ MB_API int mb_boids_step_f32(const float* pos_in, const float* dir_in, float* po
                 if (rc) return rc;
                 attr_set = true;
             }
-            if (margin < 0.5) {
-                const float reject2 = (float)(vision * vision * (1.0 + margin));
-                boids_update_tiled<<<(unsigned)(tiles_x * tiles_y), kTileThreads, sizeof(TileSmem), stream>>>(
-                    ws.packed, order, ws.cell_start, ws.cell_end, g, bp, reject2, tiles_x, (float2*)pos_out,
-                    (float2*)dir_out, neighbor_count, ovf_tiles, ovf_count);
-            } else {
-                boids_update<<<(unsigned)mb::ceil_div(n, 128), 128, 0, stream>>>(ws.packed, order, ws.cell_start, ws.cell_end, n,
-                                                                             g, bp, (float2*)pos_out, (float2*)dir_out,
-                                                                             neighbor_count);
-            }
+            // float32 classification bands (see the kernel comment); d2 in float32 is within 3e-7 relative of the
+            // reference's float64 value, the bands are +-1e-6.  Seam: a pair whose |dx| exceeds size - vision(1+)
+            // may be a neighbour through the torus wrap.
+            const double band = 1e-6;
+            FastParams fp;
+            fp.vis_lo2 = (float)(bp.vision2_le * (1.0 - band));
+            fp.vis_hi2 = (float)(bp.vision2_le * (1.0 + band));
+            fp.sep_lo2 = (float)(bp.separation2_lt * (1.0 - band));
+            fp.sep_hi2 = (float)(bp.separation2_lt * (1.0 + band));
+            fp.seam_x = (float)((g.sx - vision * 1.001) * (1.0 - band));
+            fp.seam_y = (float)((g.sy - vision * 1.001) * (1.0 - band));
+            boids_update_tiled<<<(unsigned)(tiles_x * tiles_y), kTileThreads, sizeof(TileSmem), stream>>>(
+                ws.packed, order, ws.cell_start, ws.cell_end, g, bp, fp, tiles_x, (float2*)pos_out,
+                (float2*)dir_out, neighbor_count, ovf_tiles, ovf_count);
             boids_update_overflow<<<mb::sm_count(), 128, 0, stream>>>(ws.packed, order, ws.cell_start, ws.cell_end, g, bp,
                                                                     tiles_x, ovf_tiles, ovf_count, (float2*)pos_out,
                                                                     (float2*)dir_out, neighbor_count);

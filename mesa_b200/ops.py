@@ -49,6 +49,102 @@ def gol_step(state: torch.Tensor, out: torch.Tensor | None = None, torus: bool =
     return out
 
 
+GOL_BITS_MAX_GENERATIONS = 8
+
+
+def gol_pack(state: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """uint8 0/1 [rows, cols] layer -> int32 [rows, cols/32] bit planes (bit k of word w = column 32w+k)."""
+    _need_cuda(state, out)
+    if state.dtype != torch.uint8 or state.dim() != 2:
+        raise ValueError("gol_pack expects a uint8 [rows, cols] tensor")
+    rows, cols = state.shape
+    if cols % 32:
+        raise ValueError("the bit-packed layer needs cols to be a multiple of 32")
+    if out is None:
+        out = torch.empty((rows, cols // 32), dtype=torch.int32, device=state.device)
+    with torch.cuda.device(state.device):
+        N.check(N.lib().mb_gol_pack_u8(N.ptr(_c(state)), N.ptr(_c(out)), rows, cols, N.stream_ptr(state.device)))
+    return out
+
+
+def gol_unpack(bits: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """int32 [rows, cols/32] bit planes -> uint8 0/1 [rows, cols] layer."""
+    _need_cuda(bits, out)
+    if bits.dtype != torch.int32 or bits.dim() != 2:
+        raise ValueError("gol_unpack expects an int32 [rows, cols/32] tensor")
+    rows, wpr = bits.shape
+    if out is None:
+        out = torch.empty((rows, wpr * 32), dtype=torch.uint8, device=bits.device)
+    if out.dtype != torch.uint8 or tuple(out.shape) != (rows, wpr * 32):
+        raise ValueError("gol_unpack: out must be uint8 [rows, 32 * words]")
+    with torch.cuda.device(bits.device):
+        N.check(N.lib().mb_gol_unpack_u8(N.ptr(_c(bits)), N.ptr(_c(out)), rows, wpr * 32, N.stream_ptr(bits.device)))
+    return out
+
+
+def gol_step_bits(bits: torch.Tensor, out: torch.Tensor, generations: int = 1, torus: bool = True,
+                  halo_top: torch.Tensor | None = None, halo_bot: torch.Tensor | None = None,
+                  col_torus: bool | None = None, rows_per_segment: int = 0) -> torch.Tensor:
+    """`generations` (1..8) Game of Life generations of a bit-packed layer in ONE launch (csrc/gol_bits.cu).
+
+    `halo_top/halo_bot` are [generations, words] packed rows of the neighbouring row blocks; a single-GPU torus
+    takes them from the opposite edge of `bits` itself."""
+    _need_cuda(bits, out, halo_top, halo_bot)
+    if bits.dtype != torch.int32 or bits.dim() != 2 or out.dtype != torch.int32 or out.shape != bits.shape:
+        raise ValueError("gol_step_bits expects int32 [rows, cols/32] tensors")
+    rows, wpr = bits.shape
+    generations = int(generations)
+    if col_torus is None:
+        col_torus = torus
+    if halo_top is None and halo_bot is None and torus and rows > 0:
+        if rows < 3 or rows < generations:
+            raise ValueError("torus needs rows >= max(3, generations)")
+        halo_top, halo_bot = bits[rows - generations:], bits[:generations]
+    for h in (halo_top, halo_bot):
+        if h is not None and (h.dtype != torch.int32 or tuple(h.shape) != (generations, wpr)):
+            raise ValueError("halo rows must be int32 [generations, cols/32]")
+    with torch.cuda.device(bits.device):
+        N.check(N.lib().mb_gol_step_bits(N.ptr(_c(bits)), N.ptr(halo_top), N.ptr(halo_bot), N.ptr(_c(out)), rows,
+                                         wpr * 32, int(bool(col_torus)), generations, int(rows_per_segment),
+                                         N.stream_ptr(bits.device)))
+    return out
+
+
+class BitLife:
+    """Game of Life state held bit-packed on one GPU (two ping-pong planes), stepped several generations per
+    launch.  `load` / `store` convert from / to the uint8 property layer."""
+
+    def __init__(self, rows: int, cols: int, device, torus: bool = True, generations_per_launch: int = 4,
+                 rows_per_segment: int = 0):
+        if cols % 32:
+            raise ValueError("the bit-packed layer needs cols to be a multiple of 32")
+        if torus and (rows < 3 or cols < 3):
+            raise ValueError("torus needs rows, cols >= 3")
+        self.rows, self.cols, self.torus = int(rows), int(cols), bool(torus)
+        self.device = torch.device(device)
+        self.rows_per_segment = int(rows_per_segment)
+        t = max(1, min(int(generations_per_launch), GOL_BITS_MAX_GENERATIONS))
+        self.generations_per_launch = min(t, self.rows) if torus else t
+        self.cur = torch.zeros((self.rows, self.cols // 32), dtype=torch.int32, device=self.device)
+        self.nxt = torch.empty_like(self.cur)
+        self.launches = 0
+
+    def load(self, state: torch.Tensor) -> None:
+        gol_pack(state, out=self.cur)
+
+    def store(self, out: torch.Tensor | None = None) -> torch.Tensor:
+        return gol_unpack(self.cur, out=out)
+
+    def run(self, generations: int) -> None:
+        left = int(generations)
+        while left > 0:
+            t = min(left, self.generations_per_launch)
+            gol_step_bits(self.cur, self.nxt, t, torus=self.torus, rows_per_segment=self.rows_per_segment)
+            self.cur, self.nxt = self.nxt, self.cur
+            self.launches += 1
+            left -= t
+
+
 def happy_threshold_table(homophily: float, radius: int):
     """min_similar[valid] evaluated with Python floats exactly like agents.py:31-39:
     `frac = similar / valid if valid > 0 else 0.0; happy = not (frac < homophily)`."""

@@ -227,3 +227,48 @@ class FusedPeerGol:
         """Raise if a wait timed out (a neighbour never published its edge rows)."""
         if int(self.local[2].item()) != 0:
             raise RuntimeError("FusedPeerGol: timed out waiting for a neighbouring rank")
+
+
+class PeerBitLife:
+    """Row-sharded Game of Life on the BIT-PACKED layer (csrc/gol_bits.cu): each rank keeps its row block as two
+    ping-pong bit planes in symmetric memory; one launch advances `generations_per_launch` generations and reads
+    that many edge rows of each neighbour in place over NVLink, then one device-side barrier orders the ping-pong
+    buffers -- one barrier per T generations instead of one exchange per generation."""
+
+    def __init__(self, rows: int, cols: int, torus: bool, device, generations_per_launch: int = 4,
+                 rows_per_segment: int = 0, group=None):
+        from . import ops
+
+        if cols % 32:
+            raise ValueError("the bit-packed layer needs cols to be a multiple of 32")
+        self._ops = ops
+        self.rows, self.cols, self.torus = int(rows), int(cols), bool(torus)
+        self.generations_per_launch = max(1, min(int(generations_per_launch), ops.GOL_BITS_MAX_GENERATIONS))
+        self.rows_per_segment = int(rows_per_segment)
+        self.layer = PeerHaloLayer(self.rows, self.cols // 32, torch.int32, self.generations_per_launch, torus,
+                                   device, group)
+        self.device = torch.device(device)
+        self.launches = 0
+
+    def load(self, block: torch.Tensor) -> None:
+        """Set the current generation from this rank's uint8 row block (collective)."""
+        self._ops.gol_pack(block, out=self.layer.state)
+        self.layer.hdl.barrier()
+
+    def store(self, out: torch.Tensor | None = None) -> torch.Tensor:
+        return self._ops.gol_unpack(self.layer.state, out=out)
+
+    def run(self, generations: int) -> None:
+        left = int(generations)
+        while left > 0:
+            t = min(left, self.generations_per_launch)
+
+            def kernel(src, dst, top, bot, t=t):
+                self._ops.gol_step_bits(src, dst, t, torus=False, col_torus=self.torus,
+                                        halo_top=None if top is None else top[top.shape[0] - t:],
+                                        halo_bot=None if bot is None else bot[:t],
+                                        rows_per_segment=self.rows_per_segment)
+
+            self.layer.step(kernel)
+            self.launches += 1
+            left -= t

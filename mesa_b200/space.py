@@ -49,6 +49,31 @@ def _torch_dtype(dtype):
     return _TORCH_DTYPES[np.dtype(dtype).type]
 
 
+class _LayerDict(dict):
+    """`Grid.property_layers` (grid.py:112): a plain dict of [d0, d1] tensors, plus optional per-layer access hooks
+    so that a model may keep a layer in another device format between reads (e.g. the bit-packed Game of Life
+    state) and bring the tensor up to date only when somebody asks for it."""
+
+    def __init__(self):
+        super().__init__()
+        self.hooks: dict = {}
+
+    def __getitem__(self, name):
+        hook = self.hooks.get(name)
+        if hook is not None:
+            hook()
+        return super().__getitem__(name)
+
+    def get(self, name, default=None):
+        return self[name] if name in self else default
+
+    def values(self):
+        return [self[k] for k in self]
+
+    def items(self):
+        return [(k, self[k]) for k in self]
+
+
 class CellProxy:
     """A cell of a DeviceGrid: coordinate + accessors that read the device layers (debug speed)."""
 
@@ -124,7 +149,7 @@ class DeviceGrid:
             raise NotImplementedError("mesa_b200 device grids are two-dimensional")
         self.random = random if random is not None else Random()
         self.device = torch.device(device)
-        self.property_layers: dict[str, torch.Tensor] = {}
+        self.property_layers: dict[str, torch.Tensor] = _LayerDict()
         self._read_only_layers: set[str] = set()
         self.create_property_layer("empty", default_value=True, dtype=bool)
 
