@@ -163,6 +163,20 @@ int mb_sort_pairs_u64(uint64_t* keys0, uint32_t* vals0, uint64_t* keys1, uint32_
                       int begin_bit, int end_bit, void* workspace, size_t workspace_bytes, int* result_buffer,
                       mb_stream_t stream);
 
+/* Boids in the reference's SEQUENTIAL activation order (AgentSet.shuffle_do("step"), agentset.py:772-787, over
+ * boid_flockers/agents.py:63-92): boid a sees the new position / direction of every boid activated before it and the
+ * old state of the others.  Order = ascending Philox priority64(seed, epoch, agent) (the order oracle/replay.py feeds to
+ * the unmodified reference).  Computed in dependency passes (csrc/continuous.cu, boids_seq_pass): identical to the
+ * sequential loop, float64 inside the step, float32 state at the step boundary like mb_boids_step_f32.  `reach` bounds
+ * the distance a boid moves in one step (speed * max(1, max |direction|)); a longer move returns MB_ERR_INVALID.
+ * Synchronises `stream`; *out_passes receives the number of dependency passes. */
+int mb_boids_seq_workspace_bytes(int64_t n, double size_x, double size_y, double vision, double reach, size_t* out);
+int mb_boids_step_seq_f32(const float* pos_in, const float* dir_in, float* pos_out, float* dir_out, int64_t n,
+                          double x0, double y0, double size_x, double size_y, int torus, double vision,
+                          double separation, double cohere, double separate, double match, double speed,
+                          double reach, uint64_t seed, uint32_t epoch, uint32_t* neighbor_count, void* workspace,
+                          size_t workspace_bytes, int* out_passes, mb_stream_t stream);
+
 /* ---- continuous space (replaces experimental/continuous_space/continuous_space.py:169-298 and
  * examples/basic/boid_flockers/agents.py:63-92 for all agents at once) -------------------------
  * Positions / directions are float32 [n, 2] in storage-index order (ContinuousSpace._agent_positions

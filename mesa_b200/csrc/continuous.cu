@@ -26,6 +26,7 @@
 // AgentSet.shuffle_do is sequential; DESIGN.md discusses the mode and how parity is checked
 // (reference Boid.step driven on frozen snapshots).
 #include "common.cuh"
+#include "philox.cuh"
 #include "sort.cuh"
 
 #include <math.h>
@@ -133,23 +134,29 @@ struct BoidAcc {
     unsigned k = 0;
 };
 
-__device__ __forceinline__ void boid_pair(const Geometry& g, const BoidParams& bp, double px, double py,
-                                          const float4& o, BoidAcc& acc) {
-    const double d2 = ref_distance2(g, px, py, (double)o.x, (double)o.y);
+// one candidate (position o, direction od; float64) against the boid at (px, py): agents.py:66-85
+__device__ __forceinline__ void boid_pair_d(const Geometry& g, const BoidParams& bp, double px, double py,
+                                            double ox, double oy, double odx, double ody, BoidAcc& acc) {
+    const double d2 = ref_distance2(g, px, py, ox, oy);
     if (d2 <= bp.vision2_le) {
-        const double ddx = ref_delta((double)o.x, px, g.sx, g.torus);
-        const double ddy = ref_delta((double)o.y, py, g.sy, g.torus);
+        const double ddx = ref_delta(ox, px, g.sx, g.torus);
+        const double ddy = ref_delta(oy, py, g.sy, g.torus);
         acc.cohx += ddx; acc.cohy += ddy;
         if (d2 < bp.separation2_lt) { acc.sepx += ddx; acc.sepy += ddy; }
-        acc.mx += (double)o.z; acc.my += (double)o.w;
+        acc.mx += odx; acc.my += ody;
         ++acc.k;
     }
 }
 
-// direction / position update of one boid from its accumulators, stored at agent index `a`
-__device__ __forceinline__ void boid_finish(const Geometry& g, const BoidParams& bp, const float4& me,
-                                            const BoidAcc& acc, uint32_t a, float2* __restrict__ pos_out,
-                                            float2* __restrict__ dir_out, uint32_t* __restrict__ nbr_count) {
+__device__ __forceinline__ void boid_pair(const Geometry& g, const BoidParams& bp, double px, double py,
+                                          const float4& o, BoidAcc& acc) {
+    boid_pair_d(g, bp, px, py, (double)o.x, (double)o.y, (double)o.z, (double)o.w, acc);
+}
+
+// direction / position update of one boid from its accumulators (agents.py:75-92 + the position setter):
+// returns (x, y, dx, dy) in float64
+__device__ __forceinline__ double4 boid_finish_d(const Geometry& g, const BoidParams& bp, const float4& me,
+                                                 const BoidAcc& acc) {
     double dirx = me.z, diry = me.w;
     double nx = me.x, ny = me.y;
     if (acc.k > 0) {
@@ -172,8 +179,16 @@ __device__ __forceinline__ void boid_finish(const Geometry& g, const BoidParams&
         nx = g.x0 + rx;
         ny = g.y0 + ry;
     }
-    pos_out[a] = make_float2((float)nx, (float)ny);
-    dir_out[a] = make_float2((float)dirx, (float)diry);
+    return make_double4(nx, ny, dirx, diry);
+}
+
+// same, stored as float32 at agent index `a`
+__device__ __forceinline__ void boid_finish(const Geometry& g, const BoidParams& bp, const float4& me,
+                                            const BoidAcc& acc, uint32_t a, float2* __restrict__ pos_out,
+                                            float2* __restrict__ dir_out, uint32_t* __restrict__ nbr_count) {
+    const double4 s = boid_finish_d(g, bp, me, acc);
+    pos_out[a] = make_float2((float)s.x, (float)s.y);
+    dir_out[a] = make_float2((float)s.z, (float)s.w);
     if (nbr_count != nullptr) nbr_count[a] = acc.k;
 }
 
@@ -401,6 +416,114 @@ boids_update_overflow(const float4* __restrict__ packed, const uint32_t* __restr
     }
 }
 
+// ---- sequential activation (the reference's shuffle_do semantics, exactly) -------------------------------------
+// AgentSet.shuffle_do("step") (agentset.py:772-787) activates the boids one after the other: boid a sees the NEW
+// position / direction of every boid that acted before it and the OLD state of the others.  With the activation
+// order given by the Philox priorities (csrc/philox.cuh) this is a dependency graph, not a chain: a only depends
+// on the earlier boids that can be within `vision` of it when it acts, i.e. whose OLD position is within
+// vision + reach (reach >= the longest move of a step).  The step is therefore computed in passes over the boids
+// that are still pending: a boid whose relevant earlier neighbours are all done computes its new state (float64,
+// kept in `newst` until the end of the step so that later boids read exactly what the reference would), publishes
+// it (st.release) and is done; the others go to the next pass.  The pending boid of lowest priority is always
+// ready, so every pass makes progress; on uniform random flocks the number of passes is ~ the longest chain of
+// decreasing priorities through overlapping neighbourhoods (a few tens), and the pending set shrinks geometrically.
+// The cell list is built on the OLD positions with edge >= vision + reach, so both the old and the new position
+// of every relevant boid are covered by the 3x3 cells around a.
+struct SeqParams {
+    float relevant2;   // float32 bound on d2(old, old) beyond which two boids cannot interact in this step
+    float far2;        // float32 bound on d2 beyond which an OLD-state candidate is surely not within vision
+    double reach2;     // (reach (1 + 1e-9))^2: a longer move is reported as an error
+    float fsx, fsy;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u8(const uint8_t* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u8(uint8_t* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void boids_seq_priorities(const uint32_t* __restrict__ order, int64_t n, uint64_t seed, uint32_t epoch,
+                                     uint64_t* __restrict__ prio) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) prio[i] = mb::priority64(seed, epoch, (uint64_t)order[i]);
+}
+
+template <bool kFirst>
+__global__ void __launch_bounds__(128)
+boids_seq_pass(const float4* __restrict__ packed, const uint64_t* __restrict__ prio, double2* newst, uint8_t* done,
+               const uint32_t* __restrict__ order, const uint32_t* __restrict__ cell_start,
+               const uint32_t* __restrict__ cell_end, int64_t n, Geometry g, BoidParams bp, SeqParams sp,
+               const uint32_t* __restrict__ pending_in, const uint32_t* __restrict__ count_in,
+               uint32_t* __restrict__ pending_out, uint32_t* __restrict__ count_out, float2* __restrict__ pos_out,
+               float2* __restrict__ dir_out, uint32_t* __restrict__ nbr_count, uint32_t* __restrict__ error) {
+    const int64_t total = kFirst ? n : (int64_t)*count_in;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    // whole warps iterate together (the pending append below is warp-aggregated)
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < total; base += stride) {
+        const int64_t idx = base + lane;
+        const bool active = idx < total;
+        uint32_t i = 0;
+        bool ready = true;
+        if (active) {
+            i = kFirst ? (uint32_t)idx : pending_in[idx];
+            const float4 me = packed[i];
+            const uint64_t pi = prio[i];
+            const double px = me.x, py = me.y;
+            const int cx = cell_coord(px, g.x0, g.sx, g.ncx), cy = cell_coord(py, g.y0, g.sy, g.ncy);
+            BoidAcc acc;
+            for_neighbor_cells(g, cx, cy, [&](unsigned c) {
+                if (!ready) return;
+                const uint32_t e = cell_end[c];
+                for (uint32_t j = cell_start[c]; j < e; ++j) {
+                    if (j == i) continue;
+                    const float4 o = packed[j];
+                    float dx = fabsf(me.x - o.x), dy = fabsf(me.y - o.y);
+                    if (g.torus) {
+                        dx = fminf(dx, sp.fsx - dx);
+                        dy = fminf(dy, sp.fsy - dy);
+                    }
+                    const float d2 = fmaf(dx, dx, dy * dy);
+                    if (d2 > sp.relevant2) continue;           // cannot be within vision before or after its move
+                    if (prio[j] < pi) {                        // acts before me: I see its NEW state
+                        if (ld_acquire_u8(done + j) == 0u) {   // not computed yet: try again in the next pass
+                            ready = false;
+                            return;
+                        }
+                        const double2 sp_ = __ldcg(newst + 2 * (size_t)j), sd_ = __ldcg(newst + 2 * (size_t)j + 1);
+                        boid_pair_d(g, bp, px, py, sp_.x, sp_.y, sd_.x, sd_.y, acc);
+                    } else if (d2 <= sp.far2) {                // acts after me: its OLD state
+                        boid_pair(g, bp, px, py, o, acc);
+                    }
+                }
+            });
+            if (ready) {
+                const double4 s = boid_finish_d(g, bp, me, acc);
+                // the move of this step (before the wrap) must not exceed `reach`, or a dependency was missed
+                const double mvx = (s.z * bp.speed), mvy = (s.w * bp.speed);
+                if (mvx * mvx + mvy * mvy > sp.reach2) atomicExch(error, 1u);
+                __stcg(newst + 2 * (size_t)i, make_double2(s.x, s.y));
+                __stcg(newst + 2 * (size_t)i + 1, make_double2(s.z, s.w));
+                st_release_u8(done + i, 1u);
+                const uint32_t a = order[i];
+                pos_out[a] = make_float2((float)s.x, (float)s.y);
+                dir_out[a] = make_float2((float)s.z, (float)s.w);
+                if (nbr_count != nullptr) nbr_count[a] = acc.k;
+            }
+        }
+        const unsigned waiting = __ballot_sync(0xffffffffu, active && !ready);
+        if (waiting) {
+            unsigned slot = 0;
+            if (lane == __ffs(waiting) - 1) slot = atomicAdd(count_out, (unsigned)__popc(waiting));
+            slot = __shfl_sync(0xffffffffu, slot, __ffs(waiting) - 1);
+            if (active && !ready) pending_out[slot + __popc(waiting & ((1u << lane) - 1u))] = i;
+        }
+    }
+}
+
 // ---- radius queries (get_agents_in_radius for a batch of points) ---------------------------
 // pass 0 (out_idx == nullptr): counts[q] = #{agents with dist <= radius} (minus `exclude[q]` if given)
 // pass 1: fills out_idx/out_dist at offsets[q] .. in ascending agent index (storage order)
@@ -603,6 +726,137 @@ MB_API int mb_boids_step_f32(const float* pos_in, const float* dir_in, float* po
     boids_update<<<(unsigned)mb::ceil_div(n, 128), 128, 0, stream>>>(ws.packed, order, ws.cell_start, ws.cell_end, n, g, bp,
                                                                      (float2*)pos_out, (float2*)dir_out, neighbor_count);
     MB_LAUNCH_CHECK("mb_boids_step_f32");
+    return MB_OK;
+}
+
+// ---- sequential Boids step (shuffle_do semantics, see boids_seq_pass) -----------------------------------------
+namespace {
+
+constexpr int kSeqMaxPasses = 4096;
+
+struct SeqWs {
+    CellListWs cl;
+    uint64_t* prio;
+    double2* newst;
+    uint8_t* done;
+    uint32_t *pend0, *pend1, *counts, *error;
+};
+
+size_t carve_seq(SeqWs* ws, char* base, int64_t n, int64_t ncells) {
+    size_t off = carve(ws ? &ws->cl : nullptr, base, n, ncells);
+    auto take = [&](size_t bytes) {
+        char* p = base ? base + off : nullptr;
+        off += (bytes + 255) & ~(size_t)255;
+        return p;
+    };
+    SeqWs t;
+    if (ws) t.cl = ws->cl;
+    t.prio = (uint64_t*)take(8 * n);
+    t.newst = (double2*)take(32 * n);
+    t.done = (uint8_t*)take(n);
+    t.pend0 = (uint32_t*)take(4 * n);
+    t.pend1 = (uint32_t*)take(4 * n);
+    t.counts = (uint32_t*)take(4 * (kSeqMaxPasses + 1));
+    t.error = (uint32_t*)take(4);
+    if (ws) *ws = t;
+    return off;
+}
+
+}  // namespace
+
+MB_API int mb_boids_seq_workspace_bytes(int64_t n, double size_x, double size_y, double vision, double reach,
+                                        size_t* out) {
+    MB_REQUIRE(out != nullptr && n >= 0 && reach >= 0.0, "mb_boids_seq_workspace_bytes: bad argument");
+    Geometry g;
+    int rc = make_geometry(&g, 0.0, 0.0, size_x, size_y, vision + reach, 1);
+    if (rc) return rc;
+    *out = carve_seq(nullptr, nullptr, n, (int64_t)g.ncx * g.ncy);
+    return MB_OK;
+}
+
+// One Boid step of all agents in the reference's SEQUENTIAL activation order (ascending Philox priority of
+// (seed, epoch, agent)): identical to model.agents.shuffle_do("step") driven with that order.  `reach` must bound the
+// distance any boid moves in one step (speed * max(1, max |direction|)); a longer move returns MB_ERR_INVALID.
+// Synchronises `stream` (the host reads the number of pending boids between batches of passes).
+MB_API int mb_boids_step_seq_f32(const float* pos_in, const float* dir_in, float* pos_out, float* dir_out, int64_t n,
+                                 double x0, double y0, double size_x, double size_y, int torus, double vision,
+                                 double separation, double cohere, double separate, double match, double speed,
+                                 double reach, uint64_t seed, uint32_t epoch, uint32_t* neighbor_count,
+                                 void* workspace, size_t workspace_bytes, int* out_passes, cudaStream_t stream) {
+    MB_REQUIRE(n >= 0 && n < (1ll << 31), "mb_boids_step_seq_f32: n out of range");
+    if (out_passes) *out_passes = 0;
+    if (n == 0) return MB_OK;
+    MB_REQUIRE(pos_in && dir_in && pos_out && dir_out && workspace, "mb_boids_step_seq_f32: null buffer");
+    MB_REQUIRE(pos_in != pos_out && dir_in != dir_out, "mb_boids_step_seq_f32: in/out must not alias");
+    MB_REQUIRE(reach >= 0.0, "mb_boids_step_seq_f32: reach must be >= 0");
+    Geometry g;
+    int rc = make_geometry(&g, x0, y0, size_x, size_y, vision + reach, torus);
+    if (rc) return rc;
+    SeqWs ws;
+    if (carve_seq(&ws, (char*)workspace, n, (int64_t)g.ncx * g.ncy) > workspace_bytes) {
+        mb::set_error("mb_boids_step_seq_f32: workspace too small");
+        return MB_ERR_WORKSPACE;
+    }
+    uint32_t* order = nullptr;
+    rc = build_cell_list((const float2*)pos_in, (const float2*)dir_in, n, g, ws.cl, &order, stream);
+    if (rc) return rc;
+    rc = mb::check_cuda(cudaMemsetAsync(ws.done, 0, n, stream), "memset");
+    if (rc) return rc;
+    rc = mb::check_cuda(cudaMemsetAsync(ws.counts, 0, 4 * (kSeqMaxPasses + 1), stream), "memset");
+    if (rc) return rc;
+    rc = mb::check_cuda(cudaMemsetAsync(ws.error, 0, 4, stream), "memset");
+    if (rc) return rc;
+    const BoidParams bp{sq_threshold_le(vision), sq_threshold_ge(separation), cohere, separate, match, speed};
+    // float32 pre-filters (conservative): d2 of the torus minimum image in float32 is off by at most ~ulp(size) per
+    // component, i.e. a relative error of about 64 eps size / radius on d2; beyond relevant2 two boids cannot see each
+    // other before or after a move of `reach`, beyond far2 an unmoved boid is surely outside `vision`
+    const double smax = size_x > size_y ? size_x : size_y;
+    const double margin = 64.0 * 1.1920929e-7 * (smax / vision) + 1e-5;
+    SeqParams sp;
+    const double rel = vision + reach;
+    sp.relevant2 = margin < 0.5 ? (float)(rel * rel * (1.0 + margin)) : INFINITY;
+    sp.far2 = margin < 0.5 ? (float)(vision * vision * (1.0 + margin)) : INFINITY;
+    sp.reach2 = reach * reach * (1.0 + 1e-9) * (1.0 + 1e-9);
+    sp.fsx = (float)size_x;
+    sp.fsy = (float)size_y;
+    const unsigned blocks = (unsigned)mb::ceil_div(n, 256);
+    boids_seq_priorities<<<blocks, 256, 0, stream>>>(order, n, seed, epoch, ws.prio);
+    boids_seq_pass<true><<<(unsigned)mb::ceil_div(n, 128), 128, 0, stream>>>(
+        ws.cl.packed, ws.prio, ws.newst, ws.done, order, ws.cl.cell_start, ws.cl.cell_end, n, g, bp, sp, nullptr, nullptr,
+        ws.pend0, ws.counts, (float2*)pos_out, (float2*)dir_out, neighbor_count, ws.error);
+    MB_LAUNCH_CHECK("mb_boids_step_seq_f32");
+    int pass = 1;  // passes launched so far; pass p reads counts[p-1] / pend[(p-1)&1] and writes counts[p] / pend[p&1]
+    uint32_t pending = (uint32_t)n;
+    const int grid_cap = mb::sm_count() * 16;
+    while (true) {
+        const int batch = pass == 1 ? 4 : 8;
+        for (int b = 0; b < batch && pass < kSeqMaxPasses; ++b, ++pass) {
+            uint32_t* pin = ((pass - 1) & 1) ? ws.pend1 : ws.pend0;
+            uint32_t* pout = (pass & 1) ? ws.pend1 : ws.pend0;
+            const int64_t want = mb::ceil_div((int64_t)pending, 128);
+            const unsigned grid = (unsigned)(want < 1 ? 1 : (want > grid_cap ? grid_cap : want));
+            boids_seq_pass<false><<<grid, 128, 0, stream>>>(
+                ws.cl.packed, ws.prio, ws.newst, ws.done, order, ws.cl.cell_start, ws.cl.cell_end, n, g, bp, sp, pin,
+                ws.counts + (pass - 1), pout, ws.counts + pass, (float2*)pos_out, (float2*)dir_out, neighbor_count,
+                ws.error);
+        }
+        MB_LAUNCH_CHECK("mb_boids_step_seq_f32");
+        uint32_t host[2] = {0u, 0u};
+        rc = mb::check_cuda(cudaMemcpyAsync(&host[0], ws.counts + (pass - 1), 4, cudaMemcpyDeviceToHost, stream), "read pending");
+        if (rc) return rc;
+        rc = mb::check_cuda(cudaMemcpyAsync(&host[1], ws.error, 4, cudaMemcpyDeviceToHost, stream), "read error");
+        if (rc) return rc;
+        rc = mb::check_cuda(cudaStreamSynchronize(stream), "mb_boids_step_seq_f32");
+        if (rc) return rc;
+        MB_REQUIRE(host[1] == 0u, "mb_boids_step_seq_f32: a boid moved farther than `reach` in one step");
+        pending = host[0];
+        if (pending == 0u) break;
+        if (pass >= kSeqMaxPasses) {
+            mb::set_error("mb_boids_step_seq_f32: dependency chains longer than %d passes", kSeqMaxPasses);
+            return MB_ERR_UNSUPPORTED;
+        }
+    }
+    if (out_passes) *out_passes = pass;
     return MB_OK;
 }
 

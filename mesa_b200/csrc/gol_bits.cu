@@ -25,7 +25,6 @@
 
 namespace {
 
-constexpr int kBitWarps = 4;          // warps per CTA (independent of each other)
 constexpr int kStripWords = 30;       // useful words per warp; lanes 0 / 31 are halo
 constexpr int kMaxGenerations = 8;    // generations per launch (template instances 1..8)
 
@@ -47,35 +46,44 @@ __device__ __forceinline__ uint32_t fetch_word(const BitRows& g, int j, int col,
     return __ldg(p + col);
 }
 
+// one 3-input logic op (LOP3.LUT); kLut = the function evaluated on a = 0xF0, b = 0xCC, c = 0xAA
+template <int kLut>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(kLut));
+    return d;
+}
+constexpr int kXor3 = 0x96, kMaj = 0xE8;
+
 // horizontal 3-sums of one packed row: bit k of (h0, h1) = cells k-1, k, k+1 summed (two bit planes)
 __device__ __forceinline__ void row_sums(uint32_t x, uint32_t& h0, uint32_t& h1) {
     const uint32_t lw = __shfl_up_sync(0xffffffffu, x, 1), rw = __shfl_down_sync(0xffffffffu, x, 1);
     const uint32_t l = __funnelshift_l(lw, x, 1);   // (x << 1) | (lw >> 31): the cell to the left of each cell
     const uint32_t r = __funnelshift_r(x, rw, 1);   // (x >> 1) | (rw << 31): the cell to the right
-    h0 = l ^ x ^ r;
-    h1 = (l & x) | (l & r) | (x & r);
+    h0 = lop3<kXor3>(l, x, r);
+    h1 = lop3<kMaj>(l, x, r);
 }
 
-// next state of the centre row from the (h0, h1) planes of the rows above / centre / below and the centre word
+// next state of the centre row from the (h0, h1) planes of the rows above / centre / below and the centre word:
+// total = t0 + 2 (k0 + u0 + 2 u1) counts the cell itself; alive' = total == 3 | (alive & total == 4).  8 LOP3.
 __device__ __forceinline__ uint32_t life_rule(uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1, uint32_t c0,
                                               uint32_t c1, uint32_t centre) {
-    const uint32_t t0 = a0 ^ b0 ^ c0;                          // total bit 0
-    const uint32_t k0 = (a0 & b0) | (a0 & c0) | (b0 & c0);     // carry into bit 1
-    const uint32_t u0 = a1 ^ b1 ^ c1;
-    const uint32_t u1 = (a1 & b1) | (a1 & c1) | (b1 & c1);
-    const uint32_t t1 = k0 ^ u0;                               // total bit 1
-    const uint32_t k1 = k0 & u0;
-    const uint32_t t2 = u1 ^ k1;                               // total bit 2
-    const uint32_t t3 = u1 & k1;                               // total bit 3 (totals 8, 9)
-    const uint32_t is3 = t0 & t1 & ~t2;
-    const uint32_t is4 = ~t0 & ~t1 & t2;
-    return ~t3 & (is3 | (centre & is4));
+    const uint32_t t0 = lop3<kXor3>(a0, b0, c0);   // total bit 0
+    const uint32_t k0 = lop3<kMaj>(a0, b0, c0);    // carry of the low planes   (weight 2)
+    const uint32_t u0 = lop3<kXor3>(a1, b1, c1);   // sum of the high planes    (weight 2)
+    const uint32_t u1 = lop3<kMaj>(a1, b1, c1);    // carry of the high planes  (weight 4)
+    const uint32_t is1 = lop3<0x14>(k0, u0, u1);   // k0 + u0 + 2 u1 == 1: (k0 ^ u0) & ~u1          -> total 2 or 3
+    const uint32_t is2 = lop3<0x42>(k0, u0, u1);   // == 2: (k0 & u0 & ~u1) | (~k0 & ~u0 & u1)      -> total 4 or 5
+    const uint32_t four = lop3<0x08>(t0, centre, is2);  // ~t0 & centre & is2: alive and total == 4
+    return lop3<0xEA>(t0, is1, four);                   // (t0 & is1) | four
 }
 
 // One input row (row j of generation 0) through all T stages: stage s turns row j-s of generation s into row
 // j-s-1 of generation s+1.  Slot kOlder of every stage holds the planes of row-2, the other slot those of row-1;
 // the caller alternates kOlder, so the window slides without register moves.  Returns row j-T of generation T.
-template <int T, bool kClamp, int kOlder>
+// kRowCheck: rows outside a clamped grid are forced dead at every stage (segments that touch the grid edge);
+// kColMask: lanes outside a clamped grid are forced dead (edge strips).
+template <int T, bool kRowCheck, bool kColMask, int kOlder>
 __device__ __forceinline__ uint32_t advance_row(uint32_t x, int j, uint32_t (&h0)[T][2], uint32_t (&h1)[T][2],
                                                 uint32_t (&cw)[T][2], int rows, bool top_dead, bool bot_dead,
                                                 uint32_t cmask) {
@@ -85,11 +93,11 @@ __device__ __forceinline__ uint32_t advance_row(uint32_t x, int j, uint32_t (&h0
         uint32_t c0, c1;
         row_sums(x, c0, c1);
         uint32_t y = life_rule(h0[s][kOlder], h1[s][kOlder], h0[s][kNewer], h1[s][kNewer], c0, c1, cw[s][kNewer]);
-        if (kClamp) {
-            const int jj = j - s - 1;  // row index of y; rows outside a clamped grid stay dead
-            const bool dead = (jj < 0 && top_dead) || (jj >= rows && bot_dead);
-            y = dead ? 0u : (y & cmask);
+        if (kRowCheck) {
+            const int jj = j - s - 1;  // row index of y
+            if ((jj < 0 && top_dead) || (jj >= rows && bot_dead)) y = 0u;
         }
+        if (kColMask) y &= cmask;
         h0[s][kOlder] = c0;  // the slot of row-2 is free now: it becomes the new row-1
         h1[s][kOlder] = c1;
         cw[s][kOlder] = x;
@@ -98,12 +106,77 @@ __device__ __forceinline__ uint32_t advance_row(uint32_t x, int j, uint32_t (&h0
     return x;
 }
 
+// The T-generation wavefront over the input rows jstart .. jstart+nsteps-1 of one strip (nsteps = segment rows
+// + 2T); the first 2T steps only fill the pipeline.  kFast: every row touched (including the two prefetched past
+// the end) lies inside the block, so rows are addressed by pointer increments; otherwise fetch_word resolves
+// halos / dead rows per row.
+template <int T, int kAhead, bool kFast, bool kRowCheck, bool kColMask>
+__device__ __forceinline__ void run_segment(const BitRows& g, uint32_t* __restrict__ op, int jstart, int nsteps,
+                                            int col, bool colvalid, bool stores, uint32_t cmask) {
+    const bool top_dead = g.halo_top == nullptr, bot_dead = g.halo_bot == nullptr;
+    uint32_t h0[T][2], h1[T][2], cw[T][2];
+#pragma unroll
+    for (int s = 0; s < T; ++s) {
+        h0[s][0] = h0[s][1] = h1[s][0] = h1[s][1] = cw[s][0] = cw[s][1] = 0u;
+    }
+    const size_t pitch = (size_t)g.wpr;
+    const uint32_t* ip = g.in + (ptrdiff_t)jstart * (ptrdiff_t)pitch + col;  // only dereferenced when kFast
+    auto fetch = [&](int j) -> uint32_t {
+        if (kFast) return (!kColMask || colvalid) ? __ldg(ip + (size_t)(j - jstart) * pitch) : 0u;
+        return fetch_word<T>(g, j, col, colvalid);
+    };
+    // rows are loaded kAhead iterations (2 rows each) before they are used
+    uint32_t n0 = fetch(jstart), n1 = fetch(jstart + 1), m0 = 0u, m1 = 0u;
+    if (kAhead == 2) {
+        m0 = fetch(jstart + 2);
+        m1 = fetch(jstart + 3);
+    }
+    int j = jstart;
+    auto next_rows = [&](uint32_t& x0, uint32_t& x1) {
+        x0 = n0;
+        x1 = n1;
+        if (kAhead == 2) {
+            n0 = m0;
+            n1 = m1;
+            m0 = fetch(j + 4);   // rows past the last needed one are never used for a stored word
+            m1 = fetch(j + 5);
+        } else {
+            n0 = fetch(j + 2);
+            n1 = fetch(j + 3);
+        }
+    };
+    // fill: 2T rows, nothing to store yet
+#pragma unroll 1
+    for (int s = 0; s < 2 * T; s += 2, j += 2) {
+        uint32_t x0, x1;
+        next_rows(x0, x1);
+        advance_row<T, kRowCheck, kColMask, 0>(x0, j, h0, h1, cw, g.rows, top_dead, bot_dead, cmask);
+        advance_row<T, kRowCheck, kColMask, 1>(x1, j + 1, h0, h1, cw, g.rows, top_dead, bot_dead, cmask);
+    }
+    // steady state: every input row completes one output row
+    const int jend = jstart + nsteps;
+#pragma unroll 1
+    for (; j + 1 < jend; j += 2) {
+        uint32_t x0, x1;
+        next_rows(x0, x1);
+        const uint32_t y0 = advance_row<T, kRowCheck, kColMask, 0>(x0, j, h0, h1, cw, g.rows, top_dead, bot_dead, cmask);
+        if (stores) op[0] = y0;
+        const uint32_t y1 = advance_row<T, kRowCheck, kColMask, 1>(x1, j + 1, h0, h1, cw, g.rows, top_dead, bot_dead, cmask);
+        if (stores) op[pitch] = y1;
+        op += 2 * pitch;
+    }
+    if (j < jend) {  // odd number of rows in the segment
+        const uint32_t y0 = advance_row<T, kRowCheck, kColMask, 0>(n0, j, h0, h1, cw, g.rows, top_dead, bot_dead, cmask);
+        if (stores) op[0] = y0;
+    }
+}
+
 // T generations of the rows [seg*rps, seg*rps + rps) of one 30-word strip.
-template <int T, bool kClamp>
-__global__ void __launch_bounds__(kBitWarps * 32)
+template <int T, int kWarps, int kAhead>
+__global__ void __launch_bounds__(kWarps * 32)
 gol_bits_kernel(const BitRows g, uint32_t* __restrict__ out, int col_torus, int nstrips, int rps) {
     const int lane = threadIdx.x & 31;
-    const unsigned task = blockIdx.x * kBitWarps + (threadIdx.x >> 5);
+    const unsigned task = blockIdx.x * kWarps + (threadIdx.x >> 5);
     const unsigned strip = task % (unsigned)nstrips, seg = task / (unsigned)nstrips;
     const int r0 = (int)seg * rps;
     if (r0 >= g.rows) return;  // whole warp
@@ -117,39 +190,22 @@ gol_bits_kernel(const BitRows g, uint32_t* __restrict__ out, int col_torus, int 
         if (col < 0) col += g.wpr;
         colvalid = true;
     }
+    if (!colvalid) col = 0;
     const bool stores = lane >= 1 && lane <= kStripWords && rawcol < g.wpr;
     const uint32_t cmask = colvalid ? 0xffffffffu : 0u;
-    const bool top_dead = g.halo_top == nullptr, bot_dead = g.halo_bot == nullptr;
+    const bool masked = __any_sync(0xffffffffu, !colvalid);  // an edge strip of a column-clamped grid
 
-    // per stage: planes of the two previous rows (slots alternate, so no register moves) + their centre words
-    uint32_t h0[T][2], h1[T][2], cw[T][2];
-#pragma unroll
-    for (int s = 0; s < T; ++s) {
-        h0[s][0] = h0[s][1] = h1[s][0] = h1[s][1] = cw[s][0] = cw[s][1] = 0u;
-    }
-
-    // one input row through all T stages (advance_row); slot kOlder of every stage holds row-2, the other row-1.
     const int jstart = r0 - T;
     const int nsteps = (r1 - r0) + 2 * T;  // input rows r0-T .. r1+T-1
     uint32_t* op = out + (size_t)r0 * g.wpr + (stores ? rawcol : 0);
-    uint32_t n0 = fetch_word<T>(g, jstart, col, colvalid), n1 = fetch_word<T>(g, jstart + 1, col, colvalid);
-    for (int s = 0; s < nsteps; s += 2) {
-        const uint32_t x0 = n0, x1 = n1;
-        const int j = jstart + s;
-        n0 = fetch_word<T>(g, j + 2, col, colvalid);   // rows past r1+T-1 are never used for a stored word
-        n1 = fetch_word<T>(g, j + 3, col, colvalid);
-        const uint32_t y0 = advance_row<T, kClamp, 0>(x0, j, h0, h1, cw, g.rows, top_dead, bot_dead, cmask);
-        if (s >= 2 * T) {
-            if (stores) *op = y0;
-            op += g.wpr;
-        }
-        if (s + 1 < nsteps) {
-            const uint32_t y1 = advance_row<T, kClamp, 1>(x1, j + 1, h0, h1, cw, g.rows, top_dead, bot_dead, cmask);
-            if (s + 1 >= 2 * T) {
-                if (stores) *op = y1;
-                op += g.wpr;
-            }
-        }
+    // interior segment: all rows it reads (and the two it prefetches past its end) are rows of this block; rows
+    // outside the grid then lie outside the cone of the rows it stores, so no row needs to be forced dead
+    const bool interior = jstart >= 0 && jstart + nsteps + 2 * kAhead + 1 <= g.rows;
+    if (interior) {
+        if (masked) run_segment<T, kAhead, true, false, true>(g, op, jstart, nsteps, col, colvalid, stores, cmask);
+        else run_segment<T, kAhead, true, false, false>(g, op, jstart, nsteps, col, colvalid, stores, cmask);
+    } else {
+        run_segment<T, kAhead, false, true, true>(g, op, jstart, nsteps, col, colvalid, stores, cmask);
     }
 }
 
@@ -179,12 +235,16 @@ __global__ void gol_unpack_kernel(const uint32_t* __restrict__ bits, uint8_t* __
     stg_na_v4(p + 1, b);
 }
 
-template <bool kClamp>
-int launch_bits(int T, const BitRows& g, uint32_t* out, int col_torus, int nstrips, int rps, unsigned blocks,
-                cudaStream_t stream) {
-#define MB_BITS_CASE(TT)                                                                                      \
-    case TT:                                                                                                  \
-        gol_bits_kernel<TT, kClamp><<<blocks, kBitWarps * 32, 0, stream>>>(g, out, col_torus, nstrips, rps); \
+// variant = 10 * rows-ahead-iterations + warps per CTA (developer sweep: MB_GOL_BITS_VARIANT)
+constexpr int kDefaultVariant = 14;
+
+template <int kWarps, int kAhead>
+int launch_bits_v(int T, const BitRows& g, uint32_t* out, int col_torus, int nstrips, int rps, int64_t tasks,
+                  cudaStream_t stream) {
+    const unsigned blocks = (unsigned)mb::ceil_div(tasks, kWarps);
+#define MB_BITS_CASE(TT)                                                                                            \
+    case TT:                                                                                                        \
+        gol_bits_kernel<TT, kWarps, kAhead><<<blocks, kWarps * 32, 0, stream>>>(g, out, col_torus, nstrips, rps); \
         break;
     switch (T) {
         MB_BITS_CASE(1) MB_BITS_CASE(2) MB_BITS_CASE(3) MB_BITS_CASE(4)
@@ -193,6 +253,18 @@ int launch_bits(int T, const BitRows& g, uint32_t* out, int col_torus, int nstri
     }
 #undef MB_BITS_CASE
     return MB_OK;
+}
+
+int launch_bits(int variant, int T, const BitRows& g, uint32_t* out, int col_torus, int nstrips, int rps,
+                int64_t tasks, cudaStream_t stream) {
+    switch (variant) {
+        case 12: return launch_bits_v<2, 1>(T, g, out, col_torus, nstrips, rps, tasks, stream);
+        case 18: return launch_bits_v<8, 1>(T, g, out, col_torus, nstrips, rps, tasks, stream);
+        case 22: return launch_bits_v<2, 2>(T, g, out, col_torus, nstrips, rps, tasks, stream);
+        case 24: return launch_bits_v<4, 2>(T, g, out, col_torus, nstrips, rps, tasks, stream);
+        case 28: return launch_bits_v<8, 2>(T, g, out, col_torus, nstrips, rps, tasks, stream);
+        default: return launch_bits_v<4, 1>(T, g, out, col_torus, nstrips, rps, tasks, stream);
+    }
 }
 
 }  // namespace
@@ -238,12 +310,10 @@ MB_API int mb_gol_step_bits(const uint32_t* in, const uint32_t* halo_top, const 
     rows_per_segment = (rows_per_segment + 1) & ~1;
     const int nstrips = (int)mb::ceil_div(wpr, kStripWords);
     const int64_t tasks = (int64_t)nstrips * mb::ceil_div(rows, rows_per_segment);
-    const unsigned blocks = (unsigned)mb::ceil_div(tasks, kBitWarps);
+    const char* env_variant = getenv("MB_GOL_BITS_VARIANT");  // read per call: the developer sweep changes it
+    const int variant = env_variant ? atoi(env_variant) : kDefaultVariant;
     const BitRows g{in, halo_top, halo_bot, (int)rows, wpr};
-    // rows / columns outside a clamped edge must stay dead through every fused generation
-    const bool clamp = !col_torus || halo_top == nullptr || halo_bot == nullptr;
-    const int rc = clamp ? launch_bits<true>(generations, g, out, col_torus, nstrips, rows_per_segment, blocks, stream)
-                         : launch_bits<false>(generations, g, out, col_torus, nstrips, rows_per_segment, blocks, stream);
+    const int rc = launch_bits(variant, generations, g, out, col_torus, nstrips, rows_per_segment, tasks, stream);
     if (rc != MB_OK) return rc;
     MB_LAUNCH_CHECK("mb_gol_step_bits");
     return MB_OK;

@@ -1,8 +1,10 @@
 """Boids flocking on the device (mirror of mesa/examples/basic/boid_flockers/model.py:22-120, agents.py:12-92).
 
-ACTIVATION MODE: the reference's `shuffle_do("step")` is sequential (each boid sees the boids moved
-before it); the device step is SYNCHRONOUS -- every boid reads the pre-step positions/directions --
-which is the reference's own `Boid.step` arithmetic applied to a frozen snapshot."""
+ACTIVATION MODE (`BoidFlockers(activation=...)`): the reference's `shuffle_do("step")` is sequential -- each boid
+sees the boids moved before it.  "sequential" reproduces exactly that in the Philox activation order
+(ops.boids_step_sequential: dependency passes, csrc/continuous.cu); "synchronous" (default, ~one pass) lets every boid
+read the pre-step positions / directions, i.e. the reference's own `Boid.step` arithmetic applied to a frozen
+snapshot."""
 from __future__ import annotations
 
 import numpy as np
@@ -38,10 +40,16 @@ def _step(agents: DeviceAgentSet, epoch: int | None = None, **_):
     m = agents.model
     s = m.scenario
     pos, dirs = m.space._agent_positions, m._direction
-    ops.boids_step(pos[: m.space._n_agents], dirs, m.space.size, vision=s.vision, separation=s.separation,
-                   cohere=s.cohere, separate=s.separate, match=s.match, speed=s.speed, torus=m.space.torus,
-                   origin=m.space.dimensions[:, 0], ws=m._ws, pos_out=m._pos_next, dir_out=m._dir_next,
-                   neighbor_count=m._nbr_count)
+    kw = dict(vision=s.vision, separation=s.separation, cohere=s.cohere, separate=s.separate, match=s.match,
+              speed=s.speed, torus=m.space.torus, origin=m.space.dimensions[:, 0], pos_out=m._pos_next,
+              dir_out=m._dir_next, neighbor_count=m._nbr_count)
+    if m.activation == "sequential":
+        if epoch is None:
+            epoch = m._next_epoch()
+        _, _, m.last_passes = ops.boids_step_sequential(pos[: m.space._n_agents], dirs, m.space.size, seed=m.philox_seed,
+                                                        epoch=epoch, reach=m._reach, ws=m._seq_ws, **kw)
+    else:
+        ops.boids_step(pos[: m.space._n_agents], dirs, m.space.size, ws=m._ws, **kw)
     # ping-pong: the new state becomes the space's positions / the agents' direction column
     m.space._agent_positions, m._pos_next = m._pos_next, m.space._agent_positions
     m._direction, m._dir_next = m._dir_next, m._direction
@@ -53,10 +61,14 @@ class BoidFlockers(DeviceModel):
     """Flocker model class. Handles agent creation, placement and scheduling."""
 
     def __init__(self, scenario: BoidsScenario = BoidsScenario, initial_positions=None, initial_directions=None,
-                 device="cuda"):
+                 device="cuda", activation: str = "synchronous"):
         if isinstance(scenario, type):
             scenario = scenario()
+        if activation not in ("synchronous", "sequential"):
+            raise ValueError("activation must be 'synchronous' or 'sequential'")
         super().__init__(scenario=scenario)
+        self.activation = activation
+        self.last_passes = 0
         n = scenario.population_size
         self.space = DeviceContinuousSpace([[0, scenario.width], [0, scenario.height]], torus=True,
                                            random=self.random, n_agents=n, device=device)
@@ -70,7 +82,13 @@ class BoidFlockers(DeviceModel):
         self._pos_next = torch.empty_like(self.space._agent_positions)
         self._dir_next = torch.empty_like(self._direction)
         self._nbr_count = torch.zeros(n, dtype=torch.int32, device=dev)
-        self._ws = ops.CellListWorkspace(n, self.space.size, scenario.vision, dev)
+        self._ws = self._seq_ws = None
+        if activation == "sequential":
+            # a boid never moves farther than this in one step (constant over the run, ops.boids_reach)
+            self._reach = ops.boids_reach(self._direction, scenario.speed)
+            self._seq_ws = ops.BoidsSeqWorkspace(n, self.space.size, scenario.vision, self._reach, dev)
+        else:
+            self._ws = ops.CellListWorkspace(n, self.space.size, scenario.vision, dev)
         self.agents = DeviceAgentSet(self, Boid, n, {"position": self.space._agent_positions,
                                                      "direction": self._direction}, self.random)
         self.agent_angles = torch.zeros(n, device=dev)

@@ -313,6 +313,60 @@ def boids_step(pos: torch.Tensor, direction: torch.Tensor, size, *, vision: floa
     return pos_out, dir_out
 
 
+class BoidsSeqWorkspace:
+    """Scratch of the sequential Boids step for up to `n` agents (cell list with edge >= vision + reach, priorities,
+    float64 intra-step state, done flags, pending lists)."""
+
+    def __init__(self, n: int, size, vision: float, reach: float, device):
+        import ctypes
+
+        nbytes = ctypes.c_size_t(0)
+        N.check(N.lib().mb_boids_seq_workspace_bytes(int(n), float(size[0]), float(size[1]), float(vision),
+                                                     float(reach), ctypes.byref(nbytes)))
+        self.n, self.vision, self.reach, self.nbytes = int(n), float(vision), float(reach), int(nbytes.value)
+        self.buf = torch.empty(max(self.nbytes, 1), dtype=torch.uint8, device=device)
+
+
+def boids_reach(direction: torch.Tensor, speed: float) -> float:
+    """Upper bound on the distance a boid moves in one step: a boid with neighbours moves `speed` along a unit
+    vector (agents.py:87-92), a lonely one `speed * |direction|` with its direction unchanged -- so the bound computed
+    once from the initial directions holds for the whole run."""
+    norm = float(torch.linalg.vector_norm(direction.to(torch.float64), dim=1).max().item()) if direction.numel() else 1.0
+    return float(speed) * max(1.0, norm) * (1.0 + 1e-12)
+
+
+def boids_step_sequential(pos: torch.Tensor, direction: torch.Tensor, size, *, seed: int, epoch: int, vision: float,
+                          separation: float, cohere: float = 0.03, separate: float = 0.015, match: float = 0.05,
+                          speed: float = 1.0, torus: bool = True, origin=(0.0, 0.0), reach: float | None = None,
+                          ws: BoidsSeqWorkspace | None = None, pos_out: torch.Tensor | None = None,
+                          dir_out: torch.Tensor | None = None, neighbor_count: torch.Tensor | None = None):
+    """One Boid step of all agents in the reference's sequential shuffle_do order (ascending Philox priority of
+    (seed, epoch, agent)).  Returns (pos_out, dir_out, passes)."""
+    import ctypes
+
+    _need_cuda(pos, direction, pos_out, dir_out, neighbor_count)
+    if pos.dtype != torch.float32 or direction.dtype != torch.float32 or pos.shape != direction.shape or pos.dim() != 2 or pos.shape[1] != 2:
+        raise ValueError("boids_step_sequential expects float32 [n, 2] positions and directions")
+    n = pos.shape[0]
+    if reach is None:
+        reach = boids_reach(direction, speed)
+    if ws is None:
+        ws = BoidsSeqWorkspace(n, size, vision, reach, pos.device)
+    if pos_out is None:
+        pos_out = torch.empty_like(pos)
+    if dir_out is None:
+        dir_out = torch.empty_like(direction)
+    passes = ctypes.c_int(0)
+    with torch.cuda.device(pos.device):
+        N.check(N.lib().mb_boids_step_seq_f32(
+            N.ptr(_c(pos)), N.ptr(_c(direction)), N.ptr(_c(pos_out)), N.ptr(_c(dir_out)), n, float(origin[0]),
+            float(origin[1]), float(size[0]), float(size[1]), int(bool(torus)), float(vision), float(separation),
+            float(cohere), float(separate), float(match), float(speed), float(reach), int(seed) & 0xFFFFFFFFFFFFFFFF,
+            int(epoch) & 0xFFFFFFFF, N.ptr(neighbor_count), N.ptr(ws.buf), ws.nbytes, ctypes.byref(passes),
+            N.stream_ptr(pos.device)))
+    return pos_out, dir_out, int(passes.value)
+
+
 def radius_query(pos: torch.Tensor, queries: torch.Tensor, size, radius: float, torus: bool = True,
                  origin=(0.0, 0.0), exclude: torch.Tensor | None = None, ws: CellListWorkspace | None = None):
     """Batched get_agents_in_radius: CSR (offsets[nq+1] int64, indices int32, distances float64)."""

@@ -86,3 +86,65 @@ def test_boids_and_radius_match_oracle(n, side, vision, torus):
         wi, wdist = oracle.radius_query(pos.astype(np.float64), p.astype(np.float64), size, vision, torus)
         assert np.array_equal(idx[off[i]:off[i + 1]], wi)
         assert np.array_equal(dist[off[i]:off[i + 1]], wdist)  # float64 distances are bit-exact
+
+
+# ---- sequential activation: the reference's shuffle_do semantics (csrc/continuous.cu, boids_seq_pass) ----------
+@pytest.mark.parametrize("name", BOIDS)
+def test_boids_sequential_matches_reference_model_step(name):
+    """One model.step() of the UNMODIFIED reference under the replayed activation order (golden seq_*_1)."""
+    from mesa_b200 import ops
+
+    g = np.load(os.path.join(GOLDEN, name))
+    n, seed, size = int(g["n"]), int(g["philox_seed"]), g["size"]
+    pos0, dir0 = g["seq_pos_0"], g["seq_dir_0"]
+    assert np.array_equal(pos0, pos0.astype(np.float32)) and np.array_equal(dir0, dir0.astype(np.float32))
+    po, do, passes = ops.boids_step_sequential(torch.from_numpy(pos0.astype(np.float32)).cuda(),
+                                               torch.from_numpy(dir0.astype(np.float32)).cuda(), size, seed=seed,
+                                               epoch=0, **_kw(g))
+    assert passes >= 1
+    assert np.max(np.abs(po.cpu().numpy().astype(np.float64) - g["seq_pos_1"]) / size) <= RTOL
+    assert np.max(np.abs(do.cpu().numpy().astype(np.float64) - g["seq_dir_1"])) <= RTOL
+
+
+@pytest.mark.parametrize("n,side,vision,torus,speed", [(2000, 200.0, 10.0, True, 1.0), (500, 25.0, 10.0, True, 1.0),
+                                                       (3000, 300.0, 7.5, False, 1.0), (64, 8.0, 5.0, True, 1.0),
+                                                       (1, 10.0, 3.0, True, 1.0), (4000, 260.0, 9.0, True, 2.5)])
+def test_boids_sequential_matches_oracle(n, side, vision, torus, speed):
+    """Several steps against the oracle's sequential mode (pinned to the reference in tests/test_oracle_golden.py)
+    in the same activation order; neighbour counts exact, state within the north-star tolerance."""
+    from mesa_b200 import ops
+
+    rng = np.random.default_rng(n + 1)
+    size = np.array([side, side * 0.75])
+    pos = (rng.random((n, 2)) * size).astype(np.float32)
+    dirs = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+    seed = 1234
+    kw = dict(vision=vision, separation=2.0, torus=torus, speed=speed)
+    if not torus:
+        # keep the flock inside the clamped space for the steps tested (the reference raises when a boid leaves)
+        pos = (size * 0.25 + rng.random((n, 2)) * size * 0.5).astype(np.float32)
+    reach = ops.boids_reach(torch.from_numpy(dirs).cuda(), speed)
+    for epoch in range(3):
+        order = oracle.activation_order(seed, epoch, n)
+        wp, wd, wc = oracle.boids_step(pos, dirs, size, order=order, **kw)
+        cnt = torch.zeros(n, dtype=torch.int32, device="cuda")
+        po, do, passes = ops.boids_step_sequential(torch.from_numpy(pos).cuda(), torch.from_numpy(dirs).cuda(), size,
+                                                   seed=seed, epoch=epoch, reach=reach, neighbor_count=cnt, **kw)
+        assert np.array_equal(cnt.cpu().numpy(), wc), (epoch, passes)
+        assert np.max(np.abs(po.cpu().numpy() - wp) / size) <= RTOL
+        assert np.max(np.abs(do.cpu().numpy() - wd)) <= RTOL
+        pos, dirs = po.cpu().numpy(), do.cpu().numpy()   # float32 state at the step boundary on both sides
+
+
+def test_boids_sequential_differs_from_synchronous_and_rejects_short_reach():
+    from mesa_b200 import ops
+
+    rng = np.random.default_rng(0)
+    size = (150.0, 150.0)
+    pos = torch.from_numpy((rng.random((3000, 2)) * 150).astype(np.float32)).cuda()
+    dirs = torch.from_numpy(rng.uniform(-1, 1, (3000, 2)).astype(np.float32)).cuda()
+    ps, ds = ops.boids_step(pos, dirs, size, vision=10.0, separation=2.0)
+    pq, dq, passes = ops.boids_step_sequential(pos, dirs, size, seed=5, epoch=0, vision=10.0, separation=2.0)
+    assert passes > 1 and float((ps - pq).abs().max()) > 1e-3   # Gauss-Seidel is not Jacobi
+    with pytest.raises(ValueError):
+        ops.boids_step_sequential(pos, dirs, size, seed=5, epoch=0, vision=10.0, separation=2.0, reach=0.5)

@@ -269,3 +269,21 @@ def test_example_boids_matches_oracle():
         assert np.max(np.abs(got_p - wp) / m.space.size) <= 1e-5 and np.max(np.abs(got_d - wd)) <= 1e-5
         pos, dirs = got_p.copy(), got_d.copy()
     assert m.agent_angles.shape == (500,) and -np.pi <= m.average_heading <= np.pi
+
+
+def test_example_boids_sequential_activation_matches_oracle():
+    """BoidFlockers(activation="sequential") == the oracle's sequential shuffle_do in the model's Philox order."""
+    from mesa_b200.examples import BoidFlockers, BoidsScenario
+
+    sc = BoidsScenario(population_size=400, width=100, height=80, vision=10.0, rng=3)
+    m = BoidFlockers(sc, activation="sequential")
+    pos = m.agents.get("position").cpu().numpy().copy()
+    dirs = m.agents.get("direction").cpu().numpy().copy()
+    for epoch in range(3):
+        m.step()
+        order = oracle.activation_order(m.philox_seed, epoch, 400)
+        wp, wd, _ = oracle.boids_step(pos, dirs, m.space.size, vision=10.0, separation=2.0, order=order)
+        got_p, got_d = m.agents.get("position").cpu().numpy(), m.agents.get("direction").cpu().numpy()
+        assert np.max(np.abs(got_p - wp) / m.space.size) <= 1e-5 and np.max(np.abs(got_d - wd)) <= 1e-5
+        assert m.last_passes >= 1
+        pos, dirs = got_p.copy(), got_d.copy()

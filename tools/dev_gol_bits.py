@@ -25,8 +25,13 @@ del y
 
 bits = ops.gol_pack(a)
 results = []
-for T in (1, 2, 3, 4, 6, 8):
-    for rps in (32, 64, 128, 256):
+SWEEP = [(v, T, rps) for v in (14, 24, 12, 22, 18, 28) for T in (4, 6, 8) for rps in (32, 48, 64, 96, 128)]
+SWEEP += [(14, T, rps) for T in (1, 2, 3) for rps in (32, 64)]
+if len(sys.argv) > 2 and sys.argv[2] == "quick":
+    SWEEP = [(14, 4, 64), (24, 4, 64), (24, 8, 64)]
+for variant, T, rps in SWEEP:
+    os.environ["MB_GOL_BITS_VARIANT"] = str(variant)
+    if True:
         cur, nxt = bits.clone(), torch.empty_like(bits)
         gens = 0
         while gens < 16:  # correctness: 16 generations in launches of T
@@ -47,7 +52,7 @@ for T in (1, 2, 3, 4, 6, 8):
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / (launches * T)
-        results.append({"T": T, "rps": rps, "ok": ok, "us_per_generation": us, "updates_per_s": G * G / us * 1e6})
+        results.append({"variant": variant, "T": T, "rps": rps, "ok": ok, "us_per_generation": us, "updates_per_s": G * G / us * 1e6})
         print(json.dumps(results[-1]), flush=True)
 # pack / unpack cost
 for name, fn in (("pack", lambda: ops.gol_pack(a, out=bits)), ("unpack", lambda: ops.gol_unpack(bits, out=b))):
