@@ -7,7 +7,7 @@
 Workload (config.workload): BASELINE.json configs[1], Conway's Game of Life on a 16384 x 16384
 uint8 torus layer; one "step" = one synchronous generation = 16384^2 agent-updates per GPU.
 The layer is resident on the device in the stepping format of the backend: bit-packed (1 bit per
-cell, csrc/gol_bits.cu), MB_GOL_T generations fused per launch (default 4); MB_GOL_PATH=u8 times
+cell, csrc/gol_bits.cu), MB_GOL_T generations fused per launch (default 8); MB_GOL_PATH=u8 times
 the uint8-layer kernel instead (csrc/gol.cu, the HBM-bound stencil; also reported under
 `workloads`).  With N GPUs the grid is row-sharded weak-scaling style: N blocks of 16384 x 16384
 stacked into a [16384*N, 16384] torus, one block per rank, the neighbours' edge rows read in place
@@ -180,7 +180,7 @@ def run_ours(args):
     a = (torch.rand((GRID, GRID), device=dev, generator=g) < 0.2).to(torch.uint8)
     b = torch.empty_like(a)
     path = os.environ.get("MB_GOL_PATH", "bits")
-    gens_per_launch = int(os.environ.get("MB_GOL_T", "4")) if path == "bits" else 1
+    gens_per_launch = int(os.environ.get("MB_GOL_T", "8")) if path == "bits" else 1
     halo_mode = os.environ.get("MB_HALO", "fused") if (world > 1 and path != "bits") else "none"
     hx = HaloExchanger(GRID, torch.uint8, 1, True, dev) if halo_mode != "none" else None
     peer = fused = life = None

@@ -163,6 +163,12 @@ int mb_sort_pairs_u64(uint64_t* keys0, uint32_t* vals0, uint64_t* keys1, uint32_
                       int begin_bit, int end_bit, void* workspace, size_t workspace_bytes, int* result_buffer,
                       mb_stream_t stream);
 
+/* The activation order of shuffle / shuffle_do number `epoch` as an explicit permutation (agentset.py:415-437,
+ * 772-787): order_out[r] = index of the agent activated r-th = agents 0..n-1 sorted by priority64(seed, epoch, agent). */
+int mb_activation_order_workspace_bytes(int64_t n, size_t* out);
+int mb_activation_order(uint64_t seed, uint32_t epoch, int64_t n, uint32_t* order_out, void* workspace,
+                        size_t workspace_bytes, mb_stream_t stream);
+
 /* Boids in the reference's SEQUENTIAL activation order (AgentSet.shuffle_do("step"), agentset.py:772-787, over
  * boid_flockers/agents.py:63-92): boid a sees the new position / direction of every boid activated before it and the
  * old state of the others.  Order = ascending Philox priority64(seed, epoch, agent) (the order oracle/replay.py feeds to

@@ -80,6 +80,8 @@ SIGNATURES: dict[str, tuple] = {
     "mb_boids_step_f32": (c_int, [_P, _P, _P, _P, c_int64, c_double, c_double, c_double, c_double, c_int,
                                   c_double, c_double, c_double, c_double, c_double, c_double, _P, _P,
                                   ctypes.c_size_t, _S]),
+    "mb_activation_order_workspace_bytes": (c_int, [c_int64, ctypes.POINTER(ctypes.c_size_t)]),
+    "mb_activation_order": (c_int, [c_uint64, c_uint32, c_int64, _P, _P, ctypes.c_size_t, _S]),
     "mb_boids_seq_workspace_bytes": (c_int, [c_int64, c_double, c_double, c_double, c_double,
                                              ctypes.POINTER(ctypes.c_size_t)]),
     "mb_boids_step_seq_f32": (c_int, [_P, _P, _P, _P, c_int64, c_double, c_double, c_double, c_double, c_int,

@@ -216,9 +216,14 @@ class DeviceAgentSet:
         from . import rng
 
         epoch = self.model._next_epoch()
-        base = torch.arange(self.n, device=self._device()) if self.index is None else self.index
-        pri = rng.priority64(self.model.philox_seed, epoch, base)
-        idx = base[torch.argsort(pri.view(torch.int64) ^ (-2**63), stable=True)]
+        if self.index is None and self._device().type == "cuda":
+            from . import ops
+
+            idx = ops.activation_order(self.model.philox_seed, epoch, self.n, self._device()).to(torch.int64)
+        else:
+            base = torch.arange(self.n, device=self._device()) if self.index is None else self.index
+            pri = rng.priority64(self.model.philox_seed, epoch, base)
+            idx = base[torch.argsort(pri.view(torch.int64) ^ (-2**63), stable=True)]
         if inplace:
             self.index = idx
             return self

@@ -31,6 +31,7 @@
 
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -436,13 +437,19 @@ struct SeqParams {
     float fsx, fsy;
 };
 
-__device__ __forceinline__ unsigned ld_acquire_u8(const uint8_t* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+// Publication of a new state without flags or fences: `newst` holds two 16-byte halves per boid, (x, y) and (dx, dy),
+// preset to NaN at the start of the step.  A half is written with ONE 16-byte store and read with ONE 16-byte
+// L2-coherent load (ld.global.cg bypasses the non-coherent L1), so a reader sees either NaN ("not finished") or the
+// complete half; it needs both halves to be valid.  No ordering between the halves is required, hence no
+// acquire/release pair -- on sm_100a every ld.acquire.gpu costs an L1 invalidation (CCTL.IVALL).
+__device__ __forceinline__ bool load_new_state(const double2* newst, uint32_t j, double2& p, double2& d) {
+    p = __ldcg(newst + 2 * (size_t)j);
+    d = __ldcg(newst + 2 * (size_t)j + 1);
+    return p.x == p.x && d.x == d.x;  // NaN != NaN
 }
-__device__ __forceinline__ void st_release_u8(uint8_t* p, unsigned v) {
-    asm volatile("st.release.gpu.global.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void store_new_state(double2* newst, uint32_t i, const double4& s) {
+    __stcg(newst + 2 * (size_t)i, make_double2(s.x, s.y));
+    __stcg(newst + 2 * (size_t)i + 1, make_double2(s.z, s.w));
 }
 
 __global__ void boids_seq_priorities(const uint32_t* __restrict__ order, int64_t n, uint64_t seed, uint32_t epoch,
@@ -451,15 +458,43 @@ __global__ void boids_seq_priorities(const uint32_t* __restrict__ order, int64_t
     if (i < n) prio[i] = mb::priority64(seed, epoch, (uint64_t)order[i]);
 }
 
-template <bool kFirst>
+// round of a slot = top bits of its priority; members = slots sorted by round (stable: cell order inside a round)
+__global__ void boids_seq_round_keys(const uint64_t* __restrict__ prio, int64_t n, int shift, uint32_t* __restrict__ keys,
+                                     uint32_t* __restrict__ vals) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = (uint32_t)(prio[i] >> shift);
+    vals[i] = (uint32_t)i;
+}
+// round_start[k] = first position of the sorted key array with key >= k (k = 0 .. rounds)
+__global__ void boids_seq_round_starts(const uint32_t* __restrict__ keys, int64_t n, int rounds,
+                                       uint32_t* __restrict__ round_start) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t k = keys[i];
+    const uint32_t prev = i == 0 ? 0u : keys[i - 1] + 1u;
+    if (i == 0 || keys[i - 1] != k)
+        for (uint32_t kk = prev; kk <= k; ++kk) round_start[kk] = (uint32_t)i;
+    if (i == n - 1)
+        for (uint32_t kk = k + 1u; kk <= (uint32_t)rounds; ++kk) round_start[kk] = (uint32_t)n;
+}
+
+// One pass: the `fresh` boids of round `round` (members[round_start[round] .. round_start[round+1]), cell order;
+// round < 0: none) plus the boids left pending by the previous pass.  Rounds partition the boids by priority (round k
+// holds the k-th slice of the activation order), so when round k is fresh every earlier round has been offered at
+// least one pass: almost all of a boid's earlier neighbours are finished, and because a round is processed in CELL
+// order its neighbourhood reads are spatially coherent (the rank-ordered chained kernel below reads at random).
 __global__ void __launch_bounds__(128)
-boids_seq_pass(const float4* __restrict__ packed, const uint64_t* __restrict__ prio, double2* newst, uint8_t* done,
+boids_seq_pass(const float4* __restrict__ packed, const uint64_t* __restrict__ prio, double2* newst,
                const uint32_t* __restrict__ order, const uint32_t* __restrict__ cell_start,
                const uint32_t* __restrict__ cell_end, int64_t n, Geometry g, BoidParams bp, SeqParams sp,
+               const uint32_t* __restrict__ members, const uint32_t* __restrict__ round_start, int round,
                const uint32_t* __restrict__ pending_in, const uint32_t* __restrict__ count_in,
                uint32_t* __restrict__ pending_out, uint32_t* __restrict__ count_out, float2* __restrict__ pos_out,
                float2* __restrict__ dir_out, uint32_t* __restrict__ nbr_count, uint32_t* __restrict__ error) {
-    const int64_t total = kFirst ? n : (int64_t)*count_in;
+    const int64_t fresh0 = round >= 0 ? (int64_t)round_start[round] : 0;
+    const int64_t fresh = round >= 0 ? (int64_t)round_start[round + 1] - fresh0 : 0;
+    const int64_t total = fresh + (count_in != nullptr ? (int64_t)*count_in : 0);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
     // whole warps iterate together (the pending append below is warp-aggregated)
@@ -469,7 +504,8 @@ boids_seq_pass(const float4* __restrict__ packed, const uint64_t* __restrict__ p
         uint32_t i = 0;
         bool ready = true;
         if (active) {
-            i = kFirst ? (uint32_t)idx : pending_in[idx];
+            if (idx < fresh) i = members != nullptr ? members[fresh0 + idx] : (uint32_t)(fresh0 + idx);
+            else i = pending_in[idx - fresh];
             const float4 me = packed[i];
             const uint64_t pi = prio[i];
             const double px = me.x, py = me.y;
@@ -489,11 +525,11 @@ boids_seq_pass(const float4* __restrict__ packed, const uint64_t* __restrict__ p
                     const float d2 = fmaf(dx, dx, dy * dy);
                     if (d2 > sp.relevant2) continue;           // cannot be within vision before or after its move
                     if (prio[j] < pi) {                        // acts before me: I see its NEW state
-                        if (ld_acquire_u8(done + j) == 0u) {   // not computed yet: try again in the next pass
+                        double2 sp_, sd_;
+                        if (!load_new_state(newst, j, sp_, sd_)) {   // not computed yet: try again in the next pass
                             ready = false;
                             return;
                         }
-                        const double2 sp_ = __ldcg(newst + 2 * (size_t)j), sd_ = __ldcg(newst + 2 * (size_t)j + 1);
                         boid_pair_d(g, bp, px, py, sp_.x, sp_.y, sd_.x, sd_.y, acc);
                     } else if (d2 <= sp.far2) {                // acts after me: its OLD state
                         boid_pair(g, bp, px, py, o, acc);
@@ -505,9 +541,7 @@ boids_seq_pass(const float4* __restrict__ packed, const uint64_t* __restrict__ p
                 // the move of this step (before the wrap) must not exceed `reach`, or a dependency was missed
                 const double mvx = (s.z * bp.speed), mvy = (s.w * bp.speed);
                 if (mvx * mvx + mvy * mvy > sp.reach2) atomicExch(error, 1u);
-                __stcg(newst + 2 * (size_t)i, make_double2(s.x, s.y));
-                __stcg(newst + 2 * (size_t)i + 1, make_double2(s.z, s.w));
-                st_release_u8(done + i, 1u);
+                store_new_state(newst, i, s);
                 const uint32_t a = order[i];
                 pos_out[a] = make_float2((float)s.x, (float)s.y);
                 dir_out[a] = make_float2((float)s.z, (float)s.w);
@@ -520,6 +554,147 @@ boids_seq_pass(const float4* __restrict__ packed, const uint64_t* __restrict__ p
             if (lane == __ffs(waiting) - 1) slot = atomicAdd(count_out, (unsigned)__popc(waiting));
             slot = __shfl_sync(0xffffffffu, slot, __ffs(waiting) - 1);
             if (active && !ready) pending_out[slot + __popc(waiting & ((1u << lane) - 1u))] = i;
+        }
+    }
+}
+
+// ---- sequential activation in ONE launch: rank-ordered chained kernel -------------------------------------------
+// The pass scheme above re-launches over the pending boids until the dependency chains are exhausted (~50 passes on
+// a uniform flock).  The chained kernel instead activates the boids in RANK order (rank = position in the Philox
+// activation order): thread r of the grid owns the boid of rank r, CTAs take their rank range from a ticket counter
+// (so a CTA with a lower range has always started earlier), and a boid whose relevant earlier neighbour is not
+// finished simply waits for it -- the neighbour has a lower rank, hence sits in a CTA that is already running, so
+// the wait always ends (the pattern of a decoupled look-back scan).  Within a warp nobody blocks: the lanes loop,
+// every iteration each unfinished lane re-tries, lanes that depend on a lane of the same warp see its result one
+// iteration later.  `rank` holds the activation rank of every cell-sorted slot (read-only during the launch); new
+// states are published through `newst` (load_new_state / store_new_state).
+// sort keys: the high word of priority64 of every cell-sorted slot (the low word, the agent index, breaks ties)
+__global__ void boids_seq_keys(const uint32_t* __restrict__ order, int64_t n, uint64_t seed, uint32_t epoch,
+                               uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = (uint32_t)(mb::priority64(seed, epoch, order != nullptr ? (uint64_t)order[i] : (uint64_t)i) >> 32);
+    vals[i] = (uint32_t)i;
+}
+
+// runs of equal high words (rare) are ordered by agent index, like priority64 orders them
+__global__ void boids_seq_fix_ties(const uint32_t* __restrict__ keys, uint32_t* __restrict__ slots,
+                                   const uint32_t* __restrict__ order, int64_t n) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const uint32_t k = keys[r];
+    if ((r > 0 && keys[r - 1] == k) || r + 1 >= n || keys[r + 1] != k) return;  // not the start of a run
+    int64_t e = r + 1;
+    while (e < n && keys[e] == k) ++e;
+    auto agent_of = [&](uint32_t slot) { return order != nullptr ? order[slot] : slot; };
+    for (int64_t a = r + 1; a < e; ++a) {  // insertion sort by agent index
+        const uint32_t s = slots[a];
+        const uint32_t ag = agent_of(s);
+        int64_t b = a;
+        while (b > r && agent_of(slots[b - 1]) > ag) {
+            slots[b] = slots[b - 1];
+            --b;
+        }
+        slots[b] = s;
+    }
+}
+
+__global__ void boids_seq_ranks(const uint32_t* __restrict__ slots, int64_t n, uint32_t* __restrict__ rank) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) rank[slots[r]] = (uint32_t)r;
+}
+
+constexpr int kChainThreads = 128;
+
+__global__ void __launch_bounds__(kChainThreads)
+boids_seq_chain(const float4* __restrict__ packed, const uint32_t* __restrict__ byrank,
+                const uint32_t* __restrict__ rank, double2* newst, const uint32_t* __restrict__ order,
+                const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end, int64_t n, Geometry g,
+                BoidParams bp, SeqParams sp, uint32_t* __restrict__ ticket, float2* __restrict__ pos_out,
+                float2* __restrict__ dir_out, uint32_t* __restrict__ nbr_count, uint32_t* __restrict__ error) {
+    __shared__ uint32_t s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int64_t r = (int64_t)s_ticket * kChainThreads + threadIdx.x;
+    bool finished = r >= n;
+    uint32_t i = 0, blocker = 0xffffffffu;
+    float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cx = 0, cy = 0;
+    if (!finished) {
+        i = byrank[r];
+        me = packed[i];
+        cx = cell_coord((double)me.x, g.x0, g.sx, g.ncx);
+        cy = cell_coord((double)me.y, g.y0, g.sy, g.ncy);
+    }
+    const uint32_t myrank = (uint32_t)r;
+    unsigned spins = 0;
+    while (!__all_sync(0xffffffffu, finished)) {
+        bool waiting = false;
+        if (!finished) {
+            double2 np_, nd_;
+            if (blocker != 0xffffffffu && !load_new_state(newst, blocker, np_, nd_)) {
+                waiting = true;  // the neighbour that stopped the last attempt is still not finished
+            } else {
+                blocker = 0xffffffffu;
+                const double px = me.x, py = me.y;
+                BoidAcc acc;
+                for_neighbor_cells(g, cx, cy, [&](unsigned c) {
+                    if (blocker != 0xffffffffu) return;
+                    const uint32_t e = cell_end[c];
+                    for (uint32_t j0 = cell_start[c]; j0 < e; j0 += 4) {
+                        // four candidates per batch: their loads are issued together (memory-level parallelism)
+                        float4 o[4];
+                        uint32_t rj[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const uint32_t j = min(j0 + u, e - 1u);
+                            o[u] = __ldg(packed + j);
+                            rj[u] = __ldg(rank + j);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const uint32_t j = j0 + u;
+                            if (j >= e || j == i) continue;
+                            float dx = fabsf(me.x - o[u].x), dy = fabsf(me.y - o[u].y);
+                            if (g.torus) {
+                                dx = fminf(dx, sp.fsx - dx);
+                                dy = fminf(dy, sp.fsy - dy);
+                            }
+                            const float d2 = fmaf(dx, dx, dy * dy);
+                            if (d2 > sp.relevant2) continue;        // cannot be within vision before or after its move
+                            if (rj[u] < myrank) {                   // acts before me: I see its NEW state
+                                if (!load_new_state(newst, j, np_, nd_)) {
+                                    blocker = j;
+                                    return;
+                                }
+                                boid_pair_d(g, bp, px, py, np_.x, np_.y, nd_.x, nd_.y, acc);
+                            } else if (d2 <= sp.far2) {             // acts after me: its OLD state
+                                boid_pair(g, bp, px, py, o[u], acc);
+                            }
+                        }
+                    }
+                });
+                if (blocker == 0xffffffffu) {
+                    const double4 s = boid_finish_d(g, bp, me, acc);
+                    const double mvx = s.z * bp.speed, mvy = s.w * bp.speed;
+                    if (mvx * mvx + mvy * mvy > sp.reach2) atomicExch(error, 1u);
+                    store_new_state(newst, i, s);
+                    const uint32_t a = order[i];
+                    pos_out[a] = make_float2((float)s.x, (float)s.y);
+                    dir_out[a] = make_float2((float)s.z, (float)s.w);
+                    if (nbr_count != nullptr) nbr_count[a] = acc.k;
+                    finished = true;
+                } else {
+                    waiting = true;
+                }
+            }
+        }
+        if (__any_sync(0xffffffffu, waiting)) {
+            if (++spins > (1u << 22)) {  // seconds: a NaN state or an inconsistent rank table; do not hang the GPU
+                if (!finished) atomicExch(error, 2u);
+                break;
+            }
+            __nanosleep(spins < 8 ? 20 : 200);
         }
     }
 }
@@ -733,13 +908,15 @@ MB_API int mb_boids_step_f32(const float* pos_in, const float* dir_in, float* po
 namespace {
 
 constexpr int kSeqMaxPasses = 4096;
+constexpr int kSeqMaxRounds = 256;
 
 struct SeqWs {
     CellListWs cl;
     uint64_t* prio;
     double2* newst;
-    uint8_t* done;
     uint32_t *pend0, *pend1, *counts, *error;
+    uint32_t *pk0, *pk1, *pv0, *pv1, *rank, *ticket;   // priority / round sort ping-pong, rank table (chained kernel)
+    uint32_t* round_start;                             // [kSeqMaxRounds + 1]
 };
 
 size_t carve_seq(SeqWs* ws, char* base, int64_t n, int64_t ncells) {
@@ -753,11 +930,17 @@ size_t carve_seq(SeqWs* ws, char* base, int64_t n, int64_t ncells) {
     if (ws) t.cl = ws->cl;
     t.prio = (uint64_t*)take(8 * n);
     t.newst = (double2*)take(32 * n);
-    t.done = (uint8_t*)take(n);
     t.pend0 = (uint32_t*)take(4 * n);
     t.pend1 = (uint32_t*)take(4 * n);
     t.counts = (uint32_t*)take(4 * (kSeqMaxPasses + 1));
     t.error = (uint32_t*)take(4);
+    t.pk0 = (uint32_t*)take(4 * n);
+    t.pk1 = (uint32_t*)take(4 * n);
+    t.pv0 = (uint32_t*)take(4 * n);
+    t.pv1 = (uint32_t*)take(4 * n);
+    t.rank = (uint32_t*)take(4 * n);
+    t.ticket = (uint32_t*)take(4);
+    t.round_start = (uint32_t*)take(4 * (kSeqMaxRounds + 1));
     if (ws) *ws = t;
     return off;
 }
@@ -800,7 +983,7 @@ MB_API int mb_boids_step_seq_f32(const float* pos_in, const float* dir_in, float
     uint32_t* order = nullptr;
     rc = build_cell_list((const float2*)pos_in, (const float2*)dir_in, n, g, ws.cl, &order, stream);
     if (rc) return rc;
-    rc = mb::check_cuda(cudaMemsetAsync(ws.done, 0, n, stream), "memset");
+    rc = mb::check_cuda(cudaMemsetAsync(ws.newst, 0xFF, 32 * n, stream), "memset");  // all NaN: nobody has finished
     if (rc) return rc;
     rc = mb::check_cuda(cudaMemsetAsync(ws.counts, 0, 4 * (kSeqMaxPasses + 1), stream), "memset");
     if (rc) return rc;
@@ -820,27 +1003,84 @@ MB_API int mb_boids_step_seq_f32(const float* pos_in, const float* dir_in, float
     sp.fsx = (float)size_x;
     sp.fsy = (float)size_y;
     const unsigned blocks = (unsigned)mb::ceil_div(n, 256);
-    boids_seq_priorities<<<blocks, 256, 0, stream>>>(order, n, seed, epoch, ws.prio);
-    boids_seq_pass<true><<<(unsigned)mb::ceil_div(n, 128), 128, 0, stream>>>(
-        ws.cl.packed, ws.prio, ws.newst, ws.done, order, ws.cl.cell_start, ws.cl.cell_end, n, g, bp, sp, nullptr, nullptr,
-        ws.pend0, ws.counts, (float2*)pos_out, (float2*)dir_out, neighbor_count, ws.error);
-    MB_LAUNCH_CHECK("mb_boids_step_seq_f32");
-    int pass = 1;  // passes launched so far; pass p reads counts[p-1] / pend[(p-1)&1] and writes counts[p] / pend[p&1]
-    uint32_t pending = (uint32_t)n;
-    const int grid_cap = mb::sm_count() * 16;
-    while (true) {
-        const int batch = pass == 1 ? 4 : 8;
-        for (int b = 0; b < batch && pass < kSeqMaxPasses; ++b, ++pass) {
-            uint32_t* pin = ((pass - 1) & 1) ? ws.pend1 : ws.pend0;
-            uint32_t* pout = (pass & 1) ? ws.pend1 : ws.pend0;
-            const int64_t want = mb::ceil_div((int64_t)pending, 128);
-            const unsigned grid = (unsigned)(want < 1 ? 1 : (want > grid_cap ? grid_cap : want));
-            boids_seq_pass<false><<<grid, 128, 0, stream>>>(
-                ws.cl.packed, ws.prio, ws.newst, ws.done, order, ws.cl.cell_start, ws.cl.cell_end, n, g, bp, sp, pin,
-                ws.counts + (pass - 1), pout, ws.counts + pass, (float2*)pos_out, (float2*)dir_out, neighbor_count,
-                ws.error);
-        }
+    const char* mode = getenv("MB_BOIDS_SEQ");
+    if (mode == nullptr || (strcmp(mode, "passes") != 0 && strcmp(mode, "rounds") != 0)) {
+        // rank-ordered chained kernel: sort the slots by priority, then one launch
+        boids_seq_keys<<<blocks, 256, 0, stream>>>(order, n, seed, epoch, ws.pk0, ws.pv0);
+        const int where = mb::radix_sort_pairs<uint32_t>(ws.pk0, ws.pv0, ws.pk1, ws.pv1, n, 0, 32, ws.cl.sort_ws,
+                                                         ws.cl.sort_ws_bytes, stream);
+        if (where < 0) return where;
+        uint32_t* keys = where ? ws.pk1 : ws.pk0;
+        uint32_t* byrank = where ? ws.pv1 : ws.pv0;
+        boids_seq_fix_ties<<<blocks, 256, 0, stream>>>(keys, byrank, order, n);
+        boids_seq_ranks<<<blocks, 256, 0, stream>>>(byrank, n, ws.rank);
+        rc = mb::check_cuda(cudaMemsetAsync(ws.ticket, 0, 4, stream), "memset");
+        if (rc) return rc;
+        boids_seq_chain<<<(unsigned)mb::ceil_div(n, kChainThreads), kChainThreads, 0, stream>>>(
+            ws.cl.packed, byrank, ws.rank, ws.newst, order, ws.cl.cell_start, ws.cl.cell_end, n, g, bp, sp, ws.ticket,
+            (float2*)pos_out, (float2*)dir_out, neighbor_count, ws.error);
         MB_LAUNCH_CHECK("mb_boids_step_seq_f32");
+        uint32_t err = 0u;
+        rc = mb::check_cuda(cudaMemcpyAsync(&err, ws.error, 4, cudaMemcpyDeviceToHost, stream), "read error");
+        if (rc) return rc;
+        rc = mb::check_cuda(cudaStreamSynchronize(stream), "mb_boids_step_seq_f32");
+        if (rc) return rc;
+        MB_REQUIRE(err != 1u, "mb_boids_step_seq_f32: a boid moved farther than `reach` in one step");
+        if (err != 0u) {
+            mb::set_error("mb_boids_step_seq_f32: the chained kernel timed out waiting for a dependency");
+            return MB_ERR_CUDA;
+        }
+        if (out_passes) *out_passes = 1;
+        return MB_OK;
+    }
+    // multi-pass schemes (MB_BOIDS_SEQ=rounds / passes; kept for cross-checking the chained kernel, 10^7 boids: chained
+    // 19 ms, rounds 23 ms, passes 66 ms): the boids are split into `rounds` slices of the activation order; each round
+    // is offered `subpasses` passes (the fresh members, then retries of whatever is still pending, which also rides
+    // along with the following rounds); `passes` is the one-round special case (every boid fresh in pass 0)
+    boids_seq_priorities<<<blocks, 256, 0, stream>>>(order, n, seed, epoch, ws.prio);
+    int rounds = n < 65536 ? 1 : 16, subpasses = 2;  // small flocks: a pass is cheaper than a launch
+    if (mode != nullptr && strcmp(mode, "passes") == 0) rounds = 1;
+    else if (const char* e = getenv("MB_BOIDS_SEQ_ROUNDS")) rounds = atoi(e);
+    if (const char* e = getenv("MB_BOIDS_SEQ_SUBPASSES")) subpasses = atoi(e);
+    int log_rounds = 0;
+    while ((1 << log_rounds) < rounds) ++log_rounds;
+    rounds = 1 << log_rounds;
+    MB_REQUIRE(rounds >= 1 && rounds <= kSeqMaxRounds && subpasses >= 1 && subpasses <= 8,
+               "mb_boids_step_seq_f32: bad MB_BOIDS_SEQ_ROUNDS / MB_BOIDS_SEQ_SUBPASSES");
+    const uint32_t* members = nullptr;
+    if (rounds > 1) {
+        boids_seq_round_keys<<<blocks, 256, 0, stream>>>(ws.prio, n, 64 - log_rounds, ws.pk0, ws.pv0);
+        const int where = mb::radix_sort_pairs<uint32_t>(ws.pk0, ws.pv0, ws.pk1, ws.pv1, n, 0, log_rounds > 8 ? 16 : 8,
+                                                         ws.cl.sort_ws, ws.cl.sort_ws_bytes, stream);
+        if (where < 0) return where;
+        members = where ? ws.pv1 : ws.pv0;
+        boids_seq_round_starts<<<blocks, 256, 0, stream>>>(where ? ws.pk1 : ws.pk0, n, rounds, ws.round_start);
+    } else {
+        const uint32_t host_start[2] = {0u, (uint32_t)n};
+        rc = mb::check_cuda(cudaMemcpyAsync(ws.round_start, host_start, 8, cudaMemcpyHostToDevice, stream), "round table");
+        if (rc) return rc;
+    }
+    const int grid_cap = mb::sm_count() * 16;
+    auto grid_for = [&](int64_t items) {
+        const int64_t want = mb::ceil_div(items < 1 ? 1 : items, 128);
+        return (unsigned)(want > grid_cap ? grid_cap : want);
+    };
+    int pass = 0;  // passes launched so far; pass p reads counts[p-1] / pend[(p-1)&1] and writes counts[p] / pend[p&1]
+    auto launch_pass = [&](int round, int64_t items) {
+        uint32_t* pin = ((pass - 1) & 1) ? ws.pend1 : ws.pend0;
+        uint32_t* pout = (pass & 1) ? ws.pend1 : ws.pend0;
+        boids_seq_pass<<<grid_for(items), 128, 0, stream>>>(
+            ws.cl.packed, ws.prio, ws.newst, order, ws.cl.cell_start, ws.cl.cell_end, n, g, bp, sp, members, ws.round_start,
+            round, pass > 0 ? pin : nullptr, pass > 0 ? ws.counts + (pass - 1) : nullptr, pout, ws.counts + pass,
+            (float2*)pos_out, (float2*)dir_out, neighbor_count, ws.error);
+        ++pass;
+    };
+    const int64_t per_round = mb::ceil_div(n, rounds);
+    for (int k = 0; k < rounds; ++k)
+        for (int sub = 0; sub < subpasses; ++sub) launch_pass(sub == 0 ? k : -1, sub == 0 ? 2 * per_round : per_round / 2);
+    MB_LAUNCH_CHECK("mb_boids_step_seq_f32");
+    uint32_t pending = (uint32_t)n;
+    while (true) {  // drain: whatever is still pending after the scheduled passes
         uint32_t host[2] = {0u, 0u};
         rc = mb::check_cuda(cudaMemcpyAsync(&host[0], ws.counts + (pass - 1), 4, cudaMemcpyDeviceToHost, stream), "read pending");
         if (rc) return rc;
@@ -851,13 +1091,53 @@ MB_API int mb_boids_step_seq_f32(const float* pos_in, const float* dir_in, float
         MB_REQUIRE(host[1] == 0u, "mb_boids_step_seq_f32: a boid moved farther than `reach` in one step");
         pending = host[0];
         if (pending == 0u) break;
-        if (pass >= kSeqMaxPasses) {
+        if (pass + 8 >= kSeqMaxPasses) {
             mb::set_error("mb_boids_step_seq_f32: dependency chains longer than %d passes", kSeqMaxPasses);
             return MB_ERR_UNSUPPORTED;
         }
+        for (int b = 0; b < 8; ++b) launch_pass(-1, pending);
+        MB_LAUNCH_CHECK("mb_boids_step_seq_f32");
     }
     if (out_passes) *out_passes = pass;
     return MB_OK;
+}
+
+// The activation order of AgentSet.shuffle / shuffle_do number `epoch` (agentset.py:415-437, 772-787) as an explicit
+// permutation: order[r] = index of the agent activated r-th = agents sorted by priority64(seed, epoch, agent)
+// (csrc/philox.cuh).  Same kernels as the sequential Boids step: radix sort on the high word, ties by agent index.
+// workspace: mb_activation_order_workspace_bytes(n).
+MB_API int mb_activation_order_workspace_bytes(int64_t n, size_t* out) {
+    MB_REQUIRE(out != nullptr && n >= 0, "mb_activation_order_workspace_bytes: bad argument");
+    *out = 4 * ((size_t)(4 * n + 255) & ~(size_t)255) + mb::sort_workspace_bytes(n) + 1024;
+    return MB_OK;
+}
+
+MB_API int mb_activation_order(uint64_t seed, uint32_t epoch, int64_t n, uint32_t* order_out, void* workspace,
+                               size_t workspace_bytes, cudaStream_t stream) {
+    MB_REQUIRE(n >= 0 && n < (1ll << 31), "mb_activation_order: n out of range");
+    if (n == 0) return MB_OK;
+    MB_REQUIRE(order_out && workspace, "mb_activation_order: null buffer");
+    size_t need = 0;
+    mb_activation_order_workspace_bytes(n, &need);
+    if (workspace_bytes < need) {
+        mb::set_error("mb_activation_order: workspace too small");
+        return MB_ERR_WORKSPACE;
+    }
+    const size_t stride = ((size_t)(4 * n + 255) & ~(size_t)255);
+    char* base = (char*)workspace;
+    uint32_t *k0 = (uint32_t*)base, *k1 = (uint32_t*)(base + stride), *v0 = (uint32_t*)(base + 2 * stride),
+             *v1 = (uint32_t*)(base + 3 * stride);
+    void* sort_ws = base + 4 * stride;
+    const unsigned blocks = (unsigned)mb::ceil_div(n, 256);
+    // identity "order": slot i holds agent i.  v0 doubles as that identity table (vals = slot = agent).
+    boids_seq_keys<<<blocks, 256, 0, stream>>>(nullptr, n, seed, epoch, k0, v0);
+    const int where = mb::radix_sort_pairs<uint32_t>(k0, v0, k1, v1, n, 0, 32, sort_ws, mb::sort_workspace_bytes(n), stream);
+    if (where < 0) return where;
+    uint32_t* keys = where ? k1 : k0;
+    uint32_t* vals = where ? v1 : v0;
+    boids_seq_fix_ties<<<blocks, 256, 0, stream>>>(keys, vals, nullptr, n);
+    MB_LAUNCH_CHECK("mb_activation_order");
+    return mb::check_cuda(cudaMemcpyAsync(order_out, vals, 4 * n, cudaMemcpyDeviceToDevice, stream), "mb_activation_order");
 }
 
 // Batched get_agents_in_radius.  Call with out_idx == NULL to get counts[nq]; prefix-sum them into

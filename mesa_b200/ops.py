@@ -114,7 +114,7 @@ class BitLife:
     """Game of Life state held bit-packed on one GPU (two ping-pong planes), stepped several generations per
     launch.  `load` / `store` convert from / to the uint8 property layer."""
 
-    def __init__(self, rows: int, cols: int, device, torus: bool = True, generations_per_launch: int = 4,
+    def __init__(self, rows: int, cols: int, device, torus: bool = True, generations_per_launch: int = 8,
                  rows_per_segment: int = 0):
         if cols % 32:
             raise ValueError("the bit-packed layer needs cols to be a multiple of 32")
@@ -311,6 +311,23 @@ def boids_step(pos: torch.Tensor, direction: torch.Tensor, size, *, vision: floa
             float(cohere), float(separate), float(match), float(speed), N.ptr(neighbor_count), N.ptr(ws.buf),
             ws.nbytes, N.stream_ptr(pos.device)))
     return pos_out, dir_out
+
+
+def activation_order(seed: int, epoch: int, n: int, device) -> torch.Tensor:
+    """order[r] = index of the agent activated r-th in shuffle number `epoch` (ascending Philox priority64), int32."""
+    import ctypes
+
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("mesa_b200 runs on CUDA tensors only (no CPU fallback)")
+    nbytes = ctypes.c_size_t(0)
+    N.check(N.lib().mb_activation_order_workspace_bytes(int(n), ctypes.byref(nbytes)))
+    ws = torch.empty(max(int(nbytes.value), 1), dtype=torch.uint8, device=dev)
+    out = torch.empty(int(n), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().mb_activation_order(int(seed) & 0xFFFFFFFFFFFFFFFF, int(epoch) & 0xFFFFFFFF, int(n), N.ptr(out),
+                                            N.ptr(ws), ws.numel(), N.stream_ptr(dev)))
+    return out
 
 
 class BoidsSeqWorkspace:

@@ -235,7 +235,7 @@ class PeerBitLife:
     that many edge rows of each neighbour in place over NVLink, then one device-side barrier orders the ping-pong
     buffers -- one barrier per T generations instead of one exchange per generation."""
 
-    def __init__(self, rows: int, cols: int, torus: bool, device, generations_per_launch: int = 4,
+    def __init__(self, rows: int, cols: int, torus: bool, device, generations_per_launch: int = 8,
                  rows_per_segment: int = 0, group=None):
         from . import ops
 

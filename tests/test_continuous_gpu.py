@@ -145,6 +145,48 @@ def test_boids_sequential_differs_from_synchronous_and_rejects_short_reach():
     dirs = torch.from_numpy(rng.uniform(-1, 1, (3000, 2)).astype(np.float32)).cuda()
     ps, ds = ops.boids_step(pos, dirs, size, vision=10.0, separation=2.0)
     pq, dq, passes = ops.boids_step_sequential(pos, dirs, size, seed=5, epoch=0, vision=10.0, separation=2.0)
-    assert passes > 1 and float((ps - pq).abs().max()) > 1e-3   # Gauss-Seidel is not Jacobi
+    assert passes >= 1 and float((ps - pq).abs().max()) > 1e-3   # Gauss-Seidel is not Jacobi
     with pytest.raises(ValueError):
         ops.boids_step_sequential(pos, dirs, size, seed=5, epoch=0, vision=10.0, separation=2.0, reach=0.5)
+
+
+@pytest.mark.parametrize("n", [1, 1000, 300_000, 3_000_000])
+def test_activation_order_matches_oracle(n):
+    """The device permutation (radix sort on the priority's high word + tie fix-up by agent index) equals the
+    oracle's; at n = 3e6 about a thousand pairs of agents share a high word, so the tie path is exercised."""
+    from mesa_b200 import ops
+
+    for seed, epoch in ((42, 0), (2**63 + 5, 7)):
+        got = ops.activation_order(seed, epoch, n, "cuda").cpu().numpy()
+        want = oracle.activation_order(seed, epoch, n)
+        assert np.array_equal(got, want)
+    if n >= 3_000_000:
+        import oracle.philox as ph
+
+        hi = (ph.priority64(42, 0, np.arange(n, dtype=np.uint64)) >> np.uint64(32))
+        assert len(np.unique(hi)) < n  # ties exist in this case
+
+
+def test_boids_sequential_schemes_agree(monkeypatch):
+    """The three schedules of the sequential step -- the rank-ordered chained kernel (default), priority rounds in
+    cell order (MB_BOIDS_SEQ=rounds) and one round (MB_BOIDS_SEQ=passes) -- are the same function."""
+    from mesa_b200 import ops
+
+    rng = np.random.default_rng(12)
+    n, size = 20000, (700.0, 500.0)
+    pos = torch.from_numpy((rng.random((n, 2)) * np.array(size)).astype(np.float32)).cuda()
+    dirs = torch.from_numpy(rng.uniform(-1, 1, (n, 2)).astype(np.float32)).cuda()
+    kw = dict(seed=3, epoch=1, vision=12.0, separation=2.0)
+    monkeypatch.delenv("MB_BOIDS_SEQ", raising=False)
+    results = []
+    for env in ({"MB_BOIDS_SEQ": "rounds", "MB_BOIDS_SEQ_ROUNDS": "16"},
+                {"MB_BOIDS_SEQ": "rounds", "MB_BOIDS_SEQ_ROUNDS": "4", "MB_BOIDS_SEQ_SUBPASSES": "1"},
+                {"MB_BOIDS_SEQ": "passes"}, {}):
+        for k in ("MB_BOIDS_SEQ", "MB_BOIDS_SEQ_ROUNDS", "MB_BOIDS_SEQ_SUBPASSES"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        results.append(ops.boids_step_sequential(pos, dirs, size, **kw))
+    assert results[0][2] >= 32 and results[3][2] == 1
+    for p_, d_, _ in results[1:]:
+        assert torch.equal(results[0][0], p_) and torch.equal(results[0][1], d_)

@@ -27,3 +27,25 @@ e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
 print(json.dumps({"n": n, "side": side, "ms_per_step": ms, "agent_updates_per_s": n / ms * 1e3,
                   "mean_neighbors": float(cnt.float().mean()), "ws_MB": ws.nbytes / 1e6}))
+
+# sequential activation (the reference's shuffle_do semantics): passes and time per step
+if len(sys.argv) > 3 and sys.argv[3] == "seq":
+    reach = ops.boids_reach(dirs, 1.0)
+    sws = ops.BoidsSeqWorkspace(n, (side, side), vision, reach, "cuda")
+    import time
+    for epoch in range(2):
+        ops.boids_step_sequential(pos, dirs, (side, side), seed=7, epoch=epoch, vision=vision, separation=2.0, reach=reach,
+                                  ws=sws, pos_out=po, dir_out=do)
+        pos, po = po, pos; dirs, do = do, dirs
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    passes = []
+    for epoch in range(2, 2 + max(3, steps // 4)):
+        _, _, p = ops.boids_step_sequential(pos, dirs, (side, side), seed=7, epoch=epoch, vision=vision, separation=2.0,
+                                            reach=reach, ws=sws, pos_out=po, dir_out=do)
+        passes.append(p)
+        pos, po = po, pos; dirs, do = do, dirs
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / len(passes) * 1e3
+    print(json.dumps({"mode": "sequential", "n": n, "ms_per_step": ms, "agent_updates_per_s": n / ms * 1e3,
+                      "passes": passes, "reach": reach, "ws_MB": sws.nbytes / 1e6}))
