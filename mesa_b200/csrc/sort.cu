@@ -93,44 +93,95 @@ __global__ void __launch_bounds__(1024) scan_add(uint32_t* __restrict__ data, in
         if (i0 + k < total) data[i0 + k] += off;
 }
 
+// Scatter pass.  Every element's slot inside its digit is found with warp multi-split (match_any) + per-warp digit
+// counts, as in the histogram order (sub-chunk, warp, lane) = input order, so the sort is stable.  The tile is then
+// REORDERED IN SHARED MEMORY by digit before it is written: consecutive threads store consecutive elements of one
+// digit, i.e. runs of ~tile/256 elements go to consecutive addresses instead of one 4-byte store per 32-byte sector
+// (the direct scatter reached 0.86 TB/s on 10^7 pairs).
 template <typename K>
 __global__ void __launch_bounds__(kSortThreads)
 sort_scatter(const K* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, K* __restrict__ keys_out,
              uint32_t* __restrict__ vals_out, int64_t n, int bit, const uint32_t* __restrict__ hist,
              int64_t tiles) {
-    __shared__ unsigned base[kRadix];                   // next output slot of each digit for this CTA
+    __shared__ unsigned gbase[kRadix];                  // global slot of this tile's first element of each digit
+    __shared__ unsigned lbase[kRadix];                  // position of that element in the reordered tile
+    __shared__ unsigned run[kRadix];                    // elements of each digit seen in earlier sub-chunks
     __shared__ unsigned wcount[kWarpsPerCta][kRadix];   // per-warp digit counts of the current sub-chunk
+    __shared__ unsigned wsum[kWarpsPerCta];
+    extern __shared__ __align__(16) unsigned char tile_raw[];
+    K* skey = reinterpret_cast<K*>(tile_raw);
+    uint32_t* sval = reinterpret_cast<uint32_t*>(tile_raw + sizeof(K) * kSortTile);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    base[tid] = hist[(int64_t)tid * tiles + blockIdx.x];
+    gbase[tid] = hist[(int64_t)tid * tiles + blockIdx.x];
+    run[tid] = 0u;
     const int64_t tile0 = (int64_t)blockIdx.x * kSortTile;
+    const int tile_n = (int)(n - tile0 < kSortTile ? n - tile0 : kSortTile);
+    K key[kSortItems];
+    uint32_t val[kSortItems];
+    unsigned where[kSortItems];  // digit | slot within the digit << 8
+#pragma unroll
+    for (int i = 0; i < kSortItems; ++i) {
+        const int s = i * kSortThreads + tid;
+        key[i] = s < tile_n ? keys_in[tile0 + s] : (K)0;
+        val[i] = s < tile_n ? vals_in[tile0 + s] : 0u;
+    }
+#pragma unroll
     for (int i = 0; i < kSortItems; ++i) {
 #pragma unroll
         for (int w = 0; w < kWarpsPerCta; ++w) wcount[w][tid] = 0u;
         __syncthreads();
-        const int64_t idx = tile0 + (int64_t)i * kSortThreads + tid;
-        const bool valid = idx < n;
-        K key = 0;
-        unsigned digit = 0xffffffffu;  // invalid lanes never match a real digit
-        if (valid) {
-            key = keys_in[idx];
-            digit = (unsigned)(key >> bit) & 0xffu;
-        }
+        const bool valid = i * kSortThreads + tid < tile_n;
+        const unsigned digit = valid ? (unsigned)(key[i] >> bit) & 0xffu : 0xffffffffu;  // invalid lanes match nobody real
         const unsigned peers = __match_any_sync(0xffffffffu, digit);
         const unsigned rank = __popc(peers & ((1u << lane) - 1u));
         if (valid && rank == 0) wcount[warp][digit] = __popc(peers);
         __syncthreads();
         if (valid) {
-            unsigned off = base[digit] + rank;
-            for (int w = 0; w < warp; ++w) off += wcount[w][digit];
-            keys_out[off] = key;
-            vals_out[off] = vals_in[idx];
+            unsigned slot = run[digit] + rank;
+            for (int w = 0; w < warp; ++w) slot += wcount[w][digit];
+            where[i] = digit | (slot << 8);
         }
         __syncthreads();
         unsigned add = 0;
 #pragma unroll
         for (int w = 0; w < kWarpsPerCta; ++w) add += wcount[w][tid];
-        base[tid] += add;
+        run[tid] += add;
+    }
+    __syncthreads();
+    {   // lbase = exclusive scan of the tile's digit counts (256 counters, one per thread)
+        const unsigned c = run[tid];
+        unsigned incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
         __syncthreads();
+        unsigned off = 0;
+        for (int w = 0; w < warp; ++w) off += wsum[w];
+        lbase[tid] = off + incl - c;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kSortItems; ++i) {
+        if (i * kSortThreads + tid < tile_n) {
+            const unsigned pos = lbase[where[i] & 0xffu] + (where[i] >> 8);
+            skey[pos] = key[i];
+            sval[pos] = val[i];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kSortItems; ++i) {
+        const int s = i * kSortThreads + tid;
+        if (s < tile_n) {
+            const K k = skey[s];
+            const unsigned digit = (unsigned)(k >> bit) & 0xffu;
+            const unsigned dst = gbase[digit] + ((unsigned)s - lbase[digit]);
+            keys_out[dst] = k;
+            vals_out[dst] = sval[s];
+        }
     }
 }
 
@@ -162,6 +213,14 @@ int radix_sort_pairs(K* k0, uint32_t* v0, K* k1, uint32_t* v1, int64_t n, int be
         return MB_ERR_WORKSPACE;
     }
     const int64_t tiles = sort_num_tiles(n);
+    constexpr size_t tile_smem = (sizeof(K) + sizeof(uint32_t)) * kSortTile;  // the reordered tile (32 / 48 KiB)
+    static bool attr_set = false;  // one flag per instantiation (K)
+    if (!attr_set) {
+        if (check_cuda(cudaFuncSetAttribute(sort_scatter<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem),
+                       "radix_sort_pairs") != MB_OK)
+            return MB_ERR_CUDA;
+        attr_set = true;
+    }
     uint32_t* hist = reinterpret_cast<uint32_t*>(workspace);
     K* ks[2] = {k0, k1};
     uint32_t* vs[2] = {v0, v1};
@@ -169,8 +228,8 @@ int radix_sort_pairs(K* k0, uint32_t* v0, K* k1, uint32_t* v1, int64_t n, int be
     for (int bit = begin_bit; bit < end_bit; bit += 8) {
         sort_hist<K><<<(unsigned)tiles, kSortThreads, 0, stream>>>(ks[cur], n, bit, hist, tiles);
         if (exclusive_scan_u32(hist, (int64_t)kRadix * tiles, hist + (int64_t)kRadix * tiles, stream) != MB_OK) return MB_ERR_CUDA;
-        sort_scatter<K><<<(unsigned)tiles, kSortThreads, 0, stream>>>(ks[cur], vs[cur], ks[cur ^ 1], vs[cur ^ 1], n,
-                                                                     bit, hist, tiles);
+        sort_scatter<K><<<(unsigned)tiles, kSortThreads, tile_smem, stream>>>(ks[cur], vs[cur], ks[cur ^ 1], vs[cur ^ 1],
+                                                                             n, bit, hist, tiles);
         cur ^= 1;
     }
     if (check_cuda(cudaGetLastError(), "radix_sort_pairs") != MB_OK) return MB_ERR_CUDA;
