@@ -10,8 +10,8 @@ The layer is resident on the device in the stepping format of the backend: bit-p
 cell, csrc/gol_bits.cu), MB_GOL_T generations fused per launch (default 8); MB_GOL_PATH=u8 times
 the uint8-layer kernel instead (csrc/gol.cu, the HBM-bound stencil; also reported under
 `workloads`).  With N GPUs the grid is row-sharded weak-scaling style: N blocks of 16384 x 16384
-stacked into a [16384*N, 16384] torus, one block per rank, the neighbours' edge rows read in place
-from their HBM over NVLink (mesa_b200/sharding.py).
+stacked into a [16384*N, 16384] torus, one block per rank, deep ghost zones refreshed from the
+neighbours' HBM over NVLink once per 64 generations (mesa_b200/sharding.py, PeerBitLife).
 
 Prints ONE JSON line (rank 0): `value` = agent-updates/s over all ranks with inputs resident in
 HBM (CUDA events, max over ranks); `e2e` = the same metric through the host-buffer API (pinned
@@ -185,8 +185,8 @@ def run_ours(args):
     hx = HaloExchanger(GRID, torch.uint8, 1, True, dev) if halo_mode != "none" else None
     peer = fused = life = None
     if path == "bits":
-        # bit-packed planes, gens_per_launch generations per launch; N > 1: the neighbours' edge rows are read in
-        # place from their HBM, one device barrier per launch
+        # bit-packed planes, gens_per_launch generations per launch; N > 1: deep ghost zones (64 rows of each ring
+        # neighbour, copied out of its HBM over NVLink once per 64 generations between two device barriers)
         if world > 1:
             from mesa_b200.sharding import PeerBitLife
 
@@ -296,8 +296,9 @@ def run_ours(args):
         achieved = alg_bytes / (ms / launches * 1e-3) / 1e9
         if life is not None:
             kernel = f"gol_bits_kernel<{gens_per_launch}>"
-            par = (f"row-sharded x{world}, bit-packed planes, {gens_per_launch} edge rows of each ring neighbour read in place "
-                   "from peer HBM over NVLink, one device barrier per launch") if world > 1 else "single GPU"
+            par = (f"row-sharded x{world}, bit-packed planes, {life.ghost} ghost rows of each ring neighbour copied out of its HBM "
+                   f"over NVLink (peer-mapped memory) once per {life.ghost} generations between two device barriers; no collective "
+                   "on the data path") if world > 1 else "single GPU"
             note = ("bit-packed state (1 bit/cell, 2 x 32 MiB planes resident in L2) and temporal blocking: the kernel is bound "
                     "by integer issue rate, not HBM; `achieved` is the contract's ALGORITHMIC figure (2 B per cell-update of the "
                     "uint8 layer) and exceeds the HBM peak by design (SURVEY 8d allows it); `traffic` is the measured DRAM bytes "

@@ -68,18 +68,19 @@ def test_sharded_boids_world1_matches_oracle(one_rank_group):
 
 
 @pytest.mark.parametrize("torus", [True, False])
-def test_peer_bit_life_world1_matches_oracle(one_rank_group, torus):
+@pytest.mark.parametrize("ghost,launches,exchanges", [(64, 3, 1), (8, 3, 2), (4, 3, 3)])
+def test_peer_bit_life_world1_matches_oracle(one_rank_group, torus, ghost, launches, exchanges):
     """Row-sharded bit-packed Game of Life with a 1-rank group: the ring neighbour is the rank itself (torus) or
-    absent (clamped); the symmetric-memory halo path must equal the oracle."""
+    absent (clamped); deep ghost zones refreshed every `ghost` generations must equal the oracle."""
     from mesa_b200.sharding import PeerBitLife
 
     rng = np.random.default_rng(8)
     s = (rng.random((72, 192)) < 0.35).astype(np.uint8)
-    life = PeerBitLife(72, 192, torus, "cuda", generations_per_launch=4)
+    life = PeerBitLife(72, 192, torus, "cuda", generations_per_launch=4, ghost=ghost)
     life.load(torch.from_numpy(s).cuda())
     life.run(10)
     want = s
     for _ in range(10):
         want = oracle.gol_step(want, torus)
-    assert life.launches == 3
+    assert (life.launches, life.exchanges) == (launches, exchanges)
     assert np.array_equal(life.store().cpu().numpy(), want)

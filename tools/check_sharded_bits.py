@@ -14,10 +14,10 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 
 ok_all = True
-for rows, cols, torus, T, gens in [(96, 256, True, 4, 10), (64, 1024, False, 3, 7), (2048, 4096, True, 8, 24)]:
+for rows, cols, torus, T, gens, ghost in [(96, 256, True, 4, 30, 8), (64, 1024, False, 3, 17, 6), (2048, 4096, True, 8, 100, 64)]:
     g = torch.Generator(device="cpu").manual_seed(rows + cols)
     full = (torch.rand((rows * world, cols), generator=g) < 0.3).to(torch.uint8)   # same on every rank
-    life = PeerBitLife(rows, cols, torus, dev, generations_per_launch=T)
+    life = PeerBitLife(rows, cols, torus, dev, generations_per_launch=T, ghost=ghost)
     life.load(full[rank * rows:(rank + 1) * rows].to(dev))
     life.run(gens)
     mine = life.store()
@@ -32,27 +32,27 @@ for rows, cols, torus, T, gens in [(96, 256, True, 4, 10), (64, 1024, False, 3, 
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     ok_all &= bool(flag.item())
     if rank == 0:
-        print(json.dumps({"case": f"bits {rows}x{cols} per rank torus={torus} T={T}", "world": world, "ok": bool(flag.item())}), flush=True)
+        print(json.dumps({"case": f"bits {rows}x{cols} per rank torus={torus} T={T} ghost={ghost} gens={gens}", "world": world, "ok": bool(flag.item())}), flush=True)
 
 # timing at the benchmark size: 16384^2 per GPU, weak scaling
 G = 16384
 gen = torch.Generator(device=dev).manual_seed(rank)
 blk = (torch.rand((G, G), device=dev, generator=gen) < 0.2).to(torch.uint8)
-for T in (4, 8):
-    life = PeerBitLife(G, G, True, dev, generations_per_launch=T)
+for T, ghost in ((8, 8), (8, 64), (8, 256)):
+    life = PeerBitLife(G, G, True, dev, generations_per_launch=T, ghost=ghost)
     life.load(blk)
     life.run(4 * T)
     dist.barrier(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    life.run(400)
+    life.run(1024)
     e1.record()
     dist.barrier(); torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        us = float(t.item()) * 1e3 / 400
-        print(json.dumps({"T": T, "world": world, "us_per_generation": us, "updates_per_s": G * G * world / us * 1e6}), flush=True)
+        us = float(t.item()) * 1e3 / 1024
+        print(json.dumps({"T": T, "ghost": ghost, "exchanges": life.exchanges, "world": world, "us_per_generation": us, "updates_per_s": G * G * world / us * 1e6}), flush=True)
     del life
 if rank == 0:
     print("ALL OK" if ok_all else "MISMATCH", flush=True)
