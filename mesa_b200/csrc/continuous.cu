@@ -33,6 +33,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 namespace {
 
 struct Geometry {
@@ -256,7 +258,7 @@ struct FastParams {
     float seam_x, seam_y;     // |dx| above this may be a neighbour across the torus seam
 };
 
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, 4)
 boids_update_tiled(const float4* __restrict__ packed, const uint32_t* __restrict__ order,
                    const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end, Geometry g,
                    BoidParams bp, FastParams fp, int tiles_x, float2* __restrict__ pos_out,
@@ -354,30 +356,41 @@ boids_update_tiled(const float4* __restrict__ packed, const uint32_t* __restrict
         BoidAcc acc;                                // float64: the rare exact path
         float cohx = 0.f, cohy = 0.f, sepx = 0.f, sepy = 0.f, mx = 0.f, my = 0.f;
         unsigned k = 0;
+        // The boid itself is one of the candidates (d2 = 0): instead of testing `q == p` for every pair it is counted
+        // like a neighbour -- it adds 0 to the difference sums and its own direction to the match sum -- and taken
+        // out again after the loop (get_neighbors_in_radius drops self, continuous_space_agents.py:66-78).
+        auto scan = [&](auto seam) {
 #pragma unroll
-        for (int r = iy - 1; r <= iy + 1; ++r) {
-            const unsigned e = sm.cell_off[r * kHX + ix + 2];
-            for (unsigned q = sm.cell_off[r * kHX + ix - 1]; q < e; ++q) {
-                const float4 o = sm.cand[q];
-                const float dx = o.x - me.x, dy = o.y - me.y;
-                const float d2 = fmaf(dx, dx, dy * dy);
-                if (d2 < fp.vis_lo2) {
-                    if (q == p) continue;  // get_neighbors_in_radius drops self
-                    cohx += dx; cohy += dy;
-                    mx += o.z; my += o.w;
-                    ++k;
-                    if (d2 < fp.sep_hi2) {
-                        if (d2 < fp.sep_lo2) {
-                            sepx += dx; sepy += dy;
-                        } else if (ref_distance2(g, px, py, (double)o.x, (double)o.y) < bp.separation2_lt) {
-                            sepx += dx; sepy += dy;
-                        }
+            for (int r = iy - 1; r <= iy + 1; ++r) {
+                const float4* q = sm.cand + sm.cell_off[r * kHX + ix - 1];
+                const float4* const qe = sm.cand + sm.cell_off[r * kHX + ix + 2];
+                for (; q < qe; ++q) {
+                    const float4 o = *q;
+                    const float dx = o.x - me.x, dy = o.y - me.y;
+                    const float d2 = fmaf(dx, dx, dy * dy);
+                    if (d2 > fp.vis_hi2) {  // surely not a neighbour -- unless the pair straddles the torus seam
+                        if (decltype(seam)::value && (fabsf(dx) > fp.seam_x || fabsf(dy) > fp.seam_y))
+                            boid_pair(g, bp, px, py, o, acc);
+                        continue;
                     }
-                } else if (d2 <= fp.vis_hi2 || (seam_tile && (fabsf(dx) > fp.seam_x || fabsf(dy) > fp.seam_y))) {
-                    boid_pair(g, bp, px, py, o, acc);  // borderline or across the seam: the reference's float64 test
+                    if (d2 < fp.vis_lo2) {
+                        cohx += dx; cohy += dy;
+                        mx += o.z; my += o.w;
+                        ++k;
+                        if (d2 < fp.sep_hi2) {
+                            if (d2 < fp.sep_lo2 || ref_distance2(g, px, py, (double)o.x, (double)o.y) < bp.separation2_lt) {
+                                sepx += dx; sepy += dy;
+                            }
+                        }
+                    } else {
+                        boid_pair(g, bp, px, py, o, acc);  // borderline: the reference's float64 test
+                    }
                 }
             }
-        }
+        };
+        if (seam_tile) scan(std::true_type{}); else scan(std::false_type{});
+        mx -= me.z; my -= me.w;   // take the boid itself out again
+        k -= 1u;
         acc.cohx += (double)cohx; acc.cohy += (double)cohy;
         acc.sepx += (double)sepx; acc.sepy += (double)sepy;
         acc.mx += (double)mx; acc.my += (double)my;
