@@ -172,6 +172,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep rank 0's stdout to the ONE JSON line (the banner goes to stdout)
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
@@ -431,6 +433,22 @@ def other_workloads(dev):
         boids()
     t = timed(boids, 10)
     out.append({"workload": "boids_1e7_vision15_synchronous", "ms_per_step": t * 1e3, "agent_updates_per_s": N / t})
+    # the same flock in the reference's SEQUENTIAL shuffle_do order (exact replay mode, rank-ordered chained kernel)
+    reach = ops.boids_reach(state[1], 1.0)
+    sws = ops.BoidsSeqWorkspace(N, (side, side), 15.0, reach, dev)
+    epoch = [0]
+
+    def boids_seq():
+        ops.boids_step_sequential(state[0], state[1], (side, side), seed=11, epoch=epoch[0], vision=15.0, separation=2.0,
+                                  reach=reach, ws=sws, pos_out=state[2], dir_out=state[3])
+        epoch[0] += 1
+        state[0], state[2] = state[2], state[0]
+        state[1], state[3] = state[3], state[1]
+
+    boids_seq()
+    t = timed(boids_seq, 4)
+    out.append({"workload": "boids_1e7_vision15_sequential_shuffle_do", "ms_per_step": t * 1e3, "agent_updates_per_s": N / t,
+                "note": "identical to the reference's sequential activation in the Philox order (dependency-chained kernel)"})
     return out
 
 

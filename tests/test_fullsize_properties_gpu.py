@@ -152,3 +152,45 @@ def test_boids_full_size_consistency():
     step = po.double() - pos.double()
     step = torch.where(step > side / 2, step - side, torch.where(step < -side / 2, step + side, step))
     assert float((torch.linalg.norm(step, dim=1) - torch.where(has, 1.0, torch.linalg.norm(dirs.double(), dim=1))).abs().max()) < 2e-3
+
+
+def test_gol_full_size_bit_packed_1000_generations_equal_uint8_kernel():
+    """BASELINE config 2 at full size and length: 1000 generations of 16384^2 on the bit-packed planes (8 per launch,
+    csrc/gol_bits.cu) equal 1000 launches of the uint8-layer kernel (csrc/gol.cu) bit for bit; the two kernels share
+    nothing but the rule, and the uint8 kernel is pinned to the oracle / the live reference at small sizes."""
+    from mesa_b200 import ops
+
+    n = 16384
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = (torch.rand((n, n), device="cuda", generator=g) < 0.2).to(torch.uint8)
+    life = ops.BitLife(n, n, "cuda", torus=True)
+    life.load(x)
+    y = x.clone()
+    checked = 0
+    for chunk in (1, 7, 64, 928):   # 1000 generations in total, compared at four points
+        life.run(chunk)
+        y = _gol(y, chunk)
+        checked += chunk
+        assert torch.equal(life.store(), y), f"bit-packed and uint8 kernels diverge by generation {checked}"
+    assert checked == 1000 and int(y.sum()) > 0
+
+
+def test_gol_full_size_bit_packed_patterns_and_translation():
+    """The same pattern / equivariance properties on the bit-packed path (glider across word, strip and torus seams)."""
+    from mesa_b200 import ops
+
+    n = 16384
+    x = torch.zeros((n, n), dtype=torch.uint8, device="cuda")
+    glider = [(0, 1), (1, 2), (2, 0), (2, 1), (2, 2)]
+    for oi, oj in [(n - 2, n - 2), (5000, 958), (63, 30), (8191, 16383 - 1)]:   # torus corner, strip edge (30 words), word edge
+        for i, j in glider:
+            x[(oi + i) % n, (oj + j) % n] = 1
+    life = ops.BitLife(n, n, "cuda", torus=True, generations_per_launch=8)
+    life.load(x)
+    life.run(40)                                   # a glider moves (+1, +1) every 4 generations
+    assert torch.equal(life.store(), torch.roll(x, (10, 10), (0, 1)))
+    g = torch.Generator(device="cuda").manual_seed(3)
+    r = (torch.rand((n, n), device="cuda", generator=g) < 0.3).to(torch.uint8)
+    a = ops.BitLife(n, n, "cuda", torus=True); a.load(r); a.run(12)
+    b = ops.BitLife(n, n, "cuda", torus=True); b.load(torch.roll(r, (777, -3333), (0, 1)).contiguous()); b.run(12)
+    assert torch.equal(b.store(), torch.roll(a.store(), (777, -3333), (0, 1)))
