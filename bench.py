@@ -173,7 +173,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep rank 0's stdout to the ONE JSON line (the banner goes to stdout)
+            del os.environ["NCCL_DEBUG"]   # the image's default prints a banner on stdout; rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 

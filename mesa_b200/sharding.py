@@ -229,85 +229,138 @@ class FusedPeerGol:
             raise RuntimeError("FusedPeerGol: timed out waiting for a neighbouring rank")
 
 
-class PeerBitLife:
-    """Row-sharded Game of Life on the BIT-PACKED layer (csrc/gol_bits.cu) with DEEP GHOST ZONES.
+class DeepGhostLayer:
+    """Row block of a sharded layer with DEEP GHOST ZONES: `ghost` rows of each ring neighbour on either side, two
+    ping-pong planes.  The extended block is stepped as a clamped grid: the rows next to its outer edge go wrong at one
+    row per generation, so the owned rows stay exact for `ghost` generations; only then are the ghost rows refreshed
+    from the neighbours -- ONE exchange per `ghost` generations instead of one per launch.  A clamped outer edge of the
+    grid gets no ghost rows (cells outside the grid stay dead for ever, ghost rows are ordinary cells).
 
-    Each rank keeps its row block plus `ghost` rows of each ring neighbour (two ping-pong planes in symmetric memory)
-    and steps the extended block as a clamped grid: the rows next to the outer edge go wrong at one row per
-    generation, so the owned rows stay exact for `ghost` generations.  Only then are the ghost rows refreshed -- each
-    rank copies the neighbours' edge rows out of their HBM over NVLink (peer-mapped tensors) between two device-side
-    barriers -- i.e. one exchange per `ghost` generations (default 64: 0.8 % redundant rows on a 16384-row block)
-    instead of one per launch.  No collective on the data path."""
+    transport="peer": the planes live in torch symmetric memory and every rank copies the neighbours' edge rows out
+    of their HBM over NVLink (peer-mapped tensors) between two device-side barriers (CUDA + NCCL group).
+    transport="p2p": plain tensors, the edge rows travel with send/recv (HaloExchanger; gloo on CPU in the tests)."""
+
+    def __init__(self, rows: int, width: int, dtype: torch.dtype, ghost: int, torus: bool, device, group=None,
+                 transport: str = "peer"):
+        if transport not in ("peer", "p2p"):
+            raise ValueError("transport must be 'peer' or 'p2p'")
+        self.group = group if group is not None else (dist.group.WORLD if dist.is_initialized() else None)
+        self.rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        self.rows, self.width, self.torus = int(rows), int(width), bool(torus)
+        self.ghost = g = max(1, min(int(ghost), self.rows))
+        self.device = torch.device(device)
+        self.transport = transport
+        up = self.rank - 1 if self.rank > 0 else (self.world - 1 if self.torus else None)
+        down = self.rank + 1 if self.rank < self.world - 1 else (0 if self.torus else None)
+        shape = (2, self.rows + 2 * g, self.width)
+        if transport == "peer":
+            import torch.distributed._symmetric_memory as symm_mem
+
+            self.buf = symm_mem.empty(shape, dtype=dtype, device=self.device)
+            self.buf.zero_()
+            self.hdl = symm_mem.rendezvous(self.buf, self.group)
+            self.peer_up = self.hdl.get_buffer(up, shape, dtype) if up is not None else None
+            self.peer_down = self.hdl.get_buffer(down, shape, dtype) if down is not None else None
+            self.hdl.barrier()
+        else:
+            self.buf = torch.zeros(shape, dtype=dtype, device=self.device)
+            self.hx = HaloExchanger(self.width, dtype, g, self.torus, self.device, group)
+        self.has_up, self.has_down = up is not None, down is not None
+        # rows of a plane that are stepped
+        self._lo = 0 if self.has_up else g
+        self._hi = self.rows + 2 * g if self.has_down else g + self.rows
+        self.cur = 0
+        self.valid = 0          # generations the ghost rows are still good for
+        self.exchanges = 0
+
+    @property
+    def state(self) -> torch.Tensor:
+        """The owned rows of the current generation."""
+        return self.buf[self.cur, self.ghost:self.ghost + self.rows]
+
+    def planes(self):
+        """(source, destination) row ranges to step: the owned rows plus the ghost zones that exist."""
+        return self.buf[self.cur, self._lo:self._hi], self.buf[1 - self.cur, self._lo:self._hi]
+
+    def invalidate(self) -> None:
+        self.valid = 0
+
+    def refresh(self) -> None:
+        """Bring the ghost rows of the current generation up to date (collective)."""
+        g, R, c = self.ghost, self.rows, self.cur
+        mine = self.buf[c]
+        if self.transport == "peer":
+            self.hdl.barrier()                       # every rank has finished writing the current generation
+            if self.has_up:
+                mine[:g].copy_(self.peer_up[c, R:R + g])            # the last owned rows of the rank above
+            if self.has_down:
+                mine[g + R:].copy_(self.peer_down[c, g:2 * g])      # the first owned rows of the rank below
+            self.hdl.barrier()                       # nobody overwrites a plane a neighbour is still copying from
+        else:
+            top, bot = self.hx.exchange(mine[g:g + R])
+            if self.has_up:
+                mine[:g].copy_(top)
+            if self.has_down:
+                mine[g + R:].copy_(bot)
+        self.valid = g
+        self.exchanges += 1
+
+    def advance(self, generations: int) -> None:
+        """The destination plane now holds the state `generations` later."""
+        if generations > self.valid:
+            raise ValueError("stepped further than the ghost rows allow")
+        self.cur ^= 1
+        self.valid -= int(generations)
+
+
+class PeerBitLife:
+    """Row-sharded Game of Life on the BIT-PACKED layer (csrc/gol_bits.cu) over a DeepGhostLayer: each rank keeps 64
+    rows of each ring neighbour and refreshes them from the neighbours' HBM over NVLink once per 64 generations
+    (0.8 % redundant rows on a 16384-row block).  No collective on the data path."""
 
     def __init__(self, rows: int, cols: int, torus: bool, device, generations_per_launch: int = 8,
                  rows_per_segment: int = 0, ghost: int = 64, group=None):
-        import torch.distributed._symmetric_memory as symm_mem
-
         from . import ops
 
         if cols % 32:
             raise ValueError("the bit-packed layer needs cols to be a multiple of 32")
         self._ops = ops
-        self.group = group if group is not None else dist.group.WORLD
-        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
         self.rows, self.cols, self.torus = int(rows), int(cols), bool(torus)
         self.device = torch.device(device)
         self.generations_per_launch = max(1, min(int(generations_per_launch), ops.GOL_BITS_MAX_GENERATIONS))
         self.rows_per_segment = int(rows_per_segment)
-        self.ghost = max(self.generations_per_launch, min(int(ghost), self.rows))
-        g, wpr = self.ghost, self.cols // 32
-        self.buf = symm_mem.empty((2, self.rows + 2 * g, wpr), dtype=torch.int32, device=self.device)
-        self.buf.zero_()
-        self.hdl = symm_mem.rendezvous(self.buf, self.group)
-        up = self.rank - 1 if self.rank > 0 else (self.world - 1 if self.torus else None)
-        down = self.rank + 1 if self.rank < self.world - 1 else (0 if self.torus else None)
-        shape = (2, self.rows + 2 * g, wpr)
-        self.peer_up = self.hdl.get_buffer(up, shape, torch.int32) if up is not None else None
-        self.peer_down = self.hdl.get_buffer(down, shape, torch.int32) if down is not None else None
-        # rows of the plane that are stepped: a clamped outer edge has no ghost rows (outside the grid cells stay dead
-        # for ever, whereas ghost rows are ordinary cells)
-        self._lo = 0 if self.peer_up is not None else g
-        self._hi = self.rows + 2 * g if self.peer_down is not None else g + self.rows
-        self.cur = 0
-        self.valid = 0          # generations the ghost rows are still good for
-        self.launches = self.exchanges = 0
-        self.hdl.barrier()
+        self.layer = DeepGhostLayer(self.rows, self.cols // 32, torch.int32, max(int(ghost), self.generations_per_launch),
+                                    torus, self.device, group, transport="peer")
+        self.ghost = self.layer.ghost
+        self.launches = 0
+
+    @property
+    def exchanges(self) -> int:
+        return self.layer.exchanges
 
     @property
     def state(self) -> torch.Tensor:
         """The owned rows of the current generation (bit planes)."""
-        return self.buf[self.cur, self.ghost:self.ghost + self.rows]
+        return self.layer.state
 
     def load(self, block: torch.Tensor) -> None:
         """Set the current generation from this rank's uint8 row block (collective)."""
-        self._ops.gol_pack(block, out=self.state)
-        self.valid = 0
+        self._ops.gol_pack(block, out=self.layer.state)
+        self.layer.invalidate()
 
     def store(self, out: torch.Tensor | None = None) -> torch.Tensor:
-        return self._ops.gol_unpack(self.state.contiguous(), out=out)
-
-    def _refresh_ghosts(self) -> None:
-        g, R, c = self.ghost, self.rows, self.cur
-        self.hdl.barrier()                       # every rank has finished writing the current generation
-        mine = self.buf[c]
-        if self.peer_up is not None:
-            mine[:g].copy_(self.peer_up[c, R:R + g])            # the last owned rows of the rank above
-        if self.peer_down is not None:
-            mine[g + R:].copy_(self.peer_down[c, g:2 * g])      # the first owned rows of the rank below
-        self.hdl.barrier()                       # nobody overwrites a plane a neighbour is still copying from
-        self.valid = g
-        self.exchanges += 1
+        return self._ops.gol_unpack(self.layer.state.contiguous(), out=out)
 
     def run(self, generations: int) -> None:
         left = int(generations)
         while left > 0:
-            if self.valid == 0:
-                self._refresh_ghosts()
-            t = min(left, self.generations_per_launch, self.valid)
-            src, dst = self.buf[self.cur, self._lo:self._hi], self.buf[1 - self.cur, self._lo:self._hi]
+            if self.layer.valid == 0:
+                self.layer.refresh()
+            t = min(left, self.generations_per_launch, self.layer.valid)
+            src, dst = self.layer.planes()
             # the extended block is a clamped grid: rows beyond the ghosts are dead (and never reach the owned rows)
             self._ops.gol_step_bits(src, dst, t, torus=False, col_torus=self.torus, rows_per_segment=self.rows_per_segment)
-            self.cur ^= 1
-            self.valid -= t
+            self.layer.advance(t)
             self.launches += 1
             left -= t

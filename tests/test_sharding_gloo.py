@@ -131,3 +131,62 @@ def _owner_worker(rank, world, port, out_dir):
 def test_partition_logic_of_sharded_drivers(tmp_path, world):
     mp.spawn(_owner_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all(bool(np.load(tmp_path / f"ok_{r}.npy")[0]) for r in range(world))
+
+
+# ---- deep ghost zones (mesa_b200.sharding.DeepGhostLayer, the scheme PeerBitLife runs on the GPUs) ---------------
+def _ghost_worker(rank, world, port, torus, gens, ghost, per_launch, rows, cols, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mesa_b200.sharding import DeepGhostLayer
+
+    rng = np.random.default_rng(1)
+    full = (rng.random((rows * world, cols)) < 0.35).astype(np.uint8)
+    layer = DeepGhostLayer(rows, cols, torch.uint8, ghost, torus, "cpu", transport="p2p")
+    layer.state.copy_(torch.from_numpy(full[rank * rows:(rank + 1) * rows]))
+    left, launches = gens, 0
+    while left > 0:
+        if layer.valid == 0:
+            layer.refresh()
+        t = min(left, per_launch, layer.valid)
+        src, dst = layer.planes()
+        x = src.numpy().copy()
+        for _ in range(t):                      # the extended block is stepped as a clamped grid (dead rows outside)
+            x = _gol_block(x, None, None) if torus else _gol_clamped(x)
+        dst.copy_(torch.from_numpy(x))
+        layer.advance(t)
+        left -= t
+        launches += 1
+    np.save(os.path.join(out_dir, f"ghost_{rank}.npy"), layer.state.numpy())
+    np.save(os.path.join(out_dir, f"ghost_stats_{rank}.npy"), np.array([launches, layer.exchanges]))
+    dist.destroy_process_group()
+
+
+def _gol_clamped(ext):
+    """One generation of a block whose outside is dead in both directions."""
+    p = np.pad(ext.astype(np.int32), 1)
+    n = sum(p[1 + di:1 + di + ext.shape[0], 1 + dj:1 + dj + ext.shape[1]] for di in (-1, 0, 1) for dj in (-1, 0, 1)) - ext
+    return ((n == 3) | ((ext == 1) & (n == 2))).astype(np.uint8)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("torus", [True, False])
+@pytest.mark.parametrize("ghost,per_launch,gens", [(4, 3, 11), (6, 8, 13)])
+def test_deep_ghost_zones_equal_unsharded(tmp_path, world, torus, ghost, per_launch, gens):
+    """Every rank keeps `ghost` rows of its neighbours and exchanges them once per `ghost` generations: the sharded
+    run equals the unsharded one (torus: rows and columns wrap; clamped: dead outside, no ghost rows at the edge)."""
+    rows, cols = 12, 20
+    mp.spawn(_ghost_worker, args=(world, _free_port(), torus, gens, ghost, per_launch, rows, cols, str(tmp_path)),
+             nprocs=world, join=True)
+    rng = np.random.default_rng(1)
+    want = (rng.random((rows * world, cols)) < 0.35).astype(np.uint8)
+    for _ in range(gens):
+        if torus:
+            n = sum(np.roll(np.roll(want.astype(np.int32), di, 0), dj, 1) for di in (-1, 0, 1) for dj in (-1, 0, 1)) - want
+            want = ((n == 3) | ((want == 1) & (n == 2))).astype(np.uint8)
+        else:
+            want = _gol_clamped(want)
+    got = np.concatenate([np.load(tmp_path / f"ghost_{r}.npy") for r in range(world)])
+    assert np.array_equal(got, want)
+    launches, exchanges = np.load(tmp_path / "ghost_stats_0.npy")
+    assert exchanges == -(-gens // ghost) and launches >= exchanges
