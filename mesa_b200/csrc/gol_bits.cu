@@ -172,8 +172,8 @@ __device__ __forceinline__ void run_segment(const BitRows& g, uint32_t* __restri
 }
 
 // T generations of the rows [seg*rps, seg*rps + rps) of one 30-word strip.
-template <int T, int kWarps, int kAhead>
-__global__ void __launch_bounds__(kWarps * 32)
+template <int T, int kWarps, int kAhead, int kMinBlocks = 1>
+__global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 gol_bits_kernel(const BitRows g, uint32_t* __restrict__ out, int col_torus, int nstrips, int rps) {
     const int lane = threadIdx.x & 31;
     const unsigned task = blockIdx.x * kWarps + (threadIdx.x >> 5);
@@ -238,13 +238,13 @@ __global__ void gol_unpack_kernel(const uint32_t* __restrict__ bits, uint8_t* __
 // variant = 10 * rows-ahead-iterations + warps per CTA (developer sweep: MB_GOL_BITS_VARIANT)
 constexpr int kDefaultVariant = 14;
 
-template <int kWarps, int kAhead>
+template <int kWarps, int kAhead, int kMinBlocks = 1>
 int launch_bits_v(int T, const BitRows& g, uint32_t* out, int col_torus, int nstrips, int rps, int64_t tasks,
                   cudaStream_t stream) {
     const unsigned blocks = (unsigned)mb::ceil_div(tasks, kWarps);
 #define MB_BITS_CASE(TT)                                                                                            \
     case TT:                                                                                                        \
-        gol_bits_kernel<TT, kWarps, kAhead><<<blocks, kWarps * 32, 0, stream>>>(g, out, col_torus, nstrips, rps); \
+        gol_bits_kernel<TT, kWarps, kAhead, kMinBlocks><<<blocks, kWarps * 32, 0, stream>>>(g, out, col_torus, nstrips, rps); \
         break;
     switch (T) {
         MB_BITS_CASE(1) MB_BITS_CASE(2) MB_BITS_CASE(3) MB_BITS_CASE(4)
@@ -258,6 +258,8 @@ int launch_bits_v(int T, const BitRows& g, uint32_t* out, int col_torus, int nst
 int launch_bits(int variant, int T, const BitRows& g, uint32_t* out, int col_torus, int nstrips, int rps,
                 int64_t tasks, cudaStream_t stream) {
     switch (variant) {
+        case 16: return launch_bits_v<4, 1, 6>(T, g, out, col_torus, nstrips, rps, tasks, stream);  // <= 80 registers
+        case 17: return launch_bits_v<4, 1, 7>(T, g, out, col_torus, nstrips, rps, tasks, stream);  // <= 72 registers
         case 12: return launch_bits_v<2, 1>(T, g, out, col_torus, nstrips, rps, tasks, stream);
         case 18: return launch_bits_v<8, 1>(T, g, out, col_torus, nstrips, rps, tasks, stream);
         case 22: return launch_bits_v<2, 2>(T, g, out, col_torus, nstrips, rps, tasks, stream);
@@ -305,7 +307,9 @@ MB_API int mb_gol_step_bits(const uint32_t* in, const uint32_t* halo_top, const 
     const int wpr = (int)(cols / 32);
     if (rows_per_segment <= 0) {
         static const int env_rps = getenv("MB_GOL_BITS_RPS") ? atoi(getenv("MB_GOL_BITS_RPS")) : 0;
-        rows_per_segment = env_rps > 0 ? env_rps : 64;
+        // measured on 16384^2 (profiles/r1_gol_bits_sweep_fine.jsonl): the best trade between the 2T re-computed rows of
+        // a segment and the balance of many small CTAs is 72 rows for T >= 7 (9.7 us per generation; 64 rows: 11.0)
+        rows_per_segment = env_rps > 0 ? env_rps : (generations >= 7 ? 72 : (generations >= 5 ? 56 : 64));
     }
     rows_per_segment = (rows_per_segment + 1) & ~1;
     const int nstrips = (int)mb::ceil_div(wpr, kStripWords);
