@@ -127,12 +127,29 @@ int mb_reloc_slots_init(const void* shard /* mb_shard_t* */, mb_stream_t stream)
 /* movers = occupied && !happy of the local block; counters[0..1] = movers, occupied */
 int mb_reloc_collect(const void* shard, uint64_t seed, uint32_t epoch, void* workspace, size_t workspace_bytes,
                      int64_t max_movers, mb_stream_t stream);
-/* host4 = {movers, occupied, fallback movers of the last pass, table changed in the last pass}; synchronises */
-int mb_reloc_counters(void* workspace, size_t workspace_bytes, int64_t max_movers, uint64_t* host4,
+/* host7 = {movers, occupied, fallback movers listed, table changed since the last take / FULL pass, (unused), entries of
+ * the release write set, a FULL pass is required}; synchronises */
+int mb_reloc_counters(void* workspace, size_t workspace_bytes, int64_t max_movers, uint64_t* host7,
                       mb_stream_t stream);
-/* one pass over the local movers whose priority lies in [t_lo, t_hi] (rank-ordered buckets, earliest first) */
+/* one pass over the local movers whose priority lies in [t_lo, t_hi] (rank-ordered buckets, earliest first).
+ * mode 0 = FULL: every mover re-evaluates from its first probe (clears the fallback list, the flags and the release set);
+ * mode 1 = RESUME: a mover only checks that it still holds its pick and otherwise continues probing after it (claims only
+ * lower `arr`, so between releases a pick can only move forward); flags accumulate. */
 int mb_reloc_pass(const void* shard, int64_t nmovers, uint64_t seed, uint32_t epoch, uint64_t t_lo, uint64_t t_hi,
-                  void* workspace, size_t workspace_bytes, int64_t max_movers, mb_stream_t stream);
+                  int mode, void* workspace, size_t workspace_bytes, int64_t max_movers, mb_stream_t stream);
+/* release sets: a cell whose registered arrival leaves (a fallback pick that shifts, a mover that moves back) may be empty
+ * again for later movers that skipped it.  mb_reloc_release_take starts an incremental iteration: it moves the first
+ * `count` (<= 4096) recorded (cell, time of the leaver) pairs into caller buffers and clears the set and the changed flag;
+ * mb_reloc_release_scan lets the local movers whose EARLIER probes contain one of `nrel` (<= 4096) released cells move
+ * back to it if it is empty at their time (the probes are replayed from the Philox stream: no table traffic except for
+ * hits).  Row-sharded grids scan the union of all ranks' sets.  Protocol per bucket: a FULL iteration (pass + fallback
+ * phase), then incremental iterations (take, scan, RESUME pass, fallback phase) until one changes nothing, confirmed by a
+ * FULL iteration (csrc/relocate.cu, mb_schelling_relocate). */
+int mb_reloc_release_take(void* workspace, size_t workspace_bytes, int64_t max_movers, uint64_t* cells_out,
+                          uint64_t* times_out, int64_t count, mb_stream_t stream);
+int mb_reloc_release_scan(const void* shard, int64_t nmovers, uint64_t seed, uint32_t epoch, uint64_t t_lo, uint64_t t_hi,
+                          const uint64_t* rel_cells, const uint64_t* rel_times, int64_t nrel, void* workspace,
+                          size_t workspace_bytes, int64_t max_movers, mb_stream_t stream);
 /* argwhere fallback (grid.py:308-316), batched: export (time, k = _randbelow(nempty), mover) of the local
  * fallback movers; count the empties of the local table at <= 2048 ascending times; pick the k_local-th one;
  * commit the picks of the local movers. */

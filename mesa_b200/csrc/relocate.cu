@@ -45,6 +45,8 @@
 // the fallback (gather the fallback movers, all-gather per-rank empty counts).  Priorities and
 // draws are keyed on global agent ids, so the result is identical for every GPU count.
 #include "common.cuh"
+#include <stdio.h>
+#include <stdlib.h>
 #include "philox.cuh"
 
 #include <string.h>
@@ -56,6 +58,7 @@ constexpr unsigned long long kNoCell = ~0ull;
 constexpr int kMaxProbes = 50;   // grid.py:303 `for _ in range(50)`
 constexpr int kMaxPasses = 100000;
 constexpr int kFbBatch = 2048;   // fallback movers served per table pass
+constexpr int kRelCap = 4096;    // released cells recorded between two scans (more: answered with a full pass)
 constexpr int kFbBlocksMax = 4096;
 constexpr int kMaxPeers = 16;
 
@@ -124,6 +127,9 @@ struct RelocWs {
     unsigned long long* mv_prio;    // [cap] priority64
     int8_t* mv_type;                // [cap]
     unsigned long long* choice;     // [cap] GLOBAL cell currently chosen (claimed) by mover m, kNoCell if none
+    uint32_t* progress;             // [cap] probe index of `choice` (kMaxProbes: fallback state) | draws consumed << 8
+    unsigned long long* softmask;   // [cap] bit j: probe j was skipped only because an EARLIER ARRIVAL holds the cell
+                                    //       (vac <= t but arr < t) -- the probes a release can re-open
     uint32_t* fb_list;              // [cap] movers that missed all 50 probes in this pass
     unsigned long long* fb_t;       // [kFbBatch] sorted times of the current fallback batch
     uint32_t* fb_m;                 // [kFbBatch] local mover of each sorted entry
@@ -133,7 +139,12 @@ struct RelocWs {
     uint32_t* fb_block;             // [kFbBatch]
     uint32_t* fb_rem;               // [kFbBatch]
     uint32_t* cnt;                  // [kFbBatch][kFbBlocksMax] empties per local table block
-    unsigned long long* counters;   // [0] movers [1] occupied [2] fallback movers of the pass [3] table changed
+    unsigned long long* rel_w_cell;  // [kRelCap] cells released since the last take (write set)
+    unsigned long long* rel_w_time;  // [kRelCap] time of the mover that left each of them
+    unsigned long long* rel_r_cell;  // [kRelCap] read set of the single-GPU driver's scans
+    unsigned long long* rel_r_time;
+    unsigned long long* counters;   // [0] movers [1] occupied [2] fallback movers listed [3] table changed [4] (unused)
+                                    // [5] entries of the release write set [6] a full pass is required
 };
 
 size_t carve(RelocWs* ws, char* base, int64_t cap) {
@@ -149,6 +160,8 @@ size_t carve(RelocWs* ws, char* base, int64_t cap) {
     t.mv_prio = (unsigned long long*)take(8 * cap);
     t.mv_type = (int8_t*)take(cap);
     t.choice = (unsigned long long*)take(8 * cap);
+    t.progress = (uint32_t*)take(4 * cap);
+    t.softmask = (unsigned long long*)take(8 * cap);
     t.fb_list = (uint32_t*)take(4 * cap);
     t.fb_t = (unsigned long long*)take(8 * kFbBatch);
     t.fb_m = (uint32_t*)take(4 * kFbBatch);
@@ -158,6 +171,10 @@ size_t carve(RelocWs* ws, char* base, int64_t cap) {
     t.fb_block = (uint32_t*)take(4 * kFbBatch);
     t.fb_rem = (uint32_t*)take(4 * kFbBatch);
     t.cnt = (uint32_t*)take(4ull * kFbBlocksMax * kFbBatch);
+    t.rel_w_cell = (unsigned long long*)take(8 * kRelCap);
+    t.rel_w_time = (unsigned long long*)take(8 * kRelCap);
+    t.rel_r_cell = (unsigned long long*)take(8 * kRelCap);
+    t.rel_r_time = (unsigned long long*)take(8 * kRelCap);
     t.counters = (unsigned long long*)take(8 * 8);
     if (ws) *ws = t;
     return off;
@@ -217,6 +234,8 @@ __global__ void collect_movers(ShardView v, RelocWs ws, int64_t cap, uint64_t se
                     ws.mv_prio[slot] = pr;
                     ws.mv_type[slot] = (int8_t)t;
                     ws.choice[slot] = kNoCell;
+                    ws.progress[slot] = 0u;
+                    ws.softmask[slot] = 0ull;
                     slots[c].vac = pr + 1;  // empty for every mover that acts after this one
                 }
             }
@@ -235,7 +254,17 @@ __device__ __forceinline__ void commit_choice(const ShardView& v, RelocWs& ws, i
                                               unsigned long long pick) {
     const unsigned long long held = ws.choice[m];
     if (held != pick) {
-        if (held != kNoCell) atomicCAS(&v.slot(held)->arr, t, kNever);  // release only if I am the registered arrival
+        // release only if I am the registered arrival.  A successful release can re-open the cell for later movers that
+        // skipped it on the way to their pick: it is recorded for the next release scan (relocate_release_scan)
+        if (held != kNoCell && atomicCAS(&v.slot(held)->arr, t, kNever) == t) {
+            const unsigned long long slot = atomicAdd(&ws.counters[5], 1ull);
+            if (slot < (unsigned long long)kRelCap) {
+                ws.rel_w_cell[slot] = held;
+                ws.rel_w_time[slot] = t;
+            } else {
+                *(volatile unsigned long long*)&ws.counters[6] = 1ull;  // too many to scan for: full pass
+            }
+        }
         ws.choice[m] = pick;
         atomicMin(&v.slot(pick)->arr, t);
         mark_changed(ws);
@@ -249,22 +278,130 @@ __device__ __forceinline__ void commit_choice(const ShardView& v, RelocWs& ws, i
 // buckets (earliest first, each to convergence): a mover only depends on earlier movers, so a
 // converged bucket is final, and conflicts inside a bucket are 1/K as dense as in the whole set --
 // far fewer passes touch far fewer movers (978 M movers on 65536^2: 88 passes over everyone without).
+//
+// Three kinds of pass.  FULL (mode 0): every mover re-evaluates its probe sequence from the first probe.
+// RESUME (mode 1): as long as every release is answered by a release scan, the table is MONOTONE for a mover -- claims
+// only lower `arr` (atomicMin), so a probe that was not empty at the mover's time stays so and its pick can only move
+// FORWARD in its probe sequence.  A mover therefore only checks that it still holds its pick (one 16-byte load:
+// arr == its time) and, if an earlier mover took it, continues probing after it (the draw counter is kept in
+// `progress`).  RELEASE SCAN (relocate_release_scan): finds the movers for which a released cell re-opens an EARLIER
+// probe.  8192^2, 15.3 M movers: a full pass 3.1-4.8 ms, a resume pass 0.35 ms once the movers have settled.
 __global__ void __launch_bounds__(128)
 relocate_pass(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, uint32_t epoch, unsigned long long t_lo,
-              unsigned long long t_hi) {
+              unsigned long long t_hi, int mode) {
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= nmovers) return;
     const unsigned long long t = ws.mv_prio[m];
     if (t < t_lo || t > t_hi) return;
     mb::DrawStream ds(seed, epoch, ws.mv_agent[m]);
-    for (int j = 0; j < kMaxProbes; ++j) {
-        const unsigned long long c = ds.randbelow((uint64_t)v.ncells);
-        if (empty_at(load_slot(v.slot(c)), t)) {
-            commit_choice(v, ws, m, t, c);
+    if (mode == 1) {
+        const uint32_t pr = ws.progress[m];
+        if ((pr & 0xffu) >= (uint32_t)kMaxProbes) return;  // fallback state: served by the fallback phase
+        const unsigned long long held = ws.choice[m];
+        const unsigned long long arr = load_slot(v.slot(held)).arr;
+        if (arr == t) return;                              // still the registered arrival of my pick
+        if (arr > t) {                                     // my registration was shadowed and the shadow has left
+            atomicMin(&v.slot(held)->arr, t);
+            mark_changed(ws);
             return;
         }
+        ds.seek(pr >> 8);                                  // an earlier mover took it: go on with the next probe
+        unsigned long long soft = ws.softmask[m] | (1ull << (pr & 0xffu));   // the lost pick is such a probe itself
+        for (int j = (int)(pr & 0xffu) + 1; j < kMaxProbes; ++j) {
+            const unsigned long long c = ds.randbelow((uint64_t)v.ncells);
+            const Slot sl = load_slot(v.slot(c));
+            if (!empty_at(sl, t) || atomicMin(&v.slot(c)->arr, t) < t) {   // (the atomicMin: lost a race, not empty after all)
+                if (sl.vac <= t) soft |= 1ull << j;
+                continue;
+            }
+            ws.choice[m] = c;
+            ws.progress[m] = (uint32_t)j | (ds.c << 8);
+            ws.softmask[m] = soft;
+            mark_changed(ws);
+            return;
+        }
+        ws.choice[m] = kNoCell;
+        ws.softmask[m] = soft;
+        ws.progress[m] = (uint32_t)kMaxProbes;
+        mark_changed(ws);
+        ws.fb_list[atomicAdd(&ws.counters[2], 1ull)] = (uint32_t)m;
+        return;
     }
+    unsigned long long soft = 0ull;
+    for (int j = 0; j < kMaxProbes; ++j) {
+        const unsigned long long c = ds.randbelow((uint64_t)v.ncells);
+        const Slot sl = load_slot(v.slot(c));
+        if (empty_at(sl, t)) {
+            commit_choice(v, ws, m, t, c);
+            ws.progress[m] = (uint32_t)j | (ds.c << 8);
+            ws.softmask[m] = soft;
+            return;
+        }
+        if (sl.vac <= t) soft |= 1ull << j;
+    }
+    ws.softmask[m] = soft;
+    ws.progress[m] = (uint32_t)kMaxProbes;
     ws.fb_list[atomicAdd(&ws.counters[2], 1ull)] = (uint32_t)m;  // served by the fallback phase of this pass
+}
+
+// RELEASE SCAN.  When the registered arrival of a cell leaves it (time t_r), the cell may be empty again for the
+// movers that act later than t_r and had skipped it on the way to their pick.  Finding them needs no table traffic:
+// every mover replays the draws of the probes BEFORE its pick (Philox, registers only) and looks each cell up in a
+// shared-memory hash of the released cells; only a hit loads the slot, and if the cell is empty at the mover's time
+// the mover moves back to it (releasing its own pick in turn, which lands in the next release set).  A fallback-state
+// mover that finds one of its probes open again asks for a full pass (rare).
+__global__ void __launch_bounds__(512)
+relocate_release_scan(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, uint32_t epoch, unsigned long long t_lo,
+                      unsigned long long t_hi, const unsigned long long* __restrict__ rel_cell,
+                      const unsigned long long* __restrict__ rel_time, int nrel, int nslots) {
+    extern __shared__ __align__(16) unsigned long long hash_raw[];
+    unsigned long long* hkey = hash_raw;            // cell + 1, 0 = free slot; nslots (a power of two >= 2 nrel) entries
+    unsigned long long* htime = hash_raw + nslots;  // earliest release time of that cell in this set
+    const unsigned hmask = (unsigned)nslots - 1u;
+    for (int i = threadIdx.x; i < nslots; i += blockDim.x) { hkey[i] = 0ull; htime[i] = kNever; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nrel; i += blockDim.x) {
+        const unsigned long long key = rel_cell[i] + 1ull;
+        unsigned h = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 40) & hmask;
+        while (true) {
+            const unsigned long long prev = atomicCAS(&hkey[h], 0ull, key);
+            if (prev == 0ull || prev == key) { atomicMin(&htime[h], rel_time[i]); break; }
+            h = (h + 1) & hmask;
+        }
+    }
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < nmovers; m += stride) {
+        const unsigned long long t = ws.mv_prio[m];
+        if (t < t_lo || t > t_hi) continue;
+        const uint32_t pr = ws.progress[m];
+        const int upto = (int)(pr & 0xffu);  // probes before the pick (all kMaxProbes of a fallback-state mover)
+        // only probes that were skipped because of an earlier ARRIVAL can re-open; most movers have none
+        const unsigned long long soft = ws.softmask[m] & (upto >= 64 ? ~0ull : ((1ull << upto) - 1ull));
+        if (soft == 0ull) continue;
+        const int last = 63 - __clzll((long long)soft);
+        mb::DrawStream ds(seed, epoch, ws.mv_agent[m]);
+        for (int j = 0; j <= last; ++j) {
+            const unsigned long long c = ds.randbelow((uint64_t)v.ncells);
+            if (((soft >> j) & 1ull) == 0ull) continue;
+            const unsigned long long key = c + 1ull;
+            unsigned h = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 40) & hmask;
+            bool hit = false;
+            while (hkey[h] != 0ull) {
+                if (hkey[h] == key) { hit = htime[h] < t; break; }
+                h = (h + 1) & hmask;
+            }
+            if (!hit || !empty_at(load_slot(v.slot(c)), t)) continue;
+            if (upto >= kMaxProbes) {
+                *(volatile unsigned long long*)&ws.counters[6] = 1ull;
+            } else {
+                commit_choice(v, ws, m, t, c);
+                ws.progress[m] = (uint32_t)j | (ds.c << 8);
+                ws.softmask[m] = soft & ((1ull << j) - 1ull);
+            }
+            break;
+        }
+    }
 }
 
 // ---- argwhere fallback, batched -----------------------------------------------------------------
@@ -454,8 +591,8 @@ __global__ void relocate_arrive(ShardView v, RelocWs ws, uint32_t* agent_cell, i
     reinterpret_cast<ulonglong2*>(v.slots[o])[d] = make_ulonglong2(kNever, kNever);
 }
 
-int read_counters(const RelocWs& ws, unsigned long long* host4, cudaStream_t stream) {
-    int rc = mb::check_cuda(cudaMemcpyAsync(host4, ws.counters, 4 * sizeof(unsigned long long),
+int read_counters(const RelocWs& ws, unsigned long long* host7, cudaStream_t stream) {
+    int rc = mb::check_cuda(cudaMemcpyAsync(host7, ws.counters, 7 * sizeof(unsigned long long),
                                             cudaMemcpyDeviceToHost, stream), "read counters");
     if (rc) return rc;
     return mb::check_cuda(cudaStreamSynchronize(stream), "sync");
@@ -519,27 +656,81 @@ MB_API int mb_reloc_collect(const void* shard, uint64_t seed, uint32_t epoch, vo
     return MB_OK;
 }
 
-// copies counters [movers, occupied, fallback movers of the pass, table changed] to the host; synchronises
-MB_API int mb_reloc_counters(void* workspace, size_t workspace_bytes, int64_t max_movers, uint64_t* host4,
+// copies counters [movers, occupied, fallback movers listed, table changed since the last take / full pass, -, entries of
+// the release write set, a full pass is required] to the host (7 words); synchronises
+MB_API int mb_reloc_counters(void* workspace, size_t workspace_bytes, int64_t max_movers, uint64_t* host7,
                              cudaStream_t stream) {
     RelocWs ws;
     int rc = get_ws(&ws, workspace, workspace_bytes, max_movers);
     if (rc) return rc;
-    MB_REQUIRE(host4 != nullptr, "mb_reloc_counters: null output");
-    return read_counters(ws, (unsigned long long*)host4, stream);
+    MB_REQUIRE(host7 != nullptr, "mb_reloc_counters: null output");
+    return read_counters(ws, (unsigned long long*)host7, stream);
 }
 
+// start of an incremental iteration: moves the first `count` (<= 4096) entries of the release write set (cells whose
+// registered arrival left, and the time of the mover that left) into caller buffers, clears the set and the changed flag
+MB_API int mb_reloc_release_take(void* workspace, size_t workspace_bytes, int64_t max_movers, uint64_t* cells_out,
+                                 uint64_t* times_out, int64_t count, cudaStream_t stream) {
+    RelocWs ws;
+    int rc = get_ws(&ws, workspace, workspace_bytes, max_movers);
+    if (rc) return rc;
+    MB_REQUIRE(count >= 0 && count <= kRelCap && (count == 0 || (cells_out && times_out)), "mb_reloc_release_take: bad argument");
+    if (count > 0) {
+        if ((rc = mb::check_cuda(cudaMemcpyAsync(cells_out, ws.rel_w_cell, 8 * count, cudaMemcpyDeviceToDevice, stream), "copy"))) return rc;
+        if ((rc = mb::check_cuda(cudaMemcpyAsync(times_out, ws.rel_w_time, 8 * count, cudaMemcpyDeviceToDevice, stream), "copy"))) return rc;
+    }
+    if ((rc = mb::check_cuda(cudaMemsetAsync(ws.counters + 3, 0, sizeof(unsigned long long), stream), "memset"))) return rc;
+    return mb::check_cuda(cudaMemsetAsync(ws.counters + 5, 0, sizeof(unsigned long long), stream), "memset");
+}
+
+// release scan (see relocate_release_scan): the local movers in [t_lo, t_hi] whose EARLIER probes include one of the
+// `nrel` (<= 4096) released cells move back to it if it is empty at their time.  Flags accumulate.
+MB_API int mb_reloc_release_scan(const void* shard, int64_t nmovers, uint64_t seed, uint32_t epoch, uint64_t t_lo,
+                                 uint64_t t_hi, const uint64_t* rel_cells, const uint64_t* rel_times, int64_t nrel,
+                                 void* workspace, size_t workspace_bytes, int64_t max_movers, cudaStream_t stream) {
+    ShardView v;
+    RelocWs ws;
+    int rc = make_view((const ShardDesc*)shard, &v);
+    if (rc) return rc;
+    if ((rc = get_ws(&ws, workspace, workspace_bytes, max_movers))) return rc;
+    MB_REQUIRE(nmovers >= 0 && nmovers <= max_movers, "mb_reloc_release_scan: mover count exceeds the workspace");
+    MB_REQUIRE(nrel >= 0 && nrel <= kRelCap && (nrel == 0 || (rel_cells && rel_times)), "mb_reloc_release_scan: bad release set");
+    if (nmovers > 0 && nrel > 0) {
+        int slots = 256;  // small sets (the usual case) get a small hash so that several CTAs fit on an SM
+        while (slots < 2 * nrel) slots <<= 1;
+        const int smem = 2 * slots * (int)sizeof(unsigned long long);
+        static bool attr_set = false;
+        if (!attr_set) {
+            if ((rc = mb::check_cuda(cudaFuncSetAttribute(relocate_release_scan, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                          2 * 2 * kRelCap * (int)sizeof(unsigned long long)),
+                                     "cudaFuncSetAttribute"))) return rc;
+            attr_set = true;
+        }
+        const int64_t want = mb::ceil_div(nmovers, 512);
+        const int64_t cap = (int64_t)mb::sm_count() * (smem <= 32768 ? 4 : 1);
+        relocate_release_scan<<<(unsigned)(want < cap ? want : cap), 512, smem, stream>>>(
+            v, ws, nmovers, seed, epoch, t_lo, t_hi, (const unsigned long long*)rel_cells, (const unsigned long long*)rel_times,
+            (int)nrel, slots);
+    }
+    MB_LAUNCH_CHECK("mb_reloc_release_scan");
+    return MB_OK;
+}
+
+// mode 0: FULL pass (every mover from its first probe; clears the fallback list, the flags and the release set first);
+// mode 1: RESUME pass (movers only verify their pick and continue after it; flags accumulate).  RESUME passes are valid
+// as long as every recorded release has been answered by a release scan (or a FULL pass).
 MB_API int mb_reloc_pass(const void* shard, int64_t nmovers, uint64_t seed, uint32_t epoch, uint64_t t_lo, uint64_t t_hi,
-                         void* workspace, size_t workspace_bytes, int64_t max_movers, cudaStream_t stream) {
+                         int mode, void* workspace, size_t workspace_bytes, int64_t max_movers, cudaStream_t stream) {
     ShardView v;
     RelocWs ws;
     int rc = make_view((const ShardDesc*)shard, &v);
     if (rc) return rc;
     if ((rc = get_ws(&ws, workspace, workspace_bytes, max_movers))) return rc;
     MB_REQUIRE(nmovers >= 0 && nmovers <= max_movers, "mb_reloc_pass: mover count exceeds the workspace");
-    if ((rc = mb::check_cuda(cudaMemsetAsync(ws.counters + 2, 0, 2 * sizeof(unsigned long long), stream), "memset"))) return rc;
+    MB_REQUIRE(mode == 0 || mode == 1, "mb_reloc_pass: mode must be 0 (full) or 1 (resume)");
+    if (mode == 0 && (rc = mb::check_cuda(cudaMemsetAsync(ws.counters + 2, 0, 5 * sizeof(unsigned long long), stream), "memset"))) return rc;
     if (nmovers > 0)
-        relocate_pass<<<(unsigned)mb::ceil_div(nmovers, 128), 128, 0, stream>>>(v, ws, nmovers, seed, epoch, t_lo, t_hi);
+        relocate_pass<<<(unsigned)mb::ceil_div(nmovers, 128), 128, 0, stream>>>(v, ws, nmovers, seed, epoch, t_lo, t_hi, mode);
     MB_LAUNCH_CHECK("mb_reloc_pass");
     return MB_OK;
 }
@@ -657,7 +848,7 @@ MB_API int mb_schelling_relocate(int8_t* type, uint8_t* happy, uint32_t* agent_i
     if (rc) return rc;
     if ((rc = get_ws(&ws, workspace, workspace_bytes, max_movers))) return rc;
     if ((rc = mb_reloc_collect(&d, seed, epoch, workspace, workspace_bytes, max_movers, stream))) return rc;
-    unsigned long long hc[4];
+    unsigned long long hc[7];
     if ((rc = read_counters(ws, hc, stream))) return rc;
     const int64_t nmovers = (int64_t)hc[0], noccupied = (int64_t)hc[1];
     if (out_movers) *out_movers = nmovers;
@@ -679,12 +870,28 @@ MB_API int mb_schelling_relocate(int8_t* type, uint8_t* happy, uint32_t* agent_i
         const unsigned long long width = buckets > 1 ? (1ull << 63) / (buckets / 2) : 0ull;  // 2^64 / buckets
         const unsigned long long t_lo = buckets > 1 ? width * (unsigned long long)b : 0ull;
         const unsigned long long t_hi = (buckets > 1 && b + 1 < buckets) ? t_lo + (width - 1) : kNever;
+        // An ITERATION = [movers re-evaluate] + [fallback phase].  The first iteration of a bucket is FULL (every mover
+        // from its first probe, 3-5 ms at 15 M movers); the following ones are INCREMENTAL: a release scan for the cells
+        // whose registered arrival left in the previous iteration, then a RESUME pass (~0.4-2 ms together).  The
+        // termination criterion stays a FULL iteration that changes nothing: an incremental iteration without any change
+        // is confirmed by one.
+        bool full = true, confirmed = false;
+        int64_t nrel = 0;
         for (;; ++pass) {
             if (pass >= kMaxPasses) {
                 mb::set_error("mb_schelling_relocate: no convergence after %d passes", pass);
                 return MB_ERR_CUDA;
             }
-            if ((rc = mb_reloc_pass(&d, nmovers, seed, epoch, t_lo, t_hi, workspace, workspace_bytes, max_movers, stream))) return rc;
+            if (full) {
+                if ((rc = mb_reloc_pass(&d, nmovers, seed, epoch, t_lo, t_hi, 0, workspace, workspace_bytes, max_movers, stream))) return rc;
+            } else {
+                if ((rc = mb_reloc_release_take(workspace, workspace_bytes, max_movers, (uint64_t*)ws.rel_r_cell,
+                                                (uint64_t*)ws.rel_r_time, nrel, stream))) return rc;
+                if (nrel > 0 && (rc = mb_reloc_release_scan(&d, nmovers, seed, epoch, t_lo, t_hi, (const uint64_t*)ws.rel_r_cell,
+                                                            (const uint64_t*)ws.rel_r_time, nrel, workspace, workspace_bytes,
+                                                            max_movers, stream))) return rc;
+                if ((rc = mb_reloc_pass(&d, nmovers, seed, epoch, t_lo, t_hi, 1, workspace, workspace_bytes, max_movers, stream))) return rc;
+            }
             if ((rc = read_counters(ws, hc, stream))) return rc;
             const int64_t nfb = (int64_t)hc[2];
             if (nfb > 0) {
@@ -701,7 +908,19 @@ MB_API int mb_schelling_relocate(int8_t* type, uint8_t* happy, uint32_t* agent_i
                 }
                 if ((rc = read_counters(ws, hc, stream))) return rc;
             }
-            if (hc[3] == 0) { ++pass; break; }  // a pass without any change of the table: this bucket is final
+            const bool changed = hc[3] != 0 || hc[5] != 0 || hc[6] != 0;
+            const bool was_full = full;
+            nrel = (int64_t)hc[5];
+            if (!changed) {
+                if (was_full) { ++pass; break; }  // a full iteration without any change: this bucket is final
+                full = confirmed = true;           // confirm the incremental result with one full iteration
+                continue;
+            }
+            if (confirmed && was_full && getenv("MB_RELOC_DEBUG") != nullptr)
+                fprintf(stderr, "[mb reloc] the confirming full iteration %d changed the table (changed=%llu released=%llu)\n",
+                        pass, hc[3], hc[5]);
+            confirmed = false;
+            full = hc[6] != 0 || nrel > kRelCap;   // the release set overflowed, or a fallback-state mover found a probe open
         }
     }
     if ((rc = mb_reloc_apply(&d, 0, nmovers, agent_cell, workspace, workspace_bytes, max_movers, stream))) return rc;

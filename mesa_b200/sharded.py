@@ -115,7 +115,7 @@ class ShardedSchelling:
         self._ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=self.device)
         self._table = ops.happy_threshold_table(self.homophily, self.radius)
         self._count = torch.zeros(1, dtype=torch.int64, device=self.device)
-        self._host4 = (ctypes.c_uint64 * 4)()
+        self._host7 = (ctypes.c_uint64 * 7)()
         self.epoch = 0
         self.happy_count = 0
         self.last_movers = self.last_passes = 0
@@ -131,8 +131,36 @@ class ShardedSchelling:
         dist.barrier(group=self.group)
 
     def _counters(self):
-        N.check(N.lib().mb_reloc_counters(N.ptr(self._ws), self._ws_bytes, self.max_movers, self._host4, self._stream()))
-        return [int(x) for x in self._host4]
+        N.check(N.lib().mb_reloc_counters(N.ptr(self._ws), self._ws_bytes, self.max_movers, self._host7, self._stream()))
+        return [int(x) for x in self._host7]
+
+    _REL_CAP = 4096   # kRelCap of csrc/relocate.cu
+
+    def _pass_flags(self):
+        """(fallback movers per rank, released cells per rank, table changed anywhere, full pass required) -- the counters
+        of every rank, all-reduced; the collective also orders every rank's kernels before the next phase."""
+        c = self._counters()
+        w = self.world
+        flags = torch.zeros(2 * w + 2, dtype=torch.int64, device=self.device)
+        flags[self.rank], flags[w + self.rank], flags[2 * w], flags[2 * w + 1] = c[2], c[5], c[3], c[6]
+        dist.all_reduce(flags, group=self.group)
+        flags = flags.tolist()
+        return flags[:w], flags[w:2 * w], flags[2 * w] != 0, flags[2 * w + 1] != 0
+
+    def _take_releases(self, nrel_all):
+        """Start of an incremental iteration: the union of every rank's release write set (cells whose registered arrival
+        left, time of the leaver); clears the local set and the changed flag."""
+        width = max(max(nrel_all), 1)
+        mine = torch.zeros((2, width), dtype=torch.int64, device=self.device)
+        N.check(N.lib().mb_reloc_release_take(N.ptr(self._ws), self._ws_bytes, self.max_movers, N.ptr(mine[0]),
+                                              N.ptr(mine[1]), nrel_all[self.rank], self._stream()))
+        if sum(nrel_all) == 0:
+            return mine[0], mine[1], 0
+        everyone = torch.empty((self.world, 2, width), dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(everyone, mine, group=self.group)
+        cells = torch.cat([everyone[r, 0, :n] for r, n in enumerate(nrel_all)]).contiguous()
+        times = torch.cat([everyone[r, 1, :n] for r, n in enumerate(nrel_all)]).contiguous()
+        return cells, times, int(cells.numel())
 
     def _allreduce(self, values, op=dist.ReduceOp.SUM):
         t = torch.tensor(values, dtype=torch.int64, device=self.device)
@@ -155,7 +183,7 @@ class ShardedSchelling:
         self.epoch += 1
         with torch.cuda.device(self.device):
             N.check(lib.mb_reloc_collect(self._shard_ref, seed, epoch, ws, wb, mm, self._stream()))
-            movers, occupied, _, _ = self._counters()
+            movers, occupied = self._counters()[:2]
             tot_movers, tot_occupied = self._allreduce([movers, occupied])   # also orders collect before any pass
             self.last_movers, self.last_passes = tot_movers, 0
             if tot_movers == 0:
@@ -171,21 +199,31 @@ class ShardedSchelling:
             for b in range(buckets):
                 t_lo = b * width
                 t_hi = (t_lo + width - 1) if b + 1 < buckets else (1 << 64) - 1
+                # an ITERATION = [movers re-evaluate] + [fallback phase]; the first one of a bucket is FULL, the following ones
+                # incremental (release scan + RESUME pass), and an incremental iteration that changes nothing is confirmed
+                # by a FULL one (csrc/relocate.cu).  Every rank takes the same decisions (all-reduced flags).
+                full, nrel_all = True, [0] * self.world
                 while True:
                     self.last_passes += 1
-                    N.check(lib.mb_reloc_pass(self._shard_ref, movers, seed, epoch, t_lo, t_hi, ws, wb, mm, self._stream()))
-                    _, _, nfb, changed = self._counters()
-                    per_rank = torch.zeros(self.world, dtype=torch.int64, device=self.device)
-                    per_rank[self.rank] = nfb
-                    flags = torch.cat([per_rank, torch.tensor([changed], dtype=torch.int64, device=self.device)])
-                    dist.all_reduce(flags, group=self.group)      # every rank's pass has finished past this point
-                    nfb_all, changed = flags[:-1].tolist(), int(flags[-1].item())
+                    if full:
+                        N.check(lib.mb_reloc_pass(self._shard_ref, movers, seed, epoch, t_lo, t_hi, 0, ws, wb, mm, self._stream()))
+                    else:
+                        cells, times, total = self._take_releases(nrel_all)
+                        if total > 0:
+                            N.check(lib.mb_reloc_release_scan(self._shard_ref, movers, seed, epoch, t_lo, t_hi, N.ptr(cells),
+                                                              N.ptr(times), total, ws, wb, mm, self._stream()))
+                        N.check(lib.mb_reloc_pass(self._shard_ref, movers, seed, epoch, t_lo, t_hi, 1, ws, wb, mm, self._stream()))
+                    nfb_all, _, _, _ = self._pass_flags()       # also: every rank's pass has finished past this point
                     if sum(nfb_all) > 0:
-                        self._serve_fallback(nfb, nfb_all, nempty, seed, epoch)
-                        _, _, _, changed2 = self._counters()
-                        changed += self._allreduce([changed2])[0]
-                    if changed == 0:
-                        break
+                        self._serve_fallback(nfb_all[self.rank], nfb_all, nempty, seed, epoch)
+                    _, nrel_all, changed, force = self._pass_flags()
+                    was_full = full
+                    if not (changed or force or sum(nrel_all) > 0):
+                        if was_full:
+                            break                                   # a full iteration without any change: the bucket is final
+                        full = True                                 # confirm the incremental result
+                        continue
+                    full = force or sum(nrel_all) > self._REL_CAP
             N.check(lib.mb_reloc_apply(self._shard_ref, 0, movers, None, ws, wb, mm, self._stream()))
             self._barrier()      # every origin is empty before any arrival is written
             N.check(lib.mb_reloc_apply(self._shard_ref, 1, movers, None, ws, wb, mm, self._stream()))
