@@ -192,7 +192,8 @@ def run_ours(args):
         if world > 1:
             from mesa_b200.sharding import PeerBitLife
 
-            life = PeerBitLife(GRID, GRID, True, dev, generations_per_launch=gens_per_launch)
+            life = PeerBitLife(GRID, GRID, True, dev, generations_per_launch=gens_per_launch,
+                               ghost=int(os.environ.get("MB_GOL_GHOST", "0")) or None)
         else:
             life = ops.BitLife(GRID, GRID, dev, torus=True, generations_per_launch=gens_per_launch)
         life.load(a)

@@ -305,14 +305,32 @@ MB_API int mb_gol_step_bits(const uint32_t* in, const uint32_t* halo_top, const 
     // same restriction as mb_gol_step_u8: a torus narrower than 3 cells aliases neighbours (cell.py:239-241)
     MB_REQUIRE(!(col_torus && cols < 3), "mb_gol_step_bits: torus needs cols >= 3");
     const int wpr = (int)(cols / 32);
+    const int nstrips = (int)mb::ceil_div(wpr, kStripWords);
     if (rows_per_segment <= 0) {
         static const int env_rps = getenv("MB_GOL_BITS_RPS") ? atoi(getenv("MB_GOL_BITS_RPS")) : 0;
-        // measured on 16384^2 (profiles/r1_gol_bits_sweep_fine.jsonl): the best trade between the 2T re-computed rows of
-        // a segment and the balance of many small CTAs is 72 rows for T >= 7 (9.7 us per generation; 64 rows: 11.0)
-        rows_per_segment = env_rps > 0 ? env_rps : (generations >= 7 ? 72 : (generations >= 5 ? 56 : 64));
+        rows_per_segment = env_rps;
+    }
+    if (rows_per_segment <= 0) {
+        // Segment height by a small cost model (fitted to the sweeps in profiles/): every SM executes k = ceil(CTAs / SMs)
+        // CTAs one after the other (the kernel is bound by the SM's ALU pipe) and a CTA costs rows + 2T row steps, so the
+        // launch costs ~ (rows_per_segment + 2T) * k.  The load-balance quantisation matters more than the 2T recomputed
+        // rows: 16384 rows at 72 rows per segment are 1026 CTAs = 6.93 per SM (9.6 us per generation), 16640 rows would be
+        // 1044 = 7.05 per SM, i.e. 8 on some SMs (11.9 us).  Few CTAs per SM leave no slack for dynamic balance (measured: 7 per SM
+        // beats 6 and 5 at equal model cost), hence the small penalties.
+        const int sms = mb::sm_count();
+        double best = 1e30;
+        for (int rps = 32; rps <= 160; rps += 2) {
+            const int64_t ctas = mb::ceil_div((int64_t)nstrips * mb::ceil_div(rows, rps), 4);
+            const int64_t k = mb::ceil_div(ctas, sms);
+            // an SM with fewer than 5 CTAs (its residency at T = 8) does not run them any faster: count at least 5
+            const double cost = (double)(rps + 2 * generations) * (double)(k < 5 ? 5 : k) * (k < 6 ? 1.15 : (k == 6 ? 1.04 : 1.0));
+            if (cost < best) {
+                best = cost;
+                rows_per_segment = rps;
+            }
+        }
     }
     rows_per_segment = (rows_per_segment + 1) & ~1;
-    const int nstrips = (int)mb::ceil_div(wpr, kStripWords);
     const int64_t tasks = (int64_t)nstrips * mb::ceil_div(rows, rows_per_segment);
     const char* env_variant = getenv("MB_GOL_BITS_VARIANT");  // read per call: the developer sweep changes it
     const int variant = env_variant ? atoi(env_variant) : kDefaultVariant;

@@ -9,6 +9,7 @@ import numpy as np
 import torch
 
 from .. import ops
+from ..datacollection import DeviceDataCollector
 from ..agentset import DeviceAgent, DeviceAgentSet, batch_operator
 from ..model import DeviceModel
 from ..space import DeviceMooreGrid
@@ -71,10 +72,22 @@ class _Columns(dict):
 class Schelling(DeviceModel):
     """Model class for the Schelling segregation model."""
 
-    def __init__(self, scenario: SchellingScenario = SchellingScenario, initial_types=None, device="cuda"):
+    def __init__(self, scenario: SchellingScenario = SchellingScenario, initial_types=None, device="cuda",
+                 collect: bool = True):
         if isinstance(scenario, type):
             scenario = scenario()
         super().__init__(scenario=scenario)
+        # model.py:53-70: the reference's reporters, served from the device columns (one reduction / one bulk copy each)
+        self.datacollector = DeviceDataCollector(
+            model_reporters={
+                "happy": "happy",
+                "pct_happy": lambda m: (m.happy / len(m.agents)) * 100 if len(m.agents) > 0 else 0,
+                "population": lambda m: len(m.agents),
+                "minority_pct": lambda m: (int((m.agents.get("type") == 1).sum().item()) / len(m.agents) * 100
+                                           if len(m.agents) > 0 else 0),
+            },
+            agent_reporters={"agent_type": "type"},
+        ) if collect else None
         self.density, self.minority_pc = scenario.density, scenario.minority_pc
         self.homophily, self.radius = scenario.homophily, scenario.radius
         self.grid = DeviceMooreGrid((scenario.width, scenario.height), random=self.random, capacity=1, device=device)
@@ -100,6 +113,8 @@ class Schelling(DeviceModel):
         cols = _Columns(self, cell=cells.to(torch.int32), type=flat[cells].clone())
         self.agents = DeviceAgentSet(self, SchellingAgent, n, cols, self.random)
         self.agents.do("assign_state")  # model.py:83-85
+        if self.datacollector is not None:
+            self.datacollector.collect(self)
 
     # `grid.empty` follows the occupancy like the reference's implicit layer (grid.py:128, cell.py:143-170)
     def _sync_empty(self):
@@ -114,4 +129,6 @@ class Schelling(DeviceModel):
         self.agents.shuffle_do("step")
         self.agents.do("assign_state")
         self._sync_empty()
+        if self.datacollector is not None:
+            self.datacollector.collect(self)  # model.py:92
         self.running = self.happy < len(self.agents)

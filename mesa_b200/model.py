@@ -33,6 +33,9 @@ class DeviceModel:
         self.steps = 0
         self.time = 0.0
         self.agents = None  # set by the concrete model (a DeviceAgentSet)
+        # model.py:133-140: the user's step() is wrapped so that every call advances time by one unit
+        self._user_step = self.step
+        self.step = self._wrapped_step
 
     def _next_epoch(self) -> int:
         e = self._epoch
@@ -42,16 +45,17 @@ class DeviceModel:
     def step(self) -> None:  # pragma: no cover - user models override
         """A single step. Fill in here."""
 
-    def _advance(self) -> None:
+    def _wrapped_step(self) -> None:
+        """model.py:152-154: advance time by one unit and run the user's step."""
         self.steps += 1
         self.time += 1.0
-        self.step()
+        self._user_step()
 
     def run_for(self, duration: int) -> None:
         """model.py:395-402: advance `duration` unit-interval steps."""
         for _ in range(int(duration)):
-            self._advance()
+            self.step()
 
     def run_model(self) -> None:
         while self.running:
-            self._advance()
+            self.step()

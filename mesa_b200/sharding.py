@@ -320,8 +320,11 @@ class PeerBitLife:
     (0.8 % redundant rows on a 16384-row block).  No collective on the data path."""
 
     def __init__(self, rows: int, cols: int, torus: bool, device, generations_per_launch: int = 8,
-                 rows_per_segment: int = 0, ghost: int = 64, group=None):
+                 rows_per_segment: int = 0, ghost: int | None = None, group=None):
         from . import ops
+
+        if ghost is None:
+            ghost = 64   # measured best at 2 and at 8 GPUs (profiles/): deeper zones cost more rows than they save barriers
 
         if cols % 32:
             raise ValueError("the bit-packed layer needs cols to be a multiple of 32")

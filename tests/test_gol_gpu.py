@@ -158,7 +158,7 @@ def test_gol_model_packed_equals_unpacked():
     a.run_for(9)
     b.run_for(9)
     want = _oracle_gens(s0.astype(np.uint8), True, 12)
-    assert a.steps == b.steps == 9  # run_for counts steps; direct step() calls do not (DeviceModel)
+    assert a.steps == b.steps == 12 and a.time == 12.0  # every step() call advances time by one unit (model.py:152-154)
     assert np.array_equal(a.grid.state.cpu().numpy(), want)
     assert np.array_equal(b.grid.state.cpu().numpy(), want)
     assert np.array_equal(a.agents.get("state").cpu().numpy(), want.reshape(-1))

@@ -38,7 +38,8 @@ for rows, cols, torus, T, gens, ghost in [(96, 256, True, 4, 30, 8), (64, 1024, 
 G = 16384
 gen = torch.Generator(device=dev).manual_seed(rank)
 blk = (torch.rand((G, G), device=dev, generator=gen) < 0.2).to(torch.uint8)
-for T, ghost in ((8, 8), (8, 64), (8, 256)):
+GHOSTS = [int(x) for x in sys.argv[1].split(',')] if len(sys.argv) > 1 else [8, 64, 256]
+for T, ghost in [(8, gh) for gh in GHOSTS]:
     life = PeerBitLife(G, G, True, dev, generations_per_launch=T, ghost=ghost)
     life.load(blk)
     life.run(4 * T)
