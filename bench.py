@@ -382,11 +382,16 @@ def other_workloads(dev):
                 "hbm_frac_of_measured_peak": 2 * GRID * GRID / ms / 1e6 / peak, "traffic": _ncu_traffic("gol_step_u8_vec")})
     del ua, ub
     # config 0: Schelling 100x100, density 0.8, 100 steps (launch-latency bound: 10 KB of state)
-    m = Schelling(SchellingScenario(width=100, height=100, density=0.8, homophily=0.4, radius=1, rng=42))
+    m = Schelling(SchellingScenario(width=100, height=100, density=0.8, homophily=0.4, radius=1, rng=42), collect=False)
     n = len(m.agents)
     t = timed(m.step, 100)
     out.append({"workload": "schelling_100x100_d0.8_h0.4_r1_100steps", "agents": n, "ms_per_step": t * 1e3,
                 "agent_updates_per_s": n / t, "note": "latency-bound (L2-resident); roofline fraction not meaningful"})
+    # the same with the reference's DataCollector inside step() (model.py:92; 4 model reporters + 1 agent column per step)
+    m = Schelling(SchellingScenario(width=100, height=100, density=0.8, homophily=0.4, radius=1, rng=42), collect=True)
+    t = timed(m.step, 100)
+    out.append({"workload": "schelling_100x100_d0.8_h0.4_r1_100steps_with_datacollector", "agents": n,
+                "ms_per_step": t * 1e3, "agent_updates_per_s": n / t})
     # Schelling happiness stencil alone on 16384^2 (the >= 60 % target of the north star)
     g = torch.Generator(device=dev).manual_seed(0)
     u = torch.rand((GRID, GRID), device=dev, generator=g)

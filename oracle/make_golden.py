@@ -97,6 +97,37 @@ def schelling_fixture(name, width, height, density, homophily, radius, steps, mt
     print(name, "agents", len(agents), "happy", happy_counts[:5], "...", happy_counts[-1], "movers", movers[:5])
 
 
+def datacollector_fixture(name, width, height, density, homophily, radius, steps, mt_seed, philox_seed):
+    """The UNMODIFIED reference Schelling model's own DataCollector output (model.py:53-70, collected at construction
+    and after every step) under the replayed activation order: model-level reporters and the (Step, AgentID)-indexed
+    agent frame.  Pins mesa_b200.datacollection.DeviceDataCollector."""
+    from mesa.examples.basic.schelling.agents import SchellingAgent
+    from mesa.examples.basic.schelling.model import Schelling, SchellingScenario
+
+    with patched_model_random(philox_seed):
+        m = Schelling(SchellingScenario(width=width, height=height, density=density, minority_pc=0.5,
+                                        homophily=homophily, radius=radius, rng=mt_seed))
+    agents = sorted(m.agents, key=lambda a: a.unique_id)
+    types = np.full((width, height), -1, dtype=np.int8)
+    for a in agents:
+        types[a.cell.coordinate] = a.type
+    m.random.replay = True
+    with activation_context(SchellingAgent, "step"):
+        for _ in range(steps):
+            m.step()
+    m.random.replay = False
+    mv = m.datacollector.get_model_vars_dataframe()
+    av = m.datacollector.get_agent_vars_dataframe().reset_index()
+    out = {"width": width, "height": height, "density": density, "homophily": homophily, "radius": radius, "steps": steps,
+           "philox_seed": np.uint64(philox_seed), "types0": types,
+           "model_columns": np.array(list(mv.columns)), "agent_step": av["Step"].to_numpy(dtype=np.float64),
+           "agent_id": av["AgentID"].to_numpy(dtype=np.int64), "agent_type": av["agent_type"].to_numpy(dtype=np.int64)}
+    for c in mv.columns:
+        out["model_" + c] = mv[c].to_numpy(dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLDEN, name), **out)
+    print(name, "rows", len(mv), "agent records", len(av), "happy", list(mv["happy"])[:4])
+
+
 # ------------------------------------------------------------------------------ neighbourhoods
 def neighborhood_fixture(name):
     """Neighbourhood sums of a random integer layer computed cell by cell through the reference's
@@ -243,6 +274,9 @@ def main():
         boltzmann_fixture("boltzmann_2000_20x30.npz", 2000, 20, 30, 10, 7, 4)     # crowded cells
         boltzmann_fixture("boltzmann_10000_100x100.npz", 10000, 100, 100, 10, 1, 5)  # reference "large"
         return
+    if only == "datacollector":
+        datacollector_fixture("datacollector_schelling_20x20.npz", 20, 20, 0.8, 0.4, 1, 10, 42, 2024)
+        return
     if only == "boids":
         boids_fixture("boids_300.npz", 300, 100, 100, 10.0, 2.0, 3, 42, 5)
         boids_fixture("boids_120_wrap.npz", 120, 40, 30, 6.0, 2.0, 3, 1, 6)
@@ -252,6 +286,7 @@ def main():
     gol_fixture(64, 48, 7, 20, "gol_64x48.npz")
     schelling_fixture("schelling_20x20_r1.npz", 20, 20, 0.8, 0.4, 1, 30, 42, 2024, full_steps=range(1, 31))
     schelling_fixture("schelling_16x48_r2.npz", 16, 48, 0.9, 0.6, 2, 12, 5, 99, full_steps=range(1, 13))
+    datacollector_fixture("datacollector_schelling_20x20.npz", 20, 20, 0.8, 0.4, 1, 10, 42, 2024)
     boids_fixture("boids_300.npz", 300, 100, 100, 10.0, 2.0, 3, 42, 5)
     boids_fixture("boids_120_wrap.npz", 120, 40, 30, 6.0, 2.0, 3, 1, 6)
     boltzmann_fixture("boltzmann_100_10x10.npz", 100, 10, 10, 25, 42, 3)
