@@ -278,27 +278,12 @@ MB_API int mb_gol_step_u8(const uint8_t* in, const uint8_t* halo_top, const uint
                          (halo_bot == nullptr || (reinterpret_cast<uintptr_t>(halo_bot) & 15) == 0);
     if (aligned) {
         const int nstrips = (int)mb::ceil_div(cols, 512);
-        static const int variant = getenv("MB_GOL_VARIANT") ? atoi(getenv("MB_GOL_VARIANT")) : 0;
-#define MB_GOL_LAUNCH(RPW, UNR, MINB)                                                                     \
-    do {                                                                                                  \
-        const int64_t tasks = (int64_t)nstrips * mb::ceil_div(rows, RPW);                                 \
-        gol_step_u8_vec<RPW, UNR, MINB, false><<<(unsigned)mb::ceil_div(tasks, kWarps), kWarps * 32, 0, stream>>>( \
-            in, halo_top, halo_bot, out, (int)rows, (int)cols, col_torus, nstrips, PeerSync{});           \
-    } while (0)
-        switch (variant) {
-            // developer variants (MB_GOL_VARIANT); the default is the best of the sweep in profiles/
-            case 1: MB_GOL_LAUNCH(32, 4, 3); break;
-            case 2: MB_GOL_LAUNCH(64, 4, 3); break;
-            case 3: MB_GOL_LAUNCH(64, 2, 4); break;
-            case 4: MB_GOL_LAUNCH(32, 4, 4); break;
-            case 5: MB_GOL_LAUNCH(64, 4, 4); break;
-            case 6: MB_GOL_LAUNCH(8, 4, 4); break;
-            case 7: MB_GOL_LAUNCH(8, 2, 4); break;
-            case 8: MB_GOL_LAUNCH(16, 2, 4); break;
-            case 9: MB_GOL_LAUNCH(16, 4, 5); break;
-            default: MB_GOL_LAUNCH(16, 4, 4); break;  // 90 us / 5.96 TB/s on 16384^2 (64 rows per warp: 95.7 us)
-        }
-#undef MB_GOL_LAUNCH
+        // 16 rows per warp, 4 rows loaded ahead, 4 CTAs per SM: the best of the sweep recorded in profiles/README.md
+        // (rows-per-warp / rows-ahead / min-CTAs: 64/4/3 95.7 us ... 16/4/4 90.1 us on 16384^2)
+        constexpr int kRpw = 16;
+        const int64_t tasks = (int64_t)nstrips * mb::ceil_div(rows, kRpw);
+        gol_step_u8_vec<kRpw, 4, 4, false><<<(unsigned)mb::ceil_div(tasks, kWarps), kWarps * 32, 0, stream>>>(
+            in, halo_top, halo_bot, out, (int)rows, (int)cols, col_torus, nstrips, PeerSync{});
     } else {
         const int64_t n = rows * cols;
         gol_step_u8_scalar<<<(unsigned)mb::ceil_div(n, 256), 256, 0, stream>>>(in, halo_top, halo_bot, out,

@@ -25,6 +25,7 @@
 
 namespace {
 
+constexpr int kBitWarps = 4;          // warps per CTA (independent of each other)
 constexpr int kStripWords = 30;       // useful words per warp; lanes 0 / 31 are halo
 constexpr int kMaxGenerations = 8;    // generations per launch (template instances 1..8)
 
@@ -110,7 +111,7 @@ __device__ __forceinline__ uint32_t advance_row(uint32_t x, int j, uint32_t (&h0
 // + 2T); the first 2T steps only fill the pipeline.  kFast: every row touched (including the two prefetched past
 // the end) lies inside the block, so rows are addressed by pointer increments; otherwise fetch_word resolves
 // halos / dead rows per row.
-template <int T, int kAhead, bool kFast, bool kRowCheck, bool kColMask>
+template <int T, bool kFast, bool kRowCheck, bool kColMask>
 __device__ __forceinline__ void run_segment(const BitRows& g, uint32_t* __restrict__ op, int jstart, int nsteps,
                                             int col, bool colvalid, bool stores, uint32_t cmask) {
     const bool top_dead = g.halo_top == nullptr, bot_dead = g.halo_bot == nullptr;
@@ -125,25 +126,14 @@ __device__ __forceinline__ void run_segment(const BitRows& g, uint32_t* __restri
         if (kFast) return (!kColMask || colvalid) ? __ldg(ip + (size_t)(j - jstart) * pitch) : 0u;
         return fetch_word<T>(g, j, col, colvalid);
     };
-    // rows are loaded kAhead iterations (2 rows each) before they are used
-    uint32_t n0 = fetch(jstart), n1 = fetch(jstart + 1), m0 = 0u, m1 = 0u;
-    if (kAhead == 2) {
-        m0 = fetch(jstart + 2);
-        m1 = fetch(jstart + 3);
-    }
+    // two rows per iteration, loaded one iteration before they are used
+    uint32_t n0 = fetch(jstart), n1 = fetch(jstart + 1);
     int j = jstart;
     auto next_rows = [&](uint32_t& x0, uint32_t& x1) {
         x0 = n0;
         x1 = n1;
-        if (kAhead == 2) {
-            n0 = m0;
-            n1 = m1;
-            m0 = fetch(j + 4);   // rows past the last needed one are never used for a stored word
-            m1 = fetch(j + 5);
-        } else {
-            n0 = fetch(j + 2);
-            n1 = fetch(j + 3);
-        }
+        n0 = fetch(j + 2);   // rows past the last needed one are never used for a stored word
+        n1 = fetch(j + 3);
     };
     // fill: 2T rows, nothing to store yet
 #pragma unroll 1
@@ -172,11 +162,11 @@ __device__ __forceinline__ void run_segment(const BitRows& g, uint32_t* __restri
 }
 
 // T generations of the rows [seg*rps, seg*rps + rps) of one 30-word strip.
-template <int T, int kWarps, int kAhead, int kMinBlocks = 1>
-__global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
+template <int T>
+__global__ void __launch_bounds__(kBitWarps * 32)
 gol_bits_kernel(const BitRows g, uint32_t* __restrict__ out, int col_torus, int nstrips, int rps) {
     const int lane = threadIdx.x & 31;
-    const unsigned task = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const unsigned task = blockIdx.x * kBitWarps + (threadIdx.x >> 5);
     const unsigned strip = task % (unsigned)nstrips, seg = task / (unsigned)nstrips;
     const int r0 = (int)seg * rps;
     if (r0 >= g.rows) return;  // whole warp
@@ -200,12 +190,12 @@ gol_bits_kernel(const BitRows g, uint32_t* __restrict__ out, int col_torus, int 
     uint32_t* op = out + (size_t)r0 * g.wpr + (stores ? rawcol : 0);
     // interior segment: all rows it reads (and the two it prefetches past its end) are rows of this block; rows
     // outside the grid then lie outside the cone of the rows it stores, so no row needs to be forced dead
-    const bool interior = jstart >= 0 && jstart + nsteps + 2 * kAhead + 1 <= g.rows;
+    const bool interior = jstart >= 0 && jstart + nsteps + 3 <= g.rows;
     if (interior) {
-        if (masked) run_segment<T, kAhead, true, false, true>(g, op, jstart, nsteps, col, colvalid, stores, cmask);
-        else run_segment<T, kAhead, true, false, false>(g, op, jstart, nsteps, col, colvalid, stores, cmask);
+        if (masked) run_segment<T, true, false, true>(g, op, jstart, nsteps, col, colvalid, stores, cmask);
+        else run_segment<T, true, false, false>(g, op, jstart, nsteps, col, colvalid, stores, cmask);
     } else {
-        run_segment<T, kAhead, false, true, true>(g, op, jstart, nsteps, col, colvalid, stores, cmask);
+        run_segment<T, false, true, true>(g, op, jstart, nsteps, col, colvalid, stores, cmask);
     }
 }
 
@@ -235,16 +225,14 @@ __global__ void gol_unpack_kernel(const uint32_t* __restrict__ bits, uint8_t* __
     stg_na_v4(p + 1, b);
 }
 
-// variant = 10 * rows-ahead-iterations + warps per CTA (developer sweep: MB_GOL_BITS_VARIANT)
-constexpr int kDefaultVariant = 14;
-
-template <int kWarps, int kAhead, int kMinBlocks = 1>
-int launch_bits_v(int T, const BitRows& g, uint32_t* out, int col_torus, int nstrips, int rps, int64_t tasks,
-                  cudaStream_t stream) {
-    const unsigned blocks = (unsigned)mb::ceil_div(tasks, kWarps);
-#define MB_BITS_CASE(TT)                                                                                            \
-    case TT:                                                                                                        \
-        gol_bits_kernel<TT, kWarps, kAhead, kMinBlocks><<<blocks, kWarps * 32, 0, stream>>>(g, out, col_torus, nstrips, rps); \
+// One template instance per number of fused generations.  (Developer variants that were swept and dropped: deeper
+// row prefetch, 2 / 8 warps per CTA, register caps, shifts on the FMA pipe -- profiles/r1_gol_bits_sweep*.jsonl.)
+int launch_bits(int T, const BitRows& g, uint32_t* out, int col_torus, int nstrips, int rps, int64_t tasks,
+                cudaStream_t stream) {
+    const unsigned blocks = (unsigned)mb::ceil_div(tasks, kBitWarps);
+#define MB_BITS_CASE(TT)                                                                                  \
+    case TT:                                                                                              \
+        gol_bits_kernel<TT><<<blocks, kBitWarps * 32, 0, stream>>>(g, out, col_torus, nstrips, rps);     \
         break;
     switch (T) {
         MB_BITS_CASE(1) MB_BITS_CASE(2) MB_BITS_CASE(3) MB_BITS_CASE(4)
@@ -253,20 +241,6 @@ int launch_bits_v(int T, const BitRows& g, uint32_t* out, int col_torus, int nst
     }
 #undef MB_BITS_CASE
     return MB_OK;
-}
-
-int launch_bits(int variant, int T, const BitRows& g, uint32_t* out, int col_torus, int nstrips, int rps,
-                int64_t tasks, cudaStream_t stream) {
-    switch (variant) {
-        case 16: return launch_bits_v<4, 1, 6>(T, g, out, col_torus, nstrips, rps, tasks, stream);  // <= 80 registers
-        case 17: return launch_bits_v<4, 1, 7>(T, g, out, col_torus, nstrips, rps, tasks, stream);  // <= 72 registers
-        case 12: return launch_bits_v<2, 1>(T, g, out, col_torus, nstrips, rps, tasks, stream);
-        case 18: return launch_bits_v<8, 1>(T, g, out, col_torus, nstrips, rps, tasks, stream);
-        case 22: return launch_bits_v<2, 2>(T, g, out, col_torus, nstrips, rps, tasks, stream);
-        case 24: return launch_bits_v<4, 2>(T, g, out, col_torus, nstrips, rps, tasks, stream);
-        case 28: return launch_bits_v<8, 2>(T, g, out, col_torus, nstrips, rps, tasks, stream);
-        default: return launch_bits_v<4, 1>(T, g, out, col_torus, nstrips, rps, tasks, stream);
-    }
 }
 
 }  // namespace
@@ -320,7 +294,7 @@ MB_API int mb_gol_step_bits(const uint32_t* in, const uint32_t* halo_top, const 
         const int sms = mb::sm_count();
         double best = 1e30;
         for (int rps = 32; rps <= 160; rps += 2) {
-            const int64_t ctas = mb::ceil_div((int64_t)nstrips * mb::ceil_div(rows, rps), 4);
+            const int64_t ctas = mb::ceil_div((int64_t)nstrips * mb::ceil_div(rows, rps), kBitWarps);
             const int64_t k = mb::ceil_div(ctas, sms);
             // an SM with fewer than 5 CTAs (its residency at T = 8) does not run them any faster: count at least 5
             const double cost = (double)(rps + 2 * generations) * (double)(k < 5 ? 5 : k) * (k < 6 ? 1.15 : (k == 6 ? 1.04 : 1.0));
@@ -332,10 +306,8 @@ MB_API int mb_gol_step_bits(const uint32_t* in, const uint32_t* halo_top, const 
     }
     rows_per_segment = (rows_per_segment + 1) & ~1;
     const int64_t tasks = (int64_t)nstrips * mb::ceil_div(rows, rows_per_segment);
-    const char* env_variant = getenv("MB_GOL_BITS_VARIANT");  // read per call: the developer sweep changes it
-    const int variant = env_variant ? atoi(env_variant) : kDefaultVariant;
     const BitRows g{in, halo_top, halo_bot, (int)rows, wpr};
-    const int rc = launch_bits(variant, generations, g, out, col_torus, nstrips, rows_per_segment, tasks, stream);
+    const int rc = launch_bits(generations, g, out, col_torus, nstrips, rows_per_segment, tasks, stream);
     if (rc != MB_OK) return rc;
     MB_LAUNCH_CHECK("mb_gol_step_bits");
     return MB_OK;

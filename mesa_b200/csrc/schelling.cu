@@ -360,30 +360,16 @@ MB_API int mb_schelling_happy_i8(const int8_t* type, const int8_t* halo_top, con
                      (halo_top == nullptr || al16(halo_top)) && (halo_bot == nullptr || al16(halo_bot));
     if (vec) {
         const int nstrips = (int)mb::ceil_div(cols, 512);
-        static const int variant = getenv("MB_HAPPY_VARIANT") ? atoi(getenv("MB_HAPPY_VARIANT")) : 0;
 #define MB_HAPPY_LAUNCH3(RR, MM, RPW, MINB)                                                                        \
     schelling_happy_vec<RR, MM, RPW, MINB><<<(unsigned)mb::ceil_div((int64_t)nstrips * mb::ceil_div(rows, RPW), kWarps), \
                                              kWarps * 32, 0, stream>>>(type, halo_top, halo_bot, happy, (int)rows,  \
                                                                        (int)cols, col_torus, nstrips, rule, happy_count)
-#define MB_HAPPY_LAUNCH(RR, MM)                                              \
-    do {                                                                     \
-        if (RR == 1) {                                                       \
-            switch (variant) {                                               \
-                case 1: MB_HAPPY_LAUNCH3(1, MM, 64, 3); break;               \
-                case 2: MB_HAPPY_LAUNCH3(1, MM, 16, 3); break;               \
-                case 3: MB_HAPPY_LAUNCH3(1, MM, 16, 4); break;               \
-                case 4: MB_HAPPY_LAUNCH3(1, MM, 64, 4); break;               \
-                default: MB_HAPPY_LAUNCH3(1, MM, 32, 4); break; /* 115 us on 16384^2 (64 rows, 3 CTAs/SM: 134 us) */ \
-            }                                                                \
-        } else {                                                             \
-            switch (variant) {                                               \
-                case 1: MB_HAPPY_LAUNCH3(2, MM, 16, 3); break;               \
-                case 2: MB_HAPPY_LAUNCH3(2, MM, 32, 2); break;               \
-                case 3: MB_HAPPY_LAUNCH3(2, MM, 32, 3); break;               \
-                case 4: MB_HAPPY_LAUNCH3(2, MM, 64, 3); break;               \
-                default: MB_HAPPY_LAUNCH3(2, MM, 64, 2); break; /* 171 us; 3 CTAs/SM spills and is slower */ \
-            }                                                                \
-        }                                                                    \
+        // rows per warp / CTAs per SM, best of the sweeps on 16384^2: r = 1: 32 rows, 4 CTAs (114 us; 64 rows / 3 CTAs
+        // 134 us); r = 2: 64 rows, 2 CTAs (171 us; 3 CTAs per SM spill and are slower)
+#define MB_HAPPY_LAUNCH(RR, MM)                          \
+    do {                                                 \
+        if (RR == 1) MB_HAPPY_LAUNCH3(1, MM, 32, 4);     \
+        else MB_HAPPY_LAUNCH3(2, MM, 64, 2);             \
     } while (0)
         if (radius == 1) {
             if (rule.mode == MODE_LINEAR) MB_HAPPY_LAUNCH(1, MODE_LINEAR);

@@ -25,16 +25,14 @@ del y
 
 bits = ops.gol_pack(a)
 results = []
-SWEEP = [(v, T, rps) for v in (14, 24, 12, 22, 18, 28) for T in (4, 6, 8) for rps in (32, 48, 64, 96, 128)]
-SWEEP += [(14, T, rps) for T in (1, 2, 3) for rps in (32, 64)]
+# (the kernel variants of the first sweeps -- prefetch depth, warps per CTA, register caps -- have been removed from the
+#  library; `variant` is kept in the records for comparison with profiles/r1_gol_bits_sweep*.jsonl)
+SWEEP = [(14, T, rps) for T in (1, 2, 3, 4, 5, 6, 7, 8) for rps in (0, 32, 48, 56, 64, 72, 88, 96, 128)]
 if len(sys.argv) > 2 and sys.argv[2] == "fine":
-    SWEEP = [(v, T, rps) for v in (14, 18) for T in (5, 6, 7, 8) for rps in (48, 50, 52, 56, 64, 72, 80, 96, 100, 104, 112, 128)]
-if len(sys.argv) > 2 and sys.argv[2] == "regs":
-    SWEEP = [(v, T, rps) for v in (14, 16, 17, 24) for T in (7, 8) for rps in (56, 64, 68, 72, 76, 80, 88, 100)]
+    SWEEP = [(14, T, rps) for T in (5, 6, 7, 8) for rps in (0, 48, 50, 52, 56, 64, 72, 80, 96, 100, 104, 112, 128)]
 if len(sys.argv) > 2 and sys.argv[2] == "quick":
-    SWEEP = [(14, 4, 64), (24, 4, 64), (24, 8, 64)]
+    SWEEP = [(14, 4, 0), (14, 8, 0), (14, 8, 64), (14, 8, 72)]
 for variant, T, rps in SWEEP:
-    os.environ["MB_GOL_BITS_VARIANT"] = str(variant)
     if True:
         cur, nxt = bits.clone(), torch.empty_like(bits)
         gens = 0
