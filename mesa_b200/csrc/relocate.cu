@@ -130,6 +130,8 @@ struct RelocWs {
     uint32_t* progress;             // [cap] probe index of `choice` (kMaxProbes: fallback state) | draws consumed << 8
     unsigned long long* softmask;   // [cap] bit j: probe j was skipped only because an EARLIER ARRIVAL holds the cell
                                     //       (vac <= t but arr < t) -- the probes a release can re-open
+    uint32_t* softcell;             // [cap] the cell of the LOWEST such probe (most movers have at most one: the release
+                                    //       scan then needs no Philox replay for them)
     uint32_t* fb_list;              // [cap] movers that missed all 50 probes in this pass
     unsigned long long* fb_t;       // [kFbBatch] sorted times of the current fallback batch
     uint32_t* fb_m;                 // [kFbBatch] local mover of each sorted entry
@@ -162,6 +164,7 @@ size_t carve(RelocWs* ws, char* base, int64_t cap) {
     t.choice = (unsigned long long*)take(8 * cap);
     t.progress = (uint32_t*)take(4 * cap);
     t.softmask = (unsigned long long*)take(8 * cap);
+    t.softcell = (uint32_t*)take(4 * cap);
     t.fb_list = (uint32_t*)take(4 * cap);
     t.fb_t = (unsigned long long*)take(8 * kFbBatch);
     t.fb_m = (uint32_t*)take(4 * kFbBatch);
@@ -306,7 +309,9 @@ relocate_pass(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, uint32_t 
             return;
         }
         ds.seek(pr >> 8);                                  // an earlier mover took it: go on with the next probe
-        unsigned long long soft = ws.softmask[m] | (1ull << (pr & 0xffu));   // the lost pick is such a probe itself
+        unsigned long long soft = ws.softmask[m];
+        if (soft == 0ull) ws.softcell[m] = (uint32_t)held;   // the lost pick becomes the lowest soft-skipped probe
+        soft |= 1ull << (pr & 0xffu);                        // (it was skipped because of an earlier arrival, too)
         for (int j = (int)(pr & 0xffu) + 1; j < kMaxProbes; ++j) {
             const unsigned long long c = ds.randbelow((uint64_t)v.ncells);
             const Slot sl = load_slot(v.slot(c));
@@ -337,7 +342,10 @@ relocate_pass(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, uint32_t 
             ws.softmask[m] = soft;
             return;
         }
-        if (sl.vac <= t) soft |= 1ull << j;
+        if (sl.vac <= t) {
+            if (soft == 0ull) ws.softcell[m] = (uint32_t)c;
+            soft |= 1ull << j;
+        }
     }
     ws.softmask[m] = soft;
     ws.progress[m] = (uint32_t)kMaxProbes;
@@ -379,6 +387,16 @@ relocate_release_scan(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, u
         // only probes that were skipped because of an earlier ARRIVAL can re-open; most movers have none
         const unsigned long long soft = ws.softmask[m] & (upto >= 64 ? ~0ull : ((1ull << upto) - 1ull));
         if (soft == 0ull) continue;
+        if ((soft & (soft - 1ull)) == 0ull) {   // exactly one candidate probe: its cell is cached, no replay unless it hits
+            const unsigned long long key = (unsigned long long)ws.softcell[m] + 1ull;
+            unsigned h = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 40) & hmask;
+            bool hit = false;
+            while (hkey[h] != 0ull) {
+                if (hkey[h] == key) { hit = htime[h] < t; break; }
+                h = (h + 1) & hmask;
+            }
+            if (!hit) continue;
+        }
         const int last = 63 - __clzll((long long)soft);
         mb::DrawStream ds(seed, epoch, ws.mv_agent[m]);
         for (int j = 0; j <= last; ++j) {
