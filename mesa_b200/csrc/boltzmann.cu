@@ -127,6 +127,40 @@ __global__ void boltz_rank(const uint32_t* __restrict__ valsB, int64_t n, uint32
     if (i < n) rankB[valsB[i]] = (uint32_t)i;
 }
 
+// Sparse grids: the pairs are radix-sorted on the CELL bits only (3 passes instead of 7 for 4096^2); a run of equal
+// cells is short (mean occupancy 0.06 at BASELINE config 3) and arrives in agent order, so ordering it by the full key
+// (cell, priority high word; ties keep ascending agent index = the tie-break of priority64) is an insertion sort by
+// the thread that owns the run's first slot.  Runs longer than kMaxFixRun raise a flag and the step falls back to the
+// full-width sort.
+constexpr int kMaxFixRun = 32;
+
+__global__ void boltz_fix_runs(uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int64_t n,
+                               unsigned long long* __restrict__ too_long) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t cell = keys[i] >> 32;
+    if (i > 0 && (keys[i - 1] >> 32) == cell) return;      // not the start of a run
+    if (i + 1 >= n || (keys[i + 1] >> 32) != cell) return;  // a run of one
+    int64_t e = i + 2;
+    while (e < n && (keys[e] >> 32) == cell && e - i <= kMaxFixRun) ++e;
+    if (e - i > kMaxFixRun) {
+        *too_long = 1ull;
+        return;
+    }
+    for (int64_t a = i + 1; a < e; ++a) {
+        const uint64_t k = keys[a];
+        const uint32_t v = vals[a];
+        int64_t b = a;
+        while (b > i && keys[b - 1] > k) {   // strict: equal keys keep their (ascending agent index) order
+            keys[b] = keys[b - 1];
+            vals[b] = vals[b - 1];
+            --b;
+        }
+        keys[b] = k;
+        vals[b] = v;
+    }
+}
+
 __device__ __forceinline__ int64_t lower_bound_u64(const uint64_t* __restrict__ a, int64_t n, uint64_t v) {
     int64_t lo = 0, hi = n;
     while (lo < hi) {
@@ -257,9 +291,32 @@ MB_API int mb_boltzmann_step(uint32_t* cell, int32_t* wealth, int64_t n, int64_t
     if (rc) return rc;
     const unsigned blocks = (unsigned)mb::ceil_div(n, 256);
     boltz_move<<<blocks, 256, 0, stream>>>(cell, n, (int)rows, (int)cols, torus, seed, epoch, ws);
-    const int where = mb::radix_sort_pairs<uint64_t>(ws.keys0, ws.vals0, ws.keys1, ws.vals1, n, 0, sort_bits(rows * cols),
-                                                     ws.sort_ws, ws.sort_ws_bytes, stream);
-    if (where < 0) return where;
+    // sparse grids sort on the cell bits only and order the short runs afterwards (boltz_fix_runs)
+    bool cell_sort_only = n <= rows * cols;
+    int where = 0;
+    if (cell_sort_only) {
+        where = mb::radix_sort_pairs<uint64_t>(ws.keys0, ws.vals0, ws.keys1, ws.vals1, n, 32, sort_bits(rows * cols),
+                                               ws.sort_ws, ws.sort_ws_bytes, stream);
+        if (where < 0) return where;
+        unsigned long long* too_long = ws.counters + (kMaxIterSlots - 1);   // last slot: never reached by the iterations
+        boltz_fix_runs<<<blocks, 256, 0, stream>>>(where ? ws.keys1 : ws.keys0, where ? ws.vals1 : ws.vals0, n, too_long);
+        unsigned long long flag = 0;
+        rc = mb::check_cuda(cudaMemcpyAsync(&flag, too_long, sizeof(flag), cudaMemcpyDeviceToHost, stream), "read");
+        if (rc) return rc;
+        rc = mb::check_cuda(cudaStreamSynchronize(stream), "sync");
+        if (rc) return rc;
+        if (flag != 0) {   // a crowded cell: redo with the full-width sort (boltz_move rewrites keys0 / vals0)
+            cell_sort_only = false;
+            rc = mb::check_cuda(cudaMemsetAsync(too_long, 0, sizeof(flag), stream), "memset");
+            if (rc) return rc;
+            boltz_move<<<blocks, 256, 0, stream>>>(cell, n, (int)rows, (int)cols, torus, seed, epoch, ws);
+        }
+    }
+    if (!cell_sort_only) {
+        where = mb::radix_sort_pairs<uint64_t>(ws.keys0, ws.vals0, ws.keys1, ws.vals1, n, 0, sort_bits(rows * cols),
+                                               ws.sort_ws, ws.sort_ws_bytes, stream);
+        if (where < 0) return where;
+    }
     const uint64_t* keysB = where ? ws.keys1 : ws.keys0;
     const uint32_t* valsB = where ? ws.vals1 : ws.vals0;
     boltz_rank<<<blocks, 256, 0, stream>>>(valsB, n, ws.rankB);
