@@ -61,8 +61,9 @@ __device__ __forceinline__ unsigned cell_of(const Geometry& g, float x, float y)
 // step 1, so every cell's few agents are put into ascending agent index (insertion sort by the thread that owns the
 // cell; cells longer than kCellSortMax are handled by cooperative CTAs, rank by counting) -- the same order a stable
 // sort of (cell, agent) gives, i.e. the storage-index order in which the reference lists a cell's agents;
-// 5. gather_state packs (x, y, dx, dy) in that order.  10^7 boids / 2.5 M cells: 0.35 ms instead of 0.79 ms with the
-// three-pass radix sort (which other kernels of the library still use for 64-bit keys).
+// 5. gather_state packs (x, y, dx, dy) in that order (tried: writing the state in the scatter and permuting it with the
+// ids -- 10^7 random 16-byte stores cost 0.57 ms, the gather of 8-byte reads 0.25 ms).  10^7 boids / 2.5 M cells:
+// 0.52 ms instead of 0.79 ms with the three-pass radix sort (which other kernels of the library still use for 64-bit keys).
 __global__ void count_cells(const float2* __restrict__ pos, int64_t n, Geometry g, uint32_t* __restrict__ counts,
                             uint32_t* __restrict__ cell_of_agent, uint32_t* __restrict__ ticket) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
