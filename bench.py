@@ -357,7 +357,14 @@ def run_ours(args):
             rows = max(64, min(GRID, int(rate * 5.0 / GRID)) // 64 * 64)  # ~5 s per step, 3 steps
             v, _ = cpu_gol_rate(rows, GRID, 3, 1, threads)
             line["cpu_baseline"] = {"value": v, "unit": "agent-updates/s", "cores": threads, "kind": "port",
-                                    "sample": f"gol torus slab {rows}x{GRID} uint8, 3 steps, C oracle port"}
+                                    "sample": f"gol torus slab {rows}x{GRID} uint8, 3 steps, C oracle port",
+                                    # context only, NOT measured in this run: the unmodified pure-Python reference as
+                                    # timed in the build container (it is not on the GPU box and
+                                    # cannot construct the 16384^2 grid at all: ~1.3 KB and 14 us per cell)
+                                    "mesa_python_indicative": {"gol_200x200": 2.9e5, "schelling_100x100": 3.0e5,
+                                                               "boltzmann_1e4_100x100": 2.2e5, "boids_400": 1.5e4,
+                                                               "unit": "agent-updates/s", "cores": 1,
+                                                               "source": "BASELINE.md section 2 (build container)"}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
