@@ -60,3 +60,23 @@ def test_boltzmann_single_cell_grid_raises():
     ws = ops.BoltzmannWorkspace(cell, 1, 1)
     with pytest.raises(ValueError):
         ops.boltzmann_step(cell, wealth, ws, 1, 0)
+
+
+def test_boltzmann_sparse_grid_with_a_crowded_cell_falls_back_to_the_full_sort():
+    """n <= ncells selects the cell-bits-only sort + run fix-up; a cell holding more than 32 agents must make the step
+    fall back to the full-width sort and still match the oracle (arrival lists, gifts, wealth)."""
+    from mesa_b200 import ops
+
+    rows, cols, n = 40, 50, 1500
+    rng = np.random.default_rng(9)
+    cell0 = rng.integers(0, rows * cols, size=n)
+    cell0[:400] = 17 * cols + 23          # 400 agents start in one cell: their moves crowd its 8 neighbours (~50 each)
+    wealth0 = rng.integers(0, 3, size=n).astype(np.int32)
+    st = oracle.BoltzmannState(rows, cols, cell0, wealth0, False)
+    cell, wealth = _dev(cell0, wealth0)
+    ws = ops.BoltzmannWorkspace(cell, rows, cols)
+    for e in range(4):
+        st.step(5, e)
+        ops.boltzmann_step(cell, wealth, ws, 5, e)
+        assert np.array_equal(cell.cpu().numpy(), st.cell), e
+        assert np.array_equal(wealth.cpu().numpy(), st.wealth), e

@@ -190,3 +190,42 @@ def test_boids_sequential_schemes_agree(monkeypatch):
     assert results[0][2] >= 32 and results[3][2] == 1
     for p_, d_, _ in results[1:]:
         assert torch.equal(results[0][0], p_) and torch.equal(results[0][1], d_)
+
+
+def test_cell_list_with_crowded_cells_matches_oracle():
+    """Dense clusters: cells with more than 32 agents take the cooperative ordering path of the counting-sort cell
+    list (sort_long_cells); neighbour sets, query rows and the Boids step must still equal the oracle."""
+    from mesa_b200 import ops
+
+    rng = np.random.default_rng(21)
+    size = np.array([400.0, 300.0])
+    spread = (rng.random((1500, 2)) * size).astype(np.float32)
+    blob1 = (np.array([120.0, 80.0]) + rng.random((700, 2)) * 6.0).astype(np.float32)      # ~700 boids in one or two cells
+    blob2 = (np.array([399.0, 299.0]) + rng.random((90, 2)) * 1.0).astype(np.float32)      # a crowded corner cell at the seam
+    pos = np.concatenate([spread, blob1, np.minimum(blob2, size.astype(np.float32))]).astype(np.float32)
+    perm = rng.permutation(len(pos))                                                       # crowded cells hold scattered ids
+    pos = pos[perm]
+    n = len(pos)
+    dirs = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+    kw = dict(vision=10.0, separation=2.0, torus=True)
+    wp, wd, wc = oracle.boids_step(pos, dirs, size, **kw)
+    cnt = torch.zeros(n, dtype=torch.int32, device="cuda")
+    po, do = ops.boids_step(torch.from_numpy(pos).cuda(), torch.from_numpy(dirs).cuda(), size, neighbor_count=cnt, **kw)
+    assert int(wc.max()) > 600
+    assert np.array_equal(cnt.cpu().numpy(), wc)
+    assert np.max(np.abs(po.cpu().numpy() - wp) / size) <= RTOL
+    assert np.max(np.abs(do.cpu().numpy() - wd)) <= RTOL
+    q = pos[::37]
+    off, idx, dist = ops.radius_query(torch.from_numpy(pos).cuda(), torch.from_numpy(q.copy()).cuda(), size, 10.0, True)
+    off, idx, dist = off.cpu().numpy(), idx.cpu().numpy(), dist.cpu().numpy()
+    for i, p in enumerate(q):
+        wi, wdist = oracle.radius_query(pos.astype(np.float64), p.astype(np.float64), size, 10.0, True)
+        assert np.array_equal(idx[off[i]:off[i + 1]], wi)
+        assert np.array_equal(dist[off[i]:off[i + 1]], wdist)
+    # the sequential step runs on the same cell list
+    order = oracle.activation_order(77, 0, n)
+    sp, sd, sc = oracle.boids_step(pos, dirs, size, order=order, **kw)
+    qo, qd, _ = ops.boids_step_sequential(torch.from_numpy(pos).cuda(), torch.from_numpy(dirs).cuda(), size, seed=77, epoch=0,
+                                          neighbor_count=cnt, **kw)
+    assert np.array_equal(cnt.cpu().numpy(), sc)
+    assert np.max(np.abs(qo.cpu().numpy() - sp) / size) <= RTOL and np.max(np.abs(qd.cpu().numpy() - sd)) <= RTOL
