@@ -349,6 +349,18 @@ def run_ours(args):
                          "frac": achieved / peak, "traffic": _ncu_traffic(kernel.split("<")[0]), "peak_source": peak_src,
                          "kernel": kernel, "algorithmic_bytes_per_launch": alg_bytes, "note": note},
         }
+        if life is not None:
+            # the roofline that actually binds the bit-packed kernel: the SM's ALU pipe (LOP3 / SHF issue one warp
+            # instruction every other cycle per SM sub-partition; 12 such instructions per 32-cell word and generation,
+            # csrc/gol_bits.cu).  ALGORITHMIC count: the words of the layer only, no halo lanes / re-computed rows.
+            sms, clock_hz = 148, (clocks.summary()["sm_mhz"] or 1965) * 1e6
+            alu_peak = sms * 4 * 16 * clock_hz                       # thread-instructions / s on the ALU pipe
+            alu_achieved = 12.0 * 32 * (GRID * GRID // 32) / (ms_per_step * 1e-3)
+            line["roofline"]["alu_pipe"] = {"achieved": alu_achieved, "peak": alu_peak, "unit": "thread-instr/s",
+                                            "frac": alu_achieved / alu_peak,
+                                            "note": "12 ALU-pipe instructions per word-generation x 16384^2/32 words per generation; "
+                                                    "ncu (profiles/r1_gol_bits_T8_ncu_full.csv): ALU pipe 83 % busy while active "
+                                                    "including the re-computed halo rows / lanes"}
         if world == 1 and not args.no_others:
             line["workloads"] = other_workloads(dev)
         if world == 1 and not args.no_cpu_baseline:
