@@ -355,7 +355,7 @@ def run_ours(args):
             # csrc/gol_bits.cu).  ALGORITHMIC count: the words of the layer only, no halo lanes / re-computed rows.
             sms, clock_hz = 148, (clocks.summary()["sm_mhz"] or 1965) * 1e6
             alu_peak = sms * 4 * 16 * clock_hz                       # thread-instructions / s on the ALU pipe
-            alu_achieved = 12.0 * 32 * (GRID * GRID // 32) / (ms_per_step * 1e-3)
+            alu_achieved = 12.0 * (GRID * GRID // 32) / (ms_per_step * 1e-3)   # one thread owns a 32-cell word
             line["roofline"]["alu_pipe"] = {"achieved": alu_achieved, "peak": alu_peak, "unit": "thread-instr/s",
                                             "frac": alu_achieved / alu_peak,
                                             "note": "12 ALU-pipe instructions per word-generation x 16384^2/32 words per generation; "
