@@ -362,7 +362,7 @@ def run_ours(args):
                                                     "ncu (profiles/r1_gol_bits_T8_ncu_full.csv): ALU pipe 83 % busy while active "
                                                     "including the re-computed halo rows / lanes"}
         if world == 1 and not args.no_others:
-            line["workloads"] = other_workloads(dev)
+            line["workloads"] = other_workloads(dev) + layer_workloads(dev)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             rate, _ = cpu_gol_rate(256, GRID, 1, 1, threads)
@@ -496,6 +496,56 @@ def other_workloads(dev):
     t = timed(boids_seq, 4)
     out.append({"workload": "boids_1e7_vision15_sequential_shuffle_do", "ms_per_step": t * 1e3, "agent_updates_per_s": N / t,
                 "note": "identical to the reference's sequential activation in the Philox order (dependency-chained kernel)"})
+    return out
+
+
+def layer_workloads(dev, grid=GRID, reps=20):
+    """Property-layer kernels (csrc/layers.cu) on grid x grid layers: CUDA-event time per launch and the
+    ALGORITHMIC bytes each launch must move (inputs read once + outputs written once) against the HBM peak."""
+    import torch
+
+    from mesa_b200 import ops
+
+    peak, _ = _peaks()
+    out = []
+    n = grid * grid
+
+    def run(name, fn, alg_bytes):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        gbs = alg_bytes / ms / 1e6
+        out.append({"workload": f"layer_{name}_{grid}x{grid}", "ms_per_step": ms, "cell_updates_per_s": n / ms * 1e3,
+                    "algorithmic_bytes": alg_bytes, "hbm_gbs": gbs, "hbm_frac_of_measured_peak": gbs / peak})
+
+    g = torch.Generator(device=dev).manual_seed(3)
+    u8 = (torch.rand((grid, grid), device=dev, generator=g) * 8).to(torch.uint8)
+    u8b = torch.empty_like(u8)
+    i32 = torch.empty((grid, grid), dtype=torch.int32, device=dev)
+    run("fill_u8", lambda: ops.layer_fill(u8b, 3), n)
+    run("affine_clamp_u8 (sugar regrowth: min(x + 1, cap))", lambda: ops.layer_affine_clamp(u8, 1.0, 1.0, 0.0, 4.0, out=u8b), 2 * n)
+    run("binary_min_u8", lambda: ops.layer_binary(u8, u8b, "min", out=u8b), 3 * n)
+    run("reduce_count_nonzero_u8 (number of empty cells)", lambda: ops.layer_reduce(u8, "count_nonzero"), n)
+    run("reduce_sum_u8", lambda: ops.layer_reduce(u8, "sum"), n)
+    run("reduce_max_u8", lambda: ops.layer_reduce(u8, "max"), n)
+    run("neighborhood_sum_u8_moore_r1_torus", lambda: ops.neighborhood_sum(u8, 1, True, False, True, out=i32), 5 * n)
+    run("neighborhood_sum_u8_vonneumann_r2_clamped", lambda: ops.neighborhood_sum(u8, 2, False, False, False, out=i32), 5 * n)
+    del u8, u8b, i32
+    f32 = torch.rand((grid, grid), device=dev, generator=g)
+    f32b = torch.empty_like(f32)
+    f64 = torch.empty((grid, grid), dtype=torch.float64, device=dev)
+    run("fill_f32", lambda: ops.layer_fill(f32b, 0.5), 4 * n)
+    run("affine_clamp_f32", lambda: ops.layer_affine_clamp(f32, 0.9, 0.01, 0.0, 1.0, out=f32b), 8 * n)
+    run("binary_add_f32", lambda: ops.layer_binary(f32, f32b, "add", out=f32b), 12 * n)
+    run("reduce_sum_f32", lambda: ops.layer_reduce(f32, "sum"), 4 * n)
+    run("diffuse_f32_torus", lambda: ops.layer_diffuse(f32, 0.3, True, out=f32b), 8 * n)
+    run("neighborhood_sum_f32_moore_r1_torus", lambda: ops.neighborhood_sum(f32, 1, True, False, True, out=f64), 12 * n)
     return out
 
 

@@ -220,6 +220,21 @@ int mb_radius_query_f32(const float* pos, int64_t n, double x0, double y0, doubl
                         uint32_t* counts, const int64_t* offsets, int32_t* out_idx, double* out_dist,
                         void* workspace, size_t workspace_bytes, int reuse_cell_list, mb_stream_t stream);
 
+/* mb_knn_query_f32: batched ContinuousSpace.get_k_nearest_agents (continuous_space.py:249-283) on the cell list:
+ * out_idx / out_dist are [nq, k], each row ascending in (distance, agent index) -- "in case of ties, the earlier an
+ * agent is inserted the higher it will rank" (:256-257) -- padded with -1 / +inf when fewer than k agents exist;
+ * exclude[q] >= 0 drops that agent (ContinuousSpaceAgent.get_nearest_neighbors, continuous_space_agents.py:80-91).
+ * cell_edge sizes the cells; workspace = mb_celllist_workspace_bytes(n, size_x, size_y, cell_edge).
+ * mb_point_distances_f32: calculate_distances (:202-235; out_dist [m]) and / or calculate_difference_vector
+ * (:169-200; out_delta [m, 2]) of one point against agents sel[0..m) (sel NULL: agents 0..m), float64, in the
+ * reference's operation order. */
+int mb_knn_query_f32(const float* pos, int64_t n, double x0, double y0, double size_x, double size_y, int torus,
+                     const float* queries, const int32_t* exclude, int64_t nq, int k, double cell_edge,
+                     int32_t* out_idx, double* out_dist, void* workspace, size_t workspace_bytes,
+                     int reuse_cell_list, mb_stream_t stream);
+int mb_point_distances_f32(const float* pos, const int32_t* sel, int64_t m, double size_x, double size_y, int torus,
+                           double px, double py, double* out_dist, double* out_delta, mb_stream_t stream);
+
 /* Domain-decomposed continuous space (one rank per slab of y, mesa_b200/sharded.py ShardedBoids): the exchange
  * steps as kernels that append straight into the neighbouring ranks' peer-mapped inboxes (NVLink stores + an
  * atomic slot counter in the receiver's memory) -- no pack / send / recv / unpack.  *_count are peer-mapped

@@ -127,41 +127,52 @@ class DeviceContinuousSpace:
         _, idx, dist = self.radius_query(np.asarray(point, dtype=np.float32)[None, :], radius)
         return idx.cpu().tolist(), dist.cpu().numpy()
 
+    def _select(self, agents):
+        if agents is None:
+            return None, list(range(self._n_agents))
+        ids = [int(a) for a in agents]
+        return torch.as_tensor(ids, dtype=torch.int32, device=self.device), ids
+
     def calculate_distances(self, point, agents=None):
         """continuous_space.py:202-235 for one point against all (or the given) agents; float64."""
-        pos = self.agent_positions if agents is None else self._agent_positions[torch.as_tensor(agents, device=self.device)]
-        p = torch.as_tensor(np.asarray(point, dtype=np.float64), device=self.device)
-        delta = torch.abs(p - pos.to(torch.float64))
-        if self.torus:
-            size = torch.as_tensor(self.size, device=self.device)
-            delta = torch.minimum(delta, size - delta)
-        dists = torch.sqrt(delta[:, 0] ** 2 + delta[:, 1] ** 2)
-        ids = list(range(self._n_agents)) if agents is None else list(agents)
-        return dists.cpu().numpy(), ids
+        sel, ids = self._select(agents)
+        d, _ = ops.point_distances(self.agent_positions.contiguous(), np.asarray(point, dtype=np.float64), self.size, self.torus, sel=sel)
+        return d.cpu().numpy(), ids
 
     def calculate_difference_vector(self, point, agents=None) -> np.ndarray:
         """continuous_space.py:169-200 (torus: the strictly smaller of delta and delta - sign(delta)*size)."""
-        pos = self.agent_positions if agents is None else self._agent_positions[torch.as_tensor(agents, device=self.device)]
-        p = torch.as_tensor(np.asarray(point, dtype=np.float64), device=self.device)
-        delta = pos.to(torch.float64) - p
-        if self.torus:
-            size = torch.as_tensor(self.size, device=self.device)
-            inverse = delta - torch.sign(delta) * size
-            delta = torch.where(torch.abs(delta) < torch.abs(inverse), delta, inverse)
-        return delta.cpu().numpy()
+        sel, _ = self._select(agents)
+        _, v = ops.point_distances(self.agent_positions.contiguous(), np.asarray(point, dtype=np.float64), self.size, self.torus, sel=sel,
+                                   distances=False, deltas=True)
+        return v.cpu().numpy()
+
+    def k_nearest_query(self, points, k: int, exclude: torch.Tensor | None = None):
+        """Batched get_k_nearest_agents for `points` [q, 2] in one launch: (indices [q, k], distances [q, k]) on
+        the device, rows ascending in (distance, storage index), padded with -1 / inf."""
+        q = torch.as_tensor(np.asarray(points, dtype=np.float32)) if not isinstance(points, torch.Tensor) else points
+        q = q.to(self.device, torch.float32).contiguous()
+        return ops.knn_query(self.agent_positions.contiguous(), q, self.size, int(k), self.torus,
+                             origin=self.dimensions[:, 0], exclude=exclude)
+
+    def nearest_neighbors(self, k: int):
+        """get_nearest_neighbors(k) of EVERY agent (self excluded, continuous_space_agents.py:80-91) in one launch."""
+        me = torch.arange(self._n_agents, dtype=torch.int32, device=self.device)
+        return self.k_nearest_query(self.agent_positions, k, exclude=me)
 
     def get_k_nearest_agents(self, point, k: int = 1):
         """continuous_space.py:249-283 (ties: earlier storage index first)."""
-        dists, ids = self.calculate_distances(point)
-        n = len(dists)
+        n = self._n_agents
         if n == 0 or k <= 0:
             return [], np.array([])
         if k > n:
             warnings.warn(f"Requested k={k} nearest agents but only {n} agent(s) are present in the space. "
                           f"Returning all {n} agent(s).", UserWarning, stacklevel=2)
             k = n
-        order = np.argsort(dists, kind="stable")[:k]
-        return [ids[i] for i in order], dists[order]
+        p = np.asarray(point, dtype=np.float64)
+        if self.torus and not self.in_bounds(p):
+            p = self.torus_correct(p)
+        idx, dist = self.k_nearest_query(p[None, :], k)
+        return idx[0].cpu().tolist(), dist[0].cpu().numpy()
 
 
 ContinuousSpace = DeviceContinuousSpace

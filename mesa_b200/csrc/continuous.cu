@@ -812,6 +812,105 @@ __global__ void radius_query(const float4* __restrict__ packed, const uint32_t* 
     if (counts != nullptr) counts[q] = k;
 }
 
+// ---- k nearest agents (get_k_nearest_agents for a batch of points, continuous_space.py:249-283) -------------
+// One thread per query walks the cell list in Chebyshev RINGS of cells around the query's cell.  After ring r is
+// done every unvisited agent is at least r * min(cell edge) away, so the search stops as soon as the k-th best
+// distance is strictly below that bound (strictly: an unvisited agent at exactly the k-th distance could still win
+// the tie on the lower storage index).  The candidate list lives in the output row, kept sorted by (distance,
+// agent index) -- "in case of ties, the earlier an agent is inserted the higher it will rank" (:256-257).  On a
+// torus the ring offsets are minimal images (each cell visited once); the walk ends when the rings cover the grid.
+// Rows are padded with index -1 / distance +inf when fewer than k agents exist.
+__global__ void __launch_bounds__(128)
+knn_query(const float4* __restrict__ packed, const uint32_t* __restrict__ order, const uint32_t* __restrict__ cell_start,
+          const uint32_t* __restrict__ cell_end, Geometry g, const float2* __restrict__ queries,
+          const int32_t* __restrict__ exclude, int64_t nq, int k, int32_t* __restrict__ out_idx,
+          double* __restrict__ out_dist) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const float2 p = queries[q];
+    const double px = p.x, py = p.y;
+    const int cx = cell_coord(px, g.x0, g.sx, g.ncx), cy = cell_coord(py, g.y0, g.sy, g.ncy);
+    const int32_t skip = exclude != nullptr ? exclude[q] : -1;
+    int32_t* idx = out_idx + q * k;
+    double* d2s = out_dist + q * k;     // squared distances while searching, square-rooted at the end
+    int have = 0;
+    // offsets a cell may take on each axis
+    const int lox = g.torus ? -((g.ncx - 1) / 2) : -cx, hix = g.torus ? g.ncx / 2 : g.ncx - 1 - cx;
+    const int loy = g.torus ? -((g.ncy - 1) / 2) : -cy, hiy = g.torus ? g.ncy / 2 : g.ncy - 1 - cy;
+    int rmax = -lox;
+    if (hix > rmax) rmax = hix;
+    if (-loy > rmax) rmax = -loy;
+    if (hiy > rmax) rmax = hiy;
+    const double ex = g.sx / (double)g.ncx, ey = g.sy / (double)g.ncy;
+    const double emin = ex < ey ? ex : ey;
+
+    auto visit = [&](int ox, int oy) {
+        int xx = cx + ox, yy = cy + oy;
+        if (g.torus) {
+            xx = (xx % g.ncx + g.ncx) % g.ncx;
+            yy = (yy % g.ncy + g.ncy) % g.ncy;
+        }
+        const unsigned c = (unsigned)(yy * g.ncx + xx);
+        const uint32_t e = cell_end[c];
+        for (uint32_t j = cell_start[c]; j < e; ++j) {
+            const int32_t a = (int32_t)order[j];
+            if (a == skip) continue;
+            const float4 o = packed[j];
+            const double d2 = ref_distance2(g, px, py, (double)o.x, (double)o.y);
+            if (have == k && !(d2 < d2s[k - 1] || (d2 == d2s[k - 1] && a < idx[k - 1]))) continue;
+            int w = have < k ? have : k - 1;
+            while (w > 0 && (d2s[w - 1] > d2 || (d2s[w - 1] == d2 && idx[w - 1] > a))) {
+                d2s[w] = d2s[w - 1];
+                idx[w] = idx[w - 1];
+                --w;
+            }
+            d2s[w] = d2;
+            idx[w] = a;
+            if (have < k) ++have;
+        }
+    };
+
+    for (int r = 0; r <= rmax; ++r) {
+        if (r == 0) {
+            visit(0, 0);
+        } else {
+            for (int oy = -r; oy <= r; ++oy) {
+                if (oy < loy || oy > hiy) continue;
+                if (oy == -r || oy == r) {
+                    const int a0 = -r > lox ? -r : lox, a1 = r < hix ? r : hix;
+                    for (int ox = a0; ox <= a1; ++ox) visit(ox, oy);
+                } else {
+                    if (-r >= lox) visit(-r, oy);
+                    if (r <= hix) visit(r, oy);
+                }
+            }
+        }
+        if (have == k) {
+            const double bound = (double)r * emin * (1.0 - 1e-9);   // slack for the rounding of cell_coord
+            if (d2s[k - 1] < bound * bound) break;
+        }
+    }
+    for (int w = 0; w < have; ++w) d2s[w] = __dsqrt_rn(d2s[w]);
+    for (int w = have; w < k; ++w) {
+        idx[w] = -1;
+        d2s[w] = __longlong_as_double(0x7ff0000000000000ll);
+    }
+}
+
+// ---- calculate_distances / calculate_difference_vector of ONE point against all or selected agents
+//      (continuous_space.py:169-235): float64, the reference's operation order ----------------------------------------
+__global__ void point_distances(const float2* __restrict__ pos, const int32_t* __restrict__ sel, int64_t m, Geometry g,
+                                double px, double py, double* __restrict__ out_dist, double* __restrict__ out_delta) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const float2 a = pos[sel != nullptr ? (int64_t)sel[i] : i];
+    if (out_dist != nullptr) out_dist[i] = __dsqrt_rn(ref_distance2(g, px, py, (double)a.x, (double)a.y));
+    if (out_delta != nullptr) {
+        out_delta[2 * i] = ref_delta((double)a.x, px, g.sx, g.torus);
+        out_delta[2 * i + 1] = ref_delta((double)a.y, py, g.sy, g.torus);
+    }
+}
+
 struct CellListWs {
     uint32_t *keys0, *vals0, *keys1, *vals1, *cell_start, *cell_end, *spare;
     float4* packed;
@@ -1242,5 +1341,49 @@ MB_API int mb_radius_query_f32(const float* pos, int64_t n, double x0, double y0
                                                                       (const float2*)queries, exclude, nq, sq_threshold_le(radius), counts,
                                                                       offsets, out_idx, out_dist);
     MB_LAUNCH_CHECK("mb_radius_query_f32");
+    return MB_OK;
+}
+
+// Batched get_k_nearest_agents: out_idx / out_dist are [nq, k] (ascending (distance, agent index); -1 / +inf padding).
+// `cell_edge` sizes the cell list (a few agents per cell is the useful regime); the workspace is
+// mb_celllist_workspace_bytes(n, size_x, size_y, cell_edge).
+MB_API int mb_knn_query_f32(const float* pos, int64_t n, double x0, double y0, double size_x, double size_y, int torus,
+                            const float* queries, const int32_t* exclude, int64_t nq, int k, double cell_edge,
+                            int32_t* out_idx, double* out_dist, void* workspace, size_t workspace_bytes,
+                            int reuse_cell_list, cudaStream_t stream) {
+    MB_REQUIRE(n >= 0 && n < (1ll << 31) && nq >= 0 && k >= 0, "mb_knn_query_f32: size out of range");
+    if (nq == 0 || k == 0) return MB_OK;
+    MB_REQUIRE(queries && workspace && out_idx && out_dist && (n == 0 || pos), "mb_knn_query_f32: null buffer");
+    Geometry g;
+    int rc = make_geometry(&g, x0, y0, size_x, size_y, cell_edge, torus);
+    if (rc) return rc;
+    CellListWs ws;
+    if (carve(&ws, (char*)workspace, n, (int64_t)g.ncx * g.ncy) > workspace_bytes) {
+        mb::set_error("mb_knn_query_f32: workspace too small");
+        return MB_ERR_WORKSPACE;
+    }
+    uint32_t* order = ws.vals0;
+    if (!reuse_cell_list) {
+        rc = build_cell_list((const float2*)pos, nullptr, n, g, ws, &order, stream);
+        if (rc) return rc;
+    }
+    knn_query<<<(unsigned)mb::ceil_div(nq, 128), 128, 0, stream>>>(ws.packed, order, ws.cell_start, ws.cell_end, g,
+                                                                   (const float2*)queries, exclude, nq, k, out_idx, out_dist);
+    MB_LAUNCH_CHECK("mb_knn_query_f32");
+    return MB_OK;
+}
+
+// calculate_distances (out_dist, [m]) and / or calculate_difference_vector (out_delta, [m, 2]) of the point
+// (px, py) against agents sel[0..m) (sel == NULL: agents 0..m).  float64 results.
+MB_API int mb_point_distances_f32(const float* pos, const int32_t* sel, int64_t m, double size_x, double size_y,
+                                  int torus, double px, double py, double* out_dist, double* out_delta,
+                                  cudaStream_t stream) {
+    MB_REQUIRE(m >= 0, "mb_point_distances_f32: negative size");
+    if (m == 0) return MB_OK;
+    MB_REQUIRE(pos && (out_dist || out_delta), "mb_point_distances_f32: null buffer");
+    Geometry g;
+    g.x0 = 0.0; g.y0 = 0.0; g.sx = size_x; g.sy = size_y; g.ncx = 1; g.ncy = 1; g.torus = torus;
+    point_distances<<<(unsigned)mb::ceil_div(m, 256), 256, 0, stream>>>((const float2*)pos, sel, m, g, px, py, out_dist, out_delta);
+    MB_LAUNCH_CHECK("mb_point_distances_f32");
     return MB_OK;
 }

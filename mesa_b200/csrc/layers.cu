@@ -13,8 +13,15 @@
 // restatement of the NetLogo `diffuse` rule stated below).
 //
 // All kernels are HBM-bound streaming kernels: 16-byte vector accesses in the elementwise
-// paths, grid-stride over a grid sized to the SM count.  Reductions are two-pass with a fixed
-// partial count so floating-point sums are reproducible run to run.
+// paths (several in flight per thread), grid-stride over a grid sized to the SM count.
+// Reductions are two-pass with a fixed partial count and a fixed element-to-thread assignment, so
+// floating-point sums are reproducible run to run.  uint8 layers never go through per-element
+// float64 arithmetic (conversions run at 16 / clk / SM and would bind before HBM does): the affine
+// map of a uint8 layer is a 256-entry table built per CTA, the uint8 reductions work on packed words.
+// The radius-1 / radius-2 neighbourhood sums and the diffusion step use a COLUMN WALKER: a thread owns
+// 4 bytes' worth of adjacent columns and walks down a segment of rows with the (2r+1)-row window in
+// registers, so every input row is fetched from L1/L2 once per (2r+1) outputs and from HBM once in all;
+// other radii take the generic one-thread-per-cell kernel.
 #include "common.cuh"
 
 #include <float.h>
@@ -41,9 +48,22 @@ inline unsigned stream_blocks(int64_t work_items) {
 
 template <typename T>
 __global__ void k_fill(T* __restrict__ p, int64_t n, double value) {
+    constexpr int V = VecOf<T>::n;
     const T v = from_double<T>(value);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // scalar head up to the first 16-byte boundary, 16-byte stores, scalar tail
+    int64_t head = (int64_t)(((16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15) / sizeof(T));
+    if (head > n) head = n;
+    const int64_t nvec = (n - head) / V;
+    uint4 raw;
+    T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+    for (int k = 0; k < V; ++k) e[k] = v;
+    uint4* pv = reinterpret_cast<uint4*>(p + head);
+    for (int64_t i = tid; i < nvec; i += stride) pv[i] = raw;
+    if (tid < head) p[tid] = v;
+    for (int64_t i = head + nvec * V + tid; i < n; i += stride) p[i] = v;
 }
 
 // out = clamp(alpha * in + beta, lo, hi), evaluated in double (float in float for f32)
@@ -74,18 +94,50 @@ __global__ void k_affine(const T* __restrict__ in, T* __restrict__ out, int64_t 
     }
 }
 
-template <typename T> __device__ __forceinline__ T apply_op(T a, T b, int op) {
-    switch (op) {
-        case OP_ADD: return (T)(a + b);
-        case OP_SUB: return (T)(a - b);
-        case OP_MUL: return (T)(a * b);
-        case OP_MIN: return a < b ? a : b;
-        default: return a > b ? a : b;
+// uint8 layers: the map has 256 possible arguments -- every CTA evaluates it once per value in float64 (the
+// same expression as k_affine) into shared memory and the stream becomes byte look-ups.
+__global__ void __launch_bounds__(256) k_affine_u8(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int64_t n,
+                                                   double alpha, double beta, double lo, double hi) {
+    __shared__ uint8_t lut[256];
+    {
+        double y = alpha * (double)threadIdx.x + beta;
+        y = y < lo ? lo : (y > hi ? hi : y);
+        lut[threadIdx.x] = from_double<uint8_t>(y);
+    }
+    __syncthreads();
+    const int64_t nvec = n / 16;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (aligned) {
+        for (int64_t i = tid; i < nvec; i += stride) {
+            uint4 raw = __ldg(reinterpret_cast<const uint4*>(in) + i);
+            uint32_t* w = reinterpret_cast<uint32_t*>(&raw);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t x = w[k];
+                w[k] = (uint32_t)lut[x & 255u] | ((uint32_t)lut[(x >> 8) & 255u] << 8) |
+                       ((uint32_t)lut[(x >> 16) & 255u] << 16) | ((uint32_t)lut[x >> 24] << 24);
+            }
+            reinterpret_cast<uint4*>(out)[i] = raw;
+        }
+        for (int64_t i = nvec * 16 + tid; i < n; i += stride) out[i] = lut[in[i]];
+    } else {
+        for (int64_t i = tid; i < n; i += stride) out[i] = lut[in[i]];
     }
 }
 
-template <typename T>
-__global__ void k_binary(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int64_t n, int op) {
+template <typename T, int OP> __device__ __forceinline__ T apply_op(T a, T b) {
+    if (OP == OP_ADD) return (T)(a + b);
+    if (OP == OP_SUB) return (T)(a - b);
+    if (OP == OP_MUL) return (T)(a * b);
+    if (OP == OP_MIN) return a < b ? a : b;
+    return a > b ? a : b;
+}
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(256) k_binary(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out,
+                                                int64_t n) {
     constexpr int V = VecOf<T>::n;
     const int64_t nvec = n / V;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -99,12 +151,23 @@ __global__ void k_binary(const T* __restrict__ a, const T* __restrict__ b, T* __
             T* ea = reinterpret_cast<T*>(&ra);
             const T* eb = reinterpret_cast<const T*>(&rb);
 #pragma unroll
-            for (int k = 0; k < V; ++k) ea[k] = apply_op<T>(ea[k], eb[k], op);
+            for (int k = 0; k < V; ++k) ea[k] = apply_op<T, OP>(ea[k], eb[k]);
             reinterpret_cast<uint4*>(out)[i] = ra;
         }
-        for (int64_t i = nvec * V + tid; i < n; i += stride) out[i] = apply_op<T>(a[i], b[i], op);
+        for (int64_t i = nvec * V + tid; i < n; i += stride) out[i] = apply_op<T, OP>(a[i], b[i]);
     } else {
-        for (int64_t i = tid; i < n; i += stride) out[i] = apply_op<T>(a[i], b[i], op);
+        for (int64_t i = tid; i < n; i += stride) out[i] = apply_op<T, OP>(a[i], b[i]);
+    }
+}
+
+template <typename T>
+void launch_binary(const T* a, const T* b, T* out, int64_t n, int op, unsigned blocks, cudaStream_t stream) {
+    switch (op) {
+        case OP_ADD: k_binary<T, OP_ADD><<<blocks, 256, 0, stream>>>(a, b, out, n); break;
+        case OP_SUB: k_binary<T, OP_SUB><<<blocks, 256, 0, stream>>>(a, b, out, n); break;
+        case OP_MUL: k_binary<T, OP_MUL><<<blocks, 256, 0, stream>>>(a, b, out, n); break;
+        case OP_MIN: k_binary<T, OP_MIN><<<blocks, 256, 0, stream>>>(a, b, out, n); break;
+        default: k_binary<T, OP_MAX><<<blocks, 256, 0, stream>>>(a, b, out, n); break;
     }
 }
 
@@ -138,20 +201,101 @@ __device__ __forceinline__ A block_reduce(A v, int op) {
     return v;  // valid in thread 0
 }
 
-template <typename T, typename A>
-__global__ void __launch_bounds__(256) k_reduce1(const T* __restrict__ in, int64_t n, int op, A* __restrict__ partial) {
-    // block b owns the contiguous chunk [b*chunk, (b+1)*chunk): fixed order => reproducible
-    const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
-    const int64_t lo = (int64_t)blockIdx.x * chunk;
+// element -> accumulator for one reduction (count_nonzero counts, the others take the value)
+template <typename T, typename A, int OP> __device__ __forceinline__ A red_value(T x) {
+    return OP == RED_COUNT_NONZERO ? (A)(x != (T)0) : (A)x;
+}
+
+// One 16-byte vector folded into the accumulator.  uint8: sum by IDP.4A against 0x01010101, count_nonzero by an
+// OR-fold of each byte onto its lowest bit + POPC; min / max per byte.
+template <typename T, typename A, int OP>
+__device__ __forceinline__ A red_vec(A acc, const uint4& raw) {
+    constexpr int ROP = OP == RED_COUNT_NONZERO ? RED_SUM : OP;
+    const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+    for (int k = 0; k < VecOf<T>::n; ++k) acc = red_combine<A>(acc, red_value<T, A, OP>(e[k]), ROP);
+    return acc;
+}
+template <> __device__ __forceinline__ long long red_vec<uint8_t, long long, RED_SUM>(long long acc, const uint4& raw) {
+    unsigned s = __dp4a(raw.x, 0x01010101u, 0u);
+    s = __dp4a(raw.y, 0x01010101u, s);
+    s = __dp4a(raw.z, 0x01010101u, s);
+    s = __dp4a(raw.w, 0x01010101u, s);
+    return acc + (long long)s;
+}
+__device__ __forceinline__ unsigned nonzero_bytes(unsigned x) {
+    x |= x >> 4;
+    x |= x >> 2;
+    x |= x >> 1;
+    return __popc(x & 0x01010101u);
+}
+template <>
+__device__ __forceinline__ long long red_vec<uint8_t, long long, RED_COUNT_NONZERO>(long long acc, const uint4& raw) {
+    return acc + (long long)(nonzero_bytes(raw.x) + nonzero_bytes(raw.y) + nonzero_bytes(raw.z) + nonzero_bytes(raw.w));
+}
+
+// uint8 min / max: bytes widened to two 16-bit lanes per word, VIMNMX.U16x2 tree, one scalar fold per vector
+template <bool IS_MIN> __device__ __forceinline__ unsigned mnmx16x2(unsigned a, unsigned b) {
+    return IS_MIN ? __vminu2(a, b) : __vmaxu2(a, b);
+}
+template <bool IS_MIN> __device__ __forceinline__ long long red_vec_u8_mnmx(long long acc, const uint4& raw) {
+    const unsigned w[4] = {raw.x, raw.y, raw.z, raw.w};
+    unsigned m = mnmx16x2<IS_MIN>(w[0] & 0x00ff00ffu, (w[0] >> 8) & 0x00ff00ffu);
+#pragma unroll
+    for (int k = 1; k < 4; ++k)
+        m = mnmx16x2<IS_MIN>(m, mnmx16x2<IS_MIN>(w[k] & 0x00ff00ffu, (w[k] >> 8) & 0x00ff00ffu));
+    const unsigned lo = m & 0xffffu, hi = m >> 16;
+    const long long r = (long long)(IS_MIN ? (lo < hi ? lo : hi) : (lo > hi ? lo : hi));
+    return IS_MIN ? (acc < r ? acc : r) : (acc > r ? acc : r);
+}
+template <> __device__ __forceinline__ long long red_vec<uint8_t, long long, RED_MIN>(long long acc, const uint4& raw) {
+    return red_vec_u8_mnmx<true>(acc, raw);
+}
+template <> __device__ __forceinline__ long long red_vec<uint8_t, long long, RED_MAX>(long long acc, const uint4& raw) {
+    return red_vec_u8_mnmx<false>(acc, raw);
+}
+
+template <typename T, typename A, int OP>
+__global__ void __launch_bounds__(256) k_reduce1(const T* __restrict__ in, int64_t n, A* __restrict__ partial) {
+    // block b owns the contiguous chunk [b*chunk, (b+1)*chunk), chunk a multiple of one vector, and inside it
+    // thread t owns vectors t, t+256, ...: a fixed assignment and a fixed combination order => reproducible.
+    constexpr int V = VecOf<T>::n;
+    constexpr int ROP = OP == RED_COUNT_NONZERO ? RED_SUM : OP;
+    int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
+    chunk = (chunk + V - 1) / V * V;
+    const int64_t lo = (int64_t)blockIdx.x * chunk < n ? (int64_t)blockIdx.x * chunk : n;
     const int64_t hi = lo + chunk < n ? lo + chunk : n;
-    A acc = red_identity<A>(op);
-    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        const T x = in[i];
-        const A v = op == RED_COUNT_NONZERO ? (A)(x != (T)0) : (A)x;
-        acc = red_combine<A>(acc, v, op);
+    A acc = red_identity<A>(ROP);
+    if ((reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+        const uint4* pv = reinterpret_cast<const uint4*>(in + lo);   // lo is a multiple of V
+        const int64_t nvec = (hi - lo) / V;
+        int64_t i = threadIdx.x;
+        for (; i + 3 * 256 < nvec; i += 4 * 256) {   // four independent 16-byte loads in flight per thread
+            const uint4 r0 = ldg_nc_v4(pv + i), r1 = ldg_nc_v4(pv + i + 256), r2 = ldg_nc_v4(pv + i + 512),
+                        r3 = ldg_nc_v4(pv + i + 768);
+            acc = red_vec<T, A, OP>(acc, r0);
+            acc = red_vec<T, A, OP>(acc, r1);
+            acc = red_vec<T, A, OP>(acc, r2);
+            acc = red_vec<T, A, OP>(acc, r3);
+        }
+        for (; i < nvec; i += 256) acc = red_vec<T, A, OP>(acc, ldg_nc_v4(pv + i));
+        for (int64_t j = lo + nvec * V + threadIdx.x; j < hi; j += 256)
+            acc = red_combine<A>(acc, red_value<T, A, OP>(in[j]), ROP);
+    } else {
+        for (int64_t j = lo + threadIdx.x; j < hi; j += 256) acc = red_combine<A>(acc, red_value<T, A, OP>(in[j]), ROP);
     }
-    acc = block_reduce<A>(acc, op);
+    acc = block_reduce<A>(acc, ROP);
     if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+template <typename T, typename A>
+void launch_reduce1(const T* in, int64_t n, int op, A* partial, int parts, cudaStream_t stream) {
+    switch (op) {
+        case RED_SUM: k_reduce1<T, A, RED_SUM><<<parts, 256, 0, stream>>>(in, n, partial); break;
+        case RED_MIN: k_reduce1<T, A, RED_MIN><<<parts, 256, 0, stream>>>(in, n, partial); break;
+        case RED_MAX: k_reduce1<T, A, RED_MAX><<<parts, 256, 0, stream>>>(in, n, partial); break;
+        default: k_reduce1<T, A, RED_COUNT_NONZERO><<<parts, 256, 0, stream>>>(in, n, partial); break;
+    }
 }
 
 template <typename A>
@@ -227,6 +371,158 @@ __global__ void k_diffuse(const T* __restrict__ in, const T* __restrict__ halo_t
     out[idx] = (T)(self * (1.0 - rate * (double)k / 8.0) + rate / 8.0 * acc);
 }
 
+// ---- column walker: radius-R neighbourhood sums and diffusion -----------------------------------------
+// A thread owns V adjacent columns (V * sizeof(T) >= 4 bytes: V = 4 for uint8, 1 otherwise; cols % V == 0 and
+// V*sizeof(T)-aligned rows are checked on the host) and walks down SEG rows of the layer.  Per input row it
+// loads the 2*NL+1 vectors around its columns (the side ones are L1 hits of the neighbour threads' loads),
+// converts them once to the accumulator type and keeps the last 2R+1 rows in registers; the loop is fully
+// unrolled, so the window never moves and the loads of later rows are hoisted above the arithmetic.  Rows
+// outside the block come from halo_top / halo_bot (R rows each; nullptr = no cells there), columns outside wrap
+// (col_torus) or contribute nothing.  Sums run in the (di, dj) order of the generic kernel and of the oracle.
+template <typename T, int V> struct WalkVec;
+template <> struct WalkVec<uint8_t, 4> { using type = uint32_t; };
+template <typename T> struct WalkVec<T, 1> { using type = T; };
+
+template <typename T, typename A, int V, int NL>
+__device__ __forceinline__ void walk_load_row(const T* __restrict__ p, const int64_t (&cv)[2 * NL + 1], A (&dst)[(2 * NL + 1) * V]) {
+    using VT = typename WalkVec<T, V>::type;
+#pragma unroll
+    for (int k = 0; k < 2 * NL + 1; ++k) {
+        if (p != nullptr && cv[k] >= 0) {
+            const VT raw = __ldg(reinterpret_cast<const VT*>(p) + cv[k]);
+            const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+            for (int v = 0; v < V; ++v) dst[k * V + v] = (A)e[v];
+        } else {
+#pragma unroll
+            for (int v = 0; v < V; ++v) dst[k * V + v] = (A)0;
+        }
+    }
+}
+
+template <typename T, int R>
+__device__ __forceinline__ const T* walk_row_ptr(const T* in, const T* halo_top, const T* halo_bot, int64_t r,
+                                                 int64_t rows, int64_t cols) {
+    if (r < 0) return (halo_top != nullptr && r >= -R) ? halo_top + (R + r) * cols : nullptr;
+    if (r >= rows) return (halo_bot != nullptr && r - rows < R) ? halo_bot + (r - rows) * cols : nullptr;
+    return in + r * cols;
+}
+
+template <int V, int NL>
+__device__ __forceinline__ void walk_columns(int64_t jv, int64_t nvec, int col_torus, int64_t (&cv)[2 * NL + 1]) {
+#pragma unroll
+    for (int k = 0; k < 2 * NL + 1; ++k) {
+        int64_t c = jv + k - NL;
+        if (c < 0 || c >= nvec) c = col_torus ? ((c % nvec) + nvec) % nvec : -1;
+        cv[k] = c;
+    }
+}
+
+template <typename T, typename A, int R, bool VN, int V, int SEG, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+k_nsum_walk(const T* __restrict__ in, const T* __restrict__ halo_top, const T* __restrict__ halo_bot,
+            A* __restrict__ out, int64_t rows, int64_t cols, int include_center, int col_torus) {
+    constexpr int NL = (R + V - 1) / V, W = (2 * NL + 1) * V;
+    const int64_t nvec = cols / V;
+    const int64_t jv = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (jv >= nvec) return;
+    int64_t cv[2 * NL + 1];
+    walk_columns<V, NL>(jv, nvec, col_torus, cv);
+    const int64_t i0 = (int64_t)blockIdx.y * SEG;
+    // rows i0-R .. i0+SEG-1+R of the walk; statically indexed (only 2R+1+PF of them are live at a time):
+    // the loads run PF rows ahead of the arithmetic
+    constexpr int PF = 2;
+    A win[SEG + 2 * R][W];
+#pragma unroll
+    for (int k = 0; k < 2 * R + PF; ++k)
+        walk_load_row<T, A, V, NL>(walk_row_ptr<T, R>(in, halo_top, halo_bot, i0 - R + k, rows, cols), cv, win[k]);
+#pragma unroll
+    for (int s = 0; s < SEG; ++s) {
+        const int64_t i = i0 + s;
+        if (s + 2 * R + PF < SEG + 2 * R)
+            walk_load_row<T, A, V, NL>(walk_row_ptr<T, R>(in, halo_top, halo_bot, i + R + PF, rows, cols), cv,
+                                       win[(s + 2 * R + PF) % (SEG + 2 * R)]);
+        A res[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            A acc = 0;
+#pragma unroll
+            for (int di = -R; di <= R; ++di)
+#pragma unroll
+                for (int dj = -R; dj <= R; ++dj) {
+                    if (VN && (di < 0 ? -di : di) + (dj < 0 ? -dj : dj) > R) continue;
+                    const A x = win[s + di + R][NL * V + v + dj];
+                    if (di == 0 && dj == 0) {
+                        if (include_center) acc += x;
+                    } else {
+                        acc += x;
+                    }
+                }
+            res[v] = acc;
+        }
+        if (i >= rows) continue;
+        A* o = out + i * cols + jv * V;
+        if (V == 4) {
+            __stcs(reinterpret_cast<int4*>(o), make_int4((int)res[0], (int)res[V > 1 ? 1 : 0], (int)res[V > 2 ? 2 : 0], (int)res[V > 3 ? 3 : 0]));
+        } else {
+#pragma unroll
+            for (int v = 0; v < V; ++v) __stcs(o + v, res[v]);
+        }
+    }
+}
+
+// diffusion on the same walker (radius 1, Moore, one column per thread); k_c from the position
+template <typename T, int SEG>
+__global__ void __launch_bounds__(128, 8)
+k_diffuse_walk(const T* __restrict__ in, const T* __restrict__ halo_top, const T* __restrict__ halo_bot,
+               T* __restrict__ out, int64_t rows, int64_t cols, double rate, int col_torus) {
+    const int64_t j = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (j >= cols) return;
+    int64_t cv[3];
+    walk_columns<1, 1>(j, cols, col_torus, cv);
+    const int kcols = (cv[0] >= 0) + 1 + (cv[2] >= 0);
+    const int64_t i0 = (int64_t)blockIdx.y * SEG;
+    constexpr int PF = 2;
+    double win[SEG + 2][3];
+#pragma unroll
+    for (int k = 0; k < 2 + PF; ++k)
+        walk_load_row<T, double, 1, 1>(walk_row_ptr<T, 1>(in, halo_top, halo_bot, i0 - 1 + k, rows, cols), cv, win[k]);
+    const double share = rate / 8.0;
+#pragma unroll
+    for (int s = 0; s < SEG; ++s) {
+        const int64_t i = i0 + s;
+        if (s + 2 + PF < SEG + 2)
+            walk_load_row<T, double, 1, 1>(walk_row_ptr<T, 1>(in, halo_top, halo_bot, i + 1 + PF, rows, cols), cv,
+                                           win[(s + 2 + PF) % (SEG + 2)]);
+        const int krows = ((i > 0) || halo_top != nullptr) + 1 + ((i + 1 < rows) || halo_bot != nullptr);
+        const int k = krows * kcols - 1;
+        double acc = 0.0;
+#pragma unroll
+        for (int di = 0; di < 3; ++di)
+#pragma unroll
+            for (int dj = 0; dj < 3; ++dj)
+                if (!(di == 1 && dj == 1)) acc += win[s + di][dj];
+        const double self = win[s + 1][1];
+        if (i < rows) __stcs(out + i * cols + j, (T)(self * (1.0 - rate * (double)k / 8.0) + share * acc));
+    }
+}
+
+template <typename T, typename A, int V, int MINB1, int MINB2>
+bool launch_nsum_walk(const T* in, const T* ht, const T* hb, A* out, int64_t rows, int64_t cols, int radius,
+                      int von_neumann, int include_center, int col_torus, cudaStream_t stream) {
+    constexpr int SEG = 16;
+    const dim3 grid((unsigned)mb::ceil_div(cols / V, 128), (unsigned)mb::ceil_div(rows, SEG));
+    if (grid.y > 65535u) return false;
+    if (radius == 1) {
+        if (von_neumann) k_nsum_walk<T, A, 1, true, V, SEG, MINB1><<<grid, 128, 0, stream>>>(in, ht, hb, out, rows, cols, include_center, col_torus);
+        else k_nsum_walk<T, A, 1, false, V, SEG, MINB1><<<grid, 128, 0, stream>>>(in, ht, hb, out, rows, cols, include_center, col_torus);
+    } else {
+        if (von_neumann) k_nsum_walk<T, A, 2, true, V, SEG, MINB2><<<grid, 128, 0, stream>>>(in, ht, hb, out, rows, cols, include_center, col_torus);
+        else k_nsum_walk<T, A, 2, false, V, SEG, MINB2><<<grid, 128, 0, stream>>>(in, ht, hb, out, rows, cols, include_center, col_torus);
+    }
+    return true;
+}
+
 #define MB_DISPATCH_DTYPE(dtype, CALL)                                   \
     switch (dtype) {                                                     \
         case DT_U8: { using T = uint8_t; CALL; } break;                  \
@@ -252,8 +548,12 @@ MB_API int mb_layer_affine_clamp(const void* in, void* out, int64_t n, int dtype
     MB_REQUIRE(n >= 0, "mb_layer_affine_clamp: negative size");
     if (n == 0) return MB_OK;
     MB_REQUIRE(in && out, "mb_layer_affine_clamp: null buffer");
-    MB_DISPATCH_DTYPE(dtype, (k_affine<T><<<stream_blocks(n / VecOf<T>::n + 1), 256, 0, stream>>>(
-                                 (const T*)in, (T*)out, n, alpha, beta, lo, hi)));
+    if (dtype == DT_U8) {
+        k_affine_u8<<<stream_blocks(n / 16 + 1), 256, 0, stream>>>((const uint8_t*)in, (uint8_t*)out, n, alpha, beta, lo, hi);
+    } else {
+        MB_DISPATCH_DTYPE(dtype, (k_affine<T><<<stream_blocks(n / VecOf<T>::n + 1), 256, 0, stream>>>(
+                                     (const T*)in, (T*)out, n, alpha, beta, lo, hi)));
+    }
     MB_LAUNCH_CHECK("mb_layer_affine_clamp");
     return MB_OK;
 }
@@ -263,8 +563,8 @@ MB_API int mb_layer_binary(const void* a, const void* b, void* out, int64_t n, i
     MB_REQUIRE(n >= 0 && op >= OP_ADD && op <= OP_MAX, "mb_layer_binary: bad argument");
     if (n == 0) return MB_OK;
     MB_REQUIRE(a && b && out, "mb_layer_binary: null buffer");
-    MB_DISPATCH_DTYPE(dtype, (k_binary<T><<<stream_blocks(n / VecOf<T>::n + 1), 256, 0, stream>>>(
-                                 (const T*)a, (const T*)b, (T*)out, n, op)));
+    MB_DISPATCH_DTYPE(dtype, (launch_binary<T>((const T*)a, (const T*)b, (T*)out, n, op,
+                                               stream_blocks(n / VecOf<T>::n + 1), stream)));
     MB_LAUNCH_CHECK("mb_layer_binary");
     return MB_OK;
 }
@@ -284,11 +584,11 @@ MB_API int mb_layer_reduce(const void* in, int64_t n, int dtype, int op, void* r
     const bool as_int = dtype == DT_U8 || dtype == DT_I32 || op == RED_COUNT_NONZERO;
     if (as_int) {
         using A = long long;
-        MB_DISPATCH_DTYPE(dtype, (k_reduce1<T, A><<<parts, 256, 0, stream>>>((const T*)in, n, op, (A*)workspace)));
+        MB_DISPATCH_DTYPE(dtype, (launch_reduce1<T, A>((const T*)in, n, op, (A*)workspace, parts, stream)));
         k_reduce2<A><<<1, 1024, 0, stream>>>((const A*)workspace, parts, op == RED_COUNT_NONZERO ? RED_SUM : op, (A*)result);
     } else {
         using A = double;
-        MB_DISPATCH_DTYPE(dtype, (k_reduce1<T, A><<<parts, 256, 0, stream>>>((const T*)in, n, op, (A*)workspace)));
+        MB_DISPATCH_DTYPE(dtype, (launch_reduce1<T, A>((const T*)in, n, op, (A*)workspace, parts, stream)));
         k_reduce2<A><<<1, 1024, 0, stream>>>((const A*)workspace, parts, op, (A*)result);
     }
     MB_LAUNCH_CHECK("mb_layer_reduce");
@@ -305,6 +605,26 @@ MB_API int mb_neighborhood_sum(const void* in, const void* halo_top, const void*
                "mb_neighborhood_sum: torus needs cols >= 2*radius+1 (SURVEY A.2)");
     if (rows == 0 || cols == 0) return MB_OK;
     MB_REQUIRE(in && out, "mb_neighborhood_sum: null buffer");
+    if (radius <= 2 && dtype >= DT_U8 && dtype <= DT_F64) {
+        // column walker (see above); uint8 rows must be 4-byte aligned for the 4-column version
+        const uintptr_t align = reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(halo_top) |
+                                reinterpret_cast<uintptr_t>(halo_bot);
+        bool done = false;
+        if (dtype == DT_U8 && cols % 4 == 0 && (align & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+            done = launch_nsum_walk<uint8_t, int32_t, 4, 8, 4>((const uint8_t*)in, (const uint8_t*)halo_top, (const uint8_t*)halo_bot, (int32_t*)out, rows, cols, radius, von_neumann, include_center, col_torus, stream);
+        else if (dtype == DT_U8)
+            done = launch_nsum_walk<uint8_t, int32_t, 1, 8, 8>((const uint8_t*)in, (const uint8_t*)halo_top, (const uint8_t*)halo_bot, (int32_t*)out, rows, cols, radius, von_neumann, include_center, col_torus, stream);
+        else if (dtype == DT_I32)
+            done = launch_nsum_walk<int32_t, int32_t, 1, 8, 8>((const int32_t*)in, (const int32_t*)halo_top, (const int32_t*)halo_bot, (int32_t*)out, rows, cols, radius, von_neumann, include_center, col_torus, stream);
+        else if (dtype == DT_F32)
+            done = launch_nsum_walk<float, double, 1, 8, 4>((const float*)in, (const float*)halo_top, (const float*)halo_bot, (double*)out, rows, cols, radius, von_neumann, include_center, col_torus, stream);
+        else
+            done = launch_nsum_walk<double, double, 1, 8, 4>((const double*)in, (const double*)halo_top, (const double*)halo_bot, (double*)out, rows, cols, radius, von_neumann, include_center, col_torus, stream);
+        if (done) {
+            MB_LAUNCH_CHECK("mb_neighborhood_sum");
+            return MB_OK;
+        }
+    }
     const unsigned blocks = (unsigned)mb::ceil_div(rows * cols, 256);
     switch (dtype) {
         case DT_U8: k_neighborhood_sum<uint8_t, int32_t><<<blocks, 256, 0, stream>>>((const uint8_t*)in, (const uint8_t*)halo_top, (const uint8_t*)halo_bot, (int32_t*)out, rows, cols, radius, von_neumann, include_center, col_torus); break;
@@ -325,6 +645,18 @@ MB_API int mb_layer_diffuse(const void* in, const void* halo_top, const void* ha
     MB_REQUIRE(!(col_torus && cols > 0 && cols < 3), "mb_layer_diffuse: torus needs cols >= 3");
     if (rows == 0 || cols == 0) return MB_OK;
     MB_REQUIRE(in && out && in != out, "mb_layer_diffuse: null or aliased buffer");
+    {
+        constexpr int SEG = 16;
+        const dim3 grid((unsigned)mb::ceil_div(cols, 128), (unsigned)mb::ceil_div(rows, SEG));
+        if (grid.y <= 65535u) {
+            if (dtype == DT_F32)
+                k_diffuse_walk<float, SEG><<<grid, 128, 0, stream>>>((const float*)in, (const float*)halo_top, (const float*)halo_bot, (float*)out, rows, cols, rate, col_torus);
+            else
+                k_diffuse_walk<double, SEG><<<grid, 128, 0, stream>>>((const double*)in, (const double*)halo_top, (const double*)halo_bot, (double*)out, rows, cols, rate, col_torus);
+            MB_LAUNCH_CHECK("mb_layer_diffuse");
+            return MB_OK;
+        }
+    }
     const unsigned blocks = (unsigned)mb::ceil_div(rows * cols, 256);
     if (dtype == DT_F32)
         k_diffuse<float><<<blocks, 256, 0, stream>>>((const float*)in, (const float*)halo_top, (const float*)halo_bot, (float*)out, rows, cols, rate, col_torus);

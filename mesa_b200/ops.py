@@ -409,6 +409,50 @@ def radius_query(pos: torch.Tensor, queries: torch.Tensor, size, radius: float, 
     return offsets, idx, dist
 
 
+def knn_cell_edge(n: int, size, k: int) -> float:
+    """Cell edge for a k-nearest search: about k + 1 agents per 3 x 3 block at uniform density."""
+    area = float(size[0]) * float(size[1])
+    edge = (area * (k + 1) / (9.0 * max(n, 1))) ** 0.5
+    return min(max(edge, 1e-6 * max(float(size[0]), float(size[1]))), max(float(size[0]), float(size[1])))
+
+
+def knn_query(pos: torch.Tensor, queries: torch.Tensor, size, k: int, torus: bool = True, origin=(0.0, 0.0),
+              exclude: torch.Tensor | None = None, cell_edge: float | None = None):
+    """Batched get_k_nearest_agents (continuous_space.py:249-283): (indices int32 [nq, k], distances float64 [nq, k]),
+    rows ascending in (distance, storage index), padded with -1 / inf when fewer than k agents exist."""
+    _need_cuda(pos, queries, exclude)
+    n, nq = pos.shape[0], queries.shape[0]
+    if k < 0:
+        raise ValueError("k must be non-negative")
+    idx = torch.empty((nq, k), dtype=torch.int32, device=pos.device)
+    dist = torch.empty((nq, k), dtype=torch.float64, device=pos.device)
+    if nq == 0 or k == 0:
+        return idx, dist
+    edge = float(cell_edge) if cell_edge is not None else knn_cell_edge(n, size, k)
+    ws = CellListWorkspace(max(n, 1), size, edge, pos.device)
+    with torch.cuda.device(pos.device):
+        N.check(N.lib().mb_knn_query_f32(N.ptr(_c(pos)), n, float(origin[0]), float(origin[1]), float(size[0]),
+                                         float(size[1]), int(bool(torus)), N.ptr(_c(queries)), N.ptr(exclude), nq, int(k),
+                                         edge, N.ptr(idx), N.ptr(dist), N.ptr(ws.buf), ws.nbytes, 0,
+                                         N.stream_ptr(pos.device)))
+    return idx, dist
+
+
+def point_distances(pos: torch.Tensor, point, size, torus: bool, sel: torch.Tensor | None = None,
+                    distances: bool = True, deltas: bool = False):
+    """calculate_distances / calculate_difference_vector of one point (continuous_space.py:169-235) against all
+    agents or the agents `sel` (int32 indices): (float64 [m] or None, float64 [m, 2] or None)."""
+    _need_cuda(pos, sel)
+    m = pos.shape[0] if sel is None else sel.shape[0]
+    d = torch.empty(m, dtype=torch.float64, device=pos.device) if distances else None
+    v = torch.empty((m, 2), dtype=torch.float64, device=pos.device) if deltas else None
+    with torch.cuda.device(pos.device):
+        N.check(N.lib().mb_point_distances_f32(N.ptr(_c(pos)), N.ptr(sel), m, float(size[0]), float(size[1]),
+                                               int(bool(torus)), float(point[0]), float(point[1]), N.ptr(d), N.ptr(v),
+                                               N.stream_ptr(pos.device)))
+    return d, v
+
+
 # ----------------------------------------------------------------------------- Boltzmann wealth
 class BoltzmannWorkspace:
     """Scratch + per-cell list order of mb_boltzmann_step for `n` agents (persistent between steps)."""
@@ -510,16 +554,21 @@ def layer_reduce(layer: torch.Tensor, op: str = "sum") -> torch.Tensor:
 
 def neighborhood_sum(layer: torch.Tensor, radius: int = 1, moore: bool = True, include_center: bool = False,
                      torus: bool = False, halo_top: torch.Tensor | None = None,
-                     halo_bot: torch.Tensor | None = None) -> torch.Tensor:
-    """Sum of `layer` over each cell's radius-r neighbourhood (cell.py:225-276) for all cells at once."""
-    _need_cuda(layer, halo_top, halo_bot)
+                     halo_bot: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Sum of `layer` over each cell's radius-r neighbourhood (cell.py:225-276) for all cells at once
+    (int32 for integer layers, float64 for float layers)."""
+    _need_cuda(layer, halo_top, halo_bot, out)
     if layer.dim() != 2:
         raise ValueError("neighborhood_sum expects a [rows, cols] layer")
     if radius < 1:
         raise ValueError("radius must be at least 1")
     rows, cols = layer.shape
     integer = layer.dtype in (torch.uint8, torch.bool, torch.int32)
-    out = torch.empty((rows, cols), dtype=torch.int32 if integer else torch.float64, device=layer.device)
+    want = torch.int32 if integer else torch.float64
+    if out is None:
+        out = torch.empty((rows, cols), dtype=want, device=layer.device)
+    elif out.shape != layer.shape or out.dtype != want or not out.is_contiguous():
+        raise ValueError(f"neighborhood_sum: out must be a contiguous {want} tensor of the layer's shape")
     if torus and halo_top is None and halo_bot is None and rows > 0:
         if rows < 2 * radius + 1:
             raise ValueError("torus needs rows >= 2*radius+1")

@@ -187,6 +187,40 @@ def radius_query(pos, point, size, radius, torus=True, exclude=-1):
     return idx[:k].copy(), dist[:k].copy()
 
 
+def point_distances(pos, point, size, torus=True):
+    """calculate_distances (continuous_space.py:202-235): torus -> abs, min(d, size - d), squares summed axis by
+    axis, sqrt; bounded -> Euclidean (scipy cdist there; the same sum of squares)."""
+    pos = np.asarray(pos, dtype=np.float64)
+    delta = np.abs(np.asarray(point, dtype=np.float64)[np.newaxis, :] - pos)
+    if torus:
+        delta = np.minimum(delta, np.asarray(size, dtype=np.float64) - delta)
+    d2 = np.zeros(pos.shape[0])
+    for axis in range(pos.shape[1]):
+        d2 += delta[:, axis] ** 2
+    return np.sqrt(d2)
+
+
+def difference_vectors(pos, point, size, torus=True):
+    """calculate_difference_vector (continuous_space.py:169-200)."""
+    delta = np.asarray(pos, dtype=np.float64) - np.asarray(point, dtype=np.float64)[np.newaxis, :]
+    if torus:
+        inverse = delta - np.sign(delta) * np.asarray(size, dtype=np.float64)
+        delta = np.where(np.abs(delta) < np.abs(inverse), delta, inverse)
+    return delta
+
+
+def knn_query(pos, point, size, k, torus=True, exclude=-1):
+    """get_k_nearest_agents (continuous_space.py:249-283) with the documented tie rule made explicit: ascending
+    (distance, storage index).  Returns (indices, distances) of min(k, n) agents."""
+    d = point_distances(pos, point, size, torus)
+    ids = np.arange(len(d))
+    if exclude >= 0:
+        keep = ids != exclude
+        d, ids = d[keep], ids[keep]
+    o = np.lexsort((ids, d))[:k]
+    return ids[o], d[o]
+
+
 # ----------------------------------------------------------------------------- Boltzmann wealth
 class BoltzmannState:
     """Reference-shaped Boltzmann state: per-agent cell/wealth + per-cell agent lists in list order."""

@@ -262,12 +262,95 @@ def boids_fixture(name, n, width, height, vision, separation, steps, seed, philo
     print(name, "mean neighbours", float(np.mean(out["nbr_count_0"])))
 
 
+# ------------------------------------------------------------------------------ continuous-space queries
+def continuous_queries_fixture(name):
+    """calculate_distances / calculate_difference_vector / get_agents_in_radius / get_k_nearest_agents of the
+    UNMODIFIED ContinuousSpace on float32-representable positions (torus and bounded, origin and shifted boxes)."""
+    from mesa import Model
+    from mesa.experimental.continuous_space import ContinuousSpace, ContinuousSpaceAgent
+
+    out = {}
+    cases = []
+    rng = np.random.default_rng(2025)
+    for c, (n, dims, torus, radius, k) in enumerate([
+        (200, [[0, 50], [0, 30]], True, 4.0, 5),
+        (200, [[0, 50], [0, 30]], False, 4.0, 5),
+        (150, [[-10, 10], [5, 45]], True, 3.0, 8),
+        (150, [[-10, 10], [5, 45]], False, 6.5, 1),
+        (7, [[0, 1], [0, 1]], True, 0.3, 7),
+        (60, [[0, 8], [0, 8]], True, 3.9, 60),
+    ]):
+        dims = np.asarray(dims, dtype=float)
+        model = Model(rng=1)
+        space = ContinuousSpace(dims, torus=torus, random=model.random, n_agents=n)
+        pos = (dims[:, 0] + rng.random((n, 2)) * (dims[:, 1] - dims[:, 0])).astype(np.float32).astype(np.float64)
+        agents = []
+        for i in range(n):
+            a = ContinuousSpaceAgent(space, model)
+            a.position = pos[i]
+            agents.append(a)
+        index = {id(a): i for i, a in enumerate(agents)}
+        points = (dims[:, 0] + rng.random((12, 2)) * (dims[:, 1] - dims[:, 0])).astype(np.float32).astype(np.float64)
+        points[0] = pos[3]          # a query sitting on an agent
+        out[f"pos_{c}"] = pos
+        out[f"points_{c}"] = points
+        some = np.sort(rng.choice(n, size=min(n, 9), replace=False))
+        out[f"subset_{c}"] = some
+        dist_all, delta_all, dist_sub, delta_sub, rad_idx, rad_dist, rad_off, knn_idx, knn_dist = [], [], [], [], [], [], [0], [], []
+        for pt in points:
+            d, ag = space.calculate_distances(pt)
+            assert [index[id(a)] for a in ag] == list(range(n))
+            dist_all.append(d)
+            delta_all.append(space.calculate_difference_vector(pt))
+            sub_agents = [agents[i] for i in some]
+            d, _ = space.calculate_distances(pt, sub_agents)
+            dist_sub.append(d)
+            delta_sub.append(space.calculate_difference_vector(pt, sub_agents))
+            ag, d = space.get_agents_in_radius(pt, radius)
+            rad_idx.extend(index[id(a)] for a in ag)
+            rad_dist.extend(d)
+            rad_off.append(len(rad_idx))
+            ag, d = space.get_k_nearest_agents(pt, k)
+            ids = np.array([index[id(a)] for a in ag])
+            o = np.lexsort((ids, d))            # argpartition leaves the k unordered
+            knn_idx.append(ids[o])
+            knn_dist.append(np.asarray(d)[o])
+        out[f"dist_all_{c}"] = np.stack(dist_all)
+        out[f"delta_all_{c}"] = np.stack(delta_all)
+        out[f"dist_sub_{c}"] = np.stack(dist_sub)
+        out[f"delta_sub_{c}"] = np.stack(delta_sub)
+        out[f"rad_idx_{c}"] = np.array(rad_idx, dtype=np.int64)
+        out[f"rad_dist_{c}"] = np.array(rad_dist, dtype=np.float64)
+        out[f"rad_off_{c}"] = np.array(rad_off, dtype=np.int64)
+        out[f"knn_idx_{c}"] = np.stack(knn_idx)
+        out[f"knn_dist_{c}"] = np.stack(knn_dist)
+        # every agent's own neighbours: get_nearest_neighbors(k') excludes self
+        kk = min(3, n - 1)
+        nn_idx, nn_dist = [], []
+        for a in agents[:20]:
+            ag, d = a.get_nearest_neighbors(kk)
+            ids = np.array([index[id(b)] for b in ag])
+            o = np.lexsort((ids, d))
+            nn_idx.append(ids[o])
+            nn_dist.append(np.asarray(d)[o])
+        out[f"nn_idx_{c}"] = np.stack(nn_idx)
+        out[f"nn_dist_{c}"] = np.stack(nn_dist)
+        cases.append((n, int(torus), radius, k, kk))
+        out[f"dims_{c}"] = dims
+    out["cases"] = np.array(cases, dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLDEN, name), **out)
+    print(name, len(cases), "cases")
+
+
 def main():
     import_reference()
     os.makedirs(GOLDEN, exist_ok=True)
     only = sys.argv[1] if len(sys.argv) > 1 else ""
     if only == "neighborhoods":
         neighborhood_fixture("neighborhoods.npz")
+        return
+    if only == "continuous":
+        continuous_queries_fixture("continuous_queries.npz")
         return
     if only == "boltzmann":
         boltzmann_fixture("boltzmann_100_10x10.npz", 100, 10, 10, 25, 42, 3)      # reference "small"
@@ -289,6 +372,7 @@ def main():
     datacollector_fixture("datacollector_schelling_20x20.npz", 20, 20, 0.8, 0.4, 1, 10, 42, 2024)
     boids_fixture("boids_300.npz", 300, 100, 100, 10.0, 2.0, 3, 42, 5)
     boids_fixture("boids_120_wrap.npz", 120, 40, 30, 6.0, 2.0, 3, 1, 6)
+    continuous_queries_fixture("continuous_queries.npz")
     boltzmann_fixture("boltzmann_100_10x10.npz", 100, 10, 10, 25, 42, 3)
     boltzmann_fixture("boltzmann_2000_20x30.npz", 2000, 20, 30, 10, 7, 4)
     boltzmann_fixture("boltzmann_10000_100x100.npz", 10000, 100, 100, 10, 1, 5)

@@ -229,3 +229,93 @@ def test_cell_list_with_crowded_cells_matches_oracle():
                                           neighbor_count=cnt, **kw)
     assert np.array_equal(cnt.cpu().numpy(), sc)
     assert np.max(np.abs(qo.cpu().numpy() - sp) / size) <= RTOL and np.max(np.abs(qd.cpu().numpy() - sd)) <= RTOL
+
+
+# ---- point queries of the drop-in space vs the UNMODIFIED reference (golden) and the oracle -----------------
+def test_continuous_queries_match_reference_golden():
+    """calculate_distances, calculate_difference_vector, get_agents_in_radius, get_k_nearest_agents and
+    get_nearest_neighbors of DeviceContinuousSpace against ContinuousSpace itself: indices identical,
+    float64 distances / vectors bit-identical (positions are float32-representable)."""
+    import random
+
+    from mesa_b200.continuous_space import ContinuousSpace
+
+    g = np.load(os.path.join(GOLDEN, "continuous_queries.npz"))
+    for c, (n, torus, radius, k, kk) in enumerate(g["cases"]):
+        n, torus, k, kk = int(n), bool(torus), int(k), int(kk)
+        pos, points, dims, sub = g[f"pos_{c}"], g[f"points_{c}"], g[f"dims_{c}"], g[f"subset_{c}"]
+        space = ContinuousSpace(dims, torus=torus, random=random.Random(1), n_agents=n)
+        space.add_agents(pos)
+        for q, pt in enumerate(points):
+            d, ids = space.calculate_distances(pt)
+            assert ids == list(range(n)) and np.array_equal(d, g[f"dist_all_{c}"][q])
+            assert np.array_equal(space.calculate_difference_vector(pt), g[f"delta_all_{c}"][q])
+            d, ids = space.calculate_distances(pt, sub.tolist())
+            assert ids == sub.tolist() and np.array_equal(d, g[f"dist_sub_{c}"][q])
+            assert np.array_equal(space.calculate_difference_vector(pt, sub.tolist()), g[f"delta_sub_{c}"][q])
+            lo, hi = g[f"rad_off_{c}"][q], g[f"rad_off_{c}"][q + 1]
+            idx, dist = space.get_agents_in_radius(pt, radius)
+            assert idx == g[f"rad_idx_{c}"][lo:hi].tolist() and np.array_equal(dist, g[f"rad_dist_{c}"][lo:hi])
+            idx, dist = space.get_k_nearest_agents(pt, k)
+            assert idx == g[f"knn_idx_{c}"][q].tolist() and np.array_equal(dist, g[f"knn_dist_{c}"][q])
+        # batched: all points in one launch, and every agent's own nearest neighbours
+        idx, dist = space.k_nearest_query(points, k)
+        assert np.array_equal(idx.cpu().numpy(), g[f"knn_idx_{c}"]) and np.array_equal(dist.cpu().numpy(), g[f"knn_dist_{c}"])
+        idx, dist = space.nearest_neighbors(kk)
+        m = g[f"nn_idx_{c}"].shape[0]
+        assert np.array_equal(idx[:m].cpu().numpy(), g[f"nn_idx_{c}"]) and np.array_equal(dist[:m].cpu().numpy(), g[f"nn_dist_{c}"])
+
+
+@pytest.mark.parametrize("n,side,torus", [(20_000, (300.0, 200.0), True), (20_000, (300.0, 200.0), False),
+                                          (5_000, (40.0, 2.0), True), (3, (10.0, 10.0), True)])
+@pytest.mark.parametrize("k", [1, 4, 16])
+def test_knn_query_matches_oracle(n, side, torus, k):
+    """Ring search on the cell list vs brute force; clustered agents (empty cells force wide rings), k > n padding."""
+    from mesa_b200 import ops
+
+    rng = np.random.default_rng(n + k)
+    pos = rng.random((n, 2)) * side
+    pos[: n // 2] = pos[: n // 2] * 0.05 + np.asarray(side) * 0.6        # half of the agents in a small cluster
+    pos = pos.astype(np.float32)
+    queries = (rng.random((300, 2)) * side).astype(np.float32)
+    idx, dist = ops.knn_query(torch.from_numpy(pos).cuda(), torch.from_numpy(queries).cuda(), side, k, torus)
+    idx, dist = idx.cpu().numpy(), dist.cpu().numpy()
+    for q in range(queries.shape[0]):
+        wi, wd = oracle.knn_query(pos.astype(np.float64), queries[q].astype(np.float64), side, k, torus)
+        m = len(wi)
+        assert np.array_equal(idx[q, :m], wi) and np.array_equal(dist[q, :m], wd), q
+        assert np.all(idx[q, m:] == -1) and np.all(np.isinf(dist[q, m:]))
+
+
+def test_knn_query_ties_rank_by_storage_index():
+    """Agents on a lattice: many exactly equal distances; the earlier storage index wins (continuous_space.py:256-257)."""
+    from mesa_b200 import ops
+
+    xs, ys = np.meshgrid(np.arange(0.5, 16.0, 1.0), np.arange(0.5, 16.0, 1.0), indexing="ij")
+    pos = np.stack([xs.ravel(), ys.ravel()], axis=1).astype(np.float32)
+    pos = pos[np.random.default_rng(0).permutation(len(pos))]
+    me = torch.arange(len(pos), dtype=torch.int32, device="cuda")
+    for torus in (True, False):
+        for k, edge in ((4, None), (8, 0.7), (9, 3.0)):
+            idx, dist = ops.knn_query(torch.from_numpy(pos).cuda(), torch.from_numpy(pos).cuda(), (16.0, 16.0), k, torus,
+                                      exclude=me, cell_edge=edge)
+            idx, dist = idx.cpu().numpy(), dist.cpu().numpy()
+            for q in range(0, len(pos), 7):
+                wi, wd = oracle.knn_query(pos.astype(np.float64), pos[q].astype(np.float64), (16.0, 16.0), k, torus, exclude=q)
+                assert np.array_equal(idx[q], wi) and np.array_equal(dist[q], wd), (torus, k, q)
+
+
+def test_knn_and_point_queries_on_empty_space():
+    import random
+
+    from mesa_b200.continuous_space import ContinuousSpace
+
+    space = ContinuousSpace([[0, 1], [0, 1]], torus=True, random=random.Random(1))
+    assert space.get_k_nearest_agents([0.5, 0.5], k=3)[0] == []
+    d, ids = space.calculate_distances([0.5, 0.5])
+    assert len(d) == 0 and ids == []
+    assert space.calculate_difference_vector([0.5, 0.5]).shape == (0, 2)
+    space.add_agents([[0.2, 0.2]])
+    assert space.get_k_nearest_agents([0.5, 0.5], k=0)[0] == []
+    idx, dist = space.k_nearest_query(np.array([[0.9, 0.9]]), 2)
+    assert idx.cpu().tolist() == [[0, -1]] and np.isinf(dist[0, 1].item())

@@ -1,0 +1,233 @@
+"""CPU emulation of the index arithmetic of kernels that need no inter-thread communication.
+
+The column-walker kernels of csrc/layers.cu (k_nsum_walk, k_diffuse_walk) and the ring search of
+csrc/continuous.cu (knn_query) are extracted TEXTUALLY from the .cu sources, compiled with g++ against
+tools/emu/cuda_shim.h (threads run one after the other) and checked against brute force on ragged shapes.
+This is a development aid for a container without a GPU -- the parity tests proper run on the device
+(tests/test_layers_gpu.py, tests/test_continuous_gpu.py).
+
+    python tools/emulate_kernels.py          # exit code 0 = all cases agree
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "mesa_b200", "csrc")
+
+
+def between(text: str, start: str, end: str) -> str:
+    a = text.index(start)
+    b = text.index(end, a)
+    return text[a:b]
+
+
+HARNESS = r'''
+#include "cuda_shim.h"
+enum { DT_U8 = 0 };
+%(layers)s
+%(continuous)s
+
+template <typename T, typename A>
+static void naive_nsum(const std::vector<T>& in, std::vector<A>& out, int64_t rows, int64_t cols, int R, bool vn,
+                       bool inc, bool torus) {
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            A acc = 0;
+            for (int di = -R; di <= R; ++di)
+                for (int dj = -R; dj <= R; ++dj) {
+                    if (vn && abs(di) + abs(dj) > R) continue;
+                    if (di == 0 && dj == 0 && !inc) continue;
+                    int64_t r = i + di, c = j + dj;
+                    if (torus) { r = (r %% rows + rows) %% rows; c = (c %% cols + cols) %% cols; }
+                    else if (r < 0 || r >= rows || c < 0 || c >= cols) continue;
+                    acc += (A)in[r * cols + c];
+                }
+            out[i * cols + j] = acc;
+        }
+}
+
+template <typename T, typename A, int R, bool VN, int V>
+static int check_nsum(int64_t rows, int64_t cols, bool inc, bool torus) {
+    if (torus && (rows < 2 * R + 1 || cols < 2 * R + 1)) return 0;
+    if (cols %% V) return 0;
+    std::vector<T> in(rows * cols);
+    for (auto& x : in) x = (T)(rand() %% 251);
+    std::vector<A> want(rows * cols), got(rows * cols, (A)-7);
+    naive_nsum<T, A>(in, want, rows, cols, R, VN, inc, torus);
+    std::vector<T> top(R * cols), bot(R * cols);
+    for (int k = 0; k < R; ++k)
+        for (int64_t c = 0; c < cols; ++c) {
+            top[k * cols + c] = torus ? in[(rows - R + k) * cols + c] : (T)0;
+            bot[k * cols + c] = torus ? in[k * cols + c] : (T)0;
+        }
+    constexpr int SEG = 16;
+    gridDim.x = (unsigned)((cols / V + 127) / 128);
+    gridDim.y = (unsigned)((rows + SEG - 1) / SEG);
+    blockDim.x = 128;
+    for (blockIdx.y = 0; blockIdx.y < gridDim.y; ++blockIdx.y)
+        for (blockIdx.x = 0; blockIdx.x < gridDim.x; ++blockIdx.x)
+            for (threadIdx.x = 0; threadIdx.x < 128; ++threadIdx.x)
+                k_nsum_walk<T, A, R, VN, V, SEG, 1>(in.data(), torus ? top.data() : nullptr, torus ? bot.data() : nullptr,
+                                                    got.data(), rows, cols, inc, torus);
+    for (int64_t k = 0; k < rows * cols; ++k)
+        if (got[k] != want[k]) {
+            printf("nsum mismatch R=%%d VN=%%d V=%%d rows=%%ld cols=%%ld inc=%%d torus=%%d at %%ld: %%g vs %%g\n", R, (int)VN, V,
+                   (long)rows, (long)cols, (int)inc, (int)torus, (long)k, (double)got[k], (double)want[k]);
+            return 1;
+        }
+    return 0;
+}
+
+static int check_diffuse(int64_t rows, int64_t cols, bool torus) {
+    if (torus && (rows < 3 || cols < 3)) return 0;
+    std::vector<double> in(rows * cols), got(rows * cols, -1.0);
+    for (auto& x : in) x = (double)(rand() %% 1000) / 8.0;
+    const double rate = 0.25;
+    std::vector<double> top(cols), bot(cols);
+    for (int64_t c = 0; c < cols; ++c) { top[c] = in[(rows - 1) * cols + c]; bot[c] = in[c]; }
+    gridDim.x = (unsigned)((cols + 127) / 128);
+    gridDim.y = (unsigned)((rows + 15) / 16);
+    for (blockIdx.y = 0; blockIdx.y < gridDim.y; ++blockIdx.y)
+        for (blockIdx.x = 0; blockIdx.x < gridDim.x; ++blockIdx.x)
+            for (threadIdx.x = 0; threadIdx.x < 128; ++threadIdx.x)
+                k_diffuse_walk<double, 16>(in.data(), torus ? top.data() : nullptr, torus ? bot.data() : nullptr, got.data(),
+                                           rows, cols, rate, torus);
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            double acc = 0.0;
+            int k = 0;
+            for (int di = -1; di <= 1; ++di)
+                for (int dj = -1; dj <= 1; ++dj) {
+                    if (!di && !dj) continue;
+                    int64_t r = i + di, c = j + dj;
+                    if (torus) { r = (r + rows) %% rows; c = (c + cols) %% cols; }
+                    else if (r < 0 || r >= rows || c < 0 || c >= cols) continue;
+                    acc += in[r * cols + c];
+                    ++k;
+                }
+            const double want = in[i * cols + j] * (1.0 - rate * k / 8.0) + rate / 8.0 * acc;
+            if (fabs(want - got[i * cols + j]) > 1e-12) {
+                printf("diffuse mismatch rows=%%ld cols=%%ld torus=%%d at (%%ld,%%ld): %%g vs %%g\n", (long)rows, (long)cols,
+                       (int)torus, (long)i, (long)j, got[i * cols + j], want);
+                return 1;
+            }
+        }
+    return 0;
+}
+
+static int check_knn(int n, double sx, double sy, bool torus, int k, double edge, int nq) {
+    Geometry g;
+    g.x0 = 0; g.y0 = 0; g.sx = sx; g.sy = sy; g.torus = torus;
+    g.ncx = std::max(1, (int)floor(sx / (edge * (1.0 + 1e-6))));
+    g.ncy = std::max(1, (int)floor(sy / (edge * (1.0 + 1e-6))));
+    std::vector<float2> pos(n);
+    for (int i = 0; i < n; ++i) {
+        // half of the agents clustered, some on a lattice (exact ties)
+        if (i %% 3 == 0) pos[i] = float2{(float)(rand() %% 8) * (float)(sx / 8), (float)(rand() %% 8) * (float)(sy / 8)};
+        else if (i %% 3 == 1) pos[i] = float2{(float)(0.6 * sx + 0.05 * sx * rand() / RAND_MAX), (float)(0.6 * sy + 0.05 * sy * rand() / RAND_MAX)};
+        else pos[i] = float2{(float)(sx * (rand() / (RAND_MAX + 1.0))), (float)(sy * (rand() / (RAND_MAX + 1.0)))};
+    }
+    const int ncells = g.ncx * g.ncy;
+    std::vector<uint32_t> cell(n), start(ncells + 1, 0), order(n);
+    for (int i = 0; i < n; ++i) { cell[i] = cell_of(g, pos[i].x, pos[i].y); ++start[cell[i] + 1]; }
+    for (int c = 0; c < ncells; ++c) start[c + 1] += start[c];
+    std::vector<uint32_t> fill(start.begin(), start.end() - 1);
+    for (int i = 0; i < n; ++i) order[fill[cell[i]]++] = i;
+    std::vector<float4> packed(n);
+    for (int s = 0; s < n; ++s) packed[s] = make_float4(pos[order[s]].x, pos[order[s]].y, 0.f, 0.f);
+    std::vector<float2> queries(nq);
+    std::vector<int32_t> excl(nq);
+    for (int q = 0; q < nq; ++q) {
+        if (q %% 2 == 0 && n > 0) { excl[q] = rand() %% n; queries[q] = pos[excl[q]]; }
+        else { excl[q] = -1; queries[q] = float2{(float)(sx * (rand() / (RAND_MAX + 1.0))), (float)(sy * (rand() / (RAND_MAX + 1.0)))}; }
+    }
+    std::vector<int32_t> idx((size_t)nq * k, -9);
+    std::vector<double> dist((size_t)nq * k, -9.0);
+    gridDim.x = (unsigned)((nq + 127) / 128);
+    blockDim.x = 128;
+    for (blockIdx.x = 0; blockIdx.x < gridDim.x; ++blockIdx.x)
+        for (threadIdx.x = 0; threadIdx.x < 128; ++threadIdx.x)
+            knn_query(packed.data(), order.data(), start.data(), start.data() + 1, g, queries.data(), excl.data(), nq, k,
+                      idx.data(), dist.data());
+    for (int q = 0; q < nq; ++q) {
+        std::vector<std::pair<double, int>> all;
+        for (int i = 0; i < n; ++i)
+            if (i != excl[q]) all.push_back({ref_distance2(g, queries[q].x, queries[q].y, pos[i].x, pos[i].y), i});
+        std::sort(all.begin(), all.end());
+        for (int w = 0; w < k; ++w) {
+            const int wi = w < (int)all.size() ? all[w].second : -1;
+            const double wd = w < (int)all.size() ? sqrt(all[w].first) : INFINITY;
+            if (idx[(size_t)q * k + w] != wi || dist[(size_t)q * k + w] != wd) {
+                printf("knn mismatch n=%%d size=(%%g,%%g) torus=%%d k=%%d edge=%%g q=%%d w=%%d: (%%d,%%g) vs (%%d,%%g)\n", n, sx, sy,
+                       (int)torus, k, edge, q, w, idx[(size_t)q * k + w], dist[(size_t)q * k + w], wi, wd);
+                return 1;
+            }
+        }
+    }
+    return 0;
+}
+
+int main() {
+    int bad = 0;
+    const int64_t shapes[][2] = {{1, 1}, {1, 40}, {40, 1}, {3, 3}, {5, 8}, {16, 128}, {17, 132}, {35, 260}, {5, 516}};
+    for (auto& s : shapes)
+        for (int inc = 0; inc < 2; ++inc)
+            for (int torus = 0; torus < 2; ++torus) {
+                bad += check_nsum<uint8_t, int32_t, 1, false, 4>(s[0], s[1], inc, torus);
+                bad += check_nsum<uint8_t, int32_t, 1, true, 4>(s[0], s[1], inc, torus);
+                bad += check_nsum<uint8_t, int32_t, 2, false, 4>(s[0], s[1], inc, torus);
+                bad += check_nsum<uint8_t, int32_t, 2, true, 4>(s[0], s[1], inc, torus);
+                bad += check_nsum<uint8_t, int32_t, 1, false, 1>(s[0], s[1], inc, torus);
+                bad += check_nsum<uint8_t, int32_t, 2, true, 1>(s[0], s[1], inc, torus);
+                bad += check_nsum<float, double, 1, false, 1>(s[0], s[1], inc, torus);
+                bad += check_nsum<float, double, 2, false, 1>(s[0], s[1], inc, torus);
+                bad += check_nsum<double, double, 1, true, 1>(s[0], s[1], inc, torus);
+                bad += check_nsum<int32_t, int32_t, 2, true, 1>(s[0], s[1], inc, torus);
+                if (!inc) bad += check_diffuse(s[0], s[1], torus);
+            }
+    for (int torus = 0; torus < 2; ++torus) {
+        bad += check_knn(2000, 300.0, 200.0, torus, 1, 5.0, 200);
+        bad += check_knn(2000, 300.0, 200.0, torus, 4, 5.0, 200);
+        bad += check_knn(2000, 300.0, 200.0, torus, 16, 2.0, 200);
+        bad += check_knn(500, 40.0, 2.0, torus, 7, 0.5, 100);
+        bad += check_knn(500, 40.0, 2.0, torus, 7, 30.0, 100);
+        bad += check_knn(3, 10.0, 10.0, torus, 5, 1.0, 20);
+        bad += check_knn(64, 16.0, 16.0, torus, 9, 4.0, 64);
+        bad += check_knn(64, 16.0, 16.0, torus, 64, 7.9, 64);
+        bad += check_knn(0, 16.0, 16.0, torus, 2, 4.0, 8);
+    }
+    printf(bad ? "FAILED: %%d case(s)\n" : "all cases agree\n", bad);
+    return bad != 0;
+}
+'''
+
+
+def main() -> int:
+    layers = open(os.path.join(CSRC, "layers.cu")).read()
+    cont = open(os.path.join(CSRC, "continuous.cu")).read()
+    layers_part = between(layers, "template <typename T, int V> struct WalkVec;", "template <typename T, typename A, int V, int MINB1, int MINB2>")
+    cont_part = (between(cont, "struct Geometry {", "// ---- cell list:")
+                 + between(cont, "__device__ __forceinline__ double ref_distance2", "// one component of calculate_difference_vector")
+                 + between(cont, "__global__ void __launch_bounds__(128)\nknn_query", "// ---- calculate_distances / calculate_difference_vector of ONE point"))
+    src = HARNESS % {"layers": layers_part, "continuous": cont_part}
+    with tempfile.TemporaryDirectory() as tmp:
+        cpp = os.path.join(tmp, "emu.cpp")
+        exe = os.path.join(tmp, "emu")
+        with open(cpp, "w") as f:
+            f.write(src)
+        r = subprocess.run(["g++", "-O1", "-std=c++17", "-w", "-I", os.path.join(ROOT, "tools", "emu"), cpp, "-o", exe],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            return 2
+        r = subprocess.run([exe], capture_output=True, text=True)
+        sys.stdout.write(r.stdout[-4000:])
+        return r.returncode
+
+
+if __name__ == "__main__":
+    sys.exit(main())
