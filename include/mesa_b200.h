@@ -289,6 +289,11 @@ int mb_neighborhood_sum(const void* in, const void* halo_top, const void* halo_b
                         mb_stream_t stream);
 int mb_layer_diffuse(const void* in, const void* halo_top, const void* halo_bot, void* out, int64_t rows,
                      int64_t cols, int dtype, double rate, int col_torus, mb_stream_t stream);
+/* Neighbourhood sums on an n-dimensional layer (1 <= ndim <= 4, C order; dims[ndim]): the n-d grids of
+ * grid.py:457-462 (Moore: product([-1,0,1]^n) connections) and :488-501 (von Neumann: +-1 per axis), radius r =
+ * Chebyshev cube / Manhattan ball (cell.py:225-276).  out dtype as mb_neighborhood_sum. */
+int mb_neighborhood_sum_nd(const void* in, void* out, int ndim, const int64_t* dims_host, int dtype, int radius,
+                           int von_neumann, int include_center, int torus, mb_stream_t stream);
 
 #ifdef __cplusplus
 }

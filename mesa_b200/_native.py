@@ -112,6 +112,7 @@ SIGNATURES: dict[str, tuple] = {
     "mb_layer_reduce": (c_int, [_P, c_int64, c_int, c_int, _P, _P, ctypes.c_size_t, _S]),
     "mb_neighborhood_sum": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, _S]),
     "mb_layer_diffuse": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_double, c_int, _S]),
+    "mb_neighborhood_sum_nd": (c_int, [_P, _P, c_int, ctypes.POINTER(c_int64), c_int, c_int, c_int, c_int, c_int, _S]),
 }
 
 _lib = None

@@ -507,6 +507,90 @@ k_diffuse_walk(const T* __restrict__ in, const T* __restrict__ halo_top, const T
     }
 }
 
+// ---- float32 layers, radius-1 Moore box: 4 columns per thread, separable sums ---------------------------------
+// The generic walker spends ~130 issue slots per warp and row on a float32 layer (3 F2F conversions and 8 DADDs per
+// cell, address arithmetic per 4-byte load) and ends up pipe-bound at < 50 % of HBM.  Here a thread owns FOUR
+// adjacent columns: one 16-byte load per row plus the two side cells (L1 hits), 6 conversions and 8 DADDs for the four
+// horizontal 3-sums, and per output row (H0 + H1) + H2 minus the centre.  Everything is float64, so for float32
+// inputs the result is the exact sum of the 8 (or 9) neighbours -- identical to the (di, dj)-ordered sum of the
+// generic kernels and of the oracle -- as long as the magnitudes inside one neighbourhood span less than 2^25
+// (53 - 24 - 4 bits of headroom); beyond that the last bit may differ.  DIFFUSE selects the diffusion epilogue.
+struct Box3Row {
+    float4 own;
+    float left, right;
+};
+
+__device__ __forceinline__ Box3Row box3_load(const float* __restrict__ p, int64_t j0, int64_t jl, int64_t jr) {
+    Box3Row r;
+    if (p != nullptr) {
+        r.own = __ldg(reinterpret_cast<const float4*>(p + j0));
+        r.left = jl >= 0 ? __ldg(p + jl) : 0.f;
+        r.right = jr >= 0 ? __ldg(p + jr) : 0.f;
+    } else {
+        r.own = make_float4(0.f, 0.f, 0.f, 0.f);
+        r.left = r.right = 0.f;
+    }
+    return r;
+}
+
+template <bool DIFFUSE, int SEG>
+__global__ void __launch_bounds__(128, 4)
+k_box3_f32(const float* __restrict__ in, const float* __restrict__ halo_top, const float* __restrict__ halo_bot,
+           void* __restrict__ out_, int64_t rows, int64_t cols, int include_center, int col_torus, double rate) {
+    const int64_t jv = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    const int64_t j0 = jv * 4;
+    if (j0 >= cols) return;
+    const int64_t jl = j0 > 0 ? j0 - 1 : (col_torus ? cols - 1 : -1);
+    const int64_t jr = j0 + 4 < cols ? j0 + 4 : (col_torus ? 0 : -1);
+    const int64_t i0 = (int64_t)blockIdx.y * SEG;
+    constexpr int PF = 2;
+    Box3Row raw[SEG + 2];
+    double H[SEG + 2][4], C[SEG + 2][4];
+    auto fetch = [&](int k) { raw[k] = box3_load(walk_row_ptr<float, 1>(in, halo_top, halo_bot, i0 - 1 + k, rows, cols), j0, jl, jr); };
+    auto widen = [&](int k) {
+        const double e0 = (double)raw[k].left, e1 = (double)raw[k].own.x, e2 = (double)raw[k].own.y,
+                     e3 = (double)raw[k].own.z, e4 = (double)raw[k].own.w, e5 = (double)raw[k].right;
+        C[k][0] = e1; C[k][1] = e2; C[k][2] = e3; C[k][3] = e4;
+        H[k][0] = (e0 + e1) + e2;
+        H[k][1] = (e1 + e2) + e3;
+        H[k][2] = (e2 + e3) + e4;
+        H[k][3] = (e3 + e4) + e5;
+    };
+#pragma unroll
+    for (int k = 0; k < 2 + PF; ++k) fetch(k);
+    widen(0);
+    widen(1);
+    const double share = rate / 8.0;
+    const int kc0 = (jl >= 0) + 2, kc3 = (jr >= 0) + 2;   // existing columns around the first / last owned column
+#pragma unroll
+    for (int s = 0; s < SEG; ++s) {
+        const int64_t i = i0 + s;
+        if (s + 2 + PF < SEG + 2) fetch((s + 2 + PF) % (SEG + 2));
+        widen(s + 2);
+        if (i >= rows) continue;
+        double res[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const double box = (H[s][v] + H[s + 1][v]) + H[s + 2][v];
+            if (DIFFUSE) {
+                const int krows = ((i > 0) || halo_top != nullptr) + 1 + ((i + 1 < rows) || halo_bot != nullptr);
+                const int k = krows * (v == 0 ? kc0 : (v == 3 ? kc3 : 3)) - 1;
+                res[v] = C[s + 1][v] * (1.0 - rate * (double)k / 8.0) + share * (box - C[s + 1][v]);
+            } else {
+                res[v] = include_center ? box : box - C[s + 1][v];
+            }
+        }
+        if (DIFFUSE) {
+            float* o = reinterpret_cast<float*>(out_) + i * cols + j0;
+            __stcs(reinterpret_cast<float4*>(o), make_float4((float)res[0], (float)res[1], (float)res[2], (float)res[3]));
+        } else {
+            double* o = reinterpret_cast<double*>(out_) + i * cols + j0;
+            __stcs(reinterpret_cast<double2*>(o), make_double2(res[0], res[1]));
+            __stcs(reinterpret_cast<double2*>(o) + 1, make_double2(res[2], res[3]));
+        }
+    }
+}
+
 template <typename T, typename A, int V, int MINB1, int MINB2>
 bool launch_nsum_walk(const T* in, const T* ht, const T* hb, A* out, int64_t rows, int64_t cols, int radius,
                       int von_neumann, int include_center, int col_torus, cudaStream_t stream) {
@@ -521,6 +605,56 @@ bool launch_nsum_walk(const T* in, const T* ht, const T* hb, A* out, int64_t row
         else k_nsum_walk<T, A, 2, false, V, SEG, MINB2><<<grid, 128, 0, stream>>>(in, ht, hb, out, rows, cols, include_center, col_torus);
     }
     return true;
+}
+
+// ---- n-dimensional grids (grid.py:457-462 Moore = product([-1,0,1]^n), :488-501 von Neumann = +-1 per axis;
+//      radius r = Chebyshev cube / Manhattan ball by the same BFS, cell.py:225-276) -------------------------------
+// One thread per cell: decode the C-order coordinate, run an odometer over the (2r+1)^n box.  3-d and 4-d layers are
+// small next to the 2-d ones of the benchmark configs; the loads are served by L1 / L2.
+constexpr int kMaxDims = 4;
+struct NdShape {
+    int ndim;
+    int64_t dim[kMaxDims];
+    int64_t stride[kMaxDims];
+};
+
+template <typename T, typename A>
+__global__ void k_neighborhood_sum_nd(const T* __restrict__ in, A* __restrict__ out, int64_t n, NdShape sh, int radius,
+                                      int von_neumann, int include_center, int torus) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    int64_t c[kMaxDims];
+    {
+        int64_t rem = idx;
+        for (int d = 0; d < sh.ndim; ++d) {
+            c[d] = rem / sh.stride[d];
+            rem -= c[d] * sh.stride[d];
+        }
+    }
+    int o[kMaxDims];
+    for (int d = 0; d < sh.ndim; ++d) o[d] = -radius;
+    A acc = 0;
+    while (true) {
+        int manhattan = 0;
+        bool centre = true, inside = true;
+        int64_t at = 0;
+        for (int d = 0; d < sh.ndim; ++d) {
+            manhattan += o[d] < 0 ? -o[d] : o[d];
+            centre = centre && o[d] == 0;
+            int64_t x = c[d] + o[d];
+            if (x < 0 || x >= sh.dim[d]) {
+                if (torus) x = (x % sh.dim[d] + sh.dim[d]) % sh.dim[d];
+                else inside = false;
+            }
+            at += x * sh.stride[d];
+        }
+        if (inside && !(von_neumann && manhattan > radius) && !(centre && !include_center)) acc += (A)in[at];
+        int d = sh.ndim - 1;      // next offset, last axis fastest (the oracle's order)
+        while (d >= 0 && o[d] == radius) o[d--] = -radius;
+        if (d < 0) break;
+        ++o[d];
+    }
+    out[idx] = acc;
 }
 
 #define MB_DISPATCH_DTYPE(dtype, CALL)                                   \
@@ -616,7 +750,12 @@ MB_API int mb_neighborhood_sum(const void* in, const void* halo_top, const void*
             done = launch_nsum_walk<uint8_t, int32_t, 1, 8, 8>((const uint8_t*)in, (const uint8_t*)halo_top, (const uint8_t*)halo_bot, (int32_t*)out, rows, cols, radius, von_neumann, include_center, col_torus, stream);
         else if (dtype == DT_I32)
             done = launch_nsum_walk<int32_t, int32_t, 1, 8, 8>((const int32_t*)in, (const int32_t*)halo_top, (const int32_t*)halo_bot, (int32_t*)out, rows, cols, radius, von_neumann, include_center, col_torus, stream);
-        else if (dtype == DT_F32)
+        else if (dtype == DT_F32 && radius == 1 && !von_neumann && cols % 4 == 0 && (align & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(out) & 15) == 0 && mb::ceil_div(rows, 16) <= 65535) {
+            const dim3 grid((unsigned)mb::ceil_div(cols / 4, 128), (unsigned)mb::ceil_div(rows, 16));
+            k_box3_f32<false, 16><<<grid, 128, 0, stream>>>((const float*)in, (const float*)halo_top, (const float*)halo_bot, out, rows, cols, include_center, col_torus, 0.0);
+            done = true;
+        } else if (dtype == DT_F32)
             done = launch_nsum_walk<float, double, 1, 8, 4>((const float*)in, (const float*)halo_top, (const float*)halo_bot, (double*)out, rows, cols, radius, von_neumann, include_center, col_torus, stream);
         else
             done = launch_nsum_walk<double, double, 1, 8, 4>((const double*)in, (const double*)halo_top, (const double*)halo_bot, (double*)out, rows, cols, radius, von_neumann, include_center, col_torus, stream);
@@ -648,6 +787,14 @@ MB_API int mb_layer_diffuse(const void* in, const void* halo_top, const void* ha
     {
         constexpr int SEG = 16;
         const dim3 grid((unsigned)mb::ceil_div(cols, 128), (unsigned)mb::ceil_div(rows, SEG));
+        const uintptr_t align = reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(halo_top) |
+                                reinterpret_cast<uintptr_t>(halo_bot) | reinterpret_cast<uintptr_t>(out);
+        if (grid.y <= 65535u && dtype == DT_F32 && cols % 4 == 0 && (align & 15) == 0) {
+            const dim3 grid4((unsigned)mb::ceil_div(cols / 4, 128), grid.y);
+            k_box3_f32<true, SEG><<<grid4, 128, 0, stream>>>((const float*)in, (const float*)halo_top, (const float*)halo_bot, out, rows, cols, 0, col_torus, rate);
+            MB_LAUNCH_CHECK("mb_layer_diffuse");
+            return MB_OK;
+        }
         if (grid.y <= 65535u) {
             if (dtype == DT_F32)
                 k_diffuse_walk<float, SEG><<<grid, 128, 0, stream>>>((const float*)in, (const float*)halo_top, (const float*)halo_bot, (float*)out, rows, cols, rate, col_torus);
@@ -663,5 +810,36 @@ MB_API int mb_layer_diffuse(const void* in, const void* halo_top, const void* ha
     else
         k_diffuse<double><<<blocks, 256, 0, stream>>>((const double*)in, (const double*)halo_top, (const double*)halo_bot, (double*)out, rows, cols, rate, col_torus);
     MB_LAUNCH_CHECK("mb_layer_diffuse");
+    return MB_OK;
+}
+
+// Neighbourhood sums on an n-dimensional layer (1 <= ndim <= 4, C order).  out dtype as mb_neighborhood_sum.
+MB_API int mb_neighborhood_sum_nd(const void* in, void* out, int ndim, const int64_t* dims, int dtype, int radius,
+                                  int von_neumann, int include_center, int torus, cudaStream_t stream) {
+    MB_REQUIRE(ndim >= 1 && ndim <= kMaxDims && dims != nullptr, "mb_neighborhood_sum_nd: 1 to 4 dimensions");
+    MB_REQUIRE(radius >= 1, "radius must be at least 1");  // cell.py:234-235
+    NdShape sh;
+    sh.ndim = ndim;
+    int64_t n = 1;
+    for (int d = ndim - 1; d >= 0; --d) {
+        MB_REQUIRE(dims[d] >= 0, "mb_neighborhood_sum_nd: negative shape");
+        MB_REQUIRE(!(torus && dims[d] > 0 && dims[d] < 2 * radius + 1),
+                   "mb_neighborhood_sum_nd: torus needs every dimension >= 2*radius+1 (SURVEY A.2)");
+        sh.dim[d] = dims[d];
+        sh.stride[d] = n;
+        n *= dims[d];
+    }
+    for (int d = ndim; d < kMaxDims; ++d) { sh.dim[d] = 1; sh.stride[d] = 0; }
+    if (n == 0) return MB_OK;
+    MB_REQUIRE(in && out, "mb_neighborhood_sum_nd: null buffer");
+    const unsigned blocks = (unsigned)mb::ceil_div(n, 256);
+    switch (dtype) {
+        case DT_U8: k_neighborhood_sum_nd<uint8_t, int32_t><<<blocks, 256, 0, stream>>>((const uint8_t*)in, (int32_t*)out, n, sh, radius, von_neumann, include_center, torus); break;
+        case DT_I32: k_neighborhood_sum_nd<int32_t, int32_t><<<blocks, 256, 0, stream>>>((const int32_t*)in, (int32_t*)out, n, sh, radius, von_neumann, include_center, torus); break;
+        case DT_F32: k_neighborhood_sum_nd<float, double><<<blocks, 256, 0, stream>>>((const float*)in, (double*)out, n, sh, radius, von_neumann, include_center, torus); break;
+        case DT_F64: k_neighborhood_sum_nd<double, double><<<blocks, 256, 0, stream>>>((const double*)in, (double*)out, n, sh, radius, von_neumann, include_center, torus); break;
+        default: mb::set_error("unknown dtype %d", dtype); return MB_ERR_INVALID;
+    }
+    MB_LAUNCH_CHECK("mb_neighborhood_sum_nd");
     return MB_OK;
 }

@@ -558,10 +558,12 @@ def neighborhood_sum(layer: torch.Tensor, radius: int = 1, moore: bool = True, i
     """Sum of `layer` over each cell's radius-r neighbourhood (cell.py:225-276) for all cells at once
     (int32 for integer layers, float64 for float layers)."""
     _need_cuda(layer, halo_top, halo_bot, out)
-    if layer.dim() != 2:
-        raise ValueError("neighborhood_sum expects a [rows, cols] layer")
     if radius < 1:
         raise ValueError("radius must be at least 1")
+    if layer.dim() != 2:
+        if halo_top is not None or halo_bot is not None:
+            raise ValueError("halo rows are a feature of two-dimensional (row-sharded) layers")
+        return _neighborhood_sum_nd(layer, radius, moore, include_center, torus, out)
     rows, cols = layer.shape
     integer = layer.dtype in (torch.uint8, torch.bool, torch.int32)
     want = torch.int32 if integer else torch.float64
@@ -577,6 +579,28 @@ def neighborhood_sum(layer: torch.Tensor, radius: int = 1, moore: bool = True, i
         N.check(N.lib().mb_neighborhood_sum(N.ptr(_c(layer)), N.ptr(halo_top), N.ptr(halo_bot), N.ptr(out), rows, cols,
                                             _dt(layer), int(radius), int(not moore), int(bool(include_center)),
                                             int(bool(torus)), N.stream_ptr(layer.device)))
+    return out
+
+
+def _neighborhood_sum_nd(layer, radius, moore, include_center, torus, out):
+    """n-dimensional grids (grid.py:457-462, 488-501): 1 to 4 dimensions, one thread per cell."""
+    import ctypes
+
+    if not 1 <= layer.dim() <= 4:
+        raise ValueError("neighborhood_sum supports layers of 1 to 4 dimensions")
+    integer = layer.dtype in (torch.uint8, torch.bool, torch.int32)
+    want = torch.int32 if integer else torch.float64
+    if out is None:
+        out = torch.empty(layer.shape, dtype=want, device=layer.device)
+    elif out.shape != layer.shape or out.dtype != want or not out.is_contiguous():
+        raise ValueError(f"neighborhood_sum: out must be a contiguous {want} tensor of the layer's shape")
+    if torus and any(d < 2 * radius + 1 for d in layer.shape):
+        raise ValueError("torus needs every dimension >= 2*radius+1")
+    dims = (ctypes.c_int64 * layer.dim())(*layer.shape)
+    with torch.cuda.device(layer.device):
+        N.check(N.lib().mb_neighborhood_sum_nd(N.ptr(_c(layer)), N.ptr(out), layer.dim(), dims, _dt(layer), int(radius),
+                                               int(not moore), int(bool(include_center)), int(bool(torus)),
+                                               N.stream_ptr(layer.device)))
     return out
 
 

@@ -12,10 +12,13 @@ but WITHOUT one Python object per cell: state is a set of [d0, d1] device layers
 cells are lightweight proxies created on demand, and whole-grid neighbourhood work is one
 kernel launch (ops.neighborhood_sum, ops.schelling_happy, ops.gol_step).
 
-Two-dimensional grids only (the hot path of BASELINE.json; n-d grids are SURVEY §8f next-4).
+Grids of 1 to 4 dimensions (grid.py:457-462, 488-501 for n != 2); the tuned stencil kernels and the row-sharded
+multi-GPU paths are two-dimensional (the BASELINE.json configs), other dimensionalities use the generic
+neighbourhood kernel (mb_neighborhood_sum_nd).
 """
 from __future__ import annotations
 
+from itertools import product
 from random import Random
 
 import numpy as np
@@ -79,7 +82,7 @@ class CellProxy:
 
     __slots__ = ("grid", "coordinate")
 
-    def __init__(self, grid: "DeviceGrid", coordinate: tuple[int, int]):
+    def __init__(self, grid: "DeviceGrid", coordinate: tuple[int, ...]):
         object.__setattr__(self, "grid", grid)
         object.__setattr__(self, "coordinate", coordinate)
 
@@ -110,7 +113,7 @@ class CellProxy:
 
     @property
     def flat(self) -> int:
-        return self.coordinate[0] * self.grid.dimensions[1] + self.coordinate[1]
+        return int(np.ravel_multi_index(self.coordinate, self.grid.dimensions))
 
     @property
     def is_empty(self) -> bool:
@@ -139,14 +142,21 @@ class DeviceGrid:
     def height(self) -> int:
         return self.dimensions[1]
 
+    @staticmethod
+    def _offsets_nd(ndims: int) -> list[tuple[int, ...]]:  # pragma: no cover - overridden
+        raise NotImplementedError
+
     def __init__(self, dimensions, torus: bool = False, capacity: float | None = None,
                  random: Random | None = None, device="cuda"):
         self.torus = torus
         self.dimensions = tuple(dimensions) if not isinstance(dimensions, tuple) else dimensions
         self.capacity = capacity
         self._validate_parameters()
-        if len(self.dimensions) != 2:
-            raise NotImplementedError("mesa_b200 device grids are two-dimensional")
+        if not 1 <= len(self.dimensions) <= 4:
+            raise NotImplementedError("mesa_b200 device grids have 1 to 4 dimensions")
+        self._ndims = len(self.dimensions)
+        if self._ndims != 2:
+            self._offsets = self._offsets_nd(self._ndims)
         self.random = random if random is not None else Random()
         self.device = torch.device(device)
         self.property_layers: dict[str, torch.Tensor] = _LayerDict()
@@ -204,15 +214,15 @@ class DeviceGrid:
         raise AttributeError(f"{type(self).__name__!s} has no attribute {name!r}")
 
     # ------------------------------------------------------------------ cells
-    def _check(self, coordinate) -> tuple[int, int]:
+    def _check(self, coordinate) -> tuple[int, ...]:
         try:
-            i, j = coordinate
+            coord = tuple(coordinate)
         except Exception:
             raise CellMissingException(coordinate) from None
-        if not (isinstance(i, (int, np.integer)) and isinstance(j, (int, np.integer))
-                and 0 <= i < self.dimensions[0] and 0 <= j < self.dimensions[1]):
+        if len(coord) != len(self.dimensions) or not all(
+                isinstance(c, (int, np.integer)) and 0 <= c < d for c, d in zip(coord, self.dimensions)):
             raise CellMissingException(coordinate)
-        return int(i), int(j)
+        return tuple(int(c) for c in coord)
 
     def __getitem__(self, coordinate) -> CellProxy:
         return CellProxy(self, self._check(coordinate))
@@ -220,17 +230,18 @@ class DeviceGrid:
     @property
     def all_cells(self):
         """Row-major iterator over cell proxies (grid.py:120-126 order); lazy -- do not materialise large grids."""
-        d0, d1 = self.dimensions
-        return (CellProxy(self, (i, j)) for i in range(d0) for j in range(d1))
+        return (CellProxy(self, c) for c in product(*(range(d) for d in self.dimensions)))
 
     def __len__(self) -> int:
-        return self.dimensions[0] * self.dimensions[1]
+        return int(np.prod(self.dimensions))
+
+    def _unravel(self, k: int) -> tuple[int, ...]:
+        return tuple(int(c) for c in np.unravel_index(int(k), self.dimensions))
 
     @property
     def empties(self):
         idx = torch.nonzero(self.empty.reshape(-1)).reshape(-1).cpu().tolist()
-        d1 = self.dimensions[1]
-        return [CellProxy(self, (k // d1, k % d1)) for k in idx]
+        return [CellProxy(self, self._unravel(k)) for k in idx]
 
     def find_nearest_cell(self, position) -> CellProxy:
         """Floor of the position, wrapped on a torus (discrete_space tests test_spatial_lookups.py:20-44)."""
@@ -240,7 +251,7 @@ class DeviceGrid:
             idx = idx % np.array(self.dimensions)
         if np.any(idx < 0) or np.any(idx >= np.array(self.dimensions)):
             raise ValueError(f"Position {position} is outside the grid bounds.")
-        return CellProxy(self, (int(idx[0]), int(idx[1])))
+        return CellProxy(self, tuple(int(c) for c in idx))
 
     # ------------------------------------------------------------------ neighbourhoods
     def neighborhood_coordinates(self, coordinate, radius: int = 1, include_center: bool = False) -> list[tuple[int, int]]:
@@ -249,16 +260,16 @@ class DeviceGrid:
         if radius < 1:
             raise ValueError("radius must be at least 1")
         start = self._check(coordinate)
-        d0, d1 = self.dimensions
+        dims = self.dimensions
 
         def connections(c):
             out = []
-            for di, dj in self._offsets:
-                ni, nj = c[0] + di, c[1] + dj
+            for off in self._offsets:
+                nb = tuple(x + o for x, o in zip(c, off))
                 if self.torus:
-                    ni, nj = ni % d0, nj % d1
-                if 0 <= ni < d0 and 0 <= nj < d1:
-                    out.append((ni, nj))
+                    nb = tuple(x % d for x, d in zip(nb, dims))
+                if all(0 <= x < d for x, d in zip(nb, dims)):
+                    out.append(nb)
             return out
 
         if radius == 1:
@@ -295,7 +306,7 @@ class DeviceGrid:
         coords = self.neighborhood_coordinates(coordinate, radius, include_center)
         if coords:
             idx = torch.tensor(coords, device=self.device)
-            mask[idx[:, 0], idx[:, 1]] = True
+            mask[tuple(idx[:, d] for d in range(idx.shape[1]))] = True
         return mask
 
     def neighborhood_sum(self, layer, radius: int = 1, include_center: bool = False) -> torch.Tensor:
@@ -309,18 +320,17 @@ class DeviceGrid:
     # ------------------------------------------------------------------ empties
     def select_random_empty_cell(self) -> CellProxy:
         """grid.py:288-316: <= 50 uniform probes, first empty wins; else argwhere(empty) + one choice."""
-        d0, d1 = self.dimensions
-        ncells = d0 * d1
+        ncells = len(self)
         empty = self.empty
         for _ in range(50):
             k = self.random._randbelow(ncells)
             if bool(empty.reshape(-1)[k].item()):
-                return CellProxy(self, (k // d1, k % d1))
+                return CellProxy(self, self._unravel(k))
         empties = torch.nonzero(empty.reshape(-1)).reshape(-1)
         if empties.numel() == 0:
             raise ValueError("Grid is completely full. No empty cells available. Cannot select a random empty cell.")
         k = int(empties[self.random._randbelow(empties.numel())].item())
-        return CellProxy(self, (k // d1, k % d1))
+        return CellProxy(self, self._unravel(k))
 
 
 class DeviceMooreGrid(DeviceGrid):
@@ -333,12 +343,30 @@ class DeviceMooreGrid(DeviceGrid):
     # fmt: on
     _moore = True
 
+    @staticmethod
+    def _offsets_nd(ndims: int) -> list[tuple[int, ...]]:
+        """grid.py:457-462: product([-1, 0, 1]^n) without the centre."""
+        offsets = list(product([-1, 0, 1], repeat=ndims))
+        offsets.remove((0,) * ndims)
+        return offsets
+
 
 class DeviceVonNeumannGrid(DeviceGrid):
     """4-connected grid (OrthogonalVonNeumannGrid, grid.py:465-501)."""
 
     _offsets = [(-1, 0), (0, -1), (0, 1), (1, 0)]
     _moore = False
+
+    @staticmethod
+    def _offsets_nd(ndims: int) -> list[tuple[int, ...]]:
+        """grid.py:488-501: one step back, one step forward along every axis."""
+        offsets = []
+        for dim in range(ndims):
+            for delta in (-1, 1):
+                off = [0] * ndims
+                off[dim] = delta
+                offsets.append(tuple(off))
+        return offsets
 
 
 # names a Mesa user would look for

@@ -40,6 +40,31 @@ def neighborhood_sum(layer: np.ndarray, radius=1, moore=True, include_center=Fal
     return out
 
 
+def neighborhood_sum_nd(layer: np.ndarray, radius=1, moore=True, include_center=False, torus=False) -> np.ndarray:
+    """The same for layers of any dimensionality (grid.py:457-462: Moore connections = product([-1,0,1]^n);
+    :488-501: von Neumann = +-1 per axis; radius r by BFS = Chebyshev cube / Manhattan ball)."""
+    from itertools import product
+
+    layer = np.asarray(layer)
+    acc_t = np.float64 if layer.dtype.kind == "f" else np.int64
+    out = np.zeros(layer.shape, dtype=acc_t)
+    grids = np.meshgrid(*(np.arange(d) for d in layer.shape), indexing="ij")
+    for off in product(range(-radius, radius + 1), repeat=layer.ndim):
+        if not moore and sum(abs(o) for o in off) > radius:
+            continue
+        if not any(off) and not include_center:
+            continue
+        idx = [g + o for g, o in zip(grids, off)]
+        if torus:
+            out += layer[tuple(i % d for i, d in zip(idx, layer.shape))].astype(acc_t)
+        else:
+            ok = np.ones(layer.shape, dtype=bool)
+            for i, d in zip(idx, layer.shape):
+                ok &= (i >= 0) & (i < d)
+            out[ok] += layer[tuple(i[ok] for i in idx)].astype(acc_t)
+    return out
+
+
 def diffuse(layer: np.ndarray, rate: float, torus=False) -> np.ndarray:
     layer = np.asarray(layer)
     rows, cols = layer.shape

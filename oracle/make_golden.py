@@ -163,6 +163,45 @@ def neighborhood_fixture(name):
     print(name, k, "cases")
 
 
+def neighborhood_nd_fixture(name):
+    """The same for 1-, 3- and 4-dimensional grids (grid.py:457-462, 488-501), plus the ordered neighbour lists of a
+    few probe cells (connection / BFS order)."""
+    import random
+
+    from mesa.discrete_space import OrthogonalMooreGrid, OrthogonalVonNeumannGrid
+
+    rng = np.random.default_rng(1)
+    out, cases = {}, []
+    k = 0
+    for moore in (True, False):
+        for torus in (False, True):
+            for dims in [(9,), (4, 5, 6), (7, 3, 5), (3, 4, 3, 5)]:
+                for radius in (1, 2):
+                    if torus and min(dims) < 2 * radius + 1:
+                        continue
+                    for include_center in (False, True):
+                        klass = OrthogonalMooreGrid if moore else OrthogonalVonNeumannGrid
+                        grid = klass(dims, torus=torus, random=random.Random(1))
+                        layer = rng.integers(0, 50, size=dims).astype(np.int32)
+                        sums = np.zeros(dims, dtype=np.int64)
+                        sizes = np.zeros(dims, dtype=np.int64)
+                        for cell in grid.all_cells:
+                            nb = cell.get_neighborhood(radius=radius, include_center=include_center)
+                            sums[cell.coordinate] = sum(int(layer[c.coordinate]) for c in nb)
+                            sizes[cell.coordinate] = len(nb)
+                        probes = [tuple(0 for _ in dims), tuple(d - 1 for d in dims), tuple(d // 2 for d in dims)]
+                        for q, pc in enumerate(probes):
+                            nb = grid[pc].get_neighborhood(radius=radius, include_center=include_center)
+                            out[f"probe_{k}_{q}"] = np.array([c.coordinate for c in nb], dtype=np.int64).reshape(-1, len(dims))
+                        out[f"layer_{k}"], out[f"sums_{k}"], out[f"sizes_{k}"] = layer, sums, sizes
+                        out[f"dims_{k}"] = np.array(dims, dtype=np.int64)
+                        cases.append((int(moore), int(torus), radius, int(include_center)))
+                        k += 1
+    out["cases"] = np.array(cases, dtype=np.int64)
+    np.savez_compressed(os.path.join(GOLDEN, name), **out)
+    print(name, k, "cases")
+
+
 # ------------------------------------------------------------------------------ Boltzmann
 def boltzmann_fixture(name, n, width, height, steps, mt_seed, philox_seed):
     from mesa.examples.basic.boltzmann_wealth_model.agents import MoneyAgent
@@ -349,6 +388,9 @@ def main():
     if only == "neighborhoods":
         neighborhood_fixture("neighborhoods.npz")
         return
+    if only == "neighborhoods_nd":
+        neighborhood_nd_fixture("neighborhoods_nd.npz")
+        return
     if only == "continuous":
         continuous_queries_fixture("continuous_queries.npz")
         return
@@ -365,6 +407,7 @@ def main():
         boids_fixture("boids_120_wrap.npz", 120, 40, 30, 6.0, 2.0, 3, 1, 6)
         return
     neighborhood_fixture("neighborhoods.npz")
+    neighborhood_nd_fixture("neighborhoods_nd.npz")
     gol_fixture(37, 23, 42, 6, "gol_37x23.npz")
     gol_fixture(64, 48, 7, 20, "gol_64x48.npz")
     schelling_fixture("schelling_20x20_r1.npz", 20, 20, 0.8, 0.4, 1, 30, 42, 2024, full_steps=range(1, 31))

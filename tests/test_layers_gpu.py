@@ -187,3 +187,40 @@ def test_diffuse_walker_ragged_shapes(shape, torus):
     a = rng.random(shape)
     got = ops.layer_diffuse(torch.from_numpy(a).cuda(), 0.7, torus).cpu().numpy()
     np.testing.assert_allclose(got, olayers.diffuse(a, 0.7, torus), rtol=1e-14, atol=1e-14)
+
+
+
+def test_nd_grids_match_reference_neighbourhoods():
+    """1-, 3- and 4-dimensional device grids (grid.py:457-462, 488-501): whole-grid neighbourhood sums / sizes and the
+    ORDERED neighbour lists of probe cells against the reference's Cell.get_neighborhood."""
+    import random
+
+    from mesa_b200.space import DeviceMooreGrid, DeviceVonNeumannGrid
+
+    g = np.load(os.path.join(GOLDEN, "neighborhoods_nd.npz"))
+    for k, (moore, torus, radius, inc) in enumerate(g["cases"]):
+        dims = tuple(int(d) for d in g[f"dims_{k}"])
+        grid = (DeviceMooreGrid if moore else DeviceVonNeumannGrid)(dims, torus=bool(torus), random=random.Random(1))
+        grid.add_property_layer("v", g[f"layer_{k}"])
+        got = grid.neighborhood_sum("v", int(radius), bool(inc))
+        assert tuple(got.shape) == dims and np.array_equal(got.cpu().numpy(), g[f"sums_{k}"]), (k, dims)
+        ones = grid.neighborhood_sum(torch.ones(dims, dtype=torch.uint8, device="cuda"), int(radius), bool(inc))
+        assert np.array_equal(ones.cpu().numpy(), g[f"sizes_{k}"]), (k, dims)
+        probes = [tuple(0 for _ in dims), tuple(d - 1 for d in dims), tuple(d // 2 for d in dims)]
+        for q, pc in enumerate(probes):
+            want = [tuple(int(x) for x in row) for row in g[f"probe_{k}_{q}"]]
+            assert grid.neighborhood_coordinates(pc, int(radius), bool(inc)) == want, (k, dims, pc)
+            mask = grid.get_neighborhood_mask(pc, include_center=bool(inc), radius=int(radius))
+            assert int(mask.sum().item()) == len(want) and all(bool(mask[c].item()) for c in want[:5])
+    # float layers and the cell API on a 3-d grid
+    grid = DeviceMooreGrid((4, 5, 6), torus=True, random=random.Random(2))
+    a = np.random.default_rng(0).standard_normal((4, 5, 6))
+    got = grid.neighborhood_sum(torch.from_numpy(a).cuda(), 1).cpu().numpy()
+    assert np.array_equal(got, olayers.neighborhood_sum_nd(a, 1, True, False, True))
+    assert len(grid) == 120 and grid[(3, 4, 5)].flat == 119 and grid.find_nearest_cell([4.5, 0.2, 7.9]).coordinate == (0, 0, 1)
+    assert len(list(grid.all_cells)) == 120 and len(grid.empties) == 120
+    assert grid.select_random_empty_cell().coordinate in {c.coordinate for c in grid.all_cells}
+    with pytest.raises(Exception):
+        grid[(1, 2)]
+    with pytest.raises(ValueError):
+        DeviceMooreGrid((4, 2, 6), torus=True, random=random.Random(2)).neighborhood_sum("empty", 1)

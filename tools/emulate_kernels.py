@@ -171,9 +171,90 @@ static int check_knn(int n, double sx, double sy, bool torus, int k, double edge
     return 0;
 }
 
+template <bool DIFFUSE>
+static int check_box3(int64_t rows, int64_t cols, bool inc, bool torus) {
+    if (cols %% 4) return 0;
+    if (torus && (rows < 3 || cols < 3)) return 0;
+    std::vector<float> in(rows * cols);
+    for (auto& x : in) x = (float)(rand() %% 4096) / 64.0f;
+    std::vector<float> top(cols), bot(cols);
+    for (int64_t c = 0; c < cols; ++c) { top[c] = in[(rows - 1) * cols + c]; bot[c] = in[c]; }
+    std::vector<double> gotd(rows * cols, -1.0);
+    std::vector<float> gotf(rows * cols, -1.0f);
+    const double rate = 0.25;
+    gridDim.x = (unsigned)((cols / 4 + 127) / 128);
+    gridDim.y = (unsigned)((rows + 15) / 16);
+    for (blockIdx.y = 0; blockIdx.y < gridDim.y; ++blockIdx.y)
+        for (blockIdx.x = 0; blockIdx.x < gridDim.x; ++blockIdx.x)
+            for (threadIdx.x = 0; threadIdx.x < 128; ++threadIdx.x)
+                k_box3_f32<DIFFUSE, 16>(in.data(), torus ? top.data() : nullptr, torus ? bot.data() : nullptr,
+                                        DIFFUSE ? (void*)gotf.data() : (void*)gotd.data(), rows, cols, inc, torus, rate);
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            double acc = 0.0;
+            int k = 0;
+            for (int di = -1; di <= 1; ++di)
+                for (int dj = -1; dj <= 1; ++dj) {
+                    if (!di && !dj) continue;
+                    int64_t r = i + di, c = j + dj;
+                    if (torus) { r = (r + rows) %% rows; c = (c + cols) %% cols; }
+                    else if (r < 0 || r >= rows || c < 0 || c >= cols) continue;
+                    acc += (double)in[r * cols + c];
+                    ++k;
+                }
+            const double self = (double)in[i * cols + j];
+            bool ok;
+            if (DIFFUSE) ok = gotf[i * cols + j] == (float)(self * (1.0 - rate * k / 8.0) + rate / 8.0 * acc);
+            else ok = gotd[i * cols + j] == (inc ? acc + self : acc);
+            if (!ok) {
+                printf("box3 mismatch diffuse=%%d rows=%%ld cols=%%ld inc=%%d torus=%%d at (%%ld,%%ld)\n", (int)DIFFUSE, (long)rows,
+                       (long)cols, (int)inc, (int)torus, (long)i, (long)j);
+                return 1;
+            }
+        }
+    return 0;
+}
+
+static int check_nd(int ndim, const int64_t* dims, int radius, bool vn, bool inc, bool torus) {
+    NdShape sh;
+    sh.ndim = ndim;
+    int64_t n = 1;
+    for (int d = ndim - 1; d >= 0; --d) { sh.dim[d] = dims[d]; sh.stride[d] = n; n *= dims[d]; if (torus && dims[d] < 2 * radius + 1) return 0; }
+    for (int d = ndim; d < kMaxDims; ++d) { sh.dim[d] = 1; sh.stride[d] = 0; }
+    std::vector<int32_t> in(n), got(n, -1);
+    for (auto& x : in) x = rand() %% 100;
+    gridDim.x = (unsigned)((n + 255) / 256);
+    blockDim.x = 256;
+    for (blockIdx.x = 0; blockIdx.x < gridDim.x; ++blockIdx.x)
+        for (threadIdx.x = 0; threadIdx.x < 256; ++threadIdx.x)
+            k_neighborhood_sum_nd<int32_t, int32_t>(in.data(), got.data(), n, sh, radius, vn, inc, torus);
+    for (int64_t idx = 0; idx < n; ++idx) {
+        int64_t c[4] = {0, 0, 0, 0}, rem = idx;
+        for (int d = 0; d < ndim; ++d) { c[d] = rem / sh.stride[d]; rem %%= sh.stride[d]; }
+        int want = 0;
+        int o[4];
+        for (o[0] = -radius; o[0] <= radius; ++o[0])
+        for (o[1] = (ndim > 1 ? -radius : 0); o[1] <= (ndim > 1 ? radius : 0); ++o[1])
+        for (o[2] = (ndim > 2 ? -radius : 0); o[2] <= (ndim > 2 ? radius : 0); ++o[2])
+        for (o[3] = (ndim > 3 ? -radius : 0); o[3] <= (ndim > 3 ? radius : 0); ++o[3]) {
+            int man = abs(o[0]) + abs(o[1]) + abs(o[2]) + abs(o[3]);
+            if ((vn && man > radius) || (man == 0 && !inc)) continue;
+            int64_t at = 0; bool ok = true;
+            for (int d = 0; d < ndim; ++d) {
+                int64_t x = c[d] + o[d];
+                if (torus) x = (x + 8 * dims[d]) %% dims[d]; else if (x < 0 || x >= dims[d]) ok = false;
+                at += x * sh.stride[d];
+            }
+            if (ok) want += in[at];
+        }
+        if (want != got[idx]) { printf("nd mismatch ndim=%%d r=%%d vn=%%d inc=%%d torus=%%d at %%ld\n", ndim, radius, (int)vn, (int)inc, (int)torus, (long)idx); return 1; }
+    }
+    return 0;
+}
+
 int main() {
     int bad = 0;
-    const int64_t shapes[][2] = {{1, 1}, {1, 40}, {40, 1}, {3, 3}, {5, 8}, {16, 128}, {17, 132}, {35, 260}, {5, 516}};
+    const int64_t shapes[][2] = {{1, 1}, {1, 40}, {40, 1}, {3, 3}, {1, 4}, {3, 4}, {5, 8}, {16, 128}, {17, 132}, {35, 260}, {5, 516}, {33, 1024}};
     for (auto& s : shapes)
         for (int inc = 0; inc < 2; ++inc)
             for (int torus = 0; torus < 2; ++torus) {
@@ -188,7 +269,19 @@ int main() {
                 bad += check_nsum<double, double, 1, true, 1>(s[0], s[1], inc, torus);
                 bad += check_nsum<int32_t, int32_t, 2, true, 1>(s[0], s[1], inc, torus);
                 if (!inc) bad += check_diffuse(s[0], s[1], torus);
+                bad += check_box3<false>(s[0], s[1], inc, torus);
+                if (!inc) bad += check_box3<true>(s[0], s[1], inc, torus);
             }
+    {
+        const int64_t d1[] = {9}, d3[] = {4, 5, 6}, d3b[] = {7, 3, 5}, d4[] = {3, 4, 3, 5};
+        for (int r = 1; r <= 2; ++r)
+            for (int m = 0; m < 8; ++m) {
+                bad += check_nd(1, d1, r, m & 1, m & 2, m & 4);
+                bad += check_nd(3, d3, r, m & 1, m & 2, m & 4);
+                bad += check_nd(3, d3b, r, m & 1, m & 2, m & 4);
+                bad += check_nd(4, d4, r, m & 1, m & 2, m & 4);
+            }
+    }
     for (int torus = 0; torus < 2; ++torus) {
         bad += check_knn(2000, 300.0, 200.0, torus, 1, 5.0, 200);
         bad += check_knn(2000, 300.0, 200.0, torus, 4, 5.0, 200);
@@ -213,6 +306,7 @@ def main() -> int:
     cont_part = (between(cont, "struct Geometry {", "// ---- cell list:")
                  + between(cont, "__device__ __forceinline__ double ref_distance2", "// one component of calculate_difference_vector")
                  + between(cont, "__global__ void __launch_bounds__(128)\nknn_query", "// ---- calculate_distances / calculate_difference_vector of ONE point"))
+    layers_part += between(layers, "constexpr int kMaxDims = 4;", "#define MB_DISPATCH_DTYPE")
     src = HARNESS % {"layers": layers_part, "continuous": cont_part}
     with tempfile.TemporaryDirectory() as tmp:
         cpp = os.path.join(tmp, "emu.cpp")
