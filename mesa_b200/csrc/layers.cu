@@ -81,7 +81,20 @@ __global__ void k_affine(const T* __restrict__ in, T* __restrict__ out, int64_t 
     };
     const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
     if (aligned) {
-        for (int64_t i = tid; i < nvec; i += stride) {
+        int64_t i = tid;
+        for (; i + stride < nvec; i += 2 * stride) {   // two independent vectors in flight per thread
+            uint4 raw0 = __ldg(reinterpret_cast<const uint4*>(in) + i);
+            uint4 raw1 = __ldg(reinterpret_cast<const uint4*>(in) + i + stride);
+            T* e0 = reinterpret_cast<T*>(&raw0);
+            T* e1 = reinterpret_cast<T*>(&raw1);
+#pragma unroll
+            for (int k = 0; k < V; ++k) e0[k] = f(e0[k]);
+#pragma unroll
+            for (int k = 0; k < V; ++k) e1[k] = f(e1[k]);
+            reinterpret_cast<uint4*>(out)[i] = raw0;
+            reinterpret_cast<uint4*>(out)[i + stride] = raw1;
+        }
+        for (; i < nvec; i += stride) {
             uint4 raw = __ldg(reinterpret_cast<const uint4*>(in) + i);
             T* e = reinterpret_cast<T*>(&raw);
 #pragma unroll
@@ -135,6 +148,34 @@ template <typename T, int OP> __device__ __forceinline__ T apply_op(T a, T b) {
     return a > b ? a : b;
 }
 
+// 16 uint8 cells at a time: packed-byte add / sub / min / max (the per-byte path costs ~4 ALU ops per cell and
+// binds before HBM does: ncu showed the ALU pipe at 72 % with DRAM at 76 %)
+template <int OP> __device__ __forceinline__ unsigned apply_op_u8x4(unsigned a, unsigned b) {
+    if (OP == OP_ADD) return __vadd4(a, b);
+    if (OP == OP_SUB) return __vsub4(a, b);
+    if (OP == OP_MIN) return __vminu4(a, b);
+    if (OP == OP_MAX) return __vmaxu4(a, b);
+    unsigned r = 0;   // OP_MUL: per byte, modulo 256 like numpy uint8
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r |= ((((a >> (8 * k)) & 255u) * ((b >> (8 * k)) & 255u)) & 255u) << (8 * k);
+    return r;
+}
+
+template <typename T, int OP>
+__device__ __forceinline__ void apply_op_vec(uint4& ra, const uint4& rb) {
+    if (sizeof(T) == 1) {
+        ra.x = apply_op_u8x4<OP>(ra.x, rb.x);
+        ra.y = apply_op_u8x4<OP>(ra.y, rb.y);
+        ra.z = apply_op_u8x4<OP>(ra.z, rb.z);
+        ra.w = apply_op_u8x4<OP>(ra.w, rb.w);
+    } else {
+        T* ea = reinterpret_cast<T*>(&ra);
+        const T* eb = reinterpret_cast<const T*>(&rb);
+#pragma unroll
+        for (int k = 0; k < VecOf<T>::n; ++k) ea[k] = apply_op<T, OP>(ea[k], eb[k]);
+    }
+}
+
 template <typename T, int OP>
 __global__ void __launch_bounds__(256) k_binary(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out,
                                                 int64_t n) {
@@ -145,13 +186,10 @@ __global__ void __launch_bounds__(256) k_binary(const T* __restrict__ a, const T
     const bool aligned = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
                            reinterpret_cast<uintptr_t>(out)) & 15) == 0;
     if (aligned) {
-        for (int64_t i = tid; i < nvec; i += stride) {
+        for (int64_t i = tid; i < nvec; i += stride) {   // (two vectors per iteration measured slower: 0.527 vs 0.494 ms)
             uint4 ra = __ldg(reinterpret_cast<const uint4*>(a) + i);
-            uint4 rb = __ldg(reinterpret_cast<const uint4*>(b) + i);
-            T* ea = reinterpret_cast<T*>(&ra);
-            const T* eb = reinterpret_cast<const T*>(&rb);
-#pragma unroll
-            for (int k = 0; k < V; ++k) ea[k] = apply_op<T, OP>(ea[k], eb[k]);
+            const uint4 rb = __ldg(reinterpret_cast<const uint4*>(b) + i);
+            apply_op_vec<T, OP>(ra, rb);
             reinterpret_cast<uint4*>(out)[i] = ra;
         }
         for (int64_t i = nvec * V + tid; i < n; i += stride) out[i] = apply_op<T, OP>(a[i], b[i]);
@@ -270,13 +308,12 @@ __global__ void __launch_bounds__(256) k_reduce1(const T* __restrict__ in, int64
         const uint4* pv = reinterpret_cast<const uint4*>(in + lo);   // lo is a multiple of V
         const int64_t nvec = (hi - lo) / V;
         int64_t i = threadIdx.x;
-        for (; i + 3 * 256 < nvec; i += 4 * 256) {   // four independent 16-byte loads in flight per thread
-            const uint4 r0 = ldg_nc_v4(pv + i), r1 = ldg_nc_v4(pv + i + 256), r2 = ldg_nc_v4(pv + i + 512),
-                        r3 = ldg_nc_v4(pv + i + 768);
-            acc = red_vec<T, A, OP>(acc, r0);
-            acc = red_vec<T, A, OP>(acc, r1);
-            acc = red_vec<T, A, OP>(acc, r2);
-            acc = red_vec<T, A, OP>(acc, r3);
+        for (; i + 3 * 256 < nvec; i += 4 * 256) {   // four independent 16-byte loads in flight per thread (eight: slower)
+            uint4 r[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) r[u] = ldg_nc_v4(pv + i + u * 256);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc = red_vec<T, A, OP>(acc, r[u]);
         }
         for (; i < nvec; i += 256) acc = red_vec<T, A, OP>(acc, ldg_nc_v4(pv + i));
         for (int64_t j = lo + nvec * V + threadIdx.x; j < hi; j += 256)
@@ -383,20 +420,27 @@ template <typename T, int V> struct WalkVec;
 template <> struct WalkVec<uint8_t, 4> { using type = uint32_t; };
 template <typename T> struct WalkVec<T, 1> { using type = T; };
 
-template <typename T, typename A, int V, int NL>
-__device__ __forceinline__ void walk_load_row(const T* __restrict__ p, const int64_t (&cv)[2 * NL + 1], A (&dst)[(2 * NL + 1) * V]) {
+// The loads of a row are UNCONDITIONAL (absent rows / columns read a valid dummy address) and stay raw; the
+// conversion to the accumulator type and the zeroing of absent cells happen when the row enters the window, PF
+// rows later.  (A predicated load followed by its conversion under the same predicate makes the compiler emit
+// "@P LDG; @P F2F" back to back -- every row then waits a full memory latency; seen in the SASS of the first version.)
+template <typename T, int V, int NL>
+__device__ __forceinline__ void walk_fetch_row(const T* __restrict__ p, const int64_t (&cs)[2 * NL + 1],
+                                               typename WalkVec<T, V>::type (&dst)[2 * NL + 1]) {
     using VT = typename WalkVec<T, V>::type;
 #pragma unroll
+    for (int k = 0; k < 2 * NL + 1; ++k) dst[k] = __ldg(reinterpret_cast<const VT*>(p) + cs[k]);
+}
+
+template <typename T, typename A, int V, int NL>
+__device__ __forceinline__ void walk_widen_row(const typename WalkVec<T, V>::type (&src)[2 * NL + 1], bool row_ok,
+                                               const int64_t (&cv)[2 * NL + 1], A (&dst)[(2 * NL + 1) * V]) {
+#pragma unroll
     for (int k = 0; k < 2 * NL + 1; ++k) {
-        if (p != nullptr && cv[k] >= 0) {
-            const VT raw = __ldg(reinterpret_cast<const VT*>(p) + cv[k]);
-            const T* e = reinterpret_cast<const T*>(&raw);
+        const T* e = reinterpret_cast<const T*>(&src[k]);
+        const bool ok = row_ok && cv[k] >= 0;
 #pragma unroll
-            for (int v = 0; v < V; ++v) dst[k * V + v] = (A)e[v];
-        } else {
-#pragma unroll
-            for (int v = 0; v < V; ++v) dst[k * V + v] = (A)0;
-        }
+        for (int v = 0; v < V; ++v) dst[k * V + v] = ok ? (A)e[v] : (A)0;
     }
 }
 
@@ -426,22 +470,32 @@ k_nsum_walk(const T* __restrict__ in, const T* __restrict__ halo_top, const T* _
     const int64_t nvec = cols / V;
     const int64_t jv = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (jv >= nvec) return;
-    int64_t cv[2 * NL + 1];
+    using VT = typename WalkVec<T, V>::type;
+    int64_t cv[2 * NL + 1], cs[2 * NL + 1];
     walk_columns<V, NL>(jv, nvec, col_torus, cv);
+#pragma unroll
+    for (int k = 0; k < 2 * NL + 1; ++k) cs[k] = cv[k] >= 0 ? cv[k] : jv;
     const int64_t i0 = (int64_t)blockIdx.y * SEG;
     // rows i0-R .. i0+SEG-1+R of the walk; statically indexed (only 2R+1+PF of them are live at a time):
-    // the loads run PF rows ahead of the arithmetic
-    constexpr int PF = 2;
+    // the raw loads run PF rows ahead of the conversion + arithmetic
+    constexpr int PF = 3;
+    VT raw[SEG + 2 * R][2 * NL + 1];
+    bool ok[SEG + 2 * R];
     A win[SEG + 2 * R][W];
+    auto fetch = [&](int k) {
+        const T* p = walk_row_ptr<T, R>(in, halo_top, halo_bot, i0 - R + k, rows, cols);
+        ok[k] = p != nullptr;
+        walk_fetch_row<T, V, NL>(ok[k] ? p : in, cs, raw[k]);
+    };
 #pragma unroll
-    for (int k = 0; k < 2 * R + PF; ++k)
-        walk_load_row<T, A, V, NL>(walk_row_ptr<T, R>(in, halo_top, halo_bot, i0 - R + k, rows, cols), cv, win[k]);
+    for (int k = 0; k < 2 * R + PF; ++k) fetch(k);
+#pragma unroll
+    for (int k = 0; k < 2 * R; ++k) walk_widen_row<T, A, V, NL>(raw[k], ok[k], cv, win[k]);
 #pragma unroll
     for (int s = 0; s < SEG; ++s) {
         const int64_t i = i0 + s;
-        if (s + 2 * R + PF < SEG + 2 * R)
-            walk_load_row<T, A, V, NL>(walk_row_ptr<T, R>(in, halo_top, halo_bot, i + R + PF, rows, cols), cv,
-                                       win[(s + 2 * R + PF) % (SEG + 2 * R)]);
+        if (s + 2 * R + PF < SEG + 2 * R) fetch((s + 2 * R + PF) % (SEG + 2 * R));
+        walk_widen_row<T, A, V, NL>(raw[s + 2 * R], ok[s + 2 * R], cv, win[s + 2 * R]);
         A res[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) {
@@ -478,22 +532,31 @@ k_diffuse_walk(const T* __restrict__ in, const T* __restrict__ halo_top, const T
                T* __restrict__ out, int64_t rows, int64_t cols, double rate, int col_torus) {
     const int64_t j = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (j >= cols) return;
-    int64_t cv[3];
+    int64_t cv[3], cs[3];
     walk_columns<1, 1>(j, cols, col_torus, cv);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) cs[k] = cv[k] >= 0 ? cv[k] : j;
     const int kcols = (cv[0] >= 0) + 1 + (cv[2] >= 0);
     const int64_t i0 = (int64_t)blockIdx.y * SEG;
-    constexpr int PF = 2;
+    constexpr int PF = 3;
+    T raw[SEG + 2][3];
+    bool ok[SEG + 2];
     double win[SEG + 2][3];
+    auto fetch = [&](int k) {
+        const T* p = walk_row_ptr<T, 1>(in, halo_top, halo_bot, i0 - 1 + k, rows, cols);
+        ok[k] = p != nullptr;
+        walk_fetch_row<T, 1, 1>(ok[k] ? p : in, cs, raw[k]);
+    };
 #pragma unroll
-    for (int k = 0; k < 2 + PF; ++k)
-        walk_load_row<T, double, 1, 1>(walk_row_ptr<T, 1>(in, halo_top, halo_bot, i0 - 1 + k, rows, cols), cv, win[k]);
+    for (int k = 0; k < 2 + PF; ++k) fetch(k);
+    walk_widen_row<T, double, 1, 1>(raw[0], ok[0], cv, win[0]);
+    walk_widen_row<T, double, 1, 1>(raw[1], ok[1], cv, win[1]);
     const double share = rate / 8.0;
 #pragma unroll
     for (int s = 0; s < SEG; ++s) {
         const int64_t i = i0 + s;
-        if (s + 2 + PF < SEG + 2)
-            walk_load_row<T, double, 1, 1>(walk_row_ptr<T, 1>(in, halo_top, halo_bot, i + 1 + PF, rows, cols), cv,
-                                           win[(s + 2 + PF) % (SEG + 2)]);
+        if (s + 2 + PF < SEG + 2) fetch((s + 2 + PF) % (SEG + 2));
+        walk_widen_row<T, double, 1, 1>(raw[s + 2], ok[s + 2], cv, win[s + 2]);
         const int krows = ((i > 0) || halo_top != nullptr) + 1 + ((i + 1 < rows) || halo_bot != nullptr);
         const int k = krows * kcols - 1;
         double acc = 0.0;
@@ -520,21 +583,16 @@ struct Box3Row {
     float left, right;
 };
 
-__device__ __forceinline__ Box3Row box3_load(const float* __restrict__ p, int64_t j0, int64_t jl, int64_t jr) {
-    Box3Row r;
-    if (p != nullptr) {
-        r.own = __ldg(reinterpret_cast<const float4*>(p + j0));
-        r.left = jl >= 0 ? __ldg(p + jl) : 0.f;
-        r.right = jr >= 0 ? __ldg(p + jr) : 0.f;
-    } else {
-        r.own = make_float4(0.f, 0.f, 0.f, 0.f);
-        r.left = r.right = 0.f;
-    }
+__device__ __forceinline__ Box3Row box3_load(const float* __restrict__ p, int64_t j0, int64_t jls, int64_t jrs) {
+    Box3Row r;   // unconditional loads (see walk_fetch_row); absent cells are zeroed when the row is widened
+    r.own = __ldg(reinterpret_cast<const float4*>(p + j0));
+    r.left = __ldg(p + jls);
+    r.right = __ldg(p + jrs);
     return r;
 }
 
 template <bool DIFFUSE, int SEG>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, 5)
 k_box3_f32(const float* __restrict__ in, const float* __restrict__ halo_top, const float* __restrict__ halo_bot,
            void* __restrict__ out_, int64_t rows, int64_t cols, int include_center, int col_torus, double rate) {
     const int64_t jv = (int64_t)blockIdx.x * 128 + threadIdx.x;
@@ -543,13 +601,21 @@ k_box3_f32(const float* __restrict__ in, const float* __restrict__ halo_top, con
     const int64_t jl = j0 > 0 ? j0 - 1 : (col_torus ? cols - 1 : -1);
     const int64_t jr = j0 + 4 < cols ? j0 + 4 : (col_torus ? 0 : -1);
     const int64_t i0 = (int64_t)blockIdx.y * SEG;
-    constexpr int PF = 2;
+    constexpr int PF = 4;   // rows of loads in flight ahead of the arithmetic (6 registers each)
     Box3Row raw[SEG + 2];
+    bool ok[SEG + 2];
     double H[SEG + 2][4], C[SEG + 2][4];
-    auto fetch = [&](int k) { raw[k] = box3_load(walk_row_ptr<float, 1>(in, halo_top, halo_bot, i0 - 1 + k, rows, cols), j0, jl, jr); };
+    const int64_t jls = jl >= 0 ? jl : j0, jrs = jr >= 0 ? jr : j0;
+    auto fetch = [&](int k) {
+        const float* p = walk_row_ptr<float, 1>(in, halo_top, halo_bot, i0 - 1 + k, rows, cols);
+        ok[k] = p != nullptr;
+        raw[k] = box3_load(ok[k] ? p : in, j0, jls, jrs);
+    };
     auto widen = [&](int k) {
-        const double e0 = (double)raw[k].left, e1 = (double)raw[k].own.x, e2 = (double)raw[k].own.y,
-                     e3 = (double)raw[k].own.z, e4 = (double)raw[k].own.w, e5 = (double)raw[k].right;
+        const bool rk = ok[k];
+        const double e0 = (rk && jl >= 0) ? (double)raw[k].left : 0.0, e1 = rk ? (double)raw[k].own.x : 0.0,
+                     e2 = rk ? (double)raw[k].own.y : 0.0, e3 = rk ? (double)raw[k].own.z : 0.0,
+                     e4 = rk ? (double)raw[k].own.w : 0.0, e5 = (rk && jr >= 0) ? (double)raw[k].right : 0.0;
         C[k][0] = e1; C[k][1] = e2; C[k][2] = e3; C[k][3] = e4;
         H[k][0] = (e0 + e1) + e2;
         H[k][1] = (e1 + e2) + e3;
@@ -562,6 +628,9 @@ k_box3_f32(const float* __restrict__ in, const float* __restrict__ halo_top, con
     widen(1);
     const double share = rate / 8.0;
     const int kc0 = (jl >= 0) + 2, kc3 = (jr >= 0) + 2;   // existing columns around the first / last owned column
+    // 1 - rate * k / 8 for the first / inner / last owned column of a row with both vertical neighbours
+    // (k = 3 * kcols - 1); rows on a clamped edge (krows = 2, or 1 on a one-row grid) compute theirs on the spot
+    const double keep0 = 1.0 - rate * (double)(3 * kc0 - 1) / 8.0, keep1 = 1.0 - rate, keep3 = 1.0 - rate * (double)(3 * kc3 - 1) / 8.0;
 #pragma unroll
     for (int s = 0; s < SEG; ++s) {
         const int64_t i = i0 + s;
@@ -569,13 +638,18 @@ k_box3_f32(const float* __restrict__ in, const float* __restrict__ halo_top, con
         widen(s + 2);
         if (i >= rows) continue;
         double res[4];
+        const int krows = ((i > 0) || halo_top != nullptr) + 1 + ((i + 1 < rows) || halo_bot != nullptr);
+        double k0 = keep0, k1 = keep1, k3 = keep3;
+        if (DIFFUSE && krows != 3) {
+            k0 = 1.0 - rate * (double)(krows * kc0 - 1) / 8.0;
+            k1 = 1.0 - rate * (double)(krows * 3 - 1) / 8.0;
+            k3 = 1.0 - rate * (double)(krows * kc3 - 1) / 8.0;
+        }
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
             const double box = (H[s][v] + H[s + 1][v]) + H[s + 2][v];
             if (DIFFUSE) {
-                const int krows = ((i > 0) || halo_top != nullptr) + 1 + ((i + 1 < rows) || halo_bot != nullptr);
-                const int k = krows * (v == 0 ? kc0 : (v == 3 ? kc3 : 3)) - 1;
-                res[v] = C[s + 1][v] * (1.0 - rate * (double)k / 8.0) + share * (box - C[s + 1][v]);
+                res[v] = C[s + 1][v] * (v == 0 ? k0 : (v == 3 ? k3 : k1)) + share * (box - C[s + 1][v]);
             } else {
                 res[v] = include_center ? box : box - C[s + 1][v];
             }
