@@ -79,6 +79,65 @@ class HaloExchanger:
         return self.halo_top, self.halo_bot
 
 
+class ShardedLayer:
+    """Row block of a property layer of a row-sharded grid ("grid stencils: GoL, Schelling happiness,
+    layer diffusion" -- one exchange step per stencil).
+
+    Rank k holds rows block_bounds(rows_total, world, k) of a [rows_total, cols] layer of any dtype the layer
+    kernels support.  `neighborhood_sum` and `diffuse` exchange `radius` halo rows with the ring neighbours
+    (HaloExchanger: NCCL on GPUs, gloo on CPU) and launch the same kernels as the single-GPU path with
+    halo_top / halo_bot set; `reduce` is the local reduction kernel + one scalar all-reduce.  `kernels` is the
+    namespace providing neighborhood_sum / layer_diffuse / layer_reduce (default mesa_b200.ops; the gloo tests
+    inject CPU restatements, there is no CPU path in the product)."""
+
+    _ALLREDUCE = {"sum": "SUM", "count_nonzero": "SUM", "min": "MIN", "max": "MAX"}
+
+    def __init__(self, block: torch.Tensor, torus: bool = False, group=None, kernels=None):
+        if block.dim() != 2:
+            raise ValueError("ShardedLayer expects a [rows, cols] row block")
+        if kernels is None:
+            from . import ops as kernels
+        self.k = kernels
+        self.block = block.contiguous()
+        self.torus = bool(torus)
+        self.group = group
+        self._hx: dict[int, HaloExchanger] = {}
+        self._spare = None
+
+    def _halos(self, radius: int):
+        hx = self._hx.get(radius)
+        if hx is None:
+            hx = self._hx[radius] = HaloExchanger(self.block.shape[1], self.block.dtype, radius, self.torus,
+                                                  self.block.device, self.group)
+        return hx.exchange(self.block)
+
+    def neighborhood_sum(self, radius: int = 1, moore: bool = True, include_center: bool = False) -> torch.Tensor:
+        """Neighbourhood sums of this rank's rows (int32 / float64 like ops.neighborhood_sum)."""
+        if radius < 1:
+            raise ValueError("radius must be at least 1")
+        top, bot = self._halos(radius)
+        if self.torus and top is None:      # unreachable: a torus always has ring neighbours
+            raise RuntimeError("torus without ring neighbours")
+        return self.k.neighborhood_sum(self.block, radius, moore, include_center, self.torus, halo_top=top, halo_bot=bot)
+
+    def diffuse(self, rate: float) -> torch.Tensor:
+        """One diffusion step of the whole sharded layer; the block is replaced by its new rows."""
+        top, bot = self._halos(1)
+        if self._spare is None:
+            self._spare = torch.empty_like(self.block)
+        out = self.k.layer_diffuse(self.block, rate, self.torus, out=self._spare,
+                                   halo_top=None if top is None else top[0], halo_bot=None if bot is None else bot[0])
+        self.block, self._spare = out, self.block
+        return self.block
+
+    def reduce(self, op: str = "sum"):
+        """Aggregate over ALL ranks' rows (python int / float)."""
+        local = self.k.layer_reduce(self.block, op)
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(local, op=getattr(dist.ReduceOp, self._ALLREDUCE[op]), group=self.group)
+        return local.item()
+
+
 class PeerHaloLayer:
     """Row block of a sharded uint8/int8 layer whose halos are READ IN PLACE from the neighbours' HBM.
 

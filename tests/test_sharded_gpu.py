@@ -84,3 +84,28 @@ def test_peer_bit_life_world1_matches_oracle(one_rank_group, torus, ghost, launc
         want = oracle.gol_step(want, torus)
     assert (life.launches, life.exchanges) == (launches, exchanges)
     assert np.array_equal(life.store().cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("torus", [True, False])
+def test_sharded_layer_world1_matches_oracle(one_rank_group, torus):
+    """Row-sharded property layer with a 1-rank group (the ring neighbour is the rank itself on a torus): halo rows go
+    through HaloExchanger into halo_top / halo_bot of the walker / box kernels; results equal the oracle's."""
+    from mesa_b200.sharding import ShardedLayer
+    from oracle import layers as olayers
+
+    rng = np.random.default_rng(11)
+    counts = rng.integers(0, 256, size=(70, 96)).astype(np.uint8)
+    layer = ShardedLayer(torch.from_numpy(counts).cuda(), torus=torus)
+    for radius, moore, inc in [(1, True, False), (2, False, True), (3, True, False)]:
+        got = layer.neighborhood_sum(radius, moore, inc).cpu().numpy()
+        assert np.array_equal(got, olayers.neighborhood_sum(counts, radius, moore, inc, torus)), (radius, moore, inc)
+    assert layer.reduce("sum") == int(counts.sum()) and layer.reduce("max") == int(counts.max())
+    assert layer.reduce("count_nonzero") == int(np.count_nonzero(counts))
+    heat = rng.random((70, 96)).astype(np.float32)
+    field = ShardedLayer(torch.from_numpy(heat).cuda(), torus=torus)
+    want = heat
+    for _ in range(3):
+        field.diffuse(0.4)
+        want = olayers.diffuse(want, 0.4, torus)
+    np.testing.assert_allclose(field.block.cpu().numpy(), want, rtol=2e-6, atol=2e-6)
+    assert abs(field.reduce("sum") - float(heat.astype(np.float64).sum())) < 1e-2

@@ -190,3 +190,90 @@ def test_deep_ghost_zones_equal_unsharded(tmp_path, world, torus, ghost, per_lau
     assert np.array_equal(got, want)
     launches, exchanges = np.load(tmp_path / "ghost_stats_0.npy")
     assert exchanges == -(-gens // ghost) and launches >= exchanges
+
+
+# ---- ShardedLayer (row-sharded property layers: neighbourhood sums, diffusion, aggregates) on gloo -------------------
+class _CpuLayerKernels:
+    """CPU stand-ins with the signature of mesa_b200.ops (the oracle restatements on a halo-extended block)."""
+
+    @staticmethod
+    def _extend(block, radius, torus, top, bot, fill_exists=False):
+        x = np.ones(block.shape) if fill_exists else block.numpy().astype(np.float64)
+        rows, cols = x.shape
+
+        def halo(h):
+            if h is None:
+                return np.zeros((radius, cols))
+            return np.ones((radius, cols)) if fill_exists else h.numpy().reshape(radius, cols).astype(np.float64)
+
+        ext = np.concatenate([halo(top), x, halo(bot)], axis=0)
+        return np.pad(ext, ((0, 0), (radius, radius)), mode="wrap" if torus else "constant")
+
+    @classmethod
+    def neighborhood_sum(cls, block, radius, moore, include_center, torus, halo_top=None, halo_bot=None):
+        from oracle import layers
+
+        ext = cls._extend(block, radius, torus, halo_top, halo_bot)
+        out = layers.neighborhood_sum(ext, radius, moore, include_center, False)[radius:-radius, radius:-radius]
+        return torch.from_numpy(out.astype(np.int64 if block.dtype in (torch.uint8, torch.int32) else np.float64))
+
+    @classmethod
+    def layer_diffuse(cls, block, rate, torus, out=None, halo_top=None, halo_bot=None):
+        from oracle import layers
+
+        acc = layers.neighborhood_sum(cls._extend(block, 1, torus, halo_top, halo_bot), 1, True, False, False)[1:-1, 1:-1]
+        k = layers.neighborhood_sum(cls._extend(block, 1, torus, halo_top, halo_bot, True), 1, True, False, False)[1:-1, 1:-1]
+        x = block.numpy().astype(np.float64)
+        out.copy_(torch.from_numpy((x * (1.0 - rate * k / 8.0) + rate / 8.0 * acc).astype(block.numpy().dtype)))
+        return out
+
+    @staticmethod
+    def layer_reduce(block, op):
+        f = {"sum": np.sum, "min": np.min, "max": np.max, "count_nonzero": np.count_nonzero}[op]
+        return torch.tensor([float(f(block.numpy().astype(np.float64)))], dtype=torch.float64)
+
+
+def _layer_worker(rank, world, port, torus, rows, cols, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mesa_b200.sharding import ShardedLayer, block_bounds
+
+    rng = np.random.default_rng(3)
+    counts = rng.integers(0, 9, size=(rows, cols)).astype(np.int32)
+    heat = rng.random((rows, cols))
+    lo, hi = block_bounds(rows, world, rank)
+    layer = ShardedLayer(torch.from_numpy(counts[lo:hi].copy()), torus=torus, kernels=_CpuLayerKernels)
+    np.save(os.path.join(out_dir, f"nsum1_{rank}.npy"), layer.neighborhood_sum(1, True, False).numpy())
+    np.save(os.path.join(out_dir, f"nsum2_{rank}.npy"), layer.neighborhood_sum(2, False, True).numpy())
+    agg = [layer.reduce("sum"), layer.reduce("max"), layer.reduce("min"), layer.reduce("count_nonzero")]
+    np.save(os.path.join(out_dir, f"agg_{rank}.npy"), np.array(agg))
+    field = ShardedLayer(torch.from_numpy(heat[lo:hi].copy()), torus=torus, kernels=_CpuLayerKernels)
+    for _ in range(3):
+        field.diffuse(0.4)
+    np.save(os.path.join(out_dir, f"heat_{rank}.npy"), field.block.numpy())
+    np.save(os.path.join(out_dir, f"mass_{rank}.npy"), np.array([field.reduce("sum")]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,torus", [(2, True), (2, False), (3, True), (3, False)])
+def test_sharded_layer_equals_unsharded(tmp_path, world, torus):
+    """Neighbourhood sums (r=1 Moore, r=2 von Neumann), three diffusion steps and the aggregates of a row-sharded
+    layer equal the unsharded restatements (uneven blocks: 23 rows over 2 / 3 ranks)."""
+    from oracle import layers
+
+    rows, cols = 23, 11
+    mp.spawn(_layer_worker, args=(world, _free_port(), torus, rows, cols, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(3)
+    counts = rng.integers(0, 9, size=(rows, cols)).astype(np.int32)
+    heat = rng.random((rows, cols))
+    cat = lambda name: np.concatenate([np.load(tmp_path / f"{name}_{r}.npy") for r in range(world)])  # noqa: E731
+    assert np.array_equal(cat("nsum1"), layers.neighborhood_sum(counts, 1, True, False, torus))
+    assert np.array_equal(cat("nsum2"), layers.neighborhood_sum(counts, 2, False, True, torus))
+    want = [counts.sum(), counts.max(), counts.min(), np.count_nonzero(counts)]
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"agg_{r}.npy"), np.array(want, dtype=np.float64))
+    for _ in range(3):
+        heat = layers.diffuse(heat, 0.4, torus)
+    np.testing.assert_allclose(cat("heat"), heat, rtol=1e-13, atol=1e-13)
+    assert abs(float(np.load(tmp_path / "mass_0.npy")[0]) - heat.sum()) < 1e-9
