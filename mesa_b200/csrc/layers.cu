@@ -432,13 +432,13 @@ __device__ __forceinline__ void walk_fetch_row(const T* __restrict__ p, const in
     for (int k = 0; k < 2 * NL + 1; ++k) dst[k] = __ldg(reinterpret_cast<const VT*>(p) + cs[k]);
 }
 
-template <typename T, typename A, int V, int NL>
+template <typename T, typename A, int V, int NL, bool ALL_OK = false>
 __device__ __forceinline__ void walk_widen_row(const typename WalkVec<T, V>::type (&src)[2 * NL + 1], bool row_ok,
                                                const int64_t (&cv)[2 * NL + 1], A (&dst)[(2 * NL + 1) * V]) {
 #pragma unroll
     for (int k = 0; k < 2 * NL + 1; ++k) {
         const T* e = reinterpret_cast<const T*>(&src[k]);
-        const bool ok = row_ok && cv[k] >= 0;
+        const bool ok = ALL_OK || (row_ok && cv[k] >= 0);
 #pragma unroll
         for (int v = 0; v < V; ++v) dst[k * V + v] = ok ? (A)e[v] : (A)0;
     }
@@ -462,40 +462,51 @@ __device__ __forceinline__ void walk_columns(int64_t jv, int64_t nvec, int col_t
     }
 }
 
-template <typename T, typename A, int R, bool VN, int V, int SEG, int MINB>
-__global__ void __launch_bounds__(128, MINB)
-k_nsum_walk(const T* __restrict__ in, const T* __restrict__ halo_top, const T* __restrict__ halo_bot,
-            A* __restrict__ out, int64_t rows, int64_t cols, int include_center, int col_torus) {
+// INTERIOR = every row i0-R .. i0+SEG-1+R lies inside this block and every column vector of the CTA exists: plain pointer
+// arithmetic, no row / column selects (the generic body spends ~50 of its ~85 instructions per warp and row on them and is
+// ALU-bound: ncu 86 % ALU pipe on the uint8 layer).  The condition is uniform over the CTA.
+template <typename T, typename A, int R, bool VN, int V, int SEG, bool INTERIOR>
+__device__ __forceinline__ void nsum_walk_body(const T* __restrict__ in, const T* __restrict__ halo_top,
+                                               const T* __restrict__ halo_bot, A* __restrict__ out, int64_t rows,
+                                               int64_t cols, int include_center, int col_torus, int64_t jv, int64_t nvec,
+                                               int64_t i0) {
     constexpr int NL = (R + V - 1) / V, W = (2 * NL + 1) * V;
-    const int64_t nvec = cols / V;
-    const int64_t jv = (int64_t)blockIdx.x * 128 + threadIdx.x;
-    if (jv >= nvec) return;
     using VT = typename WalkVec<T, V>::type;
     int64_t cv[2 * NL + 1], cs[2 * NL + 1];
-    walk_columns<V, NL>(jv, nvec, col_torus, cv);
+    if (INTERIOR) {
 #pragma unroll
-    for (int k = 0; k < 2 * NL + 1; ++k) cs[k] = cv[k] >= 0 ? cv[k] : jv;
-    const int64_t i0 = (int64_t)blockIdx.y * SEG;
+        for (int k = 0; k < 2 * NL + 1; ++k) cv[k] = cs[k] = jv + k - NL;
+    } else {
+        walk_columns<V, NL>(jv, nvec, col_torus, cv);
+#pragma unroll
+        for (int k = 0; k < 2 * NL + 1; ++k) cs[k] = cv[k] >= 0 ? cv[k] : jv;
+    }
     // rows i0-R .. i0+SEG-1+R of the walk; statically indexed (only 2R+1+PF of them are live at a time):
     // the raw loads run PF rows ahead of the conversion + arithmetic
     constexpr int PF = 3;
     VT raw[SEG + 2 * R][2 * NL + 1];
     bool ok[SEG + 2 * R];
     A win[SEG + 2 * R][W];
+    const T* const first = in + (i0 - R) * cols;   // INTERIOR only
     auto fetch = [&](int k) {
-        const T* p = walk_row_ptr<T, R>(in, halo_top, halo_bot, i0 - R + k, rows, cols);
-        ok[k] = p != nullptr;
-        walk_fetch_row<T, V, NL>(ok[k] ? p : in, cs, raw[k]);
+        if (INTERIOR) {
+            ok[k] = true;
+            walk_fetch_row<T, V, NL>(first + (int64_t)k * cols, cs, raw[k]);
+        } else {
+            const T* p = walk_row_ptr<T, R>(in, halo_top, halo_bot, i0 - R + k, rows, cols);
+            ok[k] = p != nullptr;
+            walk_fetch_row<T, V, NL>(ok[k] ? p : in, cs, raw[k]);
+        }
     };
 #pragma unroll
     for (int k = 0; k < 2 * R + PF; ++k) fetch(k);
 #pragma unroll
-    for (int k = 0; k < 2 * R; ++k) walk_widen_row<T, A, V, NL>(raw[k], ok[k], cv, win[k]);
+    for (int k = 0; k < 2 * R; ++k) walk_widen_row<T, A, V, NL, INTERIOR>(raw[k], ok[k], cv, win[k]);
+    A* o = out + i0 * cols + jv * V;
 #pragma unroll
     for (int s = 0; s < SEG; ++s) {
-        const int64_t i = i0 + s;
         if (s + 2 * R + PF < SEG + 2 * R) fetch((s + 2 * R + PF) % (SEG + 2 * R));
-        walk_widen_row<T, A, V, NL>(raw[s + 2 * R], ok[s + 2 * R], cv, win[s + 2 * R]);
+        walk_widen_row<T, A, V, NL, INTERIOR>(raw[s + 2 * R], ok[s + 2 * R], cv, win[s + 2 * R]);
         A res[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) {
@@ -514,15 +525,33 @@ k_nsum_walk(const T* __restrict__ in, const T* __restrict__ halo_top, const T* _
                 }
             res[v] = acc;
         }
-        if (i >= rows) continue;
-        A* o = out + i * cols + jv * V;
-        if (V == 4) {
-            __stcs(reinterpret_cast<int4*>(o), make_int4((int)res[0], (int)res[V > 1 ? 1 : 0], (int)res[V > 2 ? 2 : 0], (int)res[V > 3 ? 3 : 0]));
-        } else {
+        if (INTERIOR || i0 + s < rows) {
+            if (V == 4) {
+                __stcs(reinterpret_cast<int4*>(o), make_int4((int)res[0], (int)res[V > 1 ? 1 : 0], (int)res[V > 2 ? 2 : 0], (int)res[V > 3 ? 3 : 0]));
+            } else {
 #pragma unroll
-            for (int v = 0; v < V; ++v) __stcs(o + v, res[v]);
+                for (int v = 0; v < V; ++v) __stcs(o + v, res[v]);
+            }
         }
+        o += cols;
     }
+}
+
+template <typename T, typename A, int R, bool VN, int V, int SEG, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+k_nsum_walk(const T* __restrict__ in, const T* __restrict__ halo_top, const T* __restrict__ halo_bot,
+            A* __restrict__ out, int64_t rows, int64_t cols, int include_center, int col_torus) {
+    constexpr int NL = (R + V - 1) / V;
+    const int64_t nvec = cols / V;
+    const int64_t jv = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (jv >= nvec) return;
+    const int64_t i0 = (int64_t)blockIdx.y * SEG;
+    const int64_t c0 = (int64_t)blockIdx.x * 128;
+    const bool interior = i0 >= R && i0 + SEG + R <= rows && c0 >= NL && c0 + 127 + NL < nvec;
+    if (interior)
+        nsum_walk_body<T, A, R, VN, V, SEG, true>(in, halo_top, halo_bot, out, rows, cols, include_center, col_torus, jv, nvec, i0);
+    else
+        nsum_walk_body<T, A, R, VN, V, SEG, false>(in, halo_top, halo_bot, out, rows, cols, include_center, col_torus, jv, nvec, i0);
 }
 
 // diffusion on the same walker (radius 1, Moore, one column per thread); k_c from the position
@@ -591,31 +620,36 @@ __device__ __forceinline__ Box3Row box3_load(const float* __restrict__ p, int64_
     return r;
 }
 
-template <bool DIFFUSE, int SEG>
-__global__ void __launch_bounds__(128, 5)
-k_box3_f32(const float* __restrict__ in, const float* __restrict__ halo_top, const float* __restrict__ halo_bot,
-           void* __restrict__ out_, int64_t rows, int64_t cols, int include_center, int col_torus, double rate) {
-    const int64_t jv = (int64_t)blockIdx.x * 128 + threadIdx.x;
-    const int64_t j0 = jv * 4;
-    if (j0 >= cols) return;
-    const int64_t jl = j0 > 0 ? j0 - 1 : (col_torus ? cols - 1 : -1);
-    const int64_t jr = j0 + 4 < cols ? j0 + 4 : (col_torus ? 0 : -1);
-    const int64_t i0 = (int64_t)blockIdx.y * SEG;
+template <bool DIFFUSE, int SEG, bool INTERIOR>
+__device__ __forceinline__ void box3_body(const float* __restrict__ in, const float* __restrict__ halo_top,
+                                          const float* __restrict__ halo_bot, void* __restrict__ out_, int64_t rows,
+                                          int64_t cols, int include_center, int col_torus, double rate, int64_t j0,
+                                          int64_t i0) {
+    // INTERIOR: all rows i0-1 .. i0+SEG exist in this block and the CTA touches neither column edge
+    const int64_t jl = INTERIOR ? j0 - 1 : (j0 > 0 ? j0 - 1 : (col_torus ? cols - 1 : -1));
+    const int64_t jr = INTERIOR ? j0 + 4 : (j0 + 4 < cols ? j0 + 4 : (col_torus ? 0 : -1));
     constexpr int PF = 4;   // rows of loads in flight ahead of the arithmetic (6 registers each)
     Box3Row raw[SEG + 2];
     bool ok[SEG + 2];
     double H[SEG + 2][4], C[SEG + 2][4];
     const int64_t jls = jl >= 0 ? jl : j0, jrs = jr >= 0 ? jr : j0;
+    const float* const first = in + (i0 - 1) * cols;   // INTERIOR only
     auto fetch = [&](int k) {
-        const float* p = walk_row_ptr<float, 1>(in, halo_top, halo_bot, i0 - 1 + k, rows, cols);
-        ok[k] = p != nullptr;
-        raw[k] = box3_load(ok[k] ? p : in, j0, jls, jrs);
+        if (INTERIOR) {
+            ok[k] = true;
+            raw[k] = box3_load(first + (int64_t)k * cols, j0, jls, jrs);
+        } else {
+            const float* p = walk_row_ptr<float, 1>(in, halo_top, halo_bot, i0 - 1 + k, rows, cols);
+            ok[k] = p != nullptr;
+            raw[k] = box3_load(ok[k] ? p : in, j0, jls, jrs);
+        }
     };
     auto widen = [&](int k) {
-        const bool rk = ok[k];
-        const double e0 = (rk && jl >= 0) ? (double)raw[k].left : 0.0, e1 = rk ? (double)raw[k].own.x : 0.0,
+        const bool rk = INTERIOR || ok[k];
+        const bool lk = INTERIOR || (rk && jl >= 0), rrk = INTERIOR || (rk && jr >= 0);
+        const double e0 = lk ? (double)raw[k].left : 0.0, e1 = rk ? (double)raw[k].own.x : 0.0,
                      e2 = rk ? (double)raw[k].own.y : 0.0, e3 = rk ? (double)raw[k].own.z : 0.0,
-                     e4 = rk ? (double)raw[k].own.w : 0.0, e5 = (rk && jr >= 0) ? (double)raw[k].right : 0.0;
+                     e4 = rk ? (double)raw[k].own.w : 0.0, e5 = rrk ? (double)raw[k].right : 0.0;
         C[k][0] = e1; C[k][1] = e2; C[k][2] = e3; C[k][3] = e4;
         H[k][0] = (e0 + e1) + e2;
         H[k][1] = (e1 + e2) + e3;
@@ -631,38 +665,59 @@ k_box3_f32(const float* __restrict__ in, const float* __restrict__ halo_top, con
     // 1 - rate * k / 8 for the first / inner / last owned column of a row with both vertical neighbours
     // (k = 3 * kcols - 1); rows on a clamped edge (krows = 2, or 1 on a one-row grid) compute theirs on the spot
     const double keep0 = 1.0 - rate * (double)(3 * kc0 - 1) / 8.0, keep1 = 1.0 - rate, keep3 = 1.0 - rate * (double)(3 * kc3 - 1) / 8.0;
+    float* of = reinterpret_cast<float*>(out_) + i0 * cols + j0;
+    double* od = reinterpret_cast<double*>(out_) + i0 * cols + j0;
 #pragma unroll
     for (int s = 0; s < SEG; ++s) {
         const int64_t i = i0 + s;
         if (s + 2 + PF < SEG + 2) fetch((s + 2 + PF) % (SEG + 2));
         widen(s + 2);
-        if (i >= rows) continue;
-        double res[4];
-        const int krows = ((i > 0) || halo_top != nullptr) + 1 + ((i + 1 < rows) || halo_bot != nullptr);
-        double k0 = keep0, k1 = keep1, k3 = keep3;
-        if (DIFFUSE && krows != 3) {
-            k0 = 1.0 - rate * (double)(krows * kc0 - 1) / 8.0;
-            k1 = 1.0 - rate * (double)(krows * 3 - 1) / 8.0;
-            k3 = 1.0 - rate * (double)(krows * kc3 - 1) / 8.0;
-        }
+        if (INTERIOR || i < rows) {
+            double res[4];
+            double k0 = keep0, k1 = keep1, k3 = keep3;
+            if (DIFFUSE && !INTERIOR) {
+                const int krows = ((i > 0) || halo_top != nullptr) + 1 + ((i + 1 < rows) || halo_bot != nullptr);
+                if (krows != 3) {
+                    k0 = 1.0 - rate * (double)(krows * kc0 - 1) / 8.0;
+                    k1 = 1.0 - rate * (double)(krows * 3 - 1) / 8.0;
+                    k3 = 1.0 - rate * (double)(krows * kc3 - 1) / 8.0;
+                }
+            }
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            const double box = (H[s][v] + H[s + 1][v]) + H[s + 2][v];
+            for (int v = 0; v < 4; ++v) {
+                const double box = (H[s][v] + H[s + 1][v]) + H[s + 2][v];
+                if (DIFFUSE) {
+                    res[v] = C[s + 1][v] * (v == 0 ? k0 : (v == 3 ? k3 : k1)) + share * (box - C[s + 1][v]);
+                } else {
+                    res[v] = include_center ? box : box - C[s + 1][v];
+                }
+            }
             if (DIFFUSE) {
-                res[v] = C[s + 1][v] * (v == 0 ? k0 : (v == 3 ? k3 : k1)) + share * (box - C[s + 1][v]);
+                __stcs(reinterpret_cast<float4*>(of), make_float4((float)res[0], (float)res[1], (float)res[2], (float)res[3]));
             } else {
-                res[v] = include_center ? box : box - C[s + 1][v];
+                __stcs(reinterpret_cast<double2*>(od), make_double2(res[0], res[1]));
+                __stcs(reinterpret_cast<double2*>(od) + 1, make_double2(res[2], res[3]));
             }
         }
-        if (DIFFUSE) {
-            float* o = reinterpret_cast<float*>(out_) + i * cols + j0;
-            __stcs(reinterpret_cast<float4*>(o), make_float4((float)res[0], (float)res[1], (float)res[2], (float)res[3]));
-        } else {
-            double* o = reinterpret_cast<double*>(out_) + i * cols + j0;
-            __stcs(reinterpret_cast<double2*>(o), make_double2(res[0], res[1]));
-            __stcs(reinterpret_cast<double2*>(o) + 1, make_double2(res[2], res[3]));
-        }
+        of += cols;
+        od += cols;
     }
+}
+
+template <bool DIFFUSE, int SEG>
+__global__ void __launch_bounds__(128, 5)
+k_box3_f32(const float* __restrict__ in, const float* __restrict__ halo_top, const float* __restrict__ halo_bot,
+           void* __restrict__ out_, int64_t rows, int64_t cols, int include_center, int col_torus, double rate) {
+    const int64_t jv = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    const int64_t j0 = jv * 4;
+    if (j0 >= cols) return;
+    const int64_t i0 = (int64_t)blockIdx.y * SEG;
+    const int64_t c0 = (int64_t)blockIdx.x * 512;   // first column of the CTA
+    const bool interior = i0 >= 1 && i0 + SEG + 1 <= rows && c0 >= 1 && c0 + 512 < cols;
+    if (interior)
+        box3_body<DIFFUSE, SEG, true>(in, halo_top, halo_bot, out_, rows, cols, include_center, col_torus, rate, j0, i0);
+    else
+        box3_body<DIFFUSE, SEG, false>(in, halo_top, halo_bot, out_, rows, cols, include_center, col_torus, rate, j0, i0);
 }
 
 template <typename T, typename A, int V, int MINB1, int MINB2>

@@ -254,7 +254,7 @@ static int check_nd(int ndim, const int64_t* dims, int radius, bool vn, bool inc
 
 int main() {
     int bad = 0;
-    const int64_t shapes[][2] = {{1, 1}, {1, 40}, {40, 1}, {3, 3}, {1, 4}, {3, 4}, {5, 8}, {16, 128}, {17, 132}, {35, 260}, {5, 516}, {33, 1024}};
+    const int64_t shapes[][2] = {{1, 1}, {1, 40}, {40, 1}, {3, 3}, {1, 4}, {3, 4}, {5, 8}, {16, 128}, {17, 132}, {35, 260}, {5, 516}, {33, 1024}, {50, 2048}};
     for (auto& s : shapes)
         for (int inc = 0; inc < 2; ++inc)
             for (int torus = 0; torus < 2; ++torus) {
