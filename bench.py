@@ -546,6 +546,12 @@ def layer_workloads(dev, grid=GRID, reps=20):
     run("reduce_sum_f32", lambda: ops.layer_reduce(f32, "sum"), 4 * n)
     run("diffuse_f32_torus", lambda: ops.layer_diffuse(f32, 0.3, True, out=f32b), 8 * n)
     run("neighborhood_sum_f32_moore_r1_torus", lambda: ops.neighborhood_sum(f32, 1, True, False, True, out=f64), 12 * n)
+    del f32, f32b
+    # float64 is the default dtype of Mesa's property layers (grid.py:130-147: dtype=float)
+    d64 = torch.rand((grid, grid), device=dev, generator=g, dtype=torch.float64)
+    run("reduce_sum_f64", lambda: ops.layer_reduce(d64, "sum"), 8 * n)
+    run("diffuse_f64_torus", lambda: ops.layer_diffuse(d64, 0.3, True, out=f64), 16 * n)
+    run("neighborhood_sum_f64_moore_r1_torus", lambda: ops.neighborhood_sum(d64, 1, True, False, True, out=f64), 16 * n)
     return out
 
 

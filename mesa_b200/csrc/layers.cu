@@ -607,65 +607,72 @@ k_diffuse_walk(const T* __restrict__ in, const T* __restrict__ halo_top, const T
 // inputs the result is the exact sum of the 8 (or 9) neighbours -- identical to the (di, dj)-ordered sum of the
 // generic kernels and of the oracle -- as long as the magnitudes inside one neighbourhood span less than 2^25
 // (53 - 24 - 4 bits of headroom); beyond that the last bit may differ.  DIFFUSE selects the diffusion epilogue.
-struct Box3Row {
-    float4 own;
-    float left, right;
+template <typename T> struct Box3Row {
+    uint4 own;      // 16 bytes = V adjacent cells (4 float32 / 2 float64)
+    T left, right;
 };
 
-__device__ __forceinline__ Box3Row box3_load(const float* __restrict__ p, int64_t j0, int64_t jls, int64_t jrs) {
-    Box3Row r;   // unconditional loads (see walk_fetch_row); absent cells are zeroed when the row is widened
-    r.own = __ldg(reinterpret_cast<const float4*>(p + j0));
+template <typename T>
+__device__ __forceinline__ Box3Row<T> box3_load(const T* __restrict__ p, int64_t j0, int64_t jls, int64_t jrs) {
+    Box3Row<T> r;   // unconditional loads (see walk_fetch_row); absent cells are zeroed when the row is widened
+    r.own = __ldg(reinterpret_cast<const uint4*>(p + j0));
     r.left = __ldg(p + jls);
     r.right = __ldg(p + jrs);
     return r;
 }
 
-template <bool DIFFUSE, int SEG, bool INTERIOR>
-__device__ __forceinline__ void box3_body(const float* __restrict__ in, const float* __restrict__ halo_top,
-                                          const float* __restrict__ halo_bot, void* __restrict__ out_, int64_t rows,
+// T = float: sums (DIFFUSE = false, float64 out) and diffusion (float out); T = double: diffusion only -- the separable
+// order is not the oracle's (di, dj) order, which float64 neighbourhood SUMS keep by using the generic walker.
+template <typename T, bool DIFFUSE, int SEG, bool INTERIOR>
+__device__ __forceinline__ void box3_body(const T* __restrict__ in, const T* __restrict__ halo_top,
+                                          const T* __restrict__ halo_bot, void* __restrict__ out_, int64_t rows,
                                           int64_t cols, int include_center, int col_torus, double rate, int64_t j0,
                                           int64_t i0) {
+    constexpr int V = 16 / sizeof(T);
     // INTERIOR: all rows i0-1 .. i0+SEG exist in this block and the CTA touches neither column edge
     const int64_t jl = INTERIOR ? j0 - 1 : (j0 > 0 ? j0 - 1 : (col_torus ? cols - 1 : -1));
-    const int64_t jr = INTERIOR ? j0 + 4 : (j0 + 4 < cols ? j0 + 4 : (col_torus ? 0 : -1));
-    constexpr int PF = 4;   // rows of loads in flight ahead of the arithmetic (6 registers each)
-    Box3Row raw[SEG + 2];
+    const int64_t jr = INTERIOR ? j0 + V : (j0 + V < cols ? j0 + V : (col_torus ? 0 : -1));
+    constexpr int PF = 4;   // rows of loads in flight ahead of the arithmetic
+    Box3Row<T> raw[SEG + 2];
     bool ok[SEG + 2];
-    double H[SEG + 2][4], C[SEG + 2][4];
+    double H[SEG + 2][V], C[SEG + 2][V];
     const int64_t jls = jl >= 0 ? jl : j0, jrs = jr >= 0 ? jr : j0;
-    const float* const first = in + (i0 - 1) * cols;   // INTERIOR only
+    const T* const first = in + (i0 - 1) * cols;   // INTERIOR only
     auto fetch = [&](int k) {
         if (INTERIOR) {
             ok[k] = true;
-            raw[k] = box3_load(first + (int64_t)k * cols, j0, jls, jrs);
+            raw[k] = box3_load<T>(first + (int64_t)k * cols, j0, jls, jrs);
         } else {
-            const float* p = walk_row_ptr<float, 1>(in, halo_top, halo_bot, i0 - 1 + k, rows, cols);
+            const T* p = walk_row_ptr<T, 1>(in, halo_top, halo_bot, i0 - 1 + k, rows, cols);
             ok[k] = p != nullptr;
-            raw[k] = box3_load(ok[k] ? p : in, j0, jls, jrs);
+            raw[k] = box3_load<T>(ok[k] ? p : in, j0, jls, jrs);
         }
     };
     auto widen = [&](int k) {
         const bool rk = INTERIOR || ok[k];
         const bool lk = INTERIOR || (rk && jl >= 0), rrk = INTERIOR || (rk && jr >= 0);
-        const double e0 = lk ? (double)raw[k].left : 0.0, e1 = rk ? (double)raw[k].own.x : 0.0,
-                     e2 = rk ? (double)raw[k].own.y : 0.0, e3 = rk ? (double)raw[k].own.z : 0.0,
-                     e4 = rk ? (double)raw[k].own.w : 0.0, e5 = rrk ? (double)raw[k].right : 0.0;
-        C[k][0] = e1; C[k][1] = e2; C[k][2] = e3; C[k][3] = e4;
-        H[k][0] = (e0 + e1) + e2;
-        H[k][1] = (e1 + e2) + e3;
-        H[k][2] = (e2 + e3) + e4;
-        H[k][3] = (e3 + e4) + e5;
+        const T* own = reinterpret_cast<const T*>(&raw[k].own);
+        double e[V + 2];
+        e[0] = lk ? (double)raw[k].left : 0.0;
+#pragma unroll
+        for (int v = 0; v < V; ++v) e[v + 1] = rk ? (double)own[v] : 0.0;
+        e[V + 1] = rrk ? (double)raw[k].right : 0.0;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            C[k][v] = e[v + 1];
+            H[k][v] = (e[v] + e[v + 1]) + e[v + 2];
+        }
     };
 #pragma unroll
     for (int k = 0; k < 2 + PF; ++k) fetch(k);
     widen(0);
     widen(1);
     const double share = rate / 8.0;
-    const int kc0 = (jl >= 0) + 2, kc3 = (jr >= 0) + 2;   // existing columns around the first / last owned column
+    const int kcf = (jl >= 0) + 2, kcl = (jr >= 0) + 2;   // existing columns around the first / last owned column
     // 1 - rate * k / 8 for the first / inner / last owned column of a row with both vertical neighbours
     // (k = 3 * kcols - 1); rows on a clamped edge (krows = 2, or 1 on a one-row grid) compute theirs on the spot
-    const double keep0 = 1.0 - rate * (double)(3 * kc0 - 1) / 8.0, keep1 = 1.0 - rate, keep3 = 1.0 - rate * (double)(3 * kc3 - 1) / 8.0;
-    float* of = reinterpret_cast<float*>(out_) + i0 * cols + j0;
+    const double keepf = 1.0 - rate * (double)(3 * kcf - 1) / 8.0, keepi = 1.0 - rate, keepl = 1.0 - rate * (double)(3 * kcl - 1) / 8.0;
+    T* ot = reinterpret_cast<T*>(out_) + i0 * cols + j0;
     double* od = reinterpret_cast<double*>(out_) + i0 * cols + j0;
 #pragma unroll
     for (int s = 0; s < SEG; ++s) {
@@ -673,51 +680,56 @@ __device__ __forceinline__ void box3_body(const float* __restrict__ in, const fl
         if (s + 2 + PF < SEG + 2) fetch((s + 2 + PF) % (SEG + 2));
         widen(s + 2);
         if (INTERIOR || i < rows) {
-            double res[4];
-            double k0 = keep0, k1 = keep1, k3 = keep3;
+            double res[V];
+            double kf = keepf, ki = keepi, kl = keepl;
             if (DIFFUSE && !INTERIOR) {
                 const int krows = ((i > 0) || halo_top != nullptr) + 1 + ((i + 1 < rows) || halo_bot != nullptr);
                 if (krows != 3) {
-                    k0 = 1.0 - rate * (double)(krows * kc0 - 1) / 8.0;
-                    k1 = 1.0 - rate * (double)(krows * 3 - 1) / 8.0;
-                    k3 = 1.0 - rate * (double)(krows * kc3 - 1) / 8.0;
+                    kf = 1.0 - rate * (double)(krows * kcf - 1) / 8.0;
+                    ki = 1.0 - rate * (double)(krows * 3 - 1) / 8.0;
+                    kl = 1.0 - rate * (double)(krows * kcl - 1) / 8.0;
                 }
             }
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
+            for (int v = 0; v < V; ++v) {
                 const double box = (H[s][v] + H[s + 1][v]) + H[s + 2][v];
                 if (DIFFUSE) {
-                    res[v] = C[s + 1][v] * (v == 0 ? k0 : (v == 3 ? k3 : k1)) + share * (box - C[s + 1][v]);
+                    res[v] = C[s + 1][v] * (v == 0 ? kf : (v == V - 1 ? kl : ki)) + share * (box - C[s + 1][v]);
                 } else {
                     res[v] = include_center ? box : box - C[s + 1][v];
                 }
             }
             if (DIFFUSE) {
-                __stcs(reinterpret_cast<float4*>(of), make_float4((float)res[0], (float)res[1], (float)res[2], (float)res[3]));
+                uint4 o;
+                T* oe = reinterpret_cast<T*>(&o);
+#pragma unroll
+                for (int v = 0; v < V; ++v) oe[v] = (T)res[v];
+                __stcs(reinterpret_cast<uint4*>(ot), o);
             } else {
-                __stcs(reinterpret_cast<double2*>(od), make_double2(res[0], res[1]));
-                __stcs(reinterpret_cast<double2*>(od) + 1, make_double2(res[2], res[3]));
+#pragma unroll
+                for (int v = 0; v < V; v += 2) __stcs(reinterpret_cast<double2*>(od + v), make_double2(res[v], res[v + 1]));
             }
         }
-        of += cols;
+        ot += cols;
         od += cols;
     }
 }
 
-template <bool DIFFUSE, int SEG>
+template <typename T, bool DIFFUSE, int SEG>
 __global__ void __launch_bounds__(128, 5)
-k_box3_f32(const float* __restrict__ in, const float* __restrict__ halo_top, const float* __restrict__ halo_bot,
-           void* __restrict__ out_, int64_t rows, int64_t cols, int include_center, int col_torus, double rate) {
+k_box3(const T* __restrict__ in, const T* __restrict__ halo_top, const T* __restrict__ halo_bot,
+       void* __restrict__ out_, int64_t rows, int64_t cols, int include_center, int col_torus, double rate) {
+    constexpr int V = 16 / sizeof(T);
     const int64_t jv = (int64_t)blockIdx.x * 128 + threadIdx.x;
-    const int64_t j0 = jv * 4;
+    const int64_t j0 = jv * V;
     if (j0 >= cols) return;
     const int64_t i0 = (int64_t)blockIdx.y * SEG;
-    const int64_t c0 = (int64_t)blockIdx.x * 512;   // first column of the CTA
-    const bool interior = i0 >= 1 && i0 + SEG + 1 <= rows && c0 >= 1 && c0 + 512 < cols;
+    const int64_t c0 = (int64_t)blockIdx.x * (128 * V);   // first column of the CTA
+    const bool interior = i0 >= 1 && i0 + SEG + 1 <= rows && c0 >= 1 && c0 + 128 * V < cols;
     if (interior)
-        box3_body<DIFFUSE, SEG, true>(in, halo_top, halo_bot, out_, rows, cols, include_center, col_torus, rate, j0, i0);
+        box3_body<T, DIFFUSE, SEG, true>(in, halo_top, halo_bot, out_, rows, cols, include_center, col_torus, rate, j0, i0);
     else
-        box3_body<DIFFUSE, SEG, false>(in, halo_top, halo_bot, out_, rows, cols, include_center, col_torus, rate, j0, i0);
+        box3_body<T, DIFFUSE, SEG, false>(in, halo_top, halo_bot, out_, rows, cols, include_center, col_torus, rate, j0, i0);
 }
 
 template <typename T, typename A, int V, int MINB1, int MINB2>
@@ -882,7 +894,7 @@ MB_API int mb_neighborhood_sum(const void* in, const void* halo_top, const void*
         else if (dtype == DT_F32 && radius == 1 && !von_neumann && cols % 4 == 0 && (align & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(out) & 15) == 0 && mb::ceil_div(rows, 16) <= 65535) {
             const dim3 grid((unsigned)mb::ceil_div(cols / 4, 128), (unsigned)mb::ceil_div(rows, 16));
-            k_box3_f32<false, 16><<<grid, 128, 0, stream>>>((const float*)in, (const float*)halo_top, (const float*)halo_bot, out, rows, cols, include_center, col_torus, 0.0);
+            k_box3<float, false, 16><<<grid, 128, 0, stream>>>((const float*)in, (const float*)halo_top, (const float*)halo_bot, out, rows, cols, include_center, col_torus, 0.0);
             done = true;
         } else if (dtype == DT_F32)
             done = launch_nsum_walk<float, double, 1, 8, 4>((const float*)in, (const float*)halo_top, (const float*)halo_bot, (double*)out, rows, cols, radius, von_neumann, include_center, col_torus, stream);
@@ -918,9 +930,13 @@ MB_API int mb_layer_diffuse(const void* in, const void* halo_top, const void* ha
         const dim3 grid((unsigned)mb::ceil_div(cols, 128), (unsigned)mb::ceil_div(rows, SEG));
         const uintptr_t align = reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(halo_top) |
                                 reinterpret_cast<uintptr_t>(halo_bot) | reinterpret_cast<uintptr_t>(out);
-        if (grid.y <= 65535u && dtype == DT_F32 && cols % 4 == 0 && (align & 15) == 0) {
-            const dim3 grid4((unsigned)mb::ceil_div(cols / 4, 128), grid.y);
-            k_box3_f32<true, SEG><<<grid4, 128, 0, stream>>>((const float*)in, (const float*)halo_top, (const float*)halo_bot, out, rows, cols, 0, col_torus, rate);
+        const int vcols = dtype == DT_F32 ? 4 : 2;   // columns per thread of the box kernel
+        if (grid.y <= 65535u && cols % vcols == 0 && (align & 15) == 0) {
+            const dim3 gridv((unsigned)mb::ceil_div(cols / vcols, 128), grid.y);
+            if (dtype == DT_F32)
+                k_box3<float, true, SEG><<<gridv, 128, 0, stream>>>((const float*)in, (const float*)halo_top, (const float*)halo_bot, out, rows, cols, 0, col_torus, rate);
+            else
+                k_box3<double, true, SEG><<<gridv, 128, 0, stream>>>((const double*)in, (const double*)halo_top, (const double*)halo_bot, out, rows, cols, 0, col_torus, rate);
             MB_LAUNCH_CHECK("mb_layer_diffuse");
             return MB_OK;
         }

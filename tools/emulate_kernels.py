@@ -171,24 +171,25 @@ static int check_knn(int n, double sx, double sy, bool torus, int k, double edge
     return 0;
 }
 
-template <bool DIFFUSE>
+template <typename T, bool DIFFUSE>
 static int check_box3(int64_t rows, int64_t cols, bool inc, bool torus) {
-    if (cols %% 4) return 0;
+    constexpr int V = 16 / sizeof(T);
+    if (cols %% V) return 0;
     if (torus && (rows < 3 || cols < 3)) return 0;
-    std::vector<float> in(rows * cols);
-    for (auto& x : in) x = (float)(rand() %% 4096) / 64.0f;
-    std::vector<float> top(cols), bot(cols);
+    std::vector<T> in(rows * cols);
+    for (auto& x : in) x = (T)(rand() %% 4096) / (T)64;
+    std::vector<T> top(cols), bot(cols);
     for (int64_t c = 0; c < cols; ++c) { top[c] = in[(rows - 1) * cols + c]; bot[c] = in[c]; }
     std::vector<double> gotd(rows * cols, -1.0);
-    std::vector<float> gotf(rows * cols, -1.0f);
+    std::vector<T> gott(rows * cols, (T)-1);
     const double rate = 0.25;
-    gridDim.x = (unsigned)((cols / 4 + 127) / 128);
+    gridDim.x = (unsigned)((cols / V + 127) / 128);
     gridDim.y = (unsigned)((rows + 15) / 16);
     for (blockIdx.y = 0; blockIdx.y < gridDim.y; ++blockIdx.y)
         for (blockIdx.x = 0; blockIdx.x < gridDim.x; ++blockIdx.x)
             for (threadIdx.x = 0; threadIdx.x < 128; ++threadIdx.x)
-                k_box3_f32<DIFFUSE, 16>(in.data(), torus ? top.data() : nullptr, torus ? bot.data() : nullptr,
-                                        DIFFUSE ? (void*)gotf.data() : (void*)gotd.data(), rows, cols, inc, torus, rate);
+                k_box3<T, DIFFUSE, 16>(in.data(), torus ? top.data() : nullptr, torus ? bot.data() : nullptr,
+                                       DIFFUSE ? (void*)gott.data() : (void*)gotd.data(), rows, cols, inc, torus, rate);
     for (int64_t i = 0; i < rows; ++i)
         for (int64_t j = 0; j < cols; ++j) {
             double acc = 0.0;
@@ -204,11 +205,11 @@ static int check_box3(int64_t rows, int64_t cols, bool inc, bool torus) {
                 }
             const double self = (double)in[i * cols + j];
             bool ok;
-            if (DIFFUSE) ok = gotf[i * cols + j] == (float)(self * (1.0 - rate * k / 8.0) + rate / 8.0 * acc);
+            if (DIFFUSE) ok = gott[i * cols + j] == (T)(self * (1.0 - rate * k / 8.0) + rate / 8.0 * acc);
             else ok = gotd[i * cols + j] == (inc ? acc + self : acc);
             if (!ok) {
-                printf("box3 mismatch diffuse=%%d rows=%%ld cols=%%ld inc=%%d torus=%%d at (%%ld,%%ld)\n", (int)DIFFUSE, (long)rows,
-                       (long)cols, (int)inc, (int)torus, (long)i, (long)j);
+                printf("box3 mismatch T=%%d diffuse=%%d rows=%%ld cols=%%ld inc=%%d torus=%%d at (%%ld,%%ld)\n", (int)sizeof(T), (int)DIFFUSE,
+                       (long)rows, (long)cols, (int)inc, (int)torus, (long)i, (long)j);
                 return 1;
             }
         }
@@ -269,8 +270,9 @@ int main() {
                 bad += check_nsum<double, double, 1, true, 1>(s[0], s[1], inc, torus);
                 bad += check_nsum<int32_t, int32_t, 2, true, 1>(s[0], s[1], inc, torus);
                 if (!inc) bad += check_diffuse(s[0], s[1], torus);
-                bad += check_box3<false>(s[0], s[1], inc, torus);
-                if (!inc) bad += check_box3<true>(s[0], s[1], inc, torus);
+                bad += check_box3<float, false>(s[0], s[1], inc, torus);
+                if (!inc) bad += check_box3<float, true>(s[0], s[1], inc, torus);
+                if (!inc) bad += check_box3<double, true>(s[0], s[1], inc, torus);
             }
     {
         const int64_t d1[] = {9}, d3[] = {4, 5, 6}, d3b[] = {7, 3, 5}, d4[] = {3, 4, 3, 5};
