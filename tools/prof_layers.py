@@ -18,6 +18,7 @@ if __name__ == "__main__":
     f32 = torch.rand((grid, grid), device=dev, generator=g)
     f32b = torch.empty_like(f32)
     f64 = torch.empty((grid, grid), dtype=torch.float64, device=dev)
+    d64 = torch.empty((grid, grid), dtype=torch.float64, device=dev)
     for _ in range(2):
         ops.layer_fill(u8b, 3)
         ops.layer_affine_clamp(u8, 1.0, 1.0, 0.0, 4.0, out=u8b)
@@ -30,5 +31,6 @@ if __name__ == "__main__":
         ops.layer_reduce(f32, "sum")
         ops.layer_diffuse(f32, 0.3, True, out=f32b)
         ops.neighborhood_sum(f32, 1, True, False, True, out=f64)
+        ops.layer_diffuse(f64, 0.3, True, out=d64)
         torch.cuda.synchronize()
     print("ok")
