@@ -405,7 +405,7 @@ __global__ void k_diffuse(const T* __restrict__ in, const T* __restrict__ halo_t
         }
     }
     const double self = (double)in[idx];
-    out[idx] = (T)(self * (1.0 - rate * (double)k / 8.0) + rate / 8.0 * acc);
+    out[idx] = (T)__fma_rn(rate / 8.0, acc, __dmul_rn(self, 1.0 - rate * (double)k / 8.0));
 }
 
 // ---- column walker: radius-R neighbourhood sums and diffusion -----------------------------------------
@@ -595,7 +595,7 @@ k_diffuse_walk(const T* __restrict__ in, const T* __restrict__ halo_top, const T
             for (int dj = 0; dj < 3; ++dj)
                 if (!(di == 1 && dj == 1)) acc += win[s + di][dj];
         const double self = win[s + 1][1];
-        if (i < rows) __stcs(out + i * cols + j, (T)(self * (1.0 - rate * (double)k / 8.0) + share * acc));
+        if (i < rows) __stcs(out + i * cols + j, (T)__fma_rn(share, acc, __dmul_rn(self, 1.0 - rate * (double)k / 8.0)));
     }
 }
 
@@ -694,7 +694,8 @@ __device__ __forceinline__ void box3_body(const T* __restrict__ in, const T* __r
             for (int v = 0; v < V; ++v) {
                 const double box = (H[s][v] + H[s + 1][v]) + H[s + 2][v];
                 if (DIFFUSE) {
-                    res[v] = C[s + 1][v] * (v == 0 ? kf : (v == V - 1 ? kl : ki)) + share * (box - C[s + 1][v]);
+                    // explicit rounding points: both bodies (and every cell) evaluate the identical expression
+                    res[v] = __fma_rn(share, box - C[s + 1][v], __dmul_rn(C[s + 1][v], v == 0 ? kf : (v == V - 1 ? kl : ki)));
                 } else {
                     res[v] = include_center ? box : box - C[s + 1][v];
                 }

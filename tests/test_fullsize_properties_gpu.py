@@ -194,3 +194,72 @@ def test_gol_full_size_bit_packed_patterns_and_translation():
     a = ops.BitLife(n, n, "cuda", torus=True); a.load(r); a.run(12)
     b = ops.BitLife(n, n, "cuda", torus=True); b.load(torch.roll(r, (777, -3333), (0, 1)).contiguous()); b.run(12)
     assert torch.equal(b.store(), torch.roll(a.store(), (777, -3333), (0, 1)))
+
+
+# ---- property layers at 16384^2 (the oracle restatements take minutes there) ------------------------------------
+def test_layer_kernels_full_size_properties():
+    """Neighbourhood sums: closed-form sizes of a clamped grid, linearity, equivariance under torus translations and
+    transposition, the walker kernel against the independent generic (radius 3) kernel through the identity
+    box(r=1) of box(r=1) = weighted r=2 box; reductions: a checksum of row-block checksums; elementwise: involution."""
+    from mesa_b200 import ops
+
+    n = 16384
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = (torch.rand((n, n), device="cuda", generator=g) * 256).to(torch.uint8)
+    # sizes of the radius-1 / radius-2 neighbourhoods of a clamped grid (cell.py:225-276): (rows seen) * (cols seen) - 1
+    ones = torch.ones((n, n), dtype=torch.uint8, device="cuda")
+    idx = torch.arange(n, device="cuda")
+    for r in (1, 2):
+        seen = torch.minimum(idx, torch.full_like(idx, r)) + 1 + torch.minimum(n - 1 - idx, torch.full_like(idx, r))
+        want = (seen[:, None] * seen[None, :] - 1).to(torch.int32)
+        assert torch.equal(ops.neighborhood_sum(ones, r, True, False, False), want)
+    del ones, want
+    s1 = ops.neighborhood_sum(a, 1, True, False, True)
+    # translation / transposition equivariance on the torus (offsets that are no multiple of a vector or a segment)
+    sh = (1237, -4099)
+    assert torch.equal(ops.neighborhood_sum(torch.roll(a, sh, (0, 1)).contiguous(), 1, True, False, True), torch.roll(s1, sh, (0, 1)))
+    assert torch.equal(ops.neighborhood_sum(a.t().contiguous(), 1, True, False, True), s1.t())
+    # linearity over int32 layers: sum(a) + sum(b) = sum(a + b)
+    b = (torch.rand((n, n), device="cuda", generator=g) * 1000).to(torch.int32)
+    ai = a.to(torch.int32)
+    lhs = ops.neighborhood_sum(ops.layer_binary(ai, b, "add"), 2, False, True, True)
+    rhs = ops.layer_binary(ops.neighborhood_sum(ai, 2, False, True, True), ops.neighborhood_sum(b, 2, False, True, True), "add")
+    assert torch.equal(lhs, rhs)
+    del b, lhs, rhs
+    # checksum of checksums: the whole-layer sum equals the sum over 64 row blocks; count_nonzero likewise
+    total = int(ops.layer_reduce(s1, "sum").item())
+    assert total == 8 * int(ops.layer_reduce(a, "sum").item())        # every cell is counted by its 8 neighbours
+    parts = sum(int(ops.layer_reduce(s1[k * 256:(k + 1) * 256], "sum").item()) for k in range(64))
+    assert parts == total
+    assert int(ops.layer_reduce(a, "count_nonzero").item()) == int((a != 0).sum().item())
+    assert int(ops.layer_reduce(a, "max").item()) == 255 and int(ops.layer_reduce(a, "min").item()) == 0
+    # elementwise: x -> 255 - x twice is the identity (uint8 table path), min / max split a + b
+    inv = ops.layer_affine_clamp(a, -1.0, 255.0, out=torch.empty_like(a))
+    assert torch.equal(ops.layer_affine_clamp(inv, -1.0, 255.0, out=torch.empty_like(a)), a)
+    lo, hi = ops.layer_binary(a, inv, "min"), ops.layer_binary(a, inv, "max")
+    assert torch.equal(ops.layer_binary(lo, hi, "add"), torch.full_like(a, 255))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_diffusion_full_size_properties(dtype):
+    """Diffusion on a 16384^2 torus: a constant layer is a fixed point, mass is conserved, the step commutes with
+    translations, and rate 0 is the identity; on a clamped grid mass is conserved as well (edge cells keep the
+    shares that have nowhere to go)."""
+    from mesa_b200 import ops
+
+    n = 16384
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.rand((n, n), device="cuda", generator=g, dtype=dtype)
+    tol = 1e-6 if dtype == torch.float32 else 1e-13
+    const = torch.full((n, n), 0.75, dtype=dtype, device="cuda")
+    assert torch.equal(ops.layer_diffuse(const, 0.5, True), const)
+    del const
+    assert torch.equal(ops.layer_diffuse(x, 0.0, True), x)
+    y = ops.layer_diffuse(x, 0.4, True)
+    mass = float(ops.layer_reduce(x, "sum").item())
+    assert abs(float(ops.layer_reduce(y, "sum").item()) - mass) <= tol * mass
+    sh = (-517, 2049)
+    assert torch.equal(ops.layer_diffuse(torch.roll(x, sh, (0, 1)).contiguous(), 0.4, True), torch.roll(y, sh, (0, 1)))
+    assert float(y.min().item()) >= 0.0 and float(y.max().item()) <= 1.0      # a convex combination of the 9 cells
+    z = ops.layer_diffuse(x, 0.4, False)
+    assert abs(float(ops.layer_reduce(z, "sum").item()) - mass) <= tol * mass

@@ -36,4 +36,5 @@ template <typename T> static inline void __stcs(T* p, T v) { *p = v; }
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 static inline double __dsqrt_rn(double a) { return sqrt(a); }
+static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
 static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }

@@ -205,7 +205,7 @@ static int check_box3(int64_t rows, int64_t cols, bool inc, bool torus) {
                 }
             const double self = (double)in[i * cols + j];
             bool ok;
-            if (DIFFUSE) ok = gott[i * cols + j] == (T)(self * (1.0 - rate * k / 8.0) + rate / 8.0 * acc);
+            if (DIFFUSE) ok = gott[i * cols + j] == (T)fma(rate / 8.0, acc, self * (1.0 - rate * k / 8.0));
             else ok = gotd[i * cols + j] == (inc ? acc + self : acc);
             if (!ok) {
                 printf("box3 mismatch T=%%d diffuse=%%d rows=%%ld cols=%%ld inc=%%d torus=%%d at (%%ld,%%ld)\n", (int)sizeof(T), (int)DIFFUSE,
