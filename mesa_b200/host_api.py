@@ -19,19 +19,45 @@ class GolHostStepper:
     wrap-around rows of the torus are uploaded first), and downloaded on the copy-out stream, so H2D of
     chunk c+2, the stencil of chunk c and D2H of chunk c-1 overlap."""
 
-    def __init__(self, rows: int, cols: int, device="cuda", chunks: int = 16):
+    def __init__(self, rows: int, cols: int, device="cuda", chunks: int = 16, ramp: bool = False):
         self.rows, self.cols = int(rows), int(cols)
         self.device = torch.device(device)
-        self.chunks = max(1, min(int(chunks), self.rows // 4 if self.rows >= 8 else 1))
         self.d_in = torch.empty((self.rows, self.cols), dtype=torch.uint8, device=self.device)
         self.d_out = torch.empty_like(self.d_in)
         self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream(self.device) for _ in range(3))
-        base, extra = divmod(self.rows, self.chunks)
-        self.bounds, lo = [], 0
-        for c in range(self.chunks):
+        self.bounds = self.chunk_bounds(self.rows, chunks, ramp)
+        self.chunks = len(self.bounds)
+
+    @staticmethod
+    def chunk_bounds(rows: int, chunks: int, ramp: bool = False) -> list[tuple[int, int]]:
+        """Row blocks [lo, hi) covering 0..rows: `chunks` equal blocks, and with `ramp` the first and the last block
+        are split again into 1/8, 1/8, 1/4, 1/2 (mirrored at the end) -- the pipeline's fill (the first upload, during
+        which nothing can be computed or downloaded) and drain (the last download) shrink from 1/chunks to
+        1/(8*chunks) of a one-way transfer.  Measured on B200 / PCIe 5 (16384^2, 16 chunks): 6.36 ms with the ramp,
+        6.34 ms without -- the step is bound by the two directions sharing the link (42 GB/s each way concurrently
+        against 55 GB/s one way), not by fill / drain, so the ramp is off by default."""
+        chunks = max(1, min(int(chunks), rows // 4 if rows >= 8 else 1))
+        base, extra = divmod(rows, chunks)
+        bounds, lo = [], 0
+        for c in range(chunks):
             hi = lo + base + (1 if c < extra else 0)
-            self.bounds.append((lo, hi))
+            bounds.append((lo, hi))
             lo = hi
+        if not ramp or chunks < 3 or base < 32:
+            return bounds
+
+        def split(lo, hi, fractions):
+            n, cuts, at = hi - lo, [], lo
+            for f in fractions[:-1]:
+                nxt = min(hi, at + max(1, round(n * f)))
+                cuts.append((at, nxt))
+                at = nxt
+            cuts.append((at, hi))
+            return [c for c in cuts if c[1] > c[0]]
+
+        head = split(*bounds[0], (0.125, 0.125, 0.25, 0.5))
+        tail = split(*bounds[-1], (0.5, 0.25, 0.125, 0.125))
+        return head + bounds[1:-1] + tail
 
     def step(self, h_in: torch.Tensor, h_out: torch.Tensor) -> torch.Tensor:
         if h_in.shape != (self.rows, self.cols) or h_in.dtype != torch.uint8 or h_in.is_cuda or h_out.is_cuda:

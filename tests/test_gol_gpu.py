@@ -49,14 +49,15 @@ def test_gol_empty():
     assert ops.gol_step(s, torus=False).shape == (0, 16)
 
 
-@pytest.mark.parametrize("shape,chunks", [((64, 64), 4), ((100, 48), 7), ((37, 23), 3), ((8, 16), 16)])
+@pytest.mark.parametrize("shape,chunks", [((64, 64), 4), ((100, 48), 7), ((37, 23), 3), ((8, 16), 16), ((1000, 64), 3),
+                                          ((521, 48), 5)])
 def test_gol_host_stepper_matches_oracle(shape, chunks):
     from mesa_b200.host_api import GolHostStepper, gol_step_host
 
     rng = np.random.default_rng(5)
     s = (rng.random(shape) < 0.4).astype(np.uint8)
     h_in = torch.from_numpy(s).pin_memory()
-    stepper = GolHostStepper(shape[0], shape[1], chunks=chunks)
+    stepper = GolHostStepper(shape[0], shape[1], chunks=chunks, ramp=shape[0] > 500)
     want = s
     for _ in range(3):
         h_out = gol_step_host(h_in, stepper=stepper)

@@ -6,15 +6,15 @@ from mesa_b200.host_api import GolHostStepper
 n = 16384
 h_in = (torch.rand((n, n)) < 0.2).to(torch.uint8).pin_memory()
 h_out = torch.empty_like(h_in).pin_memory()
-for chunks in (1, 4, 8, 16, 32, 64, 128):
-    st = GolHostStepper(n, n, "cuda", chunks=chunks)
+for chunks, ramp in [(1, False), (8, False), (16, False), (32, False), (8, True), (12, True), (16, True), (24, True), (32, True)]:
+    st = GolHostStepper(n, n, "cuda", chunks=chunks, ramp=ramp)
     for _ in range(2):
         st.step(h_in, h_out); torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(10):
         st.step(h_in, h_out); torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / 10
-    print(json.dumps({"chunks": chunks, "ms": dt * 1e3, "GBps_each_way": n * n / dt / 1e9}))
+    print(json.dumps({"chunks": chunks, "ramp": ramp, "blocks": st.chunks, "ms": dt * 1e3, "GBps_each_way": n * n / dt / 1e9}))
 # raw copies for reference
 d = torch.empty((n, n), dtype=torch.uint8, device="cuda")
 torch.cuda.synchronize(); t0 = time.perf_counter()
