@@ -455,6 +455,20 @@ def other_workloads(dev):
     out.append({"workload": "schelling_assign_state_16384x16384_r1", "ms_per_step": ms, "agents": occupied,
                 "agent_updates_per_s": occupied / ms * 1e3, "hbm_gbs": 2 * GRID * GRID / ms / 1e6,
                 "hbm_frac_of_measured_peak": 2 * GRID * GRID / ms / 1e6 / peak})
+    # the reference's "large" Schelling variant: radius 2, homophily 1 (benchmarks/configurations.py:42-49)
+    tbl2 = ops.happy_threshold_table(1.0, 2)
+    for _ in range(3):
+        ops.schelling_happy(types, 1.0, 2, False, out=happy, count=cnt, table=tbl2)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(50):
+        ops.schelling_happy(types, 1.0, 2, False, out=happy, count=cnt, table=tbl2)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 50
+    out.append({"workload": "schelling_assign_state_16384x16384_r2_h1", "ms_per_step": ms, "agents": occupied,
+                "agent_updates_per_s": occupied / ms * 1e3, "hbm_gbs": 2 * GRID * GRID / ms / 1e6,
+                "hbm_frac_of_measured_peak": 2 * GRID * GRID / ms / 1e6 / peak})
     del types, happy
     # config 2: Boltzmann wealth, 10^6 agents on 4096^2
     m = BoltzmannWealth(BoltzmannScenario(n=1_000_000, width=4096, height=4096, rng=1))

@@ -54,9 +54,17 @@ __device__ __forceinline__ unsigned splat(unsigned b) { return b * 0x01010101u; 
 template <int R>
 struct RowH {
     unsigned h[4];
-    unsigned g[R == 1 ? 1 : 4];
+    unsigned g[1];
     unsigned occ[4];  // centre cells: occupied (0/1 per byte)
     unsigned one[4];  // centre cells: type 1
+};
+//   R == 2, packed: hg[k] holds both 5-column sums per byte (low nibble = #occupied, high nibble = #type-1, each <= 5)
+//   and cen[k] the centre cells (bit 0 = occupied, bit 4 = type 1): 8 registers per row instead of 16, so the 5-row
+//   ring fits the register budget of 3 CTAs per SM (the unpacked ring: 128 registers, 2 CTAs, occupancy-bound).
+template <>
+struct RowH<2> {
+    unsigned hg[4];
+    unsigned cen[4];
 };
 
 struct LaneAddr {
@@ -107,23 +115,21 @@ __device__ __forceinline__ RowH<R> make_rowh(const RawRow& x, const LaneAddr& la
             q.h[k - 1] = e[k] + __funnelshift_r(e[k], e[k + 1], 8) + __funnelshift_l(e[k - 1], e[k], 8);
         q.g[0] = 0u;
     } else {
-        unsigned eo[6], e1[6];
+        unsigned e[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
-            eo[k] = ~(raw[k] >> 7) & 0x01010101u;
-            e1[k] = raw[k] & eo[k];
-            if (k >= 1 && k <= 4) { q.occ[k - 1] = eo[k]; q.one[k - 1] = e1[k]; }
+            const unsigned occ = ~(raw[k] >> 7) & 0x01010101u;
+            const unsigned one = raw[k] & occ;
+            e[k] = occ + (one << 4);
+            if (k >= 1 && k <= 4) q.cen[k - 1] = e[k];   // bit 0 = occupied, bit 4 = type 1
         }
 #pragma unroll
         for (int k = 1; k <= 4; ++k) {
-            unsigned a = eo[k], b = e1[k];
+            unsigned a = e[k];
 #pragma unroll
-            for (int d = 1; d <= R; ++d) {
-                a += __funnelshift_r(eo[k], eo[k + 1], 8 * d) + __funnelshift_l(eo[k - 1], eo[k], 8 * d);
-                b += __funnelshift_r(e1[k], e1[k + 1], 8 * d) + __funnelshift_l(e1[k - 1], e1[k], 8 * d);
-            }
-            q.h[k - 1] = a;
-            q.g[k - 1] = b;
+            for (int d = 1; d <= R; ++d)
+                a += __funnelshift_r(e[k], e[k + 1], 8 * d) + __funnelshift_l(e[k - 1], e[k], 8 * d);
+            q.hg[k - 1] = a;   // each nibble <= 5
         }
     }
     return q;
@@ -209,17 +215,23 @@ schelling_happy_vec(const int8_t* __restrict__ type, const int8_t* __restrict__ 
         unsigned* ow = reinterpret_cast<unsigned*>(&o);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            unsigned bocc, bone;
+            unsigned bocc, bone, occ_c, one_c;
             if constexpr (R == 1) {
                 const unsigned b = ring[0].h[k] + ring[1].h[k] + ring[2].h[k];
                 bocc = b & 0x0f0f0f0fu;
                 bone = (b >> 4) & 0x0f0f0f0fu;
+                occ_c = ring[R].occ[k];
+                one_c = ring[R].one[k];
             } else {
-                bocc = 0u; bone = 0u;
-#pragma unroll
-                for (int i = 0; i < W; ++i) { bocc += ring[i].h[k]; bone += ring[i].g[k]; }
+                // three rows (nibbles <= 15) + two rows (<= 10): no nibble overflows before the unpacking
+                const unsigned sa = ring[0].hg[k] + ring[1].hg[k] + ring[2].hg[k];
+                const unsigned sb = ring[3].hg[k] + ring[4].hg[k];
+                bocc = (sa & 0x0f0f0f0fu) + (sb & 0x0f0f0f0fu);
+                bone = ((sa >> 4) & 0x0f0f0f0fu) + ((sb >> 4) & 0x0f0f0f0fu);
+                occ_c = ring[R].cen[k] & 0x01010101u;
+                one_c = (ring[R].cen[k] >> 4) & 0x01010101u;
             }
-            const unsigned res = decide4<MODE>(bocc, bone, ring[R].occ[k], ring[R].one[k], rule);
+            const unsigned res = decide4<MODE>(bocc, bone, occ_c, one_c, rule);
             ow[k] = res;
             nhappy += __popc(res);
         }
@@ -365,11 +377,12 @@ MB_API int mb_schelling_happy_i8(const int8_t* type, const int8_t* halo_top, con
                                              kWarps * 32, 0, stream>>>(type, halo_top, halo_bot, happy, (int)rows,  \
                                                                        (int)cols, col_torus, nstrips, rule, happy_count)
         // rows per warp / CTAs per SM, best of the sweeps on 16384^2: r = 1: 32 rows, 4 CTAs (114 us; 64 rows / 3 CTAs
-        // 134 us); r = 2: 64 rows, 2 CTAs (171 us; 3 CTAs per SM spill and are slower)
+        // 134 us); r = 2 with the nibble-packed ring: 64 rows, 4 CTAs 143 us (64 / 3: 150, 32 / 3: 151, 32 / 4: 143;
+        // the unpacked 16-registers-per-row ring: 128 registers, 2 CTAs, 171 us)
 #define MB_HAPPY_LAUNCH(RR, MM)                          \
     do {                                                 \
         if (RR == 1) MB_HAPPY_LAUNCH3(1, MM, 32, 4);     \
-        else MB_HAPPY_LAUNCH3(2, MM, 64, 2);             \
+        else MB_HAPPY_LAUNCH3(2, MM, 64, 4);             \
     } while (0)
         if (radius == 1) {
             if (rule.mode == MODE_LINEAR) MB_HAPPY_LAUNCH(1, MODE_LINEAR);
