@@ -50,13 +50,13 @@ __device__ __forceinline__ unsigned splat(unsigned b) { return b * 0x01010101u; 
 
 // One input row of a lane after the horizontal pass.
 //   R == 1: h[k] holds both box-row sums per byte: low nibble = #occupied, high nibble = #type-1 (each <= 3)
-//   R == 2: h[k] = #occupied, g[k] = #type-1 over the 5 columns (each <= 5)
 template <int R>
 struct RowH {
     unsigned h[4];
-    unsigned g[1];
     unsigned occ[4];  // centre cells: occupied (0/1 per byte)
     unsigned one[4];  // centre cells: type 1
+    // (packing the centre cells like the radius-2 ring saves 15 registers but costs 12 unpacking operations per row:
+    //  121 us at 4 CTAs per SM, 119 us at 5 against 115 us -- radius 1 is instruction-bound, not occupancy-bound)
 };
 //   R == 2, packed: hg[k] holds both 5-column sums per byte (low nibble = #occupied, high nibble = #type-1, each <= 5)
 //   and cen[k] the centre cells (bit 0 = occupied, bit 4 = type 1): 8 registers per row instead of 16, so the 5-row
@@ -113,7 +113,6 @@ __device__ __forceinline__ RowH<R> make_rowh(const RawRow& x, const LaneAddr& la
 #pragma unroll
         for (int k = 1; k <= 4; ++k)
             q.h[k - 1] = e[k] + __funnelshift_r(e[k], e[k + 1], 8) + __funnelshift_l(e[k - 1], e[k], 8);
-        q.g[0] = 0u;
     } else {
         unsigned e[6];
 #pragma unroll
