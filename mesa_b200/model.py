@@ -32,10 +32,36 @@ class DeviceModel:
         self.running = True
         self.steps = 0
         self.time = 0.0
-        self.agents = None  # set by the concrete model (a DeviceAgentSet)
+        self._agents_by_type: dict = {}
+        self._agents = None  # set by the concrete model (a DeviceAgentSet) through the `agents` property
         # model.py:133-140: the user's step() is wrapped so that every call advances time by one unit
         self._user_step = self.step
         self.step = self._wrapped_step
+
+    # model.py:143-148, 221-247: `agents` is the set of all agents, `agents_by_type` maps an agent class to the set of
+    # its instances (typed activation, e.g. wolf_sheep/model.py:140-141: agents_by_type[Sheep].shuffle_do("step")).
+    # A device model registers one DeviceAgentSet per agent class; assigning `model.agents` registers that set.
+    @property
+    def agents(self):
+        return self._agents
+
+    @agents.setter
+    def agents(self, agentset) -> None:
+        self._agents = agentset
+        if agentset is not None:
+            self.register_agentset(agentset)
+
+    def register_agentset(self, agentset) -> None:
+        """Make `agentset` (one population of one agent class) reachable through `agents_by_type`."""
+        self._agents_by_type[agentset.agent_type] = agentset
+
+    @property
+    def agent_types(self) -> list[type]:
+        return list(self._agents_by_type.keys())
+
+    @property
+    def agents_by_type(self) -> dict:
+        return self._agents_by_type
 
     def _next_epoch(self) -> int:
         e = self._epoch

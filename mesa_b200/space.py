@@ -120,6 +120,14 @@ class CellProxy:
         return bool(self.grid.empty[self.coordinate].item())
 
     @property
+    def is_full(self) -> bool:
+        """cell.py:183-189: len(agents) >= capacity (never full when capacity is None)."""
+        grid = self.grid
+        if grid.capacity is None:
+            return False
+        return bool((grid.agent_counts()[self.coordinate] >= grid.capacity).item())
+
+    @property
     def neighborhood(self) -> list["CellProxy"]:
         return self.get_neighborhood()
 
@@ -330,6 +338,41 @@ class DeviceGrid:
         if empties.numel() == 0:
             raise ValueError("Grid is completely full. No empty cells available. Cannot select a random empty cell.")
         k = int(empties[self.random._randbelow(empties.numel())].item())
+        return CellProxy(self, self._unravel(k))
+
+
+    # ------------------------------------------------------------------ capacity (grid.py:318-378)
+    def agent_counts(self) -> torch.Tensor:
+        """Agents per cell: the `agent_count` property layer when the model maintains one (cells shared by several
+        agents), otherwise 1 - empty (grids of capacity 1, where `empty` is the occupancy)."""
+        layers = self.property_layers
+        if "agent_count" in layers:
+            return layers["agent_count"]
+        return (~layers["empty"]).to(torch.int32)
+
+    @property
+    def cells_with_capacity(self):
+        """All cells that are not full (grid.py:318-350); every cell when capacity is None."""
+        if self.capacity is None:
+            return self.all_cells
+        idx = torch.nonzero((self.agent_counts() < self.capacity).reshape(-1)).reshape(-1).cpu().tolist()
+        return [CellProxy(self, self._unravel(k)) for k in idx]
+
+    def select_random_cell_with_capacity(self) -> CellProxy:
+        """grid.py:352-378: <= 50 uniform probes, first cell that is not full wins; else one choice among the
+        cells with capacity; IndexError when every cell is full."""
+        ncells = len(self)
+        if self.capacity is None:
+            return CellProxy(self, self._unravel(self.random._randbelow(ncells)))
+        room = (self.agent_counts() < self.capacity).reshape(-1)
+        for _ in range(50):
+            k = self.random._randbelow(ncells)
+            if bool(room[k].item()):
+                return CellProxy(self, self._unravel(k))
+        available = torch.nonzero(room).reshape(-1)
+        if available.numel() == 0:
+            raise IndexError("No available cells exist in the grid: all cells are at full capacity.")
+        k = int(available[self.random._randbelow(available.numel())].item())
         return CellProxy(self, self._unravel(k))
 
 

@@ -287,3 +287,59 @@ def test_example_boids_sequential_activation_matches_oracle():
         assert np.max(np.abs(got_p - wp) / m.space.size) <= 1e-5 and np.max(np.abs(got_d - wd)) <= 1e-5
         assert m.last_passes >= 1
         pos, dirs = got_p.copy(), got_d.copy()
+
+
+def test_capacity_api_matches_reference_draw_protocol():
+    """cells_with_capacity / select_random_cell_with_capacity / Cell.is_full (grid.py:318-378, cell.py:178-182) on a
+    grid whose cells hold up to 2 agents: the same cells, the same consumption of the stdlib random stream
+    (<= 50 `choice(cells)` probes, then one `choice(available)`), IndexError when every cell is full."""
+    from mesa_b200.space import DeviceMooreGrid
+
+    grid = DeviceMooreGrid((6, 7), torus=False, capacity=2, random=random.Random(5))
+    rng = np.random.default_rng(0)
+    counts = rng.integers(0, 3, size=(6, 7)).astype(np.int32)
+    grid.add_property_layer("agent_count", counts)
+    room = counts < 2
+    got = sorted(c.coordinate for c in grid.cells_with_capacity)
+    assert got == sorted(map(tuple, np.argwhere(room).tolist()))
+    assert grid[(0, 0)].is_full == bool(counts[0, 0] >= 2)
+    replay = random.Random(5)
+    for _ in range(20):
+        want = None
+        for _ in range(50):
+            k = replay._randbelow(42)
+            if room.reshape(-1)[k]:
+                want = (k // 7, k % 7)
+                break
+        assert want is not None and grid.select_random_cell_with_capacity().coordinate == want
+    # nearly full: only (5, 6) has room -> the 50 probes usually miss and the fallback draws among 1 cell
+    counts[:] = 2
+    counts[5, 6] = 1
+    grid.property_layers["agent_count"].copy_(torch.from_numpy(counts))
+    for _ in range(5):
+        assert grid.select_random_cell_with_capacity().coordinate == (5, 6)
+    grid.property_layers["agent_count"].fill_(2)
+    assert list(grid.cells_with_capacity) == []
+    with pytest.raises(IndexError):
+        grid.select_random_cell_with_capacity()
+    # capacity None: nothing is ever full, one draw per call; capacity 1 without a count layer: 1 - empty
+    free = DeviceMooreGrid((3, 3), random=random.Random(1))
+    assert not free[(1, 1)].is_full and len(list(free.cells_with_capacity)) == 9
+    assert free.select_random_cell_with_capacity().coordinate == divmod(random.Random(1)._randbelow(9), 3)
+    single = DeviceMooreGrid((2, 2), capacity=1, random=random.Random(1))
+    single.empty[0, 1] = False
+    assert single[(0, 1)].is_full and sorted(c.coordinate for c in single.cells_with_capacity) == [(0, 0), (1, 0), (1, 1)]
+
+
+def test_agents_by_type_typed_activation():
+    """model.agents_by_type / agent_types (model.py:221-247): typed activation like wolf_sheep/model.py:140-141."""
+    from mesa_b200.examples import Schelling, SchellingScenario
+    from mesa_b200.examples.schelling import SchellingAgent
+
+    m = Schelling(SchellingScenario(width=20, height=20, density=0.8, homophily=0.4, radius=1, rng=3), collect=False)
+    assert m.agent_types == [SchellingAgent] and m.agents_by_type[SchellingAgent] is m.agents
+    before = m.happy
+    assert m.agents_by_type[SchellingAgent].do("assign_state") is m.agents and m.happy == before
+    m.agents_by_type[SchellingAgent].shuffle_do("step")
+    m.agents.do("assign_state")
+    assert m.happy != before or m.last_movers == 0
