@@ -1,0 +1,95 @@
+"""Host-side logic of the drop-in classes that needs no GPU: neighbour ordering of the n-dimensional grids against the
+reference's Cell.get_neighborhood (golden probes), chunking of the host stepper, cell-edge heuristic of the k-nearest
+search, DeviceModel bookkeeping (clock, epochs, agents_by_type)."""
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _bare_grid(cls, dims, torus):
+    """A device grid without its device layers: only the fields neighborhood_coordinates reads."""
+    g = cls.__new__(cls)
+    g.__dict__.update(dimensions=tuple(dims), torus=bool(torus), _ndims=len(dims))
+    if len(dims) != 2:
+        g.__dict__["_offsets"] = cls._offsets_nd(len(dims))
+    return g
+
+
+def test_nd_neighbour_order_matches_reference_probes():
+    from mesa_b200.space import DeviceMooreGrid, DeviceVonNeumannGrid
+
+    g = np.load(os.path.join(GOLDEN, "neighborhoods_nd.npz"))
+    for k, (moore, torus, radius, inc) in enumerate(g["cases"]):
+        dims = tuple(int(d) for d in g[f"dims_{k}"])
+        grid = _bare_grid(DeviceMooreGrid if moore else DeviceVonNeumannGrid, dims, torus)
+        probes = [tuple(0 for _ in dims), tuple(d - 1 for d in dims), tuple(d // 2 for d in dims)]
+        for q, pc in enumerate(probes):
+            want = [tuple(int(x) for x in row) for row in g[f"probe_{k}_{q}"]]
+            assert grid.neighborhood_coordinates(pc, int(radius), bool(inc)) == want, (k, dims, pc)
+
+
+def test_2d_neighbour_order_and_torus_dedup():
+    """connection order at a clamped corner, wrapped duplicates collapse, a dimension of 1 makes the
+    cell its own neighbour on a torus."""
+    from mesa_b200.space import DeviceMooreGrid, DeviceVonNeumannGrid
+
+    assert _bare_grid(DeviceMooreGrid, (5, 5), False).neighborhood_coordinates((0, 0)) == [(0, 1), (1, 0), (1, 1)]
+    assert _bare_grid(DeviceVonNeumannGrid, (5, 5), False).neighborhood_coordinates((2, 2)) == [(1, 2), (2, 1), (2, 3), (3, 2)]
+    assert len(_bare_grid(DeviceMooreGrid, (2, 5), True).neighborhood_coordinates((0, 0))) == 5
+    assert len(_bare_grid(DeviceMooreGrid, (2, 2), True).neighborhood_coordinates((0, 0))) == 3
+    assert (0, 1) in _bare_grid(DeviceMooreGrid, (1, 4), True).neighborhood_coordinates((0, 1))
+    assert len(_bare_grid(DeviceMooreGrid, (7, 7), True).neighborhood_coordinates((3, 3), radius=5)) == 48
+    assert len(_bare_grid(DeviceVonNeumannGrid, (9, 9), False).neighborhood_coordinates((4, 4), radius=2)) == 12
+
+
+def test_host_stepper_chunk_bounds_tile_the_rows():
+    from mesa_b200.host_api import GolHostStepper
+
+    for rows in (8, 37, 64, 100, 1000, 4096, 16384):
+        for chunks in (1, 3, 7, 16, 64):
+            for ramp in (False, True):
+                b = GolHostStepper.chunk_bounds(rows, chunks, ramp)
+                assert b[0][0] == 0 and b[-1][1] == rows
+                assert all(hi > lo for lo, hi in b) and all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
+    ramped = GolHostStepper.chunk_bounds(16384, 16, True)
+    assert len(ramped) == 22 and ramped[0] == (0, 128) and ramped[-1] == (16384 - 128, 16384)
+
+
+def test_knn_cell_edge_is_bounded_and_scales():
+    from mesa_b200 import ops
+
+    e1 = ops.knn_cell_edge(10_000, (100.0, 100.0), 4)
+    assert 0 < e1 <= 100.0 and abs(e1 - (100.0 * 100.0 * 5 / (9 * 10_000)) ** 0.5) < 1e-12
+    assert ops.knn_cell_edge(0, (10.0, 5.0), 1) <= 10.0            # empty space: one cell at most
+    assert ops.knn_cell_edge(10**9, (1.0, 1.0), 1) >= 1e-6          # never degenerate
+    assert ops.knn_cell_edge(100, (10.0, 10.0), 16) > ops.knn_cell_edge(100, (10.0, 10.0), 1)
+
+
+def test_device_model_clock_epochs_and_agents_by_type():
+    from mesa_b200.model import DeviceModel
+
+    class Dummy:
+        pass
+
+    class Set:
+        agent_type = Dummy
+
+    class M(DeviceModel):
+        def __init__(self):
+            super().__init__(rng=7)
+            self.calls = 0
+            self.agents = Set()
+
+        def step(self):
+            self.calls += 1
+
+    m = M()
+    m.step()
+    m.run_for(3)
+    assert (m.steps, m.time, m.calls) == (4, 4.0, 4)                 # model.py:152-154: every step advances time by 1
+    assert [m._next_epoch() for _ in range(3)] == [0, 1, 2]          # one epoch per shuffle
+    assert m.agent_types == [Dummy] and m.agents_by_type[Dummy] is m.agents
+    m2 = M()
+    assert m2.philox_seed == m.philox_seed and m2.random.random() == M().random.random()   # seeded identically
