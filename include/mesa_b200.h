@@ -253,6 +253,18 @@ int mb_boids_compact(const float* pos, const float* dir, const int64_t* ids, int
                      mb_stream_t stream);
 int mb_scan_scratch_words(int64_t n, size_t* out);
 
+/* ---- Dynamic populations (replaces the per-agent dict deletions of _HardKeyAgentSet.discard / remove,
+ * mesa/agentset.py:700-711, reached through Agent.remove -> Model.deregister_agent, mesa/agent.py:73-108,
+ * mesa/model.py:281-294): removing a batch of agents is one STABLE compaction of every structure-of-arrays
+ * column -- survivors keep their registration order, the base order of do / shuffle_do (agentset.py:776).
+ * mb_compact_plan: keep [n] bytes (0 = remove) -> offsets [n + 1] uint32, offsets[i] = survivors before row i,
+ * offsets[n] = number of survivors; scratch = mb_scan_scratch_words(n + 1) uint32 words.
+ * mb_compact_rows: out[offsets[i]] = in[i] for every kept row (row_bytes wide; in / out must not overlap);
+ * called once per column with the same plan. */
+int mb_compact_plan(const uint8_t* keep, int64_t n, uint32_t* offsets, uint32_t* scratch, mb_stream_t stream);
+int mb_compact_rows(const void* in, void* out, int64_t n, int64_t row_bytes, const uint8_t* keep,
+                    const uint32_t* offsets, mb_stream_t stream);
+
 /* ---- Boltzmann wealth (replaces AgentSet.shuffle_do("step") over
  * examples/basic/boltzmann_wealth_model/agents.py:24-44: Moore random walk, then give one unit to
  * a random cell mate) ---------------------------------------------------------------------------

@@ -10,6 +10,13 @@ registered for (agent type, "name").  Unregistered names raise -- there is no pe
 fallback.  `shuffle_do` consumes one activation epoch: the order is the ascending Philox
 priority64(model seed, epoch, agent) (csrc/philox.cuh), which replaces `random.shuffle`
 (agentset.py:777) and can be replayed into the reference (oracle/replay.py).
+
+Populations are dynamic (agentset.py:700-711 `add / discard / remove`, agent.py:73-108 `Agent.remove`,
+agent.py:115-160 `Agent.create_agents`): `add_agents` appends rows, `remove_agents` / `remove` /
+`discard` take rows out with ONE stable compaction shared by every column (csrc/agents.cu), so the
+survivors keep their registration order -- the base order of `do` / `shuffle_do` -- and their
+`unique_id`.  Row proxies and `select / shuffle / sort` views taken before a removal refer to row
+numbers that no longer exist; using them afterwards raises `ReferenceError`.
 """
 from __future__ import annotations
 
@@ -44,49 +51,72 @@ def _lookup(agent_type: type, name: str) -> Callable:
 class DeviceAgent:
     """Base class of device agent types; instances are row proxies handed out on demand."""
 
-    __slots__ = ("_set", "_index")
+    __slots__ = ("_set", "_index", "_gen")
 
     def __init__(self, agentset: "DeviceAgentSet", index: int):
         object.__setattr__(self, "_set", agentset)
         object.__setattr__(self, "_index", int(index))
+        object.__setattr__(self, "_gen", agentset._pop.generation)
+
+    def _row(self) -> int:
+        """The row this proxy stands for; rows are renumbered by a removal, which invalidates older proxies."""
+        if self._gen != self._set._pop.generation:
+            raise ReferenceError("agent proxy taken before agents were removed from the population; "
+                                 "look the agent up again (rows are renumbered by the compaction)")
+        return self._index
 
     @property
-    def unique_id(self) -> int:  # agent.py:51-71: ids count from 1 in registration order
-        return self._index + 1
+    def unique_id(self) -> int:  # agent.py:51-71, model.py:250-263: ids count from 1 in registration order
+        return self._set._unique_id(self._row())
 
     @property
     def model(self):
         return self._set.model
 
+    def remove(self) -> None:
+        """agent.py:73-108: take this agent out of the model's population (KeyError-free like the reference)."""
+        self._set.discard(self)
+
     def __getattr__(self, name):
         cols = object.__getattribute__(self, "_set").columns
         if name in cols:
-            v = cols[name][self._index]
+            v = cols[name][self._row()]
             return v.item() if v.dim() == 0 else v.cpu().numpy()
         raise AttributeError(name)
 
     def __setattr__(self, name, value):
         cols = self._set.columns
         if name in cols:
-            cols[name][self._index] = torch.as_tensor(value, device=cols[name].device, dtype=cols[name].dtype)
+            cols[name][self._row()] = torch.as_tensor(value, device=cols[name].device, dtype=cols[name].dtype)
             return
         raise AttributeError(name)
 
     def __eq__(self, other):
-        return isinstance(other, DeviceAgent) and other._set is self._set and other._index == self._index
+        return (isinstance(other, DeviceAgent) and other._set.columns is self._set.columns
+                and other._gen == self._gen and other._index == self._index)
 
     def __hash__(self):
-        return hash((id(self._set), self._index))
+        return hash((id(self._set.columns), self._gen, self._index))
 
     def __repr__(self):
         return f"<{type(self).__name__} {self.unique_id}>"
+
+
+class _Population:
+    """State shared by a population and its views: the removal generation (bumped whenever rows are renumbered)
+    and the unique ids (`ids` stays None while unique_id == row + 1, i.e. until the first removal)."""
+
+    def __init__(self, n: int):
+        self.generation = 0
+        self.ids: torch.Tensor | None = None
+        self.next_id = n + 1  # model.py:250-263: ids are handed out in registration order and never reused
 
 
 class DeviceAgentSet:
     """An ordered set of `n` agents of one type stored column-wise on the device."""
 
     def __init__(self, model, agent_type: type, n: int, columns: dict[str, torch.Tensor] | None = None,
-                 random=None, index: torch.Tensor | None = None):
+                 random=None, index: torch.Tensor | None = None, resizable: bool = True, _pop: _Population | None = None):
         self.model = model
         self.agent_type = agent_type
         self.n = int(n)
@@ -95,12 +125,30 @@ class DeviceAgentSet:
         self.random = random if random is not None else getattr(model, "random", None)
         # `index` selects / orders rows for views produced by select / shuffle / sort (None = all, in order)
         self.index = index
+        # False for populations whose rows are also keys of other state (grid layers holding agent rows, a
+        # continuous space's storage order): those models add / remove through their own space, not here
+        self.resizable = bool(resizable)
+        self._pop = _pop if _pop is not None else _Population(self.n)
+        self._view_gen = self._pop.generation
+        # called as hook(agentset, plan) after rows were appended (plan None) or compacted (plan = the
+        # ops.CompactionPlan): lets a model keep row-keyed side state (workspaces, layers) in step
+        self.resize_hooks: list[Callable] = []
+
+    def _view(self, idx: torch.Tensor) -> "DeviceAgentSet":
+        return DeviceAgentSet(self.model, self.agent_type, self.n, self.columns, self.random, idx, self.resizable,
+                              self._pop)
+
+    def _check_view(self) -> None:
+        if self.index is not None and self._view_gen != self._pop.generation:
+            raise ReferenceError("this view was taken before agents were removed from the population; "
+                                 "select / shuffle / sort again (rows are renumbered by the compaction)")
 
     # -- collection protocol ------------------------------------------------
     def __len__(self) -> int:
         return self.n if self.index is None else int(self.index.numel())
 
     def __iter__(self):
+        self._check_view()
         if self.index is None:
             return (self.agent_type(self, i) for i in range(self.n))
         return (self.agent_type(self, i) for i in self.index.cpu().tolist())
@@ -108,11 +156,15 @@ class DeviceAgentSet:
     def __contains__(self, agent) -> bool:
         if not isinstance(agent, DeviceAgent) or agent._set.columns is not self.columns:
             return False
+        if agent._gen != self._pop.generation:  # a proxy from before a removal names no current agent
+            return False
+        self._check_view()
         if self.index is None:
             return 0 <= agent._index < self.n
         return bool((self.index == agent._index).any().item())
 
     def __getitem__(self, item):
+        self._check_view()
         if isinstance(item, slice):
             rng = range(len(self))[item]
             return [self[i] for i in rng]
@@ -126,10 +178,132 @@ class DeviceAgentSet:
     def __repr__(self) -> str:
         return f"<{type(self).__name__} ({len(self)} agents)>"
 
-    def add(self, agent):
-        raise NotImplementedError("device populations are fixed-size in this release (SURVEY §8f)")
+    # -- unique ids -----------------------------------------------------------
+    def _unique_id(self, row: int) -> int:
+        ids = self._pop.ids
+        return row + 1 if ids is None else int(ids[row].item())
 
-    discard = remove = add
+    def unique_ids(self) -> torch.Tensor:
+        """`unique_id` of every agent of this set, in the set's order (int64, on the device)."""
+        self._check_view()
+        ids = self._pop.ids
+        if ids is None:
+            if self.index is None:
+                return torch.arange(1, self.n + 1, dtype=torch.int64, device=self._device())
+            return self.index.to(torch.int64) + 1
+        return ids if self.index is None else ids[self.index]
+
+    # -- creation and removal (agentset.py:700-711, agent.py:73-160) --------------------
+    def _require_resizable(self, what: str) -> None:
+        self._require_full(what)
+        if not self.resizable:
+            raise NotImplementedError(f"{what}: the rows of this population key other model state (grid layers / "
+                                      "space storage); the model owns its size")
+        if not isinstance(self.columns, dict) or not all(isinstance(c, torch.Tensor) for c in self.columns.values()):
+            raise NotImplementedError(f"{what} needs plain tensor columns")
+        for name, col in self.columns.items():
+            if col.shape[0] != self.n:
+                raise ValueError(f"column {name!r} has {col.shape[0]} rows for {self.n} agents")
+
+    def add_agents(self, k: int, **values) -> "DeviceAgentSet":
+        """Create `k` agents at the end of the registration order (agent.py:115-160 `create_agents`): each
+        keyword names a column and gives one value for all new agents or one per agent (torch broadcasting
+        against [k, ...]); unnamed columns start at zero.  Returns the set of the new agents."""
+        k = int(k)
+        if k < 0:
+            raise ValueError("cannot create a negative number of agents")
+        self._require_resizable("add_agents")
+        for name in values:
+            if name not in self.columns:
+                raise AttributeError(f"agents have no attribute {name!r}")
+        old_n, new_n = self.n, self.n + k
+        dev = self._device()
+        grown = {}
+        for name, col in self.columns.items():  # build everything first: a bad value must not leave half a resize
+            g = torch.empty((new_n, *col.shape[1:]), dtype=col.dtype, device=col.device)
+            g[:old_n].copy_(col)
+            if name in values:
+                g[old_n:] = torch.as_tensor(values[name], device=col.device).to(col.dtype)
+            else:
+                g[old_n:].zero_()
+            grown[name] = g
+        pop = self._pop
+        if pop.ids is not None:
+            fresh = torch.arange(pop.next_id, pop.next_id + k, dtype=torch.int64, device=pop.ids.device)
+            pop.ids = torch.cat([pop.ids, fresh])
+        pop.next_id += k
+        self.columns.update(grown)
+        self.n = new_n
+        for hook in self.resize_hooks:
+            hook(self, None)
+        return self._view(torch.arange(old_n, new_n, dtype=torch.int64, device=dev))
+
+    def remove_agents(self, which) -> "DeviceAgentSet":
+        """Remove a batch of agents: `which` is a bool mask [n] (True = remove), a tensor / sequence of row
+        numbers, or an iterable of agent proxies.  One stable compaction of every column (csrc/agents.cu): the
+        other agents keep their order and their unique_id."""
+        from . import ops
+
+        self._require_resizable("remove_agents")
+        dev = self._device()
+        if isinstance(which, DeviceAgentSet):
+            which._check_view()
+            which = torch.arange(which.n, device=dev) if which.index is None else which.index
+        if isinstance(which, torch.Tensor) and which.dtype == torch.bool:
+            if tuple(which.shape) != (self.n,):
+                raise ValueError(f"removal mask has shape {tuple(which.shape)}, expected ({self.n},)")
+            keep = ~which.to(dev)
+        else:
+            if not isinstance(which, torch.Tensor):
+                rows = []
+                for a in which:
+                    if isinstance(a, DeviceAgent):
+                        if a not in self:
+                            raise KeyError(a)
+                        a = a._index
+                    rows.append(int(a))
+                which = torch.as_tensor(rows, dtype=torch.int64)
+            rows = which.to(dev, torch.int64).reshape(-1)
+            if rows.numel() and (int(rows.min().item()) < 0 or int(rows.max().item()) >= self.n):
+                raise IndexError("agent row out of range")
+            keep = torch.ones(self.n, dtype=torch.bool, device=dev)
+            keep[rows] = False
+        plan = ops.CompactionPlan(keep)
+        if plan.kept == self.n:
+            return self
+        pop = self._pop
+        ids = pop.ids if pop.ids is not None else torch.arange(1, self.n + 1, dtype=torch.int64, device=dev)
+        compacted = {name: plan.apply(col) for name, col in self.columns.items()}
+        pop.ids = plan.apply(ids)
+        self.columns.update(compacted)
+        self.n = plan.kept
+        pop.generation += 1
+        for hook in self.resize_hooks:
+            hook(self, plan)
+        return self
+
+    def add(self, agent):
+        """agentset.py:700-702.  Device agents are created in batches (`add_agents`); adding an agent that is
+        already a member is the no-op it is in the reference."""
+        if agent in self:
+            return
+        raise TypeError("DeviceAgentSet.add takes a current member (no-op); create agents with add_agents(k, **columns)")
+
+    def discard(self, agent):
+        """agentset.py:704-707: remove the agent if it is a member."""
+        if agent in self:
+            self.remove_agents([agent._index])
+
+    def remove(self, agent):
+        """agentset.py:709-711: remove the agent, KeyError if it is not a member."""
+        if agent not in self:
+            raise KeyError(agent)
+        self.remove_agents([agent._index])
+
+    def clear(self):
+        """MutableSet.clear: remove every agent (model.py:307-320 `remove_all_agents`)."""
+        if self.n:
+            self.remove_agents(torch.ones(self.n, dtype=torch.bool, device=self._device()))
 
     # -- batch activation ---------------------------------------------------
     def _require_full(self, what: str):
@@ -162,6 +336,7 @@ class DeviceAgentSet:
 
     # -- columns --------------------------------------------------------------
     def _col(self, name: str) -> torch.Tensor:
+        self._check_view()
         try:
             col = self.columns[name]
         except KeyError:
@@ -197,6 +372,7 @@ class DeviceAgentSet:
 
     def select(self, filter_func=None, at_most=float("inf"), inplace: bool = False, agent_type=None):
         """agentset.py:66-135 with a column predicate: `filter_func(columns) -> bool mask [n]`."""
+        self._check_view()
         idx = torch.arange(self.n, device=self._device()) if self.index is None else self.index
         if agent_type is not None and not issubclass(self.agent_type, agent_type):
             idx = idx[:0]
@@ -207,14 +383,15 @@ class DeviceAgentSet:
             k = int(at_most) if at_most >= 1 else int(len(idx) * at_most)
             idx = idx[:k]
         if inplace:
-            self.index = idx
+            self.index, self._view_gen = idx, self._pop.generation
             return self
-        return DeviceAgentSet(self.model, self.agent_type, self.n, self.columns, self.random, idx)
+        return self._view(idx)
 
     def shuffle(self, inplace: bool = False):
         """agentset.py:415-437 with the Philox activation order of a fresh epoch."""
         from . import rng
 
+        self._check_view()
         epoch = self.model._next_epoch()
         if self.index is None and self._device().type == "cuda":
             from . import ops
@@ -225,20 +402,21 @@ class DeviceAgentSet:
             pri = rng.priority64(self.model.philox_seed, epoch, base)
             idx = base[torch.argsort(pri.view(torch.int64) ^ (-2**63), stable=True)]
         if inplace:
-            self.index = idx
+            self.index, self._view_gen = idx, self._pop.generation
             return self
-        return DeviceAgentSet(self.model, self.agent_type, self.n, self.columns, self.random, idx)
+        return self._view(idx)
 
     def sort(self, key, ascending: bool = False, inplace: bool = False):
         if not isinstance(key, str):
             raise NotImplementedError("DeviceAgentSet.sort takes a column name")
+        self._check_view()
         base = torch.arange(self.n, device=self._device()) if self.index is None else self.index
         order = torch.argsort(self.columns[key][base], stable=True, descending=not ascending)
         idx = base[order]
         if inplace:
-            self.index = idx
+            self.index, self._view_gen = idx, self._pop.generation
             return self
-        return DeviceAgentSet(self.model, self.agent_type, self.n, self.columns, self.random, idx)
+        return self._view(idx)
 
     def to_list(self):
         return list(self)

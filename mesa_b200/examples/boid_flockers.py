@@ -90,7 +90,7 @@ class BoidFlockers(DeviceModel):
         else:
             self._ws = ops.CellListWorkspace(n, self.space.size, scenario.vision, dev)
         self.agents = DeviceAgentSet(self, Boid, n, {"position": self.space._agent_positions,
-                                                     "direction": self._direction}, self.random)
+                                                     "direction": self._direction}, self.random, resizable=False)
         self.agent_angles = torch.zeros(n, device=dev)
         self.average_heading = None
         self.update_average_heading()

@@ -47,7 +47,7 @@ class BoltzmannWealth(DeviceModel):
             initial_cells = np.floor(self.rng.random(self.num_agents) * ncells).astype(np.int64)
         cell = torch.as_tensor(np.asarray(initial_cells)).to(torch.int32).to(dev).contiguous()
         wealth = torch.ones(self.num_agents, dtype=torch.int32, device=dev)
-        self.agents = DeviceAgentSet(self, MoneyAgent, self.num_agents, {"cell": cell, "wealth": wealth}, self.random)
+        self.agents = DeviceAgentSet(self, MoneyAgent, self.num_agents, {"cell": cell, "wealth": wealth}, self.random, resizable=False)
         self._ws = ops.BoltzmannWorkspace(cell, scenario.width, scenario.height)
         self.last_iterations = 0
         self.running = True

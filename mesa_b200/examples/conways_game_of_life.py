@@ -72,7 +72,7 @@ class ConwaysGameOfLife(DeviceModel):
         self._next_state = None if packed else torch.empty_like(state)
         if packed:
             self.grid.property_layers.hooks["state"] = self._on_layer_access
-        self.agents = DeviceAgentSet(self, Cell, width * height, _StateColumns(self), self.random)
+        self.agents = DeviceAgentSet(self, Cell, width * height, _StateColumns(self), self.random, resizable=False)
         self.running = True
 
     # -- the two representations of the state layer

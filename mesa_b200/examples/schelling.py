@@ -111,7 +111,7 @@ class Schelling(DeviceModel):
         self._ws = ops.RelocationWorkspace(types, n)
         self.last_movers = self.last_iterations = 0
         cols = _Columns(self, cell=cells.to(torch.int32), type=flat[cells].clone())
-        self.agents = DeviceAgentSet(self, SchellingAgent, n, cols, self.random)
+        self.agents = DeviceAgentSet(self, SchellingAgent, n, cols, self.random, resizable=False)
         self.agents.do("assign_state")  # model.py:83-85
         if self.datacollector is not None:
             self.datacollector.collect(self)

@@ -63,6 +63,11 @@ class DeviceModel:
     def agents_by_type(self) -> dict:
         return self._agents_by_type
 
+    def remove_all_agents(self) -> None:
+        """model.py:307-320: remove every agent of every registered population."""
+        for agentset in list(self._agents_by_type.values()):
+            agentset.clear()
+
     def _next_epoch(self) -> int:
         e = self._epoch
         self._epoch += 1

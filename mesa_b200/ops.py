@@ -620,3 +620,52 @@ def layer_diffuse(layer: torch.Tensor, rate: float, torus: bool = False, out: to
         N.check(N.lib().mb_layer_diffuse(N.ptr(_c(layer)), N.ptr(halo_top), N.ptr(halo_bot), N.ptr(_c(out)), rows, cols,
                                          _dt(layer), float(rate), int(bool(torus)), N.stream_ptr(layer.device)))
     return out
+
+
+# ----------------------------------------------------------------------------- dynamic populations
+class CompactionPlan:
+    """Keep flags + their exclusive prefix sum for one stable compaction shared by all columns of a
+    population (csrc/agents.cu).  `kept` reads the survivor count back (one 4-byte copy)."""
+
+    def __init__(self, keep: torch.Tensor):
+        import ctypes
+
+        _need_cuda(keep)
+        if keep.dim() != 1:
+            raise ValueError("keep flags must be one-dimensional")
+        if keep.dtype == torch.bool:
+            keep = keep.view(torch.uint8)
+        elif keep.dtype != torch.uint8:
+            raise TypeError("keep flags must be bool or uint8")
+        self.keep = _c(keep)
+        self.n = keep.numel()
+        self.offsets = torch.empty(self.n + 1, dtype=torch.int32, device=keep.device)
+        words = ctypes.c_size_t(0)
+        N.check(N.lib().mb_scan_scratch_words(self.n + 1, ctypes.byref(words)))
+        scratch = torch.empty(words.value, dtype=torch.int32, device=keep.device)
+        with torch.cuda.device(keep.device):
+            N.check(N.lib().mb_compact_plan(N.ptr(self.keep), self.n, N.ptr(self.offsets), N.ptr(scratch),
+                                            N.stream_ptr(keep.device)))
+        self._kept = None
+
+    @property
+    def kept(self) -> int:
+        if self._kept is None:
+            self._kept = int(self.offsets[self.n].item()) & 0xFFFFFFFF
+        return self._kept
+
+    def apply(self, column: torch.Tensor) -> torch.Tensor:
+        """The surviving rows of `column` ([n, ...]) in their original order, as a new tensor."""
+        _need_cuda(column)
+        if column.shape[0] != self.n:
+            raise ValueError(f"column has {column.shape[0]} rows, the plan {self.n}")
+        col = _c(column)
+        out = torch.empty((self.kept, *col.shape[1:]), dtype=col.dtype, device=col.device)
+        row_bytes = col.element_size()
+        for d in col.shape[1:]:
+            row_bytes *= int(d)
+        if self.n and row_bytes and self.kept:
+            with torch.cuda.device(col.device):
+                N.check(N.lib().mb_compact_rows(N.ptr(col), N.ptr(out), self.n, row_bytes, N.ptr(self.keep),
+                                                N.ptr(self.offsets), N.stream_ptr(col.device)))
+        return out

@@ -381,6 +381,48 @@ def continuous_queries_fixture(name):
     print(name, len(cases), "cases")
 
 
+# ------------------------------------------------------------------------------ dynamic populations
+def dynamic_agents_fixture(name):
+    """A scripted sequence of agent creations (Agent.create_agents, agent.py:115-160) and removals (Agent.remove,
+    agent.py:73-108) on the live Model; after every operation the (unique_id, x) columns of model.agents in
+    iteration order -- what DeviceAgentSet.add_agents / remove_agents must reproduce."""
+    import mesa
+
+    class Walker(mesa.Agent):
+        def __init__(self, model, x=0):
+            super().__init__(model)
+            self.x = x
+
+    m = mesa.Model(rng=1)
+    script = [("add", np.arange(40) * 3), ("remove_x_mod4", None), ("add", 1000 + np.arange(7)),
+              ("remove_ids", np.array([2, 41, 47, 39])), ("add", np.array([5, 6, 7])), ("remove_ids", np.array([1])),
+              ("remove_gt", np.array([45])), ("add", np.array([77])), ("remove_ids", np.array([], dtype=np.int64))]
+    out = {"n_ops": np.array(len(script))}
+    for k, (kind, arg) in enumerate(script):
+        if kind == "add":
+            Walker.create_agents(m, len(arg), x=list(arg))
+            removed = np.array([], dtype=np.int64)
+        else:
+            if kind == "remove_x_mod4":
+                victims = [a for a in m.agents if a.x % 4 == 0]
+            elif kind == "remove_gt":
+                victims = [a for a in m.agents if a.unique_id > int(arg[0])]
+            else:
+                wanted = set(int(i) for i in arg)
+                victims = [a for a in m.agents if a.unique_id in wanted]
+            removed = np.array([a.unique_id for a in victims], dtype=np.int64)
+            for a in victims:
+                a.remove()
+        out[f"op{k}_kind"] = np.array(0 if kind == "add" else 1)
+        out[f"op{k}_add_x"] = np.asarray(arg if kind == "add" else [], dtype=np.int64)
+        out[f"op{k}_removed_ids"] = removed
+        out[f"op{k}_ids"] = np.array(m.agents.get("unique_id"), dtype=np.int64)
+        out[f"op{k}_x"] = np.array(m.agents.get("x"), dtype=np.int64)
+        assert list(out[f"op{k}_ids"]) == [a.unique_id for a in m.agents_by_type[Walker]]
+    np.savez_compressed(os.path.join(GOLDEN, name), **out)
+    print(name, "final population", out[f"op{len(script) - 1}_ids"].tolist())
+
+
 def main():
     import_reference()
     os.makedirs(GOLDEN, exist_ok=True)
@@ -393,6 +435,9 @@ def main():
         return
     if only == "continuous":
         continuous_queries_fixture("continuous_queries.npz")
+        return
+    if only == "dynamic":
+        dynamic_agents_fixture("dynamic_agents.npz")
         return
     if only == "boltzmann":
         boltzmann_fixture("boltzmann_100_10x10.npz", 100, 10, 10, 25, 42, 3)      # reference "small"
@@ -416,6 +461,7 @@ def main():
     boids_fixture("boids_300.npz", 300, 100, 100, 10.0, 2.0, 3, 42, 5)
     boids_fixture("boids_120_wrap.npz", 120, 40, 30, 6.0, 2.0, 3, 1, 6)
     continuous_queries_fixture("continuous_queries.npz")
+    dynamic_agents_fixture("dynamic_agents.npz")
     boltzmann_fixture("boltzmann_100_10x10.npz", 100, 10, 10, 25, 42, 3)
     boltzmann_fixture("boltzmann_2000_20x30.npz", 2000, 20, 30, 10, 7, 4)
     boltzmann_fixture("boltzmann_10000_100x100.npz", 10000, 100, 100, 10, 1, 5)

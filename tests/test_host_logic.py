@@ -93,3 +93,60 @@ def test_device_model_clock_epochs_and_agents_by_type():
     assert m.agent_types == [Dummy] and m.agents_by_type[Dummy] is m.agents
     m2 = M()
     assert m2.philox_seed == m.philox_seed and m2.random.random() == M().random.random()   # seeded identically
+
+
+class _HostPlan:
+    """Test double for ops.CompactionPlan (the device compaction of csrc/agents.cu): lets the bookkeeping of
+    DeviceAgentSet (unique ids, order, generations, hooks) run on CPU tensors.  Not a product path."""
+
+    def __init__(self, keep):
+        self.keep = keep.to(bool)
+        self.n = keep.numel()
+        self.kept = int(self.keep.sum())
+
+    def apply(self, col):
+        return col[self.keep].clone()
+
+
+def test_dynamic_population_bookkeeping_matches_the_reference_script(monkeypatch):
+    """tests/golden/dynamic_agents.npz: Agent.create_agents / Agent.remove on the live Model (agent.py:73-160)."""
+    from _dynamic_script import replay
+    from mesa_b200 import ops
+
+    monkeypatch.setattr(ops, "CompactionPlan", _HostPlan)
+    for by_mask in (True, False):
+        replay("cpu", by_mask)
+
+
+def test_population_growth_needs_no_kernel_and_removal_has_no_cpu_fallback():
+    import pytest
+    import torch
+
+    from mesa_b200.agentset import DeviceAgent, DeviceAgentSet
+    from mesa_b200.model import DeviceModel
+
+    class Wolf(DeviceAgent):
+        pass
+
+    model = DeviceModel(rng=1)
+    agents = DeviceAgentSet(model, Wolf, 3, {"energy": torch.tensor([4, 5, 6]), "pos": torch.zeros((3, 2))})
+    model.agents = agents
+    seen = []
+    agents.resize_hooks.append(lambda s, plan: seen.append((len(s), plan)))
+    cubs = agents.add_agents(2, energy=7, pos=torch.tensor([1.0, 2.0]))       # one shared value per column
+    assert len(agents) == 5 and cubs.unique_ids().tolist() == [4, 5] and seen == [(5, None)]
+    assert agents.get("energy").tolist() == [4, 5, 6, 7, 7] and agents.get("pos")[3:].tolist() == [[1.0, 2.0]] * 2
+    assert agents.add_agents(1).get("energy").tolist() == [0]                   # unnamed columns start at zero
+    with pytest.raises(AttributeError):
+        agents.add_agents(1, speed=3)
+    with pytest.raises(ValueError):
+        agents.add_agents(-1)
+    assert len(agents) == 6                                                     # failed calls change nothing
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        agents.remove(agents[0])                                                # the compaction is a device kernel
+    assert len(agents) == 6 and agents.unique_ids().tolist() == [1, 2, 3, 4, 5, 6]
+    fixed = DeviceAgentSet(model, Wolf, 3, {"energy": torch.tensor([4, 5, 6])}, resizable=False)
+    with pytest.raises(NotImplementedError):
+        fixed.add_agents(1)
+    with pytest.raises(NotImplementedError):
+        agents.shuffle().remove_agents([0])                                     # views do not resize the population

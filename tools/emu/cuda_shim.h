@@ -28,6 +28,7 @@ struct int4 { int x, y, z, w; };
 struct double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 struct uint4 { unsigned x, y, z, w; };
+struct uint2 { unsigned x, y; };
 static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 

@@ -30,6 +30,37 @@ HARNESS = r'''
 enum { DT_U8 = 0 };
 %(layers)s
 %(continuous)s
+%(agents)s
+
+// stable compaction of csrc/agents.cu: flags -> (host) exclusive scan -> grid-stride row scatter, rows of any width
+template <typename U>
+static int check_compact(int64_t n, int upr, int blocks, int pattern) {
+    std::vector<uint8_t> keep(n);
+    for (int64_t i = 0; i < n; ++i)
+        keep[i] = pattern == 0 ? 0 : pattern == 1 ? 1 : pattern == 2 ? (uint8_t)(rand() %% 3 == 0) * 255 : (uint8_t)((i / 37) %% 2);
+    std::vector<uint32_t> offs(n + 1, 77u);
+    blockDim.x = 256;
+    gridDim.x = (unsigned)((n + 1 + 255) / 256);
+    for (blockIdx.x = 0; blockIdx.x < gridDim.x; ++blockIdx.x)
+        for (threadIdx.x = 0; threadIdx.x < 256; ++threadIdx.x) flags_to_words(keep.data(), offs.data(), n);
+    uint32_t run = 0;
+    for (int64_t i = 0; i <= n; ++i) { const uint32_t f = offs[i]; if (f > 1) return 1; offs[i] = run; run += f; }
+    const int64_t kept = offs[n];
+    std::vector<U> in(n * upr), got(kept * upr), want;
+    unsigned char* raw = (unsigned char*)in.data();
+    for (size_t b = 0; b < in.size() * sizeof(U); ++b) raw[b] = (unsigned char)rand();
+    for (int64_t i = 0; i < n; ++i)
+        if (keep[i]) for (int k = 0; k < upr; ++k) want.push_back(in[i * upr + k]);
+    gridDim.x = (unsigned)blocks;
+    for (blockIdx.x = 0; blockIdx.x < gridDim.x; ++blockIdx.x)
+        for (threadIdx.x = 0; threadIdx.x < 256; ++threadIdx.x)
+            compact_rows<U>(in.data(), got.data(), n * upr, (unsigned)upr, keep.data(), offs.data());
+    if ((int64_t)want.size() != kept * upr || memcmp(want.data(), got.data(), want.size() * sizeof(U)) != 0) {
+        printf("compact mismatch unit=%%d n=%%ld upr=%%d blocks=%%d pattern=%%d\n", (int)sizeof(U), (long)n, upr, blocks, pattern);
+        return 1;
+    }
+    return 0;
+}
 
 template <typename T, typename A>
 static void naive_nsum(const std::vector<T>& in, std::vector<A>& out, int64_t rows, int64_t cols, int R, bool vn,
@@ -295,6 +326,15 @@ int main() {
         bad += check_knn(64, 16.0, 16.0, torus, 64, 7.9, 64);
         bad += check_knn(0, 16.0, 16.0, torus, 2, 4.0, 8);
     }
+    for (int pattern = 0; pattern < 4; ++pattern)
+        for (int64_t n : {0, 1, 2, 255, 256, 257, 5000}) {
+            bad += check_compact<uint8_t>(n, 1, 3, pattern);
+            bad += check_compact<uint8_t>(n, 3, 64, pattern);
+            bad += check_compact<uint16_t>(n, 1, 1, pattern);
+            bad += check_compact<uint32_t>(n, 3, 7, pattern);
+            bad += check_compact<uint2>(n, 1, 2, pattern);
+            bad += check_compact<uint4>(n, 2, 5, pattern);
+        }
     printf(bad ? "FAILED: %%d case(s)\n" : "all cases agree\n", bad);
     return bad != 0;
 }
@@ -309,7 +349,9 @@ def main() -> int:
                  + between(cont, "__device__ __forceinline__ double ref_distance2", "// one component of calculate_difference_vector")
                  + between(cont, "__global__ void __launch_bounds__(128)\nknn_query", "// ---- calculate_distances / calculate_difference_vector of ONE point"))
     layers_part += between(layers, "constexpr int kMaxDims = 4;", "#define MB_DISPATCH_DTYPE")
-    src = HARNESS % {"layers": layers_part, "continuous": cont_part}
+    agents = open(os.path.join(CSRC, "agents.cu")).read()
+    agents_part = between(agents, "__global__ void flags_to_words", "template <typename U>\nint launch_rows")
+    src = HARNESS % {"layers": layers_part, "continuous": cont_part, "agents": agents_part}
     with tempfile.TemporaryDirectory() as tmp:
         cpp = os.path.join(tmp, "emu.cpp")
         exe = os.path.join(tmp, "emu")
