@@ -235,6 +235,13 @@ int mb_knn_query_f32(const float* pos, int64_t n, double x0, double y0, double s
 int mb_point_distances_f32(const float* pos, const int32_t* sel, int64_t m, double size_x, double size_y, int torus,
                            double px, double py, double* out_dist, double* out_delta, mb_stream_t stream);
 
+/* The same two queries in a space of any dimension (ContinuousSpace keeps a (capacity, ndims) array,
+ * continuous_space.py:85-101; distances add the squares axis by axis, :223-234): pos [n, ndim] float32, size_host and
+ * point_host [ndim] doubles in HOST memory, out_dist [m], out_delta [m, ndim] float64 (either may be NULL). */
+int mb_point_distances_nd_f32(const float* pos, int ndim, const int32_t* sel, int64_t m, const double* size_host,
+                              int torus, const double* point_host, double* out_dist, double* out_delta,
+                              mb_stream_t stream);
+
 /* Domain-decomposed continuous space (one rank per slab of y, mesa_b200/sharded.py ShardedBoids): the exchange
  * steps as kernels that append straight into the neighbouring ranks' peer-mapped inboxes (NVLink stores + an
  * atomic slot counter in the receiver's memory) -- no pack / send / recv / unpack.  *_count are peer-mapped

@@ -95,6 +95,8 @@ SIGNATURES: dict[str, tuple] = {
     "mb_knn_query_f32": (c_int, [_P, c_int64, c_double, c_double, c_double, c_double, c_int, _P, _P, c_int64, c_int,
                                  c_double, _P, _P, _P, ctypes.c_size_t, c_int, _S]),
     "mb_point_distances_f32": (c_int, [_P, _P, c_int64, c_double, c_double, c_int, c_double, c_double, _P, _P, _S]),
+    "mb_point_distances_nd_f32": (c_int, [_P, c_int, _P, c_int64, ctypes.POINTER(c_double), c_int,
+                                          ctypes.POINTER(c_double), _P, _P, _S]),
     "mb_boids_send_ghosts": (c_int, [_P, _P, c_int64, c_double, c_double, c_double, _P, _P, _P, _P, _P, _P, c_int64, _P, _S]),
     "mb_boids_route": (c_int, [_P, _P, _P, c_int64, c_double, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                c_int64, _P, _S]),

@@ -10,6 +10,10 @@ fp32-representable positions they are bit-identical to the reference's (csrc/con
 
 Single-point queries launch one small kernel each; the batched `radius_query` /
 `neighbors_in_radius` are the hot-path entry points (one cell-list build + one query kernel).
+
+Spaces of 1 to 8 dimensions are supported like the reference's (capacity, ndims) storage (continuous_space.py:85-101):
+outside two dimensions the point queries evaluate all n distances in one launch (`mb_point_distances_nd_f32`, what the
+reference does in numpy) and the cell-list based batched queries are not available.
 """
 from __future__ import annotations
 
@@ -32,13 +36,13 @@ class DeviceContinuousSpace:
         self.random = random
         self.dimensions = np.asanyarray(dimensions, dtype=float)
         self.ndims = int(self.dimensions.shape[0])
-        if self.ndims != 2:
-            raise NotImplementedError("mesa_b200 continuous spaces are two-dimensional")
+        if self.dimensions.ndim != 2 or self.dimensions.shape[1] != 2 or not 1 <= self.ndims <= 8:
+            raise ValueError("dimensions must be [[lo, hi], ...] with 1 to 8 axes")
         self.size = self.dimensions[:, 1] - self.dimensions[:, 0]
         self.center = np.sum(self.dimensions, axis=1) / 2
         self.torus = bool(torus)
         self.device = torch.device(device)
-        self._agent_positions = torch.empty((int(n_agents), 2), dtype=torch.float32, device=self.device)
+        self._agent_positions = torch.empty((int(n_agents), self.ndims), dtype=torch.float32, device=self.device)
         self._n_agents = 0
         self._ws = None
 
@@ -56,9 +60,9 @@ class DeviceContinuousSpace:
         return self.size[1]
 
     def add_agents(self, positions) -> torch.Tensor:
-        """Append agents at `positions` ([k, 2]); returns their storage indices.  Out-of-bounds points wrap on
+        """Append agents at `positions` ([k, ndims]); returns their storage indices.  Out-of-bounds points wrap on
         a torus and raise ValueError otherwise (continuous_space_agents.py:36-44)."""
-        pos = torch.as_tensor(np.asarray(positions, dtype=np.float64))
+        pos = torch.as_tensor(np.asarray(positions, dtype=np.float64).reshape(-1, self.ndims))
         lo = torch.as_tensor(self.dimensions[:, 0])
         hi = torch.as_tensor(self.dimensions[:, 1])
         bad = ~((pos >= lo) & (pos <= hi)).all(dim=1)
@@ -73,7 +77,7 @@ class DeviceContinuousSpace:
         if need > cap:
             # growth +max(20 %, 20) rows like continuous_space.py:121-129, at least what is needed
             new_cap = max(need, cap + max(int(cap * 0.2), 20))
-            grown = torch.empty((new_cap, 2), dtype=torch.float32, device=self.device)
+            grown = torch.empty((new_cap, self.ndims), dtype=torch.float32, device=self.device)
             grown[: self._n_agents] = self._agent_positions[: self._n_agents]
             self._agent_positions = grown
         self._agent_positions[self._n_agents:need] = pos.to(torch.float32).to(self.device)
@@ -104,6 +108,21 @@ class DeviceContinuousSpace:
         return self.dimensions[:, 0] + np.mod(np.asanyarray(point) - self.dimensions[:, 0], self.size)
 
     # -- queries ------------------------------------------------------------------
+    def _require_2d(self, what: str) -> None:
+        if self.ndims != 2:
+            raise NotImplementedError(f"{what} runs on the two-dimensional cell list; a {self.ndims}-dimensional space "
+                                      "answers point queries (calculate_distances, get_agents_in_radius, ...) only")
+
+    def _point_distances(self, point, sel, distances: bool, deltas: bool):
+        p = np.asarray(point, dtype=np.float64).reshape(-1)
+        if p.shape[0] != self.ndims:
+            raise ValueError(f"point must have {self.ndims} components")
+        if self.ndims == 2:
+            return ops.point_distances(self.agent_positions.contiguous(), p, self.size, self.torus, sel=sel,
+                                       distances=distances, deltas=deltas)
+        return ops.point_distances_nd(self.agent_positions.contiguous(), p, self.size, self.torus, sel=sel,
+                                      distances=distances, deltas=deltas)
+
     def _workspace(self, radius: float) -> ops.CellListWorkspace:
         if self._ws is None or self._ws.radius > radius or self._ws.n < self._n_agents:
             self._ws = ops.CellListWorkspace(max(self._n_agents, 1), self.size, radius, self.device)
@@ -111,6 +130,7 @@ class DeviceContinuousSpace:
 
     def radius_query(self, points, radius: float, exclude: torch.Tensor | None = None):
         """Batched get_agents_in_radius for `points` [q, 2]: CSR (offsets, agent indices, float64 distances)."""
+        self._require_2d("radius_query")
         q = torch.as_tensor(np.asarray(points, dtype=np.float32)) if not isinstance(points, torch.Tensor) else points
         q = q.to(self.device, torch.float32).contiguous()
         return ops.radius_query(self.agent_positions.contiguous(), q, self.size, float(radius), self.torus,
@@ -124,6 +144,10 @@ class DeviceContinuousSpace:
 
     def get_agents_in_radius(self, point, radius: float | int = 1):
         """continuous_space.py:237-247: (agent indices, distances) with dist <= radius, storage order."""
+        if self.ndims != 2:  # all n distances in one launch, then the reference's `distances <= radius` selection
+            d, _ = self._point_distances(point, None, True, False)
+            inside = torch.nonzero(d <= float(radius)).reshape(-1)
+            return inside.cpu().tolist(), d[inside].cpu().numpy()
         _, idx, dist = self.radius_query(np.asarray(point, dtype=np.float32)[None, :], radius)
         return idx.cpu().tolist(), dist.cpu().numpy()
 
@@ -136,19 +160,19 @@ class DeviceContinuousSpace:
     def calculate_distances(self, point, agents=None):
         """continuous_space.py:202-235 for one point against all (or the given) agents; float64."""
         sel, ids = self._select(agents)
-        d, _ = ops.point_distances(self.agent_positions.contiguous(), np.asarray(point, dtype=np.float64), self.size, self.torus, sel=sel)
+        d, _ = self._point_distances(point, sel, True, False)
         return d.cpu().numpy(), ids
 
     def calculate_difference_vector(self, point, agents=None) -> np.ndarray:
         """continuous_space.py:169-200 (torus: the strictly smaller of delta and delta - sign(delta)*size)."""
         sel, _ = self._select(agents)
-        _, v = ops.point_distances(self.agent_positions.contiguous(), np.asarray(point, dtype=np.float64), self.size, self.torus, sel=sel,
-                                   distances=False, deltas=True)
+        _, v = self._point_distances(point, sel, False, True)
         return v.cpu().numpy()
 
     def k_nearest_query(self, points, k: int, exclude: torch.Tensor | None = None):
         """Batched get_k_nearest_agents for `points` [q, 2] in one launch: (indices [q, k], distances [q, k]) on
         the device, rows ascending in (distance, storage index), padded with -1 / inf."""
+        self._require_2d("k_nearest_query")
         q = torch.as_tensor(np.asarray(points, dtype=np.float32)) if not isinstance(points, torch.Tensor) else points
         q = q.to(self.device, torch.float32).contiguous()
         return ops.knn_query(self.agent_positions.contiguous(), q, self.size, int(k), self.torus,
@@ -169,6 +193,10 @@ class DeviceContinuousSpace:
                           f"Returning all {n} agent(s).", UserWarning, stacklevel=2)
             k = n
         p = np.asarray(point, dtype=np.float64)
+        if self.ndims != 2:  # the reference's own method: all n distances, keep the k smallest (ties: earlier index)
+            d, _ = self._point_distances(p, None, True, False)
+            order = torch.argsort(d, stable=True)[:k]
+            return order.cpu().tolist(), d[order].cpu().numpy()
         if self.torus and not self.in_bounds(p):
             p = self.torus_correct(p)
         idx, dist = self.k_nearest_query(p[None, :], k)

@@ -911,6 +911,32 @@ __global__ void point_distances(const float2* __restrict__ pos, const int32_t* _
     }
 }
 
+// The same two queries in a space of any dimension (continuous_space.py:48-101 keeps a (capacity, ndims) array; the
+// reference's distance loop runs "for i in range(1, self.ndims)", :229-231): pos is [n, ndim] float32, squares are
+// added axis by axis in axis order -- also what scipy's Euclidean cdist does on the bounded path (:234).
+constexpr int kMaxSpaceDims = 8;
+struct NdQuery {
+    double p[kMaxSpaceDims], size[kMaxSpaceDims];
+    int ndim, torus;
+};
+
+__global__ void point_distances_nd(const float* __restrict__ pos, const int32_t* __restrict__ sel, int64_t m, NdQuery g,
+                                   double* __restrict__ out_dist, double* __restrict__ out_delta) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const float* a = pos + (sel != nullptr ? (int64_t)sel[i] : i) * g.ndim;
+    double acc = 0.0;
+    for (int d = 0; d < g.ndim; ++d) {
+        const double q = (double)a[d];
+        double del = fabs(g.p[d] - q);
+        if (g.torus) del = fmin(del, g.size[d] - del);
+        const double sq = __dmul_rn(del, del);
+        acc = d == 0 ? sq : __dadd_rn(acc, sq);
+        if (out_delta != nullptr) out_delta[i * g.ndim + d] = ref_delta(q, g.p[d], g.size[d], g.torus);
+    }
+    if (out_dist != nullptr) out_dist[i] = __dsqrt_rn(acc);
+}
+
 struct CellListWs {
     uint32_t *keys0, *vals0, *keys1, *vals1, *cell_start, *cell_end, *spare;
     float4* packed;
@@ -1385,5 +1411,27 @@ MB_API int mb_point_distances_f32(const float* pos, const int32_t* sel, int64_t 
     g.x0 = 0.0; g.y0 = 0.0; g.sx = size_x; g.sy = size_y; g.ncx = 1; g.ncy = 1; g.torus = torus;
     point_distances<<<(unsigned)mb::ceil_div(m, 256), 256, 0, stream>>>((const float2*)pos, sel, m, g, px, py, out_dist, out_delta);
     MB_LAUNCH_CHECK("mb_point_distances_f32");
+    return MB_OK;
+}
+
+// n-dimensional form of mb_point_distances_f32: pos [n, ndim] float32, size_host / point_host [ndim] doubles in HOST
+// memory, out_dist [m], out_delta [m, ndim] float64 (either may be NULL).  1 <= ndim <= 8.
+MB_API int mb_point_distances_nd_f32(const float* pos, int ndim, const int32_t* sel, int64_t m, const double* size_host,
+                                     int torus, const double* point_host, double* out_dist, double* out_delta,
+                                     cudaStream_t stream) {
+    MB_REQUIRE(m >= 0, "mb_point_distances_nd_f32: negative size");
+    MB_REQUIRE(ndim >= 1 && ndim <= kMaxSpaceDims, "mb_point_distances_nd_f32: 1 <= ndim <= %d", kMaxSpaceDims);
+    MB_REQUIRE(size_host != nullptr && point_host != nullptr, "mb_point_distances_nd_f32: null host argument");
+    if (m == 0) return MB_OK;
+    MB_REQUIRE(pos && (out_dist || out_delta), "mb_point_distances_nd_f32: null buffer");
+    NdQuery g;
+    for (int d = 0; d < kMaxSpaceDims; ++d) {
+        g.p[d] = d < ndim ? point_host[d] : 0.0;
+        g.size[d] = d < ndim ? size_host[d] : 1.0;
+    }
+    g.ndim = ndim;
+    g.torus = torus;
+    point_distances_nd<<<(unsigned)mb::ceil_div(m, 256), 256, 0, stream>>>(pos, sel, m, g, out_dist, out_delta);
+    MB_LAUNCH_CHECK("mb_point_distances_nd_f32");
     return MB_OK;
 }

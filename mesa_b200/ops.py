@@ -453,6 +453,26 @@ def point_distances(pos: torch.Tensor, point, size, torus: bool, sel: torch.Tens
     return d, v
 
 
+def point_distances_nd(pos: torch.Tensor, point, size, torus: bool, sel: torch.Tensor | None = None,
+                       distances: bool = True, deltas: bool = False):
+    """point_distances for positions [n, ndim] of any dimension 1..8: (float64 [m] or None, float64 [m, ndim] or None)."""
+    import ctypes
+
+    _need_cuda(pos, sel)
+    ndim = int(pos.shape[1])
+    if len(point) != ndim or len(size) != ndim:
+        raise ValueError(f"point / size must have {ndim} components")
+    m = pos.shape[0] if sel is None else sel.shape[0]
+    d = torch.empty(m, dtype=torch.float64, device=pos.device) if distances else None
+    v = torch.empty((m, ndim), dtype=torch.float64, device=pos.device) if deltas else None
+    arr = ctypes.c_double * ndim
+    with torch.cuda.device(pos.device):
+        N.check(N.lib().mb_point_distances_nd_f32(N.ptr(_c(pos)), ndim, N.ptr(sel), m, arr(*[float(s) for s in size]),
+                                                  int(bool(torus)), arr(*[float(p) for p in point]), N.ptr(d), N.ptr(v),
+                                                  N.stream_ptr(pos.device)))
+    return d, v
+
+
 # ----------------------------------------------------------------------------- Boltzmann wealth
 class BoltzmannWorkspace:
     """Scratch + per-cell list order of mb_boltzmann_step for `n` agents (persistent between steps)."""

@@ -381,6 +381,76 @@ def continuous_queries_fixture(name):
     print(name, len(cases), "cases")
 
 
+# ------------------------------------------------------------------------------ n-d continuous spaces
+def continuous_nd_fixture(name):
+    """The point queries of the UNMODIFIED ContinuousSpace in 1, 3 and 4 dimensions (torus and bounded, shifted boxes)
+    on float32-representable positions: all distances, difference vectors, radius selections, k nearest."""
+    from mesa import Model
+    from mesa.experimental.continuous_space import ContinuousSpace, ContinuousSpaceAgent
+
+    out = {}
+    cases = []
+    rng = np.random.default_rng(77)
+    for c, (n, dims, torus, radius, k) in enumerate([
+        (120, [[0, 20], [0, 30], [0, 10]], True, 5.0, 6),
+        (120, [[0, 20], [0, 30], [0, 10]], False, 5.0, 6),
+        (90, [[-5, 5], [2, 12], [-30, -10], [0, 7]], True, 6.0, 4),
+        (90, [[-5, 5], [2, 12], [-30, -10], [0, 7]], False, 7.5, 90),
+        (40, [[3, 19]], True, 1.5, 3),
+        (40, [[3, 19]], False, 1.5, 40),
+        (5, [[0, 2], [-2, 0], [-2, 2]], False, 1.0, 2),
+    ]):
+        dims = np.asarray(dims, dtype=float)
+        nd = dims.shape[0]
+        model = Model(rng=1)
+        space = ContinuousSpace(dims, torus=torus, random=model.random, n_agents=n)
+        pos = (dims[:, 0] + rng.random((n, nd)) * (dims[:, 1] - dims[:, 0])).astype(np.float32).astype(np.float64)
+        if n > 10:
+            pos[7] = pos[2]         # two agents on the same spot: ties rank by insertion order
+        agents = []
+        for i in range(n):
+            a = ContinuousSpaceAgent(space, model)
+            a.position = pos[i]
+            agents.append(a)
+        index = {id(a): i for i, a in enumerate(agents)}
+        points = (dims[:, 0] + rng.random((8, nd)) * (dims[:, 1] - dims[:, 0])).astype(np.float32).astype(np.float64)
+        points[0] = pos[3 % n]
+        some = np.sort(rng.choice(n, size=min(n, 7), replace=False))
+        dist_all, delta_all, dist_sub, delta_sub, rad_idx, rad_dist, rad_off, knn_idx, knn_dist = [], [], [], [], [], [], [0], [], []
+        for pt in points:
+            d, ag = space.calculate_distances(pt)
+            assert [index[id(a)] for a in ag] == list(range(n))
+            dist_all.append(d)
+            delta_all.append(space.calculate_difference_vector(pt))
+            sub_agents = [agents[i] for i in some]
+            d, _ = space.calculate_distances(pt, sub_agents)
+            dist_sub.append(d)
+            delta_sub.append(space.calculate_difference_vector(pt, sub_agents))
+            ag, d = space.get_agents_in_radius(pt, radius)
+            rad_idx.extend(index[id(a)] for a in ag)
+            rad_dist.extend(d)
+            rad_off.append(len(rad_idx))
+            ag, d = space.get_k_nearest_agents(pt, k)
+            ids = np.array([index[id(a)] for a in ag])
+            o = np.lexsort((ids, d))            # argpartition leaves the k unordered
+            knn_idx.append(ids[o])
+            knn_dist.append(np.asarray(d)[o])
+        out[f"pos_{c}"], out[f"points_{c}"], out[f"subset_{c}"], out[f"dims_{c}"] = pos, points, some, dims
+        out[f"dist_all_{c}"] = np.stack(dist_all)
+        out[f"delta_all_{c}"] = np.stack(delta_all)
+        out[f"dist_sub_{c}"] = np.stack(dist_sub)
+        out[f"delta_sub_{c}"] = np.stack(delta_sub)
+        out[f"rad_idx_{c}"] = np.array(rad_idx, dtype=np.int64)
+        out[f"rad_dist_{c}"] = np.array(rad_dist, dtype=np.float64)
+        out[f"rad_off_{c}"] = np.array(rad_off, dtype=np.int64)
+        out[f"knn_idx_{c}"] = np.stack(knn_idx)
+        out[f"knn_dist_{c}"] = np.stack(knn_dist)
+        cases.append((n, int(torus), radius, k))
+    out["cases"] = np.array(cases, dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLDEN, name), **out)
+    print(name, len(cases), "cases")
+
+
 # ------------------------------------------------------------------------------ dynamic populations
 def dynamic_agents_fixture(name):
     """A scripted sequence of agent creations (Agent.create_agents, agent.py:115-160) and removals (Agent.remove,
@@ -436,6 +506,9 @@ def main():
     if only == "continuous":
         continuous_queries_fixture("continuous_queries.npz")
         return
+    if only == "continuous_nd":
+        continuous_nd_fixture("continuous_queries_nd.npz")
+        return
     if only == "dynamic":
         dynamic_agents_fixture("dynamic_agents.npz")
         return
@@ -461,6 +534,7 @@ def main():
     boids_fixture("boids_300.npz", 300, 100, 100, 10.0, 2.0, 3, 42, 5)
     boids_fixture("boids_120_wrap.npz", 120, 40, 30, 6.0, 2.0, 3, 1, 6)
     continuous_queries_fixture("continuous_queries.npz")
+    continuous_nd_fixture("continuous_queries_nd.npz")
     dynamic_agents_fixture("dynamic_agents.npz")
     boltzmann_fixture("boltzmann_100_10x10.npz", 100, 10, 10, 25, 42, 3)
     boltzmann_fixture("boltzmann_2000_20x30.npz", 2000, 20, 30, 10, 7, 4)

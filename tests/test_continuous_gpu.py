@@ -266,6 +266,52 @@ def test_continuous_queries_match_reference_golden():
         assert np.array_equal(idx[:m].cpu().numpy(), g[f"nn_idx_{c}"]) and np.array_equal(dist[:m].cpu().numpy(), g[f"nn_dist_{c}"])
 
 
+def test_continuous_queries_nd_match_reference_golden():
+    """1-, 3- and 4-dimensional spaces (tests/experimental/test_continuous_space.py:38-56 builds a 3-d one): the point
+    queries of DeviceContinuousSpace against ContinuousSpace itself, float64 results bit-identical."""
+    import random
+
+    from mesa_b200 import ops
+    from mesa_b200.continuous_space import ContinuousSpace
+
+    g = np.load(os.path.join(GOLDEN, "continuous_queries_nd.npz"))
+    for c, (n, torus, radius, k) in enumerate(g["cases"]):
+        n, torus, k = int(n), bool(torus), int(k)
+        pos, points, dims, sub = g[f"pos_{c}"], g[f"points_{c}"], g[f"dims_{c}"], g[f"subset_{c}"]
+        space = ContinuousSpace(dims, torus=torus, random=random.Random(1), n_agents=4)
+        space.add_agents(pos[: n // 2])
+        space.add_agents(pos[n // 2:])                                   # growth keeps the earlier rows
+        assert space.ndims == dims.shape[0] and tuple(space.agent_positions.shape) == (n, dims.shape[0])
+        for q, pt in enumerate(points):
+            d, ids = space.calculate_distances(pt)
+            assert ids == list(range(n)) and np.array_equal(d, g[f"dist_all_{c}"][q])
+            assert np.array_equal(space.calculate_difference_vector(pt), g[f"delta_all_{c}"][q])
+            d, ids = space.calculate_distances(pt, sub.tolist())
+            assert ids == sub.tolist() and np.array_equal(d, g[f"dist_sub_{c}"][q])
+            assert np.array_equal(space.calculate_difference_vector(pt, sub.tolist()), g[f"delta_sub_{c}"][q])
+            lo, hi = g[f"rad_off_{c}"][q], g[f"rad_off_{c}"][q + 1]
+            idx, dist = space.get_agents_in_radius(pt, radius)
+            assert idx == g[f"rad_idx_{c}"][lo:hi].tolist() and np.array_equal(dist, g[f"rad_dist_{c}"][lo:hi])
+            idx, dist = space.get_k_nearest_agents(pt, k)
+            assert idx == g[f"knn_idx_{c}"][q].tolist() and np.array_equal(dist, g[f"knn_dist_{c}"][q])
+        with pytest.raises(NotImplementedError):
+            space.neighbors_in_radius(radius)                            # the batched queries run on the 2-d cell list
+    # the 3-d space of the reference's own test: fields and bounds
+    space = ContinuousSpace([[0, 2], [-2, 0], [-2, 2]], torus=False, random=random.Random(1))
+    assert space.ndims == 3 and space.size.tolist() == [2, 2, 4] and space.center.tolist() == [1, -1, 0]
+    assert space.in_bounds([1, -1, 0]) and not space.in_bounds([1, -1, 3]) and not space.in_bounds([2.5, -1, 0])
+    with pytest.raises(ValueError):
+        space.add_agents([[1.0, -1.0, 3.0]])
+    # in two dimensions the n-d kernel and the 2-d kernel are the same function
+    g2 = np.load(os.path.join(GOLDEN, "continuous_queries.npz"))
+    pos2 = torch.from_numpy(g2["pos_0"].astype(np.float32)).cuda()
+    size2 = g2["dims_0"][:, 1] - g2["dims_0"][:, 0]
+    for pt in g2["points_0"]:
+        a = ops.point_distances(pos2, pt, size2, True, distances=True, deltas=True)
+        b = ops.point_distances_nd(pos2, pt, size2, True, distances=True, deltas=True)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
 @pytest.mark.parametrize("n,side,torus", [(20_000, (300.0, 200.0), True), (20_000, (300.0, 200.0), False),
                                           (5_000, (40.0, 2.0), True), (3, (10.0, 10.0), True)])
 @pytest.mark.parametrize("k", [1, 4, 16])

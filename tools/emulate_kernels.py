@@ -284,8 +284,47 @@ static int check_nd(int ndim, const int64_t* dims, int radius, bool vn, bool inc
     return 0;
 }
 
-int main() {
-    int bad = 0;
+// point_distances_nd of csrc/continuous.cu against the golden vectors of the live ContinuousSpace (1, 3 and 4
+// dimensions), handed over as a flat binary file by main() below
+static int check_point_distances_nd(const char* path) {
+    FILE* fp = fopen(path, "rb");
+    if (!fp) { printf("cannot open %%s\n", path); return 1; }
+    int bad = 0, ncases = 0;
+    int64_t hdr[4];
+    while (fread(hdr, sizeof(int64_t), 4, fp) == 4) {
+        const int ndim = (int)hdr[0], torus = (int)hdr[1];
+        const int64_t n = hdr[2], nq = hdr[3];
+        std::vector<double> size(ndim), points(nq * ndim), dist(nq * n), delta(nq * n * ndim);
+        std::vector<float> pos(n * ndim);
+        if (fread(size.data(), 8, ndim, fp) != (size_t)ndim || fread(pos.data(), 4, n * ndim, fp) != (size_t)(n * ndim) ||
+            fread(points.data(), 8, nq * ndim, fp) != (size_t)(nq * ndim) || fread(dist.data(), 8, nq * n, fp) != (size_t)(nq * n) ||
+            fread(delta.data(), 8, nq * n * ndim, fp) != (size_t)(nq * n * ndim)) { printf("short read\n"); return 1; }
+        for (int64_t q = 0; q < nq; ++q) {
+            NdQuery g;
+            for (int d = 0; d < kMaxSpaceDims; ++d) { g.p[d] = d < ndim ? points[q * ndim + d] : 0.0; g.size[d] = d < ndim ? size[d] : 1.0; }
+            g.ndim = ndim; g.torus = torus;
+            std::vector<double> gd(n, -1.0), gv(n * ndim, -1.0);
+            blockDim.x = 256;
+            gridDim.x = (unsigned)((n + 255) / 256);
+            for (blockIdx.x = 0; blockIdx.x < gridDim.x; ++blockIdx.x)
+                for (threadIdx.x = 0; threadIdx.x < 256; ++threadIdx.x)
+                    point_distances_nd(pos.data(), nullptr, n, g, gd.data(), gv.data());
+            if (memcmp(gd.data(), &dist[q * n], 8 * n) != 0 || memcmp(gv.data(), &delta[q * n * ndim], 8 * n * ndim) != 0) {
+                printf("point_distances_nd mismatch ndim=%%d torus=%%d query %%ld\n", ndim, torus, (long)q);
+                ++bad;
+            }
+        }
+        ++ncases;
+    }
+    fclose(fp);
+    if (ncases < 7) { printf("only %%d n-d cases read\n", ncases); return 1; }
+    return bad;
+}
+
+int main(int argc, char** argv) {
+    if (argc > 1 && check_point_distances_nd(argv[1])) { printf("FAILED: n-d point distances\n"); return 1; }
+
+    int bad = argc > 1 ? 0 : 1;  // the golden file is part of the check
     const int64_t shapes[][2] = {{1, 1}, {1, 40}, {40, 1}, {3, 3}, {1, 4}, {3, 4}, {5, 8}, {16, 128}, {17, 132}, {35, 260}, {5, 516}, {33, 1024}, {50, 2048}};
     for (auto& s : shapes)
         for (int inc = 0; inc < 2; ++inc)
@@ -341,13 +380,31 @@ int main() {
 '''
 
 
+def _dump_nd_golden(path: str) -> None:
+    """tests/golden/continuous_queries_nd.npz (live ContinuousSpace) as a flat binary file for the C++ harness."""
+    import numpy as np
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "continuous_queries_nd.npz"))
+    with open(path, "wb") as f:
+        for c, (n, torus, _radius, _k) in enumerate(g["cases"]):
+            pos, points, dims = g[f"pos_{c}"], g[f"points_{c}"], g[f"dims_{c}"]
+            np.array([pos.shape[1], int(torus), pos.shape[0], points.shape[0]], dtype=np.int64).tofile(f)
+            (dims[:, 1] - dims[:, 0]).astype(np.float64).tofile(f)
+            pos.astype(np.float32).tofile(f)
+            points.astype(np.float64).tofile(f)
+            g[f"dist_all_{c}"].astype(np.float64).tofile(f)
+            g[f"delta_all_{c}"].astype(np.float64).tofile(f)
+
+
 def main() -> int:
     layers = open(os.path.join(CSRC, "layers.cu")).read()
     cont = open(os.path.join(CSRC, "continuous.cu")).read()
     layers_part = between(layers, "template <typename T, int V> struct WalkVec;", "template <typename T, typename A, int V, int MINB1, int MINB2>")
     cont_part = (between(cont, "struct Geometry {", "// ---- cell list:")
                  + between(cont, "__device__ __forceinline__ double ref_distance2", "// one component of calculate_difference_vector")
-                 + between(cont, "__global__ void __launch_bounds__(128)\nknn_query", "// ---- calculate_distances / calculate_difference_vector of ONE point"))
+                 + between(cont, "// one component of calculate_difference_vector", "// visit the distinct cells of the 3x3 block")
+                 + between(cont, "__global__ void __launch_bounds__(128)\nknn_query", "// ---- calculate_distances / calculate_difference_vector of ONE point")
+                 + between(cont, "constexpr int kMaxSpaceDims = 8;", "struct CellListWs {"))
     layers_part += between(layers, "constexpr int kMaxDims = 4;", "#define MB_DISPATCH_DTYPE")
     agents = open(os.path.join(CSRC, "agents.cu")).read()
     agents_part = between(agents, "__global__ void flags_to_words", "template <typename U>\nint launch_rows")
@@ -362,7 +419,9 @@ def main() -> int:
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             return 2
-        r = subprocess.run([exe], capture_output=True, text=True)
+        nd_bin = os.path.join(tmp, "nd_cases.bin")
+        _dump_nd_golden(nd_bin)
+        r = subprocess.run([exe, nd_bin], capture_output=True, text=True)
         sys.stdout.write(r.stdout[-4000:])
         return r.returncode
 
