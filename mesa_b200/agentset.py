@@ -1,7 +1,7 @@
 """DeviceAgentSet: structure-of-arrays agent populations behind the AbstractAgentSet surface.
 
 Mirrors mesa/agentset.py:27-355 (AbstractAgentSet): `do` / `shuffle_do` / `map` / `get` / `set` /
-`agg` / `select` / `shuffle` / `sort` / `__len__` / `__iter__` / `__contains__`, with `do` and
+`agg` / `select` / `groupby` / `shuffle` / `sort` / `__len__` / `__iter__` / `__contains__`, with `do` and
 `shuffle_do` returning `self` (agentset.py:756-787).  Agents are rows of device columns
 (`agents.columns[name]` is a [n] tensor); `agent.attr` on a proxy reads one element (debug speed).
 
@@ -418,6 +418,51 @@ class DeviceAgentSet:
             return self
         return self._view(idx)
 
+    def groupby(self, by, result_type: str = "agentset") -> "DeviceGroupBy":
+        """agentset.py:282-320: group the agents by a column (`by` = its name) or by `by(columns) -> key tensor [n]`.
+        Groups appear in the order of their first member and keep the set's order inside, like the reference's dict of
+        lists.  One stable radix sort of (key bits, position) on the device (csrc/sort.cu) and one read-back of the
+        group boundaries; float keys are grouped by bit pattern."""
+        from . import ops
+
+        self._check_view()
+        if result_type not in ("agentset", "list"):
+            raise ValueError(f"Unknown result_type {result_type!r}, expected 'agentset' or 'list'")
+        if isinstance(by, str) and by not in self.columns:
+            raise AttributeError(f"agents have no attribute {by!r}")
+        keys = self.columns[by] if isinstance(by, str) else by(self.columns)
+        if keys.dim() != 1:
+            raise ValueError("groupby needs one scalar key per agent")
+        rows = torch.arange(self.n, device=keys.device) if self.index is None else self.index
+        keys = keys[rows] if self.index is not None else keys
+        m = int(rows.numel())
+        if m == 0:
+            return DeviceGroupBy({})
+        if keys.dtype.is_floating_point:
+            wide = keys.element_size() > 4
+            canon = keys.to(torch.float64 if wide else torch.float32) + 0.0   # -0.0 and 0.0 are one key, as in a dict
+            bits = canon.contiguous().view(torch.int64 if wide else torch.int32)
+            keys = canon
+        elif keys.dtype in (torch.int32, torch.int64):
+            bits = keys.contiguous()
+        else:                                                              # bool and narrow integers
+            bits = keys.to(torch.int32)
+        order_in = torch.arange(m, dtype=torch.int32, device=keys.device)
+        sorted_bits, order = ops.sort_pairs(bits, order_in)             # stable: set order survives inside a group
+        order = order.to(torch.int64)
+        starts = torch.nonzero(sorted_bits[1:] != sorted_bits[:-1]).reshape(-1) + 1
+        starts = torch.cat([starts.new_zeros(1), starts])
+        first = order[starts]                                            # position of each group's first member
+        by_first = torch.argsort(first)                                  # groups in order of first appearance
+        starts_h = starts[by_first].cpu().tolist()
+        ends_h = torch.cat([starts[1:], starts.new_full((1,), m)])[by_first].cpu().tolist()
+        names = keys[first[by_first]].cpu().tolist()
+        groups = {}
+        for name, lo, hi in zip(names, starts_h, ends_h):
+            members = self._view(rows[order[lo:hi]])
+            groups[name] = members if result_type == "agentset" else list(members)
+        return DeviceGroupBy(groups)
+
     def to_list(self):
         return list(self)
 
@@ -425,6 +470,57 @@ class DeviceAgentSet:
         for c in self.columns.values():
             return c.device
         return torch.device("cuda")
+
+
+_MISSING = object()
+
+
+class DeviceGroupBy:
+    """agentset.py:837-970 (GroupBy): `groups` maps each key to the DeviceAgentSet (or list) of its agents."""
+
+    def __init__(self, groups: dict):
+        self.groups = dict(groups)
+
+    def get_group(self, name, default=_MISSING):
+        try:
+            return self.groups[name]
+        except KeyError as err:
+            if default is not _MISSING:
+                return default
+            raise KeyError(f"No group found with name: {name}") from err
+
+    def map(self, method, *args, **kwargs) -> dict:
+        if isinstance(method, str):
+            return {k: getattr(v, method)(*args, **kwargs) for k, v in self.groups.items()}
+        return {k: method(v, *args, **kwargs) for k, v in self.groups.items()}
+
+    def do(self, method, *args, **kwargs) -> "DeviceGroupBy":
+        self.map(method, *args, **kwargs)
+        return self
+
+    def count(self) -> dict:
+        return {k: len(v) for k, v in self.groups.items()}
+
+    def agg(self, attr_name: str, func) -> dict:
+        """Aggregate a column per group; `func` gets the group's device column (or names a reduction), like
+        DeviceAgentSet.agg."""
+        out = {}
+        for name, group in self.groups.items():
+            if isinstance(group, DeviceAgentSet):
+                out[name] = group.agg(attr_name, func)
+            else:
+                out[name] = func([getattr(a, attr_name) for a in group])
+        return out
+
+    def __iter__(self):
+        return iter(self.groups.items())
+
+    def __len__(self):
+        return len(self.groups)
+
+    def __repr__(self) -> str:
+        sizes = {name: len(group) for name, group in self.groups.items()}
+        return f"{type(self).__name__}({len(self)} groups: {sizes})"
 
 
 try:  # make isinstance(x, mesa.agentset.AbstractAgentSet) hold when mesa is importable

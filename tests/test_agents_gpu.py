@@ -159,3 +159,60 @@ def test_datacollector_reports_surviving_unique_ids():
     dc.collect(model)
     df = dc.get_agent_vars_dataframe().reset_index()
     assert df[df.Step == 1.0].AgentID.tolist() == [1, 3, 4] and df[df.Step == 1.0].energy.tolist() == [1, 3, 4]
+
+
+def _reference_groups(keys):
+    """agentset.py:305-313: dict of lists in first-appearance order."""
+    groups = {}
+    for i, k in enumerate(keys):
+        groups.setdefault(k, []).append(i)
+    return groups
+
+
+@pytest.mark.parametrize("dtype", [torch.int32, torch.int64, torch.uint8, torch.bool, torch.float32, torch.float64])
+def test_groupby_matches_the_reference_grouping(dtype):
+    """agentset.py:282-320 + GroupBy (:837-970); epstein_civil_violence/model.py:122 uses groupby("state").count()."""
+    from mesa_b200.agentset import DeviceAgent, DeviceAgentSet
+    from mesa_b200.model import DeviceModel
+
+    class Citizen(DeviceAgent):
+        pass
+
+    rng = np.random.default_rng(3)
+    n = 5000
+    raw = rng.integers(0, 2 if dtype == torch.bool else 7, size=n)
+    if dtype in (torch.float32, torch.float64):
+        host = (raw * 0.5 - 1.0)
+        host[host == 0.0] = np.where(rng.random((host == 0.0).sum()) < 0.5, 0.0, -0.0)     # both zeros: one key
+        state = torch.from_numpy(host).to(dtype)
+    else:
+        state = torch.from_numpy(raw).to(dtype)
+    wealth = torch.from_numpy(rng.integers(0, 100, size=n)).to(torch.int32)
+    model = DeviceModel(rng=1)
+    agents = DeviceAgentSet(model, Citizen, n, {"state": state.cuda(), "wealth": wealth.cuda()})
+    want = _reference_groups(state.tolist())
+    got = agents.groupby("state")
+    assert list(got.groups) == list(want) and got.count() == {k: len(v) for k, v in want.items()}
+    assert len(got) == len(want) and repr(got).startswith("DeviceGroupBy(")
+    for k, members in got:
+        assert members.unique_ids().tolist() == [i + 1 for i in want[k]]                     # set order inside a group
+    sums = got.agg("wealth", "sum")
+    assert sums == {k: int(wealth[v].sum()) for k, v in want.items()}
+    assert got.map("__len__") == got.count() and got.do(lambda g: None) is got
+    first = next(iter(want))
+    assert got.get_group(first) is got.groups[first] and got.get_group("missing", default=None) is None
+    with pytest.raises(KeyError):
+        got.get_group("missing")
+    # a callable key over the columns, on a selected view, as lists
+    rich = agents.select(lambda c: c["wealth"] >= 50)
+    by_parity = rich.groupby(lambda c: c["wealth"] % 2, result_type="list")
+    rows = [i for i in range(n) if wealth[i] >= 50]
+    want2 = _reference_groups([int(wealth[i]) % 2 for i in rows])
+    assert list(by_parity.groups) == list(want2)
+    for k, members in by_parity:
+        assert [a.unique_id - 1 for a in members] == [rows[j] for j in want2[k]]
+    with pytest.raises(AttributeError):
+        agents.groupby("mood")
+    with pytest.raises(ValueError):
+        agents.groupby("state", result_type="tuple")
+    assert len(agents.select(lambda c: c["wealth"] > 1000).groupby("state")) == 0

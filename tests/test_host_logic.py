@@ -150,3 +150,33 @@ def test_population_growth_needs_no_kernel_and_removal_has_no_cpu_fallback():
         fixed.add_agents(1)
     with pytest.raises(NotImplementedError):
         agents.shuffle().remove_agents([0])                                     # views do not resize the population
+
+
+def test_groupby_bookkeeping_on_the_host(monkeypatch):
+    """Group order = first appearance, set order inside a group (agentset.py:305-313); the stable device sort is replaced
+    by a host double here, the device test is tests/test_agents_gpu.py::test_groupby_matches_the_reference_grouping."""
+    import torch
+
+    from mesa_b200 import ops
+    from mesa_b200.agentset import DeviceAgent, DeviceAgentSet
+    from mesa_b200.model import DeviceModel
+
+    def host_sort(keys, vals, begin_bit=0, end_bit=None):
+        order = torch.argsort(keys, stable=True)
+        return keys[order], vals[order]
+
+    monkeypatch.setattr(ops, "sort_pairs", host_sort)
+
+    class Citizen(DeviceAgent):
+        pass
+
+    model = DeviceModel(rng=1)
+    state = torch.tensor([2, 0, 2, 1, 0, 2, 1], dtype=torch.int32)
+    agents = DeviceAgentSet(model, Citizen, 7, {"state": state, "x": torch.arange(7.0)})
+    g = agents.groupby("state")
+    assert list(g.groups) == [2, 0, 1] and g.count() == {2: 3, 0: 2, 1: 2}
+    assert g.get_group(2).unique_ids().tolist() == [1, 3, 6] and g.get_group(1).get("x").tolist() == [3.0, 6.0]
+    assert g.agg("x", torch.sum) == {2: torch.tensor(7.0), 0: torch.tensor(5.0), 1: torch.tensor(9.0)}
+    shuffled = agents.sort("x", ascending=False)                     # a reordered view groups in ITS order
+    g2 = shuffled.groupby("state", result_type="list")
+    assert list(g2.groups) == [1, 2, 0] and [a.unique_id for a in g2.get_group(2)] == [6, 3, 1]
