@@ -193,6 +193,14 @@ class DeviceAgentSet:
             return self.index.to(torch.int64) + 1
         return ids if self.index is None else ids[self.index]
 
+    def unique_ids_host(self):
+        """The same as a numpy array; a population that never shrank answers without touching the device."""
+        import numpy as np
+
+        if self._pop.ids is None and self.index is None:
+            return np.arange(1, self.n + 1, dtype=np.int64)
+        return self.unique_ids().cpu().numpy()
+
     # -- creation and removal (agentset.py:700-711, agent.py:73-160) --------------------
     def _require_resizable(self, what: str) -> None:
         self._require_full(what)

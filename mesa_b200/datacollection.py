@@ -113,7 +113,7 @@ class DeviceDataCollector:
                 self.model_vars[var].append(_to_host(value))
         if self.agent_reporters:
             agents = model.agents
-            ids = agents.unique_ids().cpu().numpy()  # ids survive removals (DeviceAgentSet.remove_agents)
+            ids = agents.unique_ids_host()  # ids survive removals (DeviceAgentSet.remove_agents)
             self._agent_records[model.time] = (ids, [self._column(agents, n, r) for n, r in self.agent_reporters.items()])
         if self.agenttype_reporters:
             self._agenttype_records[model.time] = {}
@@ -122,7 +122,7 @@ class DeviceDataCollector:
                 if not issubclass(agents.agent_type, agent_type):
                     raise ValueError(f"Agent type {agent_type} is not recognized as an Agent type in the model or Agent "
                                      f"subclass. Use an Agent (sub)class, like {[agents.agent_type]}.")
-                ids = agents.unique_ids().cpu().numpy()
+                ids = agents.unique_ids_host()
                 self._agenttype_records[model.time][agent_type] = (ids, [self._column(agents, n, r) for n, r in reps.items()])
 
     # ------------------------------------------------------------------ tables
