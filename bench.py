@@ -362,7 +362,7 @@ def run_ours(args):
                                                     "ncu (profiles/r1_gol_bits_T8_ncu_full.csv): ALU pipe 83 % busy while active "
                                                     "including the re-computed halo rows / lanes"}
         if world == 1 and not args.no_others:
-            line["workloads"] = other_workloads(dev) + layer_workloads(dev)
+            line["workloads"] = other_workloads(dev) + layer_workloads(dev) + agent_workloads(dev)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             rate, _ = cpu_gol_rate(256, GRID, 1, 1, threads)
@@ -567,6 +567,45 @@ def layer_workloads(dev, grid=GRID, reps=20):
     run("diffuse_f64_torus", lambda: ops.layer_diffuse(d64, 0.3, True, out=f64), 16 * n)
     run("neighborhood_sum_f64_moore_r1_torus", lambda: ops.neighborhood_sum(d64, 1, True, False, True, out=f64), 16 * n)
     return out
+
+
+def agent_workloads(dev, n=10_000_000, reps=20):
+    """Dynamic populations (csrc/agents.cu): removing 10 % of 10^7 agents -- the compaction plan (flags + exclusive scan)
+    and the stable row scatter of a 16-byte column (position + direction of a boid).  Algorithmic bytes of the scatter:
+    16 B read per agent + 16 B written per survivor + 5 B of flag / offset per agent.  A failure here is reported in the
+    entry instead of ending the bench line."""
+    import torch
+
+    from mesa_b200 import ops
+
+    peak, _ = _peaks()
+    try:
+        g = torch.Generator(device=dev).manual_seed(1)
+        keep = torch.rand(n, device=dev, generator=g) < 0.9
+        col = torch.zeros((n, 4), dtype=torch.float32, device=dev)
+
+        def run(fn):
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+
+        ms_plan = run(lambda: ops.CompactionPlan(keep))
+        plan = ops.CompactionPlan(keep)
+        alg = 16 * n + 16 * plan.kept + 5 * n
+        ms_rows = run(lambda: plan.apply(col))
+        return [{"workload": f"remove_agents_plan_{n} (keep flags + exclusive scan)", "ms_per_step": ms_plan,
+                 "agents_per_s": n / ms_plan * 1e3, "note": "three small launches: latency-bound"},
+                {"workload": f"remove_agents_compact_rows_f32x4_{n} (90 % kept)", "ms_per_step": ms_rows,
+                 "agents_per_s": n / ms_rows * 1e3, "algorithmic_bytes": alg, "hbm_gbs": alg / ms_rows / 1e6,
+                 "hbm_frac_of_measured_peak": alg / ms_rows / 1e6 / peak}]
+    except Exception as exc:  # pragma: no cover - reported, not fatal
+        return [{"workload": f"remove_agents_{n}", "error": repr(exc)}]
 
 
 def _ncu_traffic(kernel="gol_step_u8_vec"):

@@ -73,7 +73,12 @@ class ConwaysGameOfLife(DeviceModel):
         if packed:
             self.grid.property_layers.hooks["state"] = self._on_layer_access
         self.agents = DeviceAgentSet(self, Cell, width * height, _StateColumns(self), self.random, resizable=False)
+        self.grid.cell_agents = self._cell_agents
         self.running = True
+
+    def _cell_agents(self, cells) -> list:
+        """One FixedAgent per cell, created row-major (model.py:13-26): the agent's row is the flat cell index."""
+        return [self.agents[c.flat] for c in cells]
 
     # -- the two representations of the state layer
     def _layer(self, writable: bool = True) -> torch.Tensor:

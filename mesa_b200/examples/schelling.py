@@ -112,9 +112,17 @@ class Schelling(DeviceModel):
         self.last_movers = self.last_iterations = 0
         cols = _Columns(self, cell=cells.to(torch.int32), type=flat[cells].clone())
         self.agents = DeviceAgentSet(self, SchellingAgent, n, cols, self.random, resizable=False)
+        self.grid.cell_agents = self._cell_agents
         self.agents.do("assign_state")  # model.py:83-85
         if self.datacollector is not None:
             self.datacollector.collect(self)
+
+    def _cell_agents(self, cells) -> list:
+        """cell.py:192-195 on this capacity-1 grid: a cell's agent is the row its `agent_id` entry names."""
+        flat = torch.as_tensor([c.flat for c in cells], dtype=torch.int64, device=self.grid.device)
+        occupied = (self.grid.type.reshape(-1)[flat] >= 0).cpu().tolist()
+        rows = self.grid.agent_id.reshape(-1)[flat].cpu().tolist()
+        return [self.agents[r] for r, occ in zip(rows, occupied) if occ]
 
     # `grid.empty` follows the occupancy like the reference's implicit layer (grid.py:128, cell.py:143-170)
     def _sync_empty(self):

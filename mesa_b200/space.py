@@ -132,8 +132,79 @@ class CellProxy:
         return self.get_neighborhood()
 
     def get_neighborhood(self, radius: int = 1, include_center: bool = False) -> list["CellProxy"]:
-        """Neighbour cells in the reference's order for radius 1 (connection order)."""
-        return [CellProxy(self.grid, c) for c in self.grid.neighborhood_coordinates(self.coordinate, radius, include_center)]
+        """Neighbour cells in the reference's order (connection order for radius 1, BFS beyond) as a
+        cell collection (cell.py:202-223 returns a CellCollection)."""
+        cells = [CellProxy(self.grid, c) for c in self.grid.neighborhood_coordinates(self.coordinate, radius, include_center)]
+        return CellCollectionProxy(cells, getattr(self.grid, "random", None))
+
+    @property
+    def agents(self) -> list:
+        """cell.py:192-195: the agents in this cell, through the model's `grid.cell_agents` hook."""
+        return CellCollectionProxy([self], None).agents
+
+
+_RAISES = object()
+
+
+class CellCollectionProxy(list):
+    """An ordered collection of cell proxies with the reference CellCollection's methods
+    (cell_collection.py:33-175): `cells`, `agents`, `select_random_cell`, `select_random_agent`, `select`.  It IS
+    the list of its cells, so code that indexes or compares the result of `get_neighborhood` keeps working.
+    The random draws are the reference's (`random.choice` on the ordered cells / agents with the grid's generator),
+    so a seeded host generator gives the reference's picks."""
+
+    def __init__(self, cells=(), random: Random | None = None):
+        super().__init__(cells)
+        self.random = random
+
+    @property
+    def cells(self) -> list:
+        return list(self)
+
+    @property
+    def agents(self) -> list:
+        """Agents of the cells, cell by cell in collection order (cell_collection.py:97-99).  Which rows of the
+        model's population sit in a cell is model state (an `agent_id` layer, a per-agent `cell` column ...), so the
+        model provides `grid.cell_agents(list of cells) -> list of agents`."""
+        if not self:
+            return []
+        hook = getattr(self[0].grid, "cell_agents", None)
+        if hook is None:
+            raise NotImplementedError("this grid's model did not register grid.cell_agents (cells -> agents)")
+        return list(hook(list(self)))
+
+    def select_random_cell(self, default=_RAISES):
+        if not self:
+            if default is _RAISES:
+                raise LookupError("Cannot select random cell from empty collection")
+            return default
+        return self.random.choice(self.cells)
+
+    def select_random_agent(self, default=_RAISES):
+        agents = self.agents
+        if not agents:
+            if default is _RAISES:
+                raise LookupError("Cannot select random agent from empty collection")
+            return default
+        return self.random.choice(agents)
+
+    def select(self, filter_func=None, at_most=float("inf")) -> "CellCollectionProxy":
+        """cell_collection.py:138-175: the first `at_most` cells passing `filter_func` (a float <= 1.0 is a fraction of
+        the collection, rounded down)."""
+        if filter_func is None and at_most == float("inf"):
+            return self
+        if at_most <= 1.0 and isinstance(at_most, float):
+            at_most = int(len(self) * at_most)
+        out = []
+        for cell in self:
+            if len(out) >= at_most:
+                break
+            if not filter_func or filter_func(cell):
+                out.append(cell)
+        return CellCollectionProxy(out, self.random)
+
+    def __repr__(self):
+        return f"CellCollection({list(self)})"
 
 
 class DeviceGrid:

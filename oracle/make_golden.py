@@ -381,6 +381,36 @@ def continuous_queries_fixture(name):
     print(name, len(cases), "cases")
 
 
+# ------------------------------------------------------------------------------ cell collections
+def cell_collection_fixture(name):
+    """CellCollection of a cell's neighbourhood on the live grids (cell_collection.py:33-175): the ordered cells, the
+    draws of select_random_cell under a seeded random.Random, and select(filter / at_most)."""
+    import random
+
+    from mesa.discrete_space import OrthogonalMooreGrid, OrthogonalVonNeumannGrid
+
+    out, cases = {}, []
+    k = 0
+    for moore in (True, False):
+        for torus in (False, True):
+            for radius in (1, 2):
+                klass = OrthogonalMooreGrid if moore else OrthogonalVonNeumannGrid
+                grid = klass((7, 5), torus=torus, random=random.Random(123))
+                for probe in [(0, 0), (3, 2), (6, 4)]:
+                    nb = grid[probe].get_neighborhood(radius=radius)
+                    out[f"cells_{k}"] = np.array([c.coordinate for c in nb.cells], dtype=np.int64)
+                    out[f"draws_{k}"] = np.array([nb.select_random_cell().coordinate for _ in range(6)], dtype=np.int64)
+                    even = nb.select(lambda c: (c.coordinate[0] + c.coordinate[1]) % 2 == 0)
+                    out[f"even_{k}"] = np.array([c.coordinate for c in even.cells], dtype=np.int64).reshape(-1, 2)
+                    out[f"first3_{k}"] = np.array([c.coordinate for c in nb.select(at_most=3).cells], dtype=np.int64)
+                    out[f"half_{k}"] = np.array([c.coordinate for c in nb.select(at_most=0.5).cells], dtype=np.int64).reshape(-1, 2)
+                    cases.append((int(moore), int(torus), radius, probe[0], probe[1]))
+                    k += 1
+    out["cases"] = np.array(cases, dtype=np.int64)
+    np.savez_compressed(os.path.join(GOLDEN, name), **out)
+    print(name, k, "cases")
+
+
 # ------------------------------------------------------------------------------ n-d continuous spaces
 def continuous_nd_fixture(name):
     """The point queries of the UNMODIFIED ContinuousSpace in 1, 3 and 4 dimensions (torus and bounded, shifted boxes)
@@ -506,6 +536,9 @@ def main():
     if only == "continuous":
         continuous_queries_fixture("continuous_queries.npz")
         return
+    if only == "cell_collection":
+        cell_collection_fixture("cell_collection.npz")
+        return
     if only == "continuous_nd":
         continuous_nd_fixture("continuous_queries_nd.npz")
         return
@@ -535,6 +568,7 @@ def main():
     boids_fixture("boids_120_wrap.npz", 120, 40, 30, 6.0, 2.0, 3, 1, 6)
     continuous_queries_fixture("continuous_queries.npz")
     continuous_nd_fixture("continuous_queries_nd.npz")
+    cell_collection_fixture("cell_collection.npz")
     dynamic_agents_fixture("dynamic_agents.npz")
     boltzmann_fixture("boltzmann_100_10x10.npz", 100, 10, 10, 25, 42, 3)
     boltzmann_fixture("boltzmann_2000_20x30.npz", 2000, 20, 30, 10, 7, 4)

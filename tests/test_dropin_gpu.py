@@ -343,3 +343,25 @@ def test_agents_by_type_typed_activation():
     m.agents_by_type[SchellingAgent].shuffle_do("step")
     m.agents.do("assign_state")
     assert m.happy != before or m.last_movers == 0
+
+
+def test_cell_agents_through_the_model_hook():
+    """cell.py:192-195 `Cell.agents`, cell_collection.py:97-136 `CellCollection.agents / select_random_agent`: which agent
+    sits in a cell is model state on the device, served through `grid.cell_agents`."""
+    from mesa_b200.examples import ConwaysGameOfLife, Schelling, SchellingScenario
+
+    m = Schelling(SchellingScenario(width=12, height=9, density=0.7, homophily=0.4, radius=1, rng=3))
+    types = m.grid.type.cpu().numpy()
+    cells = m.agents.get("cell").cpu().numpy()
+    for a in list(m.agents)[:20]:
+        assert [b.unique_id for b in a.cell.agents] == [a.unique_id]     # capacity 1: the cell's agent is the agent
+    empty = [c for c in m.grid.all_cells if types[c.coordinate] < 0]
+    assert empty and empty[0].agents == []
+    nb = m.grid[(5, 4)].get_neighborhood()
+    want = [int(np.nonzero(cells == c.flat)[0][0]) + 1 for c in nb if types[c.coordinate] >= 0]
+    assert [a.unique_id for a in nb.agents] == want
+    if want:
+        assert nb.select_random_agent().unique_id in want
+    g = ConwaysGameOfLife(width=8, height=32, rng=1)
+    assert [a.unique_id for a in g.grid[(2, 3)].agents] == [2 * 32 + 3 + 1]
+    assert len(g.grid[(0, 0)].get_neighborhood().agents) == 8

@@ -180,3 +180,38 @@ def test_groupby_bookkeeping_on_the_host(monkeypatch):
     shuffled = agents.sort("x", ascending=False)                     # a reordered view groups in ITS order
     g2 = shuffled.groupby("state", result_type="list")
     assert list(g2.groups) == [1, 2, 0] and [a.unique_id for a in g2.get_group(2)] == [6, 3, 1]
+
+
+def test_cell_collection_matches_the_reference(monkeypatch):
+    """tests/golden/cell_collection.npz: CellCollection of a neighbourhood on the live grids -- ordered cells, the draws
+    of select_random_cell under random.Random(123) (cell_collection.py:101-119), select(filter / at_most) (:138-175)."""
+    import random
+
+    import pytest
+
+    from mesa_b200.space import CellCollectionProxy, DeviceMooreGrid, DeviceVonNeumannGrid
+
+    g = np.load(os.path.join(GOLDEN, "cell_collection.npz"))
+    grids = {}
+    for k, (moore, torus, radius, pi, pj) in enumerate(g["cases"]):
+        key = (int(moore), int(torus), int(radius))
+        if key not in grids:                       # the reference drew all probes of a grid from ONE generator
+            grid = _bare_grid(DeviceMooreGrid if moore else DeviceVonNeumannGrid, (7, 5), torus)
+            grid.__dict__["random"] = random.Random(123)
+            grids[key] = grid
+        nb = grids[key][(int(pi), int(pj))].get_neighborhood(radius=int(radius))
+        assert isinstance(nb, CellCollectionProxy) and [c.coordinate for c in nb.cells] == [tuple(r) for r in g[f"cells_{k}"]]
+        assert [nb.select_random_cell().coordinate for _ in range(6)] == [tuple(r) for r in g[f"draws_{k}"]]
+        even = nb.select(lambda c: (c.coordinate[0] + c.coordinate[1]) % 2 == 0)
+        assert [c.coordinate for c in even] == [tuple(r) for r in g[f"even_{k}"]]
+        assert [c.coordinate for c in nb.select(at_most=3)] == [tuple(r) for r in g[f"first3_{k}"]]
+        assert [c.coordinate for c in nb.select(at_most=0.5)] == [tuple(r) for r in g[f"half_{k}"]]
+        assert nb.select() is nb and nb == nb.cells                       # it is the list of its cells
+    empty = CellCollectionProxy([], random.Random(1))
+    assert empty.select_random_cell(default=None) is None and empty.agents == []
+    with pytest.raises(LookupError):
+        empty.select_random_cell()
+    with pytest.raises(LookupError):
+        empty.select_random_agent()
+    with pytest.raises(NotImplementedError):
+        nb.agents                                                        # no model registered grid.cell_agents
