@@ -78,14 +78,38 @@ class DeviceModel:
 
     def _wrapped_step(self) -> None:
         """model.py:152-154: advance time by one unit and run the user's step."""
+        self._step_at(self.time + 1.0)
+
+    def _step_at(self, time: float) -> None:
         self.steps += 1
-        self.time += 1.0
+        self.time = time
         self._user_step()
 
-    def run_for(self, duration: int) -> None:
-        """model.py:395-402: advance `duration` unit-interval steps."""
-        for _ in range(int(duration)):
-            self.step()
+    def _advance_time(self, until: float) -> None:
+        """model.py:156-190 for the default schedule (one step per unit of time, at the integer times): run the steps
+        that fall in (time, until], then move the clock to `until`."""
+        import math
+
+        while True:
+            nxt = float(math.floor(self.time) + 1)
+            if nxt > until:
+                break
+            self._step_at(nxt)
+        if until > self.time:
+            self.time = float(until)
+
+    def run_for(self, duration: float | int) -> None:
+        """model.py:395-402: advance the clock by `duration`, running the steps that fall due."""
+        self._advance_time(self.time + duration)
+
+    def run_until(self, end_time: float | int) -> None:
+        """model.py:404-422: run up to the absolute time `end_time`; a time in the past only warns."""
+        if self.time > end_time:
+            import warnings
+
+            warnings.warn(f"end_time {end_time} is not larger than current time {self.time}", RuntimeWarning, stacklevel=2)
+            return
+        self._advance_time(end_time)
 
     def run_model(self) -> None:
         while self.running:

@@ -215,3 +215,38 @@ def test_cell_collection_matches_the_reference(monkeypatch):
         empty.select_random_agent()
     with pytest.raises(NotImplementedError):
         nb.agents                                                        # no model registered grid.cell_agents
+
+
+def test_model_clock_run_for_run_until_like_the_reference():
+    """Probed on the live Model (mesa/model.py:156-190, 395-422): steps fall due at the integer times; run_for(2.5)
+    runs 2 steps and leaves time 2.5; run_until in the past warns and does nothing; step() itself adds one unit."""
+    import pytest
+
+    from mesa_b200.model import DeviceModel
+
+    class M(DeviceModel):
+        def __init__(self):
+            super().__init__(rng=1)
+            self.n = 0
+            self.seen = []
+
+        def step(self):
+            self.n += 1
+            self.seen.append(self.time)
+
+    m = M()
+    m.run_for(2.5)
+    assert (m.n, m.time) == (2, 2.5)
+    m.run_for(0.5)
+    assert (m.n, m.time) == (3, 3.0)
+    m.run_until(5)
+    assert (m.n, m.time) == (5, 5.0)
+    with pytest.warns(RuntimeWarning):
+        m.run_until(3)
+    assert (m.n, m.time) == (5, 5.0)
+    m.step()
+    assert (m.n, m.time) == (6, 6.0)
+    m.run_until(7.2)
+    assert (m.n, m.time) == (7, 7.2)
+    m.run_for(1)
+    assert (m.n, m.time) == (8, 8.2) and m.seen == [1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0, 8.0] and m.steps == 8
