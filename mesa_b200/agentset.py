@@ -360,6 +360,14 @@ class DeviceAgentSet:
         return [self.get(a, handle_missing, default_value) for a in attr_names]
 
     def set(self, attr_name: str, value) -> "DeviceAgentSet":
+        """agentset.py:215-227: set an attribute of every agent of this set; a name the agents do not have yet becomes a
+        new column (the reference's setattr creates the attribute), zero for agents outside a view."""
+        if attr_name not in self.columns:
+            if not isinstance(self.columns, dict):
+                raise AttributeError(f"agents have no attribute {attr_name!r}")
+            v = torch.as_tensor(value)
+            shape = (self.n, *v.shape[1:]) if v.dim() and v.shape[0] == len(self) else (self.n, *v.shape)
+            self.columns[attr_name] = torch.zeros(shape, dtype=v.dtype, device=self._device())
         col = self.columns[attr_name]
         if self.index is None:
             col[:] = torch.as_tensor(value, device=col.device, dtype=col.dtype)
@@ -388,7 +396,8 @@ class DeviceAgentSet:
             mask = filter_func(self.columns)
             idx = idx[mask[idx]]
         if at_most != float("inf"):
-            k = int(at_most) if at_most >= 1 else int(len(idx) * at_most)
+            # agentset.py:100-102: a float <= 1.0 is a fraction of the ORIGINAL set (rounded down), else a count
+            k = int(len(self) * at_most) if (at_most <= 1.0 and isinstance(at_most, float)) else int(at_most)
             idx = idx[:k]
         if inplace:
             self.index, self._view_gen = idx, self._pop.generation

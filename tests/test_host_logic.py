@@ -250,3 +250,45 @@ def test_model_clock_run_for_run_until_like_the_reference():
     assert (m.n, m.time) == (7, 7.2)
     m.run_for(1)
     assert (m.n, m.time) == (8, 8.2) and m.seen == [1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0, 8.0] and m.steps == 8
+
+
+def test_select_at_most_semantics_of_the_reference():
+    """agentset.py:95-117 (tests/test_agentset.py::test_agentset select cases): an int caps the count, a float <= 1.0
+    is a fraction of the ORIGINAL set rounded down -- also after filtering -- and 1.0 keeps everything."""
+    import torch
+
+    from mesa_b200.agentset import DeviceAgent, DeviceAgentSet
+    from mesa_b200.model import DeviceModel
+
+    class A(DeviceAgent):
+        pass
+
+    agents = DeviceAgentSet(DeviceModel(rng=1), A, 10, {"x": torch.arange(10)})
+    assert len(agents.select(at_most=3)) == 3 and len(agents.select(at_most=0.25)) == 2
+    assert len(agents.select(at_most=1.0)) == 10 and len(agents.select(at_most=1)) == 1
+    even = lambda c: c["x"] % 2 == 0                                               # noqa: E731
+    assert agents.select(even, at_most=0.3).get("x").tolist() == [0, 2, 4]          # 30 % of 10, not of the 5 matches
+    assert agents.select(even, at_most=0.9).get("x").tolist() == [0, 2, 4, 6, 8]
+    assert agents.select(even, at_most=2).get("x").tolist() == [0, 2]
+    assert len(agents.select(agent_type=DeviceModel)) == 0 and len(agents.select(agent_type=DeviceAgent)) == 10
+
+
+def test_set_creates_missing_columns_like_setattr():
+    """agentset.py:215-227: `set` does setattr on every agent, so a new name becomes a new attribute (column)."""
+    import torch
+
+    from mesa_b200.agentset import DeviceAgent, DeviceAgentSet
+    from mesa_b200.model import DeviceModel
+
+    class A(DeviceAgent):
+        pass
+
+    agents = DeviceAgentSet(DeviceModel(rng=1), A, 4, {"x": torch.arange(4)})
+    assert agents.set("x", 7) is agents and agents.get("x").tolist() == [7] * 4
+    agents.set("mood", 2.5)
+    assert agents.get("mood").tolist() == [2.5] * 4 and agents[1].mood == 2.5
+    agents.set("velocity", [1.0, -1.0])                                   # one shared vector value
+    assert agents.get("velocity").tolist() == [[1.0, -1.0]] * 4
+    agents.select(lambda c: c["x"] == 7, at_most=2).set("flag", True)     # through a view: the others stay zero
+    assert agents.get("flag").tolist() == [True, True, False, False]
+    assert agents.add_agents(1, x=3).get("mood").tolist() == [0.0] and len(agents.get("velocity")) == 5
