@@ -352,12 +352,25 @@ class DeviceAgentSet:
         return col if self.index is None else col[self.index]
 
     def get(self, attr_names, handle_missing: str = "error", default_value=None):
-        """agentset.py:171-227: attribute column(s) as device tensors (bulk copy instead of a Python loop)."""
+        """agentset.py:171-213 as bulk column reads instead of a Python loop: one name -> the column ([n, ...] device
+        tensor); a list of names -> ONE [n, k] tensor, row i = the values of agent i in the order of the names (the
+        reference's list of per-agent lists; scalar columns only, promoted to their common dtype).
+        `handle_missing="default"` fills unknown attributes with `default_value`."""
+        if handle_missing not in ("error", "default"):
+            raise ValueError(f"Unknown handle_missing option: {handle_missing}, should be one of 'error' or 'default'")
         if isinstance(attr_names, str):
             if attr_names not in self.columns and handle_missing == "default":
-                return torch.full((len(self),), default_value)
+                return torch.full((len(self),), default_value, device=self._device())
             return self._col(attr_names)
-        return [self.get(a, handle_missing, default_value) for a in attr_names]
+        cols = [self.get(a, handle_missing, default_value) for a in attr_names]
+        if any(c.dim() != 1 for c in cols):
+            raise ValueError("get() of several attributes stacks scalar columns; read vector attributes one by one")
+        if not cols:
+            return torch.empty((len(self), 0), device=self._device())
+        common = cols[0].dtype
+        for c in cols[1:]:
+            common = torch.promote_types(common, c.dtype)
+        return torch.stack([c.to(common) for c in cols], dim=1)
 
     def set(self, attr_name: str, value) -> "DeviceAgentSet":
         """agentset.py:215-227: set an attribute of every agent of this set; a name the agents do not have yet becomes a

@@ -292,3 +292,30 @@ def test_set_creates_missing_columns_like_setattr():
     agents.select(lambda c: c["x"] == 7, at_most=2).set("flag", True)     # through a view: the others stay zero
     assert agents.get("flag").tolist() == [True, True, False, False]
     assert agents.add_agents(1, x=3).get("mood").tolist() == [0.0] and len(agents.get("velocity")) == 5
+
+
+def test_get_orientation_and_missing_handling():
+    """agentset.py:171-213 (tests/test_agentset.py::test_agentset_get_attribute): several names give one row per agent."""
+    import pytest
+    import torch
+
+    from mesa_b200.agentset import DeviceAgent, DeviceAgentSet
+    from mesa_b200.model import DeviceModel
+
+    class A(DeviceAgent):
+        pass
+
+    agents = DeviceAgentSet(DeviceModel(rng=1), A, 3, {"a": torch.tensor([1, 2, 3]), "b": torch.tensor([0.5, 1.5, 2.5]),
+                                                       "pos": torch.zeros((3, 2))})
+    assert agents.get("a").tolist() == [1, 2, 3]
+    assert agents.get(["a", "b"]).tolist() == [[1.0, 0.5], [2.0, 1.5], [3.0, 2.5]]
+    assert agents.get(["a", "nope"], handle_missing="default", default_value=-1).tolist() == [[1, -1], [2, -1], [3, -1]]
+    with pytest.raises(AttributeError):
+        agents.get("nope")
+    with pytest.raises(AttributeError):
+        agents.get(["a", "nope"])
+    with pytest.raises(ValueError):
+        agents.get("a", handle_missing="ignore")
+    with pytest.raises(ValueError):
+        agents.get(["a", "pos"])
+    assert agents.sort("b", ascending=False).get(["a"]).tolist() == [[3], [2], [1]]
