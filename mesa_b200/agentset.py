@@ -48,6 +48,20 @@ def _lookup(agent_type: type, name: str) -> Callable:
     )
 
 
+def _reduction_name(func) -> str | None:
+    """The device reduction a well-known aggregation function stands for (None: call it on the column)."""
+    import builtins
+
+    import numpy as np
+
+    table = {builtins.min: "min", builtins.max: "max", builtins.sum: "sum", builtins.len: "len",
+             np.min: "min", np.max: "max", np.sum: "sum", np.mean: "mean", np.count_nonzero: "count_nonzero"}
+    try:
+        return table.get(func)
+    except TypeError:  # unhashable callable
+        return None
+
+
 class DeviceAgent:
     """Base class of device agent types; instances are row proxies handed out on demand."""
 
@@ -389,15 +403,33 @@ class DeviceAgentSet:
         return self
 
     def agg(self, attribute: str, func):
-        """agentset.py:137-169: aggregate a column; `func` gets the device tensor (e.g. torch.sum) or a name."""
-        col = self._col(attribute)
-        if isinstance(func, str):
-            from . import ops
-
-            return ops.layer_reduce(col.contiguous(), func).item()
+        """agentset.py:137-169: aggregate a column.  `func` names a device reduction ("sum", "min", "max",
+        "count_nonzero", "mean", "len") or IS one of the functions the reference's users pass -- the builtins `min`,
+        `max`, `sum`, `len` and numpy's `min / max / sum / mean` run as the same device reductions (one launch, one
+        scalar read-back) instead of iterating a device tensor; any other callable gets the device column.  A list or
+        tuple of functions gives a list of results."""
         if isinstance(func, (list, tuple)):
             return [self.agg(attribute, f) for f in func]
-        return func(col)
+        col = self._col(attribute)
+        name = func if isinstance(func, str) else _reduction_name(func)
+        if name is None:
+            return func(col)
+        n = int(col.shape[0])
+        if name == "len":
+            return n
+        if col.dim() != 1:
+            raise ValueError(f"agg({attribute!r}, {name!r}) needs a scalar attribute")
+        from . import ops
+
+        if name == "mean":
+            if n == 0:
+                return float("nan")
+            return ops.layer_reduce(col.contiguous(), "sum").item() / n
+        if n == 0:
+            if name in ("min", "max"):
+                raise ValueError(f"{name}() of an empty agent set")     # like the builtins on an empty list
+            return 0
+        return ops.layer_reduce(col.contiguous(), name).item()
 
     def select(self, filter_func=None, at_most=float("inf"), inplace: bool = False, agent_type=None):
         """agentset.py:66-135 with a column predicate: `filter_func(columns) -> bool mask [n]`."""

@@ -319,3 +319,38 @@ def test_get_orientation_and_missing_handling():
     with pytest.raises(ValueError):
         agents.get(["a", "pos"])
     assert agents.sort("b", ascending=False).get(["a"]).tolist() == [[3], [2], [1]]
+
+
+def test_agg_maps_well_known_functions_to_device_reductions(monkeypatch):
+    """tests/test_agentset.py::test_agentset_agg of the reference passes min / max / sum / np.mean / lists of them; those
+    must not iterate a device tensor: they dispatch to the named device reduction (host double here)."""
+    import torch
+
+    from mesa_b200 import ops
+    from mesa_b200.agentset import DeviceAgent, DeviceAgentSet
+    from mesa_b200.model import DeviceModel
+
+    calls = []
+
+    def host_reduce(layer, op="sum"):
+        calls.append(op)
+        fn = {"sum": torch.sum, "min": torch.min, "max": torch.max, "count_nonzero": torch.count_nonzero}[op]
+        return fn(layer).reshape(1)
+
+    monkeypatch.setattr(ops, "layer_reduce", host_reduce)
+
+    class A(DeviceAgent):
+        pass
+
+    agents = DeviceAgentSet(DeviceModel(rng=1), A, 10, {"energy": torch.arange(1, 11, dtype=torch.int32),
+                                                        "wealth": 10 * torch.arange(1, 11, dtype=torch.int32)})
+    assert agents.agg("energy", min) == 1 and agents.agg("energy", max) == 10 and agents.agg("energy", sum) == 55
+    assert agents.agg("wealth", np.mean) == 55.0 and agents.agg("energy", [min, max]) == [1, 10]
+    assert agents.agg("energy", (min, max, sum)) == [1, 10, 55] and agents.agg("energy", len) == 10
+    assert calls == ["min", "max", "sum", "sum", "min", "max", "min", "max", "sum"]
+
+    def custom(values):                                               # any other callable sees the column
+        return float(values.sum()) / len(values)
+
+    assert agents.agg("energy", custom) == 5.5 and agents.agg("wealth", [min, custom]) == [10, 55.0]
+    assert agents.select(lambda c: c["energy"] > 100).agg("energy", sum) == 0
