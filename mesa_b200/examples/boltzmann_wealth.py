@@ -5,7 +5,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .. import ops
+from .. import ops, reference_init
 from ..agentset import DeviceAgent, DeviceAgentSet, batch_operator
 from ..model import DeviceModel
 from ..space import DeviceMooreGrid
@@ -43,8 +43,12 @@ class BoltzmannWealth(DeviceModel):
         dev = self.grid.device
         ncells = scenario.width * scenario.height
         if initial_cells is None:
-            # model.py:70-74 random.choices(cells, k=n): cells[floor(random() * ncells)]
-            initial_cells = np.floor(self.rng.random(self.num_agents) * ncells).astype(np.int64)
+            # model.py:70-74 model.random.choices(cells, k=n): cells[floor(random() * ncells)] -- the same seed places
+            # the agents where the reference does (mesa_b200/reference_init.py)
+            if self.num_agents <= reference_init.MAX_REFERENCE_DRAWS:
+                initial_cells = reference_init.boltzmann_initial_cells(self.random, self.num_agents, ncells)
+            else:
+                initial_cells = np.floor(self.rng.random(self.num_agents) * ncells).astype(np.int64)
         cell = torch.as_tensor(np.asarray(initial_cells)).to(torch.int32).to(dev).contiguous()
         wealth = torch.ones(self.num_agents, dtype=torch.int32, device=dev)
         self.agents = DeviceAgentSet(self, MoneyAgent, self.num_agents, {"cell": cell, "wealth": wealth}, self.random, resizable=False)

@@ -5,7 +5,7 @@ from __future__ import annotations
 
 import torch
 
-from .. import ops
+from .. import ops, reference_init
 from ..agentset import DeviceAgent, DeviceAgentSet, batch_operator
 from ..model import DeviceModel
 from ..space import DeviceMooreGrid
@@ -61,7 +61,13 @@ class ConwaysGameOfLife(DeviceModel):
         super().__init__(rng=rng)
         self.grid = DeviceMooreGrid((width, height), capacity=1, random=self.random, torus=True, device=device)
         if initial_state is None:
-            initial_state = self.rng.random((width, height)) < initial_fraction_alive
+            # model.py:19-27: row-major over the cells, alive iff model.random.random() < fraction -- the same seed gives
+            # the reference's initial layer (mesa_b200/reference_init.py); beyond the sizes the reference can construct
+            # the same distribution comes from the numpy stream
+            if width * height <= reference_init.MAX_REFERENCE_DRAWS:
+                initial_state = reference_init.gol_initial_state(self.random, width, height, initial_fraction_alive)
+            else:
+                initial_state = self.rng.random((width, height)) < initial_fraction_alive
         state = torch.as_tensor(initial_state).to(torch.uint8).to(self.grid.device).contiguous()
         self.grid.add_property_layer("state", state)
         if packed is None:

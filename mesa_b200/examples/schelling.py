@@ -8,7 +8,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .. import ops
+from .. import ops, reference_init
 from ..datacollection import DeviceDataCollector
 from ..agentset import DeviceAgent, DeviceAgentSet, batch_operator
 from ..model import DeviceModel
@@ -93,10 +93,15 @@ class Schelling(DeviceModel):
         self.grid = DeviceMooreGrid((scenario.width, scenario.height), random=self.random, capacity=1, device=device)
         dev = self.grid.device
         if initial_types is None:
-            # model.py:72-81 draws random() < density then random() < minority_pc per cell, row-major
-            occupied = self.rng.random((scenario.width, scenario.height)) < self.density
-            minority = self.rng.random((scenario.width, scenario.height)) < self.minority_pc
-            initial_types = np.where(occupied, minority.astype(np.int8), np.int8(-1))
+            # model.py:72-81 draws random() < density and then, for an agent, random() < minority_pc per cell, row-major
+            # from model.random: the same seed gives the reference's initial grid (mesa_b200/reference_init.py)
+            if 2 * scenario.width * scenario.height <= reference_init.MAX_REFERENCE_DRAWS:
+                initial_types = reference_init.schelling_initial_types(self.random, scenario.width, scenario.height,
+                                                                       self.density, self.minority_pc)
+            else:  # sizes the reference cannot construct: the same distribution from the numpy stream
+                occupied = self.rng.random((scenario.width, scenario.height)) < self.density
+                minority = self.rng.random((scenario.width, scenario.height)) < self.minority_pc
+                initial_types = np.where(occupied, minority.astype(np.int8), np.int8(-1))
         types = torch.as_tensor(np.asarray(initial_types, dtype=np.int8)).to(dev).contiguous()
         flat = types.reshape(-1)
         cells = torch.nonzero(flat >= 0).reshape(-1)  # registration order = row-major over occupied cells

@@ -1,7 +1,8 @@
 """DeviceModel: the part of mesa.Model the hot path needs (mesa/model.py:85-150, 296-422).
 
 Seeds: like the reference, `rng` / `seed` seed both a stdlib `random.Random` (`model.random`) and a
-numpy Generator (`model.rng`); in addition `model.philox_seed` keys the device draws and
+numpy Generator (`model.rng`), with the reference's own derivation (mesa_b200/reference_init.py), so the same `rng`
+gives the same two streams -- and the example models the same initial state -- as in the reference; in addition `model.philox_seed` keys the device draws and
 `model._next_epoch()` counts activations (`shuffle_do` / `shuffle` calls) so that every shuffle is a
 fresh, replayable permutation (csrc/philox.cuh).
 """
@@ -19,15 +20,16 @@ class DeviceModel:
         if rng is None:
             rng = seed
         self.scenario = scenario
-        if isinstance(rng, np.random.Generator):
-            self.rng = rng
-            stdlib_seed = int(rng.integers(0, 2**63))
-        else:
-            self.rng = np.random.default_rng(rng)
-            stdlib_seed = rng if rng is not None else int(self.rng.integers(0, 2**63))
+        # scenario.py:156-158, 214-221 + model.py:125-129: `rng` seeds the numpy Generator, and the first word of its seed
+        # sequence seeds the stdlib generator -- the same two streams the reference model gets from the same `rng`
+        from .reference_init import seed_streams
+
+        self.rng, stdlib_seed = seed_streams(rng)
         self.random = random.Random(stdlib_seed)
         self._seed = stdlib_seed
-        self.philox_seed = int(stdlib_seed) & 0xFFFFFFFFFFFFFFFF if isinstance(stdlib_seed, int) else hash(stdlib_seed) & 0xFFFFFFFFFFFFFFFF
+        # the key of the device's Philox streams: the user's integer seed itself when there is one
+        user_int = isinstance(rng, (int, np.integer)) and not isinstance(rng, bool)
+        self.philox_seed = (int(rng) if user_int else stdlib_seed) & 0xFFFFFFFFFFFFFFFF
         self._epoch = 0
         self.running = True
         self.steps = 0

@@ -1,0 +1,101 @@
+"""mesa_b200.reference_init: the same seed gives the same streams and the same INITIAL model state as the reference
+(scenario.py:156-158, 214-221; schelling/model.py:71-81; conways_game_of_life/model.py:19-27;
+boltzmann_wealth_model/model.py:70-74; boid_flockers/model.py:79-82).  Pinned by the initial states stored in the golden
+fixtures that oracle/make_golden.py produced by constructing the unmodified reference models from these seeds."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from mesa_b200 import reference_init as ri
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_mt_uniforms_is_random_random_and_advances_the_generator():
+    a, b = random.Random(123), random.Random(123)
+    for n in (1, 7, 624, 1000):
+        want = [a.random() for _ in range(n)]
+        assert ri.mt_uniforms(b, n).tolist() == want
+        assert a.getstate() == b.getstate()
+    peek = ri.mt_uniforms(b, 5, advance=False)
+    assert a.getstate() == b.getstate() and peek.tolist() == [a.random() for _ in range(5)]
+
+
+def test_seed_streams_match_scenario_seeding():
+    gen, stdlib = ri.seed_streams(42)
+    ss = np.random.SeedSequence(42)
+    assert stdlib == int(ss.generate_state(1, dtype=np.uint32)[0])
+    assert gen.random() == np.random.default_rng(42).random()
+    g = np.random.default_rng(7)
+    assert ri.seed_streams(g)[0] is g                                     # a Generator is used as it is
+
+
+@pytest.mark.parametrize("name,seed", [("gol_37x23.npz", 42), ("gol_64x48.npz", 7)])
+def test_game_of_life_initial_state_is_the_reference(name, seed):
+    g = np.load(os.path.join(GOLDEN, name))
+    s0 = g["states"][0]
+    rnd = random.Random(ri.seed_streams(seed)[1])
+    assert np.array_equal(ri.gol_initial_state(rnd, s0.shape[0], s0.shape[1], 0.2), s0.astype(bool))
+
+
+@pytest.mark.parametrize("name,seed,density", [("schelling_20x20_r1.npz", 42, 0.8), ("schelling_16x48_r2.npz", 5, 0.9),
+                                               ("schelling_100x100_c1.npz", 42, 0.8)])
+def test_schelling_initial_grid_is_the_reference(name, seed, density):
+    g = np.load(os.path.join(GOLDEN, name))
+    w, h = int(g["width"]), int(g["height"])
+    want = np.full(w * h, -1, dtype=np.int8)
+    want[g["cell0"]] = g["atype"]
+    rnd = random.Random(ri.seed_streams(seed)[1])
+    check = random.Random(ri.seed_streams(seed)[1])
+    got = ri.schelling_initial_types(rnd, w, h, density, 0.5)
+    assert np.array_equal(got.reshape(-1), want)
+    # the generator stands exactly where the reference's stands after its per-cell loop
+    for _ in range(w * h):
+        if check.random() < density:
+            check.random()
+    assert rnd.getstate() == check.getstate()
+
+
+@pytest.mark.parametrize("name,seed", [("boltzmann_100_10x10.npz", 42), ("boltzmann_2000_20x30.npz", 7),
+                                       ("boltzmann_10000_100x100.npz", 1)])
+def test_boltzmann_initial_cells_are_the_reference(name, seed):
+    g = np.load(os.path.join(GOLDEN, name))
+    n, ncells = int(g["n"]), int(g["width"]) * int(g["height"])
+    rnd = random.Random(ri.seed_streams(seed)[1])
+    assert np.array_equal(ri.boltzmann_initial_cells(rnd, n, ncells), g["cell_0"].astype(np.int64))
+
+
+def test_example_models_start_from_the_reference_initial_state(monkeypatch):
+    """Model level, on CPU tensors with the device work stubbed out (the constructors only): `Model(rng=seed)` holds the
+    reference's initial state for that seed."""
+    import torch
+
+    from mesa_b200 import ops
+    from mesa_b200.examples import (BoltzmannScenario, BoltzmannWealth, ConwaysGameOfLife, Schelling, SchellingScenario)
+
+    class _Stub:
+        def __init__(self, *a, **k):
+            pass
+
+    monkeypatch.setattr(ops, "RelocationWorkspace", _Stub)
+    monkeypatch.setattr(ops, "BoltzmannWorkspace", _Stub)
+    monkeypatch.setattr(ops, "layer_fill", lambda layer, value: layer.fill_(value))
+    monkeypatch.setattr(ops, "schelling_happy", lambda *a, **k: (None, torch.zeros(1, dtype=torch.int64)))
+
+    g = np.load(os.path.join(GOLDEN, "gol_37x23.npz"))
+    m = ConwaysGameOfLife(width=37, height=23, rng=42, device="cpu", packed=False)
+    assert np.array_equal(m.grid.state.numpy(), g["states"][0])
+
+    g = np.load(os.path.join(GOLDEN, "schelling_20x20_r1.npz"))
+    want = np.full(400, -1, dtype=np.int8)
+    want[g["cell0"]] = g["atype"]
+    s = Schelling(SchellingScenario(width=20, height=20, density=0.8, homophily=0.4, radius=1, rng=42), device="cpu",
+                  collect=False)
+    assert np.array_equal(s.grid.type.numpy().reshape(-1), want)
+    assert np.array_equal(s.agents.get("cell").numpy(), g["cell0"]) and np.array_equal(s.agents.get("type").numpy(), g["atype"])
+
+    g = np.load(os.path.join(GOLDEN, "boltzmann_2000_20x30.npz"))
+    b = BoltzmannWealth(BoltzmannScenario(n=2000, width=20, height=30, rng=7), device="cpu")
+    assert np.array_equal(b.agents.get("cell").numpy(), g["cell_0"]) and b.agents.get("wealth").tolist() == [1] * 2000
