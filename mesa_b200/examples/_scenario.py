@@ -15,5 +15,8 @@ class Scenario:
                 raise TypeError(f"{type(self).__name__} has no parameter {k!r}")
             object.__setattr__(self, k, v)
 
-    def __setattr__(self, key, value):  # frozen after init like the reference
-        raise AttributeError("Scenario parameters are frozen")
+    def __setattr__(self, key, value):  # frozen after init like the reference (scenario.py:164-171)
+        raise TypeError(f"Scenario is frozen; cannot set '{key}'. Create a new Scenario instance instead.")
+
+    def __delattr__(self, key):  # scenario.py:173-177
+        raise TypeError(f"Scenario is frozen; cannot delete '{key}'.")
