@@ -109,3 +109,55 @@ def test_boids_initial_state_from_a_seed(replay):
     agents = sorted(m.agents, key=lambda a: a.unique_id)
     assert np.array_equal(np.array([a.position for a in agents]), pos)
     assert np.array_equal(np.array([a.direction for a in agents]), dirs)
+
+
+def test_agentset_operations_against_the_reference_agentset(replay, monkeypatch):
+    """select / sort / get / groupby / agg of DeviceAgentSet (column predicates on CPU tensors; the device sort and
+    reductions replaced by host doubles) against mesa.AgentSet on the same random attribute table."""
+    import mesa
+    import torch
+
+    from mesa_b200 import ops
+    from mesa_b200.agentset import DeviceAgent, DeviceAgentSet
+    from mesa_b200.model import DeviceModel
+
+    monkeypatch.setattr(ops, "sort_pairs", lambda k, v, b=0, e=None: (k[torch.argsort(k, stable=True)], v[torch.argsort(k, stable=True)]))
+    monkeypatch.setattr(ops, "layer_reduce", lambda layer, op="sum": {"sum": torch.sum, "min": torch.min, "max": torch.max}[op](layer).reshape(1))
+
+    class RefAgent(mesa.Agent):
+        def __init__(self, model, energy, kind):
+            super().__init__(model)
+            self.energy, self.kind = energy, kind
+
+    class DevAgent(DeviceAgent):
+        pass
+
+    rng = np.random.default_rng(5)
+    for trial in range(4):
+        n = int(rng.integers(5, 60))
+        energy = rng.integers(0, 6, size=n)
+        kind = rng.integers(0, 4, size=n)
+        ref_model = mesa.Model(rng=1)
+        RefAgent.create_agents(ref_model, n, list(energy), list(kind))
+        ref = ref_model.agents
+        dev = DeviceAgentSet(DeviceModel(rng=1), DevAgent, n, {"energy": torch.from_numpy(energy), "kind": torch.from_numpy(kind)})
+
+        def ids(agentset):
+            return [a.unique_id for a in agentset]
+
+        for at_most in (3, 0.3, 1.0, 1, float("inf")):
+            for thresh in (None, 2):
+                rf = None if thresh is None else (lambda a, t=thresh: a.energy >= t)
+                df = None if thresh is None else (lambda c, t=thresh: c["energy"] >= t)
+                assert ids(dev.select(df, at_most=at_most)) == ids(ref.select(rf, at_most=at_most)), (trial, at_most, thresh)
+        for ascending in (True, False):
+            assert ids(dev.sort("energy", ascending=ascending)) == ids(ref.sort("energy", ascending=ascending))
+        assert dev.get("energy").tolist() == ref.get("energy")
+        assert dev.get(["energy", "kind"]).tolist() == ref.get(["energy", "kind"])
+        rg, dg = ref.groupby("kind"), dev.groupby("kind")
+        assert list(dg.groups) == list(rg.groups) and dg.count() == rg.count()
+        for k in rg.groups:
+            assert ids(dg.get_group(k)) == ids(rg.get_group(k))
+        assert dg.agg("energy", sum) == rg.agg("energy", sum) and dg.agg("energy", max) == rg.agg("energy", max)
+        assert dev.agg("energy", [min, max, sum]) == ref.agg("energy", [min, max, sum])
+        assert dev.agg("energy", np.mean) == ref.agg("energy", np.mean)
