@@ -25,7 +25,8 @@ def replay():
     return rp
 
 
-@pytest.mark.parametrize("seed,width,height,density,homophily,radius", [(2027, 15, 12, 0.75, 0.5, 1), (31337, 9, 21, 0.9, 0.7, 2)])
+@pytest.mark.parametrize("seed,width,height,density,homophily,radius", [(2027, 15, 12, 0.75, 0.5, 1), (31337, 9, 21, 0.9, 0.7, 2),
+                                                                          (5150, 12, 12, 0.97, 0.6, 1)])  # dense: 50 probes miss -> argwhere fallback
 def test_schelling_from_a_seed(replay, seed, width, height, density, homophily, radius):
     from mesa.examples.basic.schelling.agents import SchellingAgent
     from mesa.examples.basic.schelling.model import Schelling, SchellingScenario
