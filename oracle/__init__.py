@@ -9,7 +9,8 @@ may import this package; nothing under mesa_b200/ does.  It holds
 * make_golden.py -- runs the live reference (build container only) and writes tests/golden/.
 
 Parity pin: tests/test_oracle_golden.py checks every function here against fixtures that
-make_golden.py produced from the live reference.
+make_golden.py produced from the live reference; tests/test_live_reference.py re-runs the
+comparison LIVE (reference model vs this oracle, from fresh seeds) wherever /root/reference exists.
 """
 from __future__ import annotations
 
