@@ -99,3 +99,20 @@ def test_example_models_start_from_the_reference_initial_state(monkeypatch):
     g = np.load(os.path.join(GOLDEN, "boltzmann_2000_20x30.npz"))
     b = BoltzmannWealth(BoltzmannScenario(n=2000, width=20, height=30, rng=7), device="cpu")
     assert np.array_equal(b.agents.get("cell").numpy(), g["cell_0"]) and b.agents.get("wealth").tolist() == [1] * 2000
+
+
+@pytest.mark.parametrize("density", [0.0, 0.05, 0.5, 0.95, 1.0])
+@pytest.mark.parametrize("minority", [0.0, 0.3, 1.0])
+def test_schelling_vectorised_draws_equal_the_per_cell_loop(density, minority):
+    """The running-maximum formulation against the reference's literal loop (schelling/model.py:71-81), including the
+    extremes where every cell takes one draw (density 0) or two (density 1: all 2 * ncells uniforms are consumed)."""
+    for seed in (0, 1, 2, 12345):
+        for (w, h) in [(1, 1), (3, 7), (16, 16), (25, 9)]:
+            a, b = random.Random(seed), random.Random(seed)
+            want = np.full(w * h, -1, dtype=np.int8)
+            for c in range(w * h):
+                if a.random() < density:
+                    want[c] = 1 if a.random() < minority else 0
+            got = ri.schelling_initial_types(b, w, h, density, minority)
+            assert got.shape == (w, h) and got.dtype == np.int8 and np.array_equal(got.reshape(-1), want)
+            assert a.getstate() == b.getstate()
