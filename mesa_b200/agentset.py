@@ -271,6 +271,10 @@ class DeviceAgentSet:
         if isinstance(which, DeviceAgentSet):
             which._check_view()
             which = torch.arange(which.n, device=dev) if which.index is None else which.index
+        if hasattr(which, "__array__") and not isinstance(which, torch.Tensor):   # numpy masks / index arrays
+            import numpy as np
+
+            which = torch.from_numpy(np.ascontiguousarray(which))
         if isinstance(which, torch.Tensor) and which.dtype == torch.bool:
             if tuple(which.shape) != (self.n,):
                 raise ValueError(f"removal mask has shape {tuple(which.shape)}, expected ({self.n},)")

@@ -115,7 +115,16 @@ def test_dynamic_population_bookkeeping_matches_the_reference_script(monkeypatch
 
     monkeypatch.setattr(ops, "CompactionPlan", _HostPlan)
     for by_mask in (True, False):
-        replay("cpu", by_mask)
+        model, agents = replay("cpu", by_mask)
+    # numpy masks and numpy index arrays mean what the torch ones mean
+    n = len(agents)
+    ids = agents.unique_ids().tolist()
+    mask = np.zeros(n, dtype=bool)
+    mask[[0, n - 1]] = True
+    agents.remove_agents(mask)
+    assert agents.unique_ids().tolist() == ids[1:-1]
+    agents.remove_agents(np.array([1, 2]))
+    assert agents.unique_ids().tolist() == [ids[1]] + ids[4:-1]
 
 
 def test_population_growth_needs_no_kernel_and_removal_has_no_cpu_fallback():
