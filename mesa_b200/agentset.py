@@ -115,6 +115,9 @@ class DeviceAgent:
     def __repr__(self):
         return f"<{type(self).__name__} {self.unique_id}>"
 
+    def __reduce__(self):  # slots + the column-routing __setattr__ rule out the default protocol
+        return (type(self), (self._set, self._row()))
+
 
 class _Population:
     """State shared by a population and its views: the removal generation (bumped whenever rows are renumbered)

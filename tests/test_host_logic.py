@@ -363,3 +363,29 @@ def test_agg_maps_well_known_functions_to_device_reductions(monkeypatch):
 
     assert agents.agg("energy", custom) == 5.5 and agents.agg("wealth", [min, custom]) == [10, 55.0]
     assert agents.select(lambda c: c["energy"] > 100).agg("energy", sum) == 0
+
+
+class _PickledAgent:
+    pass
+
+
+def test_agent_proxies_and_views_pickle():
+    """agentset.py:617-632 / test_agentset.py::test_agentset_serialization: agents and sets survive pickle."""
+    import pickle
+
+    import torch
+
+    from mesa_b200.agentset import DeviceAgent, DeviceAgentSet
+    from mesa_b200.model import DeviceModel
+
+    global _PickledAgent
+
+    class _PickledAgent(DeviceAgent):  # noqa: F811 - module-level name so that pickle can find the class
+        pass
+
+    _PickledAgent.__qualname__ = "_PickledAgent"
+    agents = DeviceAgentSet(DeviceModel(rng=1), _PickledAgent, 5, {"x": torch.arange(5) * 2})
+    a, view = agents[3], agents.select(lambda c: c["x"] > 2)
+    b, view2, agents2 = pickle.loads(pickle.dumps((a, view, agents)))
+    assert b.unique_id == 4 and b.x == 6 and b in agents2 and view2.columns is agents2.columns
+    assert [p.unique_id for p in view2] == [3, 4, 5] and len(agents2) == 5
