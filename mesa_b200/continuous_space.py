@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 from . import ops
+from .agentset import DeviceAgent
 
 
 class DeviceContinuousSpace:
@@ -204,3 +205,40 @@ class DeviceContinuousSpace:
 
 
 ContinuousSpace = DeviceContinuousSpace
+
+
+class DeviceContinuousSpaceAgent(DeviceAgent):
+    """continuous_space_agents.py:19-91 on a row proxy: the agent's row is its storage index in `model.space` (the
+    reference's `_mesa_index`).  Per-agent calls are debugging speed; the batch step uses
+    `space.neighbors_in_radius` / `space.nearest_neighbors` / the Boids kernels."""
+
+    __slots__ = ()
+
+    @property
+    def space(self) -> DeviceContinuousSpace:
+        return self.model.space
+
+    def __setattr__(self, name, value):
+        if name == "position":  # continuous_space_agents.py:36-44: wrap on a torus, refuse out-of-bounds points otherwise
+            space = self.space
+            value = np.asarray(value, dtype=float)
+            if not space.in_bounds(value):
+                if space.torus:
+                    value = space.torus_correct(value)
+                else:
+                    raise ValueError(f"point {value} is outside the bounds of the space")
+        super().__setattr__(name, value)
+
+    def _others(self, indices, dists):
+        me = self._row()
+        keep = np.asarray([i != me for i in indices], dtype=bool)
+        agents = [self._set.agent_type(self._set, i) for i in indices if i != me]
+        return agents, np.asarray(dists)[keep]
+
+    def get_neighbors_in_radius(self, radius: float | int = 1):
+        """continuous_space_agents.py:66-78: (agents, distances) within `radius` of this agent, itself dropped."""
+        return self._others(*self.space.get_agents_in_radius(self.position, radius=radius))
+
+    def get_nearest_neighbors(self, k: int = 1):
+        """continuous_space_agents.py:80-91: the k nearest other agents (asks for k + 1 and drops itself)."""
+        return self._others(*self.space.get_k_nearest_agents(self.position, k=k + 1))

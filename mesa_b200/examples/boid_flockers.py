@@ -12,7 +12,7 @@ import torch
 
 from .. import ops
 from ..agentset import DeviceAgent, DeviceAgentSet, batch_operator
-from ..continuous_space import DeviceContinuousSpace
+from ..continuous_space import DeviceContinuousSpace, DeviceContinuousSpaceAgent
 from ..model import DeviceModel
 from ._scenario import Scenario
 
@@ -31,8 +31,9 @@ class BoidsScenario(Scenario):
     match: float = 0.05
 
 
-class Boid(DeviceAgent):
-    """A Boid-style flocker agent (agents.py:12)."""
+class Boid(DeviceContinuousSpaceAgent):
+    """A Boid-style flocker agent (agents.py:12): a ContinuousSpaceAgent, so `boid.get_neighbors_in_radius(r)`,
+    `boid.get_nearest_neighbors(k)` and `boid.position = p` (wrapped on the torus) work on a row proxy."""
 
 
 @batch_operator(Boid, "step")

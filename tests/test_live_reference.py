@@ -162,3 +162,77 @@ def test_agentset_operations_against_the_reference_agentset(replay, monkeypatch)
         assert dg.agg("energy", sum) == rg.agg("energy", sum) and dg.agg("energy", max) == rg.agg("energy", max)
         assert dev.agg("energy", [min, max, sum]) == ref.agg("energy", [min, max, sum])
         assert dev.agg("energy", np.mean) == ref.agg("energy", np.mean)
+
+
+def test_continuous_space_agent_queries_against_the_reference(replay, monkeypatch):
+    """ContinuousSpaceAgent.get_neighbors_in_radius / get_nearest_neighbors / position setter
+    (continuous_space_agents.py:31-91) through DeviceContinuousSpaceAgent row proxies.  The space runs on CPU tensors
+    here with the two device queries replaced by oracle doubles (the kernels themselves are pinned by
+    tests/test_continuous_gpu.py); what is compared is the agent-level logic: self dropped, k + 1 asked for, order."""
+    import mesa
+    import torch
+    from mesa.experimental.continuous_space import ContinuousSpace, ContinuousSpaceAgent
+
+    from mesa_b200 import ops
+    from mesa_b200.agentset import DeviceAgentSet
+    from mesa_b200.continuous_space import DeviceContinuousSpace, DeviceContinuousSpaceAgent
+    from mesa_b200.model import DeviceModel
+
+    def host_radius_query(pos, queries, size, radius, torus=True, origin=(0.0, 0.0), exclude=None):
+        off, idx, dist = [0], [], []
+        p = pos.numpy().astype(np.float64)
+        for q in queries.numpy().astype(np.float64):
+            d = oracle.point_distances(p, q, size, torus)
+            inside = np.nonzero(d <= radius)[0]
+            idx.extend(inside.tolist())
+            dist.extend(d[inside].tolist())
+            off.append(len(idx))
+        return torch.tensor(off), torch.tensor(idx, dtype=torch.int64), torch.tensor(dist, dtype=torch.float64)
+
+    def host_knn_query(pos, queries, size, k, torus=True, origin=(0.0, 0.0), exclude=None):
+        p = pos.numpy().astype(np.float64)
+        rows = [oracle.knn_query(p, q, size, k, torus) for q in queries.numpy().astype(np.float64)]
+        return torch.tensor(np.stack([r[0] for r in rows])), torch.tensor(np.stack([r[1] for r in rows]))
+
+    monkeypatch.setattr(ops, "radius_query", host_radius_query)
+    monkeypatch.setattr(ops, "knn_query", host_knn_query)
+
+    class Bird(DeviceContinuousSpaceAgent):
+        pass
+
+    rng = np.random.default_rng(11)
+    for torus in (True, False):
+        dims = np.array([[0.0, 30.0], [0.0, 20.0]])
+        n = 60
+        pos = (rng.random((n, 2)) * (dims[:, 1] - dims[:, 0])).astype(np.float32).astype(np.float64)
+        ref_model = mesa.Model(rng=1)
+        ref_space = ContinuousSpace(dims, torus=torus, random=ref_model.random, n_agents=n)
+        ref_agents = []
+        for i in range(n):
+            a = ContinuousSpaceAgent(ref_space, ref_model)
+            a.position = pos[i]
+            ref_agents.append(a)
+        index = {id(a): i for i, a in enumerate(ref_agents)}
+
+        model = DeviceModel(rng=1)
+        model.space = DeviceContinuousSpace(dims, torus=torus, random=model.random, n_agents=n, device="cpu")
+        model.space.add_agents(pos)
+        birds = DeviceAgentSet(model, Bird, n, {"position": model.space._agent_positions}, resizable=False)
+        for i in range(0, n, 7):
+            ag, d = ref_agents[i].get_neighbors_in_radius(6.0)
+            got_ag, got_d = birds[i].get_neighbors_in_radius(6.0)
+            assert [b.unique_id - 1 for b in got_ag] == [index[id(a)] for a in ag] and np.array_equal(got_d, d)
+            ag, d = ref_agents[i].get_nearest_neighbors(4)
+            got_ag, got_d = birds[i].get_nearest_neighbors(4)
+            o = np.lexsort(([index[id(a)] for a in ag], d))                  # argpartition leaves the k unordered
+            assert [b.unique_id - 1 for b in got_ag] == [index[id(ag[j])] for j in o] and np.array_equal(got_d, np.asarray(d)[o])
+        # position setter: wraps on a torus, refuses out-of-bounds points otherwise
+        if torus:
+            ref_agents[0].position = np.array([31.5, -2.0])
+            birds[0].position = np.array([31.5, -2.0])
+            assert np.allclose(birds[0].position, ref_agents[0].position) and np.allclose(birds[0].position, [1.5, 18.0])
+        else:
+            with pytest.raises(ValueError):
+                ref_agents[0].position = np.array([31.5, 1.0])
+            with pytest.raises(ValueError):
+                birds[0].position = np.array([31.5, 1.0])
