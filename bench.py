@@ -26,6 +26,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import sys
 import threading
@@ -157,12 +158,218 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------
 # GPU side
 # --------------------------------------------------------------------------------------------
+def _free_port() -> int:
+    import socket
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _bind_to_gpu_numa_node(physical_index: int):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off (so that pinned host buffers are allocated
+    there: with 8 ranks on a two-socket host every H2D / D2H copy otherwise crosses the socket interconnect).
+    Returns (node, previous affinity) or (None, None)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(physical_index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None, None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        prev = os.sched_getaffinity(0)
+        cpus &= prev
+        if not cpus:
+            return None, None
+        os.sched_setaffinity(0, cpus)
+        return node, prev
+    except Exception:
+        return None, None
+
+
+def _digest_u64(values, first_index: int):
+    """Order-independent 64-bit digest of an integer tensor block whose first element has global index `first_index`:
+    sum_i (v_i + 2) * (2 * mix(i) + 1)  mod 2^64  (sums of blocks add up, so it is the same for every sharding)."""
+    import torch
+
+    v = values.reshape(-1).to(torch.int64) + 2
+    idx = torch.arange(first_index, first_index + v.numel(), dtype=torch.int64, device=v.device)
+    w = (idx * -7046029254386353131 + 2135587861) | 1      # 0x9E3779B97F4A7C15 as int64; wraps mod 2^64
+    return (v * w).sum()
+
+
+def parity_checks(dev, world, rank):
+    """Multi-GPU parity, OUTSIDE every timed region (results must be identical for every GPU count):
+    (a) the row-sharded bit-packed Game of Life against a single-GPU recompute of the whole grid with the uint8 kernel;
+    (b) row-sharded Schelling 1024^2, 5 steps, against the committed digests of the sequential CPU oracle
+        (tests/golden/bench_parity.json; the same digests for 1, 2, 4 and 8 GPUs);
+    (c) domain-decomposed Boids, 10^5 boids, 5 steps, against the single-GPU step (state within 1e-5).
+    Returns flat scalars."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from mesa_b200 import ops
+    from mesa_b200.sharded import ShardedBoids, ShardedSchelling
+    from mesa_b200.sharding import PeerBitLife, block_bounds
+
+    out = {}
+
+    def all_ok(flag: bool) -> bool:
+        t = torch.tensor([int(bool(flag))], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    # (a) Game of Life: 1024 rows per rank, 100 generations = the initial ghost refresh + one more mid-run
+    rows, cols, gens = 1024, 1024, 100
+    g = torch.Generator(device="cpu").manual_seed(2024)
+    full = (torch.rand((rows * world, cols), generator=g) < 0.3).to(torch.uint8).to(dev)
+    if world > 1:
+        life = PeerBitLife(rows, cols, True, dev, generations_per_launch=8, ghost=64)
+    else:
+        life = ops.BitLife(rows, cols, dev, torus=True, generations_per_launch=8)
+    life.load(full[rank * rows:(rank + 1) * rows])
+    life.run(gens)
+    mine = life.store()
+    a, b = full, torch.empty_like(full)
+    for _ in range(gens):
+        ops.gol_step(a, out=b, torus=True)
+        a, b = b, a
+    if world > 1:
+        life.check()
+        out["parity_gol_exchanges"] = life.exchanges
+    out["parity_gol_ok"] = all_ok(torch.equal(mine, a[rank * rows:(rank + 1) * rows]))
+    del life, full, a, b
+
+    # (b) Schelling 1024^2 d=0.8 h=0.4 r=1, 5 steps
+    with open(os.path.join(ROOT, "tests", "golden", "bench_parity.json")) as f:
+        gold = json.load(f)["schelling_1024"]
+    R = C = gold["rows"]
+    rng = np.random.Generator(np.random.Philox(gold["seed"]))
+    u, v = rng.random((R, C)), rng.random((R, C))
+    grid = np.where(u < 0.8, (v < 0.5).astype(np.int8), np.int8(-1)).astype(np.int8)
+    lo, hi = block_bounds(R, world, rank)
+    m = ShardedSchelling(R, C, grid[lo:hi], 0.4, 1, seed=gold["seed"], device=dev)
+    ok = m.happy_count == gold["happy0"]
+    digests = []
+    for s in range(len(gold["steps"])):
+        happy = m.step()
+        occ = (m.type >= 0)
+        d = torch.stack([_digest_u64(m.type, lo * C), _digest_u64(torch.where(occ, m.agent_id.to(torch.int64) & 0xFFFFFFFF, -1), lo * C)])
+        dist.all_reduce(d)
+        got = {"movers": m.last_movers, "happy": happy, "types": int(d[0].item()) & (2**64 - 1), "ids": int(d[1].item()) & (2**64 - 1)}
+        digests.append(got)
+        ok = ok and got == gold["steps"][s]
+    out["parity_schelling_ok"] = all_ok(ok)
+    out["parity_schelling_digest"] = f"{digests[-1]['types']:016x}"
+    del m
+
+    # (c) Boids 10^5, reference "large" density, vision 15, 5 steps
+    n = 100_000
+    side = 150.0 * math.sqrt(n / 400.0)
+    rng = np.random.Generator(np.random.Philox(5))
+    pos = (rng.random((n, 2)) * side).astype(np.float32)
+    dirs = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+    owner = ShardedBoids.owner_of(torch.from_numpy(pos[:, 1]), side, world).numpy()
+    sel = owner == rank
+    sb = ShardedBoids(side, side, pos[sel], dirs[sel], np.arange(n)[sel], vision=15.0, separation=2.0, device=dev)
+    p1, d1 = torch.from_numpy(pos).to(dev), torch.from_numpy(dirs).to(dev)
+    for _ in range(5):
+        sb.step()
+        p1, d1 = ops.boids_step(p1, d1, (side, side), vision=15.0, separation=2.0)
+    ids, gp, gd = sb.gather()
+    err_p = float((gp - p1).abs().max().item()) / side
+    err_d = float((gd - d1).abs().max().item())
+    out["parity_boids_ok"] = all_ok(bool(torch.equal(ids, torch.arange(n, device=dev))) and err_p <= 1e-5 and err_d <= 1e-5)
+    out["parity_boids_max_err"] = max(err_p, err_d)
+    del sb
+    out["parity_ok"] = bool(out["parity_gol_ok"] and out["parity_schelling_ok"] and out["parity_boids_ok"])
+    return out
+
+
+def sharded_workloads(dev, world, rank):
+    """The other two workloads BASELINE.json's metric names, at this GPU count (flat scalars):
+    Schelling config 5 weak-scaled (8192 x 65536 per GPU = 65536^2 at 8 GPUs, d=0.8 h=0.4 r=1, 5 steps from a random
+    state) and Boids config 4 strong-scaled (10^7 boids in total, vision 15, synchronous activation)."""
+    import torch
+    import torch.distributed as dist
+
+    from mesa_b200.sharded import ShardedBoids, ShardedSchelling
+
+    out = {}
+
+    def sync():
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    rows_per, cols, steps = 8192, 65536, 5
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    u = torch.rand((rows_per, cols), device=dev, generator=g)
+    types = torch.where(u < 0.4, 0, torch.where(u < 0.8, 1, -1)).to(torch.int8)
+    del u
+    m = ShardedSchelling(rows_per * world, cols, types, 0.4, 1, seed=7, device=dev)
+    del types
+    reloc, assign, movers, passes = [], [], [], []
+    for _ in range(steps):
+        sync()
+        t0 = time.perf_counter()
+        m.move_unhappy()
+        sync()
+        t1 = time.perf_counter()
+        m.assign_state()
+        sync()
+        t2 = time.perf_counter()
+        reloc.append((t1 - t0) * 1e3)
+        assign.append((t2 - t1) * 1e3)
+        movers.append(m.last_movers)
+        passes.append(m.last_passes)
+    total = (sum(reloc) + sum(assign)) / 1e3
+    out.update({"schelling_c5_grid_rows": rows_per * world, "schelling_c5_agents": m.n_agents,
+                "schelling_c5_updates_per_s": m.n_agents * steps / total, "schelling_c5_steps": steps,
+                "schelling_c5_sec": total, "schelling_relocate_ms_first": reloc[0], "schelling_relocate_ms_last": reloc[-1],
+                "schelling_assign_ms": min(assign), "schelling_c5_movers_first": movers[0],
+                "schelling_c5_passes_first": passes[0]})
+    del m
+    torch.cuda.empty_cache()
+
+    N = 10_000_000
+    side = 150.0 * math.sqrt(N / 400.0)
+    n_local = N // world
+    pos = torch.rand((n_local, 2), device=dev, generator=g)
+    pos[:, 0] *= side
+    pos[:, 1] = (pos[:, 1] + rank) * (side / world)
+    dirs = torch.rand((n_local, 2), device=dev, generator=g) * 2 - 1
+    b = ShardedBoids(side, side, pos, dirs, torch.arange(n_local, device=dev) + rank * n_local, vision=15.0,
+                     separation=2.0, device=dev)
+    for _ in range(3):
+        b.step()
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        b.step()
+    sync()
+    dt = time.perf_counter() - t0
+    out.update({"boids_1e7_ms_per_step": dt / 20 * 1e3, "boids_1e7_updates_per_s": N * 20 / dt})
+    del b
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     from mesa_b200 import ops
-    from mesa_b200.sharding import FusedPeerGol, HaloExchanger, PeerHaloLayer
+    from mesa_b200.host_api import GolHostStepper, ShardedGolHostStepper
+    from mesa_b200.sharding import FusedPeerGol, HaloExchanger, PeerBitLife, PeerHaloLayer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -171,10 +378,18 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (mesa_b200 has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        del os.environ["NCCL_DEBUG"]   # the image's default prints a banner on stdout; rank 0 prints ONE JSON line
+    have_group = True
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            del os.environ["NCCL_DEBUG"]   # the image's default prints a banner on stdout; rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
+    else:
+        # a 1-rank group: the sharded drivers (parity checks, Schelling / Boids workloads) need symmetric memory
+        try:
+            dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{_free_port()}", rank=0, world_size=1,
+                                    device_id=dev)
+        except Exception:
+            have_group = False
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
     # synthetic initial state: alive with p=0.2 (conways_game_of_life/model.py:9-15), Philox-seeded
@@ -184,38 +399,28 @@ def run_ours(args):
     path = os.environ.get("MB_GOL_PATH", "bits")
     gens_per_launch = int(os.environ.get("MB_GOL_T", "8")) if path == "bits" else 1
     halo_mode = os.environ.get("MB_HALO", "fused") if (world > 1 and path != "bits") else "none"
-    hx = HaloExchanger(GRID, torch.uint8, 1, True, dev) if halo_mode != "none" else None
+    hx = HaloExchanger(GRID, torch.uint8, 1, True, dev) if halo_mode not in ("none", "fused", "peer") else None
     peer = fused = life = None
     if path == "bits":
         # bit-packed planes, gens_per_launch generations per launch; N > 1: deep ghost zones (64 rows of each ring
-        # neighbour, copied out of its HBM over NVLink once per 64 generations between two device barriers)
+        # neighbour, copied out of its HBM over NVLink once per 64 generations by one kernel with a flag hand-shake)
         if world > 1:
-            from mesa_b200.sharding import PeerBitLife
-
             life = PeerBitLife(GRID, GRID, True, dev, generations_per_launch=gens_per_launch,
-                               ghost=int(os.environ.get("MB_GOL_GHOST", "0")) or None)
+                               ghost=int(os.environ.get("MB_GOL_GHOST", "0")) or None,
+                               transport=os.environ.get("MB_GHOST_TRANSPORT", "peer"))
         else:
             life = ops.BitLife(GRID, GRID, dev, torus=True, generations_per_launch=gens_per_launch)
         life.load(a)
     elif halo_mode == "fused":
-        # halos read in place from the neighbours' HBM over NVLink, hand-shake fused into the stencil kernel
         fused = FusedPeerGol(GRID, GRID, True, dev)
         fused.load(a)
     elif halo_mode == "peer":
-        # halos read in place from the neighbours' HBM (symmetric memory) + one device barrier per generation
         peer = PeerHaloLayer(GRID, GRID, torch.uint8, 1, True, dev)
         peer.state.copy_(a)
 
     def gol_rows(src, dst, top, bot):
         ops.gol_step(src, out=dst, torus=False, col_torus=True,
                      halo_top=None if top is None else top[-1], halo_bot=None if bot is None else bot[0])
-
-    def step(src, dst):
-        if hx is None:
-            ops.gol_step(src, out=dst, torus=True)
-        else:
-            top, bot = hx.exchange(src)
-            ops.gol_step(src, out=dst, torus=True, halo_top=top[0], halo_bot=bot[0])
 
     def barrier():
         if world > 1:
@@ -228,50 +433,81 @@ def run_ours(args):
             fused.step()
         elif peer is not None:
             peer.step(gol_rows)
+        elif hx is not None:
+            top, bot = hx.exchange(a)
+            ops.gol_step(a, out=b, torus=True, halo_top=top[0], halo_bot=bot[0])
+            a, b = b, a
         else:
-            step(a, b)
+            ops.gol_step(a, out=b, torus=True)
             a, b = b, a
 
-    def run_generations(k):
-        if life is not None:
-            life.run(k)
-        else:
-            for _ in range(k):
-                advance()
+    def kernel_count():
+        if life is None:
+            return 0
+        n = life.launches
+        if world > 1:
+            n += life.layer.exchanges + life.layer.waits
+        return n
 
-    run_generations(max(args.warmup, 3))
-    if life is not None:
-        # the timed region launches the T-generation kernel and, if K is not a multiple of T, one shorter variant:
-        # load both before timing (CUDA loads kernels lazily on first launch)
-        run_generations(gens_per_launch)
-        if args.steps % gens_per_launch:
-            run_generations(args.steps % gens_per_launch)
-    barrier()
-    launches0 = life.launches if life is not None else 0
-    # single GPU, bit-packed path: the K generations are captured once into a CUDA graph (the launch sequence is static:
-    # ping-pong planes, T generations per launch) and replayed inside the timed region, so a short run (small K) is not
-    # dominated by the host-side cost of the first launches
+    warm = max(args.warmup, 3)
+    use_graph = life is not None and os.environ.get("MB_BENCH_GRAPH", "1") != "0"
     graph = None
-    if life is not None and world == 1 and os.environ.get("MB_BENCH_GRAPH", "1") != "0":
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=side):
-            life.run(args.steps)          # captured, not executed
-        torch.cuda.current_stream(dev).wait_stream(side)
+    if life is not None:
+        life.run(warm)
+        # the launch sequence of the timed region, once, untimed: loads every kernel variant it uses (CUDA loads
+        # kernels lazily) -- the T-generation stencil, the shorter tail variants and, N > 1, the ghost exchange
+        if world > 1:
+            life.layer.invalidate()
+        life.run(args.steps, even_launches=use_graph)
         barrier()
+        if use_graph:
+            # the K generations are a static launch sequence (ping-pong planes, T generations per launch; N > 1: ONE ghost
+            # refresh with its device-side hand-shake first): captured once, replayed once untimed (uploads the graph),
+            # then replayed inside the timed region.  The same at every GPU count.
+            if world > 1:
+                life.layer.invalidate()           # the timed window starts with stale ghost rows: it contains the exchange
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            graph = torch.cuda.CUDAGraph()
+            k0 = kernel_count()
+            x0 = life.exchanges if world > 1 else 0
+            with torch.cuda.graph(graph, stream=side):
+                life.run(args.steps, even_launches=True)          # captured, not executed
+            torch.cuda.current_stream(dev).wait_stream(side)
+            launches = kernel_count() - k0
+            exchanges = (life.exchanges - x0) if world > 1 else 0
+            graph.replay()
+            barrier()
+    else:
+        for _ in range(warm):
+            advance()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(_physical_gpu_index(local)) as clocks:
-        e0.record()
         if graph is not None:
+            e0.record()
             graph.replay()
+            e1.record()
+        elif life is not None:
+            if world > 1:
+                life.layer.invalidate()
+            k0, x0 = kernel_count(), (life.exchanges if world > 1 else 0)
+            e0.record()
+            life.run(args.steps)
+            e1.record()
+            launches = kernel_count() - k0
+            exchanges = (life.exchanges - x0) if world > 1 else 0
         else:
-            run_generations(args.steps)
-        e1.record()
+            e0.record()
+            for _ in range(args.steps):
+                advance()
+            e1.record()
+            launches, exchanges = args.steps, (args.steps if world > 1 else 0)
         barrier()
-    launches = (life.launches - launches0) if life is not None else args.steps
     if fused is not None:
         fused.check()
+    if life is not None and world > 1:
+        life.check()
     ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -280,19 +516,27 @@ def run_ours(args):
     updates = GRID * GRID * args.steps * world
     value = updates / (ms * 1e-3)
     ms_per_step = ms / args.steps
+    stencil_launches = len([t for t in ops.gol_launch_plan(args.steps, gens_per_launch, even=use_graph) if t]) if life is not None else args.steps
 
-    # ---- e2e: host buffers in, host buffers out, every step (public API: mesa_b200.host_api.GolHostStepper;
-    # H2D / stencil / D2H pipelined over row chunks so both PCIe directions stay busy).  With N > 1 every rank
-    # steps its own block from / to its own host buffers; the two halo rows come from the resident previous
-    # generation of the neighbours (same NCCL / peer exchange as above is not needed for the copy-bound figure:
-    # each rank treats its block as a torus, which moves exactly the same bytes).
-    from mesa_b200.host_api import GolHostStepper
-
+    # post-timing verification of the replayed / stepped state: one more generation on the bit planes must equal one
+    # uint8-kernel generation of the unpacked state (N = 1), and the e2e leg below checks the host path against it
+    # ---- e2e: host buffers in, host buffers out, every step (public API: mesa_b200.host_api; H2D / stencil / D2H
+    # pipelined over row chunks so both PCIe directions stay busy).  N > 1 is the REAL sharded generation: every rank
+    # steps its own block of the [16384 N, 16384] torus from / to its own pinned host buffers, the halo rows come
+    # from the ring neighbours' edge rows (uploaded first into symmetric memory, read in place over NVLink).
     e2e_steps = max(3, min(args.steps, 20))
+    node, prev_aff = _bind_to_gpu_numa_node(_physical_gpu_index(local))
     h_in = torch.empty((GRID, GRID), dtype=torch.uint8).pin_memory()
     h_out = torch.empty((GRID, GRID), dtype=torch.uint8).pin_memory()
-    h_in.copy_((life.store() if life is not None else fused.state if fused is not None else peer.state if peer is not None else a).cpu())
-    stepper = GolHostStepper(GRID, GRID, dev, chunks=16)
+    cur_state = life.store() if life is not None else fused.state if fused is not None else peer.state if peer is not None else a
+    h_in.copy_(cur_state.cpu())
+    h_out.zero_()
+    if prev_aff is not None:
+        os.sched_setaffinity(0, prev_aff)
+    if world > 1:
+        stepper = ShardedGolHostStepper(GRID, GRID, dev, chunks=16, torus=True)
+    else:
+        stepper = GolHostStepper(GRID, GRID, dev, chunks=16)
 
     def e2e_step():
         stepper.step(h_in, h_out)
@@ -311,75 +555,148 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
     e2e_value = GRID * GRID * e2e_steps * world / e2e_dt
+    # the host path's generation == the resident path's generation of the same state (every rank, bit for bit)
+    e2e_ok = None
+    if life is not None:
+        life.run(1)
+        same = torch.tensor([int(torch.equal(h_out.to(dev), life.store()))], device=dev)
+        if world > 1:
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        e2e_ok = bool(same.item())
+    del h_in, h_out, stepper, cur_state
+
+    extras, notes = {}, []
+    if not args.no_others and have_group:
+        for fn in (parity_checks, sharded_workloads):
+            try:
+                extras.update(fn(dev, world, rank))
+            except Exception as exc:  # reported, never fatal for the headline line
+                notes.append(f"{fn.__name__}: {exc!r}"[:300])
+                if fn is parity_checks:
+                    extras["parity_ok"] = False
+                try:
+                    torch.cuda.synchronize()
+                except Exception:
+                    pass
 
     if rank == 0:
         peak, peak_src = _peaks()
-        # algorithmic bytes: 2 B per cell-update x the cell-updates one launch performs
-        gens_avg = args.steps / launches
-        alg_bytes = ALG_BYTES_PER_UPDATE * GRID * GRID * gens_avg
-        achieved = alg_bytes / (ms / launches * 1e-3) / 1e9
+        details = []
+        if world == 1 and not args.no_others:
+            try:
+                details = other_workloads(dev) + layer_workloads(dev) + agent_workloads(dev)
+            except Exception as exc:
+                notes.append(f"workloads: {exc!r}"[:300])
+        flat = _flat_workload_keys(details)
+        flat.update(extras)
         if life is not None:
             kernel = f"gol_bits_kernel<{gens_per_launch}>"
-            par = (f"row-sharded x{world}, bit-packed planes, {life.ghost} ghost rows of each ring neighbour copied out of its HBM "
-                   f"over NVLink (peer-mapped memory) once per {life.ghost} generations between two device barriers; no collective "
-                   "on the data path") if world > 1 else "single GPU"
-            note = ("bit-packed state (1 bit/cell, 2 x 32 MiB planes resident in L2) and temporal blocking: the kernel is bound "
-                    "by integer issue rate, not HBM; `achieved` is the contract's ALGORITHMIC figure (2 B per cell-update of the "
-                    "uint8 layer) and exceeds the HBM peak by design (SURVEY 8d allows it); `traffic` is the measured DRAM bytes "
-                    "per launch.  The HBM-bound uint8-layer stencil is under workloads[gol_u8_layer...]")
+            par = (f"row-sharded x{world}, bit-packed planes, {life.ghost} ghost rows of each ring neighbour copied out of its "
+                   f"HBM over NVLink once per {life.ghost} generations by one kernel with a flag hand-shake in peer memory "
+                   "(csrc/ghost.cu); no barrier, no collective") if world > 1 else "single GPU"
+            # physical roofline of the bit-packed kernel: its state is 1 bit per cell, so one launch must read and write
+            # one 32 MiB plane whatever the number of fused generations; the contract's 2 B per cell-update figure
+            # (the uint8 layer) is reported beside it as `contract_gbs`
+            us_launch = ms * 1e3 / stencil_launches
+            alg_bytes = 2 * GRID * GRID / 8
+            achieved = alg_bytes / (us_launch * 1e-6) / 1e9
+            sm_mhz = clocks.summary()["sm_mhz"] or 1965
+            alu_peak = 148 * 4 * 16 * sm_mhz * 1e6                      # thread-instructions / s on the ALU pipe
+            alu_achieved = 12.0 * (GRID * GRID // 32) / (ms_per_step * 1e-3)   # 12 LOP3 / SHF per word-generation
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": _ncu_traffic("gol_bits_kernel"), "peak_source": peak_src, "kernel": kernel,
+                    "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": us_launch,
+                    "binding_pipe": "alu (integer LOP3/SHF issue), not HBM: the planes are L2-resident",
+                    "alu_pipe_frac": alu_achieved / alu_peak,
+                    "contract_gbs": ALG_BYTES_PER_UPDATE * GRID * GRID / (ms_per_step * 1e-3) / 1e9,
+                    "note": "frac = bit-plane bytes one launch must move / launch time / HBM peak (physical, small by design: "
+                            "8 generations are fused per launch and the kernel is bound by the integer pipe, alu_pipe_frac); "
+                            "the HBM-bound grid stencils are gol_u8_hbm_frac / happy_r1_hbm_frac / happy_r2_hbm_frac"}
         else:
             kernel = "gol_step_u8_vec"
             par = (f"row-sharded x{world}, ring halos " + ("read in place from peer HBM over NVLink, hand-shake fused into the stencil kernel (1 launch / generation, no collective)" if fused is not None else "read in place from peer HBM over NVLink (symmetric memory) + device barrier" if peer is not None else "exchanged with NCCL send/recv")) if world > 1 else "single GPU"
-            note = "uint8 layer, one generation per launch"
+            alg_bytes = ALG_BYTES_PER_UPDATE * GRID * GRID
+            achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": _ncu_traffic(kernel), "peak_source": peak_src, "kernel": kernel,
+                    "algorithmic_bytes_per_launch": alg_bytes, "note": "uint8 layer, one generation per launch"}
+        for k in ("gol_u8_hbm_frac", "happy_r1_hbm_frac", "happy_r2_hbm_frac"):
+            if k in flat:
+                roof[k] = flat[k]
         line = {
             "metric": "agent_updates_per_sec", "value": value, "unit": "agent-updates/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "gol_16384x16384_u8_torus", "grid_per_gpu": [GRID, GRID],
-                       "global_grid": [GRID * world, GRID], "torus": True, "device_format": "bits" if life is not None else "u8",
+            "config": {"workload": "gol_16384x16384_u8_torus", "grid_rows_per_gpu": GRID, "grid_cols": GRID,
+                       "global_rows": GRID * world, "torus": True, "device_format": "bits" if life is not None else "u8",
                        "generations_per_launch": gens_per_launch, "parallelism": par,
-                       "launch": "one CUDA graph replay of the K-generation launch sequence" if graph is not None else "stream launches",
+                       "launch": "one CUDA graph replay of the K-generation launch sequence (same at every GPU count)" if graph is not None else "stream launches",
+                       "exchanges": exchanges,
                        "l2": L2_NOTE if life is None else "bit planes (2 x 32 MiB) are L2-resident by design; no flush: the resident working set IS the workload (1000 consecutive generations of one layer)"},
-            "e2e": {"value": e2e_value, "unit": "agent-updates/s", "h2d_bytes_per_step": GRID * GRID,
-                    "d2h_bytes_per_step": GRID * GRID, "steps": e2e_steps,
-                    "api": "mesa_b200.host_api.GolHostStepper.step (pinned host in/out, 16 row chunks, 3 streams)"},
+            "e2e": {"value": e2e_value, "unit": "agent-updates/s", "h2d_bytes_per_step": GRID * GRID * world,
+                    "d2h_bytes_per_step": GRID * GRID * world, "steps": e2e_steps, "ok": e2e_ok, "numa_node": node,
+                    "api": ("mesa_b200.host_api.ShardedGolHostStepper.step (every rank: pinned host block in/out, halo rows from the "
+                            "ring neighbours over NVLink, 16 row chunks, 3 streams)") if world > 1 else
+                           "mesa_b200.host_api.GolHostStepper.step (pinned host in/out, 16 row chunks, 3 streams)"},
             "gpu_launches": launches,
+            "exchanges": exchanges,
             "clocks": clocks.summary(),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": _ncu_traffic(kernel.split("<")[0]), "peak_source": peak_src,
-                         "kernel": kernel, "algorithmic_bytes_per_launch": alg_bytes, "note": note},
+            "roofline": roof,
         }
-        if life is not None:
-            # the roofline that actually binds the bit-packed kernel: the SM's ALU pipe (LOP3 / SHF issue one warp
-            # instruction every other cycle per SM sub-partition; 12 such instructions per 32-cell word and generation,
-            # csrc/gol_bits.cu).  ALGORITHMIC count: the words of the layer only, no halo lanes / re-computed rows.
-            sms, clock_hz = 148, (clocks.summary()["sm_mhz"] or 1965) * 1e6
-            alu_peak = sms * 4 * 16 * clock_hz                       # thread-instructions / s on the ALU pipe
-            alu_achieved = 12.0 * (GRID * GRID // 32) / (ms_per_step * 1e-3)   # one thread owns a 32-cell word
-            line["roofline"]["alu_pipe"] = {"achieved": alu_achieved, "peak": alu_peak, "unit": "thread-instr/s",
-                                            "frac": alu_achieved / alu_peak,
-                                            "note": "12 ALU-pipe instructions per word-generation x 16384^2/32 words per generation; "
-                                                    "ncu (profiles/r1_gol_bits_T8_ncu_full.csv): ALU pipe 83 % busy while active "
-                                                    "including the re-computed halo rows / lanes"}
-        if world == 1 and not args.no_others:
-            line["workloads"] = other_workloads(dev) + layer_workloads(dev) + agent_workloads(dev)
+        line.update(flat)
+        line["config"].update({k: v for k, v in flat.items() if k.startswith("parity")})
+        line["roofline"].update({k: v for k, v in flat.items() if not k.startswith("parity") and k not in roof})
+        if notes:
+            line["notes"] = notes
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             rate, _ = cpu_gol_rate(256, GRID, 1, 1, threads)
             rows = max(64, min(GRID, int(rate * 5.0 / GRID)) // 64 * 64)  # ~5 s per step, 3 steps
             v, _ = cpu_gol_rate(rows, GRID, 3, 1, threads)
             line["cpu_baseline"] = {"value": v, "unit": "agent-updates/s", "cores": threads, "kind": "port",
-                                    "sample": f"gol torus slab {rows}x{GRID} uint8, 3 steps, C oracle port",
-                                    # context only, NOT measured in this run: the unmodified pure-Python reference as
-                                    # timed in the build container (it is not on the GPU box and
-                                    # cannot construct the 16384^2 grid at all: ~1.3 KB and 14 us per cell)
-                                    "mesa_python_indicative": {"gol_200x200": 2.9e5, "schelling_100x100": 3.0e5,
-                                                               "boltzmann_1e4_100x100": 2.2e5, "boids_400": 1.5e4,
-                                                               "unit": "agent-updates/s", "cores": 1,
-                                                               "source": "BASELINE.md section 2 (build container)"}}
+                                    "sample": f"gol torus slab {rows}x{GRID} uint8, 3 steps, C oracle port"}
+        if details:
+            # the per-workload detail goes to a side file and to stderr; stdout carries ONE compact JSON line
+            try:
+                os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+                with open(os.path.join(ROOT, "gpurun_out", f"bench_workloads_n{world}.json"), "w") as f:
+                    json.dump(details, f, indent=1)
+            except Exception:
+                pass
+            print(json.dumps({"workloads": details}), file=sys.stderr, flush=True)
         print(json.dumps(line), flush=True)
-    if world > 1:
+    if dist.is_initialized():
+        try:
+            dist.barrier()
+        except Exception:
+            pass
         dist.destroy_process_group()
+
+
+def _flat_workload_keys(details):
+    """Flat scalars of the single-GPU workload list that the driver's record keeps (it drops nested lists)."""
+    flat = {}
+    names = {"gol_u8_layer": "gol_u8", "schelling_assign_state_16384x16384_r1": "happy_r1",
+             "schelling_assign_state_16384x16384_r2_h1": "happy_r2"}
+    for w in details:
+        name = w.get("workload", "")
+        for key, short in names.items():
+            if name.startswith(key) and "hbm_frac_of_measured_peak" in w:
+                flat[f"{short}_hbm_frac"] = w["hbm_frac_of_measured_peak"]
+                flat[f"{short}_us"] = w["ms_per_step"] * 1e3
+        if name.startswith("schelling_100x100") and "with_datacollector" not in name:
+            flat["schelling_c1_us_per_step"] = w["ms_per_step"] * 1e3
+            flat["schelling_c1_updates_per_s"] = w["agent_updates_per_s"]
+        if name.startswith("schelling_8192"):
+            flat["schelling_8192_first_step_ms"] = w["first_step_ms"]
+        if name.startswith("boltzmann_1e6"):
+            flat["boltzmann_1e6_ms_per_step"] = w["ms_per_step"]
+            flat["boltzmann_1e6_updates_per_s"] = w["agent_updates_per_s"]
+        if name.startswith("boids_1e7_vision15_synchronous"):
+            flat["boids_1e7_single_gpu_ms_per_step"] = w["ms_per_step"]
+        if name.startswith("boids_1e7_vision15_sequential"):
+            flat["boids_1e7_sequential_ms_per_step"] = w["ms_per_step"]
+    return flat
 
 
 def other_workloads(dev):
@@ -433,8 +750,35 @@ def other_workloads(dev):
     t = timed(m.step, 100)
     out.append({"workload": "schelling_100x100_d0.8_h0.4_r1_100steps_with_datacollector", "agents": n,
                 "ms_per_step": t * 1e3, "agent_updates_per_s": n / t})
-    # Schelling happiness stencil alone on 16384^2 (the >= 60 % target of the north star)
+    # Schelling 8192^2, d=0.8 h=0.4 r=1: relocation at scale on one GPU -- the first step from a random state
+    # (~15 M movers) and the four after it (shuffle_do("step") + do("assign_state") each)
     g = torch.Generator(device=dev).manual_seed(0)
+    R8 = 8192
+    u = torch.rand((R8, R8), device=dev, generator=g)
+    t8 = torch.where(u < 0.2, -1, torch.where(u < 0.6, 0, 1)).to(torch.int8)
+    del u
+    occ = (t8 >= 0).reshape(-1)
+    n8 = int(occ.sum().item())
+    aid = torch.where(occ, torch.cumsum(occ.to(torch.int32), 0, dtype=torch.int32) - 1, 0).reshape(R8, R8).contiguous()
+    del occ
+    h8, c8 = ops.schelling_happy(t8, 0.4, 1)
+    ws8 = ops.RelocationWorkspace(t8, n8)
+    per = []
+    for epoch in range(5):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        mv, its = ops.schelling_relocate(t8, h8, aid, ws8, 7, epoch)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        ops.schelling_happy(t8, 0.4, 1, out=h8, count=c8)
+        torch.cuda.synchronize()
+        per.append({"movers": mv, "iterations": its, "relocate_ms": (t1 - t0) * 1e3, "assign_ms": (time.perf_counter() - t1) * 1e3})
+    tot = sum(p["relocate_ms"] + p["assign_ms"] for p in per) / 1e3
+    out.append({"workload": "schelling_8192x8192_d0.8_h0.4_r1_5steps", "agents": n8, "first_step_ms": per[0]["relocate_ms"] + per[0]["assign_ms"],
+                "ms_per_step": tot / 5 * 1e3, "agent_updates_per_s": n8 * 5 / tot, "per_step": per})
+    del t8, h8, aid, ws8
+    torch.cuda.empty_cache()
+    # Schelling happiness stencil alone on 16384^2 (the >= 60 % target of the north star)
     u = torch.rand((GRID, GRID), device=dev, generator=g)
     types = torch.where(u < 0.2, -1, torch.where(u < 0.6, 0, 1)).to(torch.int8)
     del u

@@ -314,6 +314,17 @@ int mb_layer_diffuse(const void* in, const void* halo_top, const void* halo_bot,
 int mb_neighborhood_sum_nd(const void* in, void* out, int ndim, const int64_t* dims_host, int dtype, int radius,
                            int von_neumann, int include_center, int torus, mb_stream_t stream);
 
+/* ---- deep-ghost-zone refresh of a row-sharded layer without barrier or collective (csrc/ghost.cu; SURVEY 8e,
+ * no reference counterpart: the reference is single-process).  flags = this rank's 8-word uint32 flag block in
+ * peer-mapped memory (zero-initialised); up_flags / down_flags = peer-mapped addresses of the neighbours' blocks.
+ * mb_ghost_exchange: publish "my plane is ready", wait for both neighbours, copy `bytes` (multiple of 16) from
+ * src_up -> dst_top and src_down -> dst_bot over NVLink, publish "copied".  mb_ghost_wait_copied: device-side wait
+ * until the neighbours have copied out of this rank's plane (before the launch that overwrites it).  A wait that
+ * exceeds ~seconds sets flags[6] instead of hanging. */
+int mb_ghost_exchange(void* dst_top, const void* src_up, void* dst_bot, const void* src_down, int64_t bytes,
+                      unsigned* flags, unsigned* up_flags, unsigned* down_flags, mb_stream_t stream);
+int mb_ghost_wait_copied(unsigned* flags, int has_up, int has_down, mb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -118,6 +118,9 @@ SIGNATURES: dict[str, tuple] = {
     "mb_neighborhood_sum": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, _S]),
     "mb_layer_diffuse": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_double, c_int, _S]),
     "mb_neighborhood_sum_nd": (c_int, [_P, _P, c_int, ctypes.POINTER(c_int64), c_int, c_int, c_int, c_int, c_int, _S]),
+    # deep-ghost refresh with a flag hand-shake (no barrier)
+    "mb_ghost_exchange": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, _S]),
+    "mb_ghost_wait_copied": (c_int, [_P, c_int, c_int, _S]),
 }
 
 _lib = None

@@ -112,18 +112,37 @@ class DeviceDataCollector:
                     value = reporter()
                 self.model_vars[var].append(_to_host(value))
         if self.agent_reporters:
-            agents = model.agents
-            ids = agents.unique_ids_host()  # ids survive removals (DeviceAgentSet.remove_agents)
-            self._agent_records[model.time] = (ids, [self._column(agents, n, r) for n, r in self.agent_reporters.items()])
+            # datacollection.py:314-333 iterates model.agents = EVERY agent of every type: concatenate the registered
+            # populations (registration order), one bulk column copy per population and reporter
+            sets = self._populations(model)
+            ids = np.concatenate([a.unique_ids_host() for a in sets]) if sets else np.zeros(0, np.int64)
+            cols = [np.concatenate([self._column(a, n, r) for a in sets]) if sets else np.zeros(0)
+                    for n, r in self.agent_reporters.items()]
+            self._agent_records[model.time] = (ids, cols)
         if self.agenttype_reporters:
             self._agenttype_records[model.time] = {}
             for agent_type, reps in self.agenttype_reporters.items():
-                agents = model.agents
-                if not issubclass(agents.agent_type, agent_type):
+                # datacollection.py:335-365: model.agents_by_type[agent_type], else every agent that is an instance of it
+                by_type = getattr(model, "agents_by_type", {}) or {}
+                if agent_type in by_type:
+                    sets = [by_type[agent_type]]
+                else:
+                    sets = [a for a in self._populations(model) if issubclass(a.agent_type, agent_type)]
+                if not sets:
                     raise ValueError(f"Agent type {agent_type} is not recognized as an Agent type in the model or Agent "
-                                     f"subclass. Use an Agent (sub)class, like {[agents.agent_type]}.")
-                ids = agents.unique_ids_host()
-                self._agenttype_records[model.time][agent_type] = (ids, [self._column(agents, n, r) for n, r in reps.items()])
+                                     f"subclass. Use an Agent (sub)class, like {[a.agent_type for a in self._populations(model)]}.")
+                ids = np.concatenate([a.unique_ids_host() for a in sets])
+                cols = [np.concatenate([self._column(a, n, r) for a in sets]) for n, r in reps.items()]
+                self._agenttype_records[model.time][agent_type] = (ids, cols)
+
+    @staticmethod
+    def _populations(model) -> list:
+        """Every registered DeviceAgentSet of the model (agents_by_type values, registration order); a model that only
+        assigned `model.agents` has exactly that one."""
+        sets = list((getattr(model, "agents_by_type", None) or {}).values())
+        if not sets and getattr(model, "agents", None) is not None:
+            sets = [model.agents]
+        return sets
 
     # ------------------------------------------------------------------ tables
     def add_table_row(self, table_name, row, ignore_missing=False):

@@ -2,9 +2,9 @@
 
 ACTIVATION MODE (`BoidFlockers(activation=...)`): the reference's `shuffle_do("step")` is sequential -- each boid
 sees the boids moved before it.  "sequential" reproduces exactly that in the Philox activation order
-(ops.boids_step_sequential: dependency passes, csrc/continuous.cu); "synchronous" (default, ~one pass) lets every boid
-read the pre-step positions / directions, i.e. the reference's own `Boid.step` arithmetic applied to a frozen
-snapshot (DESIGN.md)."""
+(ops.boids_step_sequential, csrc/continuous.cu) and is the DEFAULT, so the drop-in example follows the reference's
+trajectory semantics; "synchronous" is the explicit fast mode (one pass): every boid reads the pre-step positions /
+directions, i.e. the reference's own `Boid.step` arithmetic applied to a frozen snapshot."""
 from __future__ import annotations
 
 import numpy as np
@@ -62,7 +62,7 @@ class BoidFlockers(DeviceModel):
     """Flocker model class. Handles agent creation, placement and scheduling."""
 
     def __init__(self, scenario: BoidsScenario = BoidsScenario, initial_positions=None, initial_directions=None,
-                 device="cuda", activation: str = "synchronous"):
+                 device="cuda", activation: str = "sequential"):
         if isinstance(scenario, type):
             scenario = scenario()
         if activation not in ("synchronous", "sequential"):

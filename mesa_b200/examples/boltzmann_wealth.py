@@ -55,6 +55,14 @@ class BoltzmannWealth(DeviceModel):
         self._ws = ops.BoltzmannWorkspace(cell, scenario.width, scenario.height)
         self.last_iterations = 0
         self.running = True
+        # grid.py:128 + cell.py:143-170: the implicit `empty` layer follows the occupancy.  Nobody on the step path reads
+        # it, so it is brought up to date when somebody asks for it (hook), from the per-agent cell column
+        self.grid.property_layers.hooks["empty"] = self._sync_empty
+
+    def _sync_empty(self):
+        empty = dict.__getitem__(self.grid.property_layers, "empty")
+        empty.fill_(True)
+        empty.view(-1)[self.agents.columns["cell"].long()] = False
 
     def step(self):
         self.agents.shuffle_do("step")  # model.py:79-81

@@ -80,6 +80,8 @@ class ConwaysGameOfLife(DeviceModel):
             self.grid.property_layers.hooks["state"] = self._on_layer_access
         self.agents = DeviceAgentSet(self, Cell, width * height, _StateColumns(self), self.random, resizable=False)
         self.grid.cell_agents = self._cell_agents
+        # one FixedAgent in every cell (model.py:13-26): no cell is ever empty (grid.py:128, cell.py:143-170)
+        dict.__getitem__(self.grid.property_layers, "empty").fill_(False)
         self.running = True
 
     def _cell_agents(self, cells) -> list:

@@ -119,6 +119,7 @@ class Schelling(DeviceModel):
         self.agents = DeviceAgentSet(self, SchellingAgent, n, cols, self.random, resizable=False)
         self.grid.cell_agents = self._cell_agents
         self.agents.do("assign_state")  # model.py:83-85
+        self._sync_empty()              # grid.py:128 + cell.py:143-170: `empty` tracks the occupancy from placement on
         if self.datacollector is not None:
             self.datacollector.collect(self)
 

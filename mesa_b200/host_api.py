@@ -98,3 +98,69 @@ def gol_step_host(h_in: torch.Tensor, h_out: torch.Tensor | None = None, stepper
     stepper.step(h_in, h_out)
     torch.cuda.current_stream(stepper.device).synchronize()
     return h_out
+
+
+class ShardedGolHostStepper(GolHostStepper):
+    """GolHostStepper for a ROW-SHARDED host layer: every rank steps its own [rows, cols] block of a
+    [rows * world, cols] grid from / to its own pinned host buffers, and the two halo rows of the block come from the
+    ring neighbours (rank k-1's last row, rank k+1's first row) -- the real sharded generation, not a private torus.
+
+    The first and the last row of the block are uploaded first into a small double-buffered tensor in symmetric
+    memory; one device-side barrier later every rank reads its neighbours' edge rows in place over NVLink as the
+    `halo_top` / `halo_bot` of its first / last chunk.  The chunk pipeline is the parent's."""
+
+    def __init__(self, rows: int, cols: int, device="cuda", chunks: int = 16, torus: bool = True, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        super().__init__(rows, cols, device, chunks)
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.torus = bool(torus)
+        self.edges = symm_mem.empty((2, 2, self.cols), dtype=torch.uint8, device=self.device)   # [parity][first, last][cols]
+        self.hdl = symm_mem.rendezvous(self.edges, self.group)
+        up = self.rank - 1 if self.rank > 0 else (self.world - 1 if self.torus else None)
+        down = self.rank + 1 if self.rank < self.world - 1 else (0 if self.torus else None)
+        shape = (2, 2, self.cols)
+        self.peer_up = self.hdl.get_buffer(up, shape, torch.uint8) if up is not None else None
+        self.peer_down = self.hdl.get_buffer(down, shape, torch.uint8) if down is not None else None
+        self.parity = 0
+        torch.cuda.current_stream(self.device).synchronize()
+        self.hdl.barrier()
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def step(self, h_in: torch.Tensor, h_out: torch.Tensor) -> torch.Tensor:
+        if h_in.shape != (self.rows, self.cols) or h_in.dtype != torch.uint8 or h_in.is_cuda or h_out.is_cuda:
+            raise ValueError("expected uint8 host tensors of the stepper's shape")
+        cur = torch.cuda.current_stream(self.device)
+        R, p = self.rows, self.parity
+        self.parity ^= 1
+        # edge rows first, then the barrier: past it every rank's edge rows of THIS generation are resident.  (The
+        # other parity is what the neighbours read in the previous step; it is rewritten two barriers later.)
+        self.edges[p, 0].copy_(h_in[0], non_blocking=True)
+        self.edges[p, 1].copy_(h_in[R - 1], non_blocking=True)
+        self.hdl.barrier()
+        for s in (self.s_in, self.s_comp, self.s_out):
+            s.wait_stream(cur)
+        top = self.peer_up[p, 1] if self.peer_up is not None else None
+        bot = self.peer_down[p, 0] if self.peer_down is not None else None
+        ev_in = []
+        with torch.cuda.stream(self.s_in):
+            for lo, hi in self.bounds:
+                self.d_in[lo:hi].copy_(h_in[lo:hi], non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(self.s_in)
+                ev_in.append(e)
+        for c, (lo, hi) in enumerate(self.bounds):
+            with torch.cuda.stream(self.s_comp):
+                self.s_comp.wait_event(ev_in[min(c + 1, self.chunks - 1)])
+                ops.gol_step(self.d_in[lo:hi], out=self.d_out[lo:hi], torus=False, col_torus=self.torus,
+                             halo_top=self.d_in[lo - 1] if lo > 0 else top,
+                             halo_bot=self.d_in[hi] if hi < R else bot)
+                done = torch.cuda.Event()
+                done.record(self.s_comp)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(done)
+                h_out[lo:hi].copy_(self.d_out[lo:hi], non_blocking=True)
+        cur.wait_stream(self.s_out)
+        return h_out

@@ -110,6 +110,32 @@ def gol_step_bits(bits: torch.Tensor, out: torch.Tensor, generations: int = 1, t
     return out
 
 
+def gol_launch_plan(generations: int, per_launch: int, valid: int | None = None, ghost: int | None = None,
+                    even: bool = False) -> list[int]:
+    """Generations of each launch of a `generations`-long run: at most `per_launch` per launch and, on a layer with deep
+    ghost zones, never past the `valid` generations the ghost rows are good for (0 = refresh first, then `ghost` more).
+    A zero entry means "refresh the ghost rows here".  even=True splits the last launch when the number of launches
+    is odd, so that the run ends on the ping-pong plane it started on (a CUDA graph of the run can then be replayed)."""
+    plan, left = [], int(generations)
+    while left > 0:
+        if valid is not None and valid == 0:
+            plan.append(0)
+            valid = ghost
+        t = min(left, per_launch) if valid is None else min(left, per_launch, valid)
+        plan.append(t)
+        left -= t
+        if valid is not None:
+            valid -= t
+    if even and sum(1 for t in plan if t) % 2:
+        for i in range(len(plan) - 1, -1, -1):
+            if plan[i] >= 2:
+                plan[i:i + 1] = [plan[i] - plan[i] // 2, plan[i] // 2]
+                break
+        else:
+            raise ValueError("a run of single-generation launches cannot be made even")
+    return plan
+
+
 class BitLife:
     """Game of Life state held bit-packed on one GPU (two ping-pong planes), stepped several generations per
     launch.  `load` / `store` convert from / to the uint8 property layer."""
@@ -135,14 +161,11 @@ class BitLife:
     def store(self, out: torch.Tensor | None = None) -> torch.Tensor:
         return gol_unpack(self.cur, out=out)
 
-    def run(self, generations: int) -> None:
-        left = int(generations)
-        while left > 0:
-            t = min(left, self.generations_per_launch)
+    def run(self, generations: int, even_launches: bool = False) -> None:
+        for t in gol_launch_plan(generations, self.generations_per_launch, even=even_launches):
             gol_step_bits(self.cur, self.nxt, t, torus=self.torus, rows_per_segment=self.rows_per_segment)
             self.cur, self.nxt = self.nxt, self.cur
             self.launches += 1
-            left -= t
 
 
 def happy_threshold_table(homophily: float, radius: int):

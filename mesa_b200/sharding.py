@@ -20,6 +20,22 @@ def block_bounds(global_rows: int, world: int, rank: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def require_equal_blocks(rows: int, group, what: str) -> None:
+    """The peer-mapped layers index a neighbour's buffer with this rank's own row count: every rank must hold the same
+    number of rows (uneven blocks: use HaloExchanger / ShardedLayer / ShardedSchelling, which carry per-rank bounds)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    mine = torch.tensor([int(rows)], dtype=torch.int64)
+    backend = dist.get_backend(group)
+    if backend == "nccl":
+        mine = mine.cuda()
+    everyone = [torch.empty_like(mine) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(everyone, mine, group=group)
+    counts = [int(t.item()) for t in everyone]
+    if len(set(counts)) != 1:
+        raise ValueError(f"{what} needs the same number of rows on every rank, got {counts}")
+
+
 class HaloExchanger:
     """Exchanges the top/bottom `radius` rows of a row block with the neighbouring ranks.
 
@@ -165,6 +181,7 @@ class PeerHaloLayer:
         self.rows, self.cols, self.radius, self.torus = int(rows), int(cols), int(radius), bool(torus)
         if self.rows < 2 * self.radius + 1:
             raise ValueError("row block thinner than 2*radius+1")
+        require_equal_blocks(self.rows, self.group, "PeerHaloLayer")
         self.buf = symm_mem.empty((2, self.rows, self.cols), dtype=dtype, device=device)
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
         self.up = self._peer(self.rank - 1)
@@ -241,6 +258,7 @@ class FusedPeerGol:
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
         self.rows, self.cols, self.torus = int(rows), int(cols), bool(torus)
         self.device = torch.device(device)
+        require_equal_blocks(self.rows, self.group, "FusedPeerGol")
         self.buf = symm_mem.empty((2, self.rows, self.cols), dtype=torch.uint8, device=self.device)
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
         self.flags = symm_mem.empty((4,), dtype=torch.int32, device=self.device)   # [wait_top, wait_bot, -, -]
@@ -295,33 +313,53 @@ class DeepGhostLayer:
     from the neighbours -- ONE exchange per `ghost` generations instead of one per launch.  A clamped outer edge of the
     grid gets no ghost rows (cells outside the grid stay dead for ever, ghost rows are ordinary cells).
 
-    transport="peer": the planes live in torch symmetric memory and every rank copies the neighbours' edge rows out
-    of their HBM over NVLink (peer-mapped tensors) between two device-side barriers (CUDA + NCCL group).
+    transport="peer" (default): the planes live in torch symmetric memory and every rank copies the neighbours' edge
+    rows out of their HBM over NVLink with ONE small kernel whose hand-shake is a pair of monotone counters per
+    neighbour in peer-mapped memory (csrc/ghost.cu: `mb_ghost_exchange`, `mb_ghost_wait_copied`) -- no barrier, no
+    collective, nothing on the host, so a run is a static launch sequence that can be captured in a CUDA graph.
+    transport="barrier": the first version, the same copies between two device-wide symmetric-memory barriers.
     transport="p2p": plain tensors, the edge rows travel with send/recv (HaloExchanger; gloo on CPU in the tests)."""
 
     def __init__(self, rows: int, width: int, dtype: torch.dtype, ghost: int, torus: bool, device, group=None,
                  transport: str = "peer"):
-        if transport not in ("peer", "p2p"):
-            raise ValueError("transport must be 'peer' or 'p2p'")
+        if transport not in ("peer", "barrier", "p2p"):
+            raise ValueError("transport must be 'peer', 'barrier' or 'p2p'")
         self.group = group if group is not None else (dist.group.WORLD if dist.is_initialized() else None)
         self.rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         self.rows, self.width, self.torus = int(rows), int(width), bool(torus)
         self.ghost = g = max(1, min(int(ghost), self.rows))
         self.device = torch.device(device)
-        self.transport = transport
         up = self.rank - 1 if self.rank > 0 else (self.world - 1 if self.torus else None)
         down = self.rank + 1 if self.rank < self.world - 1 else (0 if self.torus else None)
         shape = (2, self.rows + 2 * g, self.width)
-        if transport == "peer":
+        itemsize = torch.empty((), dtype=dtype).element_size()
+        if transport == "peer" and ((g * self.width * itemsize) % 16 or (self.rows * self.width * itemsize) % 16):
+            transport = "barrier"   # the copy kernel moves 16-byte vectors
+        self.transport = transport
+        if transport in ("peer", "barrier"):
             import torch.distributed._symmetric_memory as symm_mem
 
+            require_equal_blocks(self.rows, self.group, "DeepGhostLayer")
             self.buf = symm_mem.empty(shape, dtype=dtype, device=self.device)
             self.buf.zero_()
             self.hdl = symm_mem.rendezvous(self.buf, self.group)
             self.peer_up = self.hdl.get_buffer(up, shape, dtype) if up is not None else None
             self.peer_down = self.hdl.get_buffer(down, shape, dtype) if down is not None else None
+            if transport == "peer":
+                from . import _native as N
+
+                self._N = N
+                self.flags = symm_mem.empty((8,), dtype=torch.int32, device=self.device)
+                self.flags.zero_()
+                self._fhdl = symm_mem.rendezvous(self.flags, self.group)
+                self._up_flags = self._fhdl.buffer_ptrs[up] if up is not None else None
+                self._down_flags = self._fhdl.buffer_ptrs[down] if down is not None else None
+                self._bytes = g * self.width * itemsize
+                self._copied_pending = [False, False]   # a neighbour may still be copying out of this plane
+            torch.cuda.current_stream(self.device).synchronize()
             self.hdl.barrier()
+            torch.cuda.current_stream(self.device).synchronize()
         else:
             self.buf = torch.zeros(shape, dtype=dtype, device=self.device)
             self.hx = HaloExchanger(self.width, dtype, g, self.torus, self.device, group)
@@ -332,6 +370,7 @@ class DeepGhostLayer:
         self.cur = 0
         self.valid = 0          # generations the ghost rows are still good for
         self.exchanges = 0
+        self.waits = 0          # device-side "neighbours have copied" waits launched
 
     @property
     def state(self) -> torch.Tensor:
@@ -346,15 +385,25 @@ class DeepGhostLayer:
         self.valid = 0
 
     def refresh(self) -> None:
-        """Bring the ghost rows of the current generation up to date (collective)."""
+        """Bring the ghost rows of the current generation up to date (every rank calls it at the same generation)."""
         g, R, c = self.ghost, self.rows, self.cur
         mine = self.buf[c]
         if self.transport == "peer":
+            N = self._N
+            with torch.cuda.device(self.device):
+                N.check(N.lib().mb_ghost_exchange(
+                    mine[:g].data_ptr() if self.has_up else None,
+                    self.peer_up[c, R:R + g].data_ptr() if self.has_up else None,        # the last owned rows of the rank above
+                    mine[g + R:].data_ptr() if self.has_down else None,
+                    self.peer_down[c, g:2 * g].data_ptr() if self.has_down else None,    # the first owned rows of the rank below
+                    self._bytes, self.flags.data_ptr(), self._up_flags, self._down_flags, N.stream_ptr(self.device)))
+            self._copied_pending[c] = True
+        elif self.transport == "barrier":
             self.hdl.barrier()                       # every rank has finished writing the current generation
             if self.has_up:
-                mine[:g].copy_(self.peer_up[c, R:R + g])            # the last owned rows of the rank above
+                mine[:g].copy_(self.peer_up[c, R:R + g])
             if self.has_down:
-                mine[g + R:].copy_(self.peer_down[c, g:2 * g])      # the first owned rows of the rank below
+                mine[g + R:].copy_(self.peer_down[c, g:2 * g])
             self.hdl.barrier()                       # nobody overwrites a plane a neighbour is still copying from
         else:
             top, bot = self.hx.exchange(mine[g:g + R])
@@ -364,6 +413,23 @@ class DeepGhostLayer:
                 mine[g + R:].copy_(bot)
         self.valid = g
         self.exchanges += 1
+
+    def prepare_write(self) -> None:
+        """Call before launching a kernel that writes the destination plane: if the neighbours copied their ghost rows
+        out of that plane in the latest exchange, wait (on the device) until they have finished."""
+        d = 1 - self.cur
+        if self.transport == "peer" and self._copied_pending[d]:
+            N = self._N
+            with torch.cuda.device(self.device):
+                N.check(N.lib().mb_ghost_wait_copied(self.flags.data_ptr(), int(self.has_up), int(self.has_down),
+                                                     N.stream_ptr(self.device)))
+            self._copied_pending[d] = False
+            self.waits += 1
+
+    def check(self) -> None:
+        """Raise if a device-side wait timed out (a neighbour never showed up).  Synchronises."""
+        if self.transport == "peer" and int(self.flags[6].item()) != 0:
+            raise RuntimeError("DeepGhostLayer: timed out waiting for a neighbouring rank")
 
     def advance(self, generations: int) -> None:
         """The destination plane now holds the state `generations` later."""
@@ -376,14 +442,15 @@ class DeepGhostLayer:
 class PeerBitLife:
     """Row-sharded Game of Life on the BIT-PACKED layer (csrc/gol_bits.cu) over a DeepGhostLayer: each rank keeps 64
     rows of each ring neighbour and refreshes them from the neighbours' HBM over NVLink once per 64 generations
-    (0.8 % redundant rows on a 16384-row block).  No collective on the data path."""
+    (0.8 % redundant rows on a 16384-row block).  No collective and no barrier on the data path: the refresh is one
+    kernel with a flag hand-shake (csrc/ghost.cu), so `run(k)` is a static launch sequence (CUDA-graph capturable)."""
 
     def __init__(self, rows: int, cols: int, torus: bool, device, generations_per_launch: int = 8,
-                 rows_per_segment: int = 0, ghost: int | None = None, group=None):
+                 rows_per_segment: int = 0, ghost: int | None = None, group=None, transport: str = "peer"):
         from . import ops
 
         if ghost is None:
-            ghost = 64   # measured best at 2 and at 8 GPUs (profiles/): deeper zones cost more rows than they save barriers
+            ghost = 64   # measured best at 2 and at 8 GPUs (profiles/): deeper zones cost more rows than they save exchanges
 
         if cols % 32:
             raise ValueError("the bit-packed layer needs cols to be a multiple of 32")
@@ -393,7 +460,7 @@ class PeerBitLife:
         self.generations_per_launch = max(1, min(int(generations_per_launch), ops.GOL_BITS_MAX_GENERATIONS))
         self.rows_per_segment = int(rows_per_segment)
         self.layer = DeepGhostLayer(self.rows, self.cols // 32, torch.int32, max(int(ghost), self.generations_per_launch),
-                                    torus, self.device, group, transport="peer")
+                                    torus, self.device, group, transport=transport)
         self.ghost = self.layer.ghost
         self.launches = 0
 
@@ -414,15 +481,19 @@ class PeerBitLife:
     def store(self, out: torch.Tensor | None = None) -> torch.Tensor:
         return self._ops.gol_unpack(self.layer.state.contiguous(), out=out)
 
-    def run(self, generations: int) -> None:
-        left = int(generations)
-        while left > 0:
-            if self.layer.valid == 0:
+    def run(self, generations: int, even_launches: bool = False) -> None:
+        """Advance `generations`.  even_launches=True: end on the plane the run started on (see ops.gol_launch_plan)."""
+        for t in self._ops.gol_launch_plan(generations, self.generations_per_launch, self.layer.valid, self.ghost,
+                                           even=even_launches):
+            if t == 0:
                 self.layer.refresh()
-            t = min(left, self.generations_per_launch, self.layer.valid)
+                continue
+            self.layer.prepare_write()
             src, dst = self.layer.planes()
             # the extended block is a clamped grid: rows beyond the ghosts are dead (and never reach the owned rows)
             self._ops.gol_step_bits(src, dst, t, torus=False, col_torus=self.torus, rows_per_segment=self.rows_per_segment)
             self.layer.advance(t)
             self.launches += 1
-            left -= t
+
+    def check(self) -> None:
+        self.layer.check()

@@ -259,7 +259,7 @@ def test_example_boids_matches_oracle():
     from mesa_b200.examples import BoidFlockers, BoidsScenario
 
     sc = BoidsScenario(population_size=500, width=120, height=90, vision=10.0, rng=2)
-    m = BoidFlockers(sc)
+    m = BoidFlockers(sc, activation="synchronous")
     pos = m.agents.get("position").cpu().numpy().copy()
     dirs = m.agents.get("direction").cpu().numpy().copy()
     for _ in range(3):

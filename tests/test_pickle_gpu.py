@@ -33,7 +33,7 @@ def test_pickle_schelling_boltzmann_boids_continue_identically():
 
     s = Schelling(SchellingScenario(width=40, height=30, density=0.8, homophily=0.5, radius=1, rng=5), collect=False)
     b = BoltzmannWealth(BoltzmannScenario(n=2000, width=30, height=20, rng=5))
-    f = BoidFlockers(BoidsScenario(population_size=600, width=120, height=90, vision=10.0, rng=2))
+    f = BoidFlockers(BoidsScenario(population_size=600, width=120, height=90, vision=10.0, rng=2), activation="synchronous")
     q = BoidFlockers(BoidsScenario(population_size=300, width=100, height=80, vision=10.0, rng=4), activation="sequential")
     for m in (s, b, f, q):
         for _ in range(3):
