@@ -164,6 +164,23 @@ int mb_reloc_fb_pick(const void* shard, const uint64_t* times_sorted, const uint
 int mb_reloc_fb_commit(const void* shard, const uint64_t* times_sorted, const uint32_t* movers,
                        const uint64_t* result, int count, void* workspace, size_t workspace_bytes,
                        int64_t max_movers, mb_stream_t stream);
+/* The fallback cascade as a time-ordered EVENT LOOP (csrc/relocate.cu, reloc_event_loop): once the ordinary movers of a
+ * bucket have converged without any fallback arrival (FULL pass + RESUME passes until nothing changes), the fallback
+ * movers -- and the later movers their picks displace -- are processed in ascending time by ONE CTA: no iteration, no
+ * release.  mb_reloc_fb_count_into fills a caller-owned block-count table [2048][4096] uint32 (peer-mapped on a
+ * row-sharded grid) and totals[count] for `count` ascending fallback times; mb_reloc_event_loop (one rank) takes the
+ * `world` tables (host array of device pointers), totals [world][2048], the times and ranks k = _randbelow(nempty) of
+ * the fallback movers of all ranks, and writes the picks that changed as overrides (time of the mover, global cell;
+ * <= 4096) plus out4 = {overrides, bail reason (0 = completed), fallback events, displaced events};
+ * mb_reloc_apply_overrides writes them into the local movers' choice.  A confirming FULL iteration follows. */
+int mb_reloc_fb_count_into(const void* shard, const uint64_t* times_sorted, int count, uint32_t* totals,
+                           uint32_t* cnt_table, mb_stream_t stream);
+int mb_reloc_event_loop(const void* shard, void* const* cnt_tables_host, uint32_t* totals, const uint64_t* fb_times,
+                        const uint64_t* fb_ranks, int count, uint64_t* ov_times, uint64_t* ov_cells, uint64_t* out4,
+                        uint64_t seed, uint32_t epoch, mb_stream_t stream);
+int mb_reloc_apply_overrides(int64_t nmovers, uint64_t t_lo, uint64_t t_hi, const uint64_t* ov_times,
+                             const uint64_t* ov_cells, int count, void* workspace, size_t workspace_bytes,
+                             int64_t max_movers, mb_stream_t stream);
 /* phase 0: origins become empty; phase 1 (after ALL ranks did phase 0): arrivals are written */
 int mb_reloc_apply(const void* shard, int phase, int64_t nmovers, uint32_t* agent_cell, void* workspace,
                    size_t workspace_bytes, int64_t max_movers, mb_stream_t stream);

@@ -71,6 +71,9 @@ SIGNATURES: dict[str, tuple] = {
     "mb_reloc_fb_count": (c_int, [_P, _P, c_int, _P, _P, ctypes.c_size_t, c_int64, _S]),
     "mb_reloc_fb_pick": (c_int, [_P, _P, _P, c_int, _P, _P, ctypes.c_size_t, c_int64, _S]),
     "mb_reloc_fb_commit": (c_int, [_P, _P, _P, _P, c_int, _P, ctypes.c_size_t, c_int64, _S]),
+    "mb_reloc_fb_count_into": (c_int, [_P, _P, c_int, _P, _P, _S]),
+    "mb_reloc_event_loop": (c_int, [_P, ctypes.POINTER(c_void_p), _P, _P, _P, c_int, _P, _P, _P, c_uint64, c_uint32, _S]),
+    "mb_reloc_apply_overrides": (c_int, [c_int64, c_uint64, c_uint64, _P, _P, c_int, _P, ctypes.c_size_t, c_int64, _S]),
     "mb_reloc_apply": (c_int, [_P, c_int, c_int64, _P, _P, ctypes.c_size_t, c_int64, _S]),
     # radix sort
     "mb_sort_workspace_bytes": (c_int, [c_int64, ctypes.POINTER(ctypes.c_size_t)]),

@@ -61,6 +61,7 @@ constexpr int kFbBatch = 2048;   // fallback movers served per table pass
 constexpr int kRelCap = 4096;    // released cells recorded between two scans (more: answered with a full pass)
 constexpr int kFbBlocksMax = 4096;
 constexpr int kMaxPeers = 16;
+constexpr int kOvCapWs = 4096;   // = kOvCap (event loop overrides)
 
 struct Slot {
     unsigned long long vac, arr;
@@ -147,6 +148,9 @@ struct RelocWs {
     unsigned long long* rel_r_time;
     unsigned long long* counters;   // [0] movers [1] occupied [2] fallback movers listed [3] table changed [4] (unused)
                                     // [5] entries of the release write set [6] a full pass is required
+    unsigned long long* ov_time;    // [kOvCap] event loop overrides: time of the mover ...
+    unsigned long long* ov_cell;    // [kOvCap] ... the global cell it holds now
+    unsigned long long* ev_out;     // [4] overrides, bail reason, fallback events, displaced events
 };
 
 size_t carve(RelocWs* ws, char* base, int64_t cap) {
@@ -179,6 +183,9 @@ size_t carve(RelocWs* ws, char* base, int64_t cap) {
     t.rel_r_cell = (unsigned long long*)take(8 * kRelCap);
     t.rel_r_time = (unsigned long long*)take(8 * kRelCap);
     t.counters = (unsigned long long*)take(8 * 8);
+    t.ov_time = (unsigned long long*)take(8 * kOvCapWs);
+    t.ov_cell = (unsigned long long*)take(8 * kOvCapWs);
+    t.ev_out = (unsigned long long*)take(8 * 8);
     if (ws) *ws = t;
     return off;
 }
@@ -208,44 +215,70 @@ __global__ void init_slots(ShardView v) {
 }
 
 // movers = occupied && !happy; appended in arbitrary order (the result does not depend on it).
-__global__ void collect_movers(ShardView v, RelocWs ws, int64_t cap, uint64_t seed, uint32_t epoch) {
+// Every CTA owns one contiguous chunk of cells: it counts its movers first, reserves their slots with ONE atomic and
+// then writes them (the first version took a slot range per warp ballot: 2 M atomics on one address at 8192^2 made the
+// kernel 1.6 ms long; the chunk is re-read from L2 for the second sweep).
+__global__ void __launch_bounds__(256)
+collect_movers(ShardView v, RelocWs ws, int64_t cap, uint64_t seed, uint32_t epoch, int64_t chunk) {
     const int8_t* __restrict__ type = v.type[v.rank];
     const uint8_t* __restrict__ happy = v.happy[v.rank];
     const uint32_t* __restrict__ agent_id = v.agent_id[v.rank];
     Slot* __restrict__ slots = v.slots[v.rank];
-    const int64_t ncells = v.local_cells;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    unsigned occupied = 0;
-    for (int64_t c0 = (int64_t)blockIdx.x * blockDim.x; c0 < ncells; c0 += stride) {
-        const int64_t c = c0 + threadIdx.x;
-        const int t = c < ncells ? type[c] : -1;
-        const bool mover = t >= 0 && happy[c] == 0;
+    __shared__ unsigned warp_cnt[8], warp_occ[8];
+    __shared__ unsigned long long cta_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t lo = (int64_t)blockIdx.x * chunk;
+    const int64_t hi = min(lo + chunk, (int64_t)v.local_cells);
+    unsigned movers = 0, occupied = 0;
+    for (int64_t c = lo + threadIdx.x; c < hi; c += blockDim.x) {
+        const int t = type[c];
         occupied += t >= 0;
+        movers += t >= 0 && happy[c] == 0;
+    }
+    movers = warp_reduce_add(movers);
+    occupied = warp_reduce_add(occupied);
+    if (lane == 0) { warp_cnt[warp] = movers; warp_occ[warp] = occupied; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned m = 0, o = 0;
+        for (int w = 0; w < 8; ++w) { m += warp_cnt[w]; o += warp_occ[w]; }
+        cta_base = m ? atomicAdd(&ws.counters[0], (unsigned long long)m) : 0ull;
+        if (o) atomicAdd(&ws.counters[1], (unsigned long long)o);
+    }
+    __syncthreads();
+    unsigned long long next = cta_base;   // uniform across the CTA
+    for (int64_t c0 = lo; c0 < hi; c0 += blockDim.x) {
+        const int64_t c = c0 + threadIdx.x;
+        const int t = c < hi ? type[c] : -1;
+        const bool mover = t >= 0 && happy[c] == 0;
         const unsigned ballot = __ballot_sync(0xffffffffu, mover);
-        if (ballot) {
-            const int lane = threadIdx.x & 31;
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&ws.counters[0], (unsigned long long)__popc(ballot));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (mover) {
-                const unsigned long long slot = base + __popc(ballot & ((1u << lane) - 1u));
-                if ((int64_t)slot < cap) {
-                    const uint32_t agent = agent_id[c];
-                    const unsigned long long pr = mb::priority64(seed, epoch, agent);
-                    ws.mv_cell[slot] = (uint32_t)c;
-                    ws.mv_agent[slot] = agent;
-                    ws.mv_prio[slot] = pr;
-                    ws.mv_type[slot] = (int8_t)t;
-                    ws.choice[slot] = kNoCell;
-                    ws.progress[slot] = 0u;
-                    ws.softmask[slot] = 0ull;
-                    slots[c].vac = pr + 1;  // empty for every mover that acts after this one
-                }
+        __syncthreads();                   // warp_cnt of the previous round has been read
+        if (lane == 0) warp_cnt[warp] = __popc(ballot);
+        __syncthreads();
+        unsigned before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const unsigned n = warp_cnt[w];
+            before += w < warp ? n : 0u;
+            total += n;
+        }
+        if (mover) {
+            const unsigned long long slot = next + before + __popc(ballot & ((1u << lane) - 1u));
+            if ((int64_t)slot < cap) {
+                const uint32_t agent = agent_id[c];
+                const unsigned long long pr = mb::priority64(seed, epoch, agent);
+                ws.mv_cell[slot] = (uint32_t)c;
+                ws.mv_agent[slot] = agent;
+                ws.mv_prio[slot] = pr;
+                ws.mv_type[slot] = (int8_t)t;
+                ws.choice[slot] = kNoCell;
+                ws.progress[slot] = 0u;
+                ws.softmask[slot] = 0ull;
+                slots[c].vac = pr + 1;  // empty for every mover that acts after this one
             }
         }
+        next += total;
     }
-    occupied = warp_reduce_add(occupied);
-    if ((threadIdx.x & 31) == 0 && occupied) atomicAdd(&ws.counters[1], (unsigned long long)occupied);
 }
 
 // "the table changed in this pass": a plain store of a constant (millions of movers change in the
@@ -289,6 +322,7 @@ __device__ __forceinline__ void commit_choice(const ShardView& v, RelocWs& ws, i
 // arr == its time) and, if an earlier mover took it, continues probing after it (the draw counter is kept in
 // `progress`).  RELEASE SCAN (relocate_release_scan): finds the movers for which a released cell re-opens an EARLIER
 // probe.  8192^2, 15.3 M movers: a full pass 3.1-4.8 ms, a resume pass 0.35 ms once the movers have settled.
+template <int kBatch>   // probes whose slot loads are issued together
 __global__ void __launch_bounds__(128)
 relocate_pass(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, uint32_t epoch, unsigned long long t_lo,
               unsigned long long t_hi, int mode) {
@@ -312,18 +346,33 @@ relocate_pass(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, uint32_t 
         unsigned long long soft = ws.softmask[m];
         if (soft == 0ull) ws.softcell[m] = (uint32_t)held;   // the lost pick becomes the lowest soft-skipped probe
         soft |= 1ull << (pr & 0xffu);                        // (it was skipped because of an earlier arrival, too)
-        for (int j = (int)(pr & 0xffu) + 1; j < kMaxProbes; ++j) {
-            const unsigned long long c = ds.randbelow((uint64_t)v.ncells);
-            const Slot sl = load_slot(v.slot(c));
-            if (!empty_at(sl, t) || atomicMin(&v.slot(c)->arr, t) < t) {   // (the atomicMin: lost a race, not empty after all)
-                if (sl.vac <= t) soft |= 1ull << j;
-                continue;
+        // probes are issued kBatch at a time: the draws of a batch are state-independent, so its slot loads go out
+        // together (memory-level parallelism; a lone dependent load per probe left the pass latency-bound)
+        for (int j0 = (int)(pr & 0xffu) + 1; j0 < kMaxProbes; j0 += kBatch) {
+            unsigned long long cells[kBatch];
+            uint32_t after[kBatch];
+            Slot sl[kBatch];
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                cells[b] = ds.randbelow((uint64_t)v.ncells);
+                after[b] = ds.c;
             }
-            ws.choice[m] = c;
-            ws.progress[m] = (uint32_t)j | (ds.c << 8);
-            ws.softmask[m] = soft;
-            mark_changed(ws);
-            return;
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) sl[b] = load_slot(v.slot(cells[b]));
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const int j = j0 + b;
+                if (j >= kMaxProbes) continue;
+                if (!empty_at(sl[b], t) || atomicMin(&v.slot(cells[b])->arr, t) < t) {   // (the atomicMin: lost a race, not empty after all)
+                    if (sl[b].vac <= t) soft |= 1ull << j;
+                    continue;
+                }
+                ws.choice[m] = cells[b];
+                ws.progress[m] = (uint32_t)j | (after[b] << 8);
+                ws.softmask[m] = soft;
+                mark_changed(ws);
+                return;
+            }
         }
         ws.choice[m] = kNoCell;
         ws.softmask[m] = soft;
@@ -333,18 +382,31 @@ relocate_pass(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, uint32_t 
         return;
     }
     unsigned long long soft = 0ull;
-    for (int j = 0; j < kMaxProbes; ++j) {
-        const unsigned long long c = ds.randbelow((uint64_t)v.ncells);
-        const Slot sl = load_slot(v.slot(c));
-        if (empty_at(sl, t)) {
-            commit_choice(v, ws, m, t, c);
-            ws.progress[m] = (uint32_t)j | (ds.c << 8);
-            ws.softmask[m] = soft;
-            return;
+    for (int j0 = 0; j0 < kMaxProbes; j0 += kBatch) {
+        unsigned long long cells[kBatch];
+        uint32_t after[kBatch];
+        Slot sl[kBatch];
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            cells[b] = ds.randbelow((uint64_t)v.ncells);
+            after[b] = ds.c;
         }
-        if (sl.vac <= t) {
-            if (soft == 0ull) ws.softcell[m] = (uint32_t)c;
-            soft |= 1ull << j;
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) sl[b] = load_slot(v.slot(cells[b]));
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            const int j = j0 + b;
+            if (j >= kMaxProbes) continue;
+            if (empty_at(sl[b], t)) {
+                commit_choice(v, ws, m, t, cells[b]);
+                ws.progress[m] = (uint32_t)j | (after[b] << 8);
+                ws.softmask[m] = soft;
+                return;
+            }
+            if (sl[b].vac <= t) {
+                if (soft == 0ull) ws.softcell[m] = (uint32_t)cells[b];
+                soft |= 1ull << j;
+            }
         }
     }
     ws.softmask[m] = soft;
@@ -481,7 +543,8 @@ __device__ __forceinline__ int first_ge(const unsigned long long* __restrict__ a
 
 // cnt[f][b] = number of cells of LOCAL table block b that are empty at the time of fallback f
 __global__ void __launch_bounds__(256)
-fb_count(ShardView v, RelocWs ws, const unsigned long long* __restrict__ fb_t, int64_t block_cells, int count) {
+fb_count(ShardView v, uint32_t* __restrict__ cnt, uint32_t* __restrict__ fb_tot, const unsigned long long* __restrict__ fb_t,
+         int64_t block_cells, int count) {
     __shared__ int diff[kFbBatch + 1];
     __shared__ unsigned long long times[kFbBatch];
     __shared__ int warp_base[8];
@@ -516,8 +579,8 @@ fb_count(ShardView v, RelocWs ws, const unsigned long long* __restrict__ fb_t, i
     }
     __syncthreads();
     for (int f = threadIdx.x; f < count; f += blockDim.x) {
-        ws.cnt[(size_t)f * kFbBlocksMax + blockIdx.x] = (uint32_t)diff[f];
-        if (diff[f]) atomicAdd(&ws.fb_tot[f], (uint32_t)diff[f]);
+        cnt[(size_t)f * kFbBlocksMax + blockIdx.x] = (uint32_t)diff[f];
+        if (diff[f]) atomicAdd(&fb_tot[f], (uint32_t)diff[f]);
     }
 }
 
@@ -587,6 +650,262 @@ __global__ void fb_commit(ShardView v, RelocWs ws, const unsigned long long* __r
     else mark_changed(ws);  // the table moved under the scan (concurrent commits): force another pass
 }
 
+// ---- the fallback cascade as an EVENT LOOP ---------------------------------------------------------------------------
+// What made the first version slow (60 ms for the first 8192^2 step) was not the movers but the ~200 argwhere-fallback
+// movers among them: the k-th empty cell in row-major order at a mover's time depends on EVERY earlier move, so each
+// generic iteration fixed roughly one more of them and shifted the picks of the later ones -- ~16 full-size iterations
+// (a release scan over all movers + a pass over the whole slot table each) for a few hundred events.
+//
+// Once the ordinary movers have converged WITHOUT any fallback arrival (a fixed point of claims that only ever lower
+// `arr`), the rest is a strictly time-ordered chain of small events, and processing them in time order needs neither
+// iteration nor release:
+//   * fallback mover f (time t_f): every mover earlier than t_f is final, so its pick -- the k-th cell with
+//     vac <= t_f <= arr in row-major order -- is final too.  It is located through the per-block counts cnt[f][b]
+//     (computed for all fallback times in ONE table pass, fb_count) and a scan of one block, and claimed (arr = t_f);
+//   * a claim at time t on a cell whose registered arrival was a later mover (arr = a > t) DISPLACES that mover: it is
+//     pushed as an event at its own time a and, when its turn comes, continues probing AFTER the lost pick (its earlier
+//     probes were not empty at a and stay so: claims only lower `arr`); its new claim may displace an even later mover;
+//   * every claim lowers `arr` of one cell from a_old to t: the cell stops being empty for the fallback times in
+//     (t, a_old] -- their cnt / totals are decremented, so later fallback picks see the exact table.
+// Events are taken in ascending time (the earliest pending displaced mover or the next fallback mover), all earlier
+// movers are final at that point by induction, nothing is ever released, and the result is the sequential one.  The
+// picks that changed are returned as an override list (time of the mover, new cell) which `apply_overrides` writes
+// into the movers' `choice`; the termination criterion stays a confirming FULL iteration that changes nothing.
+// A displaced mover that runs out of probes (it becomes a fallback mover itself, ~1e-5 of them) or any inconsistency
+// ends the loop early (bail != 0) and the generic iteration takes over from the consistent state reached so far.
+//
+// One CTA: the chain is sequential by nature (each event is a handful of dependent L2 / NVLink accesses); the CTA's
+// 1024 threads cooperate on the parts that are wide (block-count walk, block scan, count updates).  Row-sharded grids
+// run it on one rank: slot tables and count tables of all ranks are peer-mapped.
+constexpr int kPendCap = 1024;   // displaced movers waiting for their turn
+constexpr int kOvCap = kOvCapWs;  // overrides returned per event loop
+
+struct EventArgs {
+    uint32_t* cnt[kMaxPeers];          // per-rank block-count tables [kFbBatch][kFbBlocksMax]
+    uint32_t* tot;                     // [world][kFbBatch] empties of each rank's table at each fallback time (updated)
+    const unsigned long long* fb_t;    // [count] ascending fallback times
+    const unsigned long long* fb_k;    // [count] rank of the empty cell to take over the WHOLE grid (row-major)
+    unsigned long long* ov_time;       // [kOvCap] overrides: time of the mover ...
+    unsigned long long* ov_cell;       //          ... and the global cell it holds now
+    unsigned long long* out;           // [0] overrides, [1] bail reason (0 = completed), [2] fallback events, [3] displaced events
+    int count;
+};
+
+__device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* warp_sums, unsigned& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned x = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += x;
+    }
+    __syncthreads();                       // warp_sums of the previous use has been read
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    unsigned before = 0, tot = 0;
+    const int nw = blockDim.x >> 5;
+    for (int w = 0; w < nw; ++w) {
+        const unsigned s = warp_sums[w];
+        before += w < warp ? s : 0u;
+        tot += s;
+    }
+    total = tot;
+    return before + incl - v;
+}
+
+__global__ void __launch_bounds__(1024, 1)
+reloc_event_loop(ShardView v, EventArgs a, uint64_t seed, uint32_t epoch) {
+    __shared__ unsigned long long times[kFbBatch];
+    __shared__ unsigned long long pend_t[kPendCap], pend_c[kPendCap];
+    __shared__ unsigned warp_sums[32];
+    __shared__ int s_npend, s_kind, s_bail, s_owner, s_block, s_found;
+    __shared__ unsigned s_need;
+    __shared__ unsigned long long s_t, s_lost, s_cell, s_aold, s_vac, s_klocal, s_nov, s_nfb, s_ndis;
+    const int tid = threadIdx.x;
+    for (int f = tid; f < a.count; f += blockDim.x) times[f] = a.fb_t[f];
+    if (tid == 0) { s_npend = 0; s_bail = 0; s_nov = 0ull; s_nfb = 0ull; s_ndis = 0ull; }
+    __syncthreads();
+    int i = 0;   // next fallback mover (uniform)
+    while (true) {
+        if (tid == 0) {
+            int best = -1;
+            unsigned long long bt = kNever;
+            for (int p = 0; p < s_npend; ++p)
+                if (pend_t[p] < bt) { bt = pend_t[p]; best = p; }
+            const unsigned long long ft = i < a.count ? times[i] : kNever;
+            if (best < 0 && i >= a.count) {
+                s_kind = 0;
+            } else if (best >= 0 && bt < ft) {
+                s_kind = 1; s_t = bt; s_lost = pend_c[best];
+                --s_npend;
+                pend_t[best] = pend_t[s_npend]; pend_c[best] = pend_c[s_npend];
+            } else {
+                s_kind = 2; s_t = ft;
+            }
+        }
+        __syncthreads();
+        if (s_kind == 0 || s_bail) break;
+        const unsigned long long t = s_t;
+        if (s_kind == 1) {
+            // ---- a displaced mover continues after the pick it lost
+            if (tid == 0) {
+                mb::DrawStream ds(seed, epoch, (uint32_t)t);   // priority64 carries the agent index in its low word
+                bool found = false, placed = false;
+                for (int j = 0; j < kMaxProbes; ++j) {
+                    const unsigned long long c = ds.randbelow((uint64_t)v.ncells);
+                    if (!found) { found = c == s_lost; continue; }
+                    Slot* sp = v.slot(c);
+                    const Slot sl = load_slot(sp);
+                    if (!empty_at(sl, t)) continue;
+                    atomicMin(&sp->arr, t);
+                    s_cell = c; s_aold = sl.arr; s_vac = sl.vac;
+                    placed = true;
+                    break;
+                }
+                if (!placed) s_bail = found ? 2 : 3;   // 2: out of probes (a new fallback mover), 3: the lost cell is not its pick
+                ++s_ndis;
+            }
+        } else {
+            // ---- fallback mover i: the k-th empty cell of the whole grid at its time
+            if (tid == 0) {
+                unsigned long long k = a.fb_k[i];
+                int owner = -1;
+                for (int r = 0; r < v.world; ++r) {
+                    const unsigned long long n = a.tot[(size_t)r * kFbBatch + i];
+                    if (k < n) { owner = r; break; }
+                    k -= n;
+                }
+                s_owner = owner; s_klocal = k; s_found = 0;
+                if (owner < 0) s_bail = 4;
+            }
+            __syncthreads();
+            if (s_bail) break;
+            const int o = s_owner;
+            const long long lc = (v.row_lo(o + 1) - v.row_lo(o)) * v.cols;
+            long long nb = (lc + 1023) / 1024;
+            if (nb > kFbBlocksMax) nb = kFbBlocksMax;
+            if (nb < 1) nb = 1;
+            const long long bc = (lc + nb - 1) / nb;
+            const uint32_t* row = a.cnt[o] + (size_t)i * kFbBlocksMax;
+            {   // walk the block counts: 4 consecutive entries per thread
+                unsigned n[4], sum = 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int b = tid * 4 + e;
+                    n[e] = b < nb ? __ldcg(row + b) : 0u;
+                    sum += n[e];
+                }
+                unsigned total;
+                unsigned excl = block_exclusive_scan(sum, warp_sums, total);
+                const unsigned long long k = s_klocal;
+                if (k >= excl && k < (unsigned long long)excl + sum) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (k >= excl && k < (unsigned long long)excl + n[e]) { s_block = tid * 4 + e; s_need = (unsigned)(k - excl); s_found = 1; }
+                        excl += n[e];
+                    }
+                }
+            }
+            __syncthreads();
+            if (!s_found) { if (tid == 0) s_bail = 5; __syncthreads(); break; }
+            const Slot* slots = v.slots[o];
+            const long long lo_c = (long long)s_block * bc;
+            const long long hi_c = min(lo_c + bc, lc);
+            unsigned need = s_need;
+            __syncthreads();
+            if (tid == 0) s_found = 0;
+            for (long long c0 = lo_c; c0 < hi_c; c0 += blockDim.x) {
+                const long long c = c0 + tid;
+                Slot sl{kNever, 0ull};
+                if (c < hi_c) sl = load_slot(slots + c);
+                const unsigned e = c < hi_c && empty_at(sl, t);
+                unsigned total;
+                const unsigned excl = block_exclusive_scan(e, warp_sums, total);
+                if (need < total) {
+                    if (e && excl == need) {
+                        s_cell = (unsigned long long)(v.row_lo(o) * v.cols + c); s_aold = sl.arr; s_vac = sl.vac; s_found = 1;
+                        atomicMin(&v.slots[o][c].arr, t);
+                    }
+                    break;
+                }
+                need -= total;
+            }
+            __syncthreads();
+            if (!s_found) { if (tid == 0) s_bail = 6; __syncthreads(); break; }
+            if (tid == 0) ++s_nfb;
+        }
+        __syncthreads();
+        if (s_bail) break;
+        // ---- the claim lowered arr of s_cell from s_aold to t: record it, wake the mover it displaced, fix the counts
+        int o; unsigned long long l;
+        v.locate(s_cell, o, l);
+        if (tid == 0) {
+            if (s_nov < (unsigned long long)kOvCap) { a.ov_time[s_nov] = t; a.ov_cell[s_nov] = s_cell; ++s_nov; }
+            else s_bail = 7;
+            if (s_aold != kNever) {
+                if (s_npend < kPendCap) { pend_t[s_npend] = s_aold; pend_c[s_npend] = s_cell; ++s_npend; }
+                else s_bail = 8;
+            }
+        }
+        {
+            const long long lc = (v.row_lo(o + 1) - v.row_lo(o)) * v.cols;
+            long long nb = (lc + 1023) / 1024;
+            if (nb > kFbBlocksMax) nb = kFbBlocksMax;
+            if (nb < 1) nb = 1;
+            const long long bc = (lc + nb - 1) / nb;
+            const unsigned blk = (unsigned)(l / (unsigned long long)bc);
+            const unsigned long long from = s_vac > t + 1ull ? s_vac : t + 1ull;
+            const int lo = first_ge(times, a.count, from);
+            const int hi = s_aold == kNever ? a.count : first_ge(times, a.count, s_aold + 1ull);
+            for (int f = lo + tid; f < hi; f += blockDim.x) {
+                atomicSub(a.cnt[o] + (size_t)f * kFbBlocksMax + blk, 1u);
+                a.tot[(size_t)o * kFbBatch + f] -= 1u;
+            }
+        }
+        if (v.world > 1) __threadfence_system(); else __threadfence();
+        if (s_kind == 2) ++i;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        a.out[0] = s_nov; a.out[1] = (unsigned long long)s_bail; a.out[2] = s_nfb; a.out[3] = s_ndis;
+    }
+}
+
+// choice[m] = the cell the event loop gave mover m (the LAST override recorded for its time); every rank applies the
+// whole list to its own movers of the bucket.
+__global__ void __launch_bounds__(512)
+apply_overrides(RelocWs ws, int64_t nmovers, unsigned long long t_lo, unsigned long long t_hi,
+                const unsigned long long* __restrict__ ov_time, const unsigned long long* __restrict__ ov_cell, int nov,
+                int nslots) {
+    extern __shared__ __align__(16) unsigned long long ov_hash[];
+    unsigned long long* hkey = ov_hash;                     // time + 1, 0 = free
+    int* hidx = reinterpret_cast<int*>(ov_hash + nslots);   // largest override index of that time
+    const unsigned hmask = (unsigned)nslots - 1u;
+    for (int i = threadIdx.x; i < nslots; i += blockDim.x) { hkey[i] = 0ull; hidx[i] = -1; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nov; i += blockDim.x) {
+        const unsigned long long key = ov_time[i] + 1ull;
+        unsigned h = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 40) & hmask;
+        while (true) {
+            const unsigned long long prev = atomicCAS(&hkey[h], 0ull, key);
+            if (prev == 0ull || prev == key) { atomicMax(&hidx[h], i); break; }
+            h = (h + 1) & hmask;
+        }
+    }
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < nmovers; m += stride) {
+        const unsigned long long t = ws.mv_prio[m];
+        if (t < t_lo || t > t_hi) continue;
+        const unsigned long long key = t + 1ull;
+        unsigned h = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 40) & hmask;
+        while (hkey[h] != 0ull) {
+            if (hkey[h] == key) { ws.choice[m] = ov_cell[hidx[h]]; break; }
+            h = (h + 1) & hmask;
+        }
+    }
+}
+
 __global__ void relocate_vacate(ShardView v, RelocWs ws, int64_t nmovers) {
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= nmovers) return;
@@ -629,7 +948,7 @@ int serve_fallback_local(const ShardView& v, RelocWs& ws, const unsigned long lo
     fb_sort<<<1, 1024, 0, stream>>>(ws, in_t, in_k, in_m, count);
     int rc = mb::check_cuda(cudaMemsetAsync(ws.fb_tot, 0, 4 * kFbBatch, stream), "memset");
     if (rc) return rc;
-    fb_count<<<(unsigned)nblocks, 256, 0, stream>>>(v, ws, ws.fb_t, block_cells, count);
+    fb_count<<<(unsigned)nblocks, 256, 0, stream>>>(v, ws.cnt, ws.fb_tot, ws.fb_t, block_cells, count);
     const unsigned wblocks = (unsigned)mb::ceil_div((int64_t)count * 32, 256);
     fb_pick<<<wblocks, 256, 0, stream>>>(v, ws, ws.fb_t, ws.fb_k, (int)nblocks, block_cells, count, ws.fb_res);
     fb_commit<<<(unsigned)mb::ceil_div(count, 128), 128, 0, stream>>>(v, ws, ws.fb_t, ws.fb_m, ws.fb_res, count);
@@ -666,9 +985,10 @@ MB_API int mb_reloc_collect(const void* shard, uint64_t seed, uint32_t epoch, vo
     if ((rc = get_ws(&ws, workspace, workspace_bytes, max_movers))) return rc;
     if ((rc = mb::check_cuda(cudaMemsetAsync(ws.counters, 0, 8 * sizeof(unsigned long long), stream), "memset"))) return rc;
     if (v.local_cells > 0) {
-        const int64_t want = mb::ceil_div(v.local_cells, 256);
-        const int64_t cap = (int64_t)mb::sm_count() * 16;
-        collect_movers<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(v, ws, max_movers, seed, epoch);
+        // one contiguous chunk of cells per CTA, a multiple of the CTA size, ~16 CTAs per SM
+        int64_t chunk = mb::ceil_div(v.local_cells, (int64_t)mb::sm_count() * 16);
+        chunk = mb::ceil_div(chunk, 256) * 256;
+        collect_movers<<<(unsigned)mb::ceil_div(v.local_cells, chunk), 256, 0, stream>>>(v, ws, max_movers, seed, epoch, chunk);
     }
     MB_LAUNCH_CHECK("mb_reloc_collect");
     return MB_OK;
@@ -747,8 +1067,17 @@ MB_API int mb_reloc_pass(const void* shard, int64_t nmovers, uint64_t seed, uint
     MB_REQUIRE(nmovers >= 0 && nmovers <= max_movers, "mb_reloc_pass: mover count exceeds the workspace");
     MB_REQUIRE(mode == 0 || mode == 1, "mb_reloc_pass: mode must be 0 (full) or 1 (resume)");
     if (mode == 0 && (rc = mb::check_cuda(cudaMemsetAsync(ws.counters + 2, 0, 5 * sizeof(unsigned long long), stream), "memset"))) return rc;
-    if (nmovers > 0)
-        relocate_pass<<<(unsigned)mb::ceil_div(nmovers, 128), 128, 0, stream>>>(v, ws, nmovers, seed, epoch, t_lo, t_hi, mode);
+    if (nmovers > 0) {
+        static int batch = -1;
+        if (batch < 0) {
+            const char* e = getenv("MB_RELOC_BATCH");
+            batch = e ? atoi(e) : 4;
+        }
+        const unsigned blocks = (unsigned)mb::ceil_div(nmovers, 128);
+        if (batch <= 1) relocate_pass<1><<<blocks, 128, 0, stream>>>(v, ws, nmovers, seed, epoch, t_lo, t_hi, mode);
+        else if (batch == 2) relocate_pass<2><<<blocks, 128, 0, stream>>>(v, ws, nmovers, seed, epoch, t_lo, t_hi, mode);
+        else relocate_pass<4><<<blocks, 128, 0, stream>>>(v, ws, nmovers, seed, epoch, t_lo, t_hi, mode);
+    }
     MB_LAUNCH_CHECK("mb_reloc_pass");
     return MB_OK;
 }
@@ -782,7 +1111,7 @@ MB_API int mb_reloc_fb_count(const void* shard, const uint64_t* times_sorted, in
     if (count == 0) return MB_OK;
     const int64_t nblocks = fb_num_blocks(v.local_cells);
     if ((rc = mb::check_cuda(cudaMemsetAsync(ws.fb_tot, 0, 4 * kFbBatch, stream), "memset"))) return rc;
-    fb_count<<<(unsigned)nblocks, 256, 0, stream>>>(v, ws, (const unsigned long long*)times_sorted,
+    fb_count<<<(unsigned)nblocks, 256, 0, stream>>>(v, ws.cnt, ws.fb_tot, (const unsigned long long*)times_sorted,
                                                    mb::ceil_div(v.local_cells, nblocks), count);
     if ((rc = mb::check_cuda(cudaMemcpyAsync(totals, ws.fb_tot, 4 * (size_t)count, cudaMemcpyDeviceToDevice, stream), "copy"))) return rc;
     MB_LAUNCH_CHECK("mb_reloc_fb_count");
@@ -843,6 +1172,80 @@ MB_API int mb_reloc_apply(const void* shard, int phase, int64_t nmovers, uint32_
     return MB_OK;
 }
 
+// Count the empties of the LOCAL table at `count` (<= 2048) ascending times into a caller-owned block-count table
+// cnt_table [2048][4096] uint32 (peer-mapped memory on a row-sharded grid: the event loop of another rank reads and
+// updates it) and totals[count].
+MB_API int mb_reloc_fb_count_into(const void* shard, const uint64_t* times_sorted, int count, uint32_t* totals,
+                                  uint32_t* cnt_table, cudaStream_t stream) {
+    ShardView v;
+    int rc = make_view((const ShardDesc*)shard, &v);
+    if (rc) return rc;
+    MB_REQUIRE(count >= 0 && count <= kFbBatch && times_sorted && totals && cnt_table, "mb_reloc_fb_count_into: bad argument");
+    if (count == 0) return MB_OK;
+    const int64_t nblocks = fb_num_blocks(v.local_cells);
+    if ((rc = mb::check_cuda(cudaMemsetAsync(totals, 0, 4 * (size_t)count, stream), "memset"))) return rc;
+    fb_count<<<(unsigned)nblocks, 256, 0, stream>>>(v, cnt_table, totals, (const unsigned long long*)times_sorted,
+                                                   mb::ceil_div(v.local_cells, nblocks), count);
+    MB_LAUNCH_CHECK("mb_reloc_fb_count_into");
+    return MB_OK;
+}
+
+// The fallback cascade of one converged bucket as a time-ordered event loop (see reloc_event_loop).  cnt_tables_host:
+// `world` device pointers (host array) to the ranks' block-count tables filled by mb_reloc_fb_count_into with the same
+// times; totals [world][2048] uint32 (this rank's memory; row r = rank r's totals, updated in place); fb_times /
+// fb_ranks [count]: ascending times and k = _randbelow(nempty) of the fallback movers of ALL ranks; overrides
+// (time, cell) [4096] and out4 = {overrides, bail reason (0 = completed), fallback events, displaced events} are
+// written.  Runs on ONE rank of a row-sharded grid (every other rank must be idle on the slot tables meanwhile).
+MB_API int mb_reloc_event_loop(const void* shard, void* const* cnt_tables_host, uint32_t* totals, const uint64_t* fb_times,
+                               const uint64_t* fb_ranks, int count, uint64_t* ov_times, uint64_t* ov_cells, uint64_t* out4,
+                               uint64_t seed, uint32_t epoch, cudaStream_t stream) {
+    ShardView v;
+    int rc = make_view((const ShardDesc*)shard, &v);
+    if (rc) return rc;
+    MB_REQUIRE(count >= 0 && count <= kFbBatch && cnt_tables_host && totals && fb_times && fb_ranks && ov_times && ov_cells && out4,
+               "mb_reloc_event_loop: bad argument");
+    EventArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int r = 0; r < v.world; ++r) {
+        MB_REQUIRE(cnt_tables_host[r] != nullptr, "mb_reloc_event_loop: null count table");
+        a.cnt[r] = (uint32_t*)cnt_tables_host[r];
+    }
+    a.tot = totals; a.fb_t = (const unsigned long long*)fb_times; a.fb_k = (const unsigned long long*)fb_ranks;
+    a.ov_time = (unsigned long long*)ov_times; a.ov_cell = (unsigned long long*)ov_cells; a.out = (unsigned long long*)out4;
+    a.count = count;
+    reloc_event_loop<<<1, 1024, 0, stream>>>(v, a, seed, epoch);
+    MB_LAUNCH_CHECK("mb_reloc_event_loop");
+    return MB_OK;
+}
+
+// choice of the local movers in [t_lo, t_hi] <- the event loop's overrides (the last one recorded for a mover wins)
+MB_API int mb_reloc_apply_overrides(int64_t nmovers, uint64_t t_lo, uint64_t t_hi, const uint64_t* ov_times,
+                                    const uint64_t* ov_cells, int count, void* workspace, size_t workspace_bytes,
+                                    int64_t max_movers, cudaStream_t stream) {
+    RelocWs ws;
+    int rc = get_ws(&ws, workspace, workspace_bytes, max_movers);
+    if (rc) return rc;
+    MB_REQUIRE(count >= 0 && count <= kOvCap && (count == 0 || (ov_times && ov_cells)), "mb_reloc_apply_overrides: bad argument");
+    MB_REQUIRE(nmovers >= 0 && nmovers <= max_movers, "mb_reloc_apply_overrides: mover count exceeds the workspace");
+    if (count == 0 || nmovers == 0) return MB_OK;
+    int slots = 256;
+    while (slots < 2 * count) slots <<= 1;
+    const int smem = slots * (int)(sizeof(unsigned long long) + sizeof(int));
+    static bool attr_set = false;
+    if (!attr_set) {
+        if ((rc = mb::check_cuda(cudaFuncSetAttribute(apply_overrides, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                      2 * kOvCap * (int)(sizeof(unsigned long long) + sizeof(int))),
+                                 "cudaFuncSetAttribute"))) return rc;
+        attr_set = true;
+    }
+    const int64_t want = mb::ceil_div(nmovers, 512);
+    const int64_t cap = (int64_t)mb::sm_count() * 2;
+    apply_overrides<<<(unsigned)(want < cap ? want : cap), 512, smem, stream>>>(
+        ws, nmovers, t_lo, t_hi, (const unsigned long long*)ov_times, (const unsigned long long*)ov_cells, count, slots);
+    MB_LAUNCH_CHECK("mb_reloc_apply_overrides");
+    return MB_OK;
+}
+
 // ================================================================================================
 // Single-GPU driver: the whole shuffle_do("step") in one call.  Synchronises `stream` (needs the mover
 // count and the per-pass flags on the host).
@@ -888,12 +1291,48 @@ MB_API int mb_schelling_relocate(int8_t* type, uint8_t* happy, uint32_t* agent_i
         const unsigned long long width = buckets > 1 ? (1ull << 63) / (buckets / 2) : 0ull;  // 2^64 / buckets
         const unsigned long long t_lo = buckets > 1 ? width * (unsigned long long)b : 0ull;
         const unsigned long long t_hi = (buckets > 1 && b + 1 < buckets) ? t_lo + (width - 1) : kNever;
-        // An ITERATION = [movers re-evaluate] + [fallback phase].  The first iteration of a bucket is FULL (every mover
-        // from its first probe, 3-5 ms at 15 M movers); the following ones are INCREMENTAL: a release scan for the cells
-        // whose registered arrival left in the previous iteration, then a RESUME pass (~0.4-2 ms together).  The
-        // termination criterion stays a FULL iteration that changes nothing: an incremental iteration without any change
-        // is confirmed by one.
-        bool full = true, confirmed = false;
+        // 1. the ordinary movers first: a FULL pass and then RESUME passes until nothing changes -- the fallback movers
+        //    (all 50 probes occupied) are only listed, they hold nothing yet, so claims only ever lower `arr` and no
+        //    release can occur: this converges to the exact sequential outcome of a world without fallback arrivals;
+        // 2. the fallback movers and everything they displace, in time order, by the event loop (reloc_event_loop);
+        // 3. the generic iteration below, starting with a FULL one, CONFIRMS: it ends at once when nothing changes
+        //    and otherwise (the event loop bailed out, > 2048 fallback movers, ...) iterates to the fixed point as before.
+        bool prefix_ok = getenv("MB_RELOC_GENERIC") == nullptr;
+        if (prefix_ok) {
+            if ((rc = mb_reloc_pass(&d, nmovers, seed, epoch, t_lo, t_hi, 0, workspace, workspace_bytes, max_movers, stream))) return rc;
+            ++pass;
+            for (int guard = 0; guard < kMaxPasses; ++guard) {
+                if ((rc = read_counters(ws, hc, stream))) return rc;
+                if (hc[5] != 0 || hc[6] != 0) { prefix_ok = false; break; }   // cannot happen (no releases); be safe
+                if (guard > 0 && hc[3] == 0) break;                            // a RESUME pass changed nothing
+                if ((rc = mb_reloc_release_take(workspace, workspace_bytes, max_movers, nullptr, nullptr, 0, stream))) return rc;
+                if ((rc = mb_reloc_pass(&d, nmovers, seed, epoch, t_lo, t_hi, 1, workspace, workspace_bytes, max_movers, stream))) return rc;
+                ++pass;
+            }
+            const int64_t nfb = (int64_t)hc[2];
+            if (prefix_ok && nfb > 0 && nfb <= kFbBatch) {
+                unsigned long long* tmp_t = ws.fb_res;
+                unsigned long long* tmp_k = reinterpret_cast<unsigned long long*>(ws.cnt);
+                uint32_t* tmp_m = ws.fb_block;
+                fb_export<<<(unsigned)mb::ceil_div(nfb, 128), 128, 0, stream>>>(v, ws, 0, (int)nfb, nempty, seed, epoch, tmp_t, tmp_k, tmp_m);
+                fb_sort<<<1, 1024, 0, stream>>>(ws, tmp_t, tmp_k, tmp_m, (int)nfb);
+                MB_LAUNCH_CHECK("relocate fallback export");
+                if ((rc = mb_reloc_fb_count_into(&d, (const uint64_t*)ws.fb_t, (int)nfb, ws.fb_tot, ws.cnt, stream))) return rc;
+                void* tables[1] = {ws.cnt};
+                if ((rc = mb_reloc_event_loop(&d, tables, ws.fb_tot, (const uint64_t*)ws.fb_t, (const uint64_t*)ws.fb_k, (int)nfb,
+                                              (uint64_t*)ws.ov_time, (uint64_t*)ws.ov_cell, (uint64_t*)ws.ev_out, seed, epoch, stream))) return rc;
+                unsigned long long ev[4];
+                if ((rc = mb::check_cuda(cudaMemcpyAsync(ev, ws.ev_out, sizeof(ev), cudaMemcpyDeviceToHost, stream), "read event loop result"))) return rc;
+                if ((rc = mb::check_cuda(cudaStreamSynchronize(stream), "sync"))) return rc;
+                if ((rc = mb_reloc_apply_overrides(nmovers, t_lo, t_hi, (const uint64_t*)ws.ov_time, (const uint64_t*)ws.ov_cell,
+                                                   (int)ev[0], workspace, workspace_bytes, max_movers, stream))) return rc;
+                if (getenv("MB_RELOC_DEBUG") != nullptr)
+                    fprintf(stderr, "[mb reloc] bucket %d: %lld fallback movers, event loop: %llu overrides, bail %llu, %llu fallback + %llu displaced events, %d passes so far\n",
+                            b, (long long)nfb, ev[0], ev[1], ev[2], ev[3], pass);
+            }
+        }
+        // An ITERATION = [movers re-evaluate] + [fallback phase].
+        bool full = true, confirmed = prefix_ok;
         int64_t nrel = 0;
         for (;; ++pass) {
             if (pass >= kMaxPasses) {

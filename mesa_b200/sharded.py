@@ -19,6 +19,7 @@ The reference has no counterpart for any of this (single process, SURVEY section
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -27,7 +28,9 @@ from . import _native as N
 from . import ops
 from .sharding import block_bounds
 
-_FB_BATCH = 2048
+_FB_BATCH = 2048     # kFbBatch of csrc/relocate.cu
+_FB_BLOCKS = 4096    # kFbBlocksMax
+_OV_CAP = 4096       # kOvCap
 _NONE64 = -1  # 0xffff_ffff_ffff_ffff as int64
 
 
@@ -113,6 +116,12 @@ class ShardedSchelling:
         N.check(N.lib().mb_reloc_workspace_bytes(self.max_movers, ctypes.byref(nbytes)))
         self._ws_bytes = int(nbytes.value)
         self._ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=self.device)
+        # event loop of the fallback cascade (csrc/relocate.cu): every rank's block-count table is peer-mapped, the loop
+        # itself runs on rank 0 and reaches all slot / count tables over NVLink
+        self._cnt_buf, self._cnt_h = symmetric((_FB_BATCH * _FB_BLOCKS,), torch.int32)
+        self._cnt_ptrs = (ctypes.c_void_p * self.world)(*[self._cnt_h.buffer_ptrs[r] for r in range(self.world)])
+        self._ov = torch.zeros(2 * _OV_CAP + 4, dtype=torch.int64, device=self.device)   # times | cells | out4
+        self.last_events = [0, 0, 0, 0]      # overrides, bail reason, fallback events, displaced events (summed over buckets)
         self._table = ops.happy_threshold_table(self.homophily, self.radius)
         self._count = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._host7 = (ctypes.c_uint64 * 7)()
@@ -186,6 +195,7 @@ class ShardedSchelling:
             movers, occupied = self._counters()[:2]
             tot_movers, tot_occupied = self._allreduce([movers, occupied])   # also orders collect before any pass
             self.last_movers, self.last_passes = tot_movers, 0
+            self.last_events = [0, 0, 0, 0]
             if tot_movers == 0:
                 return 0
             nempty = self.rows_total * self.cols - tot_occupied
@@ -199,9 +209,27 @@ class ShardedSchelling:
             for b in range(buckets):
                 t_lo = b * width
                 t_hi = (t_lo + width - 1) if b + 1 < buckets else (1 << 64) - 1
-                # an ITERATION = [movers re-evaluate] + [fallback phase]; the first one of a bucket is FULL, the following ones
-                # incremental (release scan + RESUME pass), and an incremental iteration that changes nothing is confirmed
-                # by a FULL one (csrc/relocate.cu).  Every rank takes the same decisions (all-reduced flags).
+                # 1. ordinary movers: FULL pass + RESUME passes until nothing changes anywhere (fallback movers only listed:
+                #    no release can occur); 2. the fallback movers and what they displace, in time order, by the event loop on
+                #    rank 0; 3. the generic iteration below confirms with a FULL iteration (csrc/relocate.cu).
+                prefix_ok = os.environ.get("MB_RELOC_GENERIC") is None
+                if prefix_ok:
+                    N.check(lib.mb_reloc_pass(self._shard_ref, movers, seed, epoch, t_lo, t_hi, 0, ws, wb, mm, self._stream()))
+                    self.last_passes += 1
+                    guard = 0
+                    while True:
+                        nfb_all, nrel_all, changed, force = self._pass_flags()
+                        if force or sum(nrel_all) > 0:
+                            prefix_ok = False
+                            break
+                        if guard > 0 and not changed:
+                            break
+                        guard += 1
+                        N.check(lib.mb_reloc_release_take(ws, wb, mm, None, None, 0, self._stream()))
+                        N.check(lib.mb_reloc_pass(self._shard_ref, movers, seed, epoch, t_lo, t_hi, 1, ws, wb, mm, self._stream()))
+                        self.last_passes += 1
+                    if prefix_ok and 0 < sum(nfb_all) <= _FB_BATCH:
+                        self._event_phase(movers, nfb_all, nempty, seed, epoch, t_lo, t_hi)
                 full, nrel_all = True, [0] * self.world
                 while True:
                     self.last_passes += 1
@@ -230,10 +258,10 @@ class ShardedSchelling:
             self._barrier()
         return tot_movers
 
-    def _serve_fallback(self, nfb: int, nfb_all: list[int], nempty: int, seed: int, epoch: int) -> None:
-        """grid.py:308-316 for the movers that missed all 50 probes, across ranks."""
+    def _gather_fallback(self, nfb_all: list[int], nempty: int, seed: int, epoch: int):
+        """(time, k, mover) of every rank's fallback movers sorted by time + the rank each one lives on."""
         lib, ws, wb, mm = N.lib(), N.ptr(self._ws), self._ws_bytes, self.max_movers
-        dev, world = self.device, self.world
+        dev, world, nfb = self.device, self.world, nfb_all[self.rank]
         width = max(nfb_all)
         mine = torch.zeros((width, 3), dtype=torch.int64, device=dev)     # (time, k, mover) uint64 bit patterns
         if nfb > 0:
@@ -251,7 +279,37 @@ class ShardedSchelling:
             homes.append(torch.full((n,), r, dtype=torch.int64, device=dev))
         entries, home = torch.cat(rows), torch.cat(homes)
         order = torch.argsort(_u64_sort_key(entries[:, 0]))
-        entries, home = entries[order], home[order]
+        return entries[order], home[order]
+
+    def _event_phase(self, movers: int, nfb_all: list[int], nempty: int, seed: int, epoch: int, t_lo: int, t_hi: int) -> None:
+        """The fallback cascade of a converged bucket: block counts on every rank, the time-ordered event loop on rank 0
+        (all slot / count tables peer-mapped), the changed picks broadcast back as overrides."""
+        lib, ws, wb, mm = N.lib(), N.ptr(self._ws), self._ws_bytes, self.max_movers
+        dev, world = self.device, self.world
+        entries, _ = self._gather_fallback(nfb_all, nempty, seed, epoch)
+        count = int(entries.shape[0])
+        times, ks = entries[:, 0].contiguous(), entries[:, 1].contiguous()
+        totals = torch.zeros(_FB_BATCH, dtype=torch.int32, device=dev)
+        N.check(lib.mb_reloc_fb_count_into(self._shard_ref, N.ptr(times), count, N.ptr(totals), N.ptr(self._cnt_buf), self._stream()))
+        all_totals = torch.empty((world, _FB_BATCH), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(all_totals, totals, group=self.group)      # also: every rank's table is counted
+        ov = self._ov
+        if self.rank == 0:
+            N.check(lib.mb_reloc_event_loop(self._shard_ref, self._cnt_ptrs, N.ptr(all_totals), N.ptr(times), N.ptr(ks), count,
+                                            N.ptr(ov[:_OV_CAP]), N.ptr(ov[_OV_CAP:2 * _OV_CAP]), N.ptr(ov[2 * _OV_CAP:]),
+                                            seed, epoch, self._stream()))
+        dist.broadcast(ov, dist.get_global_rank(self.group, 0) if self.group is not dist.group.WORLD else 0, group=self.group)
+        out4 = ov[2 * _OV_CAP:].tolist()
+        e = self.last_events
+        self.last_events = [e[0] + int(out4[0]), max(e[1], int(out4[1])), e[2] + int(out4[2]), e[3] + int(out4[3])]
+        N.check(lib.mb_reloc_apply_overrides(movers, t_lo, t_hi, N.ptr(ov[:_OV_CAP]), N.ptr(ov[_OV_CAP:2 * _OV_CAP]), int(out4[0]),
+                                             ws, wb, mm, self._stream()))
+
+    def _serve_fallback(self, nfb: int, nfb_all: list[int], nempty: int, seed: int, epoch: int) -> None:
+        """grid.py:308-316 for the movers that missed all 50 probes, across ranks."""
+        lib, ws, wb, mm = N.lib(), N.ptr(self._ws), self._ws_bytes, self.max_movers
+        dev, world = self.device, self.world
+        entries, home = self._gather_fallback(nfb_all, nempty, seed, epoch)
         for first in range(0, entries.shape[0], _FB_BATCH):
             batch = entries[first:first + _FB_BATCH]
             count = batch.shape[0]
