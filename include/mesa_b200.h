@@ -185,6 +185,21 @@ int mb_reloc_apply_overrides(int64_t nmovers, uint64_t t_lo, uint64_t t_hi, cons
 int mb_reloc_apply(const void* shard, int phase, int64_t nmovers, uint32_t* agent_cell, void* workspace,
                    size_t workspace_bytes, int64_t max_movers, mb_stream_t stream);
 
+/* ---- the WHOLE Schelling model step of a small grid in ONE launch (csrc/schelling_small.cu; schelling/model.py:87-93:
+ * shuffle_do("step") then do("assign_state")).  Grids of at most mb_schelling_small_max_cells() (12800) cells keep the
+ * relocation slots in shared memory; one CTA runs the same fixed-point iteration as mb_schelling_relocate between
+ * barriers, applies the moves and evaluates every agent's happiness.  Nothing is read back: out4 = device uint64[4] =
+ * {model.happy, movers, status (0 ok; 1 = grid completely full with an unhappy agent -> ValueError, grid.py:311-315;
+ * 2 = workspace too small; 3 = too many fallback movers; 4 = no convergence), passes}.  relocate == 0 only evaluates
+ * happiness (the model's initial do("assign_state")).  agent_cell [nagents] and empty_layer [rows, cols] (the grid's
+ * implicit "empty" layer, grid.py:128) are optional.  min_similar_host as in mb_schelling_happy_i8. */
+int mb_schelling_small_max_cells(void);
+int mb_schelling_small_workspace_bytes(int64_t max_movers, size_t* out);
+int mb_schelling_step_small(int8_t* type, uint8_t* happy, uint32_t* agent_id, uint32_t* agent_cell, uint8_t* empty_layer,
+                            int64_t rows, int64_t cols, int radius, int torus, const uint8_t* min_similar_host,
+                            uint64_t seed, uint32_t epoch, int relocate, void* workspace, size_t workspace_bytes,
+                            int64_t max_movers, uint64_t* out4, mb_stream_t stream);
+
 /* ---- stable LSD radix sort of (key, uint32) pairs (cell lists; no reference counterpart: the
  * reference scans all agents per query, continuous_space.py:202-235) --------------------------
  * Sorts on key bits [begin_bit, end_bit), 8 bits per pass, ping-ponging between buffer 0 and 1;
@@ -296,13 +311,17 @@ int mb_compact_rows(const void* in, void* out, int64_t n, int64_t row_bytes, con
  * The workspace carries the per-cell list order (arrival order, cell.py:143-170) between steps:
  * call mb_boltzmann_init after placing agents, then mb_boltzmann_step once per model step with
  * epoch = number of shuffles so far.  Result identical to the sequential reference driven with the
- * same keyed draws (csrc/boltzmann.cu).  mb_boltzmann_step synchronises `stream`. */
+ * same keyed draws (csrc/boltzmann.cu).  mb_boltzmann_step only ENQUEUES (no host synchronisation: crowded cells
+ * and the convergence of the give decisions are resolved on the device); iterations_dev: optional device uint32. */
 int mb_boltzmann_workspace_bytes(int64_t n, size_t* out);
 int mb_boltzmann_init(const uint32_t* cell, int64_t n, int64_t rows, int64_t cols, void* workspace,
                       size_t workspace_bytes, mb_stream_t stream);
 int mb_boltzmann_step(uint32_t* cell, int32_t* wealth, int64_t n, int64_t rows, int64_t cols, int torus,
                       uint64_t seed, uint32_t epoch, void* workspace, size_t workspace_bytes,
-                      int* out_iterations, mb_stream_t stream);
+                      uint32_t* iterations_dev, mb_stream_t stream);
+/* sticky status word of the workspace (0 = every step was exact; 1 = a step met more than 4096 cells holding more
+ * than 32 agents each, which the device path does not order).  Synchronises `stream`. */
+int mb_boltzmann_status(void* workspace, size_t workspace_bytes, int64_t n, uint64_t* status_host, mb_stream_t stream);
 
 /* ---- property layers (replace the numpy expressions users run on Grid.property_layers arrays,
  * grid.py:112,130-220; e.g. sugarscape_g1mt/model.py:123-124, grid.py:146, grid.py:308) and the

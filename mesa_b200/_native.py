@@ -75,6 +75,10 @@ SIGNATURES: dict[str, tuple] = {
     "mb_reloc_event_loop": (c_int, [_P, ctypes.POINTER(c_void_p), _P, _P, _P, c_int, _P, _P, _P, c_uint64, c_uint32, _S]),
     "mb_reloc_apply_overrides": (c_int, [c_int64, c_uint64, c_uint64, _P, _P, c_int, _P, ctypes.c_size_t, c_int64, _S]),
     "mb_reloc_apply": (c_int, [_P, c_int, c_int64, _P, _P, ctypes.c_size_t, c_int64, _S]),
+    "mb_schelling_small_max_cells": (c_int, []),
+    "mb_schelling_small_workspace_bytes": (c_int, [c_int64, ctypes.POINTER(ctypes.c_size_t)]),
+    "mb_schelling_step_small": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, _P, c_uint64, c_uint32, c_int,
+                                        _P, ctypes.c_size_t, c_int64, _P, _S]),
     # radix sort
     "mb_sort_workspace_bytes": (c_int, [c_int64, ctypes.POINTER(ctypes.c_size_t)]),
     "mb_sort_pairs_u32": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, _P, ctypes.c_size_t,
@@ -112,7 +116,8 @@ SIGNATURES: dict[str, tuple] = {
     "mb_boltzmann_workspace_bytes": (c_int, [c_int64, ctypes.POINTER(ctypes.c_size_t)]),
     "mb_boltzmann_init": (c_int, [_P, c_int64, c_int64, c_int64, _P, ctypes.c_size_t, _S]),
     "mb_boltzmann_step": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int, c_uint64, c_uint32, _P,
-                                  ctypes.c_size_t, ctypes.POINTER(c_int), _S]),
+                                  ctypes.c_size_t, _P, _S]),
+    "mb_boltzmann_status": (c_int, [_P, ctypes.c_size_t, c_int64, ctypes.POINTER(c_uint64), _S]),
     # property layers / neighbourhood sums
     "mb_layer_fill": (c_int, [_P, c_int64, c_int, c_double, _S]),
     "mb_layer_affine_clamp": (c_int, [_P, _P, c_int64, c_int, c_double, c_double, c_double, c_double, _S]),

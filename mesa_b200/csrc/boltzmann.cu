@@ -28,8 +28,7 @@ namespace {
 
 constexpr unsigned long long kNever = ~0ull;
 constexpr uint32_t kNoTarget = 0xffffffffu;
-constexpr int kIterBatch = 4;
-constexpr int kMaxIterSlots = 4096;
+constexpr int kCounterWords = 2 + 2 * 4096 + 2;   // status, queue length, (start, length) x kLongCap, 4 sync words
 
 struct BoltzWs {
     uint64_t* keysA;      // [n] sorted (cell << 32 | arrival priority hi32) of the PREVIOUS step (persistent)
@@ -45,7 +44,7 @@ struct BoltzWs {
     unsigned long long* first_gift;  // [n] earliest time a gift reaches the agent
     uint8_t* gives;       // [n]
     uint8_t* draws;       // [n] draws consumed by move()
-    unsigned long long* counters;    // [kMaxIterSlots] changed flags
+    unsigned long long* counters;    // [kCounterWords] status | crowded-cell queue | barrier / convergence words
     void* sort_ws;
     size_t sort_ws_bytes;
 };
@@ -71,7 +70,7 @@ size_t carve(BoltzWs* ws, char* base, int64_t n) {
     t.first_gift = (unsigned long long*)take(8 * n);
     t.gives = (uint8_t*)take(n);
     t.draws = (uint8_t*)take(n);
-    t.counters = (unsigned long long*)take(8 * kMaxIterSlots);
+    t.counters = (unsigned long long*)take(8 * kCounterWords);
     t.sort_ws_bytes = mb::sort_workspace_bytes(n);
     t.sort_ws = take(t.sort_ws_bytes);
     if (ws) *ws = t;
@@ -133,18 +132,26 @@ __global__ void boltz_rank(const uint32_t* __restrict__ valsB, int64_t n, uint32
 // the thread that owns the run's first slot.  Runs longer than kMaxFixRun raise a flag and the step falls back to the
 // full-width sort.
 constexpr int kMaxFixRun = 32;
+constexpr int kLongCap = 4096;       // crowded cells queued per step (more: error status)
+constexpr int kLongSmem = 4096;      // run length sorted in shared memory by one CTA (longer: in place, global memory)
 
+// longs: [0] number of queued runs, then (start, length) pairs
 __global__ void boltz_fix_runs(uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int64_t n,
-                               unsigned long long* __restrict__ too_long) {
+                               unsigned long long* __restrict__ longs) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t cell = keys[i] >> 32;
     if (i > 0 && (keys[i - 1] >> 32) == cell) return;      // not the start of a run
     if (i + 1 >= n || (keys[i + 1] >> 32) != cell) return;  // a run of one
     int64_t e = i + 2;
-    while (e < n && (keys[e] >> 32) == cell && e - i <= kMaxFixRun) ++e;
+    while (e < n && (keys[e] >> 32) == cell) ++e;
     if (e - i > kMaxFixRun) {
-        *too_long = 1ull;
+        // a crowded cell: queued for the cooperative sort (boltz_fix_long) -- no host round trip
+        const unsigned long long slot = atomicAdd(&longs[0], 1ull);
+        if (slot < (unsigned long long)kLongCap) {
+            longs[1 + 2 * slot] = (unsigned long long)i;
+            longs[2 + 2 * slot] = (unsigned long long)(e - i);
+        }
         return;
     }
     for (int64_t a = i + 1; a < e; ++a) {
@@ -158,6 +165,63 @@ __global__ void boltz_fix_runs(uint64_t* __restrict__ keys, uint32_t* __restrict
         }
         keys[b] = k;
         vals[b] = v;
+    }
+}
+
+// Crowded cells (runs longer than kMaxFixRun): one CTA per queued run, bitonic sort on (key, agent) -- the radix sort
+// on the cell bits is stable, so a run arrives in ascending agent index and ordering ties by the agent index equals the
+// stable order.  Runs of up to kLongSmem pairs are sorted in shared memory, longer ones in place.
+__global__ void __launch_bounds__(1024)
+boltz_fix_long(uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, const unsigned long long* __restrict__ longs,
+               unsigned long long* __restrict__ status) {
+    __shared__ uint64_t sk[kLongSmem];
+    __shared__ uint32_t sv[kLongSmem];
+    unsigned long long nruns = longs[0];
+    if (nruns > (unsigned long long)kLongCap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *status = 1ull;   // more crowded cells than the queue holds
+        nruns = kLongCap;
+    }
+    for (unsigned long long r = blockIdx.x; r < nruns; r += gridDim.x) {
+        const int64_t start = (int64_t)longs[1 + 2 * r];
+        const int64_t len = (int64_t)longs[2 + 2 * r];
+        int64_t pow2 = 1;
+        while (pow2 < len) pow2 <<= 1;
+        const bool in_smem = len <= kLongSmem;
+        uint64_t* K = in_smem ? sk : keys + start;
+        uint32_t* V = in_smem ? sv : vals + start;
+        if (in_smem) {
+            for (int64_t i = threadIdx.x; i < len; i += blockDim.x) {
+                sk[i] = keys[start + i];
+                sv[i] = vals[start + i];
+            }
+        }
+        __syncthreads();
+        // bitonic network in its all-ascending form (first stage of every merge pairs i with i ^ (k - 1), the others
+        // i with i ^ j): the smaller element always goes to the lower index, so the virtual +infinity elements that pad
+        // the run to a power of two never move and pairs with a partner beyond `len` are simply skipped
+        for (int64_t k = 2; k <= pow2; k <<= 1)
+            for (int64_t j = k >> 1; j > 0; j >>= 1) {
+                const int64_t mask = j == (k >> 1) ? k - 1 : j;
+                for (int64_t i = threadIdx.x; i < len; i += blockDim.x) {
+                    const int64_t p = i ^ mask;
+                    if (p > i && p < len) {
+                        const uint64_t ki = K[i], kp = K[p];
+                        const uint32_t vi = V[i], vp = V[p];
+                        if (ki > kp || (ki == kp && vi > vp)) {
+                            K[i] = kp; V[i] = vp;
+                            K[p] = ki; V[p] = vi;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        if (in_smem) {
+            for (int64_t i = threadIdx.x; i < len; i += blockDim.x) {
+                keys[start + i] = sk[i];
+                vals[start + i] = sv[i];
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -206,21 +270,51 @@ __global__ void boltz_target(const int32_t* __restrict__ wealth, int64_t n, uint
     ws.first_gift[a] = kNever;
 }
 
-// every giver announces the time of its gift to the receiver
-__global__ void boltz_push(int64_t n, BoltzWs ws) {
-    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= n || !ws.gives[a]) return;
-    atomicMin(&ws.first_gift[ws.target[a]], (unsigned long long)ws.prio[a]);
+// The give decisions as ONE persistent kernel: a giver announces the time of its gift to the receiver (atomicMin), an
+// agent that started the step broke gives iff a gift reached it before its turn, repeated until nothing changes --
+// a monotone fixed point, ~4 rounds.  The rounds are separated by a grid-wide barrier (all CTAs are resident: the
+// grid is sized from the occupancy), so the convergence test never goes to the host.
+//   sync[0]: barrier arrivals (monotone), sync[1 + (round & 1)]: "somebody changed in this round", sync[3]: rounds done
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (*(volatile unsigned*)counter < target) __nanosleep(20);
+        __threadfence();
+    }
+    __syncthreads();
 }
 
-// an agent that started the step broke gives iff a gift reached it before its turn
-__global__ void boltz_pull(int64_t n, BoltzWs ws, int iter) {
-    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= n || ws.gives[a] || ws.target[a] == kNoTarget) return;
-    if (ws.first_gift[a] < ws.prio[a]) {
-        ws.gives[a] = 1;
-        atomicAdd(&ws.counters[iter], 1ull);
+__global__ void __launch_bounds__(256)
+boltz_iterate(int64_t n, BoltzWs ws, unsigned* sync, uint32_t* iterations_out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned target = 0, round = 0;
+    for (;; ++round) {
+        // push: givers that have not announced yet (gives == 1 -> 2)
+        for (int64_t a = first; a < n; a += stride) {
+            if (__ldcg(ws.gives + a) == 1) {
+                atomicMin(&ws.first_gift[ws.target[a]], (unsigned long long)ws.prio[a]);
+                ws.gives[a] = 2;
+            }
+        }
+        grid_barrier(&sync[0], target);
+        unsigned changed = 0;
+        for (int64_t a = first; a < n; a += stride) {
+            if (__ldcg(ws.gives + a) == 0 && ws.target[a] != kNoTarget && __ldcg(ws.first_gift + a) < ws.prio[a]) {
+                ws.gives[a] = 1;
+                changed = 1;
+            }
+        }
+        if (__syncthreads_or(changed) && threadIdx.x == 0) *(volatile unsigned*)&sync[1 + (round & 1u)] = 1u;
+        if (blockIdx.x == 0 && threadIdx.x == 0) sync[1 + ((round + 1u) & 1u)] = 0u;   // the other round's flag: everybody has read it
+        grid_barrier(&sync[0], target);
+        if (*(volatile unsigned*)&sync[1 + (round & 1u)] == 0u) break;
+        if (round > 1000000u) break;
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && iterations_out != nullptr) *iterations_out = round + 1u;
 }
 
 __global__ void boltz_apply(int32_t* __restrict__ wealth, uint32_t* __restrict__ cell, int64_t n, BoltzWs ws) {
@@ -231,6 +325,7 @@ __global__ void boltz_apply(int32_t* __restrict__ wealth, uint32_t* __restrict__
         atomicAdd(&wealth[ws.target[a]], 1);
         atomicSub(&wealth[a], 1);
     }
+    // (gives is 0 / 2 here: every giver has announced its gift before the last round found nothing to change)
 }
 
 int sort_bits(int64_t ncells) {
@@ -260,6 +355,8 @@ MB_API int mb_boltzmann_init(const uint32_t* cell, int64_t n, int64_t rows, int6
         mb::set_error("mb_boltzmann_init: workspace too small");
         return MB_ERR_WORKSPACE;
     }
+    int rc0 = mb::check_cuda(cudaMemsetAsync(ws.counters, 0, 8 * kCounterWords, stream), "memset");   // status word, queue
+    if (rc0) return rc0;
     const unsigned blocks = (unsigned)mb::ceil_div(n, 256);
     init_keys<<<blocks, 256, 0, stream>>>(cell, n, ws.keys0, ws.vals0);
     const int where = mb::radix_sort_pairs<uint64_t>(ws.keys0, ws.vals0, ws.keys1, ws.vals1, n, 32, sort_bits(rows * cols),
@@ -270,16 +367,18 @@ MB_API int mb_boltzmann_init(const uint32_t* cell, int64_t n, int64_t rows, int6
     return mb::check_cuda(cudaMemcpyAsync(ws.valsA, where ? ws.vals1 : ws.vals0, 4 * n, cudaMemcpyDeviceToDevice, stream), "copy");
 }
 
-// One model step (shuffle number `epoch`).  Synchronises `stream` (convergence flag).
+// One model step (shuffle number `epoch`).  Enqueues ~20 launches on `stream` and returns: no host synchronisation
+// (crowded cells and the convergence of the give decisions are handled on the device).  iterations_dev (optional,
+// device uint32): rounds of the give-decision fixed point.  status word (device, ws.counters[0], read it with
+// mb_boltzmann_status): non-zero if more than 4096 cells held more than 32 agents in this step (not supported).
 MB_API int mb_boltzmann_step(uint32_t* cell, int32_t* wealth, int64_t n, int64_t rows, int64_t cols, int torus,
                              uint64_t seed, uint32_t epoch, void* workspace, size_t workspace_bytes,
-                             int* out_iterations, cudaStream_t stream) {
+                             uint32_t* iterations_dev, cudaStream_t stream) {
     MB_REQUIRE(n >= 0 && n < (1ll << 31), "mb_boltzmann_step: n out of range");
     MB_REQUIRE(rows > 0 && cols > 0 && rows * cols < (1ll << 32), "mb_boltzmann_step: grid must have < 2^32 cells");
     // a 1x1 grid has an empty neighbourhood: select_random_cell raises LookupError (cell_collection.py:114-117)
     MB_REQUIRE(rows * cols >= 2, "Cannot select random cell from empty collection");
     MB_REQUIRE(!torus || (rows >= 3 && cols >= 3), "mb_boltzmann_step: torus needs dims >= 3 (SURVEY A.2)");
-    if (out_iterations) *out_iterations = 0;
     if (n == 0) return MB_OK;
     MB_REQUIRE(cell && wealth && workspace, "mb_boltzmann_step: null buffer");
     BoltzWs ws;
@@ -287,32 +386,27 @@ MB_API int mb_boltzmann_step(uint32_t* cell, int32_t* wealth, int64_t n, int64_t
         mb::set_error("mb_boltzmann_step: workspace too small");
         return MB_ERR_WORKSPACE;
     }
-    int rc = mb::check_cuda(cudaMemsetAsync(ws.counters, 0, 8 * kMaxIterSlots, stream), "memset");
+    // counters: [0] status (sticky), [1] queued crowded cells, [2 ..] their (start, length) pairs; sync words at the end
+    unsigned long long* status = ws.counters;
+    unsigned long long* longs = ws.counters + 1;
+    unsigned* sync = reinterpret_cast<unsigned*>(ws.counters + kCounterWords - 2);
+    int rc = mb::check_cuda(cudaMemsetAsync(longs, 0, 8, stream), "memset");
     if (rc) return rc;
+    if ((rc = mb::check_cuda(cudaMemsetAsync(sync, 0, 16, stream), "memset"))) return rc;
     const unsigned blocks = (unsigned)mb::ceil_div(n, 256);
     boltz_move<<<blocks, 256, 0, stream>>>(cell, n, (int)rows, (int)cols, torus, seed, epoch, ws);
-    // sparse grids sort on the cell bits only and order the short runs afterwards (boltz_fix_runs)
-    bool cell_sort_only = n <= rows * cols;
+    // sparse grids sort on the cell bits only and order the (short) runs of equal cells afterwards; crowded grids
+    // sort on the full (cell, priority) key
     int where = 0;
-    if (cell_sort_only) {
+    if (n <= rows * cols) {
         where = mb::radix_sort_pairs<uint64_t>(ws.keys0, ws.vals0, ws.keys1, ws.vals1, n, 32, sort_bits(rows * cols),
                                                ws.sort_ws, ws.sort_ws_bytes, stream);
         if (where < 0) return where;
-        unsigned long long* too_long = ws.counters + (kMaxIterSlots - 1);   // last slot: never reached by the iterations
-        boltz_fix_runs<<<blocks, 256, 0, stream>>>(where ? ws.keys1 : ws.keys0, where ? ws.vals1 : ws.vals0, n, too_long);
-        unsigned long long flag = 0;
-        rc = mb::check_cuda(cudaMemcpyAsync(&flag, too_long, sizeof(flag), cudaMemcpyDeviceToHost, stream), "read");
-        if (rc) return rc;
-        rc = mb::check_cuda(cudaStreamSynchronize(stream), "sync");
-        if (rc) return rc;
-        if (flag != 0) {   // a crowded cell: redo with the full-width sort (boltz_move rewrites keys0 / vals0)
-            cell_sort_only = false;
-            rc = mb::check_cuda(cudaMemsetAsync(too_long, 0, sizeof(flag), stream), "memset");
-            if (rc) return rc;
-            boltz_move<<<blocks, 256, 0, stream>>>(cell, n, (int)rows, (int)cols, torus, seed, epoch, ws);
-        }
-    }
-    if (!cell_sort_only) {
+        uint64_t* k = where ? ws.keys1 : ws.keys0;
+        uint32_t* v = where ? ws.vals1 : ws.vals0;
+        boltz_fix_runs<<<blocks, 256, 0, stream>>>(k, v, n, longs);
+        boltz_fix_long<<<32, 1024, 0, stream>>>(k, v, longs, status);
+    } else {
         where = mb::radix_sort_pairs<uint64_t>(ws.keys0, ws.vals0, ws.keys1, ws.vals1, n, 0, sort_bits(rows * cols),
                                                ws.sort_ws, ws.sort_ws_bytes, stream);
         if (where < 0) return where;
@@ -322,25 +416,15 @@ MB_API int mb_boltzmann_step(uint32_t* cell, int32_t* wealth, int64_t n, int64_t
     boltz_rank<<<blocks, 256, 0, stream>>>(valsB, n, ws.rankB);
     boltz_target<<<blocks, 256, 0, stream>>>(wealth, n, seed, epoch, keysB, valsB, ws);
     MB_LAUNCH_CHECK("boltz_target");
-    int iter = 0;
-    for (bool done = false; !done;) {
-        if (iter + kIterBatch >= kMaxIterSlots) {
-            mb::set_error("mb_boltzmann_step: no convergence after %d iterations", iter);
-            return MB_ERR_CUDA;
-        }
-        const int first = iter;
-        for (int b = 0; b < kIterBatch; ++b, ++iter) {
-            boltz_push<<<blocks, 256, 0, stream>>>(n, ws);
-            boltz_pull<<<blocks, 256, 0, stream>>>(n, ws, iter);
-        }
-        MB_LAUNCH_CHECK("boltz_iterate");
-        unsigned long long changed[kIterBatch];
-        rc = mb::check_cuda(cudaMemcpyAsync(changed, ws.counters + first, sizeof(changed), cudaMemcpyDeviceToHost, stream), "read");
-        if (rc) return rc;
-        rc = mb::check_cuda(cudaStreamSynchronize(stream), "sync");
-        if (rc) return rc;
-        done = changed[kIterBatch - 1] == 0;
+    // persistent give-decision kernel: every CTA must be resident (grid barrier)
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        if ((rc = mb::check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, boltz_iterate, 256, 0), "occupancy"))) return rc;
+        if (per_sm < 1) per_sm = 1;
     }
+    int64_t grid = (int64_t)mb::sm_count() * per_sm;
+    if (grid > blocks) grid = blocks;
+    boltz_iterate<<<(unsigned)grid, 256, 0, stream>>>(n, ws, sync, iterations_dev);
     boltz_apply<<<blocks, 256, 0, stream>>>(wealth, cell, n, ws);
     // this step's arrival order is next step's "still sitting here" order
     rc = mb::check_cuda(cudaMemcpyAsync(ws.keysA, keysB, 8 * n, cudaMemcpyDeviceToDevice, stream), "copy");
@@ -348,6 +432,20 @@ MB_API int mb_boltzmann_step(uint32_t* cell, int32_t* wealth, int64_t n, int64_t
     rc = mb::check_cuda(cudaMemcpyAsync(ws.valsA, valsB, 4 * n, cudaMemcpyDeviceToDevice, stream), "copy");
     if (rc) return rc;
     MB_LAUNCH_CHECK("mb_boltzmann_step");
-    if (out_iterations) *out_iterations = iter;
     return MB_OK;
+}
+
+// Sticky status word of the workspace (0 = every step so far was exact).  Synchronises `stream`.
+MB_API int mb_boltzmann_status(void* workspace, size_t workspace_bytes, int64_t n, uint64_t* status_host, cudaStream_t stream) {
+    MB_REQUIRE(workspace && status_host && n >= 0, "mb_boltzmann_status: bad argument");
+    *status_host = 0;
+    if (n == 0) return MB_OK;
+    BoltzWs ws;
+    if (carve(&ws, (char*)workspace, n) > workspace_bytes) {
+        mb::set_error("mb_boltzmann_status: workspace too small");
+        return MB_ERR_WORKSPACE;
+    }
+    int rc = mb::check_cuda(cudaMemcpyAsync(status_host, ws.counters, 8, cudaMemcpyDeviceToHost, stream), "read");
+    if (rc) return rc;
+    return mb::check_cuda(cudaStreamSynchronize(stream), "sync");
 }

@@ -814,17 +814,37 @@ reloc_event_loop(ShardView v, EventArgs a, uint64_t seed, uint32_t epoch) {
             unsigned need = s_need;
             __syncthreads();
             if (tid == 0) s_found = 0;
-            for (long long c0 = lo_c; c0 < hi_c; c0 += blockDim.x) {
-                const long long c = c0 + tid;
-                Slot sl{kNever, 0ull};
-                if (c < hi_c) sl = load_slot(slots + c);
-                const unsigned e = c < hi_c && empty_at(sl, t);
+            // every thread takes kPer consecutive cells (independent 16-byte loads, all in flight at once), one block
+            // scan per 1024 * kPer cells
+            constexpr int kPer = 16;
+            for (long long c0 = lo_c; c0 < hi_c; c0 += (long long)blockDim.x * kPer) {
+                const long long mine = c0 + (long long)tid * kPer;
+                Slot sl[kPer];
+#pragma unroll
+                for (int q = 0; q < kPer; ++q) {
+                    sl[q] = Slot{kNever, 0ull};
+                    if (mine + q < hi_c) sl[q] = load_slot(slots + mine + q);
+                }
+                unsigned e = 0;
+#pragma unroll
+                for (int q = 0; q < kPer; ++q) e += empty_at(sl[q], t);
                 unsigned total;
                 const unsigned excl = block_exclusive_scan(e, warp_sums, total);
                 if (need < total) {
-                    if (e && excl == need) {
-                        s_cell = (unsigned long long)(v.row_lo(o) * v.cols + c); s_aold = sl.arr; s_vac = sl.vac; s_found = 1;
-                        atomicMin(&v.slots[o][c].arr, t);
+                    if (need >= excl && need < excl + e) {
+                        unsigned left = need - excl;
+#pragma unroll
+                        for (int q = 0; q < kPer; ++q) {
+                            if (empty_at(sl[q], t)) {
+                                if (left == 0u) {
+                                    const long long c = mine + q;
+                                    s_cell = (unsigned long long)(v.row_lo(o) * v.cols + c); s_aold = sl[q].arr; s_vac = sl[q].vac;
+                                    s_found = 1;
+                                    atomicMin(&v.slots[o][c].arr, t);
+                                }
+                                --left;
+                            }
+                        }
                     }
                     break;
                 }

@@ -27,8 +27,7 @@ class MoneyAgent(DeviceAgent):
 @batch_operator(MoneyAgent, "step")
 def _step(agents: DeviceAgentSet, epoch: int, **_):
     m = agents.model
-    m.last_iterations = ops.boltzmann_step(agents.columns["cell"], agents.columns["wealth"], m._ws, m.philox_seed, epoch,
-                                           torus=m.grid.torus)
+    ops.boltzmann_step(agents.columns["cell"], agents.columns["wealth"], m._ws, m.philox_seed, epoch, torus=m.grid.torus)
 
 
 class BoltzmannWealth(DeviceModel):
@@ -53,7 +52,6 @@ class BoltzmannWealth(DeviceModel):
         wealth = torch.ones(self.num_agents, dtype=torch.int32, device=dev)
         self.agents = DeviceAgentSet(self, MoneyAgent, self.num_agents, {"cell": cell, "wealth": wealth}, self.random, resizable=False)
         self._ws = ops.BoltzmannWorkspace(cell, scenario.width, scenario.height)
-        self.last_iterations = 0
         self.running = True
         # grid.py:128 + cell.py:143-170: the implicit `empty` layer follows the occupancy.  Nobody on the step path reads
         # it, so it is brought up to date when somebody asks for it (hook), from the per-agent cell column
@@ -63,6 +61,12 @@ class BoltzmannWealth(DeviceModel):
         empty = dict.__getitem__(self.grid.property_layers, "empty")
         empty.fill_(True)
         empty.view(-1)[self.agents.columns["cell"].long()] = False
+
+    @property
+    def last_iterations(self) -> int:
+        """Rounds of the give-decision fixed point of the last step (device word, read on demand)."""
+        self._ws.check()
+        return int(self._ws.iterations.item())
 
     def step(self):
         self.agents.shuffle_do("step")  # model.py:79-81

@@ -40,17 +40,29 @@ class SchellingAgent(DeviceAgent):
 @batch_operator(SchellingAgent, "assign_state")
 def _assign_state(agents: DeviceAgentSet, **_):
     m = agents.model
+    if m._small is not None:
+        # small grid: ONE launch for the pending shuffle_do("step") (if any) + this do("assign_state"), nothing read back
+        epoch, m._pending_epoch = m._pending_epoch, None
+        layers = m.grid.property_layers
+        m._small.step(layers["type"], layers["happy"], layers["agent_id"], m.philox_seed, epoch or 0,
+                      agent_cell=dict.__getitem__(agents.columns, "cell"), empty_layer=layers["empty"],
+                      relocate=epoch is not None)
+        m._last_small = m._last_small or epoch is not None
+        return
     g = m.grid
     ops.schelling_happy(g.type, m.homophily, m.radius, g.torus, out=g.happy, count=m._happy_count, table=m._table)
-    m._happy_dirty = True
 
 
 @batch_operator(SchellingAgent, "step")
 def _step(agents: DeviceAgentSet, epoch: int, **_):
     m = agents.model
-    g = m.grid
-    m.last_movers, m.last_iterations = ops.schelling_relocate(g.type, g.happy, g.agent_id, m._ws, m.philox_seed, epoch,
-                                                              agent_cell=agents.columns["cell"])
+    if m._small is not None:
+        # deferred: the relocation is fused with the do("assign_state") that follows it in Schelling.step (model.py:87-93);
+        # anybody who looks at the layers or the agents' cells in between gets it flushed first (_flush_pending)
+        m._flush_pending()
+        m._pending_epoch = epoch
+        return
+    m._relocate(epoch)
 
 
 class _Columns(dict):
@@ -61,6 +73,7 @@ class _Columns(dict):
         self._model = model
 
     def __getitem__(self, name):
+        self._model._flush_pending()
         if name == "happy":
             return self._model.grid.happy.reshape(-1)[dict.__getitem__(self, "cell").long()]
         return dict.__getitem__(self, name)
@@ -73,9 +86,12 @@ class Schelling(DeviceModel):
     """Model class for the Schelling segregation model."""
 
     def __init__(self, scenario: SchellingScenario = SchellingScenario, initial_types=None, device="cuda",
-                 collect: bool = True):
+                 collect: bool = True, fused: bool = True):
         if isinstance(scenario, type):
             scenario = scenario()
+        self._small = self._pending_epoch = None
+        self._last_small = False
+        self._running, self._running_pending = True, False
         super().__init__(scenario=scenario)
         # model.py:53-70: the reference's reporters, served from the device columns (one reduction / one bulk copy each)
         self.datacollector = DeviceDataCollector(
@@ -114,12 +130,19 @@ class Schelling(DeviceModel):
         self._table = ops.happy_threshold_table(self.homophily, self.radius)
         self._happy_count = torch.zeros(1, dtype=torch.int64, device=dev)
         self._ws = ops.RelocationWorkspace(types, n)
-        self.last_movers = self.last_iterations = 0
+        self._last = (0, 0)
+        if fused and ops.SchellingSmallStep.supports(int(types.numel())):
+            # the whole step in one launch (csrc/schelling_small.cu); model.happy / movers stay on the device until read
+            self._small = ops.SchellingSmallStep(types, n, self.homophily, self.radius, self.grid.torus)
+            self._happy_count = self._small.out[0:1]
+            for name in ("type", "happy", "agent_id", "empty"):
+                self.grid.property_layers.hooks[name] = self._flush_pending
         cols = _Columns(self, cell=cells.to(torch.int32), type=flat[cells].clone())
         self.agents = DeviceAgentSet(self, SchellingAgent, n, cols, self.random, resizable=False)
         self.grid.cell_agents = self._cell_agents
         self.agents.do("assign_state")  # model.py:83-85
-        self._sync_empty()              # grid.py:128 + cell.py:143-170: `empty` tracks the occupancy from placement on
+        if self._small is None:
+            self._sync_empty()          # grid.py:128 + cell.py:143-170: `empty` tracks the occupancy from placement on
         if self.datacollector is not None:
             self.datacollector.collect(self)
 
@@ -134,15 +157,52 @@ class Schelling(DeviceModel):
     def _sync_empty(self):
         torch.lt(self.grid.type, 0, out=self.grid.property_layers["empty"])
 
+    def _relocate(self, epoch: int) -> None:
+        g = self.grid
+        self._last_small = False
+        self._last = ops.schelling_relocate(g.type, g.happy, g.agent_id, self._ws, self.philox_seed, epoch,
+                                            agent_cell=dict.__getitem__(self.agents.columns, "cell"))
+
+    def _flush_pending(self) -> None:
+        """A shuffle_do("step") that was deferred for fusion and is being observed before its do("assign_state"): run it
+        now through the multi-launch path (same result)."""
+        if self._pending_epoch is not None:
+            epoch, self._pending_epoch = self._pending_epoch, None
+            self._ws.sync(dict.__getitem__(self.grid.property_layers, "type"))   # the fused steps do not maintain the slot table
+            self._relocate(epoch)
+
     @property
     def happy(self) -> int:
+        if self._small is not None:
+            return self._small.check()[0]
         return int(self._happy_count.item())
+
+    @property
+    def last_movers(self) -> int:
+        return self._small.check()[1] if self._last_small else self._last[0]
+
+    @property
+    def last_iterations(self) -> int:
+        return self._small.check()[2] if self._last_small else self._last[1]
+
+    # model.py:93 `self.running = self.happy < len(self.agents)`: evaluated when somebody reads it, so that a step
+    # enqueues its launch and returns (run_for(n) never waits for the device; run_model() reads it every step)
+    @property
+    def running(self) -> bool:
+        if self._running_pending:
+            self._running, self._running_pending = self.happy < len(self.agents), False
+        return self._running
+
+    @running.setter
+    def running(self, value) -> None:
+        self._running, self._running_pending = bool(value), False
 
     def step(self):
         """model.py:87-93."""
         self.agents.shuffle_do("step")
         self.agents.do("assign_state")
-        self._sync_empty()
+        if self._small is None:
+            self._sync_empty()
         if self.datacollector is not None:
             self.datacollector.collect(self)  # model.py:92
-        self.running = self.happy < len(self.agents)
+        self._running_pending = True

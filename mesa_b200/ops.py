@@ -274,6 +274,57 @@ def schelling_relocate(type_layer: torch.Tensor, happy: torch.Tensor, agent_id: 
     return int(movers.value), int(iters.value)
 
 
+class SchellingSmallStep:
+    """The whole Schelling model step of a small grid (<= 12800 cells, e.g. BASELINE config 1: 100 x 100) as ONE
+    kernel launch with nothing read back (csrc/schelling_small.cu): shuffle_do("step") + do("assign_state").
+
+    `out` is a device int64[4]: model.happy, movers, status, passes; `check()` reads it (synchronises) and raises the
+    reference's ValueError for a completely full grid (grid.py:311-315)."""
+
+    def __init__(self, type_layer: torch.Tensor, max_movers: int, homophily: float, radius: int, torus: bool = False):
+        import ctypes
+
+        _need_cuda(type_layer)
+        if type_layer.dtype != torch.int8 or type_layer.dim() != 2:
+            raise ValueError("expected the int8 [rows, cols] type layer")
+        self.rows, self.cols = type_layer.shape
+        if not self.supports(self.rows * self.cols):
+            raise ValueError("SchellingSmallStep: the grid has more cells than the single-launch path holds")
+        self.radius, self.torus = int(radius), bool(torus)
+        self.max_movers = int(max_movers)
+        self.table = happy_threshold_table(homophily, radius)
+        nbytes = ctypes.c_size_t(0)
+        N.check(N.lib().mb_schelling_small_workspace_bytes(self.max_movers, ctypes.byref(nbytes)))
+        self.nbytes = int(nbytes.value)
+        self.buf = torch.empty(max(self.nbytes, 1), dtype=torch.uint8, device=type_layer.device)
+        self.out = torch.zeros(4, dtype=torch.int64, device=type_layer.device)
+
+    @staticmethod
+    def supports(ncells: int) -> bool:
+        return 0 < ncells <= N.lib().mb_schelling_small_max_cells()
+
+    def step(self, type_layer, happy, agent_id, seed: int, epoch: int, agent_cell=None, empty_layer=None,
+             relocate: bool = True) -> torch.Tensor:
+        _need_cuda(type_layer, happy, agent_id, agent_cell, empty_layer)
+        e = None if empty_layer is None else (empty_layer.view(torch.uint8) if empty_layer.dtype == torch.bool else empty_layer)
+        with torch.cuda.device(type_layer.device):
+            N.check(N.lib().mb_schelling_step_small(
+                N.ptr(_c(type_layer)), N.ptr(_c(happy)), N.ptr(_c(agent_id)), N.ptr(agent_cell), N.ptr(e), self.rows,
+                self.cols, self.radius, int(self.torus), self.table.ctypes.data, int(seed) & 0xFFFFFFFFFFFFFFFF,
+                int(epoch) & 0xFFFFFFFF, int(bool(relocate)), N.ptr(self.buf), self.nbytes, self.max_movers,
+                N.ptr(self.out), N.stream_ptr(type_layer.device)))
+        return self.out
+
+    def check(self) -> tuple[int, int, int]:
+        """(model.happy, movers, passes) of the last step; raises on a failed step.  Synchronises."""
+        happy, movers, status, passes = (int(x) for x in self.out.tolist())
+        if status == 1:
+            raise ValueError("Grid is completely full. No empty cells available. Cannot select a random empty cell.")
+        if status:
+            raise N.MesaB200Error(f"mb_schelling_step_small failed with status {status}")
+        return happy, movers, passes
+
+
 # ----------------------------------------------------------------------------- sort
 def sort_pairs(keys: torch.Tensor, vals: torch.Tensor, begin_bit: int = 0, end_bit: int | None = None):
     """Stable radix sort of (keys, vals); keys int32/int64 viewed as unsigned, vals int32.  Returns new tensors."""
@@ -511,6 +562,7 @@ class BoltzmannWorkspace:
         N.check(N.lib().mb_boltzmann_workspace_bytes(self.n, ctypes.byref(nbytes)))
         self.nbytes = int(nbytes.value)
         self.buf = torch.empty(max(self.nbytes, 1), dtype=torch.uint8, device=cell.device)
+        self.iterations = torch.zeros(1, dtype=torch.int32, device=cell.device)
         self.reset(cell)
 
     def reset(self, cell: torch.Tensor) -> None:
@@ -519,21 +571,30 @@ class BoltzmannWorkspace:
             N.check(N.lib().mb_boltzmann_init(N.ptr(_c(cell)), self.n, self.rows, self.cols, N.ptr(self.buf),
                                               self.nbytes, N.stream_ptr(cell.device)))
 
+    def check(self) -> None:
+        """Raise if any step since `reset` could not be ordered exactly on the device.  Synchronises."""
+        import ctypes
+
+        status = ctypes.c_uint64(0)
+        with torch.cuda.device(self.buf.device):
+            N.check(N.lib().mb_boltzmann_status(N.ptr(self.buf), self.nbytes, self.n, ctypes.byref(status),
+                                                N.stream_ptr(self.buf.device)))
+        if status.value:
+            raise N.MesaB200Error("boltzmann_step: more than 4096 cells held more than 32 agents in one step")
+
 
 def boltzmann_step(cell: torch.Tensor, wealth: torch.Tensor, ws: BoltzmannWorkspace, seed: int, epoch: int,
-                   torus: bool = False) -> int:
-    """shuffle_do("step") of all MoneyAgents; returns the number of give-resolution iterations."""
-    import ctypes
-
+                   torus: bool = False) -> torch.Tensor:
+    """shuffle_do("step") of all MoneyAgents.  Only enqueues (no host synchronisation); returns the device int32[1]
+    holding the number of give-resolution rounds (read it lazily).  `ws.check()` raises if a step was not exact."""
     _need_cuda(cell, wealth)
     if cell.dtype != torch.int32 or wealth.dtype != torch.int32 or cell.numel() != ws.n or wealth.numel() != ws.n:
         raise ValueError("boltzmann_step expects int32 cell / wealth tensors matching the workspace")
-    iters = ctypes.c_int(0)
     with torch.cuda.device(cell.device):
         N.check(N.lib().mb_boltzmann_step(N.ptr(_c(cell)), N.ptr(_c(wealth)), ws.n, ws.rows, ws.cols,
                                           int(bool(torus)), int(seed) & 0xFFFFFFFFFFFFFFFF, int(epoch) & 0xFFFFFFFF,
-                                          N.ptr(ws.buf), ws.nbytes, ctypes.byref(iters), N.stream_ptr(cell.device)))
-    return int(iters.value)
+                                          N.ptr(ws.buf), ws.nbytes, N.ptr(ws.iterations), N.stream_ptr(cell.device)))
+    return ws.iterations
 
 
 # ----------------------------------------------------------------------------- property layers

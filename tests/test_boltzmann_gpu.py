@@ -50,6 +50,7 @@ def test_boltzmann_matches_oracle(n, rows, cols, torus, steps):
         ops.boltzmann_step(cell, wealth, ws, 11, e, torus=torus)
         assert np.array_equal(cell.cpu().numpy(), st.cell), e
         assert np.array_equal(wealth.cpu().numpy(), st.wealth), e
+    ws.check()
     assert int(wealth.sum().item()) == int(wealth0.sum())
 
 
@@ -62,15 +63,16 @@ def test_boltzmann_single_cell_grid_raises():
         ops.boltzmann_step(cell, wealth, ws, 1, 0)
 
 
-def test_boltzmann_sparse_grid_with_a_crowded_cell_falls_back_to_the_full_sort():
-    """n <= ncells selects the cell-bits-only sort + run fix-up; a cell holding more than 32 agents must make the step
-    fall back to the full-width sort and still match the oracle (arrival lists, gifts, wealth)."""
+@pytest.mark.parametrize("rows,cols,n,crowd", [(40, 50, 1500, 400), (300, 300, 60000, 45000)])
+def test_boltzmann_sparse_grid_with_a_crowded_cell_is_ordered_on_the_device(rows, cols, n, crowd):
+    """n <= ncells selects the cell-bits-only sort + run fix-up; cells holding more than 32 agents are queued and ordered
+    by the cooperative kernel (boltz_fix_long: shared memory up to 4096 agents per cell, in place beyond) without a host
+    round trip, and the step still matches the oracle (arrival lists, gifts, wealth)."""
     from mesa_b200 import ops
 
-    rows, cols, n = 40, 50, 1500
     rng = np.random.default_rng(9)
     cell0 = rng.integers(0, rows * cols, size=n)
-    cell0[:400] = 17 * cols + 23          # 400 agents start in one cell: their moves crowd its 8 neighbours (~50 each)
+    cell0[:crowd] = 17 * cols + 23        # `crowd` agents start in one cell: their moves crowd its 8 neighbours
     wealth0 = rng.integers(0, 3, size=n).astype(np.int32)
     st = oracle.BoltzmannState(rows, cols, cell0, wealth0, False)
     cell, wealth = _dev(cell0, wealth0)
@@ -80,3 +82,4 @@ def test_boltzmann_sparse_grid_with_a_crowded_cell_falls_back_to_the_full_sort()
         ops.boltzmann_step(cell, wealth, ws, 5, e)
         assert np.array_equal(cell.cpu().numpy(), st.cell), e
         assert np.array_equal(wealth.cpu().numpy(), st.wealth), e
+    ws.check()

@@ -117,3 +117,114 @@ def test_relocate_full_grid_raises_value_error():
     dev.assign()
     with pytest.raises(ValueError):
         dev.move(1, 0)
+
+
+# ---- the whole step of a small grid in ONE launch (csrc/schelling_small.cu) ------------------------------------------
+class DeviceSchellingSmall(DeviceSchelling):
+    """The same state stepped by mb_schelling_step_small: relocation + happiness fused, nothing read back per step."""
+
+    def __init__(self, st, homophily, radius, torus=False):
+        super().__init__(st, homophily, radius, torus)
+        self.small = self.ops.SchellingSmallStep(self.type, st.n, homophily, radius, torus)
+        self.empty = torch.ones((self.rows, self.cols), dtype=torch.bool, device="cuda")
+
+    def assign(self):
+        self.small.step(self.type, self.happy, self.agent_id.view(torch.int32), 0, 0, agent_cell=self.agent_cell.view(torch.int32),
+                        empty_layer=self.empty, relocate=False)
+        return self.small.check()[0]
+
+    def step(self, seed, epoch):
+        self.small.step(self.type, self.happy, self.agent_id.view(torch.int32), seed, epoch,
+                        agent_cell=self.agent_cell.view(torch.int32), empty_layer=self.empty, relocate=True)
+        return self.small.check()      # (happy, movers, passes)
+
+
+@pytest.mark.parametrize("name", SCHELLING)
+def test_small_step_matches_reference_trajectory(name):
+    g = np.load(os.path.join(GOLDEN, name))
+    rows, cols = int(g["width"]), int(g["height"])
+    from mesa_b200 import ops
+
+    if not ops.SchellingSmallStep.supports(rows * cols):
+        pytest.skip("grid larger than the single-launch path")
+    h, r, seed = float(g["homophily"]), int(g["radius"]), int(g["philox_seed"])
+    st = oracle.SchellingState(rows, cols, g["cell0"], g["atype"])
+    dev = DeviceSchellingSmall(st, h, r)
+    assert dev.assign() == int(g["happy_count0"])
+    assert np.array_equal(dev.happy_by_agent(), g["happy0"])
+    full = set(g["full_steps"].tolist())
+    for s in range(1, len(g["happy_count"]) + 1):
+        happy, movers, _ = dev.step(seed, s - 1)
+        assert movers == int(g["movers"][s - 1]), s
+        assert happy == int(g["happy_count"][s - 1]), s
+        if s in full:
+            assert np.array_equal(dev.cells(), g[f"cell_{s}"]), s
+            assert np.array_equal(dev.happy_by_agent(), g[f"happy_{s}"]), s
+            tg = dev.type.cpu().numpy().reshape(-1)
+            assert np.array_equal(tg[dev.cells()], g["atype"])
+            assert np.array_equal(dev.empty.cpu().numpy().reshape(-1), tg < 0)
+
+
+@pytest.mark.parametrize("shape,density,h,radius,torus,steps", [
+    ((24, 32), None, 0.9, 1, False, 5),       # 97 % full: the argwhere fallback dominates
+    ((100, 128), 0.8, 0.4, 1, False, 6),      # the largest grid the path takes
+    ((37, 23), 0.7, 0.3, 3, True, 6), ((16, 16), 0.5, 0.0, 1, False, 2), ((9, 11), 0.9, 1.5, 2, False, 4),
+    ((1, 40), 0.6, 0.5, 1, False, 4), ((50, 3), 0.8, 0.6, 1, True, 4),
+])
+def test_small_step_matches_oracle(shape, density, h, radius, torus, steps):
+    rng = np.random.default_rng(shape[0] * 131 + shape[1])
+    rows, cols = shape
+    if density is None:
+        grid = rng.integers(0, 2, size=shape).astype(np.int8)
+        grid.reshape(-1)[rng.choice(rows * cols, size=20, replace=False)] = -1
+    else:
+        u = rng.random(shape)
+        grid = np.where(u < density, (rng.random(shape) < 0.5).astype(np.int8), np.int8(-1)).astype(np.int8)
+    st = oracle.SchellingState.from_type_grid(grid)
+    dev = DeviceSchellingSmall(st, h, radius, torus)
+    assert st.assign_state(h, radius, torus) == dev.assign()
+    fallbacks = 0
+    for epoch in range(steps):
+        movers, nfb = st.move_unhappy(21, epoch)
+        fallbacks += nfb
+        want = st.assign_state(h, radius, torus)
+        happy, got_movers, _ = dev.step(21, epoch)
+        assert (happy, got_movers) == (want, movers), epoch
+        assert np.array_equal(dev.cells(), st.cell), epoch
+        assert np.array_equal(dev.type.cpu().numpy(), st.type_grid()) and np.array_equal(dev.happy.cpu().numpy(), st.happy_grid())
+    if density is None:
+        assert fallbacks > 0
+
+
+def test_small_step_full_grid_raises_value_error():
+    grid = np.array([[0, 1, 0], [1, 0, 1], [0, 1, 0]], dtype=np.int8)
+    st = oracle.SchellingState.from_type_grid(grid)
+    dev = DeviceSchellingSmall(st, 1.0, 1)
+    dev.assign()
+    with pytest.raises(ValueError):
+        dev.step(1, 0)
+
+
+def test_example_model_fused_equals_unfused_and_flushes_deferred_steps():
+    """Schelling(fused=True) (one launch per step, lazily read) == Schelling(fused=False) (multi-launch path); a
+    shuffle_do("step") observed before its do("assign_state") is flushed."""
+    from mesa_b200.examples import Schelling, SchellingScenario
+
+    sc = SchellingScenario(width=50, height=40, density=0.85, homophily=0.5, radius=1, rng=9)
+    a, b = Schelling(sc, collect=False, fused=True), Schelling(sc, collect=False, fused=False)
+    assert a._small is not None and b._small is None and a.happy == b.happy
+    for _ in range(6):
+        a.step()
+        b.step()
+        assert a.happy == b.happy and a.last_movers == b.last_movers and a.running == b.running
+        assert torch.equal(a.grid.type, b.grid.type) and torch.equal(a.agents.get("cell"), b.agents.get("cell"))
+        assert torch.equal(a.grid.empty, b.grid.empty)
+    a.agents.shuffle_do("step")
+    b.agents.shuffle_do("step")
+    assert torch.equal(a.grid.type, b.grid.type)          # the deferred step is flushed by the layer access
+    a.agents.do("assign_state")
+    b.agents.do("assign_state")
+    assert a.happy == b.happy
+    a.run_for(5)
+    b.run_for(5)
+    assert a.happy == b.happy and torch.equal(a.grid.type, b.grid.type)

@@ -16,7 +16,8 @@ for e in range(3):
 torch.cuda.synchronize(); t0 = time.perf_counter()
 iters = 0
 for e in range(3, 3 + steps):
-    iters += ops.boltzmann_step(cell, wealth, ws, 1, e)
+    ops.boltzmann_step(cell, wealth, ws, 1, e)
 torch.cuda.synchronize(); dt = time.perf_counter() - t0
+ws.check(); iters = int(ws.iterations.item()) * steps
 print(json.dumps({"n": n, "side": side, "ms_per_step": dt / steps * 1e3, "agent_updates_per_s": n * steps / dt,
                   "mean_iters": iters / steps, "max_wealth": int(wealth.max()), "sum": int(wealth.sum())}))
