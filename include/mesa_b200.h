@@ -96,8 +96,8 @@ int mb_schelling_happy_i8(const int8_t* type, const int8_t* halo_top, const int8
  * reference driven with the same numbers (csrc/relocate.cu explains the fixed point).
  * Layers (row-major [rows, cols]): type int8 (-1 empty), happy uint8, agent_id uint32 (agent
  * index sitting in each occupied cell), slots = 16 bytes per cell (when the cell empties / who
- * arrives; persistent, built from the type layer by mb_reloc_slots_init and to be rebuilt if the
- * type layer is edited elsewhere).  A full grid with an unhappy agent returns MB_ERR_INVALID
+ * arrives; scratch: rebuilt from the type / happy layers at the start of every step by the mover collection, followed --
+ * when the buffer is mb_reloc_table_bytes() long -- by the bitmap of the agents that stay put).  A full grid with an unhappy agent returns MB_ERR_INVALID
  * (ValueError, grid.py:311-315).
  *
  * mb_schelling_relocate: the whole step on ONE GPU (synchronises `stream`); agent_cell is an
@@ -115,10 +115,17 @@ typedef struct mb_shard {
     void* type[MB_MAX_PEERS];     /* int8 */
     void* happy[MB_MAX_PEERS];    /* uint8 */
     void* agent_id[MB_MAX_PEERS]; /* uint32, global agent index */
+    void* static_bits;            /* optional (NULL: off): uint32 [world][bits_stride], THIS rank's copy of every rank's
+                                   * "cell holds an agent that stays put this step" bitmap (bit l of section r = local cell l
+                                   * of rank r).  mb_reloc_collect writes this rank's section; the caller all-gathers the
+                                   * sections before the first pass.  Probes of such cells cost one L2-resident bit instead
+                                   * of a 16-byte random (NVLink) access */
+    int64_t bits_stride;          /* words per section, >= ceil(cells of the largest block / 32) */
 } mb_shard_t;
 
+int mb_reloc_table_bytes(int64_t rows, int64_t cols, size_t* out); /* slots + bitmap of one GPU's table buffer */
 int mb_schelling_relocate(int8_t* type, uint8_t* happy, uint32_t* agent_id, uint32_t* agent_cell, void* slots,
-                          int64_t rows, int64_t cols, uint64_t seed, uint32_t epoch, void* workspace,
+                          size_t slots_bytes, int64_t rows, int64_t cols, uint64_t seed, uint32_t epoch, void* workspace,
                           size_t workspace_bytes, int64_t max_movers, int64_t* out_movers, int* out_iterations,
                           mb_stream_t stream);
 

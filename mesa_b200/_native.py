@@ -33,7 +33,8 @@ class Shard(ctypes.Structure):
 
     _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("rows_total", c_int64), ("cols", c_int64),
                 ("slots", c_void_p * MB_MAX_PEERS), ("type", c_void_p * MB_MAX_PEERS),
-                ("happy", c_void_p * MB_MAX_PEERS), ("agent_id", c_void_p * MB_MAX_PEERS)]
+                ("happy", c_void_p * MB_MAX_PEERS), ("agent_id", c_void_p * MB_MAX_PEERS),
+                ("static_bits", c_void_p), ("bits_stride", c_int64)]
 
 
 class MesaB200Error(RuntimeError):
@@ -56,7 +57,8 @@ SIGNATURES: dict[str, tuple] = {
     "mb_gol_step_bits": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _S]),
     # Schelling
     "mb_schelling_happy_i8": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int, c_int, _P, c_int, _P, _S]),
-    "mb_schelling_relocate": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_uint64, c_uint32, _P, ctypes.c_size_t,
+    "mb_reloc_table_bytes": (c_int, [c_int64, c_int64, ctypes.POINTER(ctypes.c_size_t)]),
+    "mb_schelling_relocate": (c_int, [_P, _P, _P, _P, _P, ctypes.c_size_t, c_int64, c_int64, c_uint64, c_uint32, _P, ctypes.c_size_t,
                                       c_int64, ctypes.POINTER(c_int64), ctypes.POINTER(c_int), _S]),
     "mb_reloc_workspace_bytes": (c_int, [c_int64, ctypes.POINTER(ctypes.c_size_t)]),
     "mb_reloc_slots_init": (c_int, [_P, _S]),

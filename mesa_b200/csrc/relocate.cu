@@ -75,6 +75,8 @@ struct ShardDesc {
     void* type[kMaxPeers];
     void* happy[kMaxPeers];
     void* agent_id[kMaxPeers];
+    void* static_bits;      // optional: [world][bits_stride] uint32, bit l of section r = local cell l of rank r is occupied by
+    int64_t bits_stride;    //           an agent that does NOT move this step (this rank's copy of every rank's section)
 };
 
 // Row-block partition of the global grid (same rule as mesa_b200/sharding.py block_bounds): the first
@@ -87,6 +89,8 @@ struct ShardView {
     int8_t* type[kMaxPeers];
     uint8_t* happy[kMaxPeers];
     uint32_t* agent_id[kMaxPeers];
+    uint32_t* static_bits;    // see ShardDesc (nullptr: no filter)
+    long long bits_stride;
 
     __host__ __device__ long long row_lo(int r) const { return (long long)r * base + (r < extra ? r : extra); }
     __device__ __forceinline__ void locate(unsigned long long c, int& owner, unsigned long long& local) const {
@@ -99,6 +103,14 @@ struct ShardView {
     __device__ __forceinline__ Slot* slot(unsigned long long c) const {
         int o; unsigned long long l;
         locate(c, o, l);
+        return slots[o] + l;
+    }
+    // slot pointer + "the cell holds an agent that stays put this step" (one L2-resident bit instead of a 16-byte
+    // random DRAM access: more than half of all probes on a 0.8-dense grid end here)
+    __device__ __forceinline__ Slot* slot_and_static(unsigned long long c, bool& is_static) const {
+        int o; unsigned long long l;
+        locate(c, o, l);
+        is_static = static_bits != nullptr && ((__ldg(static_bits + (size_t)o * bits_stride + (l >> 5)) >> (l & 31u)) & 1u);
         return slots[o] + l;
     }
 };
@@ -119,6 +131,10 @@ int make_view(const ShardDesc* d, ShardView* v) {
         v->slots[r] = (Slot*)d->slots[r]; v->type[r] = (int8_t*)d->type[r];
         v->happy[r] = (uint8_t*)d->happy[r]; v->agent_id[r] = (uint32_t*)d->agent_id[r];
     }
+    v->static_bits = (uint32_t*)d->static_bits;
+    v->bits_stride = d->bits_stride;
+    MB_REQUIRE(v->static_bits == nullptr || v->bits_stride * 32 >= (v->base + (v->extra ? 1 : 0)) * v->cols,
+               "static bitmap sections are shorter than a rank's block");
     return MB_OK;
 }
 
@@ -247,11 +263,14 @@ collect_movers(ShardView v, RelocWs ws, int64_t cap, uint64_t seed, uint32_t epo
     }
     __syncthreads();
     unsigned long long next = cta_base;   // uniform across the CTA
+    uint32_t* __restrict__ bits = v.static_bits ? v.static_bits + (size_t)v.rank * v.bits_stride : nullptr;
     for (int64_t c0 = lo; c0 < hi; c0 += blockDim.x) {
         const int64_t c = c0 + threadIdx.x;
         const int t = c < hi ? type[c] : -1;
         const bool mover = t >= 0 && happy[c] == 0;
         const unsigned ballot = __ballot_sync(0xffffffffu, mover);
+        const unsigned stat = __ballot_sync(0xffffffffu, t >= 0 && !mover);
+        if (bits != nullptr && lane == 0 && c < hi) bits[c >> 5] = stat;   // chunks are multiples of 256 cells: whole words
         __syncthreads();                   // warp_cnt of the previous round has been read
         if (lane == 0) warp_cnt[warp] = __popc(ballot);
         __syncthreads();
@@ -262,11 +281,15 @@ collect_movers(ShardView v, RelocWs ws, int64_t cap, uint64_t seed, uint32_t epo
             before += w < warp ? n : 0u;
             total += n;
         }
+        // the slot of EVERY cell is rebuilt here (sequential 16-byte stores): vac = 0 for an empty cell, priority + 1 of a
+        // mover (it is gone once its turn is over), never for an agent that stays; nobody has arrived yet
+        unsigned long long vac = t >= 0 ? kNever : 0ull;
         if (mover) {
             const unsigned long long slot = next + before + __popc(ballot & ((1u << lane) - 1u));
+            const uint32_t agent = agent_id[c];
+            const unsigned long long pr = mb::priority64(seed, epoch, agent);
+            vac = pr + 1ull;
             if ((int64_t)slot < cap) {
-                const uint32_t agent = agent_id[c];
-                const unsigned long long pr = mb::priority64(seed, epoch, agent);
                 ws.mv_cell[slot] = (uint32_t)c;
                 ws.mv_agent[slot] = agent;
                 ws.mv_prio[slot] = pr;
@@ -274,9 +297,9 @@ collect_movers(ShardView v, RelocWs ws, int64_t cap, uint64_t seed, uint32_t epo
                 ws.choice[slot] = kNoCell;
                 ws.progress[slot] = 0u;
                 ws.softmask[slot] = 0ull;
-                slots[c].vac = pr + 1;  // empty for every mover that acts after this one
             }
         }
+        if (c < hi) reinterpret_cast<ulonglong2*>(slots)[c] = make_ulonglong2(vac, kNever);
         next += total;
     }
 }
@@ -284,6 +307,20 @@ collect_movers(ShardView v, RelocWs ws, int64_t cap, uint64_t seed, uint32_t epo
 // "the table changed in this pass": a plain store of a constant (millions of movers change in the
 // first pass; counting them with one atomic address would serialise the whole pass)
 __device__ __forceinline__ void mark_changed(RelocWs& ws) { *(volatile unsigned long long*)&ws.counters[3] = 1ull; }
+
+// give up `held` if I am its registered arrival.  A successful release can re-open the cell for later movers that skipped
+// it on the way to their pick: it is recorded for the next release scan (relocate_release_scan)
+__device__ __forceinline__ void release_held(const ShardView& v, RelocWs& ws, unsigned long long held, unsigned long long t) {
+    if (held != kNoCell && atomicCAS(&v.slot(held)->arr, t, kNever) == t) {
+        const unsigned long long slot = atomicAdd(&ws.counters[5], 1ull);
+        if (slot < (unsigned long long)kRelCap) {
+            ws.rel_w_cell[slot] = held;
+            ws.rel_w_time[slot] = t;
+        } else {
+            *(volatile unsigned long long*)&ws.counters[6] = 1ull;  // too many to scan for: full pass
+        }
+    }
+}
 
 // claim `pick` for mover m (and release what it held before)
 __device__ __forceinline__ void commit_choice(const ShardView& v, RelocWs& ws, int64_t m, unsigned long long t,
@@ -357,13 +394,19 @@ relocate_pass(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, uint32_t 
                 cells[b] = ds.randbelow((uint64_t)v.ncells);
                 after[b] = ds.c;
             }
+            Slot* sp[kBatch];
 #pragma unroll
-            for (int b = 0; b < kBatch; ++b) sl[b] = load_slot(v.slot(cells[b]));
+            for (int b = 0; b < kBatch; ++b) {
+                bool is_static;
+                sp[b] = v.slot_and_static(cells[b], is_static);
+                sl[b] = Slot{kNever, kNever};                    // an agent that stays: never empty, no slot load
+                if (!is_static) sl[b] = load_slot(sp[b]);
+            }
 #pragma unroll
             for (int b = 0; b < kBatch; ++b) {
                 const int j = j0 + b;
                 if (j >= kMaxProbes) continue;
-                if (!empty_at(sl[b], t) || atomicMin(&v.slot(cells[b])->arr, t) < t) {   // (the atomicMin: lost a race, not empty after all)
+                if (!empty_at(sl[b], t) || atomicMin(&sp[b]->arr, t) < t) {   // (the atomicMin: lost a race, not empty after all)
                     if (sl[b].vac <= t) soft |= 1ull << j;
                     continue;
                 }
@@ -382,23 +425,44 @@ relocate_pass(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, uint32_t 
         return;
     }
     unsigned long long soft = 0ull;
+    const unsigned long long held = ws.choice[m];
     for (int j0 = 0; j0 < kMaxProbes; j0 += kBatch) {
         unsigned long long cells[kBatch];
         uint32_t after[kBatch];
         Slot sl[kBatch];
+        Slot* sp[kBatch];
 #pragma unroll
         for (int b = 0; b < kBatch; ++b) {
             cells[b] = ds.randbelow((uint64_t)v.ncells);
             after[b] = ds.c;
         }
 #pragma unroll
-        for (int b = 0; b < kBatch; ++b) sl[b] = load_slot(v.slot(cells[b]));
+        for (int b = 0; b < kBatch; ++b) {
+            bool is_static;
+            sp[b] = v.slot_and_static(cells[b], is_static);
+            sl[b] = Slot{kNever, kNever};                        // an agent that stays: never empty, no slot load
+            if (!is_static) sl[b] = load_slot(sp[b]);
+        }
 #pragma unroll
         for (int b = 0; b < kBatch; ++b) {
             const int j = j0 + b;
             if (j >= kMaxProbes) continue;
             if (empty_at(sl[b], t)) {
-                commit_choice(v, ws, m, t, cells[b]);
+                if (cells[b] == held) {
+                    // re-assert: my registration may have been shadowed by an earlier arrival that has left since
+                    if (atomicMin(&sp[b]->arr, t) > t) mark_changed(ws);
+                } else {
+                    // claim; an earlier mover that registered between my load and my claim wins the cell: go on probing
+                    // at once instead of finding out in the next pass
+                    if (atomicMin(&sp[b]->arr, t) < t) {
+                        if (soft == 0ull) ws.softcell[m] = (uint32_t)cells[b];
+                        soft |= 1ull << j;
+                        continue;
+                    }
+                    release_held(v, ws, held, t);
+                    ws.choice[m] = cells[b];
+                    mark_changed(ws);
+                }
                 ws.progress[m] = (uint32_t)j | (after[b] << 8);
                 ws.softmask[m] = soft;
                 return;
@@ -409,6 +473,7 @@ relocate_pass(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, uint32_t 
             }
         }
     }
+    // (a pick held from an earlier pass is compared and, if need be, released by the fallback phase: commit_choice)
     ws.softmask[m] = soft;
     ws.progress[m] = (uint32_t)kMaxProbes;
     ws.fb_list[atomicAdd(&ws.counters[2], 1ull)] = (uint32_t)m;  // served by the fallback phase of this pass
@@ -747,23 +812,47 @@ reloc_event_loop(ShardView v, EventArgs a, uint64_t seed, uint32_t epoch) {
         if (s_kind == 0 || s_bail) break;
         const unsigned long long t = s_t;
         if (s_kind == 1) {
-            // ---- a displaced mover continues after the pick it lost
-            if (tid == 0) {
-                mb::DrawStream ds(seed, epoch, (uint32_t)t);   // priority64 carries the agent index in its low word
-                bool found = false, placed = false;
-                for (int j = 0; j < kMaxProbes; ++j) {
-                    const unsigned long long c = ds.randbelow((uint64_t)v.ncells);
-                    if (!found) { found = c == s_lost; continue; }
-                    Slot* sp = v.slot(c);
-                    const Slot sl = load_slot(sp);
-                    if (!empty_at(sl, t)) continue;
-                    atomicMin(&sp->arr, t);
-                    s_cell = c; s_aold = sl.arr; s_vac = sl.vac;
-                    placed = true;
-                    break;
+            // ---- a displaced mover continues after the pick it lost.  Its probe cells are state-independent: the first
+            // kDraws draws of its stream are computed by kDraws threads at once (draw d = half of Philox block d / 2),
+            // the accepted ones (r < ncells, random.py:242-250) are numbered by a block scan = the probe sequence, and
+            // the slots of the probes after the lost one are loaded by one thread each.
+            constexpr int kDraws = 512;
+            __shared__ unsigned long long probes[kMaxProbes];
+            __shared__ int s_lostidx, s_pickidx;
+            if (tid == 0) { s_lostidx = kMaxProbes; s_pickidx = kMaxProbes; }
+            unsigned long long r = 0;
+            unsigned ok = 0;
+            if (tid < kDraws) {
+                const mb::U4 blk = mb::philox_keyed(seed, epoch, (uint32_t)t, mb::kStreamDraw, (uint32_t)tid >> 1);
+                const unsigned long long d = (tid & 1) ? (((unsigned long long)blk.z << 32) | blk.w) : (((unsigned long long)blk.x << 32) | blk.y);
+                const int kbits = 64 - __clzll((long long)v.ncells);
+                r = d >> (64 - kbits);
+                ok = r < (unsigned long long)v.ncells;
+            }
+            unsigned total;
+            const unsigned idx = block_exclusive_scan(ok, warp_sums, total);
+            if (ok && idx < (unsigned)kMaxProbes) probes[idx] = r;
+            __syncthreads();
+            if (total < (unsigned)kMaxProbes) {
+                if (tid == 0) s_bail = 9;        // fewer than 50 probes in 512 draws: practically impossible
+            } else {
+                if (tid < kMaxProbes && probes[tid] == s_lost) atomicMin(&s_lostidx, tid);
+                __syncthreads();
+                Slot sl{kNever, 0ull};
+                if (tid < kMaxProbes && tid > s_lostidx) {
+                    sl = load_slot(v.slot(probes[tid]));
+                    if (empty_at(sl, t)) atomicMin(&s_pickidx, tid);
                 }
-                if (!placed) s_bail = found ? 2 : 3;   // 2: out of probes (a new fallback mover), 3: the lost cell is not its pick
-                ++s_ndis;
+                __syncthreads();
+                if (tid == 0) {
+                    if (s_lostidx >= kMaxProbes) s_bail = 3;           // the lost cell is not one of its probes
+                    else if (s_pickidx >= kMaxProbes) s_bail = 2;      // out of probes: a new fallback mover
+                    ++s_ndis;
+                }
+                if (tid == s_pickidx && tid < kMaxProbes) {
+                    atomicMin(&v.slot(probes[tid])->arr, t);
+                    s_cell = probes[tid]; s_aold = sl.arr; s_vac = sl.vac;
+                }
             }
         } else {
             // ---- fallback mover i: the k-th empty cell of the whole grid at its time
@@ -816,7 +905,7 @@ reloc_event_loop(ShardView v, EventArgs a, uint64_t seed, uint32_t epoch) {
             if (tid == 0) s_found = 0;
             // every thread takes kPer consecutive cells (independent 16-byte loads, all in flight at once), one block
             // scan per 1024 * kPer cells
-            constexpr int kPer = 16;
+            constexpr int kPer = 8;
             for (long long c0 = lo_c; c0 < hi_c; c0 += (long long)blockDim.x * kPer) {
                 const long long mine = c0 + (long long)tid * kPer;
                 Slot sl[kPer];
@@ -932,7 +1021,6 @@ __global__ void relocate_vacate(ShardView v, RelocWs ws, int64_t nmovers) {
     const uint32_t o = ws.mv_cell[m];
     v.type[v.rank][o] = -1;
     v.happy[v.rank][o] = 0;
-    reinterpret_cast<ulonglong2*>(v.slots[v.rank])[o] = make_ulonglong2(0ull, kNever);
 }
 
 __global__ void relocate_arrive(ShardView v, RelocWs ws, uint32_t* agent_cell, int64_t nmovers) {
@@ -945,7 +1033,6 @@ __global__ void relocate_arrive(ShardView v, RelocWs ws, uint32_t* agent_cell, i
     v.happy[o][d] = 0;  // the flag travels with the agent: movers are unhappy until the next assign_state
     v.agent_id[o][d] = agent;
     if (agent_cell != nullptr) agent_cell[agent] = (uint32_t)ws.choice[m];
-    reinterpret_cast<ulonglong2*>(v.slots[o])[d] = make_ulonglong2(kNever, kNever);
 }
 
 int read_counters(const RelocWs& ws, unsigned long long* host7, cudaStream_t stream) {
@@ -1270,8 +1357,15 @@ MB_API int mb_reloc_apply_overrides(int64_t nmovers, uint64_t t_lo, uint64_t t_h
 // Single-GPU driver: the whole shuffle_do("step") in one call.  Synchronises `stream` (needs the mover
 // count and the per-pass flags on the host).
 // ================================================================================================
+MB_API int mb_reloc_table_bytes(int64_t rows, int64_t cols, size_t* out) {
+    MB_REQUIRE(out != nullptr && rows >= 0 && cols >= 0, "mb_reloc_table_bytes: bad argument");
+    const int64_t n = rows * cols;
+    *out = (size_t)n * sizeof(Slot) + (size_t)mb::ceil_div(n, 32) * sizeof(uint32_t);
+    return MB_OK;
+}
+
 MB_API int mb_schelling_relocate(int8_t* type, uint8_t* happy, uint32_t* agent_id, uint32_t* agent_cell, void* slots,
-                                 int64_t rows, int64_t cols, uint64_t seed, uint32_t epoch, void* workspace,
+                                 size_t slots_bytes, int64_t rows, int64_t cols, uint64_t seed, uint32_t epoch, void* workspace,
                                  size_t workspace_bytes, int64_t max_movers, int64_t* out_movers,
                                  int* out_iterations, cudaStream_t stream) {
     if (out_movers) *out_movers = 0;
@@ -1283,6 +1377,13 @@ MB_API int mb_schelling_relocate(int8_t* type, uint8_t* happy, uint32_t* agent_i
     memset(&d, 0, sizeof(d));
     d.world = 1; d.rank = 0; d.rows_total = rows; d.cols = cols;
     d.slots[0] = slots; d.type[0] = type; d.happy[0] = happy; d.agent_id[0] = agent_id;
+    // the table buffer = 16-byte slots of all cells [+ the bitmap of the agents that stay put (mb_reloc_table_bytes)]
+    const size_t slot_bytes = (size_t)(rows * cols) * sizeof(Slot);
+    MB_REQUIRE(slots_bytes >= slot_bytes, "mb_schelling_relocate: the slot table is smaller than 16 bytes per cell");
+    if (slots_bytes >= slot_bytes + (size_t)mb::ceil_div(rows * cols, 32) * sizeof(uint32_t) && getenv("MB_RELOC_NOBITS") == nullptr) {
+        d.static_bits = (char*)slots + slot_bytes;
+        d.bits_stride = mb::ceil_div(rows * cols, 32);
+    }
     ShardView v;
     RelocWs ws;
     int rc = make_view(&d, &v);

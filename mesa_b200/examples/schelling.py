@@ -168,7 +168,6 @@ class Schelling(DeviceModel):
         now through the multi-launch path (same result)."""
         if self._pending_epoch is not None:
             epoch, self._pending_epoch = self._pending_epoch, None
-            self._ws.sync(dict.__getitem__(self.grid.property_layers, "type"))   # the fused steps do not maintain the slot table
             self._relocate(epoch)
 
     @property

@@ -218,11 +218,8 @@ def schelling_happy(type_layer: torch.Tensor, homophily: float, radius: int = 1,
 
 
 class RelocationWorkspace:
-    """Persistent state of mb_schelling_relocate on one GPU: the 16-byte-per-cell slot table (mirrors the
-    occupancy) + the private mover / fallback scratch.
-
-    Built from the int8 type layer; call `sync(type_layer)` again if the layer is edited outside
-    `schelling_relocate`."""
+    """Scratch of mb_schelling_relocate on one GPU: the 16-byte-per-cell slot table + the bitmap of the agents that stay
+    put (both rebuilt from the layers at the start of every step) + the private mover / fallback scratch."""
 
     def __init__(self, type_layer: torch.Tensor, max_movers: int):
         import ctypes
@@ -236,22 +233,16 @@ class RelocationWorkspace:
         N.check(N.lib().mb_reloc_workspace_bytes(self.max_movers, ctypes.byref(nbytes)))
         self.nbytes = int(nbytes.value)
         self.buf = torch.empty(max(self.nbytes, 1), dtype=torch.uint8, device=type_layer.device)
-        self.slots = torch.empty((max(self.ncells, 1), 2), dtype=torch.int64, device=type_layer.device)
-        self.sync(type_layer)
+        tbytes = ctypes.c_size_t(0)
+        N.check(N.lib().mb_reloc_table_bytes(self.rows, self.cols, ctypes.byref(tbytes)))
+        self.slots_bytes = int(tbytes.value)     # 16-byte slots + the bitmap of the agents that stay put
+        self.slots = torch.empty(max(-(-self.slots_bytes // 8), 1), dtype=torch.int64, device=type_layer.device)
 
     def sync(self, type_layer: torch.Tensor) -> None:
+        """Kept for callers of the first version: the slot table is scratch now (rebuilt from the layers at the start of
+        every relocation), so edits of the type layer need no notification."""
         if type_layer.dtype != torch.int8 or type_layer.numel() != self.ncells:
             raise ValueError("expected the int8 type layer this workspace was sized for")
-        if self.ncells == 0:
-            return
-        d = N.Shard()
-        d.world, d.rank, d.rows_total, d.cols = 1, 0, self.rows, self.cols
-        d.slots[0], d.type[0] = self.slots.data_ptr(), _c(type_layer).data_ptr()
-        d.happy[0] = d.agent_id[0] = type_layer.data_ptr()  # unused by the init kernel, must be non-null
-        import ctypes
-
-        with torch.cuda.device(type_layer.device):
-            N.check(N.lib().mb_reloc_slots_init(ctypes.byref(d), N.stream_ptr(type_layer.device)))
 
 
 def schelling_relocate(type_layer: torch.Tensor, happy: torch.Tensor, agent_id: torch.Tensor,
@@ -269,7 +260,7 @@ def schelling_relocate(type_layer: torch.Tensor, happy: torch.Tensor, agent_id: 
     with torch.cuda.device(type_layer.device):
         N.check(N.lib().mb_schelling_relocate(
             N.ptr(_c(type_layer)), N.ptr(_c(happy)), N.ptr(_c(agent_id)), N.ptr(agent_cell), N.ptr(ws.slots),
-            ws.rows, ws.cols, int(seed) & 0xFFFFFFFFFFFFFFFF, int(epoch) & 0xFFFFFFFF, N.ptr(ws.buf), ws.nbytes,
+            ws.slots_bytes, ws.rows, ws.cols, int(seed) & 0xFFFFFFFFFFFFFFFF, int(epoch) & 0xFFFFFFFF, N.ptr(ws.buf), ws.nbytes,
             ws.max_movers, ctypes.byref(movers), ctypes.byref(iters), N.stream_ptr(type_layer.device)))
     return int(movers.value), int(iters.value)
 

@@ -90,9 +90,16 @@ class ShardedSchelling:
         ids[occupied] = torch.arange(first, first + self.n_local, dtype=torch.int64, device=self.device)
         self.agent_id.copy_(ids.reshape(self.rows, self.cols).to(torch.int32))  # uint32 bit pattern
 
+        # bitmap of the agents that stay put in a step, one section per rank: mb_reloc_collect fills this rank's section,
+        # an all-gather replicates them, and the probe kernels test a LOCAL, L2-resident bit before touching a (mostly
+        # remote) 16-byte slot -- more than half of all probes on a 0.8-dense grid stop there
+        self._bits_stride = -(-(max_rows * self.cols) // 32)
+        self._bits = torch.zeros((self.world, self._bits_stride), dtype=torch.int32, device=self.device)
         self.shard = N.Shard()
         self.shard.world, self.shard.rank = self.world, self.rank
         self.shard.rows_total, self.shard.cols = self.rows_total, self.cols
+        if os.environ.get("MB_RELOC_NOBITS") is None:
+            self.shard.static_bits, self.shard.bits_stride = self._bits.data_ptr(), self._bits_stride
         for r in range(self.world):
             self.shard.slots[r] = self._slot_h.buffer_ptrs[r]
             self.shard.type[r] = self._type_h.buffer_ptrs[r]
@@ -194,6 +201,8 @@ class ShardedSchelling:
             N.check(lib.mb_reloc_collect(self._shard_ref, seed, epoch, ws, wb, mm, self._stream()))
             movers, occupied = self._counters()[:2]
             tot_movers, tot_occupied = self._allreduce([movers, occupied])   # also orders collect before any pass
+            if self.world > 1 and self.shard.static_bits:
+                dist.all_gather_into_tensor(self._bits, self._bits[self.rank].clone(), group=self.group)
             self.last_movers, self.last_passes = tot_movers, 0
             self.last_events = [0, 0, 0, 0]
             if tot_movers == 0:
