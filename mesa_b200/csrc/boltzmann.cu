@@ -28,7 +28,7 @@ namespace {
 
 constexpr unsigned long long kNever = ~0ull;
 constexpr uint32_t kNoTarget = 0xffffffffu;
-constexpr int kCounterWords = 2 + 2 * 4096 + 2;   // status, queue length, (start, length) x kLongCap, 4 sync words
+constexpr int kCounterWords = 2 + 2 * 4096 + 3;   // status, queue length, (start, length) x kLongCap, candidate count, 4 sync words
 
 struct BoltzWs {
     uint64_t* keysA;      // [n] sorted (cell << 32 | arrival priority hi32) of the PREVIOUS step (persistent)
@@ -45,6 +45,9 @@ struct BoltzWs {
     uint8_t* gives;       // [n]
     uint8_t* draws;       // [n] draws consumed by move()
     unsigned long long* counters;    // [kCounterWords] status | crowded-cell queue | barrier / convergence words
+    uint32_t* cand;       // [n] agents that have a cell mate to give to (the only ones the give decisions involve)
+    uint32_t* occA;       // [occ_words] hashed bitmap of the cells that hold an agent at the start of the step
+    uint32_t occ_mask;    // occ_words * 32 - 1 (a power of two)
     void* sort_ws;
     size_t sort_ws_bytes;
 };
@@ -71,6 +74,13 @@ size_t carve(BoltzWs* ws, char* base, int64_t n) {
     t.gives = (uint8_t*)take(n);
     t.draws = (uint8_t*)take(n);
     t.counters = (unsigned long long*)take(8 * kCounterWords);
+    t.cand = (uint32_t*)take(4 * n);
+    {   // >= 32 bits per agent, a power of two: a false positive only costs the binary search it would have skipped
+        uint64_t bits = 1024;
+        while (bits < 32ull * (uint64_t)(n > 0 ? n : 1) && bits < (1ull << 31)) bits <<= 1;
+        t.occ_mask = (uint32_t)(bits - 1);
+        t.occA = (uint32_t*)take((size_t)(bits / 8));
+    }
     t.sort_ws_bytes = mb::sort_workspace_bytes(n);
     t.sort_ws = take(t.sort_ws_bytes);
     if (ws) *ws = t;
@@ -92,27 +102,33 @@ __global__ void boltz_move(const uint32_t* __restrict__ cell, int64_t n, int row
     if (a >= n) return;
     const uint32_t c = cell[a];
     const int i = (int)(c / (uint32_t)cols), j = (int)(c % (uint32_t)cols);
-    // grid.py:447-451 offsets in order; clamped grids drop out-of-range cells (grid.py:398)
-    uint32_t nbr[8];
-    int cnt = 0;
+    {   // the cell holds somebody at the start of the step (boltz_target skips the search of last step's order otherwise)
+        const uint32_t h = (c * 0x9E3779B1u) & ws.occ_mask;
+        atomicOr(&ws.occA[h >> 5], 1u << (h & 31u));
+    }
+    // grid.py:447-451 offsets in order; clamped grids drop out-of-range cells (grid.py:398): count the existing
+    // neighbours, draw k = _randbelow(count), take the k-th existing one
+    int cnt = 8;
+    if (!torus) {
+        const int ni = (i > 0) + 1 + (i < rows - 1), nj = (j > 0) + 1 + (j < cols - 1);
+        cnt = ni * nj - 1;
+    }
+    mb::DrawStream ds(seed, epoch, (uint64_t)a);
+    int k = (int)ds.randbelow((uint64_t)cnt);
+    uint32_t dest = c;
 #pragma unroll
     for (int q = 0; q < 9; ++q) {
         if (q == 4) continue;
         int ni = i + q / 3 - 1, nj = j + q % 3 - 1;
+        bool exists = true;
         if (torus) {
             ni = (ni + rows) % rows;
             nj = (nj + cols) % cols;
-        } else if (ni < 0 || ni >= rows || nj < 0 || nj >= cols) {
-            continue;
+        } else {
+            exists = ni >= 0 && ni < rows && nj >= 0 && nj < cols;
         }
-        nbr[cnt++] = (uint32_t)ni * (uint32_t)cols + (uint32_t)nj;
+        if (exists && k-- == 0) dest = (uint32_t)ni * (uint32_t)cols + (uint32_t)nj;
     }
-    mb::DrawStream ds(seed, epoch, (uint64_t)a);
-    const uint32_t k = (uint32_t)ds.randbelow((uint64_t)cnt);
-    uint32_t dest = nbr[0];
-#pragma unroll
-    for (int q = 1; q < 8; ++q)
-        if ((uint32_t)q == k) dest = nbr[q];
     const uint64_t t = mb::priority64(seed, epoch, (uint64_t)a);
     ws.new_cell[a] = dest;
     ws.prio[a] = t;
@@ -236,15 +252,20 @@ __device__ __forceinline__ int64_t lower_bound_u64(const uint64_t* __restrict__ 
 
 // give_money() target of every agent (state independent) + initial give decision
 __global__ void boltz_target(const int32_t* __restrict__ wealth, int64_t n, uint64_t seed, uint32_t epoch,
-                             const uint64_t* __restrict__ keysB, const uint32_t* __restrict__ valsB, BoltzWs ws) {
+                             const uint64_t* __restrict__ keysB, const uint32_t* __restrict__ valsB, BoltzWs ws,
+                             unsigned long long* __restrict__ cand_count) {
     const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n) return;
     const uint32_t c = ws.new_cell[a];
     const uint64_t t = ws.prio[a];
-    // agents still sitting in c (old cell == c, acting later), in last step's arrival order
-    const int64_t a0 = lower_bound_u64(ws.keysA, n, (uint64_t)c << 32);
-    int64_t cntA = 0;
-    for (int64_t s = a0; s < n && (uint32_t)(ws.keysA[s] >> 32) == c; ++s) cntA += ws.prio[ws.valsA[s]] > t;
+    // agents still sitting in c (old cell == c, acting later), in last step's arrival order -- nobody if the cell was
+    // empty at the start of the step (94 % of the cells at BASELINE config 3: one bit instead of a 20-step search)
+    const uint32_t hc = (c * 0x9E3779B1u) & ws.occ_mask;
+    int64_t a0 = 0, cntA = 0;
+    if ((ws.occA[hc >> 5] >> (hc & 31u)) & 1u) {
+        a0 = lower_bound_u64(ws.keysA, n, (uint64_t)c << 32);
+        for (int64_t s = a0; s < n && (uint32_t)(ws.keysA[s] >> 32) == c; ++s) cntA += ws.prio[ws.valsA[s]] > t;
+    }
     // agents that already arrived in c, in arrival order: the run of this step's order before me
     const int64_t me = ws.rankB[a];
     int64_t b0 = me;
@@ -268,6 +289,14 @@ __global__ void boltz_target(const int32_t* __restrict__ wealth, int64_t n, uint
     ws.target[a] = tgt;
     ws.gives[a] = (tgt != kNoTarget && wealth[a] > 0) ? 1 : 0;
     ws.first_gift[a] = kNever;
+    if (tgt != kNoTarget) {   // warp-aggregated append to the candidate list
+        const unsigned peers = __activemask();
+        const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(cand_count, (unsigned long long)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        ws.cand[base + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)a;
+    }
 }
 
 // The give decisions as ONE persistent kernel: a giver announces the time of its gift to the receiver (atomicMin), an
@@ -287,23 +316,26 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256)
-boltz_iterate(int64_t n, BoltzWs ws, unsigned* sync, uint32_t* iterations_out) {
+__global__ void __launch_bounds__(1024)
+boltz_iterate(BoltzWs ws, const unsigned long long* __restrict__ cand_count, unsigned* sync, uint32_t* iterations_out) {
+    const int64_t n = (int64_t)*cand_count;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned target = 0, round = 0;
     for (;; ++round) {
         // push: givers that have not announced yet (gives == 1 -> 2)
-        for (int64_t a = first; a < n; a += stride) {
-            if (__ldcg(ws.gives + a) == 1) {
+        for (int64_t i = first; i < n; i += stride) {
+            const uint32_t a = ws.cand[i];
+            if (ws.gives[a] == 1) {
                 atomicMin(&ws.first_gift[ws.target[a]], (unsigned long long)ws.prio[a]);
                 ws.gives[a] = 2;
             }
         }
         grid_barrier(&sync[0], target);
         unsigned changed = 0;
-        for (int64_t a = first; a < n; a += stride) {
-            if (__ldcg(ws.gives + a) == 0 && ws.target[a] != kNoTarget && __ldcg(ws.first_gift + a) < ws.prio[a]) {
+        for (int64_t i = first; i < n; i += stride) {
+            const uint32_t a = ws.cand[i];
+            if (ws.gives[a] == 0 && __ldcg(ws.first_gift + a) < ws.prio[a]) {
                 ws.gives[a] = 1;
                 changed = 1;
             }
@@ -390,9 +422,11 @@ MB_API int mb_boltzmann_step(uint32_t* cell, int32_t* wealth, int64_t n, int64_t
     unsigned long long* status = ws.counters;
     unsigned long long* longs = ws.counters + 1;
     unsigned* sync = reinterpret_cast<unsigned*>(ws.counters + kCounterWords - 2);
+    unsigned long long* cand_count = ws.counters + kCounterWords - 3;
     int rc = mb::check_cuda(cudaMemsetAsync(longs, 0, 8, stream), "memset");
     if (rc) return rc;
-    if ((rc = mb::check_cuda(cudaMemsetAsync(sync, 0, 16, stream), "memset"))) return rc;
+    if ((rc = mb::check_cuda(cudaMemsetAsync(cand_count, 0, 8 + 16, stream), "memset"))) return rc;   // candidate count + sync words
+    if ((rc = mb::check_cuda(cudaMemsetAsync(ws.occA, 0, ((size_t)ws.occ_mask + 1) / 8, stream), "memset"))) return rc;
     const unsigned blocks = (unsigned)mb::ceil_div(n, 256);
     boltz_move<<<blocks, 256, 0, stream>>>(cell, n, (int)rows, (int)cols, torus, seed, epoch, ws);
     // sparse grids sort on the cell bits only and order the (short) runs of equal cells afterwards; crowded grids
@@ -414,17 +448,12 @@ MB_API int mb_boltzmann_step(uint32_t* cell, int32_t* wealth, int64_t n, int64_t
     const uint64_t* keysB = where ? ws.keys1 : ws.keys0;
     const uint32_t* valsB = where ? ws.vals1 : ws.vals0;
     boltz_rank<<<blocks, 256, 0, stream>>>(valsB, n, ws.rankB);
-    boltz_target<<<blocks, 256, 0, stream>>>(wealth, n, seed, epoch, keysB, valsB, ws);
+    boltz_target<<<blocks, 256, 0, stream>>>(wealth, n, seed, epoch, keysB, valsB, ws, cand_count);
     MB_LAUNCH_CHECK("boltz_target");
-    // persistent give-decision kernel: every CTA must be resident (grid barrier)
-    static int per_sm = 0;
-    if (per_sm == 0) {
-        if ((rc = mb::check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, boltz_iterate, 256, 0), "occupancy"))) return rc;
-        if (per_sm < 1) per_sm = 1;
-    }
-    int64_t grid = (int64_t)mb::sm_count() * per_sm;
-    if (grid > blocks) grid = blocks;
-    boltz_iterate<<<(unsigned)grid, 256, 0, stream>>>(n, ws, sync, iterations_dev);
+    // persistent give-decision kernel over the candidate list: one CTA per SM at most, all resident (grid barrier)
+    int64_t grid = mb::ceil_div(n, 1024 * 4);
+    if (grid > mb::sm_count()) grid = mb::sm_count();
+    boltz_iterate<<<(unsigned)grid, 1024, 0, stream>>>(ws, cand_count, sync, iterations_dev);
     boltz_apply<<<blocks, 256, 0, stream>>>(wealth, cell, n, ws);
     // this step's arrival order is next step's "still sitting here" order
     rc = mb::check_cuda(cudaMemcpyAsync(ws.keysA, keysB, 8 * n, cudaMemcpyDeviceToDevice, stream), "copy");

@@ -187,9 +187,37 @@ sort_scatter(const K* __restrict__ keys_in, const uint32_t* __restrict__ vals_in
 
 }  // namespace
 
+// small inputs (<= 32 chunks): ONE CTA walks the chunks with a running carry -- one launch instead of three
+__global__ void __launch_bounds__(1024) scan_single(uint32_t* __restrict__ data, int64_t total) {
+    __shared__ unsigned warp_sum[32];
+    __shared__ unsigned carry;
+    if (threadIdx.x == 0) carry = 0u;
+    __syncthreads();
+    for (int64_t c0 = 0; c0 < total; c0 += kScanChunk) {
+        const int64_t i0 = c0 + (int64_t)threadIdx.x * 4;
+        unsigned v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (i0 + k < total) ? data[i0 + k] : 0u;
+        unsigned block_total;
+        unsigned excl = carry + block_excl_scan_1024(v[0] + v[1] + v[2] + v[3], warp_sum, block_total);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i0 + k < total) data[i0 + k] = excl;
+            excl += v[k];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry += block_total;
+        __syncthreads();
+    }
+}
+
 int exclusive_scan_u32(uint32_t* data, int64_t n, uint32_t* sums, cudaStream_t stream) {
     if (n <= 0) return MB_OK;
     const int64_t nchunks = ceil_div(n, kScanChunk);
+    if (nchunks <= 32) {
+        scan_single<<<1, 1024, 0, stream>>>(data, n);
+        return check_cuda(cudaGetLastError(), "exclusive_scan_u32");
+    }
     scan_chunks<<<(unsigned)nchunks, 1024, 0, stream>>>(data, n, sums);
     scan_top<<<1, 1024, 0, stream>>>(sums, nchunks);
     scan_add<<<(unsigned)nchunks, 1024, 0, stream>>>(data, n, sums);

@@ -21,6 +21,15 @@ for fused in (True, False):
     out[f"schelling_c1_us_fused={fused}"] = round(timed(m.step, 95), 2)
     out[f"happy_after_100_fused={fused}"] = m.happy
     if fused:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        mm = Schelling(SchellingScenario(width=100, height=100, density=0.8, homophily=0.4, radius=1, rng=42), collect=False)
+        for _ in range(5):
+            mm.step()
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(95):
+            mm.step()
+        e1.record(); torch.cuda.synchronize()
+        out["schelling_c1_device_us"] = round(e0.elapsed_time(e1) * 1e3 / 95, 2)
         out["passes_last"] = m.last_iterations
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         m2 = Schelling(SchellingScenario(width=100, height=100, density=0.8, homophily=0.4, radius=1, rng=42), collect=False)
