@@ -479,6 +479,152 @@ relocate_pass(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, uint32_t 
     ws.fb_list[atomicAdd(&ws.counters[2], 1ull)] = (uint32_t)m;  // served by the fallback phase of this pass
 }
 
+// ---- the same pass with LANE REFILL -------------------------------------------------------------------------------------
+// ncu of the one-thread-per-mover kernel above (profiles/r2_reloc_pass_ncu.txt): 5.1 of 32 lanes active in a FULL pass,
+// 2.8 in a RESUME pass -- a mover needs a geometric number of probes (or, in a RESUME pass, none at all), so a warp
+// spends most of its instructions on its slowest lane; 2.3 G warp instructions for 15 M movers, issue-bound, DRAM at
+// 1.2 TB/s.  Here a warp owns a contiguous range of movers and keeps ALL lanes busy: it loads the movers 32 at a time
+// (one coalesced tile in registers), every lane that finishes its mover takes the next one of the tile by shuffle, and
+// one loop iteration advances every lane by one step of its own mover -- the verification of the held pick (RESUME) or one
+// batch of kBatch probes.  Results are identical (same draws, same claims); only the mapping of movers to lanes changes.
+template <int kBatch>
+__global__ void __launch_bounds__(128)
+relocate_pass_packed(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, uint32_t epoch, unsigned long long t_lo,
+                     unsigned long long t_hi, int mode, int64_t movers_per_warp) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t next = warp_id * movers_per_warp;                       // first mover of the next tile (warp-uniform)
+    const int64_t end = min(next + movers_per_warp, nmovers);
+    if (next >= end) return;
+    // the current tile: lane l holds mover tile0 + l; tile_mask = entries not handed out yet (in the bucket's time range)
+    int64_t tile0 = 0;
+    unsigned tile_mask = 0u;
+    unsigned long long tile_t = 0ull;
+    uint32_t tile_agent = 0u;
+    // this lane's mover
+    int64_t m = -1;
+    unsigned long long t = 0ull, held = kNoCell, soft = 0ull;
+    int j = 0;                 // next probe
+    bool verify = false;       // RESUME: the held pick has not been checked yet
+    mb::DrawStream ds(seed, epoch, 0u);
+    for (;;) {
+        // ---- refill idle lanes from the tile (loading the next tile when it runs out)
+        for (int round = 0; round < 2; ++round) {
+            const unsigned idle = __ballot_sync(0xffffffffu, m < 0);
+            if (idle == 0u) break;
+            if (tile_mask == 0u) {
+                if (next >= end) break;
+                tile0 = next;
+                next = min(next + 32, end);
+                const int64_t mine = tile0 + lane;
+                bool in_range = false;
+                if (mine < next) {
+                    tile_t = ws.mv_prio[mine];
+                    tile_agent = ws.mv_agent[mine];
+                    in_range = tile_t >= t_lo && tile_t <= t_hi;
+                }
+                tile_mask = __ballot_sync(0xffffffffu, in_range);
+                if (tile_mask == 0u) { round = -1; continue; }   // nothing of this bucket in the tile: take the next one
+            }
+            const int rank = __popc(idle & lt_mask);
+            const int avail = __popc(tile_mask);
+            const int src = (m < 0 && rank < avail) ? (int)__fns(tile_mask, 0, rank + 1) : 0;
+            const unsigned long long nt = __shfl_sync(0xffffffffu, tile_t, src);
+            const uint32_t na = __shfl_sync(0xffffffffu, tile_agent, src);
+            if (m < 0 && rank < avail) {
+                m = tile0 + src;
+                t = nt;
+                ds = mb::DrawStream(seed, epoch, na);
+                held = ws.choice[m];
+                soft = 0ull;
+                j = 0;
+                verify = mode == 1;
+            }
+            const int taken = min(__popc(idle), avail);
+            for (int q = 0; q < taken; ++q) tile_mask &= tile_mask - 1u;   // drop the entries handed out (lowest first)
+        }
+        if (__ballot_sync(0xffffffffu, m >= 0) == 0u) break;
+        if (m < 0) continue;
+        // ---- one step of this lane's mover
+        if (verify) {
+            verify = false;
+            const uint32_t pr = ws.progress[m];
+            if ((pr & 0xffu) >= (uint32_t)kMaxProbes) { m = -1; continue; }   // fallback state: served by the fallback phase
+            Slot* hp = v.slot(held);
+            const unsigned long long arr = load_slot(hp).arr;
+            if (arr == t) { m = -1; continue; }                               // still the registered arrival of my pick
+            if (arr > t) {                                                    // shadowed, and the shadow has left
+                atomicMin(&hp->arr, t);
+                mark_changed(ws);
+                m = -1;
+                continue;
+            }
+            ds.seek(pr >> 8);                                                 // an earlier mover took it: go on after it
+            soft = ws.softmask[m];
+            if (soft == 0ull) ws.softcell[m] = (uint32_t)held;
+            soft |= 1ull << (pr & 0xffu);
+            j = (int)(pr & 0xffu) + 1;
+            held = kNoCell;                                                   // nothing of mine is registered any more
+            continue;
+        }
+        unsigned long long cells[kBatch];
+        uint32_t after[kBatch];
+        Slot sl[kBatch];
+        Slot* sp[kBatch];
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            cells[b] = ds.randbelow((uint64_t)v.ncells);
+            after[b] = ds.c;
+        }
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            bool is_static;
+            sp[b] = v.slot_and_static(cells[b], is_static);
+            sl[b] = Slot{kNever, kNever};
+            if (!is_static) sl[b] = load_slot(sp[b]);
+        }
+        bool done = false;
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            const int jj = j + b;
+            if (done || jj >= kMaxProbes) continue;
+            if (empty_at(sl[b], t)) {
+                if (cells[b] == held) {
+                    if (atomicMin(&sp[b]->arr, t) > t) mark_changed(ws);      // re-assert (see relocate_pass)
+                } else {
+                    if (atomicMin(&sp[b]->arr, t) < t) {                      // lost the race for it: go on probing
+                        if (soft == 0ull) ws.softcell[m] = (uint32_t)cells[b];
+                        soft |= 1ull << jj;
+                        continue;
+                    }
+                    if (mode == 0) release_held(v, ws, held, t);
+                    ws.choice[m] = cells[b];
+                    mark_changed(ws);
+                }
+                ws.progress[m] = (uint32_t)jj | (after[b] << 8);
+                ws.softmask[m] = soft;
+                done = true;
+                continue;
+            }
+            if (sl[b].vac <= t) {
+                if (soft == 0ull) ws.softcell[m] = (uint32_t)cells[b];
+                soft |= 1ull << jj;
+            }
+        }
+        j += kBatch;
+        if (done) { m = -1; continue; }
+        if (j >= kMaxProbes) {
+            // all 50 probes occupied: fallback state
+            ws.softmask[m] = soft;
+            ws.progress[m] = (uint32_t)kMaxProbes;
+            if (mode == 1) { ws.choice[m] = kNoCell; mark_changed(ws); }
+            ws.fb_list[atomicAdd(&ws.counters[2], 1ull)] = (uint32_t)m;
+            m = -1;
+        }
+    }
+}
+
 // RELEASE SCAN.  When the registered arrival of a cell leaves it (time t_r), the cell may be empty again for the
 // movers that act later than t_r and had skipped it on the way to their pick.  Finding them needs no table traffic:
 // every mover replays the draws of the probes BEFORE its pick (Philox, registers only) and looks each cell up in a
@@ -1178,12 +1324,30 @@ MB_API int mb_reloc_pass(const void* shard, int64_t nmovers, uint64_t seed, uint
         static int batch = -1;
         if (batch < 0) {
             const char* e = getenv("MB_RELOC_BATCH");
-            batch = e ? atoi(e) : 4;
+            batch = e ? atoi(e) : 2;
         }
-        const unsigned blocks = (unsigned)mb::ceil_div(nmovers, 128);
-        if (batch <= 1) relocate_pass<1><<<blocks, 128, 0, stream>>>(v, ws, nmovers, seed, epoch, t_lo, t_hi, mode);
-        else if (batch == 2) relocate_pass<2><<<blocks, 128, 0, stream>>>(v, ws, nmovers, seed, epoch, t_lo, t_hi, mode);
-        else relocate_pass<4><<<blocks, 128, 0, stream>>>(v, ws, nmovers, seed, epoch, t_lo, t_hi, mode);
+        static int packed = -1;
+        if (packed < 0) {
+            const char* e = getenv("MB_RELOC_PACKED");
+            packed = e ? atoi(e) : 1;
+        }
+        if (packed) {
+            // one warp per `per_warp` consecutive movers: enough warps to fill the machine several times over, long
+            // enough ranges for the lane refill to pay
+            int64_t per_warp = 256;
+            const int64_t want_warps = (int64_t)mb::sm_count() * 64 * 4;
+            if (mb::ceil_div(nmovers, per_warp) < want_warps) per_warp = mb::ceil_div(mb::ceil_div(nmovers, want_warps), 32) * 32;
+            if (per_warp < 32) per_warp = 32;
+            const unsigned blocks = (unsigned)mb::ceil_div(mb::ceil_div(nmovers, per_warp), 4);
+            if (batch <= 1) relocate_pass_packed<1><<<blocks, 128, 0, stream>>>(v, ws, nmovers, seed, epoch, t_lo, t_hi, mode, per_warp);
+            else if (batch == 2) relocate_pass_packed<2><<<blocks, 128, 0, stream>>>(v, ws, nmovers, seed, epoch, t_lo, t_hi, mode, per_warp);
+            else relocate_pass_packed<4><<<blocks, 128, 0, stream>>>(v, ws, nmovers, seed, epoch, t_lo, t_hi, mode, per_warp);
+        } else {
+            const unsigned blocks = (unsigned)mb::ceil_div(nmovers, 128);
+            if (batch <= 1) relocate_pass<1><<<blocks, 128, 0, stream>>>(v, ws, nmovers, seed, epoch, t_lo, t_hi, mode);
+            else if (batch == 2) relocate_pass<2><<<blocks, 128, 0, stream>>>(v, ws, nmovers, seed, epoch, t_lo, t_hi, mode);
+            else relocate_pass<4><<<blocks, 128, 0, stream>>>(v, ws, nmovers, seed, epoch, t_lo, t_hi, mode);
+        }
     }
     MB_LAUNCH_CHECK("mb_reloc_pass");
     return MB_OK;

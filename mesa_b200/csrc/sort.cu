@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(1024) scan_single(uint32_t* __restrict__ data,
 int exclusive_scan_u32(uint32_t* data, int64_t n, uint32_t* sums, cudaStream_t stream) {
     if (n <= 0) return MB_OK;
     const int64_t nchunks = ceil_div(n, kScanChunk);
-    if (nchunks <= 32) {
+    if (nchunks <= 2) {
         scan_single<<<1, 1024, 0, stream>>>(data, n);
         return check_cuda(cudaGetLastError(), "exclusive_scan_u32");
     }
