@@ -487,12 +487,10 @@ relocate_pass(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, uint32_t 
 // (one coalesced tile in registers), every lane that finishes its mover takes the next one of the tile by shuffle, and
 // one loop iteration advances every lane by one step of its own mover -- the verification of the held pick (RESUME) or one
 // batch of kBatch probes.  Results are identical (same draws, same claims); only the mapping of movers to lanes changes.
-// Second source of divergence: _randbelow's rejection loop (ncells = 2^26 rejects every other draw) runs a Philox block per
-// iteration inside a data-dependent loop.  Here one loop iteration computes exactly ONE Philox block (two draws) per
-// active lane; the accepted draws (r < ncells, random.py:242-250) queue up as probe cells and the queue is evaluated
-// (bitmap test, slot loads, claim) once it holds two or three of them.  Same draws in the same order, so the probe
-// sequence -- and with it every result -- is unchanged.
-template <int kUnused>
+// (Tried and dropped: one Philox block per lane and loop iteration with a queue of accepted draws, to take _randbelow's
+// rejection loop out of the divergent part -- 15.8 lanes active instead of 11.9, but 4.9 ms instead of 2.8 ms for the
+// FULL pass at 8192^2: more loop iterations, each paying the refill ballots / shuffles, and 80 registers.)
+template <int kBatch>
 __global__ void __launch_bounds__(128)
 relocate_pass_packed(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, uint32_t epoch, unsigned long long t_lo,
                      unsigned long long t_hi, int mode, int64_t movers_per_warp) {
@@ -502,7 +500,6 @@ relocate_pass_packed(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, ui
     int64_t next = warp_id * movers_per_warp;                       // first mover of the next tile (warp-uniform)
     const int64_t end = min(next + movers_per_warp, nmovers);
     if (next >= end) return;
-    const int shift = __clzll((long long)v.ncells);                 // 64 - ncells.bit_length()
     // the current tile: lane l holds mover tile0 + l; tile_mask = entries not handed out yet (in the bucket's time range)
     int64_t tile0 = 0;
     unsigned tile_mask = 0u;
@@ -511,13 +508,9 @@ relocate_pass_packed(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, ui
     // this lane's mover
     int64_t m = -1;
     unsigned long long t = 0ull, held = kNoCell, soft = 0ull;
-    uint32_t agent = 0u, blk = 0u;   // next Philox block of the DRAW stream
-    bool skip = false;               // the first draw of that block is already consumed (resumed at an odd draw index)
-    int j = 0;                       // probes evaluated so far
-    int q = 0;                       // queued probe cells
-    unsigned long long qc0 = 0ull, qc1 = 0ull, qc2 = 0ull;
-    uint32_t qa0 = 0u, qa1 = 0u, qa2 = 0u;   // draws consumed after each queued probe
-    bool verify = false;             // RESUME: the held pick has not been checked yet
+    int j = 0;                 // next probe
+    bool verify = false;       // RESUME: the held pick has not been checked yet
+    mb::DrawStream ds(seed, epoch, 0u);
     for (;;) {
         // ---- refill idle lanes from the tile (loading the next tile when it runs out)
         for (int round = 0; round < 2; ++round) {
@@ -545,14 +538,14 @@ relocate_pass_packed(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, ui
             if (m < 0 && rank < avail) {
                 m = tile0 + src;
                 t = nt;
-                agent = na;
-                blk = 0u; skip = false; j = 0; q = 0;
+                ds = mb::DrawStream(seed, epoch, na);
                 held = ws.choice[m];
                 soft = 0ull;
+                j = 0;
                 verify = mode == 1;
             }
             const int taken = min(__popc(idle), avail);
-            for (int k = 0; k < taken; ++k) tile_mask &= tile_mask - 1u;   // drop the entries handed out (lowest first)
+            for (int q = 0; q < taken; ++q) tile_mask &= tile_mask - 1u;   // drop the entries handed out (lowest first)
         }
         if (__ballot_sync(0xffffffffu, m >= 0) == 0u) break;
         if (m < 0) continue;
@@ -570,8 +563,7 @@ relocate_pass_packed(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, ui
                 m = -1;
                 continue;
             }
-            blk = (pr >> 8) >> 1;                                             // an earlier mover took it: go on after it
-            skip = ((pr >> 8) & 1u) != 0u;
+            ds.seek(pr >> 8);                                                 // an earlier mover took it: go on after it
             soft = ws.softmask[m];
             if (soft == 0ull) ws.softcell[m] = (uint32_t)held;
             soft |= 1ull << (pr & 0xffu);
@@ -579,42 +571,27 @@ relocate_pass_packed(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, ui
             held = kNoCell;                                                   // nothing of mine is registered any more
             continue;
         }
-        {   // one Philox block = two draws of the mover's stream
-            const mb::U4 o = mb::philox_keyed(seed, epoch, agent, mb::kStreamDraw, blk);
-            const unsigned long long r0 = (((unsigned long long)o.x << 32) | o.y) >> shift;
-            const unsigned long long r1 = (((unsigned long long)o.z << 32) | o.w) >> shift;
-            if (!skip && r0 < (unsigned long long)v.ncells) {
-                if (q == 0) { qc0 = r0; qa0 = 2u * blk + 1u; } else { qc1 = r0; qa1 = 2u * blk + 1u; }
-                ++q;
-            }
-            if (r1 < (unsigned long long)v.ncells) {
-                if (q == 0) { qc0 = r1; qa0 = 2u * blk + 2u; } else if (q == 1) { qc1 = r1; qa1 = 2u * blk + 2u; } else { qc2 = r1; qa2 = 2u * blk + 2u; }
-                ++q;
-            }
-            skip = false;
-            ++blk;
-        }
-        if (q < 2 && j + q < kMaxProbes) continue;
-        // ---- evaluate the queued probes in order
-        const unsigned long long cells[3] = {qc0, qc1, qc2};
-        const uint32_t after[3] = {qa0, qa1, qa2};
-        Slot sl[3];
-        Slot* sp[3];
+        unsigned long long cells[kBatch];
+        uint32_t after[kBatch];
+        Slot sl[kBatch];
+        Slot* sp[kBatch];
 #pragma unroll
-        for (int b = 0; b < 3; ++b) {
+        for (int b = 0; b < kBatch; ++b) {
+            cells[b] = ds.randbelow((uint64_t)v.ncells);
+            after[b] = ds.c;
+        }
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            bool is_static;
+            sp[b] = v.slot_and_static(cells[b], is_static);
             sl[b] = Slot{kNever, kNever};
-            sp[b] = nullptr;
-            if (b < q && j + b < kMaxProbes) {
-                bool is_static;
-                sp[b] = v.slot_and_static(cells[b], is_static);
-                if (!is_static) sl[b] = load_slot(sp[b]);
-            }
+            if (!is_static) sl[b] = load_slot(sp[b]);
         }
         bool done = false;
 #pragma unroll
-        for (int b = 0; b < 3; ++b) {
+        for (int b = 0; b < kBatch; ++b) {
             const int jj = j + b;
-            if (done || b >= q || jj >= kMaxProbes) continue;
+            if (done || jj >= kMaxProbes) continue;
             if (empty_at(sl[b], t)) {
                 if (cells[b] == held) {
                     if (atomicMin(&sp[b]->arr, t) > t) mark_changed(ws);      // re-assert (see relocate_pass)
@@ -638,8 +615,7 @@ relocate_pass_packed(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, ui
                 soft |= 1ull << jj;
             }
         }
-        j += q;
-        q = 0;
+        j += kBatch;
         if (done) { m = -1; continue; }
         if (j >= kMaxProbes) {
             // all 50 probes occupied: fallback state
