@@ -92,7 +92,7 @@ def test_example_models_start_from_the_reference_initial_state(monkeypatch):
     want = np.full(400, -1, dtype=np.int8)
     want[g["cell0"]] = g["atype"]
     s = Schelling(SchellingScenario(width=20, height=20, density=0.8, homophily=0.4, radius=1, rng=42), device="cpu",
-                  collect=False)
+                  collect=False, fused=False)
     assert np.array_equal(s.grid.type.numpy().reshape(-1), want)
     assert np.array_equal(s.agents.get("cell").numpy(), g["cell0"]) and np.array_equal(s.agents.get("type").numpy(), g["atype"])
 
