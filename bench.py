@@ -446,7 +446,7 @@ def run_ours(args):
             return 0
         n = life.launches
         if world > 1:
-            n += life.layer.exchanges + life.layer.waits
+            n = life.kernel_launches + life.layer.exchanges + life.layer.waits
         return n
 
     warm = max(args.warmup, 3)
@@ -484,6 +484,11 @@ def run_ours(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(_physical_gpu_index(local)) as clocks:
+        if world > 1 and life is not None and getattr(life.layer, "hdl", None) is not None:
+            # the host barrier above leaves the ranks tens of microseconds apart, which a 0.2 ms window that opens with an
+            # exchange would book as waiting time of the early ranks: line the GPUs up with a device-side barrier
+            # (symmetric memory, one small kernel per rank) BEFORE the first event is recorded
+            life.layer.hdl.barrier()
         if graph is not None:
             e0.record()
             graph.replay()

@@ -27,10 +27,15 @@ import torch
 _OPERATORS: dict[tuple[type, str], Callable] = {}
 
 
-def batch_operator(agent_type: type, name: str):
-    """Register `fn(agentset, *, epoch=None, **kwargs)` as the device implementation of `agent_type.name`."""
+def batch_operator(agent_type: type, name: str, views: bool = False):
+    """Register `fn(agentset, *, epoch=None, **kwargs)` as the device implementation of `agent_type.name`.
+
+    views=True declares that the operator honours `agentset.index` (the row tensor of a `select / shuffle / sort` view,
+    None for the whole population), so `do / shuffle_do / map` may be called on such views like on any reference
+    AgentSet (agentset.py:66-135 `select`, :474-518); operators without it only accept whole populations."""
 
     def deco(fn):
+        fn._mb_views = bool(views)
         _OPERATORS[(agent_type, name)] = fn
         return fn
 
@@ -339,29 +344,37 @@ class DeviceAgentSet:
         if self.index is not None:
             raise NotImplementedError(f"{what} on a selected / reordered view is not supported on the device path")
 
+    def _operator(self, what: str, method: str) -> Callable:
+        fn = _lookup(self.agent_type, method)
+        if self.index is not None:
+            self._check_view()
+            if not getattr(fn, "_mb_views", False):
+                raise NotImplementedError(f"{what}({method!r}) on a selected / reordered view: the operator registered for "
+                                          f"{self.agent_type.__name__}.{method} works on whole populations only "
+                                          "(register it with batch_operator(..., views=True) to take agentset.index)")
+        return fn
+
     def do(self, method, *args, **kwargs) -> "DeviceAgentSet":
         """agentset.py:756-770: call `method` on every agent (registration order) -- one kernel launch."""
         if not isinstance(method, str):
             raise NotImplementedError("DeviceAgentSet.do takes the name of a registered batch operator, not a callable")
-        self._require_full("do")
-        _lookup(self.agent_type, method)(self, *args, **kwargs)
+        self._operator("do", method)(self, *args, **kwargs)
         return self
 
     def shuffle_do(self, method, *args, **kwargs) -> "DeviceAgentSet":
         """agentset.py:772-787: activate every agent once in a random order (Philox priority order)."""
         if not isinstance(method, str):
             raise NotImplementedError("DeviceAgentSet.shuffle_do takes the name of a registered batch operator")
-        self._require_full("shuffle_do")
+        fn = self._operator("shuffle_do", method)
         epoch = self.model._next_epoch()
-        _lookup(self.agent_type, method)(self, *args, epoch=epoch, **kwargs)
+        fn(self, *args, epoch=epoch, **kwargs)
         return self
 
     def map(self, method, *args, **kwargs):
         """agentset.py:789-804: like do, returning the operator's per-agent result tensor."""
         if not isinstance(method, str):
             raise NotImplementedError("DeviceAgentSet.map takes the name of a registered batch operator")
-        self._require_full("map")
-        return _lookup(self.agent_type, method)(self, *args, **kwargs)
+        return self._operator("map", method)(self, *args, **kwargs)
 
     # -- columns --------------------------------------------------------------
     def _col(self, name: str) -> torch.Tensor:

@@ -25,6 +25,13 @@
 #include <stdlib.h>
 #include <string.h>
 
+namespace mb {
+// csrc/schelling_bits.cu: the bit-plane kernel (radius <= 2, binary types, cols % 32 == 0, rules with a small integer form)
+int happy_bits_launch(const int8_t* type, const int8_t* halo_top, const int8_t* halo_bot, uint8_t* happy, int64_t rows,
+                      int64_t cols, int radius, int col_torus, const uint8_t* min_similar_host,
+                      unsigned long long* happy_count, cudaStream_t stream, bool* handled);
+}
+
 namespace {
 
 constexpr int kWarps = 8;
@@ -363,6 +370,12 @@ MB_API int mb_schelling_happy_i8(const int8_t* type, const int8_t* halo_top, con
     if (rows == 0 || cols == 0) return MB_OK;
     MB_REQUIRE(type != nullptr && happy != nullptr, "mb_schelling_happy_i8: null buffer");
     const int nmax = (2 * radius + 1) * (2 * radius + 1) - 1;
+    if (binary_types) {
+        bool handled = false;
+        const int rc = mb::happy_bits_launch(type, halo_top, halo_bot, happy, rows, cols, radius, col_torus, min_similar_host,
+                                             happy_count, stream, &handled);
+        if (rc != MB_OK || handled) return rc;
+    }
     HappyRule rule;
     const bool packed = make_rule(min_similar_host, nmax, &rule);
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };

@@ -114,7 +114,7 @@ def gol_launch_plan(generations: int, per_launch: int, valid: int | None = None,
                     even: bool = False) -> list[int]:
     """Generations of each launch of a `generations`-long run: at most `per_launch` per launch and, on a layer with deep
     ghost zones, never past the `valid` generations the ghost rows are good for (0 = refresh first, then `ghost` more).
-    A zero entry means "refresh the ghost rows here".  even=True splits the last launch when the number of launches
+    A zero entry means "refresh the ghost rows here".  even=True splits the longest launch when the number of launches
     is odd, so that the run ends on the ping-pong plane it started on (a CUDA graph of the run can then be replayed)."""
     plan, left = [], int(generations)
     while left > 0:
@@ -127,12 +127,13 @@ def gol_launch_plan(generations: int, per_launch: int, valid: int | None = None,
         if valid is not None:
             valid -= t
     if even and sum(1 for t in plan if t) % 2:
-        for i in range(len(plan) - 1, -1, -1):
-            if plan[i] >= 2:
-                plan[i:i + 1] = [plan[i] - plan[i] // 2, plan[i] // 2]
-                break
-        else:
+        # split the LONGEST launch (the last one among equals): two launches of 4 generations cost less than a pair of
+        # 2-generation ones (the per-generation cost falls with the number of generations chained in a launch)
+        best = max(plan)
+        if best < 2:
             raise ValueError("a run of single-generation launches cannot be made even")
+        i = len(plan) - 1 - plan[::-1].index(best)
+        plan[i:i + 1] = [best - best // 2, best // 2]
     return plan
 
 

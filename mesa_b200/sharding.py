@@ -446,7 +446,8 @@ class PeerBitLife:
     kernel with a flag hand-shake (csrc/ghost.cu), so `run(k)` is a static launch sequence (CUDA-graph capturable)."""
 
     def __init__(self, rows: int, cols: int, torus: bool, device, generations_per_launch: int = 8,
-                 rows_per_segment: int = 0, ghost: int | None = None, group=None, transport: str = "peer"):
+                 rows_per_segment: int = 0, ghost: int | None = None, group=None, transport: str = "peer",
+                 overlap: bool = True):
         from . import ops
 
         if ghost is None:
@@ -462,7 +463,10 @@ class PeerBitLife:
         self.layer = DeepGhostLayer(self.rows, self.cols // 32, torch.int32, max(int(ghost), self.generations_per_launch),
                                     torus, self.device, group, transport=transport)
         self.ghost = self.layer.ghost
-        self.launches = 0
+        self.launches = 0          # stencil steps (a step with an overlapped refresh is three kernels)
+        self.kernel_launches = 0
+        self.overlap = overlap
+        self._side = None
 
     @property
     def exchanges(self) -> int:
@@ -483,10 +487,19 @@ class PeerBitLife:
 
     def run(self, generations: int, even_launches: bool = False) -> None:
         """Advance `generations`.  even_launches=True: end on the plane the run started on (see ops.gol_launch_plan)."""
+        refresh_pending = False
         for t in self._ops.gol_launch_plan(generations, self.generations_per_launch, self.layer.valid, self.ghost,
                                            even=even_launches):
             if t == 0:
-                self.layer.refresh()
+                # the refresh is folded into the launch that follows it (when the block is tall enough to have an interior)
+                if self.overlap and self.layer.transport == "peer" and self.rows >= 4 * self.generations_per_launch:
+                    refresh_pending = True
+                else:
+                    self.layer.refresh()
+                continue
+            if refresh_pending:
+                refresh_pending = False
+                self._step_with_refresh(t)
                 continue
             self.layer.prepare_write()
             src, dst = self.layer.planes()
@@ -494,6 +507,32 @@ class PeerBitLife:
             self._ops.gol_step_bits(src, dst, t, torus=False, col_torus=self.torus, rows_per_segment=self.rows_per_segment)
             self.layer.advance(t)
             self.launches += 1
+            self.kernel_launches += 1
+
+    def _step_with_refresh(self, t: int) -> None:
+        """The first launch after a ghost refresh, with the refresh OVERLAPPED: rows further than `t` rows from the edges
+        of the owned block do not depend on the ghost rows within `t` generations, so they are stepped at once on the
+        calling stream while a side stream runs the exchange (hand-shake + copy over NVLink, csrc/ghost.cu) and then the
+        two edge strips (ghost rows + `t` owned rows each); the streams join afterwards.  Same cells from the same inputs
+        as the single launch over the extended block (the strips get the rows across the cut as halo rows)."""
+        layer, ops, g, R = self.layer, self._ops, self.ghost, self.rows
+        main = torch.cuda.current_stream(self.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.device)
+        side = self._side
+        layer.prepare_write()                       # nobody is still copying out of the plane about to be written
+        side.wait_stream(main)                      # the previous launch has written the current plane
+        src, dst = layer.buf[layer.cur], layer.buf[1 - layer.cur]
+        kw = dict(torus=False, col_torus=self.torus, rows_per_segment=self.rows_per_segment)
+        with torch.cuda.stream(side):
+            layer.refresh()
+            ops.gol_step_bits(src[layer._lo:g + t], dst[layer._lo:g + t], t, halo_bot=src[g + t:g + 2 * t], **kw)
+            ops.gol_step_bits(src[g + R - t:layer._hi], dst[g + R - t:layer._hi], t, halo_top=src[g + R - 2 * t:g + R - t], **kw)
+        ops.gol_step_bits(src[g + t:g + R - t], dst[g + t:g + R - t], t, halo_top=src[g:g + t], halo_bot=src[g + R - t:g + R], **kw)
+        main.wait_stream(side)
+        layer.advance(t)
+        self.launches += 1
+        self.kernel_launches += 3
 
     def check(self) -> None:
         self.layer.check()

@@ -128,6 +128,19 @@ class CellProxy:
         return bool((grid.agent_counts()[self.coordinate] >= grid.capacity).item())
 
     @property
+    def connections(self) -> dict:
+        """cell.py:96: {offset: neighbouring cell} in the order the grid connects them (grid.py:390-399; on a torus an offset
+        that wraps onto an already connected cell keeps its own key, like the reference's dict of connections)."""
+        grid, out = self.grid, {}
+        for off in grid._offsets:
+            nb = tuple(x + o for x, o in zip(self.coordinate, off))
+            if grid.torus:
+                nb = tuple(x % d for x, d in zip(nb, grid.dimensions))
+            if all(0 <= x < d for x, d in zip(nb, grid.dimensions)):
+                out[off] = CellProxy(grid, nb)
+        return out
+
+    @property
     def neighborhood(self) -> list["CellProxy"]:
         return self.get_neighborhood()
 
@@ -144,6 +157,9 @@ class CellProxy:
 
 
 _RAISES = object()
+# cell.py:49-58 `Cell.__slots__` (+ the two fields of the proxy): names a property layer may not take
+_CELL_SLOTS = frozenset({"_agents", "_empty", "_position", "capacity", "connections", "coordinate", "properties", "random",
+                         "grid"})
 
 
 class CellCollectionProxy(list):
@@ -207,8 +223,59 @@ class CellCollectionProxy(list):
         return f"CellCollection({list(self)})"
 
 
+class _CellMap:
+    """`space._cells` (discrete_space.py:67): coordinate -> cell, without materialising the cells."""
+
+    def __init__(self, grid: "DeviceGrid"):
+        self._grid = grid
+
+    def __getitem__(self, coordinate) -> CellProxy:
+        return self._grid[coordinate]
+
+    def __contains__(self, coordinate) -> bool:
+        try:
+            self._grid._check(coordinate)
+        except KeyError:
+            return False
+        return True
+
+    def __len__(self) -> int:
+        return len(self._grid)
+
+    def __iter__(self):
+        return product(*(range(d) for d in self._grid.dimensions))
+
+    def keys(self):
+        return iter(self)
+
+    def values(self):
+        return self._grid.all_cells
+
+    def items(self):
+        return ((c, CellProxy(self._grid, c)) for c in self)
+
+
+class _DetachedCell(CellProxy):
+    """`grid.cell_klass(coordinate)` (grid.py:100-110): a cell that belongs to no grid yet.  Like the reference's slotted
+    Cell it rejects unknown attributes."""
+
+    __slots__ = ()
+
+    def __init__(self, coordinate, capacity=None, random=None):
+        CellProxy.__init__(self, None, coordinate if isinstance(coordinate, tuple) else (coordinate,))
+
+    def __setattr__(self, name, value):
+        raise AttributeError(f"'Cell' object has no attribute {name!r}")
+
+
 class DeviceGrid:
     """Base class of the device grids (mirror of mesa.discrete_space.Grid)."""
+
+    cell_klass = _DetachedCell
+
+    @property
+    def _cells(self) -> _CellMap:
+        return _CellMap(self)
 
     _offsets: list[tuple[int, int]] = []
     _moore = True
@@ -277,8 +344,10 @@ class DeviceGrid:
         self._read_only_layers.discard(name)
 
     def _attach_property_layer(self, name: str, layer: torch.Tensor, read_only: bool = False) -> None:
-        if any(name in c.__dict__ for c in type(self).__mro__) or name in ("grid", "coordinate"):
+        if any(name in c.__dict__ for c in type(self).__mro__):
             raise ValueError(f"property_layer '{name}' conflicts with an existing Grid attribute.")
+        if name in _CELL_SLOTS:   # grid.py:194-202: the name would shadow a field of the cells
+            raise ValueError(f"property_layer name '{name}' clashes with existing slot '{name}'.")
         if name in self.property_layers:
             raise ValueError(f"property_layer '{name}' already exists.")
         self.property_layers[name] = layer

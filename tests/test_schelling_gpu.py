@@ -74,6 +74,11 @@ def test_schelling_matches_reference_trajectory(name):
     ((64, 64), 1, 0.4, False), ((100, 100), 2, 1.0, False), ((48, 528), 2, 0.55, False),
     ((130, 1040), 1, 0.375, True), ((33, 512), 2, 0.5, True), ((37, 23), 1, 0.4, False),
     ((37, 23), 3, 0.3, True), ((16, 16), 1, 0.0, False), ((16, 32), 1, 1.5, False),
+    # widths that are multiples of 32 take the bit-plane kernel (csrc/schelling_bits.cu): partial strips, several strips,
+    # fewer rows than a row group, single rows, rules with and without a small integer form
+    ((130, 1056), 1, 0.375, True), ((67, 2080), 2, 0.55, False), ((5, 32), 2, 0.4, True), ((1, 64), 1, 0.4, False),
+    ((70, 1024), 2, 1.0, True), ((200, 96), 1, 0.7, False), ((3, 1024), 1, 1.0, True), ((64, 64), 2, 0.0, False),
+    ((41, 160), 1, 0.123, False), ((41, 160), 2, 0.9, True), ((29, 32), 1, 0.5, True), ((29, 64), 2, 0.3333333333333333, False),
 ])
 def test_happy_layer_matches_oracle(shape, radius, h, torus):
     rng = np.random.default_rng(1)
@@ -86,6 +91,27 @@ def test_happy_layer_matches_oracle(shape, radius, h, torus):
     happy, count = ops.schelling_happy(torch.from_numpy(grid).cuda(), h, radius, torus)
     assert int(count.item()) == want_count
     assert np.array_equal(happy.cpu().numpy(), st.happy_grid())
+
+
+@pytest.mark.parametrize("shape,radius,h", [((96, 128), 1, 0.4), ((96, 128), 2, 0.55), ((50, 1056), 2, 1.0), ((50, 48), 1, 0.4)])
+def test_happy_row_blocks_with_halo_rows_equal_the_whole_grid(shape, radius, h):
+    """The row-sharded form: every block gets the `radius` rows above / below it as halo rows (None at the outer edges);
+    the blocks' happy layers and counts add up to the whole grid's."""
+    from mesa_b200 import ops
+
+    rng = np.random.default_rng(5)
+    u = rng.random(shape)
+    grid = torch.from_numpy(np.where(u < 0.25, -1, np.where(u < 0.6, 0, 1)).astype(np.int8)).cuda()
+    whole, count = ops.schelling_happy(grid, h, radius, False)
+    cuts = [0, 7, 7 + radius, 40, shape[0]]
+    total = 0
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        top = grid[lo - radius:lo].contiguous() if lo >= radius else None
+        bot = grid[hi:hi + radius].contiguous() if hi + radius <= shape[0] else None
+        part, c = ops.schelling_happy(grid[lo:hi].contiguous(), h, radius, False, halo_top=top, halo_bot=bot)
+        assert torch.equal(part, whole[lo:hi]), (lo, hi)
+        total += int(c.item())
+    assert total == int(count.item())
 
 
 def test_relocate_dense_grid_uses_argwhere_fallback():

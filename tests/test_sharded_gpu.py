@@ -69,16 +69,20 @@ def test_sharded_boids_world1_matches_oracle(one_rank_group):
 
 @pytest.mark.parametrize("torus", [True, False])
 @pytest.mark.parametrize("ghost,launches,exchanges", [(64, 3, 1), (8, 3, 2), (4, 3, 3)])
-def test_peer_bit_life_world1_matches_oracle(one_rank_group, torus, ghost, launches, exchanges):
+@pytest.mark.parametrize("overlap", [True, False])
+def test_peer_bit_life_world1_matches_oracle(one_rank_group, torus, ghost, launches, exchanges, overlap):
     """Row-sharded bit-packed Game of Life with a 1-rank group: the ring neighbour is the rank itself (torus) or
     absent (clamped); deep ghost zones refreshed every `ghost` generations must equal the oracle."""
     from mesa_b200.sharding import PeerBitLife
 
     rng = np.random.default_rng(8)
     s = (rng.random((72, 192)) < 0.35).astype(np.uint8)
-    life = PeerBitLife(72, 192, torus, "cuda", generations_per_launch=4, ghost=ghost)
+    # overlap=True: the launch after a refresh is split into an interior launch + the exchange and two edge strips on a
+    # side stream (PeerBitLife._step_with_refresh)
+    life = PeerBitLife(72, 192, torus, "cuda", generations_per_launch=4, ghost=ghost, overlap=overlap)
     life.load(torch.from_numpy(s).cuda())
     life.run(10)
+    assert life.kernel_launches == launches + (2 * exchanges if overlap else 0)
     want = s
     for _ in range(10):
         want = oracle.gol_step(want, torus)

@@ -32,7 +32,7 @@ for torus, T, ghost, gens in [(True, 8, 8, 40), (False, 4, 16, 50), (True, 8, 64
     full = (torch.rand((rows * world, cols), generator=g) < 0.3).to(torch.uint8).to(dev)
     res = []
     for transport in ("peer", "barrier"):
-        life = PeerBitLife(rows, cols, torus, dev, generations_per_launch=T, ghost=ghost, transport=transport)
+        life = PeerBitLife(rows, cols, torus, dev, generations_per_launch=T, ghost=ghost, transport=transport, overlap=(transport == "peer"))
         life.load(full[rank * rows:(rank + 1) * rows])
         life.run(gens)
         life.check()
