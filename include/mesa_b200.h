@@ -219,6 +219,11 @@ int mb_sort_pairs_u64(uint64_t* keys0, uint32_t* vals0, uint64_t* keys1, uint32_
                       int begin_bit, int end_bit, void* workspace, size_t workspace_bytes, int* result_buffer,
                       mb_stream_t stream);
 
+/* offsets[i] = counts[0] + ... + counts[i-1] (i = 0 .. n): the row offsets of a CSR result from its per-row counts (the
+ * batched radius queries count first, then fill).  scratch: (n + 1) + mb_scan_scratch_words(n + 1) uint32 words.  The
+ * running sum is 32 bits wide: totals >= 2^32 are the caller's to refuse. */
+int mb_offsets_from_counts(const int32_t* counts, int64_t n, int64_t* offsets, uint32_t* scratch, mb_stream_t stream);
+
 /* The activation order of shuffle / shuffle_do number `epoch` as an explicit permutation (agentset.py:415-437,
  * 772-787): order_out[r] = index of the agent activated r-th = agents 0..n-1 sorted by priority64(seed, epoch, agent). */
 int mb_activation_order_workspace_bytes(int64_t n, size_t* out);

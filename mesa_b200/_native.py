@@ -111,6 +111,7 @@ SIGNATURES: dict[str, tuple] = {
                                c_int64, _P, _S]),
     "mb_boids_compact": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P, _P, _S]),
     "mb_scan_scratch_words": (c_int, [c_int64, ctypes.POINTER(ctypes.c_size_t)]),
+    "mb_offsets_from_counts": (c_int, [_P, c_int64, _P, _P, _S]),
     # dynamic populations
     "mb_compact_plan": (c_int, [_P, c_int64, _P, _P, _S]),
     "mb_compact_rows": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _S]),

@@ -480,9 +480,11 @@ class DeviceAgentSet:
 
             idx = ops.activation_order(self.model.philox_seed, epoch, self.n, self._device()).to(torch.int64)
         else:
+            from . import ops
+
             base = torch.arange(self.n, device=self._device()) if self.index is None else self.index
-            pri = rng.priority64(self.model.philox_seed, epoch, base)
-            idx = base[torch.argsort(pri.view(torch.int64) ^ (-2**63), stable=True)]
+            pri = rng.priority64(self.model.philox_seed, epoch, base)        # uint64 bit patterns in int64
+            idx = base[ops.argsort_stable(pri.view(torch.int64) ^ (-2**63))]
         if inplace:
             self.index, self._view_gen = idx, self._pop.generation
             return self
@@ -493,7 +495,9 @@ class DeviceAgentSet:
             raise NotImplementedError("DeviceAgentSet.sort takes a column name")
         self._check_view()
         base = torch.arange(self.n, device=self._device()) if self.index is None else self.index
-        order = torch.argsort(self.columns[key][base], stable=True, descending=not ascending)
+        from . import ops
+
+        order = ops.argsort_stable(self.columns[key][base], descending=not ascending)
         idx = base[order]
         if inplace:
             self.index, self._view_gen = idx, self._pop.generation
@@ -532,10 +536,10 @@ class DeviceAgentSet:
         order_in = torch.arange(m, dtype=torch.int32, device=keys.device)
         sorted_bits, order = ops.sort_pairs(bits, order_in)             # stable: set order survives inside a group
         order = order.to(torch.int64)
-        starts = torch.nonzero(sorted_bits[1:] != sorted_bits[:-1]).reshape(-1) + 1
+        starts = ops.nonzero_indices(sorted_bits[1:] != sorted_bits[:-1]) + 1
         starts = torch.cat([starts.new_zeros(1), starts])
         first = order[starts]                                            # position of each group's first member
-        by_first = torch.argsort(first)                                  # groups in order of first appearance
+        by_first = ops.argsort_stable(first)                             # groups in order of first appearance
         starts_h = starts[by_first].cpu().tolist()
         ends_h = torch.cat([starts[1:], starts.new_full((1,), m)])[by_first].cpu().tolist()
         names = keys[first[by_first]].cpu().tolist()

@@ -59,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
-            cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+            cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("MB_NVCC_EXTRA", "").split(), "-c", src, "-o", obj]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             jobs.append(cmd)

@@ -147,7 +147,7 @@ class DeviceContinuousSpace:
         """continuous_space.py:237-247: (agent indices, distances) with dist <= radius, storage order."""
         if self.ndims != 2:  # all n distances in one launch, then the reference's `distances <= radius` selection
             d, _ = self._point_distances(point, None, True, False)
-            inside = torch.nonzero(d <= float(radius)).reshape(-1)
+            inside = ops.nonzero_indices(d <= float(radius))
             return inside.cpu().tolist(), d[inside].cpu().numpy()
         _, idx, dist = self.radius_query(np.asarray(point, dtype=np.float32)[None, :], radius)
         return idx.cpu().tolist(), dist.cpu().numpy()
@@ -196,7 +196,7 @@ class DeviceContinuousSpace:
         p = np.asarray(point, dtype=np.float64)
         if self.ndims != 2:  # the reference's own method: all n distances, keep the k smallest (ties: earlier index)
             d, _ = self._point_distances(p, None, True, False)
-            order = torch.argsort(d, stable=True)[:k]
+            order = ops.argsort_stable(d)[:k]
             return order.cpu().tolist(), d[order].cpu().numpy()
         if self.torus and not self.in_bounds(p):
             p = self.torus_correct(p)

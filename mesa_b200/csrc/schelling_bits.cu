@@ -36,6 +36,9 @@ int happy_bits_launch(const int8_t* type, const int8_t* halo_top, const int8_t* 
 namespace {
 
 constexpr int kWarpsPerCta = 4;
+#ifndef MB_HAPPY_MINB1
+#define MB_HAPPY_MINB1 5   // CTAs per SM the radius-1 kernel is compiled for
+#endif
 
 struct BitRule {
     unsigned a, b, c;        // happy (valid > 0)  <=>  a * same + c >= b * other
@@ -52,6 +55,19 @@ struct RawRow32 {
     unsigned lw, rw;    // aligned word left / right of them (strip-edge lanes only)
 };
 
+// The lane's 32 cells with ONE 256-bit load (sm_100: LDG.E.256; a warp then asks for 1 KiB of consecutive bytes in 8
+// L1 wavefronts -- two 128-bit loads per lane stride the lanes by 32 bytes and take 16), 32-byte aligned rows only
+__device__ __forceinline__ void ldg256(const void* p, uint4& lo, uint4& hi) {
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                 : "l"(p));
+}
+__device__ __forceinline__ void stg256_cs(void* p, const uint4& lo, const uint4& hi) {
+    asm volatile("st.global.cs.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z),
+                 "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+                 : "memory");
+}
+
 template <bool kChecked>
 __device__ __forceinline__ RawRow32 load_raw32(const int8_t* __restrict__ row, const LaneCols& la) {
     RawRow32 x;
@@ -60,10 +76,7 @@ __device__ __forceinline__ RawRow32 load_raw32(const int8_t* __restrict__ row, c
     x.lw = ~0u;
     x.rw = ~0u;
     if (!kChecked || row != nullptr) {
-        if (la.active) {
-            x.lo = __ldg(reinterpret_cast<const uint4*>(row + la.col));
-            x.hi = __ldg(reinterpret_cast<const uint4*>(row + la.col + 16));
-        }
+        if (la.active) ldg256(row + la.col, x.lo, x.hi);
         if (la.ld_left) x.lw = __ldg(reinterpret_cast<const unsigned*>(row + la.lcol));
         if (la.ld_right) x.rw = __ldg(reinterpret_cast<const unsigned*>(row + la.rcol));
     }
@@ -116,15 +129,28 @@ __device__ __forceinline__ RowBits<R> make_row(const RawRow32& x, const LaneCols
         Lp[p] = __shfl_up_sync(0xffffffffu, pl[p], 1);
         Rp[p] = __shfl_down_sync(0xffffffffu, pl[p], 1);
     }
-    {   // strip-edge lanes take the cells beyond the strip from the extra words (branch-free: selects)
-        const unsigned lb = ((x.lw & 0x01000000u) << 7) | ((x.lw & 0x00010000u) << 14);
-        const unsigned le = ((x.lw & 0x02000000u) << 6) | ((x.lw & 0x00020000u) << 13);
-        const unsigned rb = (x.rw & 1u) | ((x.rw & 0x00000100u) >> 7);
-        const unsigned re = ((x.rw & 2u) >> 1) | ((x.rw & 0x00000200u) >> 8);
-        Lp[0] = la.edge_l ? (lb & ~le) : Lp[0];
-        Lp[1] = la.edge_l ? (~(lb | le) & 0xc0000000u) : Lp[1];
-        Rp[0] = la.edge_r ? (rb & ~re) : Rp[0];
-        Rp[1] = la.edge_r ? (~(rb | re) & 3u) : Rp[1];
+    {   // strip-edge lanes take the R cells beyond either end of the strip from the extra words (branch-free: selects).
+        // A cell is type 1 iff bit 0 and not bit 1 of its byte, type 0 iff neither: both tests for all four bytes at once
+        const unsigned l1 = x.lw & ~(x.lw >> 1), l0 = ~(x.lw | (x.lw >> 1));   // bit 8i: cell i of the word is type 1 / type 0
+        const unsigned r1 = x.rw & ~(x.rw >> 1), r0 = ~(x.rw | (x.rw >> 1));
+        unsigned lo1, lo0, ro1, ro0;
+        if constexpr (R == 1) {
+            lo1 = (l1 & 0x01000000u) << 7;   // cell col - 1 (byte 3) -> bit 31
+            lo0 = (l0 & 0x01000000u) << 7;
+            ro1 = r1 & 1u;                   // cell col + 32 (byte 0) -> bit 0
+            ro0 = r0 & 1u;
+        } else {
+            // cells col - 1, col - 2 (bytes 3, 2) -> bits 31, 30: one multiply (bit 24 + 7, bit 16 + 14; the stray product
+            // bit 23 is masked off); cells col + 32, col + 33 (bytes 0, 1) -> bits 0, 1
+            lo1 = ((l1 & 0x01010000u) * 0x4080u) & 0xc0000000u;
+            lo0 = ((l0 & 0x01010000u) * 0x4080u) & 0xc0000000u;
+            ro1 = (r1 & 1u) | ((r1 >> 7) & 2u);
+            ro0 = (r0 & 1u) | ((r0 >> 7) & 2u);
+        }
+        Lp[0] = la.edge_l ? lo1 : Lp[0];
+        Lp[1] = la.edge_l ? lo0 : Lp[1];
+        Rp[0] = la.edge_r ? ro1 : Rp[0];
+        Rp[1] = la.edge_r ? ro0 : Rp[1];
     }
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
@@ -160,9 +186,11 @@ struct NeighbourSum;
 template <>
 struct NeighbourSum<1> {
     static constexpr int NS = 4;
+    // kIncl: the centre cell counts too (3 x 3 box sum)
+    template <bool kIncl>
     __device__ __forceinline__ static void run(const RowBits<1>* const* ring, int p, unsigned (&n)[NS]) {
         const unsigned* t = ring[0]->full[p];
-        const unsigned* m = ring[1]->nbr[p];
+        const unsigned* m = kIncl ? ring[1]->full[p] : ring[1]->nbr[p];
         const unsigned* b = ring[2]->full[p];
         const unsigned a0 = t[0] ^ b[0], k0 = t[0] & b[0];
         const unsigned a1 = t[1] ^ b[1] ^ k0, a2 = maj3(t[1], b[1], k0);
@@ -178,10 +206,11 @@ struct NeighbourSum<1> {
 template <>
 struct NeighbourSum<2> {
     static constexpr int NS = 5;
+    template <bool kIncl>
     __device__ __forceinline__ static void run(const RowBits<2>* const* ring, int p, unsigned (&n)[NS]) {
         const unsigned* t2 = ring[0]->full[p];
         const unsigned* t1 = ring[1]->full[p];
-        const unsigned* m = ring[2]->nbr[p];
+        const unsigned* m = kIncl ? ring[2]->full[p] : ring[2]->nbr[p];
         const unsigned* b1 = ring[3]->full[p];
         const unsigned* b2 = ring[4]->full[p];
         // weight 1
@@ -270,12 +299,18 @@ schelling_happy_bits(const int8_t* __restrict__ type, const int8_t* __restrict__
     constexpr int W = 2 * R + 1;
     constexpr int NS = NeighbourSum<R>::NS;
     constexpr int NX = NS + 4;   // a * same + c < 16 * 25 + 9 <= 2^(NS + 4)
+#ifndef MB_HAPPY_LUT_NIBBLE
     // bits -> uint8: 8 cells per shared-memory lookup (byte of the happy word -> two words of 0 / 1 bytes); the lookups
     // run on the load / store pipe, the arithmetic form (shift, mask, multiply, mask per 4 cells) on the ALU pipe that
-    // binds this kernel
+    // binds this kernel.  (A per-lane copy of a 16-entry nibble table is conflict-free but needs twice the index
+    // arithmetic: measured equal, profiles/r2_happy_bits_*.)
     __shared__ uint2 spread[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x)
         spread[i] = make_uint2((((unsigned)i & 0xfu) * 0x00204081u) & 0x01010101u, (((unsigned)i >> 4) * 0x00204081u) & 0x01010101u);
+#else
+    __shared__ unsigned spread[16 * 32];
+    for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) spread[i] = (((unsigned)i >> 5) * 0x00204081u) & 0x01010101u;
+#endif
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const unsigned task = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
@@ -316,16 +351,20 @@ schelling_happy_bits(const int8_t* __restrict__ type, const int8_t* __restrict__
 
     // one output row: the window is ring[(k + i) % W], i = 0 .. 2R (k: position in the group, compile-time)
     auto produce = [&](const RowBits<R>* const* win) {
+        // kA == 0 (happy <=> no neighbour of the other type, e.g. homophily 1): `same` is not needed, so the box sums may
+        // include the centre cell (it adds to the count of its own type only) -- the centre row then needs no separate
+        // centre-less horizontal sum (dead code below), and "has a neighbour" becomes "the two counts add up to >= 2"
+        constexpr bool kIncl = kA == 0;
         unsigned n1[NS], n0[NS];
-        NeighbourSum<R>::run(win, 0, n1);
-        NeighbourSum<R>::run(win, 1, n0);
+        NeighbourSum<R>::template run<kIncl>(win, 0, n1);
+        NeighbourSum<R>::template run<kIncl>(win, 1, n0);
         const unsigned c1 = win[R]->cen[0], c0 = win[R]->cen[1];
-        unsigned same[NS], other[NS], any = 0u;
+        unsigned same[NS], other[NS], any = kIncl ? (n1[0] & n0[0]) : (n1[0] | n0[0]);
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
             same[i] = (c1 & n1[i]) | (~c1 & n0[i]);
             other[i] = (c1 & n0[i]) | (~c1 & n1[i]);
-            any |= n1[i] | n0[i];
+            if (i > 0) any |= n1[i] | n0[i];
         }
         unsigned X[NX], Y[NX];
         if constexpr (kA >= 0) {
@@ -351,12 +390,22 @@ schelling_happy_bits(const int8_t* __restrict__ type, const int8_t* __restrict__
         const unsigned alone = rule.happy_if_alone ? ~0u : 0u;
         const unsigned H = (c1 | c0) & ((any & ge) | (~any & alone));
         nhappy += __popc(H);
+        uint4 o0, o1;
+#ifndef MB_HAPPY_LUT_NIBBLE
         const uint2 q0 = spread[H & 0xffu], q1 = spread[__byte_perm(H, 0u, 0x4441)];
         const uint2 q2 = spread[__byte_perm(H, 0u, 0x4442)], q3 = spread[H >> 24];
-        if (la.active) {
-            __stcs(reinterpret_cast<uint4*>(op), make_uint4(q0.x, q0.y, q1.x, q1.y));
-            __stcs(reinterpret_cast<uint4*>(op + 16), make_uint4(q2.x, q2.y, q3.x, q3.y));
-        }
+        o0 = make_uint4(q0.x, q0.y, q1.x, q1.y);
+        o1 = make_uint4(q2.x, q2.y, q3.x, q3.y);
+#else
+        // nibble 2j of H is byte j of Ha, nibble 2j + 1 byte j of Hb; address = lane + 32 * nibble
+        const unsigned Ha = H & 0x0f0f0f0fu, Hb = (H >> 4) & 0x0f0f0f0fu;
+        const unsigned* tab = spread + lane;
+        o0.x = tab[__byte_perm(Ha, 0u, 0x4440) * 32u]; o0.y = tab[__byte_perm(Hb, 0u, 0x4440) * 32u];
+        o0.z = tab[__byte_perm(Ha, 0u, 0x4441) * 32u]; o0.w = tab[__byte_perm(Hb, 0u, 0x4441) * 32u];
+        o1.x = tab[__byte_perm(Ha, 0u, 0x4442) * 32u]; o1.y = tab[__byte_perm(Hb, 0u, 0x4442) * 32u];
+        o1.z = tab[__byte_perm(Ha, 0u, 0x4443) * 32u]; o1.w = tab[__byte_perm(Hb, 0u, 0x4443) * 32u];
+#endif
+        if (la.active) stg256_cs(op, o0, o1);
         op += pitch;
     };
 
@@ -443,9 +492,9 @@ int happy_bits_launch(const int8_t* type, const int8_t* halo_top, const int8_t* 
         const char* r = getenv("MB_HAPPY_BITS_ROWS");
         rpw_env = r ? atoi(r) : 0;
     }
-    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-    if (!enabled || radius > 2 || cols % 32 != 0 || rows >= (1ll << 30) || cols >= (1ll << 30) || !al16(type) || !al16(happy) ||
-        (halo_top != nullptr && !al16(halo_top)) || (halo_bot != nullptr && !al16(halo_bot)))
+    auto al32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; };   // 256-bit loads / stores
+    if (!enabled || radius > 2 || cols % 32 != 0 || rows >= (1ll << 30) || cols >= (1ll << 30) || !al32(type) || !al32(happy) ||
+        (halo_top != nullptr && !al32(halo_top)) || (halo_bot != nullptr && !al32(halo_bot)))
         return MB_OK;
     const int nmax = (2 * radius + 1) * (2 * radius + 1) - 1;
     BitRule rule;
@@ -463,8 +512,8 @@ int happy_bits_launch(const int8_t* type, const int8_t* halo_top, const int8_t* 
         type, halo_top, halo_bot, happy, (int)rows, (int)cols, col_torus, nstrips, rpw, rule, happy_count)
 #define MB_BITS_CASE(AA, BB)                                        \
     if (!done && rule.c == 0u && rule.a == AA && rule.b == BB) {    \
-        if (radius == 1) MB_BITS_LAUNCH(1, AA, BB, 5);              \
-        else MB_BITS_LAUNCH(2, AA, BB, 3);                          \
+        if (radius == 1) MB_BITS_LAUNCH(1, AA, BB, MB_HAPPY_MINB1); \
+        else MB_BITS_LAUNCH(2, AA, BB, (AA == 0 ? 4 : 3));           \
         done = true;                                                \
     }
     bool done = false;
@@ -472,7 +521,7 @@ int happy_bits_launch(const int8_t* type, const int8_t* halo_top, const int8_t* 
     MB_BITS_CASE(0, 1) MB_BITS_CASE(1, 1) MB_BITS_CASE(3, 2) MB_BITS_CASE(2, 1) MB_BITS_CASE(1, 2)
     MB_BITS_CASE(3, 1) MB_BITS_CASE(1, 3) MB_BITS_CASE(2, 3) MB_BITS_CASE(7, 3) MB_BITS_CASE(3, 7)
     if (!done) {
-        if (radius == 1) MB_BITS_LAUNCH(1, -1, -1, 5);
+        if (radius == 1) MB_BITS_LAUNCH(1, -1, -1, MB_HAPPY_MINB1);
         else MB_BITS_LAUNCH(2, -1, -1, 3);
     }
 #undef MB_BITS_CASE

@@ -297,3 +297,29 @@ MB_API int mb_sort_pairs_u64(uint64_t* keys0, uint32_t* vals0, uint64_t* keys1, 
     if (result_buffer) *result_buffer = rc;
     return MB_OK;
 }
+
+// ---- offsets of a CSR result from its per-row counts (radius queries: csrc/continuous.cu counts first, the host sizes
+// the index / distance arrays, the second launch fills them): offsets[i] = sum of counts[0 .. i), offsets[n] = the total.
+// scratch: (n + 1) + mb_scan_scratch_words(n + 1) uint32 words.  The running sum is 32-bit: the caller checks the total
+// (a 64-bit reduction of the counts) against 2^32 first.
+namespace {
+__global__ void counts_to_words(const int32_t* __restrict__ counts, uint32_t* __restrict__ words, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) words[i] = i < n ? (uint32_t)counts[i] : 0u;
+}
+__global__ void words_to_offsets(const uint32_t* __restrict__ words, int64_t* __restrict__ offsets, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) offsets[i] = (int64_t)words[i];
+}
+}  // namespace
+
+MB_API int mb_offsets_from_counts(const int32_t* counts, int64_t n, int64_t* offsets, uint32_t* scratch, cudaStream_t stream) {
+    MB_REQUIRE(n >= 0 && offsets != nullptr && scratch != nullptr && (n == 0 || counts != nullptr), "mb_offsets_from_counts: bad argument");
+    const unsigned blocks = (unsigned)mb::ceil_div(n + 1, 256);
+    counts_to_words<<<blocks, 256, 0, stream>>>(counts, scratch, n);
+    const int rc = mb::exclusive_scan_u32(scratch, n + 1, scratch + (n + 1), stream);
+    if (rc != MB_OK) return rc;
+    words_to_offsets<<<blocks, 256, 0, stream>>>(scratch, offsets, n);
+    MB_LAUNCH_CHECK("mb_offsets_from_counts");
+    return MB_OK;
+}

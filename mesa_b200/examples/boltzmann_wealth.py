@@ -74,7 +74,8 @@ class BoltzmannWealth(DeviceModel):
     @property
     def gini(self) -> float:
         """model.py:83-101 on the device."""
-        x, _ = torch.sort(self.agents.columns["wealth"].to(torch.float64))
+        w = self.agents.columns["wealth"]
+        x = w[ops.argsort_stable(w)].to(torch.float64)
         n = self.num_agents
         i = torch.arange(n, device=x.device, dtype=torch.float64)
         b = float((x * (n - i)).sum() / (n * x.sum()))

@@ -15,14 +15,18 @@ What a maintainer adds to use the device backend from an unmodified `mesa.Model`
 from __future__ import annotations
 
 import mesa
+import mesa.exceptions
 from mesa.agentset import AbstractAgentSet
 from mesa.discrete_space import DiscreteSpace
 
 from .agentset import DeviceAgentSet
+from . import space as _space
 from .space import DeviceGrid
 
 AbstractAgentSet.register(DeviceAgentSet)
 DiscreteSpace.register(DeviceGrid)
+# the device grids raise mesa's own exception type (mesa/exceptions.py) even if they were imported before mesa was
+_space.CellMissingException = mesa.exceptions.CellMissingException
 
 
 class DeviceBackedModel(mesa.Model):

@@ -340,6 +340,73 @@ def sort_pairs(keys: torch.Tensor, vals: torch.Tensor, begin_bit: int = 0, end_b
     return (k1, v1) if which.value else (k0, v0)
 
 
+def argsort_stable(keys: torch.Tensor, descending: bool = False) -> torch.Tensor:
+    """Indices that sort a one-dimensional device column, equal keys in their original order (what `sorted(..., key=)`
+    and `sorted(..., reverse=True)` give the reference, agentset.py:443-472): the column's bits are mapped to unsigned
+    integers of the same order (sign flip for signed integers, sign-magnitude to offset for floats; complemented for a
+    descending sort) and sorted with the stable radix sort of csrc/sort.cu.  int64 result."""
+    if keys.dim() != 1:
+        raise ValueError("argsort_stable expects a one-dimensional column")
+    n = keys.numel()
+    if n >= 2**31:
+        raise ValueError("argsort_stable handles fewer than 2^31 rows")
+    dt = keys.dtype
+    if dt in (torch.bool, torch.uint8, torch.int8, torch.int16, torch.int32):
+        u = keys.to(torch.int32) ^ (-2**31)                       # signed order -> unsigned order of the same bits
+    elif dt == torch.int64:
+        u = keys ^ (-2**63)
+    elif dt in (torch.float16, torch.bfloat16, torch.float32):
+        b = keys.to(torch.float32).contiguous().view(torch.int32)
+        u = torch.where(b < 0, ~b, b ^ (-2**31))                  # negative floats: all bits flipped, others: sign bit set
+    elif dt == torch.float64:
+        b = keys.contiguous().view(torch.int64)
+        u = torch.where(b < 0, ~b, b ^ (-2**63))
+    else:
+        raise TypeError(f"argsort_stable: unsupported column dtype {dt}")
+    if descending:
+        u = ~u
+    vals = torch.arange(n, dtype=torch.int32, device=keys.device)
+    if n == 0:
+        return vals.to(torch.int64)
+    _, order = sort_pairs(u.contiguous(), vals)
+    return order.to(torch.int64)
+
+
+def nonzero_indices(mask: torch.Tensor) -> torch.Tensor:
+    """Flat indices of the set entries of a bool / uint8 tensor in ascending order (np.argwhere / np.flatnonzero order,
+    grid.py:308-316): one stable compaction of the index column (csrc/agents.cu).  int64 result."""
+    flat = mask.reshape(-1)
+    if flat.dtype not in (torch.bool, torch.uint8):
+        flat = flat != 0
+    n = flat.numel()
+    if n == 0:
+        return torch.empty(0, dtype=torch.int64, device=mask.device)
+    plan = CompactionPlan(flat.contiguous())
+    if n < 2**31:
+        return plan.apply(torch.arange(n, dtype=torch.int32, device=mask.device)).to(torch.int64)
+    return plan.apply(torch.arange(n, dtype=torch.int64, device=mask.device))
+
+
+def offsets_from_counts(counts: torch.Tensor) -> torch.Tensor:
+    """int64 [n + 1] row offsets of a CSR result from its int32 per-row counts (mb_offsets_from_counts)."""
+    import ctypes
+
+    _need_cuda(counts)
+    if counts.dtype != torch.int32 or counts.dim() != 1:
+        raise ValueError("offsets_from_counts expects an int32 [n] tensor")
+    n = counts.numel()
+    if n and int(layer_reduce(counts, "sum").item()) >= 2**32:
+        raise ValueError("the query result holds 2^32 or more entries; query in smaller batches")
+    offsets = torch.empty(n + 1, dtype=torch.int64, device=counts.device)
+    words = ctypes.c_size_t(0)
+    N.check(N.lib().mb_scan_scratch_words(n + 1, ctypes.byref(words)))
+    scratch = torch.empty(n + 1 + int(words.value), dtype=torch.int32, device=counts.device)
+    with torch.cuda.device(counts.device):
+        N.check(N.lib().mb_offsets_from_counts(N.ptr(_c(counts)), n, N.ptr(offsets), N.ptr(scratch),
+                                               N.stream_ptr(counts.device)))
+    return offsets
+
+
 # ----------------------------------------------------------------------------- continuous space
 class CellListWorkspace:
     """Scratch of the cell-list kernels for up to `n` agents and query radius >= `radius`."""
@@ -464,8 +531,7 @@ def radius_query(pos: torch.Tensor, queries: torch.Tensor, size, radius: float, 
         N.check(N.lib().mb_radius_query_f32(N.ptr(_c(pos)), n, *args, N.ptr(_c(queries)), N.ptr(exclude), nq,
                                             float(radius), N.ptr(counts), None, None, None, N.ptr(ws.buf), ws.nbytes,
                                             0, st))
-        offsets = torch.zeros(nq + 1, dtype=torch.int64, device=pos.device)
-        torch.cumsum(counts, 0, out=offsets[1:])
+        offsets = offsets_from_counts(counts)
         total = int(offsets[-1].item())
         idx = torch.empty(total, dtype=torch.int32, device=pos.device)
         dist = torch.empty(total, dtype=torch.float64, device=pos.device)

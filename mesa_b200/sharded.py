@@ -287,7 +287,7 @@ class ShardedSchelling:
             rows.append(everyone[r, :n])
             homes.append(torch.full((n,), r, dtype=torch.int64, device=dev))
         entries, home = torch.cat(rows), torch.cat(homes)
-        order = torch.argsort(_u64_sort_key(entries[:, 0]))
+        order = ops.argsort_stable(_u64_sort_key(entries[:, 0]))
         return entries[order], home[order]
 
     def _event_phase(self, movers: int, nfb_all: list[int], nempty: int, seed: int, epoch: int, t_lo: int, t_hi: int) -> None:
@@ -489,7 +489,7 @@ class ShardedBoidsNCCL:
         everyone = torch.empty((self.world, width, 5), dtype=torch.float64, device=self.device)
         dist.all_gather_into_tensor(everyone, mine, group=self.group)
         rows = torch.cat([everyone[r, : int(n[r].item())] for r in range(self.world)])
-        order = torch.argsort(rows[:, 4])
+        order = ops.argsort_stable(rows[:, 4].contiguous())
         rows = rows[order]
         return rows[:, 4].to(torch.int64), rows[:, :2].to(torch.float32), rows[:, 2:4].to(torch.float32)
 
@@ -645,5 +645,5 @@ class ShardedBoids:
         everyone = torch.empty((self.world, width, 5), dtype=torch.float64, device=self.device)
         dist.all_gather_into_tensor(everyone, mine, group=self.group)
         rows = torch.cat([everyone[r, : int(n[r].item())] for r in range(self.world)])
-        rows = rows[torch.argsort(rows[:, 4])]
+        rows = rows[ops.argsort_stable(rows[:, 4].contiguous())]
         return rows[:, 4].to(torch.int64), rows[:, :2].to(torch.float32), rows[:, 2:4].to(torch.float32)

@@ -388,7 +388,7 @@ class DeviceGrid:
 
     @property
     def empties(self):
-        idx = torch.nonzero(self.empty.reshape(-1)).reshape(-1).cpu().tolist()
+        idx = ops.nonzero_indices(self.empty).cpu().tolist()
         return [CellProxy(self, self._unravel(k)) for k in idx]
 
     def find_nearest_cell(self, position) -> CellProxy:
@@ -474,7 +474,7 @@ class DeviceGrid:
             k = self.random._randbelow(ncells)
             if bool(empty.reshape(-1)[k].item()):
                 return CellProxy(self, self._unravel(k))
-        empties = torch.nonzero(empty.reshape(-1)).reshape(-1)
+        empties = ops.nonzero_indices(empty)
         if empties.numel() == 0:
             raise ValueError("Grid is completely full. No empty cells available. Cannot select a random empty cell.")
         k = int(empties[self.random._randbelow(empties.numel())].item())
@@ -495,7 +495,7 @@ class DeviceGrid:
         """All cells that are not full (grid.py:318-350); every cell when capacity is None."""
         if self.capacity is None:
             return self.all_cells
-        idx = torch.nonzero((self.agent_counts() < self.capacity).reshape(-1)).reshape(-1).cpu().tolist()
+        idx = ops.nonzero_indices(self.agent_counts() < self.capacity).cpu().tolist()
         return [CellProxy(self, self._unravel(k)) for k in idx]
 
     def select_random_cell_with_capacity(self) -> CellProxy:
@@ -509,7 +509,7 @@ class DeviceGrid:
             k = self.random._randbelow(ncells)
             if bool(room[k].item()):
                 return CellProxy(self, self._unravel(k))
-        available = torch.nonzero(room).reshape(-1)
+        available = ops.nonzero_indices(room)
         if available.numel() == 0:
             raise IndexError("No available cells exist in the grid: all cells are at full capacity.")
         k = int(available[self.random._randbelow(available.numel())].item())

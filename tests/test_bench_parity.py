@@ -42,8 +42,8 @@ def test_launch_plan():
     from mesa_b200.ops import gol_launch_plan as plan
 
     assert plan(20, 8) == [8, 8, 4]
-    assert plan(20, 8, even=True) == [8, 8, 2, 2]
-    assert plan(20, 8, 0, 64, even=True) == [0, 8, 8, 2, 2]
+    assert plan(20, 8, even=True) == [8, 4, 4, 4]        # the LONGEST launch is split (two launches of 4 beat 2 + 2)
+    assert plan(20, 8, 0, 64, even=True) == [0, 8, 4, 4, 4]
     p = plan(1000, 8, 5, 64)
     assert sum(p) == 1000 and p[:3] == [5, 0, 8] and p.count(0) == 16
     for k in (2, 7, 16, 17, 63, 64, 65, 129):

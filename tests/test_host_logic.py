@@ -95,6 +95,15 @@ def test_device_model_clock_epochs_and_agents_by_type():
     assert m2.philox_seed == m.philox_seed and m2.random.random() == M().random.random()   # seeded identically
 
 
+def _host_sort_pairs(keys, vals, begin_bit=0, end_bit=None):
+    """Test double for ops.sort_pairs (the stable radix sort of csrc/sort.cu, keys compared as UNSIGNED integers)."""
+    import torch
+
+    wide = keys.dtype == torch.int64
+    order = torch.argsort(keys ^ (-2**63 if wide else -2**31), stable=True)
+    return keys[order], vals[order]
+
+
 class _HostPlan:
     """Test double for ops.CompactionPlan (the device compaction of csrc/agents.cu): lets the bookkeeping of
     DeviceAgentSet (unique ids, order, generations, hooks) run on CPU tensors.  Not a product path."""
@@ -127,10 +136,11 @@ def test_dynamic_population_bookkeeping_matches_the_reference_script(monkeypatch
     assert agents.unique_ids().tolist() == [ids[1]] + ids[4:-1]
 
 
-def test_population_growth_needs_no_kernel_and_removal_has_no_cpu_fallback():
+def test_population_growth_needs_no_kernel_and_removal_has_no_cpu_fallback(monkeypatch):
     import pytest
     import torch
 
+    from mesa_b200 import ops
     from mesa_b200.agentset import DeviceAgent, DeviceAgentSet
     from mesa_b200.model import DeviceModel
 
@@ -157,6 +167,7 @@ def test_population_growth_needs_no_kernel_and_removal_has_no_cpu_fallback():
     fixed = DeviceAgentSet(model, Wolf, 3, {"energy": torch.tensor([4, 5, 6])}, resizable=False)
     with pytest.raises(NotImplementedError):
         fixed.add_agents(1)
+    monkeypatch.setattr(ops, "sort_pairs", _host_sort_pairs)                    # shuffle() orders the view with the device sort
     with pytest.raises(NotImplementedError):
         agents.shuffle().remove_agents([0])                                     # views do not resize the population
 
@@ -170,11 +181,8 @@ def test_groupby_bookkeeping_on_the_host(monkeypatch):
     from mesa_b200.agentset import DeviceAgent, DeviceAgentSet
     from mesa_b200.model import DeviceModel
 
-    def host_sort(keys, vals, begin_bit=0, end_bit=None):
-        order = torch.argsort(keys, stable=True)
-        return keys[order], vals[order]
-
-    monkeypatch.setattr(ops, "sort_pairs", host_sort)
+    monkeypatch.setattr(ops, "sort_pairs", _host_sort_pairs)
+    monkeypatch.setattr(ops, "CompactionPlan", _HostPlan)
 
     class Citizen(DeviceAgent):
         pass
@@ -303,7 +311,7 @@ def test_set_creates_missing_columns_like_setattr():
     assert agents.add_agents(1, x=3).get("mood").tolist() == [0.0] and len(agents.get("velocity")) == 5
 
 
-def test_get_orientation_and_missing_handling():
+def test_get_orientation_and_missing_handling(host_kernels):
     """agentset.py:171-213 (tests/test_agentset.py::test_agentset_get_attribute): several names give one row per agent."""
     import pytest
     import torch

@@ -112,7 +112,7 @@ def test_boids_initial_state_from_a_seed(replay):
     assert np.array_equal(np.array([a.direction for a in agents]), dirs)
 
 
-def test_agentset_operations_against_the_reference_agentset(replay, monkeypatch):
+def test_agentset_operations_against_the_reference_agentset(replay, host_kernels):
     """select / sort / get / groupby / agg of DeviceAgentSet (column predicates on CPU tensors; the device sort and
     reductions replaced by host doubles) against mesa.AgentSet on the same random attribute table."""
     import mesa
@@ -122,8 +122,6 @@ def test_agentset_operations_against_the_reference_agentset(replay, monkeypatch)
     from mesa_b200.agentset import DeviceAgent, DeviceAgentSet
     from mesa_b200.model import DeviceModel
 
-    monkeypatch.setattr(ops, "sort_pairs", lambda k, v, b=0, e=None: (k[torch.argsort(k, stable=True)], v[torch.argsort(k, stable=True)]))
-    monkeypatch.setattr(ops, "layer_reduce", lambda layer, op="sum": {"sum": torch.sum, "min": torch.min, "max": torch.max}[op](layer).reshape(1))
 
     class RefAgent(mesa.Agent):
         def __init__(self, model, energy, kind):

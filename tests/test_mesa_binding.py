@@ -37,6 +37,7 @@ def live_mesa(monkeypatch):
         monkeypatch.syspath_prepend(REF)
     import mesa  # noqa: F401
 
+    import mesa_b200.mesa_binding  # noqa: F401  (registers the virtual subclasses, mesa's exception types)
     from mesa_b200 import ops
 
     monkeypatch.setattr(ops, "layer_fill", lambda layer, value: layer.fill_(value))
