@@ -356,10 +356,10 @@ def argsort_stable(keys: torch.Tensor, descending: bool = False) -> torch.Tensor
     elif dt == torch.int64:
         u = keys ^ (-2**63)
     elif dt in (torch.float16, torch.bfloat16, torch.float32):
-        b = keys.to(torch.float32).contiguous().view(torch.int32)
+        b = (keys.to(torch.float32) + 0.0).contiguous().view(torch.int32)    # + 0.0: -0.0 and 0.0 compare equal in Python
         u = torch.where(b < 0, ~b, b ^ (-2**31))                  # negative floats: all bits flipped, others: sign bit set
     elif dt == torch.float64:
-        b = keys.contiguous().view(torch.int64)
+        b = (keys + 0.0).contiguous().view(torch.int64)
         u = torch.where(b < 0, ~b, b ^ (-2**63))
     else:
         raise TypeError(f"argsort_stable: unsupported column dtype {dt}")
