@@ -373,6 +373,30 @@ int mb_ghost_exchange(void* dst_top, const void* src_up, void* dst_bot, const vo
                       unsigned* flags, unsigned* up_flags, unsigned* down_flags, mb_stream_t stream);
 int mb_ghost_wait_copied(unsigned* flags, int has_up, int has_down, mb_stream_t stream);
 
+/* ---- Wolf-Sheep predation (replaces agents_by_type[Sheep].shuffle_do("step") / agents_by_type[Wolf].shuffle_do("step"),
+ * mesa/examples/advanced/wolf_sheep/model.py:136-141 over agents.py:36-158; csrc/wolf_sheep.cu).  Sequential semantics as
+ * the fixed point of Jacobi passes: the caller repeats *_pass + mb_ws_compare_reset until the table no longer changes,
+ * then calls *_apply.  cell: int32 flat cell (row-major [height, width], von Neumann torus), energy: float64, uid: the
+ * agents' unique ids (the Philox key is uid - 1), tables: uint64 priorities, all bits set = never.  Sheep: wolves_in
+ * [ncells] int32 (mb_ws_count_cells of the wolves), grown [ncells] uint8 or NULL (no grass).  Wolves: slist = sheep rows
+ * sorted by (cell, position in the cell's list), cstart [ncells + 1] (mb_ws_segment_starts). */
+int mb_ws_count_cells(const int32_t* cell, int64_t n, int32_t* counts, int64_t ncells, mb_stream_t stream);
+int mb_ws_segment_starts(const int32_t* sorted_cell, int64_t n, int64_t ncells, int32_t* cstart, mb_stream_t stream);
+int mb_ws_sheep_pass(const int32_t* cell, const int64_t* uid, int64_t n, int height, int width, uint64_t seed, uint32_t epoch,
+                     const int32_t* wolves_in, const uint8_t* grown, const uint64_t* E_prev, uint64_t* E_next,
+                     mb_stream_t stream);
+int mb_ws_compare_reset(uint64_t* a, const uint64_t* b, int64_t n, unsigned* changed, mb_stream_t stream);
+int mb_ws_sheep_apply(int32_t* cell, double* energy, const int64_t* uid, int64_t n, int height, int width, uint64_t seed,
+                      uint32_t epoch, const int32_t* wolves_in, const uint8_t* grown, uint8_t* grown_out, int32_t* regrow_at,
+                      const uint64_t* E, double gain, double p_reproduce, int32_t regrow_time, uint8_t* moved, uint8_t* dead,
+                      uint8_t* repro, uint64_t* prio, mb_stream_t stream);
+int mb_ws_wolf_pass(const int32_t* cell, const int64_t* uid, int64_t n, int height, int width, uint64_t seed, uint32_t epoch,
+                    const int32_t* slist, const int32_t* cstart, const uint64_t* D_prev, uint64_t* D_next, mb_stream_t stream);
+int mb_ws_wolf_apply(int32_t* cell, double* energy, const int64_t* uid, int64_t n, int height, int width, uint64_t seed,
+                     uint32_t epoch, const int32_t* slist, const int32_t* cstart, const uint64_t* D, double gain,
+                     double p_reproduce, uint8_t* dead, uint8_t* repro, uint64_t* prio, mb_stream_t stream);
+int mb_ws_regrow(uint8_t* grown, int32_t* regrow_at, int64_t ncells, int32_t now, mb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -112,6 +112,16 @@ SIGNATURES: dict[str, tuple] = {
     "mb_boids_compact": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P, _P, _S]),
     "mb_scan_scratch_words": (c_int, [c_int64, ctypes.POINTER(ctypes.c_size_t)]),
     "mb_offsets_from_counts": (c_int, [_P, c_int64, _P, _P, _S]),
+    "mb_ws_count_cells": (c_int, [_P, c_int64, _P, c_int64, _S]),
+    "mb_ws_segment_starts": (c_int, [_P, c_int64, c_int64, _P, _S]),
+    "mb_ws_sheep_pass": (c_int, [_P, _P, c_int64, c_int, c_int, c_uint64, c_uint32, _P, _P, _P, _P, _S]),
+    "mb_ws_compare_reset": (c_int, [_P, _P, c_int64, _P, _S]),
+    "mb_ws_sheep_apply": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_uint64, c_uint32, _P, _P, _P, _P, _P, c_double, c_double,
+                                  ctypes.c_int32, _P, _P, _P, _P, _S]),
+    "mb_ws_wolf_pass": (c_int, [_P, _P, c_int64, c_int, c_int, c_uint64, c_uint32, _P, _P, _P, _P, _S]),
+    "mb_ws_wolf_apply": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_uint64, c_uint32, _P, _P, _P, c_double, c_double, _P, _P, _P,
+                                 _S]),
+    "mb_ws_regrow": (c_int, [_P, _P, c_int64, ctypes.c_int32, _S]),
     # dynamic populations
     "mb_compact_plan": (c_int, [_P, c_int64, _P, _P, _S]),
     "mb_compact_rows": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _S]),

@@ -235,10 +235,12 @@ class DeviceAgentSet:
             if col.shape[0] != self.n:
                 raise ValueError(f"column {name!r} has {col.shape[0]} rows for {self.n} agents")
 
-    def add_agents(self, k: int, **values) -> "DeviceAgentSet":
+    def add_agents(self, k: int, unique_ids=None, **values) -> "DeviceAgentSet":
         """Create `k` agents at the end of the registration order (agent.py:115-160 `create_agents`): each
         keyword names a column and gives one value for all new agents or one per agent (torch broadcasting
-        against [k, ...]); unnamed columns start at zero.  Returns the set of the new agents."""
+        against [k, ...]); unnamed columns start at zero.  Returns the set of the new agents.  `unique_ids` ([k] int64) gives
+        the new agents' ids explicitly -- for models whose populations share ONE id counter, as all agent types of a
+        reference model do (model.py:250-263: `agent_id_counter`); by default a population counts its own ids."""
         k = int(k)
         if k < 0:
             raise ValueError("cannot create a negative number of agents")
@@ -258,10 +260,20 @@ class DeviceAgentSet:
                 g[old_n:].zero_()
             grown[name] = g
         pop = self._pop
-        if pop.ids is not None:
-            fresh = torch.arange(pop.next_id, pop.next_id + k, dtype=torch.int64, device=pop.ids.device)
+        if unique_ids is not None:
+            fresh = torch.as_tensor(unique_ids, device=dev).to(torch.int64).reshape(-1)
+            if fresh.numel() != k:
+                raise ValueError(f"{fresh.numel()} unique ids for {k} new agents")
+            if pop.ids is None:
+                pop.ids = torch.arange(1, old_n + 1, dtype=torch.int64, device=dev)
             pop.ids = torch.cat([pop.ids, fresh])
-        pop.next_id += k
+            if k:
+                pop.next_id = max(pop.next_id, int(fresh.max().item()) + 1)
+        else:
+            if pop.ids is not None:
+                fresh = torch.arange(pop.next_id, pop.next_id + k, dtype=torch.int64, device=pop.ids.device)
+                pop.ids = torch.cat([pop.ids, fresh])
+            pop.next_id += k
         self.columns.update(grown)
         self.n = new_n
         for hook in self.resize_hooks:

@@ -51,6 +51,7 @@ class BoltzmannWealth(DeviceModel):
         cell = torch.as_tensor(np.asarray(initial_cells)).to(torch.int32).to(dev).contiguous()
         wealth = torch.ones(self.num_agents, dtype=torch.int32, device=dev)
         self.agents = DeviceAgentSet(self, MoneyAgent, self.num_agents, {"cell": cell, "wealth": wealth}, self.random, resizable=False)
+        self.grid.attach_population(self.agents)          # grid.agents / host mirror enumerate them through `cell`
         self._ws = ops.BoltzmannWorkspace(cell, scenario.width, scenario.height)
         self.running = True
         # grid.py:128 + cell.py:143-170: the implicit `empty` layer follows the occupancy.  Nobody on the step path reads

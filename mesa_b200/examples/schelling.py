@@ -140,6 +140,7 @@ class Schelling(DeviceModel):
         cols = _Columns(self, cell=cells.to(torch.int32), type=flat[cells].clone())
         self.agents = DeviceAgentSet(self, SchellingAgent, n, cols, self.random, resizable=False)
         self.grid.cell_agents = self._cell_agents
+        self.grid.attach_population(self.agents)
         self.agents.do("assign_state")  # model.py:83-85
         if self._small is None:
             self._sync_empty()          # grid.py:128 + cell.py:143-170: `empty` tracks the occupancy from placement on

@@ -21,10 +21,11 @@ from mesa.discrete_space import DiscreteSpace
 
 from .agentset import DeviceAgentSet
 from . import space as _space
-from .space import DeviceGrid
+from .space import DeviceGrid, HostSpaceMirror
 
 AbstractAgentSet.register(DeviceAgentSet)
 DiscreteSpace.register(DeviceGrid)
+DiscreteSpace.register(HostSpaceMirror)   # abstract_renderer.py:38-41 picks agent.cell.position for DiscreteSpace instances
 # the device grids raise mesa's own exception type (mesa/exceptions.py) even if they were imported before mesa was
 _space.CellMissingException = mesa.exceptions.CellMissingException
 

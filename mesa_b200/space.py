@@ -116,6 +116,11 @@ class CellProxy:
         return int(np.ravel_multi_index(self.coordinate, self.grid.dimensions))
 
     @property
+    def position(self) -> np.ndarray:
+        """cell.py:68-78: the physical position of a cell of an implicit grid is its coordinate."""
+        return np.asarray(self.coordinate, dtype=float)
+
+    @property
     def is_empty(self) -> bool:
         return bool(self.grid.empty[self.coordinate].item())
 
@@ -223,6 +228,64 @@ class CellCollectionProxy(list):
         return f"CellCollection({list(self)})"
 
 
+class HostAgentView:
+    """One agent of a host mirror: `unique_id`, `cell` (a cell proxy: `.coordinate`, `.position`) and the mirrored
+    attribute values -- what a portrayal function or a checkpoint inspector reads (visualization/backends/
+    matplotlib_backend.py:104-163: `for agent in space.agents: agent_portrayal(agent)`, `agent.cell.position`)."""
+
+    __slots__ = ("unique_id", "cell", "agent_type", "_attrs")
+
+    def __init__(self, unique_id, cell, agent_type, attrs):
+        self.unique_id, self.cell, self.agent_type, self._attrs = unique_id, cell, agent_type, attrs
+
+    def __getattr__(self, name):
+        try:
+            return object.__getattribute__(self, "_attrs")[name]
+        except KeyError:
+            raise AttributeError(name) from None
+
+    def __repr__(self):
+        return f"<{self.agent_type.__name__} {self.unique_id} at {self.cell.coordinate}>"
+
+
+class HostSpaceMirror:
+    """A read-only HOST snapshot of a device grid for consumers that walk Python objects (SURVEY.md 8(f) next-3:
+    visualization/space_renderer.py:339, backends/matplotlib_backend.py:104, 340; checkpoint inspection): every property
+    layer as a numpy array (`space.property_layers`), every agent of the populations attached to the grid as a
+    HostAgentView (`space.agents`), plus the geometry the renderers read.  Built with ONE device-to-host copy per layer and
+    per agent column; the device state is not touched afterwards."""
+
+    def __init__(self, grid: "DeviceGrid", layers=None, attributes=None):
+        self.dimensions, self.torus, self.capacity = grid.dimensions, grid.torus, grid.capacity
+        self.width = grid.dimensions[0]
+        self.height = grid.dimensions[1] if len(grid.dimensions) > 1 else 1
+        names = list(grid.property_layers) if layers is None else list(layers)
+        self.property_layers = {}
+        for name in names:
+            t = grid.property_layers[name]
+            self.property_layers[name] = t.detach().to("cpu", copy=True).numpy()
+        self._grid = grid
+        self.agents = []
+        for agentset, column in grid.populations:
+            cols = agentset.columns
+            cells = cols[column].detach().cpu().numpy().astype(np.int64).reshape(-1)[: agentset.n]
+            ids = agentset.unique_ids_host()
+            wanted = [k for k in cols if k != column] if attributes is None else [k for k in attributes if k in cols]
+            host = {k: cols[k].detach().cpu().numpy()[: agentset.n] for k in wanted}
+            coords = np.stack(np.unravel_index(cells, grid.dimensions), axis=1) if len(cells) else np.zeros((0, len(grid.dimensions)), int)
+            for r in range(agentset.n):
+                attrs = {k: (v[r].item() if v[r].ndim == 0 else v[r]) for k, v in host.items()}
+                self.agents.append(HostAgentView(int(ids[r]), CellProxy(grid, tuple(int(c) for c in coords[r])),
+                                                 agentset.agent_type, attrs))
+
+    @property
+    def all_cells(self):
+        return self._grid.all_cells
+
+    def __getitem__(self, coordinate):
+        return self._grid[coordinate]
+
+
 class _CellMap:
     """`space._cells` (discrete_space.py:67): coordinate -> cell, without materialising the cells."""
 
@@ -307,6 +370,7 @@ class DeviceGrid:
         self.device = torch.device(device)
         self.property_layers: dict[str, torch.Tensor] = _LayerDict()
         self._read_only_layers: set[str] = set()
+        self.populations: list = []     # (DeviceAgentSet, name of its flat-cell column): who lives on this grid
         self.create_property_layer("empty", default_value=True, dtype=bool)
 
     # grid.py:280-286
@@ -317,6 +381,26 @@ class DeviceGrid:
             raise TypeError("Torus must be a boolean.")
         if self.capacity is not None and not isinstance(self.capacity, float | int):
             raise TypeError("Capacity must be a number or None.")
+
+    # ------------------------------------------------------------------ agents on the grid (readback)
+    def attach_population(self, agentset, cell_column: str = "cell") -> None:
+        """Tell the grid that `agentset` lives on it, its agents' flat cell ids in column `cell_column` (the device
+        models do this; it is what `grid.agents` and the host mirror enumerate)."""
+        if all(a is not agentset for a, _ in self.populations):
+            self.populations.append((agentset, cell_column))
+
+    def host_mirror(self, layers=None, attributes=None) -> "HostSpaceMirror":
+        """A host snapshot for visualization / inspection: numpy layers + lightweight agent views (see HostSpaceMirror)."""
+        return HostSpaceMirror(self, layers, attributes)
+
+    @property
+    def agents(self) -> list:
+        """discrete_space.py:84-87 `space.agents`: every agent in the space, cell by cell in row-major cell order and,
+        inside a cell, in registration order.  A host-side list (one bulk copy per population): debugging / rendering
+        speed, not a step path."""
+        views = self.host_mirror(layers=()).agents
+        flat = [int(np.ravel_multi_index(a.cell.coordinate, self.dimensions)) for a in views]
+        return [views[i] for i in sorted(range(len(views)), key=lambda i: flat[i])]
 
     # ------------------------------------------------------------------ property layers
     def create_property_layer(self, name: str, default_value=0.0, dtype=float, read_only: bool = False) -> torch.Tensor:

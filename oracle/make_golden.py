@@ -523,6 +523,76 @@ def dynamic_agents_fixture(name):
     print(name, "final population", out[f"op{len(script) - 1}_ids"].tolist())
 
 
+# ------------------------------------------------------------------------------ Wolf-Sheep
+def wolf_sheep_fixture(name, width, height, n_sheep, n_wolves, steps, mt_seed, philox_seed, grass=True, regrowth=30,
+                       sheep_reproduce=0.04, wolf_reproduce=0.05, wolf_gain=20.0):
+    """The unmodified WolfSheep model (examples/advanced/wolf_sheep) under the replayed order / draws: after every step
+    the sheep and wolf tables (unique_id, cell, energy) in registration order and the grass layer."""
+    from mesa.examples.advanced.wolf_sheep.agents import Animal, GrassPatch, Sheep, Wolf
+    from mesa.examples.advanced.wolf_sheep.model import WolfSheep, WolfSheepScenario
+
+    with patched_model_random(philox_seed):
+        m = WolfSheep(WolfSheepScenario(width=width, height=height, initial_sheep=n_sheep, initial_wolves=n_wolves,
+                                        grass=grass, grass_regrowth_time=regrowth, sheep_reproduce=sheep_reproduce,
+                                        wolf_reproduce=wolf_reproduce, wolf_gain_from_food=float(wolf_gain),
+                                        rng=mt_seed))
+    rng = m.random
+    assert isinstance(rng, ReplayRandom)
+    H, W = m.grid.dimensions          # model.py:76: Grid([height, width])
+
+    def table(klass):
+        agents = list(m.agents_by_type.get(klass, []))
+        ids = np.array([a.unique_id for a in agents], dtype=np.int64)
+        cells = np.array([a.cell.coordinate[0] * W + a.cell.coordinate[1] for a in agents], dtype=np.int64)
+        energy = np.array([a.energy for a in agents], dtype=np.float64)
+        return ids, cells, energy
+
+    def grown():
+        g = np.zeros((H, W), dtype=np.uint8)
+        if grass:
+            for a in m.agents_by_type[GrassPatch]:
+                g[a.cell.coordinate] = a.fully_grown
+        return g
+
+    out = {"height": H, "width": W, "grass": grass, "regrowth": regrowth, "steps": steps, "mt_seed": mt_seed,
+           "philox_seed": np.uint64(philox_seed), "sheep_reproduce": sheep_reproduce, "wolf_reproduce": wolf_reproduce,
+           "sheep_gain": m.scenario.sheep_gain_from_food, "wolf_gain": m.scenario.wolf_gain_from_food,
+           "next_id_0": m.agent_id_counter}
+    for kind, klass in (("sheep", Sheep), ("wolf", Wolf)):
+        out[f"{kind}_id_0"], out[f"{kind}_cell_0"], out[f"{kind}_energy_0"] = table(klass)
+    out["grown_0"] = grown()
+    # the pending regrowth events of the initial patches (agents.py:142-144): time at which each patch regrows, -1 if grown
+    regrow_at = np.full((H, W), -1, dtype=np.int64)
+    for ev in m._event_list._events if hasattr(m._event_list, "_events") else []:
+        fn = getattr(ev, "fn", None)
+        target = fn() if callable(fn) else None
+        owner = getattr(target, "__self__", None)
+        if isinstance(owner, GrassPatch) and not getattr(ev, "CANCELED", False):
+            regrow_at[owner.cell.coordinate] = int(ev.time)
+    out["regrow_at_0"] = regrow_at
+    rng.replay = True
+    with activation_context(Animal, "step"):
+        for s in range(1, steps + 1):
+            m.step()
+            for kind, klass in (("sheep", Sheep), ("wolf", Wolf)):
+                out[f"{kind}_id_{s}"], out[f"{kind}_cell_{s}"], out[f"{kind}_energy_{s}"] = table(klass)
+            out[f"grown_{s}"] = grown()
+    rng.replay = False
+    out["counts"] = m.datacollector.get_model_vars_dataframe().to_numpy()
+    np.savez_compressed(os.path.join(GOLDEN, name), **out)
+    print(name, "sheep", [len(out[f"sheep_id_{s}"]) for s in (0, steps // 2, steps)], "wolves",
+          [len(out[f"wolf_id_{s}"]) for s in (0, steps // 2, steps)], "pending regrowths", int((regrow_at >= 0).sum()))
+
+
+def wolf_sheep_fixtures():
+    wolf_sheep_fixture("wolf_sheep_20x20.npz", 20, 20, 100, 50, 25, 42, 17)                      # the scenario's defaults
+    wolf_sheep_fixture("wolf_sheep_30x30.npz", 30, 30, 300, 25, 40, 1, 21, regrowth=20, sheep_reproduce=0.1,
+                       wolf_gain=15.0)                                                           # both species persist
+    wolf_sheep_fixture("wolf_sheep_12x15_crowded.npz", 15, 12, 400, 20, 20, 3, 18, regrowth=8, sheep_reproduce=0.2,
+                       wolf_gain=10.0)                                                           # crowded cells, many births
+    wolf_sheep_fixture("wolf_sheep_9x7_nograss.npz", 7, 9, 60, 6, 15, 5, 19, grass=False, sheep_reproduce=0.3)
+
+
 def main():
     import_reference()
     os.makedirs(GOLDEN, exist_ok=True)
@@ -544,6 +614,9 @@ def main():
         return
     if only == "dynamic":
         dynamic_agents_fixture("dynamic_agents.npz")
+        return
+    if only == "wolf_sheep":
+        wolf_sheep_fixtures()
         return
     if only == "boltzmann":
         boltzmann_fixture("boltzmann_100_10x10.npz", 100, 10, 10, 25, 42, 3)      # reference "small"
@@ -573,6 +646,7 @@ def main():
     boltzmann_fixture("boltzmann_100_10x10.npz", 100, 10, 10, 25, 42, 3)
     boltzmann_fixture("boltzmann_2000_20x30.npz", 2000, 20, 30, 10, 7, 4)
     boltzmann_fixture("boltzmann_10000_100x100.npz", 10000, 100, 100, 10, 1, 5)
+    wolf_sheep_fixtures()
     # BASELINE.json configs[0]: 100x100, density 0.8, 100 steps (h=0.4, r=1)
     schelling_fixture("schelling_100x100_c1.npz", 100, 100, 0.8, 0.4, 1, 100, 42, 7, full_steps=[1, 2, 10, 50, 100])
     # the reference's own "large" benchmark variant (benchmarks/configurations.py:42-49)

@@ -365,3 +365,27 @@ def test_cell_agents_through_the_model_hook():
     g = ConwaysGameOfLife(width=8, height=32, rng=1)
     assert [a.unique_id for a in g.grid[(2, 3)].agents] == [2 * 32 + 3 + 1]
     assert len(g.grid[(0, 0)].get_neighborhood().agents) == 8
+
+
+def test_host_mirror_of_a_running_model():
+    """SURVEY 8(f) next-3 on the device: the host snapshot of a stepped Schelling model holds the layers as numpy arrays and
+    one agent view per agent whose cell / position agree with the device columns; `grid.agents` lists them cell by cell."""
+    import numpy as np
+
+    from mesa_b200.examples import Schelling, SchellingScenario
+
+    m = Schelling(SchellingScenario(width=20, height=15, density=0.7, rng=3))
+    for _ in range(3):
+        m.step()
+    space = m.grid.host_mirror()
+    cells = m.agents.get("cell").cpu().numpy().astype(np.int64)
+    types = m.agents.get("type").cpu().numpy()
+    assert len(space.agents) == len(m.agents) == len(cells)
+    for a, c, t in zip(space.agents, cells, types):
+        assert a.cell.coordinate == tuple(int(x) for x in np.unravel_index(c, (20, 15))) and a.type == t
+        assert np.array_equal(a.cell.position, np.asarray(a.cell.coordinate, dtype=float))
+    assert np.array_equal(space.property_layers["type"], m.grid.type.cpu().numpy())
+    assert space.property_layers["empty"].dtype == bool
+    assert np.array_equal(space.property_layers["empty"], m.grid.type.cpu().numpy() < 0)
+    flat = [a.cell.coordinate[0] * 15 + a.cell.coordinate[1] for a in m.grid.agents]
+    assert flat == sorted(flat) and len(flat) == len(cells)

@@ -397,3 +397,50 @@ def test_agent_proxies_and_views_pickle():
     b, view2, agents2 = pickle.loads(pickle.dumps((a, view, agents)))
     assert b.unique_id == 4 and b.x == 6 and b in agents2 and view2.columns is agents2.columns
     assert [p.unique_id for p in view2] == [3, 4, 5] and len(agents2) == 5
+
+
+def test_host_mirror_serves_the_visualization_consumers(host_kernels):
+    """what visualization/backends/matplotlib_backend.py:104-163, 340-356 and space_renderer.py:339 read
+    from a space -- `for agent in space.agents`, `agent.cell.position` (abstract_renderer.py:38-41), `space.property_layers`
+    as numpy arrays (`layer.astype(float)` for bool layers, `(space.width, space.height) == data.shape`, np.min / np.max) --
+    from a host snapshot of a device grid (CPU tensors here)."""
+    import torch
+
+    from mesa_b200.agentset import DeviceAgent, DeviceAgentSet
+    from mesa_b200.model import DeviceModel
+    from mesa_b200.space import DeviceMooreGrid, HostSpaceMirror
+
+    class Ant(DeviceAgent):
+        pass
+
+    model = DeviceModel(rng=3)
+    grid = DeviceMooreGrid((4, 6), torus=False, random=model.random, device="cpu")
+    grid.create_property_layer("sugar", default_value=1.5)
+    grid.sugar[2, 3] = 9.0
+    cells = torch.tensor([23, 0, 7, 7], dtype=torch.int32)                  # flat ids: (3, 5), (0, 0), (1, 1), (1, 1)
+    ants = DeviceAgentSet(model, Ant, 4, {"cell": cells, "load": torch.tensor([0.5, 1.5, 2.5, 3.5])})
+    grid.attach_population(ants)
+    grid.empty.view(-1)[cells.long()] = False
+
+    space = grid.host_mirror()
+    assert isinstance(space, HostSpaceMirror) and (space.width, space.height) == (4, 6)
+    # property layers: numpy, the renderer's own expressions work on them
+    assert set(space.property_layers) == {"empty", "sugar"}
+    for name, layer in space.property_layers.items():
+        data = layer.astype(float) if layer.dtype == bool else layer
+        assert isinstance(data, np.ndarray) and (space.width, space.height) == data.shape
+    assert np.max(space.property_layers["sugar"]) == 9.0 and np.min(space.property_layers["sugar"]) == 1.5
+    assert space.property_layers["empty"].dtype == bool and int((~space.property_layers["empty"]).sum()) == 3
+    # agents: portrayal-style access
+    seen = [(a.unique_id, a.cell.coordinate, tuple(a.cell.position), a.load) for a in space.agents]
+    assert seen == [(1, (3, 5), (3.0, 5.0), 0.5), (2, (0, 0), (0.0, 0.0), 1.5), (3, (1, 1), (1.0, 1.0), 2.5),
+                    (4, (1, 1), (1.0, 1.0), 3.5)]
+    assert all(isinstance(a.cell.position, np.ndarray) and a.agent_type is Ant for a in space.agents)
+    # grid.agents: cell by cell (row-major), registration order inside a cell -- discrete_space.py:84-87
+    assert [a.unique_id for a in grid.agents] == [2, 3, 4, 1]
+    # the snapshot is detached from the device state
+    grid.sugar[0, 0] = -1.0
+    assert space.property_layers["sugar"][0, 0] == 1.5
+    # restricted snapshots (one layer, one attribute)
+    small = grid.host_mirror(layers=["sugar"], attributes=[])
+    assert list(small.property_layers) == ["sugar"] and not hasattr(small.agents[0], "load")

@@ -101,7 +101,7 @@ def test_mesa_model_steps_through_a_device_agentset(live_mesa):
 
     m = WalkerModel(rng=7)
     assert isinstance(m, mesa.Model) and isinstance(m.agents, AbstractAgentSet) and isinstance(m.agents, DeviceAgentSet)
-    assert isinstance(m.grid, DiscreteSpace)
+    assert isinstance(m.grid, DiscreteSpace) and isinstance(m.grid.host_mirror(), DiscreteSpace)
     assert m.agents_by_type[Walker] is m.agents and m.agent_types == [Walker] and len(m.agents) == 50
     m.run_for(3)                                  # mesa's event loop calls our step three times
     assert m.time == 3.0 and m._epoch == 3
