@@ -697,6 +697,9 @@ def _flat_workload_keys(details):
         if name.startswith("boltzmann_1e6"):
             flat["boltzmann_1e6_ms_per_step"] = w["ms_per_step"]
             flat["boltzmann_1e6_updates_per_s"] = w["agent_updates_per_s"]
+        if name.startswith("wolf_sheep_1e6") and "ms_per_step" in w:
+            flat["wolf_sheep_ms_per_step"] = w["ms_per_step"]
+            flat["wolf_sheep_updates_per_s"] = w["agent_updates_per_s"]
         if name.startswith("boids_1e7_vision15_synchronous"):
             flat["boids_1e7_single_gpu_ms_per_step"] = w["ms_per_step"]
         if name.startswith("boids_1e7_vision15_sequential"):
@@ -819,6 +822,30 @@ def other_workloads(dev):
                 "agent_updates_per_s": occupied / ms * 1e3, "hbm_gbs": 2 * GRID * GRID / ms / 1e6,
                 "hbm_frac_of_measured_peak": 2 * GRID * GRID / ms / 1e6 / peak})
     del types, happy
+    # Wolf-Sheep predation (typed activation + predation on dynamic populations), 10^6 sheep and
+    # 2 x 10^5 wolves on 2048^2 with grass; agent-updates = animals activated
+    try:
+        from mesa_b200.examples.wolf_sheep import Sheep, Wolf, WolfSheep, WolfSheepScenario
+
+        ws_m = WolfSheep(WolfSheepScenario(width=2048, height=2048, initial_sheep=1_000_000, initial_wolves=200_000, rng=3))
+        ws_m.step()
+        acted, passes = 0, []
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            acted += len(ws_m.agents_by_type[Sheep]) + len(ws_m.agents_by_type[Wolf])
+            ws_m.step()
+            passes.append((ws_m.last_sheep_passes, ws_m.last_wolf_passes))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out.append({"workload": "wolf_sheep_1e6_sheep_2e5_wolves_2048x2048_grass", "ms_per_step": dt / 10 * 1e3,
+                    "agent_updates_per_s": acted / dt, "sheep": len(ws_m.agents_by_type[Sheep]),
+                    "wolves": len(ws_m.agents_by_type[Wolf]), "jacobi_passes_sheep_wolf": passes[-1],
+                    "note": "sequential shuffle_do semantics of both phases as Jacobi fixed points (csrc/wolf_sheep.cu); "
+                            "host-driven passes + population compaction: latency-bound at this size"})
+        del ws_m
+    except Exception as exc:  # reported, never fatal
+        out.append({"workload": "wolf_sheep", "error": repr(exc)[:200]})
     # config 2: Boltzmann wealth, 10^6 agents on 4096^2
     m = BoltzmannWealth(BoltzmannScenario(n=1_000_000, width=4096, height=4096, rng=1))
     m.run_for(3)

@@ -174,7 +174,7 @@ int mb_reloc_fb_commit(const void* shard, const uint64_t* times_sorted, const ui
 /* The fallback cascade as a time-ordered EVENT LOOP (csrc/relocate.cu, reloc_event_loop): once the ordinary movers of a
  * bucket have converged without any fallback arrival (FULL pass + RESUME passes until nothing changes), the fallback
  * movers -- and the later movers their picks displace -- are processed in ascending time by ONE CTA: no iteration, no
- * release.  mb_reloc_fb_count_into fills a caller-owned block-count table [2048][4096] uint32 (peer-mapped on a
+ * release.  mb_reloc_fb_count_into fills a caller-owned block-count table [2048][16384] uint32 (peer-mapped on a
  * row-sharded grid) and totals[count] for `count` ascending fallback times; mb_reloc_event_loop (one rank) takes the
  * `world` tables (host array of device pointers), totals [world][2048], the times and ranks k = _randbelow(nempty) of
  * the fallback movers of all ranks, and writes the picks that changed as overrides (time of the mover, global cell;

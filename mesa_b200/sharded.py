@@ -29,7 +29,7 @@ from . import ops
 from .sharding import block_bounds
 
 _FB_BATCH = 2048     # kFbBatch of csrc/relocate.cu
-_FB_BLOCKS = 4096    # kFbBlocksMax
+_FB_BLOCKS = 16384   # kFbBlocksMax
 _OV_CAP = 4096       # kOvCap
 _NONE64 = -1  # 0xffff_ffff_ffff_ffff as int64
 
@@ -222,6 +222,7 @@ class ShardedSchelling:
                 #    no release can occur); 2. the fallback movers and what they displace, in time order, by the event loop on
                 #    rank 0; 3. the generic iteration below confirms with a FULL iteration (csrc/relocate.cu).
                 prefix_ok = os.environ.get("MB_RELOC_GENERIC") is None
+                settled = False      # the bucket reached its fixed point by construction (csrc/relocate.cu, same rule)
                 if prefix_ok:
                     N.check(lib.mb_reloc_pass(self._shard_ref, movers, seed, epoch, t_lo, t_hi, 0, ws, wb, mm, self._stream()))
                     self.last_passes += 1
@@ -237,8 +238,11 @@ class ShardedSchelling:
                         N.check(lib.mb_reloc_release_take(ws, wb, mm, None, None, 0, self._stream()))
                         N.check(lib.mb_reloc_pass(self._shard_ref, movers, seed, epoch, t_lo, t_hi, 1, ws, wb, mm, self._stream()))
                         self.last_passes += 1
+                    settled = prefix_ok and sum(nfb_all) == 0
                     if prefix_ok and 0 < sum(nfb_all) <= _FB_BATCH:
-                        self._event_phase(movers, nfb_all, nempty, seed, epoch, t_lo, t_hi)
+                        settled = self._event_phase(movers, nfb_all, nempty, seed, epoch, t_lo, t_hi)
+                if settled and os.environ.get("MB_RELOC_CONFIRM", "0") in ("", "0"):
+                    continue             # no confirming FULL iteration: claims only lowered `arr`, nothing was released
                 full, nrel_all = True, [0] * self.world
                 while True:
                     self.last_passes += 1
@@ -290,7 +294,7 @@ class ShardedSchelling:
         order = ops.argsort_stable(_u64_sort_key(entries[:, 0]))
         return entries[order], home[order]
 
-    def _event_phase(self, movers: int, nfb_all: list[int], nempty: int, seed: int, epoch: int, t_lo: int, t_hi: int) -> None:
+    def _event_phase(self, movers: int, nfb_all: list[int], nempty: int, seed: int, epoch: int, t_lo: int, t_hi: int) -> bool:
         """The fallback cascade of a converged bucket: block counts on every rank, the time-ordered event loop on rank 0
         (all slot / count tables peer-mapped), the changed picks broadcast back as overrides."""
         lib, ws, wb, mm = N.lib(), N.ptr(self._ws), self._ws_bytes, self.max_movers
@@ -313,6 +317,7 @@ class ShardedSchelling:
         self.last_events = [e[0] + int(out4[0]), max(e[1], int(out4[1])), e[2] + int(out4[2]), e[3] + int(out4[3])]
         N.check(lib.mb_reloc_apply_overrides(movers, t_lo, t_hi, N.ptr(ov[:_OV_CAP]), N.ptr(ov[_OV_CAP:2 * _OV_CAP]), int(out4[0]),
                                              ws, wb, mm, self._stream()))
+        return int(out4[1]) == 0     # bail reason 0: every event was processed in time order
 
     def _serve_fallback(self, nfb: int, nfb_all: list[int], nempty: int, seed: int, epoch: int) -> None:
         """grid.py:308-316 for the movers that missed all 50 probes, across ranks."""

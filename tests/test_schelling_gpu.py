@@ -254,3 +254,18 @@ def test_example_model_fused_equals_unfused_and_flushes_deferred_steps():
     a.run_for(5)
     b.run_for(5)
     assert a.happy == b.happy and torch.equal(a.grid.type, b.grid.type)
+
+
+def test_relocation_with_the_confirming_iteration_gives_the_same_trajectories():
+    """MB_RELOC_CONFIRM=1 re-enables the confirming FULL iteration after the event loop (csrc/relocate.cu: skipped by default
+    when the bucket is settled by construction); the golden trajectories must come out the same either way.  The switch is
+    read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+
+    env = dict(os.environ, MB_RELOC_CONFIRM="1", MB_RELOC_DEBUG="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
+                        "matches_reference_trajectory or dense_grid or sharded"], env=env, capture_output=True, text=True,
+                       timeout=900, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "the confirming full iteration" not in r.stderr          # it never finds work (debug message of relocate.cu)
