@@ -302,6 +302,14 @@ int mb_boids_route(const float* pos, const float* dir, const int64_t* ids, int64
 int mb_boids_compact(const float* pos, const float* dir, const int64_t* ids, int64_t n, const unsigned* stay_flags,
                      const unsigned* stay_offsets, float* pos_out, float* dir_out, int64_t* ids_out,
                      mb_stream_t stream);
+/* Rewrite a boid population in cell-list order (row i of the outputs = the boid at sorted slot i, perm_out[i] = its
+ * previous row; ids_in NULL: the previous rows are the ids).  A model that calls this every few steps keeps its storage
+ * order spatially sorted, which turns the gathers / scatters of mb_boids_step_f32 into coalesced accesses.  Same
+ * workspace as the step (mb_celllist_workspace_bytes with radius = vision). */
+int mb_boids_resort_f32(const float* pos_in, const float* dir_in, const int64_t* ids_in, float* pos_out, float* dir_out,
+                        int64_t* ids_out, uint32_t* perm_out, int64_t n, double x0, double y0, double size_x,
+                        double size_y, int torus, double vision, void* workspace, size_t workspace_bytes,
+                        mb_stream_t stream);
 int mb_scan_scratch_words(int64_t n, size_t* out);
 
 /* ---- Dynamic populations (replaces the per-agent dict deletions of _HardKeyAgentSet.discard / remove,

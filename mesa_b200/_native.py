@@ -110,6 +110,8 @@ SIGNATURES: dict[str, tuple] = {
     "mb_boids_route": (c_int, [_P, _P, _P, c_int64, c_double, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                c_int64, _P, _S]),
     "mb_boids_compact": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P, _P, _S]),
+    "mb_boids_resort_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_double, c_double, c_double, c_double, c_int, c_double,
+                                    _P, ctypes.c_size_t, _S]),
     "mb_scan_scratch_words": (c_int, [c_int64, ctypes.POINTER(ctypes.c_size_t)]),
     "mb_offsets_from_counts": (c_int, [_P, c_int64, _P, _P, _S]),
     "mb_ws_count_cells": (c_int, [_P, c_int64, _P, c_int64, _S]),

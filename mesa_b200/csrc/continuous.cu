@@ -1096,6 +1096,55 @@ MB_API int mb_boids_step_f32(const float* pos_in, const float* dir_in, float* po
     return MB_OK;
 }
 
+// ---- spatial re-sort of the storage order ------------------------------------------------------------------------
+// The step kernels gather every boid's state by its cell-list position and scatter the results back to storage order;
+// with a storage order that has nothing to do with space (agents created at random positions) those are 10^7 random
+// 8-byte accesses each (gather_state 0.25 ms, 2.6x write amplification in the update kernel: profiles/r1_boids_*).
+// mb_boids_resort_f32 rewrites the population in cell-list order -- row i of the outputs is the boid at sorted slot i,
+// perm_out[i] its previous row -- so that a model which re-sorts every few steps (boids move at most `speed` per step,
+// a cell edge is >= vision) keeps storage order and cell order nearly identical and all of those accesses coalesce.
+// unique ids travel with the rows (ids_in NULL: the previous row numbers are the ids).
+namespace {
+__global__ void split_sorted(const float4* __restrict__ packed, const uint32_t* __restrict__ order,
+                             const int64_t* __restrict__ ids_in, int64_t n, float2* __restrict__ pos_out,
+                             float2* __restrict__ dir_out, int64_t* __restrict__ ids_out, uint32_t* __restrict__ perm_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 s = packed[i];
+    const uint32_t a = order[i];
+    pos_out[i] = make_float2(s.x, s.y);
+    dir_out[i] = make_float2(s.z, s.w);
+    if (ids_out != nullptr) ids_out[i] = ids_in != nullptr ? ids_in[a] : (int64_t)a;
+    if (perm_out != nullptr) perm_out[i] = a;
+}
+}  // namespace
+
+MB_API int mb_boids_resort_f32(const float* pos_in, const float* dir_in, const int64_t* ids_in, float* pos_out, float* dir_out,
+                               int64_t* ids_out, uint32_t* perm_out, int64_t n, double x0, double y0, double size_x,
+                               double size_y, int torus, double vision, void* workspace, size_t workspace_bytes,
+                               cudaStream_t stream) {
+    MB_REQUIRE(n >= 0 && n < (1ll << 31), "mb_boids_resort_f32: n out of range");
+    if (n == 0) return MB_OK;
+    MB_REQUIRE(pos_in && dir_in && pos_out && dir_out && workspace, "mb_boids_resort_f32: null buffer");
+    MB_REQUIRE(pos_in != pos_out && dir_in != dir_out && (ids_in == nullptr || ids_in != ids_out),
+               "mb_boids_resort_f32: in / out must not alias");
+    Geometry g;
+    int rc = make_geometry(&g, x0, y0, size_x, size_y, vision, torus);
+    if (rc) return rc;
+    CellListWs ws;
+    if (carve(&ws, (char*)workspace, n, (int64_t)g.ncx * g.ncy) > workspace_bytes) {
+        mb::set_error("mb_boids_resort_f32: workspace too small");
+        return MB_ERR_WORKSPACE;
+    }
+    uint32_t* order = nullptr;
+    rc = build_cell_list((const float2*)pos_in, (const float2*)dir_in, n, g, ws, &order, stream);
+    if (rc) return rc;
+    split_sorted<<<(unsigned)mb::ceil_div(n, 256), 256, 0, stream>>>(ws.packed, order, ids_in, n, (float2*)pos_out, (float2*)dir_out,
+                                                                    ids_out, perm_out);
+    MB_LAUNCH_CHECK("mb_boids_resort_f32");
+    return MB_OK;
+}
+
 // ---- sequential Boids step (shuffle_do semantics, see boids_seq_pass) -----------------------------------------
 namespace {
 

@@ -50,6 +50,10 @@ def _step(agents: DeviceAgentSet, epoch: int | None = None, **_):
         _, _, m.last_passes = ops.boids_step_sequential(pos[: m.space._n_agents], dirs, m.space.size, seed=m.philox_seed,
                                                         epoch=epoch, reach=m._reach, ws=m._seq_ws, **kw)
     else:
+        if m.resort_every and m._steps_since_resort >= m.resort_every:
+            m.resort()
+            pos, dirs = m.space._agent_positions, m._direction
+        m._steps_since_resort += 1
         ops.boids_step(pos[: m.space._n_agents], dirs, m.space.size, ws=m._ws, **kw)
     # ping-pong: the new state becomes the space's positions / the agents' direction column
     m.space._agent_positions, m._pos_next = m._pos_next, m.space._agent_positions
@@ -62,7 +66,7 @@ class BoidFlockers(DeviceModel):
     """Flocker model class. Handles agent creation, placement and scheduling."""
 
     def __init__(self, scenario: BoidsScenario = BoidsScenario, initial_positions=None, initial_directions=None,
-                 device="cuda", activation: str = "sequential"):
+                 device="cuda", activation: str = "sequential", resort_every: int = 8):
         if isinstance(scenario, type):
             scenario = scenario()
         if activation not in ("synchronous", "sequential"):
@@ -70,6 +74,10 @@ class BoidFlockers(DeviceModel):
         super().__init__(scenario=scenario)
         self.activation = activation
         self.last_passes = 0
+        # synchronous activation: every `resort_every` steps the storage order is rewritten in cell-list order (ops.boids_resort),
+        # which keeps the step's gathers / scatters coalesced; the boids' unique ids travel with the rows (0 = never)
+        self.resort_every = int(resort_every) if activation == "synchronous" else 0
+        self._steps_since_resort = self.resort_every       # the first step sorts the freshly created (random) order
         n = scenario.population_size
         self.space = DeviceContinuousSpace([[0, scenario.width], [0, scenario.height]], torus=True,
                                            random=self.random, n_agents=n, device=device)
@@ -95,6 +103,24 @@ class BoidFlockers(DeviceModel):
         self.agent_angles = torch.zeros(n, device=dev)
         self.average_heading = None
         self.update_average_heading()
+
+    def resort(self) -> None:
+        """Rewrite the population in cell-list order.  Rows are renumbered (proxies taken before become invalid, like after a
+        removal); `agents.unique_ids()` keeps telling who is who."""
+        n = self.space._n_agents
+        ids = self.agents.unique_ids().contiguous()
+        pos, dirs, ids, _ = ops.boids_resort(self.space._agent_positions[:n].contiguous(), self._direction, self.space.size,
+                                             vision=self.scenario.vision, ids=ids, torus=self.space.torus,
+                                             origin=self.space.dimensions[:, 0], ws=self._ws)
+        if self.space._agent_positions.shape[0] == n:
+            self.space._agent_positions = pos
+        else:
+            self.space._agent_positions[:n].copy_(pos)
+        self._direction = dirs
+        self.agents.columns["position"], self.agents.columns["direction"] = self.space._agent_positions, self._direction
+        self.agents._pop.ids = ids
+        self.agents._pop.generation += 1
+        self._steps_since_resort = 0
 
     def calculate_angles(self):
         d = self._direction

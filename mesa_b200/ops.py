@@ -517,6 +517,30 @@ def boids_step_sequential(pos: torch.Tensor, direction: torch.Tensor, size, *, s
     return pos_out, dir_out, int(passes.value)
 
 
+def boids_resort(pos: torch.Tensor, direction: torch.Tensor, size, *, vision: float, ids: torch.Tensor | None = None,
+                 torus: bool = True, origin=(0.0, 0.0), ws: CellListWorkspace | None = None):
+    """The population rewritten in cell-list order (mb_boids_resort_f32): returns (pos, direction, ids, perm) with
+    row i = the boid at sorted slot i, perm[i] (int32) = its previous row, ids (int64) its unique id (`ids` given) or
+    its previous row.  A model that re-sorts every few steps keeps the gathers / scatters of `boids_step` coalesced."""
+    _need_cuda(pos, direction, ids)
+    if pos.dtype != torch.float32 or direction.dtype != torch.float32 or pos.shape != direction.shape or pos.dim() != 2 or pos.shape[1] != 2:
+        raise ValueError("boids_resort expects float32 [n, 2] positions and directions")
+    n = pos.shape[0]
+    if ids is not None and (ids.dtype != torch.int64 or tuple(ids.shape) != (n,)):
+        raise ValueError("ids must be int64 [n]")
+    if ws is None:
+        ws = CellListWorkspace(n, size, vision, pos.device)
+    pos_out, dir_out = torch.empty_like(pos), torch.empty_like(direction)
+    ids_out = torch.empty(n, dtype=torch.int64, device=pos.device)
+    perm = torch.empty(n, dtype=torch.int32, device=pos.device)
+    with torch.cuda.device(pos.device):
+        N.check(N.lib().mb_boids_resort_f32(
+            N.ptr(_c(pos)), N.ptr(_c(direction)), N.ptr(None if ids is None else _c(ids)), N.ptr(pos_out), N.ptr(dir_out),
+            N.ptr(ids_out), N.ptr(perm), n, float(origin[0]), float(origin[1]), float(size[0]), float(size[1]),
+            int(bool(torus)), float(vision), N.ptr(ws.buf), ws.nbytes, N.stream_ptr(pos.device)))
+    return pos_out, dir_out, ids_out, perm
+
+
 def radius_query(pos: torch.Tensor, queries: torch.Tensor, size, radius: float, torus: bool = True,
                  origin=(0.0, 0.0), exclude: torch.Tensor | None = None, ws: CellListWorkspace | None = None):
     """Batched get_agents_in_radius: CSR (offsets[nq+1] int64, indices int32, distances float64)."""

@@ -34,6 +34,31 @@ _OV_CAP = 4096       # kOvCap
 _NONE64 = -1  # 0xffff_ffff_ffff_ffff as int64
 
 
+class _Phase:
+    def __init__(self, owner, name):
+        self.o, self.name = owner, name
+        self.on = os.environ.get("MB_SHARD_PROFILE") is not None
+
+    def __enter__(self):
+        if self.on:
+            import time
+
+            torch.cuda.synchronize(self.o.device)
+            self.t0 = time.perf_counter()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            import time
+
+            torch.cuda.synchronize(self.o.device)
+            prof = self.o.__dict__.setdefault("profile", {})
+            rec = prof.setdefault(self.name, [0, 0.0])
+            rec[0] += 1
+            rec[1] += (time.perf_counter() - self.t0) * 1e3
+        return False
+
+
 def _u64_sort_key(t: torch.Tensor) -> torch.Tensor:
     """int64 bit patterns of uint64 values -> keys whose signed order is the unsigned order."""
     return t ^ torch.iinfo(torch.int64).min
@@ -142,6 +167,10 @@ class ShardedSchelling:
         self.assign_state()
 
     # ------------------------------------------------------------------ plumbing
+    def _phase(self, name: str):
+        """MB_SHARD_PROFILE=1: wall time per phase of move_unhappy (device-synchronised on both sides) in `self.profile`."""
+        return _Phase(self, name)
+
     def _barrier(self):
         torch.cuda.current_stream(self.device).synchronize()
         dist.barrier(group=self.group)
@@ -198,11 +227,13 @@ class ShardedSchelling:
         seed, epoch = self.seed & 0xFFFFFFFFFFFFFFFF, self.epoch & 0xFFFFFFFF
         self.epoch += 1
         with torch.cuda.device(self.device):
-            N.check(lib.mb_reloc_collect(self._shard_ref, seed, epoch, ws, wb, mm, self._stream()))
-            movers, occupied = self._counters()[:2]
-            tot_movers, tot_occupied = self._allreduce([movers, occupied])   # also orders collect before any pass
-            if self.world > 1 and self.shard.static_bits:
-                dist.all_gather_into_tensor(self._bits, self._bits[self.rank].clone(), group=self.group)
+            with self._phase("collect"):
+                N.check(lib.mb_reloc_collect(self._shard_ref, seed, epoch, ws, wb, mm, self._stream()))
+                movers, occupied = self._counters()[:2]
+                tot_movers, tot_occupied = self._allreduce([movers, occupied])   # also orders collect before any pass
+            with self._phase("bitmap all_gather"):
+                if self.world > 1 and self.shard.static_bits:
+                    dist.all_gather_into_tensor(self._bits, self._bits[self.rank].clone(), group=self.group)
             self.last_movers, self.last_passes = tot_movers, 0
             self.last_events = [0, 0, 0, 0]
             if tot_movers == 0:
@@ -224,23 +255,27 @@ class ShardedSchelling:
                 prefix_ok = os.environ.get("MB_RELOC_GENERIC") is None
                 settled = False      # the bucket reached its fixed point by construction (csrc/relocate.cu, same rule)
                 if prefix_ok:
-                    N.check(lib.mb_reloc_pass(self._shard_ref, movers, seed, epoch, t_lo, t_hi, 0, ws, wb, mm, self._stream()))
+                    with self._phase("FULL pass"):
+                        N.check(lib.mb_reloc_pass(self._shard_ref, movers, seed, epoch, t_lo, t_hi, 0, ws, wb, mm, self._stream()))
                     self.last_passes += 1
                     guard = 0
                     while True:
-                        nfb_all, nrel_all, changed, force = self._pass_flags()
+                        with self._phase("flags (D2H + all_reduce)"):
+                            nfb_all, nrel_all, changed, force = self._pass_flags()
                         if force or sum(nrel_all) > 0:
                             prefix_ok = False
                             break
                         if guard > 0 and not changed:
                             break
                         guard += 1
-                        N.check(lib.mb_reloc_release_take(ws, wb, mm, None, None, 0, self._stream()))
-                        N.check(lib.mb_reloc_pass(self._shard_ref, movers, seed, epoch, t_lo, t_hi, 1, ws, wb, mm, self._stream()))
+                        with self._phase("RESUME pass"):
+                            N.check(lib.mb_reloc_release_take(ws, wb, mm, None, None, 0, self._stream()))
+                            N.check(lib.mb_reloc_pass(self._shard_ref, movers, seed, epoch, t_lo, t_hi, 1, ws, wb, mm, self._stream()))
                         self.last_passes += 1
                     settled = prefix_ok and sum(nfb_all) == 0
                     if prefix_ok and 0 < sum(nfb_all) <= _FB_BATCH:
-                        settled = self._event_phase(movers, nfb_all, nempty, seed, epoch, t_lo, t_hi)
+                        with self._phase("event phase"):
+                            settled = self._event_phase(movers, nfb_all, nempty, seed, epoch, t_lo, t_hi)
                 if settled and os.environ.get("MB_RELOC_CONFIRM", "0") in ("", "0"):
                     continue             # no confirming FULL iteration: claims only lowered `arr`, nothing was released
                 full, nrel_all = True, [0] * self.world
@@ -265,10 +300,11 @@ class ShardedSchelling:
                         full = True                                 # confirm the incremental result
                         continue
                     full = force or sum(nrel_all) > self._REL_CAP
-            N.check(lib.mb_reloc_apply(self._shard_ref, 0, movers, None, ws, wb, mm, self._stream()))
-            self._barrier()      # every origin is empty before any arrival is written
-            N.check(lib.mb_reloc_apply(self._shard_ref, 1, movers, None, ws, wb, mm, self._stream()))
-            self._barrier()
+            with self._phase("vacate + arrive"):
+                N.check(lib.mb_reloc_apply(self._shard_ref, 0, movers, None, ws, wb, mm, self._stream()))
+                self._barrier()      # every origin is empty before any arrival is written
+                N.check(lib.mb_reloc_apply(self._shard_ref, 1, movers, None, ws, wb, mm, self._stream()))
+                self._barrier()
         return tot_movers
 
     def _gather_fallback(self, nfb_all: list[int], nempty: int, seed: int, epoch: int):
@@ -299,19 +335,22 @@ class ShardedSchelling:
         (all slot / count tables peer-mapped), the changed picks broadcast back as overrides."""
         lib, ws, wb, mm = N.lib(), N.ptr(self._ws), self._ws_bytes, self.max_movers
         dev, world = self.device, self.world
-        entries, _ = self._gather_fallback(nfb_all, nempty, seed, epoch)
+        with self._phase("  ev: gather fallback movers"):
+            entries, _ = self._gather_fallback(nfb_all, nempty, seed, epoch)
         count = int(entries.shape[0])
         times, ks = entries[:, 0].contiguous(), entries[:, 1].contiguous()
         totals = torch.zeros(_FB_BATCH, dtype=torch.int32, device=dev)
-        N.check(lib.mb_reloc_fb_count_into(self._shard_ref, N.ptr(times), count, N.ptr(totals), N.ptr(self._cnt_buf), self._stream()))
-        all_totals = torch.empty((world, _FB_BATCH), dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(all_totals, totals, group=self.group)      # also: every rank's table is counted
+        with self._phase("  ev: block counts + all_gather"):
+            N.check(lib.mb_reloc_fb_count_into(self._shard_ref, N.ptr(times), count, N.ptr(totals), N.ptr(self._cnt_buf), self._stream()))
+            all_totals = torch.empty((world, _FB_BATCH), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(all_totals, totals, group=self.group)      # also: every rank's table is counted
         ov = self._ov
-        if self.rank == 0:
-            N.check(lib.mb_reloc_event_loop(self._shard_ref, self._cnt_ptrs, N.ptr(all_totals), N.ptr(times), N.ptr(ks), count,
-                                            N.ptr(ov[:_OV_CAP]), N.ptr(ov[_OV_CAP:2 * _OV_CAP]), N.ptr(ov[2 * _OV_CAP:]),
-                                            seed, epoch, self._stream()))
-        dist.broadcast(ov, dist.get_global_rank(self.group, 0) if self.group is not dist.group.WORLD else 0, group=self.group)
+        with self._phase("  ev: event loop (rank 0) + broadcast"):
+            if self.rank == 0:
+                N.check(lib.mb_reloc_event_loop(self._shard_ref, self._cnt_ptrs, N.ptr(all_totals), N.ptr(times), N.ptr(ks), count,
+                                                N.ptr(ov[:_OV_CAP]), N.ptr(ov[_OV_CAP:2 * _OV_CAP]), N.ptr(ov[2 * _OV_CAP:]),
+                                                seed, epoch, self._stream()))
+            dist.broadcast(ov, dist.get_global_rank(self.group, 0) if self.group is not dist.group.WORLD else 0, group=self.group)
         out4 = ov[2 * _OV_CAP:].tolist()
         e = self.last_events
         self.last_events = [e[0] + int(out4[0]), max(e[1], int(out4[1])), e[2] + int(out4[2]), e[3] + int(out4[3])]

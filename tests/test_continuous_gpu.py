@@ -365,3 +365,39 @@ def test_knn_and_point_queries_on_empty_space():
     assert space.get_k_nearest_agents([0.5, 0.5], k=0)[0] == []
     idx, dist = space.k_nearest_query(np.array([[0.9, 0.9]]), 2)
     assert idx.cpu().tolist() == [[0, -1]] and np.isinf(dist[0, 1].item())
+
+
+def test_resort_keeps_the_flock_and_its_ids():
+    """ops.boids_resort rewrites the population in cell-list order: the same boids (ids travel with the rows), and a model that
+    re-sorts every few steps follows the same trajectory as one that never does (neighbour sets exact, state within 1e-5: the
+    float32 neighbour sums run in another order)."""
+    from mesa_b200 import ops
+    from mesa_b200.examples import BoidFlockers, BoidsScenario
+
+    rng = np.random.default_rng(4)
+    n, side = 20000, 600.0
+    pos = torch.from_numpy((rng.random((n, 2)) * side).astype(np.float32)).cuda()
+    dirs = torch.from_numpy(rng.uniform(-1, 1, (n, 2)).astype(np.float32)).cuda()
+    ids = torch.arange(100, 100 + n, dtype=torch.int64, device="cuda")
+    p2, d2, i2, perm = ops.boids_resort(pos, dirs, (side, side), vision=15.0, ids=ids)
+    assert torch.equal(p2, pos[perm.long()]) and torch.equal(d2, dirs[perm.long()]) and torch.equal(i2, ids[perm.long()])
+    assert torch.equal(torch.sort(perm.long()).values, torch.arange(n, device="cuda"))
+    ncx = int(side // (15.0 * (1 + 1e-6)))
+    cell = (torch.floor(p2[:, 1].double() * ncx / side).long().clamp(0, ncx - 1) * ncx
+            + torch.floor(p2[:, 0].double() * ncx / side).long().clamp(0, ncx - 1))
+    assert bool((cell[1:] >= cell[:-1]).all())                       # cell-list order
+    same_cell = cell[1:] == cell[:-1]
+    assert bool((perm[1:][same_cell] > perm[:-1][same_cell]).all())  # previous order inside a cell
+
+    sc = BoidsScenario(population_size=3000, width=300, height=300, vision=10.0, rng=5)
+    a = BoidFlockers(sc, activation="synchronous", resort_every=0)
+    b = BoidFlockers(sc, activation="synchronous", resort_every=3)
+    for _ in range(10):
+        a.step()
+        b.step()
+    order = torch.argsort(b.agents.unique_ids())
+    assert torch.equal(b.agents.unique_ids()[order], a.agents.unique_ids())
+    pa, pb = a.agents.get("position"), b.agents.get("position")[order]
+    da, db = a.agents.get("direction"), b.agents.get("direction")[order]
+    assert float((pa - pb).abs().max()) / 300.0 <= 1e-5 and float((da - db).abs().max()) <= 1e-5
+    assert torch.equal(a._nbr_count, b._nbr_count[order])

@@ -47,6 +47,10 @@ for s in range(steps):
                  "assign_ms": round((t2 - t1) * 1e3, 3), "happy": happy})
     if rank == 0:
         print(json.dumps(rows[-1]), flush=True)
+        if getattr(m, "profile", None):
+            print(json.dumps({"phases_ms": {k: [v[0], round(v[1], 2)] for k, v in m.profile.items()},
+                              "events": m.last_events}), flush=True)
+            m.profile.clear()
 if rank == 0:
     total = sum(r["relocate_ms"] + r["assign_ms"] for r in rows) / 1e3
     print(json.dumps({"workload": f"schelling {rows_per * world}x{cols} d=0.8 h=0.4 r=1, row-sharded x{world}",
