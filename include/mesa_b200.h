@@ -144,6 +144,14 @@ int mb_reloc_counters(void* workspace, size_t workspace_bytes, int64_t max_mover
  * lower `arr`, so between releases a pick can only move forward); flags accumulate. */
 int mb_reloc_pass(const void* shard, int64_t nmovers, uint64_t seed, uint32_t epoch, uint64_t t_lo, uint64_t t_hi,
                   int mode, void* workspace, size_t workspace_bytes, int64_t max_movers, mb_stream_t stream);
+/* Rank-ordered buckets as index lists: mb_reloc_bucket_lists groups the mover indices by bucket (top bits of the
+ * priority; nbuckets a power of two, 2..256) inside the workspace and writes the per-bucket counts to a HOST array
+ * (synchronises); mb_reloc_pass_list is mb_reloc_pass over one bucket's list [list_first, list_first + list_count). */
+int mb_reloc_bucket_lists(int64_t nmovers, int nbuckets, uint64_t* counts_host, void* workspace, size_t workspace_bytes,
+                          int64_t max_movers, mb_stream_t stream);
+int mb_reloc_pass_list(const void* shard, int64_t list_first, int64_t list_count, uint64_t seed, uint32_t epoch, uint64_t t_lo,
+                       uint64_t t_hi, int mode, void* workspace, size_t workspace_bytes, int64_t max_movers,
+                       mb_stream_t stream);
 /* release sets: a cell whose registered arrival leaves (a fallback pick that shifts, a mover that moves back) may be empty
  * again for later movers that skipped it.  mb_reloc_release_take starts an incremental iteration: it moves the first
  * `count` (<= 4096) recorded (cell, time of the leaver) pairs into caller buffers and clears the set and the changed flag;
@@ -174,7 +182,7 @@ int mb_reloc_fb_commit(const void* shard, const uint64_t* times_sorted, const ui
 /* The fallback cascade as a time-ordered EVENT LOOP (csrc/relocate.cu, reloc_event_loop): once the ordinary movers of a
  * bucket have converged without any fallback arrival (FULL pass + RESUME passes until nothing changes), the fallback
  * movers -- and the later movers their picks displace -- are processed in ascending time by ONE CTA: no iteration, no
- * release.  mb_reloc_fb_count_into fills a caller-owned block-count table [2048][16384] uint32 (peer-mapped on a
+ * release.  mb_reloc_fb_count_into fills a caller-owned count table [65536 + 1024][2048] uint32 (per block of the slot table, then per super-block of 64 blocks; block-major) (peer-mapped on a
  * row-sharded grid) and totals[count] for `count` ascending fallback times; mb_reloc_event_loop (one rank) takes the
  * `world` tables (host array of device pointers), totals [world][2048], the times and ranks k = _randbelow(nempty) of
  * the fallback movers of all ranks, and writes the picks that changed as overrides (time of the mover, global cell;

@@ -65,6 +65,9 @@ SIGNATURES: dict[str, tuple] = {
     "mb_reloc_collect": (c_int, [_P, c_uint64, c_uint32, _P, ctypes.c_size_t, c_int64, _S]),
     "mb_reloc_counters": (c_int, [_P, ctypes.c_size_t, c_int64, ctypes.POINTER(c_uint64), _S]),
     "mb_reloc_pass": (c_int, [_P, c_int64, c_uint64, c_uint32, c_uint64, c_uint64, c_int, _P, ctypes.c_size_t, c_int64, _S]),
+    "mb_reloc_bucket_lists": (c_int, [c_int64, c_int, _P, _P, ctypes.c_size_t, c_int64, _S]),
+    "mb_reloc_pass_list": (c_int, [_P, c_int64, c_int64, c_uint64, c_uint32, c_uint64, c_uint64, c_int, _P, ctypes.c_size_t, c_int64,
+                                   _S]),
     "mb_reloc_release_take": (c_int, [_P, ctypes.c_size_t, c_int64, _P, _P, c_int64, _S]),
     "mb_reloc_release_scan": (c_int, [_P, c_int64, c_uint64, c_uint32, c_uint64, c_uint64, _P, _P, c_int64, _P,
                                       ctypes.c_size_t, c_int64, _S]),

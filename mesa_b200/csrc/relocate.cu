@@ -59,7 +59,9 @@ constexpr int kMaxProbes = 50;   // grid.py:303 `for _ in range(50)`
 constexpr int kMaxPasses = 100000;
 constexpr int kFbBatch = 2048;   // fallback movers served per table pass
 constexpr int kRelCap = 4096;    // released cells recorded between two scans (more: answered with a full pass)
-constexpr int kFbBlocksMax = 16384;  // blocks of the slot table with per-fallback empty counts (finer blocks: shorter scans in the event loop)
+constexpr int kFbBlocksMax = 65536;   // blocks of a rank's slot table with per-fallback empty counts (fine blocks: short scans)
+constexpr int kFbSuper = 64;          // blocks per super-block: the count walk is two short scans (supers, then 64 blocks)
+constexpr int kFbSupersMax = kFbBlocksMax / kFbSuper;
 constexpr int kMaxPeers = 16;
 constexpr int kOvCapWs = 4096;   // = kOvCap (event loop overrides)
 
@@ -150,6 +152,8 @@ struct RelocWs {
     uint32_t* softcell;             // [cap] the cell of the LOWEST such probe (most movers have at most one: the release
                                     //       scan then needs no Philox replay for them)
     uint32_t* fb_list;              // [cap] movers that missed all 50 probes in this pass
+    uint32_t* bucket_list;          // [cap] mover indices grouped by rank-ordered bucket (mb_reloc_bucket_lists)
+    unsigned long long* bucket_cur; // [256] per-bucket counts, then write cursors
     unsigned long long* fb_t;       // [kFbBatch] sorted times of the current fallback batch
     uint32_t* fb_m;                 // [kFbBatch] local mover of each sorted entry
     unsigned long long* fb_k;       // [kFbBatch] rank of the empty cell to take (within this rank's table)
@@ -157,7 +161,8 @@ struct RelocWs {
     uint32_t* fb_tot;               // [kFbBatch] empties of the local table at each fallback time
     uint32_t* fb_block;             // [kFbBatch]
     uint32_t* fb_rem;               // [kFbBatch]
-    uint32_t* cnt;                  // [kFbBatch][kFbBlocksMax] empties per local table block
+    uint32_t* cnt;                  // [kFbBlocksMax][kFbBatch] empties per local table block, then [kFbSupersMax][kFbBatch]
+                                    // the same per super-block (fb_sup)
     unsigned long long* rel_w_cell;  // [kRelCap] cells released since the last take (write set)
     unsigned long long* rel_w_time;  // [kRelCap] time of the mover that left each of them
     unsigned long long* rel_r_cell;  // [kRelCap] read set of the single-GPU driver's scans
@@ -186,6 +191,8 @@ size_t carve(RelocWs* ws, char* base, int64_t cap) {
     t.softmask = (unsigned long long*)take(8 * cap);
     t.softcell = (uint32_t*)take(4 * cap);
     t.fb_list = (uint32_t*)take(4 * cap);
+    t.bucket_list = (uint32_t*)take(4 * cap);
+    t.bucket_cur = (unsigned long long*)take(8 * 256);
     t.fb_t = (unsigned long long*)take(8 * kFbBatch);
     t.fb_m = (uint32_t*)take(4 * kFbBatch);
     t.fb_k = (unsigned long long*)take(8 * kFbBatch);
@@ -193,7 +200,7 @@ size_t carve(RelocWs* ws, char* base, int64_t cap) {
     t.fb_tot = (uint32_t*)take(4 * kFbBatch);
     t.fb_block = (uint32_t*)take(4 * kFbBatch);
     t.fb_rem = (uint32_t*)take(4 * kFbBatch);
-    t.cnt = (uint32_t*)take(4ull * kFbBlocksMax * kFbBatch);
+    t.cnt = (uint32_t*)take(4ull * (kFbBlocksMax + kFbSupersMax) * kFbBatch);
     t.rel_w_cell = (unsigned long long*)take(8 * kRelCap);
     t.rel_w_time = (unsigned long long*)take(8 * kRelCap);
     t.rel_r_cell = (unsigned long long*)take(8 * kRelCap);
@@ -221,6 +228,10 @@ __device__ __forceinline__ Slot load_slot(const Slot* p) {
 }
 
 __device__ __forceinline__ bool empty_at(const Slot& s, unsigned long long t) { return s.vac <= t && t <= s.arr; }
+
+// the super-block counts follow the block counts in a count table
+__host__ __device__ __forceinline__ uint32_t* fb_sup(uint32_t* cnt) { return cnt + (size_t)kFbBlocksMax * kFbBatch; }
+__host__ __device__ __forceinline__ const uint32_t* fb_sup(const uint32_t* cnt) { return cnt + (size_t)kFbBlocksMax * kFbBatch; }
 
 __global__ void init_slots(ShardView v) {
     const int8_t* __restrict__ type = v.type[v.rank];
@@ -492,8 +503,9 @@ relocate_pass(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, uint32_t 
 // FULL pass at 8192^2: more loop iterations, each paying the refill ballots / shuffles, and 80 registers.)
 template <int kBatch>
 __global__ void __launch_bounds__(128)
-relocate_pass_packed(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, uint32_t epoch, unsigned long long t_lo,
-                     unsigned long long t_hi, int mode, int64_t movers_per_warp) {
+relocate_pass_packed(ShardView v, RelocWs ws, const uint32_t* __restrict__ mlist, int64_t nmovers, uint64_t seed, uint32_t epoch,
+                     unsigned long long t_lo, unsigned long long t_hi, int mode, int64_t movers_per_warp) {
+    // mlist != NULL: the movers of this pass are mlist[0 .. nmovers) (one rank-ordered bucket), otherwise 0 .. nmovers-1
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -504,7 +516,7 @@ relocate_pass_packed(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, ui
     int64_t tile0 = 0;
     unsigned tile_mask = 0u;
     unsigned long long tile_t = 0ull;
-    uint32_t tile_agent = 0u;
+    uint32_t tile_agent = 0u, tile_m = 0u;
     // this lane's mover
     int64_t m = -1;
     unsigned long long t = 0ull, held = kNoCell, soft = 0ull;
@@ -523,8 +535,9 @@ relocate_pass_packed(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, ui
                 const int64_t mine = tile0 + lane;
                 bool in_range = false;
                 if (mine < next) {
-                    tile_t = ws.mv_prio[mine];
-                    tile_agent = ws.mv_agent[mine];
+                    tile_m = mlist != nullptr ? mlist[mine] : (uint32_t)mine;
+                    tile_t = ws.mv_prio[tile_m];
+                    tile_agent = ws.mv_agent[tile_m];
                     in_range = tile_t >= t_lo && tile_t <= t_hi;
                 }
                 tile_mask = __ballot_sync(0xffffffffu, in_range);
@@ -535,8 +548,9 @@ relocate_pass_packed(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, ui
             const int src = (m < 0 && rank < avail) ? (int)__fns(tile_mask, 0, rank + 1) : 0;
             const unsigned long long nt = __shfl_sync(0xffffffffu, tile_t, src);
             const uint32_t na = __shfl_sync(0xffffffffu, tile_agent, src);
+            const uint32_t nm = __shfl_sync(0xffffffffu, tile_m, src);
             if (m < 0 && rank < avail) {
-                m = tile0 + src;
+                m = (int64_t)nm;
                 t = nt;
                 ds = mb::DrawStream(seed, epoch, na);
                 held = ws.choice[m];
@@ -625,6 +639,41 @@ relocate_pass_packed(ShardView v, RelocWs ws, int64_t nmovers, uint64_t seed, ui
             ws.fb_list[atomicAdd(&ws.counters[2], 1ull)] = (uint32_t)m;
             m = -1;
         }
+    }
+}
+
+// ---- rank-ordered buckets as index lists ---------------------------------------------------------------------------------
+// With many movers the passes work bucket by bucket (earliest priorities first).  Scanning ALL movers for the 1 / B that
+// belong to the current bucket made every pass cost at least a sweep over the mover arrays (122 M movers per GPU on the
+// 65536^2 grid: 3.1 ms per RESUME pass that did nothing else, profiles/r2_c5_shard_n1_launches.csv); here the mover
+// indices are grouped by bucket once per step (histogram, host prefix, scatter) and a pass walks only its bucket's list.
+__global__ void __launch_bounds__(256)
+bucket_hist(RelocWs ws, int64_t nmovers, int shift, unsigned long long* __restrict__ counts) {
+    __shared__ unsigned h[256];
+    h[threadIdx.x] = 0u;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < nmovers; m += stride)
+        atomicAdd(&h[(unsigned)(ws.mv_prio[m] >> shift)], 1u);
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)h[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256)
+bucket_scatter(RelocWs ws, int64_t nmovers, int shift, unsigned long long* __restrict__ cursors, int64_t per_cta) {
+    __shared__ unsigned h[256];
+    __shared__ unsigned long long base[256];
+    h[threadIdx.x] = 0u;
+    __syncthreads();
+    const int64_t lo = (int64_t)blockIdx.x * per_cta, hi = min(lo + per_cta, nmovers);
+    for (int64_t m = lo + threadIdx.x; m < hi; m += blockDim.x) atomicAdd(&h[(unsigned)(ws.mv_prio[m] >> shift)], 1u);
+    __syncthreads();
+    base[threadIdx.x] = h[threadIdx.x] ? atomicAdd(&cursors[threadIdx.x], (unsigned long long)h[threadIdx.x]) : 0ull;
+    h[threadIdx.x] = 0u;
+    __syncthreads();
+    for (int64_t m = lo + threadIdx.x; m < hi; m += blockDim.x) {
+        const unsigned b = (unsigned)(ws.mv_prio[m] >> shift);
+        ws.bucket_list[base[b] + atomicAdd(&h[b], 1u)] = (uint32_t)m;    // order inside a bucket is irrelevant
     }
 }
 
@@ -755,7 +804,8 @@ __device__ __forceinline__ int first_ge(const unsigned long long* __restrict__ a
     return lo;
 }
 
-// cnt[f][b] = number of cells of LOCAL table block b that are empty at the time of fallback f
+// cnt[b][f] = number of cells of LOCAL table block b that are empty at the time of fallback f (+ the sums per super-block,
+// which must be zero on entry)
 __global__ void __launch_bounds__(256)
 fb_count(ShardView v, uint32_t* __restrict__ cnt, uint32_t* __restrict__ fb_tot, const unsigned long long* __restrict__ fb_t,
          int64_t block_cells, int count) {
@@ -792,9 +842,13 @@ fb_count(ShardView v, uint32_t* __restrict__ cnt, uint32_t* __restrict__ fb_tot,
         }
     }
     __syncthreads();
+    uint32_t* __restrict__ sup = fb_sup(cnt) + (size_t)(blockIdx.x / kFbSuper) * kFbBatch;
     for (int f = threadIdx.x; f < count; f += blockDim.x) {
-        cnt[(size_t)f * kFbBlocksMax + blockIdx.x] = (uint32_t)diff[f];
-        if (diff[f]) atomicAdd(&fb_tot[f], (uint32_t)diff[f]);
+        cnt[(size_t)blockIdx.x * kFbBatch + f] = (uint32_t)diff[f];     // block-major: coalesced here and in the updates
+        if (diff[f]) {
+            atomicAdd(&sup[f], (uint32_t)diff[f]);
+            atomicAdd(&fb_tot[f], (uint32_t)diff[f]);
+        }
     }
 }
 
@@ -809,26 +863,37 @@ fb_pick(ShardView v, RelocWs ws, const unsigned long long* __restrict__ fb_t,
     if (f >= count) return;
     unsigned long long k = k_local[f];
     if (k == kNoCell) return;
-    const uint32_t* __restrict__ row = ws.cnt + (size_t)f * kFbBlocksMax;
-    int block = -1;
-    unsigned need = 0;
-    for (int b0 = 0; b0 < nblocks && block < 0; b0 += 32) {
-        const int b = b0 + lane;
-        const unsigned n = b < nblocks ? row[b] : 0u;
-        unsigned incl = n;
+    // two-level walk: the super-block that holds the k-th empty cell, then the block inside it
+    auto walk = [&](const uint32_t* __restrict__ base, int first, int n_entries, int& hit, unsigned long long& kk) {
+        hit = -1;
+        for (int b0 = 0; b0 < n_entries && hit < 0; b0 += 32) {
+            const int b = b0 + lane;
+            const unsigned n = b < n_entries ? base[(size_t)(first + b) * kFbBatch + f] : 0u;
+            unsigned incl = n;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned x = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += x;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned x = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += x;
+            }
+            const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+            if (kk < total) {
+                const int l = __ffs(__ballot_sync(0xffffffffu, kk < incl)) - 1;
+                kk -= __shfl_sync(0xffffffffu, incl - n, l);
+                hit = b0 + l;
+            } else {
+                kk -= total;
+            }
         }
-        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-        if (k < total) {
-            const int l = __ffs(__ballot_sync(0xffffffffu, k < incl)) - 1;
-            need = (unsigned)(k - __shfl_sync(0xffffffffu, incl - n, l));
-            block = b0 + l;
-        } else {
-            k -= total;
-        }
+    };
+    int block = -1, super = -1;
+    unsigned need = 0;
+    const int nsupers = (nblocks + kFbSuper - 1) / kFbSuper;
+    walk(fb_sup(ws.cnt), 0, nsupers, super, k);
+    if (super >= 0) {
+        const int first = super * kFbSuper;
+        int inner = -1;
+        walk(ws.cnt, first, min(kFbSuper, nblocks - first), inner, k);
+        if (inner >= 0) { block = first + inner; need = (unsigned)k; }
     }
     long long found = -1;
     if (block >= 0) {
@@ -895,7 +960,7 @@ constexpr int kPendCap = 1024;   // displaced movers waiting for their turn
 constexpr int kOvCap = kOvCapWs;  // overrides returned per event loop
 
 struct EventArgs {
-    uint32_t* cnt[kMaxPeers];          // per-rank block-count tables [kFbBatch][kFbBlocksMax]
+    uint32_t* cnt[kMaxPeers];          // per-rank count tables: [kFbBlocksMax][kFbBatch] blocks + [kFbSupersMax][kFbBatch] super-blocks
     uint32_t* tot;                     // [world][kFbBatch] empties of each rank's table at each fallback time (updated)
     const unsigned long long* fb_t;    // [count] ascending fallback times
     const unsigned long long* fb_k;    // [count] rank of the empty cell to take over the WHOLE grid (row-major)
@@ -1020,30 +1085,31 @@ reloc_event_loop(ShardView v, EventArgs a, uint64_t seed, uint32_t epoch) {
             if (s_bail) break;
             const int o = s_owner;
             const long long lc = (v.row_lo(o + 1) - v.row_lo(o)) * v.cols;
-            long long nb = (lc + 1023) / 1024;
+            long long nb = (lc + 4095) / 4096;
             if (nb > kFbBlocksMax) nb = kFbBlocksMax;
             if (nb < 1) nb = 1;
             const long long bc = (lc + nb - 1) / nb;
-            const uint32_t* row = a.cnt[o] + (size_t)i * kFbBlocksMax;
-            {   // walk the block counts: kWalk consecutive entries per thread
-                constexpr int kWalk = kFbBlocksMax / 1024;
-                unsigned n[kWalk], sum = 0;
-#pragma unroll
-                for (int e = 0; e < kWalk; ++e) {
-                    const int b = tid * kWalk + e;
-                    n[e] = b < nb ? __ldcg(row + b) : 0u;
-                    sum += n[e];
-                }
+            const int nsup = (int)((nb + kFbSuper - 1) / kFbSuper);
+            {   // two-level walk of the owner's counts at fallback time i: super-block (one entry per thread), then its blocks
+                const uint32_t* sup = fb_sup(a.cnt[o]);
+                const unsigned n = tid < nsup ? __ldcg(sup + (size_t)tid * kFbBatch + i) : 0u;
                 unsigned total;
-                unsigned excl = block_exclusive_scan(sum, warp_sums, total);
+                const unsigned excl = block_exclusive_scan(n, warp_sums, total);
                 const unsigned long long k = s_klocal;
-                if (k >= excl && k < (unsigned long long)excl + sum) {
-#pragma unroll
-                    for (int e = 0; e < kWalk; ++e) {
-                        if (k >= excl && k < (unsigned long long)excl + n[e]) { s_block = tid * kWalk + e; s_need = (unsigned)(k - excl); s_found = 1; }
-                        excl += n[e];
-                    }
-                }
+                if (k >= excl && k < (unsigned long long)excl + n) { s_block = tid; s_need = (unsigned)(k - excl); s_found = 1; }
+            }
+            __syncthreads();
+            if (!s_found) { if (tid == 0) s_bail = 5; __syncthreads(); break; }
+            {
+                const int first = s_block * kFbSuper;
+                const unsigned long long k = s_need;
+                __syncthreads();
+                if (tid == 0) s_found = 0;
+                const int b = first + tid;
+                const unsigned n = (tid < kFbSuper && b < nb) ? __ldcg(a.cnt[o] + (size_t)b * kFbBatch + i) : 0u;
+                unsigned total;
+                const unsigned excl = block_exclusive_scan(n, warp_sums, total);   // (the scan's first barrier orders the reset)
+                if (k >= excl && k < (unsigned long long)excl + n) { s_block = b; s_need = (unsigned)(k - excl); s_found = 1; }
             }
             __syncthreads();
             if (!s_found) { if (tid == 0) s_bail = 5; __syncthreads(); break; }
@@ -1108,7 +1174,7 @@ reloc_event_loop(ShardView v, EventArgs a, uint64_t seed, uint32_t epoch) {
         }
         {
             const long long lc = (v.row_lo(o + 1) - v.row_lo(o)) * v.cols;
-            long long nb = (lc + 1023) / 1024;
+            long long nb = (lc + 4095) / 4096;
             if (nb > kFbBlocksMax) nb = kFbBlocksMax;
             if (nb < 1) nb = 1;
             const long long bc = (lc + nb - 1) / nb;
@@ -1116,8 +1182,11 @@ reloc_event_loop(ShardView v, EventArgs a, uint64_t seed, uint32_t epoch) {
             const unsigned long long from = s_vac > t + 1ull ? s_vac : t + 1ull;
             const int lo = first_ge(times, a.count, from);
             const int hi = s_aold == kNever ? a.count : first_ge(times, a.count, s_aold + 1ull);
-            for (int f = lo + tid; f < hi; f += blockDim.x) {
-                atomicSub(a.cnt[o] + (size_t)f * kFbBlocksMax + blk, 1u);
+            uint32_t* cb = a.cnt[o] + (size_t)blk * kFbBatch;
+            uint32_t* cs = fb_sup(a.cnt[o]) + (size_t)(blk / kFbSuper) * kFbBatch;
+            for (int f = lo + tid; f < hi; f += blockDim.x) {     // consecutive words of one block row / super row
+                atomicSub(cb + f, 1u);
+                atomicSub(cs + f, 1u);
                 a.tot[(size_t)o * kFbBatch + f] -= 1u;
             }
         }
@@ -1193,8 +1262,14 @@ int read_counters(const RelocWs& ws, unsigned long long* host7, cudaStream_t str
 }
 
 inline int64_t fb_num_blocks(int64_t local_cells) {
-    int64_t b = mb::ceil_div(local_cells > 0 ? local_cells : 1, 1024);
+    int64_t b = mb::ceil_div(local_cells > 0 ? local_cells : 1, 4096);
     return b > kFbBlocksMax ? kFbBlocksMax : b;
+}
+
+// the super-block sums accumulate with atomics: clear them before a count pass
+inline int fb_clear_supers(uint32_t* cnt_table, int64_t nblocks, cudaStream_t stream) {
+    return mb::check_cuda(cudaMemsetAsync(fb_sup(cnt_table), 0, sizeof(uint32_t) * (size_t)mb::ceil_div(nblocks, kFbSuper) * kFbBatch, stream),
+                          "memset");
 }
 
 // serve `count` (<= kFbBatch) fallback entries whose (t, k, m) sit in device arrays, single rank
@@ -1205,6 +1280,7 @@ int serve_fallback_local(const ShardView& v, RelocWs& ws, const unsigned long lo
     fb_sort<<<1, 1024, 0, stream>>>(ws, in_t, in_k, in_m, count);
     int rc = mb::check_cuda(cudaMemsetAsync(ws.fb_tot, 0, 4 * kFbBatch, stream), "memset");
     if (rc) return rc;
+    if ((rc = fb_clear_supers(ws.cnt, nblocks, stream))) return rc;
     fb_count<<<(unsigned)nblocks, 256, 0, stream>>>(v, ws.cnt, ws.fb_tot, ws.fb_t, block_cells, count);
     const unsigned wblocks = (unsigned)mb::ceil_div((int64_t)count * 32, 256);
     fb_pick<<<wblocks, 256, 0, stream>>>(v, ws, ws.fb_t, ws.fb_k, (int)nblocks, block_cells, count, ws.fb_res);
@@ -1314,17 +1390,12 @@ MB_API int mb_reloc_release_scan(const void* shard, int64_t nmovers, uint64_t se
 // mode 0: FULL pass (every mover from its first probe; clears the fallback list, the flags and the release set first);
 // mode 1: RESUME pass (movers only verify their pick and continue after it; flags accumulate).  RESUME passes are valid
 // as long as every recorded release has been answered by a release scan (or a FULL pass).
-MB_API int mb_reloc_pass(const void* shard, int64_t nmovers, uint64_t seed, uint32_t epoch, uint64_t t_lo, uint64_t t_hi,
-                         int mode, void* workspace, size_t workspace_bytes, int64_t max_movers, cudaStream_t stream) {
-    ShardView v;
-    RelocWs ws;
-    int rc = make_view((const ShardDesc*)shard, &v);
-    if (rc) return rc;
-    if ((rc = get_ws(&ws, workspace, workspace_bytes, max_movers))) return rc;
-    MB_REQUIRE(nmovers >= 0 && nmovers <= max_movers, "mb_reloc_pass: mover count exceeds the workspace");
-    MB_REQUIRE(mode == 0 || mode == 1, "mb_reloc_pass: mode must be 0 (full) or 1 (resume)");
+namespace {
+int launch_pass(const ShardView& v, RelocWs& ws, const uint32_t* mlist, int64_t count, uint64_t seed, uint32_t epoch,
+                uint64_t t_lo, uint64_t t_hi, int mode, cudaStream_t stream) {
+    int rc;
     if (mode == 0 && (rc = mb::check_cuda(cudaMemsetAsync(ws.counters + 2, 0, 5 * sizeof(unsigned long long), stream), "memset"))) return rc;
-    if (nmovers > 0) {
+    if (count > 0) {
         static int batch = -1;
         if (batch < 0) {
             const char* e = getenv("MB_RELOC_BATCH");
@@ -1335,26 +1406,86 @@ MB_API int mb_reloc_pass(const void* shard, int64_t nmovers, uint64_t seed, uint
             const char* e = getenv("MB_RELOC_PACKED");
             packed = e ? atoi(e) : 1;
         }
-        if (packed) {
+        if (packed || mlist != nullptr) {
             // one warp per `per_warp` consecutive movers: enough warps to fill the machine several times over, long
             // enough ranges for the lane refill to pay
             int64_t per_warp = 256;
             const int64_t want_warps = (int64_t)mb::sm_count() * 64 * 4;
-            if (mb::ceil_div(nmovers, per_warp) < want_warps) per_warp = mb::ceil_div(mb::ceil_div(nmovers, want_warps), 32) * 32;
+            if (mb::ceil_div(count, per_warp) < want_warps) per_warp = mb::ceil_div(mb::ceil_div(count, want_warps), 32) * 32;
             if (per_warp < 32) per_warp = 32;
-            const unsigned blocks = (unsigned)mb::ceil_div(mb::ceil_div(nmovers, per_warp), 4);
-            if (batch <= 1) relocate_pass_packed<1><<<blocks, 128, 0, stream>>>(v, ws, nmovers, seed, epoch, t_lo, t_hi, mode, per_warp);
-            else if (batch == 2) relocate_pass_packed<2><<<blocks, 128, 0, stream>>>(v, ws, nmovers, seed, epoch, t_lo, t_hi, mode, per_warp);
-            else relocate_pass_packed<4><<<blocks, 128, 0, stream>>>(v, ws, nmovers, seed, epoch, t_lo, t_hi, mode, per_warp);
+            const unsigned blocks = (unsigned)mb::ceil_div(mb::ceil_div(count, per_warp), 4);
+            if (batch <= 1) relocate_pass_packed<1><<<blocks, 128, 0, stream>>>(v, ws, mlist, count, seed, epoch, t_lo, t_hi, mode, per_warp);
+            else if (batch == 2) relocate_pass_packed<2><<<blocks, 128, 0, stream>>>(v, ws, mlist, count, seed, epoch, t_lo, t_hi, mode, per_warp);
+            else relocate_pass_packed<4><<<blocks, 128, 0, stream>>>(v, ws, mlist, count, seed, epoch, t_lo, t_hi, mode, per_warp);
         } else {
-            const unsigned blocks = (unsigned)mb::ceil_div(nmovers, 128);
-            if (batch <= 1) relocate_pass<1><<<blocks, 128, 0, stream>>>(v, ws, nmovers, seed, epoch, t_lo, t_hi, mode);
-            else if (batch == 2) relocate_pass<2><<<blocks, 128, 0, stream>>>(v, ws, nmovers, seed, epoch, t_lo, t_hi, mode);
-            else relocate_pass<4><<<blocks, 128, 0, stream>>>(v, ws, nmovers, seed, epoch, t_lo, t_hi, mode);
+            const unsigned blocks = (unsigned)mb::ceil_div(count, 128);
+            if (batch <= 1) relocate_pass<1><<<blocks, 128, 0, stream>>>(v, ws, count, seed, epoch, t_lo, t_hi, mode);
+            else if (batch == 2) relocate_pass<2><<<blocks, 128, 0, stream>>>(v, ws, count, seed, epoch, t_lo, t_hi, mode);
+            else relocate_pass<4><<<blocks, 128, 0, stream>>>(v, ws, count, seed, epoch, t_lo, t_hi, mode);
         }
     }
     MB_LAUNCH_CHECK("mb_reloc_pass");
     return MB_OK;
+}
+}  // namespace
+
+MB_API int mb_reloc_pass(const void* shard, int64_t nmovers, uint64_t seed, uint32_t epoch, uint64_t t_lo, uint64_t t_hi,
+                         int mode, void* workspace, size_t workspace_bytes, int64_t max_movers, cudaStream_t stream) {
+    ShardView v;
+    RelocWs ws;
+    int rc = make_view((const ShardDesc*)shard, &v);
+    if (rc) return rc;
+    if ((rc = get_ws(&ws, workspace, workspace_bytes, max_movers))) return rc;
+    MB_REQUIRE(nmovers >= 0 && nmovers <= max_movers, "mb_reloc_pass: mover count exceeds the workspace");
+    MB_REQUIRE(mode == 0 || mode == 1, "mb_reloc_pass: mode must be 0 (full) or 1 (resume)");
+    return launch_pass(v, ws, nullptr, nmovers, seed, epoch, t_lo, t_hi, mode, stream);
+}
+
+// Group the mover indices by rank-ordered bucket (nbuckets: a power of two <= 256; bucket = top bits of the priority)
+// into the workspace's bucket list and return the per-bucket counts (host array of nbuckets words).  Synchronises.
+MB_API int mb_reloc_bucket_lists(int64_t nmovers, int nbuckets, uint64_t* counts_host, void* workspace, size_t workspace_bytes,
+                                 int64_t max_movers, cudaStream_t stream) {
+    RelocWs ws;
+    int rc = get_ws(&ws, workspace, workspace_bytes, max_movers);
+    if (rc) return rc;
+    MB_REQUIRE(nmovers >= 0 && nmovers <= max_movers && counts_host != nullptr, "mb_reloc_bucket_lists: bad argument");
+    MB_REQUIRE(nbuckets >= 2 && nbuckets <= 256 && (nbuckets & (nbuckets - 1)) == 0, "mb_reloc_bucket_lists: nbuckets must be a power of two in 2..256");
+    int log2b = 0;
+    while ((1 << log2b) < nbuckets) ++log2b;
+    const int shift = 64 - log2b;
+    if ((rc = mb::check_cuda(cudaMemsetAsync(ws.bucket_cur, 0, 8 * 256, stream), "memset"))) return rc;
+    if (nmovers > 0) bucket_hist<<<mb::sm_count() * 8, 256, 0, stream>>>(ws, nmovers, shift, ws.bucket_cur);
+    unsigned long long host[256];
+    if ((rc = mb::check_cuda(cudaMemcpyAsync(host, ws.bucket_cur, 8 * 256, cudaMemcpyDeviceToHost, stream), "read bucket counts"))) return rc;
+    if ((rc = mb::check_cuda(cudaStreamSynchronize(stream), "sync"))) return rc;
+    unsigned long long cursors[256], run = 0;
+    for (int b = 0; b < 256; ++b) {
+        cursors[b] = run;
+        run += host[b];
+        if (b < nbuckets) counts_host[b] = host[b];
+    }
+    if ((rc = mb::check_cuda(cudaMemcpyAsync(ws.bucket_cur, cursors, 8 * 256, cudaMemcpyHostToDevice, stream), "write bucket cursors"))) return rc;
+    if ((rc = mb::check_cuda(cudaStreamSynchronize(stream), "sync"))) return rc;     // `cursors` lives on this stack frame
+    if (nmovers > 0) {
+        const int64_t per_cta = mb::ceil_div(mb::ceil_div(nmovers, (int64_t)mb::sm_count() * 16), 256) * 256;
+        bucket_scatter<<<(unsigned)mb::ceil_div(nmovers, per_cta), 256, 0, stream>>>(ws, nmovers, shift, ws.bucket_cur, per_cta);
+    }
+    MB_LAUNCH_CHECK("mb_reloc_bucket_lists");
+    return MB_OK;
+}
+
+// mb_reloc_pass over ONE bucket's list: the movers bucket_list[list_first .. list_first + list_count)
+MB_API int mb_reloc_pass_list(const void* shard, int64_t list_first, int64_t list_count, uint64_t seed, uint32_t epoch, uint64_t t_lo,
+                              uint64_t t_hi, int mode, void* workspace, size_t workspace_bytes, int64_t max_movers,
+                              cudaStream_t stream) {
+    ShardView v;
+    RelocWs ws;
+    int rc = make_view((const ShardDesc*)shard, &v);
+    if (rc) return rc;
+    if ((rc = get_ws(&ws, workspace, workspace_bytes, max_movers))) return rc;
+    MB_REQUIRE(list_first >= 0 && list_count >= 0 && list_first + list_count <= max_movers, "mb_reloc_pass_list: list range exceeds the workspace");
+    MB_REQUIRE(mode == 0 || mode == 1, "mb_reloc_pass_list: mode must be 0 (full) or 1 (resume)");
+    return launch_pass(v, ws, ws.bucket_list + list_first, list_count, seed, epoch, t_lo, t_hi, mode, stream);
 }
 
 // (time, k = _randbelow(nempty), local mover) of this rank's fallback movers [first, first+count) of the pass
@@ -1386,6 +1517,7 @@ MB_API int mb_reloc_fb_count(const void* shard, const uint64_t* times_sorted, in
     if (count == 0) return MB_OK;
     const int64_t nblocks = fb_num_blocks(v.local_cells);
     if ((rc = mb::check_cuda(cudaMemsetAsync(ws.fb_tot, 0, 4 * kFbBatch, stream), "memset"))) return rc;
+    if ((rc = fb_clear_supers(ws.cnt, nblocks, stream))) return rc;
     fb_count<<<(unsigned)nblocks, 256, 0, stream>>>(v, ws.cnt, ws.fb_tot, (const unsigned long long*)times_sorted,
                                                    mb::ceil_div(v.local_cells, nblocks), count);
     if ((rc = mb::check_cuda(cudaMemcpyAsync(totals, ws.fb_tot, 4 * (size_t)count, cudaMemcpyDeviceToDevice, stream), "copy"))) return rc;
@@ -1448,7 +1580,7 @@ MB_API int mb_reloc_apply(const void* shard, int phase, int64_t nmovers, uint32_
 }
 
 // Count the empties of the LOCAL table at `count` (<= 2048) ascending times into a caller-owned block-count table
-// cnt_table [2048][16384] uint32 (peer-mapped memory on a row-sharded grid: the event loop of another rank reads and
+// cnt_table [65536 + 1024][2048] uint32 (blocks, then super-blocks of 64; peer-mapped memory on a row-sharded grid: the event loop of another rank reads and
 // updates it) and totals[count].
 MB_API int mb_reloc_fb_count_into(const void* shard, const uint64_t* times_sorted, int count, uint32_t* totals,
                                   uint32_t* cnt_table, cudaStream_t stream) {
@@ -1459,6 +1591,7 @@ MB_API int mb_reloc_fb_count_into(const void* shard, const uint64_t* times_sorte
     if (count == 0) return MB_OK;
     const int64_t nblocks = fb_num_blocks(v.local_cells);
     if ((rc = mb::check_cuda(cudaMemsetAsync(totals, 0, 4 * (size_t)count, stream), "memset"))) return rc;
+    if ((rc = fb_clear_supers(cnt_table, nblocks, stream))) return rc;
     fb_count<<<(unsigned)nblocks, 256, 0, stream>>>(v, cnt_table, totals, (const unsigned long long*)times_sorted,
                                                    mb::ceil_div(v.local_cells, nblocks), count);
     MB_LAUNCH_CHECK("mb_reloc_fb_count_into");
@@ -1575,7 +1708,28 @@ MB_API int mb_schelling_relocate(int8_t* type, uint8_t* happy, uint32_t* agent_i
     // measured on 8192^2 / 15 M movers, 1 bucket 79 ms, 8 buckets 96 ms)
     int buckets = 1;
     while (buckets < 256 && nmovers / buckets > (16ll << 20)) buckets <<= 1;
+    {   // MB_RELOC_BUCKETS=n (a power of two <= 256) forces the bucket count: how the parity suite covers the bucketed path
+        static int forced = -1;
+        if (forced < 0) {
+            const char* e = getenv("MB_RELOC_BUCKETS");
+            forced = e ? atoi(e) : 0;
+        }
+        if (forced >= 1 && forced <= 256 && (forced & (forced - 1)) == 0) buckets = forced;
+    }
     int pass = 0;
+    // several buckets: group the mover indices by bucket once; a pass then walks only its bucket's list
+    unsigned long long bucket_off[257] = {0};
+    if (buckets > 1) {
+        uint64_t counts[256];
+        if ((rc = mb_reloc_bucket_lists(nmovers, buckets, counts, workspace, workspace_bytes, max_movers, stream))) return rc;
+        for (int b = 0; b < buckets; ++b) bucket_off[b + 1] = bucket_off[b] + counts[b];
+    }
+    auto run_pass = [&](int b, uint64_t t_lo, uint64_t t_hi, int mode) -> int {
+        if (buckets > 1)
+            return mb_reloc_pass_list(&d, (int64_t)bucket_off[b], (int64_t)(bucket_off[b + 1] - bucket_off[b]), seed, epoch, t_lo, t_hi,
+                                      mode, workspace, workspace_bytes, max_movers, stream);
+        return mb_reloc_pass(&d, nmovers, seed, epoch, t_lo, t_hi, mode, workspace, workspace_bytes, max_movers, stream);
+    };
     for (int b = 0; b < buckets; ++b) {
         const unsigned long long width = buckets > 1 ? (1ull << 63) / (buckets / 2) : 0ull;  // 2^64 / buckets
         const unsigned long long t_lo = buckets > 1 ? width * (unsigned long long)b : 0ull;
@@ -1589,14 +1743,14 @@ MB_API int mb_schelling_relocate(int8_t* type, uint8_t* happy, uint32_t* agent_i
         bool prefix_ok = getenv("MB_RELOC_GENERIC") == nullptr;
         bool settled = false;   // the bucket reached its fixed point by construction (no confirming iteration needed)
         if (prefix_ok) {
-            if ((rc = mb_reloc_pass(&d, nmovers, seed, epoch, t_lo, t_hi, 0, workspace, workspace_bytes, max_movers, stream))) return rc;
+            if ((rc = run_pass(b, t_lo, t_hi, 0))) return rc;
             ++pass;
             for (int guard = 0; guard < kMaxPasses; ++guard) {
                 if ((rc = read_counters(ws, hc, stream))) return rc;
                 if (hc[5] != 0 || hc[6] != 0) { prefix_ok = false; break; }   // cannot happen (no releases); be safe
                 if (guard > 0 && hc[3] == 0) break;                            // a RESUME pass changed nothing
                 if ((rc = mb_reloc_release_take(workspace, workspace_bytes, max_movers, nullptr, nullptr, 0, stream))) return rc;
-                if ((rc = mb_reloc_pass(&d, nmovers, seed, epoch, t_lo, t_hi, 1, workspace, workspace_bytes, max_movers, stream))) return rc;
+                if ((rc = run_pass(b, t_lo, t_hi, 1))) return rc;
                 ++pass;
             }
             const int64_t nfb = (int64_t)hc[2];
@@ -1641,14 +1795,14 @@ MB_API int mb_schelling_relocate(int8_t* type, uint8_t* happy, uint32_t* agent_i
                 return MB_ERR_CUDA;
             }
             if (full) {
-                if ((rc = mb_reloc_pass(&d, nmovers, seed, epoch, t_lo, t_hi, 0, workspace, workspace_bytes, max_movers, stream))) return rc;
+                if ((rc = run_pass(b, t_lo, t_hi, 0))) return rc;
             } else {
                 if ((rc = mb_reloc_release_take(workspace, workspace_bytes, max_movers, (uint64_t*)ws.rel_r_cell,
                                                 (uint64_t*)ws.rel_r_time, nrel, stream))) return rc;
                 if (nrel > 0 && (rc = mb_reloc_release_scan(&d, nmovers, seed, epoch, t_lo, t_hi, (const uint64_t*)ws.rel_r_cell,
                                                             (const uint64_t*)ws.rel_r_time, nrel, workspace, workspace_bytes,
                                                             max_movers, stream))) return rc;
-                if ((rc = mb_reloc_pass(&d, nmovers, seed, epoch, t_lo, t_hi, 1, workspace, workspace_bytes, max_movers, stream))) return rc;
+                if ((rc = run_pass(b, t_lo, t_hi, 1))) return rc;
             }
             if ((rc = read_counters(ws, hc, stream))) return rc;
             const int64_t nfb = (int64_t)hc[2];

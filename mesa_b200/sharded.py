@@ -29,7 +29,7 @@ from . import ops
 from .sharding import block_bounds
 
 _FB_BATCH = 2048     # kFbBatch of csrc/relocate.cu
-_FB_BLOCKS = 16384   # kFbBlocksMax
+_FB_BLOCKS = 65536 + 1024   # kFbBlocksMax + kFbSupersMax rows of kFbBatch words (blocks, then super-blocks)
 _OV_CAP = 4096       # kOvCap
 _NONE64 = -1  # 0xffff_ffff_ffff_ffff as int64
 
@@ -245,7 +245,28 @@ class ShardedSchelling:
             buckets = 1
             while buckets < 256 and tot_movers // (buckets * self.world) > (16 << 20):
                 buckets <<= 1
+            forced = int(os.environ.get("MB_RELOC_BUCKETS", "0") or 0)      # the parity suite forces the bucketed path
+            if 1 <= forced <= 256 and forced & (forced - 1) == 0:
+                buckets = forced
             width = (1 << 64) // buckets
+            # several buckets: the local mover indices are grouped by bucket once, a pass then walks only its bucket's list
+            # instead of scanning every mover for the 1 / buckets that take part (csrc/relocate.cu, mb_reloc_bucket_lists)
+            offsets = None
+            if buckets > 1:
+                counts = (ctypes.c_uint64 * buckets)()
+                with self._phase("bucket lists"):
+                    N.check(lib.mb_reloc_bucket_lists(movers, buckets, counts, ws, wb, mm, self._stream()))
+                offsets = [0]
+                for c in counts:
+                    offsets.append(offsets[-1] + int(c))
+
+            def run_pass(b, mode):
+                if offsets is None:
+                    N.check(lib.mb_reloc_pass(self._shard_ref, movers, seed, epoch, t_lo, t_hi, mode, ws, wb, mm, self._stream()))
+                else:
+                    N.check(lib.mb_reloc_pass_list(self._shard_ref, offsets[b], offsets[b + 1] - offsets[b], seed, epoch, t_lo, t_hi,
+                                                   mode, ws, wb, mm, self._stream()))
+
             for b in range(buckets):
                 t_lo = b * width
                 t_hi = (t_lo + width - 1) if b + 1 < buckets else (1 << 64) - 1
@@ -256,7 +277,7 @@ class ShardedSchelling:
                 settled = False      # the bucket reached its fixed point by construction (csrc/relocate.cu, same rule)
                 if prefix_ok:
                     with self._phase("FULL pass"):
-                        N.check(lib.mb_reloc_pass(self._shard_ref, movers, seed, epoch, t_lo, t_hi, 0, ws, wb, mm, self._stream()))
+                        run_pass(b, 0)
                     self.last_passes += 1
                     guard = 0
                     while True:
@@ -270,7 +291,7 @@ class ShardedSchelling:
                         guard += 1
                         with self._phase("RESUME pass"):
                             N.check(lib.mb_reloc_release_take(ws, wb, mm, None, None, 0, self._stream()))
-                            N.check(lib.mb_reloc_pass(self._shard_ref, movers, seed, epoch, t_lo, t_hi, 1, ws, wb, mm, self._stream()))
+                            run_pass(b, 1)
                         self.last_passes += 1
                     settled = prefix_ok and sum(nfb_all) == 0
                     if prefix_ok and 0 < sum(nfb_all) <= _FB_BATCH:
@@ -282,13 +303,13 @@ class ShardedSchelling:
                 while True:
                     self.last_passes += 1
                     if full:
-                        N.check(lib.mb_reloc_pass(self._shard_ref, movers, seed, epoch, t_lo, t_hi, 0, ws, wb, mm, self._stream()))
+                        run_pass(b, 0)
                     else:
                         cells, times, total = self._take_releases(nrel_all)
                         if total > 0:
                             N.check(lib.mb_reloc_release_scan(self._shard_ref, movers, seed, epoch, t_lo, t_hi, N.ptr(cells),
                                                               N.ptr(times), total, ws, wb, mm, self._stream()))
-                        N.check(lib.mb_reloc_pass(self._shard_ref, movers, seed, epoch, t_lo, t_hi, 1, ws, wb, mm, self._stream()))
+                        run_pass(b, 1)
                     nfb_all, _, _, _ = self._pass_flags()       # also: every rank's pass has finished past this point
                     if sum(nfb_all) > 0:
                         self._serve_fallback(nfb_all[self.rank], nfb_all, nempty, seed, epoch)

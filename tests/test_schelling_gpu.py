@@ -269,3 +269,18 @@ def test_relocation_with_the_confirming_iteration_gives_the_same_trajectories():
                        timeout=900, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "the confirming full iteration" not in r.stderr          # it never finds work (debug message of relocate.cu)
+
+
+def test_relocation_in_rank_ordered_buckets_gives_the_same_trajectories():
+    """MB_RELOC_BUCKETS=4 forces the path that huge grids take (> 16 M movers per GPU): the movers are processed in four
+    rank-ordered buckets through per-bucket index lists (mb_reloc_bucket_lists / mb_reloc_pass_list).  Same goldens, same
+    oracle comparisons, single-GPU and row-sharded (1-rank group) drivers."""
+    import subprocess
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, MB_RELOC_BUCKETS="4")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), os.path.join(here, "test_sharded_gpu.py"), "-q", "-x",
+                        "-m", "gpu", "-k", "matches_reference_trajectory or dense_grid or sharded_driver"], env=env,
+                       capture_output=True, text=True, timeout=900, cwd=os.path.dirname(here))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
