@@ -992,8 +992,14 @@ __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* w
     return before + incl - v;
 }
 
+// kBatched: the fallback events are taken in BATCHES of up to 32 (csrc comment "batched fallback events" below)
+constexpr int kEvBatch = 32;      // events per batch = warps of the CTA
+constexpr int kEvBmWords = 256;   // bitmap words per event: blocks of at most 8192 cells
+
+template <bool kBatched>
 __global__ void __launch_bounds__(1024, 1)
 reloc_event_loop(ShardView v, EventArgs a, uint64_t seed, uint32_t epoch) {
+    extern __shared__ __align__(16) unsigned ev_bitmaps[];   // [kEvBatch][kEvBmWords] (kBatched only)
     __shared__ unsigned long long times[kFbBatch];
     __shared__ unsigned long long pend_t[kPendCap], pend_c[kPendCap];
     __shared__ unsigned warp_sums[32];
@@ -1068,6 +1074,228 @@ reloc_event_loop(ShardView v, EventArgs a, uint64_t seed, uint32_t epoch) {
                     s_cell = probes[tid]; s_aold = sl.arr; s_vac = sl.vac;
                 }
             }
+        } else if (kBatched) {
+            // ---- batched fallback events.  One event costs a chain of dependent (on a row-sharded grid: remote) accesses --
+            // walk the owner's super-block and block counts, scan the block, claim, fix the counts -- ~28 us over NVLink,
+            // and 14 000 events of a 65536^2 step were 60 % of it.  The events are sequential only through the cells the
+            // earlier ones took, so up to 32 consecutive ones (all earlier than the first pending displaced mover) are
+            // LOCATED in parallel, one warp each, on the tables as they are (phase A: owner, super-block, block, and the
+            // block's emptiness bitmap at the event's time), and then COMMITTED in time order by warp 0 (phase B): the
+            // cells the earlier events of the batch took (at most 31, lane-resident) that the stale tables still count as
+            // empty at this event's time either lie before the block -- the pick moves that many empties further -- or
+            // inside it -- their bits are cleared.  If the corrected pick leaves the block, or a claim displaces a mover
+            // (which must act before later events), the batch ends there and the rest is located again.  The first event
+            // of a batch needs no correction, so every batch makes progress; the result is the sequential one.
+            __shared__ int b_owner[kEvBatch], b_ok[kEvBatch], s_nbatch, s_done;
+            __shared__ unsigned b_need[kEvBatch], b_ncell[kEvBatch], b_blk[kEvBatch];
+            __shared__ unsigned long long b_lo[kEvBatch];
+            const int w = tid >> 5, lane = tid & 31;
+            if (tid == 0) {
+                int nbm = a.count - i < kEvBatch ? a.count - i : kEvBatch;
+                unsigned long long bt = kNever;
+                for (int p = 0; p < s_npend; ++p) bt = pend_t[p] < bt ? pend_t[p] : bt;
+                while (nbm > 1 && times[i + nbm - 1] > bt) --nbm;
+                s_nbatch = nbm;
+            }
+            __syncthreads();
+            const int nbatch = s_nbatch;
+            // ---- phase A: warp w locates event i + w
+            if (w < nbatch) {
+                const int e = i + w;
+                const unsigned long long te = times[e];
+                unsigned long long k = a.fb_k[e];
+                int ok = 1, owner = -1;
+                {   // owner rank: first rank whose cumulative number of empties at te exceeds k
+                    unsigned long long n = lane < v.world ? (unsigned long long)a.tot[(size_t)lane * kFbBatch + e] : 0ull, incl = n;
+#pragma unroll
+                    for (int o2 = 1; o2 < 32; o2 <<= 1) {
+                        const unsigned long long x = __shfl_up_sync(0xffffffffu, incl, o2);
+                        if (lane >= o2) incl += x;
+                    }
+                    const unsigned hit = __ballot_sync(0xffffffffu, k < incl);
+                    if (hit == 0u) ok = 0;
+                    else {
+                        owner = __ffs(hit) - 1;
+                        k -= __shfl_sync(0xffffffffu, incl - n, owner);
+                    }
+                }
+                unsigned need = 0, ncell = 0, blk = 0;
+                unsigned long long glo = 0;
+                if (ok) {
+                    const long long lc = (v.row_lo(owner + 1) - v.row_lo(owner)) * v.cols;
+                    long long nb = (lc + 4095) / 4096;
+                    if (nb > kFbBlocksMax) nb = kFbBlocksMax;
+                    if (nb < 1) nb = 1;
+                    const long long bc = (lc + nb - 1) / nb;
+                    const int nsup = (int)((nb + kFbSuper - 1) / kFbSuper);
+                    // one level of the walk: `cnt_n` entries base[(first + j) * kFbBatch + e], j < cnt_n <= 1024; lane l sums the
+                    // chunk [l * per, (l + 1) * per) (all loads in flight at once), the warp finds the chunk, then its entry
+                    auto level = [&](const uint32_t* base, int first, int cnt_n, int& found, unsigned long long& kk) {
+                        const int per = (cnt_n + 31) / 32;
+                        unsigned long long mine = 0;
+                        for (int j = 0; j < per; ++j) {
+                            const int idx = lane * per + j;
+                            if (idx < cnt_n) mine += __ldcg(base + (size_t)(first + idx) * kFbBatch + e);
+                        }
+                        unsigned long long incl = mine;
+#pragma unroll
+                        for (int o2 = 1; o2 < 32; o2 <<= 1) {
+                            const unsigned long long x = __shfl_up_sync(0xffffffffu, incl, o2);
+                            if (lane >= o2) incl += x;
+                        }
+                        const unsigned hit = __ballot_sync(0xffffffffu, kk < incl);
+                        if (hit == 0u) { found = -1; return; }
+                        const int L = __ffs(hit) - 1;
+                        kk -= __shfl_sync(0xffffffffu, incl - mine, L);
+                        // the chunk of lane L, one entry per lane (per <= 32)
+                        const int idx = L * per + lane;
+                        const unsigned long long n = (lane < per && idx < cnt_n) ? (unsigned long long)__ldcg(base + (size_t)(first + idx) * kFbBatch + e) : 0ull;
+                        unsigned long long inc2 = n;
+#pragma unroll
+                        for (int o2 = 1; o2 < 32; o2 <<= 1) {
+                            const unsigned long long x = __shfl_up_sync(0xffffffffu, inc2, o2);
+                            if (lane >= o2) inc2 += x;
+                        }
+                        const unsigned hit2 = __ballot_sync(0xffffffffu, kk < inc2);
+                        if (hit2 == 0u) { found = -1; return; }
+                        const int l2 = __ffs(hit2) - 1;
+                        kk -= __shfl_sync(0xffffffffu, inc2 - n, l2);
+                        found = L * per + l2;
+                    };
+                    int super = -1, inner = -1;
+                    level(fb_sup(a.cnt[owner]), 0, nsup, super, k);
+                    if (super >= 0) {
+                        const int first = super * kFbSuper;
+                        const int in_super = (int)(nb - first < kFbSuper ? nb - first : kFbSuper);
+                        level(a.cnt[owner], first, in_super, inner, k);
+                    }
+                    if (super < 0 || inner < 0 || bc > 32 * kEvBmWords) ok = 0;
+                    else {
+                        blk = (unsigned)(super * kFbSuper + inner);
+                        need = (unsigned)k;
+                        const long long lo_c = (long long)blk * bc;
+                        const long long hi_c = lo_c + bc < lc ? lo_c + bc : lc;
+                        ncell = (unsigned)(hi_c - lo_c);
+                        glo = (unsigned long long)(v.row_lo(owner) * v.cols + lo_c);
+                        // the block's emptiness bitmap at te: 8 independent 16-byte loads per lane and round
+                        const Slot* slots = v.slots[owner] + lo_c;
+                        unsigned* bm = ev_bitmaps + (size_t)w * kEvBmWords;
+                        for (unsigned w0 = 0; w0 < (unsigned)kEvBmWords; w0 += 8) {
+                            Slot sl[8];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const unsigned c = (w0 + q) * 32u + lane;
+                                sl[q] = Slot{kNever, 0ull};
+                                if (c < ncell) sl[q] = load_slot(slots + c);
+                            }
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const unsigned bits = __ballot_sync(0xffffffffu, empty_at(sl[q], te));
+                                if (lane == q) bm[w0 + q] = bits;
+                            }
+                        }
+                    }
+                }
+                if (lane == 0) { b_owner[w] = owner; b_ok[w] = ok; b_need[w] = need; b_ncell[w] = ncell; b_blk[w] = blk; b_lo[w] = glo; }
+            }
+            __syncthreads();
+            // ---- phase B: warp 0 commits the events in time order
+            if (w == 0) {
+                unsigned long long S_cell = 0, S_vac = kNever, S_aold = 0;   // lane q: the cell event q of this batch took
+                int done = 0;
+                for (int q = 0; q < nbatch; ++q) {
+                    const unsigned long long te = times[i + q];
+                    if (!b_ok[q]) {
+                        if (q == 0 && lane == 0) s_bail = 5;
+                        break;
+                    }
+                    unsigned* bm = ev_bitmaps + (size_t)q * kEvBmWords;
+                    const unsigned long long glo = b_lo[q];
+                    const bool covered = lane < q && S_vac <= te && te <= S_aold;   // still counted as empty at te by the tables
+                    const unsigned before = __popc(__ballot_sync(0xffffffffu, covered && S_cell < glo));
+                    if (covered && S_cell >= glo && S_cell < glo + b_ncell[q]) {
+                        const unsigned pos = (unsigned)(S_cell - glo);
+                        atomicAnd(&bm[pos >> 5], ~(1u << (pos & 31u)));
+                    }
+                    __syncwarp();
+                    const unsigned need = b_need[q] + before;
+                    // the need-th set bit of the bitmap: lane l owns words 8 l .. 8 l + 7
+                    unsigned wsum = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) wsum += __popc(bm[lane * 8 + j]);
+                    unsigned incl = wsum;
+#pragma unroll
+                    for (int o2 = 1; o2 < 32; o2 <<= 1) {
+                        const unsigned x = __shfl_up_sync(0xffffffffu, incl, o2);
+                        if (lane >= o2) incl += x;
+                    }
+                    const unsigned hit = __ballot_sync(0xffffffffu, need < incl);
+                    if (hit == 0u) {            // the pick left the block: locate this event again in the next batch
+                        if (q == 0 && lane == 0) s_bail = 6;
+                        break;
+                    }
+                    const int L = __ffs(hit) - 1;
+                    unsigned left = need - __shfl_sync(0xffffffffu, incl - wsum, L);
+                    int pos = -1;
+                    if (lane == L) {
+                        for (int j = 0; j < 8 && pos < 0; ++j) {
+                            const unsigned word = bm[lane * 8 + j];
+                            const unsigned n = __popc(word);
+                            if (left < n) pos = (lane * 8 + j) * 32 + (int)__fns(word, 0u, left + 1u);
+                            else left -= n;
+                        }
+                    }
+                    pos = __shfl_sync(0xffffffffu, pos, L);
+                    const int o = b_owner[q];
+                    const unsigned long long cell = glo + (unsigned long long)pos;
+                    Slot* sp = v.slots[o] + (cell - (unsigned long long)(v.row_lo(o) * v.cols));
+                    unsigned long long aold = 0ull, vac = 0ull;
+                    if (lane == 0) aold = atomicMin(&sp->arr, te);
+                    if (lane == 1) vac = load_slot(sp).vac;
+                    aold = __shfl_sync(0xffffffffu, aold, 0);
+                    vac = __shfl_sync(0xffffffffu, vac, 1);
+                    if (aold < te || vac > te) {            // not empty at te after all: the tables and the slots disagree
+                        if (lane == 0) s_bail = 6;
+                        break;
+                    }
+                    if (lane == q) { S_cell = cell; S_vac = vac; S_aold = aold; }
+                    bool cut = false;
+                    if (lane == 0) {
+                        if (s_nov < (unsigned long long)kOvCap) { a.ov_time[s_nov] = te; a.ov_cell[s_nov] = cell; ++s_nov; }
+                        else s_bail = 7;
+                        ++s_nfb;
+                        if (aold != kNever) {
+                            if (s_npend < kPendCap) { pend_t[s_npend] = aold; pend_c[s_npend] = cell; ++s_npend; }
+                            else s_bail = 8;
+                        }
+                    }
+                    cut = aold != kNever;     // the displaced mover acts before the later events of the batch may
+                    {   // the cell stops being empty for the fallback times in (te, aold]: fix the owner's counts
+                        const unsigned blk = b_blk[q];
+                        const unsigned long long from = vac > te + 1ull ? vac : te + 1ull;
+                        const int lo = first_ge(times, a.count, from);
+                        const int hi = aold == kNever ? a.count : first_ge(times, a.count, aold + 1ull);
+                        uint32_t* cb = a.cnt[o] + (size_t)blk * kFbBatch;
+                        uint32_t* cs = fb_sup(a.cnt[o]) + (size_t)(blk / kFbSuper) * kFbBatch;
+                        for (int f = lo + lane; f < hi; f += 32) {
+                            atomicSub(cb + f, 1u);
+                            atomicSub(cs + f, 1u);
+                            a.tot[(size_t)o * kFbBatch + f] -= 1u;
+                        }
+                    }
+                    done = q + 1;
+                    __syncwarp();
+                    const int bail_now = *(volatile int*)&s_bail;    // uniform: every lane reads the shared word
+                    if (cut || bail_now) break;
+                }
+                done = __shfl_sync(0xffffffffu, done, 0);
+                if (lane == 0) s_done = done;
+            }
+            if (v.world > 1) __threadfence_system(); else __threadfence();
+            __syncthreads();
+            if (s_bail) break;
+            i += s_done;
+            continue;
         } else {
             // ---- fallback mover i: the k-th empty cell of the whole grid at its time
             if (tid == 0) {
@@ -1621,7 +1849,18 @@ MB_API int mb_reloc_event_loop(const void* shard, void* const* cnt_tables_host, 
     a.tot = totals; a.fb_t = (const unsigned long long*)fb_times; a.fb_k = (const unsigned long long*)fb_ranks;
     a.ov_time = (unsigned long long*)ov_times; a.ov_cell = (unsigned long long*)ov_cells; a.out = (unsigned long long*)out4;
     a.count = count;
-    reloc_event_loop<<<1, 1024, 0, stream>>>(v, a, seed, epoch);
+    static int batched = -1;
+    if (batched < 0) {
+        const char* e = getenv("MB_RELOC_EVENT_BATCH");     // 0: one event at a time (the first version, kept for cross-checks)
+        batched = e ? atoi(e) : 1;
+        if (batched) {
+            rc = mb::check_cuda(cudaFuncSetAttribute(reloc_event_loop<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     kEvBatch * kEvBmWords * (int)sizeof(unsigned)), "cudaFuncSetAttribute");
+            if (rc) return rc;
+        }
+    }
+    if (batched) reloc_event_loop<true><<<1, 1024, kEvBatch * kEvBmWords * sizeof(unsigned), stream>>>(v, a, seed, epoch);
+    else reloc_event_loop<false><<<1, 1024, 0, stream>>>(v, a, seed, epoch);
     MB_LAUNCH_CHECK("mb_reloc_event_loop");
     return MB_OK;
 }

@@ -136,6 +136,30 @@ def test_relocate_dense_grid_uses_argwhere_fallback():
     assert total_fb > 0
 
 
+@pytest.mark.parametrize("shape,empty_frac,h", [((256, 256), 0.09, 0.9), ((192, 320), 0.12, 1.0)])
+def test_relocate_hundreds_of_fallbacks_go_through_the_batched_event_loop(shape, empty_frac, h):
+    """A crowded grid where a few hundred movers per step miss all 50 probes (between one batch and the 2048-entry limit of
+    the event loop): the time-ordered event loop takes them in batches of up to 32 (csrc/relocate.cu), and every cell must
+    still equal the sequential oracle's."""
+    rng = np.random.default_rng(11)
+    rows, cols = shape
+    grid = rng.integers(0, 2, size=shape).astype(np.int8)
+    grid.reshape(-1)[rng.choice(rows * cols, size=int(rows * cols * empty_frac), replace=False)] = -1
+    st = oracle.SchellingState.from_type_grid(grid)
+    dev = DeviceSchelling(st, h, 1)
+    st.assign_state(h, 1)
+    dev.assign()
+    seen = []
+    for epoch in range(3):
+        movers, nfb = st.move_unhappy(21, epoch)
+        seen.append(nfb)
+        got_movers, _ = dev.move(21, epoch)
+        assert got_movers == movers
+        assert np.array_equal(dev.cells(), st.cell), epoch
+        assert st.assign_state(h, 1) == dev.assign()
+    assert max(seen) > 64 and max(seen) <= 2048, seen
+
+
 def test_relocate_full_grid_raises_value_error():
     grid = np.array([[0, 1, 0], [1, 0, 1], [0, 1, 0]], dtype=np.int8)
     st = oracle.SchellingState.from_type_grid(grid)
