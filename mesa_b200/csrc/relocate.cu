@@ -1859,7 +1859,12 @@ MB_API int mb_reloc_event_loop(const void* shard, void* const* cnt_tables_host, 
             if (rc) return rc;
         }
     }
-    if (batched) reloc_event_loop<true><<<1, 1024, kEvBatch * kEvBmWords * sizeof(unsigned), stream>>>(v, a, seed, epoch);
+    // Batches pay on one GPU (8192 x 65536 cells, 1780 events: 24 -> 14 ms) and lose on a row-sharded grid, where the 32
+    // speculative block scans of a batch are remote reads of 128 KiB each through ONE SM (65536^2 on 8 GPUs, 14 926
+    // events: 419 ms one at a time, 899 ms batched) -- MB_RELOC_EVENT_BATCH=2 forces them there (the multi-GPU parity
+    // tests pass either way)
+    if (batched >= 2 || (batched == 1 && v.world == 1))
+        reloc_event_loop<true><<<1, 1024, kEvBatch * kEvBmWords * sizeof(unsigned), stream>>>(v, a, seed, epoch);
     else reloc_event_loop<false><<<1, 1024, 0, stream>>>(v, a, seed, epoch);
     MB_LAUNCH_CHECK("mb_reloc_event_loop");
     return MB_OK;
