@@ -862,46 +862,42 @@ def other_workloads(dev):
     t = timed(m.step, 30)
     out.append({"workload": "boltzmann_1e6_agents_4096x4096", "ms_per_step": t * 1e3, "agent_updates_per_s": 1e6 / t})
     del m
-    # config 3: Boids, 10^7 agents at the reference "large" density (vision 15)
+    # config 3: Boids, 10^7 agents at the reference "large" density (vision 15).  Both variants below start from the SAME
+    # initial flock (the step gets slower as the boids cluster, so simulation time matters): 3 untimed + 16 timed steps
     N = 10_000_000
     side = 150.0 * math.sqrt(N / 400.0)
-    pos = torch.rand((N, 2), device=dev, generator=g) * side
-    dirs = torch.rand((N, 2), device=dev, generator=g) * 2 - 1
+    pos0 = torch.rand((N, 2), device=dev, generator=g) * side
+    dirs0 = torch.rand((N, 2), device=dev, generator=g) * 2 - 1
     ws = ops.CellListWorkspace(N, (side, side), 15.0, dev)
-    po, do = torch.empty_like(pos), torch.empty_like(dirs)
-    state = [pos, dirs, po, do]
+    state = [None, None, None, None]
 
-    calls = [0]
+    def boids_run(resort_every):
+        state[0], state[1] = pos0.clone(), dirs0.clone()
+        state[2], state[3] = torch.empty_like(pos0), torch.empty_like(dirs0)
+        calls = [0]
 
-    def boids():
-        # what BoidFlockers(activation="synchronous") does: every 8th step the storage order is rewritten in cell-list
-        # order (ops.boids_resort, inside the timed region), which keeps the step's gathers / scatters coalesced
-        if calls[0] % 8 == 0:
-            state[0], state[1], _, _ = ops.boids_resort(state[0], state[1], (side, side), vision=15.0, ws=ws)
-            state[2], state[3] = torch.empty_like(state[0]), torch.empty_like(state[1])
-        calls[0] += 1
-        ops.boids_step(state[0], state[1], (side, side), vision=15.0, separation=2.0, ws=ws, pos_out=state[2], dir_out=state[3])
-        state[0], state[2] = state[2], state[0]
-        state[1], state[3] = state[3], state[1]
+        def one():
+            # what BoidFlockers(activation="synchronous") does: every 8th step the storage order is rewritten in
+            # cell-list order (ops.boids_resort, inside the timed region), which keeps the gathers / scatters coalesced
+            if resort_every and calls[0] % resort_every == 0:
+                state[0], state[1], _, _ = ops.boids_resort(state[0], state[1], (side, side), vision=15.0, ws=ws)
+                state[2], state[3] = torch.empty_like(state[0]), torch.empty_like(state[1])
+            calls[0] += 1
+            ops.boids_step(state[0], state[1], (side, side), vision=15.0, separation=2.0, ws=ws, pos_out=state[2], dir_out=state[3])
+            state[0], state[2] = state[2], state[0]
+            state[1], state[3] = state[3], state[1]
 
-    for _ in range(2):
-        boids()
-    calls[0] = 0
-    t = timed(boids, 16)
+        for _ in range(3):
+            one()
+        return timed(one, 16)
+
+    t = boids_run(8)
     out.append({"workload": "boids_1e7_vision15_synchronous", "ms_per_step": t * 1e3, "agent_updates_per_s": N / t,
                 "note": "storage order re-sorted spatially every 8 steps (2 re-sorts inside the 16 timed steps)"})
-
-    def boids_unsorted():
-        ops.boids_step(state[0], state[1], (side, side), vision=15.0, separation=2.0, ws=ws, pos_out=state[2], dir_out=state[3])
-        state[0], state[2] = state[2], state[0]
-        state[1], state[3] = state[3], state[1]
-
-    shuffle = torch.randperm(N, device=dev, generator=g)
-    state[0], state[1] = state[0][shuffle].contiguous(), state[1][shuffle].contiguous()
-    del shuffle
-    t = timed(boids_unsorted, 8)
+    t = boids_run(0)
     out.append({"workload": "boids_1e7_vision15_synchronous_random_storage_order", "ms_per_step": t * 1e3,
                 "agent_updates_per_s": N / t, "note": "the round-1 figure: storage order unrelated to space"})
+    del pos0, dirs0
     # the same flock in the reference's SEQUENTIAL shuffle_do order (exact replay mode, rank-ordered chained kernel)
     reach = ops.boids_reach(state[1], 1.0)
     sws = ops.BoidsSeqWorkspace(N, (side, side), 15.0, reach, dev)

@@ -28,6 +28,29 @@ ms = e0.elapsed_time(e1) / steps
 print(json.dumps({"n": n, "side": side, "ms_per_step": ms, "agent_updates_per_s": n / ms * 1e3,
                   "mean_neighbors": float(cnt.float().mean()), "ws_MB": ws.nbytes / 1e6}))
 
+# the same with the storage order re-sorted spatially every `every` steps (what BoidFlockers(activation="synchronous") does);
+# every variant starts from the SAME initial flock (the step gets slower as the boids cluster, so simulation time matters)
+g = torch.Generator(device="cuda").manual_seed(0)
+pos0 = torch.rand((n, 2), device="cuda", generator=g) * side
+dirs0 = torch.rand((n, 2), device="cuda", generator=g) * 2 - 1
+for every in (0, 8, 4, 16, 1):
+    pos, dirs = pos0.clone(), dirs0.clone()
+    po, do = torch.empty_like(pos), torch.empty_like(dirs)
+    calls = 0
+    for timed in (False, True):        # 3 untimed steps, then `steps` timed ones
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps if timed else 3):
+            if every and calls % every == 0:
+                pos, dirs, _, _ = ops.boids_resort(pos, dirs, (side, side), vision=vision, ws=ws)
+                po, do = torch.empty_like(pos), torch.empty_like(dirs)
+            calls += 1
+            ops.boids_step(pos, dirs, (side, side), vision=vision, separation=2.0, ws=ws, pos_out=po, dir_out=do)
+            pos, po = po, pos; dirs, do = do, dirs
+        e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    print(json.dumps({"n": n, "resort_every": every, "ms_per_step": ms, "agent_updates_per_s": n / ms * 1e3}), flush=True)
+
 # sequential activation (the reference's shuffle_do semantics): passes and time per step
 if len(sys.argv) > 3 and sys.argv[3] == "seq":
     reach = ops.boids_reach(dirs, 1.0)
