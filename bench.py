@@ -700,8 +700,10 @@ def _flat_workload_keys(details):
         if name.startswith("wolf_sheep_1e6") and "ms_per_step" in w:
             flat["wolf_sheep_ms_per_step"] = w["ms_per_step"]
             flat["wolf_sheep_updates_per_s"] = w["agent_updates_per_s"]
-        if name.startswith("boids_1e7_vision15_synchronous"):
+        if name == "boids_1e7_vision15_synchronous":
             flat["boids_1e7_single_gpu_ms_per_step"] = w["ms_per_step"]
+        if name == "boids_1e7_vision15_synchronous_random_storage_order":
+            flat["boids_1e7_unsorted_ms_per_step"] = w["ms_per_step"]
         if name.startswith("boids_1e7_vision15_sequential"):
             flat["boids_1e7_sequential_ms_per_step"] = w["ms_per_step"]
     return flat
@@ -897,8 +899,15 @@ def other_workloads(dev):
     t = boids_run(0)
     out.append({"workload": "boids_1e7_vision15_synchronous_random_storage_order", "ms_per_step": t * 1e3,
                 "agent_updates_per_s": N / t, "note": "the round-1 figure: storage order unrelated to space"})
+    # the same flock in the reference's SEQUENTIAL shuffle_do order (exact replay mode, rank-ordered chained kernel), from
+    # the same point of the simulation as round 1 measured it (12 synchronous steps after the start)
+    state[0], state[1] = pos0.clone(), dirs0.clone()
+    state[2], state[3] = torch.empty_like(pos0), torch.empty_like(dirs0)
+    for _ in range(12):
+        ops.boids_step(state[0], state[1], (side, side), vision=15.0, separation=2.0, ws=ws, pos_out=state[2], dir_out=state[3])
+        state[0], state[2] = state[2], state[0]
+        state[1], state[3] = state[3], state[1]
     del pos0, dirs0
-    # the same flock in the reference's SEQUENTIAL shuffle_do order (exact replay mode, rank-ordered chained kernel)
     reach = ops.boids_reach(state[1], 1.0)
     sws = ops.BoidsSeqWorkspace(N, (side, side), 15.0, reach, dev)
     epoch = [0]

@@ -15,7 +15,12 @@
  *     failure on the calling thread is mb_last_error() (valid until the next call);
  *   - `const T*` / `T*` buffer arguments are DEVICE pointers unless the name ends in `_host`;
  *   - the library never allocates, frees or retains device memory and never calls NCCL;
- *   - work is enqueued on `stream` (a cudaStream_t passed as void*), no implicit sync;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*) and the call returns without waiting for it.  The
+ *     exceptions say "synchronises" in their comment -- they hand a data-dependent size or flag back to the host:
+ *     mb_schelling_relocate and the mb_reloc_counters / mb_reloc_bucket_lists phases (mover counts, per-pass flags of
+ *     the fixed point on large grids), mb_boids_step_seq_f32 (reads back its error word: a boid that moved farther
+ *     than `reach` invalidates the schedule), mb_boltzmann_status.  The single-launch step of small Schelling grids
+ *     (mb_schelling_step_small), the Boltzmann step, every stencil / layer / query kernel never synchronise;
  *   - grids are C-order [rows, cols] = [d0, d1] of Grid((d0, d1)) (grid.py:74-82, :146), so the
  *     flat cell id is i*cols + j = index into Grid._celllist (grid.py:120-126).
  */

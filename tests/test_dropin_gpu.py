@@ -265,9 +265,12 @@ def test_example_boids_matches_oracle():
     for _ in range(3):
         m.step()
         wp, wd, _ = oracle.boids_step(pos, dirs, m.space.size, vision=10.0, separation=2.0)
-        got_p, got_d = m.agents.get("position").cpu().numpy(), m.agents.get("direction").cpu().numpy()
+        # the synchronous model keeps its storage spatially sorted (resort_every): rows are found through the unique ids
+        by_id = np.argsort(m.agents.unique_ids().cpu().numpy())
+        got_p, got_d = m.agents.get("position").cpu().numpy()[by_id], m.agents.get("direction").cpu().numpy()[by_id]
         assert np.max(np.abs(got_p - wp) / m.space.size) <= 1e-5 and np.max(np.abs(got_d - wd)) <= 1e-5
         pos, dirs = got_p.copy(), got_d.copy()
+    assert m.resort_every == 8 and not np.array_equal(by_id, np.arange(500))       # the first step re-sorted the rows
     assert m.agent_angles.shape == (500,) and -np.pi <= m.average_heading <= np.pi
 
 
