@@ -349,9 +349,22 @@ boltz_iterate(BoltzWs ws, const unsigned long long* __restrict__ cand_count, uns
     if (blockIdx.x == 0 && threadIdx.x == 0 && iterations_out != nullptr) *iterations_out = round + 1u;
 }
 
-__global__ void boltz_apply(int32_t* __restrict__ wealth, uint32_t* __restrict__ cell, int64_t n, BoltzWs ws) {
+// + the bookkeeping that used to be five more stream operations per step: this step's arrival order becomes next step's
+// "still sitting here" order (keysA / valsA), and the words the NEXT step expects cleared (crowded-cell queue length,
+// candidate count, barrier words, the occupancy filter) are cleared here, after their last reader
+__global__ void boltz_apply(int32_t* __restrict__ wealth, uint32_t* __restrict__ cell, int64_t n, BoltzWs ws,
+                            const uint64_t* __restrict__ keysB, const uint32_t* __restrict__ valsB) {
     const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a == 0) {
+        ws.counters[1] = 0ull;
+        ws.counters[kCounterWords - 3] = 0ull; ws.counters[kCounterWords - 2] = 0ull; ws.counters[kCounterWords - 1] = 0ull;
+    }
+    const int64_t total = (int64_t)gridDim.x * blockDim.x;
+    const int64_t occ_words = ((int64_t)ws.occ_mask + 1) / 32;
+    for (int64_t i = a; i < occ_words; i += total) ws.occA[i] = 0u;
     if (a >= n) return;
+    ws.keysA[a] = keysB[a];
+    ws.valsA[a] = valsB[a];
     cell[a] = ws.new_cell[a];
     if (ws.gives[a]) {
         atomicAdd(&wealth[ws.target[a]], 1);
@@ -389,6 +402,7 @@ MB_API int mb_boltzmann_init(const uint32_t* cell, int64_t n, int64_t rows, int6
     }
     int rc0 = mb::check_cuda(cudaMemsetAsync(ws.counters, 0, 8 * kCounterWords, stream), "memset");   // status word, queue
     if (rc0) return rc0;
+    if ((rc0 = mb::check_cuda(cudaMemsetAsync(ws.occA, 0, ((size_t)ws.occ_mask + 1) / 8, stream), "memset"))) return rc0;
     const unsigned blocks = (unsigned)mb::ceil_div(n, 256);
     init_keys<<<blocks, 256, 0, stream>>>(cell, n, ws.keys0, ws.vals0);
     const int where = mb::radix_sort_pairs<uint64_t>(ws.keys0, ws.vals0, ws.keys1, ws.vals1, n, 32, sort_bits(rows * cols),
@@ -423,10 +437,9 @@ MB_API int mb_boltzmann_step(uint32_t* cell, int32_t* wealth, int64_t n, int64_t
     unsigned long long* longs = ws.counters + 1;
     unsigned* sync = reinterpret_cast<unsigned*>(ws.counters + kCounterWords - 2);
     unsigned long long* cand_count = ws.counters + kCounterWords - 3;
-    int rc = mb::check_cuda(cudaMemsetAsync(longs, 0, 8, stream), "memset");
-    if (rc) return rc;
-    if ((rc = mb::check_cuda(cudaMemsetAsync(cand_count, 0, 8 + 16, stream), "memset"))) return rc;   // candidate count + sync words
-    if ((rc = mb::check_cuda(cudaMemsetAsync(ws.occA, 0, ((size_t)ws.occ_mask + 1) / 8, stream), "memset"))) return rc;
+    // (the queue length, the candidate count, the barrier words and the occupancy filter are clear: mb_boltzmann_init /
+    // the previous step's boltz_apply)
+    int rc = MB_OK;
     const unsigned blocks = (unsigned)mb::ceil_div(n, 256);
     boltz_move<<<blocks, 256, 0, stream>>>(cell, n, (int)rows, (int)cols, torus, seed, epoch, ws);
     // sparse grids sort on the cell bits only and order the (short) runs of equal cells afterwards; crowded grids
@@ -454,12 +467,8 @@ MB_API int mb_boltzmann_step(uint32_t* cell, int32_t* wealth, int64_t n, int64_t
     int64_t grid = mb::ceil_div(n, 1024 * 4);
     if (grid > mb::sm_count()) grid = mb::sm_count();
     boltz_iterate<<<(unsigned)grid, 1024, 0, stream>>>(ws, cand_count, sync, iterations_dev);
-    boltz_apply<<<blocks, 256, 0, stream>>>(wealth, cell, n, ws);
-    // this step's arrival order is next step's "still sitting here" order
-    rc = mb::check_cuda(cudaMemcpyAsync(ws.keysA, keysB, 8 * n, cudaMemcpyDeviceToDevice, stream), "copy");
-    if (rc) return rc;
-    rc = mb::check_cuda(cudaMemcpyAsync(ws.valsA, valsB, 4 * n, cudaMemcpyDeviceToDevice, stream), "copy");
-    if (rc) return rc;
+    boltz_apply<<<blocks, 256, 0, stream>>>(wealth, cell, n, ws, keysB, valsB);
+    (void)rc;
     MB_LAUNCH_CHECK("mb_boltzmann_step");
     return MB_OK;
 }

@@ -1,5 +1,6 @@
 // Stable LSD radix sort of (key, uint32) pairs -- see sort.cuh.
 #include "sort.cuh"
+#include <stdlib.h>
 
 namespace mb {
 namespace {
@@ -185,6 +186,214 @@ sort_scatter(const K* __restrict__ keys_in, const uint32_t* __restrict__ vals_in
     }
 }
 
+
+// ---- ONE SWEEP per digit (decoupled look-back) ----------------------------------------------------------------------------
+// The three launches per digit above (tile histograms, their scan -- itself three launches --, scatter) read the keys twice
+// and cost five launch gaps per digit: at 10^6 keys (Boltzmann: one sort per step) the gaps ARE the sort.  Here the digit
+// histograms of ALL passes come from one read of the keys (sort_hist_all), and a pass is ONE kernel: a CTA takes its tile
+// from a ticket counter (so every tile with a lower number is already running or done), ranks its keys exactly as
+// sort_scatter does, publishes its 256 digit counts (flag AGGREGATE), and thread d sums the counts of the preceding tiles
+// backwards until it meets a tile that has published its INCLUSIVE prefix, then publishes its own -- flag and 30-bit count
+// share one word, so plain relaxed loads / stores are enough.  The walk reads kLookWin predecessors per round trip (the
+// first wave starts in lock-step: one predecessor per L2 latency would cost ~sqrt(2 x tiles) latencies).
+// Tiles are numbered in input order and the walk adds lower tiles only: the sort stays stable.
+constexpr uint32_t kFlagAgg = 1u << 30, kFlagPre = 2u << 30, kCntMask = (1u << 30) - 1u;
+constexpr int kLookWin = 8;
+constexpr int kMaxPasses = 8;
+constexpr unsigned kSpinLimit = 1u << 26;   // polls of one status word before the kernel gives up (error word, no hang)
+
+__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// head of the one-sweep workspace: [kMaxPasses][kRadix] digit totals, then kMaxPasses tickets, then one error word
+constexpr int kHeadWords = kMaxPasses * kRadix + kMaxPasses + 8;
+
+template <typename K>
+__global__ void __launch_bounds__(kSortThreads)
+sort_hist_all(const K* __restrict__ keys, int64_t n, int begin_bit, int passes, uint32_t* __restrict__ ghist,
+              uint32_t* __restrict__ status0, int64_t status_words) {
+    __shared__ unsigned sh[kMaxPasses][kRadix];
+    for (int p = 0; p < passes; ++p) sh[p][threadIdx.x] = 0u;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * kSortThreads;
+    const int64_t first = (int64_t)blockIdx.x * kSortThreads + threadIdx.x;
+    for (int64_t i = first; i < n; i += stride) {
+        const K k = keys[i];
+        for (int p = 0; p < passes; ++p) atomicAdd(&sh[p][(unsigned)(k >> (begin_bit + 8 * p)) & 0xffu], 1u);
+    }
+    for (int64_t i = first; i < status_words; i += stride) status0[i] = 0u;   // the first pass's tile states
+    __syncthreads();
+    for (int p = 0; p < passes; ++p) {
+        const unsigned c = sh[p][threadIdx.x];
+        if (c) atomicAdd(&ghist[p * kRadix + threadIdx.x], c);
+    }
+}
+
+template <typename K, int kItems>   // kItems elements per thread: 16 (tiles of 4096), 8 for small inputs (more, shorter CTAs)
+__global__ void __launch_bounds__(kSortThreads, sizeof(K) == 4 ? 4 : 3)
+sort_onesweep(const K* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, K* __restrict__ keys_out,
+              uint32_t* __restrict__ vals_out, int64_t n, int bit, const uint32_t* __restrict__ ghist,
+              uint32_t* __restrict__ ticket, uint32_t* __restrict__ status, uint32_t* __restrict__ status_next,
+              uint32_t* __restrict__ error_word) {
+    // Ranking: warp w owns the contiguous 512 elements [512 w, 512 (w + 1)) of the tile (item i of lane l = element
+    // 512 w + 32 i + l) and keeps PRIVATE digit counters wcount[w][.]: the lanes holding one digit find each other with
+    // match_any, their leader advances the warp's counter and hands the old value out -- no block barrier inside the
+    // item loop (the three-launch kernel above pays three per item).  One pass over the 8 x 256 counters afterwards
+    // turns them into exclusive offsets across warps; (warp, item, lane) order = input order, so the sort is stable.
+    __shared__ unsigned gbase[kRadix];                  // global slot of this tile's first element of each digit
+    __shared__ unsigned lbase[kRadix];                  // position of that element in the reordered tile
+    __shared__ unsigned wcount[kWarpsPerCta][kRadix];   // per-warp digit counts, then exclusive offsets across warps
+    __shared__ unsigned wsum[kWarpsPerCta];
+    __shared__ unsigned s_tile;
+    extern __shared__ __align__(16) unsigned char tile_raw[];
+    K* skey = reinterpret_cast<K*>(tile_raw);
+    uint32_t* sval = reinterpret_cast<uint32_t*>(tile_raw + sizeof(K) * kSortThreads * kItems);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+#pragma unroll
+    for (int w = 0; w < kWarpsPerCta; ++w) wcount[w][tid] = 0u;
+    unsigned dbase;                                     // first global slot of digit `tid`: exclusive scan of the digit totals
+    {
+        const unsigned c = ghist[tid];
+        unsigned incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();                                // (also publishes s_tile and the cleared counters)
+        unsigned off = 0;
+        for (int w = 0; w < warp; ++w) off += wsum[w];
+        dbase = off + incl - c;
+    }
+    const int64_t tile = (int64_t)s_tile;
+    if (status_next != nullptr) status_next[tile * kRadix + tid] = 0u;   // the next pass's tile states (other buffer)
+    constexpr int kTile = kSortThreads * kItems;
+    const int64_t tile0 = tile * kTile;
+    const int tile_n = (int)(n - tile0 < kTile ? n - tile0 : kTile);
+    constexpr int kWarpItems = kItems * 32;
+    const int wbase = warp * kWarpItems + lane;
+    K key[kItems];
+    uint32_t val[kItems];
+    unsigned where[kItems];  // digit | slot within (digit, warp) << 8
+    if (tile_n == kTile) {                             // (CTA-uniform) a full tile: no bound checks
+        const K* kp = keys_in + tile0 + wbase;
+        const uint32_t* vp = vals_in + tile0 + wbase;
+#pragma unroll
+        for (int i = 0; i < kItems; ++i) {
+            key[i] = kp[i * 32];
+            val[i] = vp[i * 32];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kItems; ++i) {
+            const int s = wbase + i * 32;
+            key[i] = s < tile_n ? keys_in[tile0 + s] : (K)0;
+            val[i] = s < tile_n ? vals_in[tile0 + s] : 0u;
+        }
+    }
+    unsigned* mine = wcount[warp];
+#pragma unroll
+    for (int i = 0; i < kItems; ++i) {
+        const bool valid = wbase + i * 32 < tile_n;
+        const unsigned digit = valid ? (unsigned)(key[i] >> bit) & 0xffu : 0xffffffffu;  // invalid lanes match nobody real
+        const unsigned peers = __match_any_sync(0xffffffffu, digit);
+        const unsigned rank = __popc(peers & lt_mask);
+        unsigned old = 0u;
+        if (valid && rank == 0) {
+            old = mine[digit];
+            mine[digit] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1);
+        where[i] = (digit & 0xffu) | ((old + rank) << 8);
+        __syncwarp();
+    }
+    __syncthreads();
+    // ---- counts of digit `tid` per warp -> exclusive offsets across warps, the tile's count
+    unsigned count = 0u;
+#pragma unroll
+    for (int w = 0; w < kWarpsPerCta; ++w) {
+        const unsigned c = wcount[w][tid];
+        wcount[w][tid] = count;
+        count += c;
+    }
+    // ---- publish the tile's digit counts at once (the tiles behind this one can go on with them) ...
+    st_relaxed(status + tile * kRadix + tid, (tile > 0 ? kFlagAgg : kFlagPre) | count);
+    {   // lbase = exclusive scan of the tile's digit counts (256 counters, one per thread)
+        unsigned incl = count;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        __syncthreads();                                // wsum of the digit-total scan has been read by everyone
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        unsigned off = 0;
+        for (int w = 0; w < warp; ++w) off += wsum[w];
+        lbase[tid] = off + incl - count;
+    }
+    __syncthreads();
+    // ... reorder the tile in shared memory (needs local offsets only; frees the registers of the elements) ...
+#pragma unroll
+    for (int i = 0; i < kItems; ++i) {
+        if (wbase + i * 32 < tile_n) {
+            const unsigned d = where[i] & 0xffu;
+            const unsigned pos = lbase[d] + mine[d] + (where[i] >> 8);
+            skey[pos] = key[i];
+            sval[pos] = val[i];
+        }
+    }
+    // ... and only then sum the preceding tiles (look-back) and publish the inclusive prefix.  (A window of 32 tiles per
+    // round trip instead of 8 changed nothing at 10^6 pairs and cost 30 registers: the walk is not what bounds the kernel.)
+    unsigned excl = 0u;
+    if (tile > 0) {
+        int64_t s = tile - 1;
+        bool found = false;
+        unsigned spins = 0u;
+        while (!found) {
+            uint32_t v[kLookWin];
+#pragma unroll
+            for (int q = 0; q < kLookWin; ++q)
+                v[q] = s - q >= 0 ? ld_relaxed(status + (s - q) * kRadix + tid) : kFlagPre;   // before tile 0: prefix 0
+            int advanced = 0;
+#pragma unroll
+            for (int q = 0; q < kLookWin; ++q) {
+                if (found || advanced != q) continue;   // stop at the first tile that has not published yet
+                const uint32_t f = v[q] >> 30;
+                if (f == 0u) continue;
+                excl += v[q] & kCntMask;
+                found = f == 2u;
+                ++advanced;
+            }
+            s -= advanced;
+            if (advanced == 0 && ++spins > kSpinLimit) { *error_word = 1u; break; }
+        }
+        st_relaxed(status + tile * kRadix + tid, kFlagPre | (excl + count));
+    }
+    gbase[tid] = dbase + excl;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kItems; ++i) {
+        const int s = i * kSortThreads + tid;
+        if (s < tile_n) {
+            const K k = skey[s];
+            const unsigned digit = (unsigned)(k >> bit) & 0xffu;
+            const unsigned dst = gbase[digit] + ((unsigned)s - lbase[digit]);
+            keys_out[dst] = k;
+            vals_out[dst] = sval[s];
+        }
+    }
+}
+
 }  // namespace
 
 // small inputs (<= 32 chunks): ONE CTA walks the chunks with a running carry -- one launch instead of three
@@ -247,12 +456,48 @@ int radix_sort_pairs(K* k0, uint32_t* v0, K* k1, uint32_t* v1, int64_t n, int be
         if (check_cuda(cudaFuncSetAttribute(sort_scatter<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem),
                        "radix_sort_pairs") != MB_OK)
             return MB_ERR_CUDA;
+        if (check_cuda(cudaFuncSetAttribute(sort_onesweep<K, kSortItems>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem),
+                       "radix_sort_pairs") != MB_OK)
+            return MB_ERR_CUDA;
         attr_set = true;
     }
-    uint32_t* hist = reinterpret_cast<uint32_t*>(workspace);
     K* ks[2] = {k0, k1};
     uint32_t* vs[2] = {v0, v1};
     int cur = 0;
+    const int passes = (end_bit - begin_bit + 7) / 8;
+    static int legacy = -1;   // MB_SORT_LEGACY=1: the three-launch passes (cross-checks)
+    if (legacy < 0) {
+        const char* e = getenv("MB_SORT_LEGACY");
+        legacy = e ? atoi(e) : 0;
+    }
+    if (!legacy && n < (1ll << 30) && passes <= kMaxPasses) {
+        // one sweep per digit: [head: digit totals of every pass, tickets, error word][tile states A][tile states B]
+        // small inputs take tiles of 2048: one wave of 4096-element tiles leaves SMs idle and is as long as its slowest CTA
+        const bool small = false;   // (tiles of 2048 for n <= 1.2 M measured SLOWER: twice the tiles to look back over)
+        const int64_t stiles = small ? ceil_div(n, (int64_t)kSortTile / 2) : tiles;
+        uint32_t* head = reinterpret_cast<uint32_t*>(workspace);
+        uint32_t* st[2] = {head + kHeadWords, head + kHeadWords + (int64_t)kRadix * stiles};
+        if (check_cuda(cudaMemsetAsync(head, 0, sizeof(uint32_t) * kHeadWords, stream), "radix_sort_pairs") != MB_OK) return MB_ERR_CUDA;
+        const int64_t want = ceil_div(n, (int64_t)kSortThreads * 8);
+        const int64_t cap = (int64_t)sm_count() * 8;
+        sort_hist_all<K><<<(unsigned)(want < cap ? want : cap), kSortThreads, 0, stream>>>(ks[cur], n, begin_bit, passes, head, st[0],
+                                                                                       (int64_t)kRadix * stiles);
+        for (int p = 0; p < passes; ++p) {
+            uint32_t* nxt = p + 1 < passes ? st[(p + 1) & 1] : nullptr;
+            if (small)
+                sort_onesweep<K, kSortItems / 2><<<(unsigned)stiles, kSortThreads, tile_smem / 2, stream>>>(
+                    ks[cur], vs[cur], ks[cur ^ 1], vs[cur ^ 1], n, begin_bit + 8 * p, head + p * kRadix, head + kMaxPasses * kRadix + p,
+                    st[p & 1], nxt, head + kMaxPasses * kRadix + kMaxPasses);
+            else
+                sort_onesweep<K, kSortItems><<<(unsigned)stiles, kSortThreads, tile_smem, stream>>>(
+                    ks[cur], vs[cur], ks[cur ^ 1], vs[cur ^ 1], n, begin_bit + 8 * p, head + p * kRadix, head + kMaxPasses * kRadix + p,
+                    st[p & 1], nxt, head + kMaxPasses * kRadix + kMaxPasses);
+            cur ^= 1;
+        }
+        if (check_cuda(cudaGetLastError(), "radix_sort_pairs") != MB_OK) return MB_ERR_CUDA;
+        return cur;
+    }
+    uint32_t* hist = reinterpret_cast<uint32_t*>(workspace);
     for (int bit = begin_bit; bit < end_bit; bit += 8) {
         sort_hist<K><<<(unsigned)tiles, kSortThreads, 0, stream>>>(ks[cur], n, bit, hist, tiles);
         if (exclusive_scan_u32(hist, (int64_t)kRadix * tiles, hist + (int64_t)kRadix * tiles, stream) != MB_OK) return MB_ERR_CUDA;

@@ -21,11 +21,15 @@ constexpr int kRadix = 256;
 
 inline int64_t sort_num_tiles(int64_t n) { return ceil_div(n > 0 ? n : 1, kSortTile); }
 
-// workspace: histogram [kRadix][tiles] uint32 (digit-major so one scan orders digits first) + one sum per
-// 4096-counter scan chunk
+// workspace: the larger of
+//   one-sweep passes (sort.cu): digit totals of up to 8 passes + tickets (2120 words), two [tiles][kRadix] tile-state arrays
+//   three-launch passes (n >= 2^30, MB_SORT_LEGACY): histogram [kRadix][tiles] uint32 (digit-major so one scan orders digits
+//   first) + one sum per 4096-counter scan chunk
 inline size_t sort_workspace_bytes(int64_t n) {
     const size_t total = (size_t)kRadix * (size_t)sort_num_tiles(n);
-    return sizeof(uint32_t) * (total + (total + 4095) / 4096 + 64) + 256;
+    const size_t legacy = total + (total + 4095) / 4096 + 64;
+    const size_t sweep = 2 * (2 * total + (size_t)kRadix) + 2120;   // (small inputs: tiles of half the size)
+    return sizeof(uint32_t) * (legacy > sweep ? legacy : sweep) + 256;
 }
 
 // Sort n pairs on key bits [begin_bit, end_bit).  Ping-pongs between (k0,v0) and (k1,v1);
