@@ -418,6 +418,27 @@ int mb_ws_wolf_apply(int32_t* cell, double* energy, const int64_t* uid, int64_t 
                      double p_reproduce, uint8_t* dead, uint8_t* repro, uint64_t* prio, mb_stream_t stream);
 int mb_ws_regrow(uint8_t* grown, int32_t* regrow_at, int64_t ncells, int32_t now, mb_stream_t stream);
 
+/* ---- Epstein civil violence (csrc/epstein.cu) -----------------------------------------------------------------------
+ * replaces, for one model step, mesa/examples/advanced/epstein_civil_violence/model.py:100-117
+ * `self.agents.shuffle_do("step")` over citizens and cops with agents.py:14-26 (update_neighbors / move: radius-`vision`
+ * neighbourhood in BFS order, is_empty filtering), agents.py:66-103 (Citizen.step) and agents.py:124-140 (Cop.step), in the
+ * reference's sequential semantics (rank-ordered dependency graph, one launch).
+ *   occ[width * height] int32: -1 = empty cell, else agent << 2 | cop << 1 | active (flat cell = x * height + y);
+ *   kind 0 citizen / 1 cop; state = CitizenState value (1 ACTIVE, 2 QUIET, 3 ARRESTED; cops 0);
+ *   voff [nv][2] int16: neighbourhood offsets (dx, dy) in the order of Cell._neighborhood (cell.py:240-276);
+ *   woff [nw][2] int16: every offset within 2 * vision (dependency range); ptab [nv + 1]: 1 - exp(-k * m), m = 0 .. nv;
+ *   sequential != 0: registration order (`agents.do("step")`, activation_order "Sequential") instead of the Philox order;
+ *   counts_dev (device, 4 x uint32, optional): status (0 = valid), ACTIVE, QUIET, ARRESTED citizens after the step.
+ * Both dimensions must be >= 2 * vision + 1 (a torus on which the neighbourhood does not wrap onto itself; the caller checks). */
+int mb_epstein_workspace_bytes(int64_t n, int64_t ncells, size_t* out);
+int mb_epstein_build_occ(const int32_t* cell, const uint8_t* kind, const uint8_t* state, int64_t n, int32_t* occ,
+                         int64_t ncells, mb_stream_t stream);
+int mb_epstein_step(int32_t* occ, int32_t* cell, const uint8_t* kind, uint8_t* state, int32_t* jail,
+                    const double* risk_aversion, const double* grievance, double* arrest_probability, int64_t n,
+                    int64_t width, int64_t height, const int16_t* voff, int nv, const int16_t* woff, int nw,
+                    const double* ptab, int max_jail_term, double threshold, int movement, int sequential, uint64_t seed,
+                    uint32_t epoch, uint32_t* counts_dev, void* workspace, size_t workspace_bytes, mb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -593,6 +593,59 @@ def wolf_sheep_fixtures():
     wolf_sheep_fixture("wolf_sheep_9x7_nograss.npz", 7, 9, 60, 6, 15, 5, 19, grass=False, sheep_reproduce=0.3)
 
 
+def epstein_fixture(name, width, height, steps, mt_seed, philox_seed, **params):
+    """The unmodified EpsteinCivilViolence model (examples/advanced/epstein_civil_violence) under the replayed order / draws:
+    after every step every agent's cell, state, jail sentence and arrest probability (rows = unique_id - 1)."""
+    from mesa.examples.advanced.epstein_civil_violence.agents import Citizen, Cop
+    from mesa.examples.advanced.epstein_civil_violence.model import EpsteinCivilViolence, EpsteinScenario
+
+    with patched_model_random(philox_seed):
+        m = EpsteinCivilViolence(width=width, height=height, scenario=EpsteinScenario(rng=mt_seed, **params))
+    rng = m.random
+    assert isinstance(rng, ReplayRandom)
+    W, H = m.grid.dimensions
+    agents = sorted(m.agents, key=lambda a: a.unique_id)
+    assert [a.unique_id for a in agents] == list(range(1, len(agents) + 1))
+
+    def table():
+        cell = np.array([a.cell.coordinate[0] * H + a.cell.coordinate[1] for a in agents], dtype=np.int64)
+        state = np.array([a.state.value if isinstance(a, Citizen) else 0 for a in agents], dtype=np.int8)
+        jail = np.array([a.jail_sentence if isinstance(a, Citizen) else 0 for a in agents], dtype=np.int64)
+        ap = np.array([np.nan if getattr(a, "arrest_probability", None) is None else a.arrest_probability for a in agents],
+                      dtype=np.float64)
+        return cell, state, jail, ap
+
+    sc = m.scenario
+    out = {"width": W, "height": H, "steps": steps, "mt_seed": mt_seed, "philox_seed": np.uint64(philox_seed),
+           "moore": sc.grid_type == "Moore", "vision": sc.cop_vision, "legitimacy": sc.legitimacy,
+           "max_jail_term": sc.max_jail_term, "active_threshold": sc.active_threshold,
+           "arrest_prob_constant": sc.arrest_prob_constant, "movement": sc.movement,
+           "citizen_density": sc.citizen_density, "cop_density": sc.cop_density,
+           "kind": np.array([isinstance(a, Cop) for a in agents], dtype=np.int8),
+           "hardship": np.array([getattr(a, "hardship", 0.0) for a in agents], dtype=np.float64),
+           "risk_aversion": np.array([getattr(a, "risk_aversion", 0.0) for a in agents], dtype=np.float64)}
+    out["cell_0"], out["state_0"], out["jail_0"], _ = table()
+    rng.replay = True
+    with activation_context(Citizen, "step"), activation_context(Cop, "step"):
+        for s in range(1, steps + 1):
+            m.step()
+            out[f"cell_{s}"], out[f"state_{s}"], out[f"jail_{s}"], out[f"ap_{s}"] = table()
+    rng.replay = False
+    out["counts"] = m.datacollector.get_model_vars_dataframe().to_numpy()
+    np.savez_compressed(os.path.join(GOLDEN, name), **out)
+    print(name, len(agents), "agents; active / quiet / arrested:", [tuple(r) for r in out["counts"][[0, 1, steps // 2, steps]]])
+
+
+def epstein_fixtures():
+    epstein_fixture("epstein_40x40.npz", 40, 40, 12, 42, 31)                                  # the scenario's defaults (von Neumann, vision 7)
+    epstein_fixture("epstein_30x22_lively.npz", 30, 22, 25, 3, 32, legitimacy=0.55, max_jail_term=6, cop_density=0.04,
+                    cop_vision=4, citizen_vision=4)                                            # rebellions flare up and are put down
+    epstein_fixture("epstein_17x19_moore.npz", 17, 19, 15, 5, 33, grid_type="Moore", cop_vision=3, citizen_vision=3,
+                    legitimacy=0.6, max_jail_term=3, citizen_density=0.8, cop_density=0.1)     # Moore, crowded: few empty cells
+    epstein_fixture("epstein_16x16_still.npz", 16, 16, 8, 7, 34, movement=False, legitimacy=0.5, max_jail_term=4,
+                    cop_vision=2, citizen_vision=2)                                            # nobody moves
+
+
 def main():
     import_reference()
     os.makedirs(GOLDEN, exist_ok=True)
@@ -617,6 +670,9 @@ def main():
         return
     if only == "wolf_sheep":
         wolf_sheep_fixtures()
+        return
+    if only == "epstein":
+        epstein_fixtures()
         return
     if only == "boltzmann":
         boltzmann_fixture("boltzmann_100_10x10.npz", 100, 10, 10, 25, 42, 3)      # reference "small"
@@ -647,6 +703,7 @@ def main():
     boltzmann_fixture("boltzmann_2000_20x30.npz", 2000, 20, 30, 10, 7, 4)
     boltzmann_fixture("boltzmann_10000_100x100.npz", 10000, 100, 100, 10, 1, 5)
     wolf_sheep_fixtures()
+    epstein_fixtures()
     # BASELINE.json configs[0]: 100x100, density 0.8, 100 steps (h=0.4, r=1)
     schelling_fixture("schelling_100x100_c1.npz", 100, 100, 0.8, 0.4, 1, 100, 42, 7, full_steps=[1, 2, 10, 50, 100])
     # the reference's own "large" benchmark variant (benchmarks/configurations.py:42-49)
