@@ -700,6 +700,11 @@ def _flat_workload_keys(details):
         if name.startswith("wolf_sheep_1e6") and "ms_per_step" in w:
             flat["wolf_sheep_ms_per_step"] = w["ms_per_step"]
             flat["wolf_sheep_updates_per_s"] = w["agent_updates_per_s"]
+        if name == "epstein_1024x1024_vision7" and "ms_per_step" in w:
+            flat["epstein_1024_ms_per_step"] = w["ms_per_step"]
+            flat["epstein_1024_updates_per_s"] = w["agent_updates_per_s"]
+        if name == "epstein_40x40_vision7" and "ms_per_step" in w:
+            flat["epstein_40_ms_per_step"] = w["ms_per_step"]
         if name == "boids_1e7_vision15_synchronous":
             flat["boids_1e7_single_gpu_ms_per_step"] = w["ms_per_step"]
         if name == "boids_1e7_vision15_synchronous_random_storage_order":
@@ -858,6 +863,30 @@ def other_workloads(dev):
         del ws_m
     except Exception as exc:  # reported, never fatal
         out.append({"workload": "wolf_sheep", "error": repr(exc)[:200]})
+    # Epstein civil violence (radius-7 von Neumann neighbourhoods, citizens + cops in one sequential activation)
+    try:
+        import numpy as np
+
+        from mesa_b200.examples.epstein_civil_violence import EpsteinCivilViolence, EpsteinScenario
+
+        for side in (40, 1024):
+            rs = np.random.default_rng(1)
+            u = rs.random(side * side)
+            occupied = np.flatnonzero(u < 0.774)                       # the scenario's densities: 0.7 citizens + 0.074 cops
+            kind = (u[occupied] >= 0.7).astype(np.uint8)
+            init = {"kind": kind, "cell": occupied, "hardship": np.where(kind == 0, rs.random(len(kind)), 0.0),
+                    "risk_aversion": np.where(kind == 0, rs.random(len(kind)), 0.0)}
+            em = EpsteinCivilViolence(side, side, EpsteinScenario(rng=1), initial_state=init)
+            for _ in range(3):
+                em.agents.shuffle_do("step")
+            t = timed(lambda: em.agents.shuffle_do("step"), 20)
+            out.append({"workload": f"epstein_{side}x{side}_vision7", "ms_per_step": t * 1e3, "agents": em.agents.n,
+                        "agent_updates_per_s": em.agents.n / t, "active_quiet_arrested": [em.ACTIVE, em.QUIET, em.ARRESTED],
+                        "note": "one launch: rank-ordered dependency graph, one warp per agent (csrc/epstein.cu); bound by the "
+                                "depth of the dependency chains (2 x vision reach), not by bandwidth"})
+            del em
+    except Exception as exc:  # reported, never fatal
+        out.append({"workload": "epstein", "error": repr(exc)[:200]})
     # config 2: Boltzmann wealth, 10^6 agents on 4096^2
     m = BoltzmannWealth(BoltzmannScenario(n=1_000_000, width=4096, height=4096, rng=1))
     m.run_for(3)

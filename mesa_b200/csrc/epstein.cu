@@ -12,11 +12,10 @@
 // nobody moves further than `vision`, so a depends on an earlier agent b only if b STARTED the step within 2 vision of a
 // (b moved into or out of a's view, changed its state there, or arrested somebody there); influences from further away
 // reach a only through an agent in between, which itself waits.  The step is therefore a dependency graph, not a chain:
-// thread r owns the agent of activation rank r (ascending Philox priority), CTAs take their rank ranges from a ticket
-// counter (every lower rank is running or done), and a thread acts once every lower-ranked agent that started within
-// 2 vision of it has finished -- found through rank_at[cell] (the rank of the agent that started the step in a cell) and
-// done[rank].  When it acts it sees exactly the state the sequential run would show it.  Inside a warp nobody blocks: the
-// lanes loop, each scans on from where it last had to wait, and acts when it can.
+// a WARP owns the agent of activation rank r (ascending Philox priority), warps take their ranks from a ticket counter
+// (every lower rank is held by a running warp or done), and the warp acts once every lower-ranked agent that started
+// within 2 vision of it has finished -- rank_at[cell] holds the rank of the agent that started the step in a cell until
+// that agent has acted.  When it acts it sees exactly the state the sequential run would show it.
 //
 // One 4-byte word per cell carries all a neighbour scan needs: -1 = empty, else agent << 2 | cop << 1 | active, kept up to
 // date by whoever changes it (the mover, the citizen that changes its mind, the cop that arrests).  The arrest probability
@@ -25,6 +24,7 @@
 // like Python's; the comparison is the reference's float64 expression (no fused operations).
 #include "common.cuh"
 #include "philox.cuh"
+#include <stdlib.h>
 
 extern "C" int mb_activation_order_workspace_bytes(int64_t n, size_t* out);
 extern "C" int mb_activation_order(uint64_t seed, uint32_t epoch, int64_t n, uint32_t* order_out, void* workspace,
@@ -33,14 +33,13 @@ extern "C" int mb_activation_order(uint64_t seed, uint32_t epoch, int64_t n, uin
 namespace {
 
 constexpr uint32_t kNoRank = 0xffffffffu;
-constexpr int kThreads = 128;
-constexpr unsigned kSpinLimit = 1u << 24;   // warp loop iterations before a thread gives up (status word, no hang)
+constexpr int kThreads = 256;
+constexpr unsigned kSpinLimit = 1u << 22;   // polls of one block of the dependency range before a warp gives up (status word, no hang)
 constexpr uint8_t kActive = 1, kQuiet = 2, kArrested = 3;   // CitizenState (agents.py:7-10)
 
 struct EpsWs {
     uint32_t* order;     // [n] agent of rank r
-    uint32_t* rank_at;   // [ncells] rank of the agent that starts the step in the cell, kNoRank if empty
-    uint32_t* done;      // [n] by rank
+    uint32_t* rank_at;   // [ncells] rank of the agent that starts the step in the cell until it has acted, kNoRank if empty / done
     uint32_t* counters;  // [0] ticket, [1] status (non-zero: a wait ran into the spin limit), [2..4] active / quiet / arrested
     void* order_ws;
     size_t order_ws_bytes;
@@ -56,7 +55,6 @@ size_t carve(EpsWs* ws, char* base, int64_t n, int64_t ncells) {
     EpsWs t;
     t.order = (uint32_t*)take(4 * n);
     t.rank_at = (uint32_t*)take(4 * ncells);
-    t.done = (uint32_t*)take(4 * n);
     t.counters = (uint32_t*)take(4 * 16);
     mb_activation_order_workspace_bytes(n, &t.order_ws_bytes);
     t.order_ws = take(t.order_ws_bytes);
@@ -92,12 +90,14 @@ __device__ __forceinline__ void st_relaxed(uint32_t* p, uint32_t v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// (__threadfence() is the sequentially consistent fence; acquire / release is all the hand-over needs)
+__device__ __forceinline__ void fence_acq_rel() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
 __global__ void eps_prepare(EpsArgs a, EpsWs ws, int sequential) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= a.n) return;
     if (sequential) ws.order[r] = (uint32_t)r;          // agents.do("step"): registration order
     ws.rank_at[a.cell[ws.order[r]]] = (uint32_t)r;
-    ws.done[r] = 0u;
 }
 
 __device__ __forceinline__ int wrap_cell(int x, int y, short2 d, int W, int H) {
@@ -107,123 +107,171 @@ __device__ __forceinline__ int wrap_cell(int x, int y, short2 d, int W, int H) {
     return nx * H + ny;
 }
 
-// the k-th cell of the neighbourhood (BFS order) whose word satisfies `want` (empty: word < 0; active citizen: (word & 3) == 1)
+// ---- one agent = one WARP ----------------------------------------------------------------------------------------------
+// (The first version gave every agent a thread: its 421-cell dependency scan and its two 112-cell neighbourhood scans were
+// chains of dependent L2 round trips, ~48 us per agent on the critical path -- 59 ms for the 1231 agents of the 40 x 40
+// default grid, slower than the reference.)  Here the 32 lanes share the scans: every lane polls 8 cells of the dependency
+// range per round trip, the neighbourhood (<= 256 cells: vision 7 has 112 / 224) is ONE round trip with the words kept in
+// registers, the counts are ballots and the k-th empty cell / active citizen is found with ballots + fns in BFS order.
+constexpr int kPer = 8;                  // cells per lane and block
+constexpr int kBlock = 32 * kPer;
+// kWaitPer (template): cells of the dependency range per lane and poll -- 16 when the range has more than 256 cells (vision 7,
+// von Neumann: 421 = one poll; measured 3.3 -> 2.8 ms on 1024^2), 8 otherwise (fewer registers, no padding loads)
+
 template <bool kEmpty>
-__device__ __forceinline__ int kth_cell(const EpsArgs& a, int x, int y, int k, int32_t* word_out) {
-    for (int i0 = 0; i0 < a.nv; i0 += 8) {
-        int c[8];
-        int32_t w[8];
+__device__ __forceinline__ bool hit_word(int32_t w) {
+    return kEmpty ? w < 0 : (w >= 0 && (w & 3) == 1);
+}
+
+// the k-th cell (BFS order: block, q, lane) whose word satisfies the predicate; block 0 comes from the registers
+template <bool kEmpty>
+__device__ __forceinline__ int select_kth(const EpsArgs& a, int x, int y, int k, int lane, const int32_t (&w0)[kPer],
+                                          const int (&c0)[kPer], int32_t* word_out) {
+    for (int blk = 0; blk * kBlock < a.nv; ++blk) {
+        int32_t w[kPer];
+        int c[kPer];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            c[q] = i0 + q < a.nv ? wrap_cell(x, y, __ldg(a.voff + i0 + q), a.width, a.height) : -1;
-            w[q] = c[q] >= 0 ? __ldcg(a.occ + c[q]) : 0;    // 0 = agent 0, citizen, not active: matches neither predicate... (guarded below)
+        for (int q = 0; q < kPer; ++q) {
+            if (blk == 0) { w[q] = w0[q]; c[q] = c0[q]; continue; }
+            const int i = blk * kBlock + q * 32 + lane;
+            c[q] = i < a.nv ? wrap_cell(x, y, __ldg(a.voff + i), a.width, a.height) : -1;
+            w[q] = c[q] >= 0 ? __ldcg(a.occ + c[q]) : 0;         // padding word 0 satisfies no predicate
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            if (c[q] < 0) continue;
-            const bool hit = kEmpty ? w[q] < 0 : (w[q] >= 0 && (w[q] & 3) == 1);
-            if (hit && k-- == 0) { *word_out = w[q]; return c[q]; }
+        for (int q = 0; q < kPer; ++q) {
+            const unsigned b = __ballot_sync(0xffffffffu, c[q] >= 0 && hit_word<kEmpty>(w[q]));
+            const int nhit = __popc(b);
+            if (k < nhit) {
+                const int src = (int)__fns(b, 0u, (unsigned)k + 1u);
+                *word_out = __shfl_sync(0xffffffffu, w[q], src);
+                return __shfl_sync(0xffffffffu, c[q], src);
+            }
+            k -= nhit;
         }
     }
     return -1;
 }
 
-__device__ void act(const EpsArgs& a, uint32_t agent) {
-    const int p = __ldcg(a.cell + agent);
-    const int x = p / a.height, y = p - x * a.height;
+__device__ void act_warp(const EpsArgs& a, uint32_t agent, int p, int x, int y, int lane) {
     const bool cop = __ldg(a.kind + agent) != 0;
-    mb::DrawStream ds(a.seed, a.epoch, (uint64_t)agent);
-    if (!cop) {
-        const int j = __ldcg(a.jail + agent);
-        if (j != 0) {                                   // agents.py:70-72: in jail, nothing else happens
-            a.jail[agent] = j - 1;
+    const int j = cop ? 0 : __ldcg(a.jail + agent);     // (issued together with the neighbourhood loads: one round trip)
+    // the neighbourhood: empty cells, cops, active citizens
+    int nempty = 0, ncops = 0, nactive = 0;
+    int32_t w0[kPer];
+    int c0[kPer];
+    for (int blk = 0; blk * kBlock < a.nv; ++blk) {
+        int32_t w[kPer];
+        int c[kPer];
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+            const int i = blk * kBlock + q * 32 + lane;
+            c[q] = i < a.nv ? wrap_cell(x, y, __ldg(a.voff + i), a.width, a.height) : -1;
+            w[q] = c[q] >= 0 ? __ldcg(a.occ + c[q]) : 0;
+        }
+        if (blk == 0 && j != 0) {                       // agents.py:70-72: in jail, nothing else happens
+            if (lane == 0) a.jail[agent] = j - 1;
             return;
         }
-    }
-    // one scan of the neighbourhood: empty cells, cops, active citizens
-    int nempty = 0, ncops = 0, nactive = 0;
-    for (int i0 = 0; i0 < a.nv; i0 += 8) {
-        int32_t w[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-            w[q] = i0 + q < a.nv ? __ldcg(a.occ + wrap_cell(x, y, __ldg(a.voff + i0 + q), a.width, a.height)) : 0;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            if (i0 + q >= a.nv) continue;
-            nempty += w[q] < 0;
-            ncops += w[q] >= 0 && (w[q] & 2);
-            nactive += w[q] >= 0 && (w[q] & 3) == 1;
+        for (int q = 0; q < kPer; ++q) {
+            const bool v = c[q] >= 0;
+            nempty += __popc(__ballot_sync(0xffffffffu, v && w[q] < 0));
+            ncops += __popc(__ballot_sync(0xffffffffu, v && w[q] >= 0 && (w[q] & 2)));
+            nactive += __popc(__ballot_sync(0xffffffffu, v && w[q] >= 0 && (w[q] & 3) == 1));
+            if (blk == 0) { w0[q] = w[q]; c0[q] = c[q]; }
         }
     }
+    mb::DrawStream ds(a.seed, a.epoch, (uint64_t)agent);
     int32_t me = (int32_t)(agent << 2) | (cop ? 2 : 0);
     if (!cop) {
         // agents.py:86-103 (the citizen counts herself among the actives)
         const double q = (double)ncops / (double)(nactive + 1);
         const int m = __double2int_rn(q);               // round-half-even, like Python's round()
-        const double prob = a.ptab[m];
-        a.arrest_probability[agent] = prob;
+        const double prob = __ldg(a.ptab + m);
         const double net_risk = __dmul_rn(__ldg(a.risk_aversion + agent), prob);
         const bool active = __dsub_rn(__ldg(a.grievance + agent), net_risk) > a.threshold;
-        a.state[agent] = active ? kActive : kQuiet;
         me |= active ? 1 : 0;
-        a.occ[p] = me;                                  // (rewritten below if she moves)
+        if (lane == 0) {
+            a.arrest_probability[agent] = prob;
+            a.state[agent] = active ? kActive : kQuiet;
+            a.occ[p] = me;                              // (rewritten below if she moves)
+        }
     } else if (nactive > 0) {
         // agents.py:130-138
         const int pick = (int)ds.randbelow((uint64_t)nactive);
         int32_t w = 0;
-        const int c = kth_cell<false>(a, x, y, pick, &w);
-        const uint32_t arrestee = (uint32_t)w >> 2;
-        a.jail[arrestee] = (int32_t)ds.randbelow((uint64_t)a.max_jail_term + 1ull);   // randint(0, max_jail_term)
-        a.state[arrestee] = kArrested;
-        a.occ[c] = w & ~1;                              // no longer active
+        const int c = select_kth<false>(a, x, y, pick, lane, w0, c0, &w);
+        const int32_t sentence = (int32_t)ds.randbelow((uint64_t)a.max_jail_term + 1ull);   // randint(0, max_jail_term)
+        if (lane == 0) {
+            const uint32_t arrestee = (uint32_t)w >> 2;
+            a.jail[arrestee] = sentence;
+            a.state[arrestee] = kArrested;
+            a.occ[c] = w & ~1;                          // no longer active
+        }
     }
     if (a.movement && nempty > 0) {                     // agents.py:22-26
         const int pick = (int)ds.randbelow((uint64_t)nempty);
         int32_t w = 0;
-        const int dest = kth_cell<true>(a, x, y, pick, &w);
-        a.occ[p] = -1;
-        a.occ[dest] = me;
-        a.cell[agent] = dest;
+        const int dest = select_kth<true>(a, x, y, pick, lane, w0, c0, &w);
+        if (lane == 0) {
+            a.occ[p] = -1;
+            a.occ[dest] = me;
+            a.cell[agent] = dest;
+        }
     }
 }
 
+template <int kWaitPer>
 __global__ void __launch_bounds__(kThreads)
-eps_chain(EpsArgs a, EpsWs ws) {
-    __shared__ unsigned s_base;
-    if (threadIdx.x == 0) s_base = atomicAdd(&ws.counters[0], (unsigned)kThreads);
-    __syncthreads();
-    const int64_t r = (int64_t)s_base + threadIdx.x;
-    bool finished = r >= a.n;
-    uint32_t agent = 0;
-    int x = 0, y = 0, i = 0;
-    if (!finished) {
-        agent = ws.order[r];
-        const int p = a.cell[agent];                   // its own cell: nobody else moves it
-        x = p / a.height; y = p - x * a.height;
-    }
-    unsigned spins = 0;
+eps_chain(EpsArgs a, EpsWs ws, int batch) {
+    const int lane = threadIdx.x & 31;
     while (true) {
-        if (!finished) {
-            // every agent of lower rank that STARTED within 2 vision must have finished (done only ever goes 0 -> 1, so the
-            // scan resumes where it last had to wait)
-            while (i < a.nw) {
-                const uint32_t rk = __ldg(ws.rank_at + wrap_cell(x, y, __ldg(a.woff + i), a.width, a.height));
-                if (rk < (uint32_t)r && ld_relaxed(ws.done + rk) == 0u) break;
-                ++i;
+        unsigned first = 0;
+        if (lane == 0) first = atomicAdd(&ws.counters[0], (unsigned)batch);   // ranks are handed out in order: every lower rank
+        first = __shfl_sync(0xffffffffu, first, 0);                           // is held by a running warp or done
+        if ((int64_t)first >= a.n) break;
+        const int64_t end = (int64_t)first + batch < a.n ? (int64_t)first + batch : a.n;
+        for (int64_t r = first; r < end; ++r) {
+            const uint32_t agent = ws.order[r];
+            const int p = __ldcg(a.cell + agent);       // its own cell: nobody else moves it
+            const int x = p / a.height, y = p - x * a.height;
+            // every agent of lower rank that STARTED within 2 vision must have finished: pending[cell] = the rank of the agent
+            // that started the step there until it has acted, kNoRank afterwards (and for cells that were empty)
+            bool bad = false;
+            for (int i0 = 0; i0 < a.nw && !bad; i0 += 32 * kWaitPer) {
+                int wc[kWaitPer];
+                unsigned pend = 0u;
+#pragma unroll
+                for (int q = 0; q < kWaitPer; ++q) {
+                    const int i = i0 + q * 32 + lane;
+                    wc[q] = 0;
+                    if (i < a.nw) {
+                        wc[q] = wrap_cell(x, y, __ldg(a.woff + i), a.width, a.height);
+                        pend |= 1u << q;
+                    }
+                }
+                unsigned spins = 0u;
+                while (true) {
+                    uint32_t v[kWaitPer];
+#pragma unroll
+                    for (int q = 0; q < kWaitPer; ++q) v[q] = (pend >> q) & 1u ? ld_relaxed(ws.rank_at + wc[q]) : kNoRank;
+#pragma unroll
+                    for (int q = 0; q < kWaitPer; ++q)
+                        if (v[q] >= (uint32_t)r) pend &= ~(1u << q);
+                    if (!__any_sync(0xffffffffu, pend != 0u)) break;
+                    if (++spins > kSpinLimit) { bad = true; break; }
+                }
             }
-            if (i == a.nw) {
-                __threadfence();                        // their writes, before my reads
-                act(a, agent);
-                __threadfence();                        // my writes, before my flag
-                st_relaxed(ws.done + r, 1u);
-                finished = true;
-            } else if (++spins > kSpinLimit) {
-                ws.counters[1] = 1u;                    // gives up WITHOUT acting: the status word reports it
-                st_relaxed(ws.done + r, 1u);
-                finished = true;
+            fence_acq_rel();                            // their writes, before this warp's reads
+            __syncwarp();
+            if (!bad) act_warp(a, agent, p, x, y, lane);
+            __syncwarp();
+            if (lane == 0) {
+                if (bad) ws.counters[1] = 1u;           // gave up WITHOUT acting: the status word reports it
+                fence_acq_rel();                        // my writes, before my flag
+                st_relaxed(ws.rank_at + p, kNoRank);
             }
         }
-        if (__all_sync(0xffffffffu, finished)) break;
     }
 }
 
@@ -294,9 +342,22 @@ MB_API int mb_epstein_step(int32_t* occ, int32_t* cell, const uint8_t* kind, uin
     if (rc) return rc;
     if ((rc = mb::check_cuda(cudaMemsetAsync(ws.rank_at, 0xff, 4 * (size_t)(width * height), stream), "memset"))) return rc;
     if ((rc = mb::check_cuda(cudaMemsetAsync(ws.counters, 0, 4 * 16, stream), "memset"))) return rc;
-    const unsigned blocks = (unsigned)mb::ceil_div(n, kThreads);
     eps_prepare<<<(unsigned)mb::ceil_div(n, 256), 256, 0, stream>>>(a, ws, sequential);
-    eps_chain<<<blocks, kThreads, 0, stream>>>(a, ws);
+    // one warp per agent, one ticket per agent.  (Handing a warp 8 consecutive ranks per ticket saves atomics on one
+    // address but chains the 8 agents of a batch behind each other ON TOP of their real dependencies: 90 ms instead of a
+    // few for 811 k agents on 1024 x 1024.  MB_EPSTEIN_BATCH=n keeps the experiment reachable.)
+    const int warps_per_cta = kThreads / 32;
+    int64_t ctas = mb::ceil_div(n, warps_per_cta);
+    const int64_t cap = (int64_t)mb::sm_count() * 8;
+    if (ctas > cap) ctas = cap;
+    static int batch = 0;
+    if (batch == 0) {
+        const char* e = getenv("MB_EPSTEIN_BATCH");
+        batch = e ? atoi(e) : 1;
+        if (batch < 1 || batch > 64) batch = 1;
+    }
+    if (nw > 256) eps_chain<16><<<(unsigned)ctas, kThreads, 0, stream>>>(a, ws, batch);
+    else eps_chain<8><<<(unsigned)ctas, kThreads, 0, stream>>>(a, ws, batch);
     if (counts_dev != nullptr) {
         eps_counts<<<(unsigned)mb::ceil_div(n, 256), 256, 0, stream>>>(kind, state, n, ws.counters);
         if ((rc = mb::check_cuda(cudaMemcpyAsync(counts_dev, ws.counters + 1, 4 * 4, cudaMemcpyDeviceToDevice, stream), "copy"))) return rc;
