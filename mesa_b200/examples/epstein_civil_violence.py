@@ -174,19 +174,11 @@ class EpsteinCivilViolence(DeviceModel):
 
     # ------------------------------------------------------------------ initial state
     def _reference_initial_state(self, sc) -> dict:
-        """model.py:84-98 with the model's own generator, call for call: `random.choices` per cell in `all_cells` order
-        (x-major), two `random.random()` per citizen (agents.py:55-56): the same seed gives the reference's agents."""
-        cum = [sc.citizen_density, sc.citizen_density + sc.cop_density, 1]
-        kind, cell, hardship, risk = [], [], [], []
-        for c in range(self.width * self.height):
-            k = self.random.choices([0, 1, None], cum_weights=cum)[0]
-            if k is None:
-                continue
-            kind.append(k)
-            cell.append(c)
-            hardship.append(self.random.random() if k == 0 else 0.0)
-            risk.append(self.random.random() if k == 0 else 0.0)
-        return {"kind": kind, "cell": cell, "hardship": hardship, "risk_aversion": risk}
+        """model.py:84-98 on the model's own generator (reference_init.epstein_initial_state): the same seed gives the
+        reference's agents."""
+        from ..reference_init import epstein_initial_state
+
+        return epstein_initial_state(self.random, self.width, self.height, sc.citizen_density, sc.cop_density)
 
     # ------------------------------------------------------------------ device state
     def _rebuild_occ(self):

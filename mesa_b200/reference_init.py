@@ -83,3 +83,21 @@ def schelling_initial_types(rnd: _random.Random, width: int, height: int, densit
     types[occupied] = (u[occ_draws[occupied] + 1] < minority_pc).astype(np.int8)
     mt_uniforms(rnd, ncells + int(occupied.sum()))           # advance past exactly what the reference consumed
     return types.reshape(width, height)
+
+
+def epstein_initial_state(rnd: _random.Random, width: int, height: int, citizen_density: float, cop_density: float) -> dict:
+    """epstein_civil_violence/model.py:84-98 with the model's own generator, call for call: `random.choices([Citizen, Cop,
+    None], cum_weights=...)` per cell in `all_cells` order (x-major) and, for a citizen, the two `random.random()` of
+    agents.py:55-56 (hardship, risk_aversion).  Agents in creation order (unique_id - 1 = row): kind 0 citizen / 1 cop."""
+    cum = [citizen_density, citizen_density + cop_density, 1]
+    kind, cell, hardship, risk = [], [], [], []
+    for c in range(int(width) * int(height)):
+        k = rnd.choices([0, 1, None], cum_weights=cum)[0]
+        if k is None:
+            continue
+        kind.append(k)
+        cell.append(c)
+        hardship.append(rnd.random() if k == 0 else 0.0)
+        risk.append(rnd.random() if k == 0 else 0.0)
+    return {"kind": np.asarray(kind, dtype=np.uint8), "cell": np.asarray(cell, dtype=np.int64),
+            "hardship": np.asarray(hardship, dtype=np.float64), "risk_aversion": np.asarray(risk, dtype=np.float64)}

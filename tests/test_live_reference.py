@@ -234,3 +234,40 @@ def test_continuous_space_agent_queries_against_the_reference(replay, monkeypatc
                 ref_agents[0].position = np.array([31.5, 1.0])
             with pytest.raises(ValueError):
                 birds[0].position = np.array([31.5, 1.0])
+
+
+@pytest.mark.parametrize("seed,width,height,params", [
+    (77, 24, 19, dict(legitimacy=0.6, max_jail_term=5, cop_vision=4, citizen_vision=4)),
+    (4242, 15, 16, dict(grid_type="Moore", legitimacy=0.5, max_jail_term=2, cop_vision=2, citizen_vision=2, cop_density=0.1)),
+])
+def test_epstein_from_a_seed(replay, seed, width, height, params):
+    """Epstein civil violence: initial state from the seed (reference_init.epstein_initial_state), trajectory from the
+    sequential restatement (oracle/epstein.py) == the unmodified model under the replayed order / draws."""
+    from mesa.examples.advanced.epstein_civil_violence.agents import Citizen, Cop
+    from mesa.examples.advanced.epstein_civil_violence.model import EpsteinCivilViolence, EpsteinScenario
+    from oracle.epstein import EpsteinOracle
+
+    philox_seed = seed + 1
+    with replay.patched_model_random(philox_seed):
+        m = EpsteinCivilViolence(width=width, height=height, scenario=EpsteinScenario(rng=seed, **params))
+    agents = sorted(m.agents, key=lambda a: a.unique_id)
+    sc = m.scenario
+    st = ri.epstein_initial_state(random.Random(ri.seed_streams(seed)[1]), width, height, sc.citizen_density, sc.cop_density)
+    assert np.array_equal(st["kind"], np.array([isinstance(a, Cop) for a in agents], dtype=np.uint8))
+    assert np.array_equal(st["cell"], np.array([a.cell.coordinate[0] * height + a.cell.coordinate[1] for a in agents]))
+    assert np.array_equal(st["hardship"], np.array([getattr(a, "hardship", 0.0) for a in agents]))
+    assert np.array_equal(st["risk_aversion"], np.array([getattr(a, "risk_aversion", 0.0) for a in agents]))
+    o = EpsteinOracle(width, height, st["kind"], st["cell"], st["hardship"], st["risk_aversion"], moore=sc.grid_type == "Moore",
+                      vision=sc.cop_vision, legitimacy=sc.legitimacy, max_jail_term=sc.max_jail_term,
+                      active_threshold=sc.active_threshold, arrest_prob_constant=sc.arrest_prob_constant, philox_seed=philox_seed)
+    cit = st["kind"] == 0
+    m.random.replay = True
+    with replay.activation_context(Citizen, "step"), replay.activation_context(Cop, "step"):
+        for step in range(8):
+            m.step()
+            o.step()
+            assert np.array_equal(o.cell, np.array([a.cell.coordinate[0] * height + a.cell.coordinate[1] for a in agents])), step
+            assert np.array_equal(o.state[cit], np.array([a.state.value for a in agents if isinstance(a, Citizen)], dtype=np.int8)), step
+            assert np.array_equal(o.jail[cit], np.array([a.jail_sentence for a in agents if isinstance(a, Citizen)])), step
+            assert o.counts() == (m.ACTIVE, m.QUIET, m.ARRESTED), step
+    m.random.replay = False
