@@ -93,12 +93,70 @@ __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* w
     return before + incl - v;
 }
 
+// do("assign_state") on a PADDED shared-memory copy of the type layer: radius R cells of border around the grid -- empty
+// (-1) outside a clamped grid, the wrapped cells on a torus -- so the (2R+1)^2 - 1 neighbour reads need no bounds checks
+// and the loops unroll (the generic loop below costs ~365 instructions per cell, 80 % of a step without movers:
+// profiles/r2_schelling_small_ncu.csv).  Returns this thread's number of happy agents.
+template <int R>
+__device__ __forceinline__ unsigned assign_state_padded(int8_t* __restrict__ tl, const int8_t* __restrict__ type,
+                                                        uint8_t* __restrict__ happy, uint8_t* __restrict__ empty_layer, int rows,
+                                                        int cols, int torus, const SmallRule& rule) {
+    const int tid = threadIdx.x;
+    const int pc = cols + 2 * R, pr = rows + 2 * R;
+    {   // fill: padded index p = pi * pc + pj walks in steps of kThreads without divisions
+        int pi = tid / pc, pj = tid - pi * pc;
+        const int di = kThreads / pc, dj = kThreads - di * pc;
+        for (int p = tid; p < pr * pc; p += kThreads) {
+            int i = pi - R, j = pj - R;
+            int8_t v = -1;
+            if (torus) {
+                i += i < 0 ? rows : 0; i -= i >= rows ? rows : 0;
+                j += j < 0 ? cols : 0; j -= j >= cols ? cols : 0;
+                v = __ldcg(type + i * cols + j);
+            } else if (i >= 0 && i < rows && j >= 0 && j < cols) {
+                v = __ldcg(type + i * cols + j);
+            }
+            tl[p] = v;
+            pi += di; pj += dj;
+            if (pj >= pc) { pj -= pc; ++pi; }
+        }
+    }
+    __syncthreads();
+    unsigned nh = 0;
+    int i = tid / cols, j = tid - i * cols;
+    const int di = kThreads / cols, dj = kThreads - di * cols;
+    for (int c = tid; c < rows * cols; c += kThreads) {
+        const int8_t* centre = tl + (i + R) * pc + (j + R);
+        const int t = *centre;
+        unsigned h = 0;
+        if (t >= 0) {
+            int similar = 0, valid = 0;
+#pragma unroll
+            for (int a = -R; a <= R; ++a)
+#pragma unroll
+                for (int b = -R; b <= R; ++b) {
+                    if (a == 0 && b == 0) continue;
+                    const int u = centre[a * pc + b];
+                    valid += u >= 0;
+                    similar += u == t;
+                }
+            h = similar >= (int)rule.min_similar[valid];
+        }
+        happy[c] = (uint8_t)h;
+        if (empty_layer != nullptr) empty_layer[c] = t < 0;
+        nh += h;
+        i += di; j += dj;
+        if (j >= cols) { j -= cols; ++i; }
+    }
+    return nh;
+}
+
 // status word: 0 ok, 1 grid completely full with an unhappy agent (ValueError, grid.py:311-315), 2 more movers than
 // the workspace holds, 3 more than kFbCap fallback movers in a pass, 4 no convergence
 __global__ void __launch_bounds__(kThreads, 1)
 schelling_small_step(int8_t* __restrict__ type, uint8_t* __restrict__ happy, uint32_t* __restrict__ agent_id,
                      uint32_t* __restrict__ agent_cell, uint8_t* __restrict__ empty_layer, int rows, int cols, int radius,
-                     int torus, SmallRule rule, uint64_t seed, uint32_t epoch, int relocate, SmallWs ws, int cap,
+                     int torus, SmallRule rule, uint64_t seed, uint32_t epoch0, int relocate, int nsteps, SmallWs ws, int cap,
                      unsigned long long* __restrict__ out /* [0] model.happy [1] movers [2] status [3] passes */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Slot* slots = reinterpret_cast<Slot*>(smem_raw);
@@ -107,27 +165,54 @@ schelling_small_step(int8_t* __restrict__ type, uint8_t* __restrict__ happy, uin
     __shared__ uint32_t fb_list[kFbCap];
     const int tid = threadIdx.x;
     const int ncells = rows * cols;
+    // nsteps > 1: model.run_for(n) as ONE launch -- the steps of a 100 x 100 grid are shorter than the host's launch path
+    // (~10 us of kernel against ~20 us to issue a launch from Python), shuffle number epoch0 + s for step s
+    for (int step = 0; step < nsteps; ++step) {
+    const uint32_t epoch = epoch0 + (uint32_t)step;
+    __syncthreads();                       // the previous step's last readers of the shared words
     if (tid == 0) { s_nmovers = 0; s_nocc = 0; s_status = 0; s_happy = 0; s_changed = 0; s_nfb = 0; }
     __syncthreads();
     unsigned passes = 0;
     if (relocate) {
-        // ---- slots + movers (movers = occupied && !happy at the start of the step, agents.py:46)
-        for (int c0 = 0; c0 < ncells; c0 += kThreads) {
-            const int c = c0 + tid;
-            const int t = c < ncells ? type[c] : -1;
-            const bool mover = t >= 0 && happy[c] == 0;
+        // ---- slots + movers (movers = occupied && !happy at the start of the step, agents.py:46).  All of a thread's cells
+        // are loaded first (independent loads: one L2 round trip instead of one per 1024-cell slice)
+        constexpr int kSlices = (kMaxCells + kThreads - 1) / kThreads;
+        int8_t t_reg[kSlices];
+        uint8_t h_reg[kSlices];
+        uint32_t a_reg[kSlices];
+#pragma unroll
+        for (int k = 0; k < kSlices; ++k) {
+            const int c = k * kThreads + tid;
+            const bool in = c < ncells;
+            t_reg[k] = in ? type[c] : (int8_t)-1;
+            h_reg[k] = in ? happy[c] : (uint8_t)1;
+            a_reg[k] = in ? agent_id[c] : 0u;
+        }
+        // a warp reserves the slots of ALL its movers with one atomic (one per slice and warp was 832 atomics on two words)
+        unsigned wmovers = 0, wocc = 0;
+#pragma unroll
+        for (int k = 0; k < kSlices; ++k) {
+            const int t = t_reg[k];
+            wmovers += __popc(__ballot_sync(0xffffffffu, t >= 0 && h_reg[k] == 0));
+            wocc += __popc(__ballot_sync(0xffffffffu, t >= 0));
+        }
+        unsigned next = 0;
+        if ((tid & 31) == 0) {
+            if (wmovers) next = atomicAdd(&s_nmovers, wmovers);
+            if (wocc) atomicAdd(&s_nocc, wocc);
+        }
+        next = __shfl_sync(0xffffffffu, next, 0);
+#pragma unroll
+        for (int k = 0; k < kSlices; ++k) {
+            const int c = k * kThreads + tid;
+            if (k * kThreads >= ncells) break;
+            const int t = t_reg[k];
+            const bool mover = t >= 0 && h_reg[k] == 0;
             const unsigned ballot = __ballot_sync(0xffffffffu, mover);
-            const unsigned occ = __ballot_sync(0xffffffffu, t >= 0);
-            unsigned base = 0;
-            if ((tid & 31) == 0) {
-                if (ballot) base = atomicAdd(&s_nmovers, (unsigned)__popc(ballot));
-                if (occ) atomicAdd(&s_nocc, (unsigned)__popc(occ));
-            }
-            base = __shfl_sync(0xffffffffu, base, 0);
             unsigned long long vac = t >= 0 ? kNever : 0ull;
             if (mover) {
-                const unsigned m = base + __popc(ballot & ((1u << (tid & 31)) - 1u));
-                const uint32_t agent = agent_id[c];
+                const unsigned m = next + __popc(ballot & ((1u << (tid & 31)) - 1u));
+                const uint32_t agent = a_reg[k];
                 const unsigned long long pr = mb::priority64(seed, epoch, agent);
                 vac = pr + 1ull;
                 if (m < (unsigned)cap) {
@@ -135,6 +220,7 @@ schelling_small_step(int8_t* __restrict__ type, uint8_t* __restrict__ happy, uin
                     ws.fbk[m] = kNone; ws.ncached[m] = 0; ws.after[m] = 0; ws.mtype[m] = (int8_t)t;
                 }
             }
+            next += __popc(ballot);
             if (c < ncells) slots[c] = Slot{vac, kNever};
         }
         __syncthreads();
@@ -149,13 +235,19 @@ schelling_small_step(int8_t* __restrict__ type, uint8_t* __restrict__ happy, uin
                 ++passes;
                 if (passes > 100000u) { if (tid == 0) s_status = 4; break; }
                 for (unsigned m = tid; m < nmovers; m += kThreads) {
+                    // everything the pass needs of this mover in ONE round trip (independent loads)
                     const unsigned long long t = ws.prio[m];
-                    uint32_t pick = kNone;
                     const int nc = ws.ncached[m];
-                    const uint16_t* cc = ws.cache + (size_t)m * kCache;
-                    for (int j = 0; j < nc; ++j) {
-                        const uint32_t c = cc[j];
-                        if (empty_at(slots[c], t)) { pick = c; break; }
+                    const uint32_t held = ws.choice[m];
+                    const uint2* crow = reinterpret_cast<const uint2*>(ws.cache + (size_t)m * kCache);   // 24-byte rows
+                    const uint2 c01 = crow[0], c23 = crow[1], c45 = crow[2];
+                    const uint32_t cw[6] = {c01.x, c01.y, c23.x, c23.y, c45.x, c45.y};
+                    uint32_t pick = kNone;
+#pragma unroll
+                    for (int j = 0; j < kCache; ++j) {
+                        if (j >= nc || pick != kNone) continue;
+                        const uint32_t c = (cw[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+                        if (empty_at(slots[c], t)) pick = c;
                     }
                     if (pick == kNone) {
                         // beyond the cached probes: draw on from the saved stream position, extending the cache while
@@ -179,7 +271,6 @@ schelling_small_step(int8_t* __restrict__ type, uint8_t* __restrict__ happy, uin
                         if (f < (unsigned)kFbCap) fb_list[f] = m;
                         continue;
                     }
-                    const uint32_t held = ws.choice[m];
                     if (held != pick) {
                         if (held != kNone) atomicCAS(&slots[held].arr, t, kNever);
                         ws.choice[m] = pick;
@@ -265,9 +356,14 @@ schelling_small_step(int8_t* __restrict__ type, uint8_t* __restrict__ happy, uin
     // ---- do("assign_state"), agents.py:24-42, from a shared-memory copy of the type layer
     int8_t* tl = reinterpret_cast<int8_t*>(smem_raw);
     __syncthreads();
+    unsigned nh = 0;
+    if (radius == 1) {
+        nh = assign_state_padded<1>(tl, type, happy, empty_layer, rows, cols, torus, rule);
+    } else if (radius == 2) {
+        nh = assign_state_padded<2>(tl, type, happy, empty_layer, rows, cols, torus, rule);
+    } else {
     for (int c = tid; c < ncells; c += kThreads) tl[c] = __ldcg(type + c);
     __syncthreads();
-    unsigned nh = 0;
     for (int c = tid; c < ncells; c += kThreads) {
         const int t = tl[c];
         unsigned h = 0;
@@ -292,10 +388,12 @@ schelling_small_step(int8_t* __restrict__ type, uint8_t* __restrict__ happy, uin
         if (empty_layer != nullptr) empty_layer[c] = t < 0;
         nh += h;
     }
+    }
     nh = warp_reduce_add(nh);
     if ((tid & 31) == 0 && nh) atomicAdd(&s_happy, nh);
     __syncthreads();
     if (tid == 0) { out[0] = s_happy; out[1] = s_nmovers; out[2] = 0ull; out[3] = passes; }
+    }
 }
 
 }  // namespace
@@ -310,19 +408,21 @@ MB_API int mb_schelling_small_workspace_bytes(int64_t max_movers, size_t* out) {
 
 // One whole model step of a grid of at most mb_schelling_small_max_cells() cells in ONE launch, nothing read back:
 // relocate != 0: shuffle_do("step") of the agents that are unhappy according to the `happy` layer, then (always)
-// do("assign_state").  min_similar_host as in mb_schelling_happy_i8.  agent_cell / empty_layer optional.  out: device
+// do("assign_state"); nsteps > 1 repeats that with shuffle numbers epoch, epoch + 1, ... inside the same launch
+// (model.run_for(n): out4 then describes the LAST step; a failed step ends the run).  min_similar_host as in mb_schelling_happy_i8.  agent_cell / empty_layer optional.  out: device
 // uint64[4] = {model.happy, movers, status (0 ok, 1 grid completely full -> ValueError, 2 workspace too small,
 // 3 too many fallback movers, 4 no convergence), passes}.  A torus with a dimension < 2*radius+1 is rejected.
 MB_API int mb_schelling_step_small(int8_t* type, uint8_t* happy, uint32_t* agent_id, uint32_t* agent_cell, uint8_t* empty_layer,
                                    int64_t rows, int64_t cols, int radius, int torus, const uint8_t* min_similar_host,
-                                   uint64_t seed, uint32_t epoch, int relocate, void* workspace, size_t workspace_bytes,
-                                   int64_t max_movers, uint64_t* out4, cudaStream_t stream) {
+                                   uint64_t seed, uint32_t epoch, int relocate, int nsteps, void* workspace,
+                                   size_t workspace_bytes, int64_t max_movers, uint64_t* out4, cudaStream_t stream) {
     MB_REQUIRE(rows > 0 && cols > 0 && rows * cols <= kMaxCells, "mb_schelling_step_small: the grid must have 1..12800 cells");
     MB_REQUIRE(radius >= 1 && radius <= 7, "mb_schelling_step_small: radius must be 1..7");
     MB_REQUIRE(type && happy && agent_id && min_similar_host && workspace && out4, "mb_schelling_step_small: null buffer");
     MB_REQUIRE(!(torus && (rows < 2 * radius + 1 || cols < 2 * radius + 1)),
                "mb_schelling_step_small: torus needs rows, cols >= 2*radius+1 (SURVEY A.2)");
     MB_REQUIRE(max_movers >= 0 && max_movers < (1ll << 31), "mb_schelling_step_small: bad max_movers");
+    MB_REQUIRE(nsteps >= 1 && (nsteps == 1 || relocate), "mb_schelling_step_small: nsteps >= 1 (several steps only with relocate)");
     SmallWs ws;
     if (carve(&ws, (char*)workspace, max_movers) > workspace_bytes) {
         mb::set_error("mb_schelling_step_small: workspace too small");
@@ -331,7 +431,9 @@ MB_API int mb_schelling_step_small(int8_t* type, uint8_t* happy, uint32_t* agent
     SmallRule rule;
     const int nmax = (2 * radius + 1) * (2 * radius + 1) - 1;
     for (int v = 0; v < 232; ++v) rule.min_similar[v] = v <= nmax ? min_similar_host[v] : 255;
-    const int smem = (int)(rows * cols) * (int)sizeof(Slot);
+    int smem = (int)(rows * cols) * (int)sizeof(Slot);
+    const int padded = (int)((rows + 4) * (cols + 4));      // the stencil's padded copy of the type layer (radius <= 2)
+    if (smem < padded) smem = padded;
     static bool attr_set = false;
     if (!attr_set) {
         int rc = mb::check_cuda(cudaFuncSetAttribute(schelling_small_step, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -340,7 +442,7 @@ MB_API int mb_schelling_step_small(int8_t* type, uint8_t* happy, uint32_t* agent
         attr_set = true;
     }
     schelling_small_step<<<1, kThreads, smem, stream>>>(type, happy, agent_id, agent_cell, empty_layer, (int)rows, (int)cols,
-                                                       radius, torus, rule, seed, epoch, relocate, ws, (int)max_movers,
+                                                       radius, torus, rule, seed, epoch, relocate, nsteps, ws, (int)max_movers,
                                                        (unsigned long long*)out4);
     MB_LAUNCH_CHECK("mb_schelling_step_small");
     return MB_OK;

@@ -197,6 +197,28 @@ class Schelling(DeviceModel):
     def running(self, value) -> None:
         self._running, self._running_pending = bool(value), False
 
+    def run_for(self, duration) -> None:
+        """mesa/model.py:395-402.  On the single-launch path without a DataCollector the k steps that fall due run inside ONE
+        launch (csrc/schelling_small.cu, nsteps = k, shuffle numbers of k consecutive epochs): a 100 x 100 step is shorter
+        than the host's launch path, and nothing has to come back between the steps (`happy`, `running` are read lazily)."""
+        import math
+
+        until = self.time + duration
+        k = int(math.floor(until) - math.floor(self.time))
+        if self._small is None or self.datacollector is not None or k < 2 or type(self).step is not Schelling.step:
+            return super().run_for(duration)
+        self._flush_pending()
+        epoch0 = self._epoch
+        self._epoch += k
+        layers = self.grid.property_layers
+        self._small.step(dict.__getitem__(layers, "type"), dict.__getitem__(layers, "happy"), dict.__getitem__(layers, "agent_id"),
+                         self.philox_seed, epoch0, agent_cell=dict.__getitem__(self.agents.columns, "cell"),
+                         empty_layer=dict.__getitem__(layers, "empty"), relocate=True, nsteps=k)
+        self._last_small = True
+        self.steps += k
+        self.time = float(until)
+        self._running_pending = True
+
     def step(self):
         """model.py:87-93."""
         self.agents.shuffle_do("step")

@@ -290,21 +290,44 @@ class SchellingSmallStep:
         self.nbytes = int(nbytes.value)
         self.buf = torch.empty(max(self.nbytes, 1), dtype=torch.uint8, device=type_layer.device)
         self.out = torch.zeros(4, dtype=torch.int64, device=type_layer.device)
+        self._bound = None
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_bound"] = None          # (bound addresses and the ctypes entry point are per process)
+        return state
 
     @staticmethod
     def supports(ncells: int) -> bool:
         return 0 < ncells <= N.lib().mb_schelling_small_max_cells()
 
     def step(self, type_layer, happy, agent_id, seed: int, epoch: int, agent_cell=None, empty_layer=None,
-             relocate: bool = True) -> torch.Tensor:
-        _need_cuda(type_layer, happy, agent_id, agent_cell, empty_layer)
-        e = None if empty_layer is None else (empty_layer.view(torch.uint8) if empty_layer.dtype == torch.bool else empty_layer)
-        with torch.cuda.device(type_layer.device):
-            N.check(N.lib().mb_schelling_step_small(
-                N.ptr(_c(type_layer)), N.ptr(_c(happy)), N.ptr(_c(agent_id)), N.ptr(agent_cell), N.ptr(e), self.rows,
-                self.cols, self.radius, int(self.torus), self.table.ctypes.data, int(seed) & 0xFFFFFFFFFFFFFFFF,
-                int(epoch) & 0xFFFFFFFF, int(bool(relocate)), N.ptr(self.buf), self.nbytes, self.max_movers,
-                N.ptr(self.out), N.stream_ptr(type_layer.device)))
+             relocate: bool = True, nsteps: int = 1) -> torch.Tensor:
+        # A 100 x 100 step is ~10 us of kernel: the host side of the call must not cost more.  The buffers of a model do
+        # not change between steps, so their addresses are bound once (keyed on the tensors' identity and storage) and a
+        # step only passes (seed, epoch, relocate) and the current stream.
+        key = (type_layer.data_ptr(), happy.data_ptr(), agent_id.data_ptr(), None if agent_cell is None else agent_cell.data_ptr(),
+               None if empty_layer is None else empty_layer.data_ptr())
+        bound = self._bound
+        if bound is None or bound[0] != key:
+            _need_cuda(type_layer, happy, agent_id, agent_cell, empty_layer)
+            for t in (type_layer, happy, agent_id, agent_cell, empty_layer):
+                if t is not None and not t.is_contiguous():
+                    raise ValueError("SchellingSmallStep.step expects contiguous layers")
+            dev = type_layer.device
+            index = dev.index if dev.index is not None else torch.cuda.current_device()
+            bound = self._bound = (key, index, N.lib().mb_schelling_step_small, self.table.ctypes.data, N.ptr(self.buf), N.ptr(self.out))
+        _, index, fn, table, buf, out = bound
+        seed, epoch, relocate = int(seed) & 0xFFFFFFFFFFFFFFFF, int(epoch) & 0xFFFFFFFF, int(bool(relocate))
+        if torch.cuda.current_device() == index:
+            rc = fn(key[0], key[1], key[2], key[3], key[4], self.rows, self.cols, self.radius, int(self.torus), table, seed, epoch,
+                    relocate, int(nsteps), buf, self.nbytes, self.max_movers, out, torch.cuda.current_stream().cuda_stream)
+        else:
+            with torch.cuda.device(index):
+                rc = fn(key[0], key[1], key[2], key[3], key[4], self.rows, self.cols, self.radius, int(self.torus), table, seed,
+                        epoch, relocate, int(nsteps), buf, self.nbytes, self.max_movers, out, torch.cuda.current_stream().cuda_stream)
+        if rc:
+            N.check(rc)
         return self.out
 
     def check(self) -> tuple[int, int, int]:

@@ -308,3 +308,28 @@ def test_relocation_in_rank_ordered_buckets_gives_the_same_trajectories():
                         "-m", "gpu", "-k", "matches_reference_trajectory or dense_grid or sharded_driver"], env=env,
                        capture_output=True, text=True, timeout=900, cwd=os.path.dirname(here))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_run_for_in_one_launch_follows_the_reference_trajectory():
+    """model.run_for(k) on the single-launch path = k steps inside ONE launch (nsteps = k): BASELINE config 1 (100 x 100, the
+    live reference's golden trajectory) in chunks of 1, 9, 40 and 50 steps, cells and happiness at the golden checkpoints."""
+    from mesa_b200.examples import Schelling, SchellingScenario
+
+    g = np.load(os.path.join(GOLDEN, "schelling_100x100_c1.npz"))
+    W, H = int(g["width"]), int(g["height"])
+    types = np.full(W * H, -1, dtype=np.int8)
+    types[g["cell0"]] = g["atype"]
+    m = Schelling(SchellingScenario(width=W, height=H, density=0.8, homophily=float(g["homophily"]), radius=int(g["radius"]), rng=1),
+                  collect=False, initial_types=types.reshape(W, H))
+    m.philox_seed = int(g["philox_seed"])
+    assert m._small is not None and m.happy == int(g["happy_count0"])
+    done = 0
+    for chunk in (1, 9, 40, 50):
+        m.run_for(chunk)
+        done += chunk
+        assert m.time == done and m.steps == done and m._epoch == done
+        assert m.happy == int(g["happy_count"][done - 1]), done
+        assert m.last_movers == int(g["movers"][done - 1]), done
+        if done in set(g["full_steps"].tolist()):
+            assert np.array_equal(m.agents.get("cell").cpu().numpy().astype(np.int64), g[f"cell_{done}"]), done
+    assert m.running == (m.happy < len(m.agents))
