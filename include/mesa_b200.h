@@ -441,6 +441,25 @@ int mb_epstein_step(int32_t* occ, int32_t* cell, const uint8_t* kind, uint8_t* s
                     const double* ptab, int max_jail_term, double threshold, int movement, int sequential, uint64_t seed,
                     uint32_t epoch, uint32_t* counts_dev, void* workspace, size_t workspace_bytes, mb_stream_t stream);
 
+/* ---- Sugarscape G1MT, movement phase (csrc/sugarscape.cu) --------------------------------------------------------------
+ * replaces, for one model step without trade, mesa/examples/advanced/sugarscape_g1mt/model.py:118-127 (regrowth of both
+ * layers, `self.agents.shuffle_do("step")`) with agents.py:209-262 (move: empty cells of the radius-`vision` von Neumann
+ * neighbourhood in BFS order, Cobb-Douglas welfare, isclose to the best, closest, random.choice), :264-271 (eat), :273-288
+ * (starve -> remove), in the reference's sequential semantics (rank-ordered dependency graph, one launch).
+ *   flat cell = x * height + y, clamped grid; layers float64 [width * height]; count[cell] = traders in the cell;
+ *   voff [2 V (V + 1)][2] int16: the neighbourhood of the LARGEST vision V in BFS order, centre excluded (vision v = its first
+ *   2 v (v + 1) entries); woff [nw][2] int16: every offset within 2 V (dependency range); keys: unique_id - 1;
+ *   dead [n] uint8 (out): starved in this step -- the caller removes them (mb_compact_plan / mb_compact_rows);
+ *   status_dev (device, 2 x uint32, optional): status (0 valid, 1 spin limit, 2 more than 4 traders started in one cell), deaths. */
+int mb_sugarscape_workspace_bytes(int64_t n, int64_t ncells, size_t* out);
+int mb_sugarscape_build_count(const int32_t* cell, int64_t n, int32_t* count, int64_t ncells, mb_stream_t stream);
+int mb_sugarscape_step(int32_t* cell, double* sugar, double* spice, const int32_t* metabolism_sugar,
+                       const int32_t* metabolism_spice, const int32_t* vision, const int64_t* unique_id, uint8_t* dead, int64_t n,
+                       double* sugar_layer, const double* sugar_max, double* spice_layer, const double* spice_max,
+                       int32_t* count, int64_t width, int64_t height, const int16_t* voff, int max_vision, const int16_t* woff,
+                       int nw, int regrow, uint64_t seed, uint32_t epoch, uint32_t* status_dev, void* workspace,
+                       size_t workspace_bytes, mb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -646,6 +646,54 @@ def epstein_fixtures():
                     cop_vision=2, citizen_vision=2)                                            # nobody moves
 
 
+def sugarscape_fixture(name, steps, mt_seed, philox_seed, **params):
+    """The unmodified SugarscapeG1mt model (examples/advanced/sugarscape_g1mt) with enable_trade=False under the replayed
+    order / draws: after every step the traders (unique ids in model.agents order, cells, sugar, spice) and both layers."""
+    from mesa.examples.advanced.sugarscape_g1mt.agents import Trader
+    from mesa.examples.advanced.sugarscape_g1mt.model import SugarscapeG1mt, SugarScapeScenario
+
+    with patched_model_random(philox_seed):
+        m = SugarscapeG1mt(SugarScapeScenario(rng=mt_seed, enable_trade=False, **params))
+    rng = m.random
+    assert isinstance(rng, ReplayRandom)
+    W, H = m.grid.dimensions
+
+    def table():
+        agents = list(m.agents)
+        return (np.array([a.unique_id for a in agents], dtype=np.int64),
+                np.array([a.cell.coordinate[0] * H + a.cell.coordinate[1] for a in agents], dtype=np.int64),
+                np.array([a.sugar for a in agents], dtype=np.float64), np.array([a.spice for a in agents], dtype=np.float64))
+
+    agents = list(m.agents)
+    out = {"width": W, "height": H, "steps": steps, "mt_seed": mt_seed, "philox_seed": np.uint64(philox_seed),
+           "sugar_max": np.asarray(m.sugar_distribution, dtype=np.float64), "spice_max": np.asarray(m.spice_distribution, dtype=np.float64),
+           "metabolism_sugar": np.array([a.metabolism_sugar for a in agents], dtype=np.int64),
+           "metabolism_spice": np.array([a.metabolism_spice for a in agents], dtype=np.int64),
+           "vision": np.array([a.vision for a in agents], dtype=np.int64),
+           "scenario": np.array([m.scenario.initial_population, m.scenario.endowment_min, m.scenario.endowment_max,
+                                 m.scenario.metabolism_min, m.scenario.metabolism_max, m.scenario.vision_min, m.scenario.vision_max])}
+    out["id_0"], out["cell_0"], out["sugar_0"], out["spice_0"] = table()
+    rng.replay = True
+    with activation_context(Trader, "step"):
+        for s in range(1, steps + 1):
+            m.step()
+            out[f"id_{s}"], out[f"cell_{s}"], out[f"sugar_{s}"], out[f"spice_{s}"] = table()
+            if s in (1, steps // 2, steps):
+                out[f"sugar_layer_{s}"] = np.asarray(m.grid.sugar.data if hasattr(m.grid.sugar, "data") else m.grid.sugar, dtype=np.float64).copy()
+                out[f"spice_layer_{s}"] = np.asarray(m.grid.spice.data if hasattr(m.grid.spice, "data") else m.grid.spice, dtype=np.float64).copy()
+    rng.replay = False
+    out["counts"] = m.datacollector.get_model_vars_dataframe().to_numpy()
+    np.savez_compressed(os.path.join(GOLDEN, name), **out)
+    print(name, "traders", [len(out[f"id_{s}"]) for s in (0, 1, steps // 2, steps)])
+
+
+def sugarscape_fixtures():
+    sugarscape_fixture("sugarscape_200.npz", 30, 42, 41)                                                  # the scenario's defaults
+    sugarscape_fixture("sugarscape_600_crowded.npz", 20, 7, 43, initial_population=600, vision_max=3)     # shared cells at the start
+    sugarscape_fixture("sugarscape_80_farsighted.npz", 25, 3, 44, initial_population=80, vision_min=4, vision_max=5,
+                       metabolism_max=3)
+
+
 def main():
     import_reference()
     os.makedirs(GOLDEN, exist_ok=True)
@@ -673,6 +721,9 @@ def main():
         return
     if only == "epstein":
         epstein_fixtures()
+        return
+    if only == "sugarscape":
+        sugarscape_fixtures()
         return
     if only == "boltzmann":
         boltzmann_fixture("boltzmann_100_10x10.npz", 100, 10, 10, 25, 42, 3)      # reference "small"
@@ -704,6 +755,7 @@ def main():
     boltzmann_fixture("boltzmann_10000_100x100.npz", 10000, 100, 100, 10, 1, 5)
     wolf_sheep_fixtures()
     epstein_fixtures()
+    sugarscape_fixtures()
     # BASELINE.json configs[0]: 100x100, density 0.8, 100 steps (h=0.4, r=1)
     schelling_fixture("schelling_100x100_c1.npz", 100, 100, 0.8, 0.4, 1, 100, 42, 7, full_steps=[1, 2, 10, 50, 100])
     # the reference's own "large" benchmark variant (benchmarks/configurations.py:42-49)

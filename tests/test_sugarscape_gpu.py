@@ -1,0 +1,98 @@
+"""Sugarscape G1MT's movement phase on the device (mesa_b200/examples/sugarscape_g1mt.py, csrc/sugarscape.cu) against the
+unmodified reference model (enable_trade=False) run under the replayed Philox order / draws (tests/golden/sugarscape_*.npz,
+oracle/make_golden.py): after every step the same traders (unique ids in model.agents order) in the same cells with the same
+sugar and spice, the same layers; on larger landscapes against the sequential restatement (oracle/sugarscape.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+FIXTURES = ["sugarscape_200.npz", "sugarscape_600_crowded.npz", "sugarscape_80_farsighted.npz"]
+
+
+def _scenario(g, **kw):
+    from mesa_b200.examples.sugarscape_g1mt import SugarScapeScenario
+
+    n, emin, emax, mmin, mmax, vmin, vmax = (int(v) for v in g["scenario"])
+    return SugarScapeScenario(initial_population=n, endowment_min=emin, endowment_max=emax, metabolism_min=mmin,
+                              metabolism_max=mmax, vision_min=vmin, vision_max=vmax, enable_trade=False, **kw)
+
+
+def _table(m):
+    a = m.agents
+    return (a.unique_ids().cpu().numpy(), a.get("cell").cpu().numpy().astype(np.int64), a.get("sugar").cpu().numpy(),
+            a.get("spice").cpu().numpy())
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_sugarscape_matches_the_reference_trajectory(name):
+    from mesa_b200.examples.sugarscape_g1mt import SugarscapeG1mt
+
+    g = np.load(os.path.join(GOLDEN, name))
+    init = {"unique_id": g["id_0"], "cell": g["cell_0"], "sugar": g["sugar_0"], "spice": g["spice_0"],
+            "metabolism_sugar": g["metabolism_sugar"], "metabolism_spice": g["metabolism_spice"], "vision": g["vision"]}
+    m = SugarscapeG1mt(_scenario(g, rng=1), sugar_map=g["sugar_max"], initial_state=init)
+    m.philox_seed = int(g["philox_seed"])
+    assert torch.equal(m.spice_distribution.cpu(), torch.as_tensor(g["spice_max"]))          # model.py:75: the flipped sugar map
+    for s in range(1, int(g["steps"]) + 1):
+        m.step()
+        ids, cells, sugar, spice = _table(m)
+        assert np.array_equal(ids, g[f"id_{s}"]), (name, s)
+        assert np.array_equal(cells, g[f"cell_{s}"]), (name, s)
+        assert np.array_equal(sugar, g[f"sugar_{s}"]) and np.array_equal(spice, g[f"spice_{s}"]), (name, s)
+        if f"sugar_layer_{s}" in g:
+            assert np.array_equal(m.grid.sugar.cpu().numpy(), g[f"sugar_layer_{s}"]), (name, s)
+            assert np.array_equal(m.grid.spice.cpu().numpy(), g[f"spice_layer_{s}"]), (name, s)
+        count = np.bincount(cells, minlength=m.width * m.height)
+        assert np.array_equal(m._count.cpu().numpy(), count) and np.array_equal(m.grid.empty.cpu().numpy().reshape(-1), count == 0)
+    counts = m.datacollector.get_model_vars_dataframe().to_numpy()
+    assert np.array_equal(counts, g["counts"])              # #Traders, Trade Volume (0), Price (-1) as the reference's collector saw them
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_same_seed_gives_the_reference_initial_traders(name):
+    """model.py:80-116 replayed call for call on the model's own two generators."""
+    from mesa_b200.examples.sugarscape_g1mt import SugarscapeG1mt
+
+    g = np.load(os.path.join(GOLDEN, name))
+    m = SugarscapeG1mt(_scenario(g, rng=int(g["mt_seed"])), sugar_map=g["sugar_max"])
+    ids, cells, sugar, spice = _table(m)
+    assert np.array_equal(ids, g["id_0"]) and np.array_equal(cells, g["cell_0"])
+    assert np.array_equal(sugar, g["sugar_0"].astype(np.float64)) and np.array_equal(spice, g["spice_0"].astype(np.float64))
+    a = m.agents
+    assert np.array_equal(a.get("metabolism_sugar").cpu().numpy(), g["metabolism_sugar"])
+    assert np.array_equal(a.get("metabolism_spice").cpu().numpy(), g["metabolism_spice"])
+    assert np.array_equal(a.get("vision").cpu().numpy(), g["vision"])
+
+
+@pytest.mark.parametrize("side,n,vmax", [(160, 6000, 5), (96, 2500, 7)])
+def test_sugarscape_matches_the_sequential_restatement_on_larger_landscapes(side, n, vmax):
+    from mesa_b200.examples.sugarscape_g1mt import SugarScapeScenario, SugarscapeG1mt, synthetic_sugar_map
+    from oracle.sugarscape import SugarscapeOracle
+
+    rs = np.random.default_rng(side)
+    smap = synthetic_sugar_map(side, side + 7)
+    cells = rs.choice(side * (side + 7), size=n, replace=False)            # (at most a few traders per cell: distinct here)
+    init = {"cell": cells, "sugar": rs.integers(5, 30, n), "spice": rs.integers(5, 30, n), "metabolism_sugar": rs.integers(1, 5, n),
+            "metabolism_spice": rs.integers(1, 5, n), "vision": rs.integers(1, vmax + 1, n)}
+    m = SugarscapeG1mt(SugarScapeScenario(enable_trade=False, rng=5), sugar_map=smap, initial_state=init)
+    o = SugarscapeOracle(side, side + 7, smap, np.flip(smap, 1), np.arange(1, n + 1), cells, init["sugar"], init["spice"],
+                         init["metabolism_sugar"], init["metabolism_spice"], init["vision"], philox_seed=m.philox_seed)
+    for s in range(6):
+        m.step()
+        o.step()
+        ids, cell, sugar, spice = _table(m)
+        assert np.array_equal(ids, o.uid) and np.array_equal(cell, o.cell), s
+        assert np.array_equal(sugar, o.sugar) and np.array_equal(spice, o.spice), s
+        assert np.array_equal(m.grid.sugar.cpu().numpy().reshape(-1), o.sugar_layer), s
+    assert len(m.agents) < n                                                # some starved
+
+
+def test_trade_is_not_built():
+    from mesa_b200.examples.sugarscape_g1mt import SugarScapeScenario, SugarscapeG1mt
+
+    with pytest.raises(NotImplementedError):
+        SugarscapeG1mt(SugarScapeScenario(rng=1))                           # enable_trade defaults to True like the reference's
