@@ -441,7 +441,7 @@ int mb_epstein_step(int32_t* occ, int32_t* cell, const uint8_t* kind, uint8_t* s
                     const double* ptab, int max_jail_term, double threshold, int movement, int sequential, uint64_t seed,
                     uint32_t epoch, uint32_t* counts_dev, void* workspace, size_t workspace_bytes, mb_stream_t stream);
 
-/* ---- Sugarscape G1MT, movement phase (csrc/sugarscape.cu) --------------------------------------------------------------
+/* ---- Sugarscape G1MT (csrc/sugarscape.cu): movement phase --------------------------------------------------------------
  * replaces, for one model step without trade, mesa/examples/advanced/sugarscape_g1mt/model.py:118-127 (regrowth of both
  * layers, `self.agents.shuffle_do("step")`) with agents.py:209-262 (move: empty cells of the radius-`vision` von Neumann
  * neighbourhood in BFS order, Cobb-Douglas welfare, isclose to the best, closest, random.choice), :264-271 (eat), :273-288
@@ -450,15 +450,29 @@ int mb_epstein_step(int32_t* occ, int32_t* cell, const uint8_t* kind, uint8_t* s
  *   voff [2 V (V + 1)][2] int16: the neighbourhood of the LARGEST vision V in BFS order, centre excluded (vision v = its first
  *   2 v (v + 1) entries); woff [nw][2] int16: every offset within 2 V (dependency range); keys: unique_id - 1;
  *   dead [n] uint8 (out): starved in this step -- the caller removes them (mb_compact_plan / mb_compact_rows);
- *   status_dev (device, 2 x uint32, optional): status (0 valid, 1 spin limit, 2 more than 4 traders started in one cell), deaths. */
+ *   pow_table [pow_m][pow_m][pow_x] float64 (optional): x ** (ms / (ms + mp)) at [ms - 1][mp - 1][x] as the HOST's libm
+ *   computes it -- the welfare sugar ** (ms / mt) * spice ** (mp / mt) (agents.py:57-70) then is the reference's bit for bit
+ *   (amounts are integer-valued); amounts or metabolisms beyond the table use CUDA's pow and are counted;
+ *   status_dev (device, 3 x uint32, optional): status (0 valid, 1 spin limit, 2 more than 4 traders started in one cell),
+ *   deaths, pow calls that missed the table. */
 int mb_sugarscape_workspace_bytes(int64_t n, int64_t ncells, size_t* out);
 int mb_sugarscape_build_count(const int32_t* cell, int64_t n, int32_t* count, int64_t ncells, mb_stream_t stream);
 int mb_sugarscape_step(int32_t* cell, double* sugar, double* spice, const int32_t* metabolism_sugar,
                        const int32_t* metabolism_spice, const int32_t* vision, const int64_t* unique_id, uint8_t* dead, int64_t n,
                        double* sugar_layer, const double* sugar_max, double* spice_layer, const double* spice_max,
                        int32_t* count, int64_t width, int64_t height, const int16_t* voff, int max_vision, const int16_t* woff,
-                       int nw, int regrow, uint64_t seed, uint32_t epoch, uint32_t* status_dev, void* workspace,
-                       size_t workspace_bytes, mb_stream_t stream);
+                       int nw, int regrow, const double* pow_table, int pow_m, int pow_x, uint64_t seed, uint32_t epoch,
+                       uint32_t* status_dev, void* workspace, size_t workspace_bytes, mb_stream_t stream);
+/* the trade activation of a step (model.py:128-129 `shuffle_do("trade_with_neighbors")`, agents.py:290-301, 156-207, 94-153):
+ * every executed trade is appended to (rec_trader = ROW of the trader whose turn it was, rec_partner = unique id of the other
+ * side, rec_price), a trader's trades in the order it made them; status_dev = {status, number of trades (may exceed
+ * rec_cap), pow calls that missed pow_table}. */
+int mb_sugarscape_trade(const int32_t* cell, double* sugar, double* spice, const int32_t* metabolism_sugar,
+                        const int32_t* metabolism_spice, const int32_t* vision, const int64_t* unique_id, int64_t n,
+                        int64_t width, int64_t height, const int16_t* voff, int max_vision, const int16_t* woff, int nw,
+                        const double* pow_table, int pow_m, int pow_x, uint64_t seed, uint32_t epoch, uint32_t* rec_trader,
+                        int64_t* rec_partner, double* rec_price, int64_t rec_cap, uint32_t* status_dev, void* workspace,
+                        size_t workspace_bytes, mb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -136,7 +136,9 @@ SIGNATURES: dict[str, tuple] = {
     "mb_sugarscape_workspace_bytes": (c_int, [c_int64, c_int64, ctypes.POINTER(ctypes.c_size_t)]),
     "mb_sugarscape_build_count": (c_int, [_P, c_int64, _P, c_int64, _S]),
     "mb_sugarscape_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, c_int64, c_int64, _P, c_int, _P,
-                                   c_int, c_int, c_uint64, c_uint32, _P, _P, ctypes.c_size_t, _S]),
+                                   c_int, c_int, _P, c_int, c_int, c_uint64, c_uint32, _P, _P, ctypes.c_size_t, _S]),
+    "mb_sugarscape_trade": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, _P, c_int, _P, c_int, _P, c_int, c_int,
+                                    c_uint64, c_uint32, _P, _P, _P, c_int64, _P, _P, ctypes.c_size_t, _S]),
     # dynamic populations
     "mb_compact_plan": (c_int, [_P, c_int64, _P, _P, _S]),
     "mb_compact_rows": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _S]),

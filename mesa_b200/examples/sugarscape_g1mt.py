@@ -1,18 +1,19 @@
-"""Sugarscape G1MT on the device, the movement phase (mirror of mesa/examples/advanced/sugarscape_g1mt/model.py:30-134,
-agents.py:20-288 with `enable_trade=False`): sugar and spice regrow, every trader moves to the best empty cell it can see,
-eats, and starves when it runs out of either.
+"""Sugarscape G1MT on the device (mirror of mesa/examples/advanced/sugarscape_g1mt/model.py:30-134, agents.py:20-301): sugar
+and spice regrow, every trader moves to the best empty cell it can see, eats, starves when it runs out of either, and then
+trades sugar for spice with the traders it can see until nobody gains.
 
 The reference model's own step runs unchanged --
 
     self.grid.sugar[:] = np.minimum(self.grid.sugar + 1, self.sugar_distribution)      # and spice
     self.agents.shuffle_do("step")
+    if self.enable_trade: self.agents.shuffle_do("trade_with_neighbors")
 
--- on one DYNAMIC device population (the starved are compacted away after the activation, `unique_id`s persist).  The
-sequential semantics are computed exactly by one launch of a rank-ordered dependency graph (csrc/sugarscape.cu); the same seed
-gives the reference's initial traders, and with the replayed Philox order / draws the reference's trajectory
-(tests/golden/sugarscape_*.npz: ids, cells, sugar and spice of every trader and both layers, bit for bit).
+-- on one DYNAMIC device population (the starved are compacted away after the first activation, `unique_id`s persist).  The
+sequential semantics of both activations are computed exactly, each by one launch of a rank-ordered dependency graph
+(csrc/sugarscape.cu); the same seed gives the reference's initial traders, and with the replayed Philox order / draws the
+reference's trajectory (tests/golden/sugarscape_*.npz: ids, cells, sugar and spice of every trader, both layers, every trade
+with its price, bit for bit; the DataCollector's trade volume and geometric-mean price).
 
-Trade (`trade_with_neighbors`, agents.py:156-207, 290-301) is NOT built: `enable_trade=True` raises NotImplementedError.
 The landscape is the caller's (`sugar_map`: a [width, height] array or a whitespace-separated text file like the reference's
 `sugar-map.txt`); without one a synthetic two-hill landscape with levels 0..4 is used.
 """
@@ -72,6 +73,21 @@ def von_neumann_bfs_offsets(radius: int) -> np.ndarray:
     return np.asarray(found, dtype=np.int16).reshape(-1, 2)
 
 
+def welfare_power_table(max_metabolism: int, max_amount: int) -> np.ndarray:
+    """table[ms - 1][mp - 1][x] = x ** (ms / (ms + mp)) for x = 0 .. max_amount - 1, evaluated by THIS host's libm through
+    `math.pow` -- the function the reference's `sugar ** (self.metabolism_sugar / m_total)` ends in (agents.py:57-70).  The
+    kernels look the welfare up here, so the strict welfare comparisons of the trade criteria (agents.py:138-141) see the
+    reference's bits even on exact mathematical ties."""
+    import math
+
+    table = np.empty((max_metabolism, max_metabolism, max_amount), dtype=np.float64)
+    for ms in range(1, max_metabolism + 1):
+        for mp in range(1, max_metabolism + 1):
+            e = ms / (ms + mp)
+            table[ms - 1, mp - 1] = [math.pow(x, e) for x in range(max_amount)]
+    return table
+
+
 def synthetic_sugar_map(width: int, height: int) -> np.ndarray:
     """Two sugar hills with levels 0..4 (the shape of the classic landscape; NOT the reference's data file)."""
     x, y = np.meshgrid(np.arange(width), np.arange(height), indexing="ij")
@@ -91,22 +107,26 @@ def _trader_step(agents: DeviceAgentSet, epoch: int, **_):
 
 @batch_operator(Trader, "trade_with_neighbors")
 def _trade(agents: DeviceAgentSet, epoch: int, **_):
-    raise NotImplementedError("Sugarscape trade (agents.py:156-207) is not built on the device; use enable_trade=False")
+    agents.model._run_trade(epoch)
+
+
+def geometric_mean(prices) -> float:
+    """model.py:20-27 (the reference's own expression, on the host: same values in the same order, same result)."""
+    if len(prices) == 0:
+        return -1
+    return np.exp(np.log(prices).mean())
 
 
 class SugarscapeG1mt(DeviceModel):
     """Sugarscape with traders (model.py:43-134), movement phase."""
 
     def __init__(self, scenario: SugarScapeScenario = SugarScapeScenario, device="cuda", sugar_map=None, width: int = 50,
-                 height: int = 50, initial_state: dict | None = None):
+                 height: int = 50, initial_state: dict | None = None, pow_table_amounts: int = 16384):
         if isinstance(scenario, type):
             scenario = scenario()
         super().__init__(scenario=scenario)
         sc = scenario
         self.enable_trade = bool(sc.enable_trade)
-        if self.enable_trade:
-            raise NotImplementedError("Sugarscape trade (agents.py:156-207) is not built on the device; use "
-                                      "SugarScapeScenario(enable_trade=False)")
         if isinstance(sugar_map, str):
             sugar_map = np.genfromtxt(sugar_map)                       # model.py:74
         if sugar_map is not None:
@@ -146,14 +166,22 @@ class SugarscapeG1mt(DeviceModel):
         woff = [(dx, dy) for dx in range(-reach, reach + 1) for dy in range(-reach + abs(dx), reach - abs(dx) + 1)]
         self._woff = torch.as_tensor(np.asarray(woff, dtype=np.int16)).to(dev).contiguous()
         self._count = torch.zeros(self.width * self.height, dtype=torch.int32, device=dev)
-        self._status = torch.zeros(2, dtype=torch.int32, device=dev)
+        self._status = torch.zeros(3, dtype=torch.int32, device=dev)
+        mmax = int(max(cols["metabolism_sugar"].max().item(), cols["metabolism_spice"].max().item())) if n else 1
+        self._pow_m, self._pow_x = mmax, int(pow_table_amounts)
+        self._pow = torch.as_tensor(welfare_power_table(self._pow_m, self._pow_x)).to(dev).contiguous()
+        self.inexact_welfares = 0     # pow calls that missed the table so far (amounts >= pow_table_amounts): CUDA pow, <= 2 ulp
         self._ws = None
         self._regrow = False
         self.last_deaths = 0
         self._rebuild_count()
         self.grid.property_layers.hooks["empty"] = self._sync_empty
-        self.datacollector = DeviceDataCollector(model_reporters={          # model.py:62-71 (no trade: volume 0, price -1)
-            "#Traders": lambda m: len(m.agents), "Trade Volume": lambda m: 0, "Price": lambda m: -1})
+        self._trades = (np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.float64))   # this step's trades
+        self._rec = None
+        self.datacollector = DeviceDataCollector(                           # model.py:62-71
+            model_reporters={"#Traders": lambda m: len(m.agents), "Trade Volume": lambda m: len(m._trades[2]),
+                             "Price": lambda m: geometric_mean(list(m._trades[2]))},
+            agent_reporters={"Trade Network": lambda agents: agents.model.trade_partners()})
         self.running = True
 
     def _reference_initial_state(self, sc) -> dict:
@@ -192,9 +220,11 @@ class SugarscapeG1mt(DeviceModel):
                 N.ptr(c["cell"]), N.ptr(c["sugar"]), N.ptr(c["spice"]), N.ptr(c["metabolism_sugar"]), N.ptr(c["metabolism_spice"]),
                 N.ptr(c["vision"]), N.ptr(uid), N.ptr(dead), n, N.ptr(layers["sugar"]), N.ptr(self.sugar_distribution),
                 N.ptr(layers["spice"]), N.ptr(self.spice_distribution), N.ptr(self._count), self.width, self.height,
-                N.ptr(self._voff), self._vmax, N.ptr(self._woff), int(self._woff.shape[0]), int(regrow), self.philox_seed, epoch,
-                N.ptr(self._status), N.ptr(self._ws), self._ws.numel(), N.stream_ptr(dev)))
-        status, deaths = self._status.tolist()
+                N.ptr(self._voff), self._vmax, N.ptr(self._woff), int(self._woff.shape[0]), int(regrow), N.ptr(self._pow),
+                self._pow_m, self._pow_x, self.philox_seed, epoch, N.ptr(self._status), N.ptr(self._ws), self._ws.numel(),
+                N.stream_ptr(dev)))
+        status, deaths, missed = self._status.tolist()
+        self.inexact_welfares += int(missed)
         if status == 2:
             raise NotImplementedError("sugarscape: more than 4 traders started the step in one cell")
         if status:
@@ -203,8 +233,58 @@ class SugarscapeG1mt(DeviceModel):
         if deaths:
             a.remove_agents(dead[:n].bool())          # agents.py:273-281 `self.remove()` (stable: the survivors keep their order)
 
+    def _run_trade(self, epoch: int):
+        a, dev = self.agents, self.grid.device
+        n, ncells = a.n, self.width * self.height
+        nbytes = ctypes.c_size_t(0)
+        N.check(N.lib().mb_sugarscape_workspace_bytes(n, ncells, ctypes.byref(nbytes)))
+        if self._ws is None or self._ws.numel() < nbytes.value:
+            self._ws = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
+        cap = max(64 * n, 1024)
+        if self._rec is None or self._rec[0].numel() < cap:
+            self._rec = (torch.empty(cap, dtype=torch.int32, device=dev), torch.empty(cap, dtype=torch.int64, device=dev),
+                         torch.empty(cap, dtype=torch.float64, device=dev))
+        c = a.columns
+        uid = a.unique_ids().contiguous()
+        with torch.cuda.device(dev):
+            N.check(N.lib().mb_sugarscape_trade(
+                N.ptr(c["cell"]), N.ptr(c["sugar"]), N.ptr(c["spice"]), N.ptr(c["metabolism_sugar"]), N.ptr(c["metabolism_spice"]),
+                N.ptr(c["vision"]), N.ptr(uid), n, self.width, self.height, N.ptr(self._voff), self._vmax, N.ptr(self._woff),
+                int(self._woff.shape[0]), N.ptr(self._pow), self._pow_m, self._pow_x, self.philox_seed, epoch, N.ptr(self._rec[0]),
+                N.ptr(self._rec[1]), N.ptr(self._rec[2]), self._rec[0].numel(), N.ptr(self._status), N.ptr(self._ws),
+                self._ws.numel(), N.stream_ptr(dev)))
+        status, ntrades, missed = self._status.tolist()
+        self.inexact_welfares += int(missed)
+        if status == 2:
+            raise NotImplementedError("sugarscape: more than 4 traders stand in one cell")
+        if status:
+            raise RuntimeError("sugarscape: a dependency wait ran into its spin limit; the step is not valid")
+        if ntrades > self._rec[0].numel():
+            raise RuntimeError("sugarscape: more trades than the record buffer holds (the amounts are right, the record is not)")
+        rows = self._rec[0][:ntrades].cpu().numpy().astype(np.int64)
+        order = np.argsort(rows, kind="stable")          # model.agents order; a trader's trades stay in the order it made them
+        ids = uid.cpu().numpy()
+        self._trades = (ids[rows[order]], self._rec[1][:ntrades].cpu().numpy()[order], self._rec[2][:ntrades].cpu().numpy()[order])
+
+    def trade_records(self):
+        """This step's trades as (trader unique ids, partner unique ids, prices), flattened in `model.agents` order -- what
+        `[a.trade_partners for a in model.agents]` / `[a.prices ...]` hold in the reference (agents.py:196-201)."""
+        return self._trades
+
+    def trade_partners(self) -> np.ndarray:
+        """Per trader (rows of `model.agents`) the list of partner ids of this step (agents.py:201 `trade_partners`)."""
+        ids = self.agents.unique_ids().cpu().numpy()
+        out = np.empty(len(ids), dtype=object)
+        lists = {int(i): [] for i in ids}
+        for t, p in zip(self._trades[0], self._trades[1]):
+            lists[int(t)].append(int(p))
+        for k, i in enumerate(ids):
+            out[k] = lists[int(i)]
+        return out
+
     def step(self):
         """model.py:118-131."""
+        self._trades = (np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.float64))     # agents.py:284-285
         self._regrow = True                                # model.py:123-124, fused into the activation's launch sequence
         self.agents.shuffle_do("step")
         if self.enable_trade:

@@ -646,14 +646,14 @@ def epstein_fixtures():
                     cop_vision=2, citizen_vision=2)                                            # nobody moves
 
 
-def sugarscape_fixture(name, steps, mt_seed, philox_seed, **params):
+def sugarscape_fixture(name, steps, mt_seed, philox_seed, trade=False, **params):
     """The unmodified SugarscapeG1mt model (examples/advanced/sugarscape_g1mt) with enable_trade=False under the replayed
     order / draws: after every step the traders (unique ids in model.agents order, cells, sugar, spice) and both layers."""
     from mesa.examples.advanced.sugarscape_g1mt.agents import Trader
     from mesa.examples.advanced.sugarscape_g1mt.model import SugarscapeG1mt, SugarScapeScenario
 
     with patched_model_random(philox_seed):
-        m = SugarscapeG1mt(SugarScapeScenario(rng=mt_seed, enable_trade=False, **params))
+        m = SugarscapeG1mt(SugarScapeScenario(rng=mt_seed, enable_trade=trade, **params))
     rng = m.random
     assert isinstance(rng, ReplayRandom)
     W, H = m.grid.dimensions
@@ -674,10 +674,13 @@ def sugarscape_fixture(name, steps, mt_seed, philox_seed, **params):
                                  m.scenario.metabolism_min, m.scenario.metabolism_max, m.scenario.vision_min, m.scenario.vision_max])}
     out["id_0"], out["cell_0"], out["sugar_0"], out["spice_0"] = table()
     rng.replay = True
-    with activation_context(Trader, "step"):
+    with activation_context(Trader, "step"), activation_context(Trader, "trade_with_neighbors"):
         for s in range(1, steps + 1):
             m.step()
             out[f"id_{s}"], out[f"cell_{s}"], out[f"sugar_{s}"], out[f"spice_{s}"] = table()
+            if trade:   # this step's trades, flattened in model.agents order: (trader id, partner id, price)
+                rec = [(a.unique_id, p, pr) for a in m.agents for p, pr in zip(a.trade_partners, a.prices)]
+                out[f"trades_{s}"] = np.array(rec, dtype=np.float64).reshape(-1, 3)
             if s in (1, steps // 2, steps):
                 out[f"sugar_layer_{s}"] = np.asarray(m.grid.sugar.data if hasattr(m.grid.sugar, "data") else m.grid.sugar, dtype=np.float64).copy()
                 out[f"spice_layer_{s}"] = np.asarray(m.grid.spice.data if hasattr(m.grid.spice, "data") else m.grid.spice, dtype=np.float64).copy()
@@ -692,6 +695,8 @@ def sugarscape_fixtures():
     sugarscape_fixture("sugarscape_600_crowded.npz", 20, 7, 43, initial_population=600, vision_max=3)     # shared cells at the start
     sugarscape_fixture("sugarscape_80_farsighted.npz", 25, 3, 44, initial_population=80, vision_min=4, vision_max=5,
                        metabolism_max=3)
+    sugarscape_fixture("sugarscape_200_trade.npz", 30, 42, 45, trade=True)                                # the scenario's defaults
+    sugarscape_fixture("sugarscape_500_trade_crowded.npz", 15, 11, 46, trade=True, initial_population=500, vision_max=4)
 
 
 def main():

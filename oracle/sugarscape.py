@@ -1,4 +1,4 @@
-"""Sequential restatement of the Sugarscape G1MT model's movement phase -- TEST INFRASTRUCTURE (oracle; the product never
+"""Sequential restatement of the Sugarscape G1MT model (movement and trade) -- TEST INFRASTRUCTURE (oracle; the product never
 imports it).
 
 Follows mesa/examples/advanced/sugarscape_g1mt (model.py:118-127 without trade, agents.py:209-288) statement by statement
@@ -14,6 +14,9 @@ tests/golden/sugarscape_*.npz (oracle/make_golden.py runs the live reference).
                    math.isclose of the best welfare, of those the ones within 1 % of the smallest Euclidean distance,
                    random.choice of these                                                           agents.py:209-262
     eat / die      agents.py:264-281 (the cell's sugar and spice are taken whole; starved = sugar <= 0 or spice <= 0)
+    trade          model.py:128-129 a second shuffle; agents.py:290-301: every trader in the radius-vision neighbourhood (BFS
+                   order of the cells, centre excluded; a cell's traders in arrival order = ascending unique_id, since traders
+                   only ever move to EMPTY cells) is traded with until no trade happens (agents.py:156-207, 113-153)
     keys           priority / draws keyed on unique_id - 1 (agents die: rows are not ids)
 """
 from __future__ import annotations
@@ -88,3 +91,55 @@ class SugarscapeOracle:
         for name in ("uid", "cell", "sugar", "spice", "ms", "mp", "vision"):
             setattr(self, name, getattr(self, name)[keep])
         self.epoch += 1
+
+    # ------------------------------------------------------------------ trade (agents.py:84-207, 290-301)
+    def mrs(self, a, sugar, spice):
+        return (spice / self.mp[a]) / (sugar / self.ms[a])                                       # agents.py:84-92
+
+    def _maybe_sell_spice(self, seller, buyer, price, w_seller, w_buyer):
+        if price >= 1:                                                                           # agents.py:94-106
+            sugar_ex, spice_ex = 1, int(price)
+        else:
+            sugar_ex, spice_ex = int(1 / price), 1
+        s_sugar, b_sugar = self.sugar[seller] + sugar_ex, self.sugar[buyer] - sugar_ex
+        s_spice, b_spice = self.spice[seller] - spice_ex, self.spice[buyer] + spice_ex
+        if s_sugar <= 0 or b_sugar <= 0 or s_spice <= 0 or b_spice <= 0:
+            return False
+        better = (w_seller < self.welfare(seller, s_sugar, s_spice)) and (w_buyer < self.welfare(buyer, b_sugar, b_spice))
+        not_crossing = self.mrs(seller, s_sugar, s_spice) > self.mrs(buyer, b_sugar, b_spice)
+        if not (better and not_crossing):
+            return False
+        self.sugar[seller], self.sugar[buyer], self.spice[seller], self.spice[buyer] = s_sugar, b_sugar, s_spice, b_spice
+        return True
+
+    def trade_phase(self):
+        """model.py:128-129; returns per trader (rows) the lists of prices and partner ids of this step."""
+        n = len(self.uid)
+        pri = philox.priority64(self.seed, self.epoch, (self.uid - 1).astype(np.uint64))
+        order = np.argsort(pri, kind="stable")
+        by_cell = {}
+        for i in np.argsort(self.uid, kind="stable"):
+            by_cell.setdefault(int(self.cell[i]), []).append(int(i))
+        prices, partners = [[] for _ in range(n)], [[] for _ in range(n)]
+        for a in order:
+            a = int(a)
+            x, y = divmod(int(self.cell[a]), self.height)
+            for dx, dy in self.offsets[int(self.vision[a])][:-1]:
+                nx, ny = x + dx, y + dy
+                if not (0 <= nx < self.width and 0 <= ny < self.height):
+                    continue
+                for b in by_cell.get(nx * self.height + ny, ()):
+                    while True:                                                                  # agents.py:156-207 (the recursion)
+                        mrs_a, mrs_b = self.mrs(a, self.sugar[a], self.spice[a]), self.mrs(b, self.sugar[b], self.spice[b])
+                        w_a, w_b = self.welfare(a, self.sugar[a], self.spice[a]), self.welfare(b, self.sugar[b], self.spice[b])
+                        if math.isclose(mrs_a, mrs_b):
+                            break
+                        price = math.sqrt(mrs_a * mrs_b)
+                        sold = (self._maybe_sell_spice(a, b, price, w_a, w_b) if mrs_a > mrs_b else
+                                self._maybe_sell_spice(b, a, price, w_b, w_a))
+                        if not sold:
+                            break
+                        prices[a].append(price)
+                        partners[a].append(int(self.uid[b]))
+        self.epoch += 1
+        return prices, partners

@@ -1,4 +1,4 @@
-"""Sugarscape G1MT's movement phase on the device (mesa_b200/examples/sugarscape_g1mt.py, csrc/sugarscape.cu) against the
+"""Sugarscape G1MT (movement and trade) on the device (mesa_b200/examples/sugarscape_g1mt.py, csrc/sugarscape.cu) against the
 unmodified reference model (enable_trade=False) run under the replayed Philox order / draws (tests/golden/sugarscape_*.npz,
 oracle/make_golden.py): after every step the same traders (unique ids in model.agents order) in the same cells with the same
 sugar and spice, the same layers; on larger landscapes against the sequential restatement (oracle/sugarscape.py)."""
@@ -10,7 +10,8 @@ import torch
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-FIXTURES = ["sugarscape_200.npz", "sugarscape_600_crowded.npz", "sugarscape_80_farsighted.npz"]
+FIXTURES = ["sugarscape_200.npz", "sugarscape_600_crowded.npz", "sugarscape_80_farsighted.npz", "sugarscape_200_trade.npz",
+            "sugarscape_500_trade_crowded.npz"]
 
 
 def _scenario(g, **kw):
@@ -18,7 +19,7 @@ def _scenario(g, **kw):
 
     n, emin, emax, mmin, mmax, vmin, vmax = (int(v) for v in g["scenario"])
     return SugarScapeScenario(initial_population=n, endowment_min=emin, endowment_max=emax, metabolism_min=mmin,
-                              metabolism_max=mmax, vision_min=vmin, vision_max=vmax, enable_trade=False, **kw)
+                              metabolism_max=mmax, vision_min=vmin, vision_max=vmax, enable_trade="trades_1" in g, **kw)
 
 
 def _table(m):
@@ -46,10 +47,15 @@ def test_sugarscape_matches_the_reference_trajectory(name):
         if f"sugar_layer_{s}" in g:
             assert np.array_equal(m.grid.sugar.cpu().numpy(), g[f"sugar_layer_{s}"]), (name, s)
             assert np.array_equal(m.grid.spice.cpu().numpy(), g[f"spice_layer_{s}"]), (name, s)
+        if "trades_1" in g:     # every trade of the step: (trader id, partner id, price) in model.agents order, prices bit for bit
+            t, p, pr = m.trade_records()
+            want = g[f"trades_{s}"]
+            assert np.array_equal(t, want[:, 0].astype(np.int64)) and np.array_equal(p, want[:, 1].astype(np.int64)), (name, s)
+            assert np.array_equal(pr, want[:, 2]), (name, s)
         count = np.bincount(cells, minlength=m.width * m.height)
         assert np.array_equal(m._count.cpu().numpy(), count) and np.array_equal(m.grid.empty.cpu().numpy().reshape(-1), count == 0)
     counts = m.datacollector.get_model_vars_dataframe().to_numpy()
-    assert np.array_equal(counts, g["counts"])              # #Traders, Trade Volume (0), Price (-1) as the reference's collector saw them
+    assert np.array_equal(counts, g["counts"])              # #Traders, Trade Volume, Price (geometric mean) as the reference's collector saw them
 
 
 @pytest.mark.parametrize("name", FIXTURES)
@@ -91,8 +97,34 @@ def test_sugarscape_matches_the_sequential_restatement_on_larger_landscapes(side
     assert len(m.agents) < n                                                # some starved
 
 
-def test_trade_is_not_built():
-    from mesa_b200.examples.sugarscape_g1mt import SugarScapeScenario, SugarscapeG1mt
+@pytest.mark.parametrize("side,n", [(120, 5000)])
+def test_sugarscape_trade_matches_the_sequential_restatement_on_a_larger_landscape(side, n):
+    from mesa_b200.examples.sugarscape_g1mt import SugarScapeScenario, SugarscapeG1mt, synthetic_sugar_map
+    from oracle.sugarscape import SugarscapeOracle
 
-    with pytest.raises(NotImplementedError):
-        SugarscapeG1mt(SugarScapeScenario(rng=1))                           # enable_trade defaults to True like the reference's
+    rs = np.random.default_rng(3)
+    smap = synthetic_sugar_map(side, side)
+    cells = rs.choice(side * side, size=n, replace=True)                   # some cells hold two or three traders
+    keep = np.ones(n, dtype=bool)
+    for c in np.flatnonzero(np.bincount(cells, minlength=side * side) > 4):
+        keep[np.flatnonzero(cells == c)[4:]] = False
+    cells = cells[keep]
+    n = len(cells)
+    init = {"cell": cells, "sugar": rs.integers(25, 51, n), "spice": rs.integers(25, 51, n), "metabolism_sugar": rs.integers(1, 6, n),
+            "metabolism_spice": rs.integers(1, 6, n), "vision": rs.integers(1, 6, n)}
+    m = SugarscapeG1mt(SugarScapeScenario(enable_trade=True, rng=5), sugar_map=smap, initial_state=init)
+    o = SugarscapeOracle(side, side, smap, np.flip(smap, 1), np.arange(1, n + 1), cells, init["sugar"], init["spice"],
+                         init["metabolism_sugar"], init["metabolism_spice"], init["vision"], philox_seed=m.philox_seed)
+    volume = 0
+    for s in range(4):
+        m.step()
+        o.step()
+        prices, partners = o.trade_phase()
+        ids, cell, sugar, spice = _table(m)
+        assert np.array_equal(ids, o.uid) and np.array_equal(cell, o.cell), s
+        assert np.array_equal(sugar, o.sugar) and np.array_equal(spice, o.spice), s
+        t, p, pr = m.trade_records()
+        assert np.array_equal(p, np.array([q for row in partners for q in row], dtype=np.int64)), s
+        assert np.array_equal(pr, np.array([q for row in prices for q in row], dtype=np.float64)), s
+        volume += len(pr)
+    assert volume > 1000
