@@ -702,6 +702,9 @@ def _flat_workload_keys(details):
         if name.startswith("wolf_sheep_1e6") and "ms_per_step" in w:
             flat["wolf_sheep_ms_per_step"] = w["ms_per_step"]
             flat["wolf_sheep_updates_per_s"] = w["agent_updates_per_s"]
+        if name.startswith("sugarscape_g1mt_512") and "ms_per_step" in w:
+            flat["sugarscape_512_ms_per_step"] = w["ms_per_step"]
+            flat["sugarscape_512_updates_per_s"] = w["agent_updates_per_s"]
         if name == "epstein_1024x1024_vision7" and "ms_per_step" in w:
             flat["epstein_1024_ms_per_step"] = w["ms_per_step"]
             flat["epstein_1024_updates_per_s"] = w["agent_updates_per_s"]
@@ -901,6 +904,36 @@ def other_workloads(dev):
             del em
     except Exception as exc:  # reported, never fatal
         out.append({"workload": "epstein", "error": repr(exc)[:200]})
+    # Sugarscape G1MT (regrowth, move / eat / die, trade) on a synthetic 512 x 512 landscape, 40 000 traders
+    try:
+        import numpy as np
+
+        from mesa_b200.examples.sugarscape_g1mt import SugarScapeScenario, SugarscapeG1mt
+
+        rs = np.random.default_rng(1)
+        ns, side = 40_000, 512
+        init = {"cell": rs.choice(side * side, size=ns, replace=False), "sugar": rs.integers(25, 51, ns), "spice": rs.integers(25, 51, ns),
+                "metabolism_sugar": rs.integers(1, 6, ns), "metabolism_spice": rs.integers(1, 6, ns), "vision": rs.integers(1, 6, ns)}
+        sm = SugarscapeG1mt(SugarScapeScenario(enable_trade=True, rng=1), width=side, height=side, initial_state=init)
+        for _ in range(2):
+            sm.step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        acted = trades = 0
+        for _ in range(10):
+            acted += 2 * len(sm.agents)                                # two activations per step (move, trade)
+            sm.step()
+            trades += len(sm.trade_records()[2])
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out.append({"workload": "sugarscape_g1mt_512x512_40000_traders_with_trade", "ms_per_step": dt / 10 * 1e3,
+                    "agent_updates_per_s": acted / dt, "traders_end": len(sm.agents), "trades_per_step": trades / 10,
+                    "inexact_welfares": sm.inexact_welfares,
+                    "note": "two rank-ordered dependency graphs per step (csrc/sugarscape.cu) + the host side of the reference's "
+                            "collector (per-trader partner lists); the starved are compacted away every step"})
+        del sm
+    except Exception as exc:  # reported, never fatal
+        out.append({"workload": "sugarscape", "error": repr(exc)[:200]})
     # config 2: Boltzmann wealth, 10^6 agents on 4096^2
     m = BoltzmannWealth(BoltzmannScenario(n=1_000_000, width=4096, height=4096, rng=1))
     m.run_for(3)

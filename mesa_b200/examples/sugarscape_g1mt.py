@@ -177,6 +177,7 @@ class SugarscapeG1mt(DeviceModel):
         self._rebuild_count()
         self.grid.property_layers.hooks["empty"] = self._sync_empty
         self._trades = (np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.float64))   # this step's trades
+        self._trade_rows = np.zeros(0, np.int64)
         self._rec = None
         self.datacollector = DeviceDataCollector(                           # model.py:62-71
             model_reporters={"#Traders": lambda m: len(m.agents), "Trade Volume": lambda m: len(m._trades[2]),
@@ -185,14 +186,12 @@ class SugarscapeG1mt(DeviceModel):
         self.running = True
 
     def _reference_initial_state(self, sc) -> dict:
-        """model.py:80-116 with the model's own two generators, call for call (the arguments of `Trader.create_agents` are
-        evaluated left to right): the same seed gives the reference's traders."""
-        n = sc.initial_population
-        cells = np.asarray(self.random.choices(range(self.width * self.height), k=n), dtype=np.int64)
-        draw = lambda lo, hi: self.rng.integers(lo, hi, (n,), endpoint=True)       # noqa: E731
-        return {"cell": cells, "sugar": draw(sc.endowment_min, sc.endowment_max), "spice": draw(sc.endowment_min, sc.endowment_max),
-                "metabolism_sugar": draw(sc.metabolism_min, sc.metabolism_max),
-                "metabolism_spice": draw(sc.metabolism_min, sc.metabolism_max), "vision": draw(sc.vision_min, sc.vision_max)}
+        """model.py:80-116 on the model's own two generators (reference_init.sugarscape_initial_state): the same seed gives
+        the reference's traders."""
+        from ..reference_init import sugarscape_initial_state
+
+        return sugarscape_initial_state(self.random, self.rng, self.width * self.height, sc.initial_population, sc.endowment_min,
+                                        sc.endowment_max, sc.metabolism_min, sc.metabolism_max, sc.vision_min, sc.vision_max)
 
     def _rebuild_count(self):
         dev = self.grid.device
@@ -264,7 +263,8 @@ class SugarscapeG1mt(DeviceModel):
         rows = self._rec[0][:ntrades].cpu().numpy().astype(np.int64)
         order = np.argsort(rows, kind="stable")          # model.agents order; a trader's trades stay in the order it made them
         ids = uid.cpu().numpy()
-        self._trades = (ids[rows[order]], self._rec[1][:ntrades].cpu().numpy()[order], self._rec[2][:ntrades].cpu().numpy()[order])
+        self._trade_rows = rows[order]
+        self._trades = (ids[self._trade_rows], self._rec[1][:ntrades].cpu().numpy()[order], self._rec[2][:ntrades].cpu().numpy()[order])
 
     def trade_records(self):
         """This step's trades as (trader unique ids, partner unique ids, prices), flattened in `model.agents` order -- what
@@ -272,19 +272,24 @@ class SugarscapeG1mt(DeviceModel):
         return self._trades
 
     def trade_partners(self) -> np.ndarray:
-        """Per trader (rows of `model.agents`) the list of partner ids of this step (agents.py:201 `trade_partners`)."""
-        ids = self.agents.unique_ids().cpu().numpy()
-        out = np.empty(len(ids), dtype=object)
-        lists = {int(i): [] for i in ids}
-        for t, p in zip(self._trades[0], self._trades[1]):
-            lists[int(t)].append(int(p))
-        for k, i in enumerate(ids):
-            out[k] = lists[int(i)]
+        """Per trader (rows of `model.agents`) the list of partner ids of this step (agents.py:201 `trade_partners`); the
+        traders that did not trade share one empty list."""
+        n = len(self.agents)
+        out = np.empty(n, dtype=object)
+        out[:] = [[]] * n
+        rows = self._trade_rows
+        if len(rows):
+            starts = np.flatnonzero(np.r_[True, rows[1:] != rows[:-1]])
+            ends = np.r_[starts[1:], len(rows)]
+            partners = self._trades[1].tolist()
+            for r, lo, hi in zip(rows[starts].tolist(), starts.tolist(), ends.tolist()):
+                out[r] = partners[lo:hi]
         return out
 
     def step(self):
         """model.py:118-131."""
         self._trades = (np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.float64))     # agents.py:284-285
+        self._trade_rows = np.zeros(0, np.int64)
         self._regrow = True                                # model.py:123-124, fused into the activation's launch sequence
         self.agents.shuffle_do("step")
         if self.enable_trade:

@@ -101,3 +101,16 @@ def epstein_initial_state(rnd: _random.Random, width: int, height: int, citizen_
         risk.append(rnd.random() if k == 0 else 0.0)
     return {"kind": np.asarray(kind, dtype=np.uint8), "cell": np.asarray(cell, dtype=np.int64),
             "hardship": np.asarray(hardship, dtype=np.float64), "risk_aversion": np.asarray(risk, dtype=np.float64)}
+
+
+def sugarscape_initial_state(rnd: _random.Random, gen: np.random.Generator, ncells: int, initial_population: int, endowment_min: int,
+                             endowment_max: int, metabolism_min: int, metabolism_max: int, vision_min: int, vision_max: int) -> dict:
+    """sugarscape_g1mt/model.py:80-116 on the model's two generators, call for call: the cells from `random.choices(cells, k=n)`
+    (stdlib stream), then sugar, spice, metabolism_sugar, metabolism_spice and vision from `rng.integers(lo, hi, (n,),
+    endpoint=True)` (numpy stream) in the order the arguments of `Trader.create_agents` are evaluated."""
+    n = int(initial_population)
+    cells = np.asarray(rnd.choices(range(int(ncells)), k=n), dtype=np.int64)
+    draw = lambda lo, hi: gen.integers(lo, hi, (n,), endpoint=True)       # noqa: E731
+    return {"cell": cells, "sugar": draw(endowment_min, endowment_max), "spice": draw(endowment_min, endowment_max),
+            "metabolism_sugar": draw(metabolism_min, metabolism_max), "metabolism_spice": draw(metabolism_min, metabolism_max),
+            "vision": draw(vision_min, vision_max)}

@@ -271,3 +271,39 @@ def test_epstein_from_a_seed(replay, seed, width, height, params):
             assert np.array_equal(o.jail[cit], np.array([a.jail_sentence for a in agents if isinstance(a, Citizen)])), step
             assert o.counts() == (m.ACTIVE, m.QUIET, m.ARRESTED), step
     m.random.replay = False
+
+
+@pytest.mark.parametrize("seed,params", [(2718, dict(initial_population=150)), (99, dict(initial_population=400, vision_max=3, metabolism_max=4))])
+def test_sugarscape_from_a_seed(replay, seed, params):
+    """Sugarscape G1MT with trade: initial traders from the seed (reference_init.sugarscape_initial_state), trajectory and
+    every trade from the sequential restatement (oracle/sugarscape.py) == the unmodified model under the replayed order / draws."""
+    from mesa.examples.advanced.sugarscape_g1mt.agents import Trader
+    from mesa.examples.advanced.sugarscape_g1mt.model import SugarscapeG1mt, SugarScapeScenario
+    from oracle.sugarscape import SugarscapeOracle
+
+    philox_seed = seed + 1
+    with replay.patched_model_random(philox_seed):
+        m = SugarscapeG1mt(SugarScapeScenario(rng=seed, enable_trade=True, **params))
+    W, H = m.grid.dimensions
+    sc = m.scenario
+    gen, stdlib_seed = ri.seed_streams(seed)
+    st = ri.sugarscape_initial_state(random.Random(stdlib_seed), gen, W * H, sc.initial_population, sc.endowment_min, sc.endowment_max,
+                                     sc.metabolism_min, sc.metabolism_max, sc.vision_min, sc.vision_max)
+    agents = list(m.agents)
+    cells = lambda: np.array([a.cell.coordinate[0] * H + a.cell.coordinate[1] for a in m.agents], dtype=np.int64)   # noqa: E731
+    assert np.array_equal(st["cell"], cells())
+    for name in ("sugar", "spice", "metabolism_sugar", "metabolism_spice", "vision"):
+        assert np.array_equal(st[name], np.array([getattr(a, name) for a in agents])), name
+    o = SugarscapeOracle(W, H, m.sugar_distribution, m.spice_distribution, np.arange(1, len(agents) + 1), st["cell"], st["sugar"],
+                         st["spice"], st["metabolism_sugar"], st["metabolism_spice"], st["vision"], philox_seed=philox_seed)
+    m.random.replay = True
+    with replay.activation_context(Trader, "step"), replay.activation_context(Trader, "trade_with_neighbors"):
+        for step in range(6):
+            m.step()
+            o.step()
+            prices, partners = o.trade_phase()
+            assert np.array_equal(o.uid, np.array([a.unique_id for a in m.agents])) and np.array_equal(o.cell, cells()), step
+            assert np.array_equal(o.sugar, np.array([a.sugar for a in m.agents], dtype=np.float64)), step
+            assert np.array_equal(o.spice, np.array([a.spice for a in m.agents], dtype=np.float64)), step
+            assert [list(a.trade_partners) for a in m.agents] == partners and [list(a.prices) for a in m.agents] == prices, step
+    m.random.replay = False
