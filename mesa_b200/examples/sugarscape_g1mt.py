@@ -117,6 +117,22 @@ def geometric_mean(prices) -> float:
     return np.exp(np.log(prices).mean())
 
 
+def _report_traders(m):
+    return len(m.agents)
+
+
+def _report_volume(m):
+    return len(m._trades[2])
+
+
+def _report_price(m):
+    return geometric_mean(list(m._trades[2]))
+
+
+def _report_network(agents):
+    return agents.model.trade_partners()
+
+
 class SugarscapeG1mt(DeviceModel):
     """Sugarscape with traders (model.py:43-134), movement phase."""
 
@@ -179,10 +195,9 @@ class SugarscapeG1mt(DeviceModel):
         self._trades = (np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.float64))   # this step's trades
         self._trade_rows = np.zeros(0, np.int64)
         self._rec = None
-        self.datacollector = DeviceDataCollector(                           # model.py:62-71
-            model_reporters={"#Traders": lambda m: len(m.agents), "Trade Volume": lambda m: len(m._trades[2]),
-                             "Price": lambda m: geometric_mean(list(m._trades[2]))},
-            agent_reporters={"Trade Network": lambda agents: agents.model.trade_partners()})
+        self.datacollector = DeviceDataCollector(                           # model.py:62-71 (module-level functions: models pickle)
+            model_reporters={"#Traders": _report_traders, "Trade Volume": _report_volume, "Price": _report_price},
+            agent_reporters={"Trade Network": _report_network})
         self.running = True
 
     def _reference_initial_state(self, sc) -> dict:

@@ -178,6 +178,18 @@ def _wolf_step(agents: DeviceAgentSet, epoch: int, **_):
         agents.remove_agents(dead_full)
 
 
+def _report_wolves(m):
+    return len(m.agents_by_type[Wolf])
+
+
+def _report_sheep(m):
+    return len(m.agents_by_type[Sheep])
+
+
+def _report_grass(m):
+    return int(ops.layer_reduce(m.grid.grass_grown, "sum").item())
+
+
 class WolfSheep(DeviceModel):
     """Wolf-Sheep Predation Model (wolf_sheep/model.py:53-141)."""
 
@@ -218,9 +230,9 @@ class WolfSheep(DeviceModel):
             self.grid.add_property_layer("grass_regrow_at", regrow)
             self.agent_id_counter += ncells          # the reference registers one GrassPatch per cell (model.py:120-131)
         self.agent_id_counter = int(st.get("next_id", self.agent_id_counter))
-        reporters = {"Wolves": lambda m: len(m.agents_by_type[Wolf]), "Sheep": lambda m: len(m.agents_by_type[Sheep])}
+        reporters = {"Wolves": _report_wolves, "Sheep": _report_sheep}       # (module-level functions: models pickle)
         if self.grass:
-            reporters["Grass"] = lambda m: int(ops.layer_reduce(m.grid.grass_grown, "sum").item())
+            reporters["Grass"] = _report_grass
         self.datacollector = DeviceDataCollector(model_reporters=reporters)
         self.running = True
         self.datacollector.collect(self)
