@@ -722,25 +722,38 @@ boids_seq_chain(const float4* __restrict__ packed, const uint32_t* __restrict__ 
                         }
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
+                            // ONE float64 pair evaluation per candidate slot for all lanes, switched on by a predicate: with
+                            // the evaluation inside the branches (irrelevant / new state / old state) each copy ran at ~3.5 of
+                            // 32 lanes and was 65 % of the kernel's warp instructions (profiles/r2_boids_seq_chain_ncu.csv).
+                            // It only moved the step from 12.3 to 12.1 ms at 10^7 boids: the kernel is bound by the memory
+                            // traffic of rank-ordered access (21 GB of DRAM reads per step, 29 % L2 hits), not by issue.
                             const uint32_t j = j0 + u;
-                            if (j >= e || j == i) continue;
                             float dx = fabsf(me.x - o[u].x), dy = fabsf(me.y - o[u].y);
                             if (g.torus) {
                                 dx = fminf(dx, sp.fsx - dx);
                                 dy = fminf(dy, sp.fsy - dy);
                             }
                             const float d2 = fmaf(dx, dx, dy * dy);
-                            if (d2 > sp.relevant2) continue;        // cannot be within vision before or after its move
-                            if (rj[u] < myrank) {                   // acts before me: I see its NEW state
-                                if (!load_new_state(newst, j, np_, nd_)) {
-                                    blocker = j;
-                                    return;
-                                }
-                                boid_pair_d(g, bp, px, py, np_.x, np_.y, nd_.x, nd_.y, acc);
-                            } else if (d2 <= sp.far2) {             // acts after me: its OLD state
-                                boid_pair(g, bp, px, py, o[u], acc);
+                            // relevant: can be within vision before or after its move
+                            const bool valid = blocker == 0xffffffffu && j < e && j != i && d2 <= sp.relevant2;
+                            bool use_new = valid && rj[u] < myrank;                     // acts before me: I see its NEW state
+                            const bool use_old = valid && !use_new && d2 <= sp.far2;    // acts after me: its OLD state
+                            if (use_new && !load_new_state(newst, j, np_, nd_)) {
+                                blocker = j;
+                                use_new = false;
+                            }
+                            const double ox = use_new ? np_.x : (double)o[u].x, oy = use_new ? np_.y : (double)o[u].y;
+                            const double odx = use_new ? nd_.x : (double)o[u].z, ody = use_new ? nd_.y : (double)o[u].w;
+                            const double dd2 = ref_distance2(g, px, py, ox, oy);
+                            const double ddx = ref_delta(ox, px, g.sx, g.torus), ddy = ref_delta(oy, py, g.sy, g.torus);
+                            if ((use_new || use_old) && dd2 <= bp.vision2_le) {         // boid_pair_d, agents.py:66-85
+                                acc.cohx += ddx; acc.cohy += ddy;
+                                if (dd2 < bp.separation2_lt) { acc.sepx += ddx; acc.sepy += ddy; }
+                                acc.mx += odx; acc.my += ody;
+                                ++acc.k;
                             }
                         }
+                        if (blocker != 0xffffffffu) return;
                     }
                 });
                 if (blocker == 0xffffffffu) {
