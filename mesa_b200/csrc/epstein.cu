@@ -34,6 +34,7 @@ namespace {
 
 constexpr uint32_t kNoRank = 0xffffffffu;
 constexpr int kThreads = 256;
+constexpr unsigned kPollSleepNs = 100;
 constexpr unsigned kSpinLimit = 1u << 22;   // polls of one block of the dependency range before a warp gives up (status word, no hang)
 constexpr uint8_t kActive = 1, kQuiet = 2, kArrested = 3;   // CitizenState (agents.py:7-10)
 
@@ -275,6 +276,255 @@ eps_chain(EpsArgs a, EpsWs ws, int batch) {
     }
 }
 
+// ======================================================================================================================
+// The single-CTA variant for small grids: its own copy of the act code (shared-memory accessors, work moved before the
+// dependency wait) -- the multi-CTA kernel above is throughput-bound at the sizes it serves and keeps its registers low.
+// kShared: the occupancy words and the jail sentences live in SHARED memory (the single-CTA kernel for small grids below);
+// the pointers are generic, the accesses volatile instead of L2-coherent loads
+template <bool kShared>
+__device__ __forceinline__ int32_t ld_live(const int32_t* p) {
+    return kShared ? *reinterpret_cast<const volatile int32_t*>(p) : __ldcg(p);
+}
+template <bool kShared>
+__device__ __forceinline__ void st_live(int32_t* p, int32_t v) {
+    if (kShared) *reinterpret_cast<volatile int32_t*>(p) = v;
+    else *p = v;
+}
+
+template <bool kEmpty, bool kShared>
+__device__ __forceinline__ int select_kth_s(const EpsArgs& a, int x, int y, int k, int lane, const int32_t (&w0)[kPer],
+                                          const int (&c0)[kPer], int32_t* word_out) {
+    for (int blk = 0; blk * kBlock < a.nv; ++blk) {
+        int32_t w[kPer];
+        int c[kPer];
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+            if (blk == 0) { w[q] = w0[q]; c[q] = c0[q]; continue; }
+            const int i = blk * kBlock + q * 32 + lane;
+            c[q] = i < a.nv ? wrap_cell(x, y, kShared ? a.voff[i] : __ldg(a.voff + i), a.width, a.height) : -1;
+            w[q] = c[q] >= 0 ? ld_live<kShared>(a.occ + c[q]) : 0;   // padding word 0 satisfies no predicate
+        }
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+            const unsigned b = __ballot_sync(0xffffffffu, c[q] >= 0 && hit_word<kEmpty>(w[q]));
+            const int nhit = __popc(b);
+            if (k < nhit) {
+                const int src = (int)__fns(b, 0u, (unsigned)k + 1u);
+                *word_out = __shfl_sync(0xffffffffu, w[q], src);
+                return __shfl_sync(0xffffffffu, c[q], src);
+            }
+            k -= nhit;
+        }
+    }
+    return -1;
+}
+
+// What does not depend on the other agents is computed BEFORE the dependency wait (the agent's constants, the cells of its
+// neighbourhood, the first draws of its stream): the ~900 dependency levels of a step are a chain of act_warp calls, and
+// every instruction between "the last dependency is done" and "my flag is set" is paid once per level.
+struct PreAct {
+    int c0[kPer];          // cells of the first neighbourhood block (this lane's)
+    uint64_t draw[4];      // the first four 64-bit draws of the agent's stream
+    bool cop;
+    double risk_aversion, grievance;
+};
+
+template <bool kShared>
+__device__ __forceinline__ void pre_act(const EpsArgs& a, uint32_t agent, int x, int y, int lane, PreAct& pre) {
+    pre.cop = __ldg(a.kind + agent) != 0;
+    pre.risk_aversion = __ldg(a.risk_aversion + agent);
+    pre.grievance = __ldg(a.grievance + agent);
+    if (kShared) {
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+            const int i = q * 32 + lane;
+            pre.c0[q] = i < a.nv ? wrap_cell(x, y, a.voff[i], a.width, a.height) : -1;
+        }       // (the multi-CTA kernel is throughput-bound at the sizes it serves: four draws per agent up front, most
+                         // of them never used, cost it 25 %; the single-CTA kernel is latency-bound and gains 15 %)
+        mb::DrawStream ds(a.seed, a.epoch, (uint64_t)agent);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pre.draw[k] = ds.next64();
+    }
+}
+
+// _randbelow on the prefetched draws, going on with the stream when they run out (rejections: < 1 in 10^3 activations)
+struct PreDraws {
+    const uint64_t* pre;
+    mb::DrawStream ds;
+    int used;
+    __device__ PreDraws(const EpsArgs& a, uint32_t agent, const uint64_t* p, bool prefetched)
+        : pre(p), ds(a.seed, a.epoch, (uint64_t)agent), used(prefetched ? 0 : 5) {}
+    __device__ __forceinline__ uint64_t next64() {
+        if (used < 4) return pre[used++];
+        if (used == 4) { ds.seek(4u); ++used; }
+        return ds.next64();
+    }
+    __device__ __forceinline__ uint64_t randbelow(uint64_t n) {
+        const int k = 64 - __clzll((long long)n);
+        uint64_t r = next64() >> (64 - k);
+        while (r >= n) r = next64() >> (64 - k);
+        return r;
+    }
+};
+
+template <bool kShared>
+__device__ __forceinline__ void act_warp_s(const EpsArgs& a, uint32_t agent, int p, int x, int y, int lane, const PreAct& pre) {
+    const bool cop = pre.cop;
+    const int j = cop ? 0 : ld_live<kShared>(a.jail + agent);   // (issued together with the neighbourhood loads: one round trip)
+    // the neighbourhood: empty cells, cops, active citizens -- counted per lane (three 10-bit fields) and summed by shuffles
+    unsigned packed = 0u;
+    int32_t w0[kPer];
+    int c0[kPer];
+    for (int blk = 0; blk * kBlock < a.nv; ++blk) {
+        int32_t w[kPer];
+        int c[kPer];
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+            if (kShared && blk == 0) {
+                c[q] = pre.c0[q];
+            } else {
+                const int i = blk * kBlock + q * 32 + lane;
+                c[q] = i < a.nv ? wrap_cell(x, y, kShared ? a.voff[i] : __ldg(a.voff + i), a.width, a.height) : -1;
+            }
+            w[q] = c[q] >= 0 ? ld_live<kShared>(a.occ + c[q]) : 0;
+        }
+        if (blk == 0 && j != 0) {                       // agents.py:70-72: in jail, nothing else happens
+            if (lane == 0) st_live<kShared>(a.jail + agent, j - 1);
+            return;
+        }
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+            const bool v = c[q] >= 0;
+            packed += (v && w[q] < 0 ? 1u : 0u) + (v && w[q] >= 0 && (w[q] & 2) ? 1u << 10 : 0u) +
+                      (v && w[q] >= 0 && (w[q] & 3) == 1 ? 1u << 20 : 0u);
+            if (blk == 0) { w0[q] = w[q]; c0[q] = c[q]; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) packed += __shfl_xor_sync(0xffffffffu, packed, o);   // (<= 1024 cells per field)
+    const int nempty = (int)(packed & 0x3ffu), ncops = (int)((packed >> 10) & 0x3ffu), nactive = (int)(packed >> 20);
+    PreDraws ds(a, agent, pre.draw, kShared);
+    int32_t me = (int32_t)(agent << 2) | (cop ? 2 : 0);
+    if (!cop) {
+        // agents.py:86-103 (the citizen counts herself among the actives)
+        const double q = (double)ncops / (double)(nactive + 1);
+        const int m = __double2int_rn(q);               // round-half-even, like Python's round()
+        const double prob = kShared ? a.ptab[m] : __ldg(a.ptab + m);
+        const double net_risk = __dmul_rn(pre.risk_aversion, prob);
+        const bool active = __dsub_rn(pre.grievance, net_risk) > a.threshold;
+        me |= active ? 1 : 0;
+        if (lane == 0) {
+            a.arrest_probability[agent] = prob;
+            a.state[agent] = active ? kActive : kQuiet;
+            st_live<kShared>(a.occ + p, me);            // (rewritten below if she moves)
+        }
+    } else if (nactive > 0) {
+        // agents.py:130-138
+        const int pick = (int)ds.randbelow((uint64_t)nactive);
+        int32_t w = 0;
+        const int c = select_kth_s<false, kShared>(a, x, y, pick, lane, w0, c0, &w);
+        const int32_t sentence = (int32_t)ds.randbelow((uint64_t)a.max_jail_term + 1ull);   // randint(0, max_jail_term)
+        if (lane == 0) {
+            const uint32_t arrestee = (uint32_t)w >> 2;
+            st_live<kShared>(a.jail + arrestee, sentence);
+            a.state[arrestee] = kArrested;
+            st_live<kShared>(a.occ + c, w & ~1);        // no longer active
+        }
+    }
+    if (a.movement && nempty > 0) {                     // agents.py:22-26
+        const int pick = (int)ds.randbelow((uint64_t)nempty);
+        int32_t w = 0;
+        const int dest = select_kth_s<true, kShared>(a, x, y, pick, lane, w0, c0, &w);
+        if (lane == 0) {
+            st_live<kShared>(a.occ + p, -1);
+            st_live<kShared>(a.occ + dest, me);
+            a.cell[agent] = dest;
+        }
+    }
+}
+
+// ---- small grids: ONE CTA, the live words in shared memory -----------------------------------------------------------------
+// A 40 x 40 grid (the reference's default) has ~700 dependency levels whatever the machine; with the occupancy words, the
+// pending ranks and the jail sentences in shared memory a level costs shared-memory latencies instead of L2 round trips and
+// device-scope fences (1.5 ms -> see DESIGN.md section 4).  32 warps work on 32 consecutive ranks: more would only wait.
+constexpr int kSmallThreads = 1024;
+constexpr int kSmallWords = 28000;        // 2 ncells + n words of dynamic shared memory at most (a 100 x 100 grid; beyond, the
+                                          // 32 warps of one CTA are fewer than the agents that could act at once)
+constexpr int kSmallOffsets = 1024, kSmallWait = 4096;   // static tables: neighbourhood, dependency range
+
+template <int kWaitPer>
+__global__ void __launch_bounds__(kSmallThreads, 1)
+eps_chain_small(EpsArgs a, EpsWs ws) {
+    extern __shared__ int32_t sm_words[];
+    __shared__ unsigned s_ticket, s_status;
+    __shared__ short2 s_voff[kSmallOffsets], s_woff[kSmallWait];
+    __shared__ double s_ptab[kSmallOffsets + 1];
+    const int ncells = a.width * a.height;
+    int32_t* occ_s = sm_words;
+    uint32_t* pend_s = reinterpret_cast<uint32_t*>(sm_words + ncells);
+    int32_t* jail_s = sm_words + 2 * ncells;
+    for (int c = threadIdx.x; c < ncells; c += kSmallThreads) { occ_s[c] = a.occ[c]; pend_s[c] = ws.rank_at[c]; }
+    for (int64_t i = threadIdx.x; i < a.n; i += kSmallThreads) jail_s[i] = a.jail[i];
+    for (int i = threadIdx.x; i < a.nv; i += kSmallThreads) s_voff[i] = a.voff[i];
+    for (int i = threadIdx.x; i <= a.nv; i += kSmallThreads) s_ptab[i] = a.ptab[i];
+    for (int i = threadIdx.x; i < a.nw; i += kSmallThreads) s_woff[i] = a.woff[i];
+    if (threadIdx.x == 0) { s_ticket = 0u; s_status = 0u; }
+    __syncthreads();
+    EpsArgs b = a;
+    b.occ = occ_s;
+    b.jail = jail_s;
+    b.voff = s_voff;      // (generic pointers: act_warp reads the tables with plain loads when kShared)
+    b.ptab = s_ptab;
+    const int lane = threadIdx.x & 31;
+    while (true) {
+        unsigned r = 0;
+        if (lane == 0) r = atomicAdd(&s_ticket, 1u);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if ((int64_t)r >= a.n) break;
+        const uint32_t agent = ws.order[r];
+        const int p = a.cell[agent];                    // its own cell: nobody else moves it
+        const int x = p / a.height, y = p - x * a.height;
+        PreAct pre;
+        pre_act<true>(b, agent, x, y, lane, pre);
+        bool bad = false;
+        for (int i0 = 0; i0 < a.nw && !bad; i0 += 32 * kWaitPer) {
+            int wc[kWaitPer];
+            unsigned pend = 0u;
+#pragma unroll
+            for (int q = 0; q < kWaitPer; ++q) {
+                const int i = i0 + q * 32 + lane;
+                wc[q] = 0;
+                if (i < a.nw) {
+                    wc[q] = wrap_cell(x, y, s_woff[i], a.width, a.height);
+                    pend |= 1u << q;
+                }
+            }
+            unsigned spins = 0u;
+            while (true) {
+#pragma unroll
+                for (int q = 0; q < kWaitPer; ++q)
+                    if (((pend >> q) & 1u) && *reinterpret_cast<volatile uint32_t*>(pend_s + wc[q]) >= r) pend &= ~(1u << q);
+                if (!__any_sync(0xffffffffu, pend != 0u)) break;
+                if (++spins > kSpinLimit) { bad = true; break; }
+                __nanosleep(kPollSleepNs);
+            }
+        }
+        __threadfence_block();                          // their writes, before this warp's reads
+        __syncwarp();
+        if (!bad) act_warp_s<true>(b, agent, p, x, y, lane, pre);
+        __syncwarp();
+        if (lane == 0) {
+            if (bad) s_status = 1u;
+            __threadfence_block();                      // my writes, before my flag
+            *reinterpret_cast<volatile uint32_t*>(pend_s + p) = kNoRank;
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < ncells; c += kSmallThreads) a.occ[c] = occ_s[c];
+    for (int64_t i = threadIdx.x; i < a.n; i += kSmallThreads) a.jail[i] = jail_s[i];
+    if (threadIdx.x == 0 && s_status) ws.counters[1] = s_status;
+}
+
 __global__ void eps_counts(const uint8_t* __restrict__ kind, const uint8_t* __restrict__ state, int64_t n, uint32_t* counters) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int s = (i < n && kind[i] == 0) ? state[i] : 0;
@@ -356,8 +606,27 @@ MB_API int mb_epstein_step(int32_t* occ, int32_t* cell, const uint8_t* kind, uin
         batch = e ? atoi(e) : 1;
         if (batch < 1 || batch > 64) batch = 1;
     }
-    if (nw > 256) eps_chain<16><<<(unsigned)ctas, kThreads, 0, stream>>>(a, ws, batch);
-    else eps_chain<8><<<(unsigned)ctas, kThreads, 0, stream>>>(a, ws, batch);
+    static int small_ok = -1;   // MB_EPSTEIN_SMALL=0 keeps every grid on the multi-CTA kernel (cross-checks)
+    if (small_ok < 0) {
+        const char* e = getenv("MB_EPSTEIN_SMALL");
+        small_ok = e ? atoi(e) : 1;
+    }
+    const int64_t words = 2 * width * height + n;
+    if (small_ok && words <= kSmallWords && nv <= kSmallOffsets && nw <= kSmallWait) {
+        const int smem = (int)(words * 4);
+        static bool attr_set = false;
+        if (!attr_set) {
+            if ((rc = mb::check_cuda(cudaFuncSetAttribute(eps_chain_small<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallWords * 4), "cudaFuncSetAttribute"))) return rc;
+            if ((rc = mb::check_cuda(cudaFuncSetAttribute(eps_chain_small<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallWords * 4), "cudaFuncSetAttribute"))) return rc;
+            attr_set = true;
+        }
+        if (nw > 256) eps_chain_small<16><<<1, kSmallThreads, smem, stream>>>(a, ws);
+        else eps_chain_small<8><<<1, kSmallThreads, smem, stream>>>(a, ws);
+    } else if (nw > 256) {
+        eps_chain<16><<<(unsigned)ctas, kThreads, 0, stream>>>(a, ws, batch);
+    } else {
+        eps_chain<8><<<(unsigned)ctas, kThreads, 0, stream>>>(a, ws, batch);
+    }
     if (counts_dev != nullptr) {
         eps_counts<<<(unsigned)mb::ceil_div(n, 256), 256, 0, stream>>>(kind, state, n, ws.counters);
         if ((rc = mb::check_cuda(cudaMemcpyAsync(counts_dev, ws.counters + 1, 4 * 4, cudaMemcpyDeviceToDevice, stream), "copy"))) return rc;
