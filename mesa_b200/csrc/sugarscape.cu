@@ -291,7 +291,6 @@ sug_chain(SugArgs a, SugWs ws, const uint32_t* __restrict__ order) {
                 }
                 if (!__any_sync(0xffffffffu, pend != 0u)) break;
                 if (++spins > kSpinLimit) { bad = true; break; }
-                __nanosleep(100);                       // a spinning warp takes issue slots from the warp it waits for
             }
         }
         fence_acq_rel();
@@ -398,7 +397,6 @@ sug_trade_chain(SugArgs a, SugWs ws, const uint32_t* __restrict__ order, const u
                 }
                 if (!__any_sync(0xffffffffu, pend != 0u)) break;
                 if (++spins > kSpinLimit) { bad = true; break; }
-                __nanosleep(100);                       // a spinning warp takes issue slots from the warp it waits for
             }
         }
         fence_acq_rel();
