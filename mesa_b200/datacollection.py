@@ -31,6 +31,33 @@ def _to_host(value):
     return deepcopy(value)
 
 
+class RaggedColumn:
+    """A per-agent column of LISTS (e.g. the reference's `trade_partners`, sugarscape_g1mt/agents.py:201) kept as a CSR pair
+    -- `offsets` [n + 1] and the flat `values` -- until somebody asks for the DataFrame: an agent reporter may return one
+    instead of n Python lists per collection."""
+
+    def __init__(self, offsets: np.ndarray, values: np.ndarray):
+        self.offsets = np.asarray(offsets, dtype=np.int64)
+        self.values = np.asarray(values)
+        if self.offsets.ndim != 1 or len(self.offsets) < 1 or int(self.offsets[-1]) != len(self.values):
+            raise ValueError("RaggedColumn: offsets must be [n + 1] with offsets[-1] == len(values)")
+        self.shape = (len(self.offsets) - 1,)
+        self.ndim = 1
+
+    def __len__(self) -> int:
+        return self.shape[0]
+
+    def copy(self) -> "RaggedColumn":
+        return RaggedColumn(self.offsets.copy(), self.values.copy())
+
+    def materialize(self) -> np.ndarray:
+        """The object array of per-agent lists the reference would have recorded."""
+        out = np.empty(len(self), dtype=object)
+        flat = self.values.tolist()
+        out[:] = [flat[lo:hi] for lo, hi in zip(self.offsets[:-1].tolist(), self.offsets[1:].tolist())]
+        return out
+
+
 class TableMissingException(KeyError):
     """mesa/datacollection.py: raised when a table name is not part of the collector."""
 
@@ -91,7 +118,8 @@ class DeviceDataCollector:
             value = agents.get(reporter)   # raises AttributeError for an unknown column, like the reference's getattr
         else:
             value = reporter(agents)
-        value = value.detach().cpu().numpy() if isinstance(value, torch.Tensor) else np.asarray(value)
+        if not isinstance(value, RaggedColumn):
+            value = value.detach().cpu().numpy() if isinstance(value, torch.Tensor) else np.asarray(value)
         if value.shape[:1] != (len(agents),):
             raise ValueError(f"Agent reporter '{name}' must return one value per agent ({len(agents)}), got shape {value.shape}")
         return value.copy()
@@ -116,7 +144,7 @@ class DeviceDataCollector:
             # populations (registration order), one bulk column copy per population and reporter
             sets = self._populations(model)
             ids = np.concatenate([a.unique_ids_host() for a in sets]) if sets else np.zeros(0, np.int64)
-            cols = [np.concatenate([self._column(a, n, r) for a in sets]) if sets else np.zeros(0)
+            cols = [self._concat([self._column(a, n, r) for a in sets]) if sets else np.zeros(0)
                     for n, r in self.agent_reporters.items()]
             self._agent_records[model.time] = (ids, cols)
         if self.agenttype_reporters:
@@ -132,8 +160,15 @@ class DeviceDataCollector:
                     raise ValueError(f"Agent type {agent_type} is not recognized as an Agent type in the model or Agent "
                                      f"subclass. Use an Agent (sub)class, like {[a.agent_type for a in self._populations(model)]}.")
                 ids = np.concatenate([a.unique_ids_host() for a in sets])
-                cols = [np.concatenate([self._column(a, n, r) for a in sets]) for n, r in reps.items()]
+                cols = [self._concat([self._column(a, n, r) for a in sets]) for n, r in reps.items()]
                 self._agenttype_records[model.time][agent_type] = (ids, cols)
+
+    @staticmethod
+    def _concat(parts: list):
+        """The columns of several populations in a row; a single ragged column stays lazy."""
+        if len(parts) == 1:
+            return parts[0]
+        return np.concatenate([p.materialize() if isinstance(p, RaggedColumn) else p for p in parts])
 
     @staticmethod
     def _populations(model) -> list:
@@ -175,7 +210,7 @@ class DeviceDataCollector:
             steps.append(np.full(len(agent_ids), time))
             ids.append(agent_ids)
             for k, v in enumerate(values):
-                cols[k].append(v)
+                cols[k].append(v.materialize() if isinstance(v, RaggedColumn) else v)
         data = {"Step": np.concatenate(steps) if steps else [], "AgentID": np.concatenate(ids) if ids else []}
         for n, c in zip(names, cols):
             data[n] = list(np.concatenate(c)) if c and c[0].ndim > 1 else (np.concatenate(c) if c else [])

@@ -130,7 +130,12 @@ def _report_price(m):
 
 
 def _report_network(agents):
-    return agents.model.trade_partners()
+    """agent reporter "Trade Network" (model.py:70): the partner lists as a lazy ragged column (built when the DataFrame is)."""
+    from ..datacollection import RaggedColumn
+
+    m = agents.model
+    counts = np.bincount(m._trade_rows, minlength=len(agents)) if len(m._trade_rows) else np.zeros(len(agents), dtype=np.int64)
+    return RaggedColumn(np.concatenate([[0], np.cumsum(counts)]), m._trades[1])
 
 
 class SugarscapeG1mt(DeviceModel):

@@ -56,6 +56,14 @@ def test_sugarscape_matches_the_reference_trajectory(name):
         assert np.array_equal(m._count.cpu().numpy(), count) and np.array_equal(m.grid.empty.cpu().numpy().reshape(-1), count == 0)
     counts = m.datacollector.get_model_vars_dataframe().to_numpy()
     assert np.array_equal(counts, g["counts"])              # #Traders, Trade Volume, Price (geometric mean) as the reference's collector saw them
+    if "trades_1" in g:     # the agent reporter "Trade Network" (model.py:70): per-trader partner lists of the last step
+        last = int(g["steps"])
+        frame = m.datacollector.get_agent_vars_dataframe()
+        got = frame.xs(float(last), level="Step")["Trade Network"]
+        want = {int(i): [] for i in g[f"id_{last}"]}
+        for t, p, _ in g[f"trades_{last}"]:
+            want[int(t)].append(int(p))
+        assert {int(k): list(v) for k, v in got.items()} == want
 
 
 @pytest.mark.parametrize("name", FIXTURES)
