@@ -214,12 +214,14 @@ int mb_reloc_apply(const void* shard, int phase, int64_t nmovers, uint32_t* agen
  * happiness (the model's initial do("assign_state")).  agent_cell [nagents] and empty_layer [rows, cols] (the grid's
  * implicit "empty" layer, grid.py:128) are optional.  min_similar_host as in mb_schelling_happy_i8.  nsteps > 1 (with
  * relocate != 0) runs that many model steps inside the one launch -- `model.run_for(n)`, mesa/model.py:395-402 -- with the
- * shuffle numbers epoch, epoch + 1, ...; out4 then describes the last step, a failed step ends the run. */
+ * shuffle numbers epoch, epoch + 1, ...; out4 then describes the last step, a failed step ends the run.  happy_current != 0:
+ * the caller guarantees that `happy` on entry is the evaluation of `type` (true inside a model run); a step without movers
+ * then changes nothing and only reads the layers (a settled model steps at the cost of that read). */
 int mb_schelling_small_max_cells(void);
 int mb_schelling_small_workspace_bytes(int64_t max_movers, size_t* out);
 int mb_schelling_step_small(int8_t* type, uint8_t* happy, uint32_t* agent_id, uint32_t* agent_cell, uint8_t* empty_layer,
                             int64_t rows, int64_t cols, int radius, int torus, const uint8_t* min_similar_host,
-                            uint64_t seed, uint32_t epoch, int relocate, int nsteps, void* workspace,
+                            uint64_t seed, uint32_t epoch, int relocate, int nsteps, int happy_current, void* workspace,
                             size_t workspace_bytes, int64_t max_movers, uint64_t* out4, mb_stream_t stream);
 
 /* ---- stable LSD radix sort of (key, uint32) pairs (cell lists; no reference counterpart: the

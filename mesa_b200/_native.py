@@ -83,7 +83,7 @@ SIGNATURES: dict[str, tuple] = {
     "mb_schelling_small_max_cells": (c_int, []),
     "mb_schelling_small_workspace_bytes": (c_int, [c_int64, ctypes.POINTER(ctypes.c_size_t)]),
     "mb_schelling_step_small": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, _P, c_uint64, c_uint32, c_int,
-                                        c_int, _P, ctypes.c_size_t, c_int64, _P, _S]),
+                                        c_int, c_int, _P, ctypes.c_size_t, c_int64, _P, _S]),
     # radix sort
     "mb_sort_workspace_bytes": (c_int, [c_int64, ctypes.POINTER(ctypes.c_size_t)]),
     "mb_sort_pairs_u32": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, _P, ctypes.c_size_t,

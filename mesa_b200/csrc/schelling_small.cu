@@ -156,7 +156,7 @@ __device__ __forceinline__ unsigned assign_state_padded(int8_t* __restrict__ tl,
 __global__ void __launch_bounds__(kThreads, 1)
 schelling_small_step(int8_t* __restrict__ type, uint8_t* __restrict__ happy, uint32_t* __restrict__ agent_id,
                      uint32_t* __restrict__ agent_cell, uint8_t* __restrict__ empty_layer, int rows, int cols, int radius,
-                     int torus, SmallRule rule, uint64_t seed, uint32_t epoch0, int relocate, int nsteps, SmallWs ws, int cap,
+                     int torus, SmallRule rule, uint64_t seed, uint32_t epoch0, int relocate, int nsteps, int happy_current, SmallWs ws, int cap,
                      unsigned long long* __restrict__ out /* [0] model.happy [1] movers [2] status [3] passes */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Slot* slots = reinterpret_cast<Slot*>(smem_raw);
@@ -189,19 +189,32 @@ schelling_small_step(int8_t* __restrict__ type, uint8_t* __restrict__ happy, uin
             a_reg[k] = in ? agent_id[c] : 0u;
         }
         // a warp reserves the slots of ALL its movers with one atomic (one per slice and warp was 832 atomics on two words)
-        unsigned wmovers = 0, wocc = 0;
+        unsigned wmovers = 0, wocc = 0, whappy = 0;
 #pragma unroll
         for (int k = 0; k < kSlices; ++k) {
             const int t = t_reg[k];
             wmovers += __popc(__ballot_sync(0xffffffffu, t >= 0 && h_reg[k] == 0));
             wocc += __popc(__ballot_sync(0xffffffffu, t >= 0));
+            whappy += __popc(__ballot_sync(0xffffffffu, t >= 0 && h_reg[k] != 0));
         }
         unsigned next = 0;
         if ((tid & 31) == 0) {
             if (wmovers) next = atomicAdd(&s_nmovers, wmovers);
             if (wocc) atomicAdd(&s_nocc, wocc);
+            if (whappy) atomicAdd(&s_happy, whappy);
         }
         next = __shfl_sync(0xffffffffu, next, 0);
+        // A step without movers changes nothing: if the happy layer on entry IS the evaluation of the type layer (always
+        // inside a model run: the previous step's do("assign_state") wrote it), the step is over -- a settled model then
+        // costs the load of its layers per step instead of a slot table and a stencil (BASELINE config 1 settles after ~30
+        // of its 100 steps).
+        __syncthreads();
+        if (s_nmovers == 0u && (step > 0 || happy_current)) {
+            if (tid == 0) { out[0] = s_happy; out[1] = 0ull; out[2] = 0ull; out[3] = 0ull; }
+            continue;
+        }
+        __syncthreads();
+        if (tid == 0) s_happy = 0u;     // (recounted by the stencil below)
 #pragma unroll
         for (int k = 0; k < kSlices; ++k) {
             const int c = k * kThreads + tid;
@@ -409,12 +422,14 @@ MB_API int mb_schelling_small_workspace_bytes(int64_t max_movers, size_t* out) {
 // One whole model step of a grid of at most mb_schelling_small_max_cells() cells in ONE launch, nothing read back:
 // relocate != 0: shuffle_do("step") of the agents that are unhappy according to the `happy` layer, then (always)
 // do("assign_state"); nsteps > 1 repeats that with shuffle numbers epoch, epoch + 1, ... inside the same launch
-// (model.run_for(n): out4 then describes the LAST step; a failed step ends the run).  min_similar_host as in mb_schelling_happy_i8.  agent_cell / empty_layer optional.  out: device
+// (model.run_for(n): out4 then describes the LAST step; a failed step ends the run).  happy_current != 0: the caller
+// guarantees that the `happy` layer on entry is the evaluation of the `type` layer (true inside a model run) -- a step
+// without movers then changes nothing and costs only the reading of the layers.  min_similar_host as in mb_schelling_happy_i8.  agent_cell / empty_layer optional.  out: device
 // uint64[4] = {model.happy, movers, status (0 ok, 1 grid completely full -> ValueError, 2 workspace too small,
 // 3 too many fallback movers, 4 no convergence), passes}.  A torus with a dimension < 2*radius+1 is rejected.
 MB_API int mb_schelling_step_small(int8_t* type, uint8_t* happy, uint32_t* agent_id, uint32_t* agent_cell, uint8_t* empty_layer,
                                    int64_t rows, int64_t cols, int radius, int torus, const uint8_t* min_similar_host,
-                                   uint64_t seed, uint32_t epoch, int relocate, int nsteps, void* workspace,
+                                   uint64_t seed, uint32_t epoch, int relocate, int nsteps, int happy_current, void* workspace,
                                    size_t workspace_bytes, int64_t max_movers, uint64_t* out4, cudaStream_t stream) {
     MB_REQUIRE(rows > 0 && cols > 0 && rows * cols <= kMaxCells, "mb_schelling_step_small: the grid must have 1..12800 cells");
     MB_REQUIRE(radius >= 1 && radius <= 7, "mb_schelling_step_small: radius must be 1..7");
@@ -442,7 +457,7 @@ MB_API int mb_schelling_step_small(int8_t* type, uint8_t* happy, uint32_t* agent
         attr_set = true;
     }
     schelling_small_step<<<1, kThreads, smem, stream>>>(type, happy, agent_id, agent_cell, empty_layer, (int)rows, (int)cols,
-                                                       radius, torus, rule, seed, epoch, relocate, nsteps, ws, (int)max_movers,
+                                                       radius, torus, rule, seed, epoch, relocate, nsteps, happy_current, ws, (int)max_movers,
                                                        (unsigned long long*)out4);
     MB_LAUNCH_CHECK("mb_schelling_step_small");
     return MB_OK;

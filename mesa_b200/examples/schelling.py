@@ -43,10 +43,11 @@ def _assign_state(agents: DeviceAgentSet, **_):
     if m._small is not None:
         # small grid: ONE launch for the pending shuffle_do("step") (if any) + this do("assign_state"), nothing read back
         epoch, m._pending_epoch = m._pending_epoch, None
-        layers = m.grid.property_layers
-        m._small.step(layers["type"], layers["happy"], layers["agent_id"], m.philox_seed, epoch or 0,
-                      agent_cell=dict.__getitem__(agents.columns, "cell"), empty_layer=layers["empty"],
-                      relocate=epoch is not None)
+        layers = m.grid.property_layers      # (plain dict reads: an access through the hooks marks the layers as observed)
+        m._small.step(dict.__getitem__(layers, "type"), dict.__getitem__(layers, "happy"), dict.__getitem__(layers, "agent_id"),
+                      m.philox_seed, epoch or 0, agent_cell=dict.__getitem__(agents.columns, "cell"),
+                      empty_layer=dict.__getitem__(layers, "empty"), relocate=epoch is not None, happy_current=m._happy_current)
+        m._happy_current = True      # the happy layer now IS the evaluation of the type layer (until somebody writes a layer)
         m._last_small = m._last_small or epoch is not None
         return
     g = m.grid
@@ -90,6 +91,7 @@ class Schelling(DeviceModel):
         if isinstance(scenario, type):
             scenario = scenario()
         self._small = self._pending_epoch = None
+        self._happy_current = False
         self._last_small = False
         self._running, self._running_pending = True, False
         super().__init__(scenario=scenario)
@@ -136,7 +138,7 @@ class Schelling(DeviceModel):
             self._small = ops.SchellingSmallStep(types, n, self.homophily, self.radius, self.grid.torus)
             self._happy_count = self._small.out[0:1]
             for name in ("type", "happy", "agent_id", "empty"):
-                self.grid.property_layers.hooks[name] = self._flush_pending
+                self.grid.property_layers.hooks[name] = self._layer_observed
         cols = _Columns(self, cell=cells.to(torch.int32), type=flat[cells].clone())
         self.agents = DeviceAgentSet(self, SchellingAgent, n, cols, self.random, resizable=False)
         self.grid.cell_agents = self._cell_agents
@@ -164,12 +166,19 @@ class Schelling(DeviceModel):
         self._last = ops.schelling_relocate(g.type, g.happy, g.agent_id, self._ws, self.philox_seed, epoch,
                                             agent_cell=dict.__getitem__(self.agents.columns, "cell"))
 
+    def _layer_observed(self) -> None:
+        """Somebody outside the step takes a layer tensor (and may write into it): a deferred relocation is run first, and
+        the happy layer no longer counts as the evaluation of the type layer (a step without movers re-evaluates it)."""
+        self._flush_pending()
+        self._happy_current = False
+
     def _flush_pending(self) -> None:
         """A shuffle_do("step") that was deferred for fusion and is being observed before its do("assign_state"): run it
         now through the multi-launch path (same result)."""
         if self._pending_epoch is not None:
             epoch, self._pending_epoch = self._pending_epoch, None
             self._relocate(epoch)
+            self._happy_current = False      # agents moved: the happy layer is stale until the next assign_state
 
     @property
     def happy(self) -> int:
@@ -213,7 +222,7 @@ class Schelling(DeviceModel):
         layers = self.grid.property_layers
         self._small.step(dict.__getitem__(layers, "type"), dict.__getitem__(layers, "happy"), dict.__getitem__(layers, "agent_id"),
                          self.philox_seed, epoch0, agent_cell=dict.__getitem__(self.agents.columns, "cell"),
-                         empty_layer=dict.__getitem__(layers, "empty"), relocate=True, nsteps=k)
+                         empty_layer=dict.__getitem__(layers, "empty"), relocate=True, nsteps=k, happy_current=True)
         self._last_small = True
         self.steps += k
         self.time = float(until)

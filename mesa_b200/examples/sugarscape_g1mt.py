@@ -189,7 +189,8 @@ class SugarscapeG1mt(DeviceModel):
         self._count = torch.zeros(self.width * self.height, dtype=torch.int32, device=dev)
         self._status = torch.zeros(3, dtype=torch.int32, device=dev)
         mmax = int(max(cols["metabolism_sugar"].max().item(), cols["metabolism_spice"].max().item())) if n else 1
-        self._pow_m, self._pow_x = mmax, int(pow_table_amounts)
+        # (the table is mmax^2 x amounts doubles from mmax^2 x amounts libm calls: metabolisms beyond 8 use CUDA's pow and count)
+        self._pow_m, self._pow_x = min(mmax, 8), int(pow_table_amounts)
         self._pow = torch.as_tensor(welfare_power_table(self._pow_m, self._pow_x)).to(dev).contiguous()
         self.inexact_welfares = 0     # pow calls that missed the table so far (amounts >= pow_table_amounts): CUDA pow, <= 2 ulp
         self._ws = None

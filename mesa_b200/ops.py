@@ -302,7 +302,7 @@ class SchellingSmallStep:
         return 0 < ncells <= N.lib().mb_schelling_small_max_cells()
 
     def step(self, type_layer, happy, agent_id, seed: int, epoch: int, agent_cell=None, empty_layer=None,
-             relocate: bool = True, nsteps: int = 1) -> torch.Tensor:
+             relocate: bool = True, nsteps: int = 1, happy_current: bool = False) -> torch.Tensor:
         # A 100 x 100 step is ~10 us of kernel: the host side of the call must not cost more.  The buffers of a model do
         # not change between steps, so their addresses are bound once (keyed on the tensors' identity and storage) and a
         # step only passes (seed, epoch, relocate) and the current stream.
@@ -321,11 +321,13 @@ class SchellingSmallStep:
         seed, epoch, relocate = int(seed) & 0xFFFFFFFFFFFFFFFF, int(epoch) & 0xFFFFFFFF, int(bool(relocate))
         if torch.cuda.current_device() == index:
             rc = fn(key[0], key[1], key[2], key[3], key[4], self.rows, self.cols, self.radius, int(self.torus), table, seed, epoch,
-                    relocate, int(nsteps), buf, self.nbytes, self.max_movers, out, torch.cuda.current_stream().cuda_stream)
+                    relocate, int(nsteps), int(bool(happy_current)), buf, self.nbytes, self.max_movers, out,
+                    torch.cuda.current_stream().cuda_stream)
         else:
             with torch.cuda.device(index):
                 rc = fn(key[0], key[1], key[2], key[3], key[4], self.rows, self.cols, self.radius, int(self.torus), table, seed,
-                        epoch, relocate, int(nsteps), buf, self.nbytes, self.max_movers, out, torch.cuda.current_stream().cuda_stream)
+                        epoch, relocate, int(nsteps), int(bool(happy_current)), buf, self.nbytes, self.max_movers, out,
+                    torch.cuda.current_stream().cuda_stream)
         if rc:
             N.check(rc)
         return self.out

@@ -333,3 +333,30 @@ def test_run_for_in_one_launch_follows_the_reference_trajectory():
         if done in set(g["full_steps"].tolist()):
             assert np.array_equal(m.agents.get("cell").cpu().numpy().astype(np.int64), g[f"cell_{done}"]), done
     assert m.running == (m.happy < len(m.agents))
+
+
+def test_settled_steps_are_skipped_only_while_the_layers_are_untouched():
+    """A step without movers returns at once when the happy layer is known to be current; writing into a layer from outside
+    (any access through grid.property_layers / grid.<layer>) makes the next step evaluate again."""
+    from mesa_b200.examples import Schelling, SchellingScenario
+
+    sc = SchellingScenario(width=30, height=30, density=0.6, homophily=0.3, radius=1, rng=2)
+    a, b = Schelling(sc, collect=False, fused=True), Schelling(sc, collect=False, fused=False)
+    for _ in range(60):
+        a.step()
+        b.step()
+        if a.last_movers == 0:
+            break
+    assert a.last_movers == 0 and b.last_movers == 0 and a.happy == b.happy == len(a.agents)
+    a.run_for(5)                                     # five settled steps in one launch: nothing changes
+    b.run_for(5)
+    assert a.happy == b.happy and torch.equal(a.grid.type, b.grid.type)
+    for m in (a, b):                                 # an outside write: flip the type of every agent in the first rows
+        t = m.grid.type
+        t[:6] = torch.where(t[:6] >= 0, 1 - t[:6], t[:6])
+    for _ in range(3):
+        a.step()
+        b.step()
+        assert a.happy == b.happy and a.last_movers == b.last_movers
+        assert torch.equal(a.grid.type, b.grid.type) and torch.equal(a.grid.happy, b.grid.happy)
+    assert a.time == b.time
