@@ -307,3 +307,54 @@ def test_sugarscape_from_a_seed(replay, seed, params):
             assert np.array_equal(o.spice, np.array([a.spice for a in m.agents], dtype=np.float64)), step
             assert [list(a.trade_partners) for a in m.agents] == partners and [list(a.prices) for a in m.agents] == prices, step
     m.random.replay = False
+
+
+def test_neighbourhood_order_properties_the_dependency_graph_kernels_rely_on(replay):
+    """csrc/epstein.cu / csrc/sugarscape.cu take a cell's radius-r neighbourhood from ONE offset table.  That is only right
+    because, on the live reference grids, (1) a torus neighbourhood is translation invariant, (2) on a CLAMPED von Neumann
+    grid it is the interior order with the absent cells dropped, (3) the radius-r list is a prefix of the radius-(r+1) list.
+    (On clamped Moore grids (2) does NOT hold -- the Sugarscape model is von Neumann, the Epstein model a torus.)"""
+    import random as _r
+
+    from mesa.discrete_space import OrthogonalMooreGrid, OrthogonalVonNeumannGrid
+
+    import torch  # noqa: F401  (mesa_b200.examples import torch)
+    from mesa_b200.examples.sugarscape_g1mt import von_neumann_bfs_offsets
+    from oracle.epstein import neighborhood_offsets
+
+    def offsets(grid, x, y, r, wrap=None):
+        out = []
+        for c in grid._cells[(x, y)].get_neighborhood(radius=r):
+            dx, dy = c.coordinate[0] - x, c.coordinate[1] - y
+            if wrap:
+                dx, dy = (dx + wrap[0] // 2) % wrap[0] - wrap[0] // 2, (dy + wrap[1] // 2) % wrap[1] - wrap[1] // 2
+            out.append((dx, dy))
+        return out
+
+    for moore, klass in ((False, OrthogonalVonNeumannGrid), (True, OrthogonalMooreGrid)):
+        torus = klass((23, 19), torus=True, random=_r.Random(1))
+        for r in (1, 2, 4, 7):
+            want = neighborhood_offsets(moore, r)
+            for x, y in ((0, 0), (11, 9), (22, 18), (3, 17)):
+                assert offsets(torus, x, y, r, wrap=(23, 19)) == want, (moore, r, x, y)          # (1)
+            if r > 1:
+                assert want[:len(neighborhood_offsets(moore, r - 1))] == neighborhood_offsets(moore, r - 1)   # (3)
+    clamped = OrthogonalVonNeumannGrid((17, 21), torus=False, random=_r.Random(1))
+    for r in (1, 3, 5, 7):
+        table = [tuple(int(v) for v in o) for o in von_neumann_bfs_offsets(r)]
+        assert table == neighborhood_offsets(False, r)
+        for x in (0, 1, 4, 8, 15, 16):
+            for y in (0, 2, 10, 19, 20):
+                want = [(dx, dy) for dx, dy in table if 0 <= x + dx < 17 and 0 <= y + dy < 21]
+                assert offsets(clamped, x, y, r) == want, (r, x, y)                              # (2)
+
+
+def test_welfare_power_table_is_the_host_pow():
+    """sugarscape_g1mt/agents.py:57-70 evaluates `sugar ** (ms / m_total)` on numpy float64 scalars: the table entries are the
+    same bits, and the exact tie that CUDA's pow breaks (28 x 54 = 27 x 56 with equal metabolisms) holds in it."""
+    from mesa_b200.examples.sugarscape_g1mt import welfare_power_table
+
+    t = welfare_power_table(5, 200)
+    for ms, mp, x in ((1, 1, 28), (5, 5, 54), (2, 3, 77), (5, 1, 199), (3, 4, 0), (4, 2, 1)):
+        assert t[ms - 1, mp - 1, x] == np.float64(x) ** (np.int64(ms) / np.int64(ms + mp))
+    assert t[4, 4, 28] * t[4, 4, 54] == t[4, 4, 27] * t[4, 4, 56]
