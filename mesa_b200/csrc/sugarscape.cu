@@ -1,5 +1,5 @@
-// Sugarscape G1MT, the movement phase: regrowth + one shuffle_do("step") of the traders (move / eat / die) in ONE launch,
-// in the reference's sequential semantics.
+// Sugarscape G1MT: regrowth + the traders' shuffle_do("step") (move / eat / die) in ONE launch, and their
+// shuffle_do("trade_with_neighbors") in another, both in the reference's sequential semantics.
 //
 //   mesa/examples/advanced/sugarscape_g1mt/model.py:118-127   sugar / spice regrow by 1 up to the landscape's maximum,
 //                                                             then self.agents.shuffle_do("step")
@@ -7,6 +7,7 @@
 //                       order), Cobb-Douglas welfare of (own + cell) sugar and spice, the cells math.isclose to the best
 //                       welfare, of those the ones within 1 % of the smallest Euclidean distance, random.choice of these
 //   agents.py:264-288   eat: take the cell's sugar and spice, pay the metabolism; die: sugar <= 0 or spice <= 0 -> remove()
+//   agents.py:84-207, 290-301   trade_with_neighbors (second half of this file)
 //
 // The same rank-ordered dependency graph as csrc/epstein.cu: a trader reads (emptiness, sugar, spice) within its own vision
 // and changes its old and new cell, so it depends on an earlier trader only if that one STARTED within vision_a + vision_b
