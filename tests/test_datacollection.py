@@ -114,3 +114,17 @@ def test_schelling_collector_reproduces_reference_datacollector():
     assert np.array_equal(av["AgentID"].to_numpy(dtype=np.int64), g["agent_id"])
     assert np.array_equal(av["agent_type"].to_numpy(dtype=np.int64), g["agent_type"])
     assert m.time == float(g["steps"]) and m.steps == int(g["steps"])
+
+
+def test_ragged_column_is_lazy_and_materialises_to_lists():
+    """datacollection.RaggedColumn: a per-agent column of lists kept as CSR until the DataFrame is built."""
+    from mesa_b200.datacollection import DeviceDataCollector, RaggedColumn
+
+    col = RaggedColumn([0, 2, 2, 5], [7, 8, 1, 2, 3])
+    assert len(col) == 3 and col.shape == (3,) and [list(x) for x in col.materialize()] == [[7, 8], [], [1, 2, 3]]
+    assert col.copy().offsets is not col.offsets
+    with pytest.raises(ValueError):
+        RaggedColumn([0, 2], [1])
+    assert DeviceDataCollector._concat([col]) is col                       # one population: stays lazy
+    both = DeviceDataCollector._concat([col, np.array([[9], [9]], dtype=object).reshape(2, 1)[:, 0]])
+    assert len(both) == 5 and list(both[0]) == [7, 8]

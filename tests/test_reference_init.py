@@ -116,3 +116,27 @@ def test_schelling_vectorised_draws_equal_the_per_cell_loop(density, minority):
             got = ri.schelling_initial_types(b, w, h, density, minority)
             assert got.shape == (w, h) and got.dtype == np.int8 and np.array_equal(got.reshape(-1), want)
             assert a.getstate() == b.getstate()
+
+
+@pytest.mark.parametrize("name", ["epstein_40x40.npz", "epstein_30x22_lively.npz", "epstein_17x19_moore.npz", "epstein_16x16_still.npz"])
+def test_epstein_initial_agents_are_the_reference(name):
+    """epstein_civil_violence/model.py:84-98 + agents.py:55-56 from the fixture's seed: kinds, cells, hardship, risk aversion."""
+    g = np.load(os.path.join(GOLDEN, name))
+    st = ri.epstein_initial_state(random.Random(ri.seed_streams(int(g["mt_seed"]))[1]), int(g["width"]), int(g["height"]),
+                                  float(g["citizen_density"]), float(g["cop_density"]))
+    assert np.array_equal(st["kind"], g["kind"].astype(np.uint8)) and np.array_equal(st["cell"], g["cell_0"])
+    assert np.array_equal(st["hardship"], g["hardship"]) and np.array_equal(st["risk_aversion"], g["risk_aversion"])
+
+
+@pytest.mark.parametrize("name", ["sugarscape_200.npz", "sugarscape_600_crowded.npz", "sugarscape_80_farsighted.npz",
+                                  "sugarscape_200_trade.npz", "sugarscape_500_trade_crowded.npz"])
+def test_sugarscape_initial_traders_are_the_reference(name):
+    """sugarscape_g1mt/model.py:80-116 from the fixture's seed (stdlib stream for the cells, numpy stream for the rest)."""
+    g = np.load(os.path.join(GOLDEN, name))
+    n, emin, emax, mmin, mmax, vmin, vmax = (int(v) for v in g["scenario"])
+    gen, stdlib = ri.seed_streams(int(g["mt_seed"]))
+    st = ri.sugarscape_initial_state(random.Random(stdlib), gen, int(g["width"]) * int(g["height"]), n, emin, emax, mmin, mmax, vmin, vmax)
+    assert np.array_equal(st["cell"], g["cell_0"])
+    assert np.array_equal(st["sugar"], g["sugar_0"]) and np.array_equal(st["spice"], g["spice_0"])
+    assert np.array_equal(st["metabolism_sugar"], g["metabolism_sugar"]) and np.array_equal(st["metabolism_spice"], g["metabolism_spice"])
+    assert np.array_equal(st["vision"], g["vision"])
