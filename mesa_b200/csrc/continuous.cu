@@ -675,7 +675,7 @@ __global__ void boids_seq_ranks(const uint32_t* __restrict__ slots, int64_t n, u
 
 constexpr int kChainThreads = 128;
 
-__global__ void __launch_bounds__(kChainThreads)
+__global__ void __launch_bounds__(kChainThreads, 8)
 boids_seq_chain(const float4* __restrict__ packed, const uint32_t* __restrict__ byrank,
                 const uint32_t* __restrict__ rank, double2* newst, const uint32_t* __restrict__ order,
                 const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end, int64_t n, Geometry g,
